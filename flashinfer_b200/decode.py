@@ -1,0 +1,370 @@
+"""Decode attention: ``single_decode_with_kv_cache`` and ``BatchDecodeWithPagedKVCacheWrapper``.
+
+API parity: reference flashinfer/decode.py:409-604 (single decode), :606-1603 (batch wrapper,
+plan/run, CUDA-graph mode), :1605 (CUDAGraph wrapper), :2897 (fast_decode_plan).
+
+B200-first implementation: one persistent tcgen05 kernel (csrc/attention/decode_sm100.cu) driven by
+a C++ stream-K planner (csrc/runtime/planner.cpp).  There is no backend zoo: CUDA tensors always
+run the sm_100a kernel (and fail loudly when a configuration is not specialised); CPU tensors run
+the fp32 PyTorch oracle.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple, Union
+
+import torch
+
+from . import jit, reference
+from .utils import (
+    check_kv_layout,
+    check_pos_encoding_mode,
+    device_sm_count,
+    dtype_code,
+    paged_kv_strides,
+    stream_ptr,
+    unpack_paged_kv_cache,
+)
+
+_SEG_INTS = 12
+_MERGE_INTS = 8
+_TILE_KV = 128
+_MAX_Q_ROWS = 32
+
+
+def _canon_dtype(dt):
+    if isinstance(dt, str):
+        return getattr(torch, dt)
+    return dt
+
+
+def single_decode_with_kv_cache(
+    q: torch.Tensor,
+    k: torch.Tensor,
+    v: torch.Tensor,
+    kv_layout: str = "NHD",
+    pos_encoding_mode: str = "NONE",
+    use_tensor_cores: bool = False,
+    q_scale: Optional[float] = None,
+    k_scale: Optional[float] = None,
+    v_scale: Optional[float] = None,
+    window_left: int = -1,
+    logits_soft_cap: Optional[float] = None,
+    sm_scale: Optional[float] = None,
+    rope_scale: Optional[float] = None,
+    rope_theta: Optional[float] = None,
+    return_lse: bool = False,
+):
+    """Decode attention for one request: q [Hq, D], k/v [kv_len, Hkv, D] (NHD) or [Hkv, kv_len, D] (HND)."""
+    check_kv_layout(kv_layout)
+    check_pos_encoding_mode(pos_encoding_mode)
+    if pos_encoding_mode != "NONE":
+        raise NotImplementedError("in-kernel RoPE/ALiBi for decode: apply flashinfer_b200.rope first")
+    head_dim = q.shape[-1]
+    if sm_scale is None:
+        sm_scale = 1.0 / math.sqrt(head_dim)
+    if q_scale is not None:
+        sm_scale *= q_scale
+    if k_scale is not None:
+        sm_scale *= k_scale
+    kn = k if kv_layout == "NHD" else k.transpose(0, 1)
+    vn = v if kv_layout == "NHD" else v.transpose(0, 1)
+    if not q.is_cuda:
+        o, lse = reference.attention_ref(
+            q.unsqueeze(0), kn, vn, False, sm_scale, logits_soft_cap or 0.0, window_left
+        )
+        o, lse = o[0], lse[0]
+    else:
+        # run through the paged kernel with the contiguous KV viewed as pages of 128 tokens
+        kv_len = kn.shape[0]
+        hkv = kn.shape[1]
+        page = _TILE_KV
+        n_pages = max(1, (kv_len + page - 1) // page)
+        pad = n_pages * page - kv_len
+        if pad:
+            kn = torch.cat([kn, kn.new_zeros(pad, hkv, head_dim)], 0)
+            vn = torch.cat([vn, vn.new_zeros(pad, hkv, head_dim)], 0)
+        kc = kn.reshape(n_pages, page, hkv, head_dim)
+        vc = vn.reshape(n_pages, page, hkv, head_dim)
+        ws = torch.empty(8 * 1024 * 1024, dtype=torch.uint8, device=q.device)
+        w = BatchDecodeWithPagedKVCacheWrapper(ws, "NHD")
+        indptr = torch.tensor([0, n_pages], dtype=torch.int32)
+        indices = torch.arange(n_pages, dtype=torch.int32)
+        last = torch.tensor([kv_len - (n_pages - 1) * page], dtype=torch.int32)
+        w.plan(
+            indptr, indices, last, q.shape[0], hkv, head_dim, page,
+            window_left=window_left, logits_soft_cap=logits_soft_cap, q_data_type=q.dtype, sm_scale=sm_scale,
+        )
+        o, lse = w.run(q.unsqueeze(0), (kc, vc), return_lse=True)
+        o, lse = o[0], lse[0]
+    if v_scale is not None:
+        o = (o.float() * v_scale).to(o.dtype)
+    return (o, lse) if return_lse else o
+
+
+class BatchDecodeWithPagedKVCacheWrapper:
+    """Batch decode over a paged KV cache (plan once per batch composition, run once per layer)."""
+
+    def __init__(
+        self,
+        float_workspace_buffer: torch.Tensor,
+        kv_layout: str = "NHD",
+        use_cuda_graph: bool = False,
+        use_tensor_cores: bool = True,
+        paged_kv_indptr_buffer: Optional[torch.Tensor] = None,
+        paged_kv_indices_buffer: Optional[torch.Tensor] = None,
+        paged_kv_last_page_len_buffer: Optional[torch.Tensor] = None,
+        backend: str = "auto",
+        jit_args=None,
+    ) -> None:
+        check_kv_layout(kv_layout)
+        self._kv_layout = kv_layout
+        self._float_workspace_buffer = float_workspace_buffer
+        self.device = float_workspace_buffer.device
+        self._use_cuda_graph = use_cuda_graph
+        self._int_workspace_buffer = torch.empty(8 * 1024 * 1024, dtype=torch.uint8, device=self.device)
+        self._pin_int_workspace_buffer = torch.empty(
+            8 * 1024 * 1024, dtype=torch.uint8, device="cpu", pin_memory=self.device.type == "cuda"
+        )
+        if use_cuda_graph:
+            if paged_kv_indptr_buffer is None or paged_kv_indices_buffer is None or paged_kv_last_page_len_buffer is None:
+                raise ValueError("use_cuda_graph=True requires the indptr/indices/last_page_len buffers")
+            self._fixed_batch_size = paged_kv_last_page_len_buffer.numel()
+        self._paged_kv_indptr_buf = paged_kv_indptr_buffer
+        self._paged_kv_indices_buf = paged_kv_indices_buffer
+        self._paged_kv_last_page_len_buf = paged_kv_last_page_len_buffer
+        self._planned = False
+        self._backend = "sm100"
+
+    @property
+    def use_tensor_cores(self) -> bool:
+        return True
+
+    @property
+    def is_cuda_graph_enabled(self) -> bool:
+        return self._use_cuda_graph
+
+    def reset_workspace_buffer(self, float_workspace_buffer: torch.Tensor, int_workspace_buffer: torch.Tensor) -> None:
+        self._float_workspace_buffer = float_workspace_buffer
+        self._int_workspace_buffer = int_workspace_buffer
+        self._pin_int_workspace_buffer = torch.empty(
+            int_workspace_buffer.numel(), dtype=torch.uint8, device="cpu", pin_memory=self.device.type == "cuda"
+        )
+
+    # ------------------------------------------------------------------ plan
+    def plan(
+        self,
+        indptr: torch.Tensor,
+        indices: torch.Tensor,
+        last_page_len: torch.Tensor,
+        num_qo_heads: int,
+        num_kv_heads: int,
+        head_dim: int,
+        page_size: int,
+        pos_encoding_mode: str = "NONE",
+        window_left: int = -1,
+        logits_soft_cap: Optional[float] = None,
+        q_data_type: Union[str, torch.dtype] = "float16",
+        kv_data_type: Optional[Union[str, torch.dtype]] = None,
+        o_data_type: Optional[Union[str, torch.dtype]] = None,
+        data_type: Optional[Union[str, torch.dtype]] = None,
+        sm_scale: Optional[float] = None,
+        rope_scale: Optional[float] = None,
+        rope_theta: Optional[float] = None,
+        non_blocking: bool = True,
+        block_tables: Optional[torch.Tensor] = None,
+        seq_lens: Optional[torch.Tensor] = None,
+        fixed_split_size: Optional[int] = None,
+        disable_split_kv: bool = False,
+        qo_indptr: Optional[torch.Tensor] = None,
+    ) -> None:
+        """Host-side planning.  ``qo_indptr`` (extension) allows q_len>1 per request
+        (speculative decode / small append) as long as ``q_len * group <= 32``."""
+        check_pos_encoding_mode(pos_encoding_mode)
+        if pos_encoding_mode != "NONE":
+            raise NotImplementedError("decode with in-kernel positional encoding; use flashinfer_b200.rope ops")
+        if num_qo_heads % num_kv_heads != 0:
+            raise ValueError("num_qo_heads must be a multiple of num_kv_heads")
+        batch_size = last_page_len.numel()
+        if indptr.numel() != batch_size + 1:
+            raise ValueError("indptr must have batch_size + 1 entries")
+        q_dt = _canon_dtype(data_type if data_type is not None else q_data_type)
+        kv_dt = _canon_dtype(kv_data_type) if kv_data_type is not None else q_dt
+        self._q_dtype, self._kv_dtype = q_dt, kv_dt
+        self._o_dtype = _canon_dtype(o_data_type) if o_data_type is not None else q_dt
+        self._num_qo_heads, self._num_kv_heads = num_qo_heads, num_kv_heads
+        self._head_dim, self._page_size = head_dim, page_size
+        self._window_left = window_left
+        self._logits_soft_cap = float(logits_soft_cap or 0.0)
+        self._sm_scale = sm_scale if sm_scale is not None else 1.0 / math.sqrt(head_dim)
+        self._batch_size = batch_size
+
+        indptr_host = indptr.to("cpu", torch.int32)
+        last_host = last_page_len.to("cpu", torch.int32)
+        n_pages = indptr_host[1:] - indptr_host[:-1]
+        kv_lens_host = (torch.clamp(n_pages - 1, min=0) * page_size + torch.where(n_pages > 0, last_host, 0)).to(torch.int32)
+        qo_host = qo_indptr.to("cpu", torch.int32).contiguous() if qo_indptr is not None else None
+        self._qo_indptr_host = qo_host
+        self._kv_lens_host = kv_lens_host
+
+        if self._use_cuda_graph:
+            if batch_size != self._fixed_batch_size:
+                raise ValueError("batch size must stay fixed under CUDA graphs")
+            self._paged_kv_indptr_buf.copy_(indptr, non_blocking=non_blocking)
+            self._paged_kv_indices_buf[: indices.numel()].copy_(indices, non_blocking=non_blocking)
+            self._paged_kv_last_page_len_buf.copy_(last_page_len, non_blocking=non_blocking)
+            self._kv_indices = self._paged_kv_indices_buf
+        else:
+            self._kv_indices = indices.to(self.device, torch.int32, non_blocking=non_blocking)
+        self._kv_indptr_host = indptr_host
+        self._kv_last_host = last_host
+
+        # ---- C++ planner into the pinned buffer, then ONE H2D copy ----
+        num_ctas = device_sm_count(self.device if self.device.type == "cuda" else None)
+        group = num_qo_heads // num_kv_heads
+        max_segs = batch_size * num_kv_heads + num_ctas + 1
+        max_merge = num_ctas + 1
+        pin32 = self._pin_int_workspace_buffer.view(torch.int32)
+        need = max_segs * _SEG_INTS + (num_ctas + 1) + max_merge * _MERGE_INTS
+        if need > pin32.numel():
+            raise RuntimeError("int workspace too small for this batch")
+        seg = pin32[: max_segs * _SEG_INTS]
+        cta = pin32[max_segs * _SEG_INTS : max_segs * _SEG_INTS + num_ctas + 1]
+        mrg = pin32[max_segs * _SEG_INTS + num_ctas + 1 : need]
+        counts = torch.zeros(8, dtype=torch.int64)
+        planner = jit.load("planner")
+        planner.call(
+            "decode_plan",
+            indptr_host.contiguous(), kv_lens_host.contiguous(), qo_host, batch_size, num_kv_heads, group,
+            page_size, num_ctas, 2 if not disable_split_kv else 1 << 30, seg, max_segs, cta, mrg, max_merge, counts,
+        )
+        nseg, nmerge, nslots, max_q_rows = (int(x) for x in counts[:4])
+        self._num_merge = nmerge
+        self._num_slots = nslots
+        self._max_q_rows = max_q_rows
+        self._num_ctas = num_ctas
+        self._plan_counts = counts
+        dev32 = self._int_workspace_buffer.view(torch.int32)
+        if self.device.type == "cuda":
+            dev32[:need].copy_(pin32[:need], non_blocking=non_blocking)
+        else:
+            dev32[:need].copy_(pin32[:need])
+        self._seg_info = dev32[: max_segs * _SEG_INTS]
+        self._cta_seg_indptr = dev32[max_segs * _SEG_INTS : max_segs * _SEG_INTS + num_ctas + 1]
+        self._merge_items = dev32[max_segs * _SEG_INTS + num_ctas + 1 : need]
+        nv = 1
+        while nv < max_q_rows:
+            nv *= 2
+        self._rows_per_slot = nv
+        slots_cap = max(nslots, 1) if not self._use_cuda_graph else 2 * num_ctas + 2
+        fneed = slots_cap * nv * (head_dim + 1) * 4
+        if fneed > self._float_workspace_buffer.numel() * self._float_workspace_buffer.element_size():
+            raise RuntimeError("float workspace too small for split-KV partials")
+        fws = self._float_workspace_buffer.view(torch.uint8)[: fneed].view(torch.float32)
+        self._partial_o = fws[: slots_cap * nv * head_dim]
+        self._partial_lse = fws[slots_cap * nv * head_dim :]
+        self._planned = True
+
+    begin_forward = plan
+
+    # ------------------------------------------------------------------ run
+    def run(
+        self,
+        q: torch.Tensor,
+        paged_kv_cache: Union[torch.Tensor, Tuple[torch.Tensor, torch.Tensor]],
+        *args,
+        q_scale: Optional[float] = None,
+        k_scale: Optional[float] = None,
+        v_scale: Optional[float] = None,
+        out: Optional[torch.Tensor] = None,
+        lse: Optional[torch.Tensor] = None,
+        return_lse: bool = False,
+        enable_pdl: Optional[bool] = None,
+        window_left: Optional[int] = None,
+        sinks: Optional[torch.Tensor] = None,
+    ):
+        if not self._planned:
+            raise RuntimeError("plan() must be called before run()")
+        k_cache, v_cache = unpack_paged_kv_cache(paged_kv_cache, self._kv_layout)
+        sm_scale = self._sm_scale
+        if q_scale is not None:
+            sm_scale *= q_scale
+        if k_scale is not None:
+            sm_scale *= k_scale
+        window_left = self._window_left if window_left is None else window_left
+        hq = self._num_qo_heads
+        if sinks is not None:
+            raise NotImplementedError("attention sinks in decode")
+        if out is None:
+            out = torch.empty(q.shape[0], hq, self._head_dim, dtype=self._o_dtype, device=q.device)
+        if return_lse and lse is None:
+            lse = torch.empty(q.shape[0], hq, dtype=torch.float32, device=q.device)
+
+        if not q.is_cuda:
+            qo = self._qo_indptr_host
+            if qo is None:
+                qo = torch.arange(self._batch_size + 1, dtype=torch.int32)
+            o_ref, lse_ref = reference.batch_paged_attention_ref(
+                q, qo, k_cache, v_cache, self._kv_indptr_host, self._kv_indices.cpu(), self._kv_last_host,
+                self._kv_layout, True, sm_scale, self._logits_soft_cap, window_left,
+            )
+            out.copy_(o_ref)
+            if return_lse:
+                lse.copy_(lse_ref)
+        else:
+            self._run_sm100(q, k_cache, v_cache, out, lse if return_lse else None, sm_scale, window_left, enable_pdl)
+        if v_scale is not None:
+            out.copy_((out.float() * v_scale).to(out.dtype))
+        return (out, lse) if return_lse else out
+
+    forward = run
+
+    def forward_return_lse(self, q, paged_kv_cache, **kw):
+        return self.run(q, paged_kv_cache, return_lse=True, **kw)
+
+    def end_forward(self) -> None:
+        pass
+
+    def _run_sm100(self, q, k_cache, v_cache, out, lse, sm_scale, window_left, enable_pdl):
+        if self._head_dim != 128:
+            raise NotImplementedError(f"decode_sm100: head_dim {self._head_dim} not specialised yet (128 only)")
+        if q.dtype not in (torch.float16, torch.bfloat16) or k_cache.dtype != q.dtype:
+            raise NotImplementedError(f"decode_sm100: q dtype {q.dtype} / kv dtype {k_cache.dtype} not specialised yet")
+        if self._max_q_rows > _MAX_Q_ROWS:
+            raise NotImplementedError("decode_sm100: q_len * group > 32; use the prefill wrapper")
+        sp, sn, sh, page_size, hkv, d = paged_kv_strides(k_cache, self._kv_layout)
+        if paged_kv_strides(v_cache, self._kv_layout)[:3] != (sp, sn, sh):
+            raise ValueError("k_cache and v_cache must share strides")
+        if page_size != self._page_size or hkv != self._num_kv_heads:
+            raise ValueError("paged_kv_cache shape does not match plan()")
+        if q.stride(-1) != 1 or out.stride(-1) != 1:
+            raise ValueError("q/out last dim must be contiguous")
+        causal = 1 if self._qo_indptr_host is not None else 0
+        mod = jit.load("decode_sm100")
+        mod.call(
+            "decode_paged_run",
+            q, k_cache, v_cache, out, lse, self._kv_indices, self._seg_info, self._cta_seg_indptr, self._merge_items,
+            self._num_merge, self._partial_o, self._partial_lse, self._num_ctas, self._max_q_rows,
+            self._num_qo_heads, self._num_kv_heads, self._head_dim, page_size, k_cache.shape[0], sp, sn, sh,
+            1 if self._kv_layout == "HND" else 0, q.stride(0), q.stride(1), out.stride(0), out.stride(1),
+            float(sm_scale), float(self._logits_soft_cap), int(window_left), causal, dtype_code(q.dtype),
+            1 if (enable_pdl is None or enable_pdl) else 0, stream_ptr(q),
+        )
+
+
+class CUDAGraphBatchDecodeWithPagedKVCacheWrapper(BatchDecodeWithPagedKVCacheWrapper):
+    """CUDA-graph flavoured wrapper (fixed batch size, user-provided index buffers)."""
+
+    def __init__(self, workspace_buffer, indptr_buffer, indices_buffer, last_page_len_buffer, kv_layout="NHD",
+                 use_tensor_cores=True):
+        super().__init__(
+            workspace_buffer, kv_layout, use_cuda_graph=True, use_tensor_cores=use_tensor_cores,
+            paged_kv_indptr_buffer=indptr_buffer, paged_kv_indices_buffer=indices_buffer,
+            paged_kv_last_page_len_buffer=last_page_len_buffer,
+        )
+
+
+def fast_decode_plan(wrapper: BatchDecodeWithPagedKVCacheWrapper, *args, **kwargs) -> None:
+    """Reference parity: flashinfer/decode.py:2897.  Our plan() is already a single C++ call plus
+    one H2D copy, so the fast path is the same code."""
+    wrapper.plan(*args, **kwargs)

@@ -1,0 +1,91 @@
+"""Dense bf16/fp16 GEMM on the hand-written tcgen05 kernel (csrc/gemm/gemm_bf16_sm100.cu).
+
+``mm_bf16(a, b)`` follows the reference signature (flashinfer/gemm/gemm_base.py:485): ``a`` is
+``[m, k]`` row-major and ``b`` is ``[k, n]`` **column-major** (i.e. ``b.T`` is a contiguous
+``[n, k]`` weight) — exactly the K-major/K-major "NT" layout the tensor cores want.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from .. import jit
+from ..utils import dtype_code, stream_ptr
+
+_workspaces = {}
+
+
+def _workspace(device) -> torch.Tensor:
+    ws = _workspaces.get(device)
+    if ws is None:
+        ws = torch.empty(32 * 1024 * 1024, dtype=torch.uint8, device=device)
+        _workspaces[device] = ws
+    return ws
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
+           out: Optional[torch.Tensor] = None, enable_pdl: bool = True) -> torch.Tensor:
+    """``x[..., K] @ weight[N, K]^T (+ bias[N])`` — the nn.Linear contraction, tcgen05 on CUDA."""
+    if x.dtype not in (torch.float16, torch.bfloat16) or weight.dtype != x.dtype:
+        raise TypeError("linear: x/weight must both be float16 or bfloat16")
+    k = x.shape[-1]
+    n = weight.shape[0]
+    if weight.shape[1] != k:
+        raise ValueError(f"linear: K mismatch {weight.shape} vs {x.shape}")
+    x2 = x.reshape(-1, k)
+    m = x2.shape[0]
+    if out is None:
+        out = torch.empty(*x.shape[:-1], n, dtype=x.dtype, device=x.device)
+    out2 = out.view(-1, n)
+    if not x.is_cuda:
+        res = x2.float() @ weight.float().t()
+        if bias is not None:
+            res = res + bias.float()
+        out2.copy_(res.to(x.dtype))
+        return out
+    if x2.stride(-1) != 1:
+        x2 = x2.contiguous()
+    if weight.stride(-1) != 1:
+        weight = weight.contiguous()
+    ws = _workspace(x.device)
+    jit.load("gemm_sm100").call(
+        "gemm_nt", x2, weight, out2, bias, m, n, k, x2.stride(0), weight.stride(0), out2.stride(0),
+        dtype_code(x.dtype), ws, ws.numel(), 1 if enable_pdl else 0, stream_ptr(x),
+    )
+    return out
+
+
+def mm_bf16(a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = None, pdl: bool = False,
+            out: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.bfloat16, backend: str = "auto"):
+    """a [m, k] row-major, b [k, n] column-major -> [m, n]."""
+    if b.stride(0) != 1:
+        b = b.t().contiguous().t()
+    res = linear(a, b.t(), bias, out=out if (out is not None and out.dtype == a.dtype) else None, enable_pdl=pdl)
+    if out_dtype != res.dtype:
+        res = res.to(out_dtype)
+    if out is not None and out.data_ptr() != res.data_ptr():
+        out.copy_(res)
+        return out
+    return res
+
+
+mm_fp16 = mm_bf16
+
+
+def bmm_bf16(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None,
+             out_dtype: torch.dtype = torch.bfloat16, backend: str = "auto"):
+    """a [B, m, k], b [B, k, n] (column-major per batch) -> [B, m, n]."""
+    bsz, m, _ = a.shape
+    n = b.shape[-1]
+    if out is None:
+        out = torch.empty(bsz, m, n, dtype=a.dtype, device=a.device)
+    for i in range(bsz):
+        mm_bf16(a[i], b[i], out=out[i], out_dtype=a.dtype)
+    return out if out_dtype == out.dtype else out.to(out_dtype)
+
+
+def tgv_gemm_sm100(a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = None, pdl: bool = False):
+    """Low-latency small-M GEMM (reference tgv_gemm_sm100, gemm_base.py:1446): a [m,k], b [k,n] col-major.
+    The swap-AB + split-K + PDL path of gemm_nt is the low-latency kernel here."""
+    return mm_bf16(a, b, bias=bias, pdl=pdl, out_dtype=a.dtype)

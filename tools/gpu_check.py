@@ -1,0 +1,204 @@
+#!/usr/bin/env python
+"""Developer GPU check runner: every case runs in its own subprocess under a timeout so that a hung
+kernel (mbarrier deadlock) cannot take the whole gpurun call down.  Results -> gpurun_out/check.json.
+
+    python tools/gpu_check.py                 # run all cases
+    python tools/gpu_check.py --case gemm     # run one case in-process
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+import traceback
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def _time_ms(fn, iters=20, warmup=5, flush=None):
+    import torch
+
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def case_gemm():
+    import torch
+    import flashinfer_b200 as fi
+    from flashinfer_b200.gemm import linear
+
+    torch.manual_seed(0)
+    res = {}
+    shapes = [(128, 128, 64), (128, 256, 128), (256, 512, 512), (1024, 4096, 4096), (300, 1000 // 8 * 8, 520),
+              (1, 4096, 4096), (8, 512, 1024), (16, 6144, 4096), (64, 4096, 14336), (64, 28672, 4096), (100, 384, 2048),
+              (4096, 4096, 4096), (8192, 8192, 8192)]
+    for (m, n, k) in shapes:
+        for dt in (torch.bfloat16,):
+            x = torch.randn(m, k, device="cuda", dtype=dt)
+            w = torch.randn(n, k, device="cuda", dtype=dt) / (k ** 0.5)
+            y = linear(x, w)
+            ref = (x.float() @ w.float().t())
+            err = (y.float() - ref).abs().max().item()
+            tol = 2e-2 * ref.abs().max().item() + 1e-2
+            ok = err <= tol
+            res[f"{m}x{n}x{k}"] = {"err": err, "tol": tol, "ok": bool(ok)}
+            print(f"gemm {m}x{n}x{k} err={err:.4g} tol={tol:.4g} {'OK' if ok else 'FAIL'}", flush=True)
+    # bias + fp16
+    x = torch.randn(77, 512, device="cuda", dtype=torch.float16)
+    w = torch.randn(264, 512, device="cuda", dtype=torch.float16) / 22
+    b = torch.randn(264, device="cuda", dtype=torch.float16)
+    y = linear(x, w, b)
+    ref = x.float() @ w.float().t() + b.float()
+    err = (y.float() - ref).abs().max().item()
+    res["fp16_bias"] = {"err": err, "ok": bool(err < 3e-2)}
+    print("gemm fp16+bias err", err, flush=True)
+    # perf
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for (m, n, k) in [(8192, 8192, 8192), (4096, 4096, 4096), (64, 28672, 4096), (64, 4096, 14336), (64, 6144, 4096), (64, 4096, 4096)]:
+        x = torch.randn(m, k, device="cuda", dtype=torch.bfloat16)
+        w = torch.randn(n, k, device="cuda", dtype=torch.bfloat16)
+        ms = _time_ms(lambda: linear(x, w), flush=flush)
+        ms_t = _time_ms(lambda: torch.nn.functional.linear(x, w), flush=flush)
+        tf = 2 * m * n * k / ms / 1e9
+        gbs = (m * k + n * k + m * n) * 2 / ms / 1e6
+        res[f"perf_{m}x{n}x{k}"] = {"ms": ms, "tflops": tf, "gbs": gbs, "cublas_ms": ms_t}
+        print(f"gemm perf {m}x{n}x{k}: {ms:.4f} ms {tf:.1f} TFLOP/s {gbs:.0f} GB/s  (cuBLAS {ms_t:.4f} ms)", flush=True)
+    return res
+
+
+def _make_paged(batch, kv_lens, hkv, d, ps, layout, dtype, device="cuda"):
+    import torch
+
+    npages = [(l + ps - 1) // ps for l in kv_lens]
+    total = sum(npages)
+    indptr = torch.tensor([0] + list(torch.tensor(npages).cumsum(0).tolist()), dtype=torch.int32)
+    indices = torch.randperm(total + 3)[:total].int()
+    last = torch.tensor([(l - 1) % ps + 1 if l > 0 else 0 for l in kv_lens], dtype=torch.int32)
+    shape = (total + 3, ps, hkv, d) if layout == "NHD" else (total + 3, hkv, ps, d)
+    kc = torch.randn(shape, device=device, dtype=dtype)
+    vc = torch.randn(shape, device=device, dtype=dtype)
+    return indptr, indices, last, kc, vc
+
+
+def case_decode():
+    import torch
+    import flashinfer_b200 as fi
+    from flashinfer_b200 import reference
+
+    torch.manual_seed(0)
+    res = {}
+    ws = torch.empty(128 << 20, dtype=torch.uint8, device="cuda")
+    cfgs = [
+        # (kv_lens, hq, hkv, ps, layout, dtype)
+        ([128], 4, 1, 16, "NHD", torch.bfloat16),
+        ([37, 128, 300], 8, 2, 16, "NHD", torch.bfloat16),
+        ([1, 17, 1000, 4096], 32, 8, 16, "NHD", torch.bfloat16),
+        ([513, 64], 32, 8, 16, "HND", torch.float16),
+        ([700, 90, 5], 16, 16, 32, "NHD", torch.bfloat16),
+        ([700, 90, 5], 32, 4, 8, "HND", torch.bfloat16),
+        ([333], 8, 8, 128, "NHD", torch.float16),
+        ([1000, 33], 8, 1, 256, "NHD", torch.bfloat16),
+        ([77, 200], 8, 2, 1, "NHD", torch.bfloat16),
+        ([4096] * 16, 32, 8, 16, "NHD", torch.bfloat16),
+    ]
+    for (kv_lens, hq, hkv, ps, layout, dt) in cfgs:
+        name = f"kv{kv_lens[:3]}x{len(kv_lens)}_h{hq}/{hkv}_ps{ps}_{layout}_{str(dt)[6:]}"
+        try:
+            B = len(kv_lens)
+            indptr, indices, last, kc, vc = _make_paged(B, kv_lens, hkv, 128, ps, layout, dt)
+            q = torch.randn(B, hq, 128, device="cuda", dtype=dt)
+            w = fi.BatchDecodeWithPagedKVCacheWrapper(ws, layout)
+            w.plan(indptr, indices, last, hq, hkv, 128, ps, q_data_type=dt)
+            o, lse = w.run(q, (kc, vc), return_lse=True)
+            torch.cuda.synchronize()
+            qo = torch.arange(B + 1, dtype=torch.int32)
+            o_ref, lse_ref = reference.batch_paged_attention_ref(
+                q, qo, kc, vc, indptr, indices.cuda(), last, layout, True)
+            err = (o.float() - o_ref.float()).abs().max().item()
+            lerr = (lse - lse_ref).abs().max().item()
+            ok = err < 2e-2 and lerr < 2e-2
+            res[name] = {"err": err, "lse_err": lerr, "ok": bool(ok), "counts": w._plan_counts.tolist()}
+            print(f"decode {name}: err={err:.4g} lse_err={lerr:.4g} {'OK' if ok else 'FAIL'}", flush=True)
+        except Exception as e:  # noqa: BLE001
+            res[name] = {"ok": False, "exc": repr(e)}
+            print(f"decode {name}: EXC {e!r}", flush=True)
+            traceback.print_exc()
+    return res
+
+
+def case_decode_perf():
+    import torch
+    import flashinfer_b200 as fi
+
+    torch.manual_seed(0)
+    res = {}
+    ws = torch.empty(128 << 20, dtype=torch.uint8, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for (B, kv, hq, hkv, ps) in [(64, 4096, 32, 8, 16), (16, 1024, 64, 8, 16), (64, 1024, 32, 8, 16), (256, 4096, 32, 8, 16), (1, 8192, 32, 8, 16), (64, 16384, 32, 8, 16)]:
+        kv_lens = [kv] * B
+        indptr, indices, last, kc, vc = _make_paged(B, kv_lens, hkv, 128, ps, "NHD", torch.bfloat16)
+        q = torch.randn(B, hq, 128, device="cuda", dtype=torch.bfloat16)
+        w = fi.BatchDecodeWithPagedKVCacheWrapper(ws, "NHD")
+        w.plan(indptr, indices, last, hq, hkv, 128, ps, q_data_type=torch.bfloat16)
+        out = torch.empty_like(q)
+        ms = _time_ms(lambda: w.run(q, (kc, vc), out=out), flush=flush if B * kv * hkv * 512 < (200 << 20) else None)
+        byts = B * kv * hkv * 128 * 2 * 2 + 2 * q.numel() * 2
+        flops = 4 * B * hq * kv * 128
+        res[f"B{B}_kv{kv}_h{hq}/{hkv}"] = {"ms": ms, "tbs": byts / ms / 1e9, "tflops": flops / ms / 1e9}
+        print(f"decode perf B={B} kv={kv} h={hq}/{hkv}: {ms:.4f} ms  {byts / ms / 1e9:.3f} TB/s  {flops / ms / 1e9:.1f} TFLOP/s", flush=True)
+    return res
+
+
+CASES = {"gemm": case_gemm, "decode": case_decode, "decode_perf": case_decode_perf}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--case", default=None)
+    ap.add_argument("--cases", default=None, help="comma list for the driver mode")
+    ap.add_argument("--timeout", type=int, default=240)
+    args = ap.parse_args()
+    if args.case:
+        out = CASES[args.case]()
+        print("RESULT_JSON " + json.dumps(out))
+        return
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    names = args.cases.split(",") if args.cases else list(CASES)
+    summary = {}
+    for name in names:
+        t0 = time.time()
+        try:
+            p = subprocess.run([sys.executable, os.path.abspath(__file__), "--case", name], capture_output=True,
+                               text=True, timeout=args.timeout, cwd=ROOT)
+            tail = (p.stdout + "\n" + p.stderr)[-6000:]
+            js = None
+            for line in p.stdout.splitlines():
+                if line.startswith("RESULT_JSON "):
+                    js = json.loads(line[len("RESULT_JSON "):])
+            summary[name] = {"rc": p.returncode, "sec": time.time() - t0, "result": js, "tail": tail if js is None else tail[-1500:]}
+            print(f"=== {name}: rc={p.returncode} ({time.time() - t0:.1f}s)\n{p.stdout[-4000:]}\n{p.stderr[-2000:]}", flush=True)
+        except subprocess.TimeoutExpired as e:
+            summary[name] = {"rc": "timeout", "sec": time.time() - t0,
+                             "tail": ((e.stdout or b"").decode(errors="replace") if isinstance(e.stdout, bytes) else (e.stdout or ""))[-4000:]}
+            print(f"=== {name}: TIMEOUT\n{summary[name]['tail']}", flush=True)
+    with open(os.path.join(ROOT, "gpurun_out", "check.json"), "w") as f:
+        json.dump(summary, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
