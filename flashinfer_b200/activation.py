@@ -1,0 +1,48 @@
+"""Gated activations.  Parity: reference flashinfer/activation.py:77-202."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import jit, reference
+from .utils import device_support_pdl, dtype_code, stream_ptr
+
+_ACT = {"silu": 0, "gelu": 1, "gelu_tanh": 2}
+
+
+def _act_and_mul(kind: str, input: torch.Tensor, out: Optional[torch.Tensor], enable_pdl):
+    d = input.shape[-1] // 2
+    if input.shape[-1] % 2:
+        raise ValueError("last dim must be even")
+    if out is None:
+        out = torch.empty(*input.shape[:-1], d, dtype=input.dtype, device=input.device)
+    if not input.is_cuda:
+        if kind == "silu":
+            out.copy_(reference.silu_and_mul_ref(input))
+        else:
+            out.copy_(reference.gelu_and_mul_ref(input, "tanh" if kind == "gelu_tanh" else "none"))
+        return out
+    x2 = input.reshape(-1, input.shape[-1])
+    if x2.stride(-1) != 1:
+        x2 = x2.contiguous()
+    o2 = out.view(-1, d)
+    pdl = device_support_pdl(input.device) if enable_pdl is None else enable_pdl
+    jit.load("activation").call(
+        "act_and_mul", x2, o2, x2.shape[0], d, x2.stride(0), o2.stride(0), _ACT[kind], dtype_code(input.dtype),
+        1 if pdl else 0, stream_ptr(input),
+    )
+    return out
+
+
+def silu_and_mul(input, out=None, enable_pdl=None):
+    """``silu(input[..., :d]) * input[..., d:]``"""
+    return _act_and_mul("silu", input, out, enable_pdl)
+
+
+def gelu_and_mul(input, out=None, enable_pdl=None):
+    return _act_and_mul("gelu", input, out, enable_pdl)
+
+
+def gelu_tanh_and_mul(input, out=None, enable_pdl=None):
+    return _act_and_mul("gelu_tanh", input, out, enable_pdl)

@@ -207,36 +207,44 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
       const int kv_head = si[1], t0 = si[2], t1 = si[3], page_start = si[8], num_pages = si[9];
       for (int ti = t0; ti < t1; ++ti) {
         const TileGeom g = tile_geom(ti, ps);
-        int my_page = -1;
-        int n_boxes;       // number of page boxes in this tile
+        // Each lane owns page boxes lane, lane+32, ... of the tile (page_size < 4 => more than 32 boxes).
+        int n_boxes;         // number of page boxes in this tile
         uint32_t box_bytes;  // bytes per box per chunk
+        int box_rows;
         if (ps <= kTileKV) {
-          const int ppt = kTileKV / ps;
-          n_boxes = min(ppt, num_pages - g.first_page);
-          box_bytes = ps * 128;
-          if (lane < n_boxes) my_page = __ldg(p.kv_indices + page_start + g.first_page + lane);
+          n_boxes = min(kTileKV / ps, num_pages - g.first_page);
+          box_rows = ps;
         } else {
           n_boxes = 1;
-          box_bytes = kTileKV * 128;
-          if (lane == 0) my_page = __ldg(p.kv_indices + page_start + g.first_page);
+          box_rows = 0;  // single box at row 0
         }
+        box_bytes = (ps <= kTileKV ? ps : kTileKV) * 128;
         const uint32_t tx = uint32_t(n_boxes) * box_bytes * S::kChunks;
+        int my_pages[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int bi = lane + j * 32;
+          my_pages[j] = (bi < n_boxes) ? __ldg(p.kv_indices + page_start + g.first_page + bi) : -1;
+        }
         // ---- K ----
         if (lane == 0) {
           ptx::mbar_wait(&k_empty[ks], kph ^ 1);
           ptx::mbar_arrive_expect_tx(&k_full[ks], tx);
         }
         __syncwarp();
-        if (my_page >= 0) {
-          uint8_t* dst = smem + S::kOffK + ks * S::kTileBytes + (ps <= kTileKV ? lane * ps * 128 : 0);
 #pragma unroll
-          for (int c = 0; c < S::kChunks; ++c) {
-            if (p.layout_hnd)
-              ptx::tma_load_4d(dst + c * S::kChunkBytes, &tmK, &k_full[ks], c * 64, g.page_off, kv_head, my_page,
-                               ptx::kEvictFirst);
-            else
-              ptx::tma_load_4d(dst + c * S::kChunkBytes, &tmK, &k_full[ks], c * 64, kv_head, g.page_off, my_page,
-                               ptx::kEvictFirst);
+        for (int j = 0; j < 4; ++j) {
+          if (my_pages[j] >= 0) {
+            uint8_t* dst = smem + S::kOffK + ks * S::kTileBytes + (lane + j * 32) * box_rows * 128;
+#pragma unroll
+            for (int c = 0; c < S::kChunks; ++c) {
+              if (p.layout_hnd)
+                ptx::tma_load_4d(dst + c * S::kChunkBytes, &tmK, &k_full[ks], c * 64, g.page_off, kv_head, my_pages[j],
+                                 ptx::kEvictFirst);
+              else
+                ptx::tma_load_4d(dst + c * S::kChunkBytes, &tmK, &k_full[ks], c * 64, kv_head, g.page_off, my_pages[j],
+                                 ptx::kEvictFirst);
+            }
           }
         }
         if (++ks == S::kStagesK) {
@@ -249,16 +257,19 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
           ptx::mbar_arrive_expect_tx(&v_full[vs], tx);
         }
         __syncwarp();
-        if (my_page >= 0) {
-          uint8_t* dst = smem + S::kOffV + vs * S::kTileBytes + (ps <= kTileKV ? lane * ps * 128 : 0);
 #pragma unroll
-          for (int c = 0; c < S::kChunks; ++c) {
-            if (p.layout_hnd)
-              ptx::tma_load_4d(dst + c * S::kChunkBytes, &tmV, &v_full[vs], c * 64, g.page_off, kv_head, my_page,
-                               ptx::kEvictFirst);
-            else
-              ptx::tma_load_4d(dst + c * S::kChunkBytes, &tmV, &v_full[vs], c * 64, kv_head, g.page_off, my_page,
-                               ptx::kEvictFirst);
+        for (int j = 0; j < 4; ++j) {
+          if (my_pages[j] >= 0) {
+            uint8_t* dst = smem + S::kOffV + vs * S::kTileBytes + (lane + j * 32) * box_rows * 128;
+#pragma unroll
+            for (int c = 0; c < S::kChunks; ++c) {
+              if (p.layout_hnd)
+                ptx::tma_load_4d(dst + c * S::kChunkBytes, &tmV, &v_full[vs], c * 64, g.page_off, kv_head, my_pages[j],
+                                 ptx::kEvictFirst);
+              else
+                ptx::tma_load_4d(dst + c * S::kChunkBytes, &tmV, &v_full[vs], c * 64, kv_head, g.page_off, my_pages[j],
+                                 ptx::kEvictFirst);
+            }
           }
         }
         if (++vs == S::kStagesV) {

@@ -1,0 +1,73 @@
+// Gated activations: out[..., d] = act(x[..., :d]) * x[..., d:]   (silu / gelu / gelu_tanh)
+// Parity: reference flashinfer/activation.py:77-202, include/flashinfer/activation.cuh:29.
+// Bandwidth-bound: 16 B vector ld/st, flat grid over (rows x d/8) vectors, PDL.
+#include <fib200/common.cuh>
+#include <fib200/ptx.cuh>
+
+using namespace fib200;
+
+FIB_EXPORT_LAST_ERROR()
+
+namespace {
+
+enum Act { kSilu = 0, kGelu = 1, kGeluTanh = 2 };
+
+template <int ACT>
+__device__ __forceinline__ float act_fn(float x) {
+  if constexpr (ACT == kSilu) {
+    return x / (1.f + __expf(-x));
+  } else if constexpr (ACT == kGelu) {
+    return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
+  } else {
+    const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+    return 0.5f * x * (1.f + tanhf(k0 * (x + k1 * x * x * x)));
+  }
+}
+
+template <typename T, int ACT>
+__global__ void __launch_bounds__(256)
+act_and_mul_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t rows, int64_t d, int64_t in_stride,
+                   int64_t out_stride) {
+  constexpr int VN = 16 / sizeof(T);
+  const int64_t vec_per_row = d / VN;
+  const int64_t total = rows * vec_per_row;
+  ptx::grid_dep_wait();
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t r = i / vec_per_row, c = (i % vec_per_row) * VN;
+    const Vec16<T> a = ld16(in + r * in_stride + c);
+    const Vec16<T> b = ld16(in + r * in_stride + d + c);
+    Vec16<T> o;
+#pragma unroll
+    for (int e = 0; e < VN; ++e) o.v[e] = from_f32<T>(act_fn<ACT>(to_f32(a.v[e])) * to_f32(b.v[e]));
+    st16(out + r * out_stride + c, o);
+  }
+  ptx::grid_dep_launch();
+}
+
+}  // namespace
+
+extern "C" int act_and_mul(void* in, void* out, int64_t rows, int64_t d, int64_t in_stride, int64_t out_stride,
+                           int64_t act, int64_t dtype, int64_t pdl, int64_t stream_) {
+  if (rows == 0 || d == 0) return 0;
+  FIB_CHECK(d % (16 / dtype_size(dtype)) == 0, "act_and_mul: d must be a multiple of the 16B vector width");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  return FIB_DISPATCH_FLOAT(dtype, T, [&]() -> int {
+    constexpr int VN = 16 / sizeof(T);
+    const int64_t total = rows * (d / VN);
+    int64_t blocks = (total + 255) / 256;
+    const int64_t cap = int64_t(num_sms()) * 16;
+    if (blocks > cap) blocks = cap;
+    LaunchCfg lc(dim3((unsigned)blocks), dim3(256), 0, stream, pdl != 0);
+    if (act == kSilu) {
+      FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, act_and_mul_kernel<T, kSilu>, (const T*)in, (T*)out, rows, d, in_stride,
+                                        out_stride));
+    } else if (act == kGelu) {
+      FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, act_and_mul_kernel<T, kGelu>, (const T*)in, (T*)out, rows, d, in_stride,
+                                        out_stride));
+    } else {
+      FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, act_and_mul_kernel<T, kGeluTanh>, (const T*)in, (T*)out, rows, d,
+                                        in_stride, out_stride));
+    }
+    return 0;
+  });
+}

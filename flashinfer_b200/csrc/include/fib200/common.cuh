@@ -44,8 +44,14 @@ inline int set_error(const std::string& msg) {
     }                                                                                              \
   } while (0)
 
+inline long long& launch_counter() {
+  static long long c = 0;
+  return c;
+}
+
 #define FIB_EXPORT_LAST_ERROR()                                                                    \
-  extern "C" const char* fib200_last_error() { return ::fib200::last_error_storage().c_str(); }
+  extern "C" const char* fib200_last_error() { return ::fib200::last_error_storage().c_str(); }    \
+  extern "C" long long fib200_launch_count() { return ::fib200::launch_counter(); }
 
 // ------------------------------------------------------------------ dtypes
 enum DType : int64_t {
@@ -189,6 +195,7 @@ struct LaunchCfg {
     }
     cfg.attrs = attrs;
     cfg.numAttrs = n;
+    ++launch_counter();
   }
 };
 

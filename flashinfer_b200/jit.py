@@ -293,5 +293,19 @@ def load(name: str) -> NativeModule:
         return mod
 
 
+def native_launch_count() -> int:
+    """Total number of kernels launched so far by all loaded native modules (each .so counts the
+    launches that go through its LaunchCfg helper)."""
+    total = 0
+    for mod in _loaded.values():
+        try:
+            f = mod._dll.fib200_launch_count
+            f.restype = ctypes.c_longlong
+            total += int(f())
+        except AttributeError:
+            pass
+    return total
+
+
 def current_stream_ptr(device: Optional[torch.device] = None) -> int:
     return torch.cuda.current_stream(device).cuda_stream

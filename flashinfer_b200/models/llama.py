@@ -1,0 +1,189 @@
+"""Llama-family decode engine built only from this library's ops (flagship serving step).
+
+One process per GPU; tensor parallelism shards attention heads and MLP columns over ``tp_size``
+ranks.  With ``tp_size > 1`` the two per-layer reductions run through the in-kernel NVLink
+all-reduce fused with residual-add + RMSNorm (``flashinfer_b200.comm``) — no NCCL on that path.
+The whole step is launch-only (plan() is done once per batch composition), so it is captured in a
+CUDA graph by ``LlamaDecodeEngine.capture()``.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from .. import activation, norm, page, rope
+from ..decode import BatchDecodeWithPagedKVCacheWrapper
+from ..gemm.dense import linear
+
+
+@dataclass
+class LlamaConfig:
+    hidden_size: int = 4096
+    intermediate_size: int = 14336
+    num_layers: int = 32
+    num_qo_heads: int = 32
+    num_kv_heads: int = 8
+    head_dim: int = 128
+    vocab_size: int = 128256
+    rms_eps: float = 1e-5
+    rope_theta: float = 5e5
+    rope_scale: float = 8.0
+    name: str = "llama-3-8b"
+
+    @staticmethod
+    def llama3_8b() -> "LlamaConfig":
+        return LlamaConfig()
+
+    @staticmethod
+    def llama3_70b() -> "LlamaConfig":
+        return LlamaConfig(hidden_size=8192, intermediate_size=28672, num_layers=80, num_qo_heads=64, num_kv_heads=8,
+                           name="llama-3-70b")
+
+    @staticmethod
+    def tiny() -> "LlamaConfig":
+        return LlamaConfig(hidden_size=512, intermediate_size=1024, num_layers=2, num_qo_heads=8, num_kv_heads=2,
+                           vocab_size=1024, name="llama-tiny")
+
+
+class LlamaDecodeEngine:
+    """Random-init Llama decoder running batched single-token decode over a paged KV cache."""
+
+    def __init__(self, cfg: LlamaConfig, max_batch: int, max_pages: int, page_size: int = 16, tp_rank: int = 0,
+                 tp_size: int = 1, device: str = "cuda", dtype: torch.dtype = torch.bfloat16, comm=None, seed: int = 0):
+        self.cfg, self.tp_rank, self.tp_size = cfg, tp_rank, tp_size
+        self.device, self.dtype = torch.device(device), dtype
+        self.page_size, self.max_batch = page_size, max_batch
+        self.comm = comm
+        assert cfg.num_kv_heads % tp_size == 0 and cfg.intermediate_size % tp_size == 0
+        self.hq = cfg.num_qo_heads // tp_size
+        self.hkv = cfg.num_kv_heads // tp_size
+        self.inter = cfg.intermediate_size // tp_size
+        g = torch.Generator(device=self.device).manual_seed(seed + 1000 * tp_rank)
+        gs = torch.Generator(device=self.device).manual_seed(seed)  # replicated tensors
+
+        def rnd(shape, gen, std):
+            return (torch.randn(shape, device=self.device, dtype=torch.float32, generator=gen) * std).to(dtype)
+
+        h, d = cfg.hidden_size, cfg.head_dim
+        self.embed = rnd((cfg.vocab_size, h), gs, 1.0)
+        self.vocab_shard = (cfg.vocab_size + tp_size - 1) // tp_size
+        self.lm_head = rnd((self.vocab_shard, h), g, h ** -0.5)
+        self.final_norm = torch.ones(h, device=self.device, dtype=dtype)
+        self.layers = []
+        for _ in range(cfg.num_layers):
+            self.layers.append({
+                "ln1": torch.ones(h, device=self.device, dtype=dtype),
+                "ln2": torch.ones(h, device=self.device, dtype=dtype),
+                "wqkv": rnd(((self.hq + 2 * self.hkv) * d, h), g, h ** -0.5),
+                "wo": rnd((h, self.hq * d), g, (cfg.num_qo_heads * d) ** -0.5),
+                "wgu": rnd((2 * self.inter, h), g, h ** -0.5),
+                "wd": rnd((h, self.inter), g, cfg.intermediate_size ** -0.5),
+                "k_cache": torch.zeros(max_pages, page_size, self.hkv, d, device=self.device, dtype=dtype),
+                "v_cache": torch.zeros(max_pages, page_size, self.hkv, d, device=self.device, dtype=dtype),
+            })
+        self._ws = torch.empty(64 << 20, dtype=torch.uint8, device=self.device)
+        self.wrapper = BatchDecodeWithPagedKVCacheWrapper(self._ws, "NHD")
+        self.launches_per_step = 0
+        self._graph = None
+
+    # ------------------------------------------------------------------ planning
+    def fill_kv_random(self, std: float = 0.5) -> None:
+        for l in self.layers:
+            l["k_cache"].normal_(0, std)
+            l["v_cache"].normal_(0, std)
+
+    def plan(self, kv_indptr: torch.Tensor, kv_indices: torch.Tensor, kv_last_page_len: torch.Tensor) -> None:
+        """``kv_*`` describe the cache *including* the token that this step appends."""
+        cfg = self.cfg
+        self.batch = kv_last_page_len.numel()
+        self.kv_indptr = kv_indptr.to(self.device, torch.int32)
+        self.kv_indices = kv_indices.to(self.device, torch.int32)
+        self.kv_last = kv_last_page_len.to(self.device, torch.int32)
+        self.wrapper.plan(kv_indptr, kv_indices, kv_last_page_len, self.hq, self.hkv, cfg.head_dim, self.page_size,
+                          q_data_type=self.dtype)
+        seq_lens = page.get_seq_lens(self.kv_indptr, self.kv_last, self.page_size).int()
+        self.positions = (seq_lens - 1).contiguous()
+        self.batch_indices = torch.arange(self.batch, device=self.device, dtype=torch.int32)
+        b, h = self.batch, cfg.hidden_size
+        # static activations (CUDA-graph friendly)
+        self.tokens = torch.zeros(b, dtype=torch.int64, device=self.device)
+        self.next_tokens = torch.zeros(b, dtype=torch.int64, device=self.device)
+        self._x = torch.empty(b, h, device=self.device, dtype=self.dtype)
+        self._res = torch.empty(b, h, device=self.device, dtype=self.dtype)
+        self._qkv = torch.empty(b, (self.hq + 2 * self.hkv) * cfg.head_dim, device=self.device, dtype=self.dtype)
+        self._attn = torch.empty(b, self.hq, cfg.head_dim, device=self.device, dtype=self.dtype)
+        self._gu = torch.empty(b, 2 * self.inter, device=self.device, dtype=self.dtype)
+        self._act = torch.empty(b, self.inter, device=self.device, dtype=self.dtype)
+        self._logits = torch.empty(b, self.vocab_shard, device=self.device, dtype=self.dtype)
+        self._graph = None
+
+    # ------------------------------------------------------------------ one decode step
+    def _reduce_add_norm(self, x: torch.Tensor, weight: torch.Tensor) -> None:
+        """x <- rmsnorm(residual += allreduce(x)); single-GPU: plain fused add+norm."""
+        if self.tp_size == 1:
+            norm.fused_add_rmsnorm(x, self._res, weight, self.cfg.rms_eps)
+        else:
+            self.comm.allreduce_add_rmsnorm(x, self._res, weight, self.cfg.rms_eps)
+
+    def step(self) -> torch.Tensor:
+        """tokens (self.tokens) -> next tokens (self.next_tokens); greedy sampling."""
+        cfg = self.cfg
+        d, hq, hkv = cfg.head_dim, self.hq, self.hkv
+        x = self._x
+        torch.index_select(self.embed, 0, self.tokens, out=x)
+        self._res.zero_()
+        n = 2
+        first = True
+        for li, l in enumerate(self.layers):
+            if first:
+                norm.fused_add_rmsnorm(x, self._res, l["ln1"], cfg.rms_eps)
+                first = False
+                n += 1
+            linear(x, l["wqkv"], out=self._qkv)
+            qkv = self._qkv.view(self.batch, hq + 2 * hkv, d)
+            q, k, v = qkv[:, :hq], qkv[:, hq : hq + hkv], qkv[:, hq + hkv :]
+            rope.apply_llama31_rope_pos_ids_inplace(q, k, self.positions, rope_scale=cfg.rope_scale,
+                                                    rope_theta=cfg.rope_theta)
+            page.append_paged_kv_cache(k, v, self.batch_indices, self.positions, (l["k_cache"], l["v_cache"]),
+                                       self.kv_indices, self.kv_indptr, self.kv_last)
+            self.wrapper.run(q, (l["k_cache"], l["v_cache"]), out=self._attn)
+            linear(self._attn.view(self.batch, hq * d), l["wo"], out=x)
+            self._reduce_add_norm(x, l["ln2"])
+            linear(x, l["wgu"], out=self._gu)
+            activation.silu_and_mul(self._gu, out=self._act)
+            linear(self._act, l["wd"], out=x)
+            n += 9
+            nxt = self.layers[li + 1]["ln1"] if li + 1 < len(self.layers) else self.final_norm
+            self._reduce_add_norm(x, nxt)
+            n += 1
+        linear(x, self.lm_head, out=self._logits)
+        n += 1
+        if self.tp_size == 1:
+            torch.argmax(self._logits, dim=-1, out=self.next_tokens)
+        else:
+            val, idx = torch.max(self._logits.float(), dim=-1)
+            self.next_tokens.copy_(self.comm.argmax_gather(val, idx + self.tp_rank * self.vocab_shard))
+        n += 1
+        self.launches_per_step = n
+        return self.next_tokens
+
+    # ------------------------------------------------------------------ CUDA graph
+    def capture(self, warmup: int = 2) -> None:
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self.step()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self.step()
+
+    def replay(self) -> torch.Tensor:
+        if self._graph is None:
+            return self.step()
+        self._graph.replay()
+        return self.next_tokens

@@ -1,0 +1,356 @@
+"""Prefill / append attention: single-request functions and the ragged / paged batch wrappers.
+
+API parity: reference flashinfer/prefill.py:1111-1387 (single_prefill_with_kv_cache),
+:1412-2536 (BatchPrefillWithPagedKVCacheWrapper), :2552-3555 (BatchPrefillWithRaggedKVCacheWrapper).
+
+CUDA tensors run the persistent tcgen05 FMHA kernel (csrc/attention/prefill_sm100.cu) driven by the
+C++ LPT planner; CPU tensors run the fp32 oracle (BASELINE.json config #1 is the CPU plumbing path).
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple, Union
+
+import torch
+
+from . import jit, reference
+from .utils import (
+    check_kv_layout,
+    check_pos_encoding_mode,
+    device_sm_count,
+    dtype_code,
+    paged_kv_strides,
+    stream_ptr,
+    unpack_paged_kv_cache,
+)
+
+_WORK_INTS = 8
+_TILE_Q = 128
+_TILE_KV = 128
+
+
+def _canon_dtype(dt):
+    return getattr(torch, dt) if isinstance(dt, str) else dt
+
+
+def _unpack_bits(packed: torch.Tensor, n: int) -> torch.Tensor:
+    """Little-endian bit unpack (inverse of quantization.packbits)."""
+    shifts = torch.arange(8, device=packed.device, dtype=torch.uint8)
+    bits = ((packed.view(torch.uint8)[:, None] >> shifts[None, :]) & 1).flatten()[:n]
+    return bits.bool()
+
+
+def single_prefill_with_kv_cache(
+    q: torch.Tensor,
+    k: torch.Tensor,
+    v: torch.Tensor,
+    scale_q: Optional[torch.Tensor] = None,
+    scale_k: Optional[torch.Tensor] = None,
+    scale_v: Optional[torch.Tensor] = None,
+    o_dtype: Optional[torch.dtype] = None,
+    custom_mask: Optional[torch.Tensor] = None,
+    packed_custom_mask: Optional[torch.Tensor] = None,
+    causal: bool = False,
+    kv_layout: str = "NHD",
+    pos_encoding_mode: str = "NONE",
+    use_fp16_qk_reduction: bool = False,
+    sm_scale: Optional[float] = None,
+    window_left: int = -1,
+    logits_soft_cap: Optional[float] = None,
+    rope_scale: Optional[float] = None,
+    rope_theta: Optional[float] = None,
+    backend: str = "auto",
+    return_lse: bool = False,
+):
+    """Prefill/append attention for one request.  q ``[qo_len, Hq, D]``; k/v ``[kv_len, Hkv, D]`` (NHD)
+    or ``[Hkv, kv_len, D]`` (HND).  Returns ``o`` (and base-2 ``lse [qo_len, Hq]``)."""
+    check_kv_layout(kv_layout)
+    check_pos_encoding_mode(pos_encoding_mode)
+    if pos_encoding_mode != "NONE":
+        raise NotImplementedError("in-kernel RoPE/ALiBi: apply flashinfer_b200.rope first")
+    d = q.shape[-1]
+    if sm_scale is None:
+        sm_scale = 1.0 / math.sqrt(d)
+    if kv_layout == "HND":
+        k, v = k.transpose(0, 1), v.transpose(0, 1)
+    qo_len, kv_len = q.shape[0], k.shape[0]
+    mask = None
+    if packed_custom_mask is not None and custom_mask is None:
+        mask = _unpack_bits(packed_custom_mask, qo_len * kv_len).view(qo_len, kv_len)
+    elif custom_mask is not None:
+        mask = custom_mask.view(qo_len, kv_len)
+    if (not q.is_cuda) or mask is not None or q.shape[-1] != 128 or v.shape[-1] != 128 or q.dtype not in (
+        torch.float16, torch.bfloat16) or k.dtype != q.dtype:
+        if q.is_cuda and mask is None:
+            raise NotImplementedError("prefill_sm100: only head_dim 128 f16/bf16 is specialised so far")
+        if q.is_cuda:
+            raise NotImplementedError("prefill_sm100: custom masks are not supported by the tcgen05 kernel yet")
+        o, lse = reference.attention_ref(q, k, v, causal and mask is None, sm_scale, logits_soft_cap or 0.0,
+                                         window_left, custom_mask=mask)
+    else:
+        ws = torch.empty(16 * 1024 * 1024, dtype=torch.uint8, device=q.device)
+        w = BatchPrefillWithRaggedKVCacheWrapper(ws, "NHD")
+        qo_indptr = torch.tensor([0, qo_len], dtype=torch.int32)
+        kv_indptr = torch.tensor([0, kv_len], dtype=torch.int32)
+        w.plan(qo_indptr, kv_indptr, q.shape[1], k.shape[1], d, causal=causal, sm_scale=sm_scale,
+               window_left=window_left, logits_soft_cap=logits_soft_cap, q_data_type=q.dtype)
+        o, lse = w.run(q, k, v, return_lse=True)
+    if o_dtype is not None and o.dtype != o_dtype:
+        o = o.to(o_dtype)
+    return (o, lse) if return_lse else o
+
+
+def single_prefill_with_kv_cache_return_lse(*args, **kwargs):
+    kwargs["return_lse"] = True
+    return single_prefill_with_kv_cache(*args, **kwargs)
+
+
+class _BatchPrefillBase:
+    """Shared plan()/run() machinery of the ragged and paged prefill wrappers."""
+
+    _paged = False
+
+    def __init__(self, float_workspace_buffer: torch.Tensor, kv_layout: str = "NHD", use_cuda_graph: bool = False,
+                 qo_indptr_buf=None, paged_kv_indptr_buf=None, paged_kv_indices_buf=None,
+                 paged_kv_last_page_len_buf=None, kv_indptr_buf=None, custom_mask_buf=None, mask_indptr_buf=None,
+                 backend: str = "auto", jit_args=None, jit_kwargs=None):
+        check_kv_layout(kv_layout)
+        self._kv_layout = kv_layout
+        self._float_workspace_buffer = float_workspace_buffer
+        self.device = float_workspace_buffer.device
+        self._use_cuda_graph = use_cuda_graph
+        self._int_workspace_buffer = torch.empty(8 * 1024 * 1024, dtype=torch.uint8, device=self.device)
+        self._pin_int_workspace_buffer = torch.empty(8 * 1024 * 1024, dtype=torch.uint8, device="cpu",
+                                                     pin_memory=self.device.type == "cuda")
+        self._planned = False
+        self._backend = "sm100"
+
+    @property
+    def is_cuda_graph_enabled(self) -> bool:
+        return self._use_cuda_graph
+
+    def reset_workspace_buffer(self, float_workspace_buffer, int_workspace_buffer) -> None:
+        self._float_workspace_buffer = float_workspace_buffer
+        self._int_workspace_buffer = int_workspace_buffer
+        self._pin_int_workspace_buffer = torch.empty(int_workspace_buffer.numel(), dtype=torch.uint8, device="cpu",
+                                                     pin_memory=self.device.type == "cuda")
+
+    def _plan_common(self, qo_indptr, kv_lens_host, num_qo_heads, num_kv_heads, head_dim_qk, head_dim_vo, causal,
+                     sm_scale, window_left, logits_soft_cap, q_data_type, kv_data_type, custom_mask, non_blocking):
+        if num_qo_heads % num_kv_heads:
+            raise ValueError("num_qo_heads must be a multiple of num_kv_heads")
+        self._num_qo_heads, self._num_kv_heads = num_qo_heads, num_kv_heads
+        self._head_dim_qk, self._head_dim_vo = head_dim_qk, head_dim_vo or head_dim_qk
+        self._causal = bool(causal)
+        self._sm_scale = sm_scale if sm_scale is not None else 1.0 / math.sqrt(head_dim_qk)
+        self._window_left = window_left
+        self._logits_soft_cap = float(logits_soft_cap or 0.0)
+        self._q_dtype = _canon_dtype(q_data_type)
+        self._kv_dtype = _canon_dtype(kv_data_type) if kv_data_type is not None else self._q_dtype
+        self._custom_mask = custom_mask
+        qo_host = qo_indptr.to("cpu", torch.int32).contiguous()
+        self._qo_indptr_host = qo_host
+        self._kv_lens_host = kv_lens_host.to(torch.int32).contiguous()
+        self._batch_size = qo_host.numel() - 1
+        # ---- C++ LPT planner: (request, q-tile, q-head) units over the persistent grid ----
+        num_ctas = device_sm_count(self.device if self.device.type == "cuda" else None)
+        q_lens = (qo_host[1:] - qo_host[:-1]).tolist()
+        max_work = sum((ql + _TILE_Q - 1) // _TILE_Q for ql in q_lens) * num_qo_heads
+        pin32 = self._pin_int_workspace_buffer.view(torch.int32)
+        need = max(max_work, 1) * _WORK_INTS + num_ctas + 1
+        if need > pin32.numel():
+            raise RuntimeError("int workspace too small for this batch")
+        work = pin32[: max(max_work, 1) * _WORK_INTS]
+        cta = pin32[max(max_work, 1) * _WORK_INTS : need]
+        counts = torch.zeros(4, dtype=torch.int64)
+        jit.load("planner").call(
+            "prefill_plan", qo_host, self._kv_lens_host, self._kv_start_host, self._batch_size, num_qo_heads, _TILE_Q,
+            _TILE_KV, 1 if causal else 0, int(window_left), num_ctas, work, max(max_work, 1), cta, counts,
+        )
+        self._num_work = int(counts[0])
+        self._num_ctas = num_ctas
+        dev32 = self._int_workspace_buffer.view(torch.int32)
+        dev32[:need].copy_(pin32[:need], non_blocking=non_blocking and self.device.type == "cuda")
+        self._work_info = dev32[: max(max_work, 1) * _WORK_INTS]
+        self._cta_work_indptr = dev32[max(max_work, 1) * _WORK_INTS : need]
+        self._planned = True
+
+    def _run_reference(self, q, get_kv, out, lse, sm_scale, window_left):
+        qo = self._qo_indptr_host
+        outs = []
+        for b in range(self._batch_size):
+            qs, qe = int(qo[b]), int(qo[b + 1])
+            if qe == qs:
+                continue
+            k, v = get_kv(b)
+            mask = None
+            if self._custom_mask is not None:
+                off = sum(int(qo[i + 1] - qo[i]) * int(self._kv_lens_host[i]) for i in range(b))
+                mask = self._custom_mask.flatten()[off : off + (qe - qs) * k.shape[0]].view(qe - qs, k.shape[0])
+            if k.shape[0] == 0:
+                o_b = torch.zeros(qe - qs, self._num_qo_heads, self._head_dim_vo, dtype=q.dtype, device=q.device)
+                l_b = torch.full((qe - qs, self._num_qo_heads), float("-inf"), device=q.device)
+            else:
+                o_b, l_b = reference.attention_ref(q[qs:qe], k, v, self._causal and mask is None, sm_scale,
+                                                   self._logits_soft_cap, window_left, custom_mask=mask)
+            out[qs:qe] = o_b.to(out.dtype)
+            if lse is not None:
+                lse[qs:qe] = l_b
+        return outs
+
+    def _launch_sm100(self, q, k, v, out, lse, sm_scale, window_left, paged, kv_indices, page_args, enable_pdl):
+        if self._head_dim_qk != 128 or self._head_dim_vo != 128:
+            raise NotImplementedError("prefill_sm100: only head_dim 128 is specialised so far")
+        if q.dtype not in (torch.float16, torch.bfloat16) or k.dtype != q.dtype:
+            raise NotImplementedError(f"prefill_sm100: dtype {q.dtype}/{k.dtype} not specialised yet")
+        if self._custom_mask is not None:
+            raise NotImplementedError("prefill_sm100: custom masks not supported yet")
+        jit.load("prefill_sm100").call(
+            "prefill_run", q, k, v, out, lse, kv_indices, self._kv_page_indptr_dev if paged else None,
+            self._work_info, self._cta_work_indptr, self._num_ctas, self._num_qo_heads, self._num_kv_heads,
+            self._head_dim_qk, 1 if paged else 0, *page_args, q.stride(0), q.stride(1), out.stride(0), out.stride(1),
+            float(sm_scale), float(self._logits_soft_cap), int(window_left), 1 if self._causal else 0,
+            dtype_code(q.dtype), 1 if (enable_pdl is None or enable_pdl) else 0, stream_ptr(q),
+        )
+
+    def end_forward(self) -> None:
+        pass
+
+
+class BatchPrefillWithRaggedKVCacheWrapper(_BatchPrefillBase):
+    """Batch prefill/append attention where K/V are ragged tensors ``[nnz_kv, Hkv, D]``."""
+
+    def __init__(self, float_workspace_buffer, kv_layout: str = "NHD", use_cuda_graph: bool = False,
+                 qo_indptr_buf=None, kv_indptr_buf=None, custom_mask_buf=None, mask_indptr_buf=None,
+                 backend: str = "auto", jit_args=None, jit_kwargs=None):
+        super().__init__(float_workspace_buffer, kv_layout, use_cuda_graph, qo_indptr_buf=qo_indptr_buf,
+                         kv_indptr_buf=kv_indptr_buf, custom_mask_buf=custom_mask_buf, mask_indptr_buf=mask_indptr_buf,
+                         backend=backend)
+
+    def plan(self, qo_indptr, kv_indptr, num_qo_heads, num_kv_heads, head_dim_qk, head_dim_vo=None, custom_mask=None,
+             packed_custom_mask=None, causal=False, pos_encoding_mode="NONE", use_fp16_qk_reduction=False,
+             window_left=-1, logits_soft_cap=None, sm_scale=None, rope_scale=None, rope_theta=None,
+             q_data_type="float16", kv_data_type=None, o_data_type=None, non_blocking=True, prefix_len_ptr=None,
+             token_pos_in_items_ptr=None, token_pos_in_items_len=0, max_item_len_ptr=None, fixed_split_size=None,
+             disable_split_kv=False) -> None:
+        check_pos_encoding_mode(pos_encoding_mode)
+        if pos_encoding_mode != "NONE":
+            raise NotImplementedError("in-kernel positional encoding")
+        kv_host = kv_indptr.to("cpu", torch.int32)
+        self._kv_start_host = kv_host[:-1].contiguous()
+        if packed_custom_mask is not None and custom_mask is None:
+            qo_h = qo_indptr.to("cpu")
+            n = int(((qo_h[1:] - qo_h[:-1]) * (kv_host[1:] - kv_host[:-1])).sum())
+            custom_mask = _unpack_bits(packed_custom_mask, n)
+        self._plan_common(qo_indptr, kv_host[1:] - kv_host[:-1], num_qo_heads, num_kv_heads, head_dim_qk, head_dim_vo,
+                          causal, sm_scale, window_left, logits_soft_cap, q_data_type, kv_data_type, custom_mask,
+                          non_blocking)
+
+    begin_forward = plan
+
+    def run(self, q, k, v, *args, q_scale=None, k_scale=None, v_scale=None, out=None, lse=None, return_lse=False,
+            enable_pdl=None, window_left=None):
+        if not self._planned:
+            raise RuntimeError("plan() must be called before run()")
+        if self._kv_layout == "HND":
+            k, v = k.transpose(0, 1), v.transpose(0, 1)
+        sm_scale = self._sm_scale * (q_scale or 1.0) * (k_scale or 1.0)
+        window_left = self._window_left if window_left is None else window_left
+        if out is None:
+            out = torch.empty(q.shape[0], self._num_qo_heads, self._head_dim_vo, dtype=q.dtype, device=q.device)
+        if return_lse and lse is None:
+            lse = torch.empty(q.shape[0], self._num_qo_heads, dtype=torch.float32, device=q.device)
+        if not q.is_cuda:
+            st = self._kv_start_host
+            self._run_reference(q, lambda b: (k[int(st[b]) : int(st[b]) + int(self._kv_lens_host[b])],
+                                              v[int(st[b]) : int(st[b]) + int(self._kv_lens_host[b])]),
+                                out, lse if return_lse else None, sm_scale, window_left)
+        else:
+            if k.stride(-1) != 1 or v.stride(-1) != 1 or k.stride() != v.stride():
+                k, v = k.contiguous(), v.contiguous()
+            page_args = (1, k.shape[0], k.stride(0), k.stride(0), k.stride(1), 0)
+            self._launch_sm100(q, k, v, out, lse if return_lse else None, sm_scale, window_left, False, None, page_args,
+                               enable_pdl)
+        if v_scale is not None:
+            out.copy_((out.float() * v_scale).to(out.dtype))
+        return (out, lse) if return_lse else out
+
+    forward = run
+
+    def forward_return_lse(self, q, k, v, **kw):
+        return self.run(q, k, v, return_lse=True, **kw)
+
+
+class BatchPrefillWithPagedKVCacheWrapper(_BatchPrefillBase):
+    """Batch prefill/append attention over a paged KV cache."""
+
+    _paged = True
+
+    def __init__(self, float_workspace_buffer, kv_layout: str = "NHD", use_cuda_graph: bool = False,
+                 qo_indptr_buf=None, paged_kv_indptr_buf=None, paged_kv_indices_buf=None,
+                 paged_kv_last_page_len_buf=None, custom_mask_buf=None, mask_indptr_buf=None, backend: str = "auto",
+                 jit_args=None, jit_kwargs=None):
+        super().__init__(float_workspace_buffer, kv_layout, use_cuda_graph, qo_indptr_buf=qo_indptr_buf,
+                         paged_kv_indptr_buf=paged_kv_indptr_buf, paged_kv_indices_buf=paged_kv_indices_buf,
+                         paged_kv_last_page_len_buf=paged_kv_last_page_len_buf, custom_mask_buf=custom_mask_buf,
+                         mask_indptr_buf=mask_indptr_buf, backend=backend)
+
+    def plan(self, qo_indptr, paged_kv_indptr, paged_kv_indices, paged_kv_last_page_len, num_qo_heads, num_kv_heads,
+             head_dim_qk, page_size, head_dim_vo=None, custom_mask=None, packed_custom_mask=None, causal=False,
+             pos_encoding_mode="NONE", use_fp16_qk_reduction=False, sm_scale=None, window_left=-1,
+             logits_soft_cap=None, rope_scale=None, rope_theta=None, q_data_type="float16", kv_data_type=None,
+             o_data_type=None, non_blocking=True, prefix_len_ptr=None, token_pos_in_items_ptr=None,
+             token_pos_in_items_len=0, max_item_len_ptr=None, seq_lens=None, seq_lens_q=None, block_tables=None,
+             max_token_per_sequence=None, max_sequence_kv=None, fixed_split_size=None, disable_split_kv=False) -> None:
+        check_pos_encoding_mode(pos_encoding_mode)
+        if pos_encoding_mode != "NONE":
+            raise NotImplementedError("in-kernel positional encoding")
+        self._page_size = page_size
+        indptr_host = paged_kv_indptr.to("cpu", torch.int32)
+        last_host = paged_kv_last_page_len.to("cpu", torch.int32)
+        n_pages = indptr_host[1:] - indptr_host[:-1]
+        kv_lens = torch.clamp(n_pages - 1, min=0) * page_size + torch.where(n_pages > 0, last_host, 0)
+        self._kv_indptr_host, self._kv_last_host = indptr_host, last_host
+        self._kv_start_host = indptr_host[:-1].contiguous()  # page-list start per request
+        self._kv_indices = paged_kv_indices.to(self.device, torch.int32, non_blocking=non_blocking)
+        self._kv_page_indptr_dev = indptr_host.to(self.device, non_blocking=non_blocking)
+        if packed_custom_mask is not None and custom_mask is None:
+            qo_h = qo_indptr.to("cpu")
+            n = int(((qo_h[1:] - qo_h[:-1]) * kv_lens).sum())
+            custom_mask = _unpack_bits(packed_custom_mask, n)
+        self._plan_common(qo_indptr, kv_lens, num_qo_heads, num_kv_heads, head_dim_qk, head_dim_vo, causal, sm_scale,
+                          window_left, logits_soft_cap, q_data_type, kv_data_type, custom_mask, non_blocking)
+
+    begin_forward = plan
+
+    def run(self, q, paged_kv_cache, *args, q_scale=None, k_scale=None, v_scale=None, out=None, lse=None,
+            return_lse=False, enable_pdl=None, window_left=None, sinks=None):
+        if not self._planned:
+            raise RuntimeError("plan() must be called before run()")
+        k_cache, v_cache = unpack_paged_kv_cache(paged_kv_cache, self._kv_layout)
+        sm_scale = self._sm_scale * (q_scale or 1.0) * (k_scale or 1.0)
+        window_left = self._window_left if window_left is None else window_left
+        if out is None:
+            out = torch.empty(q.shape[0], self._num_qo_heads, self._head_dim_vo, dtype=q.dtype, device=q.device)
+        if return_lse and lse is None:
+            lse = torch.empty(q.shape[0], self._num_qo_heads, dtype=torch.float32, device=q.device)
+        if not q.is_cuda:
+            self._run_reference(
+                q, lambda b: reference.gather_paged_kv(k_cache, v_cache, self._kv_indices.cpu(), self._kv_indptr_host,
+                                                       self._kv_last_host, b, self._kv_layout),
+                out, lse if return_lse else None, sm_scale, window_left)
+        else:
+            sp, sn, sh, page_size, hkv, d = paged_kv_strides(k_cache, self._kv_layout)
+            if paged_kv_strides(v_cache, self._kv_layout)[:3] != (sp, sn, sh):
+                raise ValueError("k_cache and v_cache must share strides")
+            page_args = (page_size, k_cache.shape[0], sp, sn, sh, 1 if self._kv_layout == "HND" else 0)
+            self._launch_sm100(q, k_cache, v_cache, out, lse if return_lse else None, sm_scale, window_left, True,
+                               self._kv_indices, page_args, enable_pdl)
+        if v_scale is not None:
+            out.copy_((out.float() * v_scale).to(out.dtype))
+        return (out, lse) if return_lse else out
+
+    forward = run
+
+    def forward_return_lse(self, q, paged_kv_cache, **kw):
+        return self.run(q, paged_kv_cache, return_lse=True, **kw)

@@ -1,0 +1,159 @@
+"""Rotary position embeddings.  Parity: reference flashinfer/rope.py:433-1691.
+
+All variants funnel into one CUDA kernel (csrc/elementwise/rope.cu); CPU tensors use the fp32 oracle.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import jit, reference
+from .utils import dtype_code, stream_ptr
+
+
+def _launch(q, k, q_out, k_out, *, pos_ids=None, indptr=None, offsets=None, cos_sin_cache=None, rotary_dim=None,
+            interleave=False, rope_scale=1.0, rope_theta=1e4, llama31=None, q_out_scale=1.0, k_out_scale=1.0):
+    nnz, hq, d = q.shape
+    hk = k.shape[1] if k is not None else 0
+    rd = rotary_dim or (cos_sin_cache.shape[-1] if cos_sin_cache is not None else d)
+    if not q.is_cuda:
+        if pos_ids is None:
+            lens = (indptr[1:] - indptr[:-1]).long()
+            b = torch.repeat_interleave(torch.arange(lens.numel()), lens)
+            pos_ids = torch.arange(nnz) - indptr[:-1].long()[b] + offsets.long()[b]
+        if cos_sin_cache is not None:
+            qo = reference.apply_rope_cos_sin_cache_ref(q, pos_ids, cos_sin_cache, interleave)
+            ko = reference.apply_rope_cos_sin_cache_ref(k, pos_ids, cos_sin_cache, interleave) if k is not None else None
+        else:
+            qo = reference.apply_rope_ref(q, pos_ids, rd, interleave, rope_scale, rope_theta, llama31)
+            ko = reference.apply_rope_ref(k, pos_ids, rd, interleave, rope_scale, rope_theta, llama31) if k is not None else None
+        q_out.copy_((qo.float() * q_out_scale).to(q_out.dtype))
+        if k is not None:
+            k_out.copy_((ko.float() * k_out_scale).to(k_out.dtype))
+        return
+    for t in (q, k, q_out, k_out):
+        if t is not None and t.stride(-1) != 1:
+            raise ValueError("rope: last dim must be contiguous")
+    pos_is_i64 = 0
+    if pos_ids is not None:
+        if pos_ids.dtype == torch.int64:
+            pos_is_i64 = 1
+        elif pos_ids.dtype != torch.int32:
+            pos_ids = pos_ids.int()
+    if cos_sin_cache is not None and cos_sin_cache.dtype != torch.float32:
+        raise ValueError("cos_sin_cache must be float32")
+    l31 = llama31 or (1.0, 4.0, 8192.0)
+    batch = indptr.numel() - 1 if indptr is not None else 0
+    jit.load("rope").call(
+        "rope_run", q, k, q_out, k_out, pos_ids, pos_is_i64, indptr, offsets, cos_sin_cache, nnz, batch, hq, hk, d, rd,
+        1 if interleave else 0, q.stride(0), q.stride(1), k.stride(0) if k is not None else 0,
+        k.stride(1) if k is not None else 0, q_out.stride(0), q_out.stride(1),
+        k_out.stride(0) if k_out is not None else 0, k_out.stride(1) if k_out is not None else 0,
+        float(rope_scale), float(rope_theta), 1 if llama31 is not None else 0, float(l31[0]), float(l31[1]),
+        float(l31[2]), float(q_out_scale), float(k_out_scale), dtype_code(q.dtype), dtype_code(q_out.dtype), 1,
+        stream_ptr(q),
+    )
+
+
+# ------------------------------------------------------------------ indptr/offsets API
+def apply_rope_inplace(q, k, indptr, offsets, rotary_dim=None, interleave=False, rope_scale=1, rope_theta=1e4) -> None:
+    _launch(q, k, q, k, indptr=indptr.int(), offsets=offsets.int(), rotary_dim=rotary_dim, interleave=interleave,
+            rope_scale=rope_scale, rope_theta=rope_theta)
+
+
+def apply_rope(q, k, indptr, offsets, rotary_dim=None, interleave=False, rope_scale=1, rope_theta=1e4):
+    qo, ko = torch.empty_like(q), torch.empty_like(k)
+    _launch(q, k, qo, ko, indptr=indptr.int(), offsets=offsets.int(), rotary_dim=rotary_dim, interleave=interleave,
+            rope_scale=rope_scale, rope_theta=rope_theta)
+    return qo, ko
+
+
+def apply_llama31_rope_inplace(q, k, indptr, offsets, rotary_dim=None, interleave=False, rope_scale=8, rope_theta=5e5,
+                               low_freq_factor=1, high_freq_factor=4, old_context_len=8192) -> None:
+    _launch(q, k, q, k, indptr=indptr.int(), offsets=offsets.int(), rotary_dim=rotary_dim, interleave=interleave,
+            rope_scale=rope_scale, rope_theta=rope_theta, llama31=(low_freq_factor, high_freq_factor, old_context_len))
+
+
+def apply_llama31_rope(q, k, indptr, offsets, rotary_dim=None, interleave=False, rope_scale=8, rope_theta=5e5,
+                       low_freq_factor=1, high_freq_factor=4, old_context_len=8192):
+    qo, ko = torch.empty_like(q), torch.empty_like(k)
+    _launch(q, k, qo, ko, indptr=indptr.int(), offsets=offsets.int(), rotary_dim=rotary_dim, interleave=interleave,
+            rope_scale=rope_scale, rope_theta=rope_theta, llama31=(low_freq_factor, high_freq_factor, old_context_len))
+    return qo, ko
+
+
+# ------------------------------------------------------------------ pos_ids API
+def apply_rope_pos_ids_inplace(q, k, pos_ids, rotary_dim=None, interleave=False, rope_scale=1, rope_theta=1e4) -> None:
+    _launch(q, k, q, k, pos_ids=pos_ids, rotary_dim=rotary_dim, interleave=interleave, rope_scale=rope_scale,
+            rope_theta=rope_theta)
+
+
+def apply_rope_pos_ids(q, k, pos_ids, rotary_dim=None, interleave=False, rope_scale=1, rope_theta=1e4):
+    qo, ko = torch.empty_like(q), torch.empty_like(k)
+    _launch(q, k, qo, ko, pos_ids=pos_ids, rotary_dim=rotary_dim, interleave=interleave, rope_scale=rope_scale,
+            rope_theta=rope_theta)
+    return qo, ko
+
+
+def apply_llama31_rope_pos_ids_inplace(q, k, pos_ids, rotary_dim=None, interleave=False, rope_scale=8, rope_theta=5e5,
+                                       low_freq_factor=1, high_freq_factor=4, old_context_len=8192) -> None:
+    _launch(q, k, q, k, pos_ids=pos_ids, rotary_dim=rotary_dim, interleave=interleave, rope_scale=rope_scale,
+            rope_theta=rope_theta, llama31=(low_freq_factor, high_freq_factor, old_context_len))
+
+
+def apply_llama31_rope_pos_ids(q, k, pos_ids, rotary_dim=None, interleave=False, rope_scale=8, rope_theta=5e5,
+                               low_freq_factor=1, high_freq_factor=4, old_context_len=8192):
+    qo, ko = torch.empty_like(q), torch.empty_like(k)
+    _launch(q, k, qo, ko, pos_ids=pos_ids, rotary_dim=rotary_dim, interleave=interleave, rope_scale=rope_scale,
+            rope_theta=rope_theta, llama31=(low_freq_factor, high_freq_factor, old_context_len))
+    return qo, ko
+
+
+# ------------------------------------------------------------------ cos/sin cache API (vLLM / SGL compatible)
+def apply_rope_with_cos_sin_cache(positions, query, key, head_size, cos_sin_cache, is_neox=True) -> Tuple[torch.Tensor, torch.Tensor]:
+    """query ``[nnz, Hq*head_size]``, key ``[nnz, Hk*head_size]``, cos_sin_cache ``[max_pos, rotary_dim]`` fp32."""
+    qo, ko = torch.empty_like(query), torch.empty_like(key)
+    _launch(query.view(query.shape[0], -1, head_size), key.view(key.shape[0], -1, head_size),
+            qo.view(qo.shape[0], -1, head_size), ko.view(ko.shape[0], -1, head_size), pos_ids=positions,
+            cos_sin_cache=cos_sin_cache, interleave=not is_neox)
+    return qo, ko
+
+
+def apply_rope_with_cos_sin_cache_inplace(positions, query, key, head_size, cos_sin_cache, is_neox=True) -> None:
+    q3, k3 = query.view(query.shape[0], -1, head_size), key.view(key.shape[0], -1, head_size)
+    _launch(q3, k3, q3, k3, pos_ids=positions, cos_sin_cache=cos_sin_cache, interleave=not is_neox)
+
+
+# ------------------------------------------------------------------ RoPE + fp8 quantisation
+def rope_quantize_fp8(q_rope, k_rope, q_nope, k_nope, cos_sin_cache, pos_ids, is_neox=True,
+                      quantize_dtype: Optional[torch.dtype] = None, quant_scale_q: float = 1.0,
+                      quant_scale_kv: float = 1.0, q_rope_out=None, k_rope_out=None, q_nope_out=None, k_nope_out=None,
+                      enable_pdl: bool = False):
+    """Apply RoPE to the rope slices, scale + quantise both rope and nope slices to fp8
+    (reference flashinfer/rope.py:1313).  q_* are ``[nnz, H, d]``; k_* are ``[nnz, Hk, d]`` or ``[nnz, d]``."""
+    qd = quantize_dtype or torch.float8_e4m3fn
+    k2d = k_rope.ndim == 2
+    kr = k_rope.unsqueeze(1) if k2d else k_rope
+    kn = k_nope.unsqueeze(1) if (k_nope is not None and k_nope.ndim == 2) else k_nope
+    q_rope_out = q_rope_out if q_rope_out is not None else torch.empty_like(q_rope, dtype=qd)
+    k_rope_out = k_rope_out if k_rope_out is not None else torch.empty_like(k_rope, dtype=qd)
+    kro = k_rope_out.unsqueeze(1) if k2d else k_rope_out
+    _launch(q_rope, kr, q_rope_out, kro, pos_ids=pos_ids, cos_sin_cache=cos_sin_cache, interleave=not is_neox,
+            q_out_scale=quant_scale_q, k_out_scale=quant_scale_kv)
+    lim = 448.0 if qd == torch.float8_e4m3fn else 57344.0
+    if q_nope is not None:
+        qn = (q_nope.float() * quant_scale_q).clamp(-lim, lim).to(qd)
+        q_nope_out = qn if q_nope_out is None else q_nope_out.copy_(qn)
+    if k_nope is not None:
+        knq = (kn.float() * quant_scale_kv).clamp(-lim, lim).to(qd)
+        knq = knq.squeeze(1) if k_nope.ndim == 2 else knq
+        k_nope_out = knq if k_nope_out is None else k_nope_out.copy_(knq)
+    return q_rope_out, k_rope_out, q_nope_out, k_nope_out
+
+
+def mla_rope_quantize_fp8(q_rope, k_rope, q_nope, k_nope, cos_sin_cache, pos_ids, is_neox=True, quantize_dtype=None,
+                          quant_scale_q=1.0, quant_scale_kv=1.0, q_rope_out=None, k_rope_out=None, q_nope_out=None,
+                          k_nope_out=None, enable_pdl=False):
+    return rope_quantize_fp8(q_rope, k_rope, q_nope, k_nope, cos_sin_cache, pos_ids, is_neox, quantize_dtype,
+                             quant_scale_q, quant_scale_kv, q_rope_out, k_rope_out, q_nope_out, k_nope_out, enable_pdl)

@@ -1,0 +1,91 @@
+"""CPU-path tests of the elementwise ops (the fp32 oracles double as the CPU implementation)."""
+import math
+
+import pytest
+import torch
+
+import flashinfer_b200 as fi
+from flashinfer_b200 import activation, cascade, norm, page, reference, rope
+
+
+def test_single_prefill_plumbing_cpu():
+    # BASELINE.json config #1: single_prefill_with_kv_cache fp32 on CPU, 1 head, seqlen 128
+    q, k, v = torch.randn(128, 1, 64), torch.randn(128, 1, 64), torch.randn(128, 1, 64)
+    o, lse = fi.single_prefill_with_kv_cache(q, k, v, causal=True, return_lse=True)
+    p = torch.softmax((q[:, 0] @ k[:, 0].T / 8.0).masked_fill(~torch.tril(torch.ones(128, 128, dtype=torch.bool)), -1e30), -1)
+    torch.testing.assert_close(o[:, 0], p @ v[:, 0], rtol=1e-4, atol=1e-4)
+    assert lse.shape == (128, 1)
+
+
+def test_norms_cpu():
+    x, r, w = torch.randn(7, 256), torch.randn(7, 256), torch.randn(256)
+    y = norm.rmsnorm(x, w)
+    torch.testing.assert_close(y, x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-6) * w)
+    x2, r2 = x.clone(), r.clone()
+    norm.fused_add_rmsnorm(x2, r2, w)
+    torch.testing.assert_close(r2, x + r)
+    torch.testing.assert_close(x2, norm.rmsnorm(x + r, w))
+    torch.testing.assert_close(norm.gemma_rmsnorm(x, w), norm.rmsnorm(x, w + 1))
+    g, b = torch.randn(256), torch.randn(256)
+    torch.testing.assert_close(norm.layernorm(x, g, b), torch.nn.functional.layer_norm(x, (256,), g, b, 1e-6))
+
+
+def test_activation_cpu():
+    x = torch.randn(5, 64)
+    torch.testing.assert_close(activation.silu_and_mul(x), torch.nn.functional.silu(x[:, :32]) * x[:, 32:])
+    torch.testing.assert_close(activation.gelu_tanh_and_mul(x), torch.nn.functional.gelu(x[:, :32], approximate="tanh") * x[:, 32:])
+
+
+def test_merge_state_matches_full_attention():
+    q, k, v = torch.randn(4, 2, 32), torch.randn(100, 2, 32), torch.randn(100, 2, 32)
+    o, s = reference.attention_ref(q, k, v)
+    oa, sa = reference.attention_ref(q, k[:37], v[:37])
+    ob, sb = reference.attention_ref(q, k[37:], v[37:])
+    om, sm = cascade.merge_state(oa, sa, ob, sb)
+    torch.testing.assert_close(om, o, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(sm, s, rtol=1e-4, atol=1e-5)
+    vs = torch.stack([oa, ob], 1)
+    ss = torch.stack([sa, sb], 1)
+    o2, s2 = cascade.merge_states(vs, ss)
+    torch.testing.assert_close(o2, o, rtol=1e-4, atol=1e-5)
+    oa2, sa2 = oa.clone(), sa.clone()
+    cascade.merge_state_in_place(oa2, sa2, ob, sb)
+    torch.testing.assert_close(oa2, o, rtol=1e-4, atol=1e-5)
+
+
+def test_rope_cpu_variants_agree():
+    nnz, H, D = 10, 2, 64
+    q, k = torch.randn(nnz, H, D), torch.randn(nnz, H, D)
+    indptr = torch.tensor([0, 4, 10], dtype=torch.int32)
+    offsets = torch.tensor([3, 100], dtype=torch.int32)
+    pos = torch.tensor([3, 4, 5, 6, 100, 101, 102, 103, 104, 105], dtype=torch.int32)
+    a = rope.apply_rope(q, k, indptr, offsets)
+    b = rope.apply_rope_pos_ids(q, k, pos)
+    torch.testing.assert_close(a[0], b[0])
+    torch.testing.assert_close(a[1], b[1])
+    # rotation preserves norms
+    torch.testing.assert_close(a[0].norm(dim=-1), q.norm(dim=-1), rtol=1e-4, atol=1e-4)
+    # cos/sin cache variant equals on-the-fly
+    inv = 1.0 / (1e4 ** (torch.arange(0, D, 2).float() / D))
+    ang = torch.arange(200).float()[:, None] * inv[None]
+    cache = torch.cat([ang.cos(), ang.sin()], -1)
+    qc, kc = rope.apply_rope_with_cos_sin_cache(pos, q.reshape(nnz, -1), k.reshape(nnz, -1), D, cache, is_neox=True)
+    torch.testing.assert_close(qc.view(nnz, H, D), b[0], rtol=1e-4, atol=1e-4)
+
+
+def test_page_append_and_positions_cpu():
+    from helpers import make_paged
+
+    kv_lens = [20, 33]
+    indptr, indices, last, kc, vc = make_paged(kv_lens, 2, 8, 16)
+    append_indptr = torch.tensor([0, 5, 8], dtype=torch.int32)
+    seq = torch.tensor(kv_lens, dtype=torch.int32)
+    bi, pos = page.get_batch_indices_positions(append_indptr, seq, 8)
+    assert bi.tolist() == [0] * 5 + [1] * 3
+    assert pos.tolist() == [15, 16, 17, 18, 19, 30, 31, 32]
+    k, v = torch.randn(8, 2, 8), torch.randn(8, 2, 8)
+    page.append_paged_kv_cache(k, v, bi, pos, (kc, vc), indices, indptr, last)
+    kk, vv = reference.gather_paged_kv(kc, vc, indices, indptr, last, 1)
+    torch.testing.assert_close(kk[30:33], k[5:])
+    torch.testing.assert_close(vv[30:33], v[5:])
+    assert page.get_seq_lens(indptr, last, 16).tolist() == kv_lens
