@@ -94,6 +94,11 @@ def run(args, rank, world, BATCH, KV_LEN, PAGE, kv_layout_fn, clock_sampler, sum
     tokens.copy_(tok_pin)
     step()  # JIT-compiles the reference modules
     torch.cuda.synchronize()
+    if getattr(args, "eager_steps", 0) > 0:
+        for _ in range(args.eager_steps):
+            step()
+        torch.cuda.synchronize()
+        return
     graph = None
     try:
         s = torch.cuda.Stream()

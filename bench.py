@@ -96,6 +96,11 @@ def run_ours(args, rank, world):
     torch.cuda.synchronize()
     native_per_step = jit.native_launch_count() - c0
     torch_per_step = 4 if world == 1 else 6  # index_select, zero_, argmax(+max/gather)
+    if args.eager_steps > 0:  # ncu / profiler mode: plain eager launches, no timing contract
+        for _ in range(args.eager_steps):
+            eng.step()
+        torch.cuda.synchronize()
+        return
     eng.capture(warmup=1)
 
     def barrier():
@@ -186,6 +191,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--eager-steps", type=int, default=0, help="run N eager steps and exit (for ncu)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))

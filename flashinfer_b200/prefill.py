@@ -25,7 +25,7 @@ from .utils import (
 )
 
 _WORK_INTS = 8
-_TILE_Q = 128
+_TILE_Q = 256
 _TILE_KV = 128
 
 
@@ -207,7 +207,7 @@ class _BatchPrefillBase:
             raise NotImplementedError("prefill_sm100: custom masks not supported yet")
         jit.load("prefill_sm100").call(
             "prefill_run", q, k, v, out, lse, kv_indices, self._kv_page_indptr_dev if paged else None,
-            self._work_info, self._cta_work_indptr, self._num_ctas, self._num_qo_heads, self._num_kv_heads,
+            self._work_info, self._cta_work_indptr, self._num_ctas, q.shape[0], self._num_qo_heads, self._num_kv_heads,
             self._head_dim_qk, 1 if paged else 0, *page_args, q.stride(0), q.stride(1), out.stride(0), out.stride(1),
             float(sm_scale), float(self._logits_soft_cap), int(window_left), 1 if self._causal else 0,
             dtype_code(q.dtype), 1 if (enable_pdl is None or enable_pdl) else 0, stream_ptr(q),

@@ -164,7 +164,85 @@ def case_decode_perf():
     return res
 
 
-CASES = {"gemm": case_gemm, "decode": case_decode, "decode_perf": case_decode_perf}
+def case_prefill():
+    import torch
+    import flashinfer_b200 as fi
+    from flashinfer_b200 import reference
+
+    torch.manual_seed(0)
+    res = {}
+    ws = torch.empty(128 << 20, dtype=torch.uint8, device="cuda")
+    # (q_lens, kv_lens, hq, hkv, causal, dtype, paged page_size or 0)
+    cfgs = [
+        ([128], [128], 1, 1, False, torch.bfloat16, 0),
+        ([256], [256], 2, 1, True, torch.bfloat16, 0),
+        ([100, 300, 17], [100, 300, 17], 8, 2, True, torch.bfloat16, 0),
+        ([33, 257], [500, 1000], 4, 4, True, torch.float16, 0),
+        ([512], [2048], 8, 2, False, torch.bfloat16, 0),
+        ([100, 300, 17], [150, 300, 400], 8, 2, True, torch.bfloat16, 16),
+        ([64, 129], [1000, 129], 4, 1, True, torch.float16, 32),
+        ([1000], [1000], 32, 8, True, torch.bfloat16, 0),
+    ]
+    for (q_lens, kv_lens, hq, hkv, causal, dt, ps) in cfgs:
+        name = f"q{q_lens}_kv{kv_lens}_h{hq}/{hkv}_c{int(causal)}_ps{ps}_{str(dt)[6:]}"
+        try:
+            B = len(q_lens)
+            qo = torch.tensor([0] + torch.tensor(q_lens).cumsum(0).tolist(), dtype=torch.int32)
+            q = torch.randn(sum(q_lens), hq, 128, device="cuda", dtype=dt)
+            if ps == 0:
+                kvi = torch.tensor([0] + torch.tensor(kv_lens).cumsum(0).tolist(), dtype=torch.int32)
+                k = torch.randn(sum(kv_lens), hkv, 128, device="cuda", dtype=dt)
+                v = torch.randn(sum(kv_lens), hkv, 128, device="cuda", dtype=dt)
+                w = fi.BatchPrefillWithRaggedKVCacheWrapper(ws)
+                w.plan(qo, kvi, hq, hkv, 128, causal=causal, q_data_type=dt)
+                o, lse = w.run(q, k, v, return_lse=True)
+                torch.cuda.synchronize()
+                outs, lses = [], []
+                for b in range(B):
+                    o_r, l_r = reference.attention_ref(q[qo[b]:qo[b + 1]], k[kvi[b]:kvi[b + 1]], v[kvi[b]:kvi[b + 1]], causal)
+                    outs.append(o_r); lses.append(l_r)
+                o_ref, lse_ref = torch.cat(outs), torch.cat(lses)
+            else:
+                indptr, indices, last, kc, vc = _make_paged(B, kv_lens, hkv, 128, ps, "NHD", dt)
+                w = fi.BatchPrefillWithPagedKVCacheWrapper(ws)
+                w.plan(qo, indptr, indices, last, hq, hkv, 128, ps, causal=causal, q_data_type=dt)
+                o, lse = w.run(q, (kc, vc), return_lse=True)
+                torch.cuda.synchronize()
+                o_ref, lse_ref = reference.batch_paged_attention_ref(q, qo, kc, vc, indptr, indices.cuda(), last, "NHD", causal)
+            err = (o.float() - o_ref.float()).abs().max().item()
+            lerr = (lse - lse_ref).abs().max().item()
+            ok = err < 3e-2 and lerr < 2e-2
+            res[name] = {"err": err, "lse_err": lerr, "ok": bool(ok)}
+            print(f"prefill {name}: err={err:.4g} lse_err={lerr:.4g} {'OK' if ok else 'FAIL'}", flush=True)
+        except Exception as e:  # noqa: BLE001
+            res[name] = {"ok": False, "exc": repr(e)}
+            print(f"prefill {name}: EXC {e!r}", flush=True)
+            traceback.print_exc()
+    return res
+
+
+def case_prefill_perf():
+    import torch
+    import flashinfer_b200 as fi
+
+    res = {}
+    ws = torch.empty(128 << 20, dtype=torch.uint8, device="cuda")
+    for (B, s, hq, hkv, causal) in [(1, 8192, 32, 8, True), (4, 8192, 32, 8, True), (16, 1024, 32, 8, True), (2, 16384, 32, 8, True), (8, 4096, 32, 8, False)]:
+        qo = torch.arange(0, (B + 1) * s, s, dtype=torch.int32)
+        q = torch.randn(B * s, hq, 128, device="cuda", dtype=torch.bfloat16)
+        k = torch.randn(B * s, hkv, 128, device="cuda", dtype=torch.bfloat16)
+        v = torch.randn(B * s, hkv, 128, device="cuda", dtype=torch.bfloat16)
+        w = fi.BatchPrefillWithRaggedKVCacheWrapper(ws)
+        w.plan(qo, qo, hq, hkv, 128, causal=causal, q_data_type=torch.bfloat16)
+        out = torch.empty_like(q)
+        ms = _time_ms(lambda: w.run(q, k, v, out=out), iters=10, warmup=3)
+        flops = 4 * B * hq * s * s * 128 * (0.5 if causal else 1.0)
+        res[f"B{B}_s{s}_c{int(causal)}"] = {"ms": ms, "tflops": flops / ms / 1e9}
+        print(f"prefill perf B={B} s={s} causal={causal}: {ms:.3f} ms {flops / ms / 1e9:.1f} TFLOP/s", flush=True)
+    return res
+
+
+CASES = {"prefill": case_prefill, "prefill_perf": case_prefill_perf, "gemm": case_gemm, "decode": case_decode, "decode_perf": case_decode_perf}
 
 
 def main():
