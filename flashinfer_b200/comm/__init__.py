@@ -1,0 +1,3 @@
+"""Communication kernels over NVLink 5 / NVSwitch (symmetric heap + in-kernel collectives)."""
+from .allreduce import TPCommunicator  # noqa: F401
+from .symm import SymmetricHeap  # noqa: F401

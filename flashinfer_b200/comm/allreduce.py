@@ -1,0 +1,159 @@
+"""Tensor-parallel all-reduce fused with residual-add + RMSNorm, issued from inside one CUDA kernel
+over NVLink/NVSwitch (csrc/comm/allreduce.cu).  Parity: reference flashinfer/comm/trtllm_ar.py
+(trtllm_allreduce_fusion :951, trtllm_custom_all_reduce :809), comm/allreduce.py (allreduce_fusion :460),
+comm/trtllm_mnnvl_ar.py and comm/vllm_ar.py.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from .. import jit
+from ..utils import dtype_code, stream_ptr
+from .symm import SymmetricHeap
+
+_MAX_BLOCKS = 296
+
+
+class TPCommunicator:
+    """Per-process-group communicator for the TP hot path.
+
+    * ``gemm_out(tokens)`` hands out the next (ping-pong) symmetric input buffer: the producer GEMM
+      writes its partial output straight into it (zero copy).
+    * ``allreduce_add_rmsnorm`` reduces that buffer across ranks in-switch (NVLS ``multimem.ld_reduce``)
+      and applies ``residual += sum; out = rmsnorm(residual) * weight`` in the same kernel.
+    """
+
+    def __init__(self, group: Optional[dist.ProcessGroup], max_tokens: int, hidden: int,
+                 dtype: torch.dtype = torch.bfloat16, use_nvls: bool = True):
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.max_tokens, self.hidden, self.dtype = max_tokens, hidden, dtype
+        esz = torch.empty(0, dtype=dtype).element_size()
+        buf_bytes = max_tokens * hidden * esz
+        sig_bytes = 2 * _MAX_BLOCKS * 16 * 4
+        small_bytes = 1 << 20
+        self.heap = SymmetricHeap(self.group, sig_bytes + 3 * buf_bytes + small_bytes + 16384)
+        sig, self._sig_off = self.heap.alloc(sig_bytes)
+        self._in = []
+        for _ in range(2):
+            v, off = self.heap.alloc(buf_bytes)
+            self._in.append((v.view(dtype).view(max_tokens, hidden), off))
+        v, self._out_off = self.heap.alloc(buf_bytes)
+        self._out_sym = v.view(dtype).view(max_tokens, hidden)
+        v, self._small_off = self.heap.alloc(small_bytes)
+        self._small = v
+        self._sig_tab = self.heap.peer_ptr_table(self._sig_off)
+        self._in_tab = [self.heap.peer_ptr_table(off) for _, off in self._in]
+        self._out_tab = self.heap.peer_ptr_table(self._out_off)
+        self._small_tab = self.heap.peer_ptr_table(self._small_off)
+        self._epochs = torch.zeros(2 * _MAX_BLOCKS, dtype=torch.int32, device=self.heap.device)
+        self.use_nvls = bool(use_nvls and self.heap.mc_ptr)
+        self._turn = 0
+        self._mod = jit.load("comm_allreduce")
+        self.heap.barrier()
+
+    # ------------------------------------------------------------------ buffers
+    def gemm_out(self, tokens: int) -> torch.Tensor:
+        """Next symmetric input buffer ``[tokens, hidden]`` (ping-pong)."""
+        self._turn ^= 1
+        return self._in[self._turn][0][:tokens]
+
+    def _locate(self, x: torch.Tensor):
+        for i, (buf, off) in enumerate(self._in):
+            if x.data_ptr() == buf.data_ptr():
+                return i
+        return -1
+
+    # ------------------------------------------------------------------ collectives
+    def allreduce_add_rmsnorm(self, x: torch.Tensor, residual: Optional[torch.Tensor], weight: Optional[torch.Tensor],
+                              eps: float = 1e-6, out: Optional[torch.Tensor] = None, two_shot: Optional[bool] = None,
+                              weight_bias: float = 0.0, quant_out: Optional[torch.Tensor] = None,
+                              quant_scale: float = 0.0, enable_pdl: bool = True) -> torch.Tensor:
+        """``s = sum_ranks(x); residual += s; out = rmsnorm(residual) * weight`` (``weight=None``: ``out = s``).
+
+        ``x`` should be a buffer obtained from :meth:`gemm_out`; any other tensor is staged into one.
+        One-shot (default for <= 1 MB): ``residual`` is replicated.  Two-shot: rank ``r`` owns rows
+        ``r::world`` of ``residual`` (token-sharded residual stream); ``out`` is complete on every rank."""
+        tokens, hidden = x.shape
+        idx = self._locate(x)
+        if idx < 0:
+            buf = self.gemm_out(tokens)
+            buf.copy_(x)
+            idx = self._turn
+        if two_shot is None:
+            two_shot = x.numel() * x.element_size() > (1 << 20)
+        if out is None:
+            out = torch.empty_like(x)
+        mc_in = self.heap.mc(self._in[idx][1]) if self.use_nvls else 0
+        target = out
+        if two_shot:
+            target = self._out_sym[:tokens]
+        self._mod.call(
+            "allreduce_fusion_run", self._in_tab[idx], self._sig_tab, self._out_tab if two_shot else None,
+            _ptr(mc_in), _ptr(self.heap.mc(self._out_off) if (two_shot and self.use_nvls) else 0), target, residual,
+            weight, self._epochs, quant_out, tokens, hidden, self.rank, self.world, _MAX_BLOCKS, float(eps),
+            float(weight_bias), float(quant_scale), 1 if two_shot else 0, dtype_code(x.dtype), 1 if enable_pdl else 0,
+            stream_ptr(x),
+        )
+        if two_shot:
+            out.copy_(target)
+        return out
+
+    def all_reduce(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Plain sum all-reduce through the same kernel."""
+        shape = x.shape
+        x2 = x.reshape(-1, shape[-1]) if x.ndim > 1 else x.reshape(1, -1)
+        if x2.shape[1] != self.hidden or x2.dtype != self.dtype:
+            return self._all_reduce_small(x, out)
+        res = self.allreduce_add_rmsnorm(x2, None, None, out=out.view_as(x2) if out is not None else None)
+        return res.view(shape)
+
+    def _all_reduce_small(self, x: torch.Tensor, out: Optional[torch.Tensor]) -> torch.Tensor:
+        """fp32 all-reduce of a small tensor (<= 1 MB) via the symmetric scratch region."""
+        n = x.numel()
+        assert n * 4 <= self._small.numel(), "small all-reduce limited to 1 MB"
+        pad = (-n) % 4
+        stage = self._small.view(torch.float32)[: n + pad].view(1, n + pad)
+        stage.zero_()
+        stage[0, :n].copy_(x.reshape(-1).float())
+        res = torch.empty(1, n + pad, dtype=torch.float32, device=x.device)
+        self._mod.call(
+            "allreduce_fusion_run", self._small_tab, self._sig_tab, None,
+            _ptr(self.heap.mc(self._small_off) if self.use_nvls else 0), _ptr(0), res, None, None, self._epochs, None,
+            1, n + pad, self.rank, self.world, _MAX_BLOCKS, 0.0, 0.0, 0.0, 0, dtype_code(torch.float32), 1, stream_ptr(x),
+        )
+        # the scratch region is reused by the next call: fence with a second (cheap) barrier round
+        self._barrier_kernel(x)
+        r = res[0, :n].view(x.shape).to(x.dtype)
+        if out is not None:
+            out.copy_(r)
+            return out
+        return r
+
+    def _barrier_kernel(self, ref: torch.Tensor) -> None:
+        dummy = torch.zeros(1, 4, dtype=torch.float32, device=ref.device)
+        self._mod.call(
+            "allreduce_fusion_run", self._small_tab, self._sig_tab, None, _ptr(0), _ptr(0), dummy, None, None,
+            self._epochs, None, 0 + 1, 4, self.rank, self.world, _MAX_BLOCKS, 0.0, 0.0, 0.0, 0,
+            dtype_code(torch.float32), 1, stream_ptr(ref),
+        )
+
+    def argmax_gather(self, val: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+        """Global argmax over vocab shards: every rank contributes (max value, global index)."""
+        b = val.numel()
+        table = torch.zeros(self.world, 2, b, dtype=torch.float32, device=val.device)
+        table[self.rank, 0] = val.float()
+        table[self.rank, 1] = idx.float()
+        table = self._all_reduce_small(table, None)
+        best = table[:, 0].argmax(0)
+        return table[:, 1].gather(0, best[None])[0].long()
+
+
+class _ptr:
+    """Marshal a raw device address through the uniform C ABI (void*)."""
+
+    def __init__(self, v: int):
+        self.v = int(v)

@@ -44,11 +44,9 @@ inline int set_error(const std::string& msg) {
     }                                                                                              \
   } while (0)
 
-namespace {
 // per-translation-unit (internal linkage): every native module counts only its own launches
-long long g_launch_counter = 0;
-}  // namespace
-inline long long& launch_counter() { return g_launch_counter; }
+static long long g_launch_counter = 0;
+static inline long long& launch_counter() { return g_launch_counter; }
 
 #define FIB_EXPORT_LAST_ERROR()                                                                    \
   extern "C" const char* fib200_last_error() { return ::fib200::last_error_storage().c_str(); }    \

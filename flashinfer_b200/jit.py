@@ -141,7 +141,8 @@ register(ModuleSpec("mla_sm100", ["attention/mla_sm100.cu"]))
 register(ModuleSpec("gemm_blockscaled_sm100", ["gemm/gemm_blockscaled_sm100.cu"]))
 register(ModuleSpec("grouped_gemm_sm100", ["gemm/grouped_gemm_sm100.cu"]))
 register(ModuleSpec("moe", ["moe/routing.cu", "moe/moe_utils.cu"]))
-register(ModuleSpec("comm", ["comm/allreduce.cu", "comm/moe_alltoall.cu", "comm/symm.cu"]))
+register(ModuleSpec("comm_allreduce", ["comm/allreduce.cu"]))
+register(ModuleSpec("comm_alltoall", ["comm/moe_alltoall.cu"]))
 register(ModuleSpec("gemm_comm_sm100", ["comm/gemm_allreduce_sm100.cu"]))
 
 
@@ -255,6 +256,8 @@ class NativeModule:
                 cargs.append(ctypes.c_double(a))
             elif isinstance(a, (ctypes.c_void_p, ctypes.c_int64, ctypes.c_double)):
                 cargs.append(a)
+            elif hasattr(a, "v") and type(a).__name__ == "_ptr":  # raw device address
+                cargs.append(ctypes.c_void_p(a.v))
             else:
                 raise TypeError(f"cannot marshal argument of type {type(a)} for {self.name}.{sym}")
         rc = self.fn(sym)(*cargs)
