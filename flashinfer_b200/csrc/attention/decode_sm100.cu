@@ -39,6 +39,7 @@ struct DecodeParams {
   const int32_t* cta_seg_indptr;  // [grid+1]
   float* partial_o;               // [slots][rows_per_slot][D]
   float* partial_lse;             // [slots][rows_per_slot]
+  int* merge_counters;            // [slots] zero-initialised, self-resetting (in-kernel merge); may be null
   int64_t q_stride_n, q_stride_h, o_stride_n, o_stride_h;
   int num_qo_heads, num_kv_heads, group, page_size, layout_hnd, rows_per_slot;
   int window_left, causal;
@@ -135,7 +136,7 @@ __device__ __forceinline__ TileGeom tile_geom(int ti, int ps) {
 
 // NQ: MMA N (padded q rows, multiple of 16); NV: power-of-two number of columns actually processed.
 template <int NQ, int NV, int D, typename T>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(288, 1)
 decode_paged_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                     const DecodeParams p, uint32_t idesc_qk, uint32_t idesc_pv) {
   using S = DecodeSmem<NQ, D>;
@@ -198,83 +199,62 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
 
   const int ps = p.page_size;
 
-  if (warp == 0) {
-    // ============================ TMA producer ============================
-    int ks = 0, vs = 0;
-    uint32_t kph = 0, vph = 0;
+  if (warp == 0 || warp == 2 || warp == 3 || warp == 8) {
+    // ============================ TMA producers (4 warps) ============================
+    // ncu showed one producer warp saturating on UTMALDG issue (the per-lane page boxes are serialised
+    // through an ELECT/R2UR loop, ~100 cycles each), so the 32 boxes of a tile are split over four
+    // warps: group g = {K,V} x {64-column chunk}.  The chunk-0 warp of each tensor arms expect_tx
+    // with the byte count of the whole tile; complete_tx from the sibling warp may land first, which
+    // is legal (the phase cannot complete before the arming arrive).
+    const int g = (warp == 0) ? 0 : (warp == 2 ? 1 : (warp == 3 ? 2 : 3));
+    const int is_v = g >> 1;
+    const int chunk = g & 1;
+    const int nstages = is_v ? S::kStagesV : S::kStagesK;
+    uint64_t* full_bars = is_v ? v_full : k_full;
+    uint64_t* empty_bars = is_v ? v_empty : k_empty;
+    const CUtensorMap* tm = is_v ? &tmV : &tmK;
+    uint8_t* ring = smem + (is_v ? S::kOffV : S::kOffK) + chunk * S::kChunkBytes;
+    int st = 0;
+    uint32_t ph = 0;
     for (int seg = seg_begin; seg < seg_end; ++seg) {
       const int32_t* si = p.seg_info + seg * kSegInts;
       const int kv_head = si[1], t0 = si[2], t1 = si[3], page_start = si[8], num_pages = si[9];
       for (int ti = t0; ti < t1; ++ti) {
-        const TileGeom g = tile_geom(ti, ps);
-        // Each lane owns page boxes lane, lane+32, ... of the tile (page_size < 4 => more than 32 boxes).
-        int n_boxes;         // number of page boxes in this tile
-        uint32_t box_bytes;  // bytes per box per chunk
-        int box_rows;
+        const TileGeom g2 = tile_geom(ti, ps);
+        int n_boxes, box_rows;
         if (ps <= kTileKV) {
-          n_boxes = min(kTileKV / ps, num_pages - g.first_page);
+          n_boxes = min(kTileKV / ps, num_pages - g2.first_page);
           box_rows = ps;
         } else {
           n_boxes = 1;
-          box_rows = 0;  // single box at row 0
+          box_rows = 0;
         }
-        box_bytes = (ps <= kTileKV ? ps : kTileKV) * 128;
+        const uint32_t box_bytes = (ps <= kTileKV ? ps : kTileKV) * 128;
         const uint32_t tx = uint32_t(n_boxes) * box_bytes * S::kChunks;
         int my_pages[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int bi = lane + j * 32;
-          my_pages[j] = (bi < n_boxes) ? __ldg(p.kv_indices + page_start + g.first_page + bi) : -1;
+          my_pages[j] = (bi < n_boxes) ? __ldg(p.kv_indices + page_start + g2.first_page + bi) : -1;
         }
-        // ---- K ----
         if (lane == 0) {
-          ptx::mbar_wait(&k_empty[ks], kph ^ 1);
-          ptx::mbar_arrive_expect_tx(&k_full[ks], tx);
+          ptx::mbar_wait(&empty_bars[st], ph ^ 1);
+          if (chunk == 0) ptx::mbar_arrive_expect_tx(&full_bars[st], tx);
         }
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           if (my_pages[j] >= 0) {
-            uint8_t* dst = smem + S::kOffK + ks * S::kTileBytes + (lane + j * 32) * box_rows * 128;
-#pragma unroll
-            for (int c = 0; c < S::kChunks; ++c) {
-              if (p.layout_hnd)
-                ptx::tma_load_4d(dst + c * S::kChunkBytes, &tmK, &k_full[ks], c * 64, g.page_off, kv_head, my_pages[j],
-                                 ptx::kEvictFirst);
-              else
-                ptx::tma_load_4d(dst + c * S::kChunkBytes, &tmK, &k_full[ks], c * 64, kv_head, g.page_off, my_pages[j],
-                                 ptx::kEvictFirst);
-            }
+            uint8_t* dst = ring + st * S::kTileBytes + (lane + j * 32) * box_rows * 128;
+            if (p.layout_hnd)
+              ptx::tma_load_4d(dst, tm, &full_bars[st], chunk * 64, g2.page_off, kv_head, my_pages[j], ptx::kEvictFirst);
+            else
+              ptx::tma_load_4d(dst, tm, &full_bars[st], chunk * 64, kv_head, g2.page_off, my_pages[j], ptx::kEvictFirst);
           }
         }
-        if (++ks == S::kStagesK) {
-          ks = 0;
-          kph ^= 1;
-        }
-        // ---- V ----
-        if (lane == 0) {
-          ptx::mbar_wait(&v_empty[vs], vph ^ 1);
-          ptx::mbar_arrive_expect_tx(&v_full[vs], tx);
-        }
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (my_pages[j] >= 0) {
-            uint8_t* dst = smem + S::kOffV + vs * S::kTileBytes + (lane + j * 32) * box_rows * 128;
-#pragma unroll
-            for (int c = 0; c < S::kChunks; ++c) {
-              if (p.layout_hnd)
-                ptx::tma_load_4d(dst + c * S::kChunkBytes, &tmV, &v_full[vs], c * 64, g.page_off, kv_head, my_pages[j],
-                                 ptx::kEvictFirst);
-              else
-                ptx::tma_load_4d(dst + c * S::kChunkBytes, &tmV, &v_full[vs], c * 64, kv_head, g.page_off, my_pages[j],
-                                 ptx::kEvictFirst);
-            }
-          }
-        }
-        if (++vs == S::kStagesV) {
-          vs = 0;
-          vph ^= 1;
+        if (++st == nstages) {
+          st = 0;
+          ph ^= 1;
         }
       }
     }
@@ -342,7 +322,7 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
       }
       issue_pv(gt - 1);
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 8) {
     // ============================ softmax / accumulate ============================
     const int q4 = warp - 4;              // TMEM lane quadrant
     const int row = q4 * 32 + lane;       // kv row inside the tile for S^T; head-dim index for O^T
@@ -501,6 +481,40 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
           }
         }
       }
+      if (slot >= 0 && p.merge_counters) {
+        // ---- in-kernel merge: the last part of this (request, kv head) to arrive folds all partials ----
+        const int first_slot = si[10], nparts = si[11];
+        __threadfence();
+        ptx::named_bar_sync(1, 128);
+        if (threadIdx.x == 128) {
+          const int old = atomicAdd(&p.merge_counters[first_slot], 1);
+          const int last = (old == nparts - 1);
+          if (last) p.merge_counters[first_slot] = 0;
+          reinterpret_cast<volatile int*>(red_sum)[0] = last;
+        }
+        ptx::named_bar_sync(1, 128);
+        const bool last = reinterpret_cast<volatile int*>(red_sum)[0] != 0;
+        if (last) {
+          __threadfence();
+          for (int c = 0; c < nq; ++c) {
+            float mx = -INFINITY;
+            for (int sidx = 0; sidx < nparts; ++sidx)
+              mx = fmaxf(mx, __ldcg(p.partial_lse + int64_t(first_slot + sidx) * p.rows_per_slot + c));
+            float acc = 0.f, den = 0.f;
+            for (int sidx = 0; sidx < nparts; ++sidx) {
+              const float ls = __ldcg(p.partial_lse + int64_t(first_slot + sidx) * p.rows_per_slot + c);
+              const float w = (mx == -INFINITY) ? 0.f : ptx::ex2(ls - mx);
+              acc += w * __ldcg(p.partial_o + (int64_t(first_slot + sidx) * p.rows_per_slot + c) * D + row);
+              den += w;
+            }
+            const float val = den > 0.f ? acc / den : 0.f;
+            const int qi = c / G, g = c % G;
+            obase[int64_t(q_start + qi) * p.o_stride_n + int64_t(kv_head * G + g) * p.o_stride_h + row] = from_f32<T>(val);
+            if (p.lse && row == 0)
+              p.lse[int64_t(q_start + qi) * p.num_qo_heads + kv_head * G + g] = den > 0.f ? mx + ptx::lg2(den) : -INFINITY;
+          }
+        }
+      }
       ptx::named_bar_sync(1, 128);  // red_sum / Q smem reuse across segments
     }
   }
@@ -559,7 +573,7 @@ int launch_decode(const CUtensorMap& tmK, const CUtensorMap& tmV, const DecodePa
   const uint32_t fmt = f16 ? ptx::kFmtF16 : ptx::kFmtBF16;
   const uint32_t idesc_qk = ptx::make_idesc_f16(fmt, 128, NQ, 0, 0);
   const uint32_t idesc_pv = ptx::make_idesc_f16(fmt, 128, NQ, 1, 0);
-  LaunchCfg lc(dim3(grid), dim3(256), S::kTotal, stream, pdl);
+  LaunchCfg lc(dim3(grid), dim3(288), S::kTotal, stream, pdl);
   FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, kern, tmK, tmV, p, idesc_qk, idesc_pv));
   return 0;
 }
@@ -578,7 +592,7 @@ extern "C" int decode_paged_info(int64_t* tile_kv, int64_t* seg_ints, int64_t* m
 // (stride_page, stride_n (token in page), stride_h); kv dtype == q dtype (f16/bf16).
 extern "C" int decode_paged_run(void* q, void* k_cache, void* v_cache, void* out, void* lse, void* kv_indices,
                                 void* seg_info, void* cta_seg_indptr, void* merge_items, int64_t num_merge_items,
-                                void* partial_o, void* partial_lse, int64_t grid, int64_t max_q_rows,
+                                void* partial_o, void* partial_lse, void* merge_counters, int64_t grid, int64_t max_q_rows,
                                 int64_t num_qo_heads, int64_t num_kv_heads, int64_t head_dim, int64_t page_size,
                                 int64_t num_pages_total, int64_t kv_stride_page, int64_t kv_stride_n,
                                 int64_t kv_stride_h, int64_t layout_hnd, int64_t q_stride_n, int64_t q_stride_h,
@@ -617,6 +631,7 @@ extern "C" int decode_paged_run(void* q, void* k_cache, void* v_cache, void* out
   p.cta_seg_indptr = (const int32_t*)cta_seg_indptr;
   p.partial_o = (float*)partial_o;
   p.partial_lse = (float*)partial_lse;
+  p.merge_counters = (int*)merge_counters;
   p.q_stride_n = q_stride_n;
   p.q_stride_h = q_stride_h;
   p.o_stride_n = o_stride_n;
@@ -650,7 +665,7 @@ extern "C" int decode_paged_run(void* q, void* k_cache, void* v_cache, void* out
     default: FIB_DEC(32, 32); break;
   }
 #undef FIB_DEC
-  if (num_merge_items > 0) {
+  if (num_merge_items > 0 && merge_counters == nullptr) {
     int blocks = (int)num_merge_items;
     LaunchCfg lc(dim3(blocks), dim3(128), 0, stream, pdl != 0);
     if (f16) {

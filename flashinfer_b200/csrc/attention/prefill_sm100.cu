@@ -201,17 +201,12 @@ prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 
   if (warp < 4) {
     ptx::setmaxnreg_dec<80>();
-    if (warp == 0) {
-      // ============================ TMA producer ============================
-      int ks = 0, vs = 0;
-      uint32_t kph = 0, vph = 0, qph = 0;
+    if (warp == 2) {
+      // ============================ Q loader ============================
+      uint32_t qph = 0;
       for (int w = w_begin; w < w_end; ++w) {
         const int32_t* wi = p.work_info + w * kWorkInts;
-        const int req = wi[0], q0 = wi[1], head = wi[3], qo_start = wi[6], kv_start = wi[7];
-        const int kv_head = head / p.group;
-        int t_lo, t_hi;
-        unit_tiles(wi, t_lo, t_hi);
-        // ---- Q (both tiles) ----
+        const int q0 = wi[1], head = wi[3], qo_start = wi[6];
         if (lane == 0) {
           ptx::mbar_wait(q_empty, qph ^ 1);
           ptx::mbar_arrive_expect_tx(q_full, 2 * S::kTileBytes);
@@ -223,6 +218,24 @@ prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                                qo_start + q0 + t * kTileQ, ptx::kEvictFirst);
         }
         qph ^= 1;
+      }
+    } else if (warp == 0 || warp == 3) {
+      // ============================ K loader (warp 0) / V loader (warp 3) ============================
+      // (one warp per tensor: paged gathers issue one TMA per page and UTMALDG issue is the limiter)
+      const int is_v = (warp == 3);
+      const int nstages = is_v ? S::kStagesV : S::kStagesK;
+      uint64_t* full_bars = is_v ? v_full : k_full;
+      uint64_t* empty_bars = is_v ? v_empty : k_empty;
+      const CUtensorMap* tm = is_v ? &tmV : &tmK;
+      uint8_t* ring = smem + (is_v ? S::kOffV : S::kOffK);
+      int st = 0;
+      uint32_t ph = 0;
+      for (int w = w_begin; w < w_end; ++w) {
+        const int32_t* wi = p.work_info + w * kWorkInts;
+        const int req = wi[0], head = wi[3], kv_start = wi[7];
+        const int kv_head = head / p.group;
+        int t_lo, t_hi;
+        unit_tiles(wi, t_lo, t_hi);
         int page_start = 0, num_pages = 0;
         if (p.paged) {
           page_start = p.kv_page_indptr[req];
@@ -261,36 +274,27 @@ prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             else
               my_pages[j] = (bi < n_boxes) ? __ldg(p.kv_indices + page_start + first_page + bi) : -1;
           }
+          if (lane == 0) {
+            ptx::mbar_wait(&empty_bars[st], ph ^ 1);
+            ptx::mbar_arrive_expect_tx(&full_bars[st], tx);
+          }
+          __syncwarp();
 #pragma unroll
-          for (int kv = 0; kv < 2; ++kv) {
-            uint64_t* full = kv == 0 ? &k_full[ks] : &v_full[vs];
-            uint64_t* empty = kv == 0 ? &k_empty[ks] : &v_empty[vs];
-            const uint32_t ph = kv == 0 ? kph : vph;
-            uint8_t* base = smem + (kv == 0 ? S::kOffK + ks * S::kTileBytes : S::kOffV + vs * S::kTileBytes);
-            const CUtensorMap* tm = kv == 0 ? &tmK : &tmV;
-            if (lane == 0) {
-              ptx::mbar_wait(empty, ph ^ 1);
-              ptx::mbar_arrive_expect_tx(full, tx);
-            }
-            __syncwarp();
+          for (int j = 0; j < 4; ++j) {
+            if (my_pages[j] >= 0) {
+              uint8_t* dst = ring + st * S::kTileBytes + (lane + j * 32) * box_rows * 128;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (my_pages[j] >= 0) {
-                uint8_t* dst = base + (lane + j * 32) * box_rows * 128;
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                  if (p.layout_hnd)
-                    ptx::tma_load_4d(dst + c * S::kChunkBytes, tm, full, c * 64, page_off, kv_head, my_pages[j]);
-                  else
-                    ptx::tma_load_4d(dst + c * S::kChunkBytes, tm, full, c * 64, kv_head, page_off, my_pages[j]);
-                }
+              for (int c = 0; c < 2; ++c) {
+                if (p.layout_hnd)
+                  ptx::tma_load_4d(dst + c * S::kChunkBytes, tm, &full_bars[st], c * 64, page_off, kv_head, my_pages[j]);
+                else
+                  ptx::tma_load_4d(dst + c * S::kChunkBytes, tm, &full_bars[st], c * 64, kv_head, page_off, my_pages[j]);
               }
             }
-            if (kv == 0) {
-              if (++ks == S::kStagesK) { ks = 0; kph ^= 1; }
-            } else {
-              if (++vs == S::kStagesV) { vs = 0; vph ^= 1; }
-            }
+          }
+          if (++st == nstages) {
+            st = 0;
+            ph ^= 1;
           }
         }
       }

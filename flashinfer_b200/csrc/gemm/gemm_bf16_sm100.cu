@@ -32,14 +32,26 @@ struct GemmSmem {
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarOffset = kStages * kStageBytes;
-  static constexpr int kTotal = kBarOffset + 256 + 1024;  // + barriers + alignment slack
+  static constexpr int kTotal = kBarOffset + 320 + 1024;  // + barriers + flags + alignment slack
 };
 
-template <int BN, bool kSwap, typename OutT, bool kSplitK>
+// Stream-K work decomposition: the flattened (tile, k-block) space is cut into equal contiguous
+// ranges, one per CTA.  A tile that straddles CTA boundaries is finished by a deterministic in-kernel
+// fix-up: every part writes its fp32 partial to an L2-resident workspace slot and bumps the tile's
+// counter; the last arriver sums the slots in slot order (bitwise reproducible) and writes the output.
+struct StreamK {
+  int tiles_a, tiles_b, kblocks, grid;
+  int64_t units;
+  int max_parts;
+  __device__ __forceinline__ int64_t begin(int c) const { return (int64_t(c) * units) / grid; }
+  __device__ __forceinline__ int cta_of(int64_t u) const { return int(((u + 1) * grid + units - 1) / units) - 1; }
+};
+
+template <int BN, bool kSwap, typename OutT>
 __global__ void __launch_bounds__(256, 1)
 gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, OutT* __restrict__ C,
-               float* __restrict__ partial, const OutT* __restrict__ bias, int rowsA, int rowsB, int K, int64_t ldc,
-               int splits, uint32_t idesc) {
+               float* __restrict__ partial, int* __restrict__ counters, const OutT* __restrict__ bias, int rowsA,
+               int rowsB, int K, int64_t ldc, const StreamK sk, uint32_t idesc) {
   using S = GemmSmem<BN>;
   constexpr int kStages = S::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -49,15 +61,12 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tmem_full = empty_bar + kStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  int* s_flag = reinterpret_cast<int*>(tmem_ptr + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-
-  const int tiles_a = (rowsA + BM - 1) / BM;
-  const int tiles_b = (rowsB + BN - 1) / BN;
-  const int num_kb_total = (K + BK - 1) / BK;
-  const int kb_per_split = (num_kb_total + splits - 1) / splits;
-  const int num_tiles = tiles_a * tiles_b * splits;
+  const int64_t u_begin = sk.begin(blockIdx.x);
+  const int64_t u_end = sk.begin(blockIdx.x + 1);
 
   if (threadIdx.x == 0) {
     ptx::prefetch_tmap(&tmA);
@@ -88,19 +97,16 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int ta = t % tiles_a;
-        const int rest = t / tiles_a;
-        const int tb = rest % tiles_b;
-        const int sp = rest / tiles_b;
-        const int kb0 = sp * kb_per_split;
-        const int kb1 = min(num_kb_total, kb0 + kb_per_split);
+      for (int64_t u = u_begin; u < u_end;) {
+        const int t = int(u / sk.kblocks);
+        const int kb0 = int(u % sk.kblocks);
+        const int kb1 = int((kb0 + (u_end - u)) < int64_t(sk.kblocks) ? (kb0 + (u_end - u)) : int64_t(sk.kblocks));
+        const int ta = t % sk.tiles_a, tb = t / sk.tiles_a;
         for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * S::kStageBytes;
           uint8_t* sb = sa + S::kABytes;
           ptx::mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
-          // weights are streamed once (evict-first when they are the A side of a swapped GEMM)
           ptx::tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, ta * BM, kSwap ? ptx::kEvictFirst : ptx::kEvictNormal);
           ptx::tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, tb * BN, kSwap ? ptx::kEvictLast : ptx::kEvictFirst);
           if (++stage == kStages) {
@@ -108,6 +114,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             phase ^= 1;
           }
         }
+        u += kb1 - kb0;
       }
     }
   } else if (warp == 1) {
@@ -116,10 +123,9 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int sp = (t / tiles_a) / tiles_b;
-      const int kb0 = sp * kb_per_split;
-      const int kb1 = min(num_kb_total, kb0 + kb_per_split);
+    for (int64_t u = u_begin; u < u_end;) {
+      const int kb0 = int(u % sk.kblocks);
+      const int kb1 = int((kb0 + (u_end - u)) < int64_t(sk.kblocks) ? (kb0 + (u_end - u)) : int64_t(sk.kblocks));
       ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BN;
@@ -145,88 +151,125 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           phase ^= 1;
         }
       }
-      if (kb1 <= kb0) {
-        // empty split (cannot happen with the host-side split choice, kept for safety)
-        if (ptx::elect_one()) ptx::mma_commit(&tmem_full[acc]);
-        __syncwarp();
-      }
+      u += kb1 - kb0;
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
     ptx::grid_dep_launch();
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
+    // ===================== epilogue (+ stream-K fix-up) =====================
     const int q = warp - 4;  // TMEM lane quadrant == warp % 4
+    const int etid = threadIdx.x - 128;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int ta = t % tiles_a;
-      const int rest = t / tiles_a;
-      const int tb = rest % tiles_b;
-      const int sp = rest / tiles_b;
+    constexpr int CH = (BN >= 32) ? 32 : 16;
+    for (int64_t u = u_begin; u < u_end;) {
+      const int t = int(u / sk.kblocks);
+      const int kb0 = int(u % sk.kblocks);
+      const int kb1 = int((kb0 + (u_end - u)) < int64_t(sk.kblocks) ? (kb0 + (u_end - u)) : int64_t(sk.kblocks));
+      u += kb1 - kb0;
+      const int ta = t % sk.tiles_a, tb = t / sk.tiles_a;
+      const bool full_tile = (kb0 == 0 && kb1 == sk.kblocks);
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
-      const int a_row = ta * BM + q * 32 + lane;  // row of the A-side operand owned by this thread
+      const int r_in_tile = q * 32 + lane;
+      const int a_row = ta * BM + r_in_tile;  // row of the A-side operand owned by this thread
       const uint32_t taddr = tmem_base + acc * BN + (uint32_t(q * 32) << 16);
-      constexpr int CH = (BN >= 32) ? 32 : 16;
+
+      int parts = 1, c_first = 0;
+      bool i_am_last = true;
+      float* my_slot = nullptr;
+      if (!full_tile) {
+        c_first = sk.cta_of(int64_t(t) * sk.kblocks);
+        const int c_last = sk.cta_of(int64_t(t + 1) * sk.kblocks - 1);
+        parts = c_last - c_first + 1;
+        float* tile_ws = partial + int64_t(c_first) * sk.max_parts * (BM * BN);
+        my_slot = tile_ws + int64_t(blockIdx.x - c_first) * (BM * BN);
+        // 1) publish my partial
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += CH) {
-        uint32_t r[CH];
-        if constexpr (CH == 32)
-          ptx::tmem_ld_x32(taddr + c0, r);
-        else
-          ptx::tmem_ld_x16(taddr + c0, r);
-        ptx::tmem_ld_wait();
-        const int b_row0 = tb * BN + c0;
-        if constexpr (kSplitK) {
-          // fp32 partials laid out [split][rowsB][rowsA] (swap) or [split][rowsA][rowsB]
-          if (a_row < rowsA) {
-            if constexpr (kSwap) {
+        for (int c0 = 0; c0 < BN; c0 += CH) {
+          uint32_t r[CH];
+          if constexpr (CH == 32) ptx::tmem_ld_x32(taddr + c0, r); else ptx::tmem_ld_x16(taddr + c0, r);
+          ptx::tmem_ld_wait();
+          float4* dst = reinterpret_cast<float4*>(my_slot + r_in_tile * BN + c0);
 #pragma unroll
-              for (int j = 0; j < CH; ++j)
-                if (b_row0 + j < rowsB)
-                  partial[(int64_t(sp) * rowsB + (b_row0 + j)) * rowsA + a_row] = __uint_as_float(r[j]);
-            } else {
+          for (int j = 0; j < CH; j += 4)
+            __stcg(dst + j / 4, make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                            __uint_as_float(r[j + 3])));
+        }
+        __threadfence();
+        ptx::named_bar_sync(1, 128);
+        if (etid == 0) {
+          const int old = atomicAdd(&counters[c_first], 1);
+          const int last = (old == parts - 1);
+          if (last) counters[c_first] = 0;  // self-reset for the next launch / graph replay
+          *s_flag = last;
+        }
+        ptx::named_bar_sync(1, 128);
+        i_am_last = (*s_flag != 0);
+        if (i_am_last) __threadfence();
+      }
+
+      if (i_am_last) {
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += CH) {
+          float v[CH];
+          if (full_tile) {
+            uint32_t r[CH];
+            if constexpr (CH == 32) ptx::tmem_ld_x32(taddr + c0, r); else ptx::tmem_ld_x16(taddr + c0, r);
+            ptx::tmem_ld_wait();
 #pragma unroll
-              for (int j = 0; j < CH; ++j)
-                if (b_row0 + j < rowsB)
-                  partial[(int64_t(sp) * rowsA + a_row) * rowsB + b_row0 + j] = __uint_as_float(r[j]);
-            }
-          }
-        } else if constexpr (kSwap) {
-          // C[b_row][a_row]: consecutive lanes -> consecutive a_row -> coalesced 2B stores
-          if (a_row < rowsA) {
-            const float bv = bias ? to_f32(bias[a_row]) : 0.f;
+            for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]);
+          } else {
 #pragma unroll
-            for (int j = 0; j < CH; ++j) {
-              if (b_row0 + j < rowsB) C[int64_t(b_row0 + j) * ldc + a_row] = from_f32<OutT>(__uint_as_float(r[j]) + bv);
-            }
-          }
-        } else {
-          // C[a_row][b_row..]: each thread owns one output row; 16B vector stores
-          if (a_row < rowsA) {
-            OutT* dst = C + int64_t(a_row) * ldc + b_row0;
-            if (b_row0 + CH <= rowsB && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-              constexpr int VN = 16 / sizeof(OutT);
+            for (int j = 0; j < CH; ++j) v[j] = 0.f;
+            const float* tile_ws = partial + int64_t(c_first) * sk.max_parts * (BM * BN);
+            for (int pth = 0; pth < parts; ++pth) {
+              const float4* src = reinterpret_cast<const float4*>(tile_ws + int64_t(pth) * (BM * BN) + r_in_tile * BN + c0);
 #pragma unroll
-              for (int j = 0; j < CH; j += VN) {
-                Vec16<OutT> v;
-#pragma unroll
-                for (int e = 0; e < VN; ++e) {
-                  float x = __uint_as_float(r[j + e]);
-                  if (bias) x += to_f32(bias[b_row0 + j + e]);
-                  v.v[e] = from_f32<OutT>(x);
-                }
-                st16(dst + j, v);
+              for (int j = 0; j < CH; j += 4) {
+                const float4 x = __ldcg(src + j / 4);
+                v[j] += x.x;
+                v[j + 1] += x.y;
+                v[j + 2] += x.z;
+                v[j + 3] += x.w;
               }
-            } else {
+            }
+          }
+          const int b_row0 = tb * BN + c0;
+          if constexpr (kSwap) {
+            // C[b_row][a_row]: consecutive lanes -> consecutive a_row -> coalesced 2B stores
+            if (a_row < rowsA) {
+              const float bv = bias ? to_f32(bias[a_row]) : 0.f;
 #pragma unroll
               for (int j = 0; j < CH; ++j)
-                if (b_row0 + j < rowsB) {
-                  float x = __uint_as_float(r[j]);
-                  if (bias) x += to_f32(bias[b_row0 + j]);
-                  dst[j] = from_f32<OutT>(x);
+                if (b_row0 + j < rowsB) C[int64_t(b_row0 + j) * ldc + a_row] = from_f32<OutT>(v[j] + bv);
+            }
+          } else {
+            if (a_row < rowsA) {
+              OutT* dst = C + int64_t(a_row) * ldc + b_row0;
+              if (b_row0 + CH <= rowsB && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+                constexpr int VN = 16 / sizeof(OutT);
+#pragma unroll
+                for (int j = 0; j < CH; j += VN) {
+                  Vec16<OutT> o;
+#pragma unroll
+                  for (int e = 0; e < VN; ++e) {
+                    float x = v[j + e];
+                    if (bias) x += to_f32(bias[b_row0 + j + e]);
+                    o.v[e] = from_f32<OutT>(x);
+                  }
+                  st16(dst + j, o);
                 }
+              } else {
+#pragma unroll
+                for (int j = 0; j < CH; ++j)
+                  if (b_row0 + j < rowsB) {
+                    float x = v[j];
+                    if (bias) x += to_f32(bias[b_row0 + j]);
+                    dst[j] = from_f32<OutT>(x);
+                  }
+              }
             }
           }
         }
@@ -247,38 +290,53 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
-// Reduce split-K fp32 partials into the output (+bias).  partial layout [splits][R0][R1].
-template <typename OutT>
-__global__ void splitk_reduce_kernel(const float* __restrict__ partial, OutT* __restrict__ C, const OutT* __restrict__ bias,
-                                     int splits, int R0, int R1, int64_t ldc, int swap) {
-  ptx::grid_dep_wait();
-  const int64_t total = int64_t(R0) * R1;
-  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
-    float acc = 0.f;
-    for (int s = 0; s < splits; ++s) acc += partial[int64_t(s) * total + i];
-    const int r0 = int(i / R1), r1 = int(i % R1);
-    // both layouts: r0 = output row (token), r1 = output col (feature)
-    if (bias) acc += to_f32(bias[r1]);
-    C[int64_t(r0) * ldc + r1] = from_f32<OutT>(acc);
-  }
-  (void)swap;
-}
-
-template <int BN, bool kSwap, typename OutT, bool kSplitK>
-int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, OutT* C, float* partial, const OutT* bias, int rowsA,
-                int rowsB, int K, int64_t ldc, int splits, bool f16, bool pdl, cudaStream_t stream) {
+template <int BN, bool kSwap, typename OutT>
+int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, OutT* C, float* workspace, int64_t workspace_bytes,
+                const OutT* bias, int rowsA, int rowsB, int K, int64_t ldc, bool f16, bool pdl, cudaStream_t stream) {
   using S = GemmSmem<BN>;
-  auto kern = gemm_nt_kernel<BN, kSwap, OutT, kSplitK>;
+  auto kern = gemm_nt_kernel<BN, kSwap, OutT>;
   static bool attr_set = false;
   if (!attr_set) {
     FIB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     attr_set = true;
   }
-  const int tiles = ((rowsA + BM - 1) / BM) * ((rowsB + BN - 1) / BN) * splits;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
+  StreamK sk;
+  sk.tiles_a = (rowsA + BM - 1) / BM;
+  sk.tiles_b = (rowsB + BN - 1) / BN;
+  sk.kblocks = (K + BK - 1) / BK;
+  const int tiles = sk.tiles_a * sk.tiles_b;
+  sk.units = int64_t(tiles) * sk.kblocks;
+  // workspace layout: [counters: 1024 ints][partials]
+  const int64_t slot_bytes = int64_t(BM) * BN * 4;
+  const int64_t ws_partial = workspace ? workspace_bytes - 4096 : 0;
+  int grid = num_sms();
+  if (sk.units < grid) grid = (int)sk.units;
+  const bool streamk = workspace != nullptr && (tiles % grid != 0);
+  auto parts_for = [&](int g) {
+    const int64_t per = sk.units / g > 0 ? sk.units / g : 1;
+    return int((sk.kblocks + per - 1) / per) + 1;
+  };
+  if (streamk) {
+    // at least 4 k-blocks per part, and the fix-up slots must fit the workspace
+    while (grid > 1 && (sk.units / grid < 4 || int64_t(grid) * parts_for(grid) * slot_bytes > ws_partial)) --grid;
+    sk.max_parts = parts_for(grid);
+  } else {
+    sk.max_parts = 1;
+    if (tiles % grid != 0) {
+      // no workspace: keep CTA ranges tile-aligned -> largest grid <= #SM that divides the tile count
+      for (int gtry = grid; gtry >= 1; --gtry)
+        if (tiles % gtry == 0) {
+          grid = gtry;
+          break;
+        }
+    }
+  }
+  sk.grid = grid;
   const uint32_t idesc = ptx::make_idesc_f16(f16 ? ptx::kFmtF16 : ptx::kFmtBF16, BM, BN, 0, 0);
   LaunchCfg lc(dim3(grid), dim3(256), S::kTotal, stream, pdl);
-  FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, kern, tmA, tmB, C, partial, bias, rowsA, rowsB, K, ldc, splits, idesc));
+  int* counters = reinterpret_cast<int*>(workspace);
+  float* partial = workspace ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + 4096) : nullptr;
+  FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, kern, tmA, tmB, C, partial, counters, bias, rowsA, rowsB, K, ldc, sk, idesc));
   return 0;
 }
 
@@ -311,29 +369,10 @@ int gemm_dispatch(const void* A, const void* B, OutT* C, const OutT* bias, int M
     uint32_t box[2] = {BK, (uint32_t)BN};
     if (make_tmap(&tmB, dt, 2, pb, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   }
-  // split-K heuristic: fill the machine when there are too few output tiles and K is long.
-  const int tiles = ((rowsA + BM - 1) / BM) * ((rowsB + BN - 1) / BN);
-  const int num_kb = (K + BK - 1) / BK;
-  int splits = 1;
-  if (workspace && tiles * 2 <= num_sms() && num_kb >= 16) {
-    splits = num_sms() / tiles;
-    if (splits > num_kb / 4) splits = num_kb / 4;
-    if (splits > 16) splits = 16;
-    while (splits > 1 && int64_t(splits) * M * N * 4 > workspace_bytes) --splits;
-    // make every split non-empty
-    while (splits > 1 && ((num_kb + splits - 1) / splits) * (splits - 1) >= num_kb) --splits;
-    if (splits < 1) splits = 1;
-  }
-#define FIB_LAUNCH(BN_, SWAP_)                                                                                       \
-  if (splits > 1) {                                                                                                  \
-    if (launch_gemm<BN_, SWAP_, OutT, true>(tmA, tmB, C, workspace, bias, rowsA, rowsB, K, ldc, splits, f16, pdl,    \
-                                            stream))                                                                 \
-      return 1;                                                                                                      \
-  } else {                                                                                                           \
-    if (launch_gemm<BN_, SWAP_, OutT, false>(tmA, tmB, C, workspace, bias, rowsA, rowsB, K, ldc, 1, f16, pdl,        \
-                                             stream))                                                                \
-      return 1;                                                                                                      \
-  }
+#define FIB_LAUNCH(BN_, SWAP_)                                                                                 \
+  if (launch_gemm<BN_, SWAP_, OutT>(tmA, tmB, C, workspace, workspace_bytes, bias, rowsA, rowsB, K, ldc, f16, pdl, \
+                                    stream))                                                                   \
+    return 1;
   if (swap) {
     switch (BN) {
       case 16: FIB_LAUNCH(16, true); break;
@@ -349,14 +388,6 @@ int gemm_dispatch(const void* A, const void* B, OutT* C, const OutT* bias, int M
     }
   }
 #undef FIB_LAUNCH
-  if (splits > 1) {
-    const int64_t total = int64_t(M) * N;
-    int blocks = int((total + 255) / 256);
-    if (blocks > num_sms() * 8) blocks = num_sms() * 8;
-    LaunchCfg lc(dim3(blocks), dim3(256), 0, stream, pdl);
-    FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, splitk_reduce_kernel<OutT>, (const float*)workspace, C, bias, splits, M, N,
-                                      ldc, swap ? 1 : 0));
-  }
   return 0;
 }
 

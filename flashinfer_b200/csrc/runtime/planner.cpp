@@ -47,7 +47,7 @@ extern "C" const char* fib200_last_error() { return g_err.c_str(); }
 //   q_indptr [B+1] or nullptr (=> q_len 1, q_start b)
 // Outputs:
 //   seg_info [max_segs][12] : {req, kv_head, tile_begin, tile_end, slot(-1 = final), q_start, q_len,
-//                              kv_len, page_start, num_pages, 0, 0}
+//                              kv_len, page_start, num_pages, first_slot, num_parts}
 //   cta_seg_indptr [num_ctas+1]
 //   merge_items [max_merge][8] : {slot0, nparts, q_start, q_len, kv_head, req, 0, 0}
 //   counts[0]=nseg, [1]=nmerge, [2]=nslots, [3]=max_q_rows(q_len*group), [4]=total_tiles, [5]=quota
@@ -112,7 +112,11 @@ extern "C" int decode_plan(const int32_t* kv_page_indptr, const int32_t* kv_lens
       const int64_t parts = nseg - first_seg;
       if (parts > 1) {
         if (nmerge >= max_merge) return fail("decode_plan: merge_items capacity exceeded");
-        for (int64_t i = 0; i < parts; ++i) seg_info[(first_seg + i) * kSegInts + 4] = (int32_t)(nslots + i);
+        for (int64_t i = 0; i < parts; ++i) {
+          seg_info[(first_seg + i) * kSegInts + 4] = (int32_t)(nslots + i);
+          seg_info[(first_seg + i) * kSegInts + 10] = (int32_t)nslots;  // first slot of the item (= counter id)
+          seg_info[(first_seg + i) * kSegInts + 11] = (int32_t)parts;   // number of partial states to merge
+        }
         int32_t* m = merge_items + nmerge * kMergeInts;
         m[0] = (int32_t)nslots;
         m[1] = (int32_t)parts;

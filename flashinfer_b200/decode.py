@@ -126,6 +126,8 @@ class BatchDecodeWithPagedKVCacheWrapper:
         self._pin_int_workspace_buffer = torch.empty(
             8 * 1024 * 1024, dtype=torch.uint8, device="cpu", pin_memory=self.device.type == "cuda"
         )
+        # in-kernel split-KV merge: one self-resetting arrival counter per partial-state slot
+        self._merge_counters = torch.zeros(4096, dtype=torch.int32, device=self.device)
         if use_cuda_graph:
             if paged_kv_indptr_buffer is None or paged_kv_indices_buffer is None or paged_kv_last_page_len_buffer is None:
                 raise ValueError("use_cuda_graph=True requires the indptr/indices/last_page_len buffers")
@@ -344,7 +346,7 @@ class BatchDecodeWithPagedKVCacheWrapper:
         mod.call(
             "decode_paged_run",
             q, k_cache, v_cache, out, lse, self._kv_indices, self._seg_info, self._cta_seg_indptr, self._merge_items,
-            self._num_merge, self._partial_o, self._partial_lse, self._num_ctas, self._max_q_rows,
+            self._num_merge, self._partial_o, self._partial_lse, self._merge_counters, self._num_ctas, self._max_q_rows,
             self._num_qo_heads, self._num_kv_heads, self._head_dim, page_size, k_cache.shape[0], sp, sn, sh,
             1 if self._kv_layout == "HND" else 0, q.stride(0), q.stride(1), out.stride(0), out.stride(1),
             float(sm_scale), float(self._logits_soft_cap), int(window_left), causal, dtype_code(q.dtype),

@@ -19,7 +19,7 @@ _workspaces = {}
 def _workspace(device) -> torch.Tensor:
     ws = _workspaces.get(device)
     if ws is None:
-        ws = torch.empty(32 * 1024 * 1024, dtype=torch.uint8, device=device)
+        ws = torch.zeros(32 * 1024 * 1024, dtype=torch.uint8, device=device)  # stream-K counters must start at 0
         _workspaces[device] = ws
     return ws
 

@@ -120,12 +120,17 @@ class LlamaDecodeEngine:
         self._graph = None
 
     # ------------------------------------------------------------------ one decode step
-    def _reduce_add_norm(self, x: torch.Tensor, weight: torch.Tensor) -> None:
-        """x <- rmsnorm(residual += allreduce(x)); single-GPU: plain fused add+norm."""
+    def _row_parallel(self, inp: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+        """Row-parallel linear: partial sums go straight into the symmetric heap when tp > 1."""
+        out = self._x if self.tp_size == 1 else self.comm.gemm_out(self.batch)
+        return linear(inp, w, out=out)
+
+    def _reduce_add_norm(self, part: torch.Tensor, weight: torch.Tensor) -> None:
+        """self._x <- rmsnorm(residual += allreduce(part)); single-GPU: plain fused add+norm."""
         if self.tp_size == 1:
-            norm.fused_add_rmsnorm(x, self._res, weight, self.cfg.rms_eps)
+            norm.fused_add_rmsnorm(part, self._res, weight, self.cfg.rms_eps)
         else:
-            self.comm.allreduce_add_rmsnorm(x, self._res, weight, self.cfg.rms_eps)
+            self.comm.allreduce_add_rmsnorm(part, self._res, weight, self.cfg.rms_eps, out=self._x)
 
     def step(self) -> torch.Tensor:
         """tokens (self.tokens) -> next tokens (self.next_tokens); greedy sampling."""
@@ -149,14 +154,14 @@ class LlamaDecodeEngine:
             page.append_paged_kv_cache(k, v, self.batch_indices, self.positions, (l["k_cache"], l["v_cache"]),
                                        self.kv_indices, self.kv_indptr, self.kv_last)
             self.wrapper.run(q, (l["k_cache"], l["v_cache"]), out=self._attn)
-            linear(self._attn.view(self.batch, hq * d), l["wo"], out=x)
-            self._reduce_add_norm(x, l["ln2"])
+            part = self._row_parallel(self._attn.view(self.batch, hq * d), l["wo"])
+            self._reduce_add_norm(part, l["ln2"])
             linear(x, l["wgu"], out=self._gu)
             activation.silu_and_mul(self._gu, out=self._act)
-            linear(self._act, l["wd"], out=x)
+            part = self._row_parallel(self._act, l["wd"])
             n += 9
             nxt = self.layers[li + 1]["ln1"] if li + 1 < len(self.layers) else self.final_norm
-            self._reduce_add_norm(x, nxt)
+            self._reduce_add_norm(part, nxt)
             n += 1
         linear(x, self.lm_head, out=self._logits)
         n += 1
