@@ -1,0 +1,297 @@
+// Block-scaled quantisation kernels for the Blackwell low-precision formats + bit packing.
+//
+// Parity: reference flashinfer/quantization/fp4_quantization.py:790-1683 (fp4_quantize / nvfp4_quantize /
+// mxfp4_quantize / nvfp4_batched_quantize / block_scale_interleave / e2m1_and_ufp8sf_scale_to_float),
+// fp8_quantization.py:163-276 (mxfp8_quantize), packbits.py:47-139 and the TRT-LLM kernels under
+// csrc/nv_internal/.  Formats: NVFP4 = e2m1 pairs packed in uint8, block 16, UE4M3 block
+// scale + fp32 global scale; MXFP4/MXFP8 = block 32, UE8M0 scale.  Scale-factor layouts: linear [M, K/vec]
+// or the 128x4 tile-swizzled layout consumed by tcgen05 block-scaled MMA (via tcgen05.cp 32x128b).
+//
+// One thread quantises one scale block (16 or 32 contiguous elements: 2 or 4 x 16 B loads), so global
+// traffic is fully vectorised; e2m1 conversion uses cvt.rn.satfinite.e2m1x2.f32 (sm_100a).
+#include <cuda_fp4.h>
+#include <fib200/common.cuh>
+#include <fib200/ptx.cuh>
+
+using namespace fib200;
+
+FIB_EXPORT_LAST_ERROR()
+
+namespace {
+
+// offset of scale (m, kc) in the 128x4 swizzled layout; kc_pad = round_up(Kc, 4)
+__host__ __device__ __forceinline__ int64_t sf_swizzled_offset(int64_t m, int64_t kc, int64_t kc_pad) {
+  const int64_t tile = (m / 128) * (kc_pad / 4) + kc / 4;
+  return tile * 512 + (m % 32) * 16 + ((m % 128) / 32) * 4 + (kc % 4);
+}
+
+__device__ __forceinline__ uint8_t f32_to_ue8m0_ceil(float x) {
+  // smallest power of two >= x (x > 0), biased exponent; 0 -> exponent for 2^-127
+  if (!(x > 0.f)) return 0;
+  const uint32_t b = __float_as_uint(x);
+  uint32_t e = (b >> 23) & 0xff;
+  if (b & 0x7fffff) e += 1;
+  if (e > 254) e = 254;
+  return (uint8_t)e;
+}
+__device__ __forceinline__ float ue8m0_to_f32(uint8_t e) { return __uint_as_float(uint32_t(e == 0 ? 0 : e) << 23); }
+
+// ---------------------------------------------------------------- fp4 (nvfp4 / mxfp4)
+// x [B, M, K] (row stride ldx) -> q [B, M, K/2] uint8, sf [B][...] uint8
+template <typename T, int VEC, bool kUE8M0>
+__global__ void __launch_bounds__(256)
+fp4_quantize_kernel(const T* __restrict__ x, uint8_t* __restrict__ q, uint8_t* __restrict__ sf,
+                    const float* __restrict__ global_scale, int64_t batch, int64_t M, int64_t K, int64_t ldx,
+                    int64_t x_batch_stride, int swizzled, int64_t sf_batch_stride) {
+  const int64_t kc_total = K / VEC;
+  const int64_t kc_pad = (kc_total + 3) / 4 * 4;
+  const int64_t total = batch * M * kc_total;
+  ptx::grid_dep_wait();
+  const float gs = global_scale ? __ldg(global_scale) : 1.f;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t kc = i % kc_total;
+    const int64_t m = (i / kc_total) % M;
+    const int64_t b = i / (kc_total * M);
+    const T* src = x + b * x_batch_stride + m * ldx + kc * VEC;
+    float v[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; j += 8) {
+      const Vec16<T> raw = ld16(src + j);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[j + e] = to_f32(raw.v[e]);
+    }
+    float amax = 0.f;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) amax = fmaxf(amax, fabsf(v[j]));
+    uint8_t sf_byte;
+    float out_scale;
+    if constexpr (kUE8M0) {
+      sf_byte = f32_to_ue8m0_ceil(amax * (1.f / 6.f) * gs);
+      const float sfv = ue8m0_to_f32(sf_byte);
+      out_scale = sfv > 0.f ? gs / sfv : 0.f;
+    } else {
+      const float sfv_f = gs * (amax * (1.f / 6.f));
+      const __nv_fp8_e4m3 s8(sfv_f);
+      sf_byte = *reinterpret_cast<const uint8_t*>(&s8);
+      const float sfv = float(s8);
+      out_scale = sfv != 0.f ? gs / sfv : 0.f;
+    }
+    uint8_t packed[VEC / 2];
+#pragma unroll
+    for (int j = 0; j < VEC; j += 2)
+      packed[j / 2] = (uint8_t)__nv_cvt_float2_to_fp4x2(make_float2(v[j] * out_scale, v[j + 1] * out_scale), __NV_E2M1,
+                                                        cudaRoundNearest);
+    uint8_t* dst = q + (b * M + m) * (K / 2) + kc * (VEC / 2);
+    if constexpr (VEC == 16) {
+      *reinterpret_cast<int2*>(dst) = *reinterpret_cast<const int2*>(packed);
+    } else {
+      *reinterpret_cast<int4*>(dst) = *reinterpret_cast<const int4*>(packed);
+    }
+    const int64_t sf_off = swizzled ? sf_swizzled_offset(m, kc, kc_pad) : m * kc_total + kc;
+    sf[b * sf_batch_stride + sf_off] = sf_byte;
+  }
+  ptx::grid_dep_launch();
+}
+
+// ---------------------------------------------------------------- mxfp8 (e4m3 + ue8m0 / 32)
+template <typename T>
+__global__ void __launch_bounds__(256)
+mxfp8_quantize_kernel(const T* __restrict__ x, __nv_fp8_e4m3* __restrict__ q, uint8_t* __restrict__ sf, int64_t M,
+                      int64_t K, int64_t ldx, int swizzled) {
+  constexpr int VEC = 32;
+  const int64_t kc_total = K / VEC;
+  const int64_t kc_pad = (kc_total + 3) / 4 * 4;
+  const int64_t total = M * kc_total;
+  ptx::grid_dep_wait();
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t kc = i % kc_total, m = i / kc_total;
+    const T* src = x + m * ldx + kc * VEC;
+    float v[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; j += 8) {
+      const Vec16<T> raw = ld16(src + j);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[j + e] = to_f32(raw.v[e]);
+    }
+    float amax = 0.f;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) amax = fmaxf(amax, fabsf(v[j]));
+    const uint8_t sf_byte = f32_to_ue8m0_ceil(amax * (1.f / 448.f));
+    const float sfv = ue8m0_to_f32(sf_byte);
+    const float inv = sfv > 0.f ? 1.f / sfv : 0.f;
+    __nv_fp8_e4m3 out[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) out[j] = __nv_fp8_e4m3(v[j] * inv);
+    int4* dst = reinterpret_cast<int4*>(q + m * K + kc * VEC);
+    dst[0] = reinterpret_cast<const int4*>(out)[0];
+    dst[1] = reinterpret_cast<const int4*>(out)[1];
+    sf[swizzled ? sf_swizzled_offset(m, kc, kc_pad) : m * kc_total + kc] = sf_byte;
+  }
+  ptx::grid_dep_launch();
+}
+
+// ---------------------------------------------------------------- scale-factor re-layout + dequant
+__global__ void sf_interleave_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int64_t batch, int64_t M,
+                                     int64_t Kc, int64_t out_batch_stride, int to_swizzled) {
+  const int64_t kc_pad = (Kc + 3) / 4 * 4;
+  const int64_t total = batch * M * Kc;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t kc = i % Kc, m = (i / Kc) % M, b = i / (Kc * M);
+    if (to_swizzled)
+      out[b * out_batch_stride + sf_swizzled_offset(m, kc, kc_pad)] = in[i];
+    else
+      out[i] = in[b * out_batch_stride + sf_swizzled_offset(m, kc, kc_pad)];
+  }
+}
+
+__device__ __forceinline__ float e2m1_to_f32(uint8_t nib) {
+  const float mag[8] = {0.f, 0.5f, 1.f, 1.5f, 2.f, 3.f, 4.f, 6.f};
+  const float v = mag[nib & 7];
+  return (nib & 8) ? -v : v;
+}
+
+__global__ void fp4_dequant_kernel(const uint8_t* __restrict__ q, const uint8_t* __restrict__ sf,
+                                   const float* __restrict__ global_scale, float* __restrict__ out, int64_t M, int64_t K,
+                                   int vec, int ue8m0, int swizzled) {
+  const int64_t kc_total = K / vec;
+  const int64_t kc_pad = (kc_total + 3) / 4 * 4;
+  const float gs = global_scale ? __ldg(global_scale) : 1.f;
+  const int64_t total = M * K / 2;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t m = i / (K / 2), k2 = i % (K / 2);
+    const int64_t kc = (k2 * 2) / vec;
+    const uint8_t sb = sf[swizzled ? sf_swizzled_offset(m, kc, kc_pad) : m * kc_total + kc];
+    float s;
+    if (ue8m0) {
+      s = ue8m0_to_f32(sb);
+    } else {
+      __nv_fp8_e4m3 t;
+      *reinterpret_cast<uint8_t*>(&t) = sb;
+      s = float(t);
+    }
+    s = s / gs;
+    const uint8_t b = q[i];
+    out[m * K + k2 * 2] = e2m1_to_f32(b & 0xf) * s;
+    out[m * K + k2 * 2 + 1] = e2m1_to_f32(b >> 4) * s;
+  }
+}
+
+// ---------------------------------------------------------------- packbits
+// x: uint8 (0 / non-zero) -> packed bits.  Segments: output segment b starts at out_indptr[b].
+__global__ void packbits_kernel(const uint8_t* __restrict__ x, uint8_t* __restrict__ y, const int32_t* __restrict__ in_indptr,
+                                const int32_t* __restrict__ out_indptr, int64_t n, int num_segments, int big_endian) {
+  if (num_segments == 0) {
+    const int64_t nbytes = (n + 7) / 8;
+    for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < nbytes; i += int64_t(gridDim.x) * blockDim.x) {
+      uint8_t v = 0;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        const int64_t j = i * 8 + b;
+        const int bit = (j < n && x[j]) ? 1 : 0;
+        v |= bit << (big_endian ? 7 - b : b);
+      }
+      y[i] = v;
+    }
+  } else {
+    for (int s = blockIdx.y; s < num_segments; s += gridDim.y) {
+      const int64_t i0 = in_indptr[s], len = in_indptr[s + 1] - i0, o0 = out_indptr[s];
+      const int64_t nbytes = (len + 7) / 8;
+      for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < nbytes; i += int64_t(gridDim.x) * blockDim.x) {
+        uint8_t v = 0;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+          const int64_t j = i * 8 + b;
+          const int bit = (j < len && x[i0 + j]) ? 1 : 0;
+          v |= bit << (big_endian ? 7 - b : b);
+        }
+        y[o0 + i] = v;
+      }
+    }
+  }
+}
+
+inline int grid_for(int64_t total, int threads = 256) {
+  int64_t b = (total + threads - 1) / threads;
+  const int64_t cap = int64_t(num_sms()) * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace
+
+// vec = 16 (NVFP4, UE4M3 scale unless ue8m0) or 32 (MXFP4, UE8M0 scale)
+extern "C" int fp4_quantize(void* x, void* q, void* sf, void* global_scale, int64_t batch, int64_t M, int64_t K,
+                            int64_t ldx, int64_t x_batch_stride, int64_t vec, int64_t ue8m0, int64_t swizzled,
+                            int64_t sf_batch_stride, int64_t dtype, int64_t pdl, int64_t stream_) {
+  FIB_CHECK(vec == 16 || vec == 32, "fp4_quantize: sf_vec_size must be 16 or 32");
+  FIB_CHECK(K % vec == 0 && ldx % 8 == 0, "fp4_quantize: K must be a multiple of sf_vec_size and rows 16B aligned");
+  if (batch * M * K == 0) return 0;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const int64_t total = batch * M * (K / vec);
+  LaunchCfg lc(dim3(grid_for(total)), dim3(256), 0, stream, pdl != 0);
+  return FIB_DISPATCH_HALF(dtype, T, [&]() -> int {
+    auto launch = [&](auto kern) -> int {
+      FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, kern, (const T*)x, (uint8_t*)q, (uint8_t*)sf, (const float*)global_scale,
+                                        batch, M, K, ldx, x_batch_stride, (int)swizzled, sf_batch_stride));
+      return 0;
+    };
+    if (vec == 16 && !ue8m0) return launch(fp4_quantize_kernel<T, 16, false>);
+    if (vec == 16) return launch(fp4_quantize_kernel<T, 16, true>);
+    if (ue8m0) return launch(fp4_quantize_kernel<T, 32, true>);
+    return launch(fp4_quantize_kernel<T, 32, false>);
+  });
+}
+
+extern "C" int mxfp8_quantize(void* x, void* q, void* sf, int64_t M, int64_t K, int64_t ldx, int64_t swizzled,
+                              int64_t dtype, int64_t pdl, int64_t stream_) {
+  FIB_CHECK(K % 32 == 0 && ldx % 8 == 0, "mxfp8_quantize: K must be a multiple of 32");
+  if (M * K == 0) return 0;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  LaunchCfg lc(dim3(grid_for(M * (K / 32))), dim3(256), 0, stream, pdl != 0);
+  return FIB_DISPATCH_HALF(dtype, T, [&]() -> int {
+    FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, mxfp8_quantize_kernel<T>, (const T*)x, (__nv_fp8_e4m3*)q, (uint8_t*)sf, M,
+                                      K, ldx, (int)swizzled));
+    return 0;
+  });
+}
+
+extern "C" int sf_interleave(void* in, void* out, int64_t batch, int64_t M, int64_t Kc, int64_t out_batch_stride,
+                             int64_t to_swizzled, int64_t stream_) {
+  if (batch * M * Kc == 0) return 0;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ++launch_counter();
+  sf_interleave_kernel<<<grid_for(batch * M * Kc), 256, 0, stream>>>((const uint8_t*)in, (uint8_t*)out, batch, M, Kc,
+                                                                     out_batch_stride, (int)to_swizzled);
+  FIB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fp4_dequantize(void* q, void* sf, void* global_scale, void* out, int64_t M, int64_t K, int64_t vec,
+                              int64_t ue8m0, int64_t swizzled, int64_t stream_) {
+  if (M * K == 0) return 0;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ++launch_counter();
+  fp4_dequant_kernel<<<grid_for(M * K / 2), 256, 0, stream>>>((const uint8_t*)q, (const uint8_t*)sf,
+                                                              (const float*)global_scale, (float*)out, M, K, (int)vec,
+                                                              (int)ue8m0, (int)swizzled);
+  FIB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int packbits(void* x, void* y, void* in_indptr, void* out_indptr, int64_t n, int64_t num_segments,
+                        int64_t big_endian, int64_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ++launch_counter();
+  if (num_segments == 0) {
+    if (n == 0) return 0;
+    packbits_kernel<<<grid_for((n + 7) / 8), 256, 0, stream>>>((const uint8_t*)x, (uint8_t*)y, nullptr, nullptr, n, 0,
+                                                               (int)big_endian);
+  } else {
+    dim3 grid(64, (unsigned)(num_segments < 1024 ? num_segments : 1024));
+    packbits_kernel<<<grid, 256, 0, stream>>>((const uint8_t*)x, (uint8_t*)y, (const int32_t*)in_indptr,
+                                              (const int32_t*)out_indptr, n, (int)num_segments, (int)big_endian);
+  }
+  FIB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}

@@ -35,23 +35,81 @@ struct GemmSmem {
   static constexpr int kTotal = kBarOffset + 320 + 1024;  // + barriers + flags + alignment slack
 };
 
-// Stream-K work decomposition: the flattened (tile, k-block) space is cut into equal contiguous
-// ranges, one per CTA.  A tile that straddles CTA boundaries is finished by a deterministic in-kernel
-// fix-up: every part writes its fp32 partial to an L2-resident workspace slot and bumps the tile's
-// counter; the last arriver sums the slots in slot order (bitwise reproducible) and writes the output.
-struct StreamK {
+// ---------------------------------------------------------------------------------------------------
+// Scheduler: W = tiles / grid full waves are data-parallel (tile = wave * grid + cta, grouped raster so
+// that a wave covers a compact block of the output and its operands stay L2 resident); the R = tiles %
+// grid remainder tiles are cut "stream-K" style into equal (tile, k-block) ranges over g_sk CTAs and
+// finished by an in-kernel reduce-scatter fix-up: every part publishes its fp32 partial in an L2-resident
+// slot, parts rendezvous on a per-tile counter (all CTAs are co-resident: persistent grid <= #SM), then
+// each part sums and writes 1/parts of the tile (slot order => bitwise reproducible).
+// ---------------------------------------------------------------------------------------------------
+struct Sched {
   int tiles_a, tiles_b, kblocks, grid;
-  int64_t units;
-  int max_parts;
-  __device__ __forceinline__ int64_t begin(int c) const { return (int64_t(c) * units) / grid; }
-  __device__ __forceinline__ int cta_of(int64_t u) const { return int(((u + 1) * grid + units - 1) / units) - 1; }
+  int W, R, g_sk, max_parts, group_a;
+  int64_t u_r;  // R * kblocks
+  __device__ __forceinline__ int64_t sk_begin(int c) const { return (int64_t(c) * u_r) / g_sk; }
+  __device__ __forceinline__ int sk_cta_of(int64_t u) const { return int(((u + 1) * g_sk + u_r - 1) / u_r) - 1; }
+  __device__ __forceinline__ void coords(int t, int& ta, int& tb) const {
+    // grouped rasterisation: walk `group_a` A-tiles for every B-tile before moving on
+    const int per_group = group_a * tiles_b;
+    const int g = t / per_group;
+    const int first = g * group_a;
+    const int rows = min(group_a, tiles_a - first);
+    const int in = t - g * per_group;
+    ta = first + in % rows;
+    tb = in / rows;
+  }
+};
+
+// Iterates the segments (tile, kb0, kb1) of one CTA: stream-K remainder first, then its DP tiles.
+struct SegIter {
+  const Sched& s;
+  int cta;
+  int64_t u, u_end;  // stream-K cursor
+  int wave;
+  __device__ SegIter(const Sched& s_, int cta_) : s(s_), cta(cta_), wave(0) {
+    if (s.g_sk > 0 && cta < s.g_sk) {
+      u = s.sk_begin(cta);
+      u_end = s.sk_begin(cta + 1);
+    } else {
+      u = u_end = 0;
+    }
+  }
+  // returns false when done. partial=true => needs the fix-up (r_idx = remainder tile index)
+  __device__ __forceinline__ bool next(int& tile, int& kb0, int& kb1, bool& partial, int& r_idx) {
+    if (u < u_end) {
+      r_idx = int(u / s.kblocks);
+      kb0 = int(u % s.kblocks);
+      const int64_t lim = kb0 + (u_end - u);
+      kb1 = lim < int64_t(s.kblocks) ? int(lim) : s.kblocks;
+      u += kb1 - kb0;
+      tile = s.W * s.grid + r_idx;
+      partial = !(kb0 == 0 && kb1 == s.kblocks);
+      return true;
+    }
+    partial = false;
+    r_idx = 0;
+    kb0 = 0;
+    kb1 = s.kblocks;
+    if (wave < s.W) {
+      tile = wave * s.grid + cta;
+      ++wave;
+      return true;
+    }
+    if (wave == s.W && s.g_sk == 0 && cta < s.R) {  // remainder handled data-parallel
+      tile = s.W * s.grid + cta;
+      ++wave;
+      return true;
+    }
+    return false;
+  }
 };
 
 template <int BN, bool kSwap, typename OutT>
 __global__ void __launch_bounds__(256, 1)
 gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, OutT* __restrict__ C,
                float* __restrict__ partial, int* __restrict__ counters, const OutT* __restrict__ bias, int rowsA,
-               int rowsB, int K, int64_t ldc, const StreamK sk, uint32_t idesc) {
+               int rowsB, int K, int64_t ldc, const Sched sk, uint32_t idesc) {
   using S = GemmSmem<BN>;
   constexpr int kStages = S::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -61,12 +119,9 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tmem_full = empty_bar + kStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  int* s_flag = reinterpret_cast<int*>(tmem_ptr + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int64_t u_begin = sk.begin(blockIdx.x);
-  const int64_t u_end = sk.begin(blockIdx.x + 1);
 
   if (threadIdx.x == 0) {
     ptx::prefetch_tmap(&tmA);
@@ -97,24 +152,24 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int64_t u = u_begin; u < u_end;) {
-        const int t = int(u / sk.kblocks);
-        const int kb0 = int(u % sk.kblocks);
-        const int kb1 = int((kb0 + (u_end - u)) < int64_t(sk.kblocks) ? (kb0 + (u_end - u)) : int64_t(sk.kblocks));
-        const int ta = t % sk.tiles_a, tb = t / sk.tiles_a;
+      SegIter it(sk, blockIdx.x);
+      int tile, kb0, kb1, r_idx;
+      bool part;
+      while (it.next(tile, kb0, kb1, part, r_idx)) {
+        int ta, tb;
+        sk.coords(tile, ta, tb);
         for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * S::kStageBytes;
           uint8_t* sb = sa + S::kABytes;
           ptx::mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
           ptx::tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, ta * BM, kSwap ? ptx::kEvictFirst : ptx::kEvictNormal);
-          ptx::tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, tb * BN, kSwap ? ptx::kEvictLast : ptx::kEvictFirst);
+          ptx::tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, tb * BN, kSwap ? ptx::kEvictLast : ptx::kEvictNormal);
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        u += kb1 - kb0;
       }
     }
   } else if (warp == 1) {
@@ -123,9 +178,10 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int64_t u = u_begin; u < u_end;) {
-      const int kb0 = int(u % sk.kblocks);
-      const int kb1 = int((kb0 + (u_end - u)) < int64_t(sk.kblocks) ? (kb0 + (u_end - u)) : int64_t(sk.kblocks));
+    SegIter it(sk, blockIdx.x);
+    int tile, kb0, kb1, r_idx;
+    bool part;
+    while (it.next(tile, kb0, kb1, part, r_idx)) {
       ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BN;
@@ -151,91 +207,35 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           phase ^= 1;
         }
       }
-      u += kb1 - kb0;
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
     ptx::grid_dep_launch();
   } else if (warp >= 4) {
-    // ===================== epilogue (+ stream-K fix-up) =====================
+    // ===================== epilogue (+ stream-K reduce-scatter fix-up) =====================
     const int q = warp - 4;  // TMEM lane quadrant == warp % 4
     const int etid = threadIdx.x - 128;
     int acc = 0;
     uint32_t acc_phase = 0;
     constexpr int CH = (BN >= 32) ? 32 : 16;
-    for (int64_t u = u_begin; u < u_end;) {
-      const int t = int(u / sk.kblocks);
-      const int kb0 = int(u % sk.kblocks);
-      const int kb1 = int((kb0 + (u_end - u)) < int64_t(sk.kblocks) ? (kb0 + (u_end - u)) : int64_t(sk.kblocks));
-      u += kb1 - kb0;
-      const int ta = t % sk.tiles_a, tb = t / sk.tiles_a;
-      const bool full_tile = (kb0 == 0 && kb1 == sk.kblocks);
+    SegIter it(sk, blockIdx.x);
+    int tile, kb0, kb1, r_idx;
+    bool part;
+    while (it.next(tile, kb0, kb1, part, r_idx)) {
+      int ta, tb;
+      sk.coords(tile, ta, tb);
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
       const int r_in_tile = q * 32 + lane;
       const int a_row = ta * BM + r_in_tile;  // row of the A-side operand owned by this thread
       const uint32_t taddr = tmem_base + acc * BN + (uint32_t(q * 32) << 16);
 
-      int parts = 1, c_first = 0;
-      bool i_am_last = true;
-      float* my_slot = nullptr;
-      if (!full_tile) {
-        c_first = sk.cta_of(int64_t(t) * sk.kblocks);
-        const int c_last = sk.cta_of(int64_t(t + 1) * sk.kblocks - 1);
-        parts = c_last - c_first + 1;
-        float* tile_ws = partial + int64_t(c_first) * sk.max_parts * (BM * BN);
-        my_slot = tile_ws + int64_t(blockIdx.x - c_first) * (BM * BN);
-        // 1) publish my partial
+      if (!part) {
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += CH) {
           uint32_t r[CH];
           if constexpr (CH == 32) ptx::tmem_ld_x32(taddr + c0, r); else ptx::tmem_ld_x16(taddr + c0, r);
           ptx::tmem_ld_wait();
-          float4* dst = reinterpret_cast<float4*>(my_slot + r_in_tile * BN + c0);
-#pragma unroll
-          for (int j = 0; j < CH; j += 4)
-            __stcg(dst + j / 4, make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                            __uint_as_float(r[j + 3])));
-        }
-        __threadfence();
-        ptx::named_bar_sync(1, 128);
-        if (etid == 0) {
-          const int old = atomicAdd(&counters[c_first], 1);
-          const int last = (old == parts - 1);
-          if (last) counters[c_first] = 0;  // self-reset for the next launch / graph replay
-          *s_flag = last;
-        }
-        ptx::named_bar_sync(1, 128);
-        i_am_last = (*s_flag != 0);
-        if (i_am_last) __threadfence();
-      }
-
-      if (i_am_last) {
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += CH) {
-          float v[CH];
-          if (full_tile) {
-            uint32_t r[CH];
-            if constexpr (CH == 32) ptx::tmem_ld_x32(taddr + c0, r); else ptx::tmem_ld_x16(taddr + c0, r);
-            ptx::tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < CH; ++j) v[j] = 0.f;
-            const float* tile_ws = partial + int64_t(c_first) * sk.max_parts * (BM * BN);
-            for (int pth = 0; pth < parts; ++pth) {
-              const float4* src = reinterpret_cast<const float4*>(tile_ws + int64_t(pth) * (BM * BN) + r_in_tile * BN + c0);
-#pragma unroll
-              for (int j = 0; j < CH; j += 4) {
-                const float4 x = __ldcg(src + j / 4);
-                v[j] += x.x;
-                v[j + 1] += x.y;
-                v[j + 2] += x.z;
-                v[j + 3] += x.w;
-              }
-            }
-          }
           const int b_row0 = tb * BN + c0;
           if constexpr (kSwap) {
             // C[b_row][a_row]: consecutive lanes -> consecutive a_row -> coalesced 2B stores
@@ -243,7 +243,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const float bv = bias ? to_f32(bias[a_row]) : 0.f;
 #pragma unroll
               for (int j = 0; j < CH; ++j)
-                if (b_row0 + j < rowsB) C[int64_t(b_row0 + j) * ldc + a_row] = from_f32<OutT>(v[j] + bv);
+                if (b_row0 + j < rowsB) C[int64_t(b_row0 + j) * ldc + a_row] = from_f32<OutT>(__uint_as_float(r[j]) + bv);
             }
           } else {
             if (a_row < rowsA) {
@@ -255,7 +255,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   Vec16<OutT> o;
 #pragma unroll
                   for (int e = 0; e < VN; ++e) {
-                    float x = v[j + e];
+                    float x = __uint_as_float(r[j + e]);
                     if (bias) x += to_f32(bias[b_row0 + j + e]);
                     o.v[e] = from_f32<OutT>(x);
                   }
@@ -265,7 +265,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                 for (int j = 0; j < CH; ++j)
                   if (b_row0 + j < rowsB) {
-                    float x = v[j];
+                    float x = __uint_as_float(r[j]);
                     if (bias) x += to_f32(bias[b_row0 + j]);
                     dst[j] = from_f32<OutT>(x);
                   }
@@ -273,10 +273,97 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+      } else {
+        // ---- stream-K fix-up ----
+        const int64_t t0u = int64_t(r_idx) * sk.kblocks;
+        const int c_first = sk.sk_cta_of(t0u);
+        const int c_last = sk.sk_cta_of(t0u + sk.kblocks - 1);
+        const int parts = c_last - c_first + 1;
+        const int my_part = blockIdx.x - c_first;
+        float* tile_ws = partial + int64_t(r_idx) * sk.max_parts * (BM * BN);
+        float* my_slot = tile_ws + int64_t(my_part) * (BM * BN);
+        // 1) publish my partial in output-major order (swap: [col][row], else [row][col])
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += CH) {
+          uint32_t r[CH];
+          if constexpr (CH == 32) ptx::tmem_ld_x32(taddr + c0, r); else ptx::tmem_ld_x16(taddr + c0, r);
+          ptx::tmem_ld_wait();
+          if constexpr (kSwap) {
+#pragma unroll
+            for (int j = 0; j < CH; ++j) __stcg(my_slot + (c0 + j) * BM + r_in_tile, __uint_as_float(r[j]));
+          } else {
+            float4* dst = reinterpret_cast<float4*>(my_slot + r_in_tile * BN + c0);
+#pragma unroll
+            for (int j = 0; j < CH; j += 4)
+              __stcg(dst + j / 4, make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                              __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));
+          }
+        }
+        // the accumulator is drained: let the MMA warp start the next segment while we fix up
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+        // 2) rendezvous of all parts of this tile
+        __threadfence();
+        ptx::named_bar_sync(1, 128);
+        int* arrive = counters + 2 * r_idx;
+        int* done = arrive + 1;
+        if (etid == 0) {
+          atomicAdd(arrive, 1);
+          while (*reinterpret_cast<volatile int*>(arrive) < parts) {
+          }
+          __threadfence();
+        }
+        ptx::named_bar_sync(1, 128);
+        // 3) reduce my 1/parts share of the tile and write it out
+        constexpr int NV = BM * BN / 4;
+        const int v_begin = (my_part * NV) / parts, v_end = ((my_part + 1) * NV) / parts;
+        for (int v = v_begin + etid; v < v_end; v += 128) {
+          float4 accv = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int pth = 0; pth < parts; ++pth) {
+            const float4 x = __ldcg(reinterpret_cast<const float4*>(tile_ws + int64_t(pth) * (BM * BN)) + v);
+            accv.x += x.x;
+            accv.y += x.y;
+            accv.z += x.z;
+            accv.w += x.w;
+          }
+          const float vals[4] = {accv.x, accv.y, accv.z, accv.w};
+          if constexpr (kSwap) {
+            const int col = (v * 4) / BM, row = (v * 4) % BM;  // 4 consecutive a-rows of one token column
+            const int b_row = tb * BN + col;
+            const int a0 = ta * BM + row;
+            if (b_row < rowsB) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (a0 + e < rowsA)
+                  C[int64_t(b_row) * ldc + a0 + e] = from_f32<OutT>(vals[e] + (bias ? to_f32(bias[a0 + e]) : 0.f));
+            }
+          } else {
+            const int row = (v * 4) / BN, col = (v * 4) % BN;
+            const int ar = ta * BM + row;
+            const int b0 = tb * BN + col;
+            if (ar < rowsA) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (b0 + e < rowsB)
+                  C[int64_t(ar) * ldc + b0 + e] = from_f32<OutT>(vals[e] + (bias ? to_f32(bias[b0 + e]) : 0.f));
+            }
+          }
+        }
+        // 4) the last part to finish resets the counters (graph-replay safe)
+        ptx::named_bar_sync(1, 128);
+        if (etid == 0) {
+          const int old = atomicAdd(done, 1);
+          if (old == parts - 1) {
+            *reinterpret_cast<volatile int*>(done) = 0;
+            __threadfence();
+            *reinterpret_cast<volatile int*>(arrive) = 0;
+          }
+        }
       }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -300,38 +387,37 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, OutT* C, float* 
     FIB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     attr_set = true;
   }
-  StreamK sk;
+  Sched sk;
   sk.tiles_a = (rowsA + BM - 1) / BM;
   sk.tiles_b = (rowsB + BN - 1) / BN;
   sk.kblocks = (K + BK - 1) / BK;
   const int tiles = sk.tiles_a * sk.tiles_b;
-  sk.units = int64_t(tiles) * sk.kblocks;
-  // workspace layout: [counters: 1024 ints][partials]
-  const int64_t slot_bytes = int64_t(BM) * BN * 4;
-  const int64_t ws_partial = workspace ? workspace_bytes - 4096 : 0;
   int grid = num_sms();
-  if (sk.units < grid) grid = (int)sk.units;
-  const bool streamk = workspace != nullptr && (tiles % grid != 0);
-  auto parts_for = [&](int g) {
-    const int64_t per = sk.units / g > 0 ? sk.units / g : 1;
-    return int((sk.kblocks + per - 1) / per) + 1;
-  };
-  if (streamk) {
-    // at least 4 k-blocks per part, and the fix-up slots must fit the workspace
-    while (grid > 1 && (sk.units / grid < 4 || int64_t(grid) * parts_for(grid) * slot_bytes > ws_partial)) --grid;
-    sk.max_parts = parts_for(grid);
-  } else {
-    sk.max_parts = 1;
-    if (tiles % grid != 0) {
-      // no workspace: keep CTA ranges tile-aligned -> largest grid <= #SM that divides the tile count
-      for (int gtry = grid; gtry >= 1; --gtry)
-        if (tiles % gtry == 0) {
-          grid = gtry;
-          break;
-        }
+  if (tiles < grid && (workspace == nullptr || int64_t(tiles) * sk.kblocks < 2 * grid)) grid = tiles;
+  sk.grid = grid;
+  sk.W = tiles / grid;
+  sk.R = tiles % grid;
+  sk.group_a = sk.tiles_a < 8 ? sk.tiles_a : 8;
+  sk.g_sk = 0;
+  sk.max_parts = 1;
+  sk.u_r = int64_t(sk.R) * sk.kblocks;
+  // workspace layout: [counters: 2 ints per remainder tile, 4 KB][fp32 partial slots]
+  const int64_t slot_bytes = int64_t(BM) * BN * 4;
+  if (workspace != nullptr && sk.R > 0 && sk.R <= 512) {
+    int64_t mp = (workspace_bytes - 4096) / (int64_t(sk.R) * slot_bytes);
+    if (mp > 8) mp = 8;
+    if (mp >= 2) {
+      int64_t g = int64_t(sk.R) * (mp - 1);       // every tile spans at most mp CTAs
+      if (g > grid) g = grid;
+      if (g > sk.u_r / 2) g = sk.u_r / 2;          // at least 2 k-blocks per CTA
+      if (g > sk.R) {                              // otherwise plain DP is just as good
+        sk.g_sk = (int)g;
+        const int64_t per = sk.u_r / g;
+        sk.max_parts = int((sk.kblocks + per - 1) / per) + 1;
+        if (sk.max_parts > mp) sk.max_parts = (int)mp;
+      }
     }
   }
-  sk.grid = grid;
   const uint32_t idesc = ptx::make_idesc_f16(f16 ? ptx::kFmtF16 : ptx::kFmtBF16, BM, BN, 0, 0);
   LaunchCfg lc(dim3(grid), dim3(256), S::kTotal, stream, pdl);
   int* counters = reinterpret_cast<int*>(workspace);

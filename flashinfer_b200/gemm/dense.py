@@ -17,10 +17,12 @@ _workspaces = {}
 
 
 def _workspace(device) -> torch.Tensor:
-    ws = _workspaces.get(device)
+    """Per-(device, stream) stream-K workspace: [4 KB self-resetting counters | fp32 partial slots]."""
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
     if ws is None:
-        ws = torch.zeros(32 * 1024 * 1024, dtype=torch.uint8, device=device)  # stream-K counters must start at 0
-        _workspaces[device] = ws
+        ws = torch.zeros(32 * 1024 * 1024, dtype=torch.uint8, device=device)  # counters must start at 0
+        _workspaces[key] = ws
     return ws
 
 
