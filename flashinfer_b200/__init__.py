@@ -47,3 +47,40 @@ from .rope import (  # noqa: F401,E402
     apply_rope_with_cos_sin_cache,
     apply_rope_with_cos_sin_cache_inplace,
 )
+from . import quantization, sampling, topk  # noqa: F401,E402
+from .quantization import (  # noqa: F401,E402
+    SfLayout,
+    block_scale_interleave,
+    e2m1_and_ufp8sf_scale_to_float,
+    fp4_quantize,
+    mxfp4_dequantize,
+    mxfp4_dequantize_host,
+    mxfp4_quantize,
+    mxfp8_dequantize_host,
+    mxfp8_quantize,
+    nvfp4_batched_quantize,
+    nvfp4_block_scale_interleave,
+    nvfp4_kv_dequantize,
+    nvfp4_kv_quantize,
+    nvfp4_quantize,
+    packbits,
+    scaled_fp4_grouped_quantize,
+    segment_packbits,
+    shuffle_matrix_a,
+    shuffle_matrix_sf_a,
+)
+from .sampling import (  # noqa: F401,E402
+    chain_speculative_sampling,
+    min_p_sampling_from_probs,
+    sampling_from_logits,
+    sampling_from_probs,
+    softmax,
+    top_k_mask_logits,
+    top_k_renorm_probs,
+    top_k_sampling_from_probs,
+    top_k_top_p_sampling_from_logits,
+    top_k_top_p_sampling_from_probs,
+    top_p_renorm_probs,
+    top_p_sampling_from_probs,
+)
+from .topk import TopKTieBreak, top_k, top_k_page_table_transform, top_k_ragged_transform  # noqa: F401,E402

@@ -221,6 +221,8 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     SegIter it(sk, blockIdx.x);
     int tile, kb0, kb1, r_idx;
     bool part;
+    int npend = 0;
+    int pend_r[4], pend_parts[4], pend_me[4], pend_ta[4], pend_tb[4];
     while (it.next(tile, kb0, kb1, part, r_idx)) {
       int ta, tb;
       sk.coords(tile, ta, tb);
@@ -277,7 +279,8 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
       } else {
-        // ---- stream-K fix-up ----
+        // ---- stream-K part: publish the fp32 partial now, fix up later (after ALL my partials are out,
+        //      otherwise neighbouring CTAs would wait on each other in a chain) ----
         const int64_t t0u = int64_t(r_idx) * sk.kblocks;
         const int c_first = sk.sk_cta_of(t0u);
         const int c_last = sk.sk_cta_of(t0u + sk.kblocks - 1);
@@ -285,7 +288,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int my_part = blockIdx.x - c_first;
         float* tile_ws = partial + int64_t(r_idx) * sk.max_parts * (BM * BN);
         float* my_slot = tile_ws + int64_t(my_part) * (BM * BN);
-        // 1) publish my partial in output-major order (swap: [col][row], else [row][col])
+        // publish in output-major order (swap: [col][row], else [row][col])
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += CH) {
           uint32_t r[CH];
@@ -302,70 +305,84 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                               __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));
           }
         }
-        // the accumulator is drained: let the MMA warp start the next segment while we fix up
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
-        // 2) rendezvous of all parts of this tile
         __threadfence();
         ptx::named_bar_sync(1, 128);
-        int* arrive = counters + 2 * r_idx;
-        int* done = arrive + 1;
-        if (etid == 0) {
-          atomicAdd(arrive, 1);
-          while (*reinterpret_cast<volatile int*>(arrive) < parts) {
-          }
-          __threadfence();
-        }
-        ptx::named_bar_sync(1, 128);
-        // 3) reduce my 1/parts share of the tile and write it out
-        constexpr int NV = BM * BN / 4;
-        const int v_begin = (my_part * NV) / parts, v_end = ((my_part + 1) * NV) / parts;
-        for (int v = v_begin + etid; v < v_end; v += 128) {
-          float4 accv = make_float4(0.f, 0.f, 0.f, 0.f);
-          for (int pth = 0; pth < parts; ++pth) {
-            const float4 x = __ldcg(reinterpret_cast<const float4*>(tile_ws + int64_t(pth) * (BM * BN)) + v);
-            accv.x += x.x;
-            accv.y += x.y;
-            accv.z += x.z;
-            accv.w += x.w;
-          }
-          const float vals[4] = {accv.x, accv.y, accv.z, accv.w};
-          if constexpr (kSwap) {
-            const int col = (v * 4) / BM, row = (v * 4) % BM;  // 4 consecutive a-rows of one token column
-            const int b_row = tb * BN + col;
-            const int a0 = ta * BM + row;
-            if (b_row < rowsB) {
-#pragma unroll
-              for (int e = 0; e < 4; ++e)
-                if (a0 + e < rowsA)
-                  C[int64_t(b_row) * ldc + a0 + e] = from_f32<OutT>(vals[e] + (bias ? to_f32(bias[a0 + e]) : 0.f));
-            }
-          } else {
-            const int row = (v * 4) / BN, col = (v * 4) % BN;
-            const int ar = ta * BM + row;
-            const int b0 = tb * BN + col;
-            if (ar < rowsA) {
-#pragma unroll
-              for (int e = 0; e < 4; ++e)
-                if (b0 + e < rowsB)
-                  C[int64_t(ar) * ldc + b0 + e] = from_f32<OutT>(vals[e] + (bias ? to_f32(bias[b0 + e]) : 0.f));
-            }
-          }
-        }
-        // 4) the last part to finish resets the counters (graph-replay safe)
-        ptx::named_bar_sync(1, 128);
-        if (etid == 0) {
-          const int old = atomicAdd(done, 1);
-          if (old == parts - 1) {
-            *reinterpret_cast<volatile int*>(done) = 0;
-            __threadfence();
-            *reinterpret_cast<volatile int*>(arrive) = 0;
-          }
-        }
+        if (etid == 0) atomicAdd(counters + 2 * r_idx, 1);
+        pend_r[npend] = r_idx;
+        pend_parts[npend] = parts;
+        pend_me[npend] = my_part;
+        pend_ta[npend] = ta;
+        pend_tb[npend] = tb;
+        ++npend;
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
+
+      // ---- deferred fix-ups: once this CTA has published every stream-K partial it owns ----
+      if (npend > 0 && it.u >= it.u_end) {
+        for (int pi = 0; pi < npend; ++pi) {
+          const int fr = pend_r[pi], parts = pend_parts[pi], my_part = pend_me[pi];
+          const int fta = pend_ta[pi], ftb = pend_tb[pi];
+          int* arrive = counters + 2 * fr;
+          int* done = arrive + 1;
+          float* tile_ws = partial + int64_t(fr) * sk.max_parts * (BM * BN);
+          if (etid == 0) {
+            while (*reinterpret_cast<volatile int*>(arrive) < parts) {
+            }
+            __threadfence();
+          }
+          ptx::named_bar_sync(1, 128);
+          // reduce my 1/parts share of the tile (slot order => deterministic) and write it out
+          constexpr int NV = BM * BN / 4;
+          const int v_begin = (my_part * NV) / parts, v_end = ((my_part + 1) * NV) / parts;
+          for (int v = v_begin + etid; v < v_end; v += 128) {
+            float4 accv = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int pth = 0; pth < parts; ++pth) {
+              const float4 x = __ldcg(reinterpret_cast<const float4*>(tile_ws + int64_t(pth) * (BM * BN)) + v);
+              accv.x += x.x;
+              accv.y += x.y;
+              accv.z += x.z;
+              accv.w += x.w;
+            }
+            const float vals[4] = {accv.x, accv.y, accv.z, accv.w};
+            if constexpr (kSwap) {
+              const int col = (v * 4) / BM, row = (v * 4) % BM;  // 4 consecutive a-rows of one token column
+              const int b_row = ftb * BN + col;
+              const int a0 = fta * BM + row;
+              if (b_row < rowsB) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  if (a0 + e < rowsA)
+                    C[int64_t(b_row) * ldc + a0 + e] = from_f32<OutT>(vals[e] + (bias ? to_f32(bias[a0 + e]) : 0.f));
+              }
+            } else {
+              const int row = (v * 4) / BN, col = (v * 4) % BN;
+              const int ar = fta * BM + row;
+              const int b0 = ftb * BN + col;
+              if (ar < rowsA) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  if (b0 + e < rowsB)
+                    C[int64_t(ar) * ldc + b0 + e] = from_f32<OutT>(vals[e] + (bias ? to_f32(bias[b0 + e]) : 0.f));
+              }
+            }
+          }
+          // the last part to finish resets the counters (graph-replay safe)
+          ptx::named_bar_sync(1, 128);
+          if (etid == 0) {
+            const int old = atomicAdd(done, 1);
+            if (old == parts - 1) {
+              *reinterpret_cast<volatile int*>(done) = 0;
+              __threadfence();
+              *reinterpret_cast<volatile int*>(arrive) = 0;
+            }
+          }
+        }
+        npend = 0;
+      }
     }
   }
 

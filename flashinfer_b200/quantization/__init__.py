@@ -1,0 +1,20 @@
+"""Quantisation ops (NVFP4 / MXFP4 / MXFP8 / bit packing).  Parity: reference flashinfer/quantization/."""
+from .fp4 import (  # noqa: F401
+    SfLayout,
+    block_scale_interleave,
+    e2m1_and_ufp8sf_scale_to_float,
+    fp4_quantize,
+    mxfp4_dequantize,
+    mxfp4_dequantize_host,
+    mxfp4_quantize,
+    nvfp4_batched_quantize,
+    nvfp4_block_scale_interleave,
+    nvfp4_kv_dequantize,
+    nvfp4_kv_quantize,
+    nvfp4_quantize,
+    scaled_fp4_grouped_quantize,
+    shuffle_matrix_a,
+    shuffle_matrix_sf_a,
+)
+from .fp8 import mxfp8_dequantize_host, mxfp8_quantize  # noqa: F401
+from .packbits import packbits, segment_packbits  # noqa: F401

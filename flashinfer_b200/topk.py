@@ -1,0 +1,94 @@
+"""Radix top-k and the fused top-k -> page-table / ragged-index transforms.
+Parity: reference flashinfer/topk.py:508-911."""
+from __future__ import annotations
+
+from enum import IntEnum
+from typing import Optional, Tuple
+
+import torch
+
+from . import jit
+from .utils import dtype_code, stream_ptr
+
+
+class TopKTieBreak(IntEnum):
+    NONE = 0
+    SMALL = 1
+    LARGE = 2
+
+    def __str__(self) -> str:
+        return self.name.lower()
+
+
+def _run(input, k, mode, lengths=None, row_starts=None, row_to_batch=None, page_table=None, ragged_offsets=None,
+         tie_break=0, want_values=False):
+    rows, max_len = input.shape
+    x = input if input.stride(-1) == 1 else input.contiguous()
+    idx = torch.empty(rows, k, dtype=torch.int32, device=x.device)
+    vals = torch.empty(rows, k, dtype=x.dtype, device=x.device) if want_values else None
+    i32 = lambda t: t.to(torch.int32).contiguous() if t is not None else None  # noqa: E731
+    jit.load("topk").call(
+        "topk_run", x, x.stride(0), vals, idx, i32(lengths), i32(row_starts), i32(row_to_batch), i32(page_table),
+        page_table.stride(0) if page_table is not None else 0, i32(ragged_offsets), rows, max_len, k, mode,
+        int(tie_break), dtype_code(x.dtype), stream_ptr(x),
+    )
+    return vals, idx
+
+
+def top_k(input: torch.Tensor, k: int, sorted: bool = False, deterministic: bool = False,
+          tie_break: int = TopKTieBreak.NONE, dsa_graph_safe: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Top-k of every row of ``input [rows, n]``: returns ``(values [rows,k], indices [rows,k] int64)``."""
+    if not input.is_cuda:
+        v, i = torch.topk(input, k, dim=-1, sorted=sorted)
+        return v, i
+    vals, idx = _run(input, k, 0, tie_break=tie_break, want_values=True)
+    if sorted:
+        order = torch.argsort(vals.float(), dim=-1, descending=True, stable=True)
+        vals, idx = vals.gather(-1, order), idx.gather(-1, order)
+    return vals, idx.long()
+
+
+def _transform_cpu(input, lengths, k, row_starts, tie_break):
+    rows = input.shape[0]
+    out = torch.full((rows, k), -1, dtype=torch.int64)
+    for r in range(rows):
+        s = int(row_starts[r]) if row_starts is not None else 0
+        n = int(lengths[r])
+        kk = min(k, n)
+        seg = input[r, s : s + n].float()
+        if tie_break == 2:
+            order = torch.argsort(seg.flip(0), descending=True, stable=True)
+            sel = (n - 1 - order[:kk])
+        else:
+            sel = torch.argsort(seg, descending=True, stable=True)[:kk]
+        out[r, :kk] = torch.sort(sel).values if tie_break != 2 else torch.sort(sel, descending=True).values
+    return out
+
+
+def top_k_page_table_transform(input: torch.Tensor, src_page_table: torch.Tensor, lengths: torch.Tensor, k: int,
+                               row_to_batch: Optional[torch.Tensor] = None, deterministic: bool = False,
+                               tie_break: int = TopKTieBreak.NONE, dsa_graph_safe: bool = False,
+                               row_starts: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``out[i, j] = src_page_table[batch(i), row_start(i) + topk_idx(i)[j]]`` (``-1`` padded), int32."""
+    if not input.is_cuda:
+        sel = _transform_cpu(input, lengths, k, row_starts, int(tie_break))
+        out = torch.full(sel.shape, -1, dtype=torch.int32)
+        for r in range(sel.shape[0]):
+            b = int(row_to_batch[r]) if row_to_batch is not None else r
+            s = int(row_starts[r]) if row_starts is not None else 0
+            m = sel[r] >= 0
+            out[r, m] = src_page_table[b, (sel[r, m] + s).long()].int()
+        return out
+    return _run(input, k, 1, lengths, row_starts, row_to_batch, src_page_table, tie_break=tie_break)[1]
+
+
+def top_k_ragged_transform(input: torch.Tensor, offsets: torch.Tensor, lengths: torch.Tensor, k: int,
+                           deterministic: bool = False, tie_break: int = TopKTieBreak.NONE,
+                           dsa_graph_safe: bool = False, row_starts: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``out[i, j] = offsets[i] + row_start(i) + topk_idx(i)[j]`` (``-1`` padded), int32."""
+    if not input.is_cuda:
+        sel = _transform_cpu(input, lengths, k, row_starts, int(tie_break))
+        s = row_starts.long() if row_starts is not None else torch.zeros(sel.shape[0], dtype=torch.long)
+        out = torch.where(sel >= 0, sel + (offsets.long() + s)[:, None], torch.full_like(sel, -1))
+        return out.int()
+    return _run(input, k, 2, lengths, row_starts, None, None, offsets, tie_break=tie_break)[1]

@@ -1,0 +1,87 @@
+"""GPU tests: quantisation kernels (vs. the CPU reference implementation) and radix top-k."""
+import numpy as np
+import pytest
+import torch
+
+from flashinfer_b200 import quantization as Q
+from flashinfer_b200 import topk as TK
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("shape", [(130, 64), (512, 7168), (1, 128)])
+@pytest.mark.parametrize("swizzled", [True, False])
+def test_nvfp4_quantize_matches_cpu_and_roundtrips(shape, swizzled):
+    x = torch.randn(shape, dtype=torch.bfloat16)
+    gs = (448.0 * 6.0 / x.float().abs().max()).reshape(1)
+    q_c, sf_c = Q.fp4_quantize(x, gs, is_sf_swizzled_layout=swizzled)
+    q_g, sf_g = Q.fp4_quantize(x.cuda(), gs.cuda(), is_sf_swizzled_layout=swizzled)
+    assert (sf_g.cpu() == sf_c).float().mean() > 0.999
+    assert (q_g.cpu() == q_c).float().mean() > 0.99  # rare 1-ulp differences in the scaled value
+    d = Q.e2m1_and_ufp8sf_scale_to_float(q_g, sf_g, gs.cuda(), is_sf_swizzled_layout=swizzled)
+    cos = torch.nn.functional.cosine_similarity(d.flatten().cpu(), x.float().flatten(), dim=0)
+    assert cos > 0.99
+
+
+def test_mxfp4_mxfp8_batched_interleave():
+    x = torch.randn(300, 256, dtype=torch.bfloat16, device="cuda")
+    q, sf = Q.mxfp4_quantize(x)
+    d = Q.mxfp4_dequantize(q, sf)
+    assert torch.nn.functional.cosine_similarity(d.flatten(), x.float().flatten(), dim=0) > 0.99
+    q8, s8 = Q.mxfp8_quantize(x)
+    q8c, s8c = Q.mxfp8_quantize(x.cpu())
+    assert torch.equal(s8.cpu(), s8c)
+    assert (q8.cpu().float() == q8c.float()).float().mean() > 0.999
+    d8 = Q.mxfp8_dequantize_host(q8, s8)
+    torch.testing.assert_close(d8, x.float(), rtol=0.07, atol=0.02)
+    xb = torch.randn(3, 128, 64, dtype=torch.bfloat16, device="cuda")
+    gs = torch.tensor([100.0], device="cuda")
+    qb, sb = Q.nvfp4_batched_quantize(xb, gs)
+    for i in range(3):
+        qi, si = Q.fp4_quantize(xb[i], gs)
+        assert torch.equal(qb[i], qi) and torch.equal(sb[i], si.reshape(-1))
+    lin = torch.randint(0, 255, (256, 8), dtype=torch.uint8, device="cuda")
+    assert torch.equal(Q.block_scale_interleave(lin).cpu(), Q.block_scale_interleave(lin.cpu()))
+
+
+def test_packbits():
+    b = torch.rand(1003, device="cuda") > 0.5
+    assert (Q.packbits(b).cpu().numpy() == np.packbits(b.cpu().numpy())).all()
+    assert (Q.packbits(b, "little").cpu().numpy() == np.packbits(b.cpu().numpy(), bitorder="little")).all()
+    indptr = torch.tensor([0, 10, 10, 333, 1003], dtype=torch.int32, device="cuda")
+    out, new_indptr = Q.segment_packbits(b, indptr)
+    ref, ref_indptr = Q.segment_packbits(b.cpu(), indptr.cpu())
+    assert torch.equal(out.cpu(), ref) and torch.equal(new_indptr.cpu(), ref_indptr)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("n,k", [(1000, 1), (32000, 50), (128256, 2048), (100, 100)])
+def test_top_k(dtype, n, k):
+    x = torch.randn(5, n, device="cuda", dtype=dtype)
+    v, i = TK.top_k(x, k, sorted=True)
+    vr, ir = torch.topk(x, k, dim=-1, sorted=True)
+    torch.testing.assert_close(v.float(), vr.float())
+    torch.testing.assert_close(x.gather(-1, i).float(), vr.float())
+    assert all(len(set(r.tolist())) == k for r in i)
+
+
+def test_top_k_transforms_and_ties():
+    rows, max_len, k = 6, 4096, 64
+    x = torch.randn(rows, max_len, device="cuda")
+    lengths = torch.tensor([4096, 100, 64, 10, 2000, 4096], dtype=torch.int32, device="cuda")
+    table = torch.randint(0, 100000, (rows, max_len), dtype=torch.int32, device="cuda")
+    out = TK.top_k_page_table_transform(x, table, lengths, k)
+    ref = TK.top_k_page_table_transform(x.cpu(), table.cpu(), lengths.cpu(), k)
+    for r in range(rows):
+        assert sorted(out[r].tolist()) == sorted(ref[r].tolist())
+    offs = torch.arange(rows, dtype=torch.int32, device="cuda") * 10000
+    out = TK.top_k_ragged_transform(x, offs, lengths, k)
+    ref = TK.top_k_ragged_transform(x.cpu(), offs.cpu(), lengths.cpu(), k)
+    for r in range(rows):
+        assert sorted(out[r].tolist()) == sorted(ref[r].tolist())
+    # ties: all-equal row -> SMALL takes the first k indices, LARGE the last k
+    t = torch.zeros(2, 500, device="cuda")
+    _, i = TK.top_k(t, 7, tie_break=TK.TopKTieBreak.SMALL)
+    assert sorted(i[0].tolist()) == list(range(7))
+    _, i = TK.top_k(t, 7, tie_break=TK.TopKTieBreak.LARGE)
+    assert sorted(i[0].tolist()) == list(range(493, 500))
