@@ -13,6 +13,7 @@
 //     and the kernel streams weights at HBM speed; split-K spreads long-K/short-N problems over
 //     all SMs (fp32 partials + tiny reduce kernel).
 //   * PDL: griddepcontrol.wait before the first global read, launch_dependents after the mainloop.
+#include <stdlib.h>
 #include <fib200/common.cuh>
 #include <fib200/ptx.cuh>
 
@@ -25,14 +26,19 @@ namespace {
 constexpr int BM = 128;  // MMA M (rows of the "A-side" operand)
 constexpr int BK = 64;   // 64 x 2B = one 128B swizzle span
 
-template <int BN>
+// Shared-memory plan for a runtime tile width BN (multiple of 16, <= 256).
 struct GemmSmem {
-  static constexpr int kStages = (BN <= 64) ? 8 : (BN <= 128 ? 6 : 4);
+  int stages, stage_bytes, bar_offset, total;
   static constexpr int kABytes = BM * BK * 2;
-  static constexpr int kBBytes = BN * BK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kBarOffset = kStages * kStageBytes;
-  static constexpr int kTotal = kBarOffset + 320 + 1024;  // + barriers + flags + alignment slack
+  __host__ __device__ static GemmSmem make(int BN) {
+    GemmSmem g;
+    g.stage_bytes = kABytes + BN * BK * 2;
+    int st = (220 * 1024) / g.stage_bytes;
+    g.stages = st > 8 ? 8 : st;
+    g.bar_offset = g.stages * g.stage_bytes;
+    g.total = g.bar_offset + 320 + 1024;
+    return g;
+  }
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -44,7 +50,7 @@ struct GemmSmem {
 // each part sums and writes 1/parts of the tile (slot order => bitwise reproducible).
 // ---------------------------------------------------------------------------------------------------
 struct Sched {
-  int tiles_a, tiles_b, kblocks, grid;
+  int tiles_a, tiles_b, kblocks, grid, BN;
   int W, R, g_sk, max_parts, group_a;
   int64_t u_r;  // R * kblocks
   __device__ __forceinline__ int64_t sk_begin(int c) const { return (int64_t(c) * u_r) / g_sk; }
@@ -105,16 +111,17 @@ struct SegIter {
   }
 };
 
-template <int BN, bool kSwap, typename OutT>
+template <bool kSwap, typename OutT>
 __global__ void __launch_bounds__(256, 1)
 gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, OutT* __restrict__ C,
                float* __restrict__ partial, int* __restrict__ counters, const OutT* __restrict__ bias, int rowsA,
                int rowsB, int K, int64_t ldc, const Sched sk, uint32_t idesc) {
-  using S = GemmSmem<BN>;
-  constexpr int kStages = S::kStages;
+  const int BN = sk.BN;
+  const GemmSmem S = GemmSmem::make(BN);
+  const int kStages = S.stages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S.bar_offset);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full = empty_bar + kStages;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -136,8 +143,10 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     ptx::fence_mbar_init();
   }
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < uint32_t(2 * BN)) tmem_cols <<= 1;
   if (warp == 2) {
-    ptx::tmem_alloc<1>(tmem_ptr, (2 * BN < 32) ? 32 : 2 * BN);
+    ptx::tmem_alloc<1>(tmem_ptr, tmem_cols);
     ptx::tmem_relinquish<1>();
   }
   ptx::tc_fence_before();
@@ -160,9 +169,9 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         sk.coords(tile, ta, tb);
         for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * S::kStageBytes;
-          uint8_t* sb = sa + S::kABytes;
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
+          uint8_t* sa = smem + stage * S.stage_bytes;
+          uint8_t* sb = sa + GemmSmem::kABytes;
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], S.stage_bytes);
           ptx::tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, ta * BM, kSwap ? ptx::kEvictFirst : ptx::kEvictNormal);
           ptx::tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, tb * BN, kSwap ? ptx::kEvictLast : ptx::kEvictNormal);
           if (++stage == kStages) {
@@ -189,8 +198,8 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
-          const uint32_t sa = ptx::smem_u32(smem + stage * S::kStageBytes);
-          const uint32_t sb = sa + S::kABytes;
+          const uint32_t sa = ptx::smem_u32(smem + stage * S.stage_bytes);
+          const uint32_t sb = sa + GemmSmem::kABytes;
           const uint64_t da = ptx::make_smem_desc(sa, 16, 1024, ptx::kSwz128);
           const uint64_t db = ptx::make_smem_desc(sb, 16, 1024, ptx::kSwz128);
 #pragma unroll
@@ -217,7 +226,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int etid = threadIdx.x - 128;
     int acc = 0;
     uint32_t acc_phase = 0;
-    constexpr int CH = (BN >= 32) ? 32 : 16;
+    constexpr int CH = 16;
     SegIter it(sk, blockIdx.x);
     int tile, kb0, kb1, r_idx;
     bool part;
@@ -236,7 +245,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += CH) {
           uint32_t r[CH];
-          if constexpr (CH == 32) ptx::tmem_ld_x32(taddr + c0, r); else ptx::tmem_ld_x16(taddr + c0, r);
+          ptx::tmem_ld_x16(taddr + c0, r);
           ptx::tmem_ld_wait();
           const int b_row0 = tb * BN + c0;
           if constexpr (kSwap) {
@@ -292,7 +301,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += CH) {
           uint32_t r[CH];
-          if constexpr (CH == 32) ptx::tmem_ld_x32(taddr + c0, r); else ptx::tmem_ld_x16(taddr + c0, r);
+          ptx::tmem_ld_x16(taddr + c0, r);
           ptx::tmem_ld_wait();
           if constexpr (kSwap) {
 #pragma unroll
@@ -336,7 +345,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           ptx::named_bar_sync(1, 128);
           // reduce my 1/parts share of the tile (slot order => deterministic) and write it out
-          constexpr int NV = BM * BN / 4;
+          const int NV = BM * BN / 4;
           const int v_begin = (my_part * NV) / parts, v_end = ((my_part + 1) * NV) / parts;
           for (int v = v_begin + etid; v < v_end; v += 128) {
             float4 accv = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -390,27 +399,28 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc<1>(tmem_base, (2 * BN < 32) ? 32 : 2 * BN);
+    ptx::tmem_dealloc<1>(tmem_base, tmem_cols);
   }
 }
 
-template <int BN, bool kSwap, typename OutT>
-int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, OutT* C, float* workspace, int64_t workspace_bytes,
+template <bool kSwap, typename OutT>
+int launch_gemm(int BN, const CUtensorMap& tmA, const CUtensorMap& tmB, OutT* C, float* workspace, int64_t workspace_bytes,
                 const OutT* bias, int rowsA, int rowsB, int K, int64_t ldc, bool f16, bool pdl, cudaStream_t stream) {
-  using S = GemmSmem<BN>;
-  auto kern = gemm_nt_kernel<BN, kSwap, OutT>;
+  const GemmSmem S = GemmSmem::make(BN);
+  auto kern = gemm_nt_kernel<kSwap, OutT>;
   static bool attr_set = false;
   if (!attr_set) {
-    FIB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    FIB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   Sched sk;
+  sk.BN = BN;
   sk.tiles_a = (rowsA + BM - 1) / BM;
   sk.tiles_b = (rowsB + BN - 1) / BN;
   sk.kblocks = (K + BK - 1) / BK;
   const int tiles = sk.tiles_a * sk.tiles_b;
   int grid = num_sms();
-  if (tiles < grid && (workspace == nullptr || int64_t(tiles) * sk.kblocks < 2 * grid)) grid = tiles;
+  if (tiles < grid && (!kSwap || workspace == nullptr || int64_t(tiles) * sk.kblocks < 2 * grid)) grid = tiles;
   sk.grid = grid;
   sk.W = tiles / grid;
   sk.R = tiles % grid;
@@ -420,7 +430,7 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, OutT* C, float* 
   sk.u_r = int64_t(sk.R) * sk.kblocks;
   // workspace layout: [counters: 2 ints per remainder tile, 4 KB][fp32 partial slots]
   const int64_t slot_bytes = int64_t(BM) * BN * 4;
-  if (workspace != nullptr && sk.R > 0 && sk.R <= 512) {
+  if (workspace != nullptr && sk.R > 0 && sk.R <= 512 && (kSwap || sk.W >= 1)) {
     int64_t mp = (workspace_bytes - 4096) / (int64_t(sk.R) * slot_bytes);
     if (mp > 8) mp = 8;
     if (mp >= 2) {
@@ -436,29 +446,62 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, OutT* C, float* 
     }
   }
   const uint32_t idesc = ptx::make_idesc_f16(f16 ? ptx::kFmtF16 : ptx::kFmtBF16, BM, BN, 0, 0);
-  LaunchCfg lc(dim3(grid), dim3(256), S::kTotal, stream, pdl);
+  LaunchCfg lc(dim3(grid), dim3(256), S.total, stream, pdl);
   int* counters = reinterpret_cast<int*>(workspace);
   float* partial = workspace ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + 4096) : nullptr;
   FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, kern, tmA, tmB, C, partial, counters, bias, rowsA, rowsB, K, ldc, sk, idesc));
   return 0;
 }
 
+inline int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
 template <typename OutT>
 int gemm_dispatch(const void* A, const void* B, OutT* C, const OutT* bias, int M, int N, int K, int64_t lda, int64_t ldb,
                   int64_t ldc, bool f16, float* workspace, int64_t workspace_bytes, bool pdl, cudaStream_t stream) {
   const CUtensorMapDataType dt = f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-  const bool swap = (M <= 128);
+  // Small M (decode): activations take the 128-row MMA-M side (rows past M are TMA zero-fill, no traffic) and
+  // the weight matrix is cut into narrow N tiles so that ONE wave covers the machine with no split-K:
+  // BN = smallest multiple of 16 with ceil(N / BN) <= #SM (>= 64 to keep the L2 re-read of the activations
+  // below the HBM traffic).  Large M: 128x256 / 128x128 tiles, round-robin waves + stream-K remainder.
+  static const int force_swap = env_int("FIB200_GEMM_SWAP", -1);
+  static const int force_bn = env_int("FIB200_GEMM_BN", 0);
+  static const int min_bn_small = env_int("FIB200_GEMM_MIN_BN", 64);
+  bool swap = false;
+  int BN;
+  if (M <= 128) {
+    const int sms = num_sms();
+    BN = ((N + sms - 1) / sms + 15) / 16 * 16;
+    if (BN < min_bn_small) BN = min_bn_small;
+    if (BN > 256) {
+      // many waves: pick BN in [192, 256] minimising the tail of the last wave
+      int best = 256;
+      double best_eff = 0.0;
+      for (int bn = 256; bn >= 192; bn -= 16) {
+        const int t = (N + bn - 1) / bn;
+        const double eff = double(t) / (double((t + sms - 1) / sms) * sms);
+        if (eff > best_eff + 1e-9) {
+          best_eff = eff;
+          best = bn;
+        }
+      }
+      BN = best;
+    }
+  } else {
+    BN = (N >= 256 && (int64_t(M) * N >= int64_t(256) * 256 * 64)) ? 256 : 128;
+  }
+  if (force_swap == 1 && M <= 128) {
+    swap = true;
+    BN = M <= 16 ? 16 : (M <= 32 ? 32 : (M <= 64 ? 64 : 128));
+  }
+  if (force_bn > 0) BN = force_bn;
   // A-side = 128-row operand.  normal: activations; swap: weights.
   const void* pa = swap ? B : A;
   const void* pb = swap ? A : B;
   const int rowsA = swap ? N : M, rowsB = swap ? M : N;
   const int64_t ldA = swap ? ldb : lda, ldB = swap ? lda : ldb;
-  int BN;
-  if (swap) {
-    BN = M <= 16 ? 16 : (M <= 32 ? 32 : (M <= 64 ? 64 : 128));
-  } else {
-    BN = (N >= 256 && (int64_t(M) * N >= int64_t(256) * 256 * 64)) ? 256 : 128;
-  }
   CUtensorMap tmA, tmB;
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)rowsA};
@@ -472,26 +515,9 @@ int gemm_dispatch(const void* A, const void* B, OutT* C, const OutT* bias, int M
     uint32_t box[2] = {BK, (uint32_t)BN};
     if (make_tmap(&tmB, dt, 2, pb, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   }
-#define FIB_LAUNCH(BN_, SWAP_)                                                                                 \
-  if (launch_gemm<BN_, SWAP_, OutT>(tmA, tmB, C, workspace, workspace_bytes, bias, rowsA, rowsB, K, ldc, f16, pdl, \
-                                    stream))                                                                   \
-    return 1;
-  if (swap) {
-    switch (BN) {
-      case 16: FIB_LAUNCH(16, true); break;
-      case 32: FIB_LAUNCH(32, true); break;
-      case 64: FIB_LAUNCH(64, true); break;
-      default: FIB_LAUNCH(128, true); break;
-    }
-  } else {
-    if (BN == 256) {
-      FIB_LAUNCH(256, false);
-    } else {
-      FIB_LAUNCH(128, false);
-    }
-  }
-#undef FIB_LAUNCH
-  return 0;
+  if (swap)
+    return launch_gemm<true, OutT>(BN, tmA, tmB, C, workspace, workspace_bytes, bias, rowsA, rowsB, K, ldc, f16, pdl, stream);
+  return launch_gemm<false, OutT>(BN, tmA, tmB, C, workspace, workspace_bytes, bias, rowsA, rowsB, K, ldc, f16, pdl, stream);
 }
 
 }  // namespace
