@@ -23,20 +23,19 @@ FIB_EXPORT_LAST_ERROR()
 
 namespace {
 
-constexpr int BM = 128;  // MMA M (rows of the "A-side" operand)
 constexpr int BK = 64;   // 64 x 2B = one 128B swizzle span
 
 // Shared-memory plan for a runtime tile width BN (multiple of 16, <= 256).
 struct GemmSmem {
-  int stages, stage_bytes, bar_offset, total;
-  static constexpr int kABytes = BM * BK * 2;
-  __host__ __device__ static GemmSmem make(int BN) {
+  int stages, stage_bytes, a_bytes, bar_offset, total;
+  __host__ __device__ static GemmSmem make(int BMv, int BN) {
     GemmSmem g;
-    g.stage_bytes = kABytes + BN * BK * 2;
+    g.a_bytes = BMv * BK * 2;
+    g.stage_bytes = g.a_bytes + BN * BK * 2;
     int st = (220 * 1024) / g.stage_bytes;
-    g.stages = st > 8 ? 8 : st;
+    g.stages = st > 16 ? 16 : st;
     g.bar_offset = g.stages * g.stage_bytes;
-    g.total = g.bar_offset + 320 + 1024;
+    g.total = g.bar_offset + 512 + 1024;
     return g;
   }
 };
@@ -111,13 +110,13 @@ struct SegIter {
   }
 };
 
-template <bool kSwap, typename OutT>
+template <int BM, bool kSwap, typename OutT>
 __global__ void __launch_bounds__(256, 1)
 gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, OutT* __restrict__ C,
                float* __restrict__ partial, int* __restrict__ counters, const OutT* __restrict__ bias, int rowsA,
                int rowsB, int K, int64_t ldc, const Sched sk, uint32_t idesc) {
   const int BN = sk.BN;
-  const GemmSmem S = GemmSmem::make(BN);
+  const GemmSmem S = GemmSmem::make(BM, BN);
   const int kStages = S.stages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -170,7 +169,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * S.stage_bytes;
-          uint8_t* sb = sa + GemmSmem::kABytes;
+          uint8_t* sb = sa + S.a_bytes;
           ptx::mbar_arrive_expect_tx(&full_bar[stage], S.stage_bytes);
           ptx::tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, ta * BM, kSwap ? ptx::kEvictFirst : ptx::kEvictNormal);
           ptx::tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, tb * BN, kSwap ? ptx::kEvictLast : ptx::kEvictNormal);
@@ -199,7 +198,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
           const uint32_t sa = ptx::smem_u32(smem + stage * S.stage_bytes);
-          const uint32_t sb = sa + GemmSmem::kABytes;
+          const uint32_t sb = sa + S.a_bytes;
           const uint64_t da = ptx::make_smem_desc(sa, 16, 1024, ptx::kSwz128);
           const uint64_t db = ptx::make_smem_desc(sb, 16, 1024, ptx::kSwz128);
 #pragma unroll
@@ -237,8 +236,10 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       sk.coords(tile, ta, tb);
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
-      const int r_in_tile = q * 32 + lane;
-      const int a_row = ta * BM + r_in_tile;  // row of the A-side operand owned by this thread
+      // M=128: row i <-> TMEM lane i.  M=64: rows 16q..16q+15 live in the lower 16 lanes of quadrant q.
+      const bool row_ok = (BM == 128) || (lane < 16);
+      const int r_in_tile = (BM == 128) ? q * 32 + lane : q * 16 + (lane & 15);
+      const int a_row = row_ok ? ta * BM + r_in_tile : (1 << 30);  // row of the A-side operand owned by this thread
       const uint32_t taddr = tmem_base + acc * BN + (uint32_t(q * 32) << 16);
 
       if (!part) {
@@ -303,6 +304,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint32_t r[CH];
           ptx::tmem_ld_x16(taddr + c0, r);
           ptx::tmem_ld_wait();
+          if (!row_ok) continue;
           if constexpr (kSwap) {
 #pragma unroll
             for (int j = 0; j < CH; ++j) __stcg(my_slot + (c0 + j) * BM + r_in_tile, __uint_as_float(r[j]));
@@ -403,11 +405,11 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
-template <bool kSwap, typename OutT>
+template <int BM, bool kSwap, typename OutT>
 int launch_gemm(int BN, const CUtensorMap& tmA, const CUtensorMap& tmB, OutT* C, float* workspace, int64_t workspace_bytes,
                 const OutT* bias, int rowsA, int rowsB, int K, int64_t ldc, bool f16, bool pdl, cudaStream_t stream) {
-  const GemmSmem S = GemmSmem::make(BN);
-  auto kern = gemm_nt_kernel<kSwap, OutT>;
+  const GemmSmem S = GemmSmem::make(BM, BN);
+  auto kern = gemm_nt_kernel<BM, kSwap, OutT>;
   static bool attr_set = false;
   if (!attr_set) {
     FIB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -469,12 +471,16 @@ int gemm_dispatch(const void* A, const void* B, OutT* C, const OutT* bias, int M
   static const int force_swap = env_int("FIB200_GEMM_SWAP", -1);
   static const int force_bn = env_int("FIB200_GEMM_BN", 0);
   static const int min_bn_small = env_int("FIB200_GEMM_MIN_BN", 64);
+  static const int force_bm = env_int("FIB200_GEMM_BM", 0);
   bool swap = false;
   int BN;
+  int BMsel = 128;
   if (M <= 128) {
     const int sms = num_sms();
+    if (M <= 64) BMsel = 64;  // half-height MMA tile: the activation tile costs 8 KB/stage -> deeper ring
     BN = ((N + sms - 1) / sms + 15) / 16 * 16;
-    if (BN < min_bn_small) BN = min_bn_small;
+    const int min_bn = (BMsel == 64 && min_bn_small == 64) ? 32 : min_bn_small;
+    if (BN < min_bn) BN = min_bn;
     if (BN > 256) {
       // many waves: pick BN in [192, 256] minimising the tail of the last wave
       int best = 256;
@@ -494,9 +500,12 @@ int gemm_dispatch(const void* A, const void* B, OutT* C, const OutT* bias, int M
   }
   if (force_swap == 1 && M <= 128) {
     swap = true;
+    BMsel = 128;
     BN = M <= 16 ? 16 : (M <= 32 ? 32 : (M <= 64 ? 64 : 128));
   }
   if (force_bn > 0) BN = force_bn;
+  if (force_bm > 0 && !swap) BMsel = force_bm;
+  const int BM = BMsel;
   // A-side = 128-row operand.  normal: activations; swap: weights.
   const void* pa = swap ? B : A;
   const void* pb = swap ? A : B;
@@ -506,7 +515,7 @@ int gemm_dispatch(const void* A, const void* B, OutT* C, const OutT* bias, int M
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)rowsA};
     uint64_t str[1] = {(uint64_t)ldA * 2};
-    uint32_t box[2] = {BK, BM};
+    uint32_t box[2] = {BK, (uint32_t)BM};
     if (make_tmap(&tmA, dt, 2, pa, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   }
   {
@@ -516,8 +525,13 @@ int gemm_dispatch(const void* A, const void* B, OutT* C, const OutT* bias, int M
     if (make_tmap(&tmB, dt, 2, pb, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   }
   if (swap)
-    return launch_gemm<true, OutT>(BN, tmA, tmB, C, workspace, workspace_bytes, bias, rowsA, rowsB, K, ldc, f16, pdl, stream);
-  return launch_gemm<false, OutT>(BN, tmA, tmB, C, workspace, workspace_bytes, bias, rowsA, rowsB, K, ldc, f16, pdl, stream);
+    return launch_gemm<128, true, OutT>(BN, tmA, tmB, C, workspace, workspace_bytes, bias, rowsA, rowsB, K, ldc, f16, pdl,
+                                        stream);
+  if (BM == 64)
+    return launch_gemm<64, false, OutT>(BN, tmA, tmB, C, workspace, workspace_bytes, bias, rowsA, rowsB, K, ldc, f16, pdl,
+                                        stream);
+  return launch_gemm<128, false, OutT>(BN, tmA, tmB, C, workspace, workspace_bytes, bias, rowsA, rowsB, K, ldc, f16, pdl,
+                                       stream);
 }
 
 }  // namespace
