@@ -50,6 +50,7 @@ struct GemmSmem {
 // ---------------------------------------------------------------------------------------------------
 struct Sched {
   int tiles_a, tiles_b, kblocks, grid, BN;
+  int S;  // cluster split-K factor (1 = off); when > 1 the grid is exactly tiles * S (one tile per cluster)
   int W, R, g_sk, max_parts, group_a;
   int64_t u_r;  // R * kblocks
   __device__ __forceinline__ int64_t sk_begin(int c) const { return (int64_t(c) * u_r) / g_sk; }
@@ -124,10 +125,14 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full = empty_bar + kStages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* go_bar = tmem_empty + 2;        // cluster split-K: "leader smem is free, send your partial"
+  uint64_t* partials_bar = go_bar + 1;      // leader only: all peers delivered their partials
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(partials_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int S_split = sk.S;
+  const int crank = S_split > 1 ? int(ptx::cluster_ctarank()) : 0;
 
   if (threadIdx.x == 0) {
     ptx::prefetch_tmap(&tmA);
@@ -140,6 +145,8 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       ptx::mbar_init(&tmem_full[i], 1);
       ptx::mbar_init(&tmem_empty[i], 4);
     }
+    ptx::mbar_init(go_bar, 1);
+    ptx::mbar_init(partials_bar, S_split > 1 ? S_split - 1 : 1);
     ptx::fence_mbar_init();
   }
   uint32_t tmem_cols = 32;
@@ -150,10 +157,156 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (S_split > 1) ptx::cluster_sync();  // peers' mbarriers must exist before any remote arrive
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
   ptx::grid_dep_wait();
+
+  if (S_split > 1) {
+    // =====================================================================================
+    // Cluster split-K (single wave): cluster = one output tile, rank r owns k-blocks
+    // [r*KB/S, (r+1)*KB/S).  Ranks > 0 hand their fp32 partial to the leader through DSMEM.
+    // =====================================================================================
+    const int tile = blockIdx.x / S_split;
+    int ta, tb;
+    sk.coords(tile, ta, tb);
+    const int kb0 = (crank * sk.kblocks) / S_split, kb1 = ((crank + 1) * sk.kblocks) / S_split;
+    if (warp == 0) {
+      if (ptx::elect_one()) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * S.stage_bytes;
+          uint8_t* sb = sa + S.a_bytes;
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], S.stage_bytes);
+          ptx::tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, ta * BM, ptx::kEvictLast);
+          ptx::tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, tb * BN, ptx::kEvictFirst);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    } else if (warp == 1) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        ptx::mbar_wait(&full_bar[stage], phase);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const uint32_t sa = ptx::smem_u32(smem + stage * S.stage_bytes);
+          const uint32_t sb = sa + S.a_bytes;
+          const uint64_t da = ptx::make_smem_desc(sa, 16, 1024, ptx::kSwz128);
+          const uint64_t db = ptx::make_smem_desc(sb, 16, 1024, ptx::kSwz128);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            ptx::mma_f16_ss<1>(tmem_base, ptx::desc_advance(da, k * 32), ptx::desc_advance(db, k * 32), idesc,
+                               (kb > kb0 || k > 0) ? 1u : 0u);
+          ptx::mma_commit(&empty_bar[stage]);
+          if (kb == kb1 - 1) ptx::mma_commit(&tmem_full[0]);
+        }
+        __syncwarp();
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      ptx::grid_dep_launch();
+    } else if (warp >= 4) {
+      const int q = warp - 4;
+      const int etid = threadIdx.x - 128;
+      const bool row_ok = (BM == 128) || (lane < 16);
+      const int r_in_tile = (BM == 128) ? q * 32 + lane : q * 16 + (lane & 15);
+      const int a_row = row_ok ? ta * BM + r_in_tile : (1 << 30);
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16);
+      // partial exchange buffer in the LEADER's smem (its pipeline stages are idle by then):
+      // [peer-1][16-column chunk][row][16 floats]  (64 B per thread per chunk -> conflict-free)
+      const uint32_t xbuf = ptx::smem_u32(smem);
+      ptx::mbar_wait(&tmem_full[0], 0);  // my accumulator is complete => all my MMAs (smem reads) retired
+      ptx::tc_fence_after();
+      if (crank == 0) {
+        if (etid == 0) {
+          for (int r = 1; r < S_split; ++r) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(go_bar), r));
+        }
+        ptx::mbar_wait_cluster(partials_bar, 0);
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+          uint32_t r[16];
+          ptx::tmem_ld_x16(taddr + c0, r);
+          ptx::tmem_ld_wait();
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+          if (row_ok) {
+            for (int pr = 0; pr < S_split - 1; ++pr) {
+              const float4* src = reinterpret_cast<const float4*>(
+                  smem + ((int64_t(pr) * (BN / 16) + c0 / 16) * BM + r_in_tile) * 64);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float4 x = src[j];
+                v[4 * j] += x.x;
+                v[4 * j + 1] += x.y;
+                v[4 * j + 2] += x.z;
+                v[4 * j + 3] += x.w;
+              }
+            }
+          }
+          const int b_row0 = tb * BN + c0;
+          if (a_row < rowsA) {
+            OutT* dst = C + int64_t(a_row) * ldc + b_row0;
+            if (b_row0 + 16 <= rowsB && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+              constexpr int VN = 16 / sizeof(OutT);
+#pragma unroll
+              for (int j = 0; j < 16; j += VN) {
+                Vec16<OutT> o;
+#pragma unroll
+                for (int e = 0; e < VN; ++e) {
+                  float x = v[j + e];
+                  if (bias) x += to_f32(bias[b_row0 + j + e]);
+                  o.v[e] = from_f32<OutT>(x);
+                }
+                st16(dst + j, o);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (b_row0 + j < rowsB) {
+                  float x = v[j];
+                  if (bias) x += to_f32(bias[b_row0 + j]);
+                  dst[j] = from_f32<OutT>(x);
+                }
+            }
+          }
+        }
+      } else {
+        ptx::mbar_wait_cluster(go_bar, 0);
+        const uint32_t remote = ptx::mapa(xbuf, 0);
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+          uint32_t r[16];
+          ptx::tmem_ld_x16(taddr + c0, r);
+          ptx::tmem_ld_wait();
+          if (row_ok) {
+            const uint32_t dst = remote + uint32_t(((int64_t(crank - 1) * (BN / 16) + c0 / 16) * BM + r_in_tile) * 64);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              ptx::st_dsmem_v4(dst + j * 16, make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                         __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
+          }
+        }
+        ptx::named_bar_sync(1, 128);
+        if (etid == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(partials_bar), 0));
+      }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync();  // nobody leaves while a peer may still touch its shared memory
+    if (warp == 2) {
+      ptx::tc_fence_after();
+      ptx::tmem_dealloc<1>(tmem_base, tmem_cols);
+    }
+    return;
+  }
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -406,7 +559,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 template <int BM, bool kSwap, typename OutT>
-int launch_gemm(int BN, const CUtensorMap& tmA, const CUtensorMap& tmB, OutT* C, float* workspace, int64_t workspace_bytes,
+int launch_gemm(int BN, int cluster_split, const CUtensorMap& tmA, const CUtensorMap& tmB, OutT* C, float* workspace, int64_t workspace_bytes,
                 const OutT* bias, int rowsA, int rowsB, int K, int64_t ldc, bool f16, bool pdl, cudaStream_t stream) {
   const GemmSmem S = GemmSmem::make(BM, BN);
   auto kern = gemm_nt_kernel<BM, kSwap, OutT>;
@@ -447,8 +600,17 @@ int launch_gemm(int BN, const CUtensorMap& tmA, const CUtensorMap& tmB, OutT* C,
       }
     }
   }
+  sk.S = 1;
+  if (!kSwap && cluster_split > 1 && tiles * cluster_split <= (cluster_split >= 4 ? (num_sms() * 132) / 148 : num_sms()) && sk.kblocks >= 4 * cluster_split &&
+      int64_t(cluster_split - 1) * BM * BN * 4 <= int64_t(S.stages) * S.stage_bytes) {
+    sk.S = cluster_split;
+    sk.grid = grid = tiles * cluster_split;
+    sk.W = 1;
+    sk.R = 0;
+    sk.g_sk = 0;
+  }
   const uint32_t idesc = ptx::make_idesc_f16(f16 ? ptx::kFmtF16 : ptx::kFmtBF16, BM, BN, 0, 0);
-  LaunchCfg lc(dim3(grid), dim3(256), S.total, stream, pdl);
+  LaunchCfg lc(dim3(grid), dim3(256), S.total, stream, pdl, sk.S);
   int* counters = reinterpret_cast<int*>(workspace);
   float* partial = workspace ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + 4096) : nullptr;
   FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, kern, tmA, tmB, C, partial, counters, bias, rowsA, rowsB, K, ldc, sk, idesc));
@@ -475,12 +637,27 @@ int gemm_dispatch(const void* A, const void* B, OutT* C, const OutT* bias, int M
   bool swap = false;
   int BN;
   int BMsel = 128;
+  static const int force_s = env_int("FIB200_GEMM_CLUSTER", 0);
+  int Ssel = 1;
   if (M <= 128) {
     const int sms = num_sms();
     if (M <= 64) BMsel = 64;  // half-height MMA tile: the activation tile costs 8 KB/stage -> deeper ring
     BN = ((N + sms - 1) / sms + 15) / 16 * 16;
     const int min_bn = (BMsel == 64 && min_bn_small == 64) ? 32 : min_bn_small;
     if (BN < min_bn) BN = min_bn;
+    // Few, wide N tiles + K split over a 4-CTA cluster (DSMEM reduction): the activation tile is re-read
+    // from L2 once per N tile, so wide tiles cut L2 traffic 4x while the cluster keeps every SM streaming.
+    if (BN <= 64 && K >= 2048) {
+      const int s_try = force_s > 0 ? force_s : 4;
+      // clusters of 4 can only be placed on 132 of the 148 SMs (GPC granularity), clusters of 2 on all
+      const int eff = s_try >= 4 ? (sms * 132) / 148 : sms;
+      int bn4 = ((N * s_try + eff - 1) / eff + 15) / 16 * 16;
+      if (bn4 < 64) bn4 = 64;
+      if (bn4 <= 256 && s_try > 1) {
+        BN = bn4;
+        Ssel = s_try;
+      }
+    }
     if (BN > 256) {
       // many waves: pick BN in [192, 256] minimising the tail of the last wave
       int best = 256;
@@ -525,12 +702,12 @@ int gemm_dispatch(const void* A, const void* B, OutT* C, const OutT* bias, int M
     if (make_tmap(&tmB, dt, 2, pb, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   }
   if (swap)
-    return launch_gemm<128, true, OutT>(BN, tmA, tmB, C, workspace, workspace_bytes, bias, rowsA, rowsB, K, ldc, f16, pdl,
+    return launch_gemm<128, true, OutT>(BN, 1, tmA, tmB, C, workspace, workspace_bytes, bias, rowsA, rowsB, K, ldc, f16, pdl,
                                         stream);
   if (BM == 64)
-    return launch_gemm<64, false, OutT>(BN, tmA, tmB, C, workspace, workspace_bytes, bias, rowsA, rowsB, K, ldc, f16, pdl,
+    return launch_gemm<64, false, OutT>(BN, Ssel, tmA, tmB, C, workspace, workspace_bytes, bias, rowsA, rowsB, K, ldc, f16, pdl,
                                         stream);
-  return launch_gemm<128, false, OutT>(BN, tmA, tmB, C, workspace, workspace_bytes, bias, rowsA, rowsB, K, ldc, f16, pdl,
+  return launch_gemm<128, false, OutT>(BN, Ssel, tmA, tmB, C, workspace, workspace_bytes, bias, rowsA, rowsB, K, ldc, f16, pdl,
                                        stream);
 }
 
