@@ -298,7 +298,32 @@ def case_gemm_small():
     return res
 
 
-CASES = {"gemm_small": case_gemm_small, "prefill": case_prefill, "prefill_perf": case_prefill_perf, "gemm": case_gemm, "decode": case_decode, "decode_perf": case_decode_perf}
+def case_mla_perf():
+    import torch
+    from flashinfer_b200.mla import BatchMLAPagedAttentionWrapper
+
+    res = {}
+    for (B, kv, H, ps) in [(16, 1024, 128, 32), (64, 4096, 128, 64), (128, 8192, 128, 64), (1, 8192, 128, 64)]:
+        npg = (kv + ps - 1) // ps
+        kvp = torch.arange(0, (B + 1) * npg, npg, dtype=torch.int32)
+        idx = torch.randperm(B * npg).int()
+        ckv = torch.randn(B * npg, ps, 512, device="cuda", dtype=torch.bfloat16)
+        kpe = torch.randn(B * npg, ps, 64, device="cuda", dtype=torch.bfloat16)
+        qn = torch.randn(B, H, 512, device="cuda", dtype=torch.bfloat16)
+        qp = torch.randn(B, H, 64, device="cuda", dtype=torch.bfloat16)
+        w = BatchMLAPagedAttentionWrapper(torch.empty(256 << 20, dtype=torch.uint8, device="cuda"))
+        w.plan(torch.arange(B + 1, dtype=torch.int32), kvp, idx, torch.full((B,), kv, dtype=torch.int32), H, 512, 64, ps,
+               True, 0.07, torch.bfloat16, torch.bfloat16)
+        out = torch.empty(B, H, 512, device="cuda", dtype=torch.bfloat16)
+        us = _graph_time_us(lambda: w.run(qn, qp, ckv, kpe, out=out), reps=5)
+        byts = B * kv * 576 * 2
+        flops = 2 * B * H * kv * (576 + 512)
+        res[f"B{B}_kv{kv}"] = {"us": us, "tbs": byts / us / 1e6, "tflops": flops / us / 1e6}
+        print(f"mla perf B={B} kv={kv} H={H}: {us:.1f} us  {byts / us / 1e6:.3f} TB/s  {flops / us / 1e6:.1f} TFLOP/s", flush=True)
+    return res
+
+
+CASES = {"mla_perf": case_mla_perf, "gemm_small": case_gemm_small, "prefill": case_prefill, "prefill_perf": case_prefill_perf, "gemm": case_gemm, "decode": case_decode, "decode_perf": case_decode_perf}
 
 
 def main():
