@@ -54,3 +54,122 @@ def merge_states(v: torch.Tensor, s: torch.Tensor) -> Tuple[torch.Tensor, torch.
     so = torch.empty(n, h, dtype=torch.float32, device=v.device)
     jit.load("cascade").call("merge_states", v, s, vo, so, n, k, h, d, dtype_code(v.dtype), 1, stream_ptr(v))
     return vo, so
+
+
+# ------------------------------------------------------------------------------------------------
+# Cascade wrappers (reference flashinfer/cascade.py:226-1086): one prefill wrapper per level, every level
+# returns (o, lse) and the levels are folded with the merge operator.
+# ------------------------------------------------------------------------------------------------
+class MultiLevelCascadeAttentionWrapper:
+    """Multi-level cascade attention over a shared paged KV cache (level 0 = most shared prefix)."""
+
+    def __init__(self, num_levels, float_workspace_buffer: torch.Tensor, kv_layout: str = "NHD",
+                 use_cuda_graph: bool = False, qo_indptr_buf_arr=None, paged_kv_indptr_buf_arr=None,
+                 paged_kv_indices_buf_arr=None, paged_kv_last_page_len_buf_arr=None) -> None:
+        from .prefill import BatchPrefillWithPagedKVCacheWrapper
+
+        self._num_levels = num_levels
+        self._kv_layout = kv_layout
+        self._use_cuda_graph = use_cuda_graph
+        self._batch_prefill_wrappers = [
+            BatchPrefillWithPagedKVCacheWrapper(float_workspace_buffer, kv_layout, use_cuda_graph)
+            for _ in range(num_levels)
+        ]
+
+    @property
+    def is_cuda_graph_enabled(self) -> bool:
+        return self._use_cuda_graph
+
+    def reset_workspace_buffer(self, float_workspace_buffer, int_workspace_buffers) -> None:
+        for w, ib in zip(self._batch_prefill_wrappers, int_workspace_buffers):
+            w.reset_workspace_buffer(float_workspace_buffer, ib)
+
+    def plan(self, qo_indptr_arr, paged_kv_indptr_arr, paged_kv_indices_arr, paged_kv_last_page_len, num_qo_heads,
+             num_kv_heads, head_dim, page_size, causal=False, pos_encoding_mode="NONE", use_fp16_qk_reduction=False,
+             sm_scale=None, window_left=-1, logits_soft_cap=None, rope_scale=None, rope_theta=None,
+             q_data_type="float16", kv_data_type=None) -> None:
+        n = self._num_levels
+        for i, (w, qo, kvp, kvi, last) in enumerate(zip(self._batch_prefill_wrappers, qo_indptr_arr, paged_kv_indptr_arr,
+                                                        paged_kv_indices_arr, paged_kv_last_page_len)):
+            # only the last (unique-suffix) level is causal, like the reference
+            w.plan(qo, kvp, kvi, last, num_qo_heads, num_kv_heads, head_dim, page_size,
+                   causal=causal if i == n - 1 else False, pos_encoding_mode=pos_encoding_mode, sm_scale=sm_scale,
+                   window_left=window_left, logits_soft_cap=logits_soft_cap, q_data_type=q_data_type,
+                   kv_data_type=kv_data_type)
+
+    begin_forward = plan
+
+    def run(self, q: torch.Tensor, paged_kv_cache):
+        out, lse = self._batch_prefill_wrappers[-1].run(q, paged_kv_cache, return_lse=True)
+        for w in self._batch_prefill_wrappers[:-1]:
+            out_i, lse_i = w.run(q, paged_kv_cache, return_lse=True)
+            merge_state_in_place(out, lse, out_i, lse_i)
+        return out
+
+    forward = run
+
+    def end_forward(self) -> None:
+        pass
+
+
+class BatchDecodeWithSharedPrefixPagedKVCacheWrapper:
+    """Decode with one prefix (contiguous k/v) shared by the whole batch + per-request paged suffixes."""
+
+    def __init__(self, float_workspace_buffer: torch.Tensor, kv_layout: str = "NHD") -> None:
+        from .decode import BatchDecodeWithPagedKVCacheWrapper
+
+        self._batch_decode_wrapper = BatchDecodeWithPagedKVCacheWrapper(float_workspace_buffer, kv_layout)
+        self._kv_layout = kv_layout
+
+    def reset_workspace_buffer(self, float_workspace_buffer, int_workspace_buffer) -> None:
+        self._batch_decode_wrapper.reset_workspace_buffer(float_workspace_buffer, int_workspace_buffer)
+
+    def begin_forward(self, unique_kv_indptr, unique_kv_indices, unique_kv_last_page_len, num_qo_heads, num_kv_heads,
+                      head_dim, page_size, data_type="float16") -> None:
+        self._batch_decode_wrapper.plan(unique_kv_indptr, unique_kv_indices, unique_kv_last_page_len, num_qo_heads,
+                                        num_kv_heads, head_dim, page_size, q_data_type=data_type)
+
+    def forward(self, q, k_shared, v_shared, unique_kv_cache, allow_fp16_qk_reduction=False, sm_scale=None,
+                rope_scale=None, rope_theta=None):
+        from .prefill import single_prefill_with_kv_cache
+
+        v_sh, s_sh = single_prefill_with_kv_cache(q, k_shared, v_shared, causal=False, kv_layout=self._kv_layout,
+                                                  sm_scale=sm_scale, return_lse=True)
+        v_un, s_un = self._batch_decode_wrapper.run(q, unique_kv_cache, return_lse=True)
+        merge_state_in_place(v_sh, s_sh, v_un, s_un)
+        return v_sh
+
+    def end_forward(self) -> None:
+        pass
+
+
+class BatchPrefillWithSharedPrefixPagedKVCacheWrapper:
+    """Prefill/append with one shared contiguous prefix + per-request paged suffixes."""
+
+    def __init__(self, float_workspace_buffer: torch.Tensor, kv_layout: str = "NHD") -> None:
+        from .prefill import BatchPrefillWithPagedKVCacheWrapper
+
+        self._batch_prefill_wrapper = BatchPrefillWithPagedKVCacheWrapper(float_workspace_buffer, kv_layout)
+        self._kv_layout = kv_layout
+
+    def reset_workspace_buffer(self, float_workspace_buffer, int_workspace_buffer) -> None:
+        self._batch_prefill_wrapper.reset_workspace_buffer(float_workspace_buffer, int_workspace_buffer)
+
+    def begin_forward(self, qo_indptr, paged_kv_indptr, paged_kv_indices, paged_kv_last_page_len, num_qo_heads,
+                      num_kv_heads, head_dim, page_size) -> None:
+        self._plan_args = (qo_indptr, paged_kv_indptr, paged_kv_indices, paged_kv_last_page_len, num_qo_heads,
+                           num_kv_heads, head_dim, page_size)
+
+    def forward(self, q, k_shared, v_shared, unique_kv_cache, causal=False, allow_fp16_qk_reduction=False, sm_scale=None,
+                rope_scale=None, rope_theta=None):
+        from .prefill import single_prefill_with_kv_cache
+
+        self._batch_prefill_wrapper.plan(*self._plan_args, causal=causal, sm_scale=sm_scale, q_data_type=q.dtype)
+        v_sh, s_sh = single_prefill_with_kv_cache(q, k_shared, v_shared, causal=False, kv_layout=self._kv_layout,
+                                                  sm_scale=sm_scale, return_lse=True)
+        v_un, s_un = self._batch_prefill_wrapper.run(q, unique_kv_cache, return_lse=True)
+        merge_state_in_place(v_sh, s_sh, v_un, s_un)
+        return v_sh
+
+    def end_forward(self) -> None:
+        pass

@@ -137,6 +137,7 @@ class BatchDecodeWithPagedKVCacheWrapper:
         self._paged_kv_last_page_len_buf = paged_kv_last_page_len_buffer
         self._planned = False
         self._backend = "sm100"
+        self._cta_budget: Optional[int] = None  # POD: restrict the persistent grid to this many SMs
 
     @property
     def use_tensor_cores(self) -> bool:
@@ -223,6 +224,8 @@ class BatchDecodeWithPagedKVCacheWrapper:
 
         # ---- C++ planner into the pinned buffer, then ONE H2D copy ----
         num_ctas = device_sm_count(self.device if self.device.type == "cuda" else None)
+        if self._cta_budget:
+            num_ctas = max(1, min(num_ctas, int(self._cta_budget)))
         group = num_qo_heads // num_kv_heads
         max_segs = batch_size * num_kv_heads + num_ctas + 1
         max_merge = num_ctas + 1
@@ -295,11 +298,10 @@ class BatchDecodeWithPagedKVCacheWrapper:
             sm_scale *= k_scale
         window_left = self._window_left if window_left is None else window_left
         hq = self._num_qo_heads
-        if sinks is not None:
-            raise NotImplementedError("attention sinks in decode")
+        want_lse = return_lse or sinks is not None
         if out is None:
             out = torch.empty(q.shape[0], hq, self._head_dim, dtype=self._o_dtype, device=q.device)
-        if return_lse and lse is None:
+        if want_lse and lse is None:
             lse = torch.empty(q.shape[0], hq, dtype=torch.float32, device=q.device)
 
         if not q.is_cuda:
@@ -311,10 +313,17 @@ class BatchDecodeWithPagedKVCacheWrapper:
                 self._kv_layout, True, sm_scale, self._logits_soft_cap, window_left,
             )
             out.copy_(o_ref)
-            if return_lse:
+            if want_lse:
                 lse.copy_(lse_ref)
         else:
-            self._run_sm100(q, k_cache, v_cache, out, lse if return_lse else None, sm_scale, window_left, enable_pdl)
+            self._run_sm100(q, k_cache, v_cache, out, lse if want_lse else None, sm_scale, window_left, enable_pdl)
+        if sinks is not None:
+            # the sink only adds exp(sink) to the softmax denominator: fold it in from (o, lse)
+            from .attention._core import apply_attention_sink
+
+            o2, l2 = apply_attention_sink(out, lse, sinks)
+            out.copy_(o2)
+            lse.copy_(l2)
         if v_scale is not None:
             out.copy_((out.float() * v_scale).to(out.dtype))
         return (out, lse) if return_lse else out
@@ -370,3 +379,95 @@ def fast_decode_plan(wrapper: BatchDecodeWithPagedKVCacheWrapper, *args, **kwarg
     """Reference parity: flashinfer/decode.py:2897.  Our plan() is already a single C++ call plus
     one H2D copy, so the fast path is the same code."""
     wrapper.plan(*args, **kwargs)
+
+
+# ------------------------------------------------------------------------------------------------
+# Function-style decode APIs (block-table interface used by vLLM / TRT-LLM style engines).
+# Parity: reference flashinfer/decode.py:2295-2724 (trtllm_batch_decode_with_kv_cache), :2727 (xqa_...),
+# flashinfer/cudnn/decode.py:258.  There is one B200 kernel here, so they all route to it.
+# ------------------------------------------------------------------------------------------------
+def _block_tables_to_indices(block_tables: torch.Tensor, seq_lens: torch.Tensor, page_size: int):
+    seq = seq_lens.to("cpu", torch.int64).reshape(-1)
+    npages = (seq + page_size - 1) // page_size
+    indptr = torch.zeros(seq.numel() + 1, dtype=torch.int32)
+    indptr[1:] = npages.cumsum(0)
+    bt = block_tables.to("cpu")
+    if seq.numel():
+        indices = torch.cat([bt[i, : int(npages[i])] for i in range(seq.numel())]).int()
+    else:
+        indices = torch.empty(0, dtype=torch.int32)
+    last = torch.where(seq > 0, (seq - 1) % page_size + 1, torch.zeros_like(seq)).int()
+    return indptr, indices, last
+
+
+def trtllm_batch_decode_with_kv_cache(query: torch.Tensor, kv_cache, workspace_buffer: torch.Tensor,
+                                      block_tables: torch.Tensor, seq_lens: torch.Tensor, max_seq_len: int,
+                                      bmm1_scale: float = 1.0, bmm2_scale: float = 1.0, window_left: int = -1,
+                                      out: Optional[torch.Tensor] = None, out_dtype=None, o_sf_scale=None,
+                                      o_sf_vec_size=None, sinks=None, kv_layout: str = "HND", enable_pdl=None,
+                                      backend: str = "auto", q_len_per_req: Optional[int] = 1, o_scale=None,
+                                      mask=None, max_q_len=None, cum_seq_lens_q=None, kv_cache_sf=None,
+                                      skip_softmax_threshold_scale_factor=None, uses_shared_paged_kv_idx: bool = True,
+                                      lse=None, return_lse: bool = False):
+    """``query [B * q_len_per_req, Hq, D]``; ``kv_cache`` a ``(k, v)`` tuple or ``[pages, 2, ...]`` tensor in
+    ``kv_layout``; ``block_tables [B, max_pages]``; ``bmm1_scale`` is the softmax scale (q/k scales folded in)."""
+    k_cache, v_cache = unpack_paged_kv_cache(kv_cache, kv_layout)
+    _, _, _, page_size, hkv, d = paged_kv_strides(k_cache, kv_layout)
+    indptr, indices, last = _block_tables_to_indices(block_tables, seq_lens, page_size)
+    b = seq_lens.numel()
+    w = BatchDecodeWithPagedKVCacheWrapper(workspace_buffer, kv_layout)
+    ql = q_len_per_req or 1
+    qo = torch.arange(0, (b + 1) * ql, ql, dtype=torch.int32) if ql > 1 else None
+    w.plan(indptr, indices, last, query.shape[1], hkv, d, page_size, window_left=window_left, q_data_type=query.dtype,
+           sm_scale=float(bmm1_scale), qo_indptr=qo)
+    res = w.run(query, (k_cache, v_cache), out=out if (out is not None and out.dtype == query.dtype) else None,
+                return_lse=return_lse, sinks=sinks, v_scale=float(bmm2_scale) if float(bmm2_scale) != 1.0 else None)
+    if out is not None and not return_lse and res.data_ptr() != out.data_ptr():
+        out.copy_(res)
+        return out
+    return res
+
+
+def xqa_batch_decode_with_kv_cache(*args, **kwargs):
+    """XQA entry point of the reference (flashinfer/decode.py:2727): same kernel here."""
+    return trtllm_batch_decode_with_kv_cache(*args, **kwargs)
+
+
+def cudnn_batch_decode_with_kv_cache(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, scale: float,
+                                     workspace_buffer: torch.Tensor, *, max_sequence_kv: int,
+                                     actual_seq_lens_kv: Optional[torch.Tensor] = None,
+                                     block_tables: Optional[torch.Tensor] = None, is_cuda_graph_compatible: bool = False,
+                                     batch_offsets_q=None, batch_offsets_o=None, batch_offsets_k=None,
+                                     batch_offsets_v=None, out: Optional[torch.Tensor] = None):
+    """cuDNN-style decode signature (reference flashinfer/cudnn/decode.py:258): HND paged caches + block tables."""
+    return trtllm_batch_decode_with_kv_cache(q, (k_cache, v_cache), workspace_buffer, block_tables,
+                                             actual_seq_lens_kv.reshape(-1), max_sequence_kv, bmm1_scale=scale, out=out,
+                                             kv_layout="HND")
+
+
+class BatchDecodeMlaWithPagedKVCacheWrapper:
+    """Legacy MLA decode wrapper (reference flashinfer/decode.py:1677-2054): q_nope/q_pe + compressed-kv / k-pe caches."""
+
+    def __init__(self, float_workspace_buffer: torch.Tensor, use_cuda_graph: bool = False, use_tensor_cores: bool = True,
+                 paged_kv_indptr_buffer=None, paged_kv_indices_buffer=None, paged_kv_last_page_len_buffer=None) -> None:
+        from .mla import BatchMLAPagedAttentionWrapper
+
+        self._w = BatchMLAPagedAttentionWrapper(float_workspace_buffer, use_cuda_graph)
+
+    def plan(self, indptr, indices, last_page_len, num_qo_heads, head_dim_compressed_kv, page_size, sm_scale,
+             window_left: int = -1, logits_soft_cap=None, data_type="float16", q_data_type=None, rope_scale=None,
+             rope_theta=None) -> None:
+        n_pages = (indptr[1:] - indptr[:-1]).to("cpu", torch.int64)
+        kv_len = torch.clamp(n_pages - 1, min=0) * page_size + last_page_len.to("cpu", torch.int64)
+        b = kv_len.numel()
+        dt = _canon_dtype(q_data_type or data_type)
+        self._w.plan(torch.arange(b + 1, dtype=torch.int32), indptr, indices, kv_len.int(), num_qo_heads,
+                     head_dim_compressed_kv, 64, page_size, False, sm_scale, dt, dt)
+
+    begin_forward = plan
+
+    def run(self, q_nope, q_pe, paged_ckv_cache, paged_kpe_cache, q_scale=None, k_scale=None, v_scale=None, out=None,
+            lse=None, return_lse: bool = False, enable_pdl: bool = False):
+        return self._w.run(q_nope, q_pe, paged_ckv_cache, paged_kpe_cache, out=out, lse=lse, return_lse=return_lse)
+
+    forward = run

@@ -1,0 +1,173 @@
+"""POD-Attention: prefill and decode co-scheduled on disjoint SM sets.
+
+Parity: reference flashinfer/pod.py:61-1205 (PODWithPagedKVCacheWrapper, BatchPODWithPagedKVCacheWrapper) and
+include/flashinfer/attention/pod.cuh (one grid, CTAs pick PREFILL/DECODE by SM id at run time).
+
+B200-first design: both attention kernels are persistent (one CTA per SM, grid size chosen by the planner), so SM
+sharing is decided on the host: a cost model (prefill FLOPs at tensor peak vs. decode bytes at HBM peak) splits the
+148 SMs into two budgets, each phase is planned for its budget and the two kernels are launched on forked streams —
+they run concurrently on disjoint SMs, the memory-bound decode hiding under the compute-bound prefill.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple, Union
+
+import torch
+
+from .decode import BatchDecodeWithPagedKVCacheWrapper
+from .prefill import BatchPrefillWithPagedKVCacheWrapper, BatchPrefillWithRaggedKVCacheWrapper
+from .utils import device_sm_count
+
+_PEAK_FLOPS = 1.1e15  # achieved FMHA rate (profiles/), not the datasheet number
+_PEAK_BW = 6.0e12
+
+
+def _split_sms(total: int, prefill_flops: float, decode_bytes: float) -> Tuple[int, int]:
+    t_p, t_d = prefill_flops / _PEAK_FLOPS, decode_bytes / _PEAK_BW
+    if t_p <= 0:
+        return 0, total
+    if t_d <= 0:
+        return total, 0
+    p = int(round(total * t_p / (t_p + t_d)))
+    p = max(8, min(total - 8, p))
+    return p, total - p
+
+
+class _SideStream:
+    def __init__(self, device):
+        self.stream = torch.cuda.Stream(device=device) if device.type == "cuda" else None
+
+    def fork(self):
+        ev = torch.cuda.Event()
+        ev.record()
+        self.stream.wait_event(ev)
+
+    def join(self):
+        ev = torch.cuda.Event()
+        ev.record(self.stream)
+        torch.cuda.current_stream().wait_event(ev)
+
+
+class PODWithPagedKVCacheWrapper:
+    """One prefill request (contiguous k_p/v_p) fused with a batch of paged decodes."""
+
+    def __init__(self, float_workspace_buffer: torch.Tensor, kv_layout: str = "NHD", use_cuda_graph: bool = False,
+                 paged_kv_indptr_buffer=None, paged_kv_indices_buffer=None, paged_kv_last_page_len_buffer=None,
+                 jit_args=None) -> None:
+        self.device = float_workspace_buffer.device
+        half = float_workspace_buffer.numel() // 2
+        self._decode = BatchDecodeWithPagedKVCacheWrapper(float_workspace_buffer[half:], kv_layout)
+        self._prefill = BatchPrefillWithRaggedKVCacheWrapper(float_workspace_buffer[:half], kv_layout)
+        self._kv_layout = kv_layout
+        self._side = _SideStream(self.device)
+
+    def plan(self, indptr, indices, last_page_len, num_qo_heads, num_kv_heads, head_dim, page_size,
+             pos_encoding_mode="NONE", window_left=-1, q_data_type="float16", kv_data_type=None, data_type=None,
+             sm_scale=None, rope_scale=None, rope_theta=None, non_blocking=True) -> None:
+        self._dargs = (indptr, indices, last_page_len, num_qo_heads, num_kv_heads, head_dim, page_size)
+        self._dkw = dict(window_left=window_left, q_data_type=data_type or q_data_type, kv_data_type=kv_data_type,
+                         sm_scale=sm_scale)
+        self._hq, self._hkv, self._d, self._ps = num_qo_heads, num_kv_heads, head_dim, page_size
+        n_pages = (indptr[1:] - indptr[:-1]).to("cpu")
+        self._decode_tokens = int(n_pages.sum()) * page_size
+        self._decode_planned_for = None
+
+    begin_forward = plan
+
+    def run(self, q_p, k_p, v_p, q_d, paged_kv_cache_d, custom_mask_p=None, packed_custom_mask_p=None, causal_p=False,
+            kv_layout_p="NHD", pos_encoding_mode_p="NONE", sm_scale_p=None, window_left_p=-1, rope_scale_p=None,
+            rope_theta_p=None, return_lse_p=False, custom_mask_d=None, packed_custom_mask_d=None, causal_d=False,
+            kv_layout_d="NHD", pos_encoding_mode_d="NONE", sm_scale_d=None, window_left_d=-1, rope_scale_d=None,
+            rope_theta_d=None, q_scale=None, k_scale=None, v_scale=None, return_lse_d=False,
+            use_fp16_qk_reduction=False, enable_pdl=None):
+        if custom_mask_p is not None or packed_custom_mask_p is not None:
+            raise NotImplementedError("POD with custom masks")
+        total = device_sm_count(self.device if self.device.type == "cuda" else None)
+        qo_len, kv_len = q_p.shape[0], (k_p.shape[0] if kv_layout_p == "NHD" else k_p.shape[1])
+        flops = 4.0 * qo_len * kv_len * self._hq * self._d * (0.5 if causal_p else 1.0)
+        dbytes = 2.0 * self._decode_tokens * self._hkv * self._d * 2
+        sp, sd = _split_sms(total, flops, dbytes)
+        self._prefill._cta_budget, self._decode._cta_budget = sp or None, sd or None
+        if self._decode_planned_for != sd:
+            self._decode.plan(*self._dargs, **self._dkw)
+            self._decode_planned_for = sd
+        self._prefill._kv_layout = kv_layout_p
+        self._prefill.plan(torch.tensor([0, qo_len], dtype=torch.int32), torch.tensor([0, kv_len], dtype=torch.int32),
+                           self._hq, self._hkv, self._d, causal=causal_p, sm_scale=sm_scale_p,
+                           window_left=window_left_p, q_data_type=q_p.dtype)
+        if q_p.is_cuda:
+            self._side.fork()
+            with torch.cuda.stream(self._side.stream):
+                res_d = self._decode.run(q_d, paged_kv_cache_d, q_scale=q_scale, k_scale=k_scale, v_scale=v_scale,
+                                         return_lse=return_lse_d)
+            res_p = self._prefill.run(q_p, k_p, v_p, return_lse=return_lse_p)
+            self._side.join()
+        else:
+            res_d = self._decode.run(q_d, paged_kv_cache_d, return_lse=return_lse_d)
+            res_p = self._prefill.run(q_p, k_p, v_p, return_lse=return_lse_p)
+        return res_p, res_d
+
+    forward = run
+
+    def end_forward(self) -> None:
+        pass
+
+
+class BatchPODWithPagedKVCacheWrapper:
+    """Batched prefill (paged) fused with batched decode (paged)."""
+
+    def __init__(self, float_workspace_buffer: torch.Tensor, kv_layout: str = "NHD", use_cuda_graph: bool = False,
+                 **kwargs) -> None:
+        self.device = float_workspace_buffer.device
+        half = float_workspace_buffer.numel() // 2
+        self._prefill = BatchPrefillWithPagedKVCacheWrapper(float_workspace_buffer[:half], kv_layout)
+        self._decode = BatchDecodeWithPagedKVCacheWrapper(float_workspace_buffer[half:], kv_layout)
+        self._side = _SideStream(self.device)
+
+    def plan(self, qo_indptr_p, kv_indptr_p, kv_indices_p, last_page_len_p, qo_indptr_d, kv_indptr_d, kv_indices_d,
+             last_page_len_d, num_qo_heads, num_kv_heads, head_dim, page_size, pos_encoding_mode="NONE",
+             window_left=-1, q_data_type="float16", kv_data_type=None, data_type=None, sm_scale=None, rope_scale=None,
+             rope_theta=None, non_blocking=True, causal_p: bool = True) -> None:
+        total = device_sm_count(self.device if self.device.type == "cuda" else None)
+        qo_p = qo_indptr_p.to("cpu", torch.int64)
+        q_lens = qo_p[1:] - qo_p[:-1]
+        np_p = (kv_indptr_p[1:] - kv_indptr_p[:-1]).to("cpu", torch.int64)
+        kv_lens_p = np_p * page_size
+        flops = float((4.0 * q_lens * kv_lens_p).sum()) * num_qo_heads * head_dim * (0.5 if causal_p else 1.0)
+        dbytes = 2.0 * float((kv_indptr_d[1:] - kv_indptr_d[:-1]).sum()) * page_size * num_kv_heads * head_dim * 2
+        sp, sd = _split_sms(total, flops, dbytes)
+        self._prefill._cta_budget, self._decode._cta_budget = sp or None, sd or None
+        dt = data_type or q_data_type
+        self._prefill.plan(qo_indptr_p, kv_indptr_p, kv_indices_p, last_page_len_p, num_qo_heads, num_kv_heads, head_dim,
+                           page_size, causal=causal_p, sm_scale=sm_scale, window_left=window_left, q_data_type=dt,
+                           kv_data_type=kv_data_type)
+        qo_d = qo_indptr_d.to("cpu", torch.int64)
+        plain_decode = bool(((qo_d[1:] - qo_d[:-1]) == 1).all())
+        self._decode.plan(kv_indptr_d, kv_indices_d, last_page_len_d, num_qo_heads, num_kv_heads, head_dim, page_size,
+                          window_left=window_left, q_data_type=dt, kv_data_type=kv_data_type, sm_scale=sm_scale,
+                          qo_indptr=None if plain_decode else qo_indptr_d)
+        self._sm_split = (sp, sd)
+
+    begin_forward = plan
+
+    def run(self, q_p, paged_kv_cache_p, q_d, paged_kv_cache_d, custom_mask_p=None, packed_custom_mask_p=None,
+            causal_p: bool = False, q_scale=None, k_scale=None, v_scale=None, return_lse: bool = False,
+            use_fp16_qk_reduction: bool = False, enable_pdl=None):
+        if custom_mask_p is not None or packed_custom_mask_p is not None:
+            raise NotImplementedError("POD with custom masks")
+        if q_p.is_cuda:
+            self._side.fork()
+            with torch.cuda.stream(self._side.stream):
+                res_d = self._decode.run(q_d, paged_kv_cache_d, q_scale=q_scale, k_scale=k_scale, v_scale=v_scale,
+                                         return_lse=return_lse)
+            res_p = self._prefill.run(q_p, paged_kv_cache_p, return_lse=return_lse)
+            self._side.join()
+        else:
+            res_d = self._decode.run(q_d, paged_kv_cache_d, return_lse=return_lse)
+            res_p = self._prefill.run(q_p, paged_kv_cache_p, return_lse=return_lse)
+        return res_p, res_d
+
+    forward = run
+
+    def end_forward(self) -> None:
+        pass

@@ -124,6 +124,7 @@ class _BatchPrefillBase:
                                                      pin_memory=self.device.type == "cuda")
         self._planned = False
         self._backend = "sm100"
+        self._cta_budget: Optional[int] = None  # POD: restrict the persistent grid to this many SMs
 
     @property
     def is_cuda_graph_enabled(self) -> bool:
@@ -154,6 +155,8 @@ class _BatchPrefillBase:
         self._batch_size = qo_host.numel() - 1
         # ---- C++ LPT planner: (request, q-tile, q-head) units over the persistent grid ----
         num_ctas = device_sm_count(self.device if self.device.type == "cuda" else None)
+        if self._cta_budget:
+            num_ctas = max(1, min(num_ctas, int(self._cta_budget)))
         q_lens = (qo_host[1:] - qo_host[:-1]).tolist()
         max_work = sum((ql + _TILE_Q - 1) // _TILE_Q for ql in q_lens) * num_qo_heads
         pin32 = self._pin_int_workspace_buffer.view(torch.int32)
@@ -327,6 +330,8 @@ class BatchPrefillWithPagedKVCacheWrapper(_BatchPrefillBase):
             return_lse=False, enable_pdl=None, window_left=None, sinks=None):
         if not self._planned:
             raise RuntimeError("plan() must be called before run()")
+        user_return_lse = return_lse
+        return_lse = return_lse or sinks is not None
         k_cache, v_cache = unpack_paged_kv_cache(paged_kv_cache, self._kv_layout)
         sm_scale = self._sm_scale * (q_scale or 1.0) * (k_scale or 1.0)
         window_left = self._window_left if window_left is None else window_left
@@ -346,11 +351,99 @@ class BatchPrefillWithPagedKVCacheWrapper(_BatchPrefillBase):
             page_args = (page_size, k_cache.shape[0], sp, sn, sh, 1 if self._kv_layout == "HND" else 0)
             self._launch_sm100(q, k_cache, v_cache, out, lse if return_lse else None, sm_scale, window_left, True,
                                self._kv_indices, page_args, enable_pdl)
+        if sinks is not None:
+            from .attention._core import apply_attention_sink
+
+            o2, l2 = apply_attention_sink(out, lse, sinks)
+            out.copy_(o2)
+            lse.copy_(l2)
         if v_scale is not None:
             out.copy_((out.float() * v_scale).to(out.dtype))
-        return (out, lse) if return_lse else out
+        return (out, lse) if user_return_lse else out
 
     forward = run
 
     def forward_return_lse(self, q, paged_kv_cache, **kw):
         return self.run(q, paged_kv_cache, return_lse=True, **kw)
+
+
+# ------------------------------------------------------------------------------------------------
+# Function-style context (prefill) APIs.  Parity: reference flashinfer/prefill.py:3557-4435
+# (fmha_varlen, trtllm_ragged_attention_deepseek, trtllm_batch_context_with_kv_cache, trtllm_fmha_v2_prefill,
+# cudnn_batch_prefill_with_kv_cache).  One kernel family on B200, so they share the wrappers above.
+# ------------------------------------------------------------------------------------------------
+def fmha_varlen(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, qo_segment_offsets: torch.Tensor,
+                kv_segment_offsets: torch.Tensor, plan_info=None, max_qo_len: Optional[int] = None, out=None, lse=None,
+                causal: bool = False, sm_scale: Optional[float] = None, return_lse: bool = False):
+    """Ragged variable-length FMHA (q/k/v ``[nnz, H, D]`` + segment offsets)."""
+    ws = torch.empty(16 << 20, dtype=torch.uint8, device=q.device)
+    w = BatchPrefillWithRaggedKVCacheWrapper(ws)
+    w.plan(qo_segment_offsets, kv_segment_offsets, q.shape[1], k.shape[1], q.shape[2], head_dim_vo=v.shape[2],
+           causal=causal, sm_scale=sm_scale, q_data_type=q.dtype)
+    return w.run(q, k, v, out=out, lse=lse, return_lse=return_lse)
+
+
+def fmha_varlen_plan(module, qo_segment_offsets, kv_segment_offsets, num_qo_heads, causal):
+    """The reference runs a device-side plan kernel here; our C++ planner is invoked inside ``fmha_varlen``."""
+    return None
+
+
+def trtllm_ragged_attention_deepseek(query, key, value, workspace_buffer, seq_lens, max_q_len, max_kv_len, bmm1_scale,
+                                     bmm2_scale, o_sf_scale, batch_size, window_left, cum_seq_lens_q, cum_seq_lens_kv,
+                                     enable_pdl=False, is_causal=True, return_lse=False, attention_sinks=None, out=None,
+                                     lse=None, skip_softmax_threshold_scale_factor=None):
+    w = BatchPrefillWithRaggedKVCacheWrapper(workspace_buffer)
+    w.plan(cum_seq_lens_q, cum_seq_lens_kv, query.shape[1], key.shape[1], query.shape[2], head_dim_vo=value.shape[2],
+           causal=is_causal, sm_scale=float(bmm1_scale), window_left=window_left, q_data_type=query.dtype)
+    res = w.run(query, key, value, out=out, lse=lse, return_lse=return_lse,
+                v_scale=float(bmm2_scale) if float(bmm2_scale) != 1.0 else None)
+    return res
+
+
+def trtllm_batch_context_with_kv_cache(query, kv_cache, workspace_buffer, block_tables, seq_lens, max_q_len, max_kv_len,
+                                       bmm1_scale, bmm2_scale, batch_size, cum_seq_lens_q, cum_seq_lens_kv,
+                                       window_left: int = -1, out=None, out_dtype=None, o_sf_scale=None,
+                                       o_sf_vec_size=None, kv_layout: str = "HND", enable_pdl=None, sinks=None,
+                                       kv_cache_sf=None, skip_softmax_threshold_scale_factor=None,
+                                       uses_shared_paged_kv_idx: bool = True, lse=None, return_lse: bool = False):
+    """Paged context attention with a block-table interface (causal)."""
+    from .decode import _block_tables_to_indices
+
+    k_cache, v_cache = unpack_paged_kv_cache(kv_cache, kv_layout)
+    _, _, _, page_size, hkv, d = paged_kv_strides(k_cache, kv_layout)
+    indptr, indices, last = _block_tables_to_indices(block_tables, seq_lens, page_size)
+    w = BatchPrefillWithPagedKVCacheWrapper(workspace_buffer, kv_layout)
+    w.plan(cum_seq_lens_q, indptr, indices, last, query.shape[1], hkv, d, page_size, causal=True,
+           sm_scale=float(bmm1_scale), window_left=window_left, q_data_type=query.dtype)
+    return w.run(query, (k_cache, v_cache), out=out, lse=lse, return_lse=return_lse, sinks=sinks,
+                 v_scale=float(bmm2_scale) if float(bmm2_scale) != 1.0 else None)
+
+
+def trtllm_fmha_v2_prefill(*args, **kwargs):
+    """sm90/sm120-only TRT-LLM fmha_v2 path in the reference (jit/attention/modules.py:2010); B200 uses fmha_varlen."""
+    raise NotImplementedError("fmha_v2 is an sm90/sm120 path; use fmha_varlen / the prefill wrappers on B200")
+
+
+def cudnn_batch_prefill_with_kv_cache(q, k_cache, v_cache, scale, workspace_buffer, *, max_token_per_sequence,
+                                      max_sequence_kv, actual_seq_lens_q, actual_seq_lens_kv, block_tables=None,
+                                      causal: bool = True, return_lse: bool = False, batch_offsets_q=None,
+                                      batch_offsets_o=None, is_cuda_graph_compatible=False, out=None, lse=None, **kw):
+    """cuDNN-style prefill signature (reference flashinfer/cudnn/prefill.py:563)."""
+    from .decode import _block_tables_to_indices
+
+    ql = actual_seq_lens_q.reshape(-1).to("cpu", torch.int64)
+    qo = torch.zeros(ql.numel() + 1, dtype=torch.int32)
+    qo[1:] = ql.cumsum(0)
+    if block_tables is not None:
+        _, _, _, page_size, hkv, d = paged_kv_strides(k_cache, "HND")
+        indptr, indices, last = _block_tables_to_indices(block_tables, actual_seq_lens_kv.reshape(-1), page_size)
+        w = BatchPrefillWithPagedKVCacheWrapper(workspace_buffer, "HND")
+        w.plan(qo, indptr, indices, last, q.shape[1], hkv, d, page_size, causal=causal, sm_scale=scale,
+               q_data_type=q.dtype)
+        return w.run(q, (k_cache, v_cache), out=out, lse=lse, return_lse=return_lse)
+    kl = actual_seq_lens_kv.reshape(-1).to("cpu", torch.int64)
+    kvi = torch.zeros(kl.numel() + 1, dtype=torch.int32)
+    kvi[1:] = kl.cumsum(0)
+    w = BatchPrefillWithRaggedKVCacheWrapper(workspace_buffer)
+    w.plan(qo, kvi, q.shape[1], k_cache.shape[1], q.shape[2], causal=causal, sm_scale=scale, q_data_type=q.dtype)
+    return w.run(q, k_cache, v_cache, out=out, lse=lse, return_lse=return_lse)
