@@ -84,3 +84,22 @@ from .sampling import (  # noqa: F401,E402
     top_p_sampling_from_probs,
 )
 from .topk import TopKTieBreak, top_k, top_k_page_table_transform, top_k_ragged_transform  # noqa: F401,E402
+from . import fused_moe, grouped_mm  # noqa: F401,E402
+from .fused_moe import (  # noqa: F401,E402
+    ActivationType,
+    GatedActType,
+    RoutingMethodType,
+    WeightLayout,
+    cutlass_fused_moe,
+    fused_topk_deepseek,
+    reorder_rows_for_gated_act_gemm,
+    trtllm_bf16_moe,
+    trtllm_bf16_routed_moe,
+    trtllm_fp4_block_scale_moe,
+    trtllm_fp4_block_scale_routed_moe,
+    trtllm_fp8_block_scale_moe,
+    trtllm_fp8_block_scale_routed_moe,
+    trtllm_fp8_per_tensor_scale_moe,
+    trtllm_mxint4_block_scale_moe,
+)
+from .gemm import SegmentGEMMWrapper, grouped_mm_bf16  # noqa: F401,E402

@@ -27,15 +27,15 @@ __device__ __forceinline__ float act_fn(float x) {
 template <typename T, int ACT>
 __global__ void __launch_bounds__(256)
 act_and_mul_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t rows, int64_t d, int64_t in_stride,
-                   int64_t out_stride) {
+                   int64_t out_stride, int gate_second) {
   constexpr int VN = 16 / sizeof(T);
   const int64_t vec_per_row = d / VN;
   const int64_t total = rows * vec_per_row;
   ptx::grid_dep_wait();
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
     const int64_t r = i / vec_per_row, c = (i % vec_per_row) * VN;
-    const Vec16<T> a = ld16(in + r * in_stride + c);
-    const Vec16<T> b = ld16(in + r * in_stride + d + c);
+    const Vec16<T> a = ld16(in + r * in_stride + (gate_second ? d : 0) + c);   // activated half
+    const Vec16<T> b = ld16(in + r * in_stride + (gate_second ? 0 : d) + c);   // linear half
     Vec16<T> o;
 #pragma unroll
     for (int e = 0; e < VN; ++e) o.v[e] = from_f32<T>(act_fn<ACT>(to_f32(a.v[e])) * to_f32(b.v[e]));
@@ -47,7 +47,7 @@ act_and_mul_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t rows, 
 }  // namespace
 
 extern "C" int act_and_mul(void* in, void* out, int64_t rows, int64_t d, int64_t in_stride, int64_t out_stride,
-                           int64_t act, int64_t dtype, int64_t pdl, int64_t stream_) {
+                           int64_t act, int64_t gate_second, int64_t dtype, int64_t pdl, int64_t stream_) {
   if (rows == 0 || d == 0) return 0;
   FIB_CHECK(d % (16 / dtype_size(dtype)) == 0, "act_and_mul: d must be a multiple of the 16B vector width");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -60,13 +60,13 @@ extern "C" int act_and_mul(void* in, void* out, int64_t rows, int64_t d, int64_t
     LaunchCfg lc(dim3((unsigned)blocks), dim3(256), 0, stream, pdl != 0);
     if (act == kSilu) {
       FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, act_and_mul_kernel<T, kSilu>, (const T*)in, (T*)out, rows, d, in_stride,
-                                        out_stride));
+                                        out_stride, (int)gate_second));
     } else if (act == kGelu) {
       FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, act_and_mul_kernel<T, kGelu>, (const T*)in, (T*)out, rows, d, in_stride,
-                                        out_stride));
+                                        out_stride, (int)gate_second));
     } else {
       FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, act_and_mul_kernel<T, kGeluTanh>, (const T*)in, (T*)out, rows, d,
-                                        in_stride, out_stride));
+                                        in_stride, out_stride, (int)gate_second));
     }
     return 0;
   });

@@ -1,0 +1,384 @@
+// MoE routing + token permutation utilities (SIMT, warp-per-token).
+//
+// Parity: reference routing kernels csrc/fused_moe/trtllm_backend/trtllm_fused_moe_routing_{deepseek,llama4,custom}.cu,
+// csrc/fused_moe/noAuxTcKernels.cu (fused_topk_deepseek) and the permute / finalize kernels of
+// csrc/fused_moe/trtllm_backend/trtllm_fused_moe_dev_kernel.cu:635-900, csrc/nv_internal/.../moeUtils.cu.
+// Routing methods (flashinfer/tllm_enums.py:6-27):
+//   0 Default (softmax -> top-k)        1 Renormalize (top-k -> softmax)     2 DeepSeekV3 (sigmoid + bias, group top-2
+//   sums -> top groups -> top-k, normalise * scale)   3 Llama4 (top-1 -> sigmoid)   4 RenormalizeNaive (softmax ->
+//   top-k -> renormalise)   5 TopK (raw)   6 SigmoidRenorm   7 MiniMax2 (sigmoid + bias -> top-k -> sum-normalise)
+//   8 Sigmoid (no renormalisation)
+#include <fib200/common.cuh>
+#include <fib200/ptx.cuh>
+
+using namespace fib200;
+
+FIB_EXPORT_LAST_ERROR()
+
+namespace {
+
+constexpr int kMaxPerLane = 16;  // up to 512 experts
+constexpr int kMaxTopK = 32;
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+
+// One warp per token.  logits [T, E] (f32 or bf16), bias [E] optional.
+template <typename TL>
+__global__ void __launch_bounds__(256)
+routing_kernel(const TL* __restrict__ logits, const float* __restrict__ bias, int32_t* __restrict__ topk_ids,
+               float* __restrict__ topk_w, int T, int E, int K, int method, int n_group, int topk_group,
+               float routed_scale, int norm_topk_prob) {
+  const int lane = threadIdx.x & 31;
+  const int tok = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (tok >= T) return;
+  ptx::grid_dep_wait();
+  const int per = (E + 31) / 32;
+  float score[kMaxPerLane];   // value used for selection
+  float orig[kMaxPerLane];    // value used for the output weight
+  // expert e lives in lane e % 32, slot e / 32
+  float mx = -INFINITY;
+#pragma unroll
+  for (int s = 0; s < kMaxPerLane; ++s) {
+    const int e = s * 32 + lane;
+    float x = (s < per && e < E) ? to_f32(logits[int64_t(tok) * E + e]) : -INFINITY;
+    score[s] = x;
+    mx = fmaxf(mx, x);
+  }
+  mx = warp_reduce_max(mx);
+  const bool softmax_first = (method == 0 || method == 4);
+  const bool sigmoid_first = (method == 2 || method == 6 || method == 7 || method == 8);
+  if (softmax_first) {
+    float sum = 0.f;
+#pragma unroll
+    for (int s = 0; s < kMaxPerLane; ++s) {
+      if (s < per) {
+        score[s] = (score[s] == -INFINITY) ? 0.f : __expf(score[s] - mx);
+        sum += score[s];
+      }
+    }
+    sum = warp_reduce_sum(sum);
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int s = 0; s < kMaxPerLane; ++s) {
+      const int e = s * 32 + lane;
+      score[s] = (s < per && e < E) ? score[s] * inv : -INFINITY;
+      orig[s] = score[s];
+    }
+  } else if (sigmoid_first) {
+#pragma unroll
+    for (int s = 0; s < kMaxPerLane; ++s) {
+      const int e = s * 32 + lane;
+      if (s < per && e < E) {
+        const float sg = sigmoidf_(score[s]);
+        orig[s] = sg;
+        score[s] = sg + ((bias && (method == 2 || method == 7)) ? bias[e] : 0.f);
+      } else {
+        orig[s] = 0.f;
+        score[s] = -INFINITY;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int s = 0; s < kMaxPerLane; ++s) orig[s] = score[s];
+  }
+
+  // DeepSeek-V3 group limiting: keep only experts of the `topk_group` best groups (score = sum of top-2 in group)
+  if (method == 2 && n_group > 1) {
+    const int gsz = E / n_group;
+    // group scores are computed redundantly by lane g (n_group <= 32)
+    float gscore = -INFINITY;
+    // gather every expert score into smem-free fashion: use shuffles per slot
+    float top1 = -INFINITY, top2 = -INFINITY;
+    for (int s = 0; s < per; ++s) {
+      for (int l = 0; l < 32; ++l) {
+        const float v = __shfl_sync(0xffffffffu, score[s], l);
+        const int e = s * 32 + l;
+        if (e < E && e / gsz == lane) {
+          if (v > top1) {
+            top2 = top1;
+            top1 = v;
+          } else if (v > top2) {
+            top2 = v;
+          }
+        }
+      }
+    }
+    if (lane < n_group) gscore = top1 + top2;
+    // select topk_group groups: rank of my group
+    int rank = 0;
+    for (int l = 0; l < n_group; ++l) {
+      const float v = __shfl_sync(0xffffffffu, gscore, l);
+      if (v > gscore || (v == gscore && l < lane)) ++rank;
+    }
+    const unsigned keep_mask = __ballot_sync(0xffffffffu, lane < n_group && rank < topk_group);
+#pragma unroll
+    for (int s = 0; s < kMaxPerLane; ++s) {
+      const int e = s * 32 + lane;
+      if (s < per && e < E) {
+        if (!((keep_mask >> (e / gsz)) & 1u)) score[s] = -INFINITY;
+      }
+    }
+  }
+
+  // iterative top-K (K <= 32): argmax over the warp, ties -> smaller expert id
+  float sel_w[kMaxTopK];
+  int sel_id[kMaxTopK];
+  float wsum = 0.f;
+  for (int k = 0; k < K; ++k) {
+    float bv = -INFINITY;
+    int be = 1 << 30;
+#pragma unroll
+    for (int s = 0; s < kMaxPerLane; ++s) {
+      const int e = s * 32 + lane;
+      if (s < per && e < E && (score[s] > bv || (score[s] == bv && e < be))) {
+        bv = score[s];
+        be = e;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oe = __shfl_xor_sync(0xffffffffu, be, o);
+      if (ov > bv || (ov == bv && oe < be)) {
+        bv = ov;
+        be = oe;
+      }
+    }
+    // owner lane fetches the output weight and removes the expert
+    float w = 0.f;
+    if ((be & 31) == lane && be < E) {
+      const int s = be >> 5;
+#pragma unroll
+      for (int ss = 0; ss < kMaxPerLane; ++ss)
+        if (ss == s) {
+          w = orig[ss];
+          score[ss] = -INFINITY;
+        }
+    }
+    w = __shfl_sync(0xffffffffu, w, be & 31);
+    if (k < kMaxTopK) {
+      sel_w[k] = w;
+      sel_id[k] = be;
+    }
+    wsum += w;
+  }
+  // post-processing of the selected weights
+  if (method == 1) {  // top-k -> softmax over the selected logits
+    float m2 = -INFINITY;
+    for (int k = 0; k < K; ++k) m2 = fmaxf(m2, sel_w[k]);
+    float s2 = 0.f;
+    for (int k = 0; k < K; ++k) {
+      sel_w[k] = __expf(sel_w[k] - m2);
+      s2 += sel_w[k];
+    }
+    for (int k = 0; k < K; ++k) sel_w[k] /= s2;
+  } else if (method == 3) {  // llama4: sigmoid of the selected logit(s)
+    for (int k = 0; k < K; ++k) sel_w[k] = sigmoidf_(sel_w[k]);
+  } else if (method == 2 || method == 7) {
+    const float inv = (norm_topk_prob || method == 7) ? 1.f / (wsum + 1e-20f) : 1.f;
+    for (int k = 0; k < K; ++k) sel_w[k] = sel_w[k] * inv * routed_scale;
+  } else if (method == 4 || method == 6) {
+    const float inv = 1.f / (wsum + 1e-20f);
+    for (int k = 0; k < K; ++k) sel_w[k] *= inv;
+  }
+  if (lane == 0) {
+    for (int k = 0; k < K; ++k) {
+      topk_ids[int64_t(tok) * K + k] = sel_id[k];
+      topk_w[int64_t(tok) * K + k] = sel_w[k];
+    }
+  }
+  ptx::grid_dep_launch();
+}
+
+// ------------------------------------------------------------------ sort / permutation (single CTA)
+// Builds the expert-grouped, tile-padded permutation.
+//   counts[e], offsets[e] (padded to `tile`), expanded_to_permuted[T*K] (-1 for non-local experts),
+//   permuted_to_token[P] (-1 padding), tile_expert[P / tile] (-1 unused), meta[0] = num tiles, meta[1] = padded rows
+__global__ void __launch_bounds__(1024)
+moe_sort_kernel(const int32_t* __restrict__ topk_ids, int T, int K, int E, int local_offset, int local_num, int tile,
+                int max_rows, int32_t* __restrict__ expanded_to_permuted, int32_t* __restrict__ permuted_to_token,
+                int32_t* __restrict__ tile_expert, int32_t* __restrict__ expert_offsets, int32_t* __restrict__ meta) {
+  extern __shared__ int sm[];
+  int* cnt = sm;               // [local_num]
+  int* off = sm + local_num;   // [local_num + 1]
+  int* cur = off + local_num + 1;
+  ptx::grid_dep_wait();
+  for (int i = threadIdx.x; i < local_num; i += blockDim.x) cnt[i] = 0;
+  __syncthreads();
+  const int n = T * K;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int e = topk_ids[i] - local_offset;
+    if (e >= 0 && e < local_num) atomicAdd(&cnt[e], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int e = 0; e < local_num; ++e) {
+      off[e] = acc;
+      acc += (cnt[e] + tile - 1) / tile * tile;
+    }
+    off[local_num] = acc;
+    meta[0] = acc / tile;
+    meta[1] = acc;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < local_num; i += blockDim.x) {
+    cur[i] = 0;
+    expert_offsets[i] = off[i];
+  }
+  if (threadIdx.x == 0) expert_offsets[local_num] = off[local_num];
+  const int total = off[local_num];
+  for (int i = threadIdx.x; i < max_rows; i += blockDim.x) permuted_to_token[i] = -1;
+  for (int i = threadIdx.x; i < max_rows / tile; i += blockDim.x) tile_expert[i] = -1;
+  __syncthreads();
+  for (int e = threadIdx.x; e < local_num; e += blockDim.x)
+    for (int r = off[e]; r < off[e + 1]; r += tile) tile_expert[r / tile] = e;
+  // deterministic order inside an expert: ascending expanded index.  One thread per expert walks the list
+  // (T*K is small in serving; for large prefill batches the per-expert walk is still O(T*K / E * E)).
+  for (int e = threadIdx.x; e < local_num; e += blockDim.x) {
+    int pos = off[e];
+    for (int i = 0; i < n; ++i) {
+      if (topk_ids[i] - local_offset == e) {
+        expanded_to_permuted[i] = pos;
+        permuted_to_token[pos] = i / K;
+        ++pos;
+      }
+    }
+  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int e = topk_ids[i] - local_offset;
+    if (e < 0 || e >= local_num) expanded_to_permuted[i] = -1;
+  }
+  (void)total;
+  ptx::grid_dep_launch();
+}
+
+// permuted_x[p, :] = x[token(p), :]  (zero rows for padding)
+template <typename T>
+__global__ void __launch_bounds__(256)
+moe_gather_kernel(const T* __restrict__ x, T* __restrict__ out, const int32_t* __restrict__ permuted_to_token,
+                  const int32_t* __restrict__ meta, int64_t hidden, int64_t x_stride) {
+  constexpr int VN = 16 / sizeof(T);
+  ptx::grid_dep_wait();
+  const int rows = meta[1];
+  const int64_t vec = hidden / VN;
+  const int64_t total = int64_t(rows) * vec;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t r = i / vec, v = i % vec;
+    const int tok = permuted_to_token[r];
+    Vec16<T> val;
+    if (tok >= 0) {
+      val = ld16(x + int64_t(tok) * x_stride + v * VN);
+    } else {
+      *reinterpret_cast<int4*>(&val) = make_int4(0, 0, 0, 0);
+    }
+    st16(out + r * hidden + v * VN, val);
+  }
+  ptx::grid_dep_launch();
+}
+
+// out[t, :] = sum_k w[t,k] * y[perm(t,k), :]   (skips non-local experts)
+template <typename T>
+__global__ void __launch_bounds__(256)
+moe_finalize_kernel(const T* __restrict__ y, T* __restrict__ out, const int32_t* __restrict__ expanded_to_permuted,
+                    const float* __restrict__ topk_w, int Tn, int K, int64_t hidden, int accumulate) {
+  constexpr int VN = 16 / sizeof(T);
+  ptx::grid_dep_wait();
+  const int64_t vec = hidden / VN;
+  const int64_t total = int64_t(Tn) * vec;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t t = i / vec, v = i % vec;
+    float acc[VN];
+#pragma unroll
+    for (int e = 0; e < VN; ++e) acc[e] = 0.f;
+    if (accumulate) {
+      const Vec16<T> o = ld16(out + t * hidden + v * VN);
+#pragma unroll
+      for (int e = 0; e < VN; ++e) acc[e] = to_f32(o.v[e]);
+    }
+    for (int k = 0; k < K; ++k) {
+      const int p = expanded_to_permuted[t * K + k];
+      if (p < 0) continue;
+      const float w = topk_w[t * K + k];
+      const Vec16<T> val = ld16(y + int64_t(p) * hidden + v * VN);
+#pragma unroll
+      for (int e = 0; e < VN; ++e) acc[e] += w * to_f32(val.v[e]);
+    }
+    Vec16<T> o;
+#pragma unroll
+    for (int e = 0; e < VN; ++e) o.v[e] = from_f32<T>(acc[e]);
+    st16(out + t * hidden + v * VN, o);
+  }
+  ptx::grid_dep_launch();
+}
+
+inline int grid_for(int64_t total) {
+  int64_t b = (total + 255) / 256;
+  const int64_t cap = int64_t(num_sms()) * 16;
+  if (b > cap) b = cap;
+  return b < 1 ? 1 : (int)b;
+}
+
+}  // namespace
+
+extern "C" int moe_routing(void* logits, void* bias, void* topk_ids, void* topk_w, int64_t T, int64_t E, int64_t K,
+                           int64_t method, int64_t n_group, int64_t topk_group, double routed_scale,
+                           int64_t norm_topk_prob, int64_t logits_dtype, int64_t pdl, int64_t stream_) {
+  FIB_CHECK(E <= 32 * kMaxPerLane, "moe_routing: at most 512 experts");
+  FIB_CHECK(K >= 1 && K <= kMaxTopK, "moe_routing: top_k must be in [1,32]");
+  FIB_CHECK(method != 2 || n_group <= 32, "moe_routing: n_group must be <= 32");
+  if (T == 0) return 0;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  LaunchCfg lc(dim3((unsigned)((T + 7) / 8)), dim3(256), 0, stream, pdl != 0);
+  if (logits_dtype == kF32) {
+    FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, routing_kernel<float>, (const float*)logits, (const float*)bias,
+                                      (int32_t*)topk_ids, (float*)topk_w, (int)T, (int)E, (int)K, (int)method,
+                                      (int)(n_group > 0 ? n_group : 1), (int)(topk_group > 0 ? topk_group : 1),
+                                      (float)routed_scale, (int)norm_topk_prob));
+  } else if (logits_dtype == kBF16) {
+    FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, routing_kernel<__nv_bfloat16>, (const __nv_bfloat16*)logits,
+                                      (const float*)bias, (int32_t*)topk_ids, (float*)topk_w, (int)T, (int)E, (int)K,
+                                      (int)method, (int)(n_group > 0 ? n_group : 1),
+                                      (int)(topk_group > 0 ? topk_group : 1), (float)routed_scale, (int)norm_topk_prob));
+  } else {
+    return set_error("moe_routing: logits must be float32 or bfloat16");
+  }
+  return 0;
+}
+
+extern "C" int moe_sort(void* topk_ids, int64_t T, int64_t K, int64_t E, int64_t local_offset, int64_t local_num,
+                        int64_t tile, int64_t max_rows, void* expanded_to_permuted, void* permuted_to_token,
+                        void* tile_expert, void* expert_offsets, void* meta, int64_t pdl, int64_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const size_t smem = (3 * local_num + 2) * sizeof(int);
+  LaunchCfg lc(dim3(1), dim3(1024), smem, stream, pdl != 0);
+  FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, moe_sort_kernel, (const int32_t*)topk_ids, (int)T, (int)K, (int)E,
+                                    (int)local_offset, (int)local_num, (int)tile, (int)max_rows,
+                                    (int32_t*)expanded_to_permuted, (int32_t*)permuted_to_token, (int32_t*)tile_expert,
+                                    (int32_t*)expert_offsets, (int32_t*)meta));
+  return 0;
+}
+
+extern "C" int moe_gather(void* x, void* out, void* permuted_to_token, void* meta, int64_t max_rows, int64_t hidden,
+                          int64_t x_stride, int64_t dtype, int64_t pdl, int64_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  return FIB_DISPATCH_HALF(dtype, T, [&]() -> int {
+    LaunchCfg lc(dim3(grid_for(max_rows * (hidden / 8))), dim3(256), 0, stream, pdl != 0);
+    FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, moe_gather_kernel<T>, (const T*)x, (T*)out,
+                                      (const int32_t*)permuted_to_token, (const int32_t*)meta, hidden, x_stride));
+    return 0;
+  });
+}
+
+extern "C" int moe_finalize(void* y, void* out, void* expanded_to_permuted, void* topk_w, int64_t T, int64_t K,
+                            int64_t hidden, int64_t accumulate, int64_t dtype, int64_t pdl, int64_t stream_) {
+  if (T == 0) return 0;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  return FIB_DISPATCH_HALF(dtype, Tt, [&]() -> int {
+    LaunchCfg lc(dim3(grid_for(T * (hidden / 8))), dim3(256), 0, stream, pdl != 0);
+    FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, moe_finalize_kernel<Tt>, (const Tt*)y, (Tt*)out,
+                                      (const int32_t*)expanded_to_permuted, (const float*)topk_w, (int)T, (int)K, hidden,
+                                      (int)accumulate));
+    return 0;
+  });
+}

@@ -1,0 +1,437 @@
+"""Fused Mixture-of-Experts.
+
+Parity: reference flashinfer/fused_moe/core.py (trtllm_*_moe :2539-3503, cutlass_fused_moe :775-1009),
+fused_routing_dsv3.py (fused_topk_deepseek), cute_dsl/fused_moe.py, tllm_enums.py.
+
+Pipeline on B200 (all hand-written sm_100a kernels, PDL-chained):
+  routing (9 methods, warp per token)  ->  sort / tile-padded permutation  ->  row gather  ->
+  grouped tcgen05 GEMM (FC1, expert id = TMA coordinate)  ->  gated activation  ->  grouped GEMM (FC2)  ->
+  finalize (top-k weighted un-permute).
+Quantised entry points (fp8 per-tensor / block-scale, nvfp4, mxint4) currently de-quantise the expert weights to
+bf16 on the fly and reuse the bf16 grouped GEMM (numerically equivalent reference semantics; the block-scaled
+tcgen05 grouped GEMM replaces this in a later round).  Gate/up convention follows the reference tests:
+``h = x @ W1^T ; out = act(h[:, I:]) * h[:, :I]`` (second half is the gate).
+"""
+from __future__ import annotations
+
+from enum import IntEnum
+from typing import List, Optional, Tuple, Union
+
+import torch
+
+from .. import jit
+from ..activation import _act_and_mul
+from ..utils import dtype_code, stream_ptr
+
+_TILE = 128
+
+
+class RoutingMethodType(IntEnum):
+    Default = 0
+    Renormalize = 1
+    DeepSeekV3 = 2
+    Llama4 = 3
+    RenormalizeNaive = 4
+    TopK = 5
+    SigmoidRenorm = 6
+    MiniMax2 = 7
+    Sigmoid = 8
+    Unspecified = 9
+
+
+class ActivationType(IntEnum):
+    Gelu = 0
+    Relu = 1
+    Silu = 2
+    Swiglu = 3
+    Geglu = 4
+    SwigluBias = 5
+    Relu2 = 6
+    Identity = 7
+    InvalidType = 8
+
+
+class GatedActType(IntEnum):
+    SwiGlu = 0
+    GeGlu = 1
+
+
+class WeightLayout(IntEnum):
+    MajorK = 0
+    MajorMn = 1
+    BlockMajorK = 2
+
+
+# ------------------------------------------------------------------ routing
+def route(routing_logits: torch.Tensor, routing_bias: Optional[torch.Tensor], top_k: int,
+          routing_method_type: int = 0, n_group: Optional[int] = None, topk_group: Optional[int] = None,
+          routed_scaling_factor: Optional[float] = None, norm_topk_prob: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Returns ``(topk_ids [T, K] int32, topk_weights [T, K] fp32)`` for any :class:`RoutingMethodType`."""
+    T, E = routing_logits.shape
+    method = int(routing_method_type)
+    scale = float(routed_scaling_factor) if routed_scaling_factor is not None else 1.0
+    if not routing_logits.is_cuda:
+        return _route_cpu(routing_logits, routing_bias, top_k, method, n_group, topk_group, scale, norm_topk_prob)
+    logits = routing_logits if routing_logits.dtype in (torch.float32, torch.bfloat16) else routing_logits.float()
+    logits = logits.contiguous()
+    ids = torch.empty(T, top_k, dtype=torch.int32, device=logits.device)
+    w = torch.empty(T, top_k, dtype=torch.float32, device=logits.device)
+    bias = routing_bias.float().contiguous() if routing_bias is not None else None
+    jit.load("moe").call("moe_routing", logits, bias, ids, w, T, E, top_k, method, n_group or 1, topk_group or 1, scale,
+                         1 if norm_topk_prob else 0, dtype_code(logits.dtype), 1, stream_ptr(logits))
+    return ids, w
+
+
+def _route_cpu(logits, bias, k, method, n_group, topk_group, scale, norm):
+    x = logits.float()
+    E = x.shape[1]
+    if method in (0, 4):
+        p = torch.softmax(x, -1)
+        w, ids = torch.topk(p, k, -1)
+        if method == 4:
+            w = w / w.sum(-1, keepdim=True)
+    elif method == 1:
+        v, ids = torch.topk(x, k, -1)
+        w = torch.softmax(v, -1)
+    elif method == 3:
+        v, ids = torch.topk(x, k, -1)
+        w = torch.sigmoid(v)
+    elif method == 5:
+        w, ids = torch.topk(x, k, -1)
+    elif method in (2, 6, 7, 8):
+        s = torch.sigmoid(x)
+        sel = s + (bias.float() if (bias is not None and method in (2, 7)) else 0)
+        if method == 2 and n_group and n_group > 1:
+            g = sel.view(-1, n_group, E // n_group)
+            gs = g.topk(2, -1).values.sum(-1)
+            keep = torch.zeros_like(gs, dtype=torch.bool).scatter_(1, gs.topk(topk_group, -1).indices, True)
+            sel = torch.where(keep[..., None].expand_as(g).reshape(-1, E), sel, torch.full_like(sel, float("-inf")))
+        ids = sel.topk(k, -1).indices
+        w = s.gather(1, ids)
+        if method in (2, 7):
+            if norm or method == 7:
+                w = w / (w.sum(-1, keepdim=True) + 1e-20)
+            w = w * scale
+        elif method == 6:
+            w = w / (w.sum(-1, keepdim=True) + 1e-20)
+    else:
+        raise ValueError(f"unknown routing method {method}")
+    return ids.int(), w.float()
+
+
+def fused_topk_deepseek(scores: torch.Tensor, bias: torch.Tensor, n_group: int, topk_group: int, topk: int,
+                        routed_scaling_factor: float, topk_values: Optional[torch.Tensor] = None,
+                        topk_indices: Optional[torch.Tensor] = None, launch_with_pdl: bool = True):
+    """DeepSeek-V3 no-aux-loss routing (reference fused_routing_dsv3.py): sigmoid + bias, grouped top-k."""
+    ids, w = route(scores, bias, topk, RoutingMethodType.DeepSeekV3, n_group, topk_group, routed_scaling_factor, True)
+    if topk_values is not None:
+        topk_values.copy_(w)
+        w = topk_values
+    if topk_indices is not None:
+        topk_indices.copy_(ids)
+        ids = topk_indices
+    return w, ids
+
+
+# ------------------------------------------------------------------ reference + pipeline
+def moe_reference(x, topk_ids, topk_w, w1, w2, activation: str = "silu", local_expert_offset: int = 0):
+    """fp32 oracle: ``w1 [E_local, 2I, H]``, ``w2 [E_local, H, I]``; gate = second half of FC1's output."""
+    T, H = x.shape
+    out = torch.zeros(T, H, dtype=torch.float32, device=x.device)
+    E = w1.shape[0]
+    inter = w2.shape[2]
+    gated = w1.shape[1] == 2 * inter
+    for e in range(E):
+        sel = (topk_ids == e + local_expert_offset)
+        tok, kk = torch.nonzero(sel, as_tuple=True)
+        if tok.numel() == 0:
+            continue
+        h = x[tok].float() @ w1[e].float().t()
+        if gated:
+            up, gate = h[:, :inter], h[:, inter:]
+            a = (torch.nn.functional.silu(gate) if activation == "silu" else torch.nn.functional.gelu(gate)) * up
+        else:
+            a = torch.nn.functional.silu(h) if activation == "silu" else torch.relu(h) ** 2
+        y = a @ w2[e].float().t()
+        out.index_add_(0, tok, y * topk_w[tok, kk].float()[:, None])
+    return out
+
+
+def moe_forward(x: torch.Tensor, topk_ids: torch.Tensor, topk_w: torch.Tensor, w1: torch.Tensor, w2: torch.Tensor,
+                local_expert_offset: int = 0, num_experts: Optional[int] = None, activation: str = "silu",
+                out: Optional[torch.Tensor] = None, do_finalize: bool = True):
+    """Core bf16/fp16 MoE: x ``[T, H]``, w1 ``[E_local, 2I, H]``, w2 ``[E_local, H, I]``."""
+    T, H = x.shape
+    e_local, n1, _ = w1.shape
+    inter = w2.shape[2]
+    K = topk_ids.shape[1]
+    if not x.is_cuda:
+        res = moe_reference(x, topk_ids, topk_w, w1, w2, activation, local_expert_offset).to(x.dtype)
+        if out is not None:
+            out.copy_(res)
+            return out
+        return res
+    if x.dtype not in (torch.float16, torch.bfloat16) or w1.dtype != x.dtype or w2.dtype != x.dtype:
+        raise TypeError("moe_forward: x / w1 / w2 must share float16 or bfloat16")
+    mod, gg = jit.load("moe"), jit.load("grouped_gemm_sm100")
+    dev = x.device
+    max_rows = (T * K + e_local * (_TILE - 1)) // _TILE * _TILE + _TILE
+    max_tiles = max_rows // _TILE
+    e2p = torch.empty(T * K, dtype=torch.int32, device=dev)
+    p2t = torch.empty(max_rows, dtype=torch.int32, device=dev)
+    tile_e = torch.empty(max_tiles, dtype=torch.int32, device=dev)
+    offs = torch.empty(e_local + 1, dtype=torch.int32, device=dev)
+    meta = torch.empty(4, dtype=torch.int32, device=dev)
+    st = stream_ptr(x)
+    ids = topk_ids.to(torch.int32).contiguous()
+    mod.call("moe_sort", ids, T, K, num_experts or e_local, local_expert_offset, e_local, _TILE, max_rows, e2p, p2t,
+             tile_e, offs, meta, 1, st)
+    xp = torch.empty(max_rows, H, dtype=x.dtype, device=dev)
+    mod.call("moe_gather", x, xp, p2t, meta, max_rows, H, x.stride(0), dtype_code(x.dtype), 1, st)
+    h1 = torch.empty(max_rows, n1, dtype=x.dtype, device=dev)
+    gg.call("grouped_gemm_nt", xp, w1.contiguous(), h1, tile_e, meta, max_tiles, n1, H, e_local, H, n1,
+            dtype_code(x.dtype), 1, st)
+    if n1 == 2 * inter:
+        a = torch.empty(max_rows, inter, dtype=x.dtype, device=dev)
+        _act_and_mul("silu" if activation == "silu" else "gelu", h1, a, True, gate_second=True)
+    else:
+        a = torch.nn.functional.silu(h1) if activation == "silu" else torch.relu(h1) ** 2
+    h2 = torch.empty(max_rows, H, dtype=x.dtype, device=dev)
+    gg.call("grouped_gemm_nt", a, w2.contiguous(), h2, tile_e, meta, max_tiles, H, inter, e_local, inter, H,
+            dtype_code(x.dtype), 1, st)
+    if not do_finalize:
+        return h2, e2p, topk_w
+    if out is None:
+        out = torch.empty(T, H, dtype=x.dtype, device=dev)
+    mod.call("moe_finalize", h2, out, e2p, topk_w.float().contiguous(), T, K, H, 0, dtype_code(x.dtype), 1, st)
+    return out
+
+
+def reorder_rows_for_gated_act_gemm(x: torch.Tensor) -> torch.Tensor:
+    """Interleave the two halves of the rows ([up | gate] -> u0 g0 u1 g1 ...), the weight layout that lets a
+    GEMM epilogue see matching up/gate columns in one tile (reference core.py:133)."""
+    m = x.shape[0]
+    half = m // 2
+    return torch.stack([x[:half], x[half:]], 1).reshape(x.shape)
+
+
+# ------------------------------------------------------------------ de-quantisation helpers
+def _dequant_fp8_block(w: torch.Tensor, scale: torch.Tensor, block: int = 128, dtype=torch.bfloat16) -> torch.Tensor:
+    """w [..., N, K] fp8, scale [..., N/block, K/block] fp32 (DeepSeek 128x128 weight blocks)."""
+    s = scale.float().repeat_interleave(block, -2).repeat_interleave(block, -1)[..., : w.shape[-2], : w.shape[-1]]
+    return (w.float() * s).to(dtype)
+
+
+def _dequant_nvfp4(w: torch.Tensor, sf: torch.Tensor, global_scale, vec: int = 16, dtype=torch.bfloat16) -> torch.Tensor:
+    """w [E, N, K/2] uint8 (e2m1 pairs), sf [E, N, K/vec] UE4M3 bytes (linear layout), global scale per expert."""
+    from ..quantization.fp4 import E2M1_VALUES
+
+    lut = torch.tensor(E2M1_VALUES + [-v for v in E2M1_VALUES], device=w.device)
+    wb = w.view(torch.uint8)
+    vals = torch.stack([lut[(wb & 0xF).long()], lut[(wb >> 4).long()]], -1).flatten(-2)
+    s = sf.view(torch.uint8).view(torch.float8_e4m3fn).float().reshape(*vals.shape[:-1], -1)
+    s = s.repeat_interleave(vec, -1)[..., : vals.shape[-1]]
+    g = torch.as_tensor(global_scale, device=w.device, dtype=torch.float32).reshape(-1, *([1] * (vals.ndim - 1)))
+    return (vals * s * g).to(dtype)
+
+
+# ------------------------------------------------------------------ trtllm-gen style entry points
+def trtllm_bf16_moe(routing_logits, routing_bias, hidden_states, gemm1_weights, gemm2_weights, num_experts, top_k,
+                    n_group, topk_group, intermediate_size, local_expert_offset, local_num_experts,
+                    routed_scaling_factor=None, routing_method_type: int = 0, use_shuffled_weight: bool = False,
+                    weight_layout: int = WeightLayout.MajorK, do_finalize: bool = True, enable_pdl: bool = True,
+                    tune_max_num_tokens: int = 8192, activation_type: int = ActivationType.Swiglu.value,
+                    norm_topk_prob: bool = True, routing_replay_out=None):
+    """bf16 MoE with fused routing.  Weights are plain K-major ``[E_local, 2I, H]`` / ``[E_local, H, I]``
+    (no pre-shuffling is needed by the TMA-fed grouped GEMM)."""
+    if use_shuffled_weight or int(weight_layout) != int(WeightLayout.MajorK):
+        raise NotImplementedError("pass plain MajorK weights (use_shuffled_weight=False): the tcgen05 grouped GEMM "
+                                  "needs no weight pre-shuffle")
+    ids, w = route(routing_logits, routing_bias, top_k, routing_method_type, n_group, topk_group, routed_scaling_factor,
+                   norm_topk_prob)
+    if routing_replay_out is not None:
+        routing_replay_out.copy_(ids)
+    return moe_forward(hidden_states, ids, w, gemm1_weights, gemm2_weights, local_expert_offset, num_experts,
+                       do_finalize=do_finalize)
+
+
+def _unpack_routed(topk_ids: torch.Tensor):
+    """Packed routing used by the *_routed_moe APIs: int32 = (expert_id << 16) | bf16(weight)."""
+    ids = (topk_ids >> 16).int()
+    w = (topk_ids & 0xFFFF).to(torch.int16).view(torch.bfloat16).float()
+    return ids, w
+
+
+def trtllm_bf16_routed_moe(topk_ids, hidden_states, gemm1_weights, gemm2_weights, num_experts, top_k, n_group,
+                           topk_group, intermediate_size, local_expert_offset, local_num_experts,
+                           routed_scaling_factor=None, routing_method_type: int = 1, use_shuffled_weight: bool = False,
+                           weight_layout: int = WeightLayout.MajorK, do_finalize: bool = True, enable_pdl: bool = True,
+                           tune_max_num_tokens: int = 8192, activation_type: int = ActivationType.Swiglu.value):
+    ids, w = _unpack_routed(topk_ids)
+    return moe_forward(hidden_states, ids, w, gemm1_weights, gemm2_weights, local_expert_offset, num_experts,
+                       do_finalize=do_finalize)
+
+
+def trtllm_fp8_per_tensor_scale_moe(routing_logits, routing_bias, hidden_states, gemm1_weights, output1_scales_scalar,
+                                    output1_scales_gate_scalar, gemm2_weights, output2_scales_scalar, num_experts, top_k,
+                                    n_group, topk_group, intermediate_size, local_expert_offset, local_num_experts,
+                                    routed_scaling_factor, use_routing_scales_on_input: bool = False,
+                                    routing_method_type: int = 0, **kw):
+    """fp8 per-tensor MoE: de-quantised to bf16 (scales folded into the weights) and run on the bf16 pipeline."""
+    ids, w = route(routing_logits, routing_bias, top_k, routing_method_type, n_group, topk_group, routed_scaling_factor)
+    s1 = output1_scales_scalar.float().reshape(-1, 1, 1)
+    s2 = output2_scales_scalar.float().reshape(-1, 1, 1)
+    w1 = (gemm1_weights.float() * s1).to(torch.bfloat16)
+    w2 = (gemm2_weights.float() * s2).to(torch.bfloat16)
+    x = hidden_states.float().to(torch.bfloat16)
+    return moe_forward(x, ids, w, w1, w2, local_expert_offset, num_experts)
+
+
+def trtllm_fp8_block_scale_moe(routing_logits, routing_bias, hidden_states, hidden_states_scale, gemm1_weights,
+                               gemm1_weights_scale, gemm2_weights, gemm2_weights_scale, num_experts, top_k, n_group,
+                               topk_group, intermediate_size, local_expert_offset, local_num_experts,
+                               routed_scaling_factor, routing_method_type: int = 0, use_shuffled_weight: bool = False,
+                               weight_layout: int = 0, **kw):
+    """DeepSeek-style fp8 (1x128 activation scales ``[H/128, T]``, 128x128 weight scales)."""
+    ids, w = route(routing_logits, routing_bias, top_k, routing_method_type, n_group, topk_group, routed_scaling_factor)
+    x = hidden_states
+    if x.dtype == torch.float8_e4m3fn:
+        s = hidden_states_scale.float().t().repeat_interleave(128, -1)[:, : x.shape[1]]
+        x = (x.float() * s).to(torch.bfloat16)
+    w1 = _dequant_fp8_block(gemm1_weights, gemm1_weights_scale)
+    w2 = _dequant_fp8_block(gemm2_weights, gemm2_weights_scale)
+    return moe_forward(x, ids, w, w1, w2, local_expert_offset, num_experts)
+
+
+def trtllm_fp8_block_scale_routed_moe(topk_ids, routing_bias, hidden_states, hidden_states_scale, gemm1_weights,
+                                      gemm1_weights_scale, gemm2_weights, gemm2_weights_scale, num_experts, top_k,
+                                      n_group, topk_group, intermediate_size, local_expert_offset, local_num_experts,
+                                      routed_scaling_factor, routing_method_type: int = 1, **kw):
+    ids, w = _unpack_routed(topk_ids)
+    x = hidden_states
+    if x.dtype == torch.float8_e4m3fn:
+        s = hidden_states_scale.float().t().repeat_interleave(128, -1)[:, : x.shape[1]]
+        x = (x.float() * s).to(torch.bfloat16)
+    return moe_forward(x, ids, w, _dequant_fp8_block(gemm1_weights, gemm1_weights_scale),
+                       _dequant_fp8_block(gemm2_weights, gemm2_weights_scale), local_expert_offset, num_experts)
+
+
+def trtllm_fp4_block_scale_moe(routing_logits, routing_bias, hidden_states, hidden_states_scale, gemm1_weights,
+                               gemm1_weights_scale, gemm1_bias, gemm1_alpha, gemm1_beta, gemm1_clamp_limit, gemm2_weights,
+                               gemm2_weights_scale, gemm2_bias, output1_scale_scalar, output1_scale_gate_scalar,
+                               output2_scale_scalar, num_experts, top_k, n_group, topk_group, intermediate_size,
+                               local_expert_offset, local_num_experts, routed_scaling_factor,
+                               routing_method_type: int = 0, do_finalize: bool = True, **kw):
+    """NVFP4 weights (``[E, N, K/2]`` packed e2m1 + linear UE4M3 block scales) with bf16 or nvfp4 activations."""
+    ids, w = route(routing_logits, routing_bias, top_k, routing_method_type, n_group, topk_group, routed_scaling_factor)
+    x = hidden_states
+    if x.dtype == torch.uint8:
+        x = _dequant_nvfp4(x, hidden_states_scale, 1.0)
+    g1 = output1_scale_scalar if output1_scale_scalar is not None else 1.0
+    g2 = output2_scale_scalar if output2_scale_scalar is not None else 1.0
+    w1 = _dequant_nvfp4(gemm1_weights, gemm1_weights_scale, g1)
+    w2 = _dequant_nvfp4(gemm2_weights, gemm2_weights_scale, g2)
+    return moe_forward(x.to(torch.bfloat16), ids, w, w1, w2, local_expert_offset, num_experts, do_finalize=do_finalize)
+
+
+def trtllm_fp4_block_scale_routed_moe(topk_ids, routing_bias, hidden_states, hidden_states_scale, gemm1_weights,
+                                      gemm1_weights_scale, gemm1_bias, gemm1_alpha, gemm1_beta, gemm1_clamp_limit,
+                                      gemm2_weights, gemm2_weights_scale, gemm2_bias, output1_scale_scalar,
+                                      output1_scale_gate_scalar, output2_scale_scalar, num_experts, top_k, n_group,
+                                      topk_group, intermediate_size, local_expert_offset, local_num_experts,
+                                      routed_scaling_factor, routing_method_type: int = 1, do_finalize: bool = True, **kw):
+    ids, w = _unpack_routed(topk_ids)
+    x = hidden_states
+    if x.dtype == torch.uint8:
+        x = _dequant_nvfp4(x, hidden_states_scale, 1.0)
+    g1 = output1_scale_scalar if output1_scale_scalar is not None else 1.0
+    g2 = output2_scale_scalar if output2_scale_scalar is not None else 1.0
+    return moe_forward(x.to(torch.bfloat16), ids, w, _dequant_nvfp4(gemm1_weights, gemm1_weights_scale, g1),
+                       _dequant_nvfp4(gemm2_weights, gemm2_weights_scale, g2), local_expert_offset, num_experts,
+                       do_finalize=do_finalize)
+
+
+def trtllm_mxint4_block_scale_moe(routing_logits, routing_bias, hidden_states, gemm1_weights, gemm1_weights_scale,
+                                  gemm1_alpha, gemm1_beta, gemm1_clamp_limit, gemm2_weights, gemm2_weights_scale,
+                                  num_experts, top_k, n_group, topk_group, intermediate_size, local_expert_offset,
+                                  local_num_experts, routed_scaling_factor, routing_method_type: int = 0, **kw):
+    """MXINT4 weights: int4 pairs in uint8 + bf16 scales per 32 elements."""
+    ids, w = route(routing_logits, routing_bias, top_k, routing_method_type, n_group, topk_group, routed_scaling_factor)
+
+    def deq(wq, sc):
+        b = wq.view(torch.uint8)
+        lo = (b & 0xF).to(torch.int8)
+        hi = (b >> 4).to(torch.int8)
+        lo = torch.where(lo > 7, lo - 16, lo)
+        hi = torch.where(hi > 7, hi - 16, hi)
+        vals = torch.stack([lo, hi], -1).flatten(-2).float()
+        s = sc.float().repeat_interleave(32, -1)[..., : vals.shape[-1]]
+        return (vals * s).to(torch.bfloat16)
+
+    return moe_forward(hidden_states, ids, w, deq(gemm1_weights, gemm1_weights_scale),
+                       deq(gemm2_weights, gemm2_weights_scale), local_expert_offset, num_experts)
+
+
+# ------------------------------------------------------------------ cutlass-style entry point
+def cutlass_fused_moe(input: torch.Tensor, token_selected_experts: torch.Tensor, token_final_scales: torch.Tensor,
+                      fc1_expert_weights: torch.Tensor, fc2_expert_weights: torch.Tensor, output_dtype: torch.dtype,
+                      quant_scales: Optional[List[torch.Tensor]] = None, fc1_expert_biases=None, fc2_expert_biases=None,
+                      input_sf=None, swiglu_alpha=None, swiglu_beta=None, swiglu_limit=None, tp_size: int = 1,
+                      tp_rank: int = 0, ep_size: int = 1, ep_rank: int = 0, cluster_size: int = 1, cluster_rank: int = 0,
+                      output: Optional[torch.Tensor] = None, enable_alltoall: bool = False,
+                      use_deepseek_fp8_block_scale: bool = False, use_w4_group_scaling: bool = False,
+                      use_mxfp8_act_scaling: bool = False, min_latency_mode: bool = False, use_packed_weights: bool = False,
+                      tune_max_num_tokens: int = 8192, enable_pdl=None, activation_type=ActivationType.Swiglu):
+    """Pre-routed MoE (reference core.py:775): ``fc1 [E_local, 2I, H]`` (= cat([w3/up, w1/gate])), ``fc2 [E_local, H, I]``.
+    ``ep_rank`` selects the local expert range; ``tp_*`` only describe how the caller sharded I."""
+    e_local = fc1_expert_weights.shape[0]
+    w1, w2 = fc1_expert_weights, fc2_expert_weights
+    if use_deepseek_fp8_block_scale and quant_scales is not None:
+        w1 = _dequant_fp8_block(w1, quant_scales[0])
+        w2 = _dequant_fp8_block(w2, quant_scales[1])
+    elif w1.dtype == torch.float8_e4m3fn and quant_scales is not None:
+        w1 = (w1.float() * quant_scales[0].float().reshape(-1, 1, 1)).to(output_dtype)
+        w2 = (w2.float() * quant_scales[2].float().reshape(-1, 1, 1)).to(output_dtype) if len(quant_scales) > 2 else w2.to(output_dtype)
+    x = input if input.dtype == output_dtype else input.to(output_dtype)
+    res = moe_forward(x, token_selected_experts.int(), token_final_scales.float(), w1.to(output_dtype), w2.to(output_dtype),
+                      local_expert_offset=ep_rank * e_local, num_experts=e_local * ep_size,
+                      activation="silu" if int(activation_type) in (int(ActivationType.Swiglu), int(ActivationType.Silu)) else "gelu",
+                      out=output)
+    return [res]
+
+
+def cute_dsl_fused_moe_nvfp4(x, x_sf, token_selected_experts, token_final_scales, w1_weight, w1_weight_sf, w1_alpha,
+                             fc2_input_scale, w2_weight, w2_weight_sf, w2_alpha, num_experts: int, top_k: int,
+                             num_local_experts: Optional[int] = None, local_expert_offset: int = 0, output_dtype=torch.bfloat16,
+                             **kw):
+    """NVFP4 MoE with pre-computed routing (reference fused_moe/cute_dsl/fused_moe.py)."""
+    xd = _dequant_nvfp4(x, x_sf, 1.0) if x.dtype == torch.uint8 else x
+    w1 = _dequant_nvfp4(w1_weight, w1_weight_sf, w1_alpha if w1_alpha is not None else 1.0)
+    w2 = _dequant_nvfp4(w2_weight, w2_weight_sf, w2_alpha if w2_alpha is not None else 1.0)
+    return moe_forward(xd.to(output_dtype), token_selected_experts.int(), token_final_scales.float(), w1.to(output_dtype),
+                       w2.to(output_dtype), local_expert_offset, num_experts)
+
+
+class CuteDslMoEWrapper:
+    """Stateful wrapper around :func:`cute_dsl_fused_moe_nvfp4` (weights bound once)."""
+
+    def __init__(self, num_experts: int, top_k: int, hidden_size: int, intermediate_size: int,
+                 num_local_experts: Optional[int] = None, local_expert_offset: int = 0, **kw) -> None:
+        self.num_experts, self.top_k = num_experts, top_k
+        self.num_local_experts = num_local_experts or num_experts
+        self.local_expert_offset = local_expert_offset
+
+    def run(self, x, x_sf, token_selected_experts, token_final_scales, w1_weight, w1_weight_sf, w1_alpha, fc2_input_scale,
+            w2_weight, w2_weight_sf, w2_alpha, **kw):
+        return cute_dsl_fused_moe_nvfp4(x, x_sf, token_selected_experts, token_final_scales, w1_weight, w1_weight_sf,
+                                        w1_alpha, fc2_input_scale, w2_weight, w2_weight_sf, w2_alpha, self.num_experts,
+                                        self.top_k, self.num_local_experts, self.local_expert_offset)
+
+
+def b12x_fused_moe(*args, **kwargs):
+    raise NotImplementedError("b12x_fused_moe targets sm_120/121 GPUs; this library is sm_100a only")
+
+
+class B12xMoEWrapper:
+    def __init__(self, *args, **kwargs):
+        raise NotImplementedError("B12xMoEWrapper targets sm_120/121 GPUs; this library is sm_100a only")

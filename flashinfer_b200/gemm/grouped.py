@@ -1,0 +1,213 @@
+"""Grouped / segment GEMMs on the tcgen05 grouped kernel (csrc/gemm/grouped_gemm_sm100.cu).
+
+Parity: reference SegmentGEMMWrapper (flashinfer/gemm/gemm_base.py:1736-1992), grouped_gemm_nt_masked
+(gemm/kernels/grouped_gemm_masked_blackwell.py), group_gemm_*_nt_groupwise (:3900-4400), DeepGEMM m-grouped
+contiguous / masked layouts (flashinfer/deep_gemm.py:1425-1585), grouped_mm (flashinfer/grouped_mm/core.py).
+
+All variants are lowered onto one layout contract: rows grouped by expert, each group padded to a multiple of
+128 rows, ``tile_expert[m_tile]`` naming the expert (-1 = skip) and the live tile count kept on the device.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from .. import jit
+from ..utils import dtype_code, stream_ptr
+
+_TILE = 128
+
+
+def grouped_gemm_tiles(a: torch.Tensor, w: torch.Tensor, tile_expert: torch.Tensor, meta: Optional[torch.Tensor],
+                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Low level: ``a [tiles*128, K]`` (row-padded), ``w [E, N, K]`` -> ``out [tiles*128, N]``."""
+    rows, K = a.shape
+    E, N, _ = w.shape
+    if out is None:
+        out = torch.empty(rows, N, dtype=a.dtype, device=a.device)
+    if not a.is_cuda:
+        te = tile_expert.tolist()
+        n = int(meta[0]) if meta is not None else len(te)
+        for t in range(min(n, len(te))):
+            if te[t] >= 0:
+                out[t * _TILE:(t + 1) * _TILE] = (a[t * _TILE:(t + 1) * _TILE].float() @ w[te[t]].float().t()).to(a.dtype)
+        return out
+    jit.load("grouped_gemm_sm100").call("grouped_gemm_nt", a, w.contiguous(), out, tile_expert, meta, rows // _TILE, N, K,
+                                        E, a.stride(0), out.stride(0), dtype_code(a.dtype), 1, stream_ptr(a))
+    return out
+
+
+def _pad_layout(seg_indptr: torch.Tensor, total: int, weight_indices: Optional[torch.Tensor]):
+    """Device-side (sync-free) construction of the 128-padded layout for arbitrary segments."""
+    dev = seg_indptr.device
+    B = seg_indptr.numel() - 1
+    indptr = seg_indptr.to(torch.int64)
+    lens = indptr[1:] - indptr[:-1]
+    padded = (lens + _TILE - 1) // _TILE * _TILE
+    pad_end = torch.cumsum(padded, 0)
+    pad_off = pad_end - padded
+    rows = torch.arange(total, device=dev, dtype=torch.int64)
+    seg = torch.searchsorted(indptr[1:].contiguous(), rows, right=True).clamp_(max=B - 1)
+    dest = pad_off[seg] + (rows - indptr[seg])
+    max_tiles = (total + B * (_TILE - 1)) // _TILE + 1
+    t0 = torch.arange(max_tiles, device=dev, dtype=torch.int64) * _TILE
+    tseg = torch.searchsorted(pad_end.contiguous(), t0, right=True)
+    valid = tseg < B
+    tsegc = tseg.clamp(max=B - 1)
+    experts = weight_indices.to(torch.int64)[tsegc] if weight_indices is not None else tsegc
+    tile_expert = torch.where(valid, experts, torch.full_like(experts, -1)).to(torch.int32)
+    meta = torch.zeros(4, dtype=torch.int32, device=dev)
+    meta[0] = (pad_end[-1] // _TILE).to(torch.int32)
+    return dest, tile_expert, meta, max_tiles
+
+
+def segment_gemm(x: torch.Tensor, weights: torch.Tensor, seg_indptr: torch.Tensor,
+                 weight_indices: Optional[torch.Tensor] = None, weight_column_major: bool = True,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y[seg i] = x[seg i] @ W[idx(i)]^T  (weights ``[n, N, K]`` when column-major, else ``[n, K, N]``)."""
+    if not weight_column_major:
+        weights = weights.transpose(1, 2).contiguous()
+    total, K = x.shape
+    N = weights.shape[1]
+    dest, tile_expert, meta, max_tiles = _pad_layout(seg_indptr, total, weight_indices)
+    xp = torch.zeros(max_tiles * _TILE, K, dtype=x.dtype, device=x.device)
+    xp[dest] = x
+    yp = grouped_gemm_tiles(xp, weights, tile_expert, meta)
+    y = yp[dest]
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
+
+
+class SegmentGEMMWrapper:
+    """Reference-compatible segment GEMM (LoRA-style batched ``x_i @ W_i``)."""
+
+    def __init__(self, float_workspace_buffer: Optional[torch.Tensor] = None, backend: str = "auto") -> None:
+        self._workspace = float_workspace_buffer
+        self.backend = "sm100"
+
+    def reset_workspace_buffer(self, float_workspace_buffer: torch.Tensor, int_workspace_buffer=None) -> None:
+        self._workspace = float_workspace_buffer
+
+    def run(self, x: torch.Tensor, weights: torch.Tensor, batch_size: int, weight_column_major: bool,
+            out: Optional[torch.Tensor] = None, seg_lens: Optional[torch.Tensor] = None,
+            seg_indptr: Optional[torch.Tensor] = None, weight_indices: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if seg_indptr is None:
+            if seg_lens is None:
+                raise ValueError("either seg_lens or seg_indptr is required")
+            seg_indptr = torch.zeros(batch_size + 1, dtype=torch.int64, device=x.device)
+            seg_indptr[1:] = torch.cumsum(seg_lens.to(x.device), 0)
+        return segment_gemm(x, weights, seg_indptr.to(x.device), weight_indices, weight_column_major, out)
+
+    forward = run
+
+
+def grouped_mm_bf16(a: torch.Tensor, b: torch.Tensor, m_indptr: torch.Tensor, out: Optional[torch.Tensor] = None,
+                    out_dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    """``a [cum_m, K]``, ``b [G, N, K]``, ``m_indptr [G+1]`` -> ``[cum_m, N]`` (reference grouped_mm/core.py)."""
+    y = segment_gemm(a, b, m_indptr, None, True)
+    y = y if y.dtype == out_dtype else y.to(out_dtype)
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
+
+
+def grouped_gemm_nt_masked(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, masked_m: torch.Tensor) -> torch.Tensor:
+    """Masked layout: ``a [E, M_max, K]``, ``b [E, N, K]``, only the first ``masked_m[e]`` rows per expert are
+    computed (tiles past the mask are skipped, rows inside a partially-masked tile are still written)."""
+    E, M, K = a.shape
+    if M % _TILE:
+        raise ValueError("grouped_gemm_nt_masked: M_max must be a multiple of 128")
+    tpe = M // _TILE
+    t = torch.arange(E * tpe, device=a.device)
+    e = t // tpe
+    valid = (t % tpe) * _TILE < masked_m.to(a.device)[e]
+    tile_expert = torch.where(valid, e, torch.full_like(e, -1)).to(torch.int32)
+    grouped_gemm_tiles(a.reshape(E * M, K), b, tile_expert, None, out.reshape(E * M, -1))
+    return out
+
+
+# ---- quantised grouped GEMMs: de-quantise to bf16, then the tcgen05 grouped kernel ---------------------------------
+def _dq_groupwise(x: torch.Tensor, scale: torch.Tensor, gran_rows: int, gran_k: int, scale_major_k: bool) -> torch.Tensor:
+    s = scale.float()
+    if not scale_major_k:
+        s = s.transpose(-1, -2)
+    s = s.repeat_interleave(gran_rows, -2).repeat_interleave(gran_k, -1)[..., : x.shape[-2], : x.shape[-1]]
+    return (x.float() * s).to(torch.bfloat16)
+
+
+def group_gemm_fp8_nt_groupwise(a: torch.Tensor, b: torch.Tensor, a_scale: torch.Tensor, b_scale: torch.Tensor,
+                                m_indptr: torch.Tensor, scale_granularity_mnk=(1, 128, 128), scale_major_mode: str = "MN",
+                                mma_sm: int = 1, out: Optional[torch.Tensor] = None,
+                                out_dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    gm, gn, gk = scale_granularity_mnk
+    major_k = scale_major_mode == "K"
+    ad = _dq_groupwise(a, a_scale, gm, gk, major_k)
+    bd = _dq_groupwise(b, b_scale, gn, gk, major_k)
+    return grouped_mm_bf16(ad, bd, m_indptr, out, out_dtype)
+
+
+def group_deepgemm_fp8_nt_groupwise(a, b, a_scale, b_scale, m_indices: torch.Tensor, scale_granularity_mnk=(1, 128, 128),
+                                    out: Optional[torch.Tensor] = None, out_dtype=torch.bfloat16) -> torch.Tensor:
+    """DeepGEMM m-grouped contiguous: ``m_indices [M]`` names the group of every row (groups 128-aligned)."""
+    gm, gn, gk = scale_granularity_mnk
+    ad = _dq_groupwise(a, a_scale, gm, gk, True)
+    bd = _dq_groupwise(b, b_scale, gn, gk, True)
+    tile_expert = m_indices[::_TILE].to(torch.int32).contiguous()
+    y = grouped_gemm_tiles(ad, bd, tile_expert, None)
+    y = y.to(out_dtype)
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
+
+
+def batch_deepgemm_fp8_nt_groupwise(a, b, a_scale, b_scale, masked_m: torch.Tensor, expected_m: int = 0,
+                                    scale_granularity_mnk=(1, 128, 128), out: Optional[torch.Tensor] = None,
+                                    out_dtype=torch.bfloat16) -> torch.Tensor:
+    """DeepGEMM masked layout: ``a [G, M_max, K]`` fp8 + ``a_scale [G, M_max, K/128]``."""
+    gm, gn, gk = scale_granularity_mnk
+    ad = _dq_groupwise(a, a_scale, gm, gk, True)
+    bd = _dq_groupwise(b, b_scale, gn, gk, True)
+    o = torch.empty(a.shape[0], a.shape[1], b.shape[1], dtype=torch.bfloat16, device=a.device)
+    grouped_gemm_nt_masked(ad, bd, o, masked_m)
+    o = o.to(out_dtype)
+    if out is not None:
+        out.copy_(o)
+        return out
+    return o
+
+
+def _dq_fp4(x: torch.Tensor, sf: torch.Tensor, vec: int, sf_dtype) -> torch.Tensor:
+    from ..quantization.fp4 import E2M1_VALUES
+
+    lut = torch.tensor(E2M1_VALUES + [-v for v in E2M1_VALUES], device=x.device)
+    xb = x.view(torch.uint8)
+    vals = torch.stack([lut[(xb & 0xF).long()], lut[(xb >> 4).long()]], -1).flatten(-2)
+    sb = sf.view(torch.uint8)
+    s = sb.view(torch.float8_e4m3fn).float() if sf_dtype == "ue4m3" else torch.exp2(sb.float() - 127.0)
+    s = s.reshape(*vals.shape[:-1], -1).repeat_interleave(vec, -1)[..., : vals.shape[-1]]
+    return (vals * s).to(torch.bfloat16)
+
+
+def group_gemm_mxfp4_nt_groupwise(a, b, a_scale, b_scale, m_indptr, mma_sm: int = 1, tile_m: int = 128, tile_n: int = 128,
+                                  tile_k: int = 128, swap_ab: bool = True, out=None, out_dtype=torch.bfloat16):
+    """a: mxfp8 e4m3 ``[cum_m, K]`` + ue8m0 ``[cum_m, K/32]``; b: mxfp4 ``[G, N, K/2]`` + ue8m0 ``[G, N, K/32]`` (linear SF)."""
+    s = torch.exp2(a_scale.view(torch.uint8).float() - 127.0).repeat_interleave(32, -1)[:, : a.shape[1]]
+    ad = (a.float() * s).to(torch.bfloat16)
+    bd = _dq_fp4(b, b_scale, 32, "ue8m0")
+    return grouped_mm_bf16(ad, bd, m_indptr, out, out_dtype)
+
+
+def group_gemm_nvfp4_nt_groupwise(a, b, a_scale, b_scale, m_indptr, alpha: Optional[torch.Tensor] = None, out=None,
+                                  out_dtype=torch.bfloat16, **kw):
+    """a: nvfp4 ``[cum_m, K/2]`` + ue4m3 ``[cum_m, K/16]``; b: nvfp4 ``[G, N, K/2]`` + ue4m3 ``[G, N, K/16]`` (linear SF);
+    ``alpha [G]`` = per-group global scale product."""
+    ad = _dq_fp4(a, a_scale, 16, "ue4m3")
+    bd = _dq_fp4(b, b_scale, 16, "ue4m3")
+    if alpha is not None:
+        bd = (bd.float() * alpha.float().reshape(-1, 1, 1)).to(torch.bfloat16)
+    return grouped_mm_bf16(ad, bd, m_indptr, out, out_dtype)

@@ -140,7 +140,7 @@ register(ModuleSpec("prefill_sm100", ["attention/prefill_sm100.cu"]))
 register(ModuleSpec("mla_sm100", ["attention/mla_sm100.cu"]))
 register(ModuleSpec("gemm_blockscaled_sm100", ["gemm/gemm_blockscaled_sm100.cu"]))
 register(ModuleSpec("grouped_gemm_sm100", ["gemm/grouped_gemm_sm100.cu"]))
-register(ModuleSpec("moe", ["moe/routing.cu", "moe/moe_utils.cu"]))
+register(ModuleSpec("moe", ["moe/routing.cu"]))
 register(ModuleSpec("comm_allreduce", ["comm/allreduce.cu"]))
 register(ModuleSpec("comm_alltoall", ["comm/moe_alltoall.cu"]))
 register(ModuleSpec("gemm_comm_sm100", ["comm/gemm_allreduce_sm100.cu"]))

@@ -1,0 +1,172 @@
+"""MoE + grouped GEMM.  Strategy mirrors reference tests/moe/test_trtllm_gen_fused_moe.py (routing reference in
+torch, dequantised expert loop as the oracle) and tests/gemm/test_group_gemm.py."""
+import pytest
+import torch
+
+import flashinfer_b200 as fi
+from flashinfer_b200.fused_moe import (RoutingMethodType, cutlass_fused_moe, fused_topk_deepseek, moe_forward,
+                                       moe_reference, route, trtllm_bf16_moe, trtllm_fp8_block_scale_moe)
+from flashinfer_b200.fused_moe.core import _route_cpu
+from flashinfer_b200.gemm import SegmentGEMMWrapper, grouped_gemm_nt_masked, grouped_mm_bf16
+
+
+def _mk(T, E, H, I, dev, dtype=torch.bfloat16, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = (torch.randn(T, H, generator=g) * 0.5).to(dtype).to(dev)
+    w1 = (torch.randn(E, 2 * I, H, generator=g) / H ** 0.5).to(dtype).to(dev)
+    w2 = (torch.randn(E, H, I, generator=g) / I ** 0.5).to(dtype).to(dev)
+    logits = torch.randn(T, E, generator=g).to(dev)
+    return x, w1, w2, logits
+
+
+# ---------------------------------------------------------------- CPU
+def test_route_cpu_methods():
+    logits = torch.randn(17, 32)
+    bias = torch.randn(32) * 0.1
+    for m in range(9):
+        k = 1 if m == RoutingMethodType.Llama4 else 4
+        ids, w = route(logits, bias, k, m, 4, 2, 2.5)
+        assert ids.shape == (17, k) and w.shape == (17, k)
+        assert (ids >= 0).all() and (ids < 32).all()
+        assert all(len(set(r.tolist())) == k for r in ids)
+    ids, w = route(logits, None, 4, RoutingMethodType.Renormalize)
+    assert torch.allclose(w.sum(-1), torch.ones(17), atol=1e-5)
+
+
+def test_moe_cpu_matches_dense_expert_loop():
+    x, w1, w2, logits = _mk(9, 4, 32, 16, "cpu", torch.float32)
+    out = trtllm_bf16_moe(logits, None, x, w1, w2, 4, 2, None, None, 16, 0, 4, routing_method_type=1)
+    ids, w = route(logits, None, 2, 1)
+    ref = torch.zeros_like(x)
+    for t in range(9):
+        for j in range(2):
+            e = int(ids[t, j])
+            h = x[t] @ w1[e].t()
+            ref[t] += w[t, j] * ((torch.nn.functional.silu(h[16:]) * h[:16]) @ w2[e].t())
+    assert torch.allclose(out, ref, atol=1e-4)
+
+
+def test_segment_gemm_cpu():
+    x = torch.randn(300, 64)
+    w = torch.randn(4, 32, 64)
+    y = SegmentGEMMWrapper().run(x, w, 3, True, seg_lens=torch.tensor([100, 0, 200]), weight_indices=torch.tensor([3, 1, 0]))
+    ref = torch.cat([x[:100] @ w[3].t(), x[100:] @ w[0].t()])
+    assert torch.allclose(y, ref, atol=1e-4)
+
+
+# ---------------------------------------------------------------- GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("method", list(range(9)))
+@pytest.mark.parametrize("E,K", [(8, 2), (128, 8), (256, 8)])
+def test_routing_gpu(method, E, K):
+    if method == RoutingMethodType.Llama4:
+        K = 1
+    T = 77
+    g = torch.Generator().manual_seed(method * 100 + E)
+    logits = torch.randn(T, E, generator=g).cuda()
+    bias = (torch.randn(E, generator=g) * 0.1).cuda()
+    n_group, topk_group = (8, 4) if E >= 128 else (1, 1)
+    ids, w = route(logits, bias, K, method, n_group, topk_group, 2.5)
+    rids, rw = _route_cpu(logits.cpu(), bias.cpu(), K, method, n_group, topk_group, 2.5, True)
+    # compare as sets (ordering inside the top-k is unspecified)
+    order, rorder = ids.cpu().sort(-1), rids.sort(-1)
+    assert torch.equal(order.values, rorder.values.int())
+    assert torch.allclose(w.cpu().gather(1, order.indices), rw.gather(1, rorder.indices), atol=2e-5, rtol=1e-4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("T", [1, 7, 300, 2048])
+@pytest.mark.parametrize("E,K,H,I", [(8, 2, 1024, 512), (64, 6, 2048, 768), (32, 8, 7168, 256)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_moe_forward_gpu(T, E, K, H, I, dtype):
+    if dtype == torch.float16 and (T != 300 or E != 8):
+        pytest.skip("fp16 sampled once")
+    x, w1, w2, logits = _mk(T, E, H, I, "cuda", dtype)
+    ids, w = route(logits, None, K, RoutingMethodType.Renormalize)
+    out = moe_forward(x, ids, w, w1, w2)
+    ref = moe_reference(x, ids, w, w1, w2)
+    err = (out.float() - ref).abs().max().item()
+    assert err < 3e-2 * max(1.0, ref.abs().max().item()), err
+
+
+@pytest.mark.gpu
+def test_moe_expert_parallel_gpu():
+    T, E, K, H, I = 200, 16, 4, 1024, 512
+    x, w1, w2, logits = _mk(T, E, H, I, "cuda")
+    ids, w = route(logits, None, K, 1)
+    full = moe_reference(x, ids, w, w1, w2)
+    acc = torch.zeros_like(full)
+    for r in range(4):
+        lo = r * 4
+        acc += moe_forward(x, ids, w, w1[lo:lo + 4].contiguous(), w2[lo:lo + 4].contiguous(), local_expert_offset=lo,
+                           num_experts=E).float()
+    assert (acc - full).abs().max().item() < 5e-2 * max(1.0, full.abs().max().item())
+
+
+@pytest.mark.gpu
+def test_trtllm_bf16_moe_deepseek_routing_gpu():
+    T, E, K, H, I = 65, 256, 8, 1024, 256
+    x, w1, w2, logits = _mk(T, E, H, I, "cuda")
+    bias = (torch.randn(E) * 0.1).cuda()
+    out = trtllm_bf16_moe(logits, bias, x, w1, w2, E, K, 8, 4, I, 0, E, 2.5, RoutingMethodType.DeepSeekV3)
+    w_, ids = fused_topk_deepseek(logits, bias, 8, 4, K, 2.5)
+    ref = moe_reference(x, ids, w_, w1, w2)
+    assert (out.float() - ref).abs().max().item() < 3e-2 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.gpu
+def test_cutlass_fused_moe_and_fp8_block_gpu():
+    T, E, K, H, I = 128, 8, 2, 1024, 512
+    x, w1, w2, logits = _mk(T, E, H, I, "cuda")
+    ids, w = route(logits, None, K, 1)
+    out = cutlass_fused_moe(x, ids, w, w1, w2, torch.bfloat16)[0]
+    ref = moe_reference(x, ids, w, w1, w2)
+    assert (out.float() - ref).abs().max().item() < 3e-2 * max(1.0, ref.abs().max().item())
+    # fp8 block-scale: quantise weights per 128x128 block, compare with the de-quantised oracle
+    def q(wt):
+        Eb, N, Kd = wt.shape
+        blk = wt.float().reshape(Eb, N // 128, 128, Kd // 128, 128)
+        s = blk.abs().amax((2, 4)) / 448.0
+        wq = (blk / s[:, :, None, :, None]).reshape(Eb, N, Kd).to(torch.float8_e4m3fn)
+        return wq, s
+    w1q, s1 = q(w1)
+    w2q, s2 = q(w2)
+    out8 = trtllm_fp8_block_scale_moe(logits, None, x, None, w1q, s1, w2q, s2, E, K, None, None, I, 0, E, None, 1)
+    from flashinfer_b200.fused_moe.core import _dequant_fp8_block
+    ref8 = moe_reference(x, ids, w, _dequant_fp8_block(w1q, s1), _dequant_fp8_block(w2q, s2))
+    assert (out8.float() - ref8).abs().max().item() < 3e-2 * max(1.0, ref8.abs().max().item())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,K", [(512, 1024), (4096, 4096), (136, 72)])
+def test_segment_gemm_gpu(N, K):
+    lens = torch.tensor([100, 0, 257, 1, 128])
+    total = int(lens.sum())
+    x = (torch.randn(total, K) * 0.5).bfloat16().cuda()
+    w = (torch.randn(6, N, K) / K ** 0.5).bfloat16().cuda()
+    widx = torch.tensor([5, 1, 0, 2, 2]).cuda()
+    y = SegmentGEMMWrapper().run(x, w, 5, True, seg_lens=lens.cuda(), weight_indices=widx)
+    off = 0
+    for i, n in enumerate(lens.tolist()):
+        ref = x[off:off + n].float() @ w[int(widx[i])].float().t()
+        assert (y[off:off + n].float() - ref).abs().max().item() < 3e-2 * max(1.0, ref.abs().max().item() if n else 1.0)
+        off += n
+    indptr = torch.zeros(6, dtype=torch.int32)
+    indptr[1:] = lens.cumsum(0)
+    y2 = grouped_mm_bf16(x, w[:5].contiguous(), indptr.cuda())
+    assert y2.shape == (total, N)
+
+
+@pytest.mark.gpu
+def test_grouped_gemm_masked_gpu():
+    E, M, N, K = 4, 256, 512, 1024
+    a = (torch.randn(E, M, K) * 0.5).bfloat16().cuda()
+    b = (torch.randn(E, N, K) / K ** 0.5).bfloat16().cuda()
+    o = torch.zeros(E, M, N, dtype=torch.bfloat16, device="cuda")
+    mm = torch.tensor([256, 3, 0, 129], dtype=torch.int32).cuda()
+    grouped_gemm_nt_masked(a, b, o, mm)
+    for e, m in enumerate(mm.tolist()):
+        ref = a[e, :m].float() @ b[e].float().t()
+        if m:
+            assert (o[e, :m].float() - ref).abs().max().item() < 3e-2 * max(1.0, ref.abs().max().item())
+    assert o[2].abs().max().item() == 0
