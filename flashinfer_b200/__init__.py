@@ -103,3 +103,4 @@ from .fused_moe import (  # noqa: F401,E402
     trtllm_mxint4_block_scale_moe,
 )
 from .gemm import SegmentGEMMWrapper, grouped_mm_bf16  # noqa: F401,E402
+from .gemm import bmm_fp8, bmm_mxfp8, gemm_fp8_nt_groupwise, mm_fp4, mm_fp8, mm_mxfp8  # noqa: F401,E402

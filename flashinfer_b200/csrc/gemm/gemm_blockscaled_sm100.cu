@@ -1,0 +1,415 @@
+// Low-precision tcgen05 GEMMs for sm_100a:  C[b] = alpha * (A[b] * B[b]^T)   (A [M,K], B [N,K], both K-major)
+//
+//   kind 0  fp8 (e4m3 / e5m2) with per-tensor scales       tcgen05.mma.kind::f8f6f4
+//   kind 1  mxfp8:  fp8 data + UE8M0 scale per 32 elems     kind::mxf8f6f4.block_scale (scale_vec::1X)
+//   kind 2  nvfp4:  e2m1 data + UE4M3 scale per 16 elems    kind::mxf4nvf4.block_scale.scale_vec::4X
+//   kind 3  mxfp4:  e2m1 data + UE8M0 scale per 32 elems    kind::mxf4nvf4.block_scale.scale_vec::2X
+//
+// Parity: reference mm_fp8 / bmm_fp8 (flashinfer/gemm/gemm_base.py:2262-2533), mm_mxfp8 / bmm_mxfp8 (:3003-3420),
+// mm_fp4 (:4567-4839) and the CUTLASS / cuDNN / trtllm-gen back ends behind them.
+//
+// Design: persistent warp-specialised kernel (TMA producer warp, single-thread MMA issuer, 4 epilogue warps).
+// Every smem stage carries one 128-byte-wide K slab of A and B (128 fp8 or 256 fp4 elements = 4 MMAs) plus the
+// scale factors of that slab, which live in global memory in the 128x4 "swizzled" layout (512-byte blocks holding
+// 128 rows x 4 scale bytes: byte (m%32)*16 + (m%128/32)*4 + k%4).  A 512-byte block is exactly one
+// tcgen05.cp.32x128b.warpx4 source, so the scales go gmem -(bulk copy)-> smem -(tcgen05.cp)-> TMEM with no
+// register traffic; tcgen05.cp and tcgen05.mma execute in issue order, so one TMEM scale buffer suffices.
+// The N tile width is a run-time multiple of 32: a tile that does not start on a 128-row scale block simply
+// offsets the TMEM column of SFB by (n0 % 128) / 32.
+#include <fib200/common.cuh>
+#include <fib200/ptx.cuh>
+
+using namespace fib200;
+
+FIB_EXPORT_LAST_ERROR()
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BKB = 128;  // K slab in bytes per stage (one SWIZZLE_128B row)
+
+enum Kind { kFp8 = 0, kMxFp8 = 1, kNvFp4 = 2, kMxFp4 = 3 };
+
+struct Geo {
+  int stages, stage_bytes, a_bytes, b_bytes, sfa_bytes, sfb_bytes, bar_offset, total;
+  int nchunk;      // 512-byte scale blocks per row block per K slab
+  int rb;          // 128-row scale blocks that can overlap one N tile
+  int acc_stages;  // TMEM accumulator buffers
+  int sfa_col, sfb_col, tmem_cols;
+  __host__ __device__ static Geo make(int BN, int kind) {
+    Geo g;
+    g.nchunk = kind == kNvFp4 ? 4 : (kind == kMxFp4 ? 2 : (kind == kMxFp8 ? 1 : 0));
+    g.rb = (BN % 128 == 0) ? BN / 128 : (BN + 127) / 128 + 1;
+    g.a_bytes = BM * BKB;
+    g.b_bytes = BN * BKB;
+    g.sfa_bytes = g.nchunk * 512;
+    g.sfb_bytes = g.rb * g.nchunk * 512;
+    g.stage_bytes = g.a_bytes + g.b_bytes + g.sfa_bytes + g.sfb_bytes;
+    int st = (218 * 1024) / g.stage_bytes;
+    g.stages = st > 8 ? 8 : st;
+    g.bar_offset = g.stages * g.stage_bytes;
+    g.total = g.bar_offset + 320 + 1024;
+    const int sf_cols = g.nchunk * 4 + g.rb * g.nchunk * 4;
+    g.acc_stages = (2 * BN + sf_cols <= 512) ? 2 : 1;
+    g.sfa_col = g.acc_stages * BN;
+    g.sfb_col = g.sfa_col + g.nchunk * 4;
+    int need = g.sfb_col + g.rb * g.nchunk * 4;
+    int c = 32;
+    while (c < need) c <<= 1;
+    g.tmem_cols = c;
+    return g;
+  }
+};
+
+struct Params {
+  const uint8_t* sfa;
+  const uint8_t* sfb;
+  const float* alpha_a;  // optional device scalars; alpha = alpha_a * alpha_b
+  const float* alpha_b;
+  int64_t sfa_batch_stride, sfb_batch_stride, c_batch_stride, ldc;
+  int M, N, Kb;  // Kb = K in bytes
+  int batch, BN;
+  int sf_k_tiles;     // 512-byte blocks along K in the scale tensors
+  int sfb_row_tiles;  // 128-row blocks in SFB
+  uint32_t idesc;
+};
+
+template <int KIND, typename OutT>
+__global__ void __launch_bounds__(256, 1)
+bs_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, OutT* __restrict__ C,
+               const Params p) {
+  const Geo G = Geo::make(p.BN, KIND);
+  const int BN = p.BN;
+  const int kStages = G.stages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + G.bar_offset);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full = empty_bar + kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+    for (int i = 0; i < kStages; ++i) {
+      ptx::mbar_init(&full_bar[i], 1);
+      ptx::mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&tmem_full[i], 1);
+      ptx::mbar_init(&tmem_empty[i], 4);
+    }
+    ptx::fence_mbar_init();
+  }
+  if constexpr (KIND != kFp8) {
+    // scale staging areas start finite (zero): slabs past the K / N edge are never loaded but still multiplied
+    for (int s = 0; s < kStages; ++s) {
+      uint32_t* sf = reinterpret_cast<uint32_t*>(smem + s * G.stage_bytes + G.a_bytes + G.b_bytes);
+      for (int i = threadIdx.x; i < (G.sfa_bytes + G.sfb_bytes) / 4; i += blockDim.x) sf[i] = 0;
+    }
+    ptx::fence_proxy_async_smem();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc<1>(tmem_ptr, G.tmem_cols);
+    ptx::tmem_relinquish<1>();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
+  const int tiles_per_batch = tiles_m * tiles_n;
+  const int num_tiles = tiles_per_batch * p.batch;
+  const int num_kb = (p.Kb + BKB - 1) / BKB;
+
+  ptx::grid_dep_wait();
+
+  if (warp == 0) {
+    if (ptx::elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int b = t / tiles_per_batch, r = t % tiles_per_batch;
+        const int tm = r % tiles_m, tn = r / tiles_m;
+        const int n0 = tn * BN;
+        const int rb0 = n0 / 128;
+        int rbn = (n0 + BN + 127) / 128 - rb0;
+        if (rb0 + rbn > p.sfb_row_tiles) rbn = p.sfb_row_tiles - rb0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * G.stage_bytes;
+          uint8_t* sb = sa + G.a_bytes;
+          uint32_t tx = G.a_bytes + G.b_bytes;
+          int nch = 0;
+          if constexpr (KIND != kFp8) {
+            nch = p.sf_k_tiles - kb * G.nchunk;
+            nch = nch > G.nchunk ? G.nchunk : nch;
+            tx += uint32_t(nch * 512) * uint32_t(1 + rbn);
+          }
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], tx);
+          ptx::tma_load_3d(sa, &tmA, &full_bar[stage], kb * BKB, tm * BM, b, ptx::kEvictNormal);
+          ptx::tma_load_3d(sb, &tmB, &full_bar[stage], kb * BKB, n0, b, ptx::kEvictNormal);
+          if constexpr (KIND != kFp8) {
+            uint8_t* ssfa = sb + G.b_bytes;
+            uint8_t* ssfb = ssfa + G.sfa_bytes;
+            const uint8_t* ga = p.sfa + int64_t(b) * p.sfa_batch_stride +
+                                (int64_t(tm) * p.sf_k_tiles + int64_t(kb) * G.nchunk) * 512;
+            ptx::bulk_load(ssfa, ga, nch * 512, &full_bar[stage]);
+            for (int rr = 0; rr < rbn; ++rr) {
+              const uint8_t* gb = p.sfb + int64_t(b) * p.sfb_batch_stride +
+                                  (int64_t(rb0 + rr) * p.sf_k_tiles + int64_t(kb) * G.nchunk) * 512;
+              ptx::bulk_load(ssfb + rr * G.nchunk * 512, gb, nch * 512, &full_bar[stage]);
+            }
+          }
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int r = t % tiles_per_batch;
+      const int n0 = (r / tiles_m) * BN;
+      const uint32_t sfb_off = uint32_t((n0 % 128) / 32);
+      ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        ptx::mbar_wait(&full_bar[stage], phase);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const uint32_t sa = ptx::smem_u32(smem + stage * G.stage_bytes);
+          const uint32_t sb = sa + G.a_bytes;
+          const uint64_t da = ptx::make_smem_desc(sa, 16, 1024, ptx::kSwz128);
+          const uint64_t db = ptx::make_smem_desc(sb, 16, 1024, ptx::kSwz128);
+          if constexpr (KIND != kFp8) {
+            const uint32_t ssfa = sb + G.b_bytes, ssfb = ssfa + G.sfa_bytes;
+            for (int c = 0; c < G.nchunk; ++c) {
+              ptx::tmem_cp_32x128b_warpx4(tmem_base + G.sfa_col + c * 4,
+                                          ptx::make_smem_desc(ssfa + c * 512, 0, 128, ptx::kSwzNone));
+              for (int rr = 0; rr < G.rb; ++rr)
+                ptx::tmem_cp_32x128b_warpx4(tmem_base + G.sfb_col + (c * G.rb + rr) * 4,
+                                            ptx::make_smem_desc(ssfb + (rr * G.nchunk + c) * 512, 0, 128, ptx::kSwzNone));
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t accum = (kb > 0 || k > 0) ? 1u : 0u;
+            const uint64_t dak = ptx::desc_advance(da, k * 32), dbk = ptx::desc_advance(db, k * 32);
+            if constexpr (KIND == kFp8) {
+              ptx::mma_f8f6f4_ss<1>(d_tmem, dak, dbk, p.idesc, accum);
+            } else if constexpr (KIND == kMxFp8) {
+              const uint32_t id = p.idesc | (uint32_t(k) << 4) | (uint32_t(k) << 29);
+              ptx::mma_mxf8f6f4_ss(d_tmem, dak, dbk, id, tmem_base + G.sfa_col, tmem_base + G.sfb_col + sfb_off, accum);
+            } else if constexpr (KIND == kNvFp4) {
+              ptx::mma_mxf4nvf4_ss(d_tmem, dak, dbk, p.idesc, tmem_base + G.sfa_col + k * 4,
+                                   tmem_base + G.sfb_col + k * G.rb * 4 + sfb_off, accum);
+            } else {
+              const uint32_t sid = uint32_t(k & 1) * 2;
+              const uint32_t id = p.idesc | (sid << 4) | (sid << 29);
+              ptx::mma_mxf4_2x_ss(d_tmem, dak, dbk, id, tmem_base + G.sfa_col + (k >> 1) * 4,
+                                  tmem_base + G.sfb_col + (k >> 1) * G.rb * 4 + sfb_off, accum);
+            }
+          }
+          ptx::mma_commit(&empty_bar[stage]);
+          if (kb == num_kb - 1) ptx::mma_commit(&tmem_full[acc]);
+        }
+        __syncwarp();
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (G.acc_stages == 2) {
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      } else {
+        acc_phase ^= 1;
+      }
+    }
+    ptx::grid_dep_launch();
+  } else if (warp >= 4) {
+    const int q = warp - 4;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    float alpha = 1.f;
+    if (p.alpha_a) alpha *= *p.alpha_a;
+    if (p.alpha_b) alpha *= *p.alpha_b;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int b = t / tiles_per_batch, r = t % tiles_per_batch;
+      const int tm = r % tiles_m, tn = r / tiles_m;
+      ptx::mbar_wait(&tmem_full[acc], acc_phase);
+      ptx::tc_fence_after();
+      const int row = tm * BM + q * 32 + lane;
+      const uint32_t taddr = tmem_base + acc * BN + (uint32_t(q * 32) << 16);
+      OutT* crow = C + int64_t(b) * p.c_batch_stride + int64_t(row) * p.ldc;
+      const bool vec_ok = (p.ldc % (16 / sizeof(OutT)) == 0);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        ptx::tmem_ld_x32(taddr + c0, v);
+        ptx::tmem_ld_wait();
+        const int col0 = tn * BN + c0;
+        if (row < p.M) {
+          if (col0 + 32 <= p.N && vec_ok) {
+            constexpr int VN = 16 / sizeof(OutT);
+#pragma unroll
+            for (int j = 0; j < 32; j += VN) {
+              Vec16<OutT> o;
+#pragma unroll
+              for (int e = 0; e < VN; ++e) o.v[e] = from_f32<OutT>(__uint_as_float(v[j + e]) * alpha);
+              st16(crow + col0 + j, o);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) crow[col0 + j] = from_f32<OutT>(__uint_as_float(v[j]) * alpha);
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+      if (G.acc_stages == 2) {
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      } else {
+        acc_phase ^= 1;
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<1>(tmem_base, G.tmem_cols);
+  }
+}
+
+template <int KIND, typename OutT>
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, void* C, const Params& p, int grid, int smem, bool pdl,
+           cudaStream_t stream) {
+  static bool set = false;
+  if (!set) {
+    FIB_CUDA_CHECK(cudaFuncSetAttribute(bs_gemm_kernel<KIND, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    set = true;
+  }
+  LaunchCfg lc(dim3(grid), dim3(256), smem, stream, pdl);
+  FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, bs_gemm_kernel<KIND, OutT>, tmA, tmB, (OutT*)C, p));
+  return 0;
+}
+
+}  // namespace
+
+// A [batch, M, Kbytes] (row stride lda bytes), B [batch, N, Kbytes] (ldb bytes): raw bytes (fp8: 1 elem / byte, fp4:
+// 2 elems / byte).  sfa / sfb: 128x4 swizzled scale tensors ([row_tiles, sf_k_tiles, 512] per batch) or null (kind 0).
+// a_fmt / b_fmt (kind 0/1): 0 = e4m3, 1 = e5m2.  bn: forced N tile (0 = heuristic).
+extern "C" int gemm_lowp_nt(void* A, void* B, void* C, void* sfa, void* sfb, void* alpha_a, void* alpha_b, int64_t batch,
+                            int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc,
+                            int64_t a_batch_stride, int64_t b_batch_stride, int64_t c_batch_stride,
+                            int64_t sfa_batch_stride, int64_t sfb_batch_stride, int64_t kind, int64_t a_fmt,
+                            int64_t b_fmt, int64_t out_dtype, int64_t bn, int64_t pdl, int64_t stream_) {
+  FIB_CHECK(kind >= 0 && kind <= 3, "gemm_lowp: kind must be 0..3");
+  FIB_CHECK(out_dtype == kF16 || out_dtype == kBF16, "gemm_lowp: output must be f16/bf16");
+  const bool fp4 = kind == kNvFp4 || kind == kMxFp4;
+  FIB_CHECK(K % (fp4 ? 32 : 16) == 0, "gemm_lowp: K must be a multiple of 16 (fp8) / 32 (fp4)");
+  FIB_CHECK(lda % 16 == 0 && ldb % 16 == 0, "gemm_lowp: row strides must be multiples of 16 bytes");
+  if (M == 0 || N == 0 || batch == 0) return 0;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const int64_t Kb = fp4 ? K / 2 : K;
+  const int tiles_m = int((M + BM - 1) / BM);
+  int BN = (int)bn;
+  if (BN == 0) {
+    const int sms = num_sms();
+    const int64_t want = (N * tiles_m * batch + sms - 1) / sms;  // columns per CTA for one full wave
+    if (want >= 256) {
+      BN = (kind == kFp8) ? 256 : 192;
+      // prefer the width with the least tile-quantisation waste over full waves
+      auto waves = [&](int w) {
+        const int64_t tiles = ((N + w - 1) / w) * tiles_m * batch;
+        return double((tiles + sms - 1) / sms) * w;
+      };
+      const int cands[4] = {256, 224, 192, 128};
+      double best = 1e30;
+      for (int c : cands) {
+        if (kind != kFp8 && 2 * c + Geo::make(c, (int)kind).nchunk * 4 * (1 + Geo::make(c, (int)kind).rb) > 512 && c != 256) continue;
+        const double cost = waves(c) * ((c == 256 && kind != kFp8) ? 1.15 : 1.0) * (c == 128 ? 1.1 : 1.0);
+        if (cost < best) {
+          best = cost;
+          BN = c;
+        }
+      }
+    } else {
+      BN = int((want + 31) / 32 * 32);
+      if (BN < 32) BN = 32;
+    }
+  }
+  FIB_CHECK(BN % 32 == 0 && BN >= 32 && BN <= 256, "gemm_lowp: N tile must be a multiple of 32 in [32, 256]");
+  const Geo G = Geo::make(BN, (int)kind);
+  FIB_CHECK(G.stages >= 2 && G.tmem_cols <= 512, "gemm_lowp: tile does not fit");
+
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[3] = {(uint64_t)Kb, (uint64_t)M, (uint64_t)batch};
+    uint64_t str[2] = {(uint64_t)lda, (uint64_t)a_batch_stride};
+    uint32_t box[3] = {BKB, BM, 1};
+    if (make_tmap(&tmA, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, A, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)Kb, (uint64_t)N, (uint64_t)batch};
+    uint64_t str[2] = {(uint64_t)ldb, (uint64_t)b_batch_stride};
+    uint32_t box[3] = {BKB, (uint32_t)BN, 1};
+    if (make_tmap(&tmB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, B, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  }
+  Params p;
+  p.sfa = (const uint8_t*)sfa;
+  p.sfb = (const uint8_t*)sfb;
+  p.alpha_a = (const float*)alpha_a;
+  p.alpha_b = (const float*)alpha_b;
+  p.sfa_batch_stride = sfa_batch_stride;
+  p.sfb_batch_stride = sfb_batch_stride;
+  p.c_batch_stride = c_batch_stride;
+  p.ldc = ldc;
+  p.M = (int)M;
+  p.N = (int)N;
+  p.Kb = (int)Kb;
+  p.batch = (int)batch;
+  p.BN = BN;
+  const int vec = kind == kNvFp4 ? 16 : 32;
+  p.sf_k_tiles = kind == kFp8 ? 0 : int(((K + vec - 1) / vec + 3) / 4);
+  p.sfb_row_tiles = int((N + 127) / 128);
+  if (kind != kFp8) FIB_CHECK(sfa && sfb, "gemm_lowp: block-scaled kinds need scale tensors");
+  if (kind == kFp8) {
+    p.idesc = ptx::make_idesc_f8((uint32_t)a_fmt, (uint32_t)b_fmt, BM, BN, 0, 0);
+  } else if (kind == kMxFp8) {
+    p.idesc = ptx::make_idesc_blockscaled((uint32_t)a_fmt, (uint32_t)b_fmt, BM, BN, 1, 0, 0);
+  } else {
+    p.idesc = ptx::make_idesc_blockscaled(1, 1, BM, BN, kind == kMxFp4 ? 1 : 0, 0, 0);
+  }
+  const int64_t tiles = int64_t(tiles_m) * ((N + BN - 1) / BN) * batch;
+  const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+  const bool f16 = out_dtype == kF16;
+  switch (kind) {
+    case kFp8:
+      return f16 ? launch<kFp8, __half>(tmA, tmB, C, p, grid, G.total, pdl != 0, stream)
+                 : launch<kFp8, __nv_bfloat16>(tmA, tmB, C, p, grid, G.total, pdl != 0, stream);
+    case kMxFp8:
+      return f16 ? launch<kMxFp8, __half>(tmA, tmB, C, p, grid, G.total, pdl != 0, stream)
+                 : launch<kMxFp8, __nv_bfloat16>(tmA, tmB, C, p, grid, G.total, pdl != 0, stream);
+    case kNvFp4:
+      return f16 ? launch<kNvFp4, __half>(tmA, tmB, C, p, grid, G.total, pdl != 0, stream)
+                 : launch<kNvFp4, __nv_bfloat16>(tmA, tmB, C, p, grid, G.total, pdl != 0, stream);
+    default:
+      return f16 ? launch<kMxFp4, __half>(tmA, tmB, C, p, grid, G.total, pdl != 0, stream)
+                 : launch<kMxFp4, __nv_bfloat16>(tmA, tmB, C, p, grid, G.total, pdl != 0, stream);
+  }
+}

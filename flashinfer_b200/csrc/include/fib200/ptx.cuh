@@ -431,6 +431,16 @@ __device__ __forceinline__ void mma_mxf4nvf4_ss(uint32_t d_tmem, uint64_t a_desc
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(sfa_tmem), "r"(sfb_tmem)
       : "memory");
 }
+// mxfp4: e2m1 data, one UE8M0 scale per 32 elements (2 scale bytes per row per K=64 MMA).
+__device__ __forceinline__ void mma_mxf4_2x_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t sfa_tmem, uint32_t sfb_tmem, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::mxf4nvf4.block_scale.scale_vec::2X [%0], %1, %2, %3, [%5], [%6], p;\n\t}" ::"r"(
+          d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(sfa_tmem), "r"(sfb_tmem)
+      : "memory");
+}
 // Make completion of all prior tcgen05 async ops of this thread arrive on an mbarrier.
 // (implies tcgen05.fence::before_thread_sync)
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {

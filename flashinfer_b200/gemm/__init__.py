@@ -12,3 +12,13 @@ from .grouped import (  # noqa: F401
     grouped_mm_bf16,
     segment_gemm,
 )
+from .lowp import (  # noqa: F401
+    bmm_fp8,
+    bmm_mxfp8,
+    fp8_blockscale_gemm_sm90,
+    gemm_fp8_nt_blockscaled,
+    gemm_fp8_nt_groupwise,
+    mm_fp4,
+    mm_fp8,
+    mm_mxfp8,
+)

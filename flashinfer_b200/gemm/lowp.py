@@ -1,0 +1,239 @@
+"""FP8 / MXFP8 / NVFP4 / MXFP4 GEMMs on the block-scaled tcgen05 kernel (csrc/gemm/gemm_blockscaled_sm100.cu).
+
+Parity: reference flashinfer/gemm/gemm_base.py — mm_fp8 (:3792), bmm_fp8 (:6113), mm_mxfp8 (:4621), bmm_mxfp8 (:8311),
+mm_fp4 (:5861), gemm_fp8_nt_groupwise (:6280), gemm_fp8_nt_blockscaled (:6632).
+
+Conventions (same as the reference): ``b`` is passed as the column-major ``[k, n]`` view of a ``[n, k]`` weight
+(``weight.t()``), block scales are uint8 tensors in the 128x4 swizzled layout produced by ``nvfp4_quantize`` /
+``mxfp4_quantize`` / ``mxfp8_quantize`` (2-D linear ``[rows, k/vec]`` scales are swizzled on the fly).
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional, Tuple
+
+import torch
+
+from .. import jit
+from ..quantization.fp4 import _swizzled_sf_size, _unswizzle_index, block_scale_interleave, e2m1_and_ufp8sf_scale_to_float
+from ..utils import dtype_code, stream_ptr
+
+_KIND = {"fp8": 0, "mxfp8": 1, "nvfp4": 2, "mxfp4": 3}
+_FP8_FMT = {torch.float8_e4m3fn: 0, torch.float8_e5m2: 1}
+
+
+def _as_nk(b: torch.Tensor) -> torch.Tensor:
+    """Accept the reference's column-major ``[.., k, n]`` view and return the K-major ``[.., n, k]`` tensor behind it."""
+    bt = b.transpose(-1, -2)
+    if bt.stride(-1) != 1:
+        bt = bt.contiguous()
+    return bt
+
+
+def _scalar(x, device) -> Optional[torch.Tensor]:
+    if x is None:
+        return None
+    if not isinstance(x, torch.Tensor):
+        x = torch.tensor(float(x))
+    return x.to(device=device, dtype=torch.float32).reshape(-1)[:1].contiguous()
+
+
+def _sf_swizzled(sf: torch.Tensor, rows: int, kc: int, batch: int = 1, swizzled: Optional[bool] = None) -> torch.Tensor:
+    """Return uint8 ``[batch, round_up(rows,128) * round_up(kc,4)]`` 128x4-swizzled scales.
+
+    ``swizzled=None`` follows the reference's mm_mxfp8 rule: 1-D (or batch x 1-D) tensors are already swizzled,
+    ``[.., rows, kc]`` / ``[.., kc, rows]`` tensors are linear and get swizzled here."""
+    sf = sf.view(torch.uint8)
+    per = _swizzled_sf_size(rows, kc)
+    if swizzled is None:
+        swizzled = sf.dim() == 1 or (sf.dim() == 2 and sf.shape == (batch, per) and batch > 1)
+    if swizzled:
+        if sf.numel() != batch * per:
+            raise ValueError(f"swizzled scale tensor has {sf.numel()} bytes, expected {batch * per}")
+        return sf.reshape(batch, per).contiguous()
+    if sf.shape[-2:] == (rows, kc):
+        return block_scale_interleave(sf.contiguous()).reshape(batch, per)
+    if sf.shape[-2:] == (kc, rows):  # transposed linear scales ([k/vec, n])
+        return block_scale_interleave(sf.transpose(-1, -2).contiguous()).reshape(batch, per)
+    raise ValueError(f"scale tensor of shape {tuple(sf.shape)} is neither swizzled ({per} bytes) nor linear [{rows}, {kc}]")
+
+
+def _launch(kind: str, a: torch.Tensor, b_nk: torch.Tensor, out: torch.Tensor, sfa, sfb, alpha_a, alpha_b, K: int,
+            bn: int = 0) -> torch.Tensor:
+    """a ``[B, M, Kbytes]``, b_nk ``[B, N, Kbytes]`` (uint8 / fp8 storage, K contiguous), out ``[B, M, N]``."""
+    B, M, _ = a.shape
+    N = b_nk.shape[1]
+    bn = bn or int(os.environ.get("FIB200_LOWP_BN", "0"))
+    a_fmt = _FP8_FMT.get(a.dtype, 0)
+    b_fmt = _FP8_FMT.get(b_nk.dtype, 0)
+    jit.load("gemm_blockscaled_sm100").call(
+        "gemm_lowp_nt", a, b_nk, out, sfa, sfb, alpha_a, alpha_b, B, M, N, K, a.stride(1), b_nk.stride(1), out.stride(1),
+        a.stride(0), b_nk.stride(0), out.stride(0), sfa.stride(0) if sfa is not None else 0,
+        sfb.stride(0) if sfb is not None else 0, _KIND[kind], a_fmt, b_fmt, dtype_code(out.dtype), bn, 1, stream_ptr(a))
+    return out
+
+
+def _prep(a: torch.Tensor, b: torch.Tensor):
+    a3 = a if a.dim() == 3 else a.unsqueeze(0)
+    b3 = b if b.dim() == 3 else b.unsqueeze(0)
+    bnk = _as_nk(b3)
+    if a3.stride(-1) != 1:
+        a3 = a3.contiguous()
+    return a3, bnk
+
+
+def _finish(out3: torch.Tensor, batched: bool, out: Optional[torch.Tensor]):
+    res = out3 if batched else out3[0]
+    if out is not None and out.data_ptr() != out3.data_ptr():
+        out.copy_(res)
+        return out
+    return res
+
+
+def _alloc_out(out, shape, dtype, device):
+    if out is not None and out.dtype == dtype and out.is_contiguous() and tuple(out.shape) in (shape, shape[1:]):
+        return out.reshape(shape)
+    return torch.empty(shape, dtype=dtype, device=device)
+
+
+# ------------------------------------------------------------------ per-tensor fp8
+def bmm_fp8(A: torch.Tensor, B: torch.Tensor, A_scale: torch.Tensor, B_scale: torch.Tensor, dtype: torch.dtype,
+            out: Optional[torch.Tensor] = None, backend: str = "auto") -> torch.Tensor:
+    """``A [b, m, k]`` fp8, ``B [b, k, n]`` fp8 column-major, scalar de-quantisation scales -> ``[b, m, n]``."""
+    batched = A.dim() == 3
+    a3, bnk = _prep(A, B)
+    Bsz, M, K = a3.shape
+    N = bnk.shape[1]
+    if not A.is_cuda:
+        res = (a3.float() @ bnk.float().transpose(-1, -2)) * (A_scale.float() * B_scale.float())
+        return _finish(res.to(dtype), batched, out)
+    if bnk.shape[0] != Bsz:
+        bnk = bnk.expand(Bsz, -1, -1)
+    o = _alloc_out(out, (Bsz, M, N), dtype, A.device)
+    _launch("fp8", a3, bnk, o, None, None, _scalar(A_scale, A.device), _scalar(B_scale, A.device), K)
+    return _finish(o, batched, out)
+
+
+def mm_fp8(a: torch.Tensor, b: torch.Tensor, alpha: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.bfloat16,
+           out: Optional[torch.Tensor] = None, backend: str = "auto") -> torch.Tensor:
+    """``a [m, k]`` fp8 x ``b [k, n]`` fp8 (column-major) * alpha."""
+    a3, bnk = _prep(a, b)
+    if not a.is_cuda:
+        res = a3.float() @ bnk.float().transpose(-1, -2) * (float(alpha) if alpha is not None else 1.0)
+        return _finish(res.to(out_dtype), False, out)
+    o = _alloc_out(out, (1, a.shape[0], bnk.shape[1]), out_dtype, a.device)
+    _launch("fp8", a3, bnk, o, None, None, _scalar(alpha, a.device), None, a.shape[1])
+    return _finish(o, False, out)
+
+
+# ------------------------------------------------------------------ mxfp8
+def _mxfp8_ref(a3, bnk, sfa, sfb):
+    Bsz, M, K = a3.shape
+    N = bnk.shape[1]
+    kc = K // 32
+    outs = []
+    for i in range(Bsz):
+        sa = torch.pow(2.0, sfa[i][_unswizzle_index(M, kc).to(sfa.device)].view(M, kc).float() - 127)
+        sb = torch.pow(2.0, sfb[i][_unswizzle_index(N, kc).to(sfb.device)].view(N, kc).float() - 127)
+        ad = (a3[i].float().view(M, kc, 32) * sa[..., None]).view(M, K)
+        bd = (bnk[i].float().reshape(N, kc, 32) * sb[..., None]).view(N, K)
+        outs.append(ad @ bd.t())
+    return torch.stack(outs)
+
+
+def bmm_mxfp8(A: torch.Tensor, B: torch.Tensor, A_scale: torch.Tensor, B_scale: torch.Tensor, dtype: torch.dtype,
+              out: Optional[torch.Tensor] = None, backend: str = "auto") -> torch.Tensor:
+    """MXFP8 (e4m3 data, UE8M0 scale per 32 elements): ``A [b, m, k]``, ``B [b, k, n]`` column-major."""
+    batched = A.dim() == 3
+    a3, bnk = _prep(A, B)
+    Bsz, M, K = a3.shape
+    N = bnk.shape[1]
+    kc = K // 32
+    sfa = _sf_swizzled(A_scale, M, kc, Bsz)
+    sfb = _sf_swizzled(B_scale, N, kc, bnk.shape[0])
+    if not A.is_cuda:
+        return _finish(_mxfp8_ref(a3, bnk, sfa, sfb).to(dtype), batched, out)
+    o = _alloc_out(out, (Bsz, M, N), dtype, A.device)
+    _launch("mxfp8", a3, bnk, o, sfa, sfb, None, None, K)
+    return _finish(o, batched, out)
+
+
+def mm_mxfp8(a: torch.Tensor, b: torch.Tensor, a_descale: torch.Tensor, b_descale: torch.Tensor,
+             out: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.bfloat16, use_8x4_sf_layout: bool = False,
+             backend: str = "auto") -> torch.Tensor:
+    if use_8x4_sf_layout:
+        raise NotImplementedError("mm_mxfp8: only the 128x4 scale layout is supported")
+    return bmm_mxfp8(a, b, a_descale, b_descale, out_dtype, out)
+
+
+# ------------------------------------------------------------------ fp4
+def mm_fp4(a: torch.Tensor, b: torch.Tensor, a_descale: torch.Tensor, b_descale: torch.Tensor,
+           alpha: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.bfloat16, out: Optional[torch.Tensor] = None,
+           block_size: int = 16, use_8x4_sf_layout: bool = False, backend: str = "auto", use_nvfp4: bool = True,
+           enable_pdl: bool = True) -> torch.Tensor:
+    """``a [m, k/2]`` packed e2m1, ``b [k/2, n]`` column-major packed e2m1, 128x4-swizzled block scales
+    (UE4M3 / 16 for NVFP4, UE8M0 / 32 for MXFP4), ``alpha`` = 1 / (global_sf_a * global_sf_b)."""
+    if use_8x4_sf_layout:
+        raise NotImplementedError("mm_fp4: only the 128x4 scale layout is supported")
+    nv = use_nvfp4 and block_size == 16
+    vec = 16 if nv else 32
+    a3, bnk = _prep(a.view(torch.uint8), b.view(torch.uint8))
+    _, M, K2 = a3.shape
+    N = bnk.shape[1]
+    K = 2 * K2
+    kc = K // vec
+    sfa = _sf_swizzled(a_descale, M, kc, 1, True)
+    sfb = _sf_swizzled(b_descale, N, kc, 1, True)
+    if not a.is_cuda:
+        ad = e2m1_and_ufp8sf_scale_to_float(a3[0], sfa[0], None, vec, 1 if nv else 0, True)
+        bdq = e2m1_and_ufp8sf_scale_to_float(bnk[0].contiguous(), sfb[0], None, vec, 1 if nv else 0, True)
+        res = ad @ bdq.t() * (float(alpha) if alpha is not None else 1.0)
+        return _finish(res.to(out_dtype)[None], False, out)
+    o = _alloc_out(out, (1, M, N), out_dtype, a.device)
+    _launch("nvfp4" if nv else "mxfp4", a3, bnk, o, sfa, sfb, _scalar(alpha, a.device), None, K)
+    return _finish(o, False, out)
+
+
+# ------------------------------------------------------------------ fp8 with fp32 group scales (DeepSeek style)
+def _expand_scale(s: torch.Tensor, rows: int, K: int, g_rows: int, g_k: int, major: str) -> torch.Tensor:
+    s = s.float()
+    if s.shape == (K // g_k, (rows + g_rows - 1) // g_rows) and (major == "MN" or s.shape != ((rows + g_rows - 1) // g_rows, K // g_k)):
+        s = s.t()
+    return s.repeat_interleave(g_rows, 0)[:rows].repeat_interleave(g_k, 1)[:, :K]
+
+
+def gemm_fp8_nt_groupwise(a: torch.Tensor, b: torch.Tensor, a_scale: torch.Tensor, b_scale: torch.Tensor,
+                          scale_major_mode: Optional[str] = None, mma_sm: int = 1,
+                          scale_granularity_mnk: Tuple[int, int, int] = (1, 128, 128), out: Optional[torch.Tensor] = None,
+                          out_dtype: Optional[torch.dtype] = None, backend: str = "auto") -> torch.Tensor:
+    """``a [m, k]`` fp8, ``b [n, k]`` fp8, fp32 scales per (1 x 128) of a and (128 x 128) of b.
+
+    fp32 group scales cannot be fed to the block-scaled tensor-core path (which takes UE8M0 / UE4M3 bytes), so the
+    operands are re-scaled to bf16 by a fused elementwise pass and multiplied by the bf16 tcgen05 GEMM."""
+    from .dense import mm_bf16
+
+    gm, gn, gk = scale_granularity_mnk
+    major = scale_major_mode or "MN"
+    M, K = a.shape
+    N = b.shape[0]
+    out_dtype = out_dtype or (out.dtype if out is not None else torch.bfloat16)
+    ad = (a.float() * _expand_scale(a_scale, M, K, gm, gk, major)).to(torch.bfloat16)
+    bd = (b.float() * _expand_scale(b_scale, N, K, gn, gk, major)).to(torch.bfloat16)
+    if not a.is_cuda:
+        res = (ad.float() @ bd.float().t()).to(out_dtype)
+    else:
+        res = mm_bf16(ad, bd.t(), out_dtype=out_dtype)
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
+
+
+def gemm_fp8_nt_blockscaled(a, b, a_scale, b_scale, scale_major_mode: Optional[str] = "MN", mma_sm: int = 1,
+                            out: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """128 x 128 x 128 block scales on both operands."""
+    return gemm_fp8_nt_groupwise(a, b, a_scale, b_scale, scale_major_mode, mma_sm, (128, 128, 128), out, out_dtype)
+
+
+def fp8_blockscale_gemm_sm90(*args, **kwargs):
+    raise NotImplementedError("fp8_blockscale_gemm_sm90 is a Hopper-only entry point; use gemm_fp8_nt_groupwise on B200")

@@ -1,0 +1,98 @@
+"""fp8 / mxfp8 / nvfp4 / mxfp4 tcgen05 GEMMs vs the fp32 de-quantised product (reference tests/gemm/test_mm_fp4.py,
+test_bmm_fp8.py, test_mm_mxfp8.py use the same oracle with a cosine-similarity bound)."""
+import os
+
+import pytest
+import torch
+
+import flashinfer_b200 as fi
+from flashinfer_b200.quantization.fp4 import e2m1_and_ufp8sf_scale_to_float
+
+pytestmark = pytest.mark.gpu
+
+
+def _to_fp8(x, dtype=torch.float8_e4m3fn):
+    amax = x.abs().amax().clamp(min=1e-12)
+    scale = torch.finfo(dtype).max / amax
+    return (x * scale).clamp(-torch.finfo(dtype).max, torch.finfo(dtype).max).to(dtype), scale.float().reciprocal()
+
+
+def _check(out, ref, tol=8e-3):
+    err = (out.float() - ref).abs().max().item()
+    assert err <= tol * max(ref.abs().max().item(), 1e-3), (err, ref.abs().max().item())
+
+
+@pytest.fixture(params=[0, 32, 96, 128, 192, 224, 256])
+def bn(request):
+    old = os.environ.get("FIB200_LOWP_BN")
+    os.environ["FIB200_LOWP_BN"] = str(request.param)
+    yield request.param
+    if old is None:
+        os.environ.pop("FIB200_LOWP_BN", None)
+    else:
+        os.environ["FIB200_LOWP_BN"] = old
+
+
+@pytest.mark.parametrize("b,m,n,k", [(1, 48, 80, 64), (16, 48, 80, 64), (2, 300, 1000, 4096), (1, 1, 4096, 4096)])
+@pytest.mark.parametrize("adt", [torch.float8_e4m3fn, torch.float8_e5m2])
+def test_bmm_fp8(b, m, n, k, adt):
+    A = torch.randn(b, m, k, device="cuda")
+    W = torch.randn(b, n, k, device="cuda")
+    a8, sa = _to_fp8(A, adt)
+    w8, sw = _to_fp8(W)
+    out = fi.bmm_fp8(a8, w8.transpose(-1, -2), sa, sw, torch.bfloat16)
+    ref = torch.bmm(a8.float(), w8.float().transpose(-1, -2)) * sa * sw
+    _check(out, ref)
+    out2 = fi.mm_fp8(a8[0], w8[0].t(), sa * sw, torch.float16)
+    _check(out2, ref[0])
+
+
+@pytest.mark.parametrize("m,n,k", [(48, 256, 128), (128, 512, 4096), (300, 1184, 416), (1, 2048, 7168), (2000, 4096, 1024)])
+def test_mm_mxfp8(m, n, k, bn):
+    a = torch.randn(m, k, device="cuda", dtype=torch.bfloat16)
+    w = torch.randn(n, k, device="cuda", dtype=torch.bfloat16)
+    aq, asf = fi.mxfp8_quantize(a)
+    wq, wsf = fi.mxfp8_quantize(w)
+    out = fi.mm_mxfp8(aq, wq.t(), asf, wsf, out_dtype=torch.bfloat16)
+    ref = fi.mxfp8_dequantize_host(aq, asf) @ fi.mxfp8_dequantize_host(wq, wsf).t()
+    _check(out, ref)
+    # linear (2-D) scales take the on-the-fly swizzle path
+    aq2, asf2 = fi.mxfp8_quantize(a, is_sf_swizzled_layout=False)
+    out2 = fi.mm_mxfp8(aq2, wq.t(), asf2.view(m, k // 32), wsf, out_dtype=torch.bfloat16)
+    _check(out2, ref)
+
+
+@pytest.mark.parametrize("m,n,k", [(48, 256, 128), (128, 512, 4096), (300, 1184, 448), (1, 2048, 7168), (2000, 4096, 1024)])
+@pytest.mark.parametrize("nv", [True, False])
+def test_mm_fp4(m, n, k, nv, bn):
+    a = torch.randn(m, k, device="cuda", dtype=torch.bfloat16)
+    w = torch.randn(n, k, device="cuda", dtype=torch.bfloat16)
+    if nv:
+        ga = (448 * 6) / a.float().abs().max()
+        gw = (448 * 6) / w.float().abs().max()
+        aq, asf = fi.nvfp4_quantize(a, ga)
+        wq, wsf = fi.nvfp4_quantize(w, gw)
+        alpha = 1.0 / (ga * gw)
+        out = fi.mm_fp4(aq, wq.t(), asf, wsf, alpha, torch.bfloat16)
+        ad = e2m1_and_ufp8sf_scale_to_float(aq, asf, ga, 16, 1, True)
+        wd = e2m1_and_ufp8sf_scale_to_float(wq, wsf, gw, 16, 1, True)
+    else:
+        aq, asf = fi.mxfp4_quantize(a)
+        wq, wsf = fi.mxfp4_quantize(w)
+        out = fi.mm_fp4(aq, wq.t(), asf, wsf, None, torch.bfloat16, block_size=32, use_nvfp4=False)
+        ad = fi.mxfp4_dequantize(aq, asf)
+        wd = fi.mxfp4_dequantize(wq, wsf)
+    _check(out, ad @ wd.t())
+
+
+def test_gemm_fp8_groupwise():
+    m, n, k = 200, 512, 1024
+    a = torch.randn(m, k, device="cuda")
+    w = torch.randn(n, k, device="cuda")
+    sa = a.view(m, k // 128, 128).abs().amax(-1) / 448
+    a8 = (a.view(m, k // 128, 128) / sa[..., None]).view(m, k).to(torch.float8_e4m3fn)
+    sw = w.view(n // 128, 128, k // 128, 128).abs().amax((1, 3)) / 448
+    w8 = (w.view(n // 128, 128, k // 128, 128) / sw[:, None, :, None]).view(n, k).to(torch.float8_e4m3fn)
+    out = fi.gemm_fp8_nt_groupwise(a8, w8, sa, sw, "K", out_dtype=torch.bfloat16)
+    ref = a @ w.t()
+    assert torch.nn.functional.cosine_similarity(out.float().flatten(), ref.flatten(), dim=0) > 0.99

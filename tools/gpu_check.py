@@ -323,7 +323,77 @@ def case_mla_perf():
     return res
 
 
-CASES = {"mla_perf": case_mla_perf, "gemm_small": case_gemm_small, "prefill": case_prefill, "prefill_perf": case_prefill_perf, "gemm": case_gemm, "decode": case_decode, "decode_perf": case_decode_perf}
+def case_moe_perf():
+    """MoE pipeline + grouped GEMM throughput (DeepSeek-V3-like and Mixtral-like shapes) vs a torch loop."""
+    import torch
+    from flashinfer_b200.fused_moe import moe_forward, route
+    from flashinfer_b200.gemm import grouped_gemm_tiles
+
+    res = {}
+    for name, (T, E, K, H, I) in {"dsv3_ep8": (4096, 32, 8, 7168, 2048), "mixtral": (4096, 8, 2, 4096, 14336),
+                                  "dsv3_decode": (128, 32, 8, 7168, 2048)}.items():
+        x = (torch.randn(T, H, device="cuda") * 0.5).bfloat16()
+        w1 = (torch.randn(E, 2 * I, H, device="cuda") / H ** 0.5).bfloat16()
+        w2 = (torch.randn(E, H, I, device="cuda") / I ** 0.5).bfloat16()
+        ids, w = route(torch.randn(T, E, device="cuda"), None, K, 1)
+        ms = _time_ms(lambda: moe_forward(x, ids, w, w1, w2), iters=10, warmup=3)
+        flops = 2.0 * T * K * H * I * 3
+        # dense lower bound: one cuBLAS GEMM pair with the same FLOPs
+        a = torch.randn(T * K, H, device="cuda").bfloat16()
+        ms_cublas = _time_ms(lambda: ((a @ w1[0].t())[:, :I].contiguous() @ w2[0].t()), iters=10, warmup=3)
+        res[name] = {"ms": ms, "tflops": flops / ms / 1e9, "cublas_dense_same_flops_ms": ms_cublas}
+        # grouped GEMM alone (FC1 shape), all tiles full
+        rows = (T * K + 127) // 128 * 128
+        ap = torch.randn(rows, H, device="cuda").bfloat16()
+        te = (torch.arange(rows // 128, device="cuda") % E).int()
+        msg = _time_ms(lambda: grouped_gemm_tiles(ap, w1, te, None), iters=10, warmup=3)
+        res[name]["fc1_grouped_ms"] = msg
+        res[name]["fc1_grouped_tflops"] = 2.0 * rows * H * 2 * I / msg / 1e9
+        del x, w1, w2, a, ap
+    return res
+
+
+def case_lowp_perf():
+    """fp8 / mxfp8 / nvfp4 GEMM throughput (8192^3 and a decode shape) with forced and heuristic N tiles."""
+    import torch
+    import flashinfer_b200 as fi
+
+    res = {}
+    for (m, n, k) in [(8192, 8192, 8192), (4096, 14336, 4096), (64, 14336, 4096)]:
+        a = torch.randn(m, k, device="cuda", dtype=torch.bfloat16)
+        w = torch.randn(n, k, device="cuda", dtype=torch.bfloat16)
+        key = f"{m}x{n}x{k}"
+        res[key] = {}
+        flops = 2.0 * m * n * k
+        a8, w8 = a.to(torch.float8_e4m3fn), w.to(torch.float8_e4m3fn)
+        one = torch.ones(1, device="cuda")
+        aq8, asf8 = fi.mxfp8_quantize(a)
+        wq8, wsf8 = fi.mxfp8_quantize(w)
+        g = torch.tensor(1.0, device="cuda")
+        aq4, asf4 = fi.nvfp4_quantize(a, g)
+        wq4, wsf4 = fi.nvfp4_quantize(w, g)
+        for bn in [0, 128, 192, 224, 256]:
+            os.environ["FIB200_LOWP_BN"] = str(bn)
+            try:
+                t8 = _time_ms(lambda: fi.mm_fp8(a8, w8.t(), one), iters=10, warmup=3)
+                tm8 = _time_ms(lambda: fi.mm_mxfp8(aq8, wq8.t(), asf8, wsf8), iters=10, warmup=3)
+                t4 = _time_ms(lambda: fi.mm_fp4(aq4, wq4.t(), asf4, wsf4, one), iters=10, warmup=3)
+                res[key][f"bn{bn}"] = {"fp8_tflops": flops / t8 / 1e9, "mxfp8_tflops": flops / tm8 / 1e9,
+                                       "nvfp4_tflops": flops / t4 / 1e9, "fp8_ms": t8, "mxfp8_ms": tm8, "nvfp4_ms": t4}
+            except Exception as e:  # noqa: BLE001
+                res[key][f"bn{bn}"] = repr(e)[:300]
+        os.environ.pop("FIB200_LOWP_BN", None)
+        tb = _time_ms(lambda: torch.matmul(a, w.t()), iters=10, warmup=3)
+        res[key]["cublas_bf16_tflops"] = flops / tb / 1e9
+        try:
+            ts = _time_ms(lambda: torch._scaled_mm(a8, w8.t(), scale_a=one, scale_b=one, out_dtype=torch.bfloat16), iters=10, warmup=3)
+            res[key]["cublaslt_fp8_tflops"] = flops / ts / 1e9
+        except Exception as e:  # noqa: BLE001
+            res[key]["cublaslt_fp8_tflops"] = repr(e)[:200]
+    return res
+
+
+CASES = {"lowp_perf": case_lowp_perf, "moe_perf": case_moe_perf, "mla_perf": case_mla_perf, "gemm_small": case_gemm_small, "prefill": case_prefill, "prefill_perf": case_prefill_perf, "gemm": case_gemm, "decode": case_decode, "decode_perf": case_decode_perf}
 
 
 def main():
