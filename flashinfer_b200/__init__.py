@@ -104,3 +104,7 @@ from .fused_moe import (  # noqa: F401,E402
 )
 from .gemm import SegmentGEMMWrapper, grouped_mm_bf16  # noqa: F401,E402
 from .gemm import bmm_fp8, bmm_mxfp8, gemm_fp8_nt_groupwise, mm_fp4, mm_fp8, mm_mxfp8  # noqa: F401,E402
+from . import api_logging, autotuner, fi_trace, green_ctx, logits_processor, parallel_attention, profiler, testing, trace  # noqa: F401,E402
+from .autotuner import autotune  # noqa: F401,E402
+from .api_logging import flashinfer_api  # noqa: F401,E402
+from . import comm, mla, attention  # noqa: F401,E402

@@ -1,0 +1,191 @@
+"""API call logging / tensor dump / replay.  Parity: reference flashinfer/api_logging.py (@flashinfer_api :711-1075,
+dumps :1346-1700, replay_from_dump :2364, replay_sequence :2448).
+
+Environment:
+  FLASHINFER_LOGLEVEL   0 off (zero overhead: the decorator returns the function unchanged), 1 names,
+                        3 names + tensor metadata, 5 additionally min/max/mean/NaN/Inf statistics (computed by the
+                        native ``tensor_stats`` kernel; skipped while a CUDA graph is being captured)
+  FLASHINFER_LOGDEST    stdout | stderr | <file path, %i = pid>
+  FLASHINFER_DUMP_DIR   when set (and level >= 3) inputs are saved BEFORE the call (crash-safe) and outputs after;
+                        FLASHINFER_DUMP_INCLUDE / _EXCLUDE are fnmatch filters on the API name, FLASHINFER_DUMP_MAX_COUNT caps
+"""
+from __future__ import annotations
+
+import fnmatch
+import functools
+import inspect
+import json
+import os
+import sys
+import threading
+import time
+from typing import Any, Callable, Dict, List, Optional
+
+import torch
+
+_LEVEL = int(os.environ.get("FLASHINFER_LOGLEVEL", "0") or 0)
+_DEST = os.environ.get("FLASHINFER_LOGDEST", "stdout")
+_DUMP_DIR = os.environ.get("FLASHINFER_DUMP_DIR")
+_DUMP_MAX = int(os.environ.get("FLASHINFER_DUMP_MAX_COUNT", "1000"))
+_DUMP_INC = os.environ.get("FLASHINFER_DUMP_INCLUDE", "*")
+_DUMP_EXC = os.environ.get("FLASHINFER_DUMP_EXCLUDE", "")
+_lock = threading.Lock()
+_counter = 0
+_stream = None
+_REGISTRY: Dict[str, Callable] = {}
+
+
+def _out():
+    global _stream
+    if _stream is None:
+        if _DEST == "stdout":
+            _stream = sys.stdout
+        elif _DEST == "stderr":
+            _stream = sys.stderr
+        else:
+            _stream = open(_DEST.replace("%i", str(os.getpid())), "a")
+    return _stream
+
+
+def _log(msg: str) -> None:
+    with _lock:
+        s = _out()
+        s.write(f"[flashinfer_b200 {time.strftime('%H:%M:%S')}] {msg}\n")
+        s.flush()
+
+
+def _capturing() -> bool:
+    return torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
+
+
+def tensor_summary(t: torch.Tensor, level: int) -> str:
+    s = f"Tensor(shape={tuple(t.shape)}, dtype={str(t.dtype).replace('torch.', '')}, device={t.device}, stride={t.stride()}"
+    if level >= 5 and t.numel() and not _capturing() and (t.is_floating_point() or t.dtype in (torch.int32, torch.int64)):
+        try:
+            from .utils import tensor_stats
+
+            st = tensor_stats(t)
+            s += f", min={st['min']:.6g}, max={st['max']:.6g}, mean={st['mean']:.6g}, nan={st['nan']}, inf={st['inf']}"
+        except Exception as e:  # noqa: BLE001
+            s += f", stats_unavailable={type(e).__name__}"
+    return s + ")"
+
+
+def _fmt(v: Any, level: int) -> str:
+    if isinstance(v, torch.Tensor):
+        return tensor_summary(v, level)
+    if isinstance(v, (list, tuple)) and v and all(isinstance(x, torch.Tensor) for x in v):
+        return "[" + ", ".join(tensor_summary(x, level) for x in v) + "]"
+    r = repr(v)
+    return r if len(r) < 200 else r[:197] + "..."
+
+
+def _collect_tensors(bound: Dict[str, Any]) -> Dict[str, torch.Tensor]:
+    out = {}
+    for k, v in bound.items():
+        if isinstance(v, torch.Tensor):
+            out[k] = v
+        elif isinstance(v, (list, tuple)):
+            for i, x in enumerate(v):
+                if isinstance(x, torch.Tensor):
+                    out[f"{k}.{i}"] = x
+    return out
+
+
+def _dump(dirpath: str, tag: str, tensors: Dict[str, torch.Tensor], meta: Dict[str, Any]) -> None:
+    os.makedirs(dirpath, exist_ok=True)
+    torch.save({k: v.detach().cpu() for k, v in tensors.items()}, os.path.join(dirpath, f"{tag}.pt"))
+    with open(os.path.join(dirpath, f"{tag}.json"), "w") as f:
+        json.dump(meta, f, indent=1, default=repr)
+
+
+def flashinfer_api(fn: Optional[Callable] = None, *, name: Optional[str] = None):
+    """Decorator for public APIs.  Logs (and optionally dumps) the inputs before the call so that a crashing kernel
+    still leaves its arguments on disk."""
+
+    def deco(f: Callable) -> Callable:
+        api = name or f"{f.__module__.replace('flashinfer_b200.', '')}.{f.__qualname__}"
+        _REGISTRY[api] = f
+        if _LEVEL <= 0:
+            return f
+        sig = None
+
+        @functools.wraps(f)
+        def wrapper(*args, **kwargs):
+            nonlocal sig
+            global _counter
+            if _LEVEL == 1:
+                _log(api)
+                return f(*args, **kwargs)
+            if sig is None:
+                try:
+                    sig = inspect.signature(f)
+                except (TypeError, ValueError):
+                    sig = False
+            bound: Dict[str, Any] = {}
+            if sig:
+                try:
+                    ba = sig.bind(*args, **kwargs)
+                    bound = dict(ba.arguments)
+                except TypeError:
+                    bound = {f"arg{i}": a for i, a in enumerate(args)} | kwargs
+            bound.pop("self", None)
+            _log(f"{api}(" + ", ".join(f"{k}={_fmt(v, _LEVEL)}" for k, v in bound.items()) + ")")
+            dump_dir = None
+            if _DUMP_DIR and not _capturing() and fnmatch.fnmatch(api, _DUMP_INC) and not (_DUMP_EXC and fnmatch.fnmatch(api, _DUMP_EXC)):
+                with _lock:
+                    _counter += 1
+                    idx = _counter
+                if idx <= _DUMP_MAX:
+                    dump_dir = os.path.join(_DUMP_DIR, f"{idx:06d}_{api.replace('.', '_')}")
+                    meta = {"api": api, "index": idx, "scalars": {k: v for k, v in bound.items() if isinstance(v, (int, float, str, bool, type(None)))}}
+                    _dump(dump_dir, "inputs", _collect_tensors(bound), meta)
+            out = f(*args, **kwargs)
+            if _LEVEL >= 3:
+                _log(f"{api} -> {_fmt(out, _LEVEL)}")
+            if dump_dir is not None:
+                outs = out if isinstance(out, (list, tuple)) else [out]
+                _dump(dump_dir, "outputs", {f"out{i}": o for i, o in enumerate(outs) if isinstance(o, torch.Tensor)}, {"api": api})
+            return out
+
+        return wrapper
+
+    return deco(fn) if fn is not None else deco
+
+
+def replay_from_dump(dump_dir: str, device: str = "cuda", compare: bool = True, rtol: float = 1e-2, atol: float = 1e-2) -> Dict[str, Any]:
+    """Re-run one dumped call (functional APIs only) and compare against the dumped outputs."""
+    with open(os.path.join(dump_dir, "inputs.json")) as f:
+        meta = json.load(f)
+    fn = _REGISTRY.get(meta["api"])
+    if fn is None:
+        raise KeyError(f"API {meta['api']} is not registered in this process (import its module first)")
+    tensors = torch.load(os.path.join(dump_dir, "inputs.pt"))
+    kwargs: Dict[str, Any] = dict(meta.get("scalars", {}))
+    lists: Dict[str, Dict[int, torch.Tensor]] = {}
+    for k, v in tensors.items():
+        if "." in k:
+            base, i = k.rsplit(".", 1)
+            lists.setdefault(base, {})[int(i)] = v.to(device)
+        else:
+            kwargs[k] = v.to(device)
+    for base, d in lists.items():
+        kwargs[base] = [d[i] for i in sorted(d)]
+    out = fn(**kwargs)
+    res: Dict[str, Any] = {"api": meta["api"], "output": out}
+    ref_path = os.path.join(dump_dir, "outputs.pt")
+    if compare and os.path.exists(ref_path):
+        ref = torch.load(ref_path)
+        outs = out if isinstance(out, (list, tuple)) else [out]
+        ok = True
+        for i, o in enumerate(outs):
+            r = ref.get(f"out{i}")
+            if r is not None and isinstance(o, torch.Tensor):
+                ok = ok and torch.allclose(o.detach().float().cpu(), r.float(), rtol=rtol, atol=atol, equal_nan=True)
+        res["match"] = ok
+    return res
+
+
+def replay_sequence(root: str, device: str = "cuda", **kw) -> List[Dict[str, Any]]:
+    return [replay_from_dump(os.path.join(root, d), device, **kw) for d in sorted(os.listdir(root))
+            if os.path.isdir(os.path.join(root, d))]

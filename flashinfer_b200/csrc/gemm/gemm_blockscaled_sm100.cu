@@ -15,7 +15,7 @@
 // tcgen05.cp.32x128b.warpx4 source, so the scales go gmem -(bulk copy)-> smem -(tcgen05.cp)-> TMEM with no
 // register traffic; tcgen05.cp and tcgen05.mma execute in issue order, so one TMEM scale buffer suffices.
 // The N tile width is a run-time multiple of 32: a tile that does not start on a 128-row scale block simply
-// offsets the TMEM column of SFB by (n0 % 128) / 32.
+// offsets the TMEM column of SFB by (n0 % 128) / 32 (tiles are multiples of 64 rows -> offsets 0 or 2).
 #include <fib200/common.cuh>
 #include <fib200/ptx.cuh>
 
@@ -39,12 +39,12 @@ struct Geo {
   __host__ __device__ static Geo make(int BN, int kind) {
     Geo g;
     g.nchunk = kind == kNvFp4 ? 4 : (kind == kMxFp4 ? 2 : (kind == kMxFp8 ? 1 : 0));
-    g.rb = (BN % 128 == 0) ? BN / 128 : (BN + 127) / 128 + 1;
+    g.rb = (BN % 128 == 0) ? BN / 128 : (BN + 64 + 127) / 128;
     g.a_bytes = BM * BKB;
     g.b_bytes = BN * BKB;
     g.sfa_bytes = g.nchunk * 512;
     g.sfb_bytes = g.rb * g.nchunk * 512;
-    g.stage_bytes = g.a_bytes + g.b_bytes + g.sfa_bytes + g.sfb_bytes;
+    g.stage_bytes = (g.a_bytes + g.b_bytes + g.sfa_bytes + g.sfb_bytes + 1023) / 1024 * 1024;  // SWIZZLE_128B tiles need 1 KB alignment
     int st = (218 * 1024) / g.stage_bytes;
     g.stages = st > 8 ? 8 : st;
     g.bar_offset = g.stages * g.stage_bytes;
@@ -338,7 +338,7 @@ extern "C" int gemm_lowp_nt(void* A, void* B, void* C, void* sfa, void* sfb, voi
         const int64_t tiles = ((N + w - 1) / w) * tiles_m * batch;
         return double((tiles + sms - 1) / sms) * w;
       };
-      const int cands[4] = {256, 224, 192, 128};
+      const int cands[3] = {256, 192, 128};
       double best = 1e30;
       for (int c : cands) {
         if (kind != kFp8 && 2 * c + Geo::make(c, (int)kind).nchunk * 4 * (1 + Geo::make(c, (int)kind).rb) > 512 && c != 256) continue;
@@ -349,11 +349,14 @@ extern "C" int gemm_lowp_nt(void* A, void* B, void* C, void* sfa, void* sfb, voi
         }
       }
     } else {
-      BN = int((want + 31) / 32 * 32);
-      if (BN < 32) BN = 32;
+      // fp8 per-tensor: any multiple of 16; block-scaled: multiples of 64 (scale columns are consumed in 64-row units)
+      const int q = kind == kFp8 ? 32 : 64;
+      BN = int((want + q - 1) / q * q);
+      if (BN < q) BN = q;
     }
   }
   FIB_CHECK(BN % 32 == 0 && BN >= 32 && BN <= 256, "gemm_lowp: N tile must be a multiple of 32 in [32, 256]");
+  FIB_CHECK(kind == kFp8 || BN % 64 == 0, "gemm_lowp: block-scaled N tile must be a multiple of 64");
   const Geo G = Geo::make(BN, (int)kind);
   FIB_CHECK(G.stages >= 2 && G.tmem_cols <= 512, "gemm_lowp: tile does not fit");
 

@@ -86,7 +86,7 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int tm = t % num_m, tn = t / num_m;
+        const int tm = t / tiles_n, tn = t % tiles_n;
         const int e = tile_expert[tm];
         if (e < 0) continue;
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -109,7 +109,7 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int tm = t % num_m;
+      const int tm = t / tiles_n;
       if (tile_expert[tm] < 0) continue;
       ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       ptx::tc_fence_after();
@@ -144,7 +144,7 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int tm = t % num_m, tn = t / num_m;
+      const int tm = t / tiles_n, tn = t % tiles_n;
       if (tile_expert[tm] < 0) continue;
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();

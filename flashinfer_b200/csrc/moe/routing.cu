@@ -194,21 +194,45 @@ routing_kernel(const TL* __restrict__ logits, const float* __restrict__ bias, in
 // Builds the expert-grouped, tile-padded permutation.
 //   counts[e], offsets[e] (padded to `tile`), expanded_to_permuted[T*K] (-1 for non-local experts),
 //   permuted_to_token[P] (-1 padding), tile_expert[P / tile] (-1 unused), meta[0] = num tiles, meta[1] = padded rows
-__global__ void __launch_bounds__(1024)
-moe_sort_kernel(const int32_t* __restrict__ topk_ids, int T, int K, int E, int local_offset, int local_num, int tile,
-                int max_rows, int32_t* __restrict__ expanded_to_permuted, int32_t* __restrict__ permuted_to_token,
-                int32_t* __restrict__ tile_expert, int32_t* __restrict__ expert_offsets, int32_t* __restrict__ meta) {
+// Three small kernels (deterministic: rows of one expert keep ascending expanded-index order):
+//   count   : grid = chunks of 1024 expanded entries; per-chunk smem histogram -> chunk_hist[chunk][e]
+//   scan    : one CTA; per expert exclusive prefix over the chunks, padded expert offsets, tile_expert, meta
+//   scatter : grid = chunks; rank inside the chunk via warp match + warps taking turns on a smem cursor
+constexpr int kSortChunk = 1024;
+
+__global__ void __launch_bounds__(kSortChunk)
+moe_count_kernel(const int32_t* __restrict__ topk_ids, int n, int local_offset, int local_num,
+                 int32_t* __restrict__ chunk_hist) {
   extern __shared__ int sm[];
-  int* cnt = sm;               // [local_num]
-  int* off = sm + local_num;   // [local_num + 1]
-  int* cur = off + local_num + 1;
   ptx::grid_dep_wait();
-  for (int i = threadIdx.x; i < local_num; i += blockDim.x) cnt[i] = 0;
+  for (int i = threadIdx.x; i < local_num; i += blockDim.x) sm[i] = 0;
   __syncthreads();
-  const int n = T * K;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+  const int i = blockIdx.x * kSortChunk + threadIdx.x;
+  if (i < n) {
     const int e = topk_ids[i] - local_offset;
-    if (e >= 0 && e < local_num) atomicAdd(&cnt[e], 1);
+    if (e >= 0 && e < local_num) atomicAdd(&sm[e], 1);
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < local_num; e += blockDim.x) chunk_hist[int64_t(blockIdx.x) * local_num + e] = sm[e];
+  ptx::grid_dep_launch();
+}
+
+__global__ void __launch_bounds__(1024)
+moe_scan_kernel(int32_t* __restrict__ chunk_hist, int nchunks, int local_num, int tile, int max_rows,
+                int32_t* __restrict__ permuted_to_token, int32_t* __restrict__ tile_expert,
+                int32_t* __restrict__ expert_offsets, int32_t* __restrict__ meta) {
+  extern __shared__ int sm[];
+  int* cnt = sm;              // [local_num]
+  int* off = sm + local_num;  // [local_num + 1]
+  ptx::grid_dep_wait();
+  for (int e = threadIdx.x; e < local_num; e += blockDim.x) {
+    int acc = 0;
+    for (int c = 0; c < nchunks; ++c) {
+      const int v = chunk_hist[int64_t(c) * local_num + e];
+      chunk_hist[int64_t(c) * local_num + e] = acc;  // exclusive prefix: rows of earlier chunks
+      acc += v;
+    }
+    cnt[e] = acc;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -222,34 +246,55 @@ moe_sort_kernel(const int32_t* __restrict__ topk_ids, int T, int K, int E, int l
     meta[1] = acc;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < local_num; i += blockDim.x) {
-    cur[i] = 0;
-    expert_offsets[i] = off[i];
-  }
-  if (threadIdx.x == 0) expert_offsets[local_num] = off[local_num];
-  const int total = off[local_num];
-  for (int i = threadIdx.x; i < max_rows; i += blockDim.x) permuted_to_token[i] = -1;
+  for (int i = threadIdx.x; i <= local_num; i += blockDim.x) expert_offsets[i] = off[i];
   for (int i = threadIdx.x; i < max_rows / tile; i += blockDim.x) tile_expert[i] = -1;
   __syncthreads();
+  // per expert: tile -> expert map and the -1 padding rows at the tail of its last tile
+  for (int e = threadIdx.x >> 5; e < local_num; e += blockDim.x >> 5) {
+    const int lane = threadIdx.x & 31;
+    for (int r = off[e] + lane * tile; r < off[e + 1]; r += 32 * tile) tile_expert[r / tile] = e;
+    for (int r = off[e] + cnt[e] + lane; r < off[e + 1]; r += 32) permuted_to_token[r] = -1;
+  }
+  ptx::grid_dep_launch();
+}
+
+__global__ void __launch_bounds__(kSortChunk)
+moe_scatter_kernel(const int32_t* __restrict__ topk_ids, int n, int K, int local_offset, int local_num,
+                   const int32_t* __restrict__ chunk_base, const int32_t* __restrict__ expert_offsets,
+                   int32_t* __restrict__ expanded_to_permuted, int32_t* __restrict__ permuted_to_token) {
+  extern __shared__ int sm[];  // cursor[local_num]
+  ptx::grid_dep_wait();
   for (int e = threadIdx.x; e < local_num; e += blockDim.x)
-    for (int r = off[e]; r < off[e + 1]; r += tile) tile_expert[r / tile] = e;
-  // deterministic order inside an expert: ascending expanded index.  One thread per expert walks the list
-  // (T*K is small in serving; for large prefill batches the per-expert walk is still O(T*K / E * E)).
-  for (int e = threadIdx.x; e < local_num; e += blockDim.x) {
-    int pos = off[e];
-    for (int i = 0; i < n; ++i) {
-      if (topk_ids[i] - local_offset == e) {
-        expanded_to_permuted[i] = pos;
-        permuted_to_token[pos] = i / K;
-        ++pos;
-      }
+    sm[e] = expert_offsets[e] + chunk_base[int64_t(blockIdx.x) * local_num + e];
+  __syncthreads();
+  const int i = blockIdx.x * kSortChunk + threadIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int e = -1;
+  if (i < n) {
+    e = topk_ids[i] - local_offset;
+    if (e < 0 || e >= local_num) e = -1;
+  }
+  const uint32_t peers = __match_any_sync(0xffffffffu, e);
+  const int rank = __popc(peers & ((1u << lane) - 1));
+  const bool leader = rank == 0;
+  int base = 0;
+  for (int w = 0; w < kSortChunk / 32; ++w) {
+    if (w == warp && e >= 0 && leader) {
+      base = sm[e];
+      sm[e] = base + __popc(peers);
+    }
+    __syncthreads();
+  }
+  base = __shfl_sync(0xffffffffu, base, __ffs(peers) - 1);
+  if (i < n) {
+    if (e >= 0) {
+      const int pos = base + rank;
+      expanded_to_permuted[i] = pos;
+      permuted_to_token[pos] = i / K;
+    } else {
+      expanded_to_permuted[i] = -1;
     }
   }
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const int e = topk_ids[i] - local_offset;
-    if (e < 0 || e >= local_num) expanded_to_permuted[i] = -1;
-  }
-  (void)total;
   ptx::grid_dep_launch();
 }
 
@@ -346,16 +391,33 @@ extern "C" int moe_routing(void* logits, void* bias, void* topk_ids, void* topk_
   return 0;
 }
 
+// workspace: int32 [ceil(T*K / 1024) * local_num]
 extern "C" int moe_sort(void* topk_ids, int64_t T, int64_t K, int64_t E, int64_t local_offset, int64_t local_num,
                         int64_t tile, int64_t max_rows, void* expanded_to_permuted, void* permuted_to_token,
-                        void* tile_expert, void* expert_offsets, void* meta, int64_t pdl, int64_t stream_) {
+                        void* tile_expert, void* expert_offsets, void* meta, void* workspace, int64_t pdl,
+                        int64_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  const size_t smem = (3 * local_num + 2) * sizeof(int);
-  LaunchCfg lc(dim3(1), dim3(1024), smem, stream, pdl != 0);
-  FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, moe_sort_kernel, (const int32_t*)topk_ids, (int)T, (int)K, (int)E,
-                                    (int)local_offset, (int)local_num, (int)tile, (int)max_rows,
-                                    (int32_t*)expanded_to_permuted, (int32_t*)permuted_to_token, (int32_t*)tile_expert,
-                                    (int32_t*)expert_offsets, (int32_t*)meta));
+  const int n = (int)(T * K);
+  const int nchunks = n > 0 ? (n + kSortChunk - 1) / kSortChunk : 0;
+  (void)E;
+  if (nchunks > 0) {
+    LaunchCfg lc(dim3(nchunks), dim3(kSortChunk), local_num * sizeof(int), stream, pdl != 0);
+    FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, moe_count_kernel, (const int32_t*)topk_ids, n, (int)local_offset,
+                                      (int)local_num, (int32_t*)workspace));
+  }
+  {
+    LaunchCfg lc(dim3(1), dim3(1024), (2 * local_num + 1) * sizeof(int), stream, pdl != 0);
+    FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, moe_scan_kernel, (int32_t*)workspace, nchunks, (int)local_num, (int)tile,
+                                      (int)max_rows, (int32_t*)permuted_to_token, (int32_t*)tile_expert,
+                                      (int32_t*)expert_offsets, (int32_t*)meta));
+  }
+  if (nchunks > 0) {
+    LaunchCfg lc(dim3(nchunks), dim3(kSortChunk), local_num * sizeof(int), stream, pdl != 0);
+    FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, moe_scatter_kernel, (const int32_t*)topk_ids, n, (int)K,
+                                      (int)local_offset, (int)local_num, (const int32_t*)workspace,
+                                      (const int32_t*)expert_offsets, (int32_t*)expanded_to_permuted,
+                                      (int32_t*)permuted_to_token));
+  }
   return 0;
 }
 

@@ -184,8 +184,9 @@ def moe_forward(x: torch.Tensor, topk_ids: torch.Tensor, topk_w: torch.Tensor, w
     meta = torch.empty(4, dtype=torch.int32, device=dev)
     st = stream_ptr(x)
     ids = topk_ids.to(torch.int32).contiguous()
+    ws = torch.empty(((T * K + 1023) // 1024) * e_local + 1, dtype=torch.int32, device=dev)
     mod.call("moe_sort", ids, T, K, num_experts or e_local, local_expert_offset, e_local, _TILE, max_rows, e2p, p2t,
-             tile_e, offs, meta, 1, st)
+             tile_e, offs, meta, ws, 1, st)
     xp = torch.empty(max_rows, H, dtype=x.dtype, device=dev)
     mod.call("moe_gather", x, xp, p2t, meta, max_rows, H, x.stride(0), dtype_code(x.dtype), 1, st)
     h1 = torch.empty(max_rows, n1, dtype=x.dtype, device=dev)

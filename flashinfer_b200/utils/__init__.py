@@ -148,3 +148,22 @@ def device_support_pdl(device=None) -> bool:
         return False
     major, _ = torch.cuda.get_device_capability(device)
     return major >= 9
+
+
+def tensor_stats(t: torch.Tensor) -> dict:
+    """min / max / mean / NaN count / Inf count in one pass (native kernel on CUDA; used by API logging level 5)."""
+    n = t.numel()
+    if not t.is_cuda or t.dtype not in (torch.float16, torch.bfloat16, torch.float32):
+        f = t.detach().float().flatten()
+        fin = f[torch.isfinite(f)]
+        return {"min": float(fin.min()) if fin.numel() else float("nan"), "max": float(fin.max()) if fin.numel() else float("nan"),
+                "mean": float(fin.mean()) if fin.numel() else float("nan"), "nan": int(torch.isnan(f).sum()),
+                "inf": int(torch.isinf(f).sum())}
+    from .. import jit
+
+    out = torch.tensor([float("inf"), float("-inf"), 0.0, 0.0, 0.0, float("inf")], dtype=torch.float32, device=t.device)
+    x = t.contiguous()
+    jit.load("runtime").call("tensor_stats", x, n, dtype_code(x.dtype), out, stream_ptr(x))
+    o = out.tolist()
+    finite = max(n - int(o[3]) - int(o[4]), 1)
+    return {"min": o[5], "max": o[1], "mean": o[2] / finite, "nan": int(o[3]), "inf": int(o[4])}

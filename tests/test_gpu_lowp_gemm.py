@@ -22,7 +22,10 @@ def _check(out, ref, tol=8e-3):
     assert err <= tol * max(ref.abs().max().item(), 1e-3), (err, ref.abs().max().item())
 
 
-@pytest.fixture(params=[0, 32, 96, 128, 192, 224, 256])
+_BNS = [int(os.environ["FIB200_LOWP_BN_TEST"])] if "FIB200_LOWP_BN_TEST" in os.environ else [128, 256, 64, 192, 0]
+
+
+@pytest.fixture(params=_BNS)
 def bn(request):
     old = os.environ.get("FIB200_LOWP_BN")
     os.environ["FIB200_LOWP_BN"] = str(request.param)
