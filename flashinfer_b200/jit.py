@@ -142,7 +142,7 @@ register(ModuleSpec("gemm_blockscaled_sm100", ["gemm/gemm_blockscaled_sm100.cu"]
 register(ModuleSpec("grouped_gemm_sm100", ["gemm/grouped_gemm_sm100.cu"]))
 register(ModuleSpec("moe", ["moe/routing.cu"]))
 register(ModuleSpec("comm_allreduce", ["comm/allreduce.cu"]))
-register(ModuleSpec("comm_alltoall", ["comm/moe_alltoall.cu"]))
+register(ModuleSpec("comm_alltoall", ["comm/moe_a2a.cu"]))
 register(ModuleSpec("gemm_comm_sm100", ["comm/gemm_allreduce_sm100.cu"]))
 
 

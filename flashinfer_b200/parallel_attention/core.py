@@ -7,6 +7,7 @@ import torch
 import torch.distributed as dist
 
 from ..cascade import merge_state
+from ..comm._p2p import all_to_all_uneven
 from ..prefill import single_prefill_with_kv_cache
 
 
@@ -113,7 +114,7 @@ def _a2a_seq_to_head(x: torch.Tensor, group, lens: Optional[List[int]]) -> torch
         dist.all_to_all_single(out, xs, group=group)
         return out.reshape(P * S, H // P, D)
     outs = [torch.empty(n, H // P, D, dtype=x.dtype, device=x.device) for n in lens]
-    dist.all_to_all(outs, [xs[i] for i in range(P)], group=group)
+    all_to_all_uneven(outs, [xs[i].contiguous() for i in range(P)], group)
     return torch.cat(outs, 0)
 
 
@@ -132,7 +133,7 @@ def _a2a_head_to_seq(o: torch.Tensor, group, lens: Optional[List[int]], rank: in
     chunks = list(torch.split(o, lens, 0))
     S = lens[rank]
     outs = [torch.empty(S, Hp, D, dtype=o.dtype, device=o.device) for _ in range(P)]
-    dist.all_to_all(outs, [c.contiguous() for c in chunks], group=group)
+    all_to_all_uneven(outs, [c.contiguous() for c in chunks], group)
     return torch.stack(outs, 1).reshape(S, P * Hp, D)
 
 
