@@ -11,3 +11,33 @@ from .moe_alltoall import (  # noqa: F401,E402
     moe_a2a_sanitize_expert_ids,
     moe_a2a_wrap_payload_tensor_in_workspace,
 )
+from .compat import (  # noqa: F401,E402
+    AllReduceFusionOp,
+    AllReduceFusionPattern,
+    AllReduceFusionWorkspace,
+    AllReduceStrategyConfig,
+    AllReduceStrategyType,
+    MNNVLAllReduceFusionWorkspace,
+    QuantizationSFLayout,
+    TRTLLMAllReduceFusionWorkspace,
+    allreduce_fusion,
+    compute_fp4_swizzled_layout_sf_size,
+    create_allreduce_fusion_workspace,
+    trtllm_allreduce_fusion,
+    trtllm_create_ipc_workspace_for_all_reduce,
+    trtllm_create_ipc_workspace_for_all_reduce_fusion,
+    trtllm_custom_all_reduce,
+    trtllm_destroy_ipc_workspace_for_all_reduce,
+    trtllm_destroy_ipc_workspace_for_all_reduce_fusion,
+    trtllm_lamport_initialize,
+    trtllm_lamport_initialize_all,
+    trtllm_moe_allreduce_fusion,
+    trtllm_moe_finalize_allreduce_fusion,
+    vllm_all_reduce,
+    vllm_dispose,
+    vllm_get_graph_buffer_ipc_meta,
+    vllm_init_custom_ar,
+    vllm_meta_size,
+    vllm_register_buffer,
+    vllm_register_graph_buffers,
+)

@@ -1,0 +1,338 @@
+"""Reference-named communication API on top of the NVLS / NVLink kernels of this package.
+
+Parity: reference flashinfer/comm/trtllm_ar.py (enums :37-113, workspace creation :430-760, trtllm_custom_all_reduce
+:809, trtllm_allreduce_fusion :951, trtllm_moe_allreduce_fusion :1062, trtllm_moe_finalize_allreduce_fusion :1140),
+flashinfer/comm/allreduce.py (AllReduceFusionWorkspace, create_allreduce_fusion_workspace :286, allreduce_fusion :460),
+flashinfer/comm/vllm_ar.py (:94-145) and flashinfer/comm/trtllm_mnnvl_ar.py.
+
+The reference exposes three generations of workspaces (IPC buffers + Lamport flags, MNNVL multicast, vLLM signal
+buffers).  Here every one of them is a :class:`TPCommunicator` (one symmetric heap with a multicast alias); the
+"workspace" objects returned by the creation functions simply own it, so reference call sites keep working.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple, Union
+
+import torch
+import torch.distributed as dist
+
+from .allreduce import TPCommunicator
+
+
+class AllReduceStrategyType:
+    NCCL = 0
+    MIN_LATENCY = 1
+    UB = 2
+    AUTO = 3
+    ONESHOT = 4
+    TWOSHOT = 5
+    LOWPRECISION = 6
+    MNNVL = 7
+
+
+class AllReduceStrategyConfig:
+    USE_MEMCPY = 1 << 0
+    PUSH_MODE = 1 << 1
+
+
+class AllReduceFusionOp:
+    NONE = 0
+    RESIDUAL_RMS_NORM = 1
+    LAST_PROCESS_FOR_UB = 2
+    RESIDUAL_RMS_PREPOST_NORM = 3
+    RESIDUAL_RMS_NORM_QUANT_FP8 = 4
+    RESIDUAL_RMS_NORM_QUANT_NVFP4 = 5
+    RESIDUAL_RMS_NORM_OUT_QUANT_FP8 = 6
+    RESIDUAL_RMS_NORM_OUT_QUANT_NVFP4 = 7
+    MOE_ALLREDUCE_RESIDUAL_RMS_NORM = 8
+    MOE_FINALIZE_ALLREDUCE_RESIDUAL_RMS_NORM = 9
+
+
+class AllReduceFusionPattern:
+    kAllReduce = 0
+    kARResidualRMSNorm = 1
+    kARResidualRMSNormFP8Quant = 2
+    kARResidualRMSNormFP4Quant = 3
+    kARResidualRMSNormOutFP8Quant = 4
+    kARResidualRMSNormOutFP4Quant = 5
+    kMoEReductionARResidualRMSNorm = 6
+    kMoEFinalizeARResidualRMSNorm = 7
+    kARResidualRMSNormPerTokenGroupFP8PackedQuant = 8
+    kARResidualRMSNormOutPerTokenGroupFP8PackedQuant = 9
+
+
+class QuantizationSFLayout:
+    SWIZZLED_128x4 = 0
+    SWIZZLED_8x4 = 1
+    LINEAR = 2
+
+
+def compute_fp4_swizzled_layout_sf_size(total_row: int, total_column: int) -> int:
+    return (total_row + 127) // 128 * 128 * ((total_column + 3) // 4 * 4)
+
+
+# ------------------------------------------------------------------ workspaces
+class AllReduceFusionWorkspace:
+    """Owns the symmetric heap + signal pads for one TP group."""
+
+    backend = "nvls"
+
+    def __init__(self, world_size: int, rank: int, max_token_num: int, hidden_dim: int, dtype: torch.dtype = torch.bfloat16,
+                 group: Optional[dist.ProcessGroup] = None) -> None:
+        self.world_size, self.rank = world_size, rank
+        self.max_token_num, self.hidden_dim, self.dtype = max_token_num, hidden_dim, dtype
+        self.comm = TPCommunicator(group, max_token_num, hidden_dim, dtype)
+        self._destroyed = False
+
+    def is_buffer_size_sufficient(self, token_num: int, hidden_dim: int, tp_size: Optional[int] = None,
+                                  dtype: Optional[torch.dtype] = None) -> bool:
+        esz = torch.empty(0, dtype=dtype or self.dtype).element_size()
+        cap = self.max_token_num * self.hidden_dim * torch.empty(0, dtype=self.dtype).element_size()
+        return token_num * hidden_dim * esz <= cap and hidden_dim == self.hidden_dim
+
+    def destroy(self) -> None:
+        self._destroyed = True
+        self.comm = None
+
+    @property
+    def metadata(self) -> dict:
+        return {"tp_size": self.world_size, "tp_rank": self.rank, "max_token_num": self.max_token_num,
+                "hidden_dim": self.hidden_dim, "dtype": str(self.dtype)}
+
+
+class TRTLLMAllReduceFusionWorkspace(AllReduceFusionWorkspace):
+    backend = "trtllm"
+
+
+class MNNVLAllReduceFusionWorkspace(AllReduceFusionWorkspace):
+    backend = "mnnvl"
+
+
+def create_allreduce_fusion_workspace(backend: str = "auto", world_size: Optional[int] = None, rank: Optional[int] = None,
+                                      max_token_num: Optional[int] = None, hidden_dim: Optional[int] = None,
+                                      dtype: Optional[torch.dtype] = None, gpus_per_node: Optional[int] = None,
+                                      comm_backend=None, force_oneshot_support: bool = False,
+                                      group: Optional[dist.ProcessGroup] = None) -> AllReduceFusionWorkspace:
+    g = group if group is not None else dist.group.WORLD
+    world_size = world_size or dist.get_world_size(g)
+    rank = dist.get_rank(g) if rank is None else rank
+    cls = {"trtllm": TRTLLMAllReduceFusionWorkspace, "mnnvl": MNNVLAllReduceFusionWorkspace}.get(backend, AllReduceFusionWorkspace)
+    return cls(world_size, rank, max_token_num, hidden_dim, dtype or torch.bfloat16, g)
+
+
+def trtllm_create_ipc_workspace_for_all_reduce_fusion(tp_rank: int, tp_size: int, max_token_num: int, hidden_dim: int,
+                                                      use_fp32_lamport: bool = False, group: Optional[dist.ProcessGroup] = None,
+                                                      create_metadata: bool = False, dtype: torch.dtype = torch.bfloat16):
+    """Returns ``(handles, workspace)`` like the reference; ``workspace`` is the object to pass as ``workspace_ptrs``."""
+    ws = TRTLLMAllReduceFusionWorkspace(tp_size, tp_rank, max_token_num, hidden_dim, dtype, group)
+    if create_metadata:
+        return [ws], ws, ws.metadata
+    return [ws], ws
+
+
+def trtllm_destroy_ipc_workspace_for_all_reduce_fusion(workspace, group=None) -> None:
+    for w in (workspace if isinstance(workspace, (list, tuple)) else [workspace]):
+        w.destroy()
+
+
+trtllm_create_ipc_workspace_for_all_reduce = trtllm_create_ipc_workspace_for_all_reduce_fusion
+trtllm_destroy_ipc_workspace_for_all_reduce = trtllm_destroy_ipc_workspace_for_all_reduce_fusion
+
+
+def trtllm_lamport_initialize(buffer_ptr: int, size: int, dtype: torch.dtype) -> None:
+    """No-op: the NVLS kernels use epoch barriers instead of Lamport sentinels, nothing needs re-initialising."""
+
+
+def trtllm_lamport_initialize_all(buffer_0_ptr: int, buffer_1_ptr: int, buffer_2_ptr: int, size: int, dtype: torch.dtype) -> None:
+    """No-op (see :func:`trtllm_lamport_initialize`)."""
+
+
+# ------------------------------------------------------------------ fused all-reduce entry points
+def _quant_after(norm: torch.Tensor, pattern: int, quant_out, scale_out, scale_factor, layout_code):
+    P = AllReduceFusionPattern
+    if pattern in (P.kARResidualRMSNormFP8Quant, P.kARResidualRMSNormOutFP8Quant):
+        s = scale_factor if isinstance(scale_factor, torch.Tensor) else torch.tensor(float(scale_factor or 1.0), device=norm.device)
+        q = (norm.float() / s.float()).clamp(-448, 448).to(torch.float8_e4m3fn)
+        if quant_out is not None:
+            quant_out.copy_(q.view(quant_out.shape))
+        return q
+    if pattern in (P.kARResidualRMSNormFP4Quant, P.kARResidualRMSNormOutFP4Quant):
+        from ..quantization.fp4 import SfLayout, nvfp4_quantize
+
+        gs = scale_factor if isinstance(scale_factor, torch.Tensor) else torch.tensor(float(scale_factor or 1.0), device=norm.device)
+        lay = SfLayout.layout_linear if layout_code == QuantizationSFLayout.LINEAR else SfLayout.layout_128x4
+        q, sf = nvfp4_quantize(norm, gs, sfLayout=lay)
+        if quant_out is not None:
+            quant_out.view(torch.uint8).reshape(-1)[: q.numel()].copy_(q.view(torch.uint8).reshape(-1))
+        if scale_out is not None:
+            scale_out.view(torch.uint8).reshape(-1)[: sf.numel()].copy_(sf.view(torch.uint8).reshape(-1))
+        return q
+    return None
+
+
+def allreduce_fusion(input: torch.Tensor, workspace: AllReduceFusionWorkspace, pattern: int, launch_with_pdl: bool = False,
+                     trigger_completion_at_end: bool = True, output: Optional[torch.Tensor] = None,
+                     residual_out: Optional[torch.Tensor] = None, norm_out: Optional[torch.Tensor] = None,
+                     quant_out: Optional[torch.Tensor] = None, scale_out: Optional[torch.Tensor] = None,
+                     residual_in: Optional[torch.Tensor] = None, rms_gamma: Optional[torch.Tensor] = None, rms_eps: float = 1e-6,
+                     scale_factor: Optional[Union[torch.Tensor, float]] = None, layout_code: Optional[int] = None,
+                     use_oneshot: Optional[bool] = None, fp32_acc: bool = False, **moe_kwargs) -> torch.Tensor:
+    """Unified fused all-reduce (patterns 0-5): sum over ranks [+ residual add + RMSNorm [+ fp8 / nvfp4 quant]]."""
+    P = AllReduceFusionPattern
+    comm = workspace.comm
+    tokens, hidden = input.shape
+    if pattern == P.kAllReduce:
+        res = comm.allreduce_add_rmsnorm(input, None, None, out=output, enable_pdl=launch_with_pdl)
+        return res
+    if pattern in (P.kMoEReductionARResidualRMSNorm, P.kMoEFinalizeARResidualRMSNorm):
+        raise ValueError("use trtllm_moe_allreduce_fusion / trtllm_moe_finalize_allreduce_fusion for MoE patterns")
+    if residual_in is None or rms_gamma is None:
+        raise ValueError("residual_in and rms_gamma are required for the RMSNorm patterns")
+    # one-shot keeps the residual replicated (reference semantics); the token-sharded two-shot flavour is exposed by
+    # TPCommunicator directly because it changes the residual layout
+    res = residual_in if residual_out is None else residual_out
+    if residual_out is not None and residual_out.data_ptr() != residual_in.data_ptr():
+        residual_out.copy_(residual_in)
+    norm = comm.allreduce_add_rmsnorm(input, res, rms_gamma, rms_eps, out=norm_out, two_shot=False, enable_pdl=launch_with_pdl)
+    q = _quant_after(norm, pattern, quant_out, scale_out, scale_factor, layout_code)
+    return q if q is not None and norm_out is None else norm
+
+
+def trtllm_allreduce_fusion(allreduce_in: torch.Tensor, world_size: int, world_rank: int, token_num: int, hidden_dim: int,
+                            workspace_ptrs, launch_with_pdl: bool, trigger_completion_at_end: bool, fp32_acc: bool,
+                            pattern_code: int, use_oneshot: Optional[bool], allreduce_out: Optional[torch.Tensor],
+                            residual_in: Optional[torch.Tensor], residual_out: Optional[torch.Tensor],
+                            norm_out: Optional[torch.Tensor], quant_out: Optional[torch.Tensor],
+                            scale_out: Optional[torch.Tensor], rms_gamma: Optional[torch.Tensor], rms_eps: Optional[float],
+                            scale_factor=None, layout_code=None, metadata: Optional[dict] = None,
+                            block_quant_group_size: Optional[int] = None) -> None:
+    ws = workspace_ptrs[0] if isinstance(workspace_ptrs, (list, tuple)) else workspace_ptrs
+    x = allreduce_in.view(token_num, hidden_dim)
+    if pattern_code == AllReduceFusionPattern.kAllReduce:
+        allreduce_fusion(x, ws, pattern_code, launch_with_pdl, output=allreduce_out.view(token_num, hidden_dim) if allreduce_out is not None else None)
+        return
+    if norm_out is None:
+        norm_out = torch.empty_like(x)
+    allreduce_fusion(x, ws, pattern_code, launch_with_pdl, trigger_completion_at_end, None,
+                     residual_out.view(token_num, hidden_dim) if residual_out is not None else None,
+                     norm_out.view(token_num, hidden_dim), quant_out, scale_out,
+                     residual_in.view(token_num, hidden_dim) if residual_in is not None else None, rms_gamma,
+                     rms_eps if rms_eps is not None else 1e-6, scale_factor, layout_code, use_oneshot, fp32_acc)
+    if allreduce_out is not None and residual_out is not None and residual_in is not None:
+        allreduce_out.view(token_num, hidden_dim).copy_((residual_out.view(token_num, hidden_dim).float() -
+                                                         residual_in.view(token_num, hidden_dim).float()).to(allreduce_out.dtype))
+
+
+def trtllm_custom_all_reduce(inp: torch.Tensor, world_size: int, world_rank: int, token_num: int, hidden_dim: int,
+                             workspace_ptrs, launch_with_pdl: bool = False, flag_value: int = 0,
+                             peer_comm_buffer_ptrs=None, peer_barrier_ptrs_in=None, peer_barrier_ptrs_out=None,
+                             bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
+                             weight: Optional[torch.Tensor] = None, weight_pre_residual_norm=None, eps: Optional[float] = None,
+                             intermediate_buffer=None, lamport_peer_comm_buffer_ptrs_0=None, lamport_peer_comm_buffer_ptrs_1=None,
+                             lamport_peer_comm_buffer_ptrs_2=None, out: Optional[torch.Tensor] = None, strategy_code=None,
+                             config_code=None, fusion_op_code: int = AllReduceFusionOp.NONE) -> torch.Tensor:
+    ws = workspace_ptrs[0] if isinstance(workspace_ptrs, (list, tuple)) else workspace_ptrs
+    x = inp.view(token_num, hidden_dim)
+    if fusion_op_code == AllReduceFusionOp.RESIDUAL_RMS_NORM:
+        if bias is not None:
+            x = x + bias
+        return ws.comm.allreduce_add_rmsnorm(x, residual.view(token_num, hidden_dim), weight, eps or 1e-6,
+                                             out=out.view(token_num, hidden_dim) if out is not None else None, two_shot=False)
+    return ws.comm.allreduce_add_rmsnorm(x, None, None, out=out.view(token_num, hidden_dim) if out is not None else None)
+
+
+# ------------------------------------------------------------------ MoE fusions
+def trtllm_moe_allreduce_fusion(world_size: int, world_rank: int, token_num: int, hidden_dim: int, workspace_ptrs,
+                                launch_with_pdl: bool, residual_in: torch.Tensor, rms_gamma: torch.Tensor, rms_eps: float,
+                                scale_factor, moe_reduction_device_num_experts: int, moe_reduction_scale_input: torch.Tensor,
+                                moe_reduction_active_experts_token_input: torch.Tensor, moe_reduction_token_input: torch.Tensor,
+                                layout_code=None, moe_allreduce_out: Optional[torch.Tensor] = None,
+                                residual_out: Optional[torch.Tensor] = None, norm_out: Optional[torch.Tensor] = None,
+                                quant_out: Optional[torch.Tensor] = None, scale_out: Optional[torch.Tensor] = None) -> None:
+    """``x = sum_e scale[e, t] * active_experts_token[e, t, :] + token_input[t, :]`` reduced locally, then the fused
+    all-reduce + residual + RMSNorm (reference trtllm_ar.py:1062)."""
+    ws = workspace_ptrs[0] if isinstance(workspace_ptrs, (list, tuple)) else workspace_ptrs
+    E = moe_reduction_device_num_experts
+    act = moe_reduction_active_experts_token_input.view(E, token_num, hidden_dim).float()
+    sc = moe_reduction_scale_input.view(E, token_num).float()
+    x = (act * sc[..., None]).sum(0) + moe_reduction_token_input.view(token_num, hidden_dim).float()
+    x = x.to(residual_in.dtype)
+    res = residual_out if residual_out is not None else residual_in.clone()
+    if residual_out is not None:
+        residual_out.copy_(residual_in)
+    norm = ws.comm.allreduce_add_rmsnorm(x, res.view(token_num, hidden_dim), rms_gamma, rms_eps,
+                                         out=norm_out.view(token_num, hidden_dim) if norm_out is not None else None, two_shot=False)
+    if moe_allreduce_out is not None:
+        moe_allreduce_out.view(token_num, hidden_dim).copy_((res.view(token_num, hidden_dim).float() - residual_in.view(token_num, hidden_dim).float()).to(moe_allreduce_out.dtype))
+    if quant_out is not None:
+        _quant_after(norm, AllReduceFusionPattern.kARResidualRMSNormFP4Quant, quant_out, scale_out, scale_factor, layout_code)
+
+
+def trtllm_moe_finalize_allreduce_fusion(allreduce_in: torch.Tensor, residual_in: torch.Tensor, norm_weight: torch.Tensor,
+                                         expanded_idx_to_permuted_idx: torch.Tensor, norm_out: torch.Tensor,
+                                         residual_out: torch.Tensor, launch_with_pdl: bool, workspace, world_rank: int,
+                                         world_size: int, eps: float, shared_expert_output: Optional[torch.Tensor] = None,
+                                         expert_scale_factor: Optional[torch.Tensor] = None, quant_out=None, scale_out=None,
+                                         scale_factor=None, layout_code=None) -> None:
+    """MoE finalize (top-k weighted un-permute, native kernel) + shared-expert add, then AR + residual + RMSNorm."""
+    from .. import jit
+    from ..utils import dtype_code, stream_ptr
+
+    ws = workspace[0] if isinstance(workspace, (list, tuple)) else workspace
+    T, K = expanded_idx_to_permuted_idx.shape
+    H = allreduce_in.shape[-1]
+    x = torch.empty(T, H, dtype=allreduce_in.dtype, device=allreduce_in.device) if shared_expert_output is None \
+        else shared_expert_output.clone().view(T, H)
+    w = expert_scale_factor.float().contiguous() if expert_scale_factor is not None else torch.ones(T, K, device=x.device)
+    jit.load("moe").call("moe_finalize", allreduce_in.contiguous(), x, expanded_idx_to_permuted_idx.int().contiguous(), w, T, K, H,
+                         0 if shared_expert_output is None else 1, dtype_code(x.dtype), 1, stream_ptr(x))
+    residual_out.copy_(residual_in)
+    norm = ws.comm.allreduce_add_rmsnorm(x, residual_out.view(T, H), norm_weight, eps, out=norm_out.view(T, H), two_shot=False)
+    if quant_out is not None:
+        _quant_after(norm, AllReduceFusionPattern.kARResidualRMSNormFP4Quant, quant_out, scale_out, scale_factor, layout_code)
+
+
+# ------------------------------------------------------------------ vLLM-style custom all-reduce
+_VLLM: dict = {}
+
+
+def vllm_meta_size() -> int:
+    return 0
+
+
+def vllm_init_custom_ar(ipc_tensors=None, rank_data: Optional[torch.Tensor] = None, rank: int = 0, full_nvlink: bool = True,
+                        group: Optional[dist.ProcessGroup] = None, max_size: int = 8 << 20, hidden: int = 4096,
+                        dtype: torch.dtype = torch.bfloat16) -> int:
+    """Returns an opaque handle.  Buffers do not need to be IPC-registered: inputs are staged into the symmetric heap."""
+    esz = torch.empty(0, dtype=dtype).element_size()
+    comm = TPCommunicator(group, max(1, max_size // (hidden * esz)), hidden, dtype)
+    h = len(_VLLM) + 1
+    _VLLM[h] = comm
+    return h
+
+
+def vllm_dispose(fa: int) -> None:
+    _VLLM.pop(fa, None)
+
+
+def vllm_all_reduce(fa: int, inp: torch.Tensor, out: torch.Tensor, reg_buffer: int = 0, reg_buffer_sz_bytes: int = 0,
+                    num_ctas: int = 0) -> None:
+    comm = _VLLM[fa]
+    flat = inp.reshape(-1)
+    if flat.numel() % comm.hidden == 0 and inp.dtype == comm.dtype:
+        res = comm.allreduce_add_rmsnorm(flat.view(-1, comm.hidden), None, None)
+        out.copy_(res.view(out.shape))
+    else:
+        out.copy_(comm.all_reduce(inp))
+
+
+def vllm_register_buffer(fa: int, fake_ipc_ptrs: List[int]) -> None:
+    """No-op: any tensor can be reduced (staged through the symmetric heap)."""
+
+
+def vllm_register_graph_buffers(fa: int, handles: List[List[int]], offsets: List[List[int]]) -> None:
+    """No-op: epochs live in device memory, so captured graphs replay without buffer registration."""
+
+
+def vllm_get_graph_buffer_ipc_meta(fa: int) -> Tuple[List[int], List[int]]:
+    return [], []
