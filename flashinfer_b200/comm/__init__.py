@@ -41,3 +41,16 @@ from .compat import (  # noqa: F401,E402
     vllm_register_buffer,
     vllm_register_graph_buffers,
 )
+from .collectives import (  # noqa: F401,E402
+    MixedCommHandler,
+    MixedCommMode,
+    MixedCommOp,
+    NVLSCollectives,
+    decode_cp_a2a_allocate_mnnvl_workspace,
+    decode_cp_a2a_alltoall,
+    decode_cp_a2a_init_workspace,
+    decode_cp_a2a_workspace_size,
+    run_mixed_comm,
+)
+from .gemm_allreduce import GemmAllReduce, gemm_allreduce  # noqa: F401,E402
+from .all_gather_matmul import AllGatherMatmul, all_gather_matmul  # noqa: F401,E402

@@ -1,0 +1,100 @@
+"""Fused GEMM + all-reduce (row-parallel linear of tensor parallelism) in ONE kernel per rank.
+
+Parity: reference flashinfer/cute_dsl/gemm_allreduce_two_shot.py (G17) and its test
+tests/gemm/test_cute_dsl_gemm_allreduce_two_shot.py.  Kernel: csrc/gemm/gemm_allreduce_sm100.cu.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from .. import jit
+from ..utils import dtype_code, stream_ptr
+from .allreduce import _ptr
+
+_MAX_TILES = 8192
+_MAX_CTAS = 148
+
+
+class GemmAllReduce:
+    """``out = all_reduce(a @ w.T)`` with ``a [M, K_local]``, ``w [N, K_local]`` (both K-major, bf16 / fp16).
+
+    one-shot (default for small M): every rank pulls the in-switch sum of every tile -> ``out`` is an ordinary tensor.
+    two-shot: tile ``t`` is reduced by rank ``t % world`` and multicast-stored to all ranks (less switch traffic for large M).
+    """
+
+    def __init__(self, group: Optional[dist.ProcessGroup], max_m: int, n: int, dtype: torch.dtype = torch.bfloat16,
+                 use_nvls: bool = True) -> None:
+        from .symm import SymmetricHeap
+
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.max_m, self.n, self.dtype = max_m, n, dtype
+        esz = torch.empty(0, dtype=dtype).element_size()
+        cbytes = (max_m * n * esz + 1023) // 1024 * 1024
+        fbytes = _MAX_TILES * 4
+        dbytes = _MAX_CTAS * 16 * 4
+        self.heap = SymmetricHeap(self.group, 3 * cbytes + fbytes + dbytes + 16384)
+        self._stage = []
+        for _ in range(2):
+            v, off = self.heap.alloc(cbytes)
+            self._stage.append((v.view(dtype)[: max_m * n].view(max_m, n), off, self.heap.peer_ptr_table(off)))
+        v, self._out_off = self.heap.alloc(cbytes)
+        self._out = v.view(dtype)[: max_m * n].view(max_m, n)
+        self._out_tab = self.heap.peer_ptr_table(self._out_off)
+        _, self._flag_off = self.heap.alloc(fbytes)
+        self._flag_tab = self.heap.peer_ptr_table(self._flag_off)
+        _, self._done_off = self.heap.alloc(dbytes)
+        self._done_tab = self.heap.peer_ptr_table(self._done_off)
+        dev = self.heap.device
+        self._expect = torch.zeros(_MAX_TILES, dtype=torch.int32, device=dev)
+        self._done_epoch = torch.zeros(_MAX_CTAS, dtype=torch.int32, device=dev)
+        self.use_nvls = bool(use_nvls and self.heap.mc_ptr)
+        self._turn = 0
+        self._mod = jit.load("gemm_comm_sm100")
+        self.heap.barrier()
+
+    def __call__(self, a: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None, two_shot: Optional[bool] = None,
+                 bn: int = 0) -> torch.Tensor:
+        M, K = a.shape
+        N = w.shape[0]
+        if N != self.n or M > self.max_m or a.dtype != self.dtype or w.dtype != self.dtype:
+            raise ValueError("GemmAllReduce: shape / dtype does not match the communicator")
+        if a.stride(1) != 1 or w.stride(1) != 1:
+            a, w = a.contiguous(), w.contiguous()
+        if two_shot is None:
+            two_shot = M * N * a.element_size() > (4 << 20)
+        self._turn ^= 1
+        stage, soff, stab = self._stage[self._turn]
+        if two_shot:
+            target = self._out[:M]
+        else:
+            target = out if out is not None else torch.empty(M, N, dtype=a.dtype, device=a.device)
+        mc = self.heap.mc if self.use_nvls else (lambda off: 0)
+        self._mod.call("gemm_allreduce_nt", a, w, stage, target, M, N, K, a.stride(0), w.stride(0), N, dtype_code(a.dtype), stab,
+                       self._flag_tab, self._out_tab if two_shot else None, self._done_tab, _ptr(mc(soff)), _ptr(mc(self._flag_off)),
+                       _ptr(mc(self._out_off) if two_shot else 0), self._expect, self._done_epoch, self.rank, self.world,
+                       1 if two_shot else 0, _MAX_TILES, bn, 1, stream_ptr(a))
+        if two_shot:
+            if out is not None:
+                out.copy_(target)
+                return out
+            return target.clone()
+        return target
+
+
+_CACHE: dict = {}
+
+
+def gemm_allreduce(a: torch.Tensor, w: torch.Tensor, group: Optional[dist.ProcessGroup] = None, out: Optional[torch.Tensor] = None,
+                   two_shot: Optional[bool] = None) -> torch.Tensor:
+    """Functional form with a per-(group, N, dtype) cached communicator sized for ``max(M, 8192)`` rows."""
+    g = group if group is not None else dist.group.WORLD
+    key = (id(g), w.shape[0], a.dtype)
+    comm = _CACHE.get(key)
+    if comm is None or comm.max_m < a.shape[0]:
+        comm = GemmAllReduce(g, max(a.shape[0], 8192), w.shape[0], a.dtype)
+        _CACHE[key] = comm
+    return comm(a, w, out, two_shot)

@@ -1,0 +1,348 @@
+// Fused GEMM + all-reduce for tensor-parallel row-parallel linears:  out = sum_ranks( A_r[M,K_r] * W_r[N,K_r]^T )
+// ONE kernel per rank: the tcgen05 GEMM and the NVLS reduction overlap tile by tile.
+//
+// Parity: reference flashinfer/cute_dsl/gemm_allreduce_two_shot.py (PersistentDenseGemmKernel(all_reduce="two_shot")
+// :216-360: epilogue stores the tile to a symmetric C, multimem.red arrives on a per-tile flag, dedicated all-reduce
+// warps wait for the flag and multimem.ld_reduce / multimem.st the tile).
+//
+// Roles (384 threads): warp 0 TMA producer | warp 1 MMA issuer | warp 2 TMEM allocator | warps 4-7 epilogue
+// (TMEM -> bf16 -> symmetric staging buffer, then ONE multimem.red.release bumps the tile flag on every rank) |
+// warps 8-11 all-reduce (spin on the local flag until all ranks have stored that tile, then pull the in-switch sum
+// with multimem.ld_reduce and write the final tile; two-shot: only the owner rank reduces and multicast-stores).
+// All ranks walk the tiles in the same order, so the waits are short and cannot deadlock (the GEMM side never waits
+// on a peer).  Flags are monotonic counters with the expected value kept per tile in local memory (graph-replay safe).
+#include <fib200/common.cuh>
+#include <fib200/ptx.cuh>
+
+using namespace fib200;
+
+FIB_EXPORT_LAST_ERROR()
+
+namespace {
+
+constexpr int BM = 128, BK = 64;
+constexpr int kMaxRanks = 16;
+
+struct GSmem {
+  int stages, stage_bytes, a_bytes, bar_offset, total;
+  __host__ __device__ static GSmem make(int BN) {
+    GSmem g;
+    g.a_bytes = BM * BK * 2;
+    g.stage_bytes = g.a_bytes + ((BN * BK * 2 + 1023) / 1024) * 1024;
+    int st = (200 * 1024) / g.stage_bytes;
+    g.stages = st > 8 ? 8 : st;
+    g.bar_offset = g.stages * g.stage_bytes;
+    g.total = g.bar_offset + 320 + 1024;
+    return g;
+  }
+};
+
+struct ARP {
+  uint8_t* peer_stage[kMaxRanks];  // symmetric staging C of every rank (P2P fallback)
+  uint32_t* peer_flags[kMaxRanks]; // symmetric per-tile flags of every rank
+  uint8_t* peer_out[kMaxRanks];    // symmetric out of every rank (two-shot P2P fallback)
+  uint8_t* mc_stage;               // multicast alias of the staging C (or null)
+  uint32_t* mc_flags;              // multicast alias of the flags (or null)
+  uint8_t* mc_out;                 // multicast alias of the symmetric out (two-shot)
+  uint32_t* expect;                // local: expected flag value per tile
+  uint32_t* peer_done[kMaxRanks];  // two-shot end barrier slots [max_ctas][world]
+  uint32_t* done_epoch;            // local [max_ctas]
+  int rank, world, two_shot;
+};
+
+template <typename OutT>
+__global__ void __launch_bounds__(384, 1)
+gemm_ar_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, OutT* __restrict__ stage,
+               OutT* __restrict__ out, int M, int N, int K, int64_t ldc, int BN, uint32_t idesc, const ARP ar) {
+  const GSmem S = GSmem::make(BN);
+  const int kStages = S.stages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S.bar_offset);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full = empty_bar + kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmW);
+    for (int i = 0; i < kStages; ++i) {
+      ptx::mbar_init(&full_bar[i], 1);
+      ptx::mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&tmem_full[i], 1);
+      ptx::mbar_init(&tmem_empty[i], 4);
+    }
+    ptx::fence_mbar_init();
+  }
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < uint32_t(2 * BN)) tmem_cols <<= 1;
+  if (warp == 2) {
+    ptx::tmem_alloc<1>(tmem_ptr, tmem_cols);
+    ptx::tmem_relinquish<1>();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = (K + BK - 1) / BK;
+  ptx::grid_dep_wait();
+
+  if (warp == 0) {
+    if (ptx::elect_one()) {
+      int stage_i = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int tm = t % tiles_m, tn = t / tiles_m;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage_i], phase ^ 1);
+          uint8_t* sa = smem + stage_i * S.stage_bytes;
+          uint8_t* sb = sa + S.a_bytes;
+          ptx::mbar_arrive_expect_tx(&full_bar[stage_i], S.a_bytes + BN * BK * 2);
+          ptx::tma_load_2d(sa, &tmA, &full_bar[stage_i], kb * BK, tm * BM, ptx::kEvictNormal);
+          ptx::tma_load_2d(sb, &tmW, &full_bar[stage_i], kb * BK, tn * BN, ptx::kEvictFirst);
+          if (++stage_i == kStages) {
+            stage_i = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    int stage_i = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        ptx::mbar_wait(&full_bar[stage_i], phase);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const uint32_t sa = ptx::smem_u32(smem + stage_i * S.stage_bytes);
+          const uint32_t sb = sa + S.a_bytes;
+          const uint64_t da = ptx::make_smem_desc(sa, 16, 1024, ptx::kSwz128);
+          const uint64_t db = ptx::make_smem_desc(sb, 16, 1024, ptx::kSwz128);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            ptx::mma_f16_ss<1>(d_tmem, ptx::desc_advance(da, k * 32), ptx::desc_advance(db, k * 32), idesc,
+                               (kb > 0 || k > 0) ? 1u : 0u);
+          ptx::mma_commit(&empty_bar[stage_i]);
+          if (kb == num_kb - 1) ptx::mma_commit(&tmem_full[acc]);
+        }
+        __syncwarp();
+        if (++stage_i == kStages) {
+          stage_i = 0;
+          phase ^= 1;
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ---------------- epilogue: TMEM -> staging C (symmetric) -> bump the tile flag on every rank
+    const int q = warp - 4;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int tm = t % tiles_m, tn = t / tiles_m;
+      ptx::mbar_wait(&tmem_full[acc], acc_phase);
+      ptx::tc_fence_after();
+      const int row = tm * BM + q * 32 + lane;
+      const uint32_t taddr = tmem_base + acc * BN + (uint32_t(q * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        uint32_t r[16];
+        ptx::tmem_ld_x16(taddr + c0, r);
+        ptx::tmem_ld_wait();
+        const int col0 = tn * BN + c0;
+        if (row < M && col0 < N) {
+          OutT* dst = stage + int64_t(row) * ldc + col0;
+          constexpr int VN = 16 / sizeof(OutT);
+#pragma unroll
+          for (int j = 0; j < 16; j += VN) {
+            Vec16<OutT> o;
+#pragma unroll
+            for (int e2 = 0; e2 < VN; ++e2) o.v[e2] = from_f32<OutT>(__uint_as_float(r[j + e2]));
+            st16(dst + j, o);
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __threadfence_system();
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // the 4 epilogue warps
+      if (warp == 4 && lane == 0) {
+        ptx::mbar_arrive(&tmem_empty[acc]);
+        if (ar.mc_flags) {
+          ptx::multimem_red_add_u32(ar.mc_flags + t, 1u);
+        } else {
+          for (int p = 0; p < ar.world; ++p) ptx::red_add_release_sys(ar.peer_flags[p] + t, 1u);
+        }
+      } else if (lane == 0) {
+        ptx::mbar_arrive(&tmem_empty[acc]);
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    ptx::grid_dep_launch();
+  } else if (warp >= 8) {
+    // ---------------- all-reduce warps
+    constexpr int VN = 16 / sizeof(OutT);
+    const int tid = threadIdx.x - 256;  // 0..127
+    const int vec_per_row = BN / VN;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int tm = t % tiles_m, tn = t / tiles_m;
+      const uint32_t want = ar.expect[t] + uint32_t(ar.world);
+      if (tid == 0) {
+        while (int32_t(ptx::ld_acquire_sys(ar.peer_flags[ar.rank] + t) - want) < 0) {
+        }
+      }
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      const bool mine = !ar.two_shot || (t % ar.world) == ar.rank;
+      if (mine) {
+        const int rows = min(BM, M - tm * BM);
+        for (int i = tid; i < rows * vec_per_row; i += 128) {
+          const int r = i / vec_per_row, v = i % vec_per_row;
+          const int col = tn * BN + v * VN;
+          if (col >= N) continue;
+          const int64_t off = (int64_t(tm * BM + r) * ldc + col) * sizeof(OutT);
+          int4 res;
+          if (ar.mc_stage) {
+            if constexpr (std::is_same<OutT, __half>::value) res = ptx::multimem_ld_reduce_f16x8(ar.mc_stage + off);
+            else res = ptx::multimem_ld_reduce_bf16x8(ar.mc_stage + off);
+          } else {
+            float accv[VN];
+#pragma unroll
+            for (int e = 0; e < VN; ++e) accv[e] = 0.f;
+            for (int p = 0; p < ar.world; ++p) {
+              int4 x;
+              asm volatile("ld.global.relaxed.sys.v4.s32 {%0,%1,%2,%3}, [%4];"
+                           : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w)
+                           : "l"(ar.peer_stage[p] + off)
+                           : "memory");
+              const OutT* h = reinterpret_cast<const OutT*>(&x);
+#pragma unroll
+              for (int e = 0; e < VN; ++e) accv[e] += to_f32(h[e]);
+            }
+            OutT* h = reinterpret_cast<OutT*>(&res);
+#pragma unroll
+            for (int e = 0; e < VN; ++e) h[e] = from_f32<OutT>(accv[e]);
+          }
+          if (!ar.two_shot) {
+            *reinterpret_cast<int4*>(reinterpret_cast<uint8_t*>(out) + off) = res;
+          } else if (ar.mc_out) {
+            ptx::multimem_st_v4(ar.mc_out + off, res);
+          } else {
+            for (int p = 0; p < ar.world; ++p) *reinterpret_cast<int4*>(ar.peer_out[p] + off) = res;
+          }
+        }
+      }
+      if (tid == 0) ar.expect[t] = want;
+    }
+    if (ar.two_shot) {
+      // every rank must see all owner-written tiles before the kernel completes
+      __threadfence_system();
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (tid < ar.world) {
+        const uint32_t epoch = ar.done_epoch[blockIdx.x] + 1;
+        ptx::st_release_sys(ar.peer_done[tid] + blockIdx.x * ar.world + ar.rank, epoch);
+        while (int32_t(ptx::ld_acquire_sys(ar.peer_done[ar.rank] + blockIdx.x * ar.world + tid) - epoch) < 0) {
+        }
+      }
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (tid == 0) ar.done_epoch[blockIdx.x] += 1;
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<1>(tmem_base, tmem_cols);
+  }
+}
+
+}  // namespace
+
+// tables: host int64 arrays [world].  stage / out: local pointers of the symmetric staging C and of the output
+// (out must be symmetric for two_shot).  expect: local uint32[max_tiles]; done_epoch: local uint32[grid].
+extern "C" int gemm_allreduce_nt(void* A, void* W, void* stage, void* out, int64_t M, int64_t N, int64_t K, int64_t lda,
+                                 int64_t ldw, int64_t ldc, int64_t dtype, void* peer_stage_tab, void* peer_flags_tab,
+                                 void* peer_out_tab, void* peer_done_tab, void* mc_stage, void* mc_flags, void* mc_out,
+                                 void* expect, void* done_epoch, int64_t rank, int64_t world, int64_t two_shot,
+                                 int64_t max_tiles, int64_t bn, int64_t pdl, int64_t stream_) {
+  FIB_CHECK(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldc % 8 == 0 && N % 16 == 0, "gemm_allreduce: K/lda/ldw/ldc must be multiples of 8 and N of 16");
+  FIB_CHECK(dtype == kF16 || dtype == kBF16, "gemm_allreduce: dtype must be f16/bf16");
+  FIB_CHECK(world >= 1 && world <= kMaxRanks, "gemm_allreduce: world size must be in [1,16]");
+  if (M == 0 || N == 0) return 0;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const CUtensorMapDataType dt = dtype == kF16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const int tiles_m = int((M + BM - 1) / BM);
+  int BN = (int)bn;
+  if (BN == 0) {
+    const int64_t want = (N * tiles_m + num_sms() - 1) / num_sms();
+    BN = int((want + 15) / 16 * 16);
+    if (BN < 32) BN = 32;
+    if (BN > 256) BN = 256;
+  }
+  FIB_CHECK(BN % 16 == 0 && BN >= 16 && BN <= 256, "gemm_allreduce: bad N tile");
+  const int64_t tiles = int64_t(tiles_m) * ((N + BN - 1) / BN);
+  FIB_CHECK(tiles <= max_tiles, "gemm_allreduce: flag array too small for this problem");
+  CUtensorMap tmA, tmW;
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+    uint64_t str[1] = {(uint64_t)lda * 2};
+    uint32_t box[2] = {BK, BM};
+    if (make_tmap(&tmA, dt, 2, A, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+    uint64_t str[1] = {(uint64_t)ldw * 2};
+    uint32_t box[2] = {BK, (uint32_t)BN};
+    if (make_tmap(&tmW, dt, 2, W, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  }
+  ARP ar;
+  for (int i = 0; i < world; ++i) {
+    ar.peer_stage[i] = reinterpret_cast<uint8_t*>(((const int64_t*)peer_stage_tab)[i]);
+    ar.peer_flags[i] = reinterpret_cast<uint32_t*>(((const int64_t*)peer_flags_tab)[i]);
+    ar.peer_out[i] = peer_out_tab ? reinterpret_cast<uint8_t*>(((const int64_t*)peer_out_tab)[i]) : nullptr;
+    ar.peer_done[i] = reinterpret_cast<uint32_t*>(((const int64_t*)peer_done_tab)[i]);
+  }
+  ar.mc_stage = (uint8_t*)mc_stage;
+  ar.mc_flags = (uint32_t*)mc_flags;
+  ar.mc_out = (uint8_t*)mc_out;
+  ar.expect = (uint32_t*)expect;
+  ar.done_epoch = (uint32_t*)done_epoch;
+  ar.rank = (int)rank;
+  ar.world = (int)world;
+  ar.two_shot = (int)two_shot;
+  const GSmem S = GSmem::make(BN);
+  const uint32_t idesc = ptx::make_idesc_f16(dtype == kF16 ? ptx::kFmtF16 : ptx::kFmtBF16, BM, BN, 0, 0);
+  const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+  LaunchCfg lc(dim3(grid), dim3(384), S.total, stream, pdl != 0);
+  if (dtype == kF16) {
+    static bool set = false;
+    if (!set) {
+      FIB_CUDA_CHECK(cudaFuncSetAttribute(gemm_ar_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      set = true;
+    }
+    FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, gemm_ar_kernel<__half>, tmA, tmW, (__half*)stage, (__half*)out, (int)M, (int)N,
+                                      (int)K, ldc, BN, idesc, ar));
+  } else {
+    static bool set = false;
+    if (!set) {
+      FIB_CUDA_CHECK(cudaFuncSetAttribute(gemm_ar_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      set = true;
+    }
+    FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, gemm_ar_kernel<__nv_bfloat16>, tmA, tmW, (__nv_bfloat16*)stage,
+                                      (__nv_bfloat16*)out, (int)M, (int)N, (int)K, ldc, BN, idesc, ar));
+  }
+  return 0;
+}

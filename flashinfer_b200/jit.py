@@ -143,7 +143,9 @@ register(ModuleSpec("grouped_gemm_sm100", ["gemm/grouped_gemm_sm100.cu"]))
 register(ModuleSpec("moe", ["moe/routing.cu"]))
 register(ModuleSpec("comm_allreduce", ["comm/allreduce.cu"]))
 register(ModuleSpec("comm_alltoall", ["comm/moe_a2a.cu"]))
-register(ModuleSpec("gemm_comm_sm100", ["comm/gemm_allreduce_sm100.cu"]))
+register(ModuleSpec("comm_collectives", ["comm/collectives.cu"]))
+register(ModuleSpec("gemm_comm_sm100", ["gemm/gemm_allreduce_sm100.cu"]))
+register(ModuleSpec("gemm_allgather_sm100", ["gemm/gemm_allgather_sm100.cu"]))
 
 
 def _existing(spec: ModuleSpec) -> bool:
