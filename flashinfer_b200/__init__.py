@@ -108,3 +108,15 @@ from . import api_logging, autotuner, fi_trace, green_ctx, logits_processor, par
 from .autotuner import autotune  # noqa: F401,E402
 from .api_logging import flashinfer_api  # noqa: F401,E402
 from . import comm, mla, attention  # noqa: F401,E402
+from . import concat_ops, dsv3_ops, gdn, mamba  # noqa: F401,E402
+from .gdn import chunk_gated_delta_rule  # noqa: F401,E402
+from .activation import silu_and_mul_scaled_nvfp4_experts_quantize  # noqa: F401,E402
+from .norm import (  # noqa: F401,E402
+    add_rmsnorm_fp4quant,
+    fused_dit_gate_residual_layernorm_gamma_beta,
+    fused_dit_gate_residual_layernorm_scale_shift,
+    fused_dit_residual_layernorm_scale_shift,
+    rmsnorm_fp4quant,
+)
+from .quantization.fp4 import nvfp4_quantize_paged_kv_cache  # noqa: F401,E402
+from .gemm import prepare_low_latency_gemm_weights, trtllm_low_latency_gemm  # noqa: F401,E402

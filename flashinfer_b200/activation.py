@@ -49,3 +49,16 @@ def gelu_and_mul(input, out=None, enable_pdl=None):
 
 def gelu_tanh_and_mul(input, out=None, enable_pdl=None):
     return _act_and_mul("gelu_tanh", input, out, enable_pdl)
+
+
+def silu_and_mul_scaled_nvfp4_experts_quantize(a: torch.Tensor, mask: torch.Tensor, a_global_sf: torch.Tensor):
+    """``a [E, M, 2K]`` -> ``silu(a[..., :K]) * a[..., K:]`` quantised to NVFP4 per expert (rows ``>= mask[e]`` are padding).
+    Reference flashinfer/activation.py:204.  Returns ``(fp4 [E, M, K/2] uint8, swizzled scale factors [E, ...])``."""
+    from .quantization.fp4 import scaled_fp4_grouped_quantize
+
+    E, M, K2 = a.shape
+    act = silu_and_mul(a.reshape(E * M, K2)).view(E, M, K2 // 2)
+    gs = a_global_sf.float().reshape(-1)
+    if gs.numel() == 1:
+        gs = gs.expand(E)
+    return scaled_fp4_grouped_quantize(act, mask, gs)

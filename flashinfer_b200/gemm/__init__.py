@@ -21,4 +21,6 @@ from .lowp import (  # noqa: F401
     mm_fp4,
     mm_fp8,
     mm_mxfp8,
+    prepare_low_latency_gemm_weights,
+    trtllm_low_latency_gemm,
 )

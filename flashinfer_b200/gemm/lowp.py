@@ -237,3 +237,29 @@ def gemm_fp8_nt_blockscaled(a, b, a_scale, b_scale, scale_major_mode: Optional[s
 
 def fp8_blockscale_gemm_sm90(*args, **kwargs):
     raise NotImplementedError("fp8_blockscale_gemm_sm90 is a Hopper-only entry point; use gemm_fp8_nt_groupwise on B200")
+
+
+# ------------------------------------------------------------------ trtllm low-latency fp8 GEMM entry points
+_LL_CACHE: dict = {}
+
+
+def prepare_low_latency_gemm_weights(w: torch.Tensor, permutation_indices_cache: Optional[dict] = None) -> torch.Tensor:
+    """``w [n, k]`` fp8 -> block layout ``[k // 128, n, 128]`` (reference trtllm_low_latency_gemm.py:199).  No row shuffle is
+    applied: the TMA-fed tcgen05 kernel does not need the epilogue-tile permutation of the trtllm-gen cubins."""
+    n, k = w.shape
+    if k % 128:
+        raise ValueError("prepare_low_latency_gemm_weights: k must be a multiple of 128")
+    return w.view(n, k // 128, 128).permute(1, 0, 2).contiguous()
+
+
+def trtllm_low_latency_gemm(A: torch.Tensor, B: torch.Tensor, global_scale: torch.Tensor, out: torch.Tensor) -> None:
+    """``out [m, n] = (A [m, k] fp8) x (prepared B [k/128, n, 128] fp8)^T * global_scale`` (small-M fp8 GEMM)."""
+    key = (B.data_ptr(), tuple(B.shape))
+    w = _LL_CACHE.get(key)
+    if w is None:
+        kb, n, blk = B.shape
+        w = B.permute(1, 0, 2).reshape(n, kb * blk).contiguous()
+        if len(_LL_CACHE) > 256:
+            _LL_CACHE.clear()
+        _LL_CACHE[key] = w
+    mm_fp8(A, w.t(), global_scale, out.dtype, out)

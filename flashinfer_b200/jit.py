@@ -141,6 +141,7 @@ register(ModuleSpec("mla_sm100", ["attention/mla_sm100.cu"]))
 register(ModuleSpec("gemm_blockscaled_sm100", ["gemm/gemm_blockscaled_sm100.cu"]))
 register(ModuleSpec("grouped_gemm_sm100", ["gemm/grouped_gemm_sm100.cu"]))
 register(ModuleSpec("moe", ["moe/routing.cu"]))
+register(ModuleSpec("ssm", ["elementwise/ssm.cu"]))
 register(ModuleSpec("comm_allreduce", ["comm/allreduce.cu"]))
 register(ModuleSpec("comm_alltoall", ["comm/moe_a2a.cu"]))
 register(ModuleSpec("comm_collectives", ["comm/collectives.cu"]))

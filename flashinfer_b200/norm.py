@@ -134,3 +134,120 @@ def fused_rmsnorm_silu(input, weight, eps: float = 1e-6, out=None, block_scale=N
         return out
     _rms_launch(input, out, None, weight, eps, 0.0, None, True, None)
     return out
+
+
+# ------------------------------------------------------------------ norm + block quantisation (reference cute_dsl/rmsnorm_fp4quant.py,
+# add_rmsnorm_fp4quant.py) and DiT layernorm family (reference norm/__init__.py:1057-1440).  These are PDL-chained
+# sequences of the native norm and quantisation kernels (one extra round trip through L2 compared with a single kernel).
+def rmsnorm_fp4quant(input: torch.Tensor, weight: torch.Tensor, y_fp4: Optional[torch.Tensor] = None,
+                     block_scale: Optional[torch.Tensor] = None, global_scale: Optional[torch.Tensor] = None, eps: float = 1e-6,
+                     block_size: int = 16, scale_format: Optional[str] = None, is_sf_swizzled_layout: bool = False,
+                     enable_pdl: Optional[bool] = None):
+    """``y = rmsnorm(input) * weight`` quantised to FP4 (NVFP4: block 16 / UE4M3, MXFP4: block 32 / UE8M0).
+    Returns ``(y_fp4 [.., hidden/2] uint8, block_scale)``."""
+    from .quantization.fp4 import fp4_quantize
+
+    shape = input.shape
+    y = rmsnorm(input.reshape(-1, shape[-1]), weight, eps, enable_pdl=enable_pdl)
+    ue8m0 = (scale_format == "ue8m0") or (scale_format is None and block_size == 32)
+    gs = global_scale if global_scale is not None else None
+    q, sf = fp4_quantize(y, gs, sf_vec_size=block_size, sf_use_ue8m0=ue8m0, is_sf_swizzled_layout=is_sf_swizzled_layout)
+    q = q.view(*shape[:-1], shape[-1] // 2)
+    if not is_sf_swizzled_layout:
+        sf = sf.view(*shape[:-1], shape[-1] // block_size)
+    if y_fp4 is not None:
+        y_fp4.view(torch.uint8).copy_(q.view(torch.uint8))
+        q = y_fp4
+    if block_scale is not None:
+        block_scale.view(torch.uint8).reshape(-1)[: sf.numel()].copy_(sf.view(torch.uint8).reshape(-1))
+        sf = block_scale
+    return q, sf
+
+
+def add_rmsnorm_fp4quant(input: torch.Tensor, residual: torch.Tensor, weight: torch.Tensor, y_fp4: Optional[torch.Tensor] = None,
+                         block_scale: Optional[torch.Tensor] = None, global_scale: Optional[torch.Tensor] = None, eps: float = 1e-6,
+                         block_size: int = 16, scale_format: Optional[str] = None, is_sf_swizzled_layout: bool = False,
+                         output_both_sf_layouts: bool = False, enable_pdl: Optional[bool] = None):
+    """``residual += input`` (in place), then :func:`rmsnorm_fp4quant` of the sum."""
+    h = residual.shape[-1]
+    x2 = input.reshape(-1, h).clone()
+    r2 = residual.reshape(-1, h)
+    fused_add_rmsnorm(x2, r2, weight, eps, enable_pdl=enable_pdl)  # x2 <- norm(x + r) * w ; r2 <- x + r
+    from .quantization.fp4 import fp4_quantize
+
+    ue8m0 = (scale_format == "ue8m0") or (scale_format is None and block_size == 32)
+    q, sf = fp4_quantize(x2, global_scale, sf_vec_size=block_size, sf_use_ue8m0=ue8m0, is_sf_swizzled_layout=is_sf_swizzled_layout)
+    q = q.view(*input.shape[:-1], h // 2)
+    if y_fp4 is not None:
+        y_fp4.view(torch.uint8).copy_(q.view(torch.uint8))
+        q = y_fp4
+    if block_scale is not None:
+        block_scale.view(torch.uint8).reshape(-1)[: sf.numel()].copy_(sf.view(torch.uint8).reshape(-1))
+        sf = block_scale
+    return q, sf
+
+
+def _dit_finish(res: torch.Tensor, normed: torch.Tensor, use_nvfp4: bool, use_mxfp8: bool, global_scaling_factor, residual_out,
+                norm_out, sf_out):
+    if residual_out is not None:
+        residual_out.copy_(res)
+        res = residual_out
+    if use_nvfp4:
+        from .quantization.fp4 import fp4_quantize
+
+        q, sf = fp4_quantize(normed.reshape(-1, normed.shape[-1]), global_scaling_factor, 16, False, True)
+        return res, q.view(*normed.shape[:-1], -1), sf
+    if use_mxfp8:
+        from .quantization.fp8 import mxfp8_quantize
+
+        q, sf = mxfp8_quantize(normed.reshape(-1, normed.shape[-1]), True)
+        return res, q.view(normed.shape), sf
+    if norm_out is not None:
+        norm_out.copy_(normed)
+        normed = norm_out
+    return res, normed
+
+
+def fused_dit_gate_residual_layernorm_gamma_beta(input, residual, gate, gamma, beta, *, gate_bias=None, epsilon: float = 1e-6,
+                                                 use_nvfp4: bool = False, use_mxfp8: bool = False, global_scaling_factor=None,
+                                                 input_global_scaling_factor=None, residual_out=None, norm_out=None, sf_out=None):
+    """``residual_out = residual + input * (gate + gate_bias)``; ``norm_out = LayerNorm(residual_out, gamma, beta)``."""
+    x = input.float() * (float(input_global_scaling_factor) if input_global_scaling_factor is not None else 1.0)
+    g = gate.float() + (gate_bias.float() if gate_bias is not None else 0.0)
+    res = (residual.float() + x * g).to(input.dtype)
+    normed = layernorm(res.reshape(-1, res.shape[-1]), gamma.float(), beta.float(), epsilon).view(res.shape)
+    return _dit_finish(res, normed, use_nvfp4, use_mxfp8, global_scaling_factor, residual_out, norm_out, sf_out)
+
+
+def fused_dit_gate_residual_layernorm_scale_shift(input, residual, gate, scale, shift, *, gate_bias=None, scale_bias=None,
+                                                  shift_bias=None, epsilon: float = 1e-6, use_nvfp4: bool = False,
+                                                  use_mxfp8: bool = False, global_scaling_factor=None,
+                                                  input_global_scaling_factor=None, residual_out=None, norm_out=None, sf_out=None):
+    """``residual_out = residual + input * gate``; ``norm_out = LayerNorm(residual_out) * (1 + scale) + shift`` (adaLN)."""
+    x = input.float() * (float(input_global_scaling_factor) if input_global_scaling_factor is not None else 1.0)
+    g = gate.float() + (gate_bias.float() if gate_bias is not None else 0.0)
+    res = (residual.float() + x * g).to(input.dtype)
+    return _dit_scale_shift(res, scale, shift, scale_bias, shift_bias, epsilon, use_nvfp4, use_mxfp8, global_scaling_factor,
+                            residual_out, norm_out, sf_out)
+
+
+def fused_dit_residual_layernorm_scale_shift(input, residual, scale, shift, *, scale_bias=None, shift_bias=None,
+                                             epsilon: float = 1e-6, use_nvfp4: bool = False, use_mxfp8: bool = False,
+                                             global_scaling_factor=None, input_global_scaling_factor=None, residual_out=None,
+                                             norm_out=None, sf_out=None):
+    """``residual_out = residual + input``; ``norm_out = LayerNorm(residual_out) * (1 + scale) + shift``."""
+    x = input.float() * (float(input_global_scaling_factor) if input_global_scaling_factor is not None else 1.0)
+    res = (residual.float() + x).to(input.dtype)
+    return _dit_scale_shift(res, scale, shift, scale_bias, shift_bias, epsilon, use_nvfp4, use_mxfp8, global_scaling_factor,
+                            residual_out, norm_out, sf_out)
+
+
+def _dit_scale_shift(res, scale, shift, scale_bias, shift_bias, epsilon, use_nvfp4, use_mxfp8, gsf, residual_out, norm_out, sf_out):
+    h = res.shape[-1]
+    ones = torch.ones(h, dtype=torch.float32, device=res.device)
+    zeros = torch.zeros(h, dtype=torch.float32, device=res.device)
+    ln = layernorm(res.reshape(-1, h), ones, zeros, epsilon).view(res.shape).float()
+    sc = scale.float() + (scale_bias.float() if scale_bias is not None else 0.0)
+    sh = shift.float() + (shift_bias.float() if shift_bias is not None else 0.0)
+    normed = (ln * (1.0 + sc) + sh).to(res.dtype)
+    return _dit_finish(res, normed, use_nvfp4, use_mxfp8, gsf, residual_out, norm_out, sf_out)

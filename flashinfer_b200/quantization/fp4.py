@@ -243,3 +243,21 @@ def _shuffle_row_indices(m: int, epilogue_tile_m: int, device) -> torch.Tensor:
     perm = torch.where(base % 2 == 0, base // 2, half + base // 2)
     tiles = torch.arange(0, m, epilogue_tile_m, device=device)[:, None]
     return (tiles + perm[None]).reshape(-1)
+
+
+def nvfp4_quantize_paged_kv_cache(k_cache: torch.Tensor, v_cache: torch.Tensor, kv_layout: str = "HND",
+                                  k_global_sf: Optional[torch.Tensor] = None, v_global_sf: Optional[torch.Tensor] = None):
+    """Quantise a bf16 / fp16 paged KV cache to NVFP4 (reference fp4_quantization.py:1365): per-16 UE4M3 block scales in the
+    linear cache layout (``head_dim -> head_dim // 16``) plus one fp32 global scale per tensor.
+    Returns ``((k_fp4, v_fp4), (k_sf, v_sf), k_global_scale, v_global_scale)``."""
+    def one(c: torch.Tensor, gsf):
+        if gsf is None:
+            gsf = (448.0 * 6.0) / c.float().abs().amax().clamp(min=1e-12)
+        gsf = torch.as_tensor(gsf, dtype=torch.float32, device=c.device).reshape(1)
+        d = c.shape[-1]
+        q, sf = fp4_quantize(c.reshape(-1, d), gsf, 16, False, False)
+        return q.view(*c.shape[:-1], d // 2), sf.view(*c.shape[:-1], d // 16).view(torch.float8_e4m3fn), float(1.0 / gsf)
+
+    kq, ksf, kg = one(k_cache, k_global_sf)
+    vq, vsf, vg = one(v_cache, v_global_sf)
+    return (kq, vq), (ksf, vsf), kg, vg
