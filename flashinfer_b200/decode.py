@@ -336,13 +336,29 @@ class BatchDecodeWithPagedKVCacheWrapper:
     def end_forward(self) -> None:
         pass
 
+    def _run_generic(self, q, k_cache, v_cache, out, lse, sm_scale, window_left, enable_pdl):
+        """Catch-all CUDA-core kernel: head dims other than 128, fp8 KV caches, very wide GQA groups."""
+        from .attention import generic as _g
+
+        if not _g.supported(q, k_cache, self._head_dim, self._head_dim):
+            raise NotImplementedError(f"decode: unsupported configuration (q {q.dtype}, kv {k_cache.dtype}, head_dim {self._head_dim})")
+        sp, sn, sh, page_size, hkv, d = paged_kv_strides(k_cache, self._kv_layout)
+        vsp, vsn, vsh = paged_kv_strides(v_cache, self._kv_layout)[:3]
+        dev = q.device
+        if getattr(self, "_gen_key", None) != id(self._kv_indptr_host):
+            qo = self._qo_indptr_host if self._qo_indptr_host is not None else torch.arange(self._batch_size + 1, dtype=torch.int32)
+            self._gen_qo = qo.to(dev)
+            self._gen_kv = self._kv_indptr_host.to(dev)
+            self._gen_last = self._kv_last_host.to(dev)
+            self._gen_key = id(self._kv_indptr_host)
+        _g.run(q, k_cache, v_cache, out, lse, self._gen_qo, self._gen_kv, self._kv_indices, self._gen_last, page_size,
+               (sp, sn, sh), (vsp, vsn, vsh), self._num_kv_heads, True, window_left, sm_scale, self._logits_soft_cap,
+               enable_pdl=enable_pdl is None or enable_pdl)
+
     def _run_sm100(self, q, k_cache, v_cache, out, lse, sm_scale, window_left, enable_pdl):
-        if self._head_dim != 128:
-            raise NotImplementedError(f"decode_sm100: head_dim {self._head_dim} not specialised yet (128 only)")
-        if q.dtype not in (torch.float16, torch.bfloat16) or k_cache.dtype != q.dtype:
-            raise NotImplementedError(f"decode_sm100: q dtype {q.dtype} / kv dtype {k_cache.dtype} not specialised yet")
-        if self._max_q_rows > _MAX_Q_ROWS:
-            raise NotImplementedError("decode_sm100: q_len * group > 32; use the prefill wrapper")
+        if (self._head_dim != 128 or q.dtype not in (torch.float16, torch.bfloat16) or k_cache.dtype != q.dtype
+                or self._max_q_rows > _MAX_Q_ROWS):
+            return self._run_generic(q, k_cache, v_cache, out, lse, sm_scale, window_left, enable_pdl)
         sp, sn, sh, page_size, hkv, d = paged_kv_strides(k_cache, self._kv_layout)
         if paged_kv_strides(v_cache, self._kv_layout)[:3] != (sp, sn, sh):
             raise ValueError("k_cache and v_cache must share strides")

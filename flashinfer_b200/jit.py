@@ -142,6 +142,7 @@ register(ModuleSpec("gemm_blockscaled_sm100", ["gemm/gemm_blockscaled_sm100.cu"]
 register(ModuleSpec("grouped_gemm_sm100", ["gemm/grouped_gemm_sm100.cu"]))
 register(ModuleSpec("moe", ["moe/routing.cu"]))
 register(ModuleSpec("ssm", ["elementwise/ssm.cu"]))
+register(ModuleSpec("attention_generic", ["attention/generic_attention.cu"]))
 register(ModuleSpec("comm_allreduce", ["comm/allreduce.cu"]))
 register(ModuleSpec("comm_alltoall", ["comm/moe_a2a.cu"]))
 register(ModuleSpec("comm_collectives", ["comm/collectives.cu"]))

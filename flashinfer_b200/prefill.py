@@ -79,14 +79,29 @@ def single_prefill_with_kv_cache(
         mask = _unpack_bits(packed_custom_mask, qo_len * kv_len).view(qo_len, kv_len)
     elif custom_mask is not None:
         mask = custom_mask.view(qo_len, kv_len)
-    if (not q.is_cuda) or mask is not None or q.shape[-1] != 128 or v.shape[-1] != 128 or q.dtype not in (
-        torch.float16, torch.bfloat16) or k.dtype != q.dtype:
-        if q.is_cuda and mask is None:
-            raise NotImplementedError("prefill_sm100: only head_dim 128 f16/bf16 is specialised so far")
-        if q.is_cuda:
-            raise NotImplementedError("prefill_sm100: custom masks are not supported by the tcgen05 kernel yet")
+    fast = q.is_cuda and mask is None and q.shape[-1] == 128 and v.shape[-1] == 128 and q.dtype in (
+        torch.float16, torch.bfloat16) and k.dtype == q.dtype
+    if not q.is_cuda:
         o, lse = reference.attention_ref(q, k, v, causal and mask is None, sm_scale, logits_soft_cap or 0.0,
                                          window_left, custom_mask=mask)
+    elif not fast:
+        from .attention import generic as _g
+
+        if not _g.supported(q, k, q.shape[-1], v.shape[-1]):
+            raise NotImplementedError(f"attention: unsupported configuration (dtype {q.dtype}/{k.dtype}, head_dim {q.shape[-1]})")
+        o = torch.empty(qo_len, q.shape[1], v.shape[-1], dtype=q.dtype, device=q.device)
+        lse = torch.empty(qo_len, q.shape[1], dtype=torch.float32, device=q.device)
+        qi = torch.tensor([0, qo_len], dtype=torch.int32, device=q.device)
+        ki = torch.tensor([0, kv_len], dtype=torch.int32, device=q.device)
+        if k.stride(-1) != 1 or v.stride(-1) != 1:
+            k, v = k.contiguous(), v.contiguous()
+        pm = _g.pack_mask_bits(mask) if mask is not None else None
+        mi = torch.tensor([0, qo_len * kv_len], dtype=torch.int32, device=q.device) if mask is not None else None
+        ks = float(scale_k) if scale_k is not None else 1.0
+        qs_ = float(scale_q) if scale_q is not None else 1.0
+        _g.run(q, k, v, o, lse, qi, ki, None, None, 1, (0, k.stride(0), k.stride(1)), (0, v.stride(0), v.stride(1)), k.shape[1],
+               causal and mask is None, window_left, sm_scale * qs_, logits_soft_cap or 0.0, pm, mi, None, ks,
+               float(scale_v) if scale_v is not None else 1.0)
     else:
         ws = torch.empty(16 * 1024 * 1024, dtype=torch.uint8, device=q.device)
         w = BatchPrefillWithRaggedKVCacheWrapper(ws, "NHD")
@@ -201,13 +216,13 @@ class _BatchPrefillBase:
                 lse[qs:qe] = l_b
         return outs
 
-    def _launch_sm100(self, q, k, v, out, lse, sm_scale, window_left, paged, kv_indices, page_args, enable_pdl):
-        if self._head_dim_qk != 128 or self._head_dim_vo != 128:
-            raise NotImplementedError("prefill_sm100: only head_dim 128 is specialised so far")
-        if q.dtype not in (torch.float16, torch.bfloat16) or k.dtype != q.dtype:
-            raise NotImplementedError(f"prefill_sm100: dtype {q.dtype}/{k.dtype} not specialised yet")
-        if self._custom_mask is not None:
-            raise NotImplementedError("prefill_sm100: custom masks not supported yet")
+    def _launch_sm100(self, q, k, v, out, lse, sm_scale, window_left, paged, kv_indices, page_args, enable_pdl,
+                      k_scale=None, v_scale=None):
+        fast = (self._head_dim_qk == 128 and self._head_dim_vo == 128 and q.dtype in (torch.float16, torch.bfloat16)
+                and k.dtype == q.dtype and self._custom_mask is None)
+        if not fast:
+            return self._launch_generic(q, k, v, out, lse, sm_scale, window_left, paged, kv_indices, page_args, enable_pdl,
+                                        k_scale, v_scale)
         jit.load("prefill_sm100").call(
             "prefill_run", q, k, v, out, lse, kv_indices, self._kv_page_indptr_dev if paged else None,
             self._work_info, self._cta_work_indptr, self._num_ctas, q.shape[0], self._num_qo_heads, self._num_kv_heads,
@@ -215,6 +230,55 @@ class _BatchPrefillBase:
             float(sm_scale), float(self._logits_soft_cap), int(window_left), 1 if self._causal else 0,
             dtype_code(q.dtype), 1 if (enable_pdl is None or enable_pdl) else 0, stream_ptr(q),
         )
+
+
+    def _launch_generic(self, q, k, v, out, lse, sm_scale, window_left, paged, kv_indices, page_args, enable_pdl, k_scale, v_scale):
+        """Catch-all CUDA-core kernel: other head dims, fp8 KV, custom masks."""
+        from .attention import generic as _g
+
+        if not _g.supported(q, k, self._head_dim_qk, self._head_dim_vo):
+            raise NotImplementedError(f"attention: unsupported configuration (dtype {q.dtype}/{k.dtype}, "
+                                      f"head_dim {self._head_dim_qk}/{self._head_dim_vo})")
+        dev = q.device
+        if getattr(self, "_gen_cache_key", None) != id(self._qo_indptr_host):
+            self._gen_qo = self._qo_indptr_host.to(dev)
+            if paged:
+                self._gen_kv = self._kv_page_indptr_dev
+                self._gen_last = self._kv_last_host.to(dev)
+            else:
+                self._gen_kv = None
+                self._gen_last = None
+            self._gen_mask = None
+            if self._custom_mask is not None:
+                self._gen_mask = _g.pack_mask_bits(self._custom_mask.to(dev))
+                ql = (self._qo_indptr_host[1:] - self._qo_indptr_host[:-1]).long()
+                bits = torch.zeros(self._batch_size + 1, dtype=torch.int64)
+                bits[1:] = torch.cumsum(ql * self._kv_lens_host.long(), 0)
+                self._gen_mask_indptr = bits.to(torch.int32).to(dev)
+            self._gen_cache_key = id(self._qo_indptr_host)
+        causal = self._causal and self._custom_mask is None
+        if paged:
+            page_size, _, sp, sn, sh, _ = page_args
+            _g.run(q, k, v, out, lse, self._gen_qo, self._gen_kv, kv_indices, self._gen_last, page_size, (sp, sn, sh), (sp, sn, sh),
+                   self._num_kv_heads, causal, window_left, sm_scale, self._logits_soft_cap, self._gen_mask,
+                   getattr(self, "_gen_mask_indptr", None), None, 1.0, 1.0, enable_pdl is None or enable_pdl)
+        else:
+            # ragged: requests may be non-contiguous in k, so each request is one launch over its [start, start+len) slice
+            for b in range(self._batch_size):
+                qs, qe = int(self._qo_indptr_host[b]), int(self._qo_indptr_host[b + 1])
+                if qe == qs:
+                    continue
+                st, ln = int(self._kv_start_host[b]), int(self._kv_lens_host[b])
+                qi = torch.tensor([0, qe - qs], dtype=torch.int32, device=dev)
+                ki = torch.tensor([0, ln], dtype=torch.int32, device=dev)
+                pm = mi = None
+                if self._gen_mask is not None:
+                    off = int(self._gen_mask_indptr[b])
+                    pm = _g.pack_mask_bits(self._custom_mask.flatten()[off: off + (qe - qs) * ln].to(dev))
+                    mi = torch.tensor([0, (qe - qs) * ln], dtype=torch.int32, device=dev)
+                _g.run(q[qs:qe], k[st:st + ln], v[st:st + ln], out[qs:qe], lse[qs:qe] if lse is not None else None, qi, ki, None,
+                       None, 1, (0, k.stride(0), k.stride(1)), (0, v.stride(0), v.stride(1)), self._num_kv_heads, causal,
+                       window_left, sm_scale, self._logits_soft_cap, pm, mi, None, 1.0, 1.0, enable_pdl is None or enable_pdl)
 
     def end_forward(self) -> None:
         pass
