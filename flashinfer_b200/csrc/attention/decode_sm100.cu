@@ -196,6 +196,7 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   const uint32_t tmem_base = *tmem_ptr;
 
   ptx::grid_dep_wait();
+  ptx::grid_dep_launch();  // early trigger: dependents overlap their prologue, they still wait for our completion
 
   const int ps = p.page_size;
 
@@ -519,7 +520,6 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     }
   }
 
-  ptx::grid_dep_launch();
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 2) {
@@ -536,6 +536,7 @@ decode_merge_kernel(const int32_t* __restrict__ items, int num_items, const floa
                     const float* __restrict__ partial_lse, T* __restrict__ out, float* __restrict__ lse_out,
                     int rows_per_slot, int group, int num_qo_heads, int64_t o_stride_n, int64_t o_stride_h) {
   ptx::grid_dep_wait();
+  ptx::grid_dep_launch();  // early trigger: dependents overlap their prologue, they still wait for our completion
   for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
     const int32_t* mi = items + it * 8;
     const int slot0 = mi[0], nparts = mi[1], q_start = mi[2], q_len = mi[3], kv_head = mi[4];

@@ -32,6 +32,7 @@ act_and_mul_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t rows, 
   const int64_t vec_per_row = d / VN;
   const int64_t total = rows * vec_per_row;
   ptx::grid_dep_wait();
+  ptx::grid_dep_launch();  // early trigger: dependents overlap their prologue, they still wait for our completion
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
     const int64_t r = i / vec_per_row, c = (i % vec_per_row) * VN;
     const Vec16<T> a = ld16(in + r * in_stride + (gate_second ? d : 0) + c);   // activated half
@@ -41,7 +42,6 @@ act_and_mul_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t rows, 
     for (int e = 0; e < VN; ++e) o.v[e] = from_f32<T>(act_fn<ACT>(to_f32(a.v[e])) * to_f32(b.v[e]));
     st16(out + r * out_stride + c, o);
   }
-  ptx::grid_dep_launch();
 }
 
 }  // namespace

@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(1024) rmsnorm_kernel(const NormParams p) {
   const int nvec = int(p.hidden / VN);
 
   ptx::grid_dep_wait();
+  ptx::grid_dep_launch();  // early trigger: dependents overlap their prologue, they still wait for our completion
 
   float cache[VN];
   float ss = 0.f;
@@ -127,7 +128,6 @@ __global__ void __launch_bounds__(1024) rmsnorm_kernel(const NormParams p) {
       for (int e = 0; e < VN; ++e) o[v * VN + e] = ov[e];
     }
   }
-  ptx::grid_dep_launch();
 }
 
 template <typename T>
@@ -138,6 +138,7 @@ layernorm_kernel(const T* __restrict__ xin, T* __restrict__ out, const float* __
   const T* x = xin + blockIdx.x * x_stride;
   T* o = out + blockIdx.x * o_stride;
   ptx::grid_dep_wait();
+  ptx::grid_dep_launch();  // early trigger: dependents overlap their prologue, they still wait for our completion
   float s = 0.f;
   for (int i = threadIdx.x; i < hidden; i += blockDim.x) s += to_f32(x[i]);
   const float mean = block_sum(s, red) / float(hidden);
@@ -149,7 +150,6 @@ layernorm_kernel(const T* __restrict__ xin, T* __restrict__ out, const float* __
   const float rstd = rsqrtf(block_sum(ss, red) / float(hidden) + eps);
   for (int i = threadIdx.x; i < hidden; i += blockDim.x)
     o[i] = from_f32<T>((to_f32(x[i]) - mean) * rstd * gamma[i] + beta[i]);
-  ptx::grid_dep_launch();
 }
 
 template <typename T, typename OutT>

@@ -22,6 +22,7 @@ append_paged_kv_kernel(const T* __restrict__ key, const T* __restrict__ value, c
   const int vec_per_head = head_dim / VN;
   const int64_t total = nnz * num_heads * vec_per_head;
   ptx::grid_dep_wait();
+  ptx::grid_dep_launch();  // early trigger: dependents overlap their prologue, they still wait for our completion
   for (int64_t w = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; w < total; w += int64_t(gridDim.x) * blockDim.x) {
     const int v = int(w % vec_per_head);
     const int64_t rest = w / vec_per_head;
@@ -35,7 +36,6 @@ append_paged_kv_kernel(const T* __restrict__ key, const T* __restrict__ value, c
     st16(k_cache + off, ld16(key + i * key_sn + h * key_sh + v * VN));
     st16(v_cache + off, ld16(value + i * val_sn + h * val_sh + v * VN));
   }
-  ptx::grid_dep_launch();
 }
 
 template <typename T>
@@ -49,6 +49,7 @@ append_paged_mla_kernel(const T* __restrict__ ckv, const T* __restrict__ kpe, co
   const int vc = ckv_dim / VN, vk = kpe_dim / VN;
   const int64_t total = nnz * (vc + vk);
   ptx::grid_dep_wait();
+  ptx::grid_dep_launch();  // early trigger: dependents overlap their prologue, they still wait for our completion
   for (int64_t w = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; w < total; w += int64_t(gridDim.x) * blockDim.x) {
     const int v = int(w % (vc + vk));
     const int64_t i = w / (vc + vk);
@@ -63,7 +64,6 @@ append_paged_mla_kernel(const T* __restrict__ ckv, const T* __restrict__ kpe, co
            ld16(kpe + i * kpe_sn + (v - vc) * VN));
     }
   }
-  ptx::grid_dep_launch();
 }
 
 __global__ void batch_indices_positions_kernel(const int32_t* __restrict__ append_indptr,

@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(256) rope_kernel(const RopeParams p) {
   const int heads = p.num_q_heads + p.num_k_heads;
   const int64_t total = p.nnz * heads * items_per_row;
   ptx::grid_dep_wait();
+  ptx::grid_dep_launch();  // early trigger: dependents overlap their prologue, they still wait for our completion
   for (int64_t w = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; w < total; w += int64_t(gridDim.x) * blockDim.x) {
     const int item = int(w % items_per_row);
     const int64_t rest = w / items_per_row;
@@ -153,7 +154,6 @@ __global__ void __launch_bounds__(256) rope_kernel(const RopeParams p) {
       }
     }
   }
-  ptx::grid_dep_launch();
 }
 
 }  // namespace

@@ -161,7 +161,10 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  ptx::grid_dep_wait();
+  // PDL: the weight operand does not depend on the previous kernel, so the TMA producer prefetches the first
+  // pipeline stages of W before griddepcontrol.wait and only the activation loads wait (hides the pipeline ramp).
+  if (warp != 0) ptx::grid_dep_wait();
+  ptx::grid_dep_launch();
 
   if (S_split > 1) {
     // =====================================================================================
@@ -176,7 +179,18 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (ptx::elect_one()) {
         int stage = 0;
         uint32_t phase = 0;
-        for (int kb = kb0; kb < kb1; ++kb) {
+        const int npre = (kb1 - kb0) < kStages ? (kb1 - kb0) : kStages;
+        for (int i = 0; i < npre; ++i) {  // weights (B operand) first: independent of the previous kernel
+          uint8_t* sb = smem + i * S.stage_bytes + S.a_bytes;
+          ptx::mbar_arrive_expect_tx(&full_bar[i], S.stage_bytes);
+          ptx::tma_load_2d(sb, &tmB, &full_bar[i], (kb0 + i) * BK, tb * BN, ptx::kEvictFirst);
+        }
+        ptx::grid_dep_wait();
+        for (int i = 0; i < npre; ++i)
+          ptx::tma_load_2d(smem + i * S.stage_bytes, &tmA, &full_bar[i], (kb0 + i) * BK, ta * BM, ptx::kEvictLast);
+        stage = npre == kStages ? 0 : npre;
+        phase = npre == kStages ? 1 : 0;
+        for (int kb = kb0 + npre; kb < kb1; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * S.stage_bytes;
           uint8_t* sb = sa + S.a_bytes;
@@ -213,7 +227,6 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           phase ^= 1;
         }
       }
-      ptx::grid_dep_launch();
     } else if (warp >= 4) {
       const int q = warp - 4;
       const int etid = threadIdx.x - 128;
@@ -316,10 +329,32 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       SegIter it(sk, blockIdx.x);
       int tile, kb0, kb1, r_idx;
       bool part;
+      bool first = true;
       while (it.next(tile, kb0, kb1, part, r_idx)) {
         int ta, tb;
         sk.coords(tile, ta, tb);
-        for (int kb = kb0; kb < kb1; ++kb) {
+        int kb_start = kb0;
+        if (first) {
+          // first segment: weight stages before griddepcontrol.wait (kSwap: weights are the A operand)
+          first = false;
+          const int npre = (kb1 - kb0) < kStages ? (kb1 - kb0) : kStages;
+          for (int i = 0; i < npre; ++i) {
+            uint8_t* sa = smem + i * S.stage_bytes;
+            ptx::mbar_arrive_expect_tx(&full_bar[i], S.stage_bytes);
+            if constexpr (kSwap) ptx::tma_load_2d(sa, &tmA, &full_bar[i], (kb0 + i) * BK, ta * BM, ptx::kEvictFirst);
+            else ptx::tma_load_2d(sa + S.a_bytes, &tmB, &full_bar[i], (kb0 + i) * BK, tb * BN, ptx::kEvictNormal);
+          }
+          ptx::grid_dep_wait();
+          for (int i = 0; i < npre; ++i) {
+            uint8_t* sa = smem + i * S.stage_bytes;
+            if constexpr (kSwap) ptx::tma_load_2d(sa + S.a_bytes, &tmB, &full_bar[i], (kb0 + i) * BK, tb * BN, ptx::kEvictLast);
+            else ptx::tma_load_2d(sa, &tmA, &full_bar[i], (kb0 + i) * BK, ta * BM, ptx::kEvictNormal);
+          }
+          stage = npre == kStages ? 0 : npre;
+          phase = npre == kStages ? 1 : 0;
+          kb_start = kb0 + npre;
+        }
+        for (int kb = kb_start; kb < kb1; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * S.stage_bytes;
           uint8_t* sb = sa + S.a_bytes;
