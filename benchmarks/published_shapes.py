@@ -1,0 +1,188 @@
+#!/usr/bin/env python
+"""Our kernels on the exact shapes whose B200 numbers are published inside the reference tree
+(BASELINE.md §1 / SURVEY §6.1, benchmarks/samples/sample_testlist_output.txt).  Timing protocol = the reference's:
+CUDA-graph replay, cold L2 (rotating / flushed), median.  Prints a markdown table + JSON (gpurun_out/published.json)."""
+import json
+import math
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import flashinfer_b200 as fi  # noqa: E402
+from flashinfer_b200.testing import bench_gpu_time  # noqa: E402
+
+ROWS = []
+
+
+def med(ts):
+    ts = sorted(ts)
+    return ts[len(ts) // 2]
+
+
+def timeit(fn, graph=True):
+    try:
+        return med(bench_gpu_time(fn, use_cuda_graph=graph, num_iters_within_graph=5, dry_run_iters=3, repeat_iters=20))
+    except Exception as e:  # noqa: BLE001
+        print("  graph timing failed, falling back to events:", repr(e)[:200])
+        return med(bench_gpu_time(fn, use_cuda_graph=False, dry_run_iters=3, repeat_iters=20))
+
+
+def row(name, ms, ref_ms, ref_backend, tflops=None, tbps=None):
+    ROWS.append({"name": name, "ms": ms, "ref_ms": ref_ms, "ref_backend": ref_backend, "tflops": tflops, "tbps": tbps,
+                 "speedup_vs_ref": ref_ms / ms if ms else None})
+    print(f"| {name} | {ms:.4f} | {ref_ms} ({ref_backend}) | {ref_ms / ms:.2f}x | {tflops or ''} | {tbps or ''} |", flush=True)
+
+
+def paged_decode():
+    B, kv, hq, hkv, d, ps = 16, 1024, 64, 8, 128, 16
+    torch.manual_seed(0)
+    lens = torch.randint(1, kv + 1, (B,))
+    npg = (lens + ps - 1) // ps
+    indptr = torch.zeros(B + 1, dtype=torch.int32)
+    indptr[1:] = npg.cumsum(0)
+    total = int(indptr[-1])
+    indices = torch.randperm(total).int()
+    last = ((lens - 1) % ps + 1).int()
+    kc = torch.randn(total, ps, hkv, d, device="cuda", dtype=torch.bfloat16)
+    vc = torch.randn(total, ps, hkv, d, device="cuda", dtype=torch.bfloat16)
+    q = torch.randn(B, hq, d, device="cuda", dtype=torch.bfloat16)
+    w = fi.BatchDecodeWithPagedKVCacheWrapper(torch.empty(128 << 20, dtype=torch.uint8, device="cuda"), "NHD")
+    w.plan(indptr, indices, last, hq, hkv, d, ps, q_data_type=torch.bfloat16)
+    out = torch.empty_like(q)
+    ms = timeit(lambda: w.run(q, (kc, vc), out=out))
+    byts = float(lens.sum()) * hkv * d * 2 * 2 + 2 * q.numel() * 2
+    row("paged decode B=16 kv<=1024 64/8 d128 p16 bf16", ms, 0.013, "trtllm-gen", tbps=round(byts / ms / 1e9, 3))
+
+
+def mla_decode():
+    B, kv, H, ps = 16, 1024, 128, 32
+    torch.manual_seed(0)
+    npg = kv // ps
+    ckv = torch.randn(B * npg, ps, 512, device="cuda", dtype=torch.bfloat16)
+    kpe = torch.randn(B * npg, ps, 64, device="cuda", dtype=torch.bfloat16)
+    qn = torch.randn(B, H, 512, device="cuda", dtype=torch.bfloat16)
+    qp = torch.randn(B, H, 64, device="cuda", dtype=torch.bfloat16)
+    w = fi.mla.BatchMLAPagedAttentionWrapper(torch.empty(128 << 20, dtype=torch.uint8, device="cuda"))
+    qo = torch.arange(B + 1, dtype=torch.int32)
+    kvi = torch.arange(0, (B + 1) * npg, npg, dtype=torch.int32)
+    idx = torch.arange(B * npg, dtype=torch.int32)
+    lens = torch.full((B,), kv, dtype=torch.int32)
+    w.plan(qo, kvi, idx, lens, H, 512, 64, ps, False, 1.0 / math.sqrt(192), torch.bfloat16, torch.bfloat16)
+    ms = timeit(lambda: w.run(qn, qp, ckv, kpe))
+    flops = 2.0 * B * H * kv * (576 + 512)
+    byts = B * kv * 576 * 2 + B * H * (576 + 512) * 2
+    row("MLA decode B=16 kv=1024 128h ckv512+kpe64 p32 bf16", ms, 0.024, "trtllm-gen", round(flops / ms / 1e9, 1), round(byts / ms / 1e9, 3))
+
+
+def ragged_prefill_ds():
+    B, s, H, dqk, dvo = 16, 1024, 128, 192, 128
+    torch.manual_seed(0)
+    lens = torch.randint(1, s + 1, (B,))
+    indptr = torch.zeros(B + 1, dtype=torch.int32)
+    indptr[1:] = lens.cumsum(0)
+    n = int(indptr[-1])
+    q = torch.randn(n, H, dqk, device="cuda", dtype=torch.bfloat16)
+    k = torch.randn(n, H, dqk, device="cuda", dtype=torch.bfloat16)
+    v = torch.randn(n, H, dvo, device="cuda", dtype=torch.bfloat16)
+    w = fi.BatchPrefillWithRaggedKVCacheWrapper(torch.empty(128 << 20, dtype=torch.uint8, device="cuda"))
+    w.plan(indptr, indptr, H, H, dqk, head_dim_vo=dvo, causal=True, q_data_type=torch.bfloat16)
+    ms = timeit(lambda: w.run(q, k, v), graph=False)
+    flops = float((lens.double() * (lens.double() + 1) / 2).sum()) * 2 * H * (dqk + dvo)
+    row("ragged prefill B=16 s<=1024 128/128 192/128 causal bf16", ms, 0.292, "cudnn", round(flops / ms / 1e9, 1))
+
+
+def paged_prefill_small():
+    B, s, hq, hkv, d, ps = 1, 1024, 64, 8, 128, 16
+    torch.manual_seed(0)
+    L = 103
+    npg = (L + ps - 1) // ps
+    kc = torch.randn(npg, ps, hkv, d, device="cuda", dtype=torch.bfloat16)
+    vc = torch.randn(npg, ps, hkv, d, device="cuda", dtype=torch.bfloat16)
+    q = torch.randn(L, hq, d, device="cuda", dtype=torch.bfloat16)
+    w = fi.BatchPrefillWithPagedKVCacheWrapper(torch.empty(128 << 20, dtype=torch.uint8, device="cuda"))
+    w.plan(torch.tensor([0, L], dtype=torch.int32), torch.tensor([0, npg], dtype=torch.int32), torch.arange(npg, dtype=torch.int32),
+           torch.tensor([(L - 1) % ps + 1], dtype=torch.int32), hq, hkv, d, ps, causal=True, q_data_type=torch.bfloat16)
+    ms = timeit(lambda: w.run(q, (kc, vc)))
+    row("paged prefill B=1 len 103 64/8 d128 causal bf16", ms, 0.010, "trtllm-gen")
+
+
+def gemms():
+    def fp8(x):
+        s = 448.0 / x.abs().amax()
+        return (x * s).to(torch.float8_e4m3fn), (1 / s).float()
+
+    for (B, m, n, k, ref) in [(64, 4, 1024, 7168, 0.085), (256, 1, 1024, 7168, 0.266)]:
+        a, sa = fp8(torch.randn(B, m, k, device="cuda"))
+        w, sw = fp8(torch.randn(B, n, k, device="cuda"))
+        out = torch.empty(B, m, n, device="cuda", dtype=torch.bfloat16)
+        ms = timeit(lambda: fi.bmm_fp8(a, w.transpose(-1, -2), sa, sw, torch.bfloat16, out))
+        row(f"bmm_fp8 B={B} m={m} n={n} k={k}", ms, ref, "cudnn/cutlass", round(2.0 * B * m * n * k / ms / 1e9, 1),
+            round((a.numel() + w.numel()) / ms / 1e9, 3))
+    m, n, k = 512, 1024, 7168
+    a = torch.randn(m, k, device="cuda", dtype=torch.bfloat16)
+    w = torch.randn(n, k, device="cuda", dtype=torch.bfloat16)
+    g = torch.tensor(1.0, device="cuda")
+    aq, asf = fi.nvfp4_quantize(a, g)
+    wq, wsf = fi.nvfp4_quantize(w, g)
+    out = torch.empty(m, n, device="cuda", dtype=torch.bfloat16)
+    ms = timeit(lambda: fi.mm_fp4(aq, wq.t(), asf, wsf, g, torch.bfloat16, out))
+    row("mm_fp4 nvfp4 m=512 n=1024 k=7168", ms, 0.009, "cudnn", round(2.0 * m * n * k / ms / 1e9, 1))
+    m = 16
+    a8 = torch.randn(m, k, device="cuda").to(torch.float8_e4m3fn)
+    w8 = torch.randn(n, k, device="cuda").to(torch.float8_e4m3fn)
+    sa = torch.rand(m, k // 128, device="cuda")
+    sw = torch.rand(n // 128, k // 128, device="cuda")
+    ms = timeit(lambda: fi.gemm_fp8_nt_groupwise(a8, w8, sa, sw, "K", out_dtype=torch.bfloat16))
+    row("gemm_fp8_nt_groupwise m=16 n=1024 k=7168", ms, 0.016, "cutlass", round(2.0 * m * n * k / ms / 1e9, 1))
+
+
+def moe():
+    from flashinfer_b200.fused_moe import RoutingMethodType, trtllm_bf16_moe
+
+    T, H, I, E, K = 1024, 1024, 1024, 256, 8
+    x = torch.randn(T, H, device="cuda", dtype=torch.bfloat16)
+    w1 = torch.randn(E, 2 * I, H, device="cuda", dtype=torch.bfloat16) * 0.03
+    w2 = torch.randn(E, H, I, device="cuda", dtype=torch.bfloat16) * 0.03
+    logits = torch.randn(T, E, device="cuda")
+    bias = torch.randn(E, device="cuda") * 0.1
+    ms = timeit(lambda: trtllm_bf16_moe(logits, bias, x, w1, w2, E, K, 8, 4, I, 0, E, 2.5, RoutingMethodType.DeepSeekV3), graph=False)
+    row("fused MoE (bf16 weights) T=1024 h=1024 i=1024 E=256 top8 DSv3 routing", ms, 0.131, "trtllm fp4", round(2.0 * T * K * H * I * 3 / ms / 1e9, 1))
+
+
+def elementwise():
+    x = torch.randn(32, 4096, device="cuda", dtype=torch.bfloat16)
+    w = torch.ones(4096, device="cuda", dtype=torch.bfloat16)
+    out = torch.empty_like(x)
+    ms = timeit(lambda: fi.rmsnorm(x, w, out=out))
+    row("rmsnorm B=32 h=4096 bf16", ms, 0.003, "cuda", tbps=round(2 * x.numel() * 2 / ms / 1e9, 3))
+    x = torch.randn(2048, 8192, device="cuda", dtype=torch.bfloat16)
+    ms = timeit(lambda: fi.mxfp8_quantize(x))
+    row("mxfp8_quantize m=2048 k=8192", ms, 0.015, "cuda", tbps=round((x.numel() * 3 + x.numel() / 32) / ms / 1e9, 3))
+    xb = torch.randn(8, 2048, 8192, device="cuda", dtype=torch.bfloat16)
+    gs = torch.ones(1, device="cuda")
+    ms = timeit(lambda: fi.nvfp4_batched_quantize(xb, gs))
+    row("nvfp4_batched_quantize B=8 m=2048 k=8192", ms, 0.079, "cuda", tbps=round((xb.numel() * 2.5 + xb.numel() / 16) / ms / 1e9, 3))
+    lg = torch.randn(64, 128256, device="cuda")
+    ms = timeit(lambda: fi.softmax(lg))
+    row("softmax B=64 vocab=128256 fp32", ms, 0.036, "cuda", tbps=round(lg.numel() * 8 / ms / 1e9, 3))
+    pr = torch.softmax(torch.randn(32, 32000, device="cuda"), -1)
+    ms = timeit(lambda: fi.sampling_from_probs(pr), graph=False)
+    row("sampling_from_probs B=32 vocab=32000", ms, 0.014, "cuda")
+
+
+if __name__ == "__main__":
+    print("| shape | ours ms | reference published ms (backend) | speedup | TFLOP/s | TB/s |\n|---|---|---|---|---|---|")
+    for fn in (paged_decode, mla_decode, paged_prefill_small, ragged_prefill_ds, gemms, moe, elementwise):
+        try:
+            fn()
+        except Exception as e:  # noqa: BLE001
+            import traceback
+
+            traceback.print_exc()
+            print(f"| {fn.__name__} | FAILED {repr(e)[:160]} |", flush=True)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "published.json"), "w") as f:
+        json.dump(ROWS, f, indent=1)

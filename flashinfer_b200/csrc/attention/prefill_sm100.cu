@@ -32,7 +32,7 @@ constexpr int kTileQ = 128;    // rows per softmax warpgroup
 constexpr int kUnitQ = 256;    // rows per work unit (two Q tiles)
 constexpr int kTileKV = 128;
 constexpr int kWorkInts = 8;
-constexpr int D = 128;
+constexpr int D = 128;  // head_dim_vo (and the default head_dim_qk)
 
 struct PrefillParams {
   void* out;
@@ -47,14 +47,20 @@ struct PrefillParams {
   float sm_scale_log2, soft_cap, sm_scale;
 };
 
+// DQK = head_dim_qk (128, or 192 for DeepSeek-style prefill with head_dim_vo = 128).  The 192 variant trades pipeline
+// depth for the larger Q / K tiles (2 K stages, 1 V stage) to stay inside 227 KB.
+template <int DQK>
 struct Smem {
-  static constexpr int kStagesK = 3, kStagesV = 2;
-  static constexpr int kTileBytes = kTileKV * D * 2;   // 32 KB
-  static constexpr int kChunkBytes = kTileKV * 128;    // 16 KB (64 columns)
-  static constexpr int kOffQ = 0;                      // 2 x 32 KB
-  static constexpr int kOffK = 2 * kTileBytes;
-  static constexpr int kOffV = kOffK + kStagesK * kTileBytes;
-  static constexpr int kOffBar = kOffV + kStagesV * kTileBytes;
+  static constexpr int kStagesK = DQK == 128 ? 3 : 2, kStagesV = DQK == 128 ? 2 : 1;
+  static constexpr int kQChunks = DQK / 64;
+  static constexpr int kQTileBytes = kTileQ * DQK * 2;   // 32 / 48 KB
+  static constexpr int kKTileBytes = kTileKV * DQK * 2;
+  static constexpr int kVTileBytes = kTileKV * D * 2;    // 32 KB
+  static constexpr int kChunkBytes = kTileKV * 128;      // 16 KB (64 columns)
+  static constexpr int kOffQ = 0;
+  static constexpr int kOffK = 2 * kQTileBytes;
+  static constexpr int kOffV = kOffK + kStagesK * kKTileBytes;
+  static constexpr int kOffBar = kOffV + kStagesV * kVTileBytes;
   static constexpr int kNumBars = 2 * kStagesK + 2 * kStagesV + 2 /*q_full,q_empty*/ + 2 /*s_full*/ + 2 /*p_ready*/ +
                                   2 /*o_done*/ + 2 /*o_free*/;
   static constexpr int kTotal = kOffBar + kNumBars * 8 + 16 + 1024;
@@ -126,11 +132,11 @@ __device__ __forceinline__ float exp_pass(uint32_t s_tmem, int kv0, int lo, int 
   return l;
 }
 
-template <typename T>
+template <typename T, int DQK>
 __global__ void __launch_bounds__(384, 1)
 prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const PrefillParams p, uint32_t idesc_qk, uint32_t idesc_pv) {
-  using S = Smem;
+  using S = Smem<DQK>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kOffBar);
@@ -209,12 +215,12 @@ prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const int q0 = wi[1], head = wi[3], qo_start = wi[6];
         if (lane == 0) {
           ptx::mbar_wait(q_empty, qph ^ 1);
-          ptx::mbar_arrive_expect_tx(q_full, 2 * S::kTileBytes);
+          ptx::mbar_arrive_expect_tx(q_full, 2 * S::kQTileBytes);
 #pragma unroll
           for (int t = 0; t < 2; ++t)
 #pragma unroll
-            for (int c = 0; c < 2; ++c)
-              ptx::tma_load_3d(smem + S::kOffQ + t * S::kTileBytes + c * S::kChunkBytes, &tmQ, q_full, c * 64, head,
+            for (int c = 0; c < S::kQChunks; ++c)
+              ptx::tma_load_3d(smem + S::kOffQ + t * S::kQTileBytes + c * S::kChunkBytes, &tmQ, q_full, c * 64, head,
                                qo_start + q0 + t * kTileQ, ptx::kEvictFirst);
         }
         qph ^= 1;
@@ -228,6 +234,8 @@ prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       uint64_t* empty_bars = is_v ? v_empty : k_empty;
       const CUtensorMap* tm = is_v ? &tmV : &tmK;
       uint8_t* ring = smem + (is_v ? S::kOffV : S::kOffK);
+      const int tile_bytes = is_v ? S::kVTileBytes : S::kKTileBytes;
+      const int nchunks = is_v ? 2 : S::kQChunks;
       int st = 0;
       uint32_t ph = 0;
       for (int w = w_begin; w < w_end; ++w) {
@@ -264,7 +272,7 @@ prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             box_rows = 0;
             box_bytes = kTileKV * 128;
           }
-          const uint32_t tx = uint32_t(n_boxes) * box_bytes * 2;
+          const uint32_t tx = uint32_t(n_boxes) * box_bytes * uint32_t(nchunks);
           int my_pages[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -282,9 +290,8 @@ prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             if (my_pages[j] >= 0) {
-              uint8_t* dst = ring + st * S::kTileBytes + (lane + j * 32) * box_rows * 128;
-#pragma unroll
-              for (int c = 0; c < 2; ++c) {
+              uint8_t* dst = ring + st * tile_bytes + (lane + j * 32) * box_rows * 128;
+              for (int c = 0; c < nchunks; ++c) {
                 if (p.layout_hnd)
                   ptx::tma_load_4d(dst + c * S::kChunkBytes, tm, &full_bars[st], c * 64, page_off, kv_head, my_pages[j]);
                 else
@@ -311,9 +318,9 @@ prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         if (ptx::elect_one()) {
           const uint32_t d_tmem = tmem_base + t * 128;
 #pragma unroll
-          for (int k = 0; k < D / 16; ++k) {
+          for (int k = 0; k < DQK / 16; ++k) {
             const uint32_t off = (k / 4) * S::kChunkBytes + (k % 4) * 32;
-            const uint64_t da = ptx::make_smem_desc(q_addr + t * S::kTileBytes + off, 16, 1024, ptx::kSwz128);
+            const uint64_t da = ptx::make_smem_desc(q_addr + t * S::kQTileBytes + off, 16, 1024, ptx::kSwz128);
             const uint64_t db = ptx::make_smem_desc(k_addr + off, 16, 1024, ptx::kSwz128);
             ptx::mma_f16_ss<1>(d_tmem, da, db, idesc_qk, k > 0 ? 1u : 0u);
           }
@@ -355,7 +362,7 @@ prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         ptx::mbar_wait(&k_full[ks], kph);
         ptx::tc_fence_after();
         {
-          const uint32_t k_addr = ptx::smem_u32(smem + S::kOffK + ks * S::kTileBytes);
+          const uint32_t k_addr = ptx::smem_u32(smem + S::kOffK + ks * S::kKTileBytes);
           issue_qk(0, k_addr);
           issue_qk(1, k_addr);
           if (ptx::elect_one()) {
@@ -368,11 +375,11 @@ prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         for (int j = 0; j < n; ++j) {
           const bool has_next = (j + 1 < n);
           ptx::mbar_wait(&v_full[vs], vph);
-          const uint32_t v_addr = ptx::smem_u32(smem + S::kOffV + vs * S::kTileBytes);
+          const uint32_t v_addr = ptx::smem_u32(smem + S::kOffV + vs * S::kVTileBytes);
           uint32_t k_addr = 0;
           if (has_next) {
             ptx::mbar_wait(&k_full[ks], kph);
-            k_addr = ptx::smem_u32(smem + S::kOffK + ks * S::kTileBytes);
+            k_addr = ptx::smem_u32(smem + S::kOffK + ks * S::kKTileBytes);
           }
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
@@ -500,7 +507,7 @@ prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         if (t == 0 && p.paged && kv0 + kTileKV > kv_len) {
           ptx::mbar_wait(&v_full[vs], vph);
           if (kv0 + row >= kv_len) {
-            uint8_t* vrow = smem + S::kOffV + vs * S::kTileBytes + row * 128;
+            uint8_t* vrow = smem + S::kOffV + vs * S::kVTileBytes + row * 128;
 #pragma unroll
             for (int c = 0; c < 2; ++c)
 #pragma unroll
@@ -555,10 +562,10 @@ extern "C" int prefill_run(void* q, void* k, void* v, void* out, void* lse, void
                            void* work_info, void* cta_work_indptr, int64_t grid, int64_t total_q, int64_t num_qo_heads,
                            int64_t num_kv_heads, int64_t head_dim, int64_t paged, int64_t page_size,
                            int64_t num_pages_total, int64_t kv_stride_page, int64_t kv_stride_n, int64_t kv_stride_h,
-                           int64_t layout_hnd, int64_t q_stride_n, int64_t q_stride_h, int64_t o_stride_n,
+                           int64_t v_stride_page, int64_t v_stride_n, int64_t v_stride_h, int64_t layout_hnd, int64_t q_stride_n, int64_t q_stride_h, int64_t o_stride_n,
                            int64_t o_stride_h, double sm_scale, double soft_cap, int64_t window_left, int64_t causal,
                            int64_t dtype, int64_t pdl, int64_t stream_) {
-  FIB_CHECK(head_dim == 128, "prefill_sm100: only head_dim 128 is specialised");
+  FIB_CHECK(head_dim == 128 || head_dim == 192, "prefill_sm100: head_dim_qk must be 128 or 192 (head_dim_vo = 128)");
   FIB_CHECK(dtype == kF16 || dtype == kBF16, "prefill_sm100: dtype must be f16/bf16");
   FIB_CHECK(!paged || page_size <= 128 || page_size % 128 == 0, "prefill_sm100: page_size > 128 must be a multiple of 128");
   FIB_CHECK(q_stride_n % 8 == 0 && q_stride_h % 8 == 0, "q strides must be 16B multiples");
@@ -576,18 +583,20 @@ extern "C" int prefill_run(void* q, void* k, void* v, void* out, void* lse, void
   for (int i = 0; i < 2; ++i) {
     const void* base = i == 0 ? k : v;
     CUtensorMap* tm = i == 0 ? &tmK : &tmV;
+    const uint64_t hd = i == 0 ? (uint64_t)head_dim : (uint64_t)D;
+    const int64_t sp = i == 0 ? kv_stride_page : v_stride_page, sn = i == 0 ? kv_stride_n : v_stride_n,
+                  sh = i == 0 ? kv_stride_h : v_stride_h;
     if (layout_hnd && paged) {
-      uint64_t dims[4] = {(uint64_t)head_dim, (uint64_t)page_size, (uint64_t)num_kv_heads, (uint64_t)num_pages_total};
-      uint64_t str[3] = {(uint64_t)kv_stride_n * 2, (uint64_t)kv_stride_h * 2, (uint64_t)kv_stride_page * 2};
+      uint64_t dims[4] = {hd, (uint64_t)page_size, (uint64_t)num_kv_heads, (uint64_t)num_pages_total};
+      uint64_t str[3] = {(uint64_t)sn * 2, (uint64_t)sh * 2, (uint64_t)sp * 2};
       uint32_t box[4] = {64, box_rows, 1, 1};
       if (make_tmap(tm, dt, 4, base, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
     } else {
       // NHD pages, or ragged [nnz, H, D] as one giant NHD page (page_size := nnz, 1 page)
       const uint64_t psz = paged ? (uint64_t)page_size : (uint64_t)num_pages_total;
       const uint64_t npg = paged ? (uint64_t)num_pages_total : 1;
-      uint64_t dims[4] = {(uint64_t)head_dim, (uint64_t)num_kv_heads, psz, npg};
-      uint64_t str[3] = {(uint64_t)kv_stride_h * 2, (uint64_t)kv_stride_n * 2,
-                         (uint64_t)(paged ? kv_stride_page : kv_stride_n * (int64_t)psz) * 2};
+      uint64_t dims[4] = {hd, (uint64_t)num_kv_heads, psz, npg};
+      uint64_t str[3] = {(uint64_t)sh * 2, (uint64_t)sn * 2, (uint64_t)(paged ? sp : sn * (int64_t)psz) * 2};
       uint32_t box[4] = {64, 1, box_rows, 1};
       if (make_tmap(tm, dt, 4, base, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
     }
@@ -615,22 +624,17 @@ extern "C" int prefill_run(void* q, void* k, void* v, void* out, void* lse, void
   const uint32_t fmt = f16 ? ptx::kFmtF16 : ptx::kFmtBF16;
   const uint32_t idesc_qk = ptx::make_idesc_f16(fmt, 128, 128, 0, 0);
   const uint32_t idesc_pv = ptx::make_idesc_f16(fmt, 128, 128, 0, 1);
-  LaunchCfg lc(dim3((unsigned)grid), dim3(384), Smem::kTotal, stream, pdl != 0);
-  if (f16) {
-    static bool set = false;
-    if (!set) {
-      FIB_CUDA_CHECK(cudaFuncSetAttribute(prefill_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::kTotal));
-      set = true;
-    }
-    FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, prefill_kernel<__half>, tmQ, tmK, tmV, p, idesc_qk, idesc_pv));
-  } else {
-    static bool set = false;
-    if (!set) {
-      FIB_CUDA_CHECK(cudaFuncSetAttribute(prefill_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          Smem::kTotal));
-      set = true;
-    }
-    FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, prefill_kernel<__nv_bfloat16>, tmQ, tmK, tmV, p, idesc_qk, idesc_pv));
+  auto go = [&](auto kern, int smem_bytes) -> int {
+    FIB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    LaunchCfg lc(dim3((unsigned)grid), dim3(384), smem_bytes, stream, pdl != 0);
+    FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, kern, tmQ, tmK, tmV, p, idesc_qk, idesc_pv));
+    return 0;
+  };
+  if (head_dim == 128) {
+    if (f16) return go(prefill_kernel<__half, 128>, Smem<128>::kTotal);
+    return go(prefill_kernel<__nv_bfloat16, 128>, Smem<128>::kTotal);
   }
+  if (f16) return go(prefill_kernel<__half, 192>, Smem<192>::kTotal);
+  return go(prefill_kernel<__nv_bfloat16, 192>, Smem<192>::kTotal);
   return 0;
 }

@@ -52,86 +52,155 @@ extern "C" const char* fib200_last_error() { return g_err.c_str(); }
 //   merge_items [max_merge][8] : {slot0, nparts, q_start, q_len, kv_head, req, 0, 0}
 //   counts[0]=nseg, [1]=nmerge, [2]=nslots, [3]=max_q_rows(q_len*group), [4]=total_tiles, [5]=quota
 // ---------------------------------------------------------------------------------------------
+namespace {
+struct DecUnit {
+  int32_t b, h, nt, q_start, q_len, kv_len, page_start, npages;
+};
+struct DecSeg {
+  int32_t unit, t0, t1, cta;
+};
+
+// Two candidate schedules, scored by  max over CTAs of (tiles + kSegCost * segments):
+//  * stream-K: walk (request, kv_head, tile) in order, cut into equal quotas -> perfect tile balance, but units
+//    straddle CTAs (extra pipeline start-ups + split-KV merges); best when every CTA has many tiles.
+//  * LPT: units stay whole unless longer than the piece size; pieces go longest-first to the least-loaded CTA ->
+//    few segments and merges; best for small batches / short sequences where start-up latency dominates.
+constexpr double kSegCost = 2.5;  // pipeline start-up of a segment measured in KV tiles (~3.5 us vs ~1.4 us / tile)
+
+double score(const std::vector<DecSeg>& segs, int64_t num_ctas) {
+  std::vector<double> load(num_ctas, 0.0);
+  for (const DecSeg& s : segs) load[s.cta] += double(s.t1 - s.t0) + kSegCost;
+  double mx = 0;
+  for (double l : load) mx = std::max(mx, l);
+  return mx;
+}
+
+std::vector<DecSeg> plan_streamk(const std::vector<DecUnit>& units, int64_t quota) {
+  std::vector<DecSeg> segs;
+  int64_t cta = 0, room = quota;
+  for (size_t u = 0; u < units.size(); ++u) {
+    int64_t t = 0;
+    const int64_t nt = units[u].nt;
+    while (t < nt) {
+      if (room == 0) {
+        ++cta;
+        room = quota;
+      }
+      const int64_t take = std::min(room, nt - t);
+      segs.push_back({(int32_t)u, (int32_t)t, (int32_t)(t + take), (int32_t)cta});
+      t += take;
+      room -= take;
+    }
+  }
+  return segs;
+}
+
+std::vector<DecSeg> plan_lpt(const std::vector<DecUnit>& units, int64_t piece, int64_t num_ctas) {
+  std::vector<DecSeg> segs;
+  for (size_t u = 0; u < units.size(); ++u) {
+    const int64_t nt = units[u].nt;
+    const int64_t parts = (nt + piece - 1) / piece;
+    for (int64_t i = 0; i < parts; ++i)
+      segs.push_back({(int32_t)u, (int32_t)(nt * i / parts), (int32_t)(nt * (i + 1) / parts), 0});
+  }
+  std::vector<int64_t> order(segs.size());
+  for (size_t i = 0; i < order.size(); ++i) order[i] = (int64_t)i;
+  std::stable_sort(order.begin(), order.end(),
+                   [&](int64_t x, int64_t y) { return segs[x].t1 - segs[x].t0 > segs[y].t1 - segs[y].t0; });
+  using Load = std::pair<double, int64_t>;
+  std::priority_queue<Load, std::vector<Load>, std::greater<Load>> heap;
+  for (int64_t c = 0; c < num_ctas; ++c) heap.push({0.0, c});
+  for (int64_t idx : order) {
+    Load l = heap.top();
+    heap.pop();
+    segs[idx].cta = (int32_t)l.second;
+    heap.push({l.first + double(segs[idx].t1 - segs[idx].t0) + kSegCost, l.second});
+  }
+  return segs;
+}
+}  // namespace
+
 extern "C" int decode_plan(const int32_t* kv_page_indptr, const int32_t* kv_lens, const int32_t* q_indptr, int64_t batch,
                            int64_t num_kv_heads, int64_t group, int64_t page_size, int64_t num_ctas,
                            int64_t min_tiles_per_cta, int32_t* seg_info, int64_t max_segs, int32_t* cta_seg_indptr,
                            int32_t* merge_items, int64_t max_merge, int64_t* counts) {
   if (batch < 0 || num_kv_heads <= 0 || page_size <= 0 || num_ctas <= 0) return fail("decode_plan: bad arguments");
-  std::vector<int64_t> tiles(batch);
+  std::vector<DecUnit> units;
   int64_t total = 0;
   int64_t max_q_rows = 1;
   for (int64_t b = 0; b < batch; ++b) {
     if (kv_lens[b] < 0) return fail("decode_plan: negative kv_len");
-    tiles[b] = num_kv_tiles(kv_lens[b], page_size);
-    total += tiles[b] * num_kv_heads;
+    const int64_t nt = num_kv_tiles(kv_lens[b], page_size);
     const int64_t ql = q_indptr ? (q_indptr[b + 1] - q_indptr[b]) : 1;
     max_q_rows = std::max(max_q_rows, ql * group);
+    if (nt == 0 || ql <= 0) continue;
+    total += nt * num_kv_heads;
+    for (int64_t h = 0; h < num_kv_heads; ++h)
+      units.push_back({(int32_t)b, (int32_t)h, (int32_t)nt, q_indptr ? q_indptr[b] : (int32_t)b, (int32_t)ql, kv_lens[b],
+                       kv_page_indptr[b], kv_page_indptr[b + 1] - kv_page_indptr[b]});
   }
+  const bool no_split = min_tiles_per_cta >= (int64_t(1) << 29);
   int64_t quota = (total + num_ctas - 1) / num_ctas;
-  quota = std::max<int64_t>(quota, std::max<int64_t>(1, min_tiles_per_cta));
-  int64_t nseg = 0, nmerge = 0, nslots = 0;
-  int64_t cta = 0, room = quota;  // tiles still available in the current CTA
-  cta_seg_indptr[0] = 0;
-  for (int64_t b = 0; b < batch; ++b) {
-    const int64_t nt = tiles[b];
-    if (nt == 0) continue;
-    const int32_t q_start = q_indptr ? q_indptr[b] : (int32_t)b;
-    const int32_t q_len = q_indptr ? (q_indptr[b + 1] - q_indptr[b]) : 1;
-    if (q_len <= 0) continue;
-    const int32_t page_start = kv_page_indptr[b];
-    const int32_t npages = kv_page_indptr[b + 1] - kv_page_indptr[b];
-    for (int64_t h = 0; h < num_kv_heads; ++h) {
-      int64_t t = 0;
-      const int64_t first_seg = nseg;
-      while (t < nt) {
-        if (room == 0) {
-          ++cta;
-          if (cta >= num_ctas) return fail("decode_plan: internal error (cta overflow)");
-          cta_seg_indptr[cta] = (int32_t)nseg;
-          room = quota;
-        }
-        const int64_t take = std::min(room, nt - t);
-        if (nseg >= max_segs) return fail("decode_plan: seg_info capacity exceeded");
-        int32_t* s = seg_info + nseg * kSegInts;
-        s[0] = (int32_t)b;
-        s[1] = (int32_t)h;
-        s[2] = (int32_t)t;
-        s[3] = (int32_t)(t + take);
-        s[4] = -1;
-        s[5] = q_start;
-        s[6] = q_len;
-        s[7] = kv_lens[b];
-        s[8] = page_start;
-        s[9] = npages;
-        s[10] = 0;
-        s[11] = 0;
-        ++nseg;
-        t += take;
-        room -= take;
-      }
-      const int64_t parts = nseg - first_seg;
-      if (parts > 1) {
-        if (nmerge >= max_merge) return fail("decode_plan: merge_items capacity exceeded");
-        for (int64_t i = 0; i < parts; ++i) {
-          seg_info[(first_seg + i) * kSegInts + 4] = (int32_t)(nslots + i);
-          seg_info[(first_seg + i) * kSegInts + 10] = (int32_t)nslots;  // first slot of the item (= counter id)
-          seg_info[(first_seg + i) * kSegInts + 11] = (int32_t)parts;   // number of partial states to merge
-        }
-        int32_t* m = merge_items + nmerge * kMergeInts;
-        m[0] = (int32_t)nslots;
-        m[1] = (int32_t)parts;
-        m[2] = q_start;
-        m[3] = q_len;
-        m[4] = (int32_t)h;
-        m[5] = (int32_t)b;
-        m[6] = 0;
-        m[7] = 0;
-        nslots += parts;
-        ++nmerge;
-      }
+  quota = std::max<int64_t>(quota, no_split ? 1 : std::max<int64_t>(1, min_tiles_per_cta));
+  std::vector<DecSeg> segs;
+  if (no_split) {
+    segs = plan_lpt(units, int64_t(1) << 30, num_ctas);  // whole units only
+  } else {
+    segs = plan_streamk(units, quota);
+    const std::vector<DecSeg> alt = plan_lpt(units, std::max<int64_t>(quota, 8), num_ctas);
+    if (score(alt, num_ctas) < score(segs, num_ctas)) segs = alt;
+  }
+  if ((int64_t)segs.size() > max_segs) return fail("decode_plan: seg_info capacity exceeded");
+  // merge bookkeeping per unit
+  std::vector<int32_t> parts(units.size(), 0), slot0(units.size(), -1), seen(units.size(), 0);
+  for (const DecSeg& sg : segs) ++parts[sg.unit];
+  int64_t nmerge = 0, nslots = 0;
+  for (size_t u = 0; u < units.size(); ++u) {
+    if (parts[u] > 1) {
+      if (nmerge >= max_merge) return fail("decode_plan: merge_items capacity exceeded");
+      slot0[u] = (int32_t)nslots;
+      int32_t* m = merge_items + nmerge * kMergeInts;
+      m[0] = (int32_t)nslots;
+      m[1] = parts[u];
+      m[2] = units[u].q_start;
+      m[3] = units[u].q_len;
+      m[4] = units[u].h;
+      m[5] = units[u].b;
+      m[6] = 0;
+      m[7] = 0;
+      nslots += parts[u];
+      ++nmerge;
     }
   }
-  for (int64_t c = cta + 1; c <= num_ctas; ++c) cta_seg_indptr[c] = (int32_t)nseg;
+  // emit grouped by CTA (stable: keeps kv order inside a unit)
+  std::vector<int64_t> order(segs.size());
+  for (size_t i = 0; i < order.size(); ++i) order[i] = (int64_t)i;
+  std::stable_sort(order.begin(), order.end(), [&](int64_t x, int64_t y) { return segs[x].cta < segs[y].cta; });
+  int64_t nseg = 0;
+  int64_t cur = 0;
+  cta_seg_indptr[0] = 0;
+  for (int64_t idx : order) {
+    const DecSeg& sg = segs[idx];
+    if (sg.cta >= num_ctas) return fail("decode_plan: internal error (cta overflow)");
+    while (cur < sg.cta) cta_seg_indptr[++cur] = (int32_t)nseg;
+    const DecUnit& u = units[sg.unit];
+    int32_t* s = seg_info + nseg * kSegInts;
+    s[0] = u.b;
+    s[1] = u.h;
+    s[2] = sg.t0;
+    s[3] = sg.t1;
+    s[4] = parts[sg.unit] > 1 ? slot0[sg.unit] + seen[sg.unit] : -1;
+    s[5] = u.q_start;
+    s[6] = u.q_len;
+    s[7] = u.kv_len;
+    s[8] = u.page_start;
+    s[9] = u.npages;
+    s[10] = parts[sg.unit] > 1 ? slot0[sg.unit] : 0;
+    s[11] = parts[sg.unit] > 1 ? parts[sg.unit] : 0;
+    ++seen[sg.unit];
+    ++nseg;
+  }
+  for (int64_t c = cur + 1; c <= num_ctas; ++c) cta_seg_indptr[c] = (int32_t)nseg;
   counts[0] = nseg;
   counts[1] = nmerge;
   counts[2] = nslots;

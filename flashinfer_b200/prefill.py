@@ -79,7 +79,7 @@ def single_prefill_with_kv_cache(
         mask = _unpack_bits(packed_custom_mask, qo_len * kv_len).view(qo_len, kv_len)
     elif custom_mask is not None:
         mask = custom_mask.view(qo_len, kv_len)
-    fast = q.is_cuda and mask is None and q.shape[-1] == 128 and v.shape[-1] == 128 and q.dtype in (
+    fast = q.is_cuda and mask is None and q.shape[-1] in (128, 192) and v.shape[-1] == 128 and q.dtype in (
         torch.float16, torch.bfloat16) and k.dtype == q.dtype
     if not q.is_cuda:
         o, lse = reference.attention_ref(q, k, v, causal and mask is None, sm_scale, logits_soft_cap or 0.0,
@@ -107,7 +107,7 @@ def single_prefill_with_kv_cache(
         w = BatchPrefillWithRaggedKVCacheWrapper(ws, "NHD")
         qo_indptr = torch.tensor([0, qo_len], dtype=torch.int32)
         kv_indptr = torch.tensor([0, kv_len], dtype=torch.int32)
-        w.plan(qo_indptr, kv_indptr, q.shape[1], k.shape[1], d, causal=causal, sm_scale=sm_scale,
+        w.plan(qo_indptr, kv_indptr, q.shape[1], k.shape[1], d, head_dim_vo=v.shape[-1], causal=causal, sm_scale=sm_scale,
                window_left=window_left, logits_soft_cap=logits_soft_cap, q_data_type=q.dtype)
         o, lse = w.run(q, k, v, return_lse=True)
     if o_dtype is not None and o.dtype != o_dtype:
@@ -218,19 +218,20 @@ class _BatchPrefillBase:
 
     def _launch_sm100(self, q, k, v, out, lse, sm_scale, window_left, paged, kv_indices, page_args, enable_pdl,
                       k_scale=None, v_scale=None):
-        fast = (self._head_dim_qk == 128 and self._head_dim_vo == 128 and q.dtype in (torch.float16, torch.bfloat16)
-                and k.dtype == q.dtype and self._custom_mask is None)
+        fast = (self._head_dim_qk in (128, 192) and self._head_dim_vo == 128 and q.dtype in (torch.float16, torch.bfloat16)
+                and k.dtype == q.dtype and v.dtype == q.dtype and self._custom_mask is None)
         if not fast:
             return self._launch_generic(q, k, v, out, lse, sm_scale, window_left, paged, kv_indices, page_args, enable_pdl,
                                         k_scale, v_scale)
+        page_size, num_pages_total, sp, sn, sh, hnd = page_args[:6]
+        vsp, vsn, vsh = page_args[6:9] if len(page_args) >= 9 else (sp, sn, sh)
         jit.load("prefill_sm100").call(
             "prefill_run", q, k, v, out, lse, kv_indices, self._kv_page_indptr_dev if paged else None,
             self._work_info, self._cta_work_indptr, self._num_ctas, q.shape[0], self._num_qo_heads, self._num_kv_heads,
-            self._head_dim_qk, 1 if paged else 0, *page_args, q.stride(0), q.stride(1), out.stride(0), out.stride(1),
-            float(sm_scale), float(self._logits_soft_cap), int(window_left), 1 if self._causal else 0,
-            dtype_code(q.dtype), 1 if (enable_pdl is None or enable_pdl) else 0, stream_ptr(q),
+            self._head_dim_qk, 1 if paged else 0, page_size, num_pages_total, sp, sn, sh, vsp, vsn, vsh, hnd, q.stride(0),
+            q.stride(1), out.stride(0), out.stride(1), float(sm_scale), float(self._logits_soft_cap), int(window_left),
+            1 if self._causal else 0, dtype_code(q.dtype), 1 if (enable_pdl is None or enable_pdl) else 0, stream_ptr(q),
         )
-
 
     def _launch_generic(self, q, k, v, out, lse, sm_scale, window_left, paged, kv_indices, page_args, enable_pdl, k_scale, v_scale):
         """Catch-all CUDA-core kernel: other head dims, fp8 KV, custom masks."""
@@ -258,7 +259,7 @@ class _BatchPrefillBase:
             self._gen_cache_key = id(self._qo_indptr_host)
         causal = self._causal and self._custom_mask is None
         if paged:
-            page_size, _, sp, sn, sh, _ = page_args
+            page_size, _, sp, sn, sh, _ = page_args[:6]
             _g.run(q, k, v, out, lse, self._gen_qo, self._gen_kv, kv_indices, self._gen_last, page_size, (sp, sn, sh), (sp, sn, sh),
                    self._num_kv_heads, causal, window_left, sm_scale, self._logits_soft_cap, self._gen_mask,
                    getattr(self, "_gen_mask_indptr", None), None, 1.0, 1.0, enable_pdl is None or enable_pdl)
@@ -333,9 +334,9 @@ class BatchPrefillWithRaggedKVCacheWrapper(_BatchPrefillBase):
                                               v[int(st[b]) : int(st[b]) + int(self._kv_lens_host[b])]),
                                 out, lse if return_lse else None, sm_scale, window_left)
         else:
-            if k.stride(-1) != 1 or v.stride(-1) != 1 or k.stride() != v.stride():
+            if k.stride(-1) != 1 or v.stride(-1) != 1:
                 k, v = k.contiguous(), v.contiguous()
-            page_args = (1, k.shape[0], k.stride(0), k.stride(0), k.stride(1), 0)
+            page_args = (1, k.shape[0], k.stride(0), k.stride(0), k.stride(1), 0, v.stride(0), v.stride(0), v.stride(1))
             self._launch_sm100(q, k, v, out, lse if return_lse else None, sm_scale, window_left, False, None, page_args,
                                enable_pdl)
         if v_scale is not None:

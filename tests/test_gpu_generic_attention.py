@@ -112,3 +112,29 @@ def test_single_decode_head_dim_64_softcap_window():
     out = fi.single_decode_with_kv_cache(q, k, v, window_left=200, logits_soft_cap=30.0)
     ref, _ = reference.attention_ref(q[None], k, v, True, 1 / math.sqrt(d), 30.0, 200)
     assert (out.float() - ref[0].float()).abs().max() < 2e-2
+
+
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_prefill_deepseek_head_dims_tcgen05(causal, dtype):
+    """head_dim_qk 192 / head_dim_vo 128 (DeepSeek prefill) runs on the tcgen05 kernel."""
+    torch.manual_seed(5)
+    H = 16
+    qo = torch.tensor([0, 100, 100, 700, 1500], dtype=torch.int32)
+    q = torch.randn(1500, H, 192, device="cuda", dtype=dtype)
+    k = torch.randn(1500, H, 192, device="cuda", dtype=dtype)
+    v = torch.randn(1500, H, 128, device="cuda", dtype=dtype)
+    w = fi.BatchPrefillWithRaggedKVCacheWrapper(torch.empty(64 << 20, dtype=torch.uint8, device="cuda"))
+    w.plan(qo, qo, H, H, 192, head_dim_vo=128, causal=causal, q_data_type=dtype)
+    out, lse = w.run(q, k, v, return_lse=True)
+    assert out.shape == (1500, H, 128)
+    for b in range(4):
+        s, e = int(qo[b]), int(qo[b + 1])
+        if s == e:
+            continue
+        ref, lref = reference.attention_ref(q[s:e], k[s:e], v[s:e], causal, 1 / math.sqrt(192))
+        assert (out[s:e].float() - ref.float()).abs().max() < 2e-2
+        assert (lse[s:e] - lref).abs().max() < 2e-2
+    o1 = fi.single_prefill_with_kv_cache(q[:333], k[:333], v[:333], causal=causal)
+    r1, _ = reference.attention_ref(q[:333], k[:333], v[:333], causal, 1 / math.sqrt(192))
+    assert (o1.float() - r1.float()).abs().max() < 2e-2

@@ -55,7 +55,8 @@ def test_decode_plan_covers_every_tile_once(ps, kv_lens):
     assert cta[0] == 0 and cta[-1] == len(seg)
     for c in range(num_ctas):
         load = sum(s[3] - s[2] for s in seg[cta[c]:cta[c + 1]].tolist())
-        assert load <= quota
+        # the LPT schedule may trade a few tiles for fewer segments / merges (cost model in planner.cpp)
+        assert load <= max(2 * quota, quota + 8)
     # merge items reference consecutive slots of the same (req, head)
     slots = {}
     for s in seg.tolist():
