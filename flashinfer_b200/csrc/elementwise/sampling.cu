@@ -143,23 +143,79 @@ __device__ __forceinline__ float row_uniform(uint64_t seed, uint64_t offset, int
 }
 
 // ------------------------------------------------------------------ softmax
+// One thread-block CLUSTER per row: every CTA keeps its slice of the row in shared memory (the row crosses HBM once
+// in each direction), the running max and the sum are exchanged through distributed shared memory (two cluster
+// barriers), so small batches still use all SMs.  Falls back to plain strided global passes when the slice does not
+// fit (huge vocab with cluster size 1) or the row is not 16-byte aligned.
+template <bool kSmemSlice>
 __global__ void __launch_bounds__(kThreads)
 softmax_kernel(const float* __restrict__ logits, float* __restrict__ probs, const float* __restrict__ temp_arr,
-               float temp_val, int V) {
+               float temp_val, int V, int csize, int slice) {
   __shared__ float smf[32];
-  const int row = blockIdx.x;
+  __shared__ float xch[2][8];  // [max | sum][cluster rank]
+  extern __shared__ float sl[];
+  const int crank = csize > 1 ? int(ptx::cluster_ctarank()) : 0;
+  if (csize > 1) ptx::cluster_arrive();  // paired with the wait before the first DSMEM store: peers must be running
+  const int row = blockIdx.x / csize;
   const float* x = logits + int64_t(row) * V;
   float* y = probs + int64_t(row) * V;
-  float t = temp_arr ? temp_arr[row] : temp_val;
+  const float t = temp_arr ? temp_arr[row] : temp_val;
   const float inv_t = (t > 0.f) ? 1.f / t : 1.f;
+  const int i0 = crank * slice;
+  const int n = max(0, min(slice, V - i0));
   float m = -INFINITY;
-  for (int i = threadIdx.x; i < V; i += blockDim.x) m = fmaxf(m, x[i] * inv_t);
+  if constexpr (kSmemSlice) {
+    const float4* x4 = reinterpret_cast<const float4*>(x + i0);
+    for (int i = threadIdx.x; i < n / 4; i += blockDim.x) {
+      float4 v = x4[i];
+      v.x *= inv_t; v.y *= inv_t; v.z *= inv_t; v.w *= inv_t;
+      reinterpret_cast<float4*>(sl)[i] = v;
+      m = fmaxf(fmaxf(m, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+    }
+    for (int i = (n / 4) * 4 + threadIdx.x; i < n; i += blockDim.x) {
+      const float v = x[i0 + i] * inv_t;
+      sl[i] = v;
+      m = fmaxf(m, v);
+    }
+  } else {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, x[i0 + i] * inv_t);
+  }
   m = block_reduce_max(m, smf);
+  if (csize > 1) {
+    ptx::cluster_wait();
+    if (threadIdx.x < csize) ptx::st_dsmem_f32(ptx::mapa(ptx::smem_u32(&xch[0][crank]), threadIdx.x), m);
+    ptx::cluster_sync();
+    for (int r = 0; r < csize; ++r) m = fmaxf(m, xch[0][r]);
+  }
   float s = 0.f;
-  for (int i = threadIdx.x; i < V; i += blockDim.x) s += __expf(x[i] * inv_t - m);
+  if constexpr (kSmemSlice) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const float e = __expf(sl[i] - m);
+      sl[i] = e;
+      s += e;
+    }
+  } else {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += __expf(x[i0 + i] * inv_t - m);
+  }
   s = block_reduce_sum(s, smf);
+  if (csize > 1) {
+    if (threadIdx.x < csize) ptx::st_dsmem_f32(ptx::mapa(ptx::smem_u32(&xch[1][crank]), threadIdx.x), s);
+    ptx::cluster_sync();
+    s = 0.f;
+    for (int r = 0; r < csize; ++r) s += xch[1][r];
+  }
   const float inv = 1.f / s;
-  for (int i = threadIdx.x; i < V; i += blockDim.x) y[i] = __expf(x[i] * inv_t - m) * inv;
+  if constexpr (kSmemSlice) {
+    float4* y4 = reinterpret_cast<float4*>(y + i0);
+    for (int i = threadIdx.x; i < n / 4; i += blockDim.x) {
+      float4 v = reinterpret_cast<const float4*>(sl)[i];
+      v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+      y4[i] = v;
+    }
+    for (int i = (n / 4) * 4 + threadIdx.x; i < n; i += blockDim.x) y[i0 + i] = sl[i] * inv;
+  } else {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) y[i0 + i] = __expf(x[i0 + i] * inv_t - m) * inv;
+  }
 }
 
 // ------------------------------------------------------------------ unified sampling kernel
@@ -437,10 +493,26 @@ extern "C" int softmax_run(void* logits, void* probs, void* temp_arr, double tem
                            int64_t stream_) {
   if (rows == 0) return 0;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
-  ++launch_counter();
-  softmax_kernel<<<(unsigned)rows, kThreads, 0, s>>>((const float*)logits, (float*)probs, (const float*)temp_arr,
-                                                     (float)temp_val, (int)V);
-  FIB_CUDA_CHECK(cudaGetLastError());
+  // cluster size: enough CTAs to cover the SMs and a slice that fits in shared memory
+  int csize = 1;
+  while (csize < 8 && (rows * csize < 2 * num_sms() || (V + csize - 1) / csize * 4 > 200 * 1024)) csize <<= 1;
+  int slice = int((V + csize - 1) / csize);
+  slice = (slice + 3) / 4 * 4;
+  const bool smem_ok = (V % 4 == 0) && int64_t(slice) * 4 <= 200 * 1024;
+  const size_t smem = smem_ok ? size_t(slice) * 4 : 0;
+  LaunchCfg lc(dim3((unsigned)(rows * csize)), dim3(kThreads), smem, s, false, csize);
+  if (smem_ok) {
+    static bool set = false;
+    if (!set) {
+      FIB_CUDA_CHECK(cudaFuncSetAttribute(softmax_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      set = true;
+    }
+    FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, softmax_kernel<true>, (const float*)logits, (float*)probs, (const float*)temp_arr,
+                                      (float)temp_val, (int)V, csize, slice));
+  } else {
+    FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, softmax_kernel<false>, (const float*)logits, (float*)probs, (const float*)temp_arr,
+                                      (float)temp_val, (int)V, csize, slice));
+  }
   return 0;
 }
 

@@ -295,6 +295,200 @@ bs_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// fp8 GEMM with fp32 group scales (DeepSeek-V3 style: 1x128 scales on A, 128x128 on B).  fp32 scales cannot be fed to
+// the block-scaled tensor-core path, so every 128-wide K slab is multiplied into a fresh TMEM buffer (2 buffers,
+// ping-pong) and the epilogue warps promote it into fp32 register accumulators:  acc += sa[row,kb] * sb[nblk,kb] * D.
+// The promotion of slab kb overlaps the MMAs of slab kb+1.  Parity: reference gemm_fp8_nt_groupwise
+// (include/flashinfer/gemm/gemm_groupwise_sm100.cuh:40-140) / DeepGEMM's per-block promotion.
+// ---------------------------------------------------------------------------------------------------------------
+struct GwParams {
+  const float* sa;  // A scales, element strides (row, kblock)
+  const float* sb;  // B scales, element strides (n-block of 128, kblock)
+  int64_t sa_row, sa_k, sb_n, sb_k, ldc;
+  int M, N, K;
+  uint32_t idesc;
+};
+
+template <int BN, typename OutT>
+__global__ void __launch_bounds__(256, 1)
+fp8_groupwise_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, OutT* __restrict__ C,
+                     const GwParams p) {
+  const Geo G = Geo::make(BN, kFp8);
+  const int kStages = G.stages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + G.bar_offset);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full = empty_bar + kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+    for (int i = 0; i < kStages; ++i) {
+      ptx::mbar_init(&full_bar[i], 1);
+      ptx::mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&tmem_full[i], 1);
+      ptx::mbar_init(&tmem_empty[i], 4);
+    }
+    ptx::fence_mbar_init();
+  }
+  constexpr uint32_t kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
+  if (warp == 2) {
+    ptx::tmem_alloc<1>(tmem_ptr, kTmemCols);
+    ptx::tmem_relinquish<1>();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = (p.K + BKB - 1) / BKB;
+  if (warp != 0) ptx::grid_dep_wait();
+  ptx::grid_dep_launch();
+
+  if (warp == 0) {
+    if (ptx::elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      bool first = true;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int tm = t % tiles_m, tn = t / tiles_m;
+        int kb_start = 0;
+        if (first) {  // weights before griddepcontrol.wait
+          first = false;
+          const int npre = num_kb < kStages ? num_kb : kStages;
+          for (int i = 0; i < npre; ++i) {
+            ptx::mbar_arrive_expect_tx(&full_bar[i], G.a_bytes + G.b_bytes);
+            ptx::tma_load_2d(smem + i * G.stage_bytes + G.a_bytes, &tmB, &full_bar[i], i * BKB, tn * BN, ptx::kEvictFirst);
+          }
+          ptx::grid_dep_wait();
+          for (int i = 0; i < npre; ++i)
+            ptx::tma_load_2d(smem + i * G.stage_bytes, &tmA, &full_bar[i], i * BKB, tm * BM, ptx::kEvictNormal);
+          stage = npre == kStages ? 0 : npre;
+          phase = npre == kStages ? 1 : 0;
+          kb_start = npre;
+        }
+        for (int kb = kb_start; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * G.stage_bytes;
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], G.a_bytes + G.b_bytes);
+          ptx::tma_load_2d(sa, &tmA, &full_bar[stage], kb * BKB, tm * BM, ptx::kEvictNormal);
+          ptx::tma_load_2d(sa + G.a_bytes, &tmB, &full_bar[stage], kb * BKB, tn * BN, ptx::kEvictFirst);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    int stage = 0, buf = 0;
+    uint32_t phase = 0, bphase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        ptx::mbar_wait(&tmem_empty[buf], bphase ^ 1);
+        ptx::mbar_wait(&full_bar[stage], phase);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const uint32_t sa = ptx::smem_u32(smem + stage * G.stage_bytes);
+          const uint64_t da = ptx::make_smem_desc(sa, 16, 1024, ptx::kSwz128);
+          const uint64_t db = ptx::make_smem_desc(sa + G.a_bytes, 16, 1024, ptx::kSwz128);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            ptx::mma_f8f6f4_ss<1>(tmem_base + buf * BN, ptx::desc_advance(da, k * 32), ptx::desc_advance(db, k * 32), p.idesc,
+                                  k > 0 ? 1u : 0u);
+          ptx::mma_commit(&empty_bar[stage]);
+          ptx::mma_commit(&tmem_full[buf]);
+        }
+        __syncwarp();
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+        buf ^= 1;
+        if (buf == 0) bphase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp - 4;
+    int buf = 0;
+    uint32_t bphase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int tm = t % tiles_m, tn = t / tiles_m;
+      const int row = tm * BM + q * 32 + lane;
+      const int rowc = row < p.M ? row : p.M - 1;
+      const int nblk = (tn * BN) / 128;
+      float acc[BN];
+#pragma unroll
+      for (int c = 0; c < BN; ++c) acc[c] = 0.f;
+      float sc_next = p.sa[rowc * p.sa_row] * p.sb[nblk * p.sb_n];
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const float sc = sc_next;
+        if (kb + 1 < num_kb) sc_next = p.sa[rowc * p.sa_row + (kb + 1) * p.sa_k] * p.sb[nblk * p.sb_n + (kb + 1) * p.sb_k];
+        ptx::mbar_wait(&tmem_full[buf], bphase);
+        ptx::tc_fence_after();
+        const uint32_t taddr = tmem_base + buf * BN + (uint32_t(q * 32) << 16);
+#pragma unroll
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32];
+          ptx::tmem_ld_x32(taddr + c0, v);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[c0 + j] = fmaf(__uint_as_float(v[j]), sc, acc[c0 + j]);
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tmem_empty[buf]);
+        buf ^= 1;
+        if (buf == 0) bphase ^= 1;
+      }
+      if (row < p.M) {
+        OutT* crow = C + int64_t(row) * p.ldc + tn * BN;
+        constexpr int VN = 16 / sizeof(OutT);
+        const bool vec_ok = (p.ldc % VN == 0);
+#pragma unroll
+        for (int c0 = 0; c0 < BN; c0 += VN) {
+          if (tn * BN + c0 + VN <= p.N && vec_ok) {
+            Vec16<OutT> o;
+#pragma unroll
+            for (int e = 0; e < VN; ++e) o.v[e] = from_f32<OutT>(acc[c0 + e]);
+            st16(crow + c0, o);
+          } else {
+#pragma unroll
+            for (int e = 0; e < VN; ++e)
+              if (tn * BN + c0 + e < p.N) crow[c0 + e] = from_f32<OutT>(acc[c0 + e]);
+          }
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<1>(tmem_base, kTmemCols);
+  }
+}
+
+template <int BN, typename OutT>
+int launch_gw(const CUtensorMap& tmA, const CUtensorMap& tmB, void* C, const GwParams& p, int grid, bool pdl, cudaStream_t stream) {
+  static bool set = false;
+  if (!set) {
+    FIB_CUDA_CHECK(cudaFuncSetAttribute(fp8_groupwise_kernel<BN, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    set = true;
+  }
+  const Geo G = Geo::make(BN, kFp8);
+  LaunchCfg lc(dim3(grid), dim3(256), G.total, stream, pdl);
+  FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, fp8_groupwise_kernel<BN, OutT>, tmA, tmB, (OutT*)C, p));
+  return 0;
+}
+
 template <int KIND, typename OutT>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, void* C, const Params& p, int grid, int smem, bool pdl,
            cudaStream_t stream) {
@@ -415,4 +609,48 @@ extern "C" int gemm_lowp_nt(void* A, void* B, void* C, void* sfa, void* sfb, voi
       return f16 ? launch<kMxFp4, __half>(tmA, tmB, C, p, grid, G.total, pdl != 0, stream)
                  : launch<kMxFp4, __nv_bfloat16>(tmA, tmB, C, p, grid, G.total, pdl != 0, stream);
   }
+}
+
+// A [M, K] fp8 (lda bytes), B [N, K] fp8; sa fp32 with element strides (sa_row, sa_k) over [M, K/128];
+// sb fp32 with element strides (sb_n, sb_k) over [N/128, K/128].
+extern "C" int gemm_fp8_groupwise_nt(void* A, void* B, void* C, void* sa, void* sb, int64_t M, int64_t N, int64_t K, int64_t lda,
+                                     int64_t ldb, int64_t ldc, int64_t sa_row, int64_t sa_k, int64_t sb_n, int64_t sb_k,
+                                     int64_t a_fmt, int64_t b_fmt, int64_t out_dtype, int64_t bn, int64_t pdl, int64_t stream_) {
+  FIB_CHECK(out_dtype == kF16 || out_dtype == kBF16, "gemm_fp8_groupwise: output must be f16/bf16");
+  FIB_CHECK(K % 128 == 0, "gemm_fp8_groupwise: K must be a multiple of 128");
+  FIB_CHECK(lda % 16 == 0 && ldb % 16 == 0, "gemm_fp8_groupwise: row strides must be multiples of 16 bytes");
+  if (M == 0 || N == 0) return 0;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const int tiles_m = int((M + BM - 1) / BM);
+  int BN = (int)bn;
+  if (BN == 0) {
+    const int64_t want = (N * tiles_m + num_sms() - 1) / num_sms();
+    BN = want <= 32 ? 32 : (want <= 64 ? 64 : 128);
+  }
+  FIB_CHECK(BN == 32 || BN == 64 || BN == 128, "gemm_fp8_groupwise: N tile must be 32 / 64 / 128");
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+    uint64_t str[1] = {(uint64_t)lda};
+    uint32_t box[2] = {BKB, BM};
+    if (make_tmap(&tmA, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, A, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+    uint64_t str[1] = {(uint64_t)ldb};
+    uint32_t box[2] = {BKB, (uint32_t)BN};
+    if (make_tmap(&tmB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, B, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  }
+  GwParams p;
+  p.sa = (const float*)sa;
+  p.sb = (const float*)sb;
+  p.sa_row = sa_row; p.sa_k = sa_k; p.sb_n = sb_n; p.sb_k = sb_k; p.ldc = ldc;
+  p.M = (int)M; p.N = (int)N; p.K = (int)K;
+  p.idesc = ptx::make_idesc_f8((uint32_t)a_fmt, (uint32_t)b_fmt, BM, BN, 0, 0);
+  const int64_t tiles = int64_t(tiles_m) * ((N + BN - 1) / BN);
+  const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+  const bool f16 = out_dtype == kF16;
+  if (BN == 32) return f16 ? launch_gw<32, __half>(tmA, tmB, C, p, grid, pdl != 0, stream) : launch_gw<32, __nv_bfloat16>(tmA, tmB, C, p, grid, pdl != 0, stream);
+  if (BN == 64) return f16 ? launch_gw<64, __half>(tmA, tmB, C, p, grid, pdl != 0, stream) : launch_gw<64, __nv_bfloat16>(tmA, tmB, C, p, grid, pdl != 0, stream);
+  return f16 ? launch_gw<128, __half>(tmA, tmB, C, p, grid, pdl != 0, stream) : launch_gw<128, __nv_bfloat16>(tmA, tmB, C, p, grid, pdl != 0, stream);
 }

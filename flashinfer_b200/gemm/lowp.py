@@ -202,14 +202,27 @@ def _expand_scale(s: torch.Tensor, rows: int, K: int, g_rows: int, g_k: int, maj
     return s.repeat_interleave(g_rows, 0)[:rows].repeat_interleave(g_k, 1)[:, :K]
 
 
+def _scale_strides(s: torch.Tensor, rows_blocks: int, kblocks: int, major: str):
+    """(tensor, row stride, k stride) for a scale tensor stored ``[rows, K/128]`` ("K") or ``[K/128, rows]`` ("MN")."""
+    s = s.float()
+    if s.dim() != 2:
+        raise ValueError("scale tensors must be 2-D")
+    if s.shape == (rows_blocks, kblocks) and not (major == "MN" and s.shape == (kblocks, rows_blocks)):
+        return s, s.stride(0), s.stride(1)
+    if s.shape == (kblocks, rows_blocks):
+        return s, s.stride(1), s.stride(0)
+    raise ValueError(f"scale shape {tuple(s.shape)} does not match ({rows_blocks}, {kblocks})")
+
+
 def gemm_fp8_nt_groupwise(a: torch.Tensor, b: torch.Tensor, a_scale: torch.Tensor, b_scale: torch.Tensor,
                           scale_major_mode: Optional[str] = None, mma_sm: int = 1,
                           scale_granularity_mnk: Tuple[int, int, int] = (1, 128, 128), out: Optional[torch.Tensor] = None,
                           out_dtype: Optional[torch.dtype] = None, backend: str = "auto") -> torch.Tensor:
-    """``a [m, k]`` fp8, ``b [n, k]`` fp8, fp32 scales per (1 x 128) of a and (128 x 128) of b.
+    """``a [m, k]`` fp8, ``b [n, k]`` fp8, fp32 scales per (1 x 128) of a and (128 x 128) of b (DeepSeek-V3 recipe).
 
-    fp32 group scales cannot be fed to the block-scaled tensor-core path (which takes UE8M0 / UE4M3 bytes), so the
-    operands are re-scaled to bf16 by a fused elementwise pass and multiplied by the bf16 tcgen05 GEMM."""
+    Native kernel: every 128-wide K slab goes through the fp8 tensor cores into a fresh TMEM buffer and is promoted into
+    fp32 registers with its scale product (csrc/gemm/gemm_blockscaled_sm100.cu ``fp8_groupwise_kernel``).  Other
+    granularities fall back to re-scaling into bf16 + the bf16 tcgen05 GEMM."""
     from .dense import mm_bf16
 
     gm, gn, gk = scale_granularity_mnk
@@ -217,6 +230,24 @@ def gemm_fp8_nt_groupwise(a: torch.Tensor, b: torch.Tensor, a_scale: torch.Tenso
     M, K = a.shape
     N = b.shape[0]
     out_dtype = out_dtype or (out.dtype if out is not None else torch.bfloat16)
+    native = (a.is_cuda and gm == 1 and gn == 128 and gk == 128 and K % 128 == 0 and a.dtype in _FP8_FMT and b.dtype in _FP8_FMT
+              and out_dtype in (torch.float16, torch.bfloat16))
+    if native:
+        kb = K // 128
+        sa, sa_row, sa_k = _scale_strides(a_scale, M, kb, major)
+        sb, sb_n, sb_k = _scale_strides(b_scale, (N + 127) // 128, kb, major)
+        if a.stride(1) != 1:
+            a = a.contiguous()
+        if b.stride(1) != 1:
+            b = b.contiguous()
+        res = out if (out is not None and out.dtype == out_dtype and out.stride(-1) == 1) else torch.empty(M, N, dtype=out_dtype, device=a.device)
+        jit.load("gemm_blockscaled_sm100").call(
+            "gemm_fp8_groupwise_nt", a, b, res, sa, sb, M, N, K, a.stride(0), b.stride(0), res.stride(0), sa_row, sa_k, sb_n, sb_k,
+            _FP8_FMT[a.dtype], _FP8_FMT[b.dtype], dtype_code(out_dtype), int(os.environ.get("FIB200_GW_BN", "0")), 1, stream_ptr(a))
+        if out is not None and out.data_ptr() != res.data_ptr():
+            out.copy_(res)
+            return out
+        return res
     ad = (a.float() * _expand_scale(a_scale, M, K, gm, gk, major)).to(torch.bfloat16)
     bd = (b.float() * _expand_scale(b_scale, N, K, gn, gk, major)).to(torch.bfloat16)
     if not a.is_cuda:

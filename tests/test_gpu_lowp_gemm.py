@@ -88,14 +88,25 @@ def test_mm_fp4(m, n, k, nv, bn):
     _check(out, ad @ wd.t())
 
 
-def test_gemm_fp8_groupwise():
-    m, n, k = 200, 512, 1024
-    a = torch.randn(m, k, device="cuda")
-    w = torch.randn(n, k, device="cuda")
-    sa = a.view(m, k // 128, 128).abs().amax(-1) / 448
-    a8 = (a.view(m, k // 128, 128) / sa[..., None]).view(m, k).to(torch.float8_e4m3fn)
-    sw = w.view(n // 128, 128, k // 128, 128).abs().amax((1, 3)) / 448
-    w8 = (w.view(n // 128, 128, k // 128, 128) / sw[:, None, :, None]).view(n, k).to(torch.float8_e4m3fn)
-    out = fi.gemm_fp8_nt_groupwise(a8, w8, sa, sw, "K", out_dtype=torch.bfloat16)
-    ref = a @ w.t()
-    assert torch.nn.functional.cosine_similarity(out.float().flatten(), ref.flatten(), dim=0) > 0.99
+@pytest.mark.parametrize("m,n,k", [(16, 1024, 7168), (200, 512, 1024), (300, 1152, 2048), (1, 128, 128), (4096, 4096, 4096)])
+@pytest.mark.parametrize("major", ["K", "MN"])
+@pytest.mark.parametrize("gw_bn", [0, 32, 64, 128])
+def test_gemm_fp8_groupwise(m, n, k, major, gw_bn):
+    os.environ["FIB200_GW_BN"] = str(gw_bn)
+    try:
+        torch.manual_seed(0)
+        a = torch.randn(m, k, device="cuda")
+        w = torch.randn(n, k, device="cuda")
+        sa = a.view(m, k // 128, 128).abs().amax(-1) / 448
+        a8 = (a.view(m, k // 128, 128) / sa[..., None]).view(m, k).to(torch.float8_e4m3fn)
+        sw = w.view(n // 128, 128, k // 128, 128).abs().amax((1, 3)) / 448
+        w8 = (w.view(n // 128, 128, k // 128, 128) / sw[:, None, :, None]).view(n, k).to(torch.float8_e4m3fn)
+        ref = (a8.float() * sa.repeat_interleave(128, 1)) @ (w8.float() * sw.repeat_interleave(128, 0).repeat_interleave(128, 1)).t()
+        if major == "MN":
+            sa_in, sw_in = sa.t().contiguous(), sw.t().contiguous()
+        else:
+            sa_in, sw_in = sa, sw
+        out = fi.gemm_fp8_nt_groupwise(a8, w8, sa_in, sw_in, major, out_dtype=torch.bfloat16)
+        _check(out, ref)
+    finally:
+        os.environ.pop("FIB200_GW_BN", None)

@@ -115,3 +115,16 @@ def test_chain_speculative_sampling_accepts_identical_draft():
     out, acc, emi = sampling.chain_speculative_sampling(draft, ids, target, seed=3, offset=0)
     assert torch.equal(out[:, :n], ids)  # q == p -> always accepted
     assert (out[:, n] >= 0).all() and (emi == n).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,V", [(1, 128256), (64, 128256), (7, 32000), (300, 1001), (2, 999999), (1024, 4096)])
+def test_softmax_cluster_shapes(B, V):
+    torch.manual_seed(B + V)
+    logits = torch.randn(B, V, device="cuda") * 3
+    temp = torch.rand(B, device="cuda") + 0.5
+    got = sampling.softmax(logits, temp)
+    ref = torch.softmax(logits / temp[:, None], -1)
+    torch.testing.assert_close(got, ref, rtol=2e-4, atol=1e-7)
+    got2 = sampling.softmax(logits, 0.7)
+    torch.testing.assert_close(got2, torch.softmax(logits / 0.7, -1), rtol=2e-4, atol=1e-7)
