@@ -43,16 +43,33 @@ def merge_state_in_place(v, s, v_other, s_other, mask: Optional[torch.Tensor] = 
                              dtype_code(v.dtype), 1, stream_ptr(v))
 
 
-def merge_states(v: torch.Tensor, s: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-    """v [n, K, H, D], s [n, K, H] -> merged ([n, H, D], [n, H])."""
+def merge_states(v: torch.Tensor, s: torch.Tensor, out: Optional[torch.Tensor] = None,
+                 lse_out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """v [n, K, H, D], s [n, K, H] -> merged ([n, H, D], [n, H]).  Slots with ``s == -inf`` are ignored.  ``out`` (any
+    16-bit / fp32 dtype matching ``v`` or not) and ``lse_out`` may be pre-allocated contiguous tensors."""
     if not v.is_cuda:
-        return reference.merge_states_ref(v, s)
+        vo, so = reference.merge_states_ref(v, s)
+        if out is not None:
+            out.copy_(vo)
+            vo = out
+        if lse_out is not None:
+            lse_out.copy_(so)
+            so = lse_out
+        return vo, so
     v = v.contiguous()
     s = s.float().contiguous()
     n, k, h, d = v.shape
-    vo = torch.empty(n, h, d, dtype=v.dtype, device=v.device)
-    so = torch.empty(n, h, dtype=torch.float32, device=v.device)
+    direct = out is not None and out.dtype == v.dtype and out.is_contiguous()
+    vo = out if direct else torch.empty(n, h, d, dtype=v.dtype, device=v.device)
+    so = lse_out if (lse_out is not None and lse_out.is_contiguous() and lse_out.dtype == torch.float32) else \
+        torch.empty(n, h, dtype=torch.float32, device=v.device)
     jit.load("cascade").call("merge_states", v, s, vo, so, n, k, h, d, dtype_code(v.dtype), 1, stream_ptr(v))
+    if out is not None and not direct:
+        out.copy_(vo)
+        vo = out
+    if lse_out is not None and so.data_ptr() != lse_out.data_ptr():
+        lse_out.copy_(so)
+        so = lse_out
     return vo, so
 
 

@@ -63,7 +63,9 @@ merge_states_kernel(const T* __restrict__ v, const float* __restrict__ s, T* __r
     for (int e = 0; e < VN; ++e) acc[e] = 0.f;
     float den = 0.f;
     for (int k = 0; k < K; ++k) {
-      const float wk = exp2f(s[(i * K + k) * H + h] - m);
+      const float sk = s[(i * K + k) * H + h];
+      if (sk == -INFINITY) continue;  // unused split slot: its v may be uninitialised
+      const float wk = exp2f(sk - m);
       den += wk;
       const Vec16<T> x = ld16(v + ((i * K + k) * H + h) * int64_t(D) + vi * VN);
 #pragma unroll

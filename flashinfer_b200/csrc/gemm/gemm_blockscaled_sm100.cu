@@ -69,6 +69,9 @@ struct Params {
   int64_t sfa_batch_stride, sfb_batch_stride, c_batch_stride, ldc;
   int M, N, Kb;  // Kb = K in bytes
   int batch, BN;
+  const int32_t* tile_expert;  // grouped (MoE) mode: expert of every 128-row tile of A (-1 = skip); B / SFB / alpha are per expert
+  const int32_t* meta;         // grouped mode: meta[0] = number of live row tiles (device side)
+  int split;          // cluster split-K factor (1 or 2): both CTAs of a cluster own the same tile, half of K each
   int sf_k_tiles;     // 512-byte blocks along K in the scale tensors
   int sfb_row_tiles;  // 128-row blocks in SFB
   uint32_t idesc;
@@ -87,8 +90,12 @@ bs_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full = empty_bar + kStages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* go_bar = tmem_empty + 2;       // split-K: leader's pipeline smem is free, peer may deposit its partial
+  uint64_t* partials_bar = go_bar + 1;     // split-K: peer's partial has landed in the leader's smem
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(partials_bar + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int split = p.split;
+  const int crank = split > 1 ? int(ptx::cluster_ctarank()) : 0;
 
   if (threadIdx.x == 0) {
     ptx::prefetch_tmap(&tmA);
@@ -101,6 +108,8 @@ bs_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       ptx::mbar_init(&tmem_full[i], 1);
       ptx::mbar_init(&tmem_empty[i], 4);
     }
+    ptx::mbar_init(go_bar, 1);
+    ptx::mbar_init(partials_bar, 1);
     ptx::fence_mbar_init();
   }
   if constexpr (KIND != kFp8) {
@@ -117,28 +126,52 @@ bs_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (split > 1) ptx::cluster_sync();  // the peer's mbarriers must exist before any remote arrive
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
-  const int tiles_per_batch = tiles_m * tiles_n;
-  const int num_tiles = tiles_per_batch * p.batch;
-  const int num_kb = (p.Kb + BKB - 1) / BKB;
-
   ptx::grid_dep_wait();
+  ptx::grid_dep_launch();
+
+  const bool grouped = p.tile_expert != nullptr;
+  int tiles_m = (p.M + BM - 1) / BM;
+  if (grouped && p.meta) tiles_m = min(tiles_m, p.meta[0]);  // written by the MoE sort kernel
+  const int tiles_n = (p.N + BN - 1) / BN;
+  const int tiles_per_batch = tiles_m * tiles_n;
+  const int num_tiles = tiles_per_batch * (grouped ? 1 : p.batch);
+  const int num_kb_total = (p.Kb + BKB - 1) / BKB;
+  // split-K: one tile per cluster, rank r multiplies K slabs [kb_lo, kb_hi)
+  const int kb_lo = (crank * num_kb_total) / split, kb_hi = ((crank + 1) * num_kb_total) / split;
+  const int t_first = split > 1 ? int(blockIdx.x) / split : int(blockIdx.x);
+  const int t_stride = split > 1 ? num_tiles : int(gridDim.x);
+  // tile -> (a_batch, b_batch, row tile, col tile).  grouped: n-fastest so consecutive CTAs share an expert's weights
+  auto decode = [&](int t, int& ba, int& bb, int& tm, int& tn) -> bool {
+    if (grouped) {
+      tm = t / tiles_n;
+      tn = t % tiles_n;
+      ba = 0;
+      bb = p.tile_expert[tm];
+      return bb >= 0;
+    }
+    const int r = t % tiles_per_batch;
+    ba = bb = t / tiles_per_batch;
+    tm = r % tiles_m;
+    tn = r / tiles_m;
+    return true;
+  };
 
   if (warp == 0) {
     if (ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int b = t / tiles_per_batch, r = t % tiles_per_batch;
-        const int tm = r % tiles_m, tn = r / tiles_m;
+      for (int t = t_first; t < num_tiles; t += t_stride) {
+        int b, bb, tm, tn;
+        if (!decode(t, b, bb, tm, tn)) continue;
         const int n0 = tn * BN;
         const int rb0 = n0 / 128;
         int rbn = (n0 + BN + 127) / 128 - rb0;
         if (rb0 + rbn > p.sfb_row_tiles) rbn = p.sfb_row_tiles - rb0;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb_lo; kb < kb_hi; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * G.stage_bytes;
           uint8_t* sb = sa + G.a_bytes;
@@ -151,7 +184,7 @@ bs_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           ptx::mbar_arrive_expect_tx(&full_bar[stage], tx);
           ptx::tma_load_3d(sa, &tmA, &full_bar[stage], kb * BKB, tm * BM, b, ptx::kEvictNormal);
-          ptx::tma_load_3d(sb, &tmB, &full_bar[stage], kb * BKB, n0, b, ptx::kEvictNormal);
+          ptx::tma_load_3d(sb, &tmB, &full_bar[stage], kb * BKB, n0, bb, ptx::kEvictNormal);
           if constexpr (KIND != kFp8) {
             uint8_t* ssfa = sb + G.b_bytes;
             uint8_t* ssfb = ssfa + G.sfa_bytes;
@@ -159,7 +192,7 @@ bs_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 (int64_t(tm) * p.sf_k_tiles + int64_t(kb) * G.nchunk) * 512;
             ptx::bulk_load(ssfa, ga, nch * 512, &full_bar[stage]);
             for (int rr = 0; rr < rbn; ++rr) {
-              const uint8_t* gb = p.sfb + int64_t(b) * p.sfb_batch_stride +
+              const uint8_t* gb = p.sfb + int64_t(bb) * p.sfb_batch_stride +
                                   (int64_t(rb0 + rr) * p.sf_k_tiles + int64_t(kb) * G.nchunk) * 512;
               ptx::bulk_load(ssfb + rr * G.nchunk * 512, gb, nch * 512, &full_bar[stage]);
             }
@@ -176,14 +209,15 @@ bs_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int r = t % tiles_per_batch;
-      const int n0 = (r / tiles_m) * BN;
+    for (int t = t_first; t < num_tiles; t += t_stride) {
+      int b_, bb_, tm_, tn_;
+      if (!decode(t, b_, bb_, tm_, tn_)) continue;
+      const int n0 = tn_ * BN;
       const uint32_t sfb_off = uint32_t((n0 % 128) / 32);
       ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BN;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      for (int kb = kb_lo; kb < kb_hi; ++kb) {
         ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
@@ -203,7 +237,7 @@ bs_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const uint32_t accum = (kb > 0 || k > 0) ? 1u : 0u;
+            const uint32_t accum = (kb > kb_lo || k > 0) ? 1u : 0u;
             const uint64_t dak = ptx::desc_advance(da, k * 32), dbk = ptx::desc_advance(db, k * 32);
             if constexpr (KIND == kFp8) {
               ptx::mma_f8f6f4_ss<1>(d_tmem, dak, dbk, p.idesc, accum);
@@ -221,7 +255,7 @@ bs_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
           ptx::mma_commit(&empty_bar[stage]);
-          if (kb == num_kb - 1) ptx::mma_commit(&tmem_full[acc]);
+          if (kb == kb_hi - 1) ptx::mma_commit(&tmem_full[acc]);
         }
         __syncwarp();
         if (++stage == kStages) {
@@ -236,21 +270,47 @@ bs_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         acc_phase ^= 1;
       }
     }
-    ptx::grid_dep_launch();
   } else if (warp >= 4) {
     const int q = warp - 4;
     int acc = 0;
     uint32_t acc_phase = 0;
-    float alpha = 1.f;
-    if (p.alpha_a) alpha *= *p.alpha_a;
-    if (p.alpha_b) alpha *= *p.alpha_b;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int b = t / tiles_per_batch, r = t % tiles_per_batch;
-      const int tm = r % tiles_m, tn = r / tiles_m;
+    float alpha0 = 1.f;
+    if (p.alpha_a && !grouped) alpha0 *= *p.alpha_a;
+    if (p.alpha_b) alpha0 *= *p.alpha_b;
+    for (int t = t_first; t < num_tiles; t += t_stride) {
+      int b, bb, tm, tn;
+      if (!decode(t, b, bb, tm, tn)) continue;
+      const float alpha = (grouped && p.alpha_a) ? alpha0 * p.alpha_a[bb] : alpha0;
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
       const int row = tm * BM + q * 32 + lane;
       const uint32_t taddr = tmem_base + acc * BN + (uint32_t(q * 32) << 16);
+      const int r_in_tile = q * 32 + lane;
+      if (split > 1) {
+        // exchange buffer = the LEADER's pipeline smem (idle once its accumulator is complete):
+        // [4-float column group][row] x 16 B  -> conflict-free for both the remote stores and the local loads
+        if (crank == 0) {
+          if (threadIdx.x == 128) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(go_bar), 1));
+          ptx::mbar_wait_cluster(partials_bar, 0);
+        } else {
+          ptx::mbar_wait_cluster(go_bar, 0);
+          const uint32_t remote = ptx::mapa(ptx::smem_u32(smem), 0);
+#pragma unroll 1
+          for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            ptx::tmem_ld_x32(taddr + c0, v);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              ptx::st_dsmem_v4(remote + uint32_t(((c0 + j) / 4 * BM + r_in_tile) * 16),
+                               make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                           __uint_as_float(v[j + 3])));
+          }
+          ptx::named_bar_sync(1, 128);
+          if (threadIdx.x == 128) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(partials_bar), 0));
+          continue;  // only the leader writes the tile
+        }
+      }
       OutT* crow = C + int64_t(b) * p.c_batch_stride + int64_t(row) * p.ldc;
       const bool vec_ok = (p.ldc % (16 / sizeof(OutT)) == 0);
 #pragma unroll 1
@@ -258,6 +318,16 @@ bs_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t v[32];
         ptx::tmem_ld_x32(taddr + c0, v);
         ptx::tmem_ld_wait();
+        if (split > 1) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 o4 = *reinterpret_cast<const float4*>(smem + ((c0 + j) / 4 * BM + r_in_tile) * 16);
+            v[j] = __float_as_uint(__uint_as_float(v[j]) + o4.x);
+            v[j + 1] = __float_as_uint(__uint_as_float(v[j + 1]) + o4.y);
+            v[j + 2] = __float_as_uint(__uint_as_float(v[j + 2]) + o4.z);
+            v[j + 3] = __float_as_uint(__uint_as_float(v[j + 3]) + o4.w);
+          }
+        }
         const int col0 = tn * BN + c0;
         if (row < p.M) {
           if (col0 + 32 <= p.N && vec_ok) {
@@ -289,6 +359,7 @@ bs_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (split > 1) ptx::cluster_sync();  // nobody leaves while the peer may still touch its shared memory
   if (warp == 2) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<1>(tmem_base, G.tmem_cols);
@@ -492,12 +563,13 @@ int launch_gw(const CUtensorMap& tmA, const CUtensorMap& tmB, void* C, const GwP
 template <int KIND, typename OutT>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, void* C, const Params& p, int grid, int smem, bool pdl,
            cudaStream_t stream) {
+  const int cluster = p.split;
   static bool set = false;
   if (!set) {
     FIB_CUDA_CHECK(cudaFuncSetAttribute(bs_gemm_kernel<KIND, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     set = true;
   }
-  LaunchCfg lc(dim3(grid), dim3(256), smem, stream, pdl);
+  LaunchCfg lc(dim3(grid), dim3(256), smem, stream, pdl, cluster);
   FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, bs_gemm_kernel<KIND, OutT>, tmA, tmB, (OutT*)C, p));
   return 0;
 }
@@ -511,7 +583,8 @@ extern "C" int gemm_lowp_nt(void* A, void* B, void* C, void* sfa, void* sfb, voi
                             int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc,
                             int64_t a_batch_stride, int64_t b_batch_stride, int64_t c_batch_stride,
                             int64_t sfa_batch_stride, int64_t sfb_batch_stride, int64_t kind, int64_t a_fmt,
-                            int64_t b_fmt, int64_t out_dtype, int64_t bn, int64_t pdl, int64_t stream_) {
+                            int64_t b_fmt, int64_t out_dtype, int64_t bn, void* tile_expert, void* meta, int64_t pdl,
+                            int64_t stream_) {
   FIB_CHECK(kind >= 0 && kind <= 3, "gemm_lowp: kind must be 0..3");
   FIB_CHECK(out_dtype == kF16 || out_dtype == kBF16, "gemm_lowp: output must be f16/bf16");
   const bool fp4 = kind == kNvFp4 || kind == kMxFp4;
@@ -521,15 +594,16 @@ extern "C" int gemm_lowp_nt(void* A, void* B, void* C, void* sfa, void* sfb, voi
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const int64_t Kb = fp4 ? K / 2 : K;
   const int tiles_m = int((M + BM - 1) / BM);
+  const int64_t eb = tile_expert ? 1 : batch;  // grouped mode: `batch` counts experts (B / SFB), A and C are one matrix
   int BN = (int)bn;
   if (BN == 0) {
     const int sms = num_sms();
-    const int64_t want = (N * tiles_m * batch + sms - 1) / sms;  // columns per CTA for one full wave
+    const int64_t want = (N * tiles_m * eb + sms - 1) / sms;  // columns per CTA for one full wave
     if (want >= 256) {
       BN = (kind == kFp8) ? 256 : 192;
       // prefer the width with the least tile-quantisation waste over full waves
       auto waves = [&](int w) {
-        const int64_t tiles = ((N + w - 1) / w) * tiles_m * batch;
+        const int64_t tiles = ((N + w - 1) / w) * tiles_m * eb;
         return double((tiles + sms - 1) / sms) * w;
       };
       const int cands[3] = {256, 192, 128};
@@ -556,8 +630,8 @@ extern "C" int gemm_lowp_nt(void* A, void* B, void* C, void* sfa, void* sfb, voi
 
   CUtensorMap tmA, tmB;
   {
-    uint64_t dims[3] = {(uint64_t)Kb, (uint64_t)M, (uint64_t)batch};
-    uint64_t str[2] = {(uint64_t)lda, (uint64_t)a_batch_stride};
+    uint64_t dims[3] = {(uint64_t)Kb, (uint64_t)M, (uint64_t)(tile_expert ? 1 : batch)};
+    uint64_t str[2] = {(uint64_t)lda, (uint64_t)(tile_expert ? lda * M : a_batch_stride)};
     uint32_t box[3] = {BKB, BM, 1};
     if (make_tmap(&tmA, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, A, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   }
@@ -569,6 +643,8 @@ extern "C" int gemm_lowp_nt(void* A, void* B, void* C, void* sfa, void* sfb, voi
   }
   Params p;
   p.sfa = (const uint8_t*)sfa;
+  p.tile_expert = (const int32_t*)tile_expert;
+  p.meta = (const int32_t*)meta;
   p.sfb = (const uint8_t*)sfb;
   p.alpha_a = (const float*)alpha_a;
   p.alpha_b = (const float*)alpha_b;
@@ -592,8 +668,14 @@ extern "C" int gemm_lowp_nt(void* A, void* B, void* C, void* sfa, void* sfb, voi
   } else {
     p.idesc = ptx::make_idesc_blockscaled(1, 1, BM, BN, kind == kMxFp4 ? 1 : 0, 0, 0);
   }
-  const int64_t tiles = int64_t(tiles_m) * ((N + BN - 1) / BN) * batch;
-  const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+  const int64_t tiles = int64_t(tiles_m) * ((N + BN - 1) / BN) * eb;
+  // cluster split-K for latency-bound shapes: few tiles, long K -> two CTAs per tile, DSMEM reduction
+  const int64_t num_kb = (Kb + BKB - 1) / BKB;
+  const char* env_split = getenv("FIB200_LOWP_SPLIT");
+  p.split = env_split ? atoi(env_split) : ((tiles * 2 <= num_sms() && num_kb >= 8) ? 2 : 1);
+  if (tile_expert) p.split = 1;
+  if (p.split != 2 || tiles * 2 > num_sms() || num_kb < 2 || BM * BN * 4 > G.stages * G.stage_bytes) p.split = 1;
+  const int grid = p.split > 1 ? (int)(tiles * p.split) : (int)(tiles < num_sms() ? tiles : num_sms());
   const bool f16 = out_dtype == kF16;
   switch (kind) {
     case kFp8:

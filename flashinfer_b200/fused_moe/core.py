@@ -208,6 +208,83 @@ def moe_forward(x: torch.Tensor, topk_ids: torch.Tensor, topk_w: torch.Tensor, w
     return out
 
 
+_SF_CACHE: dict = {}
+
+
+def _swizzle_expert_sf(sf: torch.Tensor, E: int, N: int, kc: int) -> torch.Tensor:
+    """Per-expert linear ``[E, N, kc]`` UE4M3 scales -> 128x4-swizzled ``[E, bytes]`` (cached per weight tensor: static)."""
+    from ..quantization.fp4 import _swizzled_sf_size, block_scale_interleave
+
+    key = (sf.data_ptr(), E, N, kc)
+    hit = _SF_CACHE.get(key)
+    if hit is not None:
+        return hit
+    per = _swizzled_sf_size(N, kc)
+    b = sf.view(torch.uint8)
+    if b.numel() == E * per and not (b.dim() == 3 and b.shape[1:] == (N, kc) and per != N * kc):
+        out = b.reshape(E, per) if b.dim() != 3 else block_scale_interleave(b.reshape(E, N, kc).contiguous()).reshape(E, per)
+    else:
+        out = block_scale_interleave(b.reshape(E, N, kc).contiguous()).reshape(E, per)
+    if len(_SF_CACHE) > 64:
+        _SF_CACHE.clear()
+    _SF_CACHE[key] = out
+    return out
+
+
+def moe_forward_nvfp4(x: torch.Tensor, topk_ids: torch.Tensor, topk_w: torch.Tensor, w1_fp4: torch.Tensor, w1_sf: torch.Tensor,
+                      w1_alpha, w2_fp4: torch.Tensor, w2_sf: torch.Tensor, w2_alpha, local_expert_offset: int = 0,
+                      num_experts: Optional[int] = None, act_global_scale: float = 1.0, out: Optional[torch.Tensor] = None):
+    """NVFP4 MoE on the block-scaled tcgen05 grouped GEMM (``kind::mxf4nvf4``): activations are quantised on the fly
+    (per-16 UE4M3 scales in the 128x4 layout of the permuted matrix), ``w1_fp4 [E, 2I, H/2]`` / ``w2_fp4 [E, H, I/2]`` are packed
+    e2m1 with linear ``[E, N, K/16]`` (or pre-swizzled) UE4M3 scales, ``w*_alpha [E]`` are the per-expert output de-quantisation
+    scales (1 / (activation global scale * weight global scale))."""
+    from ..gemm.lowp import grouped_gemm_nvfp4
+    from ..quantization.fp4 import fp4_quantize
+
+    T, H = x.shape
+    e_local, n1, _ = w1_fp4.shape
+    inter = w2_fp4.shape[2] * 2
+    K = topk_ids.shape[1]
+    dev = x.device
+    mod = jit.load("moe")
+    max_rows = (T * K + e_local * (_TILE - 1)) // _TILE * _TILE + _TILE
+    max_tiles = max_rows // _TILE
+    e2p = torch.empty(T * K, dtype=torch.int32, device=dev)
+    p2t = torch.empty(max_rows, dtype=torch.int32, device=dev)
+    tile_e = torch.empty(max_tiles, dtype=torch.int32, device=dev)
+    offs = torch.empty(e_local + 1, dtype=torch.int32, device=dev)
+    meta = torch.empty(4, dtype=torch.int32, device=dev)
+    st = stream_ptr(x)
+    ids = topk_ids.to(torch.int32).contiguous()
+    ws = torch.empty(((T * K + 1023) // 1024) * e_local + 1, dtype=torch.int32, device=dev)
+    mod.call("moe_sort", ids, T, K, num_experts or e_local, local_expert_offset, e_local, _TILE, max_rows, e2p, p2t, tile_e, offs,
+             meta, ws, 1, st)
+    xb = x if x.dtype in (torch.float16, torch.bfloat16) else x.to(torch.bfloat16)
+    xp = torch.empty(max_rows, H, dtype=xb.dtype, device=dev)
+    mod.call("moe_gather", xb, xp, p2t, meta, max_rows, H, xb.stride(0), dtype_code(xb.dtype), 1, st)
+    gs = torch.full((1,), float(act_global_scale), dtype=torch.float32, device=dev)
+    xq, xsf = fp4_quantize(xp, gs, 16, False, True)
+    a1 = torch.as_tensor(w1_alpha, dtype=torch.float32, device=dev).reshape(-1)
+    a2 = torch.as_tensor(w2_alpha, dtype=torch.float32, device=dev).reshape(-1)
+    if a1.numel() == 1:
+        a1 = a1.expand(e_local)
+    if a2.numel() == 1:
+        a2 = a2.expand(e_local)
+    a1 = (a1 / act_global_scale).contiguous()
+    a2 = (a2 / act_global_scale).contiguous()
+    sf1 = _swizzle_expert_sf(w1_sf, e_local, n1, H // 16)
+    sf2 = _swizzle_expert_sf(w2_sf, e_local, H, inter // 16)
+    h1 = grouped_gemm_nvfp4(xq, xsf, w1_fp4, sf1, a1, tile_e, meta, out_dtype=xb.dtype)
+    act = torch.empty(max_rows, inter, dtype=xb.dtype, device=dev)
+    _act_and_mul("silu", h1, act, True, gate_second=True)
+    aq, asf = fp4_quantize(act, gs, 16, False, True)
+    h2 = grouped_gemm_nvfp4(aq, asf, w2_fp4, sf2, a2, tile_e, meta, out_dtype=xb.dtype)
+    if out is None:
+        out = torch.empty(T, H, dtype=xb.dtype, device=dev)
+    mod.call("moe_finalize", h2, out, e2p, topk_w.float().contiguous(), T, K, H, 0, dtype_code(xb.dtype), 1, st)
+    return out
+
+
 def reorder_rows_for_gated_act_gemm(x: torch.Tensor) -> torch.Tensor:
     """Interleave the two halves of the rows ([up | gate] -> u0 g0 u1 g1 ...), the weight layout that lets a
     GEMM epilogue see matching up/gate columns in one tile (reference core.py:133)."""
@@ -330,6 +407,9 @@ def trtllm_fp4_block_scale_moe(routing_logits, routing_bias, hidden_states, hidd
         x = _dequant_nvfp4(x, hidden_states_scale, 1.0)
     g1 = output1_scale_scalar if output1_scale_scalar is not None else 1.0
     g2 = output2_scale_scalar if output2_scale_scalar is not None else 1.0
+    if x.is_cuda and do_finalize and hidden_states.shape[-1] % 64 == 0 and intermediate_size % 64 == 0:
+        return moe_forward_nvfp4(x, ids, w, gemm1_weights, gemm1_weights_scale, g1, gemm2_weights, gemm2_weights_scale, g2,
+                                 local_expert_offset, num_experts)
     w1 = _dequant_nvfp4(gemm1_weights, gemm1_weights_scale, g1)
     w2 = _dequant_nvfp4(gemm2_weights, gemm2_weights_scale, g2)
     return moe_forward(x.to(torch.bfloat16), ids, w, w1, w2, local_expert_offset, num_experts, do_finalize=do_finalize)

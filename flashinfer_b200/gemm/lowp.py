@@ -59,9 +59,11 @@ def _sf_swizzled(sf: torch.Tensor, rows: int, kc: int, batch: int = 1, swizzled:
 
 
 def _launch(kind: str, a: torch.Tensor, b_nk: torch.Tensor, out: torch.Tensor, sfa, sfb, alpha_a, alpha_b, K: int,
-            bn: int = 0) -> torch.Tensor:
+            bn: int = 0, tile_expert: Optional[torch.Tensor] = None, meta: Optional[torch.Tensor] = None) -> torch.Tensor:
     """a ``[B, M, Kbytes]``, b_nk ``[B, N, Kbytes]`` (uint8 / fp8 storage, K contiguous), out ``[B, M, N]``."""
     B, M, _ = a.shape
+    if tile_expert is not None:
+        B = b_nk.shape[0]  # grouped: experts
     N = b_nk.shape[1]
     bn = bn or int(os.environ.get("FIB200_LOWP_BN", "0"))
     a_fmt = _FP8_FMT.get(a.dtype, 0)
@@ -69,7 +71,8 @@ def _launch(kind: str, a: torch.Tensor, b_nk: torch.Tensor, out: torch.Tensor, s
     jit.load("gemm_blockscaled_sm100").call(
         "gemm_lowp_nt", a, b_nk, out, sfa, sfb, alpha_a, alpha_b, B, M, N, K, a.stride(1), b_nk.stride(1), out.stride(1),
         a.stride(0), b_nk.stride(0), out.stride(0), sfa.stride(0) if sfa is not None else 0,
-        sfb.stride(0) if sfb is not None else 0, _KIND[kind], a_fmt, b_fmt, dtype_code(out.dtype), bn, 1, stream_ptr(a))
+        sfb.stride(0) if sfb is not None else 0, _KIND[kind], a_fmt, b_fmt, dtype_code(out.dtype), bn, tile_expert, meta, 1,
+        stream_ptr(a))
     return out
 
 
@@ -294,3 +297,20 @@ def trtllm_low_latency_gemm(A: torch.Tensor, B: torch.Tensor, global_scale: torc
             _LL_CACHE.clear()
         _LL_CACHE[key] = w
     mm_fp8(A, w.t(), global_scale, out.dtype, out)
+
+
+def grouped_gemm_nvfp4(a_fp4: torch.Tensor, a_sf: torch.Tensor, w_fp4: torch.Tensor, w_sf: torch.Tensor, alpha: Optional[torch.Tensor],
+                       tile_expert: torch.Tensor, meta: Optional[torch.Tensor], out: Optional[torch.Tensor] = None,
+                       out_dtype: torch.dtype = torch.bfloat16, vec: int = 16) -> torch.Tensor:
+    """Grouped block-scaled GEMM for MoE (tcgen05 ``kind::mxf4nvf4``): rows of ``a_fp4 [rows, K/2]`` are grouped by expert in
+    128-row tiles (``tile_expert[tile]``), ``w_fp4 [E, N, K/2]`` with swizzled scales ``w_sf [E, sf_bytes]`` and one
+    ``alpha[e]`` per expert; ``a_sf`` is the swizzled scale tensor of the whole activation matrix."""
+    rows, K2 = a_fp4.shape
+    E, N, _ = w_fp4.shape
+    if out is None:
+        out = torch.empty(rows, N, dtype=out_dtype, device=a_fp4.device)
+    kind = "nvfp4" if vec == 16 else "mxfp4"
+    _launch(kind, a_fp4.view(torch.uint8).unsqueeze(0), w_fp4.view(torch.uint8), out.unsqueeze(0), a_sf.view(torch.uint8).reshape(1, -1),
+            w_sf.view(torch.uint8).reshape(E, -1), alpha.float().contiguous() if alpha is not None else None, None, 2 * K2,
+            tile_expert=tile_expert, meta=meta)
+    return out

@@ -110,3 +110,27 @@ def test_gemm_fp8_groupwise(m, n, k, major, gw_bn):
         _check(out, ref)
     finally:
         os.environ.pop("FIB200_GW_BN", None)
+
+
+@pytest.mark.parametrize("m,n,k", [(48, 256, 4096), (512, 1024, 7168), (1, 512, 1024), (130, 448, 2048)])
+@pytest.mark.parametrize("split", ["1", "2"])
+def test_lowp_cluster_split_k(m, n, k, split):
+    """Cluster split-K (two CTAs per tile, DSMEM reduction) for fp8 / mxfp8 / nvfp4."""
+    os.environ["FIB200_LOWP_SPLIT"] = split
+    try:
+        torch.manual_seed(0)
+        a = torch.randn(m, k, device="cuda", dtype=torch.bfloat16)
+        w = torch.randn(n, k, device="cuda", dtype=torch.bfloat16)
+        a8, sa = _to_fp8(a.float())
+        w8, sw = _to_fp8(w.float())
+        _check(fi.mm_fp8(a8, w8.t(), sa * sw, torch.bfloat16), (a8.float() @ w8.float().t()) * sa * sw)
+        aq, asf = fi.mxfp8_quantize(a)
+        wq, wsf = fi.mxfp8_quantize(w)
+        _check(fi.mm_mxfp8(aq, wq.t(), asf, wsf), fi.mxfp8_dequantize_host(aq, asf) @ fi.mxfp8_dequantize_host(wq, wsf).t())
+        g = torch.tensor(1.0, device="cuda")
+        aq4, asf4 = fi.nvfp4_quantize(a, g)
+        wq4, wsf4 = fi.nvfp4_quantize(w, g)
+        ref = e2m1_and_ufp8sf_scale_to_float(aq4, asf4, g, 16, 1, True) @ e2m1_and_ufp8sf_scale_to_float(wq4, wsf4, g, 16, 1, True).t()
+        _check(fi.mm_fp4(aq4, wq4.t(), asf4, wsf4, g, torch.bfloat16), ref)
+    finally:
+        os.environ.pop("FIB200_LOWP_SPLIT", None)

@@ -171,3 +171,36 @@ def test_grouped_gemm_masked_gpu():
         if m:
             assert (o[e, :m].float() - ref).abs().max().item() < 3e-2 * max(1.0, ref.abs().max().item())
     assert o[2].abs().max().item() == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("T,E,K,H,I", [(64, 8, 2, 512, 256), (1024, 64, 8, 1024, 1024), (7, 16, 4, 2048, 768)])
+def test_moe_nvfp4_native_gpu(T, E, K, H, I):
+    """NVFP4 MoE on the block-scaled grouped tcgen05 GEMM vs the de-quantised expert loop."""
+    from flashinfer_b200.fused_moe import moe_forward_nvfp4
+    from flashinfer_b200.fused_moe.core import _dequant_nvfp4
+    from flashinfer_b200.quantization.fp4 import fp4_quantize
+
+    x, w1, w2, logits = _mk(T, E, H, I, "cuda")
+    ids, w = route(logits, None, K, 1)
+
+    def quant_w(wt):
+        gs = (448.0 * 6.0) / wt.float().abs().amax((1, 2))            # per-expert global scale
+        qs, sfs = [], []
+        for e in range(wt.shape[0]):
+            q, sf = fp4_quantize(wt[e], gs[e].reshape(1), 16, False, False)  # linear scales [N, K/16]
+            qs.append(q)
+            sfs.append(sf)
+        return torch.stack(qs), torch.stack(sfs), (1.0 / gs).float()
+
+    w1q, w1sf, a1 = quant_w(w1)
+    w2q, w2sf, a2 = quant_w(w2)
+    out = moe_forward_nvfp4(x, ids, w, w1q, w1sf, a1, w2q, w2sf, a2)
+    # oracle with the same quantised weights (activations stay bf16 in the oracle -> looser tolerance)
+    w1d = _dequant_nvfp4(w1q, w1sf, a1)
+    w2d = _dequant_nvfp4(w2q, w2sf, a2)
+    ref = moe_reference(x, ids, w, w1d, w2d)
+    cos = torch.nn.functional.cosine_similarity(out.float().flatten(), ref.flatten(), dim=0)
+    assert cos > 0.97, float(cos)
+    rel = (out.float() - ref).norm() / ref.norm()
+    assert rel < 0.25, float(rel)
