@@ -36,7 +36,7 @@ constexpr int kWorkInts = 8;
 
 struct MlaParams {
   const int32_t* kv_indices;
-  const int32_t* work;  // [nwork][8] {q_row, kv_page_start, kv_begin(token), kv_end(token), kv_len, out_slot, num_pages, 0}
+  const int32_t* work;  // [nwork][8] {q_row, kv_page_start, kv_begin(token), kv_end(token), kv_len, out_slot, num_pages, first part: (kmax << 16) | nparts else 0}
   void* out;            // final bf16/f16 [n, H, 512]            (when partial == nullptr)
   float* partial_o;     // [slots][H][512] fp32                  (split-KV)
   float* partial_lse;   // [slots][H]
@@ -328,10 +328,16 @@ mla_decode_kernel(const __grid_constant__ CUtensorMap tmQn, const __grid_constan
       }
     }
     if (row_ok && half == 0) {
-      if (p.partial_o)
+      if (p.partial_o) {
         p.partial_lse[int64_t(out_slot) * p.num_heads + row] = lse_v;
-      else if (p.lse)
+        // work[7] = (kmax << 16) | nparts on the first part of a row: mark the unused split slots so that the merge
+        // ignores them (no host-side fill of the partial buffers)
+        const int nparts = wk[7] & 0xffff, kmax = wk[7] >> 16;
+        for (int sidx = nparts; sidx < kmax; ++sidx)
+          p.partial_lse[int64_t(out_slot + sidx) * p.num_heads + row] = -INFINITY;
+      } else if (p.lse) {
         p.lse[int64_t(q_row) * p.num_heads + row] = lse_v;
+      }
     }
   }
 

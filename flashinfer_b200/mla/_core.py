@@ -78,6 +78,9 @@ class BatchMLAPagedAttentionWrapper:
         ctas = max(1, device_sm_count(self.device if self.device.type == "cuda" else None) // 2)
         chunk = max(4 * _TILE, -(-total_tokens // ctas))
         chunk = -(-chunk // _TILE) * _TILE
+        # one wave: grow the chunk until the number of (row, split) work items fits the CTA pairs of the device
+        while sum(max(1, -(-r[2] // chunk)) for r in rows) > ctas and chunk < (1 << 30):
+            chunk += _TILE
         kmax = max(1, max((-(-r[2] // chunk) for r in rows), default=1))
         self._kmax = kmax
         work = []
@@ -85,7 +88,7 @@ class BatchMLAPagedAttentionWrapper:
             nsp = max(1, -(-vis // chunk))
             for s in range(nsp):
                 lo, hi = s * chunk, min(vis, (s + 1) * chunk)
-                work.append([qr, pstart, lo, max(hi, lo), vis, qr * kmax + s, max(npages, 1), 0])
+                work.append([qr, pstart, lo, max(hi, lo), vis, qr * kmax + s, max(npages, 1), ((kmax << 16) | nsp) if s == 0 else 0])
         self._num_work = len(work)
         w = torch.tensor(work, dtype=torch.int32).reshape(-1)
         pin = self._pin_int_workspace_buffer.view(torch.int32)
@@ -133,9 +136,6 @@ class BatchMLAPagedAttentionWrapper:
             if q_nope.dtype not in (torch.float16, torch.bfloat16) or ckv_cache.dtype != q_nope.dtype:
                 raise NotImplementedError("mla_sm100: q/kv dtype must both be f16 or bf16")
             split = self._kmax > 1
-            if split:
-                self._partial_lse.fill_(float("-inf"))
-                self._partial_o.zero_()
             jit.load("mla_sm100").call(
                 "mla_decode_run", q_nope, q_pe, ckv_cache, kpe_cache, self._kv_indices, self._work, self._num_work,
                 out, self._partial_o if split else None, self._partial_lse if split else None,
@@ -145,10 +145,9 @@ class BatchMLAPagedAttentionWrapper:
                 self._sm_scale, dtype_code(q_nope.dtype), 1, stream_ptr(q_nope),
             )
             if split:
-                o_m, l_m = cascade.merge_states(self._partial_o, self._partial_lse)
+                # fp32 partials -> one merge kernel that writes (o, lse); unused slots were marked -inf by the kernel
+                o_m, l_m = cascade.merge_states(self._partial_o, self._partial_lse, lse_out=lse if return_lse else None)
                 out.copy_(o_m)
-                if return_lse:
-                    lse.copy_(l_m)
         if o_scale is not None:
             out.mul_(o_scale)
         if return_lse and return_lse_base_on_e:
