@@ -672,7 +672,7 @@ extern "C" int gemm_lowp_nt(void* A, void* B, void* C, void* sfa, void* sfb, voi
   // cluster split-K for latency-bound shapes: few tiles, long K -> two CTAs per tile, DSMEM reduction
   const int64_t num_kb = (Kb + BKB - 1) / BKB;
   const char* env_split = getenv("FIB200_LOWP_SPLIT");
-  p.split = env_split ? atoi(env_split) : 1;  // opt-in (FIB200_LOWP_SPLIT=2): measured slower than the plain wave on m=512,n=1024,k=7168
+  p.split = env_split ? atoi(env_split) : ((tiles * 2 <= num_sms() && num_kb >= 8) ? 2 : 1);  // m=512,n=1024,k=7168 nvfp4: 18.0 -> 15.2 us
   if (tile_expert) p.split = 1;
   if (p.split != 2 || tiles * 2 > num_sms() || num_kb < 2 || BM * BN * 4 > G.stages * G.stage_bytes) p.split = 1;
   const int grid = p.split > 1 ? (int)(tiles * p.split) : (int)(tiles < num_sms() ? tiles : num_sms());
