@@ -32,6 +32,16 @@ struct RopeParams {
   int llama31;
   float smooth_a, smooth_b;
   float q_out_scale, k_out_scale;  // quantisation multipliers (1 for plain)
+  // fused paged-KV append (optional): roped K and raw V go straight into the cache pages
+  const void* v;                  // [nnz, Hk, D] (strides v_sn, v_sh) or null
+  void* k_cache;                  // paged destination of K (null = k_out)
+  void* v_cache;
+  const int32_t* batch_indices;   // [nnz] request of every token
+  const int32_t* kv_indices;      // page ids
+  const int32_t* kv_indptr;       // [B+1]
+  int64_t v_sn, v_sh, c_sp, c_sn, c_sh;  // cache strides: page / in-page token / head (elements)
+  int page_size;
+  float v_out_scale;
 };
 
 __device__ __forceinline__ float rope_freq(const RopeParams& p, int i /* pair index */) {
@@ -70,7 +80,7 @@ __global__ void __launch_bounds__(256) rope_kernel(const RopeParams p) {
   const int rot_items = p.interleave ? rd / VN : rd / (2 * VN);
   const int pass_items = (D - rd) / VN;
   const int items_per_row = rot_items + pass_items;
-  const int heads = p.num_q_heads + p.num_k_heads;
+  const int heads = p.num_q_heads + p.num_k_heads + (p.v ? p.num_k_heads : 0);
   const int64_t total = p.nnz * heads * items_per_row;
   ptx::grid_dep_wait();
   ptx::grid_dep_launch();  // early trigger: dependents overlap their prologue, they still wait for our completion
@@ -80,11 +90,42 @@ __global__ void __launch_bounds__(256) rope_kernel(const RopeParams p) {
     const int head = int(rest % heads);
     const int64_t tok = rest / heads;
     const bool is_q = head < p.num_q_heads;
-    const int h = is_q ? head : head - p.num_q_heads;
-    const T* src = reinterpret_cast<const T*>(is_q ? p.q : p.k) + tok * (is_q ? p.q_sn : p.k_sn) + h * (is_q ? p.q_sh : p.k_sh);
-    OutT* dst = reinterpret_cast<OutT*>(is_q ? p.q_out : p.k_out) + tok * (is_q ? p.qo_sn : p.ko_sn) +
-                h * (is_q ? p.qo_sh : p.ko_sh);
-    const float oscale = is_q ? p.q_out_scale : p.k_out_scale;
+    const bool is_v = head >= p.num_q_heads + p.num_k_heads;
+    const int h = is_q ? head : (is_v ? head - p.num_q_heads - p.num_k_heads : head - p.num_q_heads);
+    const T* src = is_v ? reinterpret_cast<const T*>(p.v) + tok * p.v_sn + h * p.v_sh
+                        : reinterpret_cast<const T*>(is_q ? p.q : p.k) + tok * (is_q ? p.q_sn : p.k_sn) + h * (is_q ? p.q_sh : p.k_sh);
+    OutT* dst;
+    if (!is_q && p.k_cache) {
+      // paged destination: the position of the token inside its request selects page + slot
+      const int b = p.batch_indices[tok];
+      const int ppos = p.pos_ids ? p.pos_ids[tok] : int(p.pos_ids64[tok]);
+      const int page = p.kv_indices[p.kv_indptr[b] + ppos / p.page_size];
+      dst = reinterpret_cast<OutT*>(is_v ? p.v_cache : p.k_cache) + int64_t(page) * p.c_sp + int64_t(ppos % p.page_size) * p.c_sn +
+            int64_t(h) * p.c_sh;
+    } else {
+      dst = reinterpret_cast<OutT*>(is_q ? p.q_out : p.k_out) + tok * (is_q ? p.qo_sn : p.ko_sn) + h * (is_q ? p.qo_sh : p.ko_sh);
+    }
+    const float oscale = is_q ? p.q_out_scale : (is_v ? p.v_out_scale : p.k_out_scale);
+    if (is_v) {
+      // V is a plain (optionally scaled / re-typed) copy: same element pattern as the rotary items
+      if (item >= rot_items) {
+        const int c = rd + (item - rot_items) * VN;
+#pragma unroll
+        for (int e = 0; e < VN; ++e) dst[c + e] = rope_cvt<OutT>(to_f32(src[c + e]) * oscale);
+      } else if (p.interleave) {
+        const int c = item * VN;
+#pragma unroll
+        for (int e = 0; e < VN; ++e) dst[c + e] = rope_cvt<OutT>(to_f32(src[c + e]) * oscale);
+      } else {
+        const int c = item * VN;
+#pragma unroll
+        for (int e = 0; e < VN; ++e) {
+          dst[c + e] = rope_cvt<OutT>(to_f32(src[c + e]) * oscale);
+          dst[rd / 2 + c + e] = rope_cvt<OutT>(to_f32(src[rd / 2 + c + e]) * oscale);
+        }
+      }
+      continue;
+    }
     if (item >= rot_items) {
       const int c = rd + (item - rot_items) * VN;
       if ((const void*)(src + c) != (const void*)(dst + c) || oscale != 1.f) {
@@ -158,6 +199,38 @@ __global__ void __launch_bounds__(256) rope_kernel(const RopeParams p) {
 
 }  // namespace
 
+namespace {
+struct AppendArgs {
+  const void* v = nullptr;
+  void* k_cache = nullptr;
+  void* v_cache = nullptr;
+  const int32_t* batch_indices = nullptr;
+  const int32_t* kv_indices = nullptr;
+  const int32_t* kv_indptr = nullptr;
+  int64_t v_sn = 0, v_sh = 0, c_sp = 0, c_sn = 0, c_sh = 0;
+  int page_size = 1;
+  float v_out_scale = 1.f;
+};
+thread_local AppendArgs g_append;  // consumed (and cleared) by the next rope_run call of this thread
+}  // namespace
+
+// Arms the fused paged-KV append for the NEXT rope_run call: K (after RoPE) and V are written into the cache pages
+// instead of k_out.  Parity: reference rope_quantize_fp8_append_paged_kv_cache (flashinfer/rope.py:1500-1691).
+extern "C" int rope_set_append(void* v, void* k_cache, void* v_cache, void* batch_indices, void* kv_indices, void* kv_indptr,
+                               int64_t v_sn, int64_t v_sh, int64_t c_sp, int64_t c_sn, int64_t c_sh, int64_t page_size,
+                               double v_out_scale) {
+  g_append.v = v;
+  g_append.k_cache = k_cache;
+  g_append.v_cache = v_cache;
+  g_append.batch_indices = (const int32_t*)batch_indices;
+  g_append.kv_indices = (const int32_t*)kv_indices;
+  g_append.kv_indptr = (const int32_t*)kv_indptr;
+  g_append.v_sn = v_sn; g_append.v_sh = v_sh; g_append.c_sp = c_sp; g_append.c_sn = c_sn; g_append.c_sh = c_sh;
+  g_append.page_size = (int)page_size;
+  g_append.v_out_scale = (float)v_out_scale;
+  return 0;
+}
+
 extern "C" int rope_run(void* q, void* k, void* q_out, void* k_out, void* pos_ids, int64_t pos_is_i64, void* indptr,
                         void* offsets, void* cos_sin_cache, int64_t nnz, int64_t batch, int64_t num_q_heads,
                         int64_t num_k_heads, int64_t head_dim, int64_t rotary_dim, int64_t interleave, int64_t q_sn,
@@ -197,9 +270,17 @@ extern "C" int rope_run(void* q, void* k, void* q_out, void* k_out, void* pos_id
   }
   p.q_out_scale = (float)q_out_scale;
   p.k_out_scale = (float)k_out_scale;
+  {
+    const AppendArgs a = g_append;
+    g_append = AppendArgs();
+    p.v = a.v; p.k_cache = a.k_cache; p.v_cache = a.v_cache; p.batch_indices = a.batch_indices; p.kv_indices = a.kv_indices;
+    p.kv_indptr = a.kv_indptr; p.v_sn = a.v_sn; p.v_sh = a.v_sh; p.c_sp = a.c_sp; p.c_sn = a.c_sn; p.c_sh = a.c_sh;
+    p.page_size = a.page_size; p.v_out_scale = a.v_out_scale;
+    if (p.k_cache) FIB_CHECK(pos_ids != nullptr && p.batch_indices && p.kv_indices && p.kv_indptr, "rope+append needs pos_ids / batch_indices / page table");
+  }
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const int rot_items = interleave ? rotary_dim / 8 : rotary_dim / 16;
-  const int64_t total = nnz * (p.num_q_heads + p.num_k_heads) * (rot_items + (head_dim - rotary_dim) / 8);
+  const int64_t total = nnz * (p.num_q_heads + p.num_k_heads + (p.v ? p.num_k_heads : 0)) * (rot_items + (head_dim - rotary_dim) / 8);
   int64_t blocks = (total + 255) / 256;
   const int64_t cap = int64_t(num_sms()) * 16;
   if (blocks > cap) blocks = cap;

@@ -149,17 +149,17 @@ class LlamaDecodeEngine:
             linear(x, l["wqkv"], out=self._qkv)
             qkv = self._qkv.view(self.batch, hq + 2 * hkv, d)
             q, k, v = qkv[:, :hq], qkv[:, hq : hq + hkv], qkv[:, hq + hkv :]
-            rope.apply_llama31_rope_pos_ids_inplace(q, k, self.positions, rope_scale=cfg.rope_scale,
-                                                    rope_theta=cfg.rope_theta)
-            page.append_paged_kv_cache(k, v, self.batch_indices, self.positions, (l["k_cache"], l["v_cache"]),
-                                       self.kv_indices, self.kv_indptr, self.kv_last)
+            # one kernel: RoPE(q) in place, RoPE(k) and v straight into the cache pages
+            rope.apply_rope_append_paged_kv_cache(q, k, v, self.positions, self.batch_indices, (l["k_cache"], l["v_cache"]),
+                                                  self.kv_indices, self.kv_indptr, "NHD", rope_scale=cfg.rope_scale,
+                                                  rope_theta=cfg.rope_theta, llama31=(1.0, 4.0, 8192.0))
             self.wrapper.run(q, (l["k_cache"], l["v_cache"]), out=self._attn)
             part = self._row_parallel(self._attn.view(self.batch, hq * d), l["wo"])
             self._reduce_add_norm(part, l["ln2"])
             linear(x, l["wgu"], out=self._gu)
             activation.silu_and_mul(self._gu, out=self._act)
             part = self._row_parallel(self._act, l["wd"])
-            n += 9
+            n += 8
             nxt = self.layers[li + 1]["ln1"] if li + 1 < len(self.layers) else self.final_norm
             self._reduce_add_norm(part, nxt)
             n += 1

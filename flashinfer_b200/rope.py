@@ -157,3 +157,74 @@ def mla_rope_quantize_fp8(q_rope, k_rope, q_nope, k_nope, cos_sin_cache, pos_ids
                           k_nope_out=None, enable_pdl=False):
     return rope_quantize_fp8(q_rope, k_rope, q_nope, k_nope, cos_sin_cache, pos_ids, is_neox, quantize_dtype,
                              quant_scale_q, quant_scale_kv, q_rope_out, k_rope_out, q_nope_out, k_nope_out, enable_pdl)
+
+
+# ------------------------------------------------------------------ fused RoPE + paged-KV append (one kernel)
+def apply_rope_append_paged_kv_cache(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, pos_ids: torch.Tensor,
+                                     batch_indices: torch.Tensor, paged_kv_cache, kv_indices: torch.Tensor,
+                                     kv_indptr: torch.Tensor, kv_layout: str = "NHD", rotary_dim=None, interleave: bool = False,
+                                     rope_scale: float = 1.0, rope_theta: float = 1e4, llama31=None, cos_sin_cache=None,
+                                     q_out: Optional[torch.Tensor] = None, q_scale: float = 1.0, kv_scale: float = 1.0) -> torch.Tensor:
+    """``q`` gets RoPE in place (or into ``q_out``); ``k`` gets RoPE and is written, with ``v``, straight into the cache pages
+    of its request (``pos_ids`` is the token position = page slot).  One launch replaces apply_rope + append_paged_kv_cache;
+    with fp8 caches the same kernel quantises (``*_scale`` are multipliers).  Reference: rope_quantize_fp8_append_paged_kv_cache."""
+    from .utils import paged_kv_strides, unpack_paged_kv_cache
+
+    k_cache, v_cache = unpack_paged_kv_cache(paged_kv_cache, kv_layout)
+    q_out = q if q_out is None else q_out
+    if not q.is_cuda:
+        from . import page as _page
+
+        kr = torch.empty_like(k)
+        _launch(q, k, q_out, kr, pos_ids=pos_ids, cos_sin_cache=cos_sin_cache, rotary_dim=rotary_dim, interleave=interleave,
+                rope_scale=rope_scale, rope_theta=rope_theta, llama31=llama31, q_out_scale=q_scale, k_out_scale=kv_scale)
+        _page.append_paged_kv_cache(kr.to(k_cache.dtype), (v.float() * kv_scale).to(v_cache.dtype), batch_indices, pos_ids,
+                                    (k_cache, v_cache), kv_indices, kv_indptr, None, kv_layout)
+        return q_out
+    sp, sn, sh, page_size, _, _ = paged_kv_strides(k_cache, kv_layout)
+    if paged_kv_strides(v_cache, kv_layout)[:3] != (sp, sn, sh) or v_cache.dtype != k_cache.dtype:
+        raise ValueError("k_cache and v_cache must share strides and dtype")
+    if k_cache.dtype != q_out.dtype:
+        raise ValueError("q_out dtype must match the cache dtype (one output type per launch)")
+    jit.load("rope").call("rope_set_append", v, k_cache, v_cache, batch_indices.int(), kv_indices.int(), kv_indptr.int(), v.stride(0),
+                          v.stride(1), sp, sn, sh, page_size, float(kv_scale))
+    _launch(q, k, q_out, k, pos_ids=pos_ids.int() if pos_ids.dtype != torch.int32 else pos_ids, cos_sin_cache=cos_sin_cache,
+            rotary_dim=rotary_dim, interleave=interleave, rope_scale=rope_scale, rope_theta=rope_theta, llama31=llama31,
+            q_out_scale=q_scale, k_out_scale=kv_scale)
+    return q_out
+
+
+def rope_quantize_fp8_append_paged_kv_cache(q_rope, k_rope, q_nope, k_nope, v, cos_sin_cache, pos_ids, paged_kv_cache, kv_indices,
+                                            kv_indptr, batch_indices, positions, is_neox: bool = True, quantize_dtype=None,
+                                            quant_scale_q: float = 1.0, quant_scale_kv: float = 1.0, page_size: int = 16,
+                                            kv_layout: str = "NHD", q_rope_out=None, q_nope_out=None, enable_pdl: bool = False):
+    """GQA / MHA flavour of the reference op (flashinfer/rope.py:1453): RoPE on the rotary slices, fp8 quantisation of Q, K, V
+    and the paged append of K / V in ONE kernel.  Returns ``(q_rope_out, q_nope_out)`` in fp8.  (MLA caches: use
+    ``mla_rope_quantize_fp8`` + ``append_paged_mla_kv_cache``.)"""
+    qdt = quantize_dtype or torch.float8_e4m3fn
+    if v is None:
+        raise NotImplementedError("MLA layout: use mla_rope_quantize_fp8 + append_paged_mla_kv_cache")
+    rd = q_rope.shape[-1]
+    # assemble full heads [nope | rope]?  the reference keeps rope dims first in memory for GQA: [rope | nope]
+    q_full = torch.cat([q_rope, q_nope], -1) if q_nope is not None and q_nope.shape[-1] else q_rope
+    k_full = torch.cat([k_rope, k_nope], -1) if k_nope is not None and k_nope.shape[-1] else k_rope
+    q_out = torch.empty(q_full.shape, dtype=qdt, device=q_full.device)
+    if q_full.is_cuda:
+        k_cache = paged_kv_cache[0]
+        if k_cache.dtype != qdt:
+            raise ValueError("cache dtype must equal quantize_dtype")
+        apply_rope_append_paged_kv_cache(q_full, k_full, v, pos_ids, batch_indices, paged_kv_cache, kv_indices, kv_indptr, kv_layout,
+                                         rotary_dim=rd, interleave=not is_neox, cos_sin_cache=cos_sin_cache, q_out=q_out,
+                                         q_scale=quant_scale_q, kv_scale=quant_scale_kv)
+    else:
+        apply_rope_append_paged_kv_cache(q_full, k_full, v, pos_ids, batch_indices, paged_kv_cache, kv_indices, kv_indptr, kv_layout,
+                                         rotary_dim=rd, interleave=not is_neox, cos_sin_cache=cos_sin_cache, q_out=q_out,
+                                         q_scale=quant_scale_q, kv_scale=quant_scale_kv)
+    qr, qn = q_out[..., :rd], q_out[..., rd:]
+    if q_rope_out is not None:
+        q_rope_out.copy_(qr)
+        qr = q_rope_out
+    if q_nope_out is not None:
+        q_nope_out.copy_(qn)
+        qn = q_nope_out
+    return qr, qn

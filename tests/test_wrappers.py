@@ -151,3 +151,38 @@ def test_block_table_function_api(device):
         v = vc[bt[b].long()].transpose(1, 2).reshape(-1, hkv, D)[:n]
         o_r, _ = reference.attention_ref(q[b : b + 1], k, v, False)
         torch.testing.assert_close(o[b : b + 1].float(), o_r.float(), **_tol(device))
+
+
+@pytest.mark.parametrize("device", DEVICES)
+@pytest.mark.parametrize("layout", ["NHD", "HND"])
+def test_rope_append_fused_matches_separate(device, layout):
+    """apply_rope_append_paged_kv_cache == apply_rope_pos_ids + append_paged_kv_cache."""
+    from flashinfer_b200 import page, rope
+
+    torch.manual_seed(0)
+    dt = torch.bfloat16 if device == "cuda" else torch.float32
+    B, hq, hkv, d, ps = 5, 8, 2, 128, 16
+    lens = torch.tensor([3, 17, 40, 16, 1])
+    npg = (lens + ps - 1) // ps
+    indptr = torch.zeros(B + 1, dtype=torch.int32)
+    indptr[1:] = npg.cumsum(0)
+    total = int(indptr[-1])
+    indices = torch.randperm(total).int().to(device)
+    shape = (total, ps, hkv, d) if layout == "NHD" else (total, hkv, ps, d)
+    kc1, vc1 = torch.zeros(shape, dtype=dt, device=device), torch.zeros(shape, dtype=dt, device=device)
+    kc2, vc2 = torch.zeros_like(kc1), torch.zeros_like(vc1)
+    # append the LAST token of every request (decode step)
+    pos = (lens - 1).int().to(device)
+    bidx = torch.arange(B, dtype=torch.int32, device=device)
+    q = torch.randn(B, hq, d, device=device, dtype=dt)
+    k = torch.randn(B, hkv, d, device=device, dtype=dt)
+    v = torch.randn(B, hkv, d, device=device, dtype=dt)
+    q1, k1 = q.clone(), k.clone()
+    rope.apply_llama31_rope_pos_ids_inplace(q1, k1, pos)
+    page.append_paged_kv_cache(k1, v, bidx, pos, (kc1, vc1), indices, indptr.to(device), ((lens - 1) % ps + 1).int().to(device), layout)
+    q2 = q.clone()
+    rope.apply_rope_append_paged_kv_cache(q2, k.clone(), v, pos, bidx, (kc2, vc2), indices, indptr.to(device), layout,
+                                          rope_scale=8, rope_theta=5e5, llama31=(1.0, 4.0, 8192.0))
+    assert torch.equal(q1, q2)
+    assert torch.equal(kc1, kc2)
+    assert torch.equal(vc1, vc2)

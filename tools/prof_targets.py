@@ -1,0 +1,42 @@
+"""Single-kernel workloads for `ncu --set full` captures:  python tools/prof_targets.py <gemm_bf16|gemm_fp4|gemm_fp8|prefill|decode|moe>"""
+import math, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import flashinfer_b200 as fi
+
+mode = sys.argv[1]
+torch.manual_seed(0)
+if mode == "gemm_bf16":
+    a = torch.randn(8192, 8192, device="cuda", dtype=torch.bfloat16); w = torch.randn(8192, 8192, device="cuda", dtype=torch.bfloat16)
+    for _ in range(3): fi.mm_bf16(a, w.t())
+elif mode in ("gemm_fp4", "gemm_fp8"):
+    a = torch.randn(8192, 8192, device="cuda", dtype=torch.bfloat16); w = torch.randn(8192, 8192, device="cuda", dtype=torch.bfloat16)
+    g = torch.tensor(1.0, device="cuda")
+    if mode == "gemm_fp4":
+        aq, asf = fi.nvfp4_quantize(a, g); wq, wsf = fi.nvfp4_quantize(w, g)
+        for _ in range(3): fi.mm_fp4(aq, wq.t(), asf, wsf, g, torch.bfloat16)
+    else:
+        a8, w8 = a.to(torch.float8_e4m3fn), w.to(torch.float8_e4m3fn)
+        for _ in range(3): fi.mm_fp8(a8, w8.t(), g)
+elif mode == "prefill":
+    L, hq, hkv, d = 8192, 32, 8, 128
+    q = torch.randn(L, hq, d, device="cuda", dtype=torch.bfloat16); k = torch.randn(L, hkv, d, device="cuda", dtype=torch.bfloat16); v = torch.randn(L, hkv, d, device="cuda", dtype=torch.bfloat16)
+    w = fi.BatchPrefillWithRaggedKVCacheWrapper(torch.empty(128 << 20, dtype=torch.uint8, device="cuda"))
+    ip = torch.tensor([0, L], dtype=torch.int32)
+    w.plan(ip, ip, hq, hkv, d, causal=True, q_data_type=torch.bfloat16)
+    for _ in range(3): w.run(q, k, v)
+elif mode == "decode":
+    B, kv, hq, hkv, d, ps = 64, 4096, 32, 8, 128, 16
+    npg = kv // ps
+    kc = torch.randn(B * npg, ps, hkv, d, device="cuda", dtype=torch.bfloat16); vc = torch.randn(B * npg, ps, hkv, d, device="cuda", dtype=torch.bfloat16)
+    q = torch.randn(B, hq, d, device="cuda", dtype=torch.bfloat16)
+    w = fi.BatchDecodeWithPagedKVCacheWrapper(torch.empty(128 << 20, dtype=torch.uint8, device="cuda"), "NHD")
+    w.plan(torch.arange(0, (B + 1) * npg, npg, dtype=torch.int32), torch.randperm(B * npg).int(), torch.full((B,), ps, dtype=torch.int32), hq, hkv, d, ps, q_data_type=torch.bfloat16)
+    for _ in range(3): w.run(q, (kc, vc))
+elif mode == "moe":
+    from flashinfer_b200.fused_moe import moe_forward, route
+    T, E, K, H, I = 4096, 32, 8, 7168, 2048
+    x = (torch.randn(T, H, device="cuda") * 0.5).bfloat16(); w1 = (torch.randn(E, 2 * I, H, device="cuda") / H ** 0.5).bfloat16(); w2 = (torch.randn(E, H, I, device="cuda") / I ** 0.5).bfloat16()
+    ids, w = route(torch.randn(T, E, device="cuda"), None, K, 1)
+    for _ in range(3): moe_forward(x, ids, w, w1, w2)
+torch.cuda.synchronize()
