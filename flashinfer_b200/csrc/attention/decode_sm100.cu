@@ -60,11 +60,11 @@ struct DecodeSmem {
   static constexpr int kOffK = 0;
   static constexpr int kOffV = kOffK + kStagesK * kTileBytes;
   static constexpr int kOffQ = kOffV + kStagesV * kTileBytes;
-  static constexpr int kOffP = kOffQ + kQBytes;
+  static constexpr int kOffP = kOffQ + 2 * kQBytes;          // Q^T is double-buffered: the next segment's Q is staged early
   static constexpr int kOffRed = kOffP + 2 * kPBytes;         // 2 x NQ x 4 floats (max) + NQ x 4 floats (sum)
   static constexpr int kRedBytes = 3 * NQ * 4 * 4;
   static constexpr int kOffBar = kOffRed + kRedBytes;
-  static constexpr int kNumBars = 2 * kStagesK + 2 * kStagesV + 2 + 2 + 2 + 1;
+  static constexpr int kNumBars = 2 * kStagesK + 2 * kStagesV + 2 + 2 + 2 + 2;
   static constexpr int kTotal = kOffBar + kNumBars * 8 + 16 + 1024;
 };
 
@@ -151,8 +151,8 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   uint64_t* s_full = v_empty + S::kStagesV;  // [2]
   uint64_t* o_full = s_full + 2;             // [2]
   uint64_t* p_ready = o_full + 2;            // [2]
-  uint64_t* q_full = p_ready + 2;            // [1]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(q_full + 1);
+  uint64_t* q_full = p_ready + 2;            // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(q_full + 2);
   float* red_max = reinterpret_cast<float*>(smem + S::kOffRed);  // [2][NV][4]
   float* red_sum = red_max + 2 * NQ * 4;                         // [NV][4]
 
@@ -179,7 +179,8 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
       ptx::mbar_init(&o_full[i], 1);
       ptx::mbar_init(&p_ready[i], 128);
     }
-    ptx::mbar_init(q_full, 128);
+    ptx::mbar_init(&q_full[0], 128);
+    ptx::mbar_init(&q_full[1], 128);
     ptx::fence_mbar_init();
   }
   if (warp == 2) {
@@ -187,7 +188,7 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     ptx::tmem_relinquish<1>();
   }
   // zero Q / P staging buffers once (padding columns stay zero forever)
-  for (int i = threadIdx.x; i < (S::kQBytes + 2 * S::kPBytes) / 16; i += blockDim.x)
+  for (int i = threadIdx.x; i < (2 * S::kQBytes + 2 * S::kPBytes) / 16; i += blockDim.x)
     reinterpret_cast<int4*>(smem + S::kOffQ)[i] = make_int4(0, 0, 0, 0);
   ptx::fence_proxy_async_smem();
   ptx::tc_fence_before();
@@ -265,7 +266,7 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     uint32_t kph = 0, vph = 0;
     uint32_t gt = 0;      // global tile counter (buffer parity)
     uint32_t seg_par = 0;
-    const uint32_t q_addr = ptx::smem_u32(smem + S::kOffQ);
+    const uint32_t q_base = ptx::smem_u32(smem + S::kOffQ);
     const uint32_t p_addr = ptx::smem_u32(smem + S::kOffP);
     auto issue_pv = [&](uint32_t tile_id) {
       const uint32_t b = tile_id & 1;
@@ -295,8 +296,10 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     for (int seg = seg_begin; seg < seg_end; ++seg) {
       const int32_t* si = p.seg_info + seg * kSegInts;
       const int t0 = si[2], t1 = si[3];
-      ptx::mbar_wait(q_full, seg_par);
-      seg_par ^= 1;
+      const int sl = seg - seg_begin;  // local segment index selects the Q buffer
+      ptx::mbar_wait(&q_full[sl & 1], (sl >> 1) & 1);
+      const uint32_t q_addr = q_base + (sl & 1) * S::kQBytes;
+      (void)seg_par;
       for (int ti = t0; ti < t1; ++ti, ++gt) {
         const uint32_t b = gt & 1;
         ptx::mbar_wait(&k_full[ks], kph);
@@ -344,21 +347,29 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
       const int nq = q_len * G;  // valid columns
 
       // ---- stage Q^T (B operand of QK) : element (c, d) at (d/8)*LBO + (c/8)*128 + (c%8)*16 + (d%8)*2
-      {
+      // Double-buffered: segment i stages the Q of segment i+1 right away, so the MMA warp never waits for a Q
+      // round trip at a segment boundary (buffer (i+1)&1 was last read by segment i-1, whose S tiles have all
+      // been consumed by these warps already).
+      auto stage_q = [&](int sg) {
+        const int32_t* sj = p.seg_info + sg * kSegInts;
+        const int kvh = sj[1], qs = sj[5], nqv = sj[6] * G;
+        uint8_t* qbuf = smem + S::kOffQ + ((sg - seg_begin) & 1) * S::kQBytes;
         const int tid = threadIdx.x - 128;
         for (int v = tid; v < NV * (D / 8); v += 128) {
           const int c = v / (D / 8), dg = v % (D / 8);
           int4 val = make_int4(0, 0, 0, 0);
-          if (c < nq) {
+          if (c < nqv) {
             const int qi = c / G, g = c % G;
-            val = __ldg(reinterpret_cast<const int4*>(qbase + int64_t(q_start + qi) * p.q_stride_n +
-                                                      int64_t(kv_head * G + g) * p.q_stride_h + dg * 8));
+            val = __ldg(reinterpret_cast<const int4*>(qbase + int64_t(qs + qi) * p.q_stride_n +
+                                                      int64_t(kvh * G + g) * p.q_stride_h + dg * 8));
           }
-          *reinterpret_cast<int4*>(smem + S::kOffQ + dg * S::kLBO + (c >> 3) * 128 + (c & 7) * 16) = val;
+          *reinterpret_cast<int4*>(qbuf + dg * S::kLBO + (c >> 3) * 128 + (c & 7) * 16) = val;
         }
         ptx::fence_proxy_async_smem();
-        ptx::mbar_arrive(q_full);
-      }
+        ptx::mbar_arrive(&q_full[(sg - seg_begin) & 1]);
+      };
+      if (seg == seg_begin) stage_q(seg);
+      if (seg + 1 < seg_end) stage_q(seg + 1);
 
       float m[NV], l[NV], o[NV], alpha_saved[NV];
 #pragma unroll
