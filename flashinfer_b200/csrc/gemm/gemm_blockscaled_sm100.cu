@@ -560,6 +560,272 @@ int launch_gw(const CUtensorMap& tmA, const CUtensorMap& tmB, void* C, const GwP
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// CTA-pair (cta_group::2) variant for large problems.  A 2-CTA cluster owns a 256 x BN output tile: CTA r holds rows
+// [r*128, r*128+128) of A (and of the accumulator, in its own TMEM) and HALF of the B tile (BN/2 rows); the leader's
+// single MMA thread issues tcgen05.mma.cta_group::2 with M = 256, which reads A / B from both CTAs' shared memory.
+// Per-SM operand traffic drops from (128 + BN) to (128 + BN/2) rows per slab, which is what lets the fp4 pipe run:
+// at 1-CTA 128x256 tiles the kernel was latency x bandwidth bound (3 stages of 56 KB = 768 clk of look-ahead, tensor
+// pipe 32 % busy in ncu); here a stage is 34 KB, 6 stages deep, with double-buffered 192-column accumulators.
+// Synchronisation: both producers credit their TMA bytes to the LEADER's full barrier (cta_group::2 TMA with the peer
+// bit cleared), tcgen05.commit multicasts "slot free" / "accumulator ready" to both CTAs, the peer's epilogue warps
+// arrive remotely on the leader's tmem_empty barrier.  Scale factors ride on 2-D tensor maps over the 512-byte blocks.
+// ---------------------------------------------------------------------------------------------------------------
+struct Geo2 {
+  int stages, stage_bytes, a_bytes, b_bytes, sfa_bytes, sfb_bytes, bar_offset, total, nchunk, rb, sfa_col, sfb_col;
+  __host__ __device__ static Geo2 make(int BN, int kind) {
+    Geo2 g;
+    g.nchunk = kind == kNvFp4 ? 4 : (kind == kMxFp4 ? 2 : (kind == kMxFp8 ? 1 : 0));
+    g.rb = (BN % 128 == 0) ? BN / 128 : (BN + 64 + 127) / 128;
+    g.a_bytes = BM * BKB;
+    g.b_bytes = (BN / 2) * BKB;
+    g.sfa_bytes = g.nchunk * 512;
+    g.sfb_bytes = g.rb * g.nchunk * 512;
+    g.stage_bytes = (g.a_bytes + g.b_bytes + g.sfa_bytes + g.sfb_bytes + 1023) / 1024 * 1024;
+    int st = (216 * 1024) / g.stage_bytes;
+    g.stages = st > 8 ? 8 : st;
+    g.bar_offset = g.stages * g.stage_bytes;
+    g.total = g.bar_offset + 320 + 1024;
+    g.sfa_col = 2 * BN;
+    g.sfb_col = g.sfa_col + g.nchunk * 4;
+    return g;
+  }
+};
+
+struct Params2 {
+  const float* alpha_a;
+  const float* alpha_b;
+  int64_t c_batch_stride, ldc;
+  int M, N, Kb, batch, BN;
+  int sf_k_tiles, sfa_row_tiles, sfb_row_tiles;  // scale tensors: [batch][row tiles][sf_k_tiles] blocks of 512 B
+  uint32_t idesc;                                // M = 256
+};
+
+template <int KIND, typename OutT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+bs_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmSFA, const __grid_constant__ CUtensorMap tmSFB, OutT* __restrict__ C,
+                const Params2 p) {
+  const Geo2 G = Geo2::make(p.BN, KIND);
+  const int BN = p.BN;
+  const int kStages = G.stages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + G.bar_offset);  // used on the leader only
+  uint64_t* empty_bar = full_bar + kStages;                              // both CTAs (multicast commit)
+  uint64_t* tmem_full = empty_bar + kStages;                             // both CTAs (multicast commit)
+  uint64_t* tmem_empty = tmem_full + 2;                                  // leader only, 8 arrivals
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int crank = int(ptx::cluster_ctarank());
+  const bool leader = crank == 0;
+
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+    if constexpr (KIND != kFp8) {
+      ptx::prefetch_tmap(&tmSFA);
+      ptx::prefetch_tmap(&tmSFB);
+    }
+    for (int i = 0; i < kStages; ++i) {
+      ptx::mbar_init(&full_bar[i], 1);
+      ptx::mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&tmem_full[i], 1);
+      ptx::mbar_init(&tmem_empty[i], 8);
+    }
+    ptx::fence_mbar_init();
+  }
+  constexpr uint32_t kTmemCols = 512;
+  if (warp == 2) {
+    ptx::tmem_alloc<2>(tmem_ptr, kTmemCols);
+    ptx::tmem_relinquish<2>();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();  // both CTAs' barriers and TMEM exist before any cross-CTA signal
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  ptx::grid_dep_wait();
+  ptx::grid_dep_launch();
+
+  const int tiles_m = (p.M + 2 * BM - 1) / (2 * BM), tiles_n = (p.N + BN - 1) / BN;
+  const int tiles_per_batch = tiles_m * tiles_n;
+  const int num_tiles = tiles_per_batch * p.batch;
+  const int num_kb = (p.Kb + BKB - 1) / BKB;
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const uint32_t stage_tx = 2u * uint32_t(G.a_bytes + G.b_bytes + G.sfa_bytes + G.sfb_bytes);
+
+  if (warp == 0) {
+    if (ptx::elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = pair; t < num_tiles; t += num_pairs) {
+        const int b = t / tiles_per_batch, r = t % tiles_per_batch;
+        const int tm = r % tiles_m, tn = r / tiles_m;
+        const int n0 = tn * BN;
+        const int row0 = tm * 2 * BM + crank * BM;
+        const int sfa_row = (tm * 2 + crank);
+        const int rb0 = n0 / 128;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * G.stage_bytes;
+          uint8_t* sb = sa + G.a_bytes;
+          if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
+          ptx::tma2_load_3d(sa, &tmA, &full_bar[stage], kb * BKB, row0, b, ptx::kEvictNormal);
+          ptx::tma2_load_3d(sb, &tmB, &full_bar[stage], kb * BKB, n0 + crank * (BN / 2), b, ptx::kEvictNormal);
+          if constexpr (KIND != kFp8) {
+            uint8_t* ssfa = sb + G.b_bytes;
+            uint8_t* ssfb = ssfa + G.sfa_bytes;
+            // scale blocks are rows of a [blocks, 128 x u32] tensor; rows past the end are zero-filled by TMA
+            ptx::tma2_load_2d(ssfa, &tmSFA, &full_bar[stage], 0,
+                              (b * p.sfa_row_tiles + sfa_row) * p.sf_k_tiles + kb * G.nchunk, ptx::kEvictNormal);
+            for (int rr = 0; rr < G.rb; ++rr) {
+              int rt = rb0 + rr;
+              if (rt >= p.sfb_row_tiles) rt = p.sfb_row_tiles - 1;  // columns past N: finite scales x zero data
+              ptx::tma2_load_2d(ssfb + rr * G.nchunk * 512, &tmSFB, &full_bar[stage], 0,
+                                (b * p.sfb_row_tiles + rt) * p.sf_k_tiles + kb * G.nchunk, ptx::kEvictNormal);
+            }
+          }
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && leader) {
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = pair; t < num_tiles; t += num_pairs) {
+      const int r = t % tiles_per_batch;
+      const int n0 = (r / tiles_m) * BN;
+      const uint32_t sfb_off = uint32_t((n0 % 128) / 32);
+      ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        ptx::mbar_wait(&full_bar[stage], phase);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const uint32_t sa = ptx::smem_u32(smem + stage * G.stage_bytes);
+          const uint32_t sb = sa + G.a_bytes;
+          const uint64_t da = ptx::make_smem_desc(sa, 16, 1024, ptx::kSwz128);
+          const uint64_t db = ptx::make_smem_desc(sb, 16, 1024, ptx::kSwz128);
+          if constexpr (KIND != kFp8) {
+            const uint32_t ssfa = sb + G.b_bytes, ssfb = ssfa + G.sfa_bytes;
+            for (int c = 0; c < G.nchunk; ++c) {
+              ptx::tmem_cp2_32x128b_warpx4(tmem_base + G.sfa_col + c * 4,
+                                           ptx::make_smem_desc(ssfa + c * 512, 0, 128, ptx::kSwzNone));
+              for (int rr = 0; rr < G.rb; ++rr)
+                ptx::tmem_cp2_32x128b_warpx4(tmem_base + G.sfb_col + (c * G.rb + rr) * 4,
+                                             ptx::make_smem_desc(ssfb + (rr * G.nchunk + c) * 512, 0, 128, ptx::kSwzNone));
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t accum = (kb > 0 || k > 0) ? 1u : 0u;
+            const uint64_t dak = ptx::desc_advance(da, k * 32), dbk = ptx::desc_advance(db, k * 32);
+            if constexpr (KIND == kFp8) {
+              ptx::mma_f8f6f4_ss<2>(d_tmem, dak, dbk, p.idesc, accum);
+            } else if constexpr (KIND == kMxFp8) {
+              const uint32_t id = p.idesc | (uint32_t(k) << 4) | (uint32_t(k) << 29);
+              ptx::mma2_mxf8f6f4_ss(d_tmem, dak, dbk, id, tmem_base + G.sfa_col, tmem_base + G.sfb_col + sfb_off, accum);
+            } else if constexpr (KIND == kNvFp4) {
+              ptx::mma2_mxf4nvf4_ss(d_tmem, dak, dbk, p.idesc, tmem_base + G.sfa_col + k * 4,
+                                    tmem_base + G.sfb_col + k * G.rb * 4 + sfb_off, accum);
+            } else {
+              const uint32_t sid = uint32_t(k & 1) * 2;
+              const uint32_t id = p.idesc | (sid << 4) | (sid << 29);
+              ptx::mma2_mxf4_2x_ss(d_tmem, dak, dbk, id, tmem_base + G.sfa_col + (k >> 1) * 4,
+                                   tmem_base + G.sfb_col + (k >> 1) * G.rb * 4 + sfb_off, accum);
+            }
+          }
+          ptx::mma_commit_2cta(&empty_bar[stage], 3);                      // slot free in BOTH CTAs
+          if (kb == num_kb - 1) ptx::mma_commit_2cta(&tmem_full[acc], 3);  // accumulator ready in BOTH CTAs
+        }
+        __syncwarp();
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else if (warp >= 4) {
+    const int q = warp - 4;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    float alpha = 1.f;
+    if (p.alpha_a) alpha *= *p.alpha_a;
+    if (p.alpha_b) alpha *= *p.alpha_b;
+    const uint32_t leader_empty = ptx::mapa(ptx::smem_u32(&tmem_empty[0]), 0);
+    for (int t = pair; t < num_tiles; t += num_pairs) {
+      const int b = t / tiles_per_batch, r = t % tiles_per_batch;
+      const int tm = r % tiles_m, tn = r / tiles_m;
+      ptx::mbar_wait(&tmem_full[acc], acc_phase);
+      ptx::tc_fence_after();
+      const int row = tm * 2 * BM + crank * BM + q * 32 + lane;
+      const uint32_t taddr = tmem_base + acc * BN + (uint32_t(q * 32) << 16);
+      OutT* crow = C + int64_t(b) * p.c_batch_stride + int64_t(row) * p.ldc;
+      const bool vec_ok = (p.ldc % (16 / sizeof(OutT)) == 0);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        ptx::tmem_ld_x32(taddr + c0, v);
+        ptx::tmem_ld_wait();
+        const int col0 = tn * BN + c0;
+        if (row < p.M) {
+          if (col0 + 32 <= p.N && vec_ok) {
+            constexpr int VN = 16 / sizeof(OutT);
+#pragma unroll
+            for (int j = 0; j < 32; j += VN) {
+              Vec16<OutT> o;
+#pragma unroll
+              for (int e = 0; e < VN; ++e) o.v[e] = from_f32<OutT>(__uint_as_float(v[j + e]) * alpha);
+              st16(crow + col0 + j, o);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) crow[col0 + j] = from_f32<OutT>(__uint_as_float(v[j]) * alpha);
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster(leader_empty + acc * 8);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();  // the leader's MMAs read the peer's shared memory: nobody leaves early
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<2>(tmem_base, kTmemCols);
+  }
+}
+
+template <int KIND, typename OutT>
+int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmSFA, const CUtensorMap& tmSFB, void* C,
+            const Params2& p, int grid, int smem, bool pdl, cudaStream_t stream) {
+  static bool set = false;
+  if (!set) {
+    FIB_CUDA_CHECK(cudaFuncSetAttribute(bs_gemm2_kernel<KIND, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    set = true;
+  }
+  LaunchCfg lc(dim3(grid), dim3(256), smem, stream, pdl);  // cluster dims are compiled in (__cluster_dims__)
+  FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, bs_gemm2_kernel<KIND, OutT>, tmA, tmB, tmSFA, tmSFB, (OutT*)C, p));
+  return 0;
+}
+
 template <int KIND, typename OutT>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, void* C, const Params& p, int grid, int smem, bool pdl,
            cudaStream_t stream) {
@@ -621,6 +887,73 @@ extern "C" int gemm_lowp_nt(void* A, void* B, void* C, void* sfa, void* sfb, voi
       const int q = kind == kFp8 ? 32 : 64;
       BN = int((want + q - 1) / q * q);
       if (BN < q) BN = q;
+    }
+  }
+  // ---- CTA-pair (cta_group::2) path for large problems ----
+  {
+    const char* env2 = getenv("FIB200_LOWP_2CTA");
+    const int BN2 = bn ? (int)bn : (kind == kFp8 ? 256 : 192);
+    const int64_t tiles2 = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN2 - 1) / BN2) * batch;
+    bool use2 = !tile_expert && M >= 512 && tiles2 >= num_sms() / 2 && K >= 512;
+    if (env2) use2 = atoi(env2) != 0 && !tile_expert;
+    if (use2 && BN2 % 64 == 0 && BN2 >= 64 && BN2 <= 256 && (kind == kFp8 || 2 * BN2 + Geo2::make(BN2, (int)kind).nchunk * 4 * (1 + Geo2::make(BN2, (int)kind).rb) <= 512)) {
+      const Geo2 G2 = Geo2::make(BN2, (int)kind);
+      CUtensorMap tmA, tmB, tmSFA, tmSFB;
+      {
+        uint64_t dims[3] = {(uint64_t)Kb, (uint64_t)M, (uint64_t)batch};
+        uint64_t str[2] = {(uint64_t)lda, (uint64_t)a_batch_stride};
+        uint32_t box[3] = {BKB, BM, 1};
+        if (make_tmap(&tmA, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, A, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+      }
+      {
+        uint64_t dims[3] = {(uint64_t)Kb, (uint64_t)N, (uint64_t)batch};
+        uint64_t str[2] = {(uint64_t)ldb, (uint64_t)b_batch_stride};
+        uint32_t box[3] = {BKB, (uint32_t)(BN2 / 2), 1};
+        if (make_tmap(&tmB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, B, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+      }
+      Params2 p2;
+      const int vec2 = kind == kNvFp4 ? 16 : 32;
+      p2.sf_k_tiles = kind == kFp8 ? 0 : int(((K + vec2 - 1) / vec2 + 3) / 4);
+      p2.sfa_row_tiles = int((M + 127) / 128);
+      p2.sfb_row_tiles = int((N + 127) / 128);
+      if (kind != kFp8) {
+        FIB_CHECK(sfa && sfb, "gemm_lowp: block-scaled kinds need scale tensors");
+        FIB_CHECK(sfa_batch_stride == int64_t(p2.sfa_row_tiles) * p2.sf_k_tiles * 512 || batch == 1, "gemm_lowp: SFA must be contiguous per batch");
+        FIB_CHECK(sfb_batch_stride == int64_t(p2.sfb_row_tiles) * p2.sf_k_tiles * 512 || batch == 1, "gemm_lowp: SFB must be contiguous per batch");
+        uint64_t dimsa[2] = {128, (uint64_t)(batch * int64_t(p2.sfa_row_tiles) * p2.sf_k_tiles)};
+        uint64_t dimsb[2] = {128, (uint64_t)(batch * int64_t(p2.sfb_row_tiles) * p2.sf_k_tiles)};
+        uint64_t str[1] = {512};
+        uint32_t box[2] = {128, (uint32_t)G2.nchunk};
+        if (make_tmap(&tmSFA, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, sfa, dimsa, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
+        if (make_tmap(&tmSFB, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, sfb, dimsb, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
+      } else {
+        tmSFA = tmA;
+        tmSFB = tmB;
+      }
+      p2.alpha_a = (const float*)alpha_a;
+      p2.alpha_b = (const float*)alpha_b;
+      p2.c_batch_stride = c_batch_stride;
+      p2.ldc = ldc;
+      p2.M = (int)M; p2.N = (int)N; p2.Kb = (int)Kb; p2.batch = (int)batch; p2.BN = BN2;
+      if (kind == kFp8) p2.idesc = ptx::make_idesc_f8((uint32_t)a_fmt, (uint32_t)b_fmt, 2 * BM, BN2, 0, 0);
+      else if (kind == kMxFp8) p2.idesc = ptx::make_idesc_blockscaled((uint32_t)a_fmt, (uint32_t)b_fmt, 2 * BM, BN2, 1, 0, 0);
+      else p2.idesc = ptx::make_idesc_blockscaled(1, 1, 2 * BM, BN2, kind == kMxFp4 ? 1 : 0, 0, 0);
+      const int pairs = (int)(tiles2 < num_sms() / 2 ? tiles2 : num_sms() / 2);
+      const bool f16o = out_dtype == kF16;
+      switch (kind) {
+        case kFp8:
+          return f16o ? launch2<kFp8, __half>(tmA, tmB, tmSFA, tmSFB, C, p2, 2 * pairs, G2.total, pdl != 0, stream)
+                      : launch2<kFp8, __nv_bfloat16>(tmA, tmB, tmSFA, tmSFB, C, p2, 2 * pairs, G2.total, pdl != 0, stream);
+        case kMxFp8:
+          return f16o ? launch2<kMxFp8, __half>(tmA, tmB, tmSFA, tmSFB, C, p2, 2 * pairs, G2.total, pdl != 0, stream)
+                      : launch2<kMxFp8, __nv_bfloat16>(tmA, tmB, tmSFA, tmSFB, C, p2, 2 * pairs, G2.total, pdl != 0, stream);
+        case kNvFp4:
+          return f16o ? launch2<kNvFp4, __half>(tmA, tmB, tmSFA, tmSFB, C, p2, 2 * pairs, G2.total, pdl != 0, stream)
+                      : launch2<kNvFp4, __nv_bfloat16>(tmA, tmB, tmSFA, tmSFB, C, p2, 2 * pairs, G2.total, pdl != 0, stream);
+        default:
+          return f16o ? launch2<kMxFp4, __half>(tmA, tmB, tmSFA, tmSFB, C, p2, 2 * pairs, G2.total, pdl != 0, stream)
+                      : launch2<kMxFp4, __nv_bfloat16>(tmA, tmB, tmSFA, tmSFB, C, p2, 2 * pairs, G2.total, pdl != 0, stream);
+      }
     }
   }
   FIB_CHECK(BN % 32 == 0 && BN >= 32 && BN <= 256, "gemm_lowp: N tile must be a multiple of 32 in [32, 256]");

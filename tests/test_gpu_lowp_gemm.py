@@ -134,3 +134,37 @@ def test_lowp_cluster_split_k(m, n, k, split):
         _check(fi.mm_fp4(aq4, wq4.t(), asf4, wsf4, g, torch.bfloat16), ref)
     finally:
         os.environ.pop("FIB200_LOWP_SPLIT", None)
+
+
+@pytest.mark.parametrize("m,n,k", [(512, 768, 1024), (300, 1184, 448), (2000, 4096, 1024), (4096, 4096, 4096)])
+@pytest.mark.parametrize("bn2", ["0", "64", "128", "192"])
+def test_lowp_cta_pair_kernel(m, n, k, bn2):
+    """cta_group::2 kernel (256 x BN tile per CTA pair) for fp8 / mxfp8 / nvfp4 / mxfp4, forced on."""
+    os.environ["FIB200_LOWP_2CTA"] = "1"
+    os.environ["FIB200_LOWP_BN"] = bn2
+    try:
+        torch.manual_seed(0)
+        a = torch.randn(m, k, device="cuda", dtype=torch.bfloat16)
+        w = torch.randn(n, k, device="cuda", dtype=torch.bfloat16)
+        a8, sa = _to_fp8(a.float())
+        w8, sw = _to_fp8(w.float())
+        _check(fi.mm_fp8(a8, w8.t(), sa * sw, torch.bfloat16), (a8.float() @ w8.float().t()) * sa * sw)
+        A3 = torch.stack([a8, a8.flip(0)])
+        W3 = torch.stack([w8, w8.flip(0)])
+        o3 = fi.bmm_fp8(A3, W3.transpose(-1, -2), sa, sw, torch.bfloat16)
+        _check(o3, torch.bmm(A3.float(), W3.float().transpose(-1, -2)) * sa * sw)
+        aq, asf = fi.mxfp8_quantize(a)
+        wq, wsf = fi.mxfp8_quantize(w)
+        _check(fi.mm_mxfp8(aq, wq.t(), asf, wsf), fi.mxfp8_dequantize_host(aq, asf) @ fi.mxfp8_dequantize_host(wq, wsf).t())
+        g = torch.tensor(1.0, device="cuda")
+        aq4, asf4 = fi.nvfp4_quantize(a, g)
+        wq4, wsf4 = fi.nvfp4_quantize(w, g)
+        ref = e2m1_and_ufp8sf_scale_to_float(aq4, asf4, g, 16, 1, True) @ e2m1_and_ufp8sf_scale_to_float(wq4, wsf4, g, 16, 1, True).t()
+        _check(fi.mm_fp4(aq4, wq4.t(), asf4, wsf4, g, torch.bfloat16), ref)
+        aqm, asfm = fi.mxfp4_quantize(a)
+        wqm, wsfm = fi.mxfp4_quantize(w)
+        _check(fi.mm_fp4(aqm, wqm.t(), asfm, wsfm, None, torch.bfloat16, block_size=32, use_nvfp4=False),
+               fi.mxfp4_dequantize(aqm, asfm) @ fi.mxfp4_dequantize(wqm, wsfm).t())
+    finally:
+        os.environ.pop("FIB200_LOWP_2CTA", None)
+        os.environ.pop("FIB200_LOWP_BN", None)
