@@ -11,7 +11,8 @@ from .utils import device_support_pdl, dtype_code, stream_ptr
 _ACT = {"silu": 0, "gelu": 1, "gelu_tanh": 2}
 
 
-def _act_and_mul(kind: str, input: torch.Tensor, out: Optional[torch.Tensor], enable_pdl, gate_second: bool = False):
+def _act_and_mul(kind: str, input: torch.Tensor, out: Optional[torch.Tensor], enable_pdl, gate_second: bool = False,
+                 row_map: Optional[torch.Tensor] = None):
     d = input.shape[-1] // 2
     if input.shape[-1] % 2:
         raise ValueError("last dim must be even")
@@ -32,7 +33,7 @@ def _act_and_mul(kind: str, input: torch.Tensor, out: Optional[torch.Tensor], en
     pdl = device_support_pdl(input.device) if enable_pdl is None else enable_pdl
     jit.load("activation").call(
         "act_and_mul", x2, o2, x2.shape[0], d, x2.stride(0), o2.stride(0), _ACT[kind], 1 if gate_second else 0,
-        dtype_code(input.dtype),
+        row_map, dtype_code(input.dtype),
         1 if pdl else 0, stream_ptr(input),
     )
     return out

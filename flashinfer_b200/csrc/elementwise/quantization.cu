@@ -42,7 +42,7 @@ template <typename T, int VEC, bool kUE8M0>
 __global__ void __launch_bounds__(256)
 fp4_quantize_kernel(const T* __restrict__ x, uint8_t* __restrict__ q, uint8_t* __restrict__ sf,
                     const float* __restrict__ global_scale, int64_t batch, int64_t M, int64_t K, int64_t ldx,
-                    int64_t x_batch_stride, int swizzled, int64_t sf_batch_stride) {
+                    int64_t x_batch_stride, int swizzled, int64_t sf_batch_stride, const int32_t* __restrict__ row_map) {
   const int64_t kc_total = K / VEC;
   const int64_t kc_pad = (kc_total + 3) / 4 * 4;
   const int64_t total = batch * M * kc_total;
@@ -52,6 +52,7 @@ fp4_quantize_kernel(const T* __restrict__ x, uint8_t* __restrict__ q, uint8_t* _
     const int64_t kc = i % kc_total;
     const int64_t m = (i / kc_total) % M;
     const int64_t b = i / (kc_total * M);
+    if (row_map && row_map[m] < 0) continue;  // MoE padding row (scale bytes stay as initialised: finite)
     const T* src = x + b * x_batch_stride + m * ldx + kc * VEC;
     float v[VEC];
 #pragma unroll
@@ -223,7 +224,7 @@ inline int grid_for(int64_t total, int threads = 256) {
 // vec = 16 (NVFP4, UE4M3 scale unless ue8m0) or 32 (MXFP4, UE8M0 scale)
 extern "C" int fp4_quantize(void* x, void* q, void* sf, void* global_scale, int64_t batch, int64_t M, int64_t K,
                             int64_t ldx, int64_t x_batch_stride, int64_t vec, int64_t ue8m0, int64_t swizzled,
-                            int64_t sf_batch_stride, int64_t dtype, int64_t pdl, int64_t stream_) {
+                            int64_t sf_batch_stride, void* row_map, int64_t dtype, int64_t pdl, int64_t stream_) {
   FIB_CHECK(vec == 16 || vec == 32, "fp4_quantize: sf_vec_size must be 16 or 32");
   FIB_CHECK(K % vec == 0 && ldx % 8 == 0, "fp4_quantize: K must be a multiple of sf_vec_size and rows 16B aligned");
   if (batch * M * K == 0) return 0;
@@ -233,7 +234,7 @@ extern "C" int fp4_quantize(void* x, void* q, void* sf, void* global_scale, int6
   return FIB_DISPATCH_HALF(dtype, T, [&]() -> int {
     auto launch = [&](auto kern) -> int {
       FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, kern, (const T*)x, (uint8_t*)q, (uint8_t*)sf, (const float*)global_scale,
-                                        batch, M, K, ldx, x_batch_stride, (int)swizzled, sf_batch_stride));
+                                        batch, M, K, ldx, x_batch_stride, (int)swizzled, sf_batch_stride, (const int32_t*)row_map));
       return 0;
     };
     if (vec == 16 && !ue8m0) return launch(fp4_quantize_kernel<T, 16, false>);

@@ -89,6 +89,38 @@ routing_kernel(const TL* __restrict__ logits, const float* __restrict__ bias, in
     float gscore = -INFINITY;
     // gather every expert score into smem-free fashion: use shuffles per slot
     float top1 = -INFINITY, top2 = -INFINITY;
+    if (gsz % 32 == 0) {
+      // fast path: a group is a whole number of register slots -> per-lane top-2 of the group's slots, then a
+      // butterfly merge of (top1, top2) pairs; lane g keeps the score of group g
+      const int spg = gsz / 32;
+      for (int g = 0; g < n_group; ++g) {
+        float a1 = -INFINITY, a2 = -INFINITY;
+#pragma unroll
+        for (int s = 0; s < kMaxPerLane; ++s) {
+          if (s >= g * spg && s < (g + 1) * spg) {
+            const float v = score[s];
+            if (v > a1) {
+              a2 = a1;
+              a1 = v;
+            } else if (v > a2) {
+              a2 = v;
+            }
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float b1 = __shfl_xor_sync(0xffffffffu, a1, o), b2 = __shfl_xor_sync(0xffffffffu, a2, o);
+          const float hi = fmaxf(a1, b1);
+          const float lo = fmaxf(fminf(a1, b1), fmaxf(a2, b2));
+          a1 = hi;
+          a2 = lo;
+        }
+        if (lane == g) {
+          top1 = a1;
+          top2 = a2;
+        }
+      }
+    } else {
     for (int s = 0; s < per; ++s) {
       for (int l = 0; l < 32; ++l) {
         const float v = __shfl_sync(0xffffffffu, score[s], l);
@@ -102,6 +134,7 @@ routing_kernel(const TL* __restrict__ logits, const float* __restrict__ bias, in
           }
         }
       }
+    }
     }
     if (lane < n_group) gscore = top1 + top2;
     // select topk_group groups: rank of my group
@@ -120,9 +153,9 @@ routing_kernel(const TL* __restrict__ logits, const float* __restrict__ bias, in
     }
   }
 
-  // iterative top-K (K <= 32): argmax over the warp, ties -> smaller expert id
-  float sel_w[kMaxTopK];
-  int sel_id[kMaxTopK];
+  // iterative top-K (K <= 32): argmax over the warp, ties -> smaller expert id.  Selection k is kept by lane k.
+  float my_w = 0.f;
+  int my_id = 0;
   float wsum = 0.f;
   for (int k = 0; k < K; ++k) {
     float bv = -INFINITY;
@@ -156,36 +189,30 @@ routing_kernel(const TL* __restrict__ logits, const float* __restrict__ bias, in
         }
     }
     w = __shfl_sync(0xffffffffu, w, be & 31);
-    if (k < kMaxTopK) {
-      sel_w[k] = w;
-      sel_id[k] = be;
+    if (lane == k) {
+      my_w = w;
+      my_id = be;
     }
     wsum += w;
   }
-  // post-processing of the selected weights
+  const bool have = lane < K;
+  // post-processing of the selected weights (lane k owns selection k)
   if (method == 1) {  // top-k -> softmax over the selected logits
-    float m2 = -INFINITY;
-    for (int k = 0; k < K; ++k) m2 = fmaxf(m2, sel_w[k]);
-    float s2 = 0.f;
-    for (int k = 0; k < K; ++k) {
-      sel_w[k] = __expf(sel_w[k] - m2);
-      s2 += sel_w[k];
-    }
-    for (int k = 0; k < K; ++k) sel_w[k] /= s2;
+    const float m2 = warp_reduce_max(have ? my_w : -INFINITY);
+    const float ex = have ? __expf(my_w - m2) : 0.f;
+    const float s2 = warp_reduce_sum(ex);
+    my_w = ex / s2;
   } else if (method == 3) {  // llama4: sigmoid of the selected logit(s)
-    for (int k = 0; k < K; ++k) sel_w[k] = sigmoidf_(sel_w[k]);
+    my_w = sigmoidf_(my_w);
   } else if (method == 2 || method == 7) {
     const float inv = (norm_topk_prob || method == 7) ? 1.f / (wsum + 1e-20f) : 1.f;
-    for (int k = 0; k < K; ++k) sel_w[k] = sel_w[k] * inv * routed_scale;
+    my_w = my_w * inv * routed_scale;
   } else if (method == 4 || method == 6) {
-    const float inv = 1.f / (wsum + 1e-20f);
-    for (int k = 0; k < K; ++k) sel_w[k] *= inv;
+    my_w *= 1.f / (wsum + 1e-20f);
   }
-  if (lane == 0) {
-    for (int k = 0; k < K; ++k) {
-      topk_ids[int64_t(tok) * K + k] = sel_id[k];
-      topk_w[int64_t(tok) * K + k] = sel_w[k];
-    }
+  if (have) {
+    topk_ids[int64_t(tok) * K + lane] = my_id;
+    topk_w[int64_t(tok) * K + lane] = my_w;
   }
   ptx::grid_dep_launch();
 }
@@ -248,6 +275,7 @@ moe_scan_kernel(int32_t* __restrict__ chunk_hist, int nchunks, int local_num, in
   __syncthreads();
   for (int i = threadIdx.x; i <= local_num; i += blockDim.x) expert_offsets[i] = off[i];
   for (int i = threadIdx.x; i < max_rows / tile; i += blockDim.x) tile_expert[i] = -1;
+  for (int i = off[local_num] + threadIdx.x; i < max_rows; i += blockDim.x) permuted_to_token[i] = -1;  // dead tail rows
   __syncthreads();
   // per expert: tile -> expert map and the -1 padding rows at the tail of its last tile
   for (int e = threadIdx.x >> 5; e < local_num; e += blockDim.x >> 5) {
@@ -302,7 +330,7 @@ moe_scatter_kernel(const int32_t* __restrict__ topk_ids, int n, int K, int local
 template <typename T>
 __global__ void __launch_bounds__(256)
 moe_gather_kernel(const T* __restrict__ x, T* __restrict__ out, const int32_t* __restrict__ permuted_to_token,
-                  const int32_t* __restrict__ meta, int64_t hidden, int64_t x_stride) {
+                  const int32_t* __restrict__ meta, int64_t hidden, int64_t x_stride, int zero_pad) {
   constexpr int VN = 16 / sizeof(T);
   ptx::grid_dep_wait();
   const int rows = meta[1];
@@ -315,6 +343,7 @@ moe_gather_kernel(const T* __restrict__ x, T* __restrict__ out, const int32_t* _
     if (tok >= 0) {
       val = ld16(x + int64_t(tok) * x_stride + v * VN);
     } else {
+      if (!zero_pad) continue;  // consumers that skip padding rows do not need them initialised
       *reinterpret_cast<int4*>(&val) = make_int4(0, 0, 0, 0);
     }
     st16(out + r * hidden + v * VN, val);
@@ -422,12 +451,12 @@ extern "C" int moe_sort(void* topk_ids, int64_t T, int64_t K, int64_t E, int64_t
 }
 
 extern "C" int moe_gather(void* x, void* out, void* permuted_to_token, void* meta, int64_t max_rows, int64_t hidden,
-                          int64_t x_stride, int64_t dtype, int64_t pdl, int64_t stream_) {
+                          int64_t x_stride, int64_t zero_pad, int64_t dtype, int64_t pdl, int64_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   return FIB_DISPATCH_HALF(dtype, T, [&]() -> int {
     LaunchCfg lc(dim3(grid_for(max_rows * (hidden / 8))), dim3(256), 0, stream, pdl != 0);
     FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, moe_gather_kernel<T>, (const T*)x, (T*)out,
-                                      (const int32_t*)permuted_to_token, (const int32_t*)meta, hidden, x_stride));
+                                      (const int32_t*)permuted_to_token, (const int32_t*)meta, hidden, x_stride, (int)zero_pad));
     return 0;
   });
 }

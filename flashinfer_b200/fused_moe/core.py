@@ -188,13 +188,13 @@ def moe_forward(x: torch.Tensor, topk_ids: torch.Tensor, topk_w: torch.Tensor, w
     mod.call("moe_sort", ids, T, K, num_experts or e_local, local_expert_offset, e_local, _TILE, max_rows, e2p, p2t,
              tile_e, offs, meta, ws, 1, st)
     xp = torch.empty(max_rows, H, dtype=x.dtype, device=dev)
-    mod.call("moe_gather", x, xp, p2t, meta, max_rows, H, x.stride(0), dtype_code(x.dtype), 1, st)
+    mod.call("moe_gather", x, xp, p2t, meta, max_rows, H, x.stride(0), 1, dtype_code(x.dtype), 1, st)
     h1 = torch.empty(max_rows, n1, dtype=x.dtype, device=dev)
     gg.call("grouped_gemm_nt", xp, w1.contiguous(), h1, tile_e, meta, max_tiles, n1, H, e_local, H, n1,
             dtype_code(x.dtype), 1, st)
     if n1 == 2 * inter:
         a = torch.empty(max_rows, inter, dtype=x.dtype, device=dev)
-        _act_and_mul("silu" if activation == "silu" else "gelu", h1, a, True, gate_second=True)
+        _act_and_mul("silu" if activation == "silu" else "gelu", h1, a, True, gate_second=True, row_map=p2t)
     else:
         a = torch.nn.functional.silu(h1) if activation == "silu" else torch.relu(h1) ** 2
     h2 = torch.empty(max_rows, H, dtype=x.dtype, device=dev)
@@ -261,9 +261,9 @@ def moe_forward_nvfp4(x: torch.Tensor, topk_ids: torch.Tensor, topk_w: torch.Ten
              meta, ws, 1, st)
     xb = x if x.dtype in (torch.float16, torch.bfloat16) else x.to(torch.bfloat16)
     xp = torch.empty(max_rows, H, dtype=xb.dtype, device=dev)
-    mod.call("moe_gather", xb, xp, p2t, meta, max_rows, H, xb.stride(0), dtype_code(xb.dtype), 1, st)
+    mod.call("moe_gather", xb, xp, p2t, meta, max_rows, H, xb.stride(0), 0, dtype_code(xb.dtype), 1, st)
     gs = torch.full((1,), float(act_global_scale), dtype=torch.float32, device=dev)
-    xq, xsf = fp4_quantize(xp, gs, 16, False, True)
+    xq, xsf = fp4_quantize(xp, gs, 16, False, True, row_map=p2t)
     a1 = torch.as_tensor(w1_alpha, dtype=torch.float32, device=dev).reshape(-1)
     a2 = torch.as_tensor(w2_alpha, dtype=torch.float32, device=dev).reshape(-1)
     if a1.numel() == 1:
@@ -276,8 +276,8 @@ def moe_forward_nvfp4(x: torch.Tensor, topk_ids: torch.Tensor, topk_w: torch.Ten
     sf2 = _swizzle_expert_sf(w2_sf, e_local, H, inter // 16)
     h1 = grouped_gemm_nvfp4(xq, xsf, w1_fp4, sf1, a1, tile_e, meta, out_dtype=xb.dtype)
     act = torch.empty(max_rows, inter, dtype=xb.dtype, device=dev)
-    _act_and_mul("silu", h1, act, True, gate_second=True)
-    aq, asf = fp4_quantize(act, gs, 16, False, True)
+    _act_and_mul("silu", h1, act, True, gate_second=True, row_map=p2t)
+    aq, asf = fp4_quantize(act, gs, 16, False, True, row_map=p2t)
     h2 = grouped_gemm_nvfp4(aq, asf, w2_fp4, sf2, a2, tile_e, meta, out_dtype=xb.dtype)
     if out is None:
         out = torch.empty(T, H, dtype=xb.dtype, device=dev)

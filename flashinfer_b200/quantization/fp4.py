@@ -68,7 +68,7 @@ def _quant_cpu(x: torch.Tensor, gs: float, vec: int, ue8m0: bool):
 def fp4_quantize(input: torch.Tensor, global_scale: Optional[torch.Tensor] = None, sf_vec_size: int = 16,
                  sf_use_ue8m0: bool = False, is_sf_swizzled_layout: bool = True, is_sf_8x4_layout: bool = False,
                  is_global_scale_inversed: bool = False, enable_pdl: Optional[bool] = None,
-                 backend: str = "cuda") -> Tuple[torch.Tensor, torch.Tensor]:
+                 backend: str = "cuda", row_map: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """Quantise ``[..., k]`` f16/bf16 to FP4.  Returns (packed uint8 ``[..., k/2]``, uint8 scale factors)."""
     if is_sf_8x4_layout:
         raise NotImplementedError("8x4 scale-factor layout")
@@ -96,7 +96,7 @@ def fp4_quantize(input: torch.Tensor, global_scale: Optional[torch.Tensor] = Non
         gst = gs.float().reshape(1).contiguous() if gs is not None else None
         jit.load("quantization").call(
             "fp4_quantize", x, packed, sf, gst, 1, m, k, x.stride(0), 0, sf_vec_size, 1 if sf_use_ue8m0 else 0,
-            1 if is_sf_swizzled_layout else 0, 0, dtype_code(x.dtype), 1, stream_ptr(x),
+            1 if is_sf_swizzled_layout else 0, 0, row_map, dtype_code(x.dtype), 1, stream_ptr(x),
         )
     sf = sf.view(-1, round_up(kc, 4)) if is_sf_swizzled_layout else sf.view(m, kc)
     return packed.view(*shape[:-1], k // 2), sf
@@ -131,7 +131,7 @@ def nvfp4_batched_quantize(a: torch.Tensor, a_global_sf: torch.Tensor, sf_vec_si
     sf = torch.zeros(b, per, dtype=torch.uint8, device=a.device)
     jit.load("quantization").call(
         "fp4_quantize", x, packed, sf, a_global_sf.float().reshape(1).contiguous(), b, m, k, x.stride(1), x.stride(0),
-        sf_vec_size, 0, 1, per, dtype_code(x.dtype), 1, stream_ptr(x),
+        sf_vec_size, 0, 1, per, None, dtype_code(x.dtype), 1, stream_ptr(x),
     )
     return packed, sf
 
