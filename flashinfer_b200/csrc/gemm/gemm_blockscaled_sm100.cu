@@ -615,7 +615,9 @@ bs_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* empty_bar = full_bar + kStages;                              // both CTAs (multicast commit)
   uint64_t* tmem_full = empty_bar + kStages;                             // both CTAs (multicast commit)
   uint64_t* tmem_empty = tmem_full + 2;                                  // leader only, 8 arrivals
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* sf_ready = tmem_empty + 2;                                   // leader: scale copies of a slab landed in TMEM
+  uint64_t* sf_free = sf_ready + 2;                                      // leader: MMAs that read a scale buffer retired
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sf_free + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int crank = int(ptx::cluster_ctarank());
   const bool leader = crank == 0;
@@ -634,6 +636,8 @@ bs_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tmem_full[i], 1);
       ptx::mbar_init(&tmem_empty[i], 8);
+      ptx::mbar_init(&sf_ready[i], 1);
+      ptx::mbar_init(&sf_free[i], 1);
     }
     ptx::fence_mbar_init();
   }
@@ -701,6 +705,9 @@ bs_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    int sfb_i = 0;              // scale buffer (ping-pong), filled by the copy warp
+    uint32_t sf_phase = 0;
+    const uint32_t sf_stride = uint32_t(G.nchunk * 4 * (1 + G.rb));
     for (int t = pair; t < num_tiles; t += num_pairs) {
       const int r = t % tiles_per_batch;
       const int n0 = (r / tiles_m) * BN;
@@ -710,22 +717,14 @@ bs_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const uint32_t d_tmem = tmem_base + acc * BN;
       for (int kb = 0; kb < num_kb; ++kb) {
         ptx::mbar_wait(&full_bar[stage], phase);
+        if constexpr (KIND != kFp8) ptx::mbar_wait(&sf_ready[sfb_i], sf_phase);
         ptx::tc_fence_after();
+        const uint32_t sfa_t = tmem_base + G.sfa_col + sfb_i * sf_stride, sfb_t = sfa_t + G.nchunk * 4;
         if (ptx::elect_one()) {
           const uint32_t sa = ptx::smem_u32(smem + stage * G.stage_bytes);
           const uint32_t sb = sa + G.a_bytes;
           const uint64_t da = ptx::make_smem_desc(sa, 16, 1024, ptx::kSwz128);
           const uint64_t db = ptx::make_smem_desc(sb, 16, 1024, ptx::kSwz128);
-          if constexpr (KIND != kFp8) {
-            const uint32_t ssfa = sb + G.b_bytes, ssfb = ssfa + G.sfa_bytes;
-            for (int c = 0; c < G.nchunk; ++c) {
-              ptx::tmem_cp2_32x128b_warpx4(tmem_base + G.sfa_col + c * 4,
-                                           ptx::make_smem_desc(ssfa + c * 512, 0, 128, ptx::kSwzNone));
-              for (int rr = 0; rr < G.rb; ++rr)
-                ptx::tmem_cp2_32x128b_warpx4(tmem_base + G.sfb_col + (c * G.rb + rr) * 4,
-                                             ptx::make_smem_desc(ssfb + (rr * G.nchunk + c) * 512, 0, 128, ptx::kSwzNone));
-            }
-          }
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint32_t accum = (kb > 0 || k > 0) ? 1u : 0u;
@@ -734,18 +733,17 @@ bs_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               ptx::mma_f8f6f4_ss<2>(d_tmem, dak, dbk, p.idesc, accum);
             } else if constexpr (KIND == kMxFp8) {
               const uint32_t id = p.idesc | (uint32_t(k) << 4) | (uint32_t(k) << 29);
-              ptx::mma2_mxf8f6f4_ss(d_tmem, dak, dbk, id, tmem_base + G.sfa_col, tmem_base + G.sfb_col + sfb_off, accum);
+              ptx::mma2_mxf8f6f4_ss(d_tmem, dak, dbk, id, sfa_t, sfb_t + sfb_off, accum);
             } else if constexpr (KIND == kNvFp4) {
-              ptx::mma2_mxf4nvf4_ss(d_tmem, dak, dbk, p.idesc, tmem_base + G.sfa_col + k * 4,
-                                    tmem_base + G.sfb_col + k * G.rb * 4 + sfb_off, accum);
+              ptx::mma2_mxf4nvf4_ss(d_tmem, dak, dbk, p.idesc, sfa_t + k * 4, sfb_t + k * G.rb * 4 + sfb_off, accum);
             } else {
               const uint32_t sid = uint32_t(k & 1) * 2;
               const uint32_t id = p.idesc | (sid << 4) | (sid << 29);
-              ptx::mma2_mxf4_2x_ss(d_tmem, dak, dbk, id, tmem_base + G.sfa_col + (k >> 1) * 4,
-                                   tmem_base + G.sfb_col + (k >> 1) * G.rb * 4 + sfb_off, accum);
+              ptx::mma2_mxf4_2x_ss(d_tmem, dak, dbk, id, sfa_t + (k >> 1) * 4, sfb_t + (k >> 1) * G.rb * 4 + sfb_off, accum);
             }
           }
           ptx::mma_commit_2cta(&empty_bar[stage], 3);                      // slot free in BOTH CTAs
+          if constexpr (KIND != kFp8) ptx::mma_commit_2cta(&sf_free[sfb_i], 1);  // scale buffer reusable (leader's barrier)
           if (kb == num_kb - 1) ptx::mma_commit_2cta(&tmem_full[acc], 3);  // accumulator ready in BOTH CTAs
         }
         __syncwarp();
@@ -753,9 +751,45 @@ bs_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           stage = 0;
           phase ^= 1;
         }
+        sfb_i ^= 1;
+        if (sfb_i == 0) sf_phase ^= 1;
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
+    }
+  } else if (warp == 3 && leader) {
+    // ---- scale-factor copy warp: smem -> TMEM (both CTAs) one slab ahead of the MMA issuer, so that the 12 tcgen05.cp
+    //      of an nvfp4 slab overlap the previous slab's MMAs instead of serialising with them on one thread
+    if constexpr (KIND != kFp8) {
+      int stage = 0, sfb_i = 0;
+      uint32_t phase = 0, sf_phase = 0;
+      const uint32_t sf_stride = uint32_t(G.nchunk * 4 * (1 + G.rb));
+      for (int t = pair; t < num_tiles; t += num_pairs) {
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&sf_free[sfb_i], sf_phase ^ 1);
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            const uint32_t sb = ptx::smem_u32(smem + stage * G.stage_bytes) + G.a_bytes;
+            const uint32_t ssfa = sb + G.b_bytes, ssfb = ssfa + G.sfa_bytes;
+            const uint32_t sfa_t = tmem_base + G.sfa_col + sfb_i * sf_stride, sfb_t = sfa_t + G.nchunk * 4;
+            for (int c = 0; c < G.nchunk; ++c) {
+              ptx::tmem_cp2_32x128b_warpx4(sfa_t + c * 4, ptx::make_smem_desc(ssfa + c * 512, 0, 128, ptx::kSwzNone));
+              for (int rr = 0; rr < G.rb; ++rr)
+                ptx::tmem_cp2_32x128b_warpx4(sfb_t + (c * G.rb + rr) * 4,
+                                             ptx::make_smem_desc(ssfb + (rr * G.nchunk + c) * 512, 0, 128, ptx::kSwzNone));
+            }
+            ptx::mma_commit_2cta(&sf_ready[sfb_i], 1);  // cta_group::2 copies -> cta_group::2 commit, leader's barrier only
+          }
+          __syncwarp();
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+          sfb_i ^= 1;
+          if (sfb_i == 0) sf_phase ^= 1;
+        }
+      }
     }
   } else if (warp >= 4) {
     const int q = warp - 4;
@@ -896,7 +930,7 @@ extern "C" int gemm_lowp_nt(void* A, void* B, void* C, void* sfa, void* sfb, voi
     const int64_t tiles2 = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN2 - 1) / BN2) * batch;
     bool use2 = !tile_expert && M >= 512 && tiles2 >= num_sms() / 2 && K >= 512;
     if (env2) use2 = atoi(env2) != 0 && !tile_expert;
-    if (use2 && BN2 % 64 == 0 && BN2 >= 64 && BN2 <= 256 && (kind == kFp8 || 2 * BN2 + Geo2::make(BN2, (int)kind).nchunk * 4 * (1 + Geo2::make(BN2, (int)kind).rb) <= 512)) {
+    if (use2 && BN2 % 64 == 0 && BN2 >= 64 && BN2 <= 256 && (kind == kFp8 || 2 * BN2 + 2 * Geo2::make(BN2, (int)kind).nchunk * 4 * (1 + Geo2::make(BN2, (int)kind).rb) <= 512)) {
       const Geo2 G2 = Geo2::make(BN2, (int)kind);
       CUtensorMap tmA, tmB, tmSFA, tmSFB;
       {

@@ -251,35 +251,63 @@ moe_scan_kernel(int32_t* __restrict__ chunk_hist, int nchunks, int local_num, in
   extern __shared__ int sm[];
   int* cnt = sm;              // [local_num]
   int* off = sm + local_num;  // [local_num + 1]
+  __shared__ int warp_tot[32];
   ptx::grid_dep_wait();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // one thread per expert (strided): exclusive prefix over the chunks, independent loads in flight
   for (int e = threadIdx.x; e < local_num; e += blockDim.x) {
     int acc = 0;
-    for (int c = 0; c < nchunks; ++c) {
+    int c = 0;
+    for (; c + 4 <= nchunks; c += 4) {
+      const int v0 = chunk_hist[int64_t(c) * local_num + e], v1 = chunk_hist[int64_t(c + 1) * local_num + e];
+      const int v2 = chunk_hist[int64_t(c + 2) * local_num + e], v3 = chunk_hist[int64_t(c + 3) * local_num + e];
+      chunk_hist[int64_t(c) * local_num + e] = acc;
+      chunk_hist[int64_t(c + 1) * local_num + e] = acc + v0;
+      chunk_hist[int64_t(c + 2) * local_num + e] = acc + v0 + v1;
+      chunk_hist[int64_t(c + 3) * local_num + e] = acc + v0 + v1 + v2;
+      acc += v0 + v1 + v2 + v3;
+    }
+    for (; c < nchunks; ++c) {
       const int v = chunk_hist[int64_t(c) * local_num + e];
-      chunk_hist[int64_t(c) * local_num + e] = acc;  // exclusive prefix: rows of earlier chunks
+      chunk_hist[int64_t(c) * local_num + e] = acc;
       acc += v;
     }
     cnt[e] = acc;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    int acc = 0;
-    for (int e = 0; e < local_num; ++e) {
-      off[e] = acc;
-      acc += (cnt[e] + tile - 1) / tile * tile;
+  // block-wide exclusive scan of the tile-padded counts (local_num <= 1024 per pass)
+  int base = 0;
+  for (int e0 = 0; e0 < local_num; e0 += blockDim.x) {
+    const int e = e0 + threadIdx.x;
+    const int padded = e < local_num ? (cnt[e] + tile - 1) / tile * tile : 0;
+    int incl = padded;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
     }
-    off[local_num] = acc;
-    meta[0] = acc / tile;
-    meta[1] = acc;
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    int wbase = 0, total = 0;
+    for (int w = 0; w < 32; ++w) {
+      if (w < warp) wbase += warp_tot[w];
+      total += warp_tot[w];
+    }
+    if (e < local_num) off[e] = base + wbase + incl - padded;
+    base += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    off[local_num] = base;
+    meta[0] = base / tile;
+    meta[1] = base;
   }
   __syncthreads();
   for (int i = threadIdx.x; i <= local_num; i += blockDim.x) expert_offsets[i] = off[i];
-  for (int i = threadIdx.x; i < max_rows / tile; i += blockDim.x) tile_expert[i] = -1;
+  for (int i = off[local_num] / tile + threadIdx.x; i < max_rows / tile; i += blockDim.x) tile_expert[i] = -1;
   for (int i = off[local_num] + threadIdx.x; i < max_rows; i += blockDim.x) permuted_to_token[i] = -1;  // dead tail rows
-  __syncthreads();
   // per expert: tile -> expert map and the -1 padding rows at the tail of its last tile
-  for (int e = threadIdx.x >> 5; e < local_num; e += blockDim.x >> 5) {
-    const int lane = threadIdx.x & 31;
+  for (int e = warp; e < local_num; e += blockDim.x >> 5) {
     for (int r = off[e] + lane * tile; r < off[e + 1]; r += 32 * tile) tile_expert[r / tile] = e;
     for (int r = off[e] + cnt[e] + lane; r < off[e + 1]; r += 32) permuted_to_token[r] = -1;
   }
