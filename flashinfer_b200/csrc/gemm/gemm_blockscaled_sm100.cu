@@ -608,6 +608,9 @@ bs_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const Params2 p) {
   const Geo2 G = Geo2::make(p.BN, KIND);
   const int BN = p.BN;
+  // fp4 slabs need 12 tcgen05.cp: a dedicated warp issues them one slab ahead.  mxfp8 (3 copies) keeps them inline:
+  // the extra hand-shake costs more than it hides (measured 2.45 -> 2.09 PFLOP/s with the copy warp).
+  constexpr bool kCopyWarp = (KIND == kNvFp4 || KIND == kMxFp4);
   const int kStages = G.stages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -717,7 +720,7 @@ bs_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const uint32_t d_tmem = tmem_base + acc * BN;
       for (int kb = 0; kb < num_kb; ++kb) {
         ptx::mbar_wait(&full_bar[stage], phase);
-        if constexpr (KIND != kFp8) ptx::mbar_wait(&sf_ready[sfb_i], sf_phase);
+        if constexpr (kCopyWarp) ptx::mbar_wait(&sf_ready[sfb_i], sf_phase);
         ptx::tc_fence_after();
         const uint32_t sfa_t = tmem_base + G.sfa_col + sfb_i * sf_stride, sfb_t = sfa_t + G.nchunk * 4;
         if (ptx::elect_one()) {
@@ -725,6 +728,15 @@ bs_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const uint32_t sb = sa + G.a_bytes;
           const uint64_t da = ptx::make_smem_desc(sa, 16, 1024, ptx::kSwz128);
           const uint64_t db = ptx::make_smem_desc(sb, 16, 1024, ptx::kSwz128);
+          if constexpr (KIND != kFp8 && !kCopyWarp) {
+            const uint32_t ssfa = sb + G.b_bytes, ssfb = ssfa + G.sfa_bytes;
+            for (int c = 0; c < G.nchunk; ++c) {
+              ptx::tmem_cp2_32x128b_warpx4(sfa_t + c * 4, ptx::make_smem_desc(ssfa + c * 512, 0, 128, ptx::kSwzNone));
+              for (int rr = 0; rr < G.rb; ++rr)
+                ptx::tmem_cp2_32x128b_warpx4(sfb_t + (c * G.rb + rr) * 4,
+                                             ptx::make_smem_desc(ssfb + (rr * G.nchunk + c) * 512, 0, 128, ptx::kSwzNone));
+            }
+          }
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint32_t accum = (kb > 0 || k > 0) ? 1u : 0u;
@@ -743,7 +755,7 @@ bs_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
           }
           ptx::mma_commit_2cta(&empty_bar[stage], 3);                      // slot free in BOTH CTAs
-          if constexpr (KIND != kFp8) ptx::mma_commit_2cta(&sf_free[sfb_i], 1);  // scale buffer reusable (leader's barrier)
+          if constexpr (kCopyWarp) ptx::mma_commit_2cta(&sf_free[sfb_i], 1);  // scale buffer reusable (leader's barrier)
           if (kb == num_kb - 1) ptx::mma_commit_2cta(&tmem_full[acc], 3);  // accumulator ready in BOTH CTAs
         }
         __syncwarp();
@@ -751,8 +763,10 @@ bs_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           stage = 0;
           phase ^= 1;
         }
-        sfb_i ^= 1;
-        if (sfb_i == 0) sf_phase ^= 1;
+        if constexpr (kCopyWarp) {
+          sfb_i ^= 1;
+          if (sfb_i == 0) sf_phase ^= 1;
+        }
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
@@ -760,7 +774,7 @@ bs_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else if (warp == 3 && leader) {
     // ---- scale-factor copy warp: smem -> TMEM (both CTAs) one slab ahead of the MMA issuer, so that the 12 tcgen05.cp
     //      of an nvfp4 slab overlap the previous slab's MMAs instead of serialising with them on one thread
-    if constexpr (KIND != kFp8) {
+    if constexpr (kCopyWarp) {
       int stage = 0, sfb_i = 0;
       uint32_t phase = 0, sf_phase = 0;
       const uint32_t sf_stride = uint32_t(G.nchunk * 4 * (1 + G.rb));

@@ -218,8 +218,25 @@ class _BatchPrefillBase:
 
     def _launch_sm100(self, q, k, v, out, lse, sm_scale, window_left, paged, kv_indices, page_args, enable_pdl,
                       k_scale=None, v_scale=None):
-        fast = (self._head_dim_qk in (128, 192) and self._head_dim_vo == 128 and q.dtype in (torch.float16, torch.bfloat16)
-                and k.dtype == q.dtype and v.dtype == q.dtype and self._custom_mask is None)
+        shape_ok = (self._head_dim_qk in (128, 192) and self._head_dim_vo == 128 and q.dtype in (torch.float16, torch.bfloat16)
+                    and self._custom_mask is None)
+        if shape_ok and k.dtype in (torch.float8_e4m3fn, torch.float8_e5m2) and q.shape[0] >= 4 * self._batch_size:
+            # fp8 KV with a compute-bound (prefill-sized) query: widen the KV that this call touches to the query dtype
+            # once (1 B read + 2 B write per element, negligible next to the O(q * kv) attention work) and stay on the
+            # tcgen05 kernel.  Scales were folded into sm_scale (k) and are applied to the output (v) by the caller.
+            if paged:
+                kv_indices_l = kv_indices.long()
+                k = k.index_select(0, kv_indices_l).to(q.dtype)
+                v = v.index_select(0, kv_indices_l).to(q.dtype)
+                kv_indices = torch.arange(kv_indices.numel(), dtype=torch.int32, device=q.device)
+                from .utils import paged_kv_strides as _pks
+
+                sp, sn, sh, page_size, _, _ = _pks(k, self._kv_layout)
+                page_args = (page_size, k.shape[0], sp, sn, sh, 1 if self._kv_layout == "HND" else 0)
+            else:
+                k, v = k.to(q.dtype), v.to(q.dtype)
+                page_args = (1, k.shape[0], k.stride(0), k.stride(0), k.stride(1), 0, v.stride(0), v.stride(0), v.stride(1))
+        fast = shape_ok and k.dtype == q.dtype and v.dtype == q.dtype
         if not fast:
             return self._launch_generic(q, k, v, out, lse, sm_scale, window_left, paged, kv_indices, page_args, enable_pdl,
                                         k_scale, v_scale)

@@ -138,3 +138,32 @@ def test_prefill_deepseek_head_dims_tcgen05(causal, dtype):
     o1 = fi.single_prefill_with_kv_cache(q[:333], k[:333], v[:333], causal=causal)
     r1, _ = reference.attention_ref(q[:333], k[:333], v[:333], causal, 1 / math.sqrt(192))
     assert (o1.float() - r1.float()).abs().max() < 2e-2
+
+
+@pytest.mark.parametrize("paged", [False, True])
+def test_prefill_fp8_kv_stays_on_tensor_cores(paged):
+    """fp8 KV + 16-bit Q prefill: KV is widened once and the tcgen05 kernel runs (BASELINE config: 8k prefill, fp8 KV)."""
+    torch.manual_seed(6)
+    hq, hkv, d, ps, L = 32, 8, 128, 16, 1024
+    q = torch.randn(L, hq, d, device="cuda", dtype=torch.bfloat16)
+    k = (torch.randn(L, hkv, d, device="cuda") * 0.5)
+    v = (torch.randn(L, hkv, d, device="cuda") * 0.5)
+    k8, v8 = k.to(torch.float8_e4m3fn), v.to(torch.float8_e4m3fn)
+    ref, _ = reference.attention_ref(q, k8.float().bfloat16(), v8.float().bfloat16(), True, 1 / math.sqrt(d))
+    ip = torch.tensor([0, L], dtype=torch.int32)
+    if not paged:
+        w = fi.BatchPrefillWithRaggedKVCacheWrapper(torch.empty(64 << 20, dtype=torch.uint8, device="cuda"))
+        w.plan(ip, ip, hq, hkv, d, causal=True, q_data_type=torch.bfloat16, kv_data_type=torch.float8_e4m3fn)
+        out = w.run(q, k8, v8)
+    else:
+        npg = L // ps
+        perm = torch.randperm(npg + 5, device="cuda")[:npg]
+        kc = torch.zeros(npg + 5, ps, hkv, d, device="cuda", dtype=torch.float8_e4m3fn)
+        vc = torch.zeros_like(kc)
+        kc[perm] = k8.view(npg, ps, hkv, d)
+        vc[perm] = v8.view(npg, ps, hkv, d)
+        w = fi.BatchPrefillWithPagedKVCacheWrapper(torch.empty(64 << 20, dtype=torch.uint8, device="cuda"))
+        w.plan(ip, torch.tensor([0, npg], dtype=torch.int32), perm.int(), torch.tensor([ps], dtype=torch.int32), hq, hkv, d, ps,
+               causal=True, q_data_type=torch.bfloat16, kv_data_type=torch.float8_e4m3fn)
+        out = w.run(q, (kc, vc))
+    assert (out.float() - ref.float()).abs().max() < 2e-2
