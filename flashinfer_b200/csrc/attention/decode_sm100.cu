@@ -20,6 +20,7 @@
 //  * LSE is returned in base-2 units like the reference (include/flashinfer/attention/state.cuh:46).
 #include <fib200/common.cuh>
 #include <fib200/ptx.cuh>
+#include <cuda_fp8.h>
 
 using namespace fib200;
 
@@ -48,15 +49,18 @@ struct DecodeParams {
   float sm_scale;
 };
 
-template <int NQ, int D>
+// KVB = bytes per KV element: 2 (f16 / bf16 cache) or 1 (fp8 cache: Q and P are converted to e4m3 and both MMAs run
+// as tcgen05 kind::f8f6f4 -- half the shared memory per tile, twice the MMA rate, no de-quantisation pass).
+template <int NQ, int D, int KVB = 2>
 struct DecodeSmem {
   static constexpr int kStagesK = 3, kStagesV = 3;
-  static constexpr int kChunks = D / 64;
-  static constexpr int kTileBytes = kTileKV * D * 2;          // 32 KB for D=128
+  static constexpr int kChunks = D * KVB / 128;              // 128-byte (SWIZZLE_128B) column chunks per row
+  static constexpr int kCore = 16 / KVB;                      // elements per 16-byte core-matrix row
+  static constexpr int kTileBytes = kTileKV * D * KVB;        // 32 KB (16-bit) / 16 KB (fp8) for D=128
   static constexpr int kChunkBytes = kTileKV * 128;           // one 64-col chunk of 128 rows
   static constexpr int kLBO = NQ * 16 + 16;                   // padded core-matrix stride (bank-conflict free)
-  static constexpr int kQBytes = ((D / 8) * kLBO + 1023) / 1024 * 1024;
-  static constexpr int kPBytes = ((kTileKV / 8) * kLBO + 1023) / 1024 * 1024;
+  static constexpr int kQBytes = ((D / kCore) * kLBO + 1023) / 1024 * 1024;
+  static constexpr int kPBytes = ((kTileKV / kCore) * kLBO + 1023) / 1024 * 1024;
   static constexpr int kOffK = 0;
   static constexpr int kOffV = kOffK + kStagesK * kTileBytes;
   static constexpr int kOffQ = kOffV + kStagesV * kTileBytes;
@@ -135,12 +139,14 @@ __device__ __forceinline__ TileGeom tile_geom(int ti, int ps) {
 }
 
 // NQ: MMA N (padded q rows, multiple of 16); NV: power-of-two number of columns actually processed.
-template <int NQ, int NV, int D, typename T>
+template <int NQ, int NV, int D, typename T, int KVB>
 __global__ void __launch_bounds__(288, 1)
 decode_paged_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                     const DecodeParams p, uint32_t idesc_qk, uint32_t idesc_pv) {
-  using S = DecodeSmem<NQ, D>;
+  using S = DecodeSmem<NQ, D, KVB>;
   static_assert(D == 128, "head_dim 128 specialisation");
+  constexpr bool kKV8 = KVB == 1;
+  constexpr float kPScale = kKV8 ? 256.f : 1.f;  // fp8 P is stored as p * 256 (<= 256 < 448): keeps small probabilities
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kOffBar);
@@ -215,7 +221,9 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     uint64_t* full_bars = is_v ? v_full : k_full;
     uint64_t* empty_bars = is_v ? v_empty : k_empty;
     const CUtensorMap* tm = is_v ? &tmV : &tmK;
-    uint8_t* ring = smem + (is_v ? S::kOffV : S::kOffK) + chunk * S::kChunkBytes;
+    // 16-bit cache: warp `chunk` loads column chunk `chunk` of every page box; fp8 cache (one chunk per row): the two
+    // warps of a tensor split the page boxes by parity instead
+    uint8_t* ring = smem + (is_v ? S::kOffV : S::kOffK) + (kKV8 ? 0 : chunk * S::kChunkBytes);
     int st = 0;
     uint32_t ph = 0;
     for (int seg = seg_begin; seg < seg_end; ++seg) {
@@ -237,7 +245,7 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int bi = lane + j * 32;
-          my_pages[j] = (bi < n_boxes) ? __ldg(p.kv_indices + page_start + g2.first_page + bi) : -1;
+          my_pages[j] = (bi < n_boxes && (!kKV8 || (bi & 1) == chunk)) ? __ldg(p.kv_indices + page_start + g2.first_page + bi) : -1;
         }
         if (lane == 0) {
           ptx::mbar_wait(&empty_bars[st], ph ^ 1);
@@ -249,9 +257,9 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
           if (my_pages[j] >= 0) {
             uint8_t* dst = ring + st * S::kTileBytes + (lane + j * 32) * box_rows * 128;
             if (p.layout_hnd)
-              ptx::tma_load_4d(dst, tm, &full_bars[st], chunk * 64, g2.page_off, kv_head, my_pages[j], ptx::kEvictFirst);
+              ptx::tma_load_4d(dst, tm, &full_bars[st], kKV8 ? 0 : chunk * 64, g2.page_off, kv_head, my_pages[j], ptx::kEvictFirst);
             else
-              ptx::tma_load_4d(dst, tm, &full_bars[st], chunk * 64, kv_head, g2.page_off, my_pages[j], ptx::kEvictFirst);
+              ptx::tma_load_4d(dst, tm, &full_bars[st], kKV8 ? 0 : chunk * 64, kv_head, g2.page_off, my_pages[j], ptx::kEvictFirst);
           }
         }
         if (++st == nstages) {
@@ -280,10 +288,17 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
         // B = P^T : K-major, no swizzle, core matrices [8 q][8 kv]
         const uint64_t db = ptx::make_smem_desc(p_addr + b * S::kPBytes, S::kLBO, 128, ptx::kSwzNone);
         const uint32_t d_tmem = tmem_base + 2 * NQ + b * NQ;
+        if constexpr (kKV8) {
 #pragma unroll
-        for (int k = 0; k < kTileKV / 16; ++k)
-          ptx::mma_f16_ss<1>(d_tmem, ptx::desc_advance(da, k * 16 * 128), ptx::desc_advance(db, k * 2 * S::kLBO),
-                             idesc_pv, k > 0 ? 1u : 0u);
+          for (int k = 0; k < kTileKV / 32; ++k)
+            ptx::mma_f8f6f4_ss<1>(d_tmem, ptx::desc_advance(da, k * 32 * 128), ptx::desc_advance(db, k * 2 * S::kLBO),
+                                  idesc_pv, k > 0 ? 1u : 0u);
+        } else {
+#pragma unroll
+          for (int k = 0; k < kTileKV / 16; ++k)
+            ptx::mma_f16_ss<1>(d_tmem, ptx::desc_advance(da, k * 16 * 128), ptx::desc_advance(db, k * 2 * S::kLBO),
+                               idesc_pv, k > 0 ? 1u : 0u);
+        }
         ptx::mma_commit(&v_empty[vs]);
         ptx::mma_commit(&o_full[b]);
       }
@@ -308,11 +323,19 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
           const uint32_t k_addr = ptx::smem_u32(smem + S::kOffK + ks * S::kTileBytes);
           const uint64_t db = ptx::make_smem_desc(q_addr, S::kLBO, 128, ptx::kSwzNone);
           const uint32_t d_tmem = tmem_base + b * NQ;
+          if constexpr (kKV8) {
 #pragma unroll
-          for (int k = 0; k < D / 16; ++k) {
-            const uint64_t da =
-                ptx::make_smem_desc(k_addr + (k / 4) * S::kChunkBytes + (k % 4) * 32, 16, 1024, ptx::kSwz128);
-            ptx::mma_f16_ss<1>(d_tmem, da, ptx::desc_advance(db, k * 2 * S::kLBO), idesc_qk, k > 0 ? 1u : 0u);
+            for (int k = 0; k < D / 32; ++k) {  // K = 32 fp8 elements = 32 bytes per MMA
+              const uint64_t da = ptx::make_smem_desc(k_addr + k * 32, 16, 1024, ptx::kSwz128);
+              ptx::mma_f8f6f4_ss<1>(d_tmem, da, ptx::desc_advance(db, k * 2 * S::kLBO), idesc_qk, k > 0 ? 1u : 0u);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < D / 16; ++k) {
+              const uint64_t da =
+                  ptx::make_smem_desc(k_addr + (k / 4) * S::kChunkBytes + (k % 4) * 32, 16, 1024, ptx::kSwz128);
+              ptx::mma_f16_ss<1>(d_tmem, da, ptx::desc_advance(db, k * 2 * S::kLBO), idesc_qk, k > 0 ? 1u : 0u);
+            }
           }
           ptx::mma_commit(&k_empty[ks]);
           ptx::mma_commit(&s_full[b]);
@@ -355,6 +378,28 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
         const int kvh = sj[1], qs = sj[5], nqv = sj[6] * G;
         uint8_t* qbuf = smem + S::kOffQ + ((sg - seg_begin) & 1) * S::kQBytes;
         const int tid = threadIdx.x - 128;
+        if constexpr (kKV8) {
+          // 16 query elements -> 16 e4m3 bytes = one core-matrix row
+          for (int v = tid; v < NV * (D / 16); v += 128) {
+            const int c = v / (D / 16), dg = v % (D / 16);
+            int4 val = make_int4(0, 0, 0, 0);
+            if (c < nqv) {
+              const int qi = c / G, g = c % G;
+              const T* src = qbase + int64_t(qs + qi) * p.q_stride_n + int64_t(kvh * G + g) * p.q_stride_h + dg * 16;
+              const int4 lo = __ldg(reinterpret_cast<const int4*>(src)), hi = __ldg(reinterpret_cast<const int4*>(src + 8));
+              const T* l8 = reinterpret_cast<const T*>(&lo);
+              const T* h8 = reinterpret_cast<const T*>(&hi);
+              uint8_t* ob = reinterpret_cast<uint8_t*>(&val);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const __nv_fp8_e4m3 a(fminf(fmaxf(to_f32(l8[e]), -448.f), 448.f)), b(fminf(fmaxf(to_f32(h8[e]), -448.f), 448.f));
+                ob[e] = *reinterpret_cast<const uint8_t*>(&a);
+                ob[8 + e] = *reinterpret_cast<const uint8_t*>(&b);
+              }
+            }
+            *reinterpret_cast<int4*>(qbuf + dg * S::kLBO + (c >> 3) * 128 + (c & 7) * 16) = val;
+          }
+        } else {
         for (int v = tid; v < NV * (D / 8); v += 128) {
           const int c = v / (D / 8), dg = v % (D / 8);
           int4 val = make_int4(0, 0, 0, 0);
@@ -364,6 +409,7 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
                                                       int64_t(kvh * G + g) * p.q_stride_h + dg * 8));
           }
           *reinterpret_cast<int4*>(qbuf + dg * S::kLBO + (c >> 3) * 128 + (c & 7) * 16) = val;
+        }
         }
         ptx::fence_proxy_async_smem();
         ptx::mbar_arrive(&q_full[(sg - seg_begin) & 1]);
@@ -388,7 +434,7 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
         tmem_ld_n<NV>(tmem_base + lane_addr + 2 * NQ + b * NQ, r);
         ptx::tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < NV; ++c) o[c] = o[c] * alpha_saved[c] + __uint_as_float(r[c]);
+        for (int c = 0; c < NV; ++c) o[c] = o[c] * alpha_saved[c] + __uint_as_float(r[c]) * (1.f / kPScale);
       };
 
       for (int ti = t0; ti < t1; ++ti, ++gt) {
@@ -437,8 +483,14 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
           l[c] = l[c] * alpha[c] + pv;
           m[c] = m_new;
           // P^T element (c, row)
-          *reinterpret_cast<T*>(smem + S::kOffP + b * S::kPBytes + (row >> 3) * S::kLBO + (c >> 3) * 128 + (c & 7) * 16 +
-                                (row & 7) * 2) = from_f32<T>(pv);
+          if constexpr (kKV8) {
+            const __nv_fp8_e4m3 p8(pv * kPScale);
+            smem[S::kOffP + b * S::kPBytes + (row >> 4) * S::kLBO + (c >> 3) * 128 + (c & 7) * 16 + (row & 15)] =
+                *reinterpret_cast<const uint8_t*>(&p8);
+          } else {
+            *reinterpret_cast<T*>(smem + S::kOffP + b * S::kPBytes + (row >> 3) * S::kLBO + (c >> 3) * 128 + (c & 7) * 16 +
+                                  (row & 7) * 2) = from_f32<T>(pv);
+          }
         }
         if (valid < kTileKV) {
           // rows past the end of the sequence: V may hold stale / uninitialised data -> zero it so
@@ -572,19 +624,20 @@ decode_merge_kernel(const int32_t* __restrict__ items, int num_items, const floa
   }
 }
 
-template <int NQ, int NV, typename T>
+template <int NQ, int NV, typename T, int KVB>
 int launch_decode(const CUtensorMap& tmK, const CUtensorMap& tmV, const DecodeParams& p, int grid, bool f16, bool pdl,
-                  cudaStream_t stream) {
-  using S = DecodeSmem<NQ, 128>;
-  auto kern = decode_paged_kernel<NQ, NV, 128, T>;
+                  cudaStream_t stream, int kv_fmt) {
+  using S = DecodeSmem<NQ, 128, KVB>;
+  auto kern = decode_paged_kernel<NQ, NV, 128, T, KVB>;
   static bool attr_set = false;
   if (!attr_set) {
     FIB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     attr_set = true;
   }
   const uint32_t fmt = f16 ? ptx::kFmtF16 : ptx::kFmtBF16;
-  const uint32_t idesc_qk = ptx::make_idesc_f16(fmt, 128, NQ, 0, 0);
-  const uint32_t idesc_pv = ptx::make_idesc_f16(fmt, 128, NQ, 1, 0);
+  // fp8 cache: A = K / V in the cache format (e4m3 = 0, e5m2 = 1), B = Q / P converted to e4m3
+  const uint32_t idesc_qk = KVB == 1 ? ptx::make_idesc_f8((uint32_t)kv_fmt, ptx::kFmtE4M3, 128, NQ, 0, 0) : ptx::make_idesc_f16(fmt, 128, NQ, 0, 0);
+  const uint32_t idesc_pv = KVB == 1 ? ptx::make_idesc_f8((uint32_t)kv_fmt, ptx::kFmtE4M3, 128, NQ, 1, 0) : ptx::make_idesc_f16(fmt, 128, NQ, 1, 0);
   LaunchCfg lc(dim3(grid), dim3(288), S::kTotal, stream, pdl);
   FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, kern, tmK, tmV, p, idesc_qk, idesc_pv));
   return 0;
@@ -609,14 +662,21 @@ extern "C" int decode_paged_run(void* q, void* k_cache, void* v_cache, void* out
                                 int64_t num_pages_total, int64_t kv_stride_page, int64_t kv_stride_n,
                                 int64_t kv_stride_h, int64_t layout_hnd, int64_t q_stride_n, int64_t q_stride_h,
                                 int64_t o_stride_n, int64_t o_stride_h, double sm_scale, double soft_cap,
-                                int64_t window_left, int64_t causal, int64_t dtype, int64_t pdl, int64_t stream_) {
+                                int64_t window_left, int64_t causal, int64_t dtype, int64_t kv_dtype, int64_t pdl,
+                                int64_t stream_) {
   FIB_CHECK(head_dim == 128, "decode_sm100: only head_dim 128 is specialised");
-  FIB_CHECK(dtype == kF16 || dtype == kBF16, "decode_sm100: q/kv dtype must be f16/bf16");
+  FIB_CHECK(dtype == kF16 || dtype == kBF16, "decode_sm100: q dtype must be f16/bf16");
+  const bool kv8 = kv_dtype == kE4M3 || kv_dtype == kE5M2;
+  FIB_CHECK(kv8 || kv_dtype == dtype, "decode_sm100: kv dtype must equal the q dtype or be fp8 (e4m3 / e5m2)");
   FIB_CHECK(max_q_rows >= 1 && max_q_rows <= 32, "decode_sm100: q_len*group must be <= 32");
-  FIB_CHECK(kv_stride_n % 8 == 0 && kv_stride_h % 8 == 0 && kv_stride_page % 8 == 0, "kv strides must be 16B multiples");
+  FIB_CHECK(kv_stride_n % (kv8 ? 16 : 8) == 0 && kv_stride_h % (kv8 ? 16 : 8) == 0 && kv_stride_page % (kv8 ? 16 : 8) == 0,
+            "kv strides must be 16B multiples");
   FIB_CHECK(page_size <= 128 || true, "");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  const CUtensorMapDataType dt = dtype == kF16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUtensorMapDataType dt = kv8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8
+                                      : (dtype == kF16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+  const uint64_t esz = kv8 ? 1 : 2;
+  const uint32_t box_cols = kv8 ? 128 : 64;  // 128 bytes either way
   CUtensorMap tmK, tmV;
   const uint32_t box_rows = page_size <= kTileKV ? (uint32_t)page_size : (uint32_t)kTileKV;
   for (int i = 0; i < 2; ++i) {
@@ -624,13 +684,13 @@ extern "C" int decode_paged_run(void* q, void* k_cache, void* v_cache, void* out
     CUtensorMap* tm = i == 0 ? &tmK : &tmV;
     if (layout_hnd) {
       uint64_t dims[4] = {(uint64_t)head_dim, (uint64_t)page_size, (uint64_t)num_kv_heads, (uint64_t)num_pages_total};
-      uint64_t str[3] = {(uint64_t)kv_stride_n * 2, (uint64_t)kv_stride_h * 2, (uint64_t)kv_stride_page * 2};
-      uint32_t box[4] = {64, box_rows, 1, 1};
+      uint64_t str[3] = {(uint64_t)kv_stride_n * esz, (uint64_t)kv_stride_h * esz, (uint64_t)kv_stride_page * esz};
+      uint32_t box[4] = {box_cols, box_rows, 1, 1};
       if (make_tmap(tm, dt, 4, base, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
     } else {
       uint64_t dims[4] = {(uint64_t)head_dim, (uint64_t)num_kv_heads, (uint64_t)page_size, (uint64_t)num_pages_total};
-      uint64_t str[3] = {(uint64_t)kv_stride_h * 2, (uint64_t)kv_stride_n * 2, (uint64_t)kv_stride_page * 2};
-      uint32_t box[4] = {64, 1, box_rows, 1};
+      uint64_t str[3] = {(uint64_t)kv_stride_h * esz, (uint64_t)kv_stride_n * esz, (uint64_t)kv_stride_page * esz};
+      uint32_t box[4] = {box_cols, 1, box_rows, 1};
       if (make_tmap(tm, dt, 4, base, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
     }
   }
@@ -664,8 +724,14 @@ extern "C" int decode_paged_run(void* q, void* k_cache, void* v_cache, void* out
   p.rows_per_slot = NV;
 #define FIB_DEC(NQ_, NV_)                                                                                     \
   {                                                                                                           \
-    int rc = f16 ? launch_decode<NQ_, NV_, __half>(tmK, tmV, p, (int)grid, true, pdl != 0, stream)            \
-                 : launch_decode<NQ_, NV_, __nv_bfloat16>(tmK, tmV, p, (int)grid, false, pdl != 0, stream);   \
+    const int kvf = kv_dtype == kE5M2 ? 1 : 0;                                                                \
+    int rc;                                                                                                   \
+    if (kv8)                                                                                                  \
+      rc = f16 ? launch_decode<NQ_, NV_, __half, 1>(tmK, tmV, p, (int)grid, true, pdl != 0, stream, kvf)      \
+               : launch_decode<NQ_, NV_, __nv_bfloat16, 1>(tmK, tmV, p, (int)grid, false, pdl != 0, stream, kvf); \
+    else                                                                                                      \
+      rc = f16 ? launch_decode<NQ_, NV_, __half, 2>(tmK, tmV, p, (int)grid, true, pdl != 0, stream, 0)        \
+               : launch_decode<NQ_, NV_, __nv_bfloat16, 2>(tmK, tmV, p, (int)grid, false, pdl != 0, stream, 0); \
     if (rc) return rc;                                                                                        \
   }
   switch (NV) {

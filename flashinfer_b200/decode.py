@@ -356,7 +356,8 @@ class BatchDecodeWithPagedKVCacheWrapper:
                enable_pdl=enable_pdl is None or enable_pdl)
 
     def _run_sm100(self, q, k_cache, v_cache, out, lse, sm_scale, window_left, enable_pdl):
-        if (self._head_dim != 128 or q.dtype not in (torch.float16, torch.bfloat16) or k_cache.dtype != q.dtype
+        kv_ok = k_cache.dtype == q.dtype or k_cache.dtype in (torch.float8_e4m3fn, torch.float8_e5m2)
+        if (self._head_dim != 128 or q.dtype not in (torch.float16, torch.bfloat16) or not kv_ok or v_cache.dtype != k_cache.dtype
                 or self._max_q_rows > _MAX_Q_ROWS):
             return self._run_generic(q, k_cache, v_cache, out, lse, sm_scale, window_left, enable_pdl)
         sp, sn, sh, page_size, hkv, d = paged_kv_strides(k_cache, self._kv_layout)
@@ -375,7 +376,7 @@ class BatchDecodeWithPagedKVCacheWrapper:
             self._num_qo_heads, self._num_kv_heads, self._head_dim, page_size, k_cache.shape[0], sp, sn, sh,
             1 if self._kv_layout == "HND" else 0, q.stride(0), q.stride(1), out.stride(0), out.stride(1),
             float(sm_scale), float(self._logits_soft_cap), int(window_left), causal, dtype_code(q.dtype),
-            1 if (enable_pdl is None or enable_pdl) else 0, stream_ptr(q),
+            dtype_code(k_cache.dtype), 1 if (enable_pdl is None or enable_pdl) else 0, stream_ptr(q),
         )
 
 

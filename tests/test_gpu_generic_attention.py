@@ -52,7 +52,10 @@ def test_decode_fp8_kv(kv_dtype):
     out = w.run(q, (k, v))
     ref, _ = reference.batch_paged_attention_ref(q, torch.arange(B + 1, dtype=torch.int32), k.float().bfloat16(), v.float().bfloat16(),
                                                  indptr, indices.cpu(), last, "NHD", True, 1 / math.sqrt(d), 0.0, -1)
-    assert (out.float() - ref.float()).abs().max() < 2e-2
+    # fp8 cache runs both MMAs as tcgen05 kind::f8f6f4 (Q and P are converted to e4m3): fp8-level error
+    assert (out.float() - ref.float()).abs().max() < 4e-2
+    cos = torch.nn.functional.cosine_similarity(out.float().flatten(), ref.float().flatten(), dim=0)
+    assert cos > 0.995
 
 
 @pytest.mark.parametrize("d", [64, 256])
