@@ -683,22 +683,36 @@ bs_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
           ptx::tma2_load_3d(sa, &tmA, &full_bar[stage], kb * BKB, row0, b, ptx::kEvictNormal);
           ptx::tma2_load_3d(sb, &tmB, &full_bar[stage], kb * BKB, n0 + crank * (BN / 2), b, ptx::kEvictNormal);
-          if constexpr (KIND != kFp8) {
-            uint8_t* ssfa = sb + G.b_bytes;
-            uint8_t* ssfb = ssfa + G.sfa_bytes;
-            // scale blocks are rows of a [blocks, 128 x u32] tensor; rows past the end are zero-filled by TMA
-            ptx::tma2_load_2d(ssfa, &tmSFA, &full_bar[stage], 0,
-                              (b * p.sfa_row_tiles + sfa_row) * p.sf_k_tiles + kb * G.nchunk, ptx::kEvictNormal);
-            for (int rr = 0; rr < G.rb; ++rr) {
-              int rt = rb0 + rr;
-              if (rt >= p.sfb_row_tiles) rt = p.sfb_row_tiles - 1;  // columns past N: finite scales x zero data
-              ptx::tma2_load_2d(ssfb + rr * G.nchunk * 512, &tmSFB, &full_bar[stage], 0,
-                                (b * p.sfb_row_tiles + rt) * p.sf_k_tiles + kb * G.nchunk, ptx::kEvictNormal);
-            }
-          }
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ---- second producer warp: scale-factor tiles (UTMALDG issue costs ~100 clk each; with A, B, SFA, SFB on one warp
+    //      an nvfp4 slab (393 clk of MMA) was issue-bound).  Same full barrier; warp 0 arms the byte count.
+    if constexpr (KIND != kFp8) {
+      if (ptx::elect_one()) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int t = pair; t < num_tiles; t += num_pairs) {
+          const int b = t / tiles_per_batch, r = t % tiles_per_batch;
+          const int tm = r % tiles_m, tn = r / tiles_m;
+          const int sfa_row = tm * 2 + crank;
+          const int rb0 = (tn * BN) / 128;
+          for (int kb = 0; kb < num_kb; ++kb) {
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* ssfa = smem + stage * G.stage_bytes + G.a_bytes + G.b_bytes;
+            uint8_t* ssfb = ssfa + G.sfa_bytes;
+            // scale tensors are [batch * row_tiles][sf_k_tiles][128 x u32]; out-of-range blocks are zero-filled by TMA
+            ptx::tma2_load_3d(ssfa, &tmSFA, &full_bar[stage], 0, kb * G.nchunk, b * p.sfa_row_tiles + sfa_row, ptx::kEvictNormal);
+            ptx::tma2_load_3d(ssfb, &tmSFB, &full_bar[stage], 0, kb * G.nchunk, b * p.sfb_row_tiles + rb0, ptx::kEvictNormal);
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
           }
         }
       }
@@ -968,12 +982,14 @@ extern "C" int gemm_lowp_nt(void* A, void* B, void* C, void* sfa, void* sfb, voi
         FIB_CHECK(sfa && sfb, "gemm_lowp: block-scaled kinds need scale tensors");
         FIB_CHECK(sfa_batch_stride == int64_t(p2.sfa_row_tiles) * p2.sf_k_tiles * 512 || batch == 1, "gemm_lowp: SFA must be contiguous per batch");
         FIB_CHECK(sfb_batch_stride == int64_t(p2.sfb_row_tiles) * p2.sf_k_tiles * 512 || batch == 1, "gemm_lowp: SFB must be contiguous per batch");
-        uint64_t dimsa[2] = {128, (uint64_t)(batch * int64_t(p2.sfa_row_tiles) * p2.sf_k_tiles)};
-        uint64_t dimsb[2] = {128, (uint64_t)(batch * int64_t(p2.sfb_row_tiles) * p2.sf_k_tiles)};
-        uint64_t str[1] = {512};
-        uint32_t box[2] = {128, (uint32_t)G2.nchunk};
-        if (make_tmap(&tmSFA, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, sfa, dimsa, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
-        if (make_tmap(&tmSFB, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, sfb, dimsb, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
+        // [rows = batch * row_tiles][sf_k_tiles][128 x u32]: one TMA box = (all scale blocks of a K slab) x (row tiles of the tile)
+        uint64_t dimsa[3] = {128, (uint64_t)p2.sf_k_tiles, (uint64_t)(batch * int64_t(p2.sfa_row_tiles))};
+        uint64_t dimsb[3] = {128, (uint64_t)p2.sf_k_tiles, (uint64_t)(batch * int64_t(p2.sfb_row_tiles))};
+        uint64_t str[2] = {512, (uint64_t)p2.sf_k_tiles * 512};
+        uint32_t boxa[3] = {128, (uint32_t)G2.nchunk, 1};
+        uint32_t boxb[3] = {128, (uint32_t)G2.nchunk, (uint32_t)G2.rb};
+        if (make_tmap(&tmSFA, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, sfa, dimsa, str, boxa, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
+        if (make_tmap(&tmSFB, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, sfb, dimsb, str, boxb, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
       } else {
         tmSFA = tmA;
         tmSFB = tmB;
