@@ -39,8 +39,10 @@ struct MlaParams {
   const int32_t* work;  // [nwork][8] {q_row, kv_page_start, kv_begin(token), kv_end(token), kv_len, out_slot, num_pages, first part: (kmax << 16) | nparts else 0}
   void* out;            // final bf16/f16 [n, H, 512]            (when partial == nullptr)
   float* partial_o;     // [slots][H][512] fp32                  (split-KV)
-  float* partial_lse;   // [slots][H]
+  float* partial_lse;   // [2 dv-halves][slots][H] (each half-CTA keeps its own copy: the halves merge independently)
   float* lse;           // optional final lse [n, H]
+  int* merge_counters;  // [n_q][2] zero-initialised, self-resetting; null = no in-kernel merge
+  int64_t lse_half_stride;  // slots * H
   int num_heads, page_size;
   int64_t o_stride_n, o_stride_h;
   float sm_scale_log2;
@@ -327,17 +329,57 @@ mla_decode_kernel(const __grid_constant__ CUtensorMap tmQn, const __grid_constan
         }
       }
     }
-    if (row_ok && half == 0) {
-      if (p.partial_o) {
-        p.partial_lse[int64_t(out_slot) * p.num_heads + row] = lse_v;
-        // work[7] = (kmax << 16) | nparts on the first part of a row: mark the unused split slots so that the merge
-        // ignores them (no host-side fill of the partial buffers)
-        const int nparts = wk[7] & 0xffff, kmax = wk[7] >> 16;
-        for (int sidx = nparts; sidx < kmax; ++sidx)
-          p.partial_lse[int64_t(out_slot + sidx) * p.num_heads + row] = -INFINITY;
-      } else if (p.lse) {
-        p.lse[int64_t(q_row) * p.num_heads + row] = lse_v;
+    const int nparts = wk[7] & 0xffff, kmax = wk[7] >> 16;
+    if (p.partial_o) {
+      if (row_ok) p.partial_lse[half * p.lse_half_stride + int64_t(out_slot) * p.num_heads + row] = lse_v;
+      // ---- in-kernel split-KV merge: the last part of this (query row, dv half) to arrive folds all parts and writes the
+      //      final bf16 output (no separate merge / copy kernels, no host-side initialisation of the partial buffers)
+      __threadfence();
+      ptx::named_bar_sync(1, 128);
+      __shared__ int s_last;
+      if (threadIdx.x == 128) {
+        const int old = atomicAdd(&p.merge_counters[q_row * 2 + half], 1);
+        const int last = (old == nparts - 1);
+        if (last) p.merge_counters[q_row * 2 + half] = 0;
+        s_last = last;
       }
+      ptx::named_bar_sync(1, 128);
+      if (s_last && row_ok) {
+        __threadfence();
+        const int64_t slot0 = int64_t(q_row) * kmax;
+        float mx = -INFINITY;
+        for (int sidx = 0; sidx < nparts; ++sidx)
+          mx = fmaxf(mx, __ldcg(p.partial_lse + half * p.lse_half_stride + (slot0 + sidx) * p.num_heads + row));
+        float wgt[8];
+        float den = 0.f;
+        for (int sidx = 0; sidx < nparts && sidx < 8; ++sidx) {
+          const float ls = __ldcg(p.partial_lse + half * p.lse_half_stride + (slot0 + sidx) * p.num_heads + row);
+          wgt[sidx] = (mx == -INFINITY) ? 0.f : ptx::ex2(ls - mx);
+          den += wgt[sidx];
+        }
+        const float invd = den > 0.f ? 1.f / den : 0.f;
+        T* dst = reinterpret_cast<T*>(p.out) + int64_t(q_row) * p.o_stride_n + int64_t(row) * p.o_stride_h + half * kDvHalf;
+#pragma unroll 1
+        for (int c = 0; c < kDvHalf; c += 8) {
+          float acc[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+          for (int sidx = 0; sidx < nparts && sidx < 8; ++sidx) {
+            const float* src = p.partial_o + ((slot0 + sidx) * p.num_heads + row) * kCkv + half * kDvHalf + c;
+            const float4 a = __ldcg(reinterpret_cast<const float4*>(src)), b2 = __ldcg(reinterpret_cast<const float4*>(src + 4));
+            acc[0] += wgt[sidx] * a.x; acc[1] += wgt[sidx] * a.y; acc[2] += wgt[sidx] * a.z; acc[3] += wgt[sidx] * a.w;
+            acc[4] += wgt[sidx] * b2.x; acc[5] += wgt[sidx] * b2.y; acc[6] += wgt[sidx] * b2.z; acc[7] += wgt[sidx] * b2.w;
+          }
+          Vec16<T> v;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v.v[e] = from_f32<T>(acc[e] * invd);
+          st16(dst + c, v);
+        }
+        if (half == 0 && p.lse) p.lse[int64_t(q_row) * p.num_heads + row] = den > 0.f ? mx + ptx::lg2(den) : -INFINITY;
+      }
+      ptx::named_bar_sync(1, 128);  // s_last is reused by the next work item
+    } else if (row_ok && half == 0 && p.lse) {
+      p.lse[int64_t(q_row) * p.num_heads + row] = lse_v;
     }
   }
 
@@ -354,8 +396,8 @@ mla_decode_kernel(const __grid_constant__ CUtensorMap tmQn, const __grid_constan
 
 // q_nope [n, H, 512], q_pe [n, H, 64] (strides in elements), ckv_cache [pages, page, 512], kpe_cache [pages, page, 64]
 extern "C" int mla_decode_run(void* q_nope, void* q_pe, void* ckv_cache, void* kpe_cache, void* kv_indices, void* work,
-                              int64_t num_work, void* out, void* partial_o, void* partial_lse, void* lse, int64_t n_q,
-                              int64_t num_heads, int64_t page_size, int64_t num_pages_total, int64_t qn_sn, int64_t qn_sh,
+                              int64_t num_work, void* out, void* partial_o, void* partial_lse, void* merge_counters,
+                              int64_t lse_half_stride, void* lse, int64_t n_q, int64_t num_heads, int64_t page_size, int64_t num_pages_total, int64_t qn_sn, int64_t qn_sh,
                               int64_t qp_sn, int64_t qp_sh, int64_t ckv_sp, int64_t ckv_sn, int64_t kpe_sp, int64_t kpe_sn,
                               int64_t o_sn, int64_t o_sh, double sm_scale, int64_t dtype, int64_t pdl, int64_t stream_) {
   FIB_CHECK(num_heads >= 1 && num_heads <= kHeads, "mla_sm100: num_heads must be <= 128");
@@ -397,6 +439,9 @@ extern "C" int mla_decode_run(void* q_nope, void* q_pe, void* ckv_cache, void* k
   p.out = out;
   p.partial_o = (float*)partial_o;
   p.partial_lse = (float*)partial_lse;
+  p.merge_counters = (int*)merge_counters;
+  p.lse_half_stride = lse_half_stride;
+  FIB_CHECK(!partial_o || merge_counters, "mla_sm100: split-KV needs merge counters");
   p.lse = (float*)lse;
   p.num_heads = (int)num_heads;
   p.page_size = (int)page_size;

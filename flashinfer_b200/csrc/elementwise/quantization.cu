@@ -42,7 +42,8 @@ template <typename T, int VEC, bool kUE8M0>
 __global__ void __launch_bounds__(256)
 fp4_quantize_kernel(const T* __restrict__ x, uint8_t* __restrict__ q, uint8_t* __restrict__ sf,
                     const float* __restrict__ global_scale, int64_t batch, int64_t M, int64_t K, int64_t ldx,
-                    int64_t x_batch_stride, int swizzled, int64_t sf_batch_stride, const int32_t* __restrict__ row_map) {
+                    int64_t x_batch_stride, int swizzled, int64_t sf_batch_stride, const int32_t* __restrict__ row_map,
+                    int gather, int gated) {
   const int64_t kc_total = K / VEC;
   const int64_t kc_pad = (kc_total + 3) / 4 * 4;
   const int64_t total = batch * M * kc_total;
@@ -52,14 +53,31 @@ fp4_quantize_kernel(const T* __restrict__ x, uint8_t* __restrict__ q, uint8_t* _
     const int64_t kc = i % kc_total;
     const int64_t m = (i / kc_total) % M;
     const int64_t b = i / (kc_total * M);
-    if (row_map && row_map[m] < 0) continue;  // MoE padding row (scale bytes stay as initialised: finite)
-    const T* src = x + b * x_batch_stride + m * ldx + kc * VEC;
+    int64_t src_row = m;
+    if (row_map) {
+      const int rm = row_map[m];
+      if (rm < 0) continue;     // MoE padding row (scale bytes stay as initialised: finite)
+      if (gather) src_row = rm; // fused MoE gather: quantise x[token(m)] straight into the permuted row m
+    }
+    const T* src = x + b * x_batch_stride + src_row * ldx + kc * VEC;
     float v[VEC];
 #pragma unroll
     for (int j = 0; j < VEC; j += 8) {
       const Vec16<T> raw = ld16(src + j);
 #pragma unroll
       for (int e = 0; e < 8; ++e) v[j + e] = to_f32(raw.v[e]);
+    }
+    if (gated) {
+      // fused SwiGLU: the row holds [linear | gate] halves of width K; quantise silu(gate) * linear
+#pragma unroll
+      for (int j = 0; j < VEC; j += 8) {
+        const Vec16<T> raw = ld16(src + K + j);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float g = to_f32(raw.v[e]);
+          v[j + e] *= g / (1.f + __expf(-g));
+        }
+      }
     }
     float amax = 0.f;
 #pragma unroll
@@ -224,7 +242,8 @@ inline int grid_for(int64_t total, int threads = 256) {
 // vec = 16 (NVFP4, UE4M3 scale unless ue8m0) or 32 (MXFP4, UE8M0 scale)
 extern "C" int fp4_quantize(void* x, void* q, void* sf, void* global_scale, int64_t batch, int64_t M, int64_t K,
                             int64_t ldx, int64_t x_batch_stride, int64_t vec, int64_t ue8m0, int64_t swizzled,
-                            int64_t sf_batch_stride, void* row_map, int64_t dtype, int64_t pdl, int64_t stream_) {
+                            int64_t sf_batch_stride, void* row_map, int64_t gather, int64_t gated, int64_t dtype, int64_t pdl,
+                            int64_t stream_) {
   FIB_CHECK(vec == 16 || vec == 32, "fp4_quantize: sf_vec_size must be 16 or 32");
   FIB_CHECK(K % vec == 0 && ldx % 8 == 0, "fp4_quantize: K must be a multiple of sf_vec_size and rows 16B aligned");
   if (batch * M * K == 0) return 0;
@@ -234,7 +253,8 @@ extern "C" int fp4_quantize(void* x, void* q, void* sf, void* global_scale, int6
   return FIB_DISPATCH_HALF(dtype, T, [&]() -> int {
     auto launch = [&](auto kern) -> int {
       FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, kern, (const T*)x, (uint8_t*)q, (uint8_t*)sf, (const float*)global_scale,
-                                        batch, M, K, ldx, x_batch_stride, (int)swizzled, sf_batch_stride, (const int32_t*)row_map));
+                                        batch, M, K, ldx, x_batch_stride, (int)swizzled, sf_batch_stride, (const int32_t*)row_map,
+                                        (int)gather, (int)gated));
       return 0;
     };
     if (vec == 16 && !ue8m0) return launch(fp4_quantize_kernel<T, 16, false>);

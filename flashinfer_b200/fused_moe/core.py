@@ -209,6 +209,17 @@ def moe_forward(x: torch.Tensor, topk_ids: torch.Tensor, topk_w: torch.Tensor, w
 
 
 _SF_CACHE: dict = {}
+_UNIT: dict = {}
+
+
+def _unit_scale(dev, v: float = 1.0) -> torch.Tensor:
+    """Cached 1-element fp32 tensor (avoids a fill kernel per MoE call)."""
+    key = (str(dev), float(v))
+    t = _UNIT.get(key)
+    if t is None:
+        t = torch.full((1,), float(v), dtype=torch.float32, device=dev)
+        _UNIT[key] = t
+    return t
 
 
 def _swizzle_expert_sf(sf: torch.Tensor, E: int, N: int, kc: int) -> torch.Tensor:
@@ -239,7 +250,7 @@ def moe_forward_nvfp4(x: torch.Tensor, topk_ids: torch.Tensor, topk_w: torch.Ten
     e2m1 with linear ``[E, N, K/16]`` (or pre-swizzled) UE4M3 scales, ``w*_alpha [E]`` are the per-expert output de-quantisation
     scales (1 / (activation global scale * weight global scale))."""
     from ..gemm.lowp import grouped_gemm_nvfp4
-    from ..quantization.fp4 import fp4_quantize
+    from ..quantization.fp4 import moe_fp4_quantize
 
     T, H = x.shape
     e_local, n1, _ = w1_fp4.shape
@@ -260,24 +271,25 @@ def moe_forward_nvfp4(x: torch.Tensor, topk_ids: torch.Tensor, topk_w: torch.Ten
     mod.call("moe_sort", ids, T, K, num_experts or e_local, local_expert_offset, e_local, _TILE, max_rows, e2p, p2t, tile_e, offs,
              meta, ws, 1, st)
     xb = x if x.dtype in (torch.float16, torch.bfloat16) else x.to(torch.bfloat16)
-    xp = torch.empty(max_rows, H, dtype=xb.dtype, device=dev)
-    mod.call("moe_gather", xb, xp, p2t, meta, max_rows, H, xb.stride(0), 0, dtype_code(xb.dtype), 1, st)
-    gs = torch.full((1,), float(act_global_scale), dtype=torch.float32, device=dev)
-    xq, xsf = fp4_quantize(xp, gs, 16, False, True, row_map=p2t)
+    if xb.stride(-1) != 1:
+        xb = xb.contiguous()
+    gs = _unit_scale(dev, act_global_scale)
+    # gather + quantise in one kernel: token rows go straight into the permuted NVFP4 activation matrix
+    xq, xsf = moe_fp4_quantize(xb, max_rows, H, p2t, gs, gather=True, gated=False)
     a1 = torch.as_tensor(w1_alpha, dtype=torch.float32, device=dev).reshape(-1)
     a2 = torch.as_tensor(w2_alpha, dtype=torch.float32, device=dev).reshape(-1)
     if a1.numel() == 1:
         a1 = a1.expand(e_local)
     if a2.numel() == 1:
         a2 = a2.expand(e_local)
-    a1 = (a1 / act_global_scale).contiguous()
-    a2 = (a2 / act_global_scale).contiguous()
+    if act_global_scale != 1.0:
+        a1, a2 = a1 / act_global_scale, a2 / act_global_scale
+    a1, a2 = a1.contiguous(), a2.contiguous()
     sf1 = _swizzle_expert_sf(w1_sf, e_local, n1, H // 16)
     sf2 = _swizzle_expert_sf(w2_sf, e_local, H, inter // 16)
     h1 = grouped_gemm_nvfp4(xq, xsf, w1_fp4, sf1, a1, tile_e, meta, out_dtype=xb.dtype)
-    act = torch.empty(max_rows, inter, dtype=xb.dtype, device=dev)
-    _act_and_mul("silu", h1, act, True, gate_second=True, row_map=p2t)
-    aq, asf = fp4_quantize(act, gs, 16, False, True, row_map=p2t)
+    # SwiGLU + quantisation of the FC2 input in one kernel
+    aq, asf = moe_fp4_quantize(h1, max_rows, inter, p2t, gs, gather=False, gated=True)
     h2 = grouped_gemm_nvfp4(aq, asf, w2_fp4, sf2, a2, tile_e, meta, out_dtype=xb.dtype)
     if out is None:
         out = torch.empty(T, H, dtype=xb.dtype, device=dev)

@@ -96,7 +96,7 @@ def fp4_quantize(input: torch.Tensor, global_scale: Optional[torch.Tensor] = Non
         gst = gs.float().reshape(1).contiguous() if gs is not None else None
         jit.load("quantization").call(
             "fp4_quantize", x, packed, sf, gst, 1, m, k, x.stride(0), 0, sf_vec_size, 1 if sf_use_ue8m0 else 0,
-            1 if is_sf_swizzled_layout else 0, 0, row_map, dtype_code(x.dtype), 1, stream_ptr(x),
+            1 if is_sf_swizzled_layout else 0, 0, row_map, 0, 0, dtype_code(x.dtype), 1, stream_ptr(x),
         )
     sf = sf.view(-1, round_up(kc, 4)) if is_sf_swizzled_layout else sf.view(m, kc)
     return packed.view(*shape[:-1], k // 2), sf
@@ -131,7 +131,7 @@ def nvfp4_batched_quantize(a: torch.Tensor, a_global_sf: torch.Tensor, sf_vec_si
     sf = torch.zeros(b, per, dtype=torch.uint8, device=a.device)
     jit.load("quantization").call(
         "fp4_quantize", x, packed, sf, a_global_sf.float().reshape(1).contiguous(), b, m, k, x.stride(1), x.stride(0),
-        sf_vec_size, 0, 1, per, None, dtype_code(x.dtype), 1, stream_ptr(x),
+        sf_vec_size, 0, 1, per, None, 0, 0, dtype_code(x.dtype), 1, stream_ptr(x),
     )
     return packed, sf
 
@@ -261,3 +261,17 @@ def nvfp4_quantize_paged_kv_cache(k_cache: torch.Tensor, v_cache: torch.Tensor, 
     kq, ksf, kg = one(k_cache, k_global_sf)
     vq, vsf, vg = one(v_cache, v_global_sf)
     return (kq, vq), (ksf, vsf), kg, vg
+
+
+def moe_fp4_quantize(x: torch.Tensor, rows: int, k: int, row_map: torch.Tensor, global_scale: torch.Tensor, gather: bool,
+                     gated: bool, sf_vec_size: int = 16) -> Tuple[torch.Tensor, torch.Tensor]:
+    """MoE-fused NVFP4 quantiser (one kernel): ``gather`` reads row ``row_map[m]`` of ``x`` (token gather) instead of row
+    ``m``; ``gated`` treats a row as ``[linear | gate]`` halves of width ``k`` and quantises ``silu(gate) * linear``
+    (SwiGLU fused with the quantisation of the FC2 input).  Rows with ``row_map[m] < 0`` are skipped.  Returns
+    (``[rows, k/2]`` uint8, 128x4-swizzled UE4M3 scales)."""
+    kc = k // sf_vec_size
+    packed = torch.empty(rows, k // 2, dtype=torch.uint8, device=x.device)
+    sf = torch.zeros(_swizzled_sf_size(rows, kc), dtype=torch.uint8, device=x.device)
+    jit.load("quantization").call("fp4_quantize", x, packed, sf, global_scale, 1, rows, k, x.stride(0), 0, sf_vec_size, 0, 1, 0,
+                                  row_map, 1 if gather else 0, 1 if gated else 0, dtype_code(x.dtype), 1, stream_ptr(x))
+    return packed, sf.view(-1, round_up(kc, 4))
