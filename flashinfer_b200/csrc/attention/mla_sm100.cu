@@ -344,38 +344,43 @@ mla_decode_kernel(const __grid_constant__ CUtensorMap tmQn, const __grid_constan
         s_last = last;
       }
       ptx::named_bar_sync(1, 128);
-      if (s_last && row_ok) {
+      if (s_last) {
         __threadfence();
+        __shared__ float s_w[8][kHeads];  // normalised merge weight of (part, head)
         const int64_t slot0 = int64_t(q_row) * kmax;
-        float mx = -INFINITY;
-        for (int sidx = 0; sidx < nparts; ++sidx)
-          mx = fmaxf(mx, __ldcg(p.partial_lse + half * p.lse_half_stride + (slot0 + sidx) * p.num_heads + row));
-        float wgt[8];
-        float den = 0.f;
-        for (int sidx = 0; sidx < nparts && sidx < 8; ++sidx) {
-          const float ls = __ldcg(p.partial_lse + half * p.lse_half_stride + (slot0 + sidx) * p.num_heads + row);
-          wgt[sidx] = (mx == -INFINITY) ? 0.f : ptx::ex2(ls - mx);
-          den += wgt[sidx];
-        }
-        const float invd = den > 0.f ? 1.f / den : 0.f;
-        T* dst = reinterpret_cast<T*>(p.out) + int64_t(q_row) * p.o_stride_n + int64_t(row) * p.o_stride_h + half * kDvHalf;
-#pragma unroll 1
-        for (int c = 0; c < kDvHalf; c += 8) {
-          float acc[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-          for (int sidx = 0; sidx < nparts && sidx < 8; ++sidx) {
-            const float* src = p.partial_o + ((slot0 + sidx) * p.num_heads + row) * kCkv + half * kDvHalf + c;
-            const float4 a = __ldcg(reinterpret_cast<const float4*>(src)), b2 = __ldcg(reinterpret_cast<const float4*>(src + 4));
-            acc[0] += wgt[sidx] * a.x; acc[1] += wgt[sidx] * a.y; acc[2] += wgt[sidx] * a.z; acc[3] += wgt[sidx] * a.w;
-            acc[4] += wgt[sidx] * b2.x; acc[5] += wgt[sidx] * b2.y; acc[6] += wgt[sidx] * b2.z; acc[7] += wgt[sidx] * b2.w;
+        if (row_ok) {
+          float mx = -INFINITY;
+          for (int sidx = 0; sidx < nparts; ++sidx)
+            mx = fmaxf(mx, __ldcg(p.partial_lse + half * p.lse_half_stride + (slot0 + sidx) * p.num_heads + row));
+          float den = 0.f;
+          for (int sidx = 0; sidx < nparts; ++sidx) {
+            const float ls = __ldcg(p.partial_lse + half * p.lse_half_stride + (slot0 + sidx) * p.num_heads + row);
+            const float w = (mx == -INFINITY) ? 0.f : ptx::ex2(ls - mx);
+            s_w[sidx][row] = w;
+            den += w;
           }
-          Vec16<T> v;
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v.v[e] = from_f32<T>(acc[e] * invd);
-          st16(dst + c, v);
+          const float invd = den > 0.f ? 1.f / den : 0.f;
+          for (int sidx = 0; sidx < nparts; ++sidx) s_w[sidx][row] *= invd;
+          if (half == 0 && p.lse) p.lse[int64_t(q_row) * p.num_heads + row] = den > 0.f ? mx + ptx::lg2(den) : -INFINITY;
         }
-        if (half == 0 && p.lse) p.lse[int64_t(q_row) * p.num_heads + row] = den > 0.f ? mx + ptx::lg2(den) : -INFINITY;
+        ptx::named_bar_sync(1, 128);
+        // cooperative, coalesced fold: the 128 threads sweep one head row (256 fp32 = 1 KB per part) at a time
+        const int t2 = (threadIdx.x - 128) * 2;  // two columns per thread
+        T* obase = reinterpret_cast<T*>(p.out) + int64_t(q_row) * p.o_stride_n + half * kDvHalf + t2;
+        const float* pbase = p.partial_o + slot0 * p.num_heads * kCkv + half * kDvHalf + t2;
+#pragma unroll 4
+        for (int h = 0; h < p.num_heads; ++h) {
+          float a0 = 0.f, a1 = 0.f;
+          for (int sidx = 0; sidx < nparts; ++sidx) {
+            const float2 v = __ldcg(reinterpret_cast<const float2*>(pbase + (int64_t(sidx) * p.num_heads + h) * kCkv));
+            const float w = s_w[sidx][h];
+            a0 += w * v.x;
+            a1 += w * v.y;
+          }
+          T* dst = obase + int64_t(h) * p.o_stride_h;
+          struct alignas(4) Pair { T a, b; } pr{from_f32<T>(a0), from_f32<T>(a1)};
+          *reinterpret_cast<Pair*>(dst) = pr;  // one 4-byte store per thread -> 512 B contiguous per head row
+        }
       }
       ptx::named_bar_sync(1, 128);  // s_last is reused by the next work item
     } else if (row_ok && half == 0 && p.lse) {

@@ -71,6 +71,7 @@ struct Params {
   int batch, BN;
   const int32_t* tile_expert;  // grouped (MoE) mode: expert of every 128-row tile of A (-1 = skip); B / SFB / alpha are per expert
   const int32_t* meta;         // grouped mode: meta[0] = number of live row tiles (device side)
+  int tab_tiles, tab_experts;  // capacity of the shared-memory tile->expert / alpha tables (grouped mode)
   int split;          // cluster split-K factor (1 or 2): both CTAs of a cluster own the same tile, half of K each
   int sf_k_tiles;     // 512-byte blocks along K in the scale tensors
   int sfb_row_tiles;  // 128-row blocks in SFB
@@ -136,6 +137,16 @@ bs_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const bool grouped = p.tile_expert != nullptr;
   int tiles_m = (p.M + BM - 1) / BM;
   if (grouped && p.meta) tiles_m = min(tiles_m, p.meta[0]);  // written by the MoE sort kernel
+  // grouped mode: the tile -> expert table and the per-expert alphas are staged in shared memory once; reading them from
+  // global memory per tile put an L2 round trip (~1 us) on the critical path of every role (ncu: long-scoreboard stalls)
+  int32_t* s_expert = reinterpret_cast<int32_t*>(smem + G.bar_offset + 320);
+  float* s_alpha = reinterpret_cast<float*>(s_expert + p.tab_tiles);
+  if (grouped) {
+    for (int i = threadIdx.x; i < tiles_m && i < p.tab_tiles; i += blockDim.x) s_expert[i] = p.tile_expert[i];
+    if (p.alpha_a)
+      for (int i = threadIdx.x; i < p.batch && i < p.tab_experts; i += blockDim.x) s_alpha[i] = p.alpha_a[i];
+    __syncthreads();
+  }
   const int tiles_n = (p.N + BN - 1) / BN;
   const int tiles_per_batch = tiles_m * tiles_n;
   const int num_tiles = tiles_per_batch * (grouped ? 1 : p.batch);
@@ -150,7 +161,7 @@ bs_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tm = t / tiles_n;
       tn = t % tiles_n;
       ba = 0;
-      bb = p.tile_expert[tm];
+      bb = tm < p.tab_tiles ? s_expert[tm] : p.tile_expert[tm];
       return bb >= 0;
     }
     const int r = t % tiles_per_batch;
@@ -280,7 +291,7 @@ bs_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int t = t_first; t < num_tiles; t += t_stride) {
       int b, bb, tm, tn;
       if (!decode(t, b, bb, tm, tn)) continue;
-      const float alpha = (grouped && p.alpha_a) ? alpha0 * p.alpha_a[bb] : alpha0;
+      const float alpha = (grouped && p.alpha_a) ? alpha0 * (bb < p.tab_experts ? s_alpha[bb] : p.alpha_a[bb]) : alpha0;
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
       const int row = tm * BM + q * 32 + lane;
@@ -1042,6 +1053,9 @@ extern "C" int gemm_lowp_nt(void* A, void* B, void* C, void* sfa, void* sfb, voi
   p.sfa = (const uint8_t*)sfa;
   p.tile_expert = (const int32_t*)tile_expert;
   p.meta = (const int32_t*)meta;
+  p.tab_tiles = tile_expert ? (tiles_m < 1024 ? tiles_m : 1024) : 0;
+  p.tab_experts = tile_expert ? (int)(batch < 1024 ? batch : 1024) : 0;
+  const int tab_bytes = (p.tab_tiles + p.tab_experts) * 4;
   p.sfb = (const uint8_t*)sfb;
   p.alpha_a = (const float*)alpha_a;
   p.alpha_b = (const float*)alpha_b;
@@ -1076,17 +1090,17 @@ extern "C" int gemm_lowp_nt(void* A, void* B, void* C, void* sfa, void* sfb, voi
   const bool f16 = out_dtype == kF16;
   switch (kind) {
     case kFp8:
-      return f16 ? launch<kFp8, __half>(tmA, tmB, C, p, grid, G.total, pdl != 0, stream)
-                 : launch<kFp8, __nv_bfloat16>(tmA, tmB, C, p, grid, G.total, pdl != 0, stream);
+      return f16 ? launch<kFp8, __half>(tmA, tmB, C, p, grid, G.total + tab_bytes, pdl != 0, stream)
+                 : launch<kFp8, __nv_bfloat16>(tmA, tmB, C, p, grid, G.total + tab_bytes, pdl != 0, stream);
     case kMxFp8:
-      return f16 ? launch<kMxFp8, __half>(tmA, tmB, C, p, grid, G.total, pdl != 0, stream)
-                 : launch<kMxFp8, __nv_bfloat16>(tmA, tmB, C, p, grid, G.total, pdl != 0, stream);
+      return f16 ? launch<kMxFp8, __half>(tmA, tmB, C, p, grid, G.total + tab_bytes, pdl != 0, stream)
+                 : launch<kMxFp8, __nv_bfloat16>(tmA, tmB, C, p, grid, G.total + tab_bytes, pdl != 0, stream);
     case kNvFp4:
-      return f16 ? launch<kNvFp4, __half>(tmA, tmB, C, p, grid, G.total, pdl != 0, stream)
-                 : launch<kNvFp4, __nv_bfloat16>(tmA, tmB, C, p, grid, G.total, pdl != 0, stream);
+      return f16 ? launch<kNvFp4, __half>(tmA, tmB, C, p, grid, G.total + tab_bytes, pdl != 0, stream)
+                 : launch<kNvFp4, __nv_bfloat16>(tmA, tmB, C, p, grid, G.total + tab_bytes, pdl != 0, stream);
     default:
-      return f16 ? launch<kMxFp4, __half>(tmA, tmB, C, p, grid, G.total, pdl != 0, stream)
-                 : launch<kMxFp4, __nv_bfloat16>(tmA, tmB, C, p, grid, G.total, pdl != 0, stream);
+      return f16 ? launch<kMxFp4, __half>(tmA, tmB, C, p, grid, G.total + tab_bytes, pdl != 0, stream)
+                 : launch<kMxFp4, __nv_bfloat16>(tmA, tmB, C, p, grid, G.total + tab_bytes, pdl != 0, stream);
   }
 }
 

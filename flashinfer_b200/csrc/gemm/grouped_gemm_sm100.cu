@@ -38,7 +38,7 @@ template <typename OutT>
 __global__ void __launch_bounds__(256, 1)
 grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                     OutT* __restrict__ C, const int32_t* __restrict__ tile_expert, const int32_t* __restrict__ meta,
-                    int max_m_tiles, int N, int K, int64_t ldc, int BN, uint32_t idesc) {
+                    int max_m_tiles, int N, int K, int64_t ldc, int BN, uint32_t idesc, int tab_tiles) {
   const GSmem S = GSmem::make(BN);
   const int kStages = S.stages;
   extern __shared__ uint8_t smem_raw[];
@@ -77,6 +77,12 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   ptx::grid_dep_wait();
   int num_m = meta ? meta[0] : max_m_tiles;
   if (num_m > max_m_tiles) num_m = max_m_tiles;
+  // stage the tile -> expert table in shared memory (a global read per tile is an L2 round trip on every role's critical path)
+  int32_t* s_expert = reinterpret_cast<int32_t*>(smem + S.bar_offset + 320);
+  const int tab = num_m < tab_tiles ? num_m : tab_tiles;
+  for (int i = threadIdx.x; i < tab; i += blockDim.x) s_expert[i] = tile_expert[i];
+  __syncthreads();
+  auto expert_of = [&](int tm) { return tm < tab ? s_expert[tm] : tile_expert[tm]; };
   const int tiles_n = (N + BN - 1) / BN;
   const int num_tiles = num_m * tiles_n;
   const int num_kb = (K + BK - 1) / BK;
@@ -87,7 +93,7 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int tm = t / tiles_n, tn = t % tiles_n;
-        const int e = tile_expert[tm];
+        const int e = expert_of(tm);
         if (e < 0) continue;
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -110,7 +116,7 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int tm = t / tiles_n;
-      if (tile_expert[tm] < 0) continue;
+      if (expert_of(tm) < 0) continue;
       ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BN;
@@ -145,7 +151,7 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int tm = t / tiles_n, tn = t % tiles_n;
-      if (tile_expert[tm] < 0) continue;
+      if (expert_of(tm) < 0) continue;
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
       const int row = tm * BM + q * 32 + lane;
@@ -216,7 +222,8 @@ extern "C" int grouped_gemm_nt(void* A, void* W, void* C, void* tile_expert, voi
   const uint32_t idesc = ptx::make_idesc_f16(dtype == kF16 ? ptx::kFmtF16 : ptx::kFmtBF16, BM, BN, 0, 0);
   const int64_t tiles = max_m_tiles * ((N + BN - 1) / BN);
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-  LaunchCfg lc(dim3(grid), dim3(256), S.total, stream, pdl != 0);
+  const int tab_tiles = (int)(max_m_tiles < 2048 ? max_m_tiles : 2048);
+  LaunchCfg lc(dim3(grid), dim3(256), S.total + tab_tiles * 4, stream, pdl != 0);
   if (dtype == kF16) {
     static bool set = false;
     if (!set) {
@@ -225,7 +232,7 @@ extern "C" int grouped_gemm_nt(void* A, void* W, void* C, void* tile_expert, voi
     }
     FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, grouped_gemm_kernel<__half>, tmA, tmW, (__half*)C,
                                       (const int32_t*)tile_expert, (const int32_t*)meta, (int)max_m_tiles, (int)N, (int)K,
-                                      ldc, BN, idesc));
+                                      ldc, BN, idesc, tab_tiles));
   } else {
     static bool set = false;
     if (!set) {
@@ -235,7 +242,7 @@ extern "C" int grouped_gemm_nt(void* A, void* W, void* C, void* tile_expert, voi
     }
     FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, grouped_gemm_kernel<__nv_bfloat16>, tmA, tmW, (__nv_bfloat16*)C,
                                       (const int32_t*)tile_expert, (const int32_t*)meta, (int)max_m_tiles, (int)N, (int)K,
-                                      ldc, BN, idesc));
+                                      ldc, BN, idesc, tab_tiles));
   }
   return 0;
 }
