@@ -12,7 +12,7 @@ _ACT = {"silu": 0, "gelu": 1, "gelu_tanh": 2}
 
 
 def _act_and_mul(kind: str, input: torch.Tensor, out: Optional[torch.Tensor], enable_pdl, gate_second: bool = False,
-                 row_map: Optional[torch.Tensor] = None):
+                 row_map: Optional[torch.Tensor] = None, row_list: bool = False):
     d = input.shape[-1] // 2
     if input.shape[-1] % 2:
         raise ValueError("last dim must be even")
@@ -31,9 +31,10 @@ def _act_and_mul(kind: str, input: torch.Tensor, out: Optional[torch.Tensor], en
         x2 = x2.contiguous()
     o2 = out.view(-1, d)
     pdl = device_support_pdl(input.device) if enable_pdl is None else enable_pdl
+    # row_list: row_map is the list of live rows (visit only those) instead of a per-row validity map
     jit.load("activation").call(
-        "act_and_mul", x2, o2, x2.shape[0], d, x2.stride(0), o2.stride(0), _ACT[kind], 1 if gate_second else 0,
-        row_map, dtype_code(input.dtype),
+        "act_and_mul", x2, o2, row_map.numel() if row_list else x2.shape[0], d, x2.stride(0), o2.stride(0), _ACT[kind],
+        1 if gate_second else 0, row_map, 1 if row_list else 0, dtype_code(input.dtype),
         1 if pdl else 0, stream_ptr(input),
     )
     return out

@@ -52,5 +52,5 @@ from .collectives import (  # noqa: F401,E402
     decode_cp_a2a_workspace_size,
     run_mixed_comm,
 )
-from .gemm_allreduce import GemmAllReduce, gemm_allreduce  # noqa: F401,E402
+from .gemm_allreduce import GemmAllReduce, gemm_allreduce, gemm_reduce_scatter  # noqa: F401,E402
 from .all_gather_matmul import AllGatherMatmul, all_gather_matmul  # noqa: F401,E402

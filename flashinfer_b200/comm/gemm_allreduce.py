@@ -76,13 +76,61 @@ class GemmAllReduce:
         self._mod.call("gemm_allreduce_nt", a, w, stage, target, M, N, K, a.stride(0), w.stride(0), N, dtype_code(a.dtype), stab,
                        self._flag_tab, self._out_tab if two_shot else None, self._done_tab, _ptr(mc(soff)), _ptr(mc(self._flag_off)),
                        _ptr(mc(self._out_off) if two_shot else 0), self._expect, self._done_epoch, self.rank, self.world,
-                       1 if two_shot else 0, _MAX_TILES, bn, 1, stream_ptr(a))
+                       1 if two_shot else 0, _MAX_TILES, bn, 0, 0, None, None, 1, stream_ptr(a))
         if two_shot:
             if out is not None:
                 out.copy_(target)
                 return out
             return target.clone()
         return target
+
+
+    def reduce_scatter(self, a: torch.Tensor, w: torch.Tensor, residual: Optional[torch.Tensor] = None,
+                       rms_weight: Optional[torch.Tensor] = None, eps: float = 1e-6, out: Optional[torch.Tensor] = None,
+                       bn: int = 0):
+        """``GEMM -> reduce-scatter (-> + residual -> RMSNorm)`` of sequence-parallel tensor parallelism, one GEMM kernel per
+        rank: rank ``r`` ends up with rows ``[r * M / world, (r + 1) * M / world)`` of ``sum_ranks(a @ w.T)``.
+
+        The GEMM epilogue stores tiles to the symmetric staging buffer; the same kernel's reduce warps pull ONLY the rows
+        this rank owns through the switch (``multimem.ld_reduce``), add the ``residual`` shard, write the local shard and
+        accumulate each row's sum of squares, so the RMSNorm that follows is a single scale pass (``rs_rmsnorm``).
+
+        Returns ``shard`` (``[M / world, N]``; it is ``sum + residual`` when ``residual`` is given), or
+        ``(normed, shard)`` when ``rms_weight`` is given.  BASELINE config "Llama-3-70B TP=8 GEMM->reduce-scatter +
+        add-RMSNorm fusion"; reference analogue: flashinfer/comm/trtllm_ar.py allreduce-fusion patterns applied per shard."""
+        M, K = a.shape
+        N = w.shape[0]
+        if N != self.n or M > self.max_m or a.dtype != self.dtype or w.dtype != self.dtype:
+            raise ValueError("GemmAllReduce.reduce_scatter: shape / dtype does not match the communicator")
+        if M % self.world:
+            raise ValueError("reduce_scatter: M must be divisible by the group size")
+        rpr = M // self.world
+        if a.stride(1) != 1 or w.stride(1) != 1:
+            a, w = a.contiguous(), w.contiguous()
+        if residual is not None:
+            if residual.shape != (rpr, N) or residual.dtype != a.dtype:
+                raise ValueError("reduce_scatter: residual must be the local [M / world, N] shard")
+            residual = residual.contiguous()
+        shard = out if out is not None else torch.empty(rpr, N, dtype=a.dtype, device=a.device)
+        if shard.stride(1) != 1 or shard.stride(0) != N:
+            raise ValueError("reduce_scatter: out must be a contiguous [M / world, N] tensor")
+        sumsq = None
+        if rms_weight is not None:
+            if getattr(self, "_sumsq", None) is None or self._sumsq.numel() < rpr:
+                self._sumsq = torch.zeros(max(rpr, self.max_m // self.world + 1), dtype=torch.float32, device=a.device)
+            sumsq = self._sumsq
+        self._turn ^= 1
+        stage, soff, stab = self._stage[self._turn]
+        mc = self.heap.mc if self.use_nvls else (lambda off: 0)
+        self._mod.call("gemm_allreduce_nt", a, w, stage, shard, M, N, K, a.stride(0), w.stride(0), N, dtype_code(a.dtype), stab,
+                       self._flag_tab, None, self._done_tab, _ptr(mc(soff)), _ptr(mc(self._flag_off)), _ptr(0), self._expect,
+                       self._done_epoch, self.rank, self.world, 2, _MAX_TILES, bn, rpr, N, residual, sumsq, 1, stream_ptr(a))
+        if rms_weight is None:
+            return shard
+        normed = torch.empty_like(shard)
+        self._mod.call("rs_rmsnorm", shard, normed, rms_weight.to(a.dtype).contiguous(), sumsq, rpr, N, N, N, float(eps),
+                       dtype_code(a.dtype), 1, stream_ptr(a))
+        return normed, shard
 
 
 _CACHE: dict = {}
@@ -98,3 +146,16 @@ def gemm_allreduce(a: torch.Tensor, w: torch.Tensor, group: Optional[dist.Proces
         comm = GemmAllReduce(g, max(a.shape[0], 8192), w.shape[0], a.dtype)
         _CACHE[key] = comm
     return comm(a, w, out, two_shot)
+
+
+def gemm_reduce_scatter(a: torch.Tensor, w: torch.Tensor, group: Optional[dist.ProcessGroup] = None,
+                        residual: Optional[torch.Tensor] = None, rms_weight: Optional[torch.Tensor] = None, eps: float = 1e-6,
+                        out: Optional[torch.Tensor] = None):
+    """Functional form of :meth:`GemmAllReduce.reduce_scatter` (cached communicator)."""
+    g = group if group is not None else dist.group.WORLD
+    key = (id(g), w.shape[0], a.dtype)
+    comm = _CACHE.get(key)
+    if comm is None or comm.max_m < a.shape[0]:
+        comm = GemmAllReduce(g, max(a.shape[0], 8192), w.shape[0], a.dtype)
+        _CACHE[key] = comm
+    return comm.reduce_scatter(a, w, residual, rms_weight, eps, out)

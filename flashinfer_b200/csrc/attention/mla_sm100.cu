@@ -10,13 +10,17 @@
 //
 // B200-first design:
 //  * all (<=128) heads of one query token form the MMA-M dimension (MQA: every head shares the latent KV).
-//  * O (128 x 512 fp32) would fill all 512 TMEM columns, so a CTA owns one 256-wide half of d_v
-//    (grid.y = 2) and recomputes S; TMEM map: S0 | S1 (32 cols each) | O (256 cols).
-//  * Q (128 x 576 bf16 = 144 KB) stays resident in smem as the K-major A operand; the latent cache is
-//    streamed in 32-token tiles (36 KB: 9 x 64-column SW128 chunks) through a 2-stage TMA ring; the
-//    same smem tile is the B operand of QK^T (K-major) and, for its 256-column half, of P.V (MN-major).
-//  * P (bf16) is written over S in TMEM and consumed as the TMEM A operand; O is rescaled lazily.
-//  * split-KV: grid.x = sum of per-request chunk counts; partial (o, lse) are merged by the cascade op.
+//  * O (128 x 512 fp32) would fill all 512 TMEM columns, so a work item runs on a CLUSTER OF TWO CTAs that split the
+//    576-wide latent dimension: CTA 0 owns ckv[0:256), CTA 1 owns ckv[256:512) + kpe.  Each CTA keeps only ITS slice of Q
+//    resident (64 / 80 KB instead of 144 KB), streams only ITS slice of the latent cache (half the bytes, which leaves room
+//    for a 5-deep TMA ring of 32-token tiles), computes a PARTIAL S over its slice of the reduction dimension, and the two
+//    partials are exchanged through distributed shared memory (st.shared::cluster + a remote mbarrier arrive per thread)
+//    and summed; both CTAs then run the same softmax and each accumulates O for its own 256 d_v columns - which are exactly
+//    the ckv columns it already holds (the same smem tile is the K-major B operand of QK^T and the MN-major B of P.V).
+//    No FLOP and no cache byte is duplicated across the pair.
+//  * TMEM map: S0 | S1 (32 cols each, P is written over S as the TMEM A operand of P.V) | O (256 cols); O rescaled lazily.
+//  * split-KV: grid = 2 x sum of per-request chunk counts; partial (o, lse) are folded by mla_merge_kernel (PDL-chained in
+//    the same host call, all SMs).
 #include <fib200/common.cuh>
 #include <fib200/ptx.cuh>
 #include <type_traits>
@@ -36,29 +40,31 @@ constexpr int kWorkInts = 8;
 
 struct MlaParams {
   const int32_t* kv_indices;
-  const int32_t* work;  // [nwork][8] {q_row, kv_page_start, kv_begin(token), kv_end(token), kv_len, out_slot, num_pages, first part: (kmax << 16) | nparts else 0}
+  const int32_t* work;  // [nwork][8] {q_row, kv_page_start, kv_begin(token), kv_end(token), kv_len, out_slot, num_pages, -}
   void* out;            // final bf16/f16 [n, H, 512]            (when partial == nullptr)
   float* partial_o;     // [slots][H][512] fp32                  (split-KV)
-  float* partial_lse;   // [2 dv-halves][slots][H] (each half-CTA keeps its own copy: the halves merge independently)
+  float* partial_lse;   // [slots][H]
   float* lse;           // optional final lse [n, H]
-  int* merge_counters;  // [n_q][2] zero-initialised, self-resetting; null = no in-kernel merge
-  int64_t lse_half_stride;  // slots * H
   int num_heads, page_size;
   int64_t o_stride_n, o_stride_h;
   float sm_scale_log2;
 };
 
 struct Smem {
-  static constexpr int kStages = 2;
-  static constexpr int kQBytes = kChunksQK * kHeads * 128;   // 147456
-  static constexpr int kTileBytes = kChunksQK * kTile * 128;  // 36864
-  static constexpr int kChunkBytes = kTile * 128;             // 4096
+  static constexpr int kStages = 5;
+  static constexpr int kMaxChunks = 5;                         // CTA 1: 4 ckv chunks + kpe
+  static constexpr int kQBytes = kMaxChunks * kHeads * 128;    // 81920
+  static constexpr int kChunkBytes = kTile * 128;              // 4096
+  static constexpr int kTileBytes = kMaxChunks * kChunkBytes;  // 20480
+  static constexpr int kXchgBytes = kHeads * kTile * 4;        // 16384: partial S of the peer, one buffer per S buffer
   static constexpr int kOffQ = 0;
   static constexpr int kOffK = kQBytes;
-  static constexpr int kOffBar = kOffK + kStages * kTileBytes;
-  static constexpr int kNumBars = 2 * kStages + 1 /*q_full*/ + 2 /*s_full*/ + 2 /*p_ready*/ + 1 /*o_done*/;
+  static constexpr int kOffX = kOffK + kStages * kTileBytes;
+  static constexpr int kOffBar = kOffX + 2 * kXchgBytes;
+  static constexpr int kNumBars = 2 * kStages + 1 /*q_full*/ + 2 /*s_full*/ + 2 /*p_ready*/ + 1 /*o_done*/ + 2 /*x_full*/;
   static constexpr int kTotal = kOffBar + kNumBars * 8 + 16 + 1024;
 };
+static_assert(Smem::kTotal <= 227 * 1024, "MLA smem budget");
 
 __device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
   uint32_t r;
@@ -72,7 +78,7 @@ __device__ __forceinline__ uint32_t pack2_f16(float lo, float hi) {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
 mla_decode_kernel(const __grid_constant__ CUtensorMap tmQn, const __grid_constant__ CUtensorMap tmQp,
                   const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmP, const MlaParams p,
                   uint32_t idesc_qk, uint32_t idesc_pv) {
@@ -86,11 +92,13 @@ mla_decode_kernel(const __grid_constant__ CUtensorMap tmQn, const __grid_constan
   uint64_t* s_full = q_full + 1;   // [2]
   uint64_t* p_ready = s_full + 2;  // [2]
   uint64_t* o_done = p_ready + 2;  // [1]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_done + 1);
+  uint64_t* x_full = o_done + 1;   // [2] peer's partial S landed in my exchange buffer (128 remote arrivals)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(x_full + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int half = blockIdx.y;  // which 256-wide slice of d_v
-  const int32_t* wk = p.work + blockIdx.x * kWorkInts;
+  const int half = int(ptx::cluster_ctarank());  // 0: ckv[0:256)   1: ckv[256:512) + kpe   (also: which d_v half)
+  const int nch = half == 0 ? 4 : 5;             // 64-column chunks of the latent dimension this CTA owns
+  const int32_t* wk = p.work + (blockIdx.x >> 1) * kWorkInts;
   const int q_row = wk[0], page_start = wk[1], kv_begin = wk[2], kv_end = wk[3], out_slot = wk[5], num_pages = wk[6];
   const int ntiles = (kv_end - kv_begin + kTile - 1) / kTile;
   const int ps = p.page_size;
@@ -108,6 +116,7 @@ mla_decode_kernel(const __grid_constant__ CUtensorMap tmQn, const __grid_constan
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&s_full[i], 1);
       ptx::mbar_init(&p_ready[i], 128);
+      ptx::mbar_init(&x_full[i], 128);
     }
     ptx::mbar_init(o_done, 1);
     ptx::fence_mbar_init();
@@ -117,7 +126,7 @@ mla_decode_kernel(const __grid_constant__ CUtensorMap tmQn, const __grid_constan
     ptx::tmem_relinquish<1>();
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  ptx::cluster_sync();  // barriers of both CTAs are initialised before any remote arrive (also a CTA-wide barrier)
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t tm_s = tmem_base;        // S0 at +0, S1 at +32
@@ -128,16 +137,19 @@ mla_decode_kernel(const __grid_constant__ CUtensorMap tmQn, const __grid_constan
   if (warp == 2) {
     // ============================ Q loader (once) ============================
     if (lane == 0) {
-      ptx::mbar_arrive_expect_tx(q_full, S::kQBytes);
-#pragma unroll
-      for (int c = 0; c < 8; ++c)
-        ptx::tma_load_3d(smem + S::kOffQ + c * (kHeads * 128), &tmQn, q_full, c * 64, 0, q_row, ptx::kEvictFirst);
-      ptx::tma_load_3d(smem + S::kOffQ + 8 * (kHeads * 128), &tmQp, q_full, 0, 0, q_row, ptx::kEvictFirst);
+      ptx::mbar_arrive_expect_tx(q_full, nch * kHeads * 128);
+      for (int lc = 0; lc < nch; ++lc) {
+        const int gc = half * 4 + lc;  // chunk of the 576-wide latent dimension
+        if (gc < 8)
+          ptx::tma_load_3d(smem + S::kOffQ + lc * (kHeads * 128), &tmQn, q_full, gc * 64, 0, q_row, ptx::kEvictFirst);
+        else
+          ptx::tma_load_3d(smem + S::kOffQ + lc * (kHeads * 128), &tmQp, q_full, 0, 0, q_row, ptx::kEvictFirst);
+      }
     }
   } else if (warp == 0 || warp == 3) {
     // ============================ latent-cache producers ============================
-    // warp 0: ckv chunks 0..4, warp 3: ckv chunks 5..7 + kpe.  One TMA box = (rows of one page) x 64 columns.
-    const int c_lo = (warp == 0) ? 0 : 5, c_hi = (warp == 0) ? 5 : 9;
+    // warp 0: local chunks 0..1, warp 3: the rest.  One TMA box = (rows of one page) x 64 columns.
+    const int c_lo = (warp == 0) ? 0 : 2, c_hi = (warp == 0) ? 2 : nch;
     int st = 0;
     uint32_t ph = 0;
     for (int j = 0; j < ntiles; ++j) {
@@ -147,7 +159,7 @@ mla_decode_kernel(const __grid_constant__ CUtensorMap tmQn, const __grid_constan
       const int nbox = kTile / rows_per_box;
       if (lane == 0) {
         ptx::mbar_wait(&k_empty[st], ph ^ 1);
-        if (warp == 0) ptx::mbar_arrive_expect_tx(&k_full[st], S::kTileBytes);
+        if (warp == 0) ptx::mbar_arrive_expect_tx(&k_full[st], nch * S::kChunkBytes);
       }
       __syncwarp();
       if (lane < nbox) {
@@ -159,8 +171,9 @@ mla_decode_kernel(const __grid_constant__ CUtensorMap tmQn, const __grid_constan
         const int off = tok % ps;
         uint8_t* dst = smem + S::kOffK + st * S::kTileBytes + lane * rows_per_box * 128;
         for (int c = c_lo; c < c_hi; ++c) {
-          if (c < 8)
-            ptx::tma_load_3d(dst + c * S::kChunkBytes, &tmC, &k_full[st], c * 64, off, page, ptx::kEvictFirst);
+          const int gc = half * 4 + c;
+          if (gc < 8)
+            ptx::tma_load_3d(dst + c * S::kChunkBytes, &tmC, &k_full[st], gc * 64, off, page, ptx::kEvictFirst);
           else
             ptx::tma_load_3d(dst + c * S::kChunkBytes, &tmP, &k_full[st], 0, off, page, ptx::kEvictFirst);
         }
@@ -182,7 +195,7 @@ mla_decode_kernel(const __grid_constant__ CUtensorMap tmQn, const __grid_constan
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
         // B = ckv[kv rows, my 256 dv columns]: MN-major SW128; chunk stride (LBO) = 4096, 8-row group (SBO) = 1024
-        const uint32_t v_addr = ptx::smem_u32(smem + S::kOffK + stage * S::kTileBytes) + half * 4 * S::kChunkBytes;
+        const uint32_t v_addr = ptx::smem_u32(smem + S::kOffK + stage * S::kTileBytes);  // local chunks 0..3 = my d_v half
         const uint64_t db = ptx::make_smem_desc(v_addr, S::kChunkBytes, 1024, ptx::kSwz128);
 #pragma unroll
         for (int k = 0; k < kTile / 16; ++k)
@@ -200,8 +213,7 @@ mla_decode_kernel(const __grid_constant__ CUtensorMap tmQn, const __grid_constan
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
         const uint32_t k_addr = ptx::smem_u32(smem + S::kOffK + st * S::kTileBytes);
-#pragma unroll
-        for (int k = 0; k < kDqk / 16; ++k) {
+        for (int k = 0; k < nch * 4; ++k) {
           const int c = k / 4, o = (k % 4) * 32;
           const uint64_t da = ptx::make_smem_desc(q_addr + c * (kHeads * 128) + o, 16, 1024, ptx::kSwz128);
           const uint64_t db = ptx::make_smem_desc(k_addr + c * S::kChunkBytes + o, 16, 1024, ptx::kSwz128);
@@ -234,6 +246,30 @@ mla_decode_kernel(const __grid_constant__ CUtensorMap tmQn, const __grid_constan
       uint32_t r[32];
       ptx::tmem_ld_x32(tm_s + lane_addr + b * 32, r);
       ptx::tmem_ld_wait();
+      {
+        // ---- exchange partial S with the peer CTA (it reduced over the other slice of the latent dimension) ----
+        // row-major [128][32] fp32 with the 16-byte vectors of a row XOR-swizzled by (row & 7): conflict-free both ways.
+        // Buffer reuse needs no extra handshake: the peer only writes buffer b for tile j + 2 after it has received ALL
+        // 128 of my tile-(j + 1) arrivals, and each of my threads arrives for j + 1 after it has read tile j's buffer.
+        const uint32_t xoff = uint32_t(S::kOffX + b * S::kXchgBytes + row * 128);
+        const uint32_t x_remote = ptx::mapa(ptx::smem_u32(smem + xoff), uint32_t(half ^ 1));
+#pragma unroll
+        for (int v = 0; v < 8; ++v)
+          ptx::st_dsmem_v4(x_remote + ((v ^ (row & 7)) << 4),
+                           make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]), __uint_as_float(r[4 * v + 2]),
+                                       __uint_as_float(r[4 * v + 3])));
+        ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&x_full[b]), uint32_t(half ^ 1)));
+        ptx::mbar_wait_cluster(&x_full[b], (j >> 1) & 1);
+        const float4* xl = reinterpret_cast<const float4*>(smem + xoff);
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+          const float4 t = xl[v ^ (row & 7)];
+          r[4 * v] = __float_as_uint(__uint_as_float(r[4 * v]) + t.x);
+          r[4 * v + 1] = __float_as_uint(__uint_as_float(r[4 * v + 1]) + t.y);
+          r[4 * v + 2] = __float_as_uint(__uint_as_float(r[4 * v + 2]) + t.z);
+          r[4 * v + 3] = __float_as_uint(__uint_as_float(r[4 * v + 3]) + t.w);
+        }
+      }
       const int valid = kv_end - tok0;  // columns >= valid are past the chunk
       float tmax = -INFINITY;
 #pragma unroll
@@ -281,9 +317,9 @@ mla_decode_kernel(const __grid_constant__ CUtensorMap tmQn, const __grid_constan
         const int stg = j % S::kStages;
         ptx::mbar_wait(&k_full[stg], (j / S::kStages) & 1);
         uint8_t* tile = smem + S::kOffK + stg * S::kTileBytes;
-        const int nz = (kTile - valid) * 8 * 8;  // rows x 8 ckv chunks x 8 int4 per 128 B row
+        const int nz = (kTile - valid) * 4 * 8;  // rows x my 4 ckv chunks x 8 int4 per 128 B row
         for (int i = threadIdx.x - 128; i < nz; i += 128) {
-          const int rrow = valid + i / 64, c = (i / 8) % 8, e = i % 8;
+          const int rrow = valid + i / 32, c = (i / 8) % 4, e = i % 8;
           reinterpret_cast<int4*>(tile + c * S::kChunkBytes + rrow * 128)[e] = make_int4(0, 0, 0, 0);
         }
         ptx::fence_proxy_async_smem();
@@ -329,60 +365,8 @@ mla_decode_kernel(const __grid_constant__ CUtensorMap tmQn, const __grid_constan
         }
       }
     }
-    const int nparts = wk[7] & 0xffff, kmax = wk[7] >> 16;
     if (p.partial_o) {
-      if (row_ok) p.partial_lse[half * p.lse_half_stride + int64_t(out_slot) * p.num_heads + row] = lse_v;
-      // ---- in-kernel split-KV merge: the last part of this (query row, dv half) to arrive folds all parts and writes the
-      //      final bf16 output (no separate merge / copy kernels, no host-side initialisation of the partial buffers)
-      __threadfence();
-      ptx::named_bar_sync(1, 128);
-      __shared__ int s_last;
-      if (threadIdx.x == 128) {
-        const int old = atomicAdd(&p.merge_counters[q_row * 2 + half], 1);
-        const int last = (old == nparts - 1);
-        if (last) p.merge_counters[q_row * 2 + half] = 0;
-        s_last = last;
-      }
-      ptx::named_bar_sync(1, 128);
-      if (s_last) {
-        __threadfence();
-        __shared__ float s_w[8][kHeads];  // normalised merge weight of (part, head)
-        const int64_t slot0 = int64_t(q_row) * kmax;
-        if (row_ok) {
-          float mx = -INFINITY;
-          for (int sidx = 0; sidx < nparts; ++sidx)
-            mx = fmaxf(mx, __ldcg(p.partial_lse + half * p.lse_half_stride + (slot0 + sidx) * p.num_heads + row));
-          float den = 0.f;
-          for (int sidx = 0; sidx < nparts; ++sidx) {
-            const float ls = __ldcg(p.partial_lse + half * p.lse_half_stride + (slot0 + sidx) * p.num_heads + row);
-            const float w = (mx == -INFINITY) ? 0.f : ptx::ex2(ls - mx);
-            s_w[sidx][row] = w;
-            den += w;
-          }
-          const float invd = den > 0.f ? 1.f / den : 0.f;
-          for (int sidx = 0; sidx < nparts; ++sidx) s_w[sidx][row] *= invd;
-          if (half == 0 && p.lse) p.lse[int64_t(q_row) * p.num_heads + row] = den > 0.f ? mx + ptx::lg2(den) : -INFINITY;
-        }
-        ptx::named_bar_sync(1, 128);
-        // cooperative, coalesced fold: the 128 threads sweep one head row (256 fp32 = 1 KB per part) at a time
-        const int t2 = (threadIdx.x - 128) * 2;  // two columns per thread
-        T* obase = reinterpret_cast<T*>(p.out) + int64_t(q_row) * p.o_stride_n + half * kDvHalf + t2;
-        const float* pbase = p.partial_o + slot0 * p.num_heads * kCkv + half * kDvHalf + t2;
-#pragma unroll 4
-        for (int h = 0; h < p.num_heads; ++h) {
-          float a0 = 0.f, a1 = 0.f;
-          for (int sidx = 0; sidx < nparts; ++sidx) {
-            const float2 v = __ldcg(reinterpret_cast<const float2*>(pbase + (int64_t(sidx) * p.num_heads + h) * kCkv));
-            const float w = s_w[sidx][h];
-            a0 += w * v.x;
-            a1 += w * v.y;
-          }
-          T* dst = obase + int64_t(h) * p.o_stride_h;
-          struct alignas(4) Pair { T a, b; } pr{from_f32<T>(a0), from_f32<T>(a1)};
-          *reinterpret_cast<Pair*>(dst) = pr;  // one 4-byte store per thread -> 512 B contiguous per head row
-        }
-      }
-      ptx::named_bar_sync(1, 128);  // s_last is reused by the next work item
+      if (row_ok && half == 0) p.partial_lse[int64_t(out_slot) * p.num_heads + row] = lse_v;
     } else if (row_ok && half == 0 && p.lse) {
       p.lse[int64_t(q_row) * p.num_heads + row] = lse_v;
     }
@@ -390,19 +374,63 @@ mla_decode_kernel(const __grid_constant__ CUtensorMap tmQn, const __grid_constan
 
   ptx::grid_dep_launch();
   ptx::tc_fence_before();
-  __syncthreads();
+  ptx::cluster_sync();  // neither CTA may retire while its peer can still write into its exchange buffers
   if (warp == 2) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<1>(tmem_base, 512);
   }
 }
 
+// Fold the split-KV partials of one query row: out[h] = sum_s w_s * partial_o[s][h], w_s = 2^(lse_s - max) / sum.
+// grid (n_q, ceil(H / 8)), one warp per head, each lane 4 x float4 -> 512 B coalesced per load instruction.
+template <typename T>
+__global__ void __launch_bounds__(256)
+mla_merge_kernel(const float* __restrict__ partial_o, const float* __restrict__ partial_lse,
+                 const int32_t* __restrict__ row_parts, T* __restrict__ out, float* __restrict__ lse, int num_heads, int kmax,
+                 int64_t o_stride_n, int64_t o_stride_h) {
+  ptx::grid_dep_wait();
+  ptx::grid_dep_launch();
+  const int q_row = blockIdx.x, h = blockIdx.y * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (h >= num_heads) return;
+  const int nparts = row_parts[q_row];
+  const int64_t slot0 = int64_t(q_row) * kmax;
+  float mx = -INFINITY;
+  for (int s = 0; s < nparts; ++s) mx = fmaxf(mx, partial_lse[(slot0 + s) * num_heads + h]);
+  float den = 0.f;
+  float4 acc[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = 0; s < nparts; ++s) {
+    const float ls = partial_lse[(slot0 + s) * num_heads + h];
+    const float w = (mx == -INFINITY) ? 0.f : ptx::ex2(ls - mx);
+    den += w;
+    const float4* src = reinterpret_cast<const float4*>(partial_o + ((slot0 + s) * num_heads + h) * kCkv);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 v = __ldcs(src + lane + 32 * i);
+      acc[i].x += w * v.x;
+      acc[i].y += w * v.y;
+      acc[i].z += w * v.z;
+      acc[i].w += w * v.w;
+    }
+  }
+  const float inv = den > 0.f ? 1.f / den : 0.f;
+  T* dst = out + int64_t(q_row) * o_stride_n + int64_t(h) * o_stride_h;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    struct alignas(8) Quad { T a, b, c, d; } q{from_f32<T>(acc[i].x * inv), from_f32<T>(acc[i].y * inv),
+                                               from_f32<T>(acc[i].z * inv), from_f32<T>(acc[i].w * inv)};
+    *reinterpret_cast<Quad*>(dst + (lane + 32 * i) * 4) = q;
+  }
+  if (lse && lane == 0) lse[int64_t(q_row) * num_heads + h] = den > 0.f ? mx + ptx::lg2(den) : -INFINITY;
+}
+
 }  // namespace
 
 // q_nope [n, H, 512], q_pe [n, H, 64] (strides in elements), ckv_cache [pages, page, 512], kpe_cache [pages, page, 64]
 extern "C" int mla_decode_run(void* q_nope, void* q_pe, void* ckv_cache, void* kpe_cache, void* kv_indices, void* work,
-                              int64_t num_work, void* out, void* partial_o, void* partial_lse, void* merge_counters,
-                              int64_t lse_half_stride, void* lse, int64_t n_q, int64_t num_heads, int64_t page_size, int64_t num_pages_total, int64_t qn_sn, int64_t qn_sh,
+                              int64_t num_work, void* out, void* partial_o, void* partial_lse, void* row_parts,
+                              int64_t kmax, void* lse, int64_t n_q, int64_t num_heads, int64_t page_size, int64_t num_pages_total, int64_t qn_sn, int64_t qn_sh,
                               int64_t qp_sn, int64_t qp_sh, int64_t ckv_sp, int64_t ckv_sn, int64_t kpe_sp, int64_t kpe_sn,
                               int64_t o_sn, int64_t o_sh, double sm_scale, int64_t dtype, int64_t pdl, int64_t stream_) {
   FIB_CHECK(num_heads >= 1 && num_heads <= kHeads, "mla_sm100: num_heads must be <= 128");
@@ -444,9 +472,7 @@ extern "C" int mla_decode_run(void* q_nope, void* q_pe, void* ckv_cache, void* k
   p.out = out;
   p.partial_o = (float*)partial_o;
   p.partial_lse = (float*)partial_lse;
-  p.merge_counters = (int*)merge_counters;
-  p.lse_half_stride = lse_half_stride;
-  FIB_CHECK(!partial_o || merge_counters, "mla_sm100: split-KV needs merge counters");
+  FIB_CHECK(!partial_o || (row_parts && partial_lse && kmax >= 1), "mla_sm100: split-KV needs the per-row part counts");
   p.lse = (float*)lse;
   p.num_heads = (int)num_heads;
   p.page_size = (int)page_size;
@@ -457,7 +483,8 @@ extern "C" int mla_decode_run(void* q_nope, void* q_pe, void* ckv_cache, void* k
   const uint32_t fmt = f16 ? ptx::kFmtF16 : ptx::kFmtBF16;
   const uint32_t idesc_qk = ptx::make_idesc_f16(fmt, kHeads, kTile, 0, 0);
   const uint32_t idesc_pv = ptx::make_idesc_f16(fmt, kHeads, kDvHalf, 0, 1);
-  LaunchCfg lc(dim3((unsigned)num_work, 2), dim3(256), Smem::kTotal, stream, pdl != 0);
+  LaunchCfg lc(dim3((unsigned)num_work * 2), dim3(256), Smem::kTotal, stream, pdl != 0);  // clusters of 2 (kernel attribute)
+  LaunchCfg lm(dim3((unsigned)n_q, (unsigned)((num_heads + 7) / 8)), dim3(256), 0, stream, pdl != 0);
   if (f16) {
     static bool set = false;
     if (!set) {
@@ -465,6 +492,9 @@ extern "C" int mla_decode_run(void* q_nope, void* q_pe, void* ckv_cache, void* k
       set = true;
     }
     FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, mla_decode_kernel<__half>, tmQn, tmQp, tmC, tmP, p, idesc_qk, idesc_pv));
+    if (partial_o)
+      FIB_CUDA_CHECK(cudaLaunchKernelEx(&lm.cfg, mla_merge_kernel<__half>, (const float*)partial_o, (const float*)partial_lse,
+                                        (const int32_t*)row_parts, (__half*)out, (float*)lse, (int)num_heads, (int)kmax, o_sn, o_sh));
   } else {
     static bool set = false;
     if (!set) {
@@ -473,6 +503,10 @@ extern "C" int mla_decode_run(void* q_nope, void* q_pe, void* ckv_cache, void* k
       set = true;
     }
     FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, mla_decode_kernel<__nv_bfloat16>, tmQn, tmQp, tmC, tmP, p, idesc_qk, idesc_pv));
+    if (partial_o)
+      FIB_CUDA_CHECK(cudaLaunchKernelEx(&lm.cfg, mla_merge_kernel<__nv_bfloat16>, (const float*)partial_o,
+                                        (const float*)partial_lse, (const int32_t*)row_parts, (__nv_bfloat16*)out, (float*)lse,
+                                        (int)num_heads, (int)kmax, o_sn, o_sh));
   }
   return 0;
 }

@@ -43,18 +43,25 @@ __global__ void __launch_bounds__(256)
 fp4_quantize_kernel(const T* __restrict__ x, uint8_t* __restrict__ q, uint8_t* __restrict__ sf,
                     const float* __restrict__ global_scale, int64_t batch, int64_t M, int64_t K, int64_t ldx,
                     int64_t x_batch_stride, int swizzled, int64_t sf_batch_stride, const int32_t* __restrict__ row_map,
-                    int gather, int gated) {
+                    int gather, int gated, const int32_t* __restrict__ row_list, int64_t n_list, int list_div) {
   const int64_t kc_total = K / VEC;
   const int64_t kc_pad = (kc_total + 3) / 4 * 4;
-  const int64_t total = batch * M * kc_total;
+  // row_list (MoE): only the n_list live destination rows are visited (row_list[j] = permuted row of expanded entry j, -1 =
+  // not local); with `gather` the source row is token j / list_div.  Otherwise all batch * M rows are walked.
+  const int64_t total = row_list ? n_list * kc_total : batch * M * kc_total;
   ptx::grid_dep_wait();
   const float gs = global_scale ? __ldg(global_scale) : 1.f;
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
     const int64_t kc = i % kc_total;
-    const int64_t m = (i / kc_total) % M;
-    const int64_t b = i / (kc_total * M);
+    int64_t m = (i / kc_total) % M;
+    const int64_t b = row_list ? 0 : i / (kc_total * M);
     int64_t src_row = m;
-    if (row_map) {
+    if (row_list) {
+      const int64_t j = i / kc_total;
+      m = row_list[j];
+      if (m < 0) continue;
+      src_row = gather ? j / list_div : m;
+    } else if (row_map) {
       const int rm = row_map[m];
       if (rm < 0) continue;     // MoE padding row (scale bytes stay as initialised: finite)
       if (gather) src_row = rm; // fused MoE gather: quantise x[token(m)] straight into the permuted row m
@@ -108,6 +115,77 @@ fp4_quantize_kernel(const T* __restrict__ x, uint8_t* __restrict__ q, uint8_t* _
     }
     const int64_t sf_off = swizzled ? sf_swizzled_offset(m, kc, kc_pad) : m * kc_total + kc;
     sf[b * sf_batch_stride + sf_off] = sf_byte;
+  }
+  ptx::grid_dep_launch();
+}
+
+// ---------------------------------------------------------------- fp8 e4m3 with fp32 scales per 1 x 128 group (DeepSeek)
+// x [M, K] -> q [M, K] e4m3, scale [M, K/128] fp32 (scale = amax / 448).  8 lanes x 16 elements cover one group.
+// MoE modes as in fp4_quantize_kernel: row_list (visit only live rows; `gather`: source row = j / list_div) and `gated`
+// (row = [linear | gate] halves of width K, quantise silu(gate) * linear).
+template <typename T>
+__global__ void __launch_bounds__(256)
+fp8_group_quantize_kernel(const T* __restrict__ x, __nv_fp8_e4m3* __restrict__ q, float* __restrict__ scale, int64_t M,
+                          int64_t K, int64_t ldx, int gated, const int32_t* __restrict__ row_list, int64_t n_list,
+                          int gather, int list_div) {
+  const int64_t per_row = K / 16;  // threads per row
+  const int64_t total = (row_list ? n_list : M) * per_row;
+  ptx::grid_dep_wait();
+  // the grid-stride loop keeps whole warps together (total is a multiple of 8 lanes per group; per_row % 8 == 0)
+  for (int64_t i0 = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) & ~int64_t(31); i0 < total;
+       i0 += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t i = i0 + (threadIdx.x & 31);
+    const bool live = i < total;
+    const int64_t ii = live ? i : total - 1;
+    const int64_t c = ii % per_row;
+    int64_t m = ii / per_row, src_row = m;
+    bool skip = !live;
+    if (row_list) {
+      const int64_t j = m;
+      m = row_list[j];
+      if (m < 0) {
+        skip = true;
+        m = 0;
+      }
+      src_row = gather ? j / list_div : m;
+    }
+    float v[16];
+    if (!skip) {
+      const T* src = x + src_row * ldx + c * 16;
+#pragma unroll
+      for (int j = 0; j < 16; j += 8) {
+        const Vec16<T> raw = ld16(src + j);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[j + e] = to_f32(raw.v[e]);
+      }
+      if (gated) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 8) {
+          const Vec16<T> raw = ld16(src + K + j);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float g = to_f32(raw.v[e]);
+            v[j + e] *= g / (1.f + __expf(-g));
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = 0.f;
+    }
+    float amax = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) amax = fmaxf(amax, fabsf(v[j]));
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if (skip) continue;
+    const float sc = fmaxf(amax, 1e-10f) * (1.f / 448.f);
+    const float inv = 1.f / sc;
+    __nv_fp8_e4m3 o8[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) o8[j] = __nv_fp8_e4m3(v[j] * inv);
+    *reinterpret_cast<int4*>(q + m * K + c * 16) = *reinterpret_cast<const int4*>(o8);
+    if ((c & 7) == 0) scale[m * (K / 128) + c / 8] = sc;
   }
   ptx::grid_dep_launch();
 }
@@ -242,25 +320,43 @@ inline int grid_for(int64_t total, int threads = 256) {
 // vec = 16 (NVFP4, UE4M3 scale unless ue8m0) or 32 (MXFP4, UE8M0 scale)
 extern "C" int fp4_quantize(void* x, void* q, void* sf, void* global_scale, int64_t batch, int64_t M, int64_t K,
                             int64_t ldx, int64_t x_batch_stride, int64_t vec, int64_t ue8m0, int64_t swizzled,
-                            int64_t sf_batch_stride, void* row_map, int64_t gather, int64_t gated, int64_t dtype, int64_t pdl,
-                            int64_t stream_) {
+                            int64_t sf_batch_stride, void* row_map, int64_t gather, int64_t gated, void* row_list,
+                            int64_t n_list, int64_t list_div, int64_t dtype, int64_t pdl, int64_t stream_) {
   FIB_CHECK(vec == 16 || vec == 32, "fp4_quantize: sf_vec_size must be 16 or 32");
   FIB_CHECK(K % vec == 0 && ldx % 8 == 0, "fp4_quantize: K must be a multiple of sf_vec_size and rows 16B aligned");
   if (batch * M * K == 0) return 0;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  const int64_t total = batch * M * (K / vec);
+  FIB_CHECK(!row_list || (batch == 1 && list_div >= 1), "fp4_quantize: row_list needs batch == 1");
+  const int64_t total = (row_list ? n_list : batch * M) * (K / vec);
+  if (total == 0) return 0;
   LaunchCfg lc(dim3(grid_for(total)), dim3(256), 0, stream, pdl != 0);
   return FIB_DISPATCH_HALF(dtype, T, [&]() -> int {
     auto launch = [&](auto kern) -> int {
       FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, kern, (const T*)x, (uint8_t*)q, (uint8_t*)sf, (const float*)global_scale,
                                         batch, M, K, ldx, x_batch_stride, (int)swizzled, sf_batch_stride, (const int32_t*)row_map,
-                                        (int)gather, (int)gated));
+                                        (int)gather, (int)gated, (const int32_t*)row_list, n_list, (int)list_div));
       return 0;
     };
     if (vec == 16 && !ue8m0) return launch(fp4_quantize_kernel<T, 16, false>);
     if (vec == 16) return launch(fp4_quantize_kernel<T, 16, true>);
     if (ue8m0) return launch(fp4_quantize_kernel<T, 32, true>);
     return launch(fp4_quantize_kernel<T, 32, false>);
+  });
+}
+
+// 1 x 128 group fp8 quantisation (DeepSeek activations); see fp8_group_quantize_kernel for the MoE modes.
+extern "C" int fp8_group_quantize(void* x, void* q, void* scale, int64_t M, int64_t K, int64_t ldx, int64_t gated, void* row_list,
+                                  int64_t n_list, int64_t gather, int64_t list_div, int64_t dtype, int64_t pdl, int64_t stream_) {
+  FIB_CHECK(K % 128 == 0 && ldx % 8 == 0, "fp8_group_quantize: K must be a multiple of 128");
+  const int64_t total = (row_list ? n_list : M) * (K / 16);
+  if (total == 0) return 0;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  LaunchCfg lc(dim3(grid_for(total)), dim3(256), 0, stream, pdl != 0);
+  return FIB_DISPATCH_HALF(dtype, T, [&]() -> int {
+    FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, fp8_group_quantize_kernel<T>, (const T*)x, (__nv_fp8_e4m3*)q, (float*)scale, M, K,
+                                      ldx, (int)gated, (const int32_t*)row_list, n_list, (int)gather,
+                                      (int)(list_div > 0 ? list_div : 1)));
+    return 0;
   });
 }
 

@@ -62,8 +62,11 @@ __device__ __forceinline__ int block_reduce_sum_int(int v, int* sm) {
 
 // Block-wide inverse-CDF draw from the entries of `p` that satisfy `keep(x)`: returns the first index
 // whose running sum of kept entries exceeds `target` (or the last kept index for round-off), -1 if none.
-template <typename Keep>
+// kFraction: `target` is a fraction in [0, 1) of the kept mass (the scan's own total is used, no separate sum pass).
+template <bool kFraction = false, typename Keep>
 __device__ int block_sample(const float* __restrict__ p, int V, float target, Keep keep, float* smf, int* smi) {
+  // One pass + one block scan: thread t owns the contiguous index range [t * per, (t + 1) * per), sums its kept entries,
+  // a single block-wide exclusive scan locates the owner of `target`, and only that thread walks its range again.
   __shared__ float s_warp[32];
   __shared__ int s_found;
   __shared__ int s_last;
@@ -72,61 +75,85 @@ __device__ int block_sample(const float* __restrict__ p, int V, float target, Ke
     s_last = -1;
   }
   __syncthreads();
-  float running = 0.f;
-  const int chunk = blockDim.x * 4;
-  for (int base = 0; base < V; base += chunk) {
-    const int i0 = base + threadIdx.x * 4;
-    float x[4];
+  const int per = (((V + int(blockDim.x) - 1) / int(blockDim.x)) + 3) & ~3;
+  const int i0 = threadIdx.x * per;
+  const int i1 = min(V, i0 + per);
+  float local = 0.f;
+  int last_here = -1;
+  if (i0 < V) {
+    if ((reinterpret_cast<uintptr_t>(p + i0) & 15) == 0) {
+      int i = i0;
+      for (; i + 4 <= i1; i += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(p + i);
+        const float x[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int i = i0 + e;
-      const float v = (i < V) ? p[i] : 0.f;
-      x[e] = (i < V && keep(v)) ? v : 0.f;
+        for (int e = 0; e < 4; ++e)
+          if (keep(x[e]) && x[e] > 0.f) {
+            local += x[e];
+            last_here = i + e;
+          }
+      }
+      for (; i < i1; ++i) {
+        const float v = p[i];
+        if (keep(v) && v > 0.f) {
+          local += v;
+          last_here = i;
+        }
+      }
+    } else {
+      for (int i = i0; i < i1; ++i) {
+        const float v = p[i];
+        if (keep(v) && v > 0.f) {
+          local += v;
+          last_here = i;
+        }
+      }
     }
-    const float local = x[0] + x[1] + x[2] + x[3];
-    // warp inclusive scan of `local`
-    float incl = local;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  }
+  if (last_here >= 0) atomicMax(&s_last, last_here);
+  // block exclusive scan of `local`
+  float incl = local;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  float warp_off = 0.f;
+  {
+    const float wv = (lane < int(blockDim.x >> 5)) ? s_warp[lane] : 0.f;
+    float wincl = wv;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const float t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += t;
+      const float t = __shfl_up_sync(0xffffffffu, wincl, o);
+      if (lane >= o) wincl += t;
     }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    float warp_off = 0.f, total = 0.f;
+    warp_off = __shfl_sync(0xffffffffu, wincl - wv, warp);
+  }
+  const float excl = warp_off + incl - local;
+  if constexpr (kFraction) {
+    // total = inclusive value of the last thread; every warp's lane 31 wrote its inclusive warp sum to s_warp
+    float total = 0.f;
     {
-      const float wv = (lane < (blockDim.x >> 5)) ? s_warp[lane] : 0.f;
-      float wincl = wv;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const float t = __shfl_up_sync(0xffffffffu, wincl, o);
-        if (lane >= o) wincl += t;
-      }
-      warp_off = __shfl_sync(0xffffffffu, wincl - wv, warp);
-      total = __shfl_sync(0xffffffffu, wincl, 31);
+      const float wv = (lane < int(blockDim.x >> 5)) ? s_warp[lane] : 0.f;
+      total = warp_reduce_sum(wv);
     }
-    float excl = running + warp_off + incl - local;
-    // last kept index in this chunk (fallback for round-off)
-    int last_here = -1;
-#pragma unroll
-    for (int e = 0; e < 4; ++e)
-      if (x[e] > 0.f) last_here = i0 + e;
-    if (last_here >= 0) atomicMax(&s_last, last_here);
-    if (excl <= target && target < excl + local) {
-      float acc = excl;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        if (x[e] > 0.f && target < acc + x[e]) {
-          atomicCAS(&s_found, -1, i0 + e);
+    target *= total;
+  }
+  if (local > 0.f && excl <= target && target < excl + local) {
+    float acc = excl;
+    for (int i = i0; i < i1; ++i) {
+      const float v = p[i];
+      if (keep(v) && v > 0.f) {
+        if (target < acc + v) {
+          atomicCAS(&s_found, -1, i);
           break;
         }
-        acc += x[e];
+        acc += v;
       }
     }
-    running += total;
-    __syncthreads();
-    if (s_found >= 0) break;
   }
   __syncthreads();
   const int f = s_found >= 0 ? s_found : s_last;
@@ -246,14 +273,9 @@ sampling_kernel(const float* __restrict__ probs, int32_t* __restrict__ out, cons
       mx = block_reduce_max(mx, smf);
       thresh = mx * min_p;
     }
-    for (int i = threadIdx.x; i < V; i += blockDim.x) {
-      const float v = p[i];
-      if (v >= thresh) total += v;
-    }
-    total = block_reduce_sum(total, smf);
+    (void)total;
     const float u = curand_uniform(&st);
-    const float target = (1.f - u) * total;  // [0, total)
-    const int tok = block_sample(p, V, target, [=](float v) { return v >= thresh && v > 0.f; }, smf, smi);
+    const int tok = block_sample<true>(p, V, 1.f - u, [=](float v) { return v >= thresh; }, smf, smi);
     if (threadIdx.x == 0) {
       out[row] = tok < 0 ? 0 : tok;
       if (success) success[row] = tok >= 0;

@@ -47,8 +47,105 @@ struct ARP {
   uint32_t* expect;                // local: expected flag value per tile
   uint32_t* peer_done[kMaxRanks];  // two-shot end barrier slots [max_ctas][world]
   uint32_t* done_epoch;            // local [max_ctas]
-  int rank, world, two_shot;
+  int rank, world, two_shot;      // two_shot: 0 one-shot all-reduce | 1 two-shot all-reduce | 2 reduce-scatter (row shards)
+  int rows_per_rank;               // reduce-scatter: rank r owns rows [r * rows_per_rank, (r + 1) * rows_per_rank)
+  int64_t ldo;                     // reduce-scatter: leading dimension of the local out / residual shard
+  const void* residual;            // reduce-scatter: optional residual shard added to the reduced rows
+  float* sumsq;                    // reduce-scatter: optional per-row sum of squares of (sum + residual) for the fused RMSNorm
 };
+
+// Reduce-scatter tail of one tile: only the rows this rank owns are pulled (in-switch sum), the optional residual shard is
+// added, the result goes to the LOCAL out shard, and (optionally) the per-row sum of squares is accumulated for the RMSNorm
+// that follows (rs_norm_kernel).  Ranks that own no row of the tile neither wait nor read.
+template <typename OutT>
+__device__ __forceinline__ void rs_reduce_tile(const ARP& ar, OutT* __restrict__ out, int tm, int tn, int M, int N, int BN,
+                                               int64_t ldc, uint32_t want, int t, int tid) {
+  constexpr int VN = 16 / sizeof(OutT);
+  __shared__ float s_sq[BM];
+  const int lo = max(tm * BM, ar.rank * ar.rows_per_rank);
+  const int hi = min(min(tm * BM + BM, M), (ar.rank + 1) * ar.rows_per_rank);
+  if (lo >= hi) return;  // uniform over the 128 all-reduce threads
+  if (tid == 0) {
+    while (int32_t(ptx::ld_acquire_sys(ar.peer_flags[ar.rank] + t) - want) < 0) {
+    }
+  }
+  s_sq[tid] = 0.f;
+  asm volatile("bar.sync 2, 128;" ::: "memory");
+  const int vec_per_row = BN / VN;
+  const int rows = hi - lo;
+  for (int i = tid; i < rows * vec_per_row; i += 128) {
+    const int r = i / vec_per_row, v = i % vec_per_row;
+    const int col = tn * BN + v * VN;
+    if (col >= N) continue;
+    const int64_t off = (int64_t(lo + r) * ldc + col) * sizeof(OutT);
+    int4 res;
+    float accv[VN];
+    if (ar.mc_stage) {
+      if constexpr (std::is_same<OutT, __half>::value) res = ptx::multimem_ld_reduce_f16x8(ar.mc_stage + off);
+      else res = ptx::multimem_ld_reduce_bf16x8(ar.mc_stage + off);
+      const OutT* h = reinterpret_cast<const OutT*>(&res);
+#pragma unroll
+      for (int e = 0; e < VN; ++e) accv[e] = to_f32(h[e]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < VN; ++e) accv[e] = 0.f;
+      for (int p = 0; p < ar.world; ++p) {
+        int4 x;
+        asm volatile("ld.global.relaxed.sys.v4.s32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w)
+                     : "l"(ar.peer_stage[p] + off)
+                     : "memory");
+        const OutT* h = reinterpret_cast<const OutT*>(&x);
+#pragma unroll
+        for (int e = 0; e < VN; ++e) accv[e] += to_f32(h[e]);
+      }
+    }
+    const int64_t ooff = int64_t(lo + r - ar.rank * ar.rows_per_rank) * ar.ldo + col;
+    if (ar.residual) {
+      const Vec16<OutT> rv = ld16(reinterpret_cast<const OutT*>(ar.residual) + ooff);
+#pragma unroll
+      for (int e = 0; e < VN; ++e) accv[e] += to_f32(rv.v[e]);
+    }
+    Vec16<OutT> o;
+    float sq = 0.f;
+#pragma unroll
+    for (int e = 0; e < VN; ++e) {
+      o.v[e] = from_f32<OutT>(accv[e]);
+      sq += accv[e] * accv[e];
+    }
+    st16(out + ooff, o);
+    if (ar.sumsq) atomicAdd(&s_sq[lo + r - tm * BM], sq);
+  }
+  if (ar.sumsq) {
+    asm volatile("bar.sync 2, 128;" ::: "memory");
+    const int row = tm * BM + tid;
+    if (row >= lo && row < hi) atomicAdd(ar.sumsq + (row - ar.rank * ar.rows_per_rank), s_sq[tid]);
+  }
+  asm volatile("bar.sync 2, 128;" ::: "memory");  // s_sq is reused by the next tile
+}
+
+// RMSNorm over a reduce-scattered shard whose per-row sum of squares was accumulated by the GEMM kernel's reduce warps.
+// x [rows, n] (already sum + residual), out = x * rsqrt(sumsq / n + eps) * weight; sumsq is reset for the next call.
+template <typename T>
+__global__ void __launch_bounds__(256)
+rs_norm_kernel(const T* __restrict__ x, T* __restrict__ y, const T* __restrict__ weight, float* __restrict__ sumsq, int n,
+               int64_t ldx, int64_t ldy, float eps) {
+  constexpr int VN = 16 / sizeof(T);
+  ptx::grid_dep_wait();
+  ptx::grid_dep_launch();
+  const int row = blockIdx.x;
+  const float scale = rsqrtf(sumsq[row] / float(n) + eps);
+  __syncthreads();
+  if (threadIdx.x == 0) sumsq[row] = 0.f;
+  for (int c = threadIdx.x * VN; c < n; c += blockDim.x * VN) {
+    const Vec16<T> v = ld16(x + int64_t(row) * ldx + c);
+    const Vec16<T> w = ld16(weight + c);
+    Vec16<T> o;
+#pragma unroll
+    for (int e = 0; e < VN; ++e) o.v[e] = from_f32<T>(to_f32(v.v[e]) * scale * to_f32(w.v[e]));
+    st16(y + int64_t(row) * ldy + c, o);
+  }
+}
 
 template <typename OutT>
 __global__ void __launch_bounds__(384, 1)
@@ -201,6 +298,11 @@ gemm_ar_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int tm = t % tiles_m, tn = t / tiles_m;
       const uint32_t want = ar.expect[t] + uint32_t(ar.world);
+      if (ar.two_shot == 2) {
+        rs_reduce_tile<OutT>(ar, out, tm, tn, M, N, BN, ldc, want, t, tid);
+        if (tid == 0) ar.expect[t] = want;
+        continue;
+      }
       if (tid == 0) {
         while (int32_t(ptx::ld_acquire_sys(ar.peer_flags[ar.rank] + t) - want) < 0) {
         }
@@ -247,7 +349,7 @@ gemm_ar_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       if (tid == 0) ar.expect[t] = want;
     }
-    if (ar.two_shot) {
+    if (ar.two_shot == 1) {
       // every rank must see all owner-written tiles before the kernel completes
       __threadfence_system();
       asm volatile("bar.sync 2, 128;" ::: "memory");
@@ -277,7 +379,8 @@ extern "C" int gemm_allreduce_nt(void* A, void* W, void* stage, void* out, int64
                                  int64_t ldw, int64_t ldc, int64_t dtype, void* peer_stage_tab, void* peer_flags_tab,
                                  void* peer_out_tab, void* peer_done_tab, void* mc_stage, void* mc_flags, void* mc_out,
                                  void* expect, void* done_epoch, int64_t rank, int64_t world, int64_t two_shot,
-                                 int64_t max_tiles, int64_t bn, int64_t pdl, int64_t stream_) {
+                                 int64_t max_tiles, int64_t bn, int64_t rows_per_rank, int64_t ldo, void* residual,
+                                 void* sumsq, int64_t pdl, int64_t stream_) {
   FIB_CHECK(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldc % 8 == 0 && N % 16 == 0, "gemm_allreduce: K/lda/ldw/ldc must be multiples of 8 and N of 16");
   FIB_CHECK(dtype == kF16 || dtype == kBF16, "gemm_allreduce: dtype must be f16/bf16");
   FIB_CHECK(world >= 1 && world <= kMaxRanks, "gemm_allreduce: world size must be in [1,16]");
@@ -323,6 +426,11 @@ extern "C" int gemm_allreduce_nt(void* A, void* W, void* stage, void* out, int64
   ar.rank = (int)rank;
   ar.world = (int)world;
   ar.two_shot = (int)two_shot;
+  ar.rows_per_rank = (int)rows_per_rank;
+  ar.ldo = ldo;
+  ar.residual = residual;
+  ar.sumsq = (float*)sumsq;
+  if (two_shot == 2) FIB_CHECK(rows_per_rank > 0 && ldo % 8 == 0, "gemm_reduce_scatter: bad shard geometry");
   const GSmem S = GSmem::make(BN);
   const uint32_t idesc = ptx::make_idesc_f16(dtype == kF16 ? ptx::kFmtF16 : ptx::kFmtBF16, BM, BN, 0, 0);
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
@@ -343,6 +451,24 @@ extern "C" int gemm_allreduce_nt(void* A, void* W, void* stage, void* out, int64
     }
     FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, gemm_ar_kernel<__nv_bfloat16>, tmA, tmW, (__nv_bfloat16*)stage,
                                       (__nv_bfloat16*)out, (int)M, (int)N, (int)K, ldc, BN, idesc, ar));
+  }
+  return 0;
+}
+
+// Second half of GEMM -> reduce-scatter -> add-RMSNorm: normalise the local shard with the sums the GEMM kernel left behind.
+extern "C" int rs_rmsnorm(void* x, void* y, void* weight, void* sumsq, int64_t rows, int64_t n, int64_t ldx, int64_t ldy,
+                          double eps, int64_t dtype, int64_t pdl, int64_t stream_) {
+  FIB_CHECK(dtype == kF16 || dtype == kBF16, "rs_rmsnorm: dtype must be f16/bf16");
+  FIB_CHECK(n % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0, "rs_rmsnorm: n / strides must be multiples of 8");
+  if (rows == 0) return 0;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  LaunchCfg lc(dim3((unsigned)rows), dim3(256), 0, stream, pdl != 0);
+  if (dtype == kF16) {
+    FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, rs_norm_kernel<__half>, (const __half*)x, (__half*)y, (const __half*)weight,
+                                      (float*)sumsq, (int)n, ldx, ldy, (float)eps));
+  } else {
+    FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, rs_norm_kernel<__nv_bfloat16>, (const __nv_bfloat16*)x, (__nv_bfloat16*)y,
+                                      (const __nv_bfloat16*)weight, (float*)sumsq, (int)n, ldx, ldy, (float)eps));
   }
   return 0;
 }

@@ -390,6 +390,11 @@ struct GwParams {
   int64_t sa_row, sa_k, sb_n, sb_k, ldc;
   int M, N, K;
   uint32_t idesc;
+  // m-grouped contiguous mode (MoE / DeepGEMM): A [M, K] is tile-aligned per expert, B is [E * N, K], row tile tm uses the
+  // weights + scales of expert tile_expert[tm]; meta[0] = number of live row tiles (device-side, produced by the sort).
+  const int32_t* tile_expert;
+  const int32_t* meta;
+  int64_t sb_e;  // expert stride of the B scales
 };
 
 template <int BN, typename OutT>
@@ -428,26 +433,43 @@ fp8_groupwise_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
+  const bool grouped = p.tile_expert != nullptr;
+  if (warp != 0 || grouped) ptx::grid_dep_wait();
+  ptx::grid_dep_launch();
+  const int tiles_n = (p.N + BN - 1) / BN;
+  const int tiles_m = grouped ? (p.meta ? p.meta[0] : (p.M + BM - 1) / BM) : (p.M + BM - 1) / BM;
   const int num_tiles = tiles_m * tiles_n;
   const int num_kb = (p.K + BKB - 1) / BKB;
-  if (warp != 0) ptx::grid_dep_wait();
-  ptx::grid_dep_launch();
+  // dense: m fastest (neighbouring CTAs share the weight tile); grouped: n fastest (they share the expert's A tile)
+  auto decode = [&](int t, int& tm, int& tn, int& e) {
+    if (grouped) {
+      tn = t % tiles_n;
+      tm = t / tiles_n;
+      e = p.tile_expert[tm];
+    } else {
+      tm = t % tiles_m;
+      tn = t / tiles_m;
+      e = 0;
+    }
+  };
 
   if (warp == 0) {
     if (ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      bool first = true;
+      bool first = !grouped;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int tm = t % tiles_m, tn = t / tiles_m;
+        int tm, tn, e;
+        decode(t, tm, tn, e);
+        if (e < 0) continue;
+        const int brow = e * p.N + tn * BN;
         int kb_start = 0;
         if (first) {  // weights before griddepcontrol.wait
           first = false;
           const int npre = num_kb < kStages ? num_kb : kStages;
           for (int i = 0; i < npre; ++i) {
             ptx::mbar_arrive_expect_tx(&full_bar[i], G.a_bytes + G.b_bytes);
-            ptx::tma_load_2d(smem + i * G.stage_bytes + G.a_bytes, &tmB, &full_bar[i], i * BKB, tn * BN, ptx::kEvictFirst);
+            ptx::tma_load_2d(smem + i * G.stage_bytes + G.a_bytes, &tmB, &full_bar[i], i * BKB, brow, ptx::kEvictFirst);
           }
           ptx::grid_dep_wait();
           for (int i = 0; i < npre; ++i)
@@ -461,7 +483,7 @@ fp8_groupwise_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           uint8_t* sa = smem + stage * G.stage_bytes;
           ptx::mbar_arrive_expect_tx(&full_bar[stage], G.a_bytes + G.b_bytes);
           ptx::tma_load_2d(sa, &tmA, &full_bar[stage], kb * BKB, tm * BM, ptx::kEvictNormal);
-          ptx::tma_load_2d(sa + G.a_bytes, &tmB, &full_bar[stage], kb * BKB, tn * BN, ptx::kEvictFirst);
+          ptx::tma_load_2d(sa + G.a_bytes, &tmB, &full_bar[stage], kb * BKB, brow, ptx::kEvictFirst);
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -473,6 +495,7 @@ fp8_groupwise_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     int stage = 0, buf = 0;
     uint32_t phase = 0, bphase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      if (grouped && p.tile_expert[t / tiles_n] < 0) continue;
       for (int kb = 0; kb < num_kb; ++kb) {
         ptx::mbar_wait(&tmem_empty[buf], bphase ^ 1);
         ptx::mbar_wait(&full_bar[stage], phase);
@@ -502,17 +525,20 @@ fp8_groupwise_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     int buf = 0;
     uint32_t bphase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int tm = t % tiles_m, tn = t / tiles_m;
+      int tm, tn, e;
+      decode(t, tm, tn, e);
+      if (e < 0) continue;
       const int row = tm * BM + q * 32 + lane;
       const int rowc = row < p.M ? row : p.M - 1;
       const int nblk = (tn * BN) / 128;
+      const float* sbp = p.sb + e * p.sb_e + nblk * p.sb_n;
       float acc[BN];
 #pragma unroll
       for (int c = 0; c < BN; ++c) acc[c] = 0.f;
-      float sc_next = p.sa[rowc * p.sa_row] * p.sb[nblk * p.sb_n];
+      float sc_next = p.sa[rowc * p.sa_row] * sbp[0];
       for (int kb = 0; kb < num_kb; ++kb) {
         const float sc = sc_next;
-        if (kb + 1 < num_kb) sc_next = p.sa[rowc * p.sa_row + (kb + 1) * p.sa_k] * p.sb[nblk * p.sb_n + (kb + 1) * p.sb_k];
+        if (kb + 1 < num_kb) sc_next = p.sa[rowc * p.sa_row + (kb + 1) * p.sa_k] * sbp[(kb + 1) * p.sb_k];
         ptx::mbar_wait(&tmem_full[buf], bphase);
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + buf * BN + (uint32_t(q * 32) << 16);
@@ -1108,7 +1134,9 @@ extern "C" int gemm_lowp_nt(void* A, void* B, void* C, void* sfa, void* sfb, voi
 // sb fp32 with element strides (sb_n, sb_k) over [N/128, K/128].
 extern "C" int gemm_fp8_groupwise_nt(void* A, void* B, void* C, void* sa, void* sb, int64_t M, int64_t N, int64_t K, int64_t lda,
                                      int64_t ldb, int64_t ldc, int64_t sa_row, int64_t sa_k, int64_t sb_n, int64_t sb_k,
-                                     int64_t a_fmt, int64_t b_fmt, int64_t out_dtype, int64_t bn, int64_t pdl, int64_t stream_) {
+                                     int64_t a_fmt, int64_t b_fmt, int64_t out_dtype, int64_t bn, void* tile_expert, void* meta,
+                                     int64_t num_experts, int64_t sb_e, int64_t pdl, int64_t stream_) {
+  // tile_expert != null: m-grouped contiguous mode, B is [num_experts * N, K], sb has an expert stride sb_e, M = padded rows
   FIB_CHECK(out_dtype == kF16 || out_dtype == kBF16, "gemm_fp8_groupwise: output must be f16/bf16");
   FIB_CHECK(K % 128 == 0, "gemm_fp8_groupwise: K must be a multiple of 128");
   FIB_CHECK(lda % 16 == 0 && ldb % 16 == 0, "gemm_fp8_groupwise: row strides must be multiples of 16 bytes");
@@ -1121,6 +1149,11 @@ extern "C" int gemm_fp8_groupwise_nt(void* A, void* B, void* C, void* sa, void* 
     BN = want <= 32 ? 32 : (want <= 64 ? 64 : 128);
   }
   FIB_CHECK(BN == 32 || BN == 64 || BN == 128, "gemm_fp8_groupwise: N tile must be 32 / 64 / 128");
+  if (tile_expert) {
+    while (BN > 32 && N % BN) BN >>= 1;
+    FIB_CHECK(N % BN == 0 && num_experts >= 1, "gemm_fp8_groupwise (grouped): N must be a multiple of 32");
+  }
+  const int64_t b_rows = tile_expert ? num_experts * N : N;
   CUtensorMap tmA, tmB;
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
@@ -1129,12 +1162,15 @@ extern "C" int gemm_fp8_groupwise_nt(void* A, void* B, void* C, void* sa, void* 
     if (make_tmap(&tmA, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, A, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   }
   {
-    uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)b_rows};
     uint64_t str[1] = {(uint64_t)ldb};
     uint32_t box[2] = {BKB, (uint32_t)BN};
     if (make_tmap(&tmB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, B, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   }
   GwParams p;
+  p.tile_expert = (const int32_t*)tile_expert;
+  p.meta = (const int32_t*)meta;
+  p.sb_e = sb_e;
   p.sa = (const float*)sa;
   p.sb = (const float*)sb;
   p.sa_row = sa_row; p.sa_k = sa_k; p.sb_n = sb_n; p.sb_k = sb_k; p.ldc = ldc;

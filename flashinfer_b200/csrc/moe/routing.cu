@@ -354,15 +354,136 @@ moe_scatter_kernel(const int32_t* __restrict__ topk_ids, int n, int K, int local
   ptx::grid_dep_launch();
 }
 
+// Small problems (T * K <= 32 K entries, 32 * local_num ints of smem): the whole sort in ONE CTA, still deterministic.
+// Warp w owns the contiguous entry range [w * per, (w + 1) * per) and walks it 32 entries at a time, so every step is
+// warp-local (match.any + a warp-private histogram row); the only block-wide steps are the expert scan in the middle.
+__global__ void __launch_bounds__(1024)
+moe_sort_small_kernel(const int32_t* __restrict__ topk_ids, int n, int K, int local_offset, int local_num, int tile,
+                      int max_rows, int32_t* __restrict__ expanded_to_permuted, int32_t* __restrict__ permuted_to_token,
+                      int32_t* __restrict__ tile_expert, int32_t* __restrict__ expert_offsets, int32_t* __restrict__ meta) {
+  extern __shared__ int sm[];
+  int* hist = sm;                          // [32][local_num] per-warp counts, then per-warp cursors
+  int* cnt = sm + 32 * local_num;          // [local_num]
+  int* off = cnt + local_num;              // [local_num + 1]
+  __shared__ int warp_tot[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 32 * local_num; i += blockDim.x) hist[i] = 0;
+  ptx::grid_dep_wait();
+  __syncthreads();
+  const int per = ((n + 31) / 32 + 31) & ~31;  // entries per warp, multiple of 32
+  const int lo = warp * per, hi = min(n, lo + per);
+  int* myh = hist + warp * local_num;
+  for (int i0 = lo; i0 < hi; i0 += 32) {
+    const int i = i0 + lane;
+    int e = -1;
+    if (i < hi) {
+      e = topk_ids[i] - local_offset;
+      if (e < 0 || e >= local_num) e = -1;
+    }
+    const uint32_t peers = __match_any_sync(0xffffffffu, e);
+    if (e >= 0 && (peers & ((1u << lane) - 1)) == 0) myh[e] += __popc(peers);
+    __syncwarp();
+  }
+  __syncthreads();
+  // per expert: exclusive prefix over the 32 warps (in place), total count
+  for (int e = threadIdx.x; e < local_num; e += blockDim.x) {
+    int acc = 0;
+#pragma unroll 8
+    for (int w = 0; w < 32; ++w) {
+      const int v = hist[w * local_num + e];
+      hist[w * local_num + e] = acc;
+      acc += v;
+    }
+    cnt[e] = acc;
+  }
+  __syncthreads();
+  int base = 0;
+  for (int e0 = 0; e0 < local_num; e0 += blockDim.x) {
+    const int e = e0 + threadIdx.x;
+    const int padded = e < local_num ? (cnt[e] + tile - 1) / tile * tile : 0;
+    int incl = padded;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    int wbase = 0, total = 0;
+    for (int w = 0; w < 32; ++w) {
+      if (w < warp) wbase += warp_tot[w];
+      total += warp_tot[w];
+    }
+    if (e < local_num) off[e] = base + wbase + incl - padded;
+    base += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    off[local_num] = base;
+    meta[0] = base / tile;
+    meta[1] = base;
+  }
+  __syncthreads();
+  ptx::grid_dep_launch();
+  for (int i = threadIdx.x; i <= local_num; i += blockDim.x) expert_offsets[i] = off[i];
+  for (int i = off[local_num] / tile + threadIdx.x; i < max_rows / tile; i += blockDim.x) tile_expert[i] = -1;
+  for (int i = off[local_num] + threadIdx.x; i < max_rows; i += blockDim.x) permuted_to_token[i] = -1;
+  for (int e = warp; e < local_num; e += blockDim.x >> 5) {
+    for (int r = off[e] + lane * tile; r < off[e + 1]; r += 32 * tile) tile_expert[r / tile] = e;
+    for (int r = off[e] + cnt[e] + lane; r < off[e + 1]; r += 32) permuted_to_token[r] = -1;
+  }
+  // scatter: same walk, positions = expert offset + warp prefix + running cursor + rank inside the 32-entry group
+  for (int i0 = lo; i0 < hi; i0 += 32) {
+    const int i = i0 + lane;
+    int e = -1;
+    if (i < hi) {
+      e = topk_ids[i] - local_offset;
+      if (e < 0 || e >= local_num) e = -1;
+    }
+    const uint32_t peers = __match_any_sync(0xffffffffu, e);
+    const int rank = __popc(peers & ((1u << lane) - 1));
+    int b = 0;
+    if (e >= 0 && rank == 0) {
+      b = myh[e];
+      myh[e] = b + __popc(peers);
+    }
+    b = __shfl_sync(0xffffffffu, b, __ffs(peers) - 1);
+    if (i < hi) {
+      if (e >= 0) {
+        const int pos = off[e] + b + rank;
+        expanded_to_permuted[i] = pos;
+        permuted_to_token[pos] = i / K;
+      } else {
+        expanded_to_permuted[i] = -1;
+      }
+    }
+    __syncwarp();
+  }
+}
+
 // permuted_x[p, :] = x[token(p), :]  (zero rows for padding)
 template <typename T>
 __global__ void __launch_bounds__(256)
 moe_gather_kernel(const T* __restrict__ x, T* __restrict__ out, const int32_t* __restrict__ permuted_to_token,
-                  const int32_t* __restrict__ meta, int64_t hidden, int64_t x_stride, int zero_pad) {
+                  const int32_t* __restrict__ meta, int64_t hidden, int64_t x_stride, int zero_pad,
+                  const int32_t* __restrict__ row_list, int64_t n_list, int list_div) {
   constexpr int VN = 16 / sizeof(T);
   ptx::grid_dep_wait();
-  const int rows = meta[1];
   const int64_t vec = hidden / VN;
+  if (row_list) {
+    // live rows only: entry j of the expanded (token, k) list lands in permuted row row_list[j]; padding rows stay
+    // uninitialised (GEMM rows are independent and nothing reads the padding rows of the result)
+    const int64_t total = n_list * vec;
+    for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+      const int64_t j = i / vec, v = i % vec;
+      const int r = row_list[j];
+      if (r < 0) continue;
+      st16(out + int64_t(r) * hidden + v * VN, ld16(x + (j / list_div) * x_stride + v * VN));
+    }
+    ptx::grid_dep_launch();
+    return;
+  }
+  const int rows = meta[1];
   const int64_t total = int64_t(rows) * vec;
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
     const int64_t r = i / vec, v = i % vec;
@@ -457,6 +578,15 @@ extern "C" int moe_sort(void* topk_ids, int64_t T, int64_t K, int64_t E, int64_t
   const int n = (int)(T * K);
   const int nchunks = n > 0 ? (n + kSortChunk - 1) / kSortChunk : 0;
   (void)E;
+  const size_t small_smem = (size_t(34) * local_num + 1) * sizeof(int);
+  if (n > 0 && n <= 32768 && small_smem <= 48 * 1024) {
+    LaunchCfg lc(dim3(1), dim3(1024), small_smem, stream, pdl != 0);
+    FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, moe_sort_small_kernel, (const int32_t*)topk_ids, n, (int)K, (int)local_offset,
+                                      (int)local_num, (int)tile, (int)max_rows, (int32_t*)expanded_to_permuted,
+                                      (int32_t*)permuted_to_token, (int32_t*)tile_expert, (int32_t*)expert_offsets,
+                                      (int32_t*)meta));
+    return 0;
+  }
   if (nchunks > 0) {
     LaunchCfg lc(dim3(nchunks), dim3(kSortChunk), local_num * sizeof(int), stream, pdl != 0);
     FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, moe_count_kernel, (const int32_t*)topk_ids, n, (int)local_offset,
@@ -479,12 +609,14 @@ extern "C" int moe_sort(void* topk_ids, int64_t T, int64_t K, int64_t E, int64_t
 }
 
 extern "C" int moe_gather(void* x, void* out, void* permuted_to_token, void* meta, int64_t max_rows, int64_t hidden,
-                          int64_t x_stride, int64_t zero_pad, int64_t dtype, int64_t pdl, int64_t stream_) {
+                          int64_t x_stride, int64_t zero_pad, void* row_list, int64_t n_list, int64_t list_div, int64_t dtype,
+                          int64_t pdl, int64_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   return FIB_DISPATCH_HALF(dtype, T, [&]() -> int {
-    LaunchCfg lc(dim3(grid_for(max_rows * (hidden / 8))), dim3(256), 0, stream, pdl != 0);
+    LaunchCfg lc(dim3(grid_for((row_list ? n_list : max_rows) * (hidden / 8))), dim3(256), 0, stream, pdl != 0);
     FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, moe_gather_kernel<T>, (const T*)x, (T*)out,
-                                      (const int32_t*)permuted_to_token, (const int32_t*)meta, hidden, x_stride, (int)zero_pad));
+                                      (const int32_t*)permuted_to_token, (const int32_t*)meta, hidden, x_stride, (int)zero_pad,
+                                      (const int32_t*)row_list, n_list, (int)(list_div > 0 ? list_div : 1)));
     return 0;
   });
 }

@@ -188,13 +188,13 @@ def moe_forward(x: torch.Tensor, topk_ids: torch.Tensor, topk_w: torch.Tensor, w
     mod.call("moe_sort", ids, T, K, num_experts or e_local, local_expert_offset, e_local, _TILE, max_rows, e2p, p2t,
              tile_e, offs, meta, ws, 1, st)
     xp = torch.empty(max_rows, H, dtype=x.dtype, device=dev)
-    mod.call("moe_gather", x, xp, p2t, meta, max_rows, H, x.stride(0), 1, dtype_code(x.dtype), 1, st)
+    mod.call("moe_gather", x, xp, p2t, meta, max_rows, H, x.stride(0), 0, e2p, T * K, K, dtype_code(x.dtype), 1, st)
     h1 = torch.empty(max_rows, n1, dtype=x.dtype, device=dev)
     gg.call("grouped_gemm_nt", xp, w1.contiguous(), h1, tile_e, meta, max_tiles, n1, H, e_local, H, n1,
             dtype_code(x.dtype), 1, st)
     if n1 == 2 * inter:
         a = torch.empty(max_rows, inter, dtype=x.dtype, device=dev)
-        _act_and_mul("silu" if activation == "silu" else "gelu", h1, a, True, gate_second=True, row_map=p2t)
+        _act_and_mul("silu" if activation == "silu" else "gelu", h1, a, True, gate_second=True, row_map=e2p, row_list=True)
     else:
         a = torch.nn.functional.silu(h1) if activation == "silu" else torch.relu(h1) ** 2
     h2 = torch.empty(max_rows, H, dtype=x.dtype, device=dev)
@@ -275,7 +275,7 @@ def moe_forward_nvfp4(x: torch.Tensor, topk_ids: torch.Tensor, topk_w: torch.Ten
         xb = xb.contiguous()
     gs = _unit_scale(dev, act_global_scale)
     # gather + quantise in one kernel: token rows go straight into the permuted NVFP4 activation matrix
-    xq, xsf = moe_fp4_quantize(xb, max_rows, H, p2t, gs, gather=True, gated=False)
+    xq, xsf = moe_fp4_quantize(xb, max_rows, H, p2t, gs, gather=True, gated=False, row_list=e2p, list_div=K)
     a1 = torch.as_tensor(w1_alpha, dtype=torch.float32, device=dev).reshape(-1)
     a2 = torch.as_tensor(w2_alpha, dtype=torch.float32, device=dev).reshape(-1)
     if a1.numel() == 1:
@@ -289,7 +289,7 @@ def moe_forward_nvfp4(x: torch.Tensor, topk_ids: torch.Tensor, topk_w: torch.Ten
     sf2 = _swizzle_expert_sf(w2_sf, e_local, H, inter // 16)
     h1 = grouped_gemm_nvfp4(xq, xsf, w1_fp4, sf1, a1, tile_e, meta, out_dtype=xb.dtype)
     # SwiGLU + quantisation of the FC2 input in one kernel
-    aq, asf = moe_fp4_quantize(h1, max_rows, inter, p2t, gs, gather=False, gated=True)
+    aq, asf = moe_fp4_quantize(h1, max_rows, inter, p2t, gs, gather=False, gated=True, row_list=e2p)
     h2 = grouped_gemm_nvfp4(aq, asf, w2_fp4, sf2, a2, tile_e, meta, out_dtype=xb.dtype)
     if out is None:
         out = torch.empty(T, H, dtype=xb.dtype, device=dev)

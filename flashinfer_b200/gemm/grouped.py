@@ -150,31 +150,59 @@ def group_gemm_fp8_nt_groupwise(a: torch.Tensor, b: torch.Tensor, a_scale: torch
     return grouped_mm_bf16(ad, bd, m_indptr, out, out_dtype)
 
 
+def _native_fp8_groupwise(a, b, a_scale, b_scale, gran) -> bool:
+    return (a.is_cuda and tuple(gran) == (1, 128, 128) and a.dtype == torch.float8_e4m3fn and b.dtype == torch.float8_e4m3fn
+            and a.shape[-1] % 128 == 0 and b.shape[-2] % 32 == 0 and a_scale.shape[-1] == a.shape[-1] // 128
+            and b_scale.shape[-1] == a.shape[-1] // 128 and b_scale.dim() == 3)
+
+
 def group_deepgemm_fp8_nt_groupwise(a, b, a_scale, b_scale, m_indices: torch.Tensor, scale_granularity_mnk=(1, 128, 128),
                                     out: Optional[torch.Tensor] = None, out_dtype=torch.bfloat16) -> torch.Tensor:
-    """DeepGEMM m-grouped contiguous: ``m_indices [M]`` names the group of every row (groups 128-aligned)."""
+    """DeepGEMM m-grouped contiguous: ``m_indices [M]`` names the group of every row (groups 128-aligned).  With the
+    DeepSeek (1, 128, 128) granularity this is ONE native fp8 tcgen05 kernel (per-slab TMEM promotion with the scale
+    product, ``gemm_fp8_groupwise_nt`` grouped mode); other granularities de-quantise into the bf16 grouped GEMM."""
     gm, gn, gk = scale_granularity_mnk
-    ad = _dq_groupwise(a, a_scale, gm, gk, True)
-    bd = _dq_groupwise(b, b_scale, gn, gk, True)
     tile_expert = m_indices[::_TILE].to(torch.int32).contiguous()
-    y = grouped_gemm_tiles(ad, bd, tile_expert, None)
-    y = y.to(out_dtype)
-    if out is not None:
+    if _native_fp8_groupwise(a, b, a_scale, b_scale, scale_granularity_mnk) and a.shape[0] % _TILE == 0 and a_scale.dim() == 2:
+        from .lowp import grouped_gemm_fp8_groupwise
+
+        odt = out_dtype if out_dtype in (torch.float16, torch.bfloat16) else torch.bfloat16
+        y = grouped_gemm_fp8_groupwise(a, a_scale, b, b_scale, tile_expert, None, odt,
+                                       out if (out is not None and out.dtype == odt and out.is_contiguous()) else None)
+    else:
+        ad = _dq_groupwise(a, a_scale, gm, gk, True)
+        bd = _dq_groupwise(b, b_scale, gn, gk, True)
+        y = grouped_gemm_tiles(ad, bd, tile_expert, None)
+    if out is not None and y.data_ptr() != out.data_ptr():
         out.copy_(y)
         return out
-    return y
+    return y if y.dtype == out_dtype else y.to(out_dtype)
 
 
 def batch_deepgemm_fp8_nt_groupwise(a, b, a_scale, b_scale, masked_m: torch.Tensor, expected_m: int = 0,
                                     scale_granularity_mnk=(1, 128, 128), out: Optional[torch.Tensor] = None,
                                     out_dtype=torch.bfloat16) -> torch.Tensor:
-    """DeepGEMM masked layout: ``a [G, M_max, K]`` fp8 + ``a_scale [G, M_max, K/128]``."""
+    """DeepGEMM masked layout: ``a [G, M_max, K]`` fp8 + ``a_scale [G, M_max, K/128]``; rows ``>= masked_m[g]`` are padding.
+    Native for (1, 128, 128) scales and ``M_max % 128 == 0``: the batch is one m-grouped problem whose tile -> expert map
+    marks the tiles past ``masked_m`` as skipped (built on the device, no host sync)."""
     gm, gn, gk = scale_granularity_mnk
-    ad = _dq_groupwise(a, a_scale, gm, gk, True)
-    bd = _dq_groupwise(b, b_scale, gn, gk, True)
-    o = torch.empty(a.shape[0], a.shape[1], b.shape[1], dtype=torch.bfloat16, device=a.device)
-    grouped_gemm_nt_masked(ad, bd, o, masked_m)
-    o = o.to(out_dtype)
+    G, Mx, K = a.shape
+    if _native_fp8_groupwise(a, b, a_scale, b_scale, scale_granularity_mnk) and Mx % _TILE == 0 and a.is_contiguous():
+        from .lowp import grouped_gemm_fp8_groupwise
+
+        mt = Mx // _TILE
+        t = torch.arange(G * mt, device=a.device, dtype=torch.int32)
+        g = t // mt
+        te = torch.where((t % mt) * _TILE < masked_m.to(torch.int32)[g.long()], g, torch.full_like(g, -1)).contiguous()
+        odt = out_dtype if out_dtype in (torch.float16, torch.bfloat16) else torch.bfloat16
+        o = grouped_gemm_fp8_groupwise(a.view(G * Mx, K), a_scale.reshape(G * Mx, K // 128), b, b_scale, te, None, odt)
+        o = o.view(G, Mx, b.shape[1])
+    else:
+        ad = _dq_groupwise(a, a_scale, gm, gk, True)
+        bd = _dq_groupwise(b, b_scale, gn, gk, True)
+        o = torch.empty(a.shape[0], a.shape[1], b.shape[1], dtype=torch.bfloat16, device=a.device)
+        grouped_gemm_nt_masked(ad, bd, o, masked_m)
+    o = o if o.dtype == out_dtype else o.to(out_dtype)
     if out is not None:
         out.copy_(o)
         return out

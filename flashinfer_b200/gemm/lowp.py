@@ -246,7 +246,8 @@ def gemm_fp8_nt_groupwise(a: torch.Tensor, b: torch.Tensor, a_scale: torch.Tenso
         res = out if (out is not None and out.dtype == out_dtype and out.stride(-1) == 1) else torch.empty(M, N, dtype=out_dtype, device=a.device)
         jit.load("gemm_blockscaled_sm100").call(
             "gemm_fp8_groupwise_nt", a, b, res, sa, sb, M, N, K, a.stride(0), b.stride(0), res.stride(0), sa_row, sa_k, sb_n, sb_k,
-            _FP8_FMT[a.dtype], _FP8_FMT[b.dtype], dtype_code(out_dtype), int(os.environ.get("FIB200_GW_BN", "0")), 1, stream_ptr(a))
+            _FP8_FMT[a.dtype], _FP8_FMT[b.dtype], dtype_code(out_dtype), int(os.environ.get("FIB200_GW_BN", "0")), None, None, 1, 0,
+            1, stream_ptr(a))
         if out is not None and out.data_ptr() != res.data_ptr():
             out.copy_(res)
             return out
@@ -260,6 +261,58 @@ def gemm_fp8_nt_groupwise(a: torch.Tensor, b: torch.Tensor, a_scale: torch.Tenso
     if out is not None:
         out.copy_(res)
         return out
+    return res
+
+
+def fp8_group_quantize(x: torch.Tensor, rows: Optional[int] = None, gated: bool = False, row_list: Optional[torch.Tensor] = None,
+                       gather: bool = False, list_div: int = 1) -> Tuple[torch.Tensor, torch.Tensor]:
+    """DeepSeek activation quantisation: ``x [M, K]`` (bf16 / fp16) -> (e4m3 ``[rows, K]``, fp32 scales ``[rows, K / 128]``), one
+    scale per 1 x 128 group (``amax / 448``).  MoE modes mirror :func:`flashinfer_b200.quantization.fp4.moe_fp4_quantize`:
+    ``row_list`` (expanded -> permuted destination row, only live rows are visited; with ``gather`` the source row of entry
+    ``j`` is ``j // list_div``) and ``gated`` (``x`` rows are ``[linear | gate]``, quantise ``silu(gate) * linear``)."""
+    K = x.shape[1] // 2 if gated else x.shape[1]
+    rows = x.shape[0] if rows is None else rows
+    if x.stride(1) != 1:
+        x = x.contiguous()
+    if not x.is_cuda:
+        if row_list is not None:
+            raise NotImplementedError("fp8_group_quantize row_list mode is CUDA only")
+        v = x.float()
+        if gated:
+            v = v[:, :K] * torch.nn.functional.silu(v[:, K:])
+        g = v.view(rows, K // 128, 128)
+        sc = g.abs().amax(-1).clamp_min(1e-10) / 448.0
+        return (g / sc[..., None]).view(rows, K).to(torch.float8_e4m3fn), sc
+    q = torch.empty(rows, K, dtype=torch.float8_e4m3fn, device=x.device)
+    sc = torch.empty(rows, K // 128, dtype=torch.float32, device=x.device)
+    jit.load("quantization").call("fp8_group_quantize", x, q, sc, rows, K, x.stride(0), 1 if gated else 0, row_list,
+                                  row_list.numel() if row_list is not None else 0, 1 if gather else 0, list_div, dtype_code(x.dtype),
+                                  1, stream_ptr(x))
+    return q, sc
+
+
+def grouped_gemm_fp8_groupwise(a: torch.Tensor, a_scale: torch.Tensor, w: torch.Tensor, w_scale: torch.Tensor,
+                               tile_expert: torch.Tensor, meta: Optional[torch.Tensor] = None,
+                               out_dtype: torch.dtype = torch.bfloat16, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """m-grouped contiguous fp8 GEMM with DeepSeek scales, native tcgen05 (``fp8_groupwise_kernel`` grouped mode).
+
+    ``a [M, K]`` e4m3 (rows grouped per expert in 128-row tiles), ``a_scale [M, K/128]`` fp32, ``w [E, N, K]`` e4m3,
+    ``w_scale [E, N/128, K/128]`` fp32, ``tile_expert [M/128]`` int32 (-1 = skip the tile), ``meta[0]`` = live row tiles
+    (device-side; ``None`` = all).  Reference: DeepGEMM m-grouped contiguous layout (flashinfer/gemm/gemm_base.py
+    group_deepgemm_fp8_nt_groupwise) and the fp8 block-scale MoE GEMMs."""
+    M, K = a.shape
+    E, N, _ = w.shape
+    if K % 128 or N % 32 or M % 128:
+        raise ValueError("grouped_gemm_fp8_groupwise: K % 128, N % 32 and M % 128 must be 0")
+    a = a if a.stride(1) == 1 else a.contiguous()
+    w = w.contiguous()
+    sa = a_scale.float()
+    sb = w_scale.float().contiguous()
+    res = out if out is not None else torch.empty(M, N, dtype=out_dtype, device=a.device)
+    jit.load("gemm_blockscaled_sm100").call(
+        "gemm_fp8_groupwise_nt", a, w, res, sa, sb, M, N, K, a.stride(0), K, res.stride(0), sa.stride(0), sa.stride(1), sb.stride(1),
+        sb.stride(2), _FP8_FMT[a.dtype], _FP8_FMT[w.dtype], dtype_code(res.dtype), int(os.environ.get("FIB200_GW_BN", "0")),
+        tile_expert, meta, E, sb.stride(0), 1, stream_ptr(a))
     return res
 
 

@@ -78,37 +78,35 @@ class BatchMLAPagedAttentionWrapper:
         ctas = max(1, device_sm_count(self.device if self.device.type == "cuda" else None) // 2)
         chunk = max(4 * _TILE, -(-total_tokens // ctas))
         chunk = -(-chunk // _TILE) * _TILE
-        max_vis = max((r[2] for r in rows), default=0)
-        chunk = max(chunk, -(-(-(-max_vis // 8)) // _TILE) * _TILE)  # at most 8 splits per row (in-kernel merge)
         # one wave: grow the chunk until the number of (row, split) work items fits the CTA pairs of the device
         while sum(max(1, -(-r[2] // chunk)) for r in rows) > ctas and chunk < (1 << 30):
             chunk += _TILE
         kmax = max(1, max((-(-r[2] // chunk) for r in rows), default=1))
         self._kmax = kmax
         work = []
+        row_parts = [1] * max(self._n_q, 1)
         for (qr, pstart, vis, npages) in rows:
             nsp = max(1, -(-vis // chunk))
+            row_parts[qr] = nsp
             for s in range(nsp):
                 lo, hi = s * chunk, min(vis, (s + 1) * chunk)
                 work.append([qr, pstart, lo, max(hi, lo), vis, qr * kmax + s, max(npages, 1), (kmax << 16) | nsp])
         self._num_work = len(work)
-        w = torch.tensor(work, dtype=torch.int32).reshape(-1)
+        w = torch.cat([torch.tensor(work, dtype=torch.int32).reshape(-1), torch.tensor(row_parts, dtype=torch.int32)])
         pin = self._pin_int_workspace_buffer.view(torch.int32)
         pin[: w.numel()].copy_(w)
         dev = self._int_workspace_buffer.view(torch.int32)
         dev[: w.numel()].copy_(pin[: w.numel()], non_blocking=self.device.type == "cuda")
-        self._work = dev[: w.numel()]
+        self._work = dev[: len(work) * 8]
+        self._row_parts = dev[len(work) * 8 : w.numel()]
         if kmax > 1:
-            if kmax > 8:
-                raise RuntimeError("mla_sm100: more than 8 KV splits per row (increase the chunk size)")
             need = self._n_q * kmax * num_heads * (512 + 2) * 4
             if need > self._float_workspace_buffer.numel() * self._float_workspace_buffer.element_size():
                 raise RuntimeError("float workspace too small for MLA split-KV partials")
             f = self._float_workspace_buffer.view(torch.uint8)[:need].view(torch.float32)
             self._partial_o = f[: self._n_q * kmax * num_heads * 512].view(self._n_q, kmax, num_heads, 512)
-            self._partial_lse = f[self._n_q * kmax * num_heads * 512 :].view(2, self._n_q, kmax, num_heads)
-            # self-resetting arrival counters of the in-kernel merge (zeroed once, here)
-            self._merge_counters = torch.zeros(max(self._n_q, 1) * 2, dtype=torch.int32, device=self.device)
+            self._partial_lse = f[self._n_q * kmax * num_heads * 512 : self._n_q * kmax * num_heads * 513].view(
+                self._n_q, kmax, num_heads)
         self._planned = True
 
     def run(self, q_nope: torch.Tensor, q_pe: torch.Tensor, ckv_cache: torch.Tensor, kpe_cache: torch.Tensor,
@@ -145,7 +143,7 @@ class BatchMLAPagedAttentionWrapper:
             jit.load("mla_sm100").call(
                 "mla_decode_run", q_nope, q_pe, ckv_cache, kpe_cache, self._kv_indices, self._work, self._num_work,
                 out, self._partial_o if split else None, self._partial_lse if split else None,
-                self._merge_counters if split else None, self._n_q * self._kmax * h if split else 0,
+                self._row_parts if split else None, self._kmax,
                 lse if return_lse else None, n, h, self._page_size, ckv_cache.shape[0],
                 q_nope.stride(0), q_nope.stride(1), q_pe.stride(0), q_pe.stride(1), ckv_cache.stride(0),
                 ckv_cache.stride(1), kpe_cache.stride(0), kpe_cache.stride(1), out.stride(0), out.stride(1),

@@ -96,7 +96,7 @@ def fp4_quantize(input: torch.Tensor, global_scale: Optional[torch.Tensor] = Non
         gst = gs.float().reshape(1).contiguous() if gs is not None else None
         jit.load("quantization").call(
             "fp4_quantize", x, packed, sf, gst, 1, m, k, x.stride(0), 0, sf_vec_size, 1 if sf_use_ue8m0 else 0,
-            1 if is_sf_swizzled_layout else 0, 0, row_map, 0, 0, dtype_code(x.dtype), 1, stream_ptr(x),
+            1 if is_sf_swizzled_layout else 0, 0, row_map, 0, 0, None, 0, 1, dtype_code(x.dtype), 1, stream_ptr(x),
         )
     sf = sf.view(-1, round_up(kc, 4)) if is_sf_swizzled_layout else sf.view(m, kc)
     return packed.view(*shape[:-1], k // 2), sf
@@ -131,7 +131,7 @@ def nvfp4_batched_quantize(a: torch.Tensor, a_global_sf: torch.Tensor, sf_vec_si
     sf = torch.zeros(b, per, dtype=torch.uint8, device=a.device)
     jit.load("quantization").call(
         "fp4_quantize", x, packed, sf, a_global_sf.float().reshape(1).contiguous(), b, m, k, x.stride(1), x.stride(0),
-        sf_vec_size, 0, 1, per, None, 0, 0, dtype_code(x.dtype), 1, stream_ptr(x),
+        sf_vec_size, 0, 1, per, None, 0, 0, None, 0, 1, dtype_code(x.dtype), 1, stream_ptr(x),
     )
     return packed, sf
 
@@ -264,14 +264,21 @@ def nvfp4_quantize_paged_kv_cache(k_cache: torch.Tensor, v_cache: torch.Tensor, 
 
 
 def moe_fp4_quantize(x: torch.Tensor, rows: int, k: int, row_map: torch.Tensor, global_scale: torch.Tensor, gather: bool,
-                     gated: bool, sf_vec_size: int = 16) -> Tuple[torch.Tensor, torch.Tensor]:
+                     gated: bool, sf_vec_size: int = 16, row_list: Optional[torch.Tensor] = None,
+                     list_div: int = 1) -> Tuple[torch.Tensor, torch.Tensor]:
     """MoE-fused NVFP4 quantiser (one kernel): ``gather`` reads row ``row_map[m]`` of ``x`` (token gather) instead of row
     ``m``; ``gated`` treats a row as ``[linear | gate]`` halves of width ``k`` and quantises ``silu(gate) * linear``
-    (SwiGLU fused with the quantisation of the FC2 input).  Rows with ``row_map[m] < 0`` are skipped.  Returns
+    (SwiGLU fused with the quantisation of the FC2 input).  Rows with ``row_map[m] < 0`` are skipped.  ``row_list``
+    (expanded -> permuted row, -1 = not local) makes the kernel visit only the live rows instead of the tile-padded
+    matrix (source token of entry ``j`` = ``j // list_div`` when gathering); padding rows / scales stay uninitialised -
+    GEMM rows are independent and nothing reads the padding rows of the result.  Returns
     (``[rows, k/2]`` uint8, 128x4-swizzled UE4M3 scales)."""
     kc = k // sf_vec_size
     packed = torch.empty(rows, k // 2, dtype=torch.uint8, device=x.device)
-    sf = torch.zeros(_swizzled_sf_size(rows, kc), dtype=torch.uint8, device=x.device)
+    alloc = torch.empty if row_list is not None else torch.zeros
+    sf = alloc(_swizzled_sf_size(rows, kc), dtype=torch.uint8, device=x.device)
     jit.load("quantization").call("fp4_quantize", x, packed, sf, global_scale, 1, rows, k, x.stride(0), 0, sf_vec_size, 0, 1, 0,
-                                  row_map, 1 if gather else 0, 1 if gated else 0, dtype_code(x.dtype), 1, stream_ptr(x))
+                                  row_map, 1 if gather else 0, 1 if gated else 0, row_list,
+                                  row_list.numel() if row_list is not None else 0, list_div, dtype_code(x.dtype), 1,
+                                  stream_ptr(x))
     return packed, sf.view(-1, round_up(kc, 4))

@@ -36,6 +36,27 @@ def _worker(rank, world, port, errs):
                 got = gar(a, w, two_shot=two_shot)
                 torch.cuda.synchronize()
                 worst = max(worst, float((got.float() - ref).abs().max() / ref.abs().max()))
+            # GEMM -> reduce-scatter (+ residual + RMSNorm) in the same kernel (BASELINE config 5)
+            for it, M in enumerate([world * 8, world * 128, 2048, world * 72]):
+                torch.manual_seed(91 * it + rank)
+                a = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
+                w = (torch.randn(N, K, device="cuda") / K ** 0.5).bfloat16()
+                rpr = M // world
+                res = torch.randn(rpr, N, device="cuda").bfloat16()
+                gamma = (1 + 0.1 * torch.randn(N, device="cuda")).bfloat16()
+                full = (a.float() @ w.float().t()).bfloat16().float()
+                dist.all_reduce(full)
+                mine = full[rank * rpr:(rank + 1) * rpr]
+                got = gar.reduce_scatter(a, w)
+                torch.cuda.synchronize()
+                worst = max(worst, float((got.float() - mine).abs().max() / full.abs().max()))
+                for _ in range(2):  # twice: the sum-of-squares scratch must be left clean
+                    normed, shard = gar.reduce_scatter(a, w, residual=res, rms_weight=gamma, eps=1e-5)
+                    torch.cuda.synchronize()
+                    x = mine + res.float()
+                    ref_n = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-5) * gamma.float()
+                    worst = max(worst, float((shard.float() - x).abs().max() / x.abs().max()))
+                    worst = max(worst, float((normed.float() - ref_n).abs().max() / ref_n.abs().max()))
             agm = AllGatherMatmul(None, 512, K, torch.bfloat16, use_nvls=use_nvls)
             for it, Ml in enumerate([128, 512, 256]):
                 torch.manual_seed(31 * it + rank)

@@ -204,3 +204,43 @@ def test_moe_nvfp4_native_gpu(T, E, K, H, I):
     assert cos > 0.97, float(cos)
     rel = (out.float() - ref).norm() / ref.norm()
     assert rel < 0.25, float(rel)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("T,E,K,off,local", [(1000, 256, 8, 0, 256), (4096, 64, 8, 0, 64), (8192, 64, 8, 16, 32), (33, 8, 2, 0, 8),
+                                             (5000, 256, 8, 64, 64)])
+def test_moe_sort_paths_gpu(T, E, K, off, local):
+    """Single-CTA sort (T*K <= 32K) and the 3-kernel sort must both produce the deterministic tile-padded permutation."""
+    from flashinfer_b200 import jit
+    from flashinfer_b200.utils import stream_ptr
+
+    mod = jit.load("moe")
+    tile = 128
+    torch.manual_seed(T + E)
+    ids = torch.stack([torch.randperm(E)[:K] for _ in range(T)]).int().cuda()
+    max_rows = (T * K + local * (tile - 1)) // tile * tile + tile
+    e2p = torch.empty(T * K, dtype=torch.int32, device="cuda")
+    p2t = torch.full((max_rows,), -7, dtype=torch.int32, device="cuda")
+    tile_e = torch.full((max_rows // tile,), -7, dtype=torch.int32, device="cuda")
+    offs = torch.empty(local + 1, dtype=torch.int32, device="cuda")
+    meta = torch.empty(4, dtype=torch.int32, device="cuda")
+    ws = torch.empty(((T * K + 1023) // 1024) * local + 1, dtype=torch.int32, device="cuda")
+    mod.call("moe_sort", ids, T, K, E, off, local, tile, max_rows, e2p, p2t, tile_e, offs, meta, ws, 0, stream_ptr(ids))
+    torch.cuda.synchronize()
+    flat = ids.flatten().cpu() - off
+    valid = (flat >= 0) & (flat < local)
+    cnt = torch.bincount(flat[valid], minlength=local)
+    padded = (cnt + tile - 1) // tile * tile
+    ref_off = torch.cat([torch.zeros(1, dtype=torch.long), padded.cumsum(0)])
+    assert torch.equal(offs.cpu().long(), ref_off)
+    assert int(meta[1]) == int(ref_off[-1]) and int(meta[0]) == int(ref_off[-1]) // tile
+    e2p_c, p2t_c, te = e2p.cpu().long(), p2t.cpu().long(), tile_e.cpu().long()
+    assert (e2p_c[~valid] == -1).all()
+    # deterministic: rows of one expert keep ascending expanded-index order
+    for e in range(local):
+        idx = torch.nonzero(flat == e).flatten()
+        assert torch.equal(e2p_c[idx], ref_off[e] + torch.arange(idx.numel())), e
+        assert torch.equal(p2t_c[ref_off[e]:ref_off[e] + idx.numel()], idx // K)
+        assert (p2t_c[ref_off[e] + idx.numel():ref_off[e + 1]] == -1).all()
+        assert (te[ref_off[e] // tile:ref_off[e + 1] // tile] == e).all()
+    assert (p2t_c[ref_off[-1]:] == -1).all() and (te[ref_off[-1] // tile:] == -1).all()
