@@ -24,7 +24,9 @@
 
 using namespace fib200;
 
+#ifndef FIB_POD_TU
 FIB_EXPORT_LAST_ERROR()
+#endif
 
 namespace {
 
@@ -139,10 +141,11 @@ __device__ __forceinline__ TileGeom tile_geom(int ti, int ps) {
 }
 
 // NQ: MMA N (padded q rows, multiple of 16); NV: power-of-two number of columns actually processed.
+// Body as a device function of the CTA index (shared with the fused POD kernel, pod_sm100.cu, where it runs with a
+// 384-thread block: warps 9..11 have no role and only take part in the CTA-wide barriers).
 template <int NQ, int NV, int D, typename T, int KVB>
-__global__ void __launch_bounds__(288, 1)
-decode_paged_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
-                    const DecodeParams p, uint32_t idesc_qk, uint32_t idesc_pv) {
+__device__ __forceinline__ void decode_body(const CUtensorMap& tmK, const CUtensorMap& tmV, const DecodeParams& p,
+                                            uint32_t idesc_qk, uint32_t idesc_pv, int cta) {
   using S = DecodeSmem<NQ, D, KVB>;
   static_assert(D == 128, "head_dim 128 specialisation");
   constexpr bool kKV8 = KVB == 1;
@@ -164,8 +167,8 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int seg_begin = p.cta_seg_indptr[blockIdx.x];
-  const int seg_end = p.cta_seg_indptr[blockIdx.x + 1];
+  const int seg_begin = p.cta_seg_indptr[cta];
+  const int seg_end = p.cta_seg_indptr[cta + 1];
   if (seg_begin >= seg_end) return;
 
   constexpr uint32_t kTmemCols = (4 * NQ < 32) ? 32 : 4 * NQ;
@@ -591,6 +594,13 @@ decode_paged_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   }
 }
 
+template <int NQ, int NV, int D, typename T, int KVB>
+__global__ void __launch_bounds__(288, 1)
+decode_paged_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                    const DecodeParams p, uint32_t idesc_qk, uint32_t idesc_pv) {
+  decode_body<NQ, NV, D, T, KVB>(tmK, tmV, p, idesc_qk, idesc_pv, blockIdx.x);
+}
+
 // Merge split-KV partials: one CTA per merge item, thread = head-dim index.
 // item = {slot0, nparts, q_start, q_len, kv_head, pad...} (8 ints)
 template <int D, typename T>
@@ -638,6 +648,16 @@ int launch_decode(const CUtensorMap& tmK, const CUtensorMap& tmV, const DecodePa
   // fp8 cache: A = K / V in the cache format (e4m3 = 0, e5m2 = 1), B = Q / P converted to e4m3
   const uint32_t idesc_qk = KVB == 1 ? ptx::make_idesc_f8((uint32_t)kv_fmt, ptx::kFmtE4M3, 128, NQ, 0, 0) : ptx::make_idesc_f16(fmt, 128, NQ, 0, 0);
   const uint32_t idesc_pv = KVB == 1 ? ptx::make_idesc_f8((uint32_t)kv_fmt, ptx::kFmtE4M3, 128, NQ, 1, 0) : ptx::make_idesc_f16(fmt, 128, NQ, 1, 0);
+#ifdef FIB_POD_TU
+  if (pod_stage().armed) {
+    // POD: a prefill launch is parked -> run both bodies in ONE grid (prefill CTAs first, then the decode CTAs)
+    if (!pod_stage().have_prefill) return set_error("pod: decode launched before the prefill side was staged");
+    if constexpr (KVB == 2 && NQ == 16 && (NV == 1 || NV == 4 || NV == 8))
+      return pod_launch<NV, T>(tmK, tmV, &p, sizeof(p), idesc_qk, idesc_pv, grid, (int)S::kTotal, pdl, stream);
+    else
+      return set_error("pod: this decode variant (fp8 KV or q rows not in {1, 4, 8}) has no fused POD kernel");
+  }
+#endif
   LaunchCfg lc(dim3(grid), dim3(288), S::kTotal, stream, pdl);
   FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, kern, tmK, tmV, p, idesc_qk, idesc_pv));
   return 0;

@@ -51,7 +51,9 @@ struct MlaParams {
 };
 
 struct Smem {
-  static constexpr int kStages = 5;
+  static constexpr int kStages = 4;
+  static constexpr int kSBufs = 4;   // S / P TMEM buffers: QK^T runs two tiles ahead of the softmax
+  static constexpr int kXBufs = 3;   // partial-S exchange buffers (see the protocol note in the softmax loop)
   static constexpr int kMaxChunks = 5;                         // CTA 1: 4 ckv chunks + kpe
   static constexpr int kQBytes = kMaxChunks * kHeads * 128;    // 81920
   static constexpr int kChunkBytes = kTile * 128;              // 4096
@@ -60,8 +62,8 @@ struct Smem {
   static constexpr int kOffQ = 0;
   static constexpr int kOffK = kQBytes;
   static constexpr int kOffX = kOffK + kStages * kTileBytes;
-  static constexpr int kOffBar = kOffX + 2 * kXchgBytes;
-  static constexpr int kNumBars = 2 * kStages + 1 /*q_full*/ + 2 /*s_full*/ + 2 /*p_ready*/ + 1 /*o_done*/ + 2 /*x_full*/;
+  static constexpr int kOffBar = kOffX + kXBufs * kXchgBytes;
+  static constexpr int kNumBars = 2 * kStages + 1 /*q_full*/ + kSBufs /*s_full*/ + kSBufs /*p_ready*/ + 1 /*o_done*/ + kXBufs;
   static constexpr int kTotal = kOffBar + kNumBars * 8 + 16 + 1024;
 };
 static_assert(Smem::kTotal <= 227 * 1024, "MLA smem budget");
@@ -89,11 +91,11 @@ mla_decode_kernel(const __grid_constant__ CUtensorMap tmQn, const __grid_constan
   uint64_t* k_full = bars;
   uint64_t* k_empty = k_full + S::kStages;
   uint64_t* q_full = k_empty + S::kStages;
-  uint64_t* s_full = q_full + 1;   // [2]
-  uint64_t* p_ready = s_full + 2;  // [2]
-  uint64_t* o_done = p_ready + 2;  // [1]
-  uint64_t* x_full = o_done + 1;   // [2] peer's partial S landed in my exchange buffer (128 remote arrivals)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(x_full + 2);
+  uint64_t* s_full = q_full + 1;            // [kSBufs]
+  uint64_t* p_ready = s_full + S::kSBufs;   // [kSBufs]
+  uint64_t* o_done = p_ready + S::kSBufs;   // [1]
+  uint64_t* x_full = o_done + 1;            // [kXBufs] peer's partial S landed in my exchange buffer (tx-count: 16 KB of st.async)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(x_full + S::kXBufs);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int half = int(ptx::cluster_ctarank());  // 0: ckv[0:256)   1: ckv[256:512) + kpe   (also: which d_v half)
@@ -113,10 +115,13 @@ mla_decode_kernel(const __grid_constant__ CUtensorMap tmQn, const __grid_constan
       ptx::mbar_init(&k_empty[i], 1);
     }
     ptx::mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < S::kSBufs; ++i) {
       ptx::mbar_init(&s_full[i], 1);
       ptx::mbar_init(&p_ready[i], 128);
-      ptx::mbar_init(&x_full[i], 128);
+    }
+    for (int i = 0; i < S::kXBufs; ++i) {
+      ptx::mbar_init(&x_full[i], 1);
+      if (i < ntiles) ptx::mbar_arrive_expect_tx(&x_full[i], S::kXchgBytes);  // first use of every exchange buffer
     }
     ptx::mbar_init(o_done, 1);
     ptx::fence_mbar_init();
@@ -129,8 +134,8 @@ mla_decode_kernel(const __grid_constant__ CUtensorMap tmQn, const __grid_constan
   ptx::cluster_sync();  // barriers of both CTAs are initialised before any remote arrive (also a CTA-wide barrier)
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  const uint32_t tm_s = tmem_base;        // S0 at +0, S1 at +32
-  const uint32_t tm_o = tmem_base + 64;   // 256 columns
+  const uint32_t tm_s = tmem_base;                        // S buffer i at +32 * i
+  const uint32_t tm_o = tmem_base + 32 * S::kSBufs;       // 256 columns
 
   ptx::grid_dep_wait();
 
@@ -189,9 +194,30 @@ mla_decode_kernel(const __grid_constant__ CUtensorMap tmQn, const __grid_constan
     uint32_t ph = 0;
     const uint32_t q_addr = ptx::smem_u32(smem + S::kOffQ);
     ptx::mbar_wait(q_full, 0);
-    auto issue_pv = [&](int j, int stage) {
-      const uint32_t b = j & 1;
-      ptx::mbar_wait(&p_ready[b], (j >> 1) & 1);
+    auto issue_qk = [&](int j) {
+      const uint32_t b = j & (S::kSBufs - 1);
+      ptx::mbar_wait(&k_full[st], ph);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        const uint32_t k_addr = ptx::smem_u32(smem + S::kOffK + st * S::kTileBytes);
+        for (int k = 0; k < nch * 4; ++k) {
+          const int c = k / 4, o = (k % 4) * 32;
+          const uint64_t da = ptx::make_smem_desc(q_addr + c * (kHeads * 128) + o, 16, 1024, ptx::kSwz128);
+          const uint64_t db = ptx::make_smem_desc(k_addr + c * S::kChunkBytes + o, 16, 1024, ptx::kSwz128);
+          ptx::mma_f16_ss<1>(tm_s + b * 32, da, db, idesc_qk, k > 0 ? 1u : 0u);
+        }
+        ptx::mma_commit(&s_full[b]);
+      }
+      __syncwarp();
+      if (++st == S::kStages) {
+        st = 0;
+        ph ^= 1;
+      }
+    };
+    auto issue_pv = [&](int j) {
+      const uint32_t b = j & (S::kSBufs - 1);
+      const int stage = j % S::kStages;
+      ptx::mbar_wait(&p_ready[b], (j / S::kSBufs) & 1);
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
         // B = ckv[kv rows, my 256 dv columns]: MN-major SW128; chunk stride (LBO) = 4096, 8-row group (SBO) = 1024
@@ -206,30 +232,14 @@ mla_decode_kernel(const __grid_constant__ CUtensorMap tmQn, const __grid_constan
       }
       __syncwarp();
     };
-    int prev_stage = 0;
+    // QK^T runs two tiles ahead of P.V: S(j + 1) is complete (and its partial already on its way to the peer) while the
+    // softmax of tile j runs.  S buffer (j + 2) & 3 was last read by P.V(j - 2), issued earlier on the same in-order pipe.
+    if (ntiles > 0) issue_qk(0);
+    if (ntiles > 1) issue_qk(1);
     for (int j = 0; j < ntiles; ++j) {
-      const uint32_t b = j & 1;
-      ptx::mbar_wait(&k_full[st], ph);
-      ptx::tc_fence_after();
-      if (ptx::elect_one()) {
-        const uint32_t k_addr = ptx::smem_u32(smem + S::kOffK + st * S::kTileBytes);
-        for (int k = 0; k < nch * 4; ++k) {
-          const int c = k / 4, o = (k % 4) * 32;
-          const uint64_t da = ptx::make_smem_desc(q_addr + c * (kHeads * 128) + o, 16, 1024, ptx::kSwz128);
-          const uint64_t db = ptx::make_smem_desc(k_addr + c * S::kChunkBytes + o, 16, 1024, ptx::kSwz128);
-          ptx::mma_f16_ss<1>(tm_s + b * 32, da, db, idesc_qk, k > 0 ? 1u : 0u);
-        }
-        ptx::mma_commit(&s_full[b]);
-      }
-      __syncwarp();
-      if (j > 0) issue_pv(j - 1, prev_stage);
-      prev_stage = st;
-      if (++st == S::kStages) {
-        st = 0;
-        ph ^= 1;
-      }
+      if (j + 2 < ntiles) issue_qk(j + 2);
+      issue_pv(j);
     }
-    if (ntiles > 0) issue_pv(ntiles - 1, prev_stage);
   } else if (warp >= 4) {
     // ============================ softmax + epilogue ============================
     const int q4 = warp - 4;
@@ -238,29 +248,39 @@ mla_decode_kernel(const __grid_constant__ CUtensorMap tmQn, const __grid_constan
     constexpr bool kIsBf16 = std::is_same<T, __nv_bfloat16>::value;
     float m_used = -INFINITY, l = 0.f;
     uint32_t od_cnt = 0;
-    for (int j = 0; j < ntiles; ++j) {
-      const uint32_t b = j & 1;
-      const int tok0 = kv_begin + j * kTile;
-      ptx::mbar_wait(&s_full[b], (j >> 1) & 1);
-      ptx::tc_fence_after();
-      uint32_t r[32];
-      ptx::tmem_ld_x32(tm_s + lane_addr + b * 32, r);
-      ptx::tmem_ld_wait();
-      {
-        // ---- exchange partial S with the peer CTA (it reduced over the other slice of the latent dimension) ----
-        // row-major [128][32] fp32 with the 16-byte vectors of a row XOR-swizzled by (row & 7): conflict-free both ways.
-        // Buffer reuse needs no extra handshake: the peer only writes buffer b for tile j + 2 after it has received ALL
-        // 128 of my tile-(j + 1) arrivals, and each of my threads arrives for j + 1 after it has read tile j's buffer.
-        const uint32_t xoff = uint32_t(S::kOffX + b * S::kXchgBytes + row * 128);
-        const uint32_t x_remote = ptx::mapa(ptx::smem_u32(smem + xoff), uint32_t(half ^ 1));
+    // ---- partial-S exchange with the peer CTA (it reduced over the other slice of the latent dimension) ----
+    // The partial of tile j + 1 is pushed with st.async (16-byte stores that credit the PEER's x_full barrier: no release
+    // fence, no per-thread arrive) right after the peer's partial of tile j has landed, so it travels while the softmax of
+    // tile j runs.  Layout: row-major [128][32] fp32, the 16-byte vectors of a row XOR-swizzled by (row & 7).
+    // Buffer reuse (3 buffers, no extra handshake): when I push tile j + 1 I have received the peer's tile j, which it
+    // pushed after finishing its iteration j - 2 -> it is done reading buffer (j - 2) % 3 == (j + 1) % 3.
+    const uint32_t peer = uint32_t(half ^ 1);
+    auto push = [&](int jn, const uint32_t(&v)[32]) {
+      const int xb = jn % S::kXBufs;
+      const uint32_t x_remote = ptx::mapa(ptx::smem_u32(smem + S::kOffX + xb * S::kXchgBytes + row * 128), peer);
+      const uint32_t bar_remote = ptx::mapa(ptx::smem_u32(&x_full[xb]), peer);
 #pragma unroll
-        for (int v = 0; v < 8; ++v)
-          ptx::st_dsmem_v4(x_remote + ((v ^ (row & 7)) << 4),
-                           make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]), __uint_as_float(r[4 * v + 2]),
-                                       __uint_as_float(r[4 * v + 3])));
-        ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&x_full[b]), uint32_t(half ^ 1)));
-        ptx::mbar_wait_cluster(&x_full[b], (j >> 1) & 1);
-        const float4* xl = reinterpret_cast<const float4*>(smem + xoff);
+      for (int q = 0; q < 8; ++q)
+        ptx::st_async_v4(x_remote + ((q ^ (row & 7)) << 4),
+                         make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                                     __uint_as_float(v[4 * q + 3])),
+                         bar_remote);
+    };
+    uint32_t r[32];
+    if (ntiles > 0) {
+      ptx::mbar_wait(&s_full[0], 0);
+      ptx::tc_fence_after();
+      ptx::tmem_ld_x32(tm_s + lane_addr, r);
+      ptx::tmem_ld_wait();
+      push(0, r);
+    }
+    for (int j = 0; j < ntiles; ++j) {
+      const uint32_t b = j & (S::kSBufs - 1);
+      const int tok0 = kv_begin + j * kTile;
+      const int xb = j % S::kXBufs;
+      ptx::mbar_wait(&x_full[xb], (j / S::kXBufs) & 1);  // tx-count completion (like a TMA write): plain acquire.cta
+      {
+        const float4* xl = reinterpret_cast<const float4*>(smem + S::kOffX + xb * S::kXchgBytes + row * 128);
 #pragma unroll
         for (int v = 0; v < 8; ++v) {
           const float4 t = xl[v ^ (row & 7)];
@@ -270,6 +290,18 @@ mla_decode_kernel(const __grid_constant__ CUtensorMap tmQn, const __grid_constan
           r[4 * v + 3] = __float_as_uint(__uint_as_float(r[4 * v + 3]) + t.w);
         }
       }
+      uint32_t rn[32];
+      if (j + 1 < ntiles) {
+        const uint32_t bn = (j + 1) & (S::kSBufs - 1);
+        ptx::mbar_wait(&s_full[bn], ((j + 1) / S::kSBufs) & 1);
+        ptx::tc_fence_after();
+        ptx::tmem_ld_x32(tm_s + lane_addr + bn * 32, rn);
+        ptx::tmem_ld_wait();
+        push(j + 1, rn);
+      }
+      // re-arm this exchange buffer for tile j + 3 (one thread; the 128 waits above have not necessarily all passed, but
+      // the next phase cannot complete before the peer's tile-(j + 3) bytes arrive, three tiles from now)
+      if (threadIdx.x == 128 && j + S::kXBufs < ntiles) ptx::mbar_arrive_expect_tx(&x_full[xb], S::kXchgBytes);
       const int valid = kv_end - tok0;  // columns >= valid are past the chunk
       float tmax = -INFINITY;
 #pragma unroll
@@ -327,6 +359,10 @@ mla_decode_kernel(const __grid_constant__ CUtensorMap tmQn, const __grid_constan
       ptx::tc_fence_before();
       ptx::mbar_arrive(&p_ready[b]);
       ++od_cnt;
+      if (j + 1 < ntiles) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) r[e] = rn[e];
+      }
     }
     // ---- epilogue ----
     const float inv = l > 0.f ? 1.f / l : 0.f;

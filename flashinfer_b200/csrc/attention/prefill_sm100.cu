@@ -24,7 +24,9 @@
 
 using namespace fib200;
 
+#ifndef FIB_POD_TU
 FIB_EXPORT_LAST_ERROR()
+#endif
 
 namespace {
 
@@ -132,10 +134,11 @@ __device__ __forceinline__ float exp_pass(uint32_t s_tmem, int kv0, int lo, int 
   return l;
 }
 
+// The kernel body is a device function of the CTA index so that the fused POD kernel (pod_sm100.cu) can run it on a subset
+// of the grid next to the decode body; tensor maps are passed by reference to the __grid_constant__ kernel parameters.
 template <typename T, int DQK>
-__global__ void __launch_bounds__(384, 1)
-prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-               const __grid_constant__ CUtensorMap tmV, const PrefillParams p, uint32_t idesc_qk, uint32_t idesc_pv) {
+__device__ __forceinline__ void prefill_body(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
+                                             const PrefillParams& p, uint32_t idesc_qk, uint32_t idesc_pv, int cta) {
   using S = Smem<DQK>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -154,8 +157,8 @@ prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int w_begin = p.cta_work_indptr[blockIdx.x];
-  const int w_end = p.cta_work_indptr[blockIdx.x + 1];
+  const int w_begin = p.cta_work_indptr[cta];
+  const int w_end = p.cta_work_indptr[cta + 1];
   if (w_begin >= w_end) return;
 
   if (threadIdx.x == 0) {
@@ -556,6 +559,13 @@ prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   }
 }
 
+template <typename T, int DQK>
+__global__ void __launch_bounds__(384, 1)
+prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+               const __grid_constant__ CUtensorMap tmV, const PrefillParams p, uint32_t idesc_qk, uint32_t idesc_pv) {
+  prefill_body<T, DQK>(tmQ, tmK, tmV, p, idesc_qk, idesc_pv, blockIdx.x);
+}
+
 }  // namespace
 
 extern "C" int prefill_run(void* q, void* k, void* v, void* out, void* lse, void* kv_indices, void* kv_page_indptr,
@@ -625,6 +635,25 @@ extern "C" int prefill_run(void* q, void* k, void* v, void* out, void* lse, void
   const uint32_t idesc_qk = ptx::make_idesc_f16(fmt, 128, 128, 0, 0);
   const uint32_t idesc_pv = ptx::make_idesc_f16(fmt, 128, 128, 0, 1);
   auto go = [&](auto kern, int smem_bytes) -> int {
+#ifdef FIB_POD_TU
+    // POD: park the fully-built prefill launch; the decode launcher that follows fuses both into one grid
+    if (pod_stage().armed) {
+      PodStage& st = pod_stage();
+      static_assert(sizeof(PrefillParams) <= sizeof(st.params), "PodStage params buffer too small");
+      st.tm[0] = tmQ;
+      st.tm[1] = tmK;
+      st.tm[2] = tmV;
+      memcpy(st.params, &p, sizeof(p));
+      st.idesc[0] = idesc_qk;
+      st.idesc[1] = idesc_pv;
+      st.grid = (int)grid;
+      st.smem = smem_bytes;
+      st.f16 = f16 ? 1 : 0;
+      st.dqk = (int)head_dim;
+      st.have_prefill = true;
+      return 0;
+    }
+#endif
     FIB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     LaunchCfg lc(dim3((unsigned)grid), dim3(384), smem_bytes, stream, pdl != 0);
     FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, kern, tmQ, tmK, tmV, p, idesc_qk, idesc_pv));

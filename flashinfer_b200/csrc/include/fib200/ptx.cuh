@@ -268,6 +268,15 @@ __device__ __forceinline__ void st_dsmem_v4(uint32_t addr, float4 v) {
   asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                : "memory");
 }
+// Asynchronous 16-byte store into a peer CTA's shared memory that credits 16 bytes on the peer's mbarrier when it lands
+// (no release fence on the sender: completion is tracked by the barrier's tx-count, like a TMA write).
+__device__ __forceinline__ void st_async_v4(uint32_t remote_addr, float4 v, uint32_t remote_mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
+                   remote_addr),
+               "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)), "r"(__float_as_uint(v.w)),
+               "r"(remote_mbar)
+               : "memory");
+}
 __device__ __forceinline__ float4 ld_dsmem_v4(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"

@@ -297,6 +297,55 @@ def moe_forward_nvfp4(x: torch.Tensor, topk_ids: torch.Tensor, topk_w: torch.Ten
     return out
 
 
+def moe_forward_fp8_block(x: torch.Tensor, x_scale: Optional[torch.Tensor], topk_ids: torch.Tensor, topk_w: torch.Tensor,
+                          w1: torch.Tensor, w1_scale: torch.Tensor, w2: torch.Tensor, w2_scale: torch.Tensor,
+                          local_expert_offset: int = 0, num_experts: Optional[int] = None,
+                          out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """DeepSeek-V3 fp8 MoE on the native fp8 tensor-core path: ``w1 [E, 2I, H]`` / ``w2 [E, H, I]`` e4m3 with 128 x 128 fp32
+    block scales ``[E, N/128, K/128]``; activations are quantised per 1 x 128 group on the fly.
+
+    sort -> (gather + 1x128 quant) -> grouped fp8 GEMM (per-slab TMEM promotion) -> (SwiGLU + 1x128 quant) -> grouped fp8
+    GEMM -> finalize: six kernels, no weight de-quantisation.  ``x`` may be bf16 / fp16, or e4m3 with ``x_scale [H/128, T]``
+    (the trtllm layout).  Reference: trtllm_fp8_block_scale_moe (flashinfer/fused_moe/core.py)."""
+    from ..gemm.lowp import fp8_group_quantize, grouped_gemm_fp8_groupwise
+
+    T, H = x.shape
+    e_local, n1, _ = w1.shape
+    inter = w2.shape[2]
+    K = topk_ids.shape[1]
+    if x.dtype == torch.float8_e4m3fn:
+        s = x_scale.float().t().repeat_interleave(128, -1)[:, :H]
+        x = (x.float() * s).to(torch.bfloat16)
+    if (not x.is_cuda) or H % 128 or inter % 128 or n1 != 2 * inter:
+        res = moe_forward(x, topk_ids, topk_w, _dequant_fp8_block(w1, w1_scale, dtype=x.dtype),
+                          _dequant_fp8_block(w2, w2_scale, dtype=x.dtype), local_expert_offset, num_experts)
+        if out is not None:
+            out.copy_(res)
+            return out
+        return res
+    dev = x.device
+    mod = jit.load("moe")
+    max_rows = (T * K + e_local * (_TILE - 1)) // _TILE * _TILE + _TILE
+    e2p = torch.empty(T * K, dtype=torch.int32, device=dev)
+    p2t = torch.empty(max_rows, dtype=torch.int32, device=dev)
+    tile_e = torch.empty(max_rows // _TILE, dtype=torch.int32, device=dev)
+    offs = torch.empty(e_local + 1, dtype=torch.int32, device=dev)
+    meta = torch.empty(4, dtype=torch.int32, device=dev)
+    st = stream_ptr(x)
+    ids = topk_ids.to(torch.int32).contiguous()
+    ws = torch.empty(((T * K + 1023) // 1024) * e_local + 1, dtype=torch.int32, device=dev)
+    mod.call("moe_sort", ids, T, K, num_experts or e_local, local_expert_offset, e_local, _TILE, max_rows, e2p, p2t, tile_e, offs,
+             meta, ws, 1, st)
+    xq, xs = fp8_group_quantize(x, max_rows, gated=False, row_list=e2p, gather=True, list_div=K)
+    h1 = grouped_gemm_fp8_groupwise(xq, xs, w1, w1_scale, tile_e, meta, x.dtype)
+    aq, a_s = fp8_group_quantize(h1, max_rows, gated=True, row_list=e2p)
+    h2 = grouped_gemm_fp8_groupwise(aq, a_s, w2, w2_scale, tile_e, meta, x.dtype)
+    if out is None:
+        out = torch.empty(T, H, dtype=x.dtype, device=dev)
+    mod.call("moe_finalize", h2, out, e2p, topk_w.float().contiguous(), T, K, H, 0, dtype_code(x.dtype), 1, st)
+    return out
+
+
 def reorder_rows_for_gated_act_gemm(x: torch.Tensor) -> torch.Tensor:
     """Interleave the two halves of the rows ([up | gate] -> u0 g0 u1 g1 ...), the weight layout that lets a
     GEMM epilogue see matching up/gate columns in one tile (reference core.py:133)."""
@@ -384,13 +433,8 @@ def trtllm_fp8_block_scale_moe(routing_logits, routing_bias, hidden_states, hidd
                                weight_layout: int = 0, **kw):
     """DeepSeek-style fp8 (1x128 activation scales ``[H/128, T]``, 128x128 weight scales)."""
     ids, w = route(routing_logits, routing_bias, top_k, routing_method_type, n_group, topk_group, routed_scaling_factor)
-    x = hidden_states
-    if x.dtype == torch.float8_e4m3fn:
-        s = hidden_states_scale.float().t().repeat_interleave(128, -1)[:, : x.shape[1]]
-        x = (x.float() * s).to(torch.bfloat16)
-    w1 = _dequant_fp8_block(gemm1_weights, gemm1_weights_scale)
-    w2 = _dequant_fp8_block(gemm2_weights, gemm2_weights_scale)
-    return moe_forward(x, ids, w, w1, w2, local_expert_offset, num_experts)
+    return moe_forward_fp8_block(hidden_states, hidden_states_scale, ids, w, gemm1_weights, gemm1_weights_scale, gemm2_weights,
+                                 gemm2_weights_scale, local_expert_offset, num_experts)
 
 
 def trtllm_fp8_block_scale_routed_moe(topk_ids, routing_bias, hidden_states, hidden_states_scale, gemm1_weights,
@@ -398,12 +442,8 @@ def trtllm_fp8_block_scale_routed_moe(topk_ids, routing_bias, hidden_states, hid
                                       n_group, topk_group, intermediate_size, local_expert_offset, local_num_experts,
                                       routed_scaling_factor, routing_method_type: int = 1, **kw):
     ids, w = _unpack_routed(topk_ids)
-    x = hidden_states
-    if x.dtype == torch.float8_e4m3fn:
-        s = hidden_states_scale.float().t().repeat_interleave(128, -1)[:, : x.shape[1]]
-        x = (x.float() * s).to(torch.bfloat16)
-    return moe_forward(x, ids, w, _dequant_fp8_block(gemm1_weights, gemm1_weights_scale),
-                       _dequant_fp8_block(gemm2_weights, gemm2_weights_scale), local_expert_offset, num_experts)
+    return moe_forward_fp8_block(hidden_states, hidden_states_scale, ids, w, gemm1_weights, gemm1_weights_scale, gemm2_weights,
+                                 gemm2_weights_scale, local_expert_offset, num_experts)
 
 
 def trtllm_fp4_block_scale_moe(routing_logits, routing_bias, hidden_states, hidden_states_scale, gemm1_weights,

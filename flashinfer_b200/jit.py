@@ -20,6 +20,7 @@ cf. reference flashinfer/jit/core.py:217-402 and flashinfer/jit/cpp_ext.py:238-3
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
 import hashlib
 import os
@@ -66,6 +67,7 @@ class ModuleSpec:
     sources: Sequence[str]  # relative to csrc/
     extra_flags: Sequence[str] = field(default_factory=list)
     ldflags: Sequence[str] = field(default_factory=list)
+    deps: Sequence[str] = field(default_factory=list)  # files #included by the sources (hashed, not compiled)
 
     @property
     def so_path(self) -> Path:
@@ -80,7 +82,7 @@ class ModuleSpec:
 
     def content_hash(self) -> str:
         h = hashlib.sha256()
-        for p in self.source_paths():
+        for p in self.source_paths() + [CSRC / d for d in self.deps]:
             h.update(p.name.encode())
             h.update(p.read_bytes())
         for inc in INCLUDE_DIRS:
@@ -138,6 +140,7 @@ register(ModuleSpec("gemm_sm100", ["gemm/gemm_bf16_sm100.cu"]))
 register(ModuleSpec("decode_sm100", ["attention/decode_sm100.cu"]))
 register(ModuleSpec("prefill_sm100", ["attention/prefill_sm100.cu"]))
 register(ModuleSpec("mla_sm100", ["attention/mla_sm100.cu"]))
+register(ModuleSpec("pod_sm100", ["attention/pod_sm100.cu"], deps=["attention/prefill_sm100.cu", "attention/decode_sm100.cu"]))
 register(ModuleSpec("gemm_blockscaled_sm100", ["gemm/gemm_blockscaled_sm100.cu"]))
 register(ModuleSpec("grouped_gemm_sm100", ["gemm/grouped_gemm_sm100.cu"]))
 register(ModuleSpec("moe", ["moe/routing.cu"]))
@@ -276,8 +279,26 @@ class NativeModule:
 _loaded: Dict[str, NativeModule] = {}
 
 
+_redirect = threading.local()
+
+
+@contextlib.contextmanager
+def redirect(mapping: Dict[str, str]):
+    """Within the block, ``load(a)`` returns module ``mapping[a]`` (same C ABI compiled into another library).  Used by
+    POD: ``pod_sm100`` contains the prefill and decode launchers plus the fused kernel."""
+    prev = getattr(_redirect, "map", None)
+    _redirect.map = dict(mapping)
+    try:
+        yield
+    finally:
+        _redirect.map = prev
+
+
 def load(name: str) -> NativeModule:
     """Load (JIT-building if needed) a native module. Fails loudly."""
+    rmap = getattr(_redirect, "map", None)
+    if rmap:
+        name = rmap.get(name, name)
     mod = _loaded.get(name)
     if mod is not None:
         return mod

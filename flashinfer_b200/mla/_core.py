@@ -79,8 +79,18 @@ class BatchMLAPagedAttentionWrapper:
         chunk = max(4 * _TILE, -(-total_tokens // ctas))
         chunk = -(-chunk // _TILE) * _TILE
         # one wave: grow the chunk until the number of (row, split) work items fits the CTA pairs of the device
-        while sum(max(1, -(-r[2] // chunk)) for r in rows) > ctas and chunk < (1 << 30):
-            chunk += _TILE
+        # (every row is at least one item, so the target is max(ctas, rows); bisect instead of stepping)
+        target = max(ctas, len(rows))
+        count = lambda c: sum(max(1, -(-r[2] // c)) for r in rows)  # noqa: E731
+        if count(chunk) > target:
+            lo, hi = chunk // _TILE, max(chunk // _TILE, -(-max((r[2] for r in rows), default=_TILE) // _TILE))
+            while lo < hi:
+                mid = (lo + hi) // 2
+                if count(mid * _TILE) > target:
+                    lo = mid + 1
+                else:
+                    hi = mid
+            chunk = lo * _TILE
         kmax = max(1, max((-(-r[2] // chunk) for r in rows), default=1))
         self._kmax = kmax
         work = []

@@ -14,6 +14,7 @@ from typing import Optional, Tuple, Union
 
 import torch
 
+from . import jit
 from .decode import BatchDecodeWithPagedKVCacheWrapper
 from .prefill import BatchPrefillWithPagedKVCacheWrapper, BatchPrefillWithRaggedKVCacheWrapper
 from .utils import device_sm_count
@@ -31,6 +32,33 @@ def _split_sms(total: int, prefill_flops: float, decode_bytes: float) -> Tuple[i
     p = int(round(total * t_p / (t_p + t_d)))
     p = max(8, min(total - 8, p))
     return p, total - p
+
+
+def _fusable(q_p: torch.Tensor, q_d: torch.Tensor, kv_d, hq: int, hkv: int, head_dim: int) -> bool:
+    """Conditions of the single-kernel path (csrc/attention/pod_sm100.cu): 16-bit q of one dtype on both sides, 16-bit decode
+    KV cache, head_dim 128, decode rows per KV head (GQA group, q_len 1) in {1, 4, 8}."""
+    kd = kv_d[0] if isinstance(kv_d, (tuple, list)) else kv_d
+    return (q_p.is_cuda and q_p.dtype in (torch.float16, torch.bfloat16) and q_d.dtype == q_p.dtype and kd.dtype == q_p.dtype
+            and head_dim == 128 and hq % hkv == 0 and (hq // hkv) in (1, 4, 8) and q_d.shape[0] > 0 and q_p.shape[0] > 0)
+
+
+def _run_fused(prefill_call, decode_call):
+    """ONE launch for both phases: with the stage armed, the prefill launcher parks its launch inside ``pod_sm100`` and the
+    decode launcher that follows fuses both into ``pod_kernel`` (prefill CTAs first, decode CTAs after them).  If the
+    prefill side did not take the tcgen05 path (nothing parked) the decode simply runs after it."""
+    mod = jit.load("pod_sm100")
+    flag = torch.zeros(1, dtype=torch.int64)
+    mod.call("pod_arm", 1)
+    try:
+        with jit.redirect({"prefill_sm100": "pod_sm100", "decode_sm100": "pod_sm100"}):
+            res_p = prefill_call()
+            mod.call("pod_query", flag)
+            if int(flag[0]) == 0:
+                mod.call("pod_arm", 0)
+            res_d = decode_call()
+    finally:
+        mod.call("pod_arm", 0)
+    return res_p, res_d
 
 
 class _SideStream:
@@ -60,6 +88,7 @@ class PODWithPagedKVCacheWrapper:
         self._prefill = BatchPrefillWithRaggedKVCacheWrapper(float_workspace_buffer[:half], kv_layout)
         self._kv_layout = kv_layout
         self._side = _SideStream(self.device)
+        self._fused = True  # single-kernel POD when the shapes allow it (set False to force the two-stream composition)
 
     def plan(self, indptr, indices, last_page_len, num_qo_heads, num_kv_heads, head_dim, page_size,
              pos_encoding_mode="NONE", window_left=-1, q_data_type="float16", kv_data_type=None, data_type=None,
@@ -95,7 +124,11 @@ class PODWithPagedKVCacheWrapper:
         self._prefill.plan(torch.tensor([0, qo_len], dtype=torch.int32), torch.tensor([0, kv_len], dtype=torch.int32),
                            self._hq, self._hkv, self._d, causal=causal_p, sm_scale=sm_scale_p,
                            window_left=window_left_p, q_data_type=q_p.dtype)
-        if q_p.is_cuda:
+        if _fusable(q_p, q_d, paged_kv_cache_d, self._hq, self._hkv, self._d) and k_p.dtype == q_p.dtype \
+                and q_scale is None and k_scale is None and v_scale is None and self._fused:
+            res_p, res_d = _run_fused(lambda: self._prefill.run(q_p, k_p, v_p, return_lse=return_lse_p),
+                                      lambda: self._decode.run(q_d, paged_kv_cache_d, return_lse=return_lse_d))
+        elif q_p.is_cuda:
             self._side.fork()
             with torch.cuda.stream(self._side.stream):
                 res_d = self._decode.run(q_d, paged_kv_cache_d, q_scale=q_scale, k_scale=k_scale, v_scale=v_scale,
@@ -123,6 +156,7 @@ class BatchPODWithPagedKVCacheWrapper:
         self._prefill = BatchPrefillWithPagedKVCacheWrapper(float_workspace_buffer[:half], kv_layout)
         self._decode = BatchDecodeWithPagedKVCacheWrapper(float_workspace_buffer[half:], kv_layout)
         self._side = _SideStream(self.device)
+        self._fused = True
 
     def plan(self, qo_indptr_p, kv_indptr_p, kv_indices_p, last_page_len_p, qo_indptr_d, kv_indptr_d, kv_indices_d,
              last_page_len_d, num_qo_heads, num_kv_heads, head_dim, page_size, pos_encoding_mode="NONE",
@@ -147,6 +181,7 @@ class BatchPODWithPagedKVCacheWrapper:
                           window_left=window_left, q_data_type=dt, kv_data_type=kv_data_type, sm_scale=sm_scale,
                           qo_indptr=None if plain_decode else qo_indptr_d)
         self._sm_split = (sp, sd)
+        self._hq, self._hkv, self._d, self._plain_decode = num_qo_heads, num_kv_heads, head_dim, plain_decode
 
     begin_forward = plan
 
@@ -155,7 +190,12 @@ class BatchPODWithPagedKVCacheWrapper:
             use_fp16_qk_reduction: bool = False, enable_pdl=None):
         if custom_mask_p is not None or packed_custom_mask_p is not None:
             raise NotImplementedError("POD with custom masks")
-        if q_p.is_cuda:
+        kp = paged_kv_cache_p[0] if isinstance(paged_kv_cache_p, (tuple, list)) else paged_kv_cache_p
+        if self._fused and self._plain_decode and _fusable(q_p, q_d, paged_kv_cache_d, self._hq, self._hkv, self._d) \
+                and kp.dtype == q_p.dtype and q_scale is None and k_scale is None and v_scale is None:
+            res_p, res_d = _run_fused(lambda: self._prefill.run(q_p, paged_kv_cache_p, return_lse=return_lse),
+                                      lambda: self._decode.run(q_d, paged_kv_cache_d, return_lse=return_lse))
+        elif q_p.is_cuda:
             self._side.fork()
             with torch.cuda.stream(self._side.stream):
                 res_d = self._decode.run(q_d, paged_kv_cache_d, q_scale=q_scale, k_scale=k_scale, v_scale=v_scale,

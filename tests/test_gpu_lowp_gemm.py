@@ -168,3 +168,88 @@ def test_lowp_cta_pair_kernel(m, n, k, bn2):
     finally:
         os.environ.pop("FIB200_LOWP_2CTA", None)
         os.environ.pop("FIB200_LOWP_BN", None)
+
+
+def _q128(x):
+    """1x128 group quantisation oracle -> (e4m3, fp32 scales, de-quantised fp32)."""
+    g = x.float().view(x.shape[0], -1, 128)
+    sc = g.abs().amax(-1).clamp_min(1e-10) / 448.0
+    q = (g / sc[..., None]).view_as(x).to(torch.float8_e4m3fn)
+    return q, sc, (q.float().view_as(g) * sc[..., None]).view_as(x)
+
+
+def _qblk(w):
+    E, N, K = w.shape
+    blk = w.float().reshape(E, N // 128, 128, K // 128, 128)
+    s = blk.abs().amax((2, 4)).clamp_min(1e-10) / 448.0
+    q = (blk / s[:, :, None, :, None]).reshape(E, N, K).to(torch.float8_e4m3fn)
+    dq = (q.float().reshape(E, N // 128, 128, K // 128, 128) * s[:, :, None, :, None]).reshape(E, N, K)
+    return q, s, dq
+
+
+def test_fp8_group_quantize_gpu():
+    from flashinfer_b200.gemm.lowp import fp8_group_quantize
+
+    torch.manual_seed(0)
+    x = (torch.randn(300, 1024, device="cuda") * 3).bfloat16()
+    q, sc = fp8_group_quantize(x)
+    q_ref, sc_ref, _ = _q128(x)
+    assert torch.allclose(sc, sc_ref, rtol=1e-5, atol=1e-9)
+    assert (q.float() - q_ref.float()).abs().max().item() <= 32.0  # at most one e4m3 ulp at the top binade (rounding of 1/scale)
+    assert ((q.float() - q_ref.float()) != 0).float().mean().item() < 0.02
+    # gated + row_list + gather
+    h = (torch.randn(64, 2 * 256, device="cuda")).bfloat16()
+    rows = torch.tensor([5, -1, 0, 17, 33, 2], dtype=torch.int32, device="cuda")
+    qg, sg = fp8_group_quantize(h, rows=64, gated=True, row_list=rows)
+    act = h.float()[:, :256] * torch.nn.functional.silu(h.float()[:, 256:])
+    for j, r in enumerate(rows.tolist()):
+        if r < 0:
+            continue
+        _, s_ref, dq_ref = _q128(act[r:r + 1])
+        assert torch.allclose(sg[r], s_ref[0], rtol=2e-2)
+        got = qg[r].float().view(-1, 128) * sg[r][:, None]
+        assert (got.flatten() - act[r]).abs().max().item() < 0.08 * act[r].abs().max().item() + 1e-3
+    src = (torch.randn(10, 256, device="cuda")).bfloat16()
+    lst = torch.tensor([3, 1, -1, 7, 2, 0], dtype=torch.int32, device="cuda")  # entry j reads token j // 2
+    qq, ss = fp8_group_quantize(src, rows=8, row_list=lst, gather=True, list_div=2)
+    for j, r in enumerate(lst.tolist()):
+        if r >= 0:
+            q_ref, s_ref, _ = _q128(src[j // 2:j // 2 + 1])
+            assert torch.allclose(ss[r], s_ref[0], rtol=1e-5)
+
+
+@pytest.mark.parametrize("E,N,K", [(4, 256, 512), (8, 1024, 1024), (3, 96, 256)])
+def test_grouped_fp8_groupwise_gpu(E, N, K):
+    """m-grouped contiguous fp8 GEMM with DeepSeek scales (native grouped mode) + the DeepGEMM-style wrappers."""
+    from flashinfer_b200.gemm import batch_deepgemm_fp8_nt_groupwise, group_deepgemm_fp8_nt_groupwise
+
+    torch.manual_seed(E + N)
+    tiles = [2, 1, 3, 1, 2, 1, 1, 2][:E]
+    m_idx = torch.cat([torch.full((t * 128,), e, dtype=torch.int32) for e, t in enumerate(tiles)]).cuda()
+    M = m_idx.numel()
+    a = torch.randn(M, K, device="cuda")
+    w = torch.randn(E, (N + 127) // 128 * 128, K, device="cuda") / K ** 0.5
+    aq, a_s, a_dq = _q128(a)
+    wq, w_s, w_dq = _qblk(w)
+    wq, w_dq = wq[:, :N].contiguous(), w_dq[:, :N]
+    ref = torch.stack([a_dq[i] @ w_dq[int(m_idx[i])].t() for i in range(0, M, 1)]) if M <= 512 else None
+    if ref is None:
+        ref = torch.empty(M, N, device="cuda")
+        for e in range(E):
+            sel = m_idx == e
+            ref[sel] = a_dq[sel] @ w_dq[e].t()
+    out = group_deepgemm_fp8_nt_groupwise(aq, wq, a_s, w_s, m_idx)
+    err = (out.float() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 1e-2, err
+    if N % 128 == 0:
+        # masked layout: group g has masked_m[g] live rows out of 256
+        G = min(E, 4)
+        masked = torch.tensor([256, 100, 0, 129][:G], dtype=torch.int32, device="cuda")
+        a3 = torch.randn(G, 256, K, device="cuda")
+        a3q, a3s, a3dq = _q128(a3.view(-1, K))
+        o = batch_deepgemm_fp8_nt_groupwise(a3q.view(G, 256, K), wq[:G], a3s.view(G, 256, -1), w_s[:G], masked)
+        for g in range(G):
+            n = int(masked[g])
+            if n:
+                r = a3dq.view(G, 256, K)[g, :n] @ w_dq[g].t()
+                assert (o[g, :n].float() - r).abs().max().item() / r.abs().max().item() < 1e-2

@@ -186,3 +186,43 @@ def test_rope_append_fused_matches_separate(device, layout):
     assert torch.equal(q1, q2)
     assert torch.equal(kc1, kc2)
     assert torch.equal(vc1, vc2)
+
+
+@pytest.mark.gpu
+def test_pod_runs_as_one_fused_kernel():
+    """On the GPU the POD wrappers must take the single-kernel path (csrc/attention/pod_sm100.cu): the launches are
+    counted inside pod_sm100.so, none in the stand-alone prefill / decode libraries, and the results match the
+    two-stream composition (same kernel bodies, same plans)."""
+    import ctypes
+
+    from flashinfer_b200 import jit
+
+    def count(name):
+        f = jit.load(name)._dll.fib200_launch_count
+        f.restype = ctypes.c_longlong
+        return int(f())
+
+    dt, ps, hq, hkv, device = torch.bfloat16, 16, 32, 8, "cuda"
+    ws = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    torch.manual_seed(3)
+    q_p = torch.randn(2048, hq, D, device=device, dtype=dt)
+    k_p = torch.randn(2048, hkv, D, device=device, dtype=dt)
+    v_p = torch.randn(2048, hkv, D, device=device, dtype=dt)
+    kv_lens = [1000 + 37 * i for i in range(24)]
+    indptr, indices, last, kc, vc = make_paged(kv_lens, hkv, D, ps, "NHD", dt, device)
+    q_d = torch.randn(len(kv_lens), hq, D, device=device, dtype=dt)
+    w = PODWithPagedKVCacheWrapper(ws)
+    w.plan(indptr, indices, last, hq, hkv, D, ps, q_data_type=dt)
+    w.run(q_p, k_p, v_p, q_d, (kc, vc), causal_p=True)  # warm-up (loads the libraries)
+    c_pod, c_p, c_d = count("pod_sm100"), count("prefill_sm100"), count("decode_sm100")
+    o_p, o_d = w.run(q_p, k_p, v_p, q_d, (kc, vc), causal_p=True)
+    torch.cuda.synchronize()
+    assert 1 <= count("pod_sm100") - c_pod <= 2  # fused kernel (+ the decode split-KV merge when the planner splits)
+    assert count("prefill_sm100") == c_p and count("decode_sm100") == c_d
+    w._fused = False
+    r_p, r_d = w.run(q_p, k_p, v_p, q_d, (kc, vc), causal_p=True)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(o_p.float(), r_p.float(), rtol=0, atol=1e-2)
+    torch.testing.assert_close(o_d.float(), r_d.float(), rtol=0, atol=1e-2)
+    ref_p, _ = reference.attention_ref(q_p[:256], k_p[:256], v_p[:256], True)
+    torch.testing.assert_close(o_p[:256].float(), ref_p.float(), rtol=3e-2, atol=3e-2)

@@ -1,4 +1,4 @@
-"""Single-kernel workloads for `ncu --set full` captures:  python tools/prof_targets.py <gemm_bf16|gemm_fp4|gemm_fp8|prefill|decode|moe>"""
+"""Single-kernel workloads for `ncu --set full` captures:  python tools/prof_targets.py <gemm_bf16|gemm_fp4|gemm_fp8|prefill|decode|moe|mla|mla_small>"""
 import math, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -39,4 +39,14 @@ elif mode == "moe":
     x = (torch.randn(T, H, device="cuda") * 0.5).bfloat16(); w1 = (torch.randn(E, 2 * I, H, device="cuda") / H ** 0.5).bfloat16(); w2 = (torch.randn(E, H, I, device="cuda") / I ** 0.5).bfloat16()
     ids, w = route(torch.randn(T, E, device="cuda"), None, K, 1)
     for _ in range(3): moe_forward(x, ids, w, w1, w2)
+elif mode in ("mla", "mla_small"):
+    from flashinfer_b200.mla import BatchMLAPagedAttentionWrapper
+    B, kv, H, ps = (64, 4096, 128, 64) if mode == "mla" else (16, 1024, 128, 32)
+    npg = kv // ps
+    ckv = torch.randn(B * npg, ps, 512, device="cuda", dtype=torch.bfloat16); kpe = torch.randn(B * npg, ps, 64, device="cuda", dtype=torch.bfloat16)
+    qn = torch.randn(B, H, 512, device="cuda", dtype=torch.bfloat16); qp = torch.randn(B, H, 64, device="cuda", dtype=torch.bfloat16)
+    w = BatchMLAPagedAttentionWrapper(torch.empty(256 << 20, dtype=torch.uint8, device="cuda"))
+    w.plan(torch.arange(B + 1, dtype=torch.int32), torch.arange(0, (B + 1) * npg, npg, dtype=torch.int32), torch.randperm(B * npg).int(),
+           torch.full((B,), kv, dtype=torch.int32), H, 512, 64, ps, True, 0.07, torch.bfloat16, torch.bfloat16)
+    for _ in range(3): w.run(qn, qp, ckv, kpe)
 torch.cuda.synchronize()
