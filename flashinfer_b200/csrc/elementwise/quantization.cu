@@ -37,6 +37,38 @@ __device__ __forceinline__ uint8_t f32_to_ue8m0_ceil(float x) {
 __device__ __forceinline__ float ue8m0_to_f32(uint8_t e) { return __uint_as_float(uint32_t(e == 0 ? 0 : e) << 23); }
 
 // ---------------------------------------------------------------- fp4 (nvfp4 / mxfp4)
+// Quantise one block of VEC values: returns the scale byte (UE4M3 or UE8M0) and stores VEC / 2 packed e2m1 bytes at dst.
+template <int VEC, bool kUE8M0>
+__device__ __forceinline__ uint8_t fp4_quantize_block(const float (&v)[VEC], float gs, uint8_t* __restrict__ dst) {
+  float amax = 0.f;
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) amax = fmaxf(amax, fabsf(v[j]));
+  uint8_t sf_byte;
+  float out_scale;
+  if constexpr (kUE8M0) {
+    sf_byte = f32_to_ue8m0_ceil(amax * (1.f / 6.f) * gs);
+    const float sfv = ue8m0_to_f32(sf_byte);
+    out_scale = sfv > 0.f ? gs / sfv : 0.f;
+  } else {
+    const float sfv_f = gs * (amax * (1.f / 6.f));
+    const __nv_fp8_e4m3 s8(sfv_f);
+    sf_byte = *reinterpret_cast<const uint8_t*>(&s8);
+    const float sfv = float(s8);
+    out_scale = sfv != 0.f ? gs / sfv : 0.f;
+  }
+  uint8_t packed[VEC / 2];
+#pragma unroll
+  for (int j = 0; j < VEC; j += 2)
+    packed[j / 2] = (uint8_t)__nv_cvt_float2_to_fp4x2(make_float2(v[j] * out_scale, v[j + 1] * out_scale), __NV_E2M1,
+                                                      cudaRoundNearest);
+  if constexpr (VEC == 16) {
+    *reinterpret_cast<int2*>(dst) = *reinterpret_cast<const int2*>(packed);
+  } else {
+    *reinterpret_cast<int4*>(dst) = *reinterpret_cast<const int4*>(packed);
+  }
+  return sf_byte;
+}
+
 // x [B, M, K] (row stride ldx) -> q [B, M, K/2] uint8, sf [B][...] uint8
 template <typename T, int VEC, bool kUE8M0>
 __global__ void __launch_bounds__(256)
@@ -86,37 +118,77 @@ fp4_quantize_kernel(const T* __restrict__ x, uint8_t* __restrict__ q, uint8_t* _
         }
       }
     }
-    float amax = 0.f;
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) amax = fmaxf(amax, fabsf(v[j]));
-    uint8_t sf_byte;
-    float out_scale;
-    if constexpr (kUE8M0) {
-      sf_byte = f32_to_ue8m0_ceil(amax * (1.f / 6.f) * gs);
-      const float sfv = ue8m0_to_f32(sf_byte);
-      out_scale = sfv > 0.f ? gs / sfv : 0.f;
-    } else {
-      const float sfv_f = gs * (amax * (1.f / 6.f));
-      const __nv_fp8_e4m3 s8(sfv_f);
-      sf_byte = *reinterpret_cast<const uint8_t*>(&s8);
-      const float sfv = float(s8);
-      out_scale = sfv != 0.f ? gs / sfv : 0.f;
-    }
-    uint8_t packed[VEC / 2];
-#pragma unroll
-    for (int j = 0; j < VEC; j += 2)
-      packed[j / 2] = (uint8_t)__nv_cvt_float2_to_fp4x2(make_float2(v[j] * out_scale, v[j + 1] * out_scale), __NV_E2M1,
-                                                        cudaRoundNearest);
     uint8_t* dst = q + (b * M + m) * (K / 2) + kc * (VEC / 2);
-    if constexpr (VEC == 16) {
-      *reinterpret_cast<int2*>(dst) = *reinterpret_cast<const int2*>(packed);
-    } else {
-      *reinterpret_cast<int4*>(dst) = *reinterpret_cast<const int4*>(packed);
-    }
+    const uint8_t sf_byte = fp4_quantize_block<VEC, kUE8M0>(v, gs, dst);
     const int64_t sf_off = swizzled ? sf_swizzled_offset(m, kc, kc_pad) : m * kc_total + kc;
     sf[b * sf_batch_stride + sf_off] = sf_byte;
   }
   ptx::grid_dep_launch();
+}
+
+// ---------------------------------------------------------------- (add +) RMSNorm + FP4 quantisation in one kernel
+// One CTA per row: pass 1 loads the row (adds and writes back the residual when given), keeps it in shared memory as fp32
+// and reduces the sum of squares; pass 2 normalises, applies the weight and quantises 16- / 32-element blocks straight to
+// packed e2m1 + scale bytes.  The normalised activations never touch HBM (reference: rmsnorm_fp4quant /
+// add_rmsnorm_fp4quant, flashinfer/norm/__init__.py, a CuTe-DSL kernel there).
+template <typename T, int VEC, bool kUE8M0>
+__global__ void __launch_bounds__(256)
+rmsnorm_fp4quant_kernel(const T* __restrict__ x, T* __restrict__ residual, const T* __restrict__ weight, uint8_t* __restrict__ q,
+                        uint8_t* __restrict__ sf, uint8_t* __restrict__ sf2, const float* __restrict__ global_scale, int64_t M,
+                        int64_t K, int64_t ldx, int64_t ldr, float eps, int swizzled, int weight_bias) {
+  extern __shared__ float rowbuf[];
+  __shared__ float red[8];
+  const int64_t m = blockIdx.x;
+  ptx::grid_dep_wait();
+  float ss = 0.f;
+  for (int64_t c = threadIdx.x * 8; c < K; c += blockDim.x * 8) {
+    const Vec16<T> xv = ld16(x + m * ldx + c);
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = to_f32(xv.v[e]);
+    if (residual) {
+      const Vec16<T> rv = ld16(residual + m * ldr + c);
+      Vec16<T> ro;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        f[e] += to_f32(rv.v[e]);
+        ro.v[e] = from_f32<T>(f[e]);
+        f[e] = to_f32(ro.v[e]);  // the norm sees the stored (rounded) residual, like the two-kernel composition
+      }
+      st16(residual + m * ldr + c, ro);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      rowbuf[c + e] = f[e];
+      ss += f[e] * f[e];
+    }
+  }
+  ss = warp_reduce_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) tot += red[w];
+  const float rstd = rsqrtf(tot / float(K) + eps);
+  const float gs = global_scale ? __ldg(global_scale) : 1.f;
+  const int64_t kc_total = K / VEC, kc_pad = (kc_total + 3) / 4 * 4;
+  ptx::grid_dep_launch();
+  for (int64_t kc = threadIdx.x; kc < kc_total; kc += blockDim.x) {
+    float v[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; j += 8) {
+      const Vec16<T> wv = ld16(weight + kc * VEC + j);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float wf = to_f32(wv.v[e]) + (weight_bias ? 1.f : 0.f);
+        // round through T like the composed path (rmsnorm writes T, the quantiser reads T)
+        v[j + e] = to_f32(from_f32<T>(rowbuf[kc * VEC + j + e] * rstd * wf));
+      }
+    }
+    const uint8_t sf_byte = fp4_quantize_block<VEC, kUE8M0>(v, gs, q + m * (K / 2) + kc * (VEC / 2));
+    sf[swizzled ? sf_swizzled_offset(m, kc, kc_pad) : m * kc_total + kc] = sf_byte;
+    if (sf2) sf2[swizzled ? m * kc_total + kc : sf_swizzled_offset(m, kc, kc_pad)] = sf_byte;  // the other layout as well
+  }
 }
 
 // ---------------------------------------------------------------- fp8 e4m3 with fp32 scales per 1 x 128 group (DeepSeek)
@@ -341,6 +413,32 @@ extern "C" int fp4_quantize(void* x, void* q, void* sf, void* global_scale, int6
     if (vec == 16) return launch(fp4_quantize_kernel<T, 16, true>);
     if (ue8m0) return launch(fp4_quantize_kernel<T, 32, true>);
     return launch(fp4_quantize_kernel<T, 32, false>);
+  });
+}
+
+// (add +) RMSNorm + FP4 quantisation, one kernel.  sf2: optional second scale tensor in the other layout.
+extern "C" int rmsnorm_fp4quant(void* x, void* residual, void* weight, void* q, void* sf, void* sf2, void* global_scale, int64_t M,
+                                int64_t K, int64_t ldx, int64_t ldr, double eps, int64_t vec, int64_t ue8m0, int64_t swizzled,
+                                int64_t weight_bias, int64_t dtype, int64_t pdl, int64_t stream_) {
+  FIB_CHECK(vec == 16 || vec == 32, "rmsnorm_fp4quant: block size must be 16 or 32");
+  FIB_CHECK(K % vec == 0 && K % 8 == 0 && ldx % 8 == 0 && ldr % 8 == 0, "rmsnorm_fp4quant: hidden must be a multiple of the block size");
+  FIB_CHECK(K * 4 <= 200 * 1024, "rmsnorm_fp4quant: hidden size too large for the row buffer");
+  if (M == 0) return 0;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const size_t smem = size_t(K) * 4;
+  LaunchCfg lc(dim3((unsigned)M), dim3(256), smem, stream, pdl != 0);
+  return FIB_DISPATCH_HALF(dtype, T, [&]() -> int {
+    auto launch = [&](auto kern) -> int {
+      if (smem > 48 * 1024) FIB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, kern, (const T*)x, (T*)residual, (const T*)weight, (uint8_t*)q, (uint8_t*)sf,
+                                        (uint8_t*)sf2, (const float*)global_scale, M, K, ldx, ldr, (float)eps, (int)swizzled,
+                                        (int)weight_bias));
+      return 0;
+    };
+    if (vec == 16 && !ue8m0) return launch(rmsnorm_fp4quant_kernel<T, 16, false>);
+    if (vec == 16) return launch(rmsnorm_fp4quant_kernel<T, 16, true>);
+    if (ue8m0) return launch(rmsnorm_fp4quant_kernel<T, 32, true>);
+    return launch(rmsnorm_fp4quant_kernel<T, 32, false>);
   });
 }
 

@@ -71,6 +71,7 @@ struct Params {
   int batch, BN;
   const int32_t* tile_expert;  // grouped (MoE) mode: expert of every 128-row tile of A (-1 = skip); B / SFB / alpha are per expert
   const int32_t* meta;         // grouped mode: meta[0] = number of live row tiles (device side)
+  const int32_t* row_map;      // grouped mode (optional): rows with row_map < 0 are padding, their results are not stored
   int tab_tiles, tab_experts;  // capacity of the shared-memory tile->expert / alpha tables (grouped mode)
   int split;          // cluster split-K factor (1 or 2): both CTAs of a cluster own the same tile, half of K each
   int sf_k_tiles;     // 512-byte blocks along K in the scale tensors
@@ -324,8 +325,10 @@ bs_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       OutT* crow = C + int64_t(b) * p.c_batch_stride + int64_t(row) * p.ldc;
       const bool vec_ok = (p.ldc % (16 / sizeof(OutT)) == 0);
+      const bool row_live = !p.row_map || (row < p.M && p.row_map[row] >= 0);
+      const bool warp_live = __any_sync(0xffffffffu, row_live);  // a warp of pure padding rows skips its TMEM reads too
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = 0; c0 < BN && warp_live; c0 += 32) {
         uint32_t v[32];
         ptx::tmem_ld_x32(taddr + c0, v);
         ptx::tmem_ld_wait();
@@ -340,7 +343,7 @@ bs_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         const int col0 = tn * BN + c0;
-        if (row < p.M) {
+        if (row < p.M && row_live) {
           if (col0 + 32 <= p.N && vec_ok) {
             constexpr int VN = 16 / sizeof(OutT);
 #pragma unroll
@@ -394,6 +397,7 @@ struct GwParams {
   // weights + scales of expert tile_expert[tm]; meta[0] = number of live row tiles (device-side, produced by the sort).
   const int32_t* tile_expert;
   const int32_t* meta;
+  const int32_t* row_map;  // optional: rows with row_map < 0 are padding (not stored)
   int64_t sb_e;  // expert stride of the B scales
 };
 
@@ -556,7 +560,7 @@ fp8_groupwise_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         buf ^= 1;
         if (buf == 0) bphase ^= 1;
       }
-      if (row < p.M) {
+      if (row < p.M && (!p.row_map || p.row_map[row] >= 0)) {
         OutT* crow = C + int64_t(row) * p.ldc + tn * BN;
         constexpr int VN = 16 / sizeof(OutT);
         const bool vec_ok = (p.ldc % VN == 0);
@@ -948,7 +952,7 @@ extern "C" int gemm_lowp_nt(void* A, void* B, void* C, void* sfa, void* sfb, voi
                             int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc,
                             int64_t a_batch_stride, int64_t b_batch_stride, int64_t c_batch_stride,
                             int64_t sfa_batch_stride, int64_t sfb_batch_stride, int64_t kind, int64_t a_fmt,
-                            int64_t b_fmt, int64_t out_dtype, int64_t bn, void* tile_expert, void* meta, int64_t pdl,
+                            int64_t b_fmt, int64_t out_dtype, int64_t bn, void* tile_expert, void* meta, void* row_map, int64_t pdl,
                             int64_t stream_) {
   FIB_CHECK(kind >= 0 && kind <= 3, "gemm_lowp: kind must be 0..3");
   FIB_CHECK(out_dtype == kF16 || out_dtype == kBF16, "gemm_lowp: output must be f16/bf16");
@@ -1079,6 +1083,7 @@ extern "C" int gemm_lowp_nt(void* A, void* B, void* C, void* sfa, void* sfb, voi
   p.sfa = (const uint8_t*)sfa;
   p.tile_expert = (const int32_t*)tile_expert;
   p.meta = (const int32_t*)meta;
+  p.row_map = (const int32_t*)row_map;
   p.tab_tiles = tile_expert ? (tiles_m < 1024 ? tiles_m : 1024) : 0;
   p.tab_experts = tile_expert ? (int)(batch < 1024 ? batch : 1024) : 0;
   const int tab_bytes = (p.tab_tiles + p.tab_experts) * 4;
@@ -1135,7 +1140,7 @@ extern "C" int gemm_lowp_nt(void* A, void* B, void* C, void* sfa, void* sfb, voi
 extern "C" int gemm_fp8_groupwise_nt(void* A, void* B, void* C, void* sa, void* sb, int64_t M, int64_t N, int64_t K, int64_t lda,
                                      int64_t ldb, int64_t ldc, int64_t sa_row, int64_t sa_k, int64_t sb_n, int64_t sb_k,
                                      int64_t a_fmt, int64_t b_fmt, int64_t out_dtype, int64_t bn, void* tile_expert, void* meta,
-                                     int64_t num_experts, int64_t sb_e, int64_t pdl, int64_t stream_) {
+                                     int64_t num_experts, int64_t sb_e, void* row_map, int64_t pdl, int64_t stream_) {
   // tile_expert != null: m-grouped contiguous mode, B is [num_experts * N, K], sb has an expert stride sb_e, M = padded rows
   FIB_CHECK(out_dtype == kF16 || out_dtype == kBF16, "gemm_fp8_groupwise: output must be f16/bf16");
   FIB_CHECK(K % 128 == 0, "gemm_fp8_groupwise: K must be a multiple of 128");
@@ -1170,6 +1175,7 @@ extern "C" int gemm_fp8_groupwise_nt(void* A, void* B, void* C, void* sa, void* 
   GwParams p;
   p.tile_expert = (const int32_t*)tile_expert;
   p.meta = (const int32_t*)meta;
+  p.row_map = (const int32_t*)row_map;
   p.sb_e = sb_e;
   p.sa = (const float*)sa;
   p.sb = (const float*)sb;

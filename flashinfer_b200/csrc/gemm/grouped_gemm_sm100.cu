@@ -38,7 +38,8 @@ template <typename OutT>
 __global__ void __launch_bounds__(256, 1)
 grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                     OutT* __restrict__ C, const int32_t* __restrict__ tile_expert, const int32_t* __restrict__ meta,
-                    int max_m_tiles, int N, int K, int64_t ldc, int BN, uint32_t idesc, int tab_tiles) {
+                    int max_m_tiles, int N, int K, int64_t ldc, int BN, uint32_t idesc, int tab_tiles,
+                    const int32_t* __restrict__ row_map) {
   const GSmem S = GSmem::make(BN);
   const int kStages = S.stages;
   extern __shared__ uint8_t smem_raw[];
@@ -156,13 +157,17 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       ptx::tc_fence_after();
       const int row = tm * BM + q * 32 + lane;
       const uint32_t taddr = tmem_base + acc * BN + (uint32_t(q * 32) << 16);
+      // MoE: padding rows of the tile-aligned layout (row_map < 0) are never read back -> do not spend HBM writes on them
+      const bool live = !row_map || row_map[row] >= 0;
+      const bool warp_live = __any_sync(0xffffffffu, live);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 16) {
+      for (int c0 = 0; c0 < BN && warp_live; c0 += 16) {
         uint32_t r[16];
         ptx::tmem_ld_x16(taddr + c0, r);
         ptx::tmem_ld_wait();
         const int col0 = tn * BN + c0;
         OutT* dst = C + int64_t(row) * ldc + col0;
+        if (!live) continue;
         if (col0 + 16 <= N) {
           constexpr int VN = 16 / sizeof(OutT);
 #pragma unroll
@@ -197,7 +202,7 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
 // A [max_m_tiles*128, K] (lda), W [E, N, K] contiguous, C [max_m_tiles*128, N] (ldc).
 extern "C" int grouped_gemm_nt(void* A, void* W, void* C, void* tile_expert, void* meta, int64_t max_m_tiles, int64_t N,
-                               int64_t K, int64_t E, int64_t lda, int64_t ldc, int64_t dtype, int64_t pdl,
+                               int64_t K, int64_t E, int64_t lda, int64_t ldc, void* row_map, int64_t dtype, int64_t pdl,
                                int64_t stream_) {
   FIB_CHECK(K % 8 == 0 && lda % 8 == 0 && ldc % 8 == 0 && N % 8 == 0, "grouped_gemm: K/N/lda/ldc must be multiples of 8");
   FIB_CHECK(dtype == kF16 || dtype == kBF16, "grouped_gemm: dtype must be f16/bf16");
@@ -232,7 +237,7 @@ extern "C" int grouped_gemm_nt(void* A, void* W, void* C, void* tile_expert, voi
     }
     FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, grouped_gemm_kernel<__half>, tmA, tmW, (__half*)C,
                                       (const int32_t*)tile_expert, (const int32_t*)meta, (int)max_m_tiles, (int)N, (int)K,
-                                      ldc, BN, idesc, tab_tiles));
+                                      ldc, BN, idesc, tab_tiles, (const int32_t*)row_map));
   } else {
     static bool set = false;
     if (!set) {
@@ -242,7 +247,7 @@ extern "C" int grouped_gemm_nt(void* A, void* W, void* C, void* tile_expert, voi
     }
     FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, grouped_gemm_kernel<__nv_bfloat16>, tmA, tmW, (__nv_bfloat16*)C,
                                       (const int32_t*)tile_expert, (const int32_t*)meta, (int)max_m_tiles, (int)N, (int)K,
-                                      ldc, BN, idesc, tab_tiles));
+                                      ldc, BN, idesc, tab_tiles, (const int32_t*)row_map));
   }
   return 0;
 }

@@ -190,7 +190,7 @@ def moe_forward(x: torch.Tensor, topk_ids: torch.Tensor, topk_w: torch.Tensor, w
     xp = torch.empty(max_rows, H, dtype=x.dtype, device=dev)
     mod.call("moe_gather", x, xp, p2t, meta, max_rows, H, x.stride(0), 0, e2p, T * K, K, dtype_code(x.dtype), 1, st)
     h1 = torch.empty(max_rows, n1, dtype=x.dtype, device=dev)
-    gg.call("grouped_gemm_nt", xp, w1.contiguous(), h1, tile_e, meta, max_tiles, n1, H, e_local, H, n1,
+    gg.call("grouped_gemm_nt", xp, w1.contiguous(), h1, tile_e, meta, max_tiles, n1, H, e_local, H, n1, p2t,
             dtype_code(x.dtype), 1, st)
     if n1 == 2 * inter:
         a = torch.empty(max_rows, inter, dtype=x.dtype, device=dev)
@@ -198,7 +198,7 @@ def moe_forward(x: torch.Tensor, topk_ids: torch.Tensor, topk_w: torch.Tensor, w
     else:
         a = torch.nn.functional.silu(h1) if activation == "silu" else torch.relu(h1) ** 2
     h2 = torch.empty(max_rows, H, dtype=x.dtype, device=dev)
-    gg.call("grouped_gemm_nt", a, w2.contiguous(), h2, tile_e, meta, max_tiles, H, inter, e_local, inter, H,
+    gg.call("grouped_gemm_nt", a, w2.contiguous(), h2, tile_e, meta, max_tiles, H, inter, e_local, inter, H, p2t,
             dtype_code(x.dtype), 1, st)
     if not do_finalize:
         return h2, e2p, topk_w
@@ -287,10 +287,10 @@ def moe_forward_nvfp4(x: torch.Tensor, topk_ids: torch.Tensor, topk_w: torch.Ten
     a1, a2 = a1.contiguous(), a2.contiguous()
     sf1 = _swizzle_expert_sf(w1_sf, e_local, n1, H // 16)
     sf2 = _swizzle_expert_sf(w2_sf, e_local, H, inter // 16)
-    h1 = grouped_gemm_nvfp4(xq, xsf, w1_fp4, sf1, a1, tile_e, meta, out_dtype=xb.dtype)
+    h1 = grouped_gemm_nvfp4(xq, xsf, w1_fp4, sf1, a1, tile_e, meta, out_dtype=xb.dtype, row_map=p2t)
     # SwiGLU + quantisation of the FC2 input in one kernel
     aq, asf = moe_fp4_quantize(h1, max_rows, inter, p2t, gs, gather=False, gated=True, row_list=e2p)
-    h2 = grouped_gemm_nvfp4(aq, asf, w2_fp4, sf2, a2, tile_e, meta, out_dtype=xb.dtype)
+    h2 = grouped_gemm_nvfp4(aq, asf, w2_fp4, sf2, a2, tile_e, meta, out_dtype=xb.dtype, row_map=p2t)
     if out is None:
         out = torch.empty(T, H, dtype=xb.dtype, device=dev)
     mod.call("moe_finalize", h2, out, e2p, topk_w.float().contiguous(), T, K, H, 0, dtype_code(xb.dtype), 1, st)
@@ -337,9 +337,9 @@ def moe_forward_fp8_block(x: torch.Tensor, x_scale: Optional[torch.Tensor], topk
     mod.call("moe_sort", ids, T, K, num_experts or e_local, local_expert_offset, e_local, _TILE, max_rows, e2p, p2t, tile_e, offs,
              meta, ws, 1, st)
     xq, xs = fp8_group_quantize(x, max_rows, gated=False, row_list=e2p, gather=True, list_div=K)
-    h1 = grouped_gemm_fp8_groupwise(xq, xs, w1, w1_scale, tile_e, meta, x.dtype)
+    h1 = grouped_gemm_fp8_groupwise(xq, xs, w1, w1_scale, tile_e, meta, x.dtype, row_map=p2t)
     aq, a_s = fp8_group_quantize(h1, max_rows, gated=True, row_list=e2p)
-    h2 = grouped_gemm_fp8_groupwise(aq, a_s, w2, w2_scale, tile_e, meta, x.dtype)
+    h2 = grouped_gemm_fp8_groupwise(aq, a_s, w2, w2_scale, tile_e, meta, x.dtype, row_map=p2t)
     if out is None:
         out = torch.empty(T, H, dtype=x.dtype, device=dev)
     mod.call("moe_finalize", h2, out, e2p, topk_w.float().contiguous(), T, K, H, 0, dtype_code(x.dtype), 1, st)

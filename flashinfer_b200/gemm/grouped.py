@@ -34,7 +34,7 @@ def grouped_gemm_tiles(a: torch.Tensor, w: torch.Tensor, tile_expert: torch.Tens
                 out[t * _TILE:(t + 1) * _TILE] = (a[t * _TILE:(t + 1) * _TILE].float() @ w[te[t]].float().t()).to(a.dtype)
         return out
     jit.load("grouped_gemm_sm100").call("grouped_gemm_nt", a, w.contiguous(), out, tile_expert, meta, rows // _TILE, N, K,
-                                        E, a.stride(0), out.stride(0), dtype_code(a.dtype), 1, stream_ptr(a))
+                                        E, a.stride(0), out.stride(0), None, dtype_code(a.dtype), 1, stream_ptr(a))
     return out
 
 

@@ -59,7 +59,8 @@ def _sf_swizzled(sf: torch.Tensor, rows: int, kc: int, batch: int = 1, swizzled:
 
 
 def _launch(kind: str, a: torch.Tensor, b_nk: torch.Tensor, out: torch.Tensor, sfa, sfb, alpha_a, alpha_b, K: int,
-            bn: int = 0, tile_expert: Optional[torch.Tensor] = None, meta: Optional[torch.Tensor] = None) -> torch.Tensor:
+            bn: int = 0, tile_expert: Optional[torch.Tensor] = None, meta: Optional[torch.Tensor] = None,
+            row_map: Optional[torch.Tensor] = None) -> torch.Tensor:
     """a ``[B, M, Kbytes]``, b_nk ``[B, N, Kbytes]`` (uint8 / fp8 storage, K contiguous), out ``[B, M, N]``."""
     B, M, _ = a.shape
     if tile_expert is not None:
@@ -71,8 +72,8 @@ def _launch(kind: str, a: torch.Tensor, b_nk: torch.Tensor, out: torch.Tensor, s
     jit.load("gemm_blockscaled_sm100").call(
         "gemm_lowp_nt", a, b_nk, out, sfa, sfb, alpha_a, alpha_b, B, M, N, K, a.stride(1), b_nk.stride(1), out.stride(1),
         a.stride(0), b_nk.stride(0), out.stride(0), sfa.stride(0) if sfa is not None else 0,
-        sfb.stride(0) if sfb is not None else 0, _KIND[kind], a_fmt, b_fmt, dtype_code(out.dtype), bn, tile_expert, meta, 1,
-        stream_ptr(a))
+        sfb.stride(0) if sfb is not None else 0, _KIND[kind], a_fmt, b_fmt, dtype_code(out.dtype), bn, tile_expert, meta,
+        row_map, 1, stream_ptr(a))
     return out
 
 
@@ -247,7 +248,7 @@ def gemm_fp8_nt_groupwise(a: torch.Tensor, b: torch.Tensor, a_scale: torch.Tenso
         jit.load("gemm_blockscaled_sm100").call(
             "gemm_fp8_groupwise_nt", a, b, res, sa, sb, M, N, K, a.stride(0), b.stride(0), res.stride(0), sa_row, sa_k, sb_n, sb_k,
             _FP8_FMT[a.dtype], _FP8_FMT[b.dtype], dtype_code(out_dtype), int(os.environ.get("FIB200_GW_BN", "0")), None, None, 1, 0,
-            1, stream_ptr(a))
+            None, 1, stream_ptr(a))
         if out is not None and out.data_ptr() != res.data_ptr():
             out.copy_(res)
             return out
@@ -293,7 +294,8 @@ def fp8_group_quantize(x: torch.Tensor, rows: Optional[int] = None, gated: bool 
 
 def grouped_gemm_fp8_groupwise(a: torch.Tensor, a_scale: torch.Tensor, w: torch.Tensor, w_scale: torch.Tensor,
                                tile_expert: torch.Tensor, meta: Optional[torch.Tensor] = None,
-                               out_dtype: torch.dtype = torch.bfloat16, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                               out_dtype: torch.dtype = torch.bfloat16, out: Optional[torch.Tensor] = None,
+                               row_map: Optional[torch.Tensor] = None) -> torch.Tensor:
     """m-grouped contiguous fp8 GEMM with DeepSeek scales, native tcgen05 (``fp8_groupwise_kernel`` grouped mode).
 
     ``a [M, K]`` e4m3 (rows grouped per expert in 128-row tiles), ``a_scale [M, K/128]`` fp32, ``w [E, N, K]`` e4m3,
@@ -312,7 +314,7 @@ def grouped_gemm_fp8_groupwise(a: torch.Tensor, a_scale: torch.Tensor, w: torch.
     jit.load("gemm_blockscaled_sm100").call(
         "gemm_fp8_groupwise_nt", a, w, res, sa, sb, M, N, K, a.stride(0), K, res.stride(0), sa.stride(0), sa.stride(1), sb.stride(1),
         sb.stride(2), _FP8_FMT[a.dtype], _FP8_FMT[w.dtype], dtype_code(res.dtype), int(os.environ.get("FIB200_GW_BN", "0")),
-        tile_expert, meta, E, sb.stride(0), 1, stream_ptr(a))
+        tile_expert, meta, E, sb.stride(0), row_map, 1, stream_ptr(a))
     return res
 
 
@@ -354,10 +356,11 @@ def trtllm_low_latency_gemm(A: torch.Tensor, B: torch.Tensor, global_scale: torc
 
 def grouped_gemm_nvfp4(a_fp4: torch.Tensor, a_sf: torch.Tensor, w_fp4: torch.Tensor, w_sf: torch.Tensor, alpha: Optional[torch.Tensor],
                        tile_expert: torch.Tensor, meta: Optional[torch.Tensor], out: Optional[torch.Tensor] = None,
-                       out_dtype: torch.dtype = torch.bfloat16, vec: int = 16) -> torch.Tensor:
+                       out_dtype: torch.dtype = torch.bfloat16, vec: int = 16, row_map: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Grouped block-scaled GEMM for MoE (tcgen05 ``kind::mxf4nvf4``): rows of ``a_fp4 [rows, K/2]`` are grouped by expert in
     128-row tiles (``tile_expert[tile]``), ``w_fp4 [E, N, K/2]`` with swizzled scales ``w_sf [E, sf_bytes]`` and one
-    ``alpha[e]`` per expert; ``a_sf`` is the swizzled scale tensor of the whole activation matrix."""
+    ``alpha[e]`` per expert; ``a_sf`` is the swizzled scale tensor of the whole activation matrix.  ``row_map [rows]`` (MoE
+    permuted-row -> token, -1 = padding): results of padding rows are not written (they are never read)."""
     rows, K2 = a_fp4.shape
     E, N, _ = w_fp4.shape
     if out is None:
@@ -365,5 +368,5 @@ def grouped_gemm_nvfp4(a_fp4: torch.Tensor, a_sf: torch.Tensor, w_fp4: torch.Ten
     kind = "nvfp4" if vec == 16 else "mxfp4"
     _launch(kind, a_fp4.view(torch.uint8).unsqueeze(0), w_fp4.view(torch.uint8), out.unsqueeze(0), a_sf.view(torch.uint8).reshape(1, -1),
             w_sf.view(torch.uint8).reshape(E, -1), alpha.float().contiguous() if alpha is not None else None, None, 2 * K2,
-            tile_expert=tile_expert, meta=meta)
+            tile_expert=tile_expert, meta=meta, row_map=row_map)
     return out

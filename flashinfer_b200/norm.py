@@ -139,52 +139,82 @@ def fused_rmsnorm_silu(input, weight, eps: float = 1e-6, out=None, block_scale=N
 # ------------------------------------------------------------------ norm + block quantisation (reference cute_dsl/rmsnorm_fp4quant.py,
 # add_rmsnorm_fp4quant.py) and DiT layernorm family (reference norm/__init__.py:1057-1440).  These are PDL-chained
 # sequences of the native norm and quantisation kernels (one extra round trip through L2 compared with a single kernel).
-def rmsnorm_fp4quant(input: torch.Tensor, weight: torch.Tensor, y_fp4: Optional[torch.Tensor] = None,
-                     block_scale: Optional[torch.Tensor] = None, global_scale: Optional[torch.Tensor] = None, eps: float = 1e-6,
-                     block_size: int = 16, scale_format: Optional[str] = None, is_sf_swizzled_layout: bool = False,
-                     enable_pdl: Optional[bool] = None):
-    """``y = rmsnorm(input) * weight`` quantised to FP4 (NVFP4: block 16 / UE4M3, MXFP4: block 32 / UE8M0).
-    Returns ``(y_fp4 [.., hidden/2] uint8, block_scale)``."""
-    from .quantization.fp4 import fp4_quantize
+def _norm_fp4quant(input, residual, weight, y_fp4, block_scale, global_scale, eps, block_size, scale_format, is_sf_swizzled_layout,
+                   output_both_sf_layouts, enable_pdl):
+    """One kernel: (residual += input) -> RMSNorm -> FP4 (csrc/elementwise/quantization.cu ``rmsnorm_fp4quant_kernel``)."""
+    from .quantization.fp4 import _swizzled_sf_size, fp4_quantize
 
-    shape = input.shape
-    y = rmsnorm(input.reshape(-1, shape[-1]), weight, eps, enable_pdl=enable_pdl)
+    h = input.shape[-1]
     ue8m0 = (scale_format == "ue8m0") or (scale_format is None and block_size == 32)
-    gs = global_scale if global_scale is not None else None
-    q, sf = fp4_quantize(y, gs, sf_vec_size=block_size, sf_use_ue8m0=ue8m0, is_sf_swizzled_layout=is_sf_swizzled_layout)
-    q = q.view(*shape[:-1], shape[-1] // 2)
+    x2 = input.reshape(-1, h)
+    rows, kc = x2.shape[0], h // block_size
+    native = (x2.is_cuda and x2.dtype in (torch.float16, torch.bfloat16) and weight.dtype == x2.dtype and h % block_size == 0
+              and h % 8 == 0 and h * 4 <= 200 * 1024 and (residual is None or (residual.dtype == x2.dtype and residual.is_contiguous())))
+    if not native:
+        if residual is not None:
+            x2 = x2.clone()
+            fused_add_rmsnorm(x2, residual.reshape(-1, h), weight, eps, enable_pdl=enable_pdl)
+            y = x2
+        else:
+            y = rmsnorm(x2, weight, eps, enable_pdl=enable_pdl)
+        q, sf = fp4_quantize(y, global_scale, sf_vec_size=block_size, sf_use_ue8m0=ue8m0, is_sf_swizzled_layout=is_sf_swizzled_layout)
+        sf_other = None
+        if output_both_sf_layouts:
+            _, sf_other = fp4_quantize(y, global_scale, sf_vec_size=block_size, sf_use_ue8m0=ue8m0,
+                                       is_sf_swizzled_layout=not is_sf_swizzled_layout)
+    else:
+        if x2.stride(-1) != 1:
+            x2 = x2.contiguous()
+        q = torch.empty(rows, h // 2, dtype=torch.uint8, device=x2.device)
+        sw_size = _swizzled_sf_size(rows, kc)
+
+        def alloc(swizzled):
+            return (torch.zeros(sw_size, dtype=torch.uint8, device=x2.device) if swizzled
+                    else torch.empty(rows * kc, dtype=torch.uint8, device=x2.device))
+
+        sf = alloc(is_sf_swizzled_layout)
+        sf_other = alloc(not is_sf_swizzled_layout) if output_both_sf_layouts else None
+        gs = global_scale.float().reshape(1).contiguous() if global_scale is not None else None
+        r2 = residual.view(-1, h) if residual is not None else None
+        pdl = device_support_pdl(x2.device) if enable_pdl is None else enable_pdl
+        jit.load("quantization").call(
+            "rmsnorm_fp4quant", x2, r2, weight.contiguous(), q, sf, sf_other, gs, rows, h, x2.stride(0), h, float(eps), block_size,
+            1 if ue8m0 else 0, 1 if is_sf_swizzled_layout else 0, 0, dtype_code(x2.dtype), 1 if pdl else 0, stream_ptr(x2))
+        sf = sf.view(-1, (kc + 3) // 4 * 4) if is_sf_swizzled_layout else sf.view(rows, kc)
+        if sf_other is not None:
+            sf_other = sf_other.view(rows, kc) if is_sf_swizzled_layout else sf_other.view(-1, (kc + 3) // 4 * 4)
+    q = q.view(*input.shape[:-1], h // 2)
     if not is_sf_swizzled_layout:
-        sf = sf.view(*shape[:-1], shape[-1] // block_size)
+        sf = sf.view(*input.shape[:-1], kc)
     if y_fp4 is not None:
         y_fp4.view(torch.uint8).copy_(q.view(torch.uint8))
         q = y_fp4
     if block_scale is not None:
         block_scale.view(torch.uint8).reshape(-1)[: sf.numel()].copy_(sf.view(torch.uint8).reshape(-1))
         sf = block_scale
+    if output_both_sf_layouts:
+        return q, sf, sf_other
     return q, sf
+
+
+def rmsnorm_fp4quant(input: torch.Tensor, weight: torch.Tensor, y_fp4: Optional[torch.Tensor] = None,
+                     block_scale: Optional[torch.Tensor] = None, global_scale: Optional[torch.Tensor] = None, eps: float = 1e-6,
+                     block_size: int = 16, scale_format: Optional[str] = None, is_sf_swizzled_layout: bool = False,
+                     enable_pdl: Optional[bool] = None):
+    """``y = rmsnorm(input) * weight`` quantised to FP4 (NVFP4: block 16 / UE4M3, MXFP4: block 32 / UE8M0) in ONE kernel: the
+    normalised activations never reach HBM.  Returns ``(y_fp4 [.., hidden/2] uint8, block_scale)``."""
+    return _norm_fp4quant(input, None, weight, y_fp4, block_scale, global_scale, eps, block_size, scale_format,
+                          is_sf_swizzled_layout, False, enable_pdl)
 
 
 def add_rmsnorm_fp4quant(input: torch.Tensor, residual: torch.Tensor, weight: torch.Tensor, y_fp4: Optional[torch.Tensor] = None,
                          block_scale: Optional[torch.Tensor] = None, global_scale: Optional[torch.Tensor] = None, eps: float = 1e-6,
                          block_size: int = 16, scale_format: Optional[str] = None, is_sf_swizzled_layout: bool = False,
                          output_both_sf_layouts: bool = False, enable_pdl: Optional[bool] = None):
-    """``residual += input`` (in place), then :func:`rmsnorm_fp4quant` of the sum."""
-    h = residual.shape[-1]
-    x2 = input.reshape(-1, h).clone()
-    r2 = residual.reshape(-1, h)
-    fused_add_rmsnorm(x2, r2, weight, eps, enable_pdl=enable_pdl)  # x2 <- norm(x + r) * w ; r2 <- x + r
-    from .quantization.fp4 import fp4_quantize
-
-    ue8m0 = (scale_format == "ue8m0") or (scale_format is None and block_size == 32)
-    q, sf = fp4_quantize(x2, global_scale, sf_vec_size=block_size, sf_use_ue8m0=ue8m0, is_sf_swizzled_layout=is_sf_swizzled_layout)
-    q = q.view(*input.shape[:-1], h // 2)
-    if y_fp4 is not None:
-        y_fp4.view(torch.uint8).copy_(q.view(torch.uint8))
-        q = y_fp4
-    if block_scale is not None:
-        block_scale.view(torch.uint8).reshape(-1)[: sf.numel()].copy_(sf.view(torch.uint8).reshape(-1))
-        sf = block_scale
-    return q, sf
+    """``residual += input`` (in place), then :func:`rmsnorm_fp4quant` of the sum - one kernel.  With
+    ``output_both_sf_layouts`` a third tensor holds the scales in the other (linear / swizzled) layout."""
+    return _norm_fp4quant(input, residual, weight, y_fp4, block_scale, global_scale, eps, block_size, scale_format,
+                          is_sf_swizzled_layout, output_both_sf_layouts, enable_pdl)
 
 
 def _dit_finish(res: torch.Tensor, normed: torch.Tensor, use_nvfp4: bool, use_mxfp8: bool, global_scaling_factor, residual_out,

@@ -253,3 +253,36 @@ def test_grouped_fp8_groupwise_gpu(E, N, K):
             if n:
                 r = a3dq.view(G, 256, K)[g, :n] @ w_dq[g].t()
                 assert (o[g, :n].float() - r).abs().max().item() / r.abs().max().item() < 1e-2
+
+
+@pytest.mark.parametrize("block,swz", [(16, True), (16, False), (32, True)])
+@pytest.mark.parametrize("with_res", [False, True])
+def test_fused_rmsnorm_fp4quant_gpu(block, swz, with_res):
+    """(add +) RMSNorm + FP4 quantisation in one kernel vs the two-kernel composition (norm kernel, then the quantiser)."""
+    import flashinfer_b200 as fi
+    from flashinfer_b200.quantization.fp4 import fp4_quantize
+
+    torch.manual_seed(block + with_res)
+    rows, h = 77, 4096
+    x = torch.randn(rows, h, device="cuda").bfloat16()
+    w = (1 + 0.1 * torch.randn(h, device="cuda")).bfloat16()
+    gs = torch.tensor([2.0], device="cuda")
+    if with_res:
+        r0 = torch.randn(rows, h, device="cuda").bfloat16()
+        r_fused = r0.clone()
+        out = fi.add_rmsnorm_fp4quant(x, r_fused, w, global_scale=gs, eps=1e-5, block_size=block, is_sf_swizzled_layout=swz,
+                                      output_both_sf_layouts=True)
+        q, sf, sf_other = out
+        xr, rr = x.clone(), r0.clone()
+        fi.fused_add_rmsnorm(xr, rr, w, 1e-5)
+        assert torch.equal(rr, r_fused)
+        y = xr
+    else:
+        q, sf = fi.rmsnorm_fp4quant(x, w, global_scale=gs, eps=1e-5, block_size=block, is_sf_swizzled_layout=swz)
+        y = fi.rmsnorm(x, w, 1e-5)
+    q_ref, sf_ref = fp4_quantize(y, gs, sf_vec_size=block, sf_use_ue8m0=(block == 32), is_sf_swizzled_layout=swz)
+    assert (q.view(torch.uint8) != q_ref.view(torch.uint8)).float().mean().item() < 5e-3
+    assert (sf.view(torch.uint8).reshape(-1)[: sf_ref.numel()] != sf_ref.view(torch.uint8).reshape(-1)).float().mean().item() < 5e-3
+    if with_res:
+        _, sf_o_ref = fp4_quantize(y, gs, sf_vec_size=block, sf_use_ue8m0=(block == 32), is_sf_swizzled_layout=not swz)
+        assert (sf_other.view(torch.uint8).reshape(-1)[: sf_o_ref.numel()] != sf_o_ref.view(torch.uint8).reshape(-1)).float().mean().item() < 5e-3
