@@ -51,14 +51,14 @@ struct MlaParams {
 };
 
 struct Smem {
-  static constexpr int kStages = 4;
+  static constexpr int kStages = 5;
   static constexpr int kSBufs = 4;   // S / P TMEM buffers: QK^T runs two tiles ahead of the softmax
   static constexpr int kXBufs = 3;   // partial-S exchange buffers (see the protocol note in the softmax loop)
   static constexpr int kMaxChunks = 5;                         // CTA 1: 4 ckv chunks + kpe
   static constexpr int kQBytes = kMaxChunks * kHeads * 128;    // 81920
   static constexpr int kChunkBytes = kTile * 128;              // 4096
   static constexpr int kTileBytes = kMaxChunks * kChunkBytes;  // 20480
-  static constexpr int kXchgBytes = kHeads * kTile * 4;        // 16384: partial S of the peer, one buffer per S buffer
+  static constexpr int kXchgBytes = kHeads * kTile * 2;        // 8192: the peer's partial S (pre-scaled, fp16)
   static constexpr int kOffQ = 0;
   static constexpr int kOffK = kQBytes;
   static constexpr int kOffX = kOffK + kStages * kTileBytes;
@@ -71,6 +71,11 @@ static_assert(Smem::kTotal <= 227 * 1024, "MLA smem budget");
 __device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack2_f16_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
 __device__ __forceinline__ uint32_t pack2_f16(float lo, float hi) {
@@ -249,22 +254,34 @@ mla_decode_kernel(const __grid_constant__ CUtensorMap tmQn, const __grid_constan
     float m_used = -INFINITY, l = 0.f;
     uint32_t od_cnt = 0;
     // ---- partial-S exchange with the peer CTA (it reduced over the other slice of the latent dimension) ----
-    // The partial of tile j + 1 is pushed with st.async (16-byte stores that credit the PEER's x_full barrier: no release
-    // fence, no per-thread arrive) right after the peer's partial of tile j has landed, so it travels while the softmax of
-    // tile j runs.  Layout: row-major [128][32] fp32, the 16-byte vectors of a row XOR-swizzled by (row & 7).
+    // DSMEM moves ~17 B/clk per SM, so the exchange is the scarce resource of this design: partials are pre-scaled by
+    // sm_scale * log2(e) and shipped as fp16 (64 B per row and tile; my own partial stays fp32, so a logit carries one fp16
+    // rounding of HALF of its value - below the bf16 rounding P gets anyway).  The partial of tile j + 1 is pushed with
+    // st.async (16-byte stores that credit the PEER's x_full barrier: no release fence, no per-thread arrive) right after
+    // the peer's partial of tile j has landed, so it travels while the softmax of tile j runs.
+    // Layout: row-major [128][64 B], the four 16-byte chunks of a row XOR-swizzled by (row >> 1) & 3 (conflict-free LDS.128).
     // Buffer reuse (3 buffers, no extra handshake): when I push tile j + 1 I have received the peer's tile j, which it
     // pushed after finishing its iteration j - 2 -> it is done reading buffer (j - 2) % 3 == (j + 1) % 3.
     const uint32_t peer = uint32_t(half ^ 1);
+    const int xsw = (row >> 1) & 3;
     auto push = [&](int jn, const uint32_t(&v)[32]) {
       const int xb = jn % S::kXBufs;
-      const uint32_t x_remote = ptx::mapa(ptx::smem_u32(smem + S::kOffX + xb * S::kXchgBytes + row * 128), peer);
+      const uint32_t x_remote = ptx::mapa(ptx::smem_u32(smem + S::kOffX + xb * S::kXchgBytes + row * 64), peer);
       const uint32_t bar_remote = ptx::mapa(ptx::smem_u32(&x_full[xb]), peer);
 #pragma unroll
-      for (int q = 0; q < 8; ++q)
-        ptx::st_async_v4(x_remote + ((q ^ (row & 7)) << 4),
-                         make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
-                                     __uint_as_float(v[4 * q + 3])),
+      for (int q = 0; q < 4; ++q) {
+        uint32_t h[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          h[e] = pack2_f16_sat(__uint_as_float(v[8 * q + 2 * e]), __uint_as_float(v[8 * q + 2 * e + 1]));
+        ptx::st_async_v4(x_remote + ((q ^ xsw) << 4),
+                         make_float4(__uint_as_float(h[0]), __uint_as_float(h[1]), __uint_as_float(h[2]), __uint_as_float(h[3])),
                          bar_remote);
+      }
+    };
+    auto scale32 = [&](uint32_t(&v)[32]) {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * p.sm_scale_log2);
     };
     uint32_t r[32];
     if (ntiles > 0) {
@@ -272,6 +289,7 @@ mla_decode_kernel(const __grid_constant__ CUtensorMap tmQn, const __grid_constan
       ptx::tc_fence_after();
       ptx::tmem_ld_x32(tm_s + lane_addr, r);
       ptx::tmem_ld_wait();
+      scale32(r);
       push(0, r);
     }
     for (int j = 0; j < ntiles; ++j) {
@@ -280,14 +298,17 @@ mla_decode_kernel(const __grid_constant__ CUtensorMap tmQn, const __grid_constan
       const int xb = j % S::kXBufs;
       ptx::mbar_wait(&x_full[xb], (j / S::kXBufs) & 1);  // tx-count completion (like a TMA write): plain acquire.cta
       {
-        const float4* xl = reinterpret_cast<const float4*>(smem + S::kOffX + xb * S::kXchgBytes + row * 128);
+        const int4* xl = reinterpret_cast<const int4*>(smem + S::kOffX + xb * S::kXchgBytes + row * 64);
 #pragma unroll
-        for (int v = 0; v < 8; ++v) {
-          const float4 t = xl[v ^ (row & 7)];
-          r[4 * v] = __float_as_uint(__uint_as_float(r[4 * v]) + t.x);
-          r[4 * v + 1] = __float_as_uint(__uint_as_float(r[4 * v + 1]) + t.y);
-          r[4 * v + 2] = __float_as_uint(__uint_as_float(r[4 * v + 2]) + t.z);
-          r[4 * v + 3] = __float_as_uint(__uint_as_float(r[4 * v + 3]) + t.w);
+        for (int q = 0; q < 4; ++q) {
+          const int4 t = xl[q ^ xsw];
+          const uint32_t w[4] = {uint32_t(t.x), uint32_t(t.y), uint32_t(t.z), uint32_t(t.w)};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[e]));
+            r[8 * q + 2 * e] = __float_as_uint(__uint_as_float(r[8 * q + 2 * e]) + f.x);
+            r[8 * q + 2 * e + 1] = __float_as_uint(__uint_as_float(r[8 * q + 2 * e + 1]) + f.y);
+          }
         }
       }
       uint32_t rn[32];
@@ -297,6 +318,7 @@ mla_decode_kernel(const __grid_constant__ CUtensorMap tmQn, const __grid_constan
         ptx::tc_fence_after();
         ptx::tmem_ld_x32(tm_s + lane_addr + bn * 32, rn);
         ptx::tmem_ld_wait();
+        scale32(rn);
         push(j + 1, rn);
       }
       // re-arm this exchange buffer for tile j + 3 (one thread; the 128 waits above have not necessarily all passed, but
@@ -309,7 +331,7 @@ mla_decode_kernel(const __grid_constant__ CUtensorMap tmQn, const __grid_constan
         const float x = (e < valid) ? __uint_as_float(r[e]) : -INFINITY;
         tmax = fmaxf(tmax, x);
       }
-      const float m_tile = tmax * p.sm_scale_log2;
+      const float m_tile = tmax;  // logits are already in the scaled log2 domain
       const bool grow = (m_tile > m_used + 8.f) || (m_used == -INFINITY && m_tile > -INFINITY);
       if (j > 0 && __any_sync(0xffffffffu, grow && l > 0.f)) {
         ptx::mbar_wait(o_done, (od_cnt - 1) & 1);
@@ -334,8 +356,8 @@ mla_decode_kernel(const __grid_constant__ CUtensorMap tmQn, const __grid_constan
       uint32_t pk[16];
 #pragma unroll
       for (int e = 0; e < 32; e += 2) {
-        float p0 = ptx::ex2(fmaf(__uint_as_float(r[e]), p.sm_scale_log2, -m_ref));
-        float p1 = ptx::ex2(fmaf(__uint_as_float(r[e + 1]), p.sm_scale_log2, -m_ref));
+        float p0 = ptx::ex2(__uint_as_float(r[e]) - m_ref);
+        float p1 = ptx::ex2(__uint_as_float(r[e + 1]) - m_ref);
         if (e >= valid) p0 = 0.f;
         if (e + 1 >= valid) p1 = 0.f;
         l += p0 + p1;

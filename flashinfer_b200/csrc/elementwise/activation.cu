@@ -34,8 +34,9 @@ act_and_mul_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t rows, 
   ptx::grid_dep_wait();
   ptx::grid_dep_launch();  // early trigger: dependents overlap their prologue, they still wait for our completion
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
-    int64_t r = i / vec_per_row;
-    const int64_t c = (i % vec_per_row) * VN;
+    int64_t r, c;
+    fast_divmod(i, vec_per_row, r, c);
+    c *= VN;
     if (row_list) {
       // row_map lists the live rows (expanded -> permuted row, -1 = not local): only those are visited
       r = row_map[r];

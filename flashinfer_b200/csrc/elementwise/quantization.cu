@@ -84,15 +84,16 @@ fp4_quantize_kernel(const T* __restrict__ x, uint8_t* __restrict__ q, uint8_t* _
   ptx::grid_dep_wait();
   const float gs = global_scale ? __ldg(global_scale) : 1.f;
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
-    const int64_t kc = i % kc_total;
-    int64_t m = (i / kc_total) % M;
-    const int64_t b = row_list ? 0 : i / (kc_total * M);
+    int64_t kc, rowi, m, b;
+    fast_divmod(i, kc_total, rowi, kc);
+    fast_divmod(rowi, M, b, m);
+    if (row_list) b = 0;
     int64_t src_row = m;
     if (row_list) {
-      const int64_t j = i / kc_total;
+      const int64_t j = rowi;
       m = row_list[j];
       if (m < 0) continue;
-      src_row = gather ? j / list_div : m;
+      src_row = gather ? int64_t(uint32_t(j) / uint32_t(list_div)) : m;
     } else if (row_map) {
       const int rm = row_map[m];
       if (rm < 0) continue;     // MoE padding row (scale bytes stay as initialised: finite)
@@ -209,8 +210,9 @@ fp8_group_quantize_kernel(const T* __restrict__ x, __nv_fp8_e4m3* __restrict__ q
     const int64_t i = i0 + (threadIdx.x & 31);
     const bool live = i < total;
     const int64_t ii = live ? i : total - 1;
-    const int64_t c = ii % per_row;
-    int64_t m = ii / per_row, src_row = m;
+    int64_t c, m;
+    fast_divmod(ii, per_row, m, c);
+    int64_t src_row = m;
     bool skip = !live;
     if (row_list) {
       const int64_t j = m;
@@ -219,7 +221,7 @@ fp8_group_quantize_kernel(const T* __restrict__ x, __nv_fp8_e4m3* __restrict__ q
         skip = true;
         m = 0;
       }
-      src_row = gather ? j / list_div : m;
+      src_row = gather ? int64_t(uint32_t(j) / uint32_t(list_div)) : m;
     }
     float v[16];
     if (!skip) {

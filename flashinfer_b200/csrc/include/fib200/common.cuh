@@ -52,6 +52,19 @@ static inline long long& launch_counter() { return g_launch_counter; }
   extern "C" const char* fib200_last_error() { return ::fib200::last_error_storage().c_str(); }    \
   extern "C" long long fib200_launch_count() { return ::fib200::launch_counter(); }
 
+// 64-bit integer division is ~100 instructions on the GPU; flat-index kernels decompose (row, column) with 32-bit math
+// whenever both operands fit (always, except for > 4G-element tensors).
+__host__ __device__ __forceinline__ void fast_divmod(int64_t i, int64_t d, int64_t& q, int64_t& r) {
+  if ((uint64_t(i) | uint64_t(d)) <= 0xffffffffull) {
+    const uint32_t qq = uint32_t(i) / uint32_t(d);
+    q = qq;
+    r = uint32_t(i) - qq * uint32_t(d);
+  } else {
+    q = i / d;
+    r = i - q * d;
+  }
+}
+
 // ------------------------------------------------------------------ dtypes
 enum DType : int64_t {
   kF16 = 0,

@@ -93,6 +93,7 @@ routing_kernel(const TL* __restrict__ logits, const float* __restrict__ bias, in
       // fast path: a group is a whole number of register slots -> per-lane top-2 of the group's slots, then a
       // butterfly merge of (top1, top2) pairs; lane g keeps the score of group g
       const int spg = gsz / 32;
+#pragma unroll 4
       for (int g = 0; g < n_group; ++g) {
         float a1 = -INFINITY, a2 = -INFINITY;
 #pragma unroll
@@ -168,14 +169,15 @@ routing_kernel(const TL* __restrict__ logits, const float* __restrict__ bias, in
         be = e;
       }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-      const int oe = __shfl_xor_sync(0xffffffffu, be, o);
-      if (ov > bv || (ov == bv && oe < be)) {
-        bv = ov;
-        be = oe;
-      }
+    {
+      // warp argmax with two redux.sync ops: max of the order-preserving integer image of the score, then the smallest
+      // expert id among the lanes that hold it (ties -> smaller id, like torch.topk on the sorted order)
+      const uint32_t bits = __float_as_uint(bv);
+      const uint32_t key = (bits & 0x80000000u) ? ~bits : (bits | 0x80000000u);
+      const uint32_t kmax = __reduce_max_sync(0xffffffffu, key);
+      be = (int)__reduce_min_sync(0xffffffffu, key == kmax ? (unsigned)be : 0x7fffffffu);
+      const uint32_t b2 = (kmax & 0x80000000u) ? (kmax & 0x7fffffffu) : ~kmax;
+      bv = __uint_as_float(b2);
     }
     // owner lane fetches the output weight and removes the expert
     float w = 0.f;
@@ -357,6 +359,7 @@ moe_scatter_kernel(const int32_t* __restrict__ topk_ids, int n, int K, int local
 // Small problems (T * K <= 32 K entries, 32 * local_num ints of smem): the whole sort in ONE CTA, still deterministic.
 // Warp w owns the contiguous entry range [w * per, (w + 1) * per) and walks it 32 entries at a time, so every step is
 // warp-local (match.any + a warp-private histogram row); the only block-wide steps are the expert scan in the middle.
+template <int ITERS>  // 32-entry groups per warp (entries are preloaded: one round of global latency instead of ITERS)
 __global__ void __launch_bounds__(1024)
 moe_sort_small_kernel(const int32_t* __restrict__ topk_ids, int n, int K, int local_offset, int local_num, int tile,
                       int max_rows, int32_t* __restrict__ expanded_to_permuted, int32_t* __restrict__ permuted_to_token,
@@ -370,16 +373,23 @@ moe_sort_small_kernel(const int32_t* __restrict__ topk_ids, int n, int K, int lo
   for (int i = threadIdx.x; i < 32 * local_num; i += blockDim.x) hist[i] = 0;
   ptx::grid_dep_wait();
   __syncthreads();
-  const int per = ((n + 31) / 32 + 31) & ~31;  // entries per warp, multiple of 32
+  const int per = ITERS * 32;  // entries per warp
   const int lo = warp * per, hi = min(n, lo + per);
   int* myh = hist + warp * local_num;
-  for (int i0 = lo; i0 < hi; i0 += 32) {
-    const int i = i0 + lane;
+  int ev[ITERS];
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    const int i = lo + it * 32 + lane;
     int e = -1;
     if (i < hi) {
       e = topk_ids[i] - local_offset;
       if (e < 0 || e >= local_num) e = -1;
     }
+    ev[it] = e;
+  }
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    const int e = ev[it];
     const uint32_t peers = __match_any_sync(0xffffffffu, e);
     if (e >= 0 && (peers & ((1u << lane) - 1)) == 0) myh[e] += __popc(peers);
     __syncwarp();
@@ -433,13 +443,10 @@ moe_sort_small_kernel(const int32_t* __restrict__ topk_ids, int n, int K, int lo
     for (int r = off[e] + cnt[e] + lane; r < off[e + 1]; r += 32) permuted_to_token[r] = -1;
   }
   // scatter: same walk, positions = expert offset + warp prefix + running cursor + rank inside the 32-entry group
-  for (int i0 = lo; i0 < hi; i0 += 32) {
-    const int i = i0 + lane;
-    int e = -1;
-    if (i < hi) {
-      e = topk_ids[i] - local_offset;
-      if (e < 0 || e >= local_num) e = -1;
-    }
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    const int i = lo + it * 32 + lane;
+    const int e = ev[it];
     const uint32_t peers = __match_any_sync(0xffffffffu, e);
     const int rank = __popc(peers & ((1u << lane) - 1));
     int b = 0;
@@ -475,10 +482,11 @@ moe_gather_kernel(const T* __restrict__ x, T* __restrict__ out, const int32_t* _
     // uninitialised (GEMM rows are independent and nothing reads the padding rows of the result)
     const int64_t total = n_list * vec;
     for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
-      const int64_t j = i / vec, v = i % vec;
+      int64_t j, v;
+      fast_divmod(i, vec, j, v);
       const int r = row_list[j];
       if (r < 0) continue;
-      st16(out + int64_t(r) * hidden + v * VN, ld16(x + (j / list_div) * x_stride + v * VN));
+      st16(out + int64_t(r) * hidden + v * VN, ld16(x + int64_t(uint32_t(j) / uint32_t(list_div)) * x_stride + v * VN));
     }
     ptx::grid_dep_launch();
     return;
@@ -510,7 +518,8 @@ moe_finalize_kernel(const T* __restrict__ y, T* __restrict__ out, const int32_t*
   const int64_t vec = hidden / VN;
   const int64_t total = int64_t(Tn) * vec;
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
-    const int64_t t = i / vec, v = i % vec;
+    int64_t t, v;
+    fast_divmod(i, vec, t, v);
     float acc[VN];
 #pragma unroll
     for (int e = 0; e < VN; ++e) acc[e] = 0.f;
@@ -581,11 +590,19 @@ extern "C" int moe_sort(void* topk_ids, int64_t T, int64_t K, int64_t E, int64_t
   const size_t small_smem = (size_t(34) * local_num + 1) * sizeof(int);
   if (n > 0 && n <= 32768 && small_smem <= 48 * 1024) {
     LaunchCfg lc(dim3(1), dim3(1024), small_smem, stream, pdl != 0);
-    FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, moe_sort_small_kernel, (const int32_t*)topk_ids, n, (int)K, (int)local_offset,
-                                      (int)local_num, (int)tile, (int)max_rows, (int32_t*)expanded_to_permuted,
-                                      (int32_t*)permuted_to_token, (int32_t*)tile_expert, (int32_t*)expert_offsets,
-                                      (int32_t*)meta));
-    return 0;
+    const int iters = (n + 1023) / 1024;  // 32-entry groups per warp
+    auto go = [&](auto kern) -> int {
+      FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, kern, (const int32_t*)topk_ids, n, (int)K, (int)local_offset, (int)local_num,
+                                        (int)tile, (int)max_rows, (int32_t*)expanded_to_permuted, (int32_t*)permuted_to_token,
+                                        (int32_t*)tile_expert, (int32_t*)expert_offsets, (int32_t*)meta));
+      return 0;
+    };
+    if (iters <= 1) return go(moe_sort_small_kernel<1>);
+    if (iters <= 2) return go(moe_sort_small_kernel<2>);
+    if (iters <= 4) return go(moe_sort_small_kernel<4>);
+    if (iters <= 8) return go(moe_sort_small_kernel<8>);
+    if (iters <= 16) return go(moe_sort_small_kernel<16>);
+    return go(moe_sort_small_kernel<32>);
   }
   if (nchunks > 0) {
     LaunchCfg lc(dim3(nchunks), dim3(kSortChunk), local_num * sizeof(int), stream, pdl != 0);
