@@ -28,11 +28,13 @@ constexpr int BK = 64;   // 64 x 2B = one 128B swizzle span
 // Shared-memory plan for a runtime tile width BN (multiple of 16, <= 256).
 struct GemmSmem {
   int stages, stage_bytes, a_bytes, bar_offset, total;
-  __host__ __device__ static GemmSmem make(int BMv, int BN) {
+  // budget_kb: ring budget.  220 = one CTA per SM; ~100 = two co-resident CTAs (decode GEMMs: the next kernel's CTA - launched
+  // early through PDL - sets up and prefetches its weights while the previous kernel is still in its epilogue on the same SM)
+  __host__ __device__ static GemmSmem make(int BMv, int BN, int budget_kb = 220) {
     GemmSmem g;
     g.a_bytes = BMv * BK * 2;
     g.stage_bytes = g.a_bytes + BN * BK * 2;
-    int st = (220 * 1024) / g.stage_bytes;
+    int st = (budget_kb * 1024) / g.stage_bytes;
     g.stages = st > 16 ? 16 : st;
     g.bar_offset = g.stages * g.stage_bytes;
     g.total = g.bar_offset + 512 + 1024;
@@ -51,6 +53,9 @@ struct GemmSmem {
 struct Sched {
   int tiles_a, tiles_b, kblocks, grid, BN;
   int S;  // cluster split-K factor (1 = off); when > 1 the grid is exactly tiles * S (one tile per cluster)
+  int smem_kb;  // ring budget handed to GemmSmem::make (host and device must agree)
+  int trace;  // debug (FIB200_GEMM_TRACE=1): the cluster split-K path writes clock64 stamps into the partial workspace
+  int G;  // with S > 1: N tiles per cluster that share the A operand through TMA multicast (1 or 2); cluster = S * G CTAs
   int W, R, g_sk, max_parts, group_a;
   int64_t u_r;  // R * kblocks
   __device__ __forceinline__ int64_t sk_begin(int c) const { return (int64_t(c) * u_r) / g_sk; }
@@ -116,8 +121,9 @@ __global__ void __launch_bounds__(256, 1)
 gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, OutT* __restrict__ C,
                float* __restrict__ partial, int* __restrict__ counters, const OutT* __restrict__ bias, int rowsA,
                int rowsB, int K, int64_t ldc, const Sched sk, uint32_t idesc) {
+  const long long t_entry = clock64();
   const int BN = sk.BN;
-  const GemmSmem S = GemmSmem::make(BM, BN);
+  const GemmSmem S = GemmSmem::make(BM, BN, sk.smem_kb);
   const int kStages = S.stages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -132,14 +138,15 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int S_split = sk.S;
-  const int crank = S_split > 1 ? int(ptx::cluster_ctarank()) : 0;
+  const bool clustered = S_split > 1 || sk.G > 1;  // one output tile per CTA, cluster = S (K split) x G (A multicast)
+  const int crank = clustered ? int(ptx::cluster_ctarank()) : 0;
 
   if (threadIdx.x == 0) {
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
     for (int i = 0; i < kStages; ++i) {
       ptx::mbar_init(&full_bar[i], 1);
-      ptx::mbar_init(&empty_bar[i], 1);
+      ptx::mbar_init(&empty_bar[i], clustered ? sk.G : 1);  // multicast: every CTA sharing A must have freed the slot
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tmem_full[i], 1);
@@ -157,7 +164,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (S_split > 1) ptx::cluster_sync();  // peers' mbarriers must exist before any remote arrive
+  if (clustered) ptx::cluster_sync();  // peers' mbarriers must exist before any remote arrive
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -166,15 +173,29 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp != 0) ptx::grid_dep_wait();
   ptx::grid_dep_launch();
 
-  if (S_split > 1) {
+  long long* trace = (sk.trace && partial) ? reinterpret_cast<long long*>(partial) + int64_t(blockIdx.x) * 8 : nullptr;
+  if (trace && threadIdx.x == 0) {
+    trace[7] = t_entry;
+    trace[0] = clock64();  // after setup + cluster_sync + griddepcontrol
+  }
+  if (clustered) {
     // =====================================================================================
     // Cluster split-K (single wave): cluster = one output tile, rank r owns k-blocks
     // [r*KB/S, (r+1)*KB/S).  Ranks > 0 hand their fp32 partial to the leader through DSMEM.
     // =====================================================================================
-    const int tile = blockIdx.x / S_split;
+    // Rank layout inside the cluster: ksplit = rank % S (K range), g = rank / S (which of the G N-tiles).  The G CTAs with the
+    // same ksplit read the SAME activation k-blocks: each loads 1/G of the A rows and multicasts them to the others, so the
+    // activations leave L2 once per pair instead of once per CTA (at M = 64 they were half of all L2 -> SM bytes).
+    const int G = sk.G;
+    const int ksplit = crank % S_split, gidx = crank / S_split;
+    const int tile = (blockIdx.x / (S_split * G)) * G + gidx;
     int ta, tb;
     sk.coords(tile, ta, tb);
-    const int kb0 = (crank * sk.kblocks) / S_split, kb1 = ((crank + 1) * sk.kblocks) / S_split;
+    const int kb0 = (ksplit * sk.kblocks) / S_split, kb1 = ((ksplit + 1) * sk.kblocks) / S_split;
+    uint16_t amask = 0;
+    for (int g2 = 0; g2 < G; ++g2) amask |= uint16_t(1u << (ksplit + S_split * g2));
+    const int a_rows = BM / G;  // rows of A this CTA loads (and multicasts)
+    const int leader_rank = gidx * S_split;
     if (warp == 0) {
       if (ptx::elect_one()) {
         int stage = 0;
@@ -186,8 +207,14 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           ptx::tma_load_2d(sb, &tmB, &full_bar[i], (kb0 + i) * BK, tb * BN, ptx::kEvictFirst);
         }
         ptx::grid_dep_wait();
-        for (int i = 0; i < npre; ++i)
-          ptx::tma_load_2d(smem + i * S.stage_bytes, &tmA, &full_bar[i], (kb0 + i) * BK, ta * BM, ptx::kEvictLast);
+        auto load_a = [&](int st, int kb) {
+          uint8_t* sa = smem + st * S.stage_bytes;
+          if (G > 1)
+            ptx::tma_load_2d_mcast(sa + gidx * a_rows * 128, &tmA, &full_bar[st], kb * BK, ta * BM + gidx * a_rows, amask);
+          else
+            ptx::tma_load_2d(sa, &tmA, &full_bar[st], kb * BK, ta * BM, ptx::kEvictLast);
+        };
+        for (int i = 0; i < npre; ++i) load_a(i, kb0 + i);
         stage = npre == kStages ? 0 : npre;
         phase = npre == kStages ? 1 : 0;
         for (int kb = kb0 + npre; kb < kb1; ++kb) {
@@ -195,7 +222,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint8_t* sa = smem + stage * S.stage_bytes;
           uint8_t* sb = sa + S.a_bytes;
           ptx::mbar_arrive_expect_tx(&full_bar[stage], S.stage_bytes);
-          ptx::tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, ta * BM, ptx::kEvictLast);
+          load_a(stage, kb);
           ptx::tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, tb * BN, ptx::kEvictFirst);
           if (++stage == kStages) {
             stage = 0;
@@ -209,6 +236,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int kb = kb0; kb < kb1; ++kb) {
         ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tc_fence_after();
+        if (trace && lane == 0 && (kb == kb0 || kb == kb1 - 1 || kb == kb0 + 8)) trace[kb == kb0 ? 1 : (kb == kb1 - 1 ? 3 : 2)] = clock64();
         if (ptx::elect_one()) {
           const uint32_t sa = ptx::smem_u32(smem + stage * S.stage_bytes);
           const uint32_t sb = sa + S.a_bytes;
@@ -218,7 +246,8 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int k = 0; k < BK / 16; ++k)
             ptx::mma_f16_ss<1>(tmem_base, ptx::desc_advance(da, k * 32), ptx::desc_advance(db, k * 32), idesc,
                                (kb > kb0 || k > 0) ? 1u : 0u);
-          ptx::mma_commit(&empty_bar[stage]);
+          if (G > 1) ptx::mma_commit_mcast(&empty_bar[stage], amask);
+          else ptx::mma_commit(&empty_bar[stage]);
           if (kb == kb1 - 1) ptx::mma_commit(&tmem_full[0]);
         }
         __syncwarp();
@@ -239,11 +268,12 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t xbuf = ptx::smem_u32(smem);
       ptx::mbar_wait(&tmem_full[0], 0);  // my accumulator is complete => all my MMAs (smem reads) retired
       ptx::tc_fence_after();
-      if (crank == 0) {
+      if (trace && etid == 0) trace[4] = clock64();
+      if (ksplit == 0) {
         if (etid == 0) {
-          for (int r = 1; r < S_split; ++r) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(go_bar), r));
+          for (int r = 1; r < S_split; ++r) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(go_bar), leader_rank + r));
         }
-        ptx::mbar_wait_cluster(partials_bar, 0);
+        if (S_split > 1) ptx::mbar_wait_cluster(partials_bar, 0);
         for (int c0 = 0; c0 < BN; c0 += 16) {
           uint32_t r[16];
           ptx::tmem_ld_x16(taddr + c0, r);
@@ -294,13 +324,13 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       } else {
         ptx::mbar_wait_cluster(go_bar, 0);
-        const uint32_t remote = ptx::mapa(xbuf, 0);
+        const uint32_t remote = ptx::mapa(xbuf, leader_rank);
         for (int c0 = 0; c0 < BN; c0 += 16) {
           uint32_t r[16];
           ptx::tmem_ld_x16(taddr + c0, r);
           ptx::tmem_ld_wait();
           if (row_ok) {
-            const uint32_t dst = remote + uint32_t(((int64_t(crank - 1) * (BN / 16) + c0 / 16) * BM + r_in_tile) * 64);
+            const uint32_t dst = remote + uint32_t(((int64_t(ksplit - 1) * (BN / 16) + c0 / 16) * BM + r_in_tile) * 64);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               ptx::st_dsmem_v4(dst + j * 16, make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
@@ -308,12 +338,14 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         ptx::named_bar_sync(1, 128);
-        if (etid == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(partials_bar), 0));
+        if (etid == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(partials_bar), leader_rank));
       }
     }
+    if (trace && threadIdx.x == 128) trace[5] = clock64();
     ptx::tc_fence_before();
     __syncthreads();
     ptx::cluster_sync();  // nobody leaves while a peer may still touch its shared memory
+    if (trace && threadIdx.x == 0) trace[6] = clock64();
     if (warp == 2) {
       ptx::tc_fence_after();
       ptx::tmem_dealloc<1>(tmem_base, tmem_cols);
@@ -593,10 +625,16 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+inline int env_int(const char* name, int dflt);
+
 template <int BM, bool kSwap, typename OutT>
-int launch_gemm(int BN, int cluster_split, const CUtensorMap& tmA, const CUtensorMap& tmB, OutT* C, float* workspace, int64_t workspace_bytes,
+int launch_gemm(int BN, int cluster_split, int mcast_g, const CUtensorMap& tmA, const CUtensorMap& tmB, OutT* C, float* workspace, int64_t workspace_bytes,
                 const OutT* bias, int rowsA, int rowsB, int K, int64_t ldc, bool f16, bool pdl, cudaStream_t stream) {
-  const GemmSmem S = GemmSmem::make(BM, BN);
+  // small-M cluster split-K launches (decode GEMMs, one tile per cluster, a few us long): half-size ring so that two CTAs fit
+  // an SM and consecutive PDL-chained GEMMs overlap their prologue / weight prefetch with the predecessor's epilogue
+  static const int small_kb = env_int("FIB200_GEMM_SMALL_SMEM_KB", 100);
+  const bool co_resident = !kSwap && cluster_split > 1 && small_kb > 0 && small_kb < 220;
+  GemmSmem S = GemmSmem::make(BM, BN, co_resident ? small_kb : 220);
   auto kern = gemm_nt_kernel<BM, kSwap, OutT>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -604,6 +642,7 @@ int launch_gemm(int BN, int cluster_split, const CUtensorMap& tmA, const CUtenso
     attr_set = true;
   }
   Sched sk;
+  sk.smem_kb = co_resident ? small_kb : 220;
   sk.BN = BN;
   sk.tiles_a = (rowsA + BM - 1) / BM;
   sk.tiles_b = (rowsB + BN - 1) / BN;
@@ -635,17 +674,28 @@ int launch_gemm(int BN, int cluster_split, const CUtensorMap& tmA, const CUtenso
       }
     }
   }
+  static const int trace_env = env_int("FIB200_GEMM_TRACE", 0);
+  sk.trace = trace_env;
   sk.S = 1;
-  if (!kSwap && cluster_split > 1 && tiles * cluster_split <= (cluster_split >= 4 ? (num_sms() * 132) / 148 : num_sms()) && sk.kblocks >= 4 * cluster_split &&
+  sk.G = 1;
+  if (!kSwap && (cluster_split > 1 || mcast_g > 1) &&
+      tiles * cluster_split <= (cluster_split * mcast_g >= 4 ? (num_sms() * 132) / 148 : num_sms()) && tiles % mcast_g == 0 &&
+      sk.kblocks >= 4 * cluster_split &&
       int64_t(cluster_split - 1) * BM * BN * 4 <= int64_t(S.stages) * S.stage_bytes) {
     sk.S = cluster_split;
+    sk.G = mcast_g;
     sk.grid = grid = tiles * cluster_split;
     sk.W = 1;
     sk.R = 0;
     sk.g_sk = 0;
   }
+  if (sk.S == 1 && co_resident) {  // the cluster split was rejected: plain persistent kernel with the full ring
+    sk.smem_kb = 220;
+    S = GemmSmem::make(BM, BN, 220);
+  }
   const uint32_t idesc = ptx::make_idesc_f16(f16 ? ptx::kFmtF16 : ptx::kFmtBF16, BM, BN, 0, 0);
-  LaunchCfg lc(dim3(grid), dim3(256), S.total, stream, pdl, sk.S);
+  if (sk.G != mcast_g) return set_error("gemm: A-multicast was planned but the cluster launch was rejected");
+  LaunchCfg lc(dim3(grid), dim3(256), S.total, stream, pdl, sk.S * sk.G);
   int* counters = reinterpret_cast<int*>(workspace);
   float* partial = workspace ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + 4096) : nullptr;
   FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, kern, tmA, tmB, C, partial, counters, bias, rowsA, rowsB, K, ldc, sk, idesc));
@@ -718,6 +768,28 @@ int gemm_dispatch(const void* A, const void* B, OutT* C, const OutT* bias, int M
   if (force_bn > 0) BN = force_bn;
   if (force_bm > 0 && !swap) BMsel = force_bm;
   const int BM = BMsel;
+  // Cluster split-K shapes: pair up neighbouring N tiles so that the activation k-blocks are multicast (cluster = S x 2).
+  // Clusters of 4 only fit 132 of the 148 SMs, and the pairing needs an even number of N tiles and a single M tile.
+  // measured on B200 (o_proj shape, clock64 trace): the main loop is DRAM-bound at 5.6 TB/s with or without the multicast,
+  // so it stays opt-in (FIB200_GEMM_MCAST=2)
+  static const int mcast_env = env_int("FIB200_GEMM_MCAST", 1);
+  int Gsel = 1;
+  if (!swap && Ssel == 2 && mcast_env == 2 && M <= BM) {
+    const int tb = (N + BN - 1) / BN;
+    if (tb % 2 == 0 && tb * Ssel <= 132) Gsel = 2;
+  }
+  // FIB200_GEMM_MCAST=4: no K split at all - narrow N tiles with full K, the activation k-blocks multicast over clusters of
+  // four neighbouring tiles (each CTA loads a quarter of the rows): no partial exchange in the epilogue
+  if (!swap && mcast_env == 4 && M <= 64 && Ssel == 2 && force_bn == 0) {
+    int bn = ((N + 131) / 132 + 15) / 16 * 16;
+    if (bn < 32) bn = 32;
+    const int tb = (N + bn - 1) / bn;
+    if (tb % 4 == 0 && tb <= 132 && bn <= 128) {
+      BN = bn;
+      Ssel = 1;
+      Gsel = 4;
+    }
+  }
   // A-side = 128-row operand.  normal: activations; swap: weights.
   const void* pa = swap ? B : A;
   const void* pb = swap ? A : B;
@@ -727,7 +799,7 @@ int gemm_dispatch(const void* A, const void* B, OutT* C, const OutT* bias, int M
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)rowsA};
     uint64_t str[1] = {(uint64_t)ldA * 2};
-    uint32_t box[2] = {BK, (uint32_t)BM};
+    uint32_t box[2] = {BK, (uint32_t)(BM / Gsel)};  // multicast: every CTA of a pair loads half of the rows
     if (make_tmap(&tmA, dt, 2, pa, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   }
   {
@@ -737,12 +809,12 @@ int gemm_dispatch(const void* A, const void* B, OutT* C, const OutT* bias, int M
     if (make_tmap(&tmB, dt, 2, pb, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   }
   if (swap)
-    return launch_gemm<128, true, OutT>(BN, 1, tmA, tmB, C, workspace, workspace_bytes, bias, rowsA, rowsB, K, ldc, f16, pdl,
+    return launch_gemm<128, true, OutT>(BN, 1, 1, tmA, tmB, C, workspace, workspace_bytes, bias, rowsA, rowsB, K, ldc, f16, pdl,
                                         stream);
   if (BM == 64)
-    return launch_gemm<64, false, OutT>(BN, Ssel, tmA, tmB, C, workspace, workspace_bytes, bias, rowsA, rowsB, K, ldc, f16, pdl,
+    return launch_gemm<64, false, OutT>(BN, Ssel, Gsel, tmA, tmB, C, workspace, workspace_bytes, bias, rowsA, rowsB, K, ldc, f16, pdl,
                                         stream);
-  return launch_gemm<128, false, OutT>(BN, Ssel, tmA, tmB, C, workspace, workspace_bytes, bias, rowsA, rowsB, K, ldc, f16, pdl,
+  return launch_gemm<128, false, OutT>(BN, Ssel, Gsel, tmA, tmB, C, workspace, workspace_bytes, bias, rowsA, rowsB, K, ldc, f16, pdl,
                                        stream);
 }
 

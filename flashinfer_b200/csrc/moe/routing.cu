@@ -23,7 +23,8 @@ constexpr int kMaxTopK = 32;
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
 
 // One warp per token.  logits [T, E] (f32 or bf16), bias [E] optional.
-template <typename TL>
+// kSlots = register slots per lane (experts / 32, rounded up to a power of two): every unrolled loop is sized by it.
+template <typename TL, int kSlots>
 __global__ void __launch_bounds__(256)
 routing_kernel(const TL* __restrict__ logits, const float* __restrict__ bias, int32_t* __restrict__ topk_ids,
                float* __restrict__ topk_w, int T, int E, int K, int method, int n_group, int topk_group,
@@ -33,12 +34,12 @@ routing_kernel(const TL* __restrict__ logits, const float* __restrict__ bias, in
   if (tok >= T) return;
   ptx::grid_dep_wait();
   const int per = (E + 31) / 32;
-  float score[kMaxPerLane];   // value used for selection
-  float orig[kMaxPerLane];    // value used for the output weight
+  float score[kSlots];   // value used for selection
+  float orig[kSlots];    // value used for the output weight
   // expert e lives in lane e % 32, slot e / 32
   float mx = -INFINITY;
 #pragma unroll
-  for (int s = 0; s < kMaxPerLane; ++s) {
+  for (int s = 0; s < kSlots; ++s) {
     const int e = s * 32 + lane;
     float x = (s < per && e < E) ? to_f32(logits[int64_t(tok) * E + e]) : -INFINITY;
     score[s] = x;
@@ -50,7 +51,7 @@ routing_kernel(const TL* __restrict__ logits, const float* __restrict__ bias, in
   if (softmax_first) {
     float sum = 0.f;
 #pragma unroll
-    for (int s = 0; s < kMaxPerLane; ++s) {
+    for (int s = 0; s < kSlots; ++s) {
       if (s < per) {
         score[s] = (score[s] == -INFINITY) ? 0.f : __expf(score[s] - mx);
         sum += score[s];
@@ -59,14 +60,14 @@ routing_kernel(const TL* __restrict__ logits, const float* __restrict__ bias, in
     sum = warp_reduce_sum(sum);
     const float inv = 1.f / sum;
 #pragma unroll
-    for (int s = 0; s < kMaxPerLane; ++s) {
+    for (int s = 0; s < kSlots; ++s) {
       const int e = s * 32 + lane;
       score[s] = (s < per && e < E) ? score[s] * inv : -INFINITY;
       orig[s] = score[s];
     }
   } else if (sigmoid_first) {
 #pragma unroll
-    for (int s = 0; s < kMaxPerLane; ++s) {
+    for (int s = 0; s < kSlots; ++s) {
       const int e = s * 32 + lane;
       if (s < per && e < E) {
         const float sg = sigmoidf_(score[s]);
@@ -79,7 +80,7 @@ routing_kernel(const TL* __restrict__ logits, const float* __restrict__ bias, in
     }
   } else {
 #pragma unroll
-    for (int s = 0; s < kMaxPerLane; ++s) orig[s] = score[s];
+    for (int s = 0; s < kSlots; ++s) orig[s] = score[s];
   }
 
   // DeepSeek-V3 group limiting: keep only experts of the `topk_group` best groups (score = sum of top-2 in group)
@@ -97,7 +98,7 @@ routing_kernel(const TL* __restrict__ logits, const float* __restrict__ bias, in
       for (int g = 0; g < n_group; ++g) {
         float a1 = -INFINITY, a2 = -INFINITY;
 #pragma unroll
-        for (int s = 0; s < kMaxPerLane; ++s) {
+        for (int s = 0; s < kSlots; ++s) {
           if (s >= g * spg && s < (g + 1) * spg) {
             const float v = score[s];
             if (v > a1) {
@@ -146,7 +147,7 @@ routing_kernel(const TL* __restrict__ logits, const float* __restrict__ bias, in
     }
     const unsigned keep_mask = __ballot_sync(0xffffffffu, lane < n_group && rank < topk_group);
 #pragma unroll
-    for (int s = 0; s < kMaxPerLane; ++s) {
+    for (int s = 0; s < kSlots; ++s) {
       const int e = s * 32 + lane;
       if (s < per && e < E) {
         if (!((keep_mask >> (e / gsz)) & 1u)) score[s] = -INFINITY;
@@ -162,7 +163,7 @@ routing_kernel(const TL* __restrict__ logits, const float* __restrict__ bias, in
     float bv = -INFINITY;
     int be = 1 << 30;
 #pragma unroll
-    for (int s = 0; s < kMaxPerLane; ++s) {
+    for (int s = 0; s < kSlots; ++s) {
       const int e = s * 32 + lane;
       if (s < per && e < E && (score[s] > bv || (score[s] == bv && e < be))) {
         bv = score[s];
@@ -184,7 +185,7 @@ routing_kernel(const TL* __restrict__ logits, const float* __restrict__ bias, in
     if ((be & 31) == lane && be < E) {
       const int s = be >> 5;
 #pragma unroll
-      for (int ss = 0; ss < kMaxPerLane; ++ss)
+      for (int ss = 0; ss < kSlots; ++ss)
         if (ss == s) {
           w = orig[ss];
           score[ss] = -INFINITY;
@@ -387,11 +388,25 @@ moe_sort_small_kernel(const int32_t* __restrict__ topk_ids, int n, int K, int lo
     }
     ev[it] = e;
   }
+  // rank / count among the 32 lanes by an all-to-all shuffle sweep (match.any is a long-latency serialising op here)
+  auto peers_of = [&](int e, int& rank, int& cnt, int& first) {
+    rank = 0;
+    cnt = 0;
+    first = 32;
+#pragma unroll
+    for (int l = 0; l < 32; ++l) {
+      const bool same = __shfl_sync(0xffffffffu, e, l) == e;
+      cnt += same;
+      rank += (same && l < lane);
+      if (same && first == 32) first = l;
+    }
+  };
 #pragma unroll
   for (int it = 0; it < ITERS; ++it) {
     const int e = ev[it];
-    const uint32_t peers = __match_any_sync(0xffffffffu, e);
-    if (e >= 0 && (peers & ((1u << lane) - 1)) == 0) myh[e] += __popc(peers);
+    int rank, cnt, first;
+    peers_of(e, rank, cnt, first);
+    if (e >= 0 && rank == 0) myh[e] += cnt;
     __syncwarp();
   }
   __syncthreads();
@@ -447,14 +462,14 @@ moe_sort_small_kernel(const int32_t* __restrict__ topk_ids, int n, int K, int lo
   for (int it = 0; it < ITERS; ++it) {
     const int i = lo + it * 32 + lane;
     const int e = ev[it];
-    const uint32_t peers = __match_any_sync(0xffffffffu, e);
-    const int rank = __popc(peers & ((1u << lane) - 1));
+    int rank, cnt, first;
+    peers_of(e, rank, cnt, first);
     int b = 0;
     if (e >= 0 && rank == 0) {
       b = myh[e];
-      myh[e] = b + __popc(peers);
+      myh[e] = b + cnt;
     }
-    b = __shfl_sync(0xffffffffu, b, __ffs(peers) - 1);
+    b = __shfl_sync(0xffffffffu, b, first);
     if (i < hi) {
       if (e >= 0) {
         const int pos = off[e] + b + rank;
@@ -465,6 +480,115 @@ moe_sort_small_kernel(const int32_t* __restrict__ topk_ids, int n, int K, int lo
       }
     }
     __syncwarp();
+  }
+}
+
+__device__ __forceinline__ int ld_dsmem_i32(uint32_t addr) {
+  int v;
+  asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+
+// Mid-size problems (T * K <= 16 K entries): the three phases in ONE launch on a thread-block cluster - CTA c owns the 1024
+// entries [1024 c, 1024 c + 1024), the per-CTA histograms are combined through distributed shared memory, every CTA then
+// knows the padded expert offsets and its own base inside every expert and scatters its chunk (same deterministic order as
+// the 3-kernel path: rows of an expert ascend with the expanded index).  A single SM is NOT enough for this: match.any and
+// the shuffle sweeps that could replace it are issue / unit bound (measured 26 - 34 us for 8 K entries on one SM).
+__global__ void __launch_bounds__(kSortChunk)
+moe_sort_cluster_kernel(const int32_t* __restrict__ topk_ids, int n, int K, int local_offset, int local_num, int tile,
+                        int max_rows, int32_t* __restrict__ expanded_to_permuted, int32_t* __restrict__ permuted_to_token,
+                        int32_t* __restrict__ tile_expert, int32_t* __restrict__ expert_offsets, int32_t* __restrict__ meta) {
+  extern __shared__ int sm[];
+  int* hist = sm;                   // [local_num] my chunk's histogram, later my running cursor
+  int* cnt = sm + local_num;        // [local_num] totals over the cluster
+  int* off = cnt + local_num;       // [local_num + 1] padded expert offsets
+  __shared__ int warp_tot[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int crank = int(ptx::cluster_ctarank()), csize = int(ptx::cluster_nctarank());
+  for (int i = threadIdx.x; i < local_num; i += blockDim.x) hist[i] = 0;
+  ptx::grid_dep_wait();
+  __syncthreads();
+  const int i = crank * kSortChunk + threadIdx.x;
+  int e = -1;
+  if (i < n) {
+    e = topk_ids[i] - local_offset;
+    if (e < 0 || e >= local_num) e = -1;
+  }
+  const uint32_t peers = __match_any_sync(0xffffffffu, e);
+  const int rank = __popc(peers & ((1u << lane) - 1));
+  if (e >= 0 && rank == 0) atomicAdd(&hist[e], __popc(peers));
+  ptx::cluster_sync();  // all histograms complete and visible cluster-wide
+  // totals and my prefix (CTAs of lower rank) for every expert
+  for (int x = threadIdx.x; x < local_num; x += blockDim.x) {
+    int tot = 0, before = 0;
+    for (int c = 0; c < csize; ++c) {
+      const int v = c == crank ? hist[x] : ld_dsmem_i32(ptx::mapa(ptx::smem_u32(&hist[x]), uint32_t(c)));
+      tot += v;
+      if (c < crank) before += v;
+    }
+    cnt[x] = tot;
+    off[x] = before;  // parked here until the padded offsets are known
+  }
+  ptx::cluster_sync();  // every remote read of `hist` is done: it may be overwritten (and CTAs may exit later on)
+  // block-wide exclusive scan of the tile-padded totals (every CTA computes the same offsets)
+  int base = 0;
+  for (int e0 = 0; e0 < local_num; e0 += blockDim.x) {
+    const int x = e0 + threadIdx.x;
+    const int padded = x < local_num ? (cnt[x] + tile - 1) / tile * tile : 0;
+    int incl = padded;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    int wbase = 0, total = 0;
+    for (int w = 0; w < 32; ++w) {
+      if (w < warp) wbase += warp_tot[w];
+      total += warp_tot[w];
+    }
+    if (x < local_num) {
+      const int o_x = base + wbase + incl - padded;
+      hist[x] = o_x + off[x];  // my cursor: expert offset + rows of lower-rank CTAs
+      off[x] = o_x;
+    }
+    base += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) off[local_num] = base;
+  __syncthreads();
+  ptx::grid_dep_launch();
+  // bookkeeping, spread over the cluster: expert x is written by CTA x % csize, the dead tail by everybody
+  if (crank == 0 && threadIdx.x == 0) {
+    meta[0] = base / tile;
+    meta[1] = base;
+  }
+  for (int x = crank * int(blockDim.x) + threadIdx.x; x <= local_num; x += csize * blockDim.x) expert_offsets[x] = off[x];
+  for (int x = base / tile + crank * int(blockDim.x) + threadIdx.x; x < max_rows / tile; x += csize * blockDim.x) tile_expert[x] = -1;
+  for (int x = base + crank * int(blockDim.x) + threadIdx.x; x < max_rows; x += csize * blockDim.x) permuted_to_token[x] = -1;
+  for (int x = crank + warp * csize; x < local_num; x += csize * (blockDim.x >> 5)) {
+    for (int r = off[x] + lane * tile; r < off[x + 1]; r += 32 * tile) tile_expert[r / tile] = x;
+    for (int r = off[x] + cnt[x] + lane; r < off[x + 1]; r += 32) permuted_to_token[r] = -1;
+  }
+  // scatter my chunk: rank inside the 32-entry group, warps take turns on the shared cursor (deterministic)
+  int b = 0;
+  for (int w = 0; w < kSortChunk / 32; ++w) {
+    if (w == warp && e >= 0 && rank == 0) {
+      b = hist[e];
+      hist[e] = b + __popc(peers);
+    }
+    __syncthreads();
+  }
+  b = __shfl_sync(0xffffffffu, b, __ffs(peers) - 1);
+  if (i < n) {
+    if (e >= 0) {
+      const int pos = b + rank;
+      expanded_to_permuted[i] = pos;
+      permuted_to_token[pos] = i / K;
+    } else {
+      expanded_to_permuted[i] = -1;
+    }
   }
 }
 
@@ -557,25 +681,32 @@ extern "C" int moe_routing(void* logits, void* bias, void* topk_ids, void* topk_
                            int64_t method, int64_t n_group, int64_t topk_group, double routed_scale,
                            int64_t norm_topk_prob, int64_t logits_dtype, int64_t pdl, int64_t stream_) {
   FIB_CHECK(E <= 32 * kMaxPerLane, "moe_routing: at most 512 experts");
+  FIB_CHECK(E >= 1, "moe_routing: no experts");
   FIB_CHECK(K >= 1 && K <= kMaxTopK, "moe_routing: top_k must be in [1,32]");
   FIB_CHECK(method != 2 || n_group <= 32, "moe_routing: n_group must be <= 32");
   if (T == 0) return 0;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   LaunchCfg lc(dim3((unsigned)((T + 7) / 8)), dim3(256), 0, stream, pdl != 0);
-  if (logits_dtype == kF32) {
-    FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, routing_kernel<float>, (const float*)logits, (const float*)bias,
-                                      (int32_t*)topk_ids, (float*)topk_w, (int)T, (int)E, (int)K, (int)method,
-                                      (int)(n_group > 0 ? n_group : 1), (int)(topk_group > 0 ? topk_group : 1),
-                                      (float)routed_scale, (int)norm_topk_prob));
-  } else if (logits_dtype == kBF16) {
-    FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, routing_kernel<__nv_bfloat16>, (const __nv_bfloat16*)logits,
-                                      (const float*)bias, (int32_t*)topk_ids, (float*)topk_w, (int)T, (int)E, (int)K,
-                                      (int)method, (int)(n_group > 0 ? n_group : 1),
+  auto go = [&](auto kern, auto* lg) -> int {
+    FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, kern, lg, (const float*)bias, (int32_t*)topk_ids, (float*)topk_w, (int)T, (int)E,
+                                      (int)K, (int)method, (int)(n_group > 0 ? n_group : 1),
                                       (int)(topk_group > 0 ? topk_group : 1), (float)routed_scale, (int)norm_topk_prob));
-  } else {
-    return set_error("moe_routing: logits must be float32 or bfloat16");
+    return 0;
+  };
+  const int slots = (int)((E + 31) / 32);
+#define FIB_ROUTE(TL_)                                                        \
+  {                                                                           \
+    const TL_* lg = (const TL_*)logits;                                       \
+    if (slots <= 1) return go(routing_kernel<TL_, 1>, lg);                    \
+    if (slots <= 2) return go(routing_kernel<TL_, 2>, lg);                    \
+    if (slots <= 4) return go(routing_kernel<TL_, 4>, lg);                    \
+    if (slots <= 8) return go(routing_kernel<TL_, 8>, lg);                    \
+    return go(routing_kernel<TL_, 16>, lg);                                   \
   }
-  return 0;
+  if (logits_dtype == kF32) FIB_ROUTE(float)
+  if (logits_dtype == kBF16) FIB_ROUTE(__nv_bfloat16)
+#undef FIB_ROUTE
+  return set_error("moe_routing: logits must be float32 or bfloat16");
 }
 
 // workspace: int32 [ceil(T*K / 1024) * local_num]
@@ -587,8 +718,26 @@ extern "C" int moe_sort(void* topk_ids, int64_t T, int64_t K, int64_t E, int64_t
   const int n = (int)(T * K);
   const int nchunks = n > 0 ? (n + kSortChunk - 1) / kSortChunk : 0;
   (void)E;
+  static const int sort_mode = [] {
+    const char* v = getenv("FIB200_MOE_SORT");
+    return v ? atoi(v) : 0;  // 0 auto, 1 single CTA, 2 cluster, 3 three kernels
+  }();
+  if (n > 0 && nchunks <= 16 && local_num <= 4096 && (sort_mode == 0 || sort_mode == 2)) {
+    // one launch, one cluster of ceil(n / 1024) CTAs (clusters above 8 need the non-portable opt-in)
+    static bool np_set = false;
+    if (!np_set) {
+      FIB_CUDA_CHECK(cudaFuncSetAttribute(moe_sort_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      np_set = true;
+    }
+    LaunchCfg lc(dim3(nchunks), dim3(kSortChunk), (size_t(3) * local_num + 1) * sizeof(int), stream, pdl != 0, nchunks);
+    FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, moe_sort_cluster_kernel, (const int32_t*)topk_ids, n, (int)K, (int)local_offset,
+                                      (int)local_num, (int)tile, (int)max_rows, (int32_t*)expanded_to_permuted,
+                                      (int32_t*)permuted_to_token, (int32_t*)tile_expert, (int32_t*)expert_offsets,
+                                      (int32_t*)meta));
+    return 0;
+  }
   const size_t small_smem = (size_t(34) * local_num + 1) * sizeof(int);
-  if (n > 0 && n <= 32768 && small_smem <= 48 * 1024) {
+  if (n > 0 && n <= 32768 && small_smem <= 48 * 1024 && sort_mode == 1) {
     LaunchCfg lc(dim3(1), dim3(1024), small_smem, stream, pdl != 0);
     const int iters = (n + 1023) / 1024;  // 32-entry groups per warp
     auto go = [&](auto kern) -> int {

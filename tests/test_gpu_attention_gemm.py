@@ -11,7 +11,9 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("mnk", [(128, 128, 64), (300, 1000, 520), (1, 4096, 4096), (16, 6144, 4096), (64, 4096, 14336),
-                                 (100, 384, 2048), (1024, 4096, 4096), (129, 136, 72)])
+                                 (100, 384, 2048), (1024, 4096, 4096), (129, 136, 72),
+                                 # decode shapes of the cluster split-K path with the A operand multicast across N-tile pairs
+                                 (64, 4096, 4096), (64, 6144, 4096), (33, 4096, 14336), (64, 28672, 4096), (7, 1024, 2048)])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 def test_linear(mnk, dtype):
     m, n, k = mnk

@@ -8,12 +8,19 @@ M = int(os.environ.get("M", "64"))
 shapes = {"qkv": (6144, 4096), "o": (4096, 4096), "gate_up": (28672, 4096), "down": (4096, 14336), "lm_head": (128256, 4096)}
 peak = 6.57e12
 res = {}
+only = os.environ.get("SHAPES")
+if only:
+    shapes = {k: v for k, v in shapes.items() if k in only.split(",")}
+nocublas = os.environ.get("NOCUBLAS") == "1"
 for name, (N, K) in shapes.items():
     nbuf = max(2, int(300e6 // (N * K * 2)) + 1)
     ws = [torch.randn(N, K, device="cuda", dtype=torch.bfloat16) * 0.02 for _ in range(nbuf)]
     a = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
     outs = {}
     for label, fn in (("ours", lambda w: fi.mm_bf16(a, w.t())), ("cublas", lambda w: a @ w.t())):
+        if nocublas and label == "cublas":
+            outs[label] = 0.0
+            continue
         for i in range(nbuf):
             fn(ws[i])
         g = torch.cuda.CUDAGraph()

@@ -49,4 +49,10 @@ elif mode in ("mla", "mla_small"):
     w.plan(torch.arange(B + 1, dtype=torch.int32), torch.arange(0, (B + 1) * npg, npg, dtype=torch.int32), torch.randperm(B * npg).int(),
            torch.full((B,), kv, dtype=torch.int32), H, 512, 64, ps, True, 0.07, torch.bfloat16, torch.bfloat16)
     for _ in range(3): w.run(qn, qp, ckv, kpe)
+elif mode in ("gemm_o", "gemm_qkv", "cublas_o", "cublas_qkv"):
+    N, K = (4096, 4096) if mode.endswith("_o") else (6144, 4096)
+    ws = [torch.randn(N, K, device="cuda", dtype=torch.bfloat16) * 0.02 for _ in range(6)]
+    a = torch.randn(64, K, device="cuda", dtype=torch.bfloat16)
+    for w in ws:
+        (fi.mm_bf16(a, w.t()) if mode.startswith("gemm") else a @ w.t())
 torch.cuda.synchronize()
