@@ -72,6 +72,7 @@ struct Params {
   const int32_t* tile_expert;  // grouped (MoE) mode: expert of every 128-row tile of A (-1 = skip); B / SFB / alpha are per expert
   const int32_t* meta;         // grouped mode: meta[0] = number of live row tiles (device side)
   const int32_t* row_map;      // grouped mode (optional): rows with row_map < 0 are padding, their results are not stored
+  int a_box_rows;              // rows per A TMA box: 128, or 32 in grouped mode with a row_map (only live row groups are loaded)
   int tab_tiles, tab_experts;  // capacity of the shared-memory tile->expert / alpha tables (grouped mode)
   int split;          // cluster split-K factor (1 or 2): both CTAs of a cluster own the same tile, half of K each
   int sf_k_tiles;     // 512-byte blocks along K in the scale tensors
@@ -142,8 +143,22 @@ bs_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // global memory per tile put an L2 round trip (~1 us) on the critical path of every role (ncu: long-scoreboard stalls)
   int32_t* s_expert = reinterpret_cast<int32_t*>(smem + G.bar_offset + 320);
   float* s_alpha = reinterpret_cast<float*>(s_expert + p.tab_tiles);
+  // MoE with few tokens per expert: most of a 128-row tile is padding.  The A tile is fetched in 32-row boxes and only the
+  // boxes that contain live rows are loaded (live rows are a prefix of the tile): s_nbox[tile] in 1..4.  The stale rows left
+  // in shared memory only feed accumulator rows that the epilogue never stores.  Per-SM ingest was the limiter of these
+  // weight-streaming GEMMs (A was as many bytes as B), so this is worth ~25 % on the tiny-batch MoE shapes.
+  int32_t* s_nbox = reinterpret_cast<int32_t*>(s_alpha + p.tab_experts);
   if (grouped) {
-    for (int i = threadIdx.x; i < tiles_m && i < p.tab_tiles; i += blockDim.x) s_expert[i] = p.tile_expert[i];
+    for (int i = threadIdx.x; i < tiles_m && i < p.tab_tiles; i += blockDim.x) {
+      s_expert[i] = p.tile_expert[i];
+      int nb = BM / 32;
+      if (p.a_box_rows == 32 && p.row_map) {
+        nb = 1;
+        for (int bx = 1; bx < BM / 32; ++bx)
+          if (i * BM + bx * 32 < p.M && p.row_map[i * BM + bx * 32] >= 0) nb = bx + 1;
+      }
+      s_nbox[i] = nb;
+    }
     if (p.alpha_a)
       for (int i = threadIdx.x; i < p.batch && i < p.tab_experts; i += blockDim.x) s_alpha[i] = p.alpha_a[i];
     __syncthreads();
@@ -187,7 +202,9 @@ bs_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * G.stage_bytes;
           uint8_t* sb = sa + G.a_bytes;
-          uint32_t tx = G.a_bytes + G.b_bytes;
+          const int abr = p.a_box_rows;
+          const int nbox = abr == BM ? 1 : (tm < p.tab_tiles ? s_nbox[tm] : BM / 32);
+          uint32_t tx = uint32_t(nbox * abr) * BKB + G.b_bytes;
           int nch = 0;
           if constexpr (KIND != kFp8) {
             nch = p.sf_k_tiles - kb * G.nchunk;
@@ -195,7 +212,8 @@ bs_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tx += uint32_t(nch * 512) * uint32_t(1 + rbn);
           }
           ptx::mbar_arrive_expect_tx(&full_bar[stage], tx);
-          ptx::tma_load_3d(sa, &tmA, &full_bar[stage], kb * BKB, tm * BM, b, ptx::kEvictNormal);
+          for (int bx = 0; bx < nbox; ++bx)
+            ptx::tma_load_3d(sa + bx * abr * BKB, &tmA, &full_bar[stage], kb * BKB, tm * BM + bx * abr, b, ptx::kEvictNormal);
           ptx::tma_load_3d(sb, &tmB, &full_bar[stage], kb * BKB, n0, bb, ptx::kEvictNormal);
           if constexpr (KIND != kFp8) {
             uint8_t* ssfa = sb + G.b_bytes;
@@ -398,6 +416,7 @@ struct GwParams {
   const int32_t* tile_expert;
   const int32_t* meta;
   const int32_t* row_map;  // optional: rows with row_map < 0 are padding (not stored)
+  int a_box_rows;          // 128, or 32 with a row_map: only the 32-row boxes that hold live rows are loaded
   int64_t sb_e;  // expert stride of the B scales
 };
 
@@ -467,17 +486,26 @@ fp8_groupwise_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         decode(t, tm, tn, e);
         if (e < 0) continue;
         const int brow = e * p.N + tn * BN;
+        const int abr = p.a_box_rows;
+        int nbox = 1;
+        if (abr != BM) {
+          for (int bx = 1; bx < BM / 32; ++bx)
+            if (tm * BM + bx * 32 < p.M && p.row_map[tm * BM + bx * 32] >= 0) nbox = bx + 1;
+        }
+        const uint32_t a_tx = uint32_t(nbox * abr) * BKB;
         int kb_start = 0;
         if (first) {  // weights before griddepcontrol.wait
           first = false;
           const int npre = num_kb < kStages ? num_kb : kStages;
           for (int i = 0; i < npre; ++i) {
-            ptx::mbar_arrive_expect_tx(&full_bar[i], G.a_bytes + G.b_bytes);
+            ptx::mbar_arrive_expect_tx(&full_bar[i], a_tx + G.b_bytes);
             ptx::tma_load_2d(smem + i * G.stage_bytes + G.a_bytes, &tmB, &full_bar[i], i * BKB, brow, ptx::kEvictFirst);
           }
           ptx::grid_dep_wait();
           for (int i = 0; i < npre; ++i)
-            ptx::tma_load_2d(smem + i * G.stage_bytes, &tmA, &full_bar[i], i * BKB, tm * BM, ptx::kEvictNormal);
+            for (int bx = 0; bx < nbox; ++bx)
+              ptx::tma_load_2d(smem + i * G.stage_bytes + bx * abr * BKB, &tmA, &full_bar[i], i * BKB, tm * BM + bx * abr,
+                               ptx::kEvictNormal);
           stage = npre == kStages ? 0 : npre;
           phase = npre == kStages ? 1 : 0;
           kb_start = npre;
@@ -485,8 +513,9 @@ fp8_groupwise_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         for (int kb = kb_start; kb < num_kb; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * G.stage_bytes;
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], G.a_bytes + G.b_bytes);
-          ptx::tma_load_2d(sa, &tmA, &full_bar[stage], kb * BKB, tm * BM, ptx::kEvictNormal);
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], a_tx + G.b_bytes);
+          for (int bx = 0; bx < nbox; ++bx)
+            ptx::tma_load_2d(sa + bx * abr * BKB, &tmA, &full_bar[stage], kb * BKB, tm * BM + bx * abr, ptx::kEvictNormal);
           ptx::tma_load_2d(sa + G.a_bytes, &tmB, &full_bar[stage], kb * BKB, brow, ptx::kEvictFirst);
           if (++stage == kStages) {
             stage = 0;
@@ -1066,11 +1095,12 @@ extern "C" int gemm_lowp_nt(void* A, void* B, void* C, void* sfa, void* sfb, voi
   const Geo G = Geo::make(BN, (int)kind);
   FIB_CHECK(G.stages >= 2 && G.tmem_cols <= 512, "gemm_lowp: tile does not fit");
 
+  const int a_box_rows = (tile_expert && row_map) ? 32 : BM;
   CUtensorMap tmA, tmB;
   {
     uint64_t dims[3] = {(uint64_t)Kb, (uint64_t)M, (uint64_t)(tile_expert ? 1 : batch)};
     uint64_t str[2] = {(uint64_t)lda, (uint64_t)(tile_expert ? lda * M : a_batch_stride)};
-    uint32_t box[3] = {BKB, BM, 1};
+    uint32_t box[3] = {BKB, (uint32_t)a_box_rows, 1};
     if (make_tmap(&tmA, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, A, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   }
   {
@@ -1086,7 +1116,8 @@ extern "C" int gemm_lowp_nt(void* A, void* B, void* C, void* sfa, void* sfb, voi
   p.row_map = (const int32_t*)row_map;
   p.tab_tiles = tile_expert ? (tiles_m < 1024 ? tiles_m : 1024) : 0;
   p.tab_experts = tile_expert ? (int)(batch < 1024 ? batch : 1024) : 0;
-  const int tab_bytes = (p.tab_tiles + p.tab_experts) * 4;
+  p.a_box_rows = a_box_rows;
+  const int tab_bytes = (2 * p.tab_tiles + p.tab_experts) * 4;
   p.sfb = (const uint8_t*)sfb;
   p.alpha_a = (const float*)alpha_a;
   p.alpha_b = (const float*)alpha_b;
@@ -1163,7 +1194,7 @@ extern "C" int gemm_fp8_groupwise_nt(void* A, void* B, void* C, void* sa, void* 
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
     uint64_t str[1] = {(uint64_t)lda};
-    uint32_t box[2] = {BKB, BM};
+    uint32_t box[2] = {BKB, (uint32_t)((tile_expert && row_map) ? 32 : BM)};
     if (make_tmap(&tmA, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, A, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   }
   {
@@ -1176,6 +1207,7 @@ extern "C" int gemm_fp8_groupwise_nt(void* A, void* B, void* C, void* sa, void* 
   p.tile_expert = (const int32_t*)tile_expert;
   p.meta = (const int32_t*)meta;
   p.row_map = (const int32_t*)row_map;
+  p.a_box_rows = (tile_expert && row_map) ? 32 : BM;
   p.sb_e = sb_e;
   p.sa = (const float*)sa;
   p.sb = (const float*)sb;

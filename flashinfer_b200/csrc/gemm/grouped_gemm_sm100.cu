@@ -81,7 +81,20 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   // stage the tile -> expert table in shared memory (a global read per tile is an L2 round trip on every role's critical path)
   int32_t* s_expert = reinterpret_cast<int32_t*>(smem + S.bar_offset + 320);
   const int tab = num_m < tab_tiles ? num_m : tab_tiles;
-  for (int i = threadIdx.x; i < tab; i += blockDim.x) s_expert[i] = tile_expert[i];
+  // live-row A loading (see gemm_blockscaled_sm100.cu): with a row_map the A tile is fetched in 32-row boxes and only the
+  // boxes holding live rows are loaded; stale smem rows only feed accumulator rows that are never stored
+  int32_t* s_nbox = s_expert + tab_tiles;
+  const int abr = row_map ? 32 : BM;
+  for (int i = threadIdx.x; i < tab; i += blockDim.x) {
+    s_expert[i] = tile_expert[i];
+    int nb = BM / 32;
+    if (row_map) {
+      nb = 1;
+      for (int bx = 1; bx < BM / 32; ++bx)
+        if (row_map[i * BM + bx * 32] >= 0) nb = bx + 1;
+    }
+    s_nbox[i] = nb;
+  }
   __syncthreads();
   auto expert_of = [&](int tm) { return tm < tab ? s_expert[tm] : tile_expert[tm]; };
   const int tiles_n = (N + BN - 1) / BN;
@@ -100,8 +113,10 @@ grouped_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * S.stage_bytes;
           uint8_t* sb = sa + S.a_bytes;
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], S.stage_bytes);
-          ptx::tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, tm * BM, ptx::kEvictFirst);
+          const int nbox = abr == BM ? 1 : (tm < tab ? s_nbox[tm] : BM / 32);
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], S.stage_bytes - S.a_bytes + nbox * abr * BK * 2);
+          for (int bx = 0; bx < nbox; ++bx)
+            ptx::tma_load_2d(sa + bx * abr * BK * 2, &tmA, &full_bar[stage], kb * BK, tm * BM + bx * abr, ptx::kEvictFirst);
           ptx::tma_load_3d(sb, &tmW, &full_bar[stage], kb * BK, tn * BN, e, ptx::kEvictNormal);
           if (++stage == kStages) {
             stage = 0;
@@ -214,7 +229,7 @@ extern "C" int grouped_gemm_nt(void* A, void* W, void* C, void* tile_expert, voi
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)(max_m_tiles * BM)};
     uint64_t str[1] = {(uint64_t)lda * 2};
-    uint32_t box[2] = {BK, BM};
+    uint32_t box[2] = {BK, (uint32_t)(row_map ? 32 : BM)};
     if (make_tmap(&tmA, dt, 2, A, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   }
   {
@@ -228,7 +243,7 @@ extern "C" int grouped_gemm_nt(void* A, void* W, void* C, void* tile_expert, voi
   const int64_t tiles = max_m_tiles * ((N + BN - 1) / BN);
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
   const int tab_tiles = (int)(max_m_tiles < 2048 ? max_m_tiles : 2048);
-  LaunchCfg lc(dim3(grid), dim3(256), S.total + tab_tiles * 4, stream, pdl != 0);
+  LaunchCfg lc(dim3(grid), dim3(256), S.total + tab_tiles * 8, stream, pdl != 0);
   if (dtype == kF16) {
     static bool set = false;
     if (!set) {
