@@ -287,10 +287,21 @@ class BatchDecodeWithPagedKVCacheWrapper:
         enable_pdl: Optional[bool] = None,
         window_left: Optional[int] = None,
         sinks: Optional[torch.Tensor] = None,
+        kv_cache_sf=None,
     ):
         if not self._planned:
             raise RuntimeError("plan() must be called before run()")
         k_cache, v_cache = unpack_paged_kv_cache(paged_kv_cache, self._kv_layout)
+        if k_cache.dtype == torch.uint8 or v_cache.dtype == torch.uint8:
+            # NVFP4 KV cache (reference decode.py:1293): block scales come in ``kv_cache_sf`` in the cache layout, the global
+            # scales in k_scale / v_scale.  Composed path: the cache is widened to the query dtype, then the tcgen05 kernel runs.
+            if kv_cache_sf is None:
+                raise ValueError("kv_cache_sf must be provided for NVFP4 KV cache.")
+            from .quantization.fp4 import nvfp4_dequantize_paged_kv_cache
+
+            ksf, vsf = unpack_paged_kv_cache(kv_cache_sf, self._kv_layout)
+            k_cache = nvfp4_dequantize_paged_kv_cache(k_cache, ksf, q.dtype)
+            v_cache = nvfp4_dequantize_paged_kv_cache(v_cache, vsf, q.dtype)
         sm_scale = self._sm_scale
         if q_scale is not None:
             sm_scale *= q_scale
@@ -430,6 +441,8 @@ def trtllm_batch_decode_with_kv_cache(query: torch.Tensor, kv_cache, workspace_b
     ``kv_layout``; ``block_tables [B, max_pages]``; ``bmm1_scale`` is the softmax scale (q/k scales folded in)."""
     k_cache, v_cache = unpack_paged_kv_cache(kv_cache, kv_layout)
     _, _, _, page_size, hkv, d = paged_kv_strides(k_cache, kv_layout)
+    if k_cache.dtype == torch.uint8:
+        d *= 2  # NVFP4 cache: two e2m1 values per byte
     indptr, indices, last = _block_tables_to_indices(block_tables, seq_lens, page_size)
     b = seq_lens.numel()
     w = BatchDecodeWithPagedKVCacheWrapper(workspace_buffer, kv_layout)
@@ -438,7 +451,8 @@ def trtllm_batch_decode_with_kv_cache(query: torch.Tensor, kv_cache, workspace_b
     w.plan(indptr, indices, last, query.shape[1], hkv, d, page_size, window_left=window_left, q_data_type=query.dtype,
            sm_scale=float(bmm1_scale), qo_indptr=qo)
     res = w.run(query, (k_cache, v_cache), out=out if (out is not None and out.dtype == query.dtype) else None,
-                return_lse=return_lse, sinks=sinks, v_scale=float(bmm2_scale) if float(bmm2_scale) != 1.0 else None)
+                return_lse=return_lse, sinks=sinks, v_scale=float(bmm2_scale) if float(bmm2_scale) != 1.0 else None,
+                kv_cache_sf=kv_cache_sf)
     if out is not None and not return_lse and res.data_ptr() != out.data_ptr():
         out.copy_(res)
         return out

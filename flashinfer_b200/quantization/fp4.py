@@ -263,6 +263,19 @@ def nvfp4_quantize_paged_kv_cache(k_cache: torch.Tensor, v_cache: torch.Tensor, 
     return (kq, vq), (ksf, vsf), kg, vg
 
 
+def nvfp4_dequantize_paged_kv_cache(cache_fp4: torch.Tensor, cache_sf: torch.Tensor, dtype: torch.dtype = torch.bfloat16,
+                                    global_scale: Optional[float] = None) -> torch.Tensor:
+    """NVFP4 paged KV cache (``[..., head_dim // 2]`` packed e2m1 + ``[..., head_dim // 16]`` UE4M3 block scales, both in the
+    cache layout) -> ``dtype`` cache of the same layout.  Used by the attention wrappers when they are handed an NVFP4 cache
+    (``kv_cache_sf=``): the block scales are folded in here, the per-tensor global scale rides on ``k_scale`` / ``v_scale``."""
+    d2 = cache_fp4.shape[-1]
+    flat = cache_fp4.reshape(-1, d2).view(torch.uint8)
+    sf = cache_sf.reshape(-1, d2 // 8).view(torch.uint8)
+    gs = None if global_scale is None else torch.tensor([1.0 / float(global_scale)], dtype=torch.float32, device=cache_fp4.device)
+    out = e2m1_and_ufp8sf_scale_to_float(flat.contiguous(), sf.contiguous(), gs, 16, 1, False)
+    return out.to(dtype).view(*cache_fp4.shape[:-1], d2 * 2)
+
+
 def moe_fp4_quantize(x: torch.Tensor, rows: int, k: int, row_map: torch.Tensor, global_scale: torch.Tensor, gather: bool,
                      gated: bool, sf_vec_size: int = 16, row_list: Optional[torch.Tensor] = None,
                      list_div: int = 1) -> Tuple[torch.Tensor, torch.Tensor]:

@@ -226,3 +226,30 @@ def test_pod_runs_as_one_fused_kernel():
     torch.testing.assert_close(o_d.float(), r_d.float(), rtol=0, atol=1e-2)
     ref_p, _ = reference.attention_ref(q_p[:256], k_p[:256], v_p[:256], True)
     torch.testing.assert_close(o_p[:256].float(), ref_p.float(), rtol=3e-2, atol=3e-2)
+
+
+@pytest.mark.parametrize("device", DEVICES)
+def test_decode_nvfp4_kv_cache(device):
+    """NVFP4 KV cache (packed e2m1 + per-16 UE4M3 scales in the cache layout, global scales through k_scale / v_scale)."""
+    from flashinfer_b200.decode import BatchDecodeWithPagedKVCacheWrapper
+    from flashinfer_b200.quantization.fp4 import nvfp4_dequantize_paged_kv_cache, nvfp4_quantize_paged_kv_cache
+
+    dt, ps, hq, hkv = _dt(device), 16, 8, 2
+    if device == "cpu":
+        dt = torch.bfloat16
+    kv_lens = [100, 33, 257]
+    indptr, indices, last, kc, vc = make_paged(kv_lens, hkv, D, ps, "NHD", dt, device)
+    q = torch.randn(len(kv_lens), hq, D, device=device, dtype=dt)
+    (kq, vq), (ksf, vsf), kg, vg = nvfp4_quantize_paged_kv_cache(kc, vc, "NHD")
+    assert kq.dtype == torch.uint8 and kq.shape[-1] == D // 2 and ksf.shape[-1] == D // 16
+    w = BatchDecodeWithPagedKVCacheWrapper(torch.empty(32 << 20, dtype=torch.uint8, device=device), "NHD")
+    w.plan(indptr, indices, last, hq, hkv, D, ps, q_data_type=dt)
+    o = w.run(q, (kq, vq), kv_cache_sf=(ksf, vsf), k_scale=kg, v_scale=vg)
+    kd = (nvfp4_dequantize_paged_kv_cache(kq, ksf, torch.float32) * kg).to(dt)
+    vd = (nvfp4_dequantize_paged_kv_cache(vq, vsf, torch.float32) * vg).to(dt)
+    assert (kd.float() - kc.float()).abs().mean().item() < 0.12 * kc.float().abs().mean().item()  # fp4 grid
+    ref, _ = reference.batch_paged_attention_ref(q, torch.arange(len(kv_lens) + 1, dtype=torch.int32), kd, vd, indptr,
+                                                 indices.to(device), last, "NHD", True)
+    torch.testing.assert_close(o.float(), ref.float(), rtol=5e-2, atol=5e-2)
+    with pytest.raises(ValueError):
+        w.run(q, (kq, vq))
