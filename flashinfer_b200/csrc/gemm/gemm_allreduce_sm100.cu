@@ -32,7 +32,7 @@ struct GSmem {
     int st = (200 * 1024) / g.stage_bytes;
     g.stages = st > 8 ? 8 : st;
     g.bar_offset = g.stages * g.stage_bytes;
-    g.total = g.bar_offset + 320 + 1024;
+    g.total = g.bar_offset + 320 + 512 /* per-row sum-of-squares scratch of the reduce-scatter mode */ + 1024;
     return g;
   }
 };
@@ -59,9 +59,8 @@ struct ARP {
 // that follows (rs_norm_kernel).  Ranks that own no row of the tile neither wait nor read.
 template <typename OutT>
 __device__ __forceinline__ void rs_reduce_tile(const ARP& ar, OutT* __restrict__ out, int tm, int tn, int M, int N, int BN,
-                                               int64_t ldc, uint32_t want, int t, int tid) {
-  constexpr int VN = 16 / sizeof(OutT);
-  __shared__ float s_sq[BM];
+                                               int64_t ldc, uint32_t want, int t, int tid, float* s_sq) {
+  constexpr int VN = 16 / sizeof(OutT);  // s_sq: BM floats of dynamic smem (a static array would eat into the 227 KB opt-in)
   const int lo = max(tm * BM, ar.rank * ar.rows_per_rank);
   const int hi = min(min(tm * BM + BM, M), (ar.rank + 1) * ar.rows_per_rank);
   if (lo >= hi) return;  // uniform over the 128 all-reduce threads
@@ -299,7 +298,7 @@ gemm_ar_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int tm = t % tiles_m, tn = t / tiles_m;
       const uint32_t want = ar.expect[t] + uint32_t(ar.world);
       if (ar.two_shot == 2) {
-        rs_reduce_tile<OutT>(ar, out, tm, tn, M, N, BN, ldc, want, t, tid);
+        rs_reduce_tile<OutT>(ar, out, tm, tn, M, N, BN, ldc, want, t, tid, reinterpret_cast<float*>(smem + S.bar_offset + 320));
         if (tid == 0) ar.expect[t] = want;
         continue;
       }
