@@ -9,6 +9,9 @@ Device-timed with CUDA events, max over ranks; prints one JSON line per shape on
 import argparse
 import json
 import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import torch
 import torch.distributed as dist
@@ -16,7 +19,7 @@ import torch.distributed as dist
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--tokens", type=int, default=16 * 2048)
+    ap.add_argument("--tokens", type=str, default=str(16 * 2048), help="comma-separated token counts")
     ap.add_argument("--iters", type=int, default=20)
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -26,10 +29,10 @@ def main():
     from flashinfer_b200.comm import GemmAllReduce
 
     hidden, inter = 8192, 28672
-    M = args.tokens // world * world
-    comm = GemmAllReduce(None, M, hidden, torch.bfloat16)
+    token_list = [int(t) // world * world for t in args.tokens.split(",")]
+    comm = GemmAllReduce(None, max(token_list), hidden, torch.bfloat16)
     peaks = {"bf16_tflops": 1640.0, "nvlink_gbs": 900.0}
-    for name, k_full in (("o_proj", hidden), ("down_proj", inter)):
+    for M, (name, k_full) in [(m, s) for m in token_list for s in (("o_proj", hidden), ("down_proj", inter))]:
         K = k_full // world
         torch.manual_seed(rank)
         a = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()

@@ -72,48 +72,72 @@ __device__ __forceinline__ void rs_reduce_tile(const ARP& ar, OutT* __restrict__
   asm volatile("bar.sync 2, 128;" ::: "memory");
   const int vec_per_row = BN / VN;
   const int rows = hi - lo;
-  for (int i = tid; i < rows * vec_per_row; i += 128) {
-    const int r = i / vec_per_row, v = i % vec_per_row;
-    const int col = tn * BN + v * VN;
-    if (col >= N) continue;
-    const int64_t off = (int64_t(lo + r) * ldc + col) * sizeof(OutT);
-    int4 res;
-    float accv[VN];
-    if (ar.mc_stage) {
-      if constexpr (std::is_same<OutT, __half>::value) res = ptx::multimem_ld_reduce_f16x8(ar.mc_stage + off);
-      else res = ptx::multimem_ld_reduce_bf16x8(ar.mc_stage + off);
-      const OutT* h = reinterpret_cast<const OutT*>(&res);
+  constexpr int U = 8;  // in-switch reductions in flight per thread (a multimem.ld_reduce is a ~2 us round trip)
+  for (int i0 = tid; i0 - (tid & 31) < rows * vec_per_row; i0 += 128 * U) {  // warp-uniform trip count (shuffles below)
+    int4 red[U];
+    bool ok[U];
 #pragma unroll
-      for (int e = 0; e < VN; ++e) accv[e] = to_f32(h[e]);
-    } else {
-#pragma unroll
-      for (int e = 0; e < VN; ++e) accv[e] = 0.f;
-      for (int p = 0; p < ar.world; ++p) {
-        int4 x;
-        asm volatile("ld.global.relaxed.sys.v4.s32 {%0,%1,%2,%3}, [%4];"
-                     : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w)
-                     : "l"(ar.peer_stage[p] + off)
-                     : "memory");
-        const OutT* h = reinterpret_cast<const OutT*>(&x);
-#pragma unroll
-        for (int e = 0; e < VN; ++e) accv[e] += to_f32(h[e]);
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * 128;
+      const int r = i / vec_per_row, v = i % vec_per_row;
+      const int col = tn * BN + v * VN;
+      ok[u] = i < rows * vec_per_row && col < N;
+      red[u] = make_int4(0, 0, 0, 0);
+      if (ok[u] && ar.mc_stage) {
+        const int64_t off = (int64_t(lo + r) * ldc + col) * sizeof(OutT);
+        if constexpr (std::is_same<OutT, __half>::value) red[u] = ptx::multimem_ld_reduce_f16x8(ar.mc_stage + off);
+        else red[u] = ptx::multimem_ld_reduce_bf16x8(ar.mc_stage + off);
       }
     }
-    const int64_t ooff = int64_t(lo + r - ar.rank * ar.rows_per_rank) * ar.ldo + col;
-    if (ar.residual) {
-      const Vec16<OutT> rv = ld16(reinterpret_cast<const OutT*>(ar.residual) + ooff);
+    // lanes that share a row (vec_per_row consecutive lanes when it is a power of two <= 32) combine their squares with
+    // shuffles; one shared-memory atomic per row group instead of one per lane (32-way serialised before: 3x the kernel time)
+    const int gw = (vec_per_row & (vec_per_row - 1)) == 0 ? (vec_per_row < 32 ? vec_per_row : 32) : 1;
 #pragma unroll
-      for (int e = 0; e < VN; ++e) accv[e] += to_f32(rv.v[e]);
-    }
-    Vec16<OutT> o;
-    float sq = 0.f;
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * 128;
+      const int r = i / vec_per_row, v = i % vec_per_row;
+      const int col = tn * BN + v * VN;
+      const int64_t off = (int64_t(lo + r) * ldc + col) * sizeof(OutT);
+      float sq = 0.f;
+      if (ok[u]) {
+      float accv[VN];
+      if (ar.mc_stage) {
+        const OutT* h = reinterpret_cast<const OutT*>(&red[u]);
 #pragma unroll
-    for (int e = 0; e < VN; ++e) {
-      o.v[e] = from_f32<OutT>(accv[e]);
-      sq += accv[e] * accv[e];
+        for (int e = 0; e < VN; ++e) accv[e] = to_f32(h[e]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < VN; ++e) accv[e] = 0.f;
+        for (int p = 0; p < ar.world; ++p) {
+          int4 x;
+          asm volatile("ld.global.relaxed.sys.v4.s32 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w)
+                       : "l"(ar.peer_stage[p] + off)
+                       : "memory");
+          const OutT* h = reinterpret_cast<const OutT*>(&x);
+#pragma unroll
+          for (int e = 0; e < VN; ++e) accv[e] += to_f32(h[e]);
+        }
+      }
+      const int64_t ooff = int64_t(lo + r - ar.rank * ar.rows_per_rank) * ar.ldo + col;
+      if (ar.residual) {
+        const Vec16<OutT> rv = ld16(reinterpret_cast<const OutT*>(ar.residual) + ooff);
+#pragma unroll
+        for (int e = 0; e < VN; ++e) accv[e] += to_f32(rv.v[e]);
+      }
+      Vec16<OutT> o;
+#pragma unroll
+      for (int e = 0; e < VN; ++e) {
+        o.v[e] = from_f32<OutT>(accv[e]);
+        sq += accv[e] * accv[e];
+      }
+      st16(out + ooff, o);
+      }
+      if (ar.sumsq) {
+        for (int o2 = gw >> 1; o2 > 0; o2 >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o2);
+        if (ok[u] && (gw == 1 || (v & (gw - 1)) == 0)) atomicAdd(&s_sq[lo + r - tm * BM], sq);
+      }
     }
-    st16(out + ooff, o);
-    if (ar.sumsq) atomicAdd(&s_sq[lo + r - tm * BM], sq);
   }
   if (ar.sumsq) {
     asm volatile("bar.sync 2, 128;" ::: "memory");
@@ -310,39 +334,56 @@ gemm_ar_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool mine = !ar.two_shot || (t % ar.world) == ar.rank;
       if (mine) {
         const int rows = min(BM, M - tm * BM);
-        for (int i = tid; i < rows * vec_per_row; i += 128) {
-          const int r = i / vec_per_row, v = i % vec_per_row;
-          const int col = tn * BN + v * VN;
-          if (col >= N) continue;
-          const int64_t off = (int64_t(tm * BM + r) * ldc + col) * sizeof(OutT);
-          int4 res;
-          if (ar.mc_stage) {
-            if constexpr (std::is_same<OutT, __half>::value) res = ptx::multimem_ld_reduce_f16x8(ar.mc_stage + off);
-            else res = ptx::multimem_ld_reduce_bf16x8(ar.mc_stage + off);
-          } else {
-            float accv[VN];
+        constexpr int U = 8;  // switch round trips in flight per thread
+        for (int i0 = tid; i0 < rows * vec_per_row; i0 += 128 * U) {
+          int4 red[U];
+          bool ok[U];
 #pragma unroll
-            for (int e = 0; e < VN; ++e) accv[e] = 0.f;
-            for (int p = 0; p < ar.world; ++p) {
-              int4 x;
-              asm volatile("ld.global.relaxed.sys.v4.s32 {%0,%1,%2,%3}, [%4];"
-                           : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w)
-                           : "l"(ar.peer_stage[p] + off)
-                           : "memory");
-              const OutT* h = reinterpret_cast<const OutT*>(&x);
-#pragma unroll
-              for (int e = 0; e < VN; ++e) accv[e] += to_f32(h[e]);
+          for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * 128;
+            const int r = i / vec_per_row, v = i % vec_per_row;
+            const int col = tn * BN + v * VN;
+            ok[u] = i < rows * vec_per_row && col < N;
+            red[u] = make_int4(0, 0, 0, 0);
+            if (ok[u] && ar.mc_stage) {
+              const int64_t off = (int64_t(tm * BM + r) * ldc + col) * sizeof(OutT);
+              if constexpr (std::is_same<OutT, __half>::value) red[u] = ptx::multimem_ld_reduce_f16x8(ar.mc_stage + off);
+              else red[u] = ptx::multimem_ld_reduce_bf16x8(ar.mc_stage + off);
             }
-            OutT* h = reinterpret_cast<OutT*>(&res);
-#pragma unroll
-            for (int e = 0; e < VN; ++e) h[e] = from_f32<OutT>(accv[e]);
           }
-          if (!ar.two_shot) {
-            *reinterpret_cast<int4*>(reinterpret_cast<uint8_t*>(out) + off) = res;
-          } else if (ar.mc_out) {
-            ptx::multimem_st_v4(ar.mc_out + off, res);
-          } else {
-            for (int p = 0; p < ar.world; ++p) *reinterpret_cast<int4*>(ar.peer_out[p] + off) = res;
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            if (!ok[u]) continue;
+            const int i = i0 + u * 128;
+            const int r = i / vec_per_row, v = i % vec_per_row;
+            const int col = tn * BN + v * VN;
+            const int64_t off = (int64_t(tm * BM + r) * ldc + col) * sizeof(OutT);
+            int4 res = red[u];
+            if (!ar.mc_stage) {
+              float accv[VN];
+#pragma unroll
+              for (int e = 0; e < VN; ++e) accv[e] = 0.f;
+              for (int p = 0; p < ar.world; ++p) {
+                int4 x;
+                asm volatile("ld.global.relaxed.sys.v4.s32 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w)
+                             : "l"(ar.peer_stage[p] + off)
+                             : "memory");
+                const OutT* h = reinterpret_cast<const OutT*>(&x);
+#pragma unroll
+                for (int e = 0; e < VN; ++e) accv[e] += to_f32(h[e]);
+              }
+              OutT* h = reinterpret_cast<OutT*>(&res);
+#pragma unroll
+              for (int e = 0; e < VN; ++e) h[e] = from_f32<OutT>(accv[e]);
+            }
+            if (!ar.two_shot) {
+              *reinterpret_cast<int4*>(reinterpret_cast<uint8_t*>(out) + off) = res;
+            } else if (ar.mc_out) {
+              ptx::multimem_st_v4(ar.mc_out + off, res);
+            } else {
+              for (int p = 0; p < ar.world; ++p) *reinterpret_cast<int4*>(ar.peer_out[p] + off) = res;
+            }
           }
         }
       }
