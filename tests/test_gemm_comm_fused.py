@@ -76,7 +76,7 @@ def _worker(rank, world, port, errs):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 8])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_gemm_comm_fused(world):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
