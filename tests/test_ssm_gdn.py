@@ -118,3 +118,32 @@ def test_router_gemm_gpu():
     assert (out.float() - ref).abs().max() < 2e-2 * float(ref.abs().max())
     out2 = tinygemm_bf16(a[:3], w, bias=torch.ones(256, device="cuda", dtype=torch.bfloat16))
     assert (out2.float() - (ref[:3] + 1)).abs().max() < 2e-2 * float(ref.abs().max())
+
+
+def test_ssd_combined_matches_recurrence_cpu():
+    """Mamba-2 chunked SSD vs the token-by-token recurrence (D, z, dt_bias + softplus, initial state, groups, packed seqs)."""
+    import torch
+    from flashinfer_b200.mamba import SSDCombined, ssd_reference
+
+    torch.manual_seed(0)
+    Bsz, L, H, P, G, N, Lc = 2, 64, 4, 8, 2, 16, 16
+    x = torch.randn(Bsz, L, H, P)
+    dt = torch.randn(Bsz, L, H) * 0.5
+    A = -torch.rand(H) - 0.1
+    Bm, Cm = torch.randn(Bsz, L, G, N) * 0.5, torch.randn(Bsz, L, G, N) * 0.5
+    D, z, bias = torch.randn(H), torch.randn(Bsz, L, H, P), torch.randn(H) * 0.1
+    init = torch.randn(Bsz, H, P, N) * 0.3
+    ssd = SSDCombined(Lc, H, P, N, G, io_dtype=torch.float32, state_dtype=torch.float32)
+    y, fin = ssd.run(x, dt, A, Bm, Cm, D=D, z=z, dt_bias=bias, dt_softplus=True, initial_states=init)
+    y_ref, s_ref = ssd_reference(x, dt, A, Bm, Cm, D, z, bias, True, init)
+    assert y.shape == (Bsz, H, P, L // Lc, Lc)
+    torch.testing.assert_close(y.permute(0, 3, 4, 1, 2).reshape(Bsz, L, H, P), y_ref, rtol=2e-4, atol=2e-4)
+    torch.testing.assert_close(fin, s_ref, rtol=2e-4, atol=2e-4)
+    # packed sequences: two sequences of 40 and 24 tokens in one row; the state restarts at the boundary
+    seq_idx = torch.cat([torch.zeros(40), torch.ones(24)]).long()[None]
+    y2, fin2 = ssd.run(x[:1], dt[:1], A, Bm[:1], Cm[:1], D=D, dt_bias=bias, dt_softplus=True, seq_idx=seq_idx)
+    ya, sa = ssd_reference(x[:1, :40], dt[:1, :40], A, Bm[:1, :40], Cm[:1, :40], D, None, bias, True)
+    yb, sb = ssd_reference(x[:1, 40:], dt[:1, 40:], A, Bm[:1, 40:], Cm[:1, 40:], D, None, bias, True)
+    got = y2.permute(0, 3, 4, 1, 2).reshape(1, L, H, P)
+    torch.testing.assert_close(got, torch.cat([ya, yb], 1), rtol=2e-4, atol=2e-4)
+    torch.testing.assert_close(fin2, torch.cat([sa, sb], 0), rtol=2e-4, atol=2e-4)
