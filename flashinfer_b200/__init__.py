@@ -120,3 +120,23 @@ from .norm import (  # noqa: F401,E402
 )
 from .quantization.fp4 import nvfp4_quantize_paged_kv_cache  # noqa: F401,E402
 from .gemm import prepare_low_latency_gemm_weights, trtllm_low_latency_gemm  # noqa: F401,E402
+# ---- the rest of the reference's top-level namespace (flashinfer/__init__.py) ----
+from .attention import BatchAttention, BatchAttentionWithAttentionSinkWrapper  # noqa: F401,E402
+from .cascade import (  # noqa: F401,E402
+    BatchDecodeWithSharedPrefixPagedKVCacheWrapper,
+    BatchPrefillWithSharedPrefixPagedKVCacheWrapper,
+    MultiLevelCascadeAttentionWrapper,
+)
+from .decode import BatchDecodeMlaWithPagedKVCacheWrapper, cudnn_batch_decode_with_kv_cache  # noqa: F401,E402
+from .fused_moe.core import B12xMoEWrapper, CuteDslMoEWrapper, b12x_fused_moe, cute_dsl_fused_moe_nvfp4  # noqa: F401,E402
+from .grouped_mm import grouped_mm_fp4, grouped_mm_fp8, grouped_mm_mxfp8  # noqa: F401,E402
+from .mla import BatchMLAPagedAttentionWrapper  # noqa: F401,E402
+from .pod import BatchPODWithPagedKVCacheWrapper, PODWithPagedKVCacheWrapper  # noqa: F401,E402
+from .prefill import trtllm_fmha_v2_prefill  # noqa: F401,E402
+from .sparse import BlockSparseAttentionWrapper, VariableBlockSparseAttentionWrapper  # noqa: F401,E402
+from .xqa import xqa, xqa_mla  # noqa: F401,E402
+
+
+def get_fp4_quantization_module(backend: str = "100"):
+    """Reference fp4_quantization.py: returns the JIT module object behind the FP4 quantisers; here the native library."""
+    return jit.load("quantization")

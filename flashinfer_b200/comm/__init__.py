@@ -54,3 +54,4 @@ from .collectives import (  # noqa: F401,E402
 )
 from .gemm_allreduce import GemmAllReduce, gemm_allreduce, gemm_reduce_scatter  # noqa: F401,E402
 from .all_gather_matmul import AllGatherMatmul, all_gather_matmul  # noqa: F401,E402
+from .compat import CudaRTLibrary, create_shared_buffer, free_shared_buffer, pack_strided_memory  # noqa: F401,E402

@@ -336,3 +336,79 @@ def vllm_register_graph_buffers(fa: int, handles: List[List[int]], offsets: List
 
 def vllm_get_graph_buffer_ipc_meta(fa: int) -> Tuple[List[int], List[int]]:
     return [], []
+
+
+# ------------------------------------------------------------------ reference comm/cuda_ipc.py + dlpack_utils.py names
+_SHARED_HEAPS: dict = {}
+
+
+def create_shared_buffer(size_in_bytes: int, group=None):
+    """Reference cuda_ipc.py:197: a buffer that every rank of ``group`` can address; returns the list of per-rank device
+    pointers (index = rank).  Backed by a symmetric-memory heap here (same address arithmetic as the rest of ``comm``)."""
+    from .symm import SymmetricHeap
+
+    heap = SymmetricHeap(group, int(size_in_bytes) + 1024)
+    _, off = heap.alloc(int(size_in_bytes))
+    ptrs = [int(p) for p in heap.peer_ptr_table(off).tolist()]
+    _SHARED_HEAPS[ptrs[heap.rank]] = heap
+    heap.barrier()
+    return ptrs
+
+
+def free_shared_buffer(pointers, group=None) -> None:
+    """Drop the heap behind a :func:`create_shared_buffer` result (the memory is released with the last reference)."""
+    for p in pointers:
+        _SHARED_HEAPS.pop(int(p), None)
+
+
+def pack_strided_memory(ptr: int, segment_size: int, segment_stride: int, num_segments: int, dtype: torch.dtype, dev_id):
+    """Reference dlpack_utils.py:191: view ``num_segments`` segments of ``segment_size`` bytes, ``segment_stride`` bytes apart,
+    starting at raw device address ``ptr`` as a ``[num_segments, segment_size / itemsize]`` tensor (no copy)."""
+    esz = torch.empty(0, dtype=dtype).element_size()
+
+    class _Raw:
+        def __init__(self):
+            self.__cuda_array_interface__ = {
+                "shape": (num_segments, segment_size // esz), "strides": (segment_stride, esz),
+                "typestr": {1: "|u1", 2: "<u2", 4: "<u4", 8: "<u8"}[esz], "data": (int(ptr), False), "version": 3}
+
+    dev = dev_id if isinstance(dev_id, torch.device) else torch.device("cuda", int(dev_id))
+    t = torch.as_tensor(_Raw(), device=dev)
+    return t.view(dtype) if t.dtype != dtype else t
+
+
+class CudaRTLibrary:
+    """Minimal ctypes view of libcudart with the calls the reference's IPC helpers use (cuda_ipc.py:70)."""
+
+    def __init__(self, so_file: Optional[str] = None):
+        import ctypes
+        import glob
+        import os
+
+        if so_file is None:
+            cands = glob.glob(os.path.join(os.path.dirname(torch.__file__), "lib", "libcudart*.so*")) + \
+                glob.glob("/usr/local/cuda/lib64/libcudart.so*")
+            so_file = cands[0] if cands else "libcudart.so"
+        self.lib = ctypes.CDLL(so_file)
+        self._ct = ctypes
+
+    def _chk(self, rc: int) -> None:
+        if rc != 0:
+            raise RuntimeError(f"CUDART error {rc}")
+
+    def cudaSetDevice(self, device: int) -> None:
+        self._chk(self.lib.cudaSetDevice(device))
+
+    def cudaDeviceSynchronize(self) -> None:
+        self._chk(self.lib.cudaDeviceSynchronize())
+
+    def cudaMalloc(self, size: int):
+        p = self._ct.c_void_p()
+        self._chk(self.lib.cudaMalloc(self._ct.byref(p), self._ct.c_size_t(size)))
+        return p
+
+    def cudaFree(self, p) -> None:
+        self._chk(self.lib.cudaFree(p))
+
+    def cudaMemset(self, p, value: int, count: int) -> None:
+        self._chk(self.lib.cudaMemset(p, value, self._ct.c_size_t(count)))

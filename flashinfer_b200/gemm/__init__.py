@@ -24,3 +24,16 @@ from .lowp import (  # noqa: F401
     prepare_low_latency_gemm_weights,
     trtllm_low_latency_gemm,
 )
+
+
+def __getattr__(name):
+    # router GEMMs / tinygemm live in dsv3_ops (which imports this package): resolve lazily to avoid the import cycle
+    if name in ("mm_M1_16_K7168_N256", "mm_M1_16_K7168_N128", "mm_M1_16_K6144_N256", "tinygemm_bf16"):
+        from .. import dsv3_ops
+
+        return getattr(dsv3_ops, name)
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")
+
+
+def is_cute_dsl_available() -> bool:
+    return False  # the GEMMs here are hand-written CUDA; nothing depends on nvidia-cutlass-dsl

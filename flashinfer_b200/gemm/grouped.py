@@ -115,6 +115,29 @@ def grouped_mm_bf16(a: torch.Tensor, b: torch.Tensor, m_indptr: torch.Tensor, ou
     return y
 
 
+def grouped_mm_mxfp8(a: torch.Tensor, b: torch.Tensor, a_descale: torch.Tensor, b_descale: torch.Tensor, m_indptr: torch.Tensor,
+                     out: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.bfloat16, *, backend: str = "auto",
+                     tactic: int = -1) -> torch.Tensor:
+    """Grouped MXFP8 GEMM (reference grouped_mm/core.py:346): ``a [cum_m, k]`` e4m3 / e5m2 with 128x4-swizzled UE8M0 scales
+    ``[cum_m, k/32]``, ``b [G, n, k]`` with swizzled scales ``[G, n, k/32]``, ``m_indptr [G+1]``.  Composed: the block scales are
+    folded in (exact: powers of two) and the bf16 grouped tcgen05 GEMM runs on the m_indptr segments."""
+    from ..quantization.fp4 import _swizzled_sf_size, _unswizzle_index
+
+    def dq(x, sf, rows, k):
+        kc = k // 32
+        sfb = sf.reshape(-1).view(torch.uint8)
+        if sfb.numel() >= _swizzled_sf_size(rows, kc) and not (sfb.numel() == rows * kc and rows % 128 == 0 and kc % 4 == 0 and False):
+            sfb = sfb[_unswizzle_index(rows, kc).to(sfb.device)]
+        scale = torch.exp2(sfb.float().view(rows, kc) - 127.0).repeat_interleave(32, 1)[:, :k]
+        return (x.float() * scale).to(torch.bfloat16)
+
+    cum_m, k = a.shape
+    G, n, _ = b.shape
+    ad = dq(a, a_descale, cum_m, k)
+    bd = torch.stack([dq(b[g], b_descale[g], n, k) for g in range(G)])
+    return grouped_mm_bf16(ad, bd, m_indptr, out, out_dtype if out is None else out.dtype)
+
+
 def grouped_gemm_nt_masked(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, masked_m: torch.Tensor) -> torch.Tensor:
     """Masked layout: ``a [E, M_max, K]``, ``b [E, N, K]``, only the first ``masked_m[e]`` rows per expert are
     computed (tiles past the mask are skipped, rows inside a partially-masked tile are still written)."""

@@ -91,3 +91,34 @@ def split_device_green_ctx_by_sm_count(dev: torch.device, sm_counts: List[int]):
 
 def get_sm_count(resource) -> int:
     return int(resource.sm.smCount)
+
+
+# ------------------------------------------------------------------ building blocks under the reference's names (green_ctx.py:47-125)
+def get_cudevice(dev: torch.device):
+    torch.cuda.init()
+    return _check(_drv().cuDeviceGet(torch.device(dev).index or 0))
+
+
+def get_device_resource(cu_dev):
+    drv = _drv()
+    return _check(drv.cuDeviceGetDevResource(cu_dev, drv.CUdevResourceType.CU_DEV_RESOURCE_TYPE_SM))
+
+
+def split_resource(resource, num_groups: int, min_count: int):
+    """``(groups, remaining)`` of ``cuDevSmResourceSplitByCount``."""
+    err, groups, n, remaining = _drv().cuDevSmResourceSplitByCount(num_groups, resource, 0, min_count)
+    if int(err) != 0:
+        raise RuntimeError(f"cuDevSmResourceSplitByCount failed: {err}")
+    return list(groups[:n]), remaining
+
+
+def split_resource_by_sm_count(cu_dev, resource, sm_counts: List[int]):
+    results, cur = [], resource
+    for c in sm_counts:
+        got, cur = split_resource(cur, 1, c)
+        results.extend(got)
+    return results, cur
+
+
+def create_green_ctx_streams(cu_dev, resources) -> List[torch.cuda.Stream]:
+    return _streams_from_resources(_drv(), cu_dev, resources)

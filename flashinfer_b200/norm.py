@@ -281,3 +281,22 @@ def _dit_scale_shift(res, scale, shift, scale_bias, shift_bias, epsilon, use_nvf
     sh = shift.float() + (shift_bias.float() if shift_bias is not None else 0.0)
     normed = (ln * (1.0 + sc) + sh).to(res.dtype)
     return _dit_finish(res, normed, use_nvfp4, use_mxfp8, gsf, residual_out, norm_out, sf_out)
+
+
+# ------------------------------------------------------------------ CuTe-DSL entry points of the reference (flashinfer/norm/__init__.py): same kernels here
+rmsnorm_cute = rmsnorm
+fused_add_rmsnorm_cute = fused_add_rmsnorm
+rmsnorm_quant_cute = rmsnorm_quant
+fused_add_rmsnorm_quant_cute = fused_add_rmsnorm_quant
+layernorm_cute = layernorm
+
+
+def qk_rmsnorm_cute(q: torch.Tensor, k: torch.Tensor, q_weight: torch.Tensor, k_weight: torch.Tensor, eps: float = 1e-6,
+                    enable_pdl: Optional[bool] = None):
+    """Per-head RMSNorm of q and k (``[..., heads, head_dim]``, normalised over ``head_dim``), in place like the reference."""
+    for t, w in ((q, q_weight), (k, k_weight)):
+        flat = t.reshape(-1, t.shape[-1])
+        res = rmsnorm(flat, w, eps, enable_pdl=enable_pdl)
+        if res.data_ptr() != flat.data_ptr():
+            t.copy_(res.view_as(t))
+    return q, k

@@ -18,3 +18,18 @@ from .fp4 import (  # noqa: F401
 )
 from .fp8 import mxfp8_dequantize_host, mxfp8_quantize  # noqa: F401
 from .packbits import packbits, segment_packbits  # noqa: F401
+
+# CuTe-DSL entry points of the reference resolve to the native kernels
+nvfp4_quantize_cute_dsl = nvfp4_quantize
+mxfp4_quantize_cute_dsl = mxfp4_quantize
+mxfp8_quantize_cute_dsl = mxfp8_quantize
+
+
+def is_cute_dsl_available() -> bool:
+    return False  # nothing here depends on nvidia-cutlass-dsl
+
+
+def get_fp4_quantization_module(backend: str = "100"):
+    from .. import jit
+
+    return jit.load("quantization")

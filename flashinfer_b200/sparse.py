@@ -14,6 +14,17 @@ from .decode import BatchDecodeWithPagedKVCacheWrapper
 from .prefill import BatchPrefillWithPagedKVCacheWrapper
 
 
+def convert_bsr_mask_layout(mask: torch.Tensor, indptr: torch.Tensor) -> torch.Tensor:
+    """BSR block masks ``[nnz, R, C]`` -> the flattened per-block-row layout of the reference (sparse.py:44): for every block row
+    the blocks are laid side by side, i.e. ``[R, n_blocks * C]`` flattened."""
+    nnz, R, C = mask.shape
+    out = torch.empty(nnz * R * C, dtype=mask.dtype, device=mask.device)
+    ip = indptr.tolist()
+    for i in range(len(ip) - 1):
+        out[ip[i] * R * C: ip[i + 1] * R * C] = mask[ip[i]: ip[i + 1]].transpose(0, 1).reshape(-1)
+    return out
+
+
 class BlockSparseAttentionWrapper:
     """Attention with a fixed-size block-sparse (BSR) mask ``[M/R, N/C]``."""
 

@@ -18,3 +18,5 @@ from .utils import (  # noqa: F401
     set_seed,
     sleep_after_kernel_run,
 )
+
+from .utils import bench_gpu_time as bench_gpu_time_with_cupti  # noqa: F401,E402  (CUPTI is not required: CUDA events / graphs)

@@ -92,3 +92,42 @@ def top_k_ragged_transform(input: torch.Tensor, offsets: torch.Tensor, lengths: 
         out = torch.where(sel >= 0, sel + (offsets.long() + s)[:, None], torch.full_like(sel, -1))
         return out.int()
     return _run(input, k, 2, lengths, row_starts, None, None, offsets, tie_break=tie_break)[1]
+
+
+# ------------------------------------------------------------------ reference helper names (flashinfer/topk.py:354-504)
+def can_implement_filtered_topk() -> bool:
+    """The reference's FilteredTopK needs 128 KB of dynamic shared memory; every B200 has 227 KB."""
+    return True
+
+
+def roundup_kbyte(x: int) -> int:
+    return (x + 1023) // 1024 * 1024
+
+
+def get_num_cached_for_topk(device, k: int) -> int:
+    """Candidate-cache capacity of the reference's cluster top-k (kept for callers that size buffers with it)."""
+    shared_per_block = (227 * 1024) // 2
+    return (shared_per_block - (k + 5 + 3 * 256 + 8) * 4 - 1024) // 16
+
+
+def get_fast_topk_clusters(batch_size: int) -> int:
+    return 8 if batch_size <= 32 else (4 if batch_size < 128 else (2 if batch_size < 256 else 1))
+
+
+def can_use_clusters_topk(device, deterministic: bool, dsa_graph_safe: bool) -> bool:
+    return not dsa_graph_safe and not deterministic
+
+
+def topk_clusters_exact(logits: torch.Tensor, top_k: int, output_values: bool = False, out_dtype=torch.int32, pdl: bool = False):
+    """Exact top-k indices (and optionally values) per row; the radix-select kernel of :func:`top_k` serves this entry point."""
+    vals, idx = globals()["top_k"](logits, top_k)
+    idx = idx.to(out_dtype)
+    return (idx, vals) if output_values else idx
+
+
+def topk_clusters_page_table_transform(logits, seq_lens, src_page_table, top_k: int, pdl: bool = False):
+    return top_k_page_table_transform(logits, src_page_table, seq_lens, top_k)
+
+
+def topk_clusters_ragged_transform(logits, seq_lens, offsets, top_k: int, pdl: bool = False):
+    return top_k_ragged_transform(logits, offsets, seq_lens, top_k)
