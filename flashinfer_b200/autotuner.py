@@ -70,6 +70,10 @@ class TunableRunner:
     def forward(self, inputs: List[torch.Tensor], tactic: Any = -1, do_preparation: bool = False, **kwargs):
         raise NotImplementedError
 
+    def get_cache_key_extras(self, inputs: List[torch.Tensor]) -> Tuple:
+        """Extra hashable state that distinguishes cached tactics beyond the input shapes (default: none)."""
+        return ()
+
     def __call__(self, inputs, **kwargs):
         return self.forward(inputs, **kwargs)
 
@@ -78,11 +82,61 @@ class TunableRunner:
 
 
 @dataclass
+class StaticDim:
+    """A dimension with one value (reference autotuner.py:332)."""
+    val: int
+
+    def _opt(self) -> int:
+        return self.val
+
+
+@dataclass(unsafe_hash=True)
+class DynamicDim:
+    """Range of one dimension (reference autotuner.py:340)."""
+    min: int
+    opt: int
+    max: int
+
+    def _opt(self) -> int:
+        return self.opt
+
+
+@dataclass
+class FakeTensor:
+    """Shape-only stand-in used when profiles are enumerated without allocating (reference autotuner.py:375)."""
+    dtype: torch.dtype
+    device: torch.device
+    shape: List[Any]
+
+
+@dataclass
+class AutoTunerStatistics:
+    """Counters the tuner keeps (reference autotuner.py:697)."""
+    cache_misses: int = 0
+    cache_miss_config_collection: Dict[str, set] = field(default_factory=dict)
+    failed_profiling_count: Dict[str, set] = field(default_factory=dict)
+    tuned_op_total_configs: Dict[str, int] = field(default_factory=dict)
+    tuned_op_successful_configs: Dict[str, int] = field(default_factory=dict)
+
+    def __str__(self) -> str:
+        return (f"Cache misses: {self.cache_misses}\nTuned ops: {dict(self.tuned_op_total_configs)}\n"
+                f"Successful: {dict(self.tuned_op_successful_configs)}\n")
+
+
+@dataclass
 class OptimizationProfile:
     shapes: List[Tuple[int, ...]] = field(default_factory=list)
+    tensor_initializers: List[Any] = field(default_factory=list)
 
     def key(self) -> Tuple:
         return tuple(self.shapes)
+
+    def get_opt_shapes(self) -> Tuple:
+        """Shapes with every Dim resolved to its tuning value (plain ints pass through)."""
+        return tuple(tuple(d._opt() if hasattr(d, "_opt") else int(d) for d in shp) for shp in self.shapes)
+
+    def get_hash_key(self) -> Tuple:
+        return self.get_opt_shapes()
 
 
 class AutoTuner:
@@ -95,6 +149,15 @@ class AutoTuner:
         self.profiling_cache: Dict[Tuple, Tuple[int, Any, float]] = {}
         self.stats = {"hits": 0, "misses": 0, "profiled": 0, "failed": 0}
         self._flush = None
+
+    @classmethod
+    def reset_statistics(self) -> None:
+        self.stats = {"hits": 0, "misses": 0, "profiled": 0, "failed": 0}
+
+    def get_effective_map_to_tuning_buckets(self, spec=None):
+        """The bucket mapper of a dynamic-dimension spec, or the default next-power-of-two bucketing."""
+        fn = getattr(spec, "map_to_tuning_buckets", None)
+        return fn if fn is not None else (lambda x: 1 << max(0, int(x) - 1).bit_length())
 
     @classmethod
     def get(cls) -> "AutoTuner":

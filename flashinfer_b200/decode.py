@@ -484,6 +484,18 @@ class BatchDecodeMlaWithPagedKVCacheWrapper:
         from .mla import BatchMLAPagedAttentionWrapper
 
         self._w = BatchMLAPagedAttentionWrapper(float_workspace_buffer, use_cuda_graph)
+        self._use_cuda_graph = bool(use_cuda_graph)
+
+    @property
+    def is_cuda_graph_enabled(self) -> bool:
+        return self._use_cuda_graph
+
+    @property
+    def use_tensor_cores(self) -> bool:
+        return True  # the MLA kernel is tcgen05
+
+    def reset_workspace_buffer(self, float_workspace_buffer: torch.Tensor, int_workspace_buffer: Optional[torch.Tensor] = None) -> None:
+        self._w._float_workspace_buffer = float_workspace_buffer
 
     def plan(self, indptr, indices, last_page_len, num_qo_heads, head_dim_compressed_kv, page_size, sm_scale,
              window_left: int = -1, logits_soft_cap=None, data_type="float16", q_data_type=None, rope_scale=None,

@@ -24,3 +24,10 @@ from .core import (  # noqa: F401
     trtllm_fp8_per_tensor_scale_moe,
     trtllm_mxint4_block_scale_moe,
 )
+from .core import Fp8QuantizationType, MoEInputs, RoutingInputMode, moe_forward_fp8_block  # noqa: F401,E402
+
+
+def convert_to_block_layout(input_tensor, blockK: int):
+    """``[..., M, K]`` -> ``[..., K / blockK, M, blockK]`` (the BlockMajorK weight layout of the reference's trtllm-gen MoE)."""
+    *lead, M, K = input_tensor.shape
+    return input_tensor.reshape(*lead, M, K // blockK, blockK).transpose(-3, -2).contiguous()

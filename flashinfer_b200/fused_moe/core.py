@@ -63,6 +63,42 @@ class WeightLayout(IntEnum):
 
 
 # ------------------------------------------------------------------ routing
+class RoutingInputMode(IntEnum):
+    """How routing information reaches a MoE entry point (reference fused_moe/core.py:81)."""
+    FromLogits = 0
+    PackedPrecomputed = 1
+    UnpackedPrecomputed = 2
+
+
+class Fp8QuantizationType(IntEnum):
+    NoneFp8 = 0
+    DeepSeekFp8 = 1
+    MxFp8 = 2
+    PerTensorFp8 = 3
+
+
+class MoEInputs:
+    """Flat container of the tensors a MoE runner consumes; field order = flat-list index (reference fused_moe/core.py:1011)."""
+    _FIELDS = ("output", "routing_logits", "topk_ids", "expert_weights", "hidden_states", "hidden_states_scale",
+               "per_token_scale")
+
+    def __init__(self, output=None, routing_logits=None, topk_ids=None, expert_weights=None, hidden_states=None,
+                 hidden_states_scale=None, per_token_scale=None):
+        self.output, self.routing_logits, self.topk_ids, self.expert_weights = output, routing_logits, topk_ids, expert_weights
+        self.hidden_states, self.hidden_states_scale, self.per_token_scale = hidden_states, hidden_states_scale, per_token_scale
+
+    def to_list(self):
+        return [getattr(self, n) for n in MoEInputs._FIELDS]
+
+    @classmethod
+    def from_list(cls, values):
+        return cls(**dict(zip(cls._FIELDS, values)))
+
+    @classmethod
+    def idx(cls, name: str) -> int:
+        return cls._FIELDS.index(name)
+
+
 def route(routing_logits: torch.Tensor, routing_bias: Optional[torch.Tensor], top_k: int,
           routing_method_type: int = 0, n_group: Optional[int] = None, topk_group: Optional[int] = None,
           routed_scaling_factor: Optional[float] = None, norm_topk_prob: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:

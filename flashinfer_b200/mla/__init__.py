@@ -5,3 +5,10 @@ from ._core import (  # noqa: F401
     trtllm_batch_decode_with_kv_cache_mla,
     xqa_batch_decode_with_kv_cache_mla,
 )
+from ._core import (  # noqa: F401,E402
+    MLAHeadDimensions,
+    MLALayerDimensions,
+    deepseek_mla_dimensions,
+    smaller_mla_dimensions,
+    supported_mla_layer_dimensions,
+)

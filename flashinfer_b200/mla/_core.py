@@ -5,6 +5,8 @@ CUDA tensors run the tcgen05 kernel ``csrc/attention/mla_sm100.cu`` (all heads o
 """
 from __future__ import annotations
 
+import dataclasses
+
 import math
 from typing import List, Optional, Tuple, Union
 
@@ -32,6 +34,27 @@ def mla_attention_ref(q_nope, q_pe, ckv, kpe, sm_scale, causal_offset: Optional[
     p = torch.exp(logits - lse[..., None])
     o = torch.einsum("hqk,kd->qhd", p, ckv.float())
     return o, (lse * LOG2E).transpose(0, 1).contiguous()
+
+
+@dataclasses.dataclass(frozen=True)
+class MLAHeadDimensions:
+    """Dimensions of a single MLA head (reference mla/_core.py:76)."""
+    qk_nope_head_dim: int
+    qk_rope_head_dim: int
+    v_head_dim: int
+    kv_lora_rank: int
+
+
+@dataclasses.dataclass(frozen=True)
+class MLALayerDimensions:
+    """Dimensions of an MLA layer (reference mla/_core.py:111)."""
+    head_dimensions: MLAHeadDimensions
+    num_heads: int
+
+
+deepseek_mla_dimensions = MLAHeadDimensions(qk_nope_head_dim=128, qk_rope_head_dim=64, v_head_dim=128, kv_lora_rank=512)
+smaller_mla_dimensions = MLAHeadDimensions(qk_nope_head_dim=64, qk_rope_head_dim=32, v_head_dim=64, kv_lora_rank=256)
+supported_mla_layer_dimensions = [MLALayerDimensions(deepseek_mla_dimensions, 128), MLALayerDimensions(deepseek_mla_dimensions, 64)]
 
 
 class BatchMLAPagedAttentionWrapper:

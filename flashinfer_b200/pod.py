@@ -89,6 +89,16 @@ class PODWithPagedKVCacheWrapper:
         self._kv_layout = kv_layout
         self._side = _SideStream(self.device)
         self._fused = True  # single-kernel POD when the shapes allow it (set False to force the two-stream composition)
+        self._use_cuda_graph = bool(use_cuda_graph)
+
+    @property
+    def is_cuda_graph_enabled(self) -> bool:
+        return self._use_cuda_graph
+
+    def reset_workspace_buffer(self, float_workspace_buffer: torch.Tensor, int_workspace_buffer: Optional[torch.Tensor] = None) -> None:
+        half = float_workspace_buffer.numel() // 2
+        self._prefill.reset_workspace_buffer(float_workspace_buffer[:half], int_workspace_buffer)
+        self._decode.reset_workspace_buffer(float_workspace_buffer[half:], int_workspace_buffer)
 
     def plan(self, indptr, indices, last_page_len, num_qo_heads, num_kv_heads, head_dim, page_size,
              pos_encoding_mode="NONE", window_left=-1, q_data_type="float16", kv_data_type=None, data_type=None,
@@ -157,6 +167,11 @@ class BatchPODWithPagedKVCacheWrapper:
         self._decode = BatchDecodeWithPagedKVCacheWrapper(float_workspace_buffer[half:], kv_layout)
         self._side = _SideStream(self.device)
         self._fused = True
+        self._use_cuda_graph = bool(use_cuda_graph)
+
+    @property
+    def is_cuda_graph_enabled(self) -> bool:
+        return self._use_cuda_graph
 
     def plan(self, qo_indptr_p, kv_indptr_p, kv_indices_p, last_page_len_p, qo_indptr_d, kv_indptr_d, kv_indices_d,
              last_page_len_d, num_qo_heads, num_kv_heads, head_dim, page_size, pos_encoding_mode="NONE",

@@ -98,6 +98,9 @@ class VariableBlockSparseAttentionWrapper:
         self.device = float_workspace_buffer.device
         self._prefill = BatchPrefillWithPagedKVCacheWrapper(float_workspace_buffer, "NHD")
 
+    def reset_workspace_buffer(self, float_workspace_buffer, int_workspace_buffer=None, **kw) -> None:
+        self._float_workspace_buffer = float_workspace_buffer
+
     def plan(self, block_mask_map: torch.Tensor, block_row_sz: torch.Tensor, block_col_sz: torch.Tensor,
              num_qo_heads: int, num_kv_heads: int, head_dim: int, causal: bool = False, pos_encoding_mode: str = "NONE",
              use_fp16_qk_reduction: bool = False, logits_soft_cap: Optional[float] = None,
