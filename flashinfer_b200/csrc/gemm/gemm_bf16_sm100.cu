@@ -53,6 +53,7 @@ struct GemmSmem {
 struct Sched {
   int tiles_a, tiles_b, kblocks, grid, BN;
   int S;  // cluster split-K factor (1 = off); when > 1 the grid is exactly tiles * S (one tile per cluster)
+  int gated;    // epilogue computes out[:, j] = silu(acc[:, 2j]) * acc[:, 2j + 1] (SwiGLU with row-interleaved gate / up weights)
   int smem_kb;  // ring budget handed to GemmSmem::make (host and device must agree)
   int trace;  // debug (FIB200_GEMM_TRACE=1): the cluster split-K path writes clock64 stamps into the partial workspace
   int G;  // with S > 1: N tiles per cluster that share the A operand through TMA multicast (1 or 2); cluster = S * G CTAs
@@ -477,6 +478,25 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int j = 0; j < CH; ++j)
                 if (b_row0 + j < rowsB) C[int64_t(b_row0 + j) * ldc + a_row] = from_f32<OutT>(__uint_as_float(r[j]) + bv);
             }
+          } else if (sk.gated) {
+            // fused SwiGLU: weight rows are interleaved (gate_0, up_0, gate_1, up_1, ...), so a 16-column chunk of the
+            // accumulator holds 8 (gate, up) pairs -> 8 outputs = one 16-byte store; the [M, 2I] intermediate never exists
+            if (a_row < rowsA && b_row0 < rowsB) {
+              OutT* dst = C + int64_t(a_row) * ldc + b_row0 / 2;
+              OutT o8[CH / 2];
+#pragma unroll
+              for (int j = 0; j < CH; j += 2) {
+                const float g = __uint_as_float(r[j]), u = __uint_as_float(r[j + 1]);
+                o8[j / 2] = from_f32<OutT>(g / (1.f + __expf(-g)) * u);
+              }
+              if (b_row0 + CH <= rowsB && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+                *reinterpret_cast<int4*>(dst) = *reinterpret_cast<const int4*>(o8);
+              } else {
+#pragma unroll
+                for (int j = 0; j < CH / 2; ++j)
+                  if (b_row0 + 2 * j + 1 < rowsB) dst[j] = o8[j];
+              }
+            }
           } else {
             if (a_row < rowsA) {
               OutT* dst = C + int64_t(a_row) * ldc + b_row0;
@@ -628,7 +648,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 inline int env_int(const char* name, int dflt);
 
 template <int BM, bool kSwap, typename OutT>
-int launch_gemm(int BN, int cluster_split, int mcast_g, const CUtensorMap& tmA, const CUtensorMap& tmB, OutT* C, float* workspace, int64_t workspace_bytes,
+int launch_gemm(int BN, int cluster_split, int mcast_g, int gated, const CUtensorMap& tmA, const CUtensorMap& tmB, OutT* C, float* workspace, int64_t workspace_bytes,
                 const OutT* bias, int rowsA, int rowsB, int K, int64_t ldc, bool f16, bool pdl, cudaStream_t stream) {
   // small-M cluster split-K launches (decode GEMMs, one tile per cluster, a few us long): half-size ring so that two CTAs fit
   // an SM and consecutive PDL-chained GEMMs overlap their prologue / weight prefetch with the predecessor's epilogue
@@ -642,6 +662,7 @@ int launch_gemm(int BN, int cluster_split, int mcast_g, const CUtensorMap& tmA, 
     attr_set = true;
   }
   Sched sk;
+  sk.gated = gated;
   sk.smem_kb = co_resident ? small_kb : 220;
   sk.BN = BN;
   sk.tiles_a = (rowsA + BM - 1) / BM;
@@ -709,7 +730,14 @@ inline int env_int(const char* name, int dflt) {
 
 template <typename OutT>
 int gemm_dispatch(const void* A, const void* B, OutT* C, const OutT* bias, int M, int N, int K, int64_t lda, int64_t ldb,
-                  int64_t ldc, bool f16, float* workspace, int64_t workspace_bytes, bool pdl, cudaStream_t stream) {
+                  int64_t ldc, bool f16, float* workspace, int64_t workspace_bytes, bool pdl, cudaStream_t stream,
+                  bool gated = false) {
+  if (gated) {
+    // the gated epilogue lives in the data-parallel path only: no stream-K fix-up (workspace off), no cluster split, no swap
+    FIB_CHECK(bias == nullptr && N % 16 == 0, "gemm (gated): no bias, N must be a multiple of 16");
+    workspace = nullptr;
+    workspace_bytes = 0;
+  }
   const CUtensorMapDataType dt = f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   // Small M (decode): activations take the 128-row MMA-M side (rows past M are TMA zero-fill, no traffic) and
   // the weight matrix is cut into narrow N tiles so that ONE wave covers the machine with no split-K:
@@ -760,7 +788,8 @@ int gemm_dispatch(const void* A, const void* B, OutT* C, const OutT* bias, int M
   } else {
     BN = (N >= 256 && (int64_t(M) * N >= int64_t(256) * 256 * 64)) ? 256 : 128;
   }
-  if (force_swap == 1 && M <= 128) {
+  if (gated) Ssel = 1;
+  if (force_swap == 1 && M <= 128 && !gated) {
     swap = true;
     BMsel = 128;
     BN = M <= 16 ? 16 : (M <= 32 ? 32 : (M <= 64 ? 64 : 128));
@@ -809,12 +838,12 @@ int gemm_dispatch(const void* A, const void* B, OutT* C, const OutT* bias, int M
     if (make_tmap(&tmB, dt, 2, pb, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   }
   if (swap)
-    return launch_gemm<128, true, OutT>(BN, 1, 1, tmA, tmB, C, workspace, workspace_bytes, bias, rowsA, rowsB, K, ldc, f16, pdl,
+    return launch_gemm<128, true, OutT>(BN, 1, 1, 0, tmA, tmB, C, workspace, workspace_bytes, bias, rowsA, rowsB, K, ldc, f16, pdl,
                                         stream);
   if (BM == 64)
-    return launch_gemm<64, false, OutT>(BN, Ssel, Gsel, tmA, tmB, C, workspace, workspace_bytes, bias, rowsA, rowsB, K, ldc, f16, pdl,
+    return launch_gemm<64, false, OutT>(BN, Ssel, Gsel, gated ? 1 : 0, tmA, tmB, C, workspace, workspace_bytes, bias, rowsA, rowsB, K, ldc, f16, pdl,
                                         stream);
-  return launch_gemm<128, false, OutT>(BN, Ssel, Gsel, tmA, tmB, C, workspace, workspace_bytes, bias, rowsA, rowsB, K, ldc, f16, pdl,
+  return launch_gemm<128, false, OutT>(BN, Ssel, Gsel, gated ? 1 : 0, tmA, tmB, C, workspace, workspace_bytes, bias, rowsA, rowsB, K, ldc, f16, pdl,
                                        stream);
 }
 
@@ -837,4 +866,19 @@ extern "C" int gemm_nt(void* A, void* B, void* C, void* bias, int64_t M, int64_t
                                         ldb, ldc, false, (float*)workspace, workspace_bytes, pdl != 0, s);
   }
   return set_error("gemm_nt: unsupported dtype");
+}
+
+// C[M, N/2] = silu(A W_even^T) * (A W_odd^T): W rows interleaved (gate_0, up_0, gate_1, up_1, ...); the SwiGLU runs in the
+// GEMM epilogue on the fp32 accumulators (reference: gated-activation GEMM epilogues of the trtllm-gen MoE / MLP kernels).
+extern "C" int gemm_nt_gated_silu(void* A, void* B, void* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc,
+                                  int64_t dtype, int64_t pdl, int64_t stream) {
+  FIB_CHECK(K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && ldc % 8 == 0, "K/lda/ldb/ldc must be multiples of 8");
+  if (M == 0 || N == 0) return 0;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == kF16)
+    return gemm_dispatch<__half>(A, B, (__half*)C, nullptr, (int)M, (int)N, (int)K, lda, ldb, ldc, true, nullptr, 0, pdl != 0, s, true);
+  if (dtype == kBF16)
+    return gemm_dispatch<__nv_bfloat16>(A, B, (__nv_bfloat16*)C, nullptr, (int)M, (int)N, (int)K, lda, ldb, ldc, false, nullptr, 0,
+                                        pdl != 0, s, true);
+  return set_error("gemm_nt_gated_silu: unsupported dtype");
 }

@@ -58,6 +58,37 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     return out
 
 
+def interleave_gate_up(w: torch.Tensor) -> torch.Tensor:
+    """``[2I, K]`` with the gate rows first and the up rows second -> rows ``(g0, u0, g1, u1, ...)``: the weight layout of
+    :func:`linear_gated_silu` (every N tile of the GEMM then holds matching gate / up columns)."""
+    half = w.shape[0] // 2
+    return torch.stack([w[:half], w[half:]], 1).reshape(w.shape).contiguous()
+
+
+def linear_gated_silu(x: torch.Tensor, weight_interleaved: torch.Tensor, out: Optional[torch.Tensor] = None,
+                      enable_pdl: bool = True) -> torch.Tensor:
+    """``silu(x @ Wg.T) * (x @ Wu.T)`` in ONE tcgen05 GEMM: ``weight_interleaved [2I, K]`` from :func:`interleave_gate_up`; the
+    SwiGLU runs in the epilogue on the fp32 accumulators and only the ``[M, I]`` result is written (the ``[M, 2I]``
+    intermediate and the separate activation kernel disappear).  Equivalent to ``silu_and_mul(linear(x, [Wg; Wu]))``."""
+    k = x.shape[-1]
+    n2 = weight_interleaved.shape[0]
+    x2 = x.reshape(-1, k)
+    m = x2.shape[0]
+    if out is None:
+        out = torch.empty(*x.shape[:-1], n2 // 2, dtype=x.dtype, device=x.device)
+    out2 = out.view(-1, n2 // 2)
+    if not x.is_cuda:
+        h = x2.float() @ weight_interleaved.float().t()
+        out2.copy_((torch.nn.functional.silu(h[:, 0::2]) * h[:, 1::2]).to(x.dtype))
+        return out
+    if x2.stride(-1) != 1:
+        x2 = x2.contiguous()
+    w = weight_interleaved if weight_interleaved.stride(-1) == 1 else weight_interleaved.contiguous()
+    jit.load("gemm_sm100").call("gemm_nt_gated_silu", x2, w, out2, m, n2, k, x2.stride(0), w.stride(0), out2.stride(0),
+                                dtype_code(x.dtype), 1 if enable_pdl else 0, stream_ptr(x))
+    return out
+
+
 def mm_bf16(a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = None, pdl: bool = False,
             out: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.bfloat16, backend: str = "auto"):
     """a [m, k] row-major, b [k, n] column-major -> [m, n]."""

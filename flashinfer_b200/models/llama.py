@@ -15,7 +15,7 @@ import torch
 
 from .. import activation, norm, page, rope
 from ..decode import BatchDecodeWithPagedKVCacheWrapper
-from ..gemm.dense import linear
+from ..gemm.dense import interleave_gate_up, linear, linear_gated_silu
 
 
 @dataclass
@@ -78,7 +78,7 @@ class LlamaDecodeEngine:
                 "ln2": torch.ones(h, device=self.device, dtype=dtype),
                 "wqkv": rnd(((self.hq + 2 * self.hkv) * d, h), g, h ** -0.5),
                 "wo": rnd((h, self.hq * d), g, (cfg.num_qo_heads * d) ** -0.5),
-                "wgu": rnd((2 * self.inter, h), g, h ** -0.5),
+                "wgu": interleave_gate_up(rnd((2 * self.inter, h), g, h ** -0.5)),  # (g0, u0, g1, u1, ...) rows
                 "wd": rnd((h, self.inter), g, cfg.intermediate_size ** -0.5),
                 "k_cache": torch.zeros(max_pages, page_size, self.hkv, d, device=self.device, dtype=dtype),
                 "v_cache": torch.zeros(max_pages, page_size, self.hkv, d, device=self.device, dtype=dtype),
@@ -114,7 +114,6 @@ class LlamaDecodeEngine:
         self._res = torch.empty(b, h, device=self.device, dtype=self.dtype)
         self._qkv = torch.empty(b, (self.hq + 2 * self.hkv) * cfg.head_dim, device=self.device, dtype=self.dtype)
         self._attn = torch.empty(b, self.hq, cfg.head_dim, device=self.device, dtype=self.dtype)
-        self._gu = torch.empty(b, 2 * self.inter, device=self.device, dtype=self.dtype)
         self._act = torch.empty(b, self.inter, device=self.device, dtype=self.dtype)
         self._logits = torch.empty(b, self.vocab_shard, device=self.device, dtype=self.dtype)
         self._graph = None
@@ -156,10 +155,10 @@ class LlamaDecodeEngine:
             self.wrapper.run(q, (l["k_cache"], l["v_cache"]), out=self._attn)
             part = self._row_parallel(self._attn.view(self.batch, hq * d), l["wo"])
             self._reduce_add_norm(part, l["ln2"])
-            linear(x, l["wgu"], out=self._gu)
-            activation.silu_and_mul(self._gu, out=self._act)
+            # gate / up GEMM with the SwiGLU in its epilogue (weights row-interleaved at load time): one kernel, no [B, 2I] tensor
+            linear_gated_silu(x, l["wgu"], out=self._act)
             part = self._row_parallel(self._act, l["wd"])
-            n += 8
+            n += 7
             nxt = self.layers[li + 1]["ln1"] if li + 1 < len(self.layers) else self.final_norm
             self._reduce_add_norm(part, nxt)
             n += 1

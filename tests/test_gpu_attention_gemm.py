@@ -105,3 +105,20 @@ def test_single_decode_and_cuda_graph():
     g.replay()
     torch.cuda.synchronize()
     torch.testing.assert_close(out, ref)
+
+
+@pytest.mark.parametrize("mnk", [(64, 28672, 4096), (1, 1024, 512), (200, 2048, 1024), (1024, 4096, 2048), (16, 96, 256)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_linear_gated_silu(mnk, dtype):
+    """GEMM with the SwiGLU epilogue (row-interleaved gate / up weights) vs silu_and_mul(linear(x, [Wg; Wu]))."""
+    from flashinfer_b200.gemm import interleave_gate_up, linear_gated_silu
+
+    m, n2, k = mnk
+    torch.manual_seed(m + k)
+    x = torch.randn(m, k, device="cuda", dtype=dtype)
+    w = torch.randn(n2, k, device="cuda", dtype=dtype) / k ** 0.5
+    h = x.float() @ w.float().t()
+    ref = torch.nn.functional.silu(h[:, : n2 // 2]) * h[:, n2 // 2:]
+    out = linear_gated_silu(x, interleave_gate_up(w))
+    assert out.shape == (m, n2 // 2)
+    torch.testing.assert_close(out.float(), ref, rtol=2e-2, atol=2e-2)
