@@ -760,7 +760,7 @@ int gemm_dispatch(const void* A, const void* B, OutT* C, const OutT* bias, int M
     if (BN < min_bn) BN = min_bn;
     // Few, wide N tiles + K split over a 4-CTA cluster (DSMEM reduction): the activation tile is re-read
     // from L2 once per N tile, so wide tiles cut L2 traffic 4x while the cluster keeps every SM streaming.
-    if (BN <= 64 && K >= 2048) {
+    if (BN <= 64 && K >= 2048 && !gated) {  // (the gated epilogue has no split-K path: it keeps the narrow one-wave tiles)
       const int s_try = force_s > 0 ? force_s : 2;
       // clusters of 4 can only be placed on 132 of the 148 SMs (GPC granularity), clusters of 2 on all
       const int eff = s_try >= 4 ? (sms * 132) / 148 : sms;
