@@ -1,0 +1,88 @@
+"""API-surface parity: every public name the reference exports at top level (flashinfer/__init__.py) must exist here,
+plus the main wrapper classes must expose the reference's public methods.  The list is frozen from the reference tree."""
+import flashinfer_b200 as fi
+
+REFERENCE_TOP_LEVEL = [
+    "ActivationType", "B12xMoEWrapper", "BatchAttention", "BatchAttentionWithAttentionSinkWrapper",
+    "BatchDecodeMlaWithPagedKVCacheWrapper", "BatchDecodeWithPagedKVCacheWrapper",
+    "BatchDecodeWithSharedPrefixPagedKVCacheWrapper", "BatchMLAPagedAttentionWrapper",
+    "BatchPODWithPagedKVCacheWrapper", "BatchPrefillWithPagedKVCacheWrapper", "BatchPrefillWithRaggedKVCacheWrapper",
+    "BatchPrefillWithSharedPrefixPagedKVCacheWrapper", "BlockSparseAttentionWrapper",
+    "CUDAGraphBatchDecodeWithPagedKVCacheWrapper", "CuteDslMoEWrapper", "MultiLevelCascadeAttentionWrapper",
+    "PODWithPagedKVCacheWrapper", "RoutingMethodType", "SegmentGEMMWrapper", "SfLayout", "TopKTieBreak",
+    "VariableBlockSparseAttentionWrapper", "add_rmsnorm_fp4quant", "append_paged_kv_cache",
+    "append_paged_mla_kv_cache", "apply_llama31_rope", "apply_llama31_rope_inplace", "apply_llama31_rope_pos_ids",
+    "apply_llama31_rope_pos_ids_inplace", "apply_rope", "apply_rope_inplace", "apply_rope_pos_ids",
+    "apply_rope_pos_ids_inplace", "apply_rope_with_cos_sin_cache", "apply_rope_with_cos_sin_cache_inplace",
+    "autotune", "b12x_fused_moe", "block_scale_interleave", "bmm_bf16", "bmm_fp8", "bmm_mxfp8",
+    "chain_speculative_sampling", "chunk_gated_delta_rule", "cudnn_batch_decode_with_kv_cache",
+    "cute_dsl_fused_moe_nvfp4", "cutlass_fused_moe", "e2m1_and_ufp8sf_scale_to_float", "fast_decode_plan",
+    "fi_trace", "fp4_quantize", "fused_add_rmsnorm", "fused_add_rmsnorm_quant", "fused_rmsnorm_silu", "gelu_and_mul",
+    "gelu_tanh_and_mul", "gemma_fused_add_rmsnorm", "gemma_rmsnorm", "get_batch_indices_positions",
+    "get_fp4_quantization_module", "get_seq_lens", "grouped_mm_bf16", "grouped_mm_fp4", "grouped_mm_fp8",
+    "grouped_mm_mxfp8", "jit", "layernorm", "mamba", "merge_state", "merge_state_in_place", "merge_states",
+    "min_p_sampling_from_probs", "mm_bf16", "mm_fp4", "mm_fp8", "mm_mxfp8", "mxfp4_dequantize",
+    "mxfp4_dequantize_host", "mxfp4_quantize", "mxfp8_dequantize_host", "mxfp8_quantize", "next_positive_power_of_2",
+    "nvfp4_batched_quantize", "nvfp4_block_scale_interleave", "nvfp4_kv_dequantize", "nvfp4_kv_quantize",
+    "nvfp4_quantize", "nvfp4_quantize_paged_kv_cache", "packbits", "prepare_low_latency_gemm_weights",
+    "reorder_rows_for_gated_act_gemm", "rmsnorm", "rmsnorm_fp4quant", "rmsnorm_quant", "sampling_from_logits",
+    "sampling_from_probs", "scaled_fp4_grouped_quantize", "segment_packbits", "shuffle_matrix_a",
+    "shuffle_matrix_sf_a", "silu_and_mul", "silu_and_mul_scaled_nvfp4_experts_quantize",
+    "single_decode_with_kv_cache", "single_prefill_with_kv_cache", "single_prefill_with_kv_cache_return_lse",
+    "softmax", "tgv_gemm_sm100", "top_k", "top_k_mask_logits", "top_k_page_table_transform",
+    "top_k_ragged_transform", "top_k_renorm_probs", "top_k_sampling_from_probs", "top_k_top_p_sampling_from_logits",
+    "top_k_top_p_sampling_from_probs", "top_p_renorm_probs", "top_p_sampling_from_probs", "topk", "trtllm_bf16_moe",
+    "trtllm_bf16_routed_moe", "trtllm_fmha_v2_prefill", "trtllm_fp4_block_scale_moe",
+    "trtllm_fp4_block_scale_routed_moe", "trtllm_fp8_block_scale_moe", "trtllm_fp8_block_scale_routed_moe",
+    "trtllm_fp8_per_tensor_scale_moe", "xqa", "xqa_mla",
+]
+
+WRAPPER_METHODS = {
+    "BatchDecodeWithPagedKVCacheWrapper": ["plan", "run", "forward", "begin_forward", "end_forward", "reset_workspace_buffer",
+                                           "is_cuda_graph_enabled", "use_tensor_cores"],
+    "BatchPrefillWithPagedKVCacheWrapper": ["plan", "run", "forward", "begin_forward", "end_forward", "reset_workspace_buffer"],
+    "BatchPrefillWithRaggedKVCacheWrapper": ["plan", "run", "forward", "begin_forward", "end_forward", "reset_workspace_buffer"],
+    "BatchMLAPagedAttentionWrapper": ["plan", "run"],
+    "MultiLevelCascadeAttentionWrapper": ["plan", "run"],
+    "PODWithPagedKVCacheWrapper": ["plan", "run", "is_cuda_graph_enabled", "reset_workspace_buffer"],
+    "BatchPODWithPagedKVCacheWrapper": ["plan", "run", "is_cuda_graph_enabled"],
+    "BlockSparseAttentionWrapper": ["plan", "run", "reset_workspace_buffer"],
+    "VariableBlockSparseAttentionWrapper": ["plan", "run", "reset_workspace_buffer"],
+    "SegmentGEMMWrapper": ["run", "reset_workspace_buffer"],
+    "BatchDecodeMlaWithPagedKVCacheWrapper": ["plan", "run", "is_cuda_graph_enabled", "use_tensor_cores", "reset_workspace_buffer"],
+}
+
+
+def test_reference_top_level_names_exist():
+    missing = [n for n in REFERENCE_TOP_LEVEL if not hasattr(fi, n)]
+    assert not missing, missing
+
+
+def test_wrapper_methods_exist():
+    missing = [(c, m) for c, ms in WRAPPER_METHODS.items() for m in ms if not hasattr(getattr(fi, c), m)]
+    assert not missing, missing
+
+
+def test_submodule_entry_points():
+    from flashinfer_b200 import comm, fused_moe, gemm, green_ctx, mamba, mla, norm, quantization, sparse, testing, topk
+
+    for mod, names in [
+        (comm, ["trtllm_allreduce_fusion", "MoeAlltoAll", "GemmAllReduce", "gemm_reduce_scatter", "AllGatherMatmul", "create_shared_buffer",
+                "free_shared_buffer", "pack_strided_memory", "CudaRTLibrary"]),
+        (fused_moe, ["trtllm_fp8_block_scale_moe", "moe_forward_fp8_block", "moe_forward_nvfp4", "MoEInputs", "RoutingInputMode",
+                     "Fp8QuantizationType", "convert_to_block_layout"]),
+        (gemm, ["mm_fp4", "bmm_fp8", "gemm_fp8_nt_groupwise", "group_deepgemm_fp8_nt_groupwise", "batch_deepgemm_fp8_nt_groupwise",
+                "linear_gated_silu", "interleave_gate_up", "tinygemm_bf16", "mm_M1_16_K7168_N256"]),
+        (green_ctx, ["split_device_green_ctx", "split_device_green_ctx_by_sm_count", "get_cudevice", "get_device_resource",
+                     "split_resource", "split_resource_by_sm_count", "create_green_ctx_streams"]),
+        (mamba, ["selective_state_update", "SSDCombined"]),
+        (mla, ["BatchMLAPagedAttentionWrapper", "MLAHeadDimensions", "MLALayerDimensions", "supported_mla_layer_dimensions"]),
+        (norm, ["rmsnorm_fp4quant", "add_rmsnorm_fp4quant", "qk_rmsnorm_cute", "rmsnorm_cute"]),
+        (quantization, ["nvfp4_quantize", "nvfp4_quantize_cute_dsl", "get_fp4_quantization_module"]),
+        (sparse, ["convert_bsr_mask_layout"]),
+        (testing, ["bench_gpu_time", "bench_gpu_time_with_cupti"]),
+        (topk, ["top_k", "topk_clusters_exact", "topk_clusters_page_table_transform", "topk_clusters_ragged_transform",
+                "can_implement_filtered_topk", "get_fast_topk_clusters"]),
+    ]:
+        missing = [n for n in names if not hasattr(mod, n)]
+        assert not missing, (mod.__name__, missing)
