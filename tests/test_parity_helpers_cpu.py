@@ -1,0 +1,104 @@
+"""CPU checks of the host-side / reference paths of ops added late in the round (their CUDA kernels have GPU tests)."""
+import torch
+
+import flashinfer_b200 as fi
+
+
+def test_fp8_group_quantize_cpu_roundtrip():
+    from flashinfer_b200.gemm.lowp import fp8_group_quantize
+
+    torch.manual_seed(0)
+    x = torch.randn(6, 256) * 3
+    q, sc = fp8_group_quantize(x)
+    assert q.dtype == torch.float8_e4m3fn and sc.shape == (6, 2)
+    dq = (q.float().view(6, 2, 128) * sc[..., None]).view(6, 256)
+    assert (dq - x).abs().max().item() < 0.07 * x.abs().max().item()
+    # gated: rows are [linear | gate]
+    h = torch.randn(4, 512)
+    qg, sg = fp8_group_quantize(h, gated=True)
+    ref = h[:, :256] * torch.nn.functional.silu(h[:, 256:])
+    dqg = (qg.float().view(4, 2, 128) * sg[..., None]).view(4, 256)
+    assert (dqg - ref).abs().max().item() < 0.07 * ref.abs().max().item() + 1e-3
+
+
+def test_linear_gated_silu_cpu_matches_unfused():
+    from flashinfer_b200.gemm import interleave_gate_up, linear_gated_silu
+
+    x, w = torch.randn(7, 64), torch.randn(48, 64)
+    ref = fi.silu_and_mul(x @ w.t())
+    torch.testing.assert_close(linear_gated_silu(x, interleave_gate_up(w)), ref, rtol=1e-5, atol=1e-5)
+
+
+def test_fp8_block_moe_cpu_fallback_matches_dequant():
+    from flashinfer_b200.fused_moe import moe_forward, moe_forward_fp8_block, route
+    from flashinfer_b200.fused_moe.core import _dequant_fp8_block
+
+    torch.manual_seed(1)
+    T, E, K, H, I = 16, 4, 2, 128, 128
+    x = torch.randn(T, H).bfloat16()
+
+    def q(wt):
+        Eb, N, Kd = wt.shape
+        blk = wt.float().reshape(Eb, N // 128, 128, Kd // 128, 128)
+        s = blk.abs().amax((2, 4)) / 448.0
+        return (blk / s[:, :, None, :, None]).reshape(Eb, N, Kd).to(torch.float8_e4m3fn), s
+
+    w1q, s1 = q(torch.randn(E, 2 * I, H) / H ** 0.5)
+    w2q, s2 = q(torch.randn(E, H, I) / I ** 0.5)
+    ids, w = route(torch.randn(T, E), None, K, 1)
+    out = moe_forward_fp8_block(x, None, ids, w, w1q, s1, w2q, s2)
+    ref = moe_forward(x, ids, w, _dequant_fp8_block(w1q, s1), _dequant_fp8_block(w2q, s2))
+    torch.testing.assert_close(out.float(), ref.float(), rtol=2e-2, atol=2e-2)
+
+
+def test_deepgemm_wrappers_cpu():
+    from flashinfer_b200.gemm import batch_deepgemm_fp8_nt_groupwise, group_deepgemm_fp8_nt_groupwise
+
+    torch.manual_seed(2)
+    E, N, K = 2, 128, 256
+    m_idx = torch.cat([torch.zeros(128), torch.ones(256)]).int()
+    a = torch.randn(384, K)
+    g = a.view(384, K // 128, 128)
+    a_s = g.abs().amax(-1) / 448.0
+    aq = (g / a_s[..., None]).view(384, K).to(torch.float8_e4m3fn)
+    w = torch.randn(E, N, K) / K ** 0.5
+    blk = w.view(E, 1, 128, K // 128, 128)
+    w_s = blk.abs().amax((2, 4)) / 448.0
+    wq = (blk / w_s[:, :, None, :, None]).reshape(E, N, K).to(torch.float8_e4m3fn)
+    a_dq = (aq.float().view(384, K // 128, 128) * a_s[..., None]).view(384, K)
+    w_dq = (wq.float().view(E, 1, 128, K // 128, 128) * w_s[:, :, None, :, None]).reshape(E, N, K)
+    ref = torch.cat([a_dq[:128] @ w_dq[0].t(), a_dq[128:] @ w_dq[1].t()])
+    out = group_deepgemm_fp8_nt_groupwise(aq, wq, a_s, w_s, m_idx)
+    torch.testing.assert_close(out.float(), ref, rtol=3e-2, atol=3e-2)
+    masked = torch.tensor([100, 128], dtype=torch.int32)
+    o = batch_deepgemm_fp8_nt_groupwise(aq[:256].view(2, 128, K), wq, a_s[:256].view(2, 128, -1), w_s, masked)
+    torch.testing.assert_close(o[0, :100].float(), (a_dq[:100] @ w_dq[0].t()), rtol=3e-2, atol=3e-2)
+
+
+def test_topk_cluster_entry_points_cpu():
+    from flashinfer_b200 import topk
+
+    x = torch.randn(3, 100)
+    idx = topk.topk_clusters_exact(x, 5)
+    assert idx.dtype == torch.int32 and idx.shape == (3, 5)
+    assert set(idx[0].tolist()) == set(torch.topk(x[0], 5).indices.tolist())
+    idx2, vals = topk.topk_clusters_exact(x, 5, output_values=True, out_dtype=torch.int64)
+    assert idx2.dtype == torch.int64 and torch.allclose(vals.sort(-1).values, torch.topk(x, 5).values.sort(-1).values)
+    assert topk.get_fast_topk_clusters(8) == 8 and topk.roundup_kbyte(1) == 1024 and topk.can_implement_filtered_topk()
+
+
+def test_misc_parity_helpers_cpu():
+    from flashinfer_b200 import norm, sparse
+    from flashinfer_b200.fused_moe import MoEInputs, convert_to_block_layout
+
+    m = torch.rand(5, 2, 3) > 0.5
+    flat = sparse.convert_bsr_mask_layout(m, torch.tensor([0, 2, 5]))
+    assert flat.shape == (30,) and torch.equal(flat[:12], m[:2].transpose(0, 1).reshape(-1))
+    q, k = torch.randn(4, 2, 8), torch.randn(4, 1, 8)
+    norm.qk_rmsnorm_cute(q, k, torch.ones(8), torch.ones(8))
+    assert (q.pow(2).mean(-1) - 1).abs().max().item() < 1e-3 and (k.pow(2).mean(-1) - 1).abs().max().item() < 1e-3
+    w = torch.arange(2 * 4 * 8).float().view(2, 4, 8)
+    b = convert_to_block_layout(w, 4)
+    assert b.shape == (2, 2, 4, 4) and torch.equal(b[0, 1, 2], w[0, 2, 4:8])
+    mi = MoEInputs(hidden_states=torch.zeros(1))
+    assert MoEInputs.from_list(mi.to_list()).hidden_states is mi.hidden_states and MoEInputs.idx("output") == 0
