@@ -108,7 +108,7 @@ from . import api_logging, autotuner, fi_trace, green_ctx, logits_processor, par
 from .autotuner import autotune  # noqa: F401,E402
 from .api_logging import flashinfer_api  # noqa: F401,E402
 from . import comm, mla, attention  # noqa: F401,E402
-from . import concat_ops, dsv3_ops, gdn, mamba  # noqa: F401,E402
+from . import concat_ops, diffusion_ops, dsv3_ops, gdn, mamba  # noqa: F401,E402
 from .gdn import chunk_gated_delta_rule  # noqa: F401,E402
 from .activation import silu_and_mul_scaled_nvfp4_experts_quantize  # noqa: F401,E402
 from .norm import (  # noqa: F401,E402

@@ -55,3 +55,9 @@ from .collectives import (  # noqa: F401,E402
 from .gemm_allreduce import GemmAllReduce, gemm_allreduce, gemm_reduce_scatter  # noqa: F401,E402
 from .all_gather_matmul import AllGatherMatmul, all_gather_matmul  # noqa: F401,E402
 from .compat import CudaRTLibrary, create_shared_buffer, free_shared_buffer, pack_strided_memory  # noqa: F401,E402
+from . import mixed_comm, mnnvl, nvshmem, trtllm_alltoall, trtllm_mnnvl_ar  # noqa: F401,E402
+from .trtllm_mnnvl_ar import (  # noqa: F401,E402
+    MNNVLAllreduceFusionStrategy,
+    trtllm_mnnvl_allreduce,
+    trtllm_mnnvl_fused_allreduce_add_rmsnorm,
+)

@@ -35,5 +35,8 @@ def __getattr__(name):
     raise AttributeError(f"module {__name__!r} has no attribute {name!r}")
 
 
+from .grouped import group_gemm_mxfp4_nt_groupwise as group_gemm_mxfp8_mxfp4_nt_groupwise  # noqa: F401,E402  (reference name)
+
+
 def is_cute_dsl_available() -> bool:
     return False  # the GEMMs here are hand-written CUDA; nothing depends on nvidia-cutlass-dsl

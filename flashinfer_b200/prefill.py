@@ -501,6 +501,33 @@ def trtllm_batch_context_with_kv_cache(query, kv_cache, workspace_buffer, block_
                  v_scale=float(bmm2_scale) if float(bmm2_scale) != 1.0 else None)
 
 
+def fmha_v2_prefill_deepseek(query: torch.Tensor, key: torch.Tensor, value: torch.Tensor, out: torch.Tensor, num_heads: int,
+                             head_dim: int, seq_len: int, scale_softmax: float, scale_bmm1: Optional[float] = None,
+                             scale_bmm2: Optional[float] = None, return_lse: bool = False, lse: Optional[torch.Tensor] = None):
+    """DeepSeek-R1 context attention (reference prefill.py:4345, an sm_120 fmha_v2 kernel there): ``query / key [B, S, H, 192]``,
+    ``value [B, S, H, 128]``, causal.  Runs the tcgen05 192 / 128 ragged prefill kernel; ``scale_softmax`` (0 = default
+    ``1 / sqrt(192)``) and the bmm scales fold into the softmax scale / output."""
+    B, S, H, dqk = query.shape
+    dvo = value.shape[-1]
+    sm = float(scale_softmax) if scale_softmax else dqk ** -0.5
+    sm *= float(scale_bmm1) if scale_bmm1 is not None else 1.0
+    indptr = torch.arange(0, (B + 1) * S, S, dtype=torch.int32)
+    w = BatchPrefillWithRaggedKVCacheWrapper(torch.empty(64 << 20, dtype=torch.uint8, device=query.device))
+    w.plan(indptr, indptr, H, H, dqk, head_dim_vo=dvo, causal=True, sm_scale=sm, q_data_type=query.dtype)
+    res = w.run(query.reshape(B * S, H, dqk), key.reshape(B * S, H, dqk), value.reshape(B * S, H, dvo), return_lse=return_lse)
+    o, l = res if return_lse else (res, None)
+    if scale_bmm2 is not None and float(scale_bmm2) != 1.0:
+        o = (o.float() * float(scale_bmm2)).to(o.dtype)
+    out.copy_(o.view(B, S, H, dvo).to(out.dtype))
+    if return_lse:
+        l = l.view(B, S, H)
+        if lse is not None:
+            lse.copy_(l)
+            l = lse
+        return out, l
+    return out
+
+
 def trtllm_fmha_v2_prefill(*args, **kwargs):
     """sm90/sm120-only TRT-LLM fmha_v2 path in the reference (jit/attention/modules.py:2010); B200 uses fmha_varlen."""
     raise NotImplementedError("fmha_v2 is an sm90/sm120 path; use fmha_varlen / the prefill wrappers on B200")

@@ -63,6 +63,35 @@ def test_wrapper_methods_exist():
     assert not missing, missing
 
 
+def test_appendix_a_module_level_names():
+    """module-level extras and the comm sub-modules."""
+    from flashinfer_b200 import comm, decode, diffusion_ops, dsv3_ops, gemm, mla, prefill, rope
+
+    want = {
+        decode: ["trtllm_batch_decode_with_kv_cache", "xqa_batch_decode_with_kv_cache"],
+        prefill: ["trtllm_batch_context_with_kv_cache", "trtllm_ragged_attention_deepseek", "fmha_varlen", "fmha_varlen_plan",
+                  "fmha_v2_prefill_deepseek"],
+        mla: ["trtllm_batch_decode_with_kv_cache_mla", "xqa_batch_decode_with_kv_cache_mla"],
+        rope: ["rope_quantize_fp8", "mla_rope_quantize_fp8", "rope_quantize_fp8_append_paged_kv_cache"],
+        gemm: ["gemm_fp8_nt_groupwise", "gemm_fp8_nt_blockscaled", "group_gemm_fp8_nt_groupwise", "group_gemm_mxfp8_mxfp4_nt_groupwise",
+               "group_gemm_nvfp4_nt_groupwise", "group_deepgemm_fp8_nt_groupwise", "batch_deepgemm_fp8_nt_groupwise",
+               "fp8_blockscale_gemm_sm90", "trtllm_low_latency_gemm"],
+        comm: ["Mapping", "AllReduceFusionOp", "AllReduceFusionPattern", "AllReduceStrategyConfig", "AllReduceStrategyType",
+               "QuantizationSFLayout", "trtllm_allreduce_fusion", "trtllm_custom_all_reduce", "trtllm_moe_allreduce_fusion",
+               "trtllm_moe_finalize_allreduce_fusion", "trtllm_create_ipc_workspace_for_all_reduce",
+               "trtllm_destroy_ipc_workspace_for_all_reduce", "trtllm_create_ipc_workspace_for_all_reduce_fusion",
+               "trtllm_destroy_ipc_workspace_for_all_reduce_fusion", "trtllm_lamport_initialize", "trtllm_lamport_initialize_all",
+               "compute_fp4_swizzled_layout_sf_size", "allreduce_fusion", "create_allreduce_fusion_workspace",
+               "AllReduceFusionWorkspace", "TRTLLMAllReduceFusionWorkspace", "MNNVLAllReduceFusionWorkspace", "MoeAlltoAll",
+               "all_gather_matmul", "mnnvl", "nvshmem", "mixed_comm", "trtllm_alltoall", "trtllm_mnnvl_ar", "vllm_all_reduce",
+               "vllm_init_custom_ar", "moe_a2a_dispatch", "moe_a2a_combine", "decode_cp_a2a_alltoall"],
+        dsv3_ops: ["mm_M1_16_K7168_N128", "mm_M1_16_K7168_N256", "fused_topk_deepseek", "concat_mla_k"],
+        diffusion_ops: ["fused_dit_gate_residual_layernorm_gamma_beta"],
+    }
+    missing = [(m.__name__, n) for m, names in want.items() for n in names if not hasattr(m, n)]
+    assert not missing, missing
+
+
 def test_submodule_entry_points():
     from flashinfer_b200 import comm, fused_moe, gemm, green_ctx, mamba, mla, norm, quantization, sparse, testing, topk
 

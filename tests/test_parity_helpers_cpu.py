@@ -102,3 +102,16 @@ def test_misc_parity_helpers_cpu():
     assert b.shape == (2, 2, 4, 4) and torch.equal(b[0, 1, 2], w[0, 2, 4:8])
     mi = MoEInputs(hidden_states=torch.zeros(1))
     assert MoEInputs.from_list(mi.to_list()).hidden_states is mi.hidden_states and MoEInputs.idx("output") == 0
+
+
+def test_fmha_v2_prefill_deepseek_cpu():
+    from flashinfer_b200 import prefill, reference
+
+    torch.manual_seed(0)
+    q, k, v = torch.randn(2, 33, 2, 192), torch.randn(2, 33, 2, 192), torch.randn(2, 33, 2, 128)
+    out = torch.empty(2, 33, 2, 128)
+    o, lse = prefill.fmha_v2_prefill_deepseek(q, k, v, out, 2, 192, 33, 0.0, return_lse=True)
+    for b in range(2):
+        ref, _ = reference.attention_ref(q[b], k[b], v[b], True)
+        torch.testing.assert_close(o[b], ref, rtol=1e-4, atol=1e-4)
+    assert lse.shape == (2, 33, 2)
