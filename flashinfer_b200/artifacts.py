@@ -1,0 +1,27 @@
+"""Reference flashinfer/artifacts.py downloads pre-built cubins (trtllm-gen FMHA / GEMM / MoE) from an artifact server.
+This library ships no binary kernels: every kernel is compiled from ``csrc/`` (see ``jit.py`` / ``aot.py``), so the artifact
+functions report an empty set."""
+from typing import List
+
+
+class ArtifactPath:
+    TRTLLM_GEN_FMHA = ""
+    TRTLLM_GEN_BMM = ""
+    TRTLLM_GEN_GEMM = ""
+    DEEPGEMM = ""
+
+
+def get_available_cubin_files(*args, **kwargs) -> List[str]:
+    return []
+
+
+def download_artifacts(*args, **kwargs) -> bool:
+    return True  # nothing to download: all kernels are built from source
+
+
+def get_artifacts_status(*args, **kwargs):
+    return []
+
+
+def clear_cubin() -> None:
+    return None

@@ -20,3 +20,13 @@ from .utils import (  # noqa: F401
 )
 
 from .utils import bench_gpu_time as bench_gpu_time_with_cupti  # noqa: F401,E402  (CUPTI is not required: CUDA events / graphs)
+from .utils import (  # noqa: F401,E402
+    aggregate_gpu_time_across_ranks,
+    bench_kineto,
+    calculate_rotation_count,
+    count_bytes,
+    empty_suppress,
+    per_block_cast_to_fp8,
+    per_token_cast_to_fp8,
+    suppress_stdout_stderr,
+)

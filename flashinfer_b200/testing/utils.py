@@ -274,3 +274,118 @@ def dequantize_fp8(x_fp8: torch.Tensor, scale: torch.Tensor, scale_major_mode: s
         s = s.repeat_interleave(rep, d)
     s = s[tuple(slice(0, d) for d in x_fp8.shape)]
     return x_fp8.float() * s
+
+
+# ------------------------------------------------------------------ DeepGEMM-style casts, byte counting, misc (reference testing/utils.py)
+def _ceil_to_ue8m0(x: torch.Tensor) -> torch.Tensor:
+    return torch.pow(2.0, torch.ceil(torch.log2(x.abs())))
+
+
+def per_token_cast_to_fp8(x: torch.Tensor):
+    """``[m, n]`` -> (e4m3 ``[m, n]``, power-of-two scales ``[m, n / 128]``), one scale per 1 x 128 group."""
+    assert x.dim() == 2 and x.size(1) % 128 == 0
+    m, n = x.shape
+    xv = x.view(m, -1, 128)
+    sf = _ceil_to_ue8m0(xv.abs().float().amax(dim=2).view(m, -1).clamp(1e-4) / 448.0)
+    return (xv * (1.0 / sf.unsqueeze(2))).to(torch.float8_e4m3fn).view(m, n), sf
+
+
+def per_block_cast_to_fp8(x: torch.Tensor):
+    """``[m, n]`` -> (e4m3 ``[m, n]``, power-of-two scales ``[ceil(m/128), ceil(n/128)]``), one scale per 128 x 128 block."""
+    assert x.dim() == 2
+    m, n = x.shape
+    mp, np_ = (m + 127) // 128 * 128, (n + 127) // 128 * 128
+    xp = torch.zeros(mp, np_, dtype=x.dtype, device=x.device)
+    xp[:m, :n] = x
+    xv = xp.view(-1, 128, np_ // 128, 128)
+    sf = _ceil_to_ue8m0(xv.abs().float().amax(dim=(1, 3), keepdim=True).clamp(1e-4) / 448.0)
+    return (xv * (1.0 / sf)).to(torch.float8_e4m3fn).view_as(xp)[:m, :n].contiguous(), sf.view(xv.size(0), xv.size(2))
+
+
+def count_bytes(*tensors) -> int:
+    total = 0
+    for t in tensors:
+        if isinstance(t, (tuple, list)):
+            total += count_bytes(*t)
+        elif t is not None:
+            total += t.numel() * t.element_size()
+    return total
+
+
+def calculate_rotation_count(tensors, device=None, min_rotations: int = 2) -> int:
+    """How many rotating copies of ``tensors`` keep the L2 cold between benchmark iterations (1 if they dwarf the L2)."""
+    nbytes = count_bytes(*tensors)
+    l2 = 126 << 20
+    if torch.cuda.is_available():
+        l2 = torch.cuda.get_device_properties(device if device is not None else torch.cuda.current_device()).L2_cache_size or l2
+    if nbytes >= 5 * l2:
+        return 1
+    return max(min_rotations, int(-(-2 * l2 // max(nbytes, 1))) + 1)
+
+
+def aggregate_gpu_time_across_ranks(x, op):
+    """Combine a per-rank time (or list of times) over the process group with ``op`` (e.g. ``max``)."""
+    import torch.distributed as dist
+
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        allx = [None] * dist.get_world_size()
+        dist.all_gather_object(allx, x)
+        if isinstance(x, list):
+            return [op(v) for v in zip(*allx)]
+        return op(allx)
+    return x
+
+
+class empty_suppress:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+class suppress_stdout_stderr:
+    """Silence fd 1 / 2 inside the block (native libraries included)."""
+
+    def __enter__(self):
+        import os
+        import sys
+
+        sys.stdout.flush()
+        sys.stderr.flush()
+        self._null = os.open(os.devnull, os.O_WRONLY)
+        self._saved = (os.dup(1), os.dup(2))
+        os.dup2(self._null, 1)
+        os.dup2(self._null, 2)
+        return self
+
+    def __exit__(self, *exc):
+        import os
+
+        os.dup2(self._saved[0], 1)
+        os.dup2(self._saved[1], 2)
+        for fd in (self._null, *self._saved):
+            os.close(fd)
+        return False
+
+
+def bench_kineto(fn, kernel_names, num_tests: int = 30, suppress_kineto_output: bool = False, trace_path=None, barrier_comm_profiling=False,
+                 flush_l2: bool = True):
+    """Average device time (seconds) of the kernels whose name contains ``kernel_names`` (str or tuple), via torch.profiler."""
+    from torch.profiler import ProfilerActivity, profile
+
+    names = (kernel_names,) if isinstance(kernel_names, str) else tuple(kernel_names)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if flush_l2 else None
+    fn()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(num_tests):
+            if flush is not None:
+                flush.zero_()
+            fn()
+        torch.cuda.synchronize()
+    out = []
+    for name in names:
+        evs = [e for e in prof.key_averages() if name in e.key]
+        tot = sum(getattr(e, "device_time_total", getattr(e, "cuda_time_total", 0.0)) for e in evs)
+        out.append(tot / num_tests / 1e6)
+    return out[0] if isinstance(kernel_names, str) else tuple(out)

@@ -167,3 +167,261 @@ def tensor_stats(t: torch.Tensor) -> dict:
     o = out.tolist()
     finite = max(n - int(o[3]) - int(o[4]), 1)
     return {"min": o[5], "max": o[1], "mean": o[2] / finite, "nan": int(o[3]), "inf": int(o[4])}
+
+
+# ====================================================================================================================
+# Helper names of the reference's flashinfer/utils.py that serving frameworks import (capability probes, dtype / shape
+# helpers, backend selectors).  This library has ONE backend (hand-written sm_100a kernels), so the selectors answer that.
+# ====================================================================================================================
+import functools as _functools
+import math as _math
+from typing import Callable, Iterable, Sequence, Tuple, Union
+
+
+class GPUArchitectureError(RuntimeError):
+    """Raised when an op is asked to run on a GPU architecture it does not support."""
+
+
+class LibraryError(RuntimeError):
+    """Raised when a required library / native module is missing."""
+
+
+class BackendSupportedError(RuntimeError):
+    """Raised when a requested backend cannot serve the call."""
+
+
+class LogLevel(Enum):
+    NOTSET = 0
+    DEBUG = 10
+    INFO = 20
+    WARNING = 30
+    ERROR = 40
+    CRITICAL = 50
+
+
+def set_log_level(lvl_str: str) -> None:
+    import logging
+
+    logging.getLogger("flashinfer_b200").setLevel(getattr(logging, str(lvl_str).upper(), logging.INFO))
+
+
+def get_logging_module():
+    import logging
+
+    return logging.getLogger("flashinfer_b200")
+
+
+def calculate_tile_tokens_dim(num_tokens: int, num_experts: int, top_k: int, max_tile_tokens_dim: int = 128) -> int:
+    """Token-tile size heuristic of the reference's trtllm-gen MoE (expected tokens per expert x 1.3, next power of two, [8, max])."""
+    per_expert = int(((num_tokens * top_k) // max(num_experts, 1)) * 1.3)
+    return min(max(next_positive_power_of_2(max(per_expert, 1)), 8), max_tile_tokens_dim)
+
+
+def is_float8(x: torch.Tensor) -> bool:
+    return x.dtype in (torch.float8_e4m3fn, torch.float8_e5m2)
+
+
+def get_indptr(x: torch.Tensor) -> torch.Tensor:
+    x = x.to(torch.int64)
+    ret = torch.zeros(x.shape[0] + 1, dtype=x.dtype, device=x.device)
+    ret[1:] = x.cumsum(0)
+    return ret
+
+
+def get_alibi_slopes(n_heads: int, device: Optional[torch.device] = None) -> torch.Tensor:
+    n = 2 ** _math.floor(_math.log2(n_heads))
+    m = torch.pow(2.0 ** (-8.0 / n), torch.arange(1, 1 + n, device=device))
+    if n < n_heads:
+        m = torch.cat([m, torch.pow(2.0 ** (-4.0 / n), torch.arange(1, 1 + 2 * (n_heads - n), 2, device=device))])
+    return m.float()
+
+
+def canonicalize_torch_dtype(dtype: Union[torch.dtype, str]) -> torch.dtype:
+    if isinstance(dtype, str):
+        return getattr(torch, dtype)
+    if isinstance(dtype, torch.dtype):
+        return dtype
+    raise TypeError(f"dtype must be a string or torch.dtype, got {type(dtype)}")
+
+
+@_functools.lru_cache(maxsize=None)
+def get_compute_capability(device: torch.device) -> Tuple[int, int]:
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise ValueError("device must be a cuda device")
+    return torch.cuda.get_device_capability(device.index)
+
+
+def get_device_sm_count(device=None) -> int:
+    return device_sm_count(device)
+
+
+def get_gpu_memory_bandwidth(device) -> float:
+    """Peak DRAM bandwidth in GB/s from the device properties (memory clock x bus width x 2)."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise ValueError("device must be a cuda device")
+    p = torch.cuda.get_device_properties(device)
+    clk = getattr(p, "memory_clock_rate", 0)
+    width = getattr(p, "memory_bus_width", 0)
+    return clk * 1e3 * (width / 8) * 2 / 1e9 if clk and width else 8000.0  # B200 HBM3e nominal
+
+
+def get_shared_bytes_per_block_optin(device=None) -> int:
+    return 227 * 1024
+
+
+def _cc(device) -> Tuple[int, int]:
+    try:
+        return get_compute_capability(torch.device(device) if device is not None else torch.device("cuda", 0))
+    except Exception:  # noqa: BLE001  (no GPU in this process)
+        return (0, 0)
+
+
+def is_sm90a_supported(device=None) -> bool:
+    return _cc(device)[0] == 9
+
+
+def is_sm100f_supported(device=None) -> bool:
+    return _cc(device)[0] == 10
+
+
+def is_sm110a_supported(device=None) -> bool:
+    return _cc(device)[0] == 11
+
+
+def is_sm120a_supported(device=None) -> bool:
+    return _cc(device) == (12, 0)
+
+
+def is_sm120f_supported(device=None) -> bool:
+    return _cc(device)[0] == 12
+
+
+def is_sm121a_supported(device=None) -> bool:
+    return _cc(device) == (12, 1)
+
+
+def is_sm12x_supported(device=None) -> bool:
+    return _cc(device)[0] == 12
+
+
+def is_cvt_rs_supported(device=None) -> bool:
+    return _cc(device)[0] in (10, 11)
+
+
+def version_at_least(version: str, base_version: str) -> bool:
+    from packaging import version as _v
+
+    return _v.parse(version) >= _v.parse(base_version)
+
+
+def has_cuda_cudart() -> bool:
+    import importlib.util
+
+    try:
+        return importlib.util.find_spec("cuda.cudart") is not None
+    except ModuleNotFoundError:
+        return False
+
+
+def get_cuda_python_version() -> str:
+    try:
+        import cuda
+
+        return getattr(cuda, "__version__", "0")
+    except ImportError:
+        return "0"
+
+
+def determine_gemm_backend(device) -> str:
+    return "sm100"
+
+
+def determine_attention_backend(device, pos_encoding_mode: int, use_fp16_qk_reductions: bool, use_custom_mask: bool, dtype_q,
+                                dtype_kv) -> str:
+    """The reference picks fa2 / fa3; here every attention call runs the sm_100a kernels."""
+    return "sm100"
+
+
+def determine_mla_backend(device) -> str:
+    return "sm100"
+
+
+def is_fa3_backend_supported(*args, **kwargs) -> bool:
+    return False
+
+
+def is_cutlass_backend_supported(*args, **kwargs) -> bool:
+    return False
+
+
+def check_shape_dtype_device(x: torch.Tensor, expected_shape: Optional[Sequence[int]], expected_dtype: Optional[torch.dtype],
+                             expected_device: Optional[torch.device], name: str) -> None:
+    if expected_shape and x.shape != torch.Size(expected_shape):
+        raise ValueError(f"Invalid shape of {name}: expected {expected_shape}, got {x.shape}")
+    if expected_dtype and x.dtype != expected_dtype:
+        raise ValueError(f"Invalid dtype of {name}: expected {expected_dtype}, got {x.dtype}")
+    if expected_device and x.device != expected_device:
+        raise ValueError(f"Invalid device of {name}: expected {expected_device}, got {x.device}")
+
+
+class FP4Tensor:
+    """Packed e2m1 data (two values per uint8) + UE4M3 block scales (reference utils.py:727)."""
+
+    def __init__(self, data: torch.Tensor, scale: torch.Tensor, scale_start_index: int = 0,
+                 original_shape: Optional[Tuple[int, ...]] = None):
+        if data.dtype != torch.uint8:
+            raise ValueError(f"data must be uint8 tensor, got {data.dtype}")
+        if original_shape is None:
+            original_shape = tuple(data.shape[:-1]) + (data.shape[-1] * 2,)
+        self.data, self.scale, self.scale_start_index, self.original_shape = data, scale, scale_start_index, tuple(original_shape)
+        self.dtype = "nvfp4"
+
+
+def get_shuffle_block_size(epilogue_tile_m: int) -> int:
+    return 32 if epilogue_tile_m % 128 == 0 else 16
+
+
+def get_shuffle_matrix_a_row_indices(input_tensor: torch.Tensor, epilogue_tile_m: int) -> torch.Tensor:
+    from ..quantization.fp4 import _shuffle_row_indices
+
+    assert input_tensor.dim() == 2, f"input_tensor should be a 2D tensor, not {input_tensor.dim()}"
+    return _shuffle_row_indices(input_tensor.shape[0], epilogue_tile_m, input_tensor.device)
+
+
+def get_shuffle_matrix_sf_a_row_indices(input_tensor: torch.Tensor, epilogue_tile_m: int, num_elts_per_sf: int = 16) -> torch.Tensor:
+    return get_shuffle_matrix_a_row_indices(input_tensor, epilogue_tile_m)
+
+
+def get_native_fp4_dtype():
+    return getattr(torch, "float4_e2m1fn_x2", torch.uint8)
+
+
+def supported_compute_capability(supported_ccs: Iterable[int]) -> Callable:
+    """Decorator: annotate a function with the compute capabilities it supports (``fn.is_compute_capability_supported(cc)``)."""
+    ccs = set(supported_ccs)
+
+    def deco(fn):
+        fn._supported_ccs = ccs
+        fn.is_compute_capability_supported = lambda cc: cc in ccs
+        return fn
+
+    return deco
+
+
+def backend_requirement(backend_checks=None, common_check=None, heuristic_func=None):
+    """Decorator of the reference that validates ``backend=`` choices; the single backend here always qualifies."""
+    def deco(fn):
+        fn.is_backend_supported = lambda backend=None, cc=None: True
+        fn.is_compute_capability_supported = lambda cc: True
+        fn.has_backend = lambda backend: True
+        fn.has_backend_choices = lambda: False
+        return fn
+
+    return deco
+
+
+def get_default_generators(device):
+    torch.cuda.init()
+    return torch.cuda.default_generators[torch.device(device).index or 0]
