@@ -132,6 +132,16 @@ def flashinfer_api(fn: Optional[Callable] = None, *, name: Optional[str] = None)
             bound.pop("self", None)
             _log(f"{api}(" + ", ".join(f"{k}={_fmt(v, _LEVEL)}" for k, v in bound.items()) + ")")
             dump_dir = None
+            deferred = None
+            if _DUMP_DIR and _capturing() and fnmatch.fnmatch(api, _DUMP_INC) and not (_DUMP_EXC and fnmatch.fnmatch(api, _DUMP_EXC)):
+                # inside torch.cuda.graph(...): no D2H copies may be captured -> keep references, write after replay
+                with _lock:
+                    _counter += 1
+                    idx = _counter
+                if idx <= _DUMP_MAX:
+                    deferred = {"dir": os.path.join(_DUMP_DIR, f"{idx:06d}_{api.replace('.', '_')}"), "api": api, "index": idx,
+                                "inputs": _collect_tensors(bound), "outputs": {},
+                                "scalars": {k: v for k, v in bound.items() if isinstance(v, (int, float, str, bool, type(None)))}}
             if _DUMP_DIR and not _capturing() and fnmatch.fnmatch(api, _DUMP_INC) and not (_DUMP_EXC and fnmatch.fnmatch(api, _DUMP_EXC)):
                 with _lock:
                     _counter += 1
@@ -146,11 +156,47 @@ def flashinfer_api(fn: Optional[Callable] = None, *, name: Optional[str] = None)
             if dump_dir is not None:
                 outs = out if isinstance(out, (list, tuple)) else [out]
                 _dump(dump_dir, "outputs", {f"out{i}": o for i, o in enumerate(outs) if isinstance(o, torch.Tensor)}, {"api": api})
+            if deferred is not None:
+                outs = out if isinstance(out, (list, tuple)) else [out]
+                deferred["outputs"] = {f"out{i}": o for i, o in enumerate(outs) if isinstance(o, torch.Tensor)}
+                with _lock:
+                    _PENDING_GRAPH_DUMPS.append(deferred)
             return out
 
         return wrapper
 
     return deco(fn) if fn is not None else deco
+
+
+_PENDING_GRAPH_DUMPS: List[Dict[str, Any]] = []
+_FLUSH_COUNTS: Dict[str, int] = {}
+
+
+def flush_graph_dumps(synchronize: bool = True) -> int:
+    """Write the dumps that were deferred during CUDA-graph capture (reference api_logging.py:1075): after ``g.replay()`` the
+    recorded input / output tensors hold that replay's values; they are written to the original dump directory (latest
+    flush) and to ``graph_flushes/flush_XXXX/`` under it (history).  Returns the number of API calls written."""
+    if synchronize and torch.cuda.is_available():
+        torch.cuda.synchronize()
+    with _lock:
+        pending = list(_PENDING_GRAPH_DUMPS)
+    for d in pending:
+        n = _FLUSH_COUNTS.get(d["dir"], 0)
+        _FLUSH_COUNTS[d["dir"]] = n + 1
+        meta = {"api": d["api"], "index": d["index"], "scalars": d["scalars"], "graph_flush": n}
+        for target in (d["dir"], os.path.join(d["dir"], "graph_flushes", f"flush_{n:04d}")):
+            _dump(target, "inputs", d["inputs"], meta)
+            _dump(target, "outputs", d["outputs"], {"api": d["api"]})
+    return len(pending)
+
+
+def clear_graph_dumps() -> int:
+    """Forget the deferred graph dumps (the captured tensors themselves belong to PyTorch).  Returns how many were dropped."""
+    with _lock:
+        n = len(_PENDING_GRAPH_DUMPS)
+        _PENDING_GRAPH_DUMPS.clear()
+        _FLUSH_COUNTS.clear()
+    return n
 
 
 def replay_from_dump(dump_dir: str, device: str = "cuda", compare: bool = True, rtol: float = 1e-2, atol: float = 1e-2) -> Dict[str, Any]:

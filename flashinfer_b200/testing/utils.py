@@ -320,7 +320,7 @@ def calculate_rotation_count(tensors, device=None, min_rotations: int = 2) -> in
         l2 = torch.cuda.get_device_properties(device if device is not None else torch.cuda.current_device()).L2_cache_size or l2
     if nbytes >= 5 * l2:
         return 1
-    return max(min_rotations, int(-(-2 * l2 // max(nbytes, 1))) + 1)
+    return min(128, max(min_rotations, int(-(-2 * l2 // max(nbytes, 1))) + 1))
 
 
 def aggregate_gpu_time_across_ranks(x, op):
