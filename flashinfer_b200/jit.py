@@ -337,3 +337,197 @@ def native_launch_count() -> int:
 
 def current_stream_ptr(device: Optional[torch.device] = None) -> int:
     return torch.cuda.current_stream(device).cuda_stream
+
+
+# ============================================================================
+# Reference JIT API names (flashinfer/jit/__init__.py, core.py): the same
+# concepts on top of ModuleSpec.  ``gen_jit_spec`` also lets users compile their
+# own .cu files with this toolchain (arch flags, include path with fib200/*.cuh,
+# uniform C ABI loader).
+# ============================================================================
+from enum import Enum as _Enum
+from types import SimpleNamespace as _NS
+
+MissingJITCacheError = MissingNativeModuleError
+
+env = _NS(
+    FLASHINFER_WORKSPACE_DIR=_PKG,
+    FLASHINFER_JIT_DIR=LIB_DIR,
+    FLASHINFER_GEN_SRC_DIR=CSRC,
+    FLASHINFER_CSRC_DIR=CSRC,
+    FLASHINFER_INCLUDE_DIR=CSRC / "include",
+    FLASHINFER_AOT_DIR=LIB_DIR,
+    FLASHINFER_CUBIN_DIR=LIB_DIR,
+    CUTLASS_INCLUDE_DIRS=[],
+    SPDLOG_INCLUDE_DIR=None,
+)
+
+sm100a_nvcc_flags = list(ARCH_FLAGS)
+sm100f_nvcc_flags = ["-gencode", "arch=compute_100f,code=sm_100f"]
+sm103a_nvcc_flags = ["-gencode", "arch=compute_103a,code=sm_103a"]
+sm110a_nvcc_flags = ["-gencode", "arch=compute_110a,code=sm_110a"]
+sm120a_nvcc_flags = ["-gencode", "arch=compute_120a,code=sm_120a"]
+sm120f_nvcc_flags = ["-gencode", "arch=compute_120f,code=sm_120f"]
+sm121a_nvcc_flags = ["-gencode", "arch=compute_121a,code=sm_121a"]
+sm90a_nvcc_flags = ["-gencode", "arch=compute_90a,code=sm_90a"]
+
+
+class JitSpecStatus(_Enum):
+    NOT_COMPILED = 0
+    COMPILED = 1
+    STALE = 2
+
+
+class JitSpec(ModuleSpec):
+    """ModuleSpec under the reference's name, with its convenience methods."""
+
+    @property
+    def jit_library_path(self) -> Path:
+        return self.so_path
+
+    @property
+    def aot_path(self) -> Path:
+        return self.so_path
+
+    @property
+    def is_compiled(self) -> bool:
+        return self.so_path.exists()
+
+    @property
+    def status(self) -> JitSpecStatus:
+        if not self.so_path.exists():
+            return JitSpecStatus.NOT_COMPILED
+        return JitSpecStatus.COMPILED if self.is_fresh() else JitSpecStatus.STALE
+
+    def build(self, verbose: bool = False, need_lock: bool = True) -> None:
+        build_module(self, verbose=verbose)
+
+    def load(self, so_path=None) -> "NativeModule":
+        return load(self.name)
+
+    def build_and_load(self) -> "NativeModule":
+        return load(self.name)
+
+
+_USER_SPECS: Dict[str, JitSpec] = {}
+
+
+def gen_jit_spec(name: str, sources: Sequence, extra_cflags: Optional[Sequence[str]] = None,
+                 extra_cuda_cflags: Optional[Sequence[str]] = None, extra_ldflags: Optional[Sequence[str]] = None,
+                 extra_include_paths: Optional[Sequence] = None, needs_device_linking: bool = False) -> JitSpec:
+    """Declare a native module from ``sources`` (paths relative to ``csrc/`` or absolute: user kernels are welcome).  The
+    result builds with the sm_100a flags of this package and loads through the uniform C-ABI caller (``spec.build_and_load()``)."""
+    flags = list(extra_cuda_cflags or [])
+    for inc in extra_include_paths or []:
+        flags += ["-I", str(inc)]
+    spec = JitSpec(name, [str(s) for s in sources], extra_flags=flags, ldflags=list(extra_ldflags or []))
+    REGISTRY[name] = spec
+    _USER_SPECS[name] = spec
+    return spec
+
+
+class JitSpecRegistry:
+    """View of the module registry (reference jit/core.py JitSpecRegistry)."""
+
+    def register(self, spec: ModuleSpec) -> None:
+        REGISTRY[spec.name] = spec
+
+    def get_all_specs(self) -> Dict[str, ModuleSpec]:
+        return dict(REGISTRY)
+
+    def get_spec_status(self, name: str):
+        spec = REGISTRY.get(name)
+        if spec is None:
+            return None
+        return _NS(name=name, status=(JitSpecStatus.NOT_COMPILED if not spec.so_path.exists() else
+                                      (JitSpecStatus.COMPILED if spec.is_fresh() else JitSpecStatus.STALE)),
+                   library_path=spec.so_path, sources=spec.source_paths())
+
+    def get_all_statuses(self):
+        return [self.get_spec_status(n) for n in REGISTRY]
+
+    def get_stats(self) -> Dict[str, int]:
+        st = [s.status for s in self.get_all_statuses()]
+        return {"total": len(st), "compiled": sum(x == JitSpecStatus.COMPILED for x in st),
+                "not_compiled": sum(x == JitSpecStatus.NOT_COMPILED for x in st), "stale": sum(x == JitSpecStatus.STALE for x in st)}
+
+
+jit_spec_registry = JitSpecRegistry()
+
+
+def build_jit_specs(specs: Sequence[ModuleSpec], verbose: bool = False, skip_prebuilt: bool = True) -> None:
+    for spec in specs:
+        build_module(spec, verbose=verbose, force=not skip_prebuilt and False)
+
+
+def clear_cache_dir() -> None:
+    """Remove the libraries of user-declared modules (``gen_jit_spec``) and the in-process module cache; the package's own
+    libraries are sources of truth for the in-tree build and are rebuilt by ``build_all(force=True)`` instead."""
+    for name, spec in list(_USER_SPECS.items()):
+        for p in (spec.so_path, spec.hash_path):
+            if p.exists():
+                p.unlink()
+        _loaded.pop(name, None)
+
+
+from .compilation_context import current_compilation_context  # noqa: E402,F401
+
+
+cubin_loader = _NS(get_cubin=lambda *a, **k: b"", setup_cubin_loader=lambda *a, **k: None)
+
+
+def setup_cubin_loader(*args, **kwargs) -> None:
+    return None  # no pre-built cubins: every kernel is compiled from csrc/
+
+
+_GEN_MAP = {
+    "gen_act_and_mul_module": "activation", "gen_batch_attention_module": "prefill_sm100", "gen_batch_decode_mla_module": "mla_sm100",
+    "gen_batch_decode_module": "decode_sm100", "gen_batch_mla_module": "mla_sm100", "gen_batch_pod_module": "pod_sm100",
+    "gen_batch_prefill_module": "prefill_sm100", "gen_comm_alltoall_module": "comm_alltoall", "gen_cudnn_fmha_module": "prefill_sm100",
+    "gen_customize_batch_decode_module": "attention_generic", "gen_customize_batch_prefill_module": "attention_generic",
+    "gen_customize_single_decode_module": "attention_generic", "gen_customize_single_prefill_module": "attention_generic",
+    "gen_dcp_alltoall_module": "comm_collectives", "gen_dsv3_fused_routing_module": "moe", "gen_dsv3_router_gemm_module": "gemm_sm100",
+    "gen_fmha_cutlass_sm100a_module": "prefill_sm100", "gen_fmha_v2_module": "prefill_sm100", "gen_fp4_kv_dequantization_module": "quantization",
+    "gen_fp4_kv_quantization_module": "quantization", "gen_moe_alltoall_module": "comm_alltoall", "gen_moe_utils_module": "moe",
+    "gen_pod_module": "pod_sm100", "gen_single_decode_module": "decode_sm100", "gen_single_prefill_module": "prefill_sm100",
+    "gen_tinygemm2_module": "gemm_sm100", "gen_trtllm_comm_module": "comm_allreduce", "gen_trtllm_fmha_v2_sm120_module": "prefill_sm100",
+    "gen_trtllm_gen_fmha_module": "decode_sm100", "gen_trtllm_mnnvl_comm_module": "comm_allreduce", "gen_vllm_comm_module": "comm_allreduce",
+}
+
+
+def _make_gen(fn_name: str, module: str):
+    def gen(*args, **kwargs):
+        """Reference JIT generator name: the template arguments select an instance there; here the native module covers them."""
+        spec = REGISTRY[module]
+        js = JitSpec(spec.name, list(spec.sources), list(spec.extra_flags), list(spec.ldflags), list(spec.deps))
+        return js
+    gen.__name__ = fn_name
+    return gen
+
+
+for _fn, _mod in _GEN_MAP.items():
+    globals()[_fn] = _make_gen(_fn, _mod)
+
+
+def _uri(prefix: str):
+    def f(*args, **kwargs) -> str:
+        parts = [str(a).replace("torch.", "") for a in args] + [f"{k}_{v}" for k, v in sorted(kwargs.items())]
+        return "_".join([prefix] + parts)
+    f.__name__ = f"get_{prefix}_uri"
+    return f
+
+
+get_single_decode_uri = _uri("single_decode")
+get_single_prefill_uri = _uri("single_prefill")
+get_batch_decode_uri = _uri("batch_decode")
+get_batch_prefill_uri = _uri("batch_prefill")
+get_batch_decode_mla_uri = _uri("batch_decode_mla")
+get_batch_mla_uri = _uri("batch_mla")
+get_batch_attention_uri = _uri("batch_attention")
+get_pod_uri = _uri("pod")
+
+
+def get_act_and_mul_cu_str(act_func_name: str, act_func_def: str) -> str:
+    """Source of a custom gated activation in the style of csrc/elementwise/activation.cu (for ``gen_jit_spec``)."""
+    return (f"// generated: {act_func_name}\\n#include <fib200/common.cuh>\\n__device__ __forceinline__ float {act_func_name}(float x)"
+            f" {{ {act_func_def} }}\\n")

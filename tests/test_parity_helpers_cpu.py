@@ -115,3 +115,39 @@ def test_fmha_v2_prefill_deepseek_cpu():
         ref, _ = reference.attention_ref(q[b], k[b], v[b], True)
         torch.testing.assert_close(o[b], ref, rtol=1e-4, atol=1e-4)
     assert lse.shape == (2, 33, 2)
+
+
+def test_user_jit_spec_builds_and_loads(tmp_path):
+    """gen_jit_spec: users compile their own .cu with the package toolchain (sm_100a flags, fib200 headers, uniform C ABI)."""
+    import pytest
+
+    from flashinfer_b200 import jit
+
+    if not jit.have_nvcc():
+        pytest.skip("nvcc not available")
+    src = tmp_path / "user_axpy.cu"
+    src.write_text(
+        '#include <fib200/common.cuh>\n'
+        'using namespace fib200;\n'
+        'FIB_EXPORT_LAST_ERROR()\n'
+        '__global__ void axpy_kernel(const float* x, float* y, float a, int64_t n) {\n'
+        '  int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;\n'
+        '  if (i < n) y[i] += a * x[i];\n'
+        '}\n'
+        'extern "C" int user_axpy(void* x, void* y, double a, int64_t n, int64_t stream) {\n'
+        '  if (n == 0) return 0;\n'
+        '  axpy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>((const float*)x, (float*)y, (float)a, n);\n'
+        '  FIB_CUDA_CHECK(cudaGetLastError());\n'
+        '  return 0;\n'
+        '}\n')
+    spec = jit.gen_jit_spec("user_axpy_test", [src])
+    try:
+        assert spec.status == jit.JitSpecStatus.NOT_COMPILED
+        mod = spec.build_and_load()
+        assert spec.status == jit.JitSpecStatus.COMPILED and mod.has("user_axpy")
+        assert jit.jit_spec_registry.get_spec_status("user_axpy_test").status == jit.JitSpecStatus.COMPILED
+        mod.call("user_axpy", None, None, 2.0, 0, 0)  # n = 0: returns before touching the GPU
+    finally:
+        jit.clear_cache_dir()
+        jit.REGISTRY.pop("user_axpy_test", None)
+    assert not spec.so_path.exists()
