@@ -57,6 +57,12 @@ COMMON_NVCC_FLAGS = [
 ]
 
 
+def debug_flags() -> List[str]:
+    """``FIB200_JIT_DEBUG=1``: device debug build (``-G -g --ptxas-options=-v``), like the reference's FLASHINFER_JIT_DEBUG; the
+    flags enter the content hash, so switching the variable rebuilds the affected modules."""
+    return ["-G", "-g", "--ptxas-options=-v"] if os.environ.get("FIB200_JIT_DEBUG", "0") == "1" else []
+
+
 class MissingNativeModuleError(RuntimeError):
     """Raised when a native module is required but is neither built nor buildable."""
 
@@ -90,7 +96,7 @@ class ModuleSpec:
                 if p.is_file():
                     h.update(p.name.encode())
                     h.update(p.read_bytes())
-        h.update(" ".join(list(ARCH_FLAGS) + list(COMMON_NVCC_FLAGS) + list(self.extra_flags) + list(self.ldflags)).encode())
+        h.update(" ".join(list(ARCH_FLAGS) + list(COMMON_NVCC_FLAGS) + debug_flags() + list(self.extra_flags) + list(self.ldflags)).encode())
         return h.hexdigest()
 
     def is_fresh(self) -> bool:
@@ -103,7 +109,7 @@ class ModuleSpec:
 
     def nvcc_command(self) -> List[str]:
         nvcc = os.environ.get("FIB200_NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-        cmd = [nvcc, "-shared", *ARCH_FLAGS, *COMMON_NVCC_FLAGS]
+        cmd = [nvcc, "-shared", *ARCH_FLAGS, *COMMON_NVCC_FLAGS, *debug_flags()]
         for inc in INCLUDE_DIRS:
             cmd += ["-I", str(inc)]
         cmd += list(self.extra_flags)
