@@ -42,6 +42,61 @@ def gated_delta_rule_ref(q, k, v, state, g_log, beta, scale, l2norm):
     return out
 
 
+def gated_delta_rule_chunked(q, k, v, state, g_log, beta, scale, l2norm, chunk: int = 64, compute_dtype: torch.dtype = torch.float32):
+    """Chunk-parallel gated delta rule (WY form), composed of batched GEMMs + one triangular solve per chunk - the algorithm of
+    the reference's tcgen05 chunked-prefill kernel (gdn_kernels/blackwell/gated_delta_net_chunked.py), here as tensor ops.
+
+    Same contract as :func:`gated_delta_rule_ref` (``state`` is updated in place).  Inside a chunk with entering state ``S0``,
+    cumulative log-gates ``G_i`` and ``Gamma_i = exp(G_i)``::
+
+        (I + A) U = beta * (V - Gamma * K S0),      A[j, l] = beta_j exp(G_j - G_l) (k_j . k_l)   (l < j)
+        O = scale * (Gamma * Q S0 + tril(Q K^T * exp(G_i - G_j)) U)
+        S_C = Gamma_C S0 + (K * exp(G_C - G))^T U
+
+    All decay factors are ratios ``exp(G_i - G_j) <= 1`` (``g_log <= 0``), so nothing overflows.  Everything that does not
+    depend on ``S0`` (A, its inverse applied to ``beta V`` and ``beta Gamma K``, the masked ``Q K^T``) is computed for all chunks
+    at once; the sequential part is three small GEMMs per chunk."""
+    B, T, H, K = q.shape
+    HV, V = v.shape[2], v.shape[3]
+    rep = HV // H
+    C = chunk
+    pad = (-T) % C
+    f = lambda t: t.float()  # noqa: E731
+    qf, kf = f(q).repeat_interleave(rep, 2), f(k).repeat_interleave(rep, 2)
+    if l2norm:
+        qf = qf * torch.rsqrt((qf * qf).sum(-1, keepdim=True) + 1e-6)
+        kf = kf * torch.rsqrt((kf * kf).sum(-1, keepdim=True) + 1e-6)
+    vf, gl, bt = f(v), f(g_log), f(beta)
+    if pad:  # identity steps: no decay (g = 0), no write (beta = 0)
+        z = lambda t: torch.cat([t, t.new_zeros(B, pad, *t.shape[2:])], 1)  # noqa: E731
+        qf, kf, vf, gl, bt = z(qf), z(kf), z(vf), z(gl), z(bt)
+    N = (T + pad) // C
+    # [B, HV, N, C, *]
+    r = lambda t: t.view(B, N, C, HV, -1).permute(0, 3, 1, 2, 4)  # noqa: E731
+    Q, Kc, Vc = r(qf), r(kf), r(vf)
+    G = r(gl[..., None])[..., 0].cumsum(-1)                      # cumulative log gate inside the chunk
+    Bt = r(bt[..., None])[..., 0]
+    Gam = torch.exp(G)
+    ratio = torch.exp((G.unsqueeze(-1) - G.unsqueeze(-2)).clamp(max=0.0))  # exp(G_i - G_j), only i >= j is used
+    KK = torch.matmul(Kc.to(compute_dtype), Kc.to(compute_dtype).transpose(-1, -2)).float()
+    eye = torch.eye(C, device=q.device)
+    A = (KK * ratio * Bt.unsqueeze(-1)).tril(-1)
+    rhs = torch.cat([Vc * Bt.unsqueeze(-1), Kc * (Bt * Gam).unsqueeze(-1)], -1)      # [.., C, V + K]
+    sol = torch.linalg.solve_triangular(eye + A, rhs, upper=False, unitriangular=True)
+    UV, W = sol[..., :V], sol[..., V:]                                                # U = UV - W S0
+    QK = (torch.matmul(Q.to(compute_dtype), Kc.to(compute_dtype).transpose(-1, -2)).float() * ratio).tril()
+    Kdec = Kc * torch.exp(G[..., -1:] - G).unsqueeze(-1)                              # K * exp(G_C - G)
+    QG = Q * Gam.unsqueeze(-1)
+    out = torch.empty(B, HV, N, C, V, dtype=torch.float32, device=q.device)
+    S = state.float().clone()                                                         # [B, HV, K, V]
+    for c in range(N):
+        U = UV[:, :, c] - torch.matmul(W[:, :, c], S)
+        out[:, :, c] = torch.matmul(QG[:, :, c], S) + torch.matmul(QK[:, :, c], U)
+        S = S * Gam[:, :, c, -1, None, None] + torch.matmul(Kdec[:, :, c].transpose(-1, -2), U)
+    state.copy_(S.to(state.dtype))
+    return (out * scale).permute(0, 2, 3, 1, 4).reshape(B, N * C, HV, V)[:, :T]
+
+
 def _run(q, k, v, state, a, bgate, g_log, A_log, dt_bias, scale, l2norm, beta_is_logit, update_state, state_idx=None,
          cu_seqlens=None, out=None):
     B, T, H, K = q.shape
@@ -117,9 +172,13 @@ def chunk_gated_delta_rule(q, k, v, g: Optional[torch.Tensor] = None, beta: Opti
                            output_final_state: bool = False, cu_seqlens: Optional[torch.Tensor] = None,
                            use_qk_l2norm_in_kernel: bool = False, output: Optional[torch.Tensor] = None,
                            output_state: Optional[torch.Tensor] = None, state_checkpoints=None, checkpoint_cu_starts=None,
-                           checkpoint_every_n_tokens: int = 0) -> Union[torch.Tensor, Tuple[torch.Tensor, torch.Tensor]]:
+                           checkpoint_every_n_tokens: int = 0, chunked: Optional[bool] = None,
+                           chunk_size: int = 64) -> Union[torch.Tensor, Tuple[torch.Tensor, torch.Tensor]]:
     """Prefill: ``q/k [total, H, K]``, ``v [total, HV, V]``, ``g`` (multiplicative forget gate) / ``beta`` ``[total, HV]``
-    fp32, packed sequences described by ``cu_seqlens``."""
+    fp32, packed sequences described by ``cu_seqlens``.
+
+    ``chunked=True`` (or ``FIB200_GDN_CHUNKED=1``) runs the chunk-parallel WY algorithm (:func:`gated_delta_rule_chunked`:
+    batched GEMMs + a triangular solve per 64-token chunk) instead of the token-sequential kernel."""
     if state_checkpoints is not None:
         raise NotImplementedError("state checkpoints are not implemented")
     total, H, K = q.shape
@@ -138,6 +197,24 @@ def chunk_gated_delta_rule(q, k, v, g: Optional[torch.Tensor] = None, beta: Opti
         state.copy_(initial_state)
     elif output_state is not None:
         state.zero_()
+    import os
+
+    if chunked is None:
+        chunked = os.environ.get("FIB200_GDN_CHUNKED", "0") == "1"
+    if chunked:
+        sc = scale if scale is not None else 1.0 / math.sqrt(K)
+        o = torch.empty(total, HV, V, dtype=torch.float32, device=dev)
+        cu = cu_seqlens.tolist()
+        for i in range(n):
+            sl = slice(cu[i], cu[i + 1])
+            if cu[i + 1] > cu[i]:
+                o[sl] = gated_delta_rule_chunked(q[None, sl], k[None, sl], v[None, sl], state[i:i + 1], g_log[None, sl], bt[None, sl], sc,
+                                                 use_qk_l2norm_in_kernel, chunk_size)[0]
+        o = o.to(q.dtype)
+        if output is not None:
+            output.copy_(o)
+            o = output
+        return (o, state) if output_final_state else o
     o = _run(q[None], k[None], v[None], state, None, bt[None], g_log[None], None, None, scale, use_qk_l2norm_in_kernel, False, True,
              cu_seqlens=cu_seqlens, out=output[None] if output is not None else None)[0]
     return (o, state) if output_final_state else o

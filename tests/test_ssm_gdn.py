@@ -147,3 +147,24 @@ def test_ssd_combined_matches_recurrence_cpu():
     got = y2.permute(0, 3, 4, 1, 2).reshape(1, L, H, P)
     torch.testing.assert_close(got, torch.cat([ya, yb], 1), rtol=2e-4, atol=2e-4)
     torch.testing.assert_close(fin2, torch.cat([sa, sb], 0), rtol=2e-4, atol=2e-4)
+
+
+def test_chunked_gated_delta_rule_matches_sequential_cpu():
+    """Chunk-parallel WY form of the gated delta rule vs the token-sequential path (packed sequences, GQA, l2norm)."""
+    import torch
+    from flashinfer_b200.gdn import chunk_gated_delta_rule
+
+    torch.manual_seed(0)
+    total, H, K, HV, V = 230, 2, 16, 4, 8
+    q, k = torch.randn(total, H, K), torch.randn(total, H, K)
+    v = torch.randn(total, HV, V)
+    g = torch.exp(-torch.rand(total, HV) * 0.3)
+    beta = torch.rand(total, HV)
+    cu = torch.tensor([0, 100, 101, 230], dtype=torch.int32)
+    init = torch.randn(3, HV, K, V) * 0.1
+    o1, s1 = chunk_gated_delta_rule(q, k, v, g, beta, initial_state=init.clone(), output_final_state=True, cu_seqlens=cu,
+                                    use_qk_l2norm_in_kernel=True)
+    o2, s2 = chunk_gated_delta_rule(q, k, v, g, beta, initial_state=init.clone(), output_final_state=True, cu_seqlens=cu,
+                                    use_qk_l2norm_in_kernel=True, chunked=True, chunk_size=32)
+    torch.testing.assert_close(o2.float(), o1.float(), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(s2.float(), s1.float(), rtol=1e-4, atol=1e-5)
