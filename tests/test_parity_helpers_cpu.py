@@ -151,3 +151,39 @@ def test_user_jit_spec_builds_and_loads(tmp_path):
         jit.clear_cache_dir()
         jit.REGISTRY.pop("user_axpy_test", None)
     assert not spec.so_path.exists()
+
+
+def test_utils_helper_names_cpu():
+    import pytest
+
+    from flashinfer_b200 import utils as u
+
+    assert torch.equal(u.get_indptr(torch.tensor([2, 0, 3])), torch.tensor([0, 2, 2, 5]))
+    s = u.get_alibi_slopes(12)
+    assert s.shape == (12,) and abs(float(s[0]) - 2 ** -1) < 1e-6 and abs(float(s[8]) - 2 ** -0.5) < 1e-6
+    assert u.canonicalize_torch_dtype("bfloat16") is torch.bfloat16 and u.is_float8(torch.zeros(1).to(torch.float8_e4m3fn))
+    assert u.calculate_tile_tokens_dim(1024, 256, 8) == 64 and u.calculate_tile_tokens_dim(1, 256, 8) == 8
+    with pytest.raises(ValueError):
+        u.check_shape_dtype_device(torch.zeros(2, 3), (3, 2), None, None, "x")
+    u.check_shape_dtype_device(torch.zeros(2, 3), (2, 3), torch.float32, torch.device("cpu"), "x")
+    t = u.FP4Tensor(torch.zeros(4, 8, dtype=torch.uint8), torch.zeros(4, 1))
+    assert t.original_shape == (4, 16)
+    assert u.get_shuffle_block_size(128) == 32 and u.get_shuffle_block_size(64) == 16
+    idx = u.get_shuffle_matrix_a_row_indices(torch.zeros(256, 4), 128)
+    assert sorted(idx.tolist()) == list(range(256))
+    assert u.version_at_least("2.11.0", "2.8") and u.determine_attention_backend(None, 0, False, False, None, None) == "sm100"
+
+    @u.supported_compute_capability([100, 103])
+    def f():
+        return 1
+
+    assert f.is_compute_capability_supported(100) and not f.is_compute_capability_supported(90)
+    from flashinfer_b200 import tllm_enums as te
+
+    assert int(te.DtypeTrtllmGen.Bfloat16) == (1 << 20) | (16 << 8) and te.trtllm_gen_dtype_has_scale(te.DtypeTrtllmGen.MxE2m1)
+    assert te.deduce_trtllm_gen_tensor_dtype(torch.zeros(2, 8, dtype=torch.uint8), torch.zeros(2)) == te.DtypeTrtllmGen.E2m1
+    from flashinfer_b200 import cuda_utils
+
+    assert cuda_utils.checkCudaErrors((0, 5)) == 5 and cuda_utils.checkCudaErrors((0,)) is None
+    with pytest.raises(RuntimeError):
+        cuda_utils.checkCudaErrors((1, None))
