@@ -61,3 +61,14 @@ from .trtllm_mnnvl_ar import (  # noqa: F401,E402
     trtllm_mnnvl_allreduce,
     trtllm_mnnvl_fused_allreduce_add_rmsnorm,
 )
+from . import (  # noqa: F401,E402
+    cuda_ipc,
+    dcp_alltoall,
+    dlpack_utils,
+    nvshmem_allreduce,
+    torch_symmetric_memory,
+    trtllm_ar,
+    trtllm_moe_alltoall,
+    vllm_ar,
+    workspace_base,
+)
