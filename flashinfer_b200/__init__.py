@@ -1,5 +1,5 @@
 """flashinfer_b200 — a B200-native (sm_100a) LLM-inference kernel library with FlashInfer's API surface."""
-__version__ = "0.1.0"
+from .version import __version__  # noqa: F401
 
 from . import jit, reference, utils  # noqa: F401
 from .decode import (  # noqa: F401

@@ -31,3 +31,7 @@ def convert_to_block_layout(input_tensor, blockK: int):
     """``[..., M, K]`` -> ``[..., K / blockK, M, blockK]`` (the BlockMajorK weight layout of the reference's trtllm-gen MoE)."""
     *lead, M, K = input_tensor.shape
     return input_tensor.reshape(*lead, M, K // blockK, blockK).transpose(-3, -2).contiguous()
+
+from .. import _alias  # noqa: E402
+
+_alias.install(__name__, ['fused_routing_dsv3'])  # the reference's per-file module paths

@@ -40,3 +40,7 @@ from .grouped import group_gemm_mxfp4_nt_groupwise as group_gemm_mxfp8_mxfp4_nt_
 
 def is_cute_dsl_available() -> bool:
     return False  # the GEMMs here are hand-written CUDA; nothing depends on nvidia-cutlass-dsl
+
+from .. import _alias  # noqa: E402
+
+_alias.install(__name__, ['gemm_base', 'routergemm'])  # the reference's per-file module paths

@@ -4,3 +4,7 @@ from ..gemm.grouped import group_gemm_fp8_nt_groupwise as grouped_mm_fp8  # noqa
 from ..gemm.grouped import group_gemm_mxfp4_nt_groupwise as grouped_mm_mxfp4  # noqa: F401
 from ..gemm.grouped import group_gemm_nvfp4_nt_groupwise as grouped_mm_fp4  # noqa: F401
 from ..gemm.grouped import grouped_mm_mxfp8  # noqa: F401
+
+from .. import _alias  # noqa: E402
+
+_alias.install(__name__, ['core'])  # the reference's per-file module paths

@@ -32,3 +32,7 @@ from .pipeline import (  # noqa: F401
     compile_pipeline,
     legalize_processors,
 )
+
+from .. import _alias  # noqa: E402
+
+_alias.install(__name__, ['types', 'op', 'operators', 'processors', 'compiler', 'fusion_rules', 'legalization', 'validators'])  # the reference's per-file module paths

@@ -17,3 +17,7 @@ from .core import (  # noqa: F401
     ulysses_varlen_config,
     uneven_cp_config,
 )
+
+from .. import _alias  # noqa: E402
+
+_alias.install(__name__, ['parallel_attention', 'parallel_config', 'parallel_wrapper', 'attention_ops', 'utils'])  # the reference's per-file module paths

@@ -33,3 +33,7 @@ def get_fp4_quantization_module(backend: str = "100"):
     from .. import jit
 
     return jit.load("quantization")
+
+from .. import _alias  # noqa: E402
+
+_alias.install(__name__, ['fp4_quantization', 'fp8_quantization'])  # the reference's per-file module paths

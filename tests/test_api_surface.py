@@ -1,5 +1,7 @@
 """API-surface parity: every public name the reference exports at top level (flashinfer/__init__.py) must exist here,
 plus the main wrapper classes must expose the reference's public methods.  The list is frozen from the reference tree."""
+import pytest
+
 import flashinfer_b200 as fi
 
 REFERENCE_TOP_LEVEL = [
@@ -115,3 +117,36 @@ def test_submodule_entry_points():
     ]:
         missing = [n for n in names if not hasattr(mod, n)]
         assert not missing, (mod.__name__, missing)
+
+
+# reference file-level module paths (flashinfer/<path>.py) and one public name each must import from here too
+_REFERENCE_MODULE_PATHS = [
+    ("gemm.routergemm", "mm_M1_16_K7168_N256"), ("gemm.gemm_base", "mm_fp4"), ("fused_moe.fused_routing_dsv3", "fused_topk_deepseek"),
+    ("fused_moe.utils", "get_hybrid_num_tokens_buckets"), ("grouped_mm.core", "grouped_mm_fp8"),
+    ("quantization.fp4_quantization", "fp4_quantize"), ("quantization.fp8_quantization", "mxfp8_quantize"),
+    ("logits_processor.processors", "TopK"), ("logits_processor.types", "TensorType"), ("logits_processor.compiler", "compile_pipeline"),
+    ("parallel_attention.parallel_config", "VarlenCPConfig"), ("parallel_attention.parallel_attention", "ParallelAttention"),
+    ("parallel_attention.utils", "get_parallel_groups"), ("cudnn.prefill", "cudnn_batch_prefill_with_kv_cache"),
+    ("cudnn.decode", "cudnn_batch_decode_with_kv_cache"), ("version", "__version__"), ("moe_ep", "available_backends"),
+    ("comm.trtllm_ar", "trtllm_allreduce_fusion"), ("comm.vllm_ar", "all_reduce"), ("comm.trtllm_moe_alltoall", "MoeAlltoAll"),
+    ("fp4_quantization", "fp4_quantize"), ("fp8_quantization", "mxfp8_quantize"), ("gdn_decode", "gated_delta_rule_decode"),
+    ("deep_gemm", "m_grouped_fp8_gemm_nt_contiguous"), ("tllm_enums", "ActivationType"),
+]
+
+
+@pytest.mark.parametrize("path,name", _REFERENCE_MODULE_PATHS)
+def test_reference_module_paths_import(path, name):
+    import importlib
+
+    mod = importlib.import_module(f"flashinfer_b200.{path}")
+    assert hasattr(mod, name), f"flashinfer_b200.{path} lacks {name}"
+
+
+def test_moe_ep_probe_is_truthful():
+    from flashinfer_b200 import moe_ep
+
+    assert moe_ep.available_backends() == ["nvlink_a2a"] and not moe_ep.have_nccl_ep() and not moe_ep.have_nixl_ep()
+    with pytest.raises(moe_ep.MoEEpNotBuiltError):
+        moe_ep.create_fleet(None, 8, 2, 8, 64, backend="nccl_ep")
+    with pytest.raises(ValueError):
+        moe_ep.create_fleet(None, 8, 2, 8, 64, backend="bogus")

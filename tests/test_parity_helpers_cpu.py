@@ -187,3 +187,33 @@ def test_utils_helper_names_cpu():
     assert cuda_utils.checkCudaErrors((0, 5)) == 5 and cuda_utils.checkCudaErrors((0,)) is None
     with pytest.raises(RuntimeError):
         cuda_utils.checkCudaErrors((1, None))
+
+
+def test_fused_moe_utils_buckets_and_swizzle():
+    from flashinfer_b200.fused_moe import utils as u
+
+    assert u.get_hybrid_num_tokens_buckets(10000) == (1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 768, 1024, 1280, 1536, 1792, 2048,
+                                                      2560, 3072, 3584, 4096, 8192, 10000)
+    assert u.get_hybrid_num_tokens_buckets(300) == (1, 2, 4, 8, 16, 32, 64, 128, 256, 300)
+    grid = u.get_hybrid_num_tokens_buckets(10000)
+    for x in (1, 3, 255, 256, 257, 1000, 2048, 2049, 4000, 4097, 9999, 20000):
+        b = u.map_to_hybrid_bucket(x, 10000)
+        assert b in grid and (b >= x or b == 10000)
+        assert b == min(g for g in grid if g >= min(x, 10000))       # the smallest grid point that covers x
+    assert u.map_to_hybrid_bucket_uncapped(5000) == 8192 and u.map_to_hybrid_bucket(0, 64) == 1
+    assert u.round_to_nearest_bucket(350, [100, 200, 500, 1000]) == 200
+    assert u.round_to_nearest_bucket(350, [100, 200, 500, 1000], round_map=True) == 500
+    assert u.round_to_nearest_bucket(2000, [100, 200, 500, 1000], round_map=True) == 1000
+    assert u.make_bucket_mapper((500, 100, 100, 200))(5) == 100
+    assert (u.next_positive_power_of_2(5), u.last_positive_power_of_2(5), u.last_positive_power_of_2(8)) == (8, 4, 8)
+    sf = torch.randint(0, 255, (2, 200, 6), dtype=torch.uint8)
+    sw = u.swizzle_sf(sf, 200, 96)
+    assert sw.numel() == 2 * 256 * 8 and u.compute_swizzled_sf_shape(200, 6) == (256, 8)
+    assert torch.equal(u.unswizzle_sf(sw, 200, 96).view(2, 200, 6), sf)
+    sf2 = torch.randint(0, 255, (2, 128, 8), dtype=torch.uint8)
+    parts = torch.cat([u.swizzle_sf(sf2[i], 128, 128) for i in range(2)])
+    assert torch.equal(u.reswizzle_sf(parts, 128, 128), u.swizzle_sf(sf2.reshape(256, 8), 256, 128))
+    assert u.get_fp4_shape([4, 100, 64], 16) == ([4, 100, 32], 2048)
+    with u.model_extra_attrs({"a": 1}):
+        assert u.get_model_extra_attrs() == {"a": 1}
+    assert u.get_model_extra_attrs() is None
