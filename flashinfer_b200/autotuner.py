@@ -139,25 +139,102 @@ class OptimizationProfile:
         return self.get_opt_shapes()
 
 
+_measure = threading.local()
+
+
+def is_in_profile_measurement() -> bool:
+    """True while the tuner is timing a candidate on this thread (ops use it to skip logging / validation side effects)."""
+    return getattr(_measure, "depth", 0) > 0
+
+
+@contextlib.contextmanager
+def _profile_measurement_scope():
+    _measure.depth = getattr(_measure, "depth", 0) + 1
+    try:
+        yield
+    finally:
+        _measure.depth -= 1
+
+
+def _collect_metadata() -> Dict[str, str]:
+    """What a tuned-config file was measured on; a mismatch at load time is reported, not fatal."""
+    from .version import __version__
+
+    meta = {"package": f"flashinfer_b200 {__version__}", "torch": torch.__version__, "cuda": str(torch.version.cuda)}
+    if torch.cuda.is_available():
+        prop = torch.cuda.get_device_properties(torch.cuda.current_device())
+        meta.update(device=prop.name, sm=f"{prop.major}{prop.minor}", sm_count=str(prop.multi_processor_count))
+    else:
+        meta["device"] = "cpu"
+    return meta
+
+
+def get_config_path(is_module: bool = False) -> str:
+    """Where shipped tuned configs for the current device live: ``tuning_configs/<device>.json`` next to this file
+    (``is_module`` returns the dotted module-style name the reference uses for the same file)."""
+    dev = torch.cuda.get_device_name().replace(" ", "_") if torch.cuda.is_available() else "cpu"
+    name = f"v0_1_{dev}"
+    return f"flashinfer_b200.tuning_configs.{name}" if is_module else os.path.join(os.path.dirname(__file__), "tuning_configs", name + ".json")
+
+
+def _tactic_to_json(t):
+    return {"__tuple__": [_tactic_to_json(x) for x in t]} if isinstance(t, tuple) else t
+
+
+def _json_to_tactic(v):
+    if isinstance(v, dict) and "__tuple__" in v:
+        return tuple(_json_to_tactic(x) for x in v["__tuple__"])
+    return tuple(_json_to_tactic(x) for x in v) if isinstance(v, list) else v
+
+
 class AutoTuner:
     _instance: Optional["AutoTuner"] = None
     _lock = threading.Lock()
 
-    def __init__(self, warmup: int = 3, repeat: int = 10) -> None:
+    def __init__(self, warmup: int = 3, repeat: int = 10, stream_delay_micro_secs: int = 0) -> None:
         self.is_tuning_mode = False
         self.warmup, self.repeat = warmup, repeat
         self.profiling_cache: Dict[Tuple, Tuple[int, Any, float]] = {}
         self.stats = {"hits": 0, "misses": 0, "profiled": 0, "failed": 0}
         self._flush = None
+        self._overrides = threading.local()
 
-    @classmethod
     def reset_statistics(self) -> None:
         self.stats = {"hits": 0, "misses": 0, "profiled": 0, "failed": 0}
 
-    def get_effective_map_to_tuning_buckets(self, spec=None):
-        """The bucket mapper of a dynamic-dimension spec, or the default next-power-of-two bucketing."""
+    # ---- per-thread bucket overrides pushed by ``autotune(tuning_buckets=..., round_up=...)``
+    def _get_override_stack(self) -> List:
+        if not hasattr(self._overrides, "stack"):
+            self._overrides.stack = []
+        return self._overrides.stack
+
+    def _override_tuning_buckets(self) -> Optional[Tuple[int, ...]]:
+        for buckets, _ in reversed(self._get_override_stack()):
+            if buckets is not None:
+                return buckets
+        return None
+
+    def _override_round_up(self) -> bool:
+        for _, up in reversed(self._get_override_stack()):
+            if up is not None:
+                return up
+        return False
+
+    def get_effective_map_to_tuning_buckets(self, spec=None) -> Callable[[int], int]:
+        """The live-size -> bucket map in force: the innermost ``autotune()`` override, else the spec's own mapper, else
+        next-power-of-two."""
+        buckets, up = self._override_tuning_buckets(), self._override_round_up()
+        if buckets is not None:
+            from .fused_moe.utils import make_bucket_mapper
+
+            return make_bucket_mapper(buckets, round_map=up)
+        gen = tuple(sorted(set(getattr(spec, "gen_tuning_buckets", ()) or ())))
+        if up and gen:
+            from .fused_moe.utils import make_bucket_mapper
+
+            return make_bucket_mapper(gen, round_map=True)
         fn = getattr(spec, "map_to_tuning_buckets", None)
-        return fn if fn is not None else (lambda x: 1 << max(0, int(x) - 1).bit_length())
+        return fn if fn is not None else next_positive_power_of_2
 
     @classmethod
     def get(cls) -> "AutoTuner":
@@ -167,14 +244,13 @@ class AutoTuner:
             return cls._instance
 
     # ---- cache
-    @staticmethod
-    def _bucket_shapes(inputs: Sequence[Any], cfg: TuningConfig) -> Tuple:
-        shapes = [tuple(t.shape) if isinstance(t, torch.Tensor) else () for t in inputs]
-        shapes = [list(s) for s in shapes]
+    def _bucket_shapes(self, inputs: Sequence[Any], cfg: TuningConfig) -> Tuple:
+        shapes = [list(t.shape) if isinstance(t, (torch.Tensor, FakeTensor)) else [] for t in inputs]
         for spec in cfg.dynamic_tensor_specs:
+            mapper = self.get_effective_map_to_tuning_buckets(spec)
             for ii, dd in zip(spec.input_idx, spec.dim_idx):
                 if ii < len(shapes) and dd < len(shapes[ii]):
-                    shapes[ii][dd] = spec.map_to_tuning_buckets(shapes[ii][dd])
+                    shapes[ii][dd] = mapper(shapes[ii][dd])
         for c in cfg.constraint_specs:
             if c.input_idx < len(shapes) and c.dim_idx < len(shapes[c.input_idx]):
                 shapes[c.input_idx][c.dim_idx] = c.infer_shape([tuple(s) for s in shapes])
@@ -187,31 +263,55 @@ class AutoTuner:
         for i, r in enumerate(runners):
             hit = self.profiling_cache.get(self._key(op, r, shapes, extras))
             if hit is not None:
-                return True, hit[0], hit[1]
+                return True, i, hit[1]
         return False, 0, -1
 
     def clear_cache(self) -> None:
         self.profiling_cache.clear()
 
     def save_configs(self, path: str) -> None:
-        rows = [{"op": k[0], "runner": k[1], "shapes": [list(s) for s in k[2]], "extras": list(k[3]), "runner_id": v[0],
-                 "tactic": v[1], "ms": v[2]} for k, v in self.profiling_cache.items()]
-        with open(path, "w") as f:
-            json.dump({"device": torch.cuda.get_device_name() if torch.cuda.is_available() else "cpu", "configs": rows}, f, indent=1)
+        """Merge this process' choices into ``path`` (entries already in the file for other shapes are kept) and replace
+        the file atomically, so concurrent writers lose at most their own update, never the file."""
+        merged: Dict[Tuple, Tuple[int, Any, float]] = {}
+        if os.path.exists(path):
+            try:
+                other = AutoTuner()
+                other.load_configs(path)
+                merged.update(other.profiling_cache)
+            except (OSError, ValueError, KeyError):
+                pass
+        merged.update(self.profiling_cache)
+        rows = [{"op": k[0], "runner": k[1], "shapes": [list(s) for s in k[2]], "extras": _tactic_to_json(tuple(k[3])),
+                 "runner_id": v[0], "tactic": _tactic_to_json(v[1]), "ms": v[2]} for k, v in sorted(merged.items(), key=repr)]
+        tmp = f"{path}.{os.getpid()}.tmp"
+        with open(tmp, "w") as f:
+            json.dump({"metadata": _collect_metadata(), "configs": rows}, f, indent=1)
+        os.replace(tmp, path)
 
     def load_configs(self, path: str) -> int:
         with open(path) as f:
             data = json.load(f)
+        meta = data.get("metadata", {})
+        here = _collect_metadata()
+        for field_ in ("device", "sm"):
+            if field_ in meta and field_ in here and meta[field_] != here[field_]:
+                import warnings
+
+                warnings.warn(f"tuned configs in {path} were measured on {field_}={meta[field_]!r}, this process runs on "
+                              f"{here[field_]!r}; the choices are still valid tactics but may not be the fastest", RuntimeWarning)
+                break
         for r in data.get("configs", []):
-            tactic = r["tactic"]
-            if isinstance(tactic, list):
-                tactic = tuple(tactic)
-            key = (r["op"], r["runner"], tuple(tuple(s) for s in r["shapes"]), tuple(r.get("extras", [])))
-            self.profiling_cache[key] = (r.get("runner_id", 0), tactic, r.get("ms", 0.0))
+            extras = _json_to_tactic(r.get("extras", []))
+            key = (r["op"], r["runner"], tuple(tuple(s) for s in r["shapes"]), tuple(extras) if isinstance(extras, tuple) else ())
+            self.profiling_cache[key] = (r.get("runner_id", 0), _json_to_tactic(r["tactic"]), r.get("ms", 0.0))
         return len(data.get("configs", []))
 
     # ---- profiling
     def _time(self, runner: TunableRunner, inputs, tactic, cfg: TuningConfig, **kwargs) -> float:
+        with _profile_measurement_scope():
+            return self._time_inner(runner, inputs, tactic, cfg, **kwargs)
+
+    def _time_inner(self, runner: TunableRunner, inputs, tactic, cfg: TuningConfig, **kwargs) -> float:
         if not torch.cuda.is_available():
             import time
 
@@ -244,23 +344,32 @@ class AutoTuner:
         ts.sort()
         return ts[len(ts) // 2]
 
-    def choose_one(self, custom_op: str, runners: Sequence[TunableRunner], tuning_config: TuningConfig,
-                   inputs: List[torch.Tensor], extras: Tuple = (), **kwargs) -> Tuple[TunableRunner, Any]:
-        """Returns ``(runner, tactic)``: the cached best, or — inside ``autotune()`` — the freshly profiled best."""
-        shapes = self._bucket_shapes(inputs, tuning_config)
-        hit, rid, tactic = self.search_cache(custom_op, runners, shapes, extras)
-        if hit:
-            self.stats["hits"] += 1
-            return runners[rid], tactic
-        if not self.is_tuning_mode:
-            self.stats["misses"] += 1
-            return runners[0], -1
+    def _resized(self, inputs: List[Any], cfg: TuningConfig, spec: DynamicTensorSpec, size: int) -> List[Any]:
+        """Inputs with every dimension named by ``spec`` set to ``size`` (fresh tensors from the spec's initialisers,
+        default: random normal cast to the dtype) and the constraint dims re-derived."""
+        out = list(inputs)
+        for n, (ii, dd) in enumerate(zip(spec.input_idx, spec.dim_idx)):
+            t = out[ii]
+            shape = list(t.shape)
+            shape[dd] = size
+            init = spec.tensor_initializers[n] if n < len(spec.tensor_initializers) else None
+            out[ii] = init(shape, t.dtype, t.device) if init is not None else _default_init(shape, t.dtype, t.device)
+        for c in cfg.constraint_specs:
+            t = out[c.input_idx]
+            want = c.infer_shape([tuple(x.shape) if isinstance(x, torch.Tensor) else () for x in out])
+            if t.shape[c.dim_idx] != want:
+                shape = list(t.shape)
+                shape[c.dim_idx] = want
+                out[c.input_idx] = _default_init(shape, t.dtype, t.device)
+        return out
+
+    def _profile(self, custom_op, runners, cfg, inputs, shapes, extras, **kwargs):
         best = (float("inf"), 0, -1)
         prof = OptimizationProfile([tuple(s) for s in shapes])
         for rid, r in enumerate(runners):
             for tac in r.get_valid_tactics(inputs, prof):
                 try:
-                    ms = self._time(r, inputs, tac, tuning_config, **kwargs)
+                    ms = self._time(r, inputs, tac, cfg, **kwargs)
                     self.stats["profiled"] += 1
                 except Exception:  # noqa: BLE001 - a tactic that cannot run is simply not a candidate
                     self.stats["failed"] += 1
@@ -269,22 +378,81 @@ class AutoTuner:
                     best = (ms, rid, tac)
         ms, rid, tac = best
         self.profiling_cache[self._key(custom_op, runners[rid], shapes, extras)] = (rid, tac, ms)
-        return runners[rid], tac
+        return rid, tac
+
+    def choose_one(self, custom_op: str, runners: Sequence[TunableRunner], tuning_config: TuningConfig,
+                   inputs: List[torch.Tensor], extras: Tuple = (), **kwargs) -> Tuple[TunableRunner, Any]:
+        """Returns ``(runner, tactic)``: the cached best, or - inside ``autotune()`` - the freshly profiled best.
+
+        In tuning mode a miss profiles the live shape's bucket and, when the config names ``gen_tuning_buckets`` (or an
+        ``autotune(tuning_buckets=...)`` override is active), every other listed bucket as well on synthetic inputs, so
+        one warm-up pass covers the whole serving range (reference autotuner.py:1045-1330)."""
+        shapes = self._bucket_shapes(inputs, tuning_config)
+        hit, rid, tactic = self.search_cache(custom_op, runners, shapes, extras)
+        if hit:
+            self.stats["hits"] += 1
+            return runners[rid], tactic
+        if not self.is_tuning_mode:
+            self.stats["misses"] += 1
+            return runners[0], -1
+        rid, tactic = self._profile(custom_op, runners, tuning_config, inputs, shapes, extras, **kwargs)
+        for spec in tuning_config.dynamic_tensor_specs:
+            sizes = self._override_tuning_buckets() or tuple(spec.gen_tuning_buckets or ())
+            for size in sizes:
+                try:
+                    alt = self._resized(inputs, tuning_config, spec, int(size))
+                except Exception:  # noqa: BLE001 - inputs that cannot be synthesised are tuned when they show up live
+                    continue
+                alt_shapes = self._bucket_shapes(alt, tuning_config)
+                if not self.search_cache(custom_op, runners, alt_shapes, extras)[0]:
+                    self._profile(custom_op, runners, tuning_config, alt, alt_shapes, extras, **kwargs)
+        return runners[rid], tactic
+
+
+def _default_init(shape, dtype, device):
+    if dtype.is_floating_point and dtype.itemsize >= 2:
+        return torch.randn(shape, device=device, dtype=torch.float32).to(dtype)
+    if dtype.is_floating_point:                      # fp8: cast from a bounded normal
+        return (torch.randn(shape, device=device) * 0.5).to(dtype)
+    return torch.zeros(shape, dtype=dtype, device=device)
 
 
 @contextlib.contextmanager
-def autotune(tune_mode: bool = True, cache_path: Optional[str] = None):
+def autotune(tune_mode: bool = True, cache: Optional[str] = None, tuning_buckets: Optional[Sequence[int]] = None,
+             round_up: Optional[bool] = None, cache_path: Optional[str] = None):
     """``with autotune():`` profiles every tunable op reached inside the block and caches the winners.
-    ``cache_path`` (or ``$FLASHINFER_AUTOTUNER_CACHE``) loads existing choices first and saves on exit."""
+
+    ``cache`` (or ``$FLASHINFER_AUTOTUNER_CACHE``; ``cache_path`` is the older spelling) names a JSON file that is loaded on
+    entry and merged + saved on exit when tuning.  ``tuning_buckets`` replaces every op's dynamic-dimension buckets inside
+    the block; ``round_up`` picks ceil instead of floor when mapping a live size onto them.  Overrides nest per thread and
+    ``None`` inherits from the enclosing block (reference autotuner.py:465-660)."""
+    if tuning_buckets is not None:
+        tuning_buckets = tuple(sorted({int(b) for b in tuning_buckets}))
+        if not tuning_buckets:
+            raise ValueError("tuning_buckets must contain at least one value")
     tuner = AutoTuner.get()
-    cache_path = cache_path or os.environ.get("FLASHINFER_AUTOTUNER_CACHE")
-    if cache_path and os.path.exists(cache_path):
-        tuner.load_configs(cache_path)
+    path = cache or cache_path or os.environ.get("FLASHINFER_AUTOTUNER_CACHE")
+    if path and os.path.exists(path):
+        tuner.load_configs(path)
     old = tuner.is_tuning_mode
     tuner.is_tuning_mode = tune_mode
+    stack = tuner._get_override_stack()
+    stack.append((tuning_buckets, round_up))
     try:
         yield tuner
     finally:
+        stack.pop()
         tuner.is_tuning_mode = old
-        if cache_path and tune_mode:
-            tuner.save_configs(cache_path)
+        if path and tune_mode:
+            tuner.save_configs(path)
+
+
+def load_from_file(key) -> Tuple[bool, int, Any]:
+    """Look ``key = (op, runner class name, shapes, extras)`` up in the shipped config file for this device."""
+    path = get_config_path()
+    if not os.path.exists(path):
+        return False, 0, -1
+    t = AutoTuner()
+    t.load_configs(path)
+    hit = t.profiling_cache.get(tuple(key))
+    return (True, hit[0], hit[1]) if hit is not None else (False, 0, -1)

@@ -15,6 +15,7 @@ from typing import Optional, Tuple
 import torch
 
 from .. import jit
+from ..autotuner import AutoTuner, DynamicTensorSpec, TunableRunner, TuningConfig
 from ..quantization.fp4 import _swizzled_sf_size, _unswizzle_index, block_scale_interleave, e2m1_and_ufp8sf_scale_to_float
 from ..utils import dtype_code, stream_ptr
 
@@ -58,15 +59,11 @@ def _sf_swizzled(sf: torch.Tensor, rows: int, kc: int, batch: int = 1, swizzled:
     raise ValueError(f"scale tensor of shape {tuple(sf.shape)} is neither swizzled ({per} bytes) nor linear [{rows}, {kc}]")
 
 
-def _launch(kind: str, a: torch.Tensor, b_nk: torch.Tensor, out: torch.Tensor, sfa, sfb, alpha_a, alpha_b, K: int,
-            bn: int = 0, tile_expert: Optional[torch.Tensor] = None, meta: Optional[torch.Tensor] = None,
-            row_map: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """a ``[B, M, Kbytes]``, b_nk ``[B, N, Kbytes]`` (uint8 / fp8 storage, K contiguous), out ``[B, M, N]``."""
+def _launch_raw(kind: str, a, b_nk, out, sfa, sfb, alpha_a, alpha_b, K: int, bn: int, tile_expert, meta, row_map):
     B, M, _ = a.shape
     if tile_expert is not None:
         B = b_nk.shape[0]  # grouped: experts
     N = b_nk.shape[1]
-    bn = bn or int(os.environ.get("FIB200_LOWP_BN", "0"))
     a_fmt = _FP8_FMT.get(a.dtype, 0)
     b_fmt = _FP8_FMT.get(b_nk.dtype, 0)
     jit.load("gemm_blockscaled_sm100").call(
@@ -75,6 +72,43 @@ def _launch(kind: str, a: torch.Tensor, b_nk: torch.Tensor, out: torch.Tensor, s
         sfb.stride(0) if sfb is not None else 0, _KIND[kind], a_fmt, b_fmt, dtype_code(out.dtype), bn, tile_expert, meta,
         row_map, 1, stream_ptr(a))
     return out
+
+
+class _TileNRunner(TunableRunner):
+    """Tactic = the N-tile width of the tcgen05 pipeline (``-1``: the launcher's wave-quantisation heuristic)."""
+
+    def __init__(self, kind, sfa, sfb, alpha_a, alpha_b, K):
+        self.args = (kind, sfa, sfb, alpha_a, alpha_b, K)
+
+    def get_valid_tactics(self, inputs, profile):
+        n = inputs[1].shape[1]
+        return [-1] + [w for w in (64, 128, 192, 256) if w <= max(64, n)]
+
+    def forward(self, inputs, tactic=-1, do_preparation=False, **kwargs):
+        kind, sfa, sfb, alpha_a, alpha_b, K = self.args
+        a, b_nk, out = inputs
+        return _launch_raw(kind, a, b_nk, out, sfa, sfb, alpha_a, alpha_b, K, max(int(tactic), 0), None, None, None)
+
+
+_TILE_N_CFG = TuningConfig(dynamic_tensor_specs=(DynamicTensorSpec((0, 2), (1, 1)),), use_cold_l2_cache=True)
+
+
+def _launch(kind: str, a: torch.Tensor, b_nk: torch.Tensor, out: torch.Tensor, sfa, sfb, alpha_a, alpha_b, K: int,
+            bn: int = 0, tile_expert: Optional[torch.Tensor] = None, meta: Optional[torch.Tensor] = None,
+            row_map: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """a ``[B, M, Kbytes]``, b_nk ``[B, N, Kbytes]`` (uint8 / fp8 storage, K contiguous), out ``[B, M, N]``.
+
+    ``bn == 0`` lets the launcher pick the N tile; inside ``with autotune():`` (or once tuned configs are loaded) the dense
+    path asks the tuner first, keyed by (kind, dtypes, batch, bucketed M, N, K)."""
+    bn = bn or int(os.environ.get("FIB200_LOWP_BN", "0"))
+    if bn == 0 and tile_expert is None:
+        tuner = AutoTuner.get()
+        if tuner.is_tuning_mode or tuner.profiling_cache:
+            runner = _TileNRunner(kind, sfa, sfb, alpha_a, alpha_b, K)
+            _, tactic = tuner.choose_one("gemm_lowp_nt", [runner], _TILE_N_CFG, [a, b_nk, out],
+                                         extras=(kind, str(a.dtype), str(out.dtype)))
+            bn = max(int(tactic), 0)
+    return _launch_raw(kind, a, b_nk, out, sfa, sfb, alpha_a, alpha_b, K, bn, tile_expert, meta, row_map)
 
 
 def _prep(a: torch.Tensor, b: torch.Tensor):

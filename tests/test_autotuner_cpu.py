@@ -1,0 +1,137 @@
+"""Autotuner host logic on CPU: tactic choice, bucket mapping + overrides, config file round trip (reference
+tests/autotuner/test_autotuner_core.py, test_autotuner_tile_mismatch.py for the strategy)."""
+import json
+import time
+
+import pytest
+import torch
+
+from flashinfer_b200.autotuner import (AutoTuner, ConstraintSpec, DynamicTensorSpec, TunableRunner, TuningConfig, autotune,
+                                       is_in_profile_measurement)
+
+
+class SleepRunner(TunableRunner):
+    """Tactic t sleeps cost[t] ms; tactic 3 always fails."""
+    cost = {-1: 3.0, 0: 2.0, 1: 0.2, 2: 1.0}
+
+    def __init__(self):
+        self.calls = []
+        self.seen_measure_flag = []
+
+    def get_valid_tactics(self, inputs, profile):
+        return [0, 1, 2, 3]
+
+    def forward(self, inputs, tactic=-1, do_preparation=False, **kwargs):
+        self.calls.append((tuple(inputs[0].shape), tactic))
+        self.seen_measure_flag.append(is_in_profile_measurement())
+        if tactic == 3:
+            raise RuntimeError("unsupported tile")
+        time.sleep(self.cost[tactic] * 1e-3)
+        return inputs[0] * 2
+
+
+@pytest.fixture()
+def tuner():
+    t = AutoTuner.get()
+    t.clear_cache()
+    t.reset_statistics()
+    yield t
+    t.clear_cache()
+
+
+def _cfg(buckets=()):
+    return TuningConfig(dynamic_tensor_specs=(DynamicTensorSpec((0, 1), (0, 0), tuple(buckets)),),
+                        constraint_specs=(ConstraintSpec(1, 1, lambda shapes: shapes[0][1] * 2),), use_cold_l2_cache=False)
+
+
+def test_choose_one_profiles_only_inside_autotune(tuner):
+    r = SleepRunner()
+    x = [torch.zeros(5, 8), torch.zeros(5, 16)]
+    runner, tac = tuner.choose_one("op", [r], _cfg(), x)
+    assert tac == -1 and not r.calls and tuner.stats["misses"] == 1
+    with autotune():
+        runner, tac = tuner.choose_one("op", [r], _cfg(), x)
+    assert runner is r and tac == 1 and tuner.stats["failed"] == 1 and tuner.stats["profiled"] == 3
+    assert all(r.seen_measure_flag) and not is_in_profile_measurement()
+    n = len(r.calls)
+    # 5 and 7 share the bucket 8: served from the cache, outside tuning mode too
+    runner, tac = tuner.choose_one("op", [r], _cfg(), [torch.zeros(7, 8), torch.zeros(7, 16)])
+    assert tac == 1 and len(r.calls) == n and tuner.stats["hits"] == 1
+    # a different static dim is a different key
+    assert tuner.choose_one("op", [r], _cfg(), [torch.zeros(7, 4), torch.zeros(7, 8)])[1] == -1
+
+
+def test_gen_tuning_buckets_are_all_profiled(tuner):
+    r = SleepRunner()
+    with autotune():
+        tuner.choose_one("op", [r], _cfg((2, 64)), [torch.zeros(5, 8), torch.zeros(5, 16)])
+    keys = {k[2] for k in tuner.profiling_cache}
+    assert keys == {((8, 8), (8, 16)), ((2, 8), (2, 16)), ((64, 8), (64, 16))}
+    assert {c[0][0] for c in r.calls} == {5, 2, 64}            # live shape + one synthetic input per listed bucket
+
+
+def test_bucket_overrides_nest_and_round(tuner):
+    spec = DynamicTensorSpec((0,), (0,), (16, 32, 64))
+    assert tuner.get_effective_map_to_tuning_buckets(spec)(200) == 256
+    with autotune(False, tuning_buckets=(512, 128, 128, 256)):
+        m = tuner.get_effective_map_to_tuning_buckets(spec)
+        assert (m(200), m(100), m(5000)) == (128, 128, 512)     # floor, clamped
+        with autotune(False, round_up=True):
+            m = tuner.get_effective_map_to_tuning_buckets(spec)
+            assert (m(200), m(100), m(5000)) == (256, 128, 512)  # buckets inherited, ceil
+        assert tuner.get_effective_map_to_tuning_buckets(spec)(200) == 128
+    with autotune(False, round_up=True):
+        assert tuner.get_effective_map_to_tuning_buckets(spec)(20) == 32   # ceil over the spec's own buckets
+    assert tuner.get_effective_map_to_tuning_buckets(spec)(200) == 256
+    with pytest.raises(ValueError):
+        with autotune(tuning_buckets=()):
+            pass
+
+
+def test_config_file_roundtrip_and_merge(tuner, tmp_path):
+    path = str(tmp_path / "tuned.json")
+    r = SleepRunner()
+    with autotune(cache=path):
+        tuner.choose_one("op_a", [r], _cfg(), [torch.zeros(5, 8), torch.zeros(5, 16)], extras=("bf16", (1, 2)))
+    data = json.load(open(path))
+    assert data["metadata"]["device"] == "cpu" and len(data["configs"]) == 1
+    tuner.clear_cache()
+    with autotune(cache=path):                                   # second process: adds op_b, must keep op_a
+        tuner.clear_cache()
+        tuner.choose_one("op_b", [r], _cfg(), [torch.zeros(9, 8), torch.zeros(9, 16)])
+    fresh = AutoTuner()
+    assert fresh.load_configs(path) == 2
+    hit, rid, tac = fresh.search_cache("op_a", [r], ((8, 8), (8, 16)), ("bf16", (1, 2)))
+    assert hit and tac == 1
+    assert fresh.search_cache("op_b", [r], ((16, 8), (16, 16)))[0]
+    # a file from another device loads with a warning
+    data["metadata"]["device"] = "NVIDIA H100"
+    json.dump(data, open(path, "w"))
+    with pytest.warns(RuntimeWarning):
+        AutoTuner().load_configs(path)
+
+
+def test_lowp_gemm_asks_the_tuner_for_its_n_tile(tuner, monkeypatch):
+    """The block-scaled GEMM wrapper consults the tuner only when it is tuning or holds configs, passes the chosen N tile
+    to the launcher and keys the choice by the bucketed M (the native launch is replaced: no GPU here)."""
+    from flashinfer_b200.gemm import lowp
+
+    seen = []
+
+    def fake_raw(kind, a, b_nk, out, sfa, sfb, alpha_a, alpha_b, K, bn, tile_expert, meta, row_map):
+        seen.append(bn)
+        time.sleep({0: 2e-3, 64: 3e-3, 128: 2e-4, 192: 1e-3, 256: 1e-3}[bn])
+        return out
+
+    monkeypatch.setattr(lowp, "_launch_raw", fake_raw)
+    a, b, o = torch.zeros(1, 48, 64, dtype=torch.uint8), torch.zeros(1, 512, 64, dtype=torch.uint8), torch.zeros(1, 48, 512)
+    lowp._launch("fp8", a, b, o, None, None, None, None, 64)
+    assert seen == [0]                                           # idle tuner: one launch, heuristic tile
+    with autotune():
+        lowp._launch("fp8", a, b, o, None, None, None, None, 64)
+    assert seen[-1] == 128 and set(seen) == {0, 64, 128, 192, 256}
+    seen.clear()
+    a2, o2 = torch.zeros(1, 60, 64, dtype=torch.uint8), torch.zeros(1, 60, 512)
+    lowp._launch("fp8", a2, b, o2, None, None, None, None, 64)   # same M bucket (64): cached choice, no profiling
+    lowp._launch("fp8", a2, b, o2, None, None, None, None, 64, bn=256)   # an explicit tile always wins
+    assert seen == [128, 256]
