@@ -106,6 +106,7 @@ from .gemm import SegmentGEMMWrapper, grouped_mm_bf16  # noqa: F401,E402
 from .gemm import bmm_fp8, bmm_mxfp8, gemm_fp8_nt_groupwise, mm_fp4, mm_fp8, mm_mxfp8  # noqa: F401,E402
 from . import api_logging, autotuner, fi_trace, green_ctx, logits_processor, parallel_attention, profiler, testing, trace  # noqa: F401,E402
 from .autotuner import autotune  # noqa: F401,E402
+from .fi_trace import fi_trace  # noqa: F401,E402,F811  (the function shadows the module attribute, as in the reference)
 from .api_logging import flashinfer_api  # noqa: F401,E402
 from . import comm, mla, attention  # noqa: F401,E402
 from . import concat_ops, diffusion_ops, dsv3_ops, gdn, mamba  # noqa: F401,E402
@@ -140,3 +141,6 @@ from .xqa import xqa, xqa_mla  # noqa: F401,E402
 def get_fp4_quantization_module(backend: str = "100"):
     """Reference fp4_quantization.py: returns the JIT module object behind the FP4 quantisers; here the native library."""
     return jit.load("quantization")
+
+
+trace.attach()  # bind op templates (wraps the ops only when FLASHINFER_TRACE_DUMP / FLASHINFER_TRACE_DIR is set)

@@ -1,0 +1,97 @@
+"""Which public function carries which template.
+
+``attach()`` runs at package import: with dumping off it only hangs ``.fi_trace`` / ``.__fi_trace_template__`` on the
+functions (the objects users call are the undecorated originals); with dumping on - at import through the environment,
+or later through :func:`enable` - it swaps the bound names for tracing wrappers, in their home module and wherever
+``flashinfer_b200`` re-exports them."""
+from __future__ import annotations
+
+import importlib
+import sys
+from typing import Dict, List, Optional, Tuple
+
+from . import template as _t
+from . import templates as T
+
+# (home module, attribute path, template)
+BINDINGS: List[Tuple[str, str, "_t.TraceTemplate"]] = [
+    ("norm", "rmsnorm", T.rmsnorm_trace),
+    ("norm", "fused_add_rmsnorm", T.fused_add_rmsnorm_trace),
+    ("norm", "gemma_rmsnorm", T.gemma_rmsnorm_trace),
+    ("norm", "gemma_fused_add_rmsnorm", T.gemma_fused_add_rmsnorm_trace),
+    ("norm", "layernorm", T.layernorm_trace),
+    ("norm", "rmsnorm_quant", T.rmsnorm_quant_trace),
+    ("norm", "fused_add_rmsnorm_quant", T.fused_add_rmsnorm_quant_trace),
+    ("activation", "silu_and_mul", T.silu_and_mul_trace),
+    ("activation", "gelu_and_mul", T.gelu_and_mul_trace),
+    ("activation", "gelu_tanh_and_mul", T.gelu_tanh_and_mul_trace),
+]
+
+_PKG = __name__.rsplit(".", 2)[0]
+_originals: Dict[Tuple[str, str], object] = {}
+
+
+def _resolve(mod_name: str, path: str):
+    owner = importlib.import_module(f"{_PKG}.{mod_name}")
+    parts = path.split(".")
+    for p in parts[:-1]:
+        owner = getattr(owner, p)
+    return owner, parts[-1]
+
+
+def _rebind(old, new) -> None:
+    """Point every re-export of ``old`` inside the package at ``new``."""
+    for name, mod in list(sys.modules.items()):
+        if mod is None or not (name == _PKG or name.startswith(_PKG + ".")):
+            continue
+        for attr, val in list(vars(mod).items()):
+            if val is old:
+                setattr(mod, attr, new)
+
+
+def attach() -> int:
+    """Bind templates to functions (idempotent).  Returns the number of bound callables."""
+    n = 0
+    for mod_name, path, tpl in BINDINGS:
+        try:
+            owner, attr = _resolve(mod_name, path)
+            fn = getattr(owner, attr)
+        except (ImportError, AttributeError):
+            continue
+        base = getattr(fn, "__wrapped_untraced__", fn)
+        tpl.fi_api = f"{_PKG}.{mod_name}.{path}"
+        _originals.setdefault((mod_name, path), base)
+        if _t.dump_dir():
+            if fn is base:
+                wrapped = _t.traced(base, tpl)
+                setattr(owner, attr, wrapped)
+                if "." not in path:
+                    _rebind(base, wrapped)
+        else:
+            if fn is not base:
+                setattr(owner, attr, base)
+                if "." not in path:
+                    _rebind(fn, base)
+            try:
+                base.__fi_trace_template__ = tpl
+                base.fi_trace = tpl.build_fi_trace_fn()
+            except AttributeError:
+                pass
+        n += 1
+    return n
+
+
+def enable(directory: str) -> None:
+    """Start writing one definition file per unique traced call under ``directory``."""
+    _t._State.dump_dir = str(directory)
+    attach()
+
+
+def disable() -> None:
+    _t._State.dump_dir = None
+    attach()
+
+
+def template_of(fn) -> Optional["_t.TraceTemplate"]:
+    fn = getattr(fn, "__func__", fn)
+    return getattr(fn, "__fi_trace_template__", None)

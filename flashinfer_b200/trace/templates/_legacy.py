@@ -1,13 +1,5 @@
 """Op templates (one per category; reference flashinfer/trace/templates/*.py)."""
-from .. import reference as _ref
-from .template import Const, Scalar, Tensor, TraceTemplate, Var
-
-rmsnorm_trace = TraceTemplate(
-    op_type="rmsnorm", name_fmt="rmsnorm_h{hidden_size}",
-    axes=[Var("batch_size"), Const("hidden_size")],
-    inputs=[Tensor("input", ("batch_size", "hidden_size")), Tensor("weight", ("hidden_size",)), Scalar("eps")],
-    outputs=[Tensor("output", ("batch_size", "hidden_size"))], reference=getattr(_ref, "rmsnorm", None), tags=("norm",),
-    description="Root-mean-square layer normalisation")
+from ..template import Const, Scalar, Tensor, TraceTemplate, Var
 
 gemm_bf16_trace = TraceTemplate(
     op_type="gemm", name_fmt="gemm_bf16_n{N}_k{K}", axes=[Var("M"), Const("N"), Const("K")],

@@ -1,0 +1,118 @@
+"""fi_trace templates: every bound template must (1) name real parameters of the API it is bound to, (2) produce a
+well-formed definition, and (3) carry a reference implementation that agrees with the API on inputs built by its own
+``init`` (reference tests/trace/test_*_reference_correctness.py + test_fi_trace_template_consistency.py, as one generic
+test).  Runs on CPU through the ops' eager paths; the same harness is device-agnostic."""
+import inspect
+import json
+
+import pytest
+import torch
+
+import flashinfer_b200 as fi
+from flashinfer_b200.trace import BINDINGS, Const, Scalar, Tensor, Var
+from flashinfer_b200.trace.bindings import _resolve
+
+# tolerance classes (reference tests/trace/reference_correctness_standards.md)
+TOLERANCE = {
+    "exact": dict(atol=0.0, rtol=0.0),
+    "bf16_norm": dict(atol=2e-2, rtol=2e-2),
+    "bf16": dict(atol=3e-2, rtol=3e-2),
+    "fp32": dict(atol=1e-5, rtol=1e-5),
+    "fp8_quant": dict(atol=0.0, rtol=0.13),     # one e4m3 step
+}
+
+_IDS = [f"{m}.{p}" for m, p, _ in BINDINGS]
+
+
+def _api(mod, path):
+    owner, attr = _resolve(mod, path)
+    return getattr(owner, attr)
+
+
+@pytest.mark.parametrize("mod,path,tpl", BINDINGS, ids=_IDS)
+def test_template_names_real_parameters(mod, path, tpl):
+    params = inspect.signature(_api(mod, path)).parameters
+    for spec in tpl.inputs:
+        assert spec.source in params, f"{tpl.key}: input '{spec.name}' reads API parameter '{spec.source}' which does not exist"
+    for spec in tpl.outputs:
+        if spec.param is not None:
+            assert spec.param in params
+    axis_names = {a.name for a in tpl.axes}
+    assert all(isinstance(a, (Const, Var)) for a in tpl.axes)
+    derived = set()
+    for spec in list(tpl.inputs) + list(tpl.outputs):
+        if isinstance(spec, Tensor):
+            derived |= set(spec.axes) - axis_names
+    # axes used in shapes but not declared must be explained by a constraint
+    for ax in derived:
+        assert any(ax in c for c in tpl.constraints), f"{tpl.key}: axis '{ax}' is neither declared nor constrained"
+    if tpl.reference is not None:
+        ref_params = set(inspect.signature(tpl.reference).parameters)
+        assert ref_params <= {s.name for s in tpl.inputs}, f"{tpl.key}: reference takes arguments the template does not list"
+
+
+@pytest.mark.parametrize("mod,path,tpl", [b for b in BINDINGS if b[2].init is not None], ids=[i for i, b in zip(_IDS, BINDINGS) if b[2].init is not None])
+def test_reference_matches_api(mod, path, tpl):
+    api = _api(mod, path)
+    sizes = dict(tpl.test_sizes or {})
+    accepted = inspect.signature(tpl.init).parameters
+    for a in tpl.axes:
+        if a.name in accepted and a.name not in sizes:
+            sizes[a.name] = 5 if isinstance(a, Var) else (128 if "size" in a.name or "dim" in a.name else 4)
+    kwargs = tpl.make_inputs(device="cpu", seed=1, **sizes)
+    ref_in = {k: (v.clone() if isinstance(v, torch.Tensor) else tuple(t.clone() for t in v) if isinstance(v, tuple) else v)
+              for k, v in kwargs.items()}
+    expect = tpl.run_reference(ref_in)
+    expect = list(expect) if isinstance(expect, (tuple, list)) else [expect]
+    got = tpl.collect_outputs(api(**kwargs), kwargs)
+    assert len(got) >= len(expect) > 0
+    tol = TOLERANCE[tpl.tolerance]
+    for spec, g, e in zip(tpl.outputs, got, expect):
+        assert isinstance(g, torch.Tensor), f"{tpl.key}: output '{spec.name}' missing"
+        assert g.shape == e.shape, f"{tpl.key}: output '{spec.name}' shape {tuple(g.shape)} vs reference {tuple(e.shape)}"
+        if tol["atol"] == 0.0 and tol["rtol"] == 0.0:
+            assert torch.equal(g, e), f"{tpl.key}: output '{spec.name}' differs"
+        else:
+            torch.testing.assert_close(g.float(), e.float(), **tol, msg=lambda m: f"{tpl.key}/{spec.name}: {m}")
+    # the definition of this very call is well formed and names the const axes
+    d = api.fi_trace(**kwargs) if hasattr(api, "fi_trace") else tpl.definition(kwargs)
+    json.dumps(d)
+    assert d["op_type"] == tpl.op_type and "{" not in d["name"]
+    for a in tpl.axes:
+        if isinstance(a, Const):
+            assert d["axes"][a.name]["value"] is not None, f"{tpl.key}: const axis '{a.name}' not resolved from the call"
+    assert all(v["dtype"] != "unknown" for k, v in d["inputs"].items() if not v.get("optional"))
+
+
+def test_enable_disable_swaps_wrappers_and_dumps_once(tmp_path):
+    x, w = torch.randn(4, 256).bfloat16(), torch.ones(256).bfloat16()
+    plain = fi.rmsnorm
+    assert fi.trace.dump_dir() is None and not hasattr(plain, "__wrapped_untraced__")
+    fi.trace.enable(str(tmp_path))
+    try:
+        assert fi.rmsnorm is not plain and fi.norm.rmsnorm is fi.rmsnorm and fi.rmsnorm.__wrapped_untraced__ is plain
+        fi.rmsnorm(x, w)
+        f = tmp_path / "rmsnorm" / "rmsnorm_h256.json"
+        stamp = f.stat().st_mtime_ns
+        fi.rmsnorm(x, w)                                   # same definition: not rewritten
+        assert f.stat().st_mtime_ns == stamp
+        fi.rmsnorm(torch.randn(2, 512).bfloat16(), torch.ones(512).bfloat16())
+        assert (tmp_path / "rmsnorm" / "rmsnorm_h512.json").exists()
+        d = json.loads(f.read_text())
+        assert d["axes"]["hidden_size"] == {"type": "const", "value": 256} and "def _rmsnorm_reference" in d["reference"]
+        ns = {"torch": torch}
+        exec(d["reference"], ns)                           # the embedded source runs on its own
+        torch.testing.assert_close(ns["_rmsnorm_reference"](x, w).float(), plain(x, w).float(), atol=2e-2, rtol=2e-2)
+    finally:
+        fi.trace.disable()
+    assert fi.rmsnorm is plain and fi.norm.rmsnorm is plain
+
+
+def test_fi_trace_user_api(tmp_path):
+    x = torch.randn(3, 512).bfloat16()
+    d = fi.fi_trace(fi.silu_and_mul, input=x)
+    assert d["name"] == "silu_and_mul_h256" and d["tags"][0] == "fi_api:flashinfer_b200.activation.silu_and_mul"
+    fi.fi_trace(fi.silu_and_mul, save_dir=str(tmp_path), input=x)
+    assert (tmp_path / "activation" / "silu_and_mul_h256.json").exists()
+    with pytest.raises(ValueError):
+        fi.fi_trace(torch.relu, input=x)
