@@ -25,6 +25,28 @@ BINDINGS: List[Tuple[str, str, "_t.TraceTemplate"]] = [
     ("activation", "silu_and_mul", T.silu_and_mul_trace),
     ("activation", "gelu_and_mul", T.gelu_and_mul_trace),
     ("activation", "gelu_tanh_and_mul", T.gelu_tanh_and_mul_trace),
+    ("rope", "apply_rope", T.apply_rope_trace),
+    ("rope", "apply_rope_inplace", T.apply_rope_inplace_trace),
+    ("rope", "apply_rope_pos_ids", T.apply_rope_pos_ids_trace),
+    ("rope", "apply_rope_pos_ids_inplace", T.apply_rope_pos_ids_inplace_trace),
+    ("rope", "apply_llama31_rope", T.apply_llama31_rope_trace),
+    ("rope", "apply_llama31_rope_inplace", T.apply_llama31_rope_inplace_trace),
+    ("rope", "apply_llama31_rope_pos_ids", T.apply_llama31_rope_pos_ids_trace),
+    ("rope", "apply_llama31_rope_pos_ids_inplace", T.apply_llama31_rope_pos_ids_inplace_trace),
+    ("rope", "apply_rope_with_cos_sin_cache", T.apply_rope_with_cos_sin_cache_trace),
+    ("rope", "apply_rope_with_cos_sin_cache_inplace", T.apply_rope_with_cos_sin_cache_inplace_trace),
+    ("sampling", "softmax", T.softmax_trace),
+    ("sampling", "top_k_renorm_probs", T.top_k_renorm_probs_trace),
+    ("sampling", "top_p_renorm_probs", T.top_p_renorm_probs_trace),
+    ("sampling", "top_k_mask_logits", T.top_k_mask_logits_trace),
+    ("sampling", "sampling_from_probs", T.sampling_from_probs_trace),
+    ("sampling", "sampling_from_logits", T.sampling_from_logits_trace),
+    ("sampling", "top_k_sampling_from_probs", T.top_k_sampling_from_probs_trace),
+    ("sampling", "top_p_sampling_from_probs", T.top_p_sampling_from_probs_trace),
+    ("sampling", "min_p_sampling_from_probs", T.min_p_sampling_from_probs_trace),
+    ("sampling", "top_k_top_p_sampling_from_probs", T.top_k_top_p_sampling_from_probs_trace),
+    ("sampling", "top_k_top_p_sampling_from_logits", T.top_k_top_p_sampling_from_logits_trace),
+    ("sampling", "chain_speculative_sampling", T.chain_speculative_sampling_trace),
 ]
 
 _PKG = __name__.rsplit(".", 2)[0]

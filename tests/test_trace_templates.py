@@ -19,6 +19,7 @@ TOLERANCE = {
     "bf16": dict(atol=3e-2, rtol=3e-2),
     "fp32": dict(atol=1e-5, rtol=1e-5),
     "fp8_quant": dict(atol=0.0, rtol=0.13),     # one e4m3 step
+    "support": None,                            # stochastic: the reference is the mask of tokens that may be emitted
 }
 
 _IDS = [f"{m}.{p}" for m, p, _ in BINDINGS]
@@ -69,6 +70,12 @@ def test_reference_matches_api(mod, path, tpl):
     tol = TOLERANCE[tpl.tolerance]
     for spec, g, e in zip(tpl.outputs, got, expect):
         assert isinstance(g, torch.Tensor), f"{tpl.key}: output '{spec.name}' missing"
+        if tol is None:
+            assert e.dtype == torch.bool and g.shape == e.shape[:1]
+            assert e[torch.arange(g.numel()), g.long()].all(), f"{tpl.key}: sampled a token outside the filtered support"
+            if len(tpl.inputs) > 1:                          # a filtered sampler: the filter must actually remove something
+                assert not e.all(), f"{tpl.key}: degenerate test, the filter keeps everything"
+            continue
         assert g.shape == e.shape, f"{tpl.key}: output '{spec.name}' shape {tuple(g.shape)} vs reference {tuple(e.shape)}"
         if tol["atol"] == 0.0 and tol["rtol"] == 0.0:
             assert torch.equal(g, e), f"{tpl.key}: output '{spec.name}' differs"
