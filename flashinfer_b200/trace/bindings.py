@@ -47,6 +47,12 @@ BINDINGS: List[Tuple[str, str, "_t.TraceTemplate"]] = [
     ("sampling", "top_k_top_p_sampling_from_probs", T.top_k_top_p_sampling_from_probs_trace),
     ("sampling", "top_k_top_p_sampling_from_logits", T.top_k_top_p_sampling_from_logits_trace),
     ("sampling", "chain_speculative_sampling", T.chain_speculative_sampling_trace),
+    ("cascade", "merge_state", T.merge_state_trace),
+    ("cascade", "merge_state_in_place", T.merge_state_in_place_trace),
+    ("cascade", "merge_states", T.merge_states_trace),
+    ("page", "append_paged_kv_cache", T.append_paged_kv_cache_trace),
+    ("page", "append_paged_mla_kv_cache", T.append_paged_mla_kv_cache_trace),
+    ("page", "get_batch_indices_positions", T.get_batch_indices_positions_trace),
 ]
 
 _PKG = __name__.rsplit(".", 2)[0]

@@ -74,7 +74,7 @@ class Tensor:
     dtype: Optional[str] = None
     optional: bool = False
     description: str = ""
-    param: Optional[str] = None
+    param: Optional[str] = None        # API argument, or "self.<attr>" for state a wrapper captured in plan()
     tuple_idx: Optional[int] = None
     dtype_from: Optional[str] = None
 
@@ -97,7 +97,13 @@ class Scalar:
 
 
 def _pick(bound: Dict[str, Any], spec) -> Any:
-    v = bound.get(spec.source)
+    src = spec.source
+    if src.startswith("self."):                      # plan()-time state of a wrapper object: "self._kv_indptr_host"
+        v = bound.get("self")
+        for part in src[5:].split("."):
+            v = getattr(v, part, None)
+    else:
+        v = bound.get(src)
     idx = getattr(spec, "tuple_idx", None)
     if idx is not None:
         v = v[idx] if isinstance(v, (tuple, list)) and len(v) > idx else None
@@ -293,7 +299,6 @@ def traced(fn: Callable, template: TraceTemplate) -> Callable:
             except TypeError:
                 bound = None
             if bound is not None:
-                bound.pop("self", None)
                 _emit_once(template, bound, out_dir)
         return fn(*args, **kwargs)
 
