@@ -323,6 +323,7 @@ class BatchPrefillWithRaggedKVCacheWrapper(_BatchPrefillBase):
             raise NotImplementedError("in-kernel positional encoding")
         kv_host = kv_indptr.to("cpu", torch.int32)
         self._kv_start_host = kv_host[:-1].contiguous()
+        self._kv_indptr_ragged_host = kv_host
         if packed_custom_mask is not None and custom_mask is None:
             qo_h = qo_indptr.to("cpu")
             n = int(((qo_h[1:] - qo_h[:-1]) * (kv_host[1:] - kv_host[:-1])).sum())

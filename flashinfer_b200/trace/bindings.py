@@ -53,6 +53,12 @@ BINDINGS: List[Tuple[str, str, "_t.TraceTemplate"]] = [
     ("page", "append_paged_kv_cache", T.append_paged_kv_cache_trace),
     ("page", "append_paged_mla_kv_cache", T.append_paged_mla_kv_cache_trace),
     ("page", "get_batch_indices_positions", T.get_batch_indices_positions_trace),
+    ("decode", "single_decode_with_kv_cache", T.single_decode_with_kv_cache_trace),
+    ("prefill", "single_prefill_with_kv_cache", T.single_prefill_with_kv_cache_trace),
+    ("decode", "BatchDecodeWithPagedKVCacheWrapper.run", T.gqa_paged_decode_trace),
+    ("prefill", "BatchPrefillWithPagedKVCacheWrapper.run", T.gqa_paged_prefill_trace),
+    ("prefill", "BatchPrefillWithRaggedKVCacheWrapper.run", T.gqa_ragged_prefill_trace),
+    ("mla", "BatchMLAPagedAttentionWrapper.run", T.mla_paged_trace),
 ]
 
 _PKG = __name__.rsplit(".", 2)[0]

@@ -227,7 +227,8 @@ class TraceTemplate:
         """API keyword arguments for the given axis sizes (defaults come from the template's ``init``)."""
         if self.init is None:
             raise ValueError(f"template {self.key} has no input builder")
-        return self.init(device=device, seed=seed, **sizes)
+        accepted = inspect.signature(self.init).parameters
+        return self.init(device=device, seed=seed, **{k: v for k, v in sizes.items() if k in accepted})
 
     def reference_kwargs(self, bound: Dict[str, Any]) -> Dict[str, Any]:
         """The arguments of ``reference`` picked out of API keyword arguments (optional inputs that are absent are dropped)."""

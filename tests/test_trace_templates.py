@@ -34,6 +34,9 @@ def _api(mod, path):
 def test_template_names_real_parameters(mod, path, tpl):
     params = inspect.signature(_api(mod, path)).parameters
     for spec in tpl.inputs:
+        if spec.source.startswith("self."):
+            assert "self" in params                   # plan()-time state: checked on a live instance below
+            continue
         assert spec.source in params, f"{tpl.key}: input '{spec.name}' reads API parameter '{spec.source}' which does not exist"
     for spec in tpl.outputs:
         if spec.param is not None:
@@ -63,6 +66,10 @@ def test_reference_matches_api(mod, path, tpl):
     kwargs = tpl.make_inputs(device="cpu", seed=1, **sizes)
     ref_in = {k: (v.clone() if isinstance(v, torch.Tensor) else tuple(t.clone() for t in v) if isinstance(v, tuple) else v)
               for k, v in kwargs.items()}
+    from flashinfer_b200.trace.template import _pick
+
+    for spec in tpl.inputs:
+        assert spec.optional or _pick(kwargs, spec) is not None, f"{tpl.key}: input '{spec.name}' ({spec.source}) did not resolve"
     expect = tpl.run_reference(ref_in)
     expect = list(expect) if isinstance(expect, (tuple, list)) else [expect]
     got = tpl.collect_outputs(api(**kwargs), kwargs)
