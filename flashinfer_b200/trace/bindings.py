@@ -59,6 +59,13 @@ BINDINGS: List[Tuple[str, str, "_t.TraceTemplate"]] = [
     ("prefill", "BatchPrefillWithPagedKVCacheWrapper.run", T.gqa_paged_prefill_trace),
     ("prefill", "BatchPrefillWithRaggedKVCacheWrapper.run", T.gqa_ragged_prefill_trace),
     ("mla", "BatchMLAPagedAttentionWrapper.run", T.mla_paged_trace),
+    ("gemm.dense", "mm_bf16", T.mm_bf16_trace),
+    ("gemm.dense", "tgv_gemm_sm100", T.tgv_gemm_sm100_trace),
+    ("gemm.dense", "bmm_bf16", T.bmm_bf16_trace),
+    ("gemm.lowp", "bmm_fp8", T.bmm_fp8_trace),
+    ("gemm.lowp", "mm_fp8", T.mm_fp8_trace),
+    ("gemm.lowp", "gemm_fp8_nt_groupwise", T.gemm_fp8_nt_groupwise_trace),
+    ("gemm.grouped", "SegmentGEMMWrapper.run", T.segment_gemm_trace),
 ]
 
 _PKG = __name__.rsplit(".", 2)[0]

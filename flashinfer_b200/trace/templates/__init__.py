@@ -1,5 +1,5 @@
 """Op templates, one module per category (reference flashinfer/trace/templates/*.py)."""
-from . import activation, attention, cascade, norm, page, rope, sampling  # noqa: F401
+from . import activation, attention, cascade, gemm, norm, page, rope, sampling  # noqa: F401
 from ._legacy import *  # noqa: F401,F403
 from .activation import *  # noqa: F401,F403
 from .norm import *  # noqa: F401,F403
@@ -8,3 +8,4 @@ from .sampling import *  # noqa: F401,F403
 from .cascade import *  # noqa: F401,F403
 from .page import *  # noqa: F401,F403
 from .attention import *  # noqa: F401,F403
+from .gemm import *  # noqa: F401,F403

@@ -1,11 +1,6 @@
 """Op templates (one per category; reference flashinfer/trace/templates/*.py)."""
 from ..template import Const, Scalar, Tensor, TraceTemplate, Var
 
-gemm_bf16_trace = TraceTemplate(
-    op_type="gemm", name_fmt="gemm_bf16_n{N}_k{K}", axes=[Var("M"), Const("N"), Const("K")],
-    inputs=[Tensor("a", ("M", "K")), Tensor("b", ("K", "N"))], outputs=[Tensor("out", ("M", "N"))], tags=("gemm", "bf16"),
-    description="C = A @ B with a column-major B ([N, K] weight passed as .T)")
-
 sampling_trace = TraceTemplate(
     op_type="sampling", name_fmt="top_k_top_p_sampling_v{vocab_size}", axes=[Var("batch_size"), Const("vocab_size")],
     inputs=[Tensor("probs", ("batch_size", "vocab_size"), "float32")], outputs=[Tensor("samples", ("batch_size",), "int32")],
