@@ -66,6 +66,13 @@ BINDINGS: List[Tuple[str, str, "_t.TraceTemplate"]] = [
     ("gemm.lowp", "mm_fp8", T.mm_fp8_trace),
     ("gemm.lowp", "gemm_fp8_nt_groupwise", T.gemm_fp8_nt_groupwise_trace),
     ("gemm.grouped", "SegmentGEMMWrapper.run", T.segment_gemm_trace),
+    ("quantization.fp8", "mxfp8_quantize", T.mxfp8_quantize_trace),
+    ("quantization.fp4", "fp4_quantize", T.fp4_quantize_trace),
+    ("fused_moe.core", "cutlass_fused_moe", T.cutlass_fused_moe_trace),
+    ("fused_moe.core", "fused_topk_deepseek", T.fused_topk_deepseek_trace),
+    ("topk", "top_k", T.top_k_trace),
+    ("concat_ops", "concat_mla_k", T.concat_mla_k_trace),
+    ("mamba.selective_state_update", "selective_state_update", T.selective_state_update_trace),
 ]
 
 _PKG = __name__.rsplit(".", 2)[0]

@@ -126,6 +126,7 @@ class TraceTemplate:
     fi_api: str = ""                   # filled by bindings: dotted name of the bound function
     derive: Optional[Callable] = None  # derive(sizes) -> extra axis sizes computed from the resolved ones
     test_sizes: Optional[Dict[str, int]] = None   # small axis sizes for the generic reference-correctness test
+    compare: Optional[Callable] = None  # compare(got, expected, kwargs): op-specific check replacing the tolerance class
 
     def __post_init__(self):
         _TEMPLATES[self.key] = self

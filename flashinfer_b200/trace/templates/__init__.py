@@ -1,6 +1,6 @@
 """Op templates, one module per category (reference flashinfer/trace/templates/*.py)."""
-from . import activation, attention, cascade, gemm, norm, page, rope, sampling  # noqa: F401
-from ._legacy import *  # noqa: F401,F403
+from . import activation, attention, cascade, gemm, misc, moe, norm, page, quantize, rope, sampling  # noqa: F401
+from .comm import *  # noqa: F401,F403
 from .activation import *  # noqa: F401,F403
 from .norm import *  # noqa: F401,F403
 from .rope import *  # noqa: F401,F403
@@ -9,3 +9,6 @@ from .cascade import *  # noqa: F401,F403
 from .page import *  # noqa: F401,F403
 from .attention import *  # noqa: F401,F403
 from .gemm import *  # noqa: F401,F403
+from .quantize import *  # noqa: F401,F403
+from .moe import *  # noqa: F401,F403
+from .misc import *  # noqa: F401,F403

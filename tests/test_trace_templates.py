@@ -76,6 +76,9 @@ def test_reference_matches_api(mod, path, tpl):
     got = tpl.collect_outputs(api(**kwargs), kwargs)
     assert len(got) >= len(expect) > 0
     tol = TOLERANCE[tpl.tolerance]
+    if tpl.compare is not None:
+        tpl.compare(got, expect, ref_in)
+        got, expect = [], []
     for spec, g, e in zip(tpl.outputs, got, expect):
         assert isinstance(g, torch.Tensor), f"{tpl.key}: output '{spec.name}' missing"
         if tol == "cos":
@@ -137,3 +140,42 @@ def test_fi_trace_user_api(tmp_path):
     assert (tmp_path / "activation" / "silu_and_mul_h256.json").exists()
     with pytest.raises(ValueError):
         fi.fi_trace(torch.relu, input=x)
+
+
+def test_mxfp4_template_against_fp4_quantize():
+    """The MXFP4 flavour shares fp4_quantize with NVFP4 (only one template can be bound to a function)."""
+    from flashinfer_b200.trace.templates import mxfp4_quantize_trace as tpl
+
+    kw = tpl.make_inputs(device="cpu", seed=3, M=5, K=128)
+    tpl.compare(list(fi.fp4_quantize(**kw)), list(tpl.run_reference(kw)), kw)
+    assert tpl.definition(kw)["name"] == "mxfp4_quantize_k128"
+
+
+def test_enable_wraps_wrapper_methods(tmp_path):
+    from flashinfer_b200.trace.templates import gqa_paged_decode_trace as tpl
+
+    kw = tpl.make_inputs(device="cpu", seed=0, batch_size=2, num_qo_heads=4, num_kv_heads=2, head_dim=64, page_size=4)
+    w = kw.pop("self")
+    plain = fi.BatchDecodeWithPagedKVCacheWrapper.run
+    fi.trace.enable(str(tmp_path))
+    try:
+        assert fi.BatchDecodeWithPagedKVCacheWrapper.run is not plain
+        w.run(kw["q"], kw["paged_kv_cache"])
+        files = list((tmp_path / "gqa_paged").iterdir())
+        assert [f.name for f in files] == ["gqa_paged_decode_h4_kv2_d64_ps4.json"]
+        d = json.loads(files[0].read_text())
+        assert d["inputs"]["kv_indptr"]["dtype"] == "int32" and d["axes"]["page_size"]["value"] == 4
+        assert d["tags"][0] == "fi_api:flashinfer_b200.decode.BatchDecodeWithPagedKVCacheWrapper.run"
+    finally:
+        fi.trace.disable()
+    assert fi.BatchDecodeWithPagedKVCacheWrapper.run is plain
+    assert fi.fi_trace(w.run, q=kw["q"], paged_kv_cache=kw["paged_kv_cache"])["axes"]["head_dim"]["value"] == 64
+
+
+def test_every_category_of_the_reference_has_templates():
+    from flashinfer_b200.trace import registered_templates
+
+    cats = {k.split(":")[0] for k in registered_templates()}
+    assert {"rmsnorm", "layernorm", "activation", "rope", "sampling", "cascade", "page", "gemm", "quantize", "gqa_single", "gqa_paged",
+            "gqa_ragged", "mla_paged", "moe", "comm"} <= cats
+    assert len(registered_templates()) >= 60
