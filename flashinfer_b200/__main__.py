@@ -1,7 +1,7 @@
 """Command line interface:  python -m flashinfer_b200 <command>
 
 Parity: reference flashinfer/__main__.py:64-393 (show-config, module-status, list-modules, clear-cache, build / AOT,
-replay).  click is used when available, argparse otherwise."""
+replay, export-compile-commands, list-/download-/clear-cubin)."""
 from __future__ import annotations
 
 import argparse
@@ -91,6 +91,50 @@ def _cmd_trace_templates(args) -> int:
     return 0
 
 
+def _cmd_export_compile_commands(args) -> int:
+    """compile_commands.json for clangd / IDEs: one entry per translation unit of every (or the named) native module
+    (reference __main__.py:334 export-compile-commands)."""
+    from . import jit
+
+    names = args.modules or list(jit.REGISTRY)
+    entries = []
+    for name in names:
+        spec = jit.REGISTRY[name]
+        cmd = spec.nvcc_command()
+        srcs = {str(p) for p in spec.source_paths()}
+        shared = [c for c in cmd if c not in srcs]
+        for src in sorted(srcs):
+            entries.append({"directory": str(jit.CSRC), "file": src, "arguments": shared[:1] + ["-c", src] + shared[1:],
+                            "output": str(spec.so_path)})
+    out = args.output or "compile_commands.json"
+    with open(out, "w") as f:
+        json.dump(entries, f, indent=1)
+    print(f"wrote {len(entries)} entries to {out}")
+    return 0
+
+
+def _cmd_list_cubins(args) -> int:
+    """The reference downloads prebuilt cubins (trtllm-gen, cuDNN-frontend ...) from an artifact server; every kernel here is
+    compiled from the in-tree sources, so the 'cubin store' is the in-tree library directory."""
+    from . import artifacts, jit
+
+    st = jit.module_status()
+    for name, spec in jit.REGISTRY.items():
+        size = spec.so_path.stat().st_size if spec.so_path.exists() else 0
+        print(f"{name:<28} {st.get(name, '?'):<8} {size:>10} B  {spec.so_path}")
+    print(f"downloadable artifacts: {len(getattr(artifacts, 'get_available_cubin_files', lambda *a, **k: [])())} (none: built from source)")
+    return 0
+
+
+def _cmd_download_cubin(args) -> int:
+    print("nothing to download: flashinfer_b200 has no prebuilt-cubin dependencies; run `python -m flashinfer_b200 build`")
+    return 0
+
+
+def _cmd_clear_cubin(args) -> int:
+    return _cmd_clear_cache(args)
+
+
 def main(argv=None) -> int:
     ap = argparse.ArgumentParser(prog="flashinfer_b200")
     sub = ap.add_subparsers(dest="cmd", required=True)
@@ -107,6 +151,13 @@ def main(argv=None) -> int:
     r.add_argument("--sequence", action="store_true")
     r.set_defaults(fn=_cmd_replay)
     sub.add_parser("trace-templates").set_defaults(fn=_cmd_trace_templates)
+    e = sub.add_parser("export-compile-commands", help="write compile_commands.json for the native modules")
+    e.add_argument("modules", nargs="*")
+    e.add_argument("-o", "--output", default=None)
+    e.set_defaults(fn=_cmd_export_compile_commands)
+    sub.add_parser("list-cubins").set_defaults(fn=_cmd_list_cubins)
+    sub.add_parser("download-cubin").set_defaults(fn=_cmd_download_cubin)
+    sub.add_parser("clear-cubin", help="same as clear-cache: the compiled libraries are the only binary artifacts").set_defaults(fn=_cmd_clear_cubin)
     args = ap.parse_args(argv)
     return args.fn(args)
 

@@ -217,3 +217,18 @@ def test_fused_moe_utils_buckets_and_swizzle():
     with u.model_extra_attrs({"a": 1}):
         assert u.get_model_extra_attrs() == {"a": 1}
     assert u.get_model_extra_attrs() is None
+
+
+def test_cli_export_compile_commands_and_cubin_commands(tmp_path, capsys):
+    import json
+
+    from flashinfer_b200.__main__ import main
+
+    out = tmp_path / "cc.json"
+    assert main(["export-compile-commands", "norm", "pod_sm100", "-o", str(out)]) == 0
+    entries = json.loads(out.read_text())
+    assert len(entries) == 2 and all(e["file"].endswith(".cu") and "arch=compute_100a,code=sm_100a" in e["arguments"] for e in entries)
+    assert entries[0]["arguments"][1:3] == ["-c", entries[0]["file"]]
+    assert main(["list-cubins"]) == 0 and main(["download-cubin"]) == 0
+    text = capsys.readouterr().out
+    assert "gemm_sm100" in text and "built from source" in text
