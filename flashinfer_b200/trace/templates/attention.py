@@ -98,11 +98,12 @@ def _gqa_paged_decode_reference(q, k_cache, v_cache, kv_indptr, kv_indices, kv_l
     return out.to(q.dtype), lse
 
 
-def _gqa_paged_decode_init(*, batch_size=8, num_qo_heads=32, num_kv_heads=8, head_dim=128, page_size=16, device="cuda", seed=0):
+def _gqa_paged_decode_init(*, batch_size=8, num_qo_heads=32, num_kv_heads=8, head_dim=128, page_size=16, kv_len=None, device="cuda", seed=0):
+    """``kv_len=None``: ragged lengths in [1, 6 pages); an integer gives every request that many cached tokens."""
     import flashinfer_b200 as fi
 
     g = torch.Generator(device="cpu").manual_seed(seed)
-    lens = [int(x) for x in torch.randint(1, 6 * page_size, (batch_size,), generator=g)]
+    lens = [int(x) for x in torch.randint(1, 6 * page_size, (batch_size,), generator=g)] if kv_len is None else [int(kv_len)] * batch_size
     indices, indptr, last, num_pages = _paged_tables(lens, page_size, device, g)
     mk = lambda *s: torch.randn(*s, generator=g).to(torch.bfloat16).to(device)  # noqa: E731
     w = fi.BatchDecodeWithPagedKVCacheWrapper(torch.empty(32 << 20, dtype=torch.uint8, device=device), "NHD")
@@ -151,12 +152,15 @@ def _gqa_paged_prefill_reference(q, k_cache, v_cache, qo_indptr, kv_indptr, kv_i
     return out.to(q.dtype), lse
 
 
-def _gqa_paged_prefill_init(*, batch_size=4, num_qo_heads=32, num_kv_heads=8, head_dim=128, page_size=16, device="cuda", seed=0):
+def _gqa_paged_prefill_init(*, batch_size=4, num_qo_heads=32, num_kv_heads=8, head_dim=128, page_size=16, qo_len=None, kv_len=None,
+                            device="cuda", seed=0):
+    """``qo_len`` / ``kv_len`` None: ragged; integers give every request that many new / total tokens."""
     import flashinfer_b200 as fi
 
     g = torch.Generator(device="cpu").manual_seed(seed)
-    q_lens = [int(x) for x in torch.randint(1, 3 * page_size, (batch_size,), generator=g)]
-    kv_lens = [ql + int(x) for ql, x in zip(q_lens, torch.randint(0, 4 * page_size, (batch_size,), generator=g))]
+    q_lens = [int(x) for x in torch.randint(1, 3 * page_size, (batch_size,), generator=g)] if qo_len is None else [int(qo_len)] * batch_size
+    kv_lens = [ql + int(x) for ql, x in zip(q_lens, torch.randint(0, 4 * page_size, (batch_size,), generator=g))] if kv_len is None \
+        else [max(int(kv_len), ql) for ql in q_lens]
     indices, indptr, last, num_pages = _paged_tables(kv_lens, page_size, device, g)
     qo_indptr = torch.tensor([0] + list(torch.tensor(q_lens).cumsum(0)), dtype=torch.int32, device=device)
     mk = lambda *s: torch.randn(*s, generator=g).to(torch.bfloat16).to(device)  # noqa: E731
@@ -202,11 +206,11 @@ def _gqa_ragged_prefill_reference(q, k, v, qo_indptr, kv_indptr, causal=True, sm
     return out.to(q.dtype), lse
 
 
-def _gqa_ragged_prefill_init(*, batch_size=4, num_qo_heads=32, num_kv_heads=8, head_dim=128, device="cuda", seed=0):
+def _gqa_ragged_prefill_init(*, batch_size=4, num_qo_heads=32, num_kv_heads=8, head_dim=128, seq_len=None, device="cuda", seed=0):
     import flashinfer_b200 as fi
 
     g = torch.Generator(device="cpu").manual_seed(seed)
-    lens = [int(x) for x in torch.randint(1, 40, (batch_size,), generator=g)]
+    lens = [int(x) for x in torch.randint(1, 40, (batch_size,), generator=g)] if seq_len is None else [int(seq_len)] * batch_size
     indptr = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device=device)
     mk = lambda *s: torch.randn(*s, generator=g).to(torch.bfloat16).to(device)  # noqa: E731
     w = fi.BatchPrefillWithRaggedKVCacheWrapper(torch.empty(32 << 20, dtype=torch.uint8, device=device), "NHD")
@@ -250,11 +254,11 @@ def _mla_paged_reference(q_nope, q_pe, ckv_cache, kpe_cache, qo_indptr, kv_indpt
     return out.to(q_nope.dtype), lse
 
 
-def _mla_paged_init(*, batch_size=4, num_heads=128, head_dim_ckv=512, head_dim_kpe=64, page_size=64, device="cuda", seed=0):
+def _mla_paged_init(*, batch_size=4, num_heads=128, head_dim_ckv=512, head_dim_kpe=64, page_size=64, kv_len=None, device="cuda", seed=0):
     import flashinfer_b200 as fi
 
     g = torch.Generator(device="cpu").manual_seed(seed)
-    kv_lens = [int(x) for x in torch.randint(1, 3 * page_size, (batch_size,), generator=g)]
+    kv_lens = [int(x) for x in torch.randint(1, 3 * page_size, (batch_size,), generator=g)] if kv_len is None else [int(kv_len)] * batch_size
     indices, indptr, _, num_pages = _paged_tables(kv_lens, page_size, device, g)
     qo_indptr = torch.arange(batch_size + 1, dtype=torch.int32, device=device)
     mk = lambda *s: (torch.randn(*s, generator=g) * 0.5).to(torch.bfloat16).to(device)  # noqa: E731
