@@ -84,13 +84,11 @@ def _flops(tpl, sizes: Dict[str, int], kwargs: Dict[str, Any]) -> Optional[float
 
 
 def _peaks() -> Dict[str, float]:
-    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
-    try:
-        with open(path) as f:
-            d = json.load(f)
-        return {"hbm_tbs": float(d.get("copy_bandwidth_tbs", d.get("hbm_tbs", 0)) or 0), "bf16_tflops": float(d.get("cublas_bf16_tflops", d.get("bf16_tflops", 0)) or 0)}
-    except (OSError, ValueError):
-        return {"hbm_tbs": 0.0, "bf16_tflops": 0.0}
+    from flashinfer_b200.testing import measured_peaks
+
+    d = measured_peaks()
+    gbs = d.get("hbm_gbs", d.get("hbm_gbps", 0.0)) or 0.0
+    return {"hbm_tbs": float(gbs) / 1e3, "bf16_tflops": float(d.get("bf16_tflops", 0.0) or 0.0)}
 
 
 def _clone(v):
