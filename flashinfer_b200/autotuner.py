@@ -59,6 +59,7 @@ class TuningConfig:
     constraint_specs: Tuple[ConstraintSpec, ...] = ()
     use_cuda_graph: bool = False
     use_cold_l2_cache: bool = True
+    synthesize_buckets: bool = True   # False: only ever profile live inputs (runners that hold state sized by a dynamic dim)
 
 
 class TunableRunner:
@@ -396,7 +397,7 @@ class AutoTuner:
             self.stats["misses"] += 1
             return runners[0], -1
         rid, tactic = self._profile(custom_op, runners, tuning_config, inputs, shapes, extras, **kwargs)
-        for spec in tuning_config.dynamic_tensor_specs:
+        for spec in (tuning_config.dynamic_tensor_specs if tuning_config.synthesize_buckets else ()):
             sizes = self._override_tuning_buckets() or tuple(spec.gen_tuning_buckets or ())
             for size in sizes:
                 try:

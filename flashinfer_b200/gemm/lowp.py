@@ -90,7 +90,8 @@ class _TileNRunner(TunableRunner):
         return _launch_raw(kind, a, b_nk, out, sfa, sfb, alpha_a, alpha_b, K, max(int(tactic), 0), None, None, None)
 
 
-_TILE_N_CFG = TuningConfig(dynamic_tensor_specs=(DynamicTensorSpec((0, 2), (1, 1)),), use_cold_l2_cache=True)
+# the runner carries scale tensors laid out for the live M, so other buckets are tuned when they show up, never synthesised
+_TILE_N_CFG = TuningConfig(dynamic_tensor_specs=(DynamicTensorSpec((0, 2), (1, 1)),), use_cold_l2_cache=True, synthesize_buckets=False)
 
 
 def _launch(kind: str, a: torch.Tensor, b_nk: torch.Tensor, out: torch.Tensor, sfa, sfb, alpha_a, alpha_b, K: int,

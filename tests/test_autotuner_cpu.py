@@ -130,6 +130,10 @@ def test_lowp_gemm_asks_the_tuner_for_its_n_tile(tuner, monkeypatch):
     with autotune():
         lowp._launch("fp8", a, b, o, None, None, None, None, 64)
     assert seen[-1] == 128 and set(seen) == {0, 64, 128, 192, 256}
+    n = len(seen)
+    with autotune(tuning_buckets=(16, 256)):                     # scale tensors are tied to the live M: no synthetic buckets
+        lowp._launch("fp8", a, b, o, None, None, None, None, 64)
+    assert all(s_ in (0, 64, 128, 192, 256) for s_ in seen[n:]) and len(seen) - n <= 6
     seen.clear()
     a2, o2 = torch.zeros(1, 60, 64, dtype=torch.uint8), torch.zeros(1, 60, 512)
     lowp._launch("fp8", a2, b, o2, None, None, None, None, 64)   # same M bucket (64): cached choice, no profiling
