@@ -73,6 +73,10 @@ BINDINGS: List[Tuple[str, str, "_t.TraceTemplate"]] = [
     ("topk", "top_k", T.top_k_trace),
     ("concat_ops", "concat_mla_k", T.concat_mla_k_trace),
     ("mamba.selective_state_update", "selective_state_update", T.selective_state_update_trace),
+    ("decode", "trtllm_batch_decode_with_kv_cache", T.trtllm_batch_decode_trace),
+    ("decode", "cudnn_batch_decode_with_kv_cache", T.cudnn_batch_decode_trace),
+    ("gdn", "gated_delta_rule_decode", T.gated_delta_rule_decode_trace),
+    ("gdn", "chunk_gated_delta_rule", T.chunk_gated_delta_rule_trace),
 ]
 
 _PKG = __name__.rsplit(".", 2)[0]

@@ -284,3 +284,88 @@ mla_paged_trace = TraceTemplate(
     reference=_mla_paged_reference, init=_mla_paged_init, tags=("attention", "mla", "paged"), constraints=("len_indptr == batch_size + 1",),
     description="Multi-head latent attention over paged compressed KV (matrix-absorbed form)", tolerance="bf16",
     test_sizes={"num_heads": 4, "head_dim_ckv": 512, "head_dim_kpe": 64, "page_size": 4, "batch_size": 3})
+
+
+# ------------------------------------------------------------------ block-table entry points (TRT-LLM / cuDNN / XQA call styles)
+def _block_table_decode_reference(query, k_cache, v_cache, block_tables, seq_lens, bmm1_scale=1.0, bmm2_scale=1.0):
+    """HND pages: k_cache / v_cache [pages, Hkv, page_size, D]; request b reads pages block_tables[b, :ceil(len / page_size)]."""
+    b, h, d = query.shape
+    hkv, page_size = k_cache.shape[1], k_cache.shape[2]
+    group = h // hkv
+    out = torch.zeros(b, h, d, dtype=torch.float32, device=query.device)
+    for i in range(b):
+        n = int(seq_lens[i])
+        pages = block_tables[i, : (n + page_size - 1) // page_size].long()
+        k = k_cache[pages].permute(0, 2, 1, 3).reshape(-1, hkv, d)[:n].to(torch.float32).repeat_interleave(group, dim=1)
+        v = v_cache[pages].permute(0, 2, 1, 3).reshape(-1, hkv, d)[:n].to(torch.float32).repeat_interleave(group, dim=1)
+        logits = torch.einsum("hd,lhd->hl", query[i].to(torch.float32), k) * bmm1_scale
+        out[i] = torch.einsum("hl,lhd->hd", torch.softmax(logits, -1), v) * bmm2_scale
+    return out.to(query.dtype)
+
+
+def _block_table_inputs(batch_size, num_qo_heads, num_kv_heads, head_dim, page_size, kv_len, device, seed):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    lens = [int(x) for x in torch.randint(1, 6 * page_size, (batch_size,), generator=g)] if kv_len is None else [int(kv_len)] * batch_size
+    per = [(n + page_size - 1) // page_size for n in lens]
+    total = sum(per)
+    ids = torch.randperm(total + 2, generator=g)[:total].int()
+    table = torch.zeros(batch_size, max(per), dtype=torch.int32)
+    o = 0
+    for i, p in enumerate(per):
+        table[i, :p] = ids[o:o + p]
+        o += p
+    mk = lambda *s: torch.randn(*s, generator=g).to(torch.bfloat16).to(device)  # noqa: E731
+    return (mk(batch_size, num_qo_heads, head_dim), mk(total + 2, num_kv_heads, page_size, head_dim), mk(total + 2, num_kv_heads, page_size, head_dim),
+            table.to(device), torch.tensor(lens, dtype=torch.int32, device=device), max(lens))
+
+
+def _trtllm_decode_init(*, batch_size=8, num_qo_heads=32, num_kv_heads=8, head_dim=128, page_size=16, kv_len=None, device="cuda", seed=0):
+    q, k, v, table, lens, mx = _block_table_inputs(batch_size, num_qo_heads, num_kv_heads, head_dim, page_size, kv_len, device, seed)
+    return {"query": q, "kv_cache": (k, v), "workspace_buffer": torch.empty(32 << 20, dtype=torch.uint8, device=device), "block_tables": table,
+            "seq_lens": lens, "max_seq_len": mx, "bmm1_scale": 1.0 / math.sqrt(head_dim), "bmm2_scale": 1.0, "kv_layout": "HND"}
+
+
+_HND = ("num_pages", "num_kv_heads", "page_size", "head_dim")
+trtllm_batch_decode_trace = TraceTemplate(
+    op_type="gqa_paged", name_fmt="trtllm_batch_decode_h{num_qo_heads}_kv{num_kv_heads}_d{head_dim}_ps{page_size}",
+    axes=[Var("batch_size"), Var("num_pages"), Var("max_pages_per_seq")] + _H + [Const("page_size", abbrev="ps")],
+    inputs=[Tensor("query", ("batch_size", "num_qo_heads", "head_dim")), Tensor("k_cache", _HND, param="kv_cache", tuple_idx=0),
+            Tensor("v_cache", _HND, param="kv_cache", tuple_idx=1), Tensor("block_tables", ("batch_size", "max_pages_per_seq"), "int32"),
+            Tensor("seq_lens", ("batch_size",), "int32"), Scalar("bmm1_scale", description="softmax scale with q / k de-quantisation folded in"),
+            Scalar("bmm2_scale", optional=True, description="output scale (v de-quantisation)")],
+    outputs=[Tensor("output", ("batch_size", "num_qo_heads", "head_dim"), dtype_from="query")], reference=_block_table_decode_reference,
+    init=_trtllm_decode_init, tags=("attention", "decode", "paged", "block_table"),
+    description="Batched GQA decode addressed by a dense block table over HND pages (TRT-LLM call style)", tolerance="bf16", test_sizes=_SIZES)
+
+
+def _cudnn_decode_reference(q, k_cache, v_cache, scale, actual_seq_lens_kv, block_tables):
+    b, h, d = q.shape
+    hkv, page_size = k_cache.shape[1], k_cache.shape[2]
+    group = h // hkv
+    lens = actual_seq_lens_kv.reshape(-1)
+    out = torch.zeros(b, h, d, dtype=torch.float32, device=q.device)
+    for i in range(b):
+        n = int(lens[i])
+        pages = block_tables[i, : (n + page_size - 1) // page_size].long()
+        k = k_cache[pages].permute(0, 2, 1, 3).reshape(-1, hkv, d)[:n].to(torch.float32).repeat_interleave(group, dim=1)
+        v = v_cache[pages].permute(0, 2, 1, 3).reshape(-1, hkv, d)[:n].to(torch.float32).repeat_interleave(group, dim=1)
+        logits = torch.einsum("hd,lhd->hl", q[i].to(torch.float32), k) * scale
+        out[i] = torch.einsum("hl,lhd->hd", torch.softmax(logits, -1), v)
+    return out.to(q.dtype)
+
+
+def _cudnn_decode_init(*, batch_size=8, num_qo_heads=32, num_kv_heads=8, head_dim=128, page_size=16, kv_len=None, device="cuda", seed=0):
+    q, k, v, table, lens, mx = _block_table_inputs(batch_size, num_qo_heads, num_kv_heads, head_dim, page_size, kv_len, device, seed)
+    return {"q": q, "k_cache": k, "v_cache": v, "scale": 1.0 / math.sqrt(head_dim), "workspace_buffer": torch.empty(32 << 20, dtype=torch.uint8, device=device),
+            "max_sequence_kv": mx, "actual_seq_lens_kv": lens.view(-1, 1, 1, 1), "block_tables": table}
+
+
+cudnn_batch_decode_trace = TraceTemplate(
+    op_type="gqa_paged", name_fmt="cudnn_batch_decode_h{num_qo_heads}_kv{num_kv_heads}_d{head_dim}_ps{page_size}",
+    axes=[Var("batch_size"), Var("num_pages"), Var("max_pages_per_seq")] + _H + [Const("page_size", abbrev="ps")],
+    inputs=[Tensor("q", ("batch_size", "num_qo_heads", "head_dim")), Tensor("k_cache", _HND), Tensor("v_cache", _HND), Scalar("scale"),
+            Tensor("actual_seq_lens_kv", ("batch_size", "one", "one_", "one__"), "int32"),
+            Tensor("block_tables", ("batch_size", "max_pages_per_seq"), "int32")],
+    outputs=[Tensor("output", ("batch_size", "num_qo_heads", "head_dim"), dtype_from="q")], reference=_cudnn_decode_reference,
+    init=_cudnn_decode_init, tags=("attention", "decode", "paged", "block_table"), constraints=("one == 1", "one_ == 1", "one__ == 1"),
+    description="cuDNN-style call signature of the paged decode kernel", tolerance="bf16", test_sizes=_SIZES)
