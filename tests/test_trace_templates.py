@@ -4,6 +4,7 @@ well-formed definition, and (3) carry a reference implementation that agrees wit
 test).  Runs on CPU through the ops' eager paths; the same harness is device-agnostic."""
 import inspect
 import json
+import os
 
 import pytest
 import torch
@@ -11,6 +12,9 @@ import torch
 import flashinfer_b200 as fi
 from flashinfer_b200.trace import BINDINGS, Const, Scalar, Tensor, Var
 from flashinfer_b200.trace.bindings import _resolve
+
+# FIB200_TRACE_TEST_DEVICE=cuda runs the same checks against the native kernels (opt-in: not part of the gpu-marked suite yet)
+DEVICE = os.environ.get("FIB200_TRACE_TEST_DEVICE", "cpu")
 
 # tolerance classes (reference tests/trace/reference_correctness_standards.md)
 TOLERANCE = {
@@ -64,7 +68,7 @@ def test_reference_matches_api(mod, path, tpl):
     for a in tpl.axes:
         if a.name in accepted and a.name not in sizes:
             sizes[a.name] = 5 if isinstance(a, Var) else (128 if "size" in a.name or "dim" in a.name else 4)
-    kwargs = tpl.make_inputs(device="cpu", seed=1, **sizes)
+    kwargs = tpl.make_inputs(device=DEVICE, seed=1, **sizes)
     ref_in = {k: (v.clone() if isinstance(v, torch.Tensor) else tuple(t.clone() for t in v) if isinstance(v, tuple) else v)
               for k, v in kwargs.items()}
     from flashinfer_b200.trace.template import _pick
@@ -89,7 +93,7 @@ def test_reference_matches_api(mod, path, tpl):
             continue
         if tol is None:
             assert e.dtype == torch.bool and g.shape == e.shape[:1]
-            assert e[torch.arange(g.numel()), g.long()].all(), f"{tpl.key}: sampled a token outside the filtered support"
+            assert e[torch.arange(g.numel(), device=g.device), g.long()].all(), f"{tpl.key}: sampled a token outside the filtered support"
             if len(tpl.inputs) > 1:                          # a filtered sampler: the filter must actually remove something
                 assert not e.all(), f"{tpl.key}: degenerate test, the filter keeps everything"
             continue
