@@ -6,6 +6,7 @@ than the L2), multi-rank numbers are the MAX over ranks.
 """
 from __future__ import annotations
 
+import contextlib
 import json
 import os
 import time
@@ -389,3 +390,37 @@ def bench_kineto(fn, kernel_names, num_tests: int = 30, suppress_kineto_output: 
         tot = sum(getattr(e, "device_time_total", getattr(e, "cuda_time_total", 0.0)) for e in evs)
         out.append(tot / num_tests / 1e6)
     return out[0] if isinstance(kernel_names, str) else tuple(out)
+
+
+class empty_suppress:
+    """No-op stand-in for :class:`suppress_stdout_stderr` (reference testing/utils.py:1701)."""
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *_):
+        return False
+
+
+class suppress_stdout_stderr(contextlib.ExitStack):
+    """Silence both the Python-level streams and file descriptors 1 / 2 (what native libraries print to) inside the block
+    (reference testing/utils.py:1709)."""
+
+    def __enter__(self):
+        super().__enter__()
+        import sys
+
+        sink = self.enter_context(open(os.devnull, "w"))
+        for stream in (sys.stdout, sys.stderr):
+            try:
+                fd = stream.fileno()
+            except (AttributeError, OSError, ValueError):
+                continue                                      # a captured / replaced stream without a descriptor
+            stream.flush()
+            saved = os.dup(fd)
+            self.callback(os.close, saved)
+            self.callback(os.dup2, saved, fd)
+            os.dup2(sink.fileno(), fd)
+        self.enter_context(contextlib.redirect_stdout(sink))
+        self.enter_context(contextlib.redirect_stderr(sink))
+        return self
