@@ -64,3 +64,10 @@ def silu_and_mul_scaled_nvfp4_experts_quantize(a: torch.Tensor, mask: torch.Tens
     if gs.numel() == 1:
         gs = gs.expand(E)
     return scaled_fp4_grouped_quantize(act, mask, gs)
+
+
+def get_act_and_mul_module(*args, **kwargs):
+    """The native module behind this file's ops (reference activation.py get_act_and_mul_module: the JIT module accessor)."""
+    from . import jit
+
+    return jit.load("activation")

@@ -190,3 +190,10 @@ class BatchPrefillWithSharedPrefixPagedKVCacheWrapper:
 
     def end_forward(self) -> None:
         pass
+
+
+def get_cascade_module(*args, **kwargs):
+    """The native module behind this file's ops (reference cascade.py get_cascade_module: the JIT module accessor)."""
+    from . import jit
+
+    return jit.load("cascade")

@@ -20,3 +20,10 @@ def concat_mla_k(k: torch.Tensor, k_nope: torch.Tensor, k_rope: torch.Tensor) ->
         raise ValueError("concat_mla_k: last dims must be contiguous")
     jit.load("ssm").call("concat_mla_k", k, k_nope, k_rope, T, H, nope, rope, k.stride(0), k.stride(1), k_nope.stride(0),
                          k_nope.stride(1), k_rope.stride(0), k.element_size(), 1, stream_ptr(k))
+
+
+def get_concat_mla_module(*args, **kwargs):
+    """The native module behind this file's ops (reference concat_ops.py get_concat_mla_module: the JIT module accessor)."""
+    from . import jit
+
+    return jit.load("ssm")

@@ -81,3 +81,10 @@ def append_paged_mla_kv_cache(append_ckv: torch.Tensor, append_kpe: torch.Tensor
         append_kpe.stride(0), ckv_cache.stride(0), ckv_cache.stride(1), kpe_cache.stride(0), kpe_cache.stride(1),
         dtype_code(ckv_cache.dtype), 1, stream_ptr(append_ckv),
     )
+
+
+def get_page_module(*args, **kwargs):
+    """The native module behind this file's ops (reference page.py get_page_module: the JIT module accessor)."""
+    from . import jit
+
+    return jit.load("page")

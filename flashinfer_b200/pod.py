@@ -226,3 +226,17 @@ class BatchPODWithPagedKVCacheWrapper:
 
     def end_forward(self) -> None:
         pass
+
+
+def get_pod_module(*args, **kwargs):
+    """The native module behind this file's ops (reference pod.py get_pod_module: the JIT module accessor)."""
+    from . import jit
+
+    return jit.load("pod_sm100")
+
+
+def get_batch_pod_module(*args, **kwargs):
+    """The native module behind this file's ops (reference pod.py get_batch_pod_module: the JIT module accessor)."""
+    from . import jit
+
+    return jit.load("pod_sm100")

@@ -4,11 +4,33 @@ Chrome/Perfetto ``traceEvents`` JSON (no external dependency)."""
 from __future__ import annotations
 
 import json
+from enum import Enum
 from typing import Dict, List, Optional, Sequence
 
 import torch
 
 START, END, INSTANT = 0, 1, 2
+
+
+class EventType(Enum):
+    """Low two bits of a tag (reference profiler/__init__.py EventType)."""
+    kBegin = 0
+    kEnd = 1
+    kInstant = 2
+
+
+def decode_tag(tag: int, num_blocks: int = 0, num_groups: int = 0):
+    """``(block_idx, group_idx, event_idx, event_type, sm_id)`` of one 32-bit tag.
+
+    The reference packs block / group / SM into the tag itself (bits 12-23 and 24-31); tags written by ``profiler.cuh``
+    carry only ``event << 2 | type`` - block, group and SM id live in the header word of each (block, group) slot - so
+    both layouts decode here: fields that a fib200 tag does not hold come back as 0."""
+    event_type = tag & 0x3
+    if tag >> 12:                                   # reference layout
+        bg = (tag >> 12) & 0xFFF
+        return (bg // num_groups if num_groups else 0, bg % num_groups if num_groups else bg, (tag >> 2) & 0x3FF, event_type,
+                (tag >> 24) & 0xFF)
+    return 0, 0, tag >> 2, event_type, 0
 
 
 def alloc_profiler_buffer(num_blocks: int, num_groups: int, max_events_per_group: int = 256, device="cuda") -> torch.Tensor:

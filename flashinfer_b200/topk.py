@@ -131,3 +131,10 @@ def topk_clusters_page_table_transform(logits, seq_lens, src_page_table, top_k: 
 
 def topk_clusters_ragged_transform(logits, seq_lens, offsets, top_k: int, pdl: bool = False):
     return top_k_ragged_transform(logits, offsets, seq_lens, top_k)
+
+
+def get_topk_module(*args, **kwargs):
+    """The native module behind this file's ops (reference topk.py get_topk_module: the JIT module accessor)."""
+    from . import jit
+
+    return jit.load("topk")

@@ -425,3 +425,12 @@ def backend_requirement(backend_checks=None, common_check=None, heuristic_func=N
 def get_default_generators(device):
     torch.cuda.init()
     return torch.cuda.default_generators[torch.device(device).index or 0]
+
+
+def prepare_jit_additional_args(*args, **kwargs):
+    """Reference utils.py: marshals extra tensor / scalar arguments of user-defined attention variants for its JIT templates.
+    Variants here are compiled C++ functors selected by name (``attention/generic``), so there is nothing to marshal: the
+    arguments are returned unchanged as ``(tensors, scalars)``."""
+    tensors = [a for a in args if hasattr(a, "data_ptr")]
+    scalars = [a for a in args if not hasattr(a, "data_ptr")]
+    return tensors, scalars

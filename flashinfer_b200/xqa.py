@@ -36,3 +36,17 @@ def xqa_mla(q, k_cache, v_cache, page_table, seq_lens, output, workspace_buffer,
                                                 page_table, seq_lens.reshape(-1), int(seq_lens.max()), bmm1_scale=sm)
     output.copy_(res.reshape(output.shape))
     return output
+
+
+def get_xqa_module(*args, **kwargs):
+    """The native module behind this file's ops (reference xqa.py get_xqa_module: the JIT module accessor)."""
+    from . import jit
+
+    return jit.load("decode_sm100")
+
+
+def get_xqa_module_mla(*args, **kwargs):
+    """The native module behind this file's ops (reference xqa.py get_xqa_module_mla: the JIT module accessor)."""
+    from . import jit
+
+    return jit.load("mla_sm100")
