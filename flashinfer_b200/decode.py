@@ -514,3 +514,21 @@ class BatchDecodeMlaWithPagedKVCacheWrapper:
         return self._w.run(q_nope, q_pe, paged_ckv_cache, paged_kpe_cache, out=out, lse=lse, return_lse=return_lse)
 
     forward = run
+
+
+from . import jit as _jit_acc  # noqa: E402
+
+get_batch_decode_module = _jit_acc.module_accessor("decode_sm100")
+get_batch_decode_jit_module = _jit_acc.module_accessor("decode_sm100")
+get_single_decode_module = _jit_acc.module_accessor("decode_sm100")
+get_batch_decode_mla_module = _jit_acc.module_accessor("mla_sm100")
+get_trtllm_gen_decode_module = _jit_acc.module_accessor("decode_sm100")
+get_trtllm_gen_fmha_module = _jit_acc.module_accessor("decode_sm100")
+
+
+def single_decode_with_kv_cache_with_jit_module(jit_module, q, k, v, *args, kv_layout: str = "NHD", window_left: int = -1,
+                                                return_lse: bool = False, **kwargs):
+    """Reference decode.py: run single-request decode through an explicitly supplied JIT module (custom attention variants).
+    Variants here live in the generic attention module and are selected by arguments, so ``jit_module`` only has to be a loaded
+    native module; the call is :func:`single_decode_with_kv_cache`."""
+    return single_decode_with_kv_cache(q, k, v, kv_layout=kv_layout, window_left=window_left, return_lse=return_lse, **kwargs)

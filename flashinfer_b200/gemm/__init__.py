@@ -44,3 +44,12 @@ def is_cute_dsl_available() -> bool:
 from .. import _alias  # noqa: E402
 
 _alias.install(__name__, ['gemm_base', 'routergemm'])  # the reference's per-file module paths
+
+
+from .. import jit as _jit_acc  # noqa: E402
+
+get_gemm_module = _jit_acc.module_accessor("gemm_sm100")
+get_gemm_sm100_module = _jit_acc.module_accessor("gemm_sm100")
+get_cutlass_fp4_gemm_module = _jit_acc.module_accessor("gemm_blockscaled_sm100")
+get_cutlass_mxfp8_gemm_module = _jit_acc.module_accessor("gemm_blockscaled_sm100")
+get_deepgemm_sm100_module = _jit_acc.module_accessor("gemm_blockscaled_sm100")

@@ -537,3 +537,14 @@ def get_act_and_mul_cu_str(act_func_name: str, act_func_def: str) -> str:
     """Source of a custom gated activation in the style of csrc/elementwise/activation.cu (for ``gen_jit_spec``)."""
     return (f"// generated: {act_func_name}\\n#include <fib200/common.cuh>\\n__device__ __forceinline__ float {act_func_name}(float x)"
             f" {{ {act_func_def} }}\\n")
+
+
+def module_accessor(name: str, doc: str = ""):
+    """``get_<x>_module()`` of the reference's op files: returns the loaded native module ``name`` (arguments that select a
+    JIT specialisation in the reference - dtypes, head dims, backends - are accepted and ignored: one library serves all)."""
+
+    def get(*args, **kwargs):
+        return load(name)
+
+    get.__doc__ = doc or f"The native module '{name}' (reference: the JIT-module accessor of the same name)."
+    return get

@@ -12,3 +12,10 @@ from ._core import (  # noqa: F401,E402
     smaller_mla_dimensions,
     supported_mla_layer_dimensions,
 )
+
+
+from .. import jit as _jit_acc  # noqa: E402
+
+get_mla_module = _jit_acc.module_accessor("mla_sm100")
+get_batch_mla_module = _jit_acc.module_accessor("mla_sm100")
+get_trtllm_gen_fmha_module = _jit_acc.module_accessor("mla_sm100")

@@ -300,3 +300,8 @@ def qk_rmsnorm_cute(q: torch.Tensor, k: torch.Tensor, q_weight: torch.Tensor, k_
         if res.data_ptr() != flat.data_ptr():
             t.copy_(res.view_as(t))
     return q, k
+
+
+from . import jit as _jit_acc  # noqa: E402
+
+get_norm_module = _jit_acc.module_accessor("norm")

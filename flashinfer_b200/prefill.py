@@ -557,3 +557,47 @@ def cudnn_batch_prefill_with_kv_cache(q, k_cache, v_cache, scale, workspace_buff
     w = BatchPrefillWithRaggedKVCacheWrapper(workspace_buffer)
     w.plan(qo, kvi, q.shape[1], k_cache.shape[1], q.shape[2], causal=causal, sm_scale=scale, q_data_type=q.dtype)
     return w.run(q, k_cache, v_cache, out=out, lse=lse, return_lse=return_lse)
+
+
+from . import jit as _jit_acc  # noqa: E402
+
+get_batch_prefill_module = _jit_acc.module_accessor("prefill_sm100")
+get_batch_prefill_jit_module = _jit_acc.module_accessor("prefill_sm100")
+get_single_prefill_module = _jit_acc.module_accessor("prefill_sm100")
+get_customize_batch_prefill_module = _jit_acc.module_accessor("attention_generic")
+get_fmha_module = _jit_acc.module_accessor("prefill_sm100")
+get_trtllm_fmha_v2_module = _jit_acc.module_accessor("prefill_sm100")
+get_trtllm_gen_prefill_module = _jit_acc.module_accessor("prefill_sm100")
+get_trtllm_gen_fmha_module = _jit_acc.module_accessor("prefill_sm100")
+
+
+def single_prefill_with_kv_cache_with_jit_module(jit_module, q, k, v, *args, kv_layout: str = "NHD", mask_mode: int = 0,
+                                                 window_left: int = -1, return_lse: bool = False, **kwargs):
+    """Reference prefill.py: single-request prefill through an explicitly supplied JIT module; ``mask_mode`` 1 = causal."""
+    return single_prefill_with_kv_cache(q, k, v, causal=(mask_mode == 1), kv_layout=kv_layout, window_left=window_left,
+                                        return_lse=return_lse, **kwargs)
+
+
+def make_hashable_cache(func):
+    """``functools.cache`` that tolerates unhashable arguments (lists / dicts are frozen into tuples) - the reference uses it
+    to memoise JIT-module getters keyed by lists of extra tensor names."""
+    import functools
+
+    def freeze(x):
+        if isinstance(x, (list, tuple)):
+            return tuple(freeze(i) for i in x)
+        if isinstance(x, dict):
+            return tuple(sorted((k, freeze(v)) for k, v in x.items()))
+        return x
+
+    memo = {}
+
+    @functools.wraps(func)
+    def wrapper(*args, **kwargs):
+        key = (freeze(args), freeze(kwargs))
+        if key not in memo:
+            memo[key] = func(*args, **kwargs)
+        return memo[key]
+
+    wrapper.cache_clear = memo.clear
+    return wrapper

@@ -37,3 +37,11 @@ def get_fp4_quantization_module(backend: str = "100"):
 from .. import _alias  # noqa: E402
 
 _alias.install(__name__, ['fp4_quantization', 'fp8_quantization'])  # the reference's per-file module paths
+
+
+from .. import jit as _jit_acc  # noqa: E402
+
+get_mxfp8_quantization_sm100_module = _jit_acc.module_accessor("quantization")
+get_fp4_kv_quantization_module = _jit_acc.module_accessor("quantization")
+get_fp4_kv_dequantization_module = _jit_acc.module_accessor("quantization")
+gen_fp4_quantization_sm100_module = _jit_acc.module_accessor("quantization")

@@ -228,3 +228,8 @@ def rope_quantize_fp8_append_paged_kv_cache(q_rope, k_rope, q_nope, k_nope, v, c
         q_nope_out.copy_(qn)
         qn = q_nope_out
     return qr, qn
+
+
+from . import jit as _jit_acc  # noqa: E402
+
+get_rope_module = _jit_acc.module_accessor("rope")

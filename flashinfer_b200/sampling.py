@@ -240,3 +240,8 @@ def chain_speculative_sampling(draft_probs, draft_token_ids, target_probs, maybe
         stream_ptr(draft_probs),
     )
     return out, acc, emi
+
+
+from . import jit as _jit_acc  # noqa: E402
+
+get_sampling_module = _jit_acc.module_accessor("sampling")

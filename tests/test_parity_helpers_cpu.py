@@ -232,3 +232,19 @@ def test_cli_export_compile_commands_and_cubin_commands(tmp_path, capsys):
     assert main(["list-cubins"]) == 0 and main(["download-cubin"]) == 0
     text = capsys.readouterr().out
     assert "gemm_sm100" in text and "built from source" in text
+
+
+def test_module_accessors_and_moe_layout_helpers():
+    import torch
+
+    from flashinfer_b200 import decode, fused_moe, gemm, jit, mla, norm, prefill
+
+    for get, name in ((decode.get_batch_decode_module, "decode_sm100"), (prefill.get_batch_prefill_module, "prefill_sm100"),
+                      (norm.get_norm_module, "norm"), (gemm.get_gemm_sm100_module, "gemm_sm100"), (mla.get_batch_mla_module, "mla_sm100")):
+        assert get("ignored", dtype=torch.bfloat16) is jit.load(name)
+    assert fused_moe.get_reorder_rows_for_gated_act_gemm_row_indices(torch.zeros(8, 2)).tolist() == [0, 4, 1, 5, 2, 6, 3, 7]
+    idx = fused_moe.get_w2_permute_indices_with_cache({}, torch.zeros(256, 16), 128)
+    assert sorted(idx.tolist()) == list(range(256))
+    calls = []
+    cached = prefill.make_hashable_cache(lambda names, opts=None: calls.append(1) or len(calls))
+    assert cached(["a", "b"], opts={"k": [1]}) == cached(["a", "b"], opts={"k": [1]}) == 1 and cached(["a"]) == 2
