@@ -242,7 +242,18 @@ class AutoTuner:
         with cls._lock:
             if cls._instance is None:
                 cls._instance = AutoTuner()
+                cls._instance._load_shipped()
             return cls._instance
+
+    def _load_shipped(self) -> None:
+        """Seed the cache with the tuned-config file shipped for this device (``tuning_configs/``), then with the user's
+        ``$FLASHINFER_AUTOTUNER_CACHE``; a missing or unreadable file is not an error."""
+        for path in (get_config_path(), os.environ.get("FLASHINFER_AUTOTUNER_CACHE")):
+            if path and os.path.exists(path):
+                try:
+                    self.load_configs(path)
+                except (OSError, ValueError, KeyError):
+                    pass
 
     # ---- cache
     def _bucket_shapes(self, inputs: Sequence[Any], cfg: TuningConfig) -> Tuple:

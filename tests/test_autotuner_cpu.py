@@ -139,3 +139,21 @@ def test_lowp_gemm_asks_the_tuner_for_its_n_tile(tuner, monkeypatch):
     lowp._launch("fp8", a2, b, o2, None, None, None, None, 64)   # same M bucket (64): cached choice, no profiling
     lowp._launch("fp8", a2, b, o2, None, None, None, None, 64, bn=256)   # an explicit tile always wins
     assert seen == [128, 256]
+
+
+def test_shipped_and_env_configs_seed_the_singleton(tmp_path, monkeypatch):
+    import flashinfer_b200.autotuner as at
+
+    shipped, user = tmp_path / "shipped.json", tmp_path / "user.json"
+    a = AutoTuner()
+    a.profiling_cache[("op_s", "R", ((8,),), ())] = (0, 64, 0.1)
+    a.save_configs(str(shipped))
+    b = AutoTuner()
+    b.profiling_cache[("op_u", "R", ((8,),), ())] = (0, 128, 0.1)
+    b.save_configs(str(user))
+    monkeypatch.setattr(at, "get_config_path", lambda is_module=False: str(shipped))
+    monkeypatch.setenv("FLASHINFER_AUTOTUNER_CACHE", str(user))
+    monkeypatch.setattr(AutoTuner, "_instance", None)
+    t = AutoTuner.get()
+    assert t.profiling_cache[("op_s", "R", ((8,),), ())][1] == 64 and t.profiling_cache[("op_u", "R", ((8,),), ())][1] == 128
+    monkeypatch.setattr(AutoTuner, "_instance", None)          # the next get() builds a clean singleton for the other tests
