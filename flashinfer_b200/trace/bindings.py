@@ -77,6 +77,8 @@ BINDINGS: List[Tuple[str, str, "_t.TraceTemplate"]] = [
     ("decode", "cudnn_batch_decode_with_kv_cache", T.cudnn_batch_decode_trace),
     ("gdn", "gated_delta_rule_decode", T.gated_delta_rule_decode_trace),
     ("gdn", "chunk_gated_delta_rule", T.chunk_gated_delta_rule_trace),
+    ("rope", "rope_quantize_fp8", T.rope_quantize_fp8_trace),
+    ("rope", "mla_rope_quantize_fp8", T.mla_rope_quantize_fp8_trace),
 ]
 
 _PKG = __name__.rsplit(".", 2)[0]

@@ -228,3 +228,63 @@ def _make_cache(name, inplace):
 
 apply_rope_with_cos_sin_cache_trace = _make_cache("apply_rope_with_cos_sin_cache", False)
 apply_rope_with_cos_sin_cache_inplace_trace = _make_cache("apply_rope_with_cos_sin_cache_inplace", True)
+
+
+# ---- RoPE + fp8 quantisation of split (rope | nope) heads: the MLA / DeepSeek pre-attention step
+def _rope_quantize_fp8_reference(q_rope, k_rope, q_nope, k_nope, cos_sin_cache, pos_ids, is_neox=True, quant_scale_q=1.0, quant_scale_kv=1.0):
+    """Rotate the rope slices with the cached cos / sin of each token's position, multiply every slice by its quantisation
+    scale and cast to e4m3 (saturating).  k slices may be [nnz, d] (one shared head, MLA) or [nnz, Hk, d]."""
+    rd = cos_sin_cache.shape[-1]
+    cs = cos_sin_cache[pos_ids.long()].to(torch.float32)
+    cos, sin = cs[:, None, : rd // 2], cs[:, None, rd // 2:]
+
+    def rotate(x):
+        xf = x.to(torch.float32)
+        xf = xf[:, None, :] if x.dim() == 2 else xf
+        if is_neox:
+            a, b = xf[..., : rd // 2], xf[..., rd // 2: rd]
+            rot = torch.cat([a * cos - b * sin, b * cos + a * sin], dim=-1)
+        else:
+            a, b = xf[..., 0:rd:2], xf[..., 1:rd:2]
+            rot = torch.stack([a * cos - b * sin, b * cos + a * sin], dim=-1).flatten(-2)
+        rot = torch.cat([rot, xf[..., rd:]], dim=-1)
+        return rot[:, 0, :] if x.dim() == 2 else rot
+
+    def quant(x, s):
+        return (x.to(torch.float32) * s).clamp(-448.0, 448.0).to(torch.float8_e4m3fn)
+
+    return quant(rotate(q_rope), quant_scale_q), quant(rotate(k_rope), quant_scale_kv), quant(q_nope, quant_scale_q), quant(k_nope, quant_scale_kv)
+
+
+def _rope_quantize_fp8_init(*, nnz=64, num_heads=128, rope_dim=64, nope_dim=512, max_position=4096, device="cuda", seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    inv = 1.0 / (1e4 ** (torch.arange(0, rope_dim, 2, dtype=torch.float32) / rope_dim))
+    ang = torch.arange(max_position, dtype=torch.float32)[:, None] * inv[None, :]
+    mk = lambda *s: torch.randn(*s, generator=g).to(torch.bfloat16).to(device)  # noqa: E731
+    return {"q_rope": mk(nnz, num_heads, rope_dim), "k_rope": mk(nnz, rope_dim), "q_nope": mk(nnz, num_heads, nope_dim), "k_nope": mk(nnz, nope_dim),
+            "cos_sin_cache": torch.cat([torch.cos(ang), torch.sin(ang)], dim=-1).to(device),
+            "pos_ids": torch.randint(0, max_position, (nnz,), generator=g, dtype=torch.int32).to(device), "is_neox": True,
+            "quant_scale_q": 0.5, "quant_scale_kv": 0.25}
+
+
+def _fp8_pairs_compare(got, expected, kwargs):
+    for g_, e_ in zip(got, expected):
+        assert g_.dtype == torch.float8_e4m3fn and g_.shape == e_.shape
+        torch.testing.assert_close(g_.to(torch.float32), e_.to(torch.float32), atol=2.0 ** -6, rtol=0.13)     # one e4m3 step
+
+
+def _make_rq(name, desc):
+    return TraceTemplate(
+        op_type="rope", name_fmt=name + "_h{num_heads}_r{rope_dim}_n{nope_dim}",
+        axes=[Var("nnz"), Var("max_position"), Const("num_heads", abbrev="h"), Const("rope_dim", abbrev="r"), Const("nope_dim", abbrev="n")],
+        inputs=[Tensor("q_rope", ("nnz", "num_heads", "rope_dim")), Tensor("k_rope", ("nnz", "rope_dim")), Tensor("q_nope", ("nnz", "num_heads", "nope_dim")),
+                Tensor("k_nope", ("nnz", "nope_dim")), Tensor("cos_sin_cache", ("max_position", "rope_dim"), "float32"), Tensor("pos_ids", ("nnz",), "int32"),
+                Scalar("is_neox", "bool", optional=True), Scalar("quant_scale_q", optional=True), Scalar("quant_scale_kv", optional=True)],
+        outputs=[Tensor("q_rope_out", ("nnz", "num_heads", "rope_dim"), dtype="float8_e4m3fn"), Tensor("k_rope_out", ("nnz", "rope_dim"), dtype="float8_e4m3fn"),
+                 Tensor("q_nope_out", ("nnz", "num_heads", "nope_dim"), dtype="float8_e4m3fn"), Tensor("k_nope_out", ("nnz", "nope_dim"), dtype="float8_e4m3fn")],
+        reference=_rope_quantize_fp8_reference, init=_rope_quantize_fp8_init, compare=_fp8_pairs_compare, tags=("rope", "fp8", "mla"),
+        description=desc, test_sizes={"num_heads": 4, "rope_dim": 16, "nope_dim": 32, "max_position": 64})
+
+
+rope_quantize_fp8_trace = _make_rq("rope_quantize_fp8", "RoPE on the rotary slices + fp8 quantisation of rope and no-rope slices of q and k")
+mla_rope_quantize_fp8_trace = _make_rq("mla_rope_quantize_fp8", "MLA spelling of rope_quantize_fp8 (shared 2-D k slices)")
