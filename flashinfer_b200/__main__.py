@@ -84,10 +84,14 @@ def _cmd_replay(args) -> int:
 
 
 def _cmd_trace_templates(args) -> int:
-    from .trace import registered_templates
+    from .trace import Const, registered_templates
 
-    for k in registered_templates():
-        print(k)
+    for k, t in sorted(registered_templates().items()):
+        if getattr(args, "verbose", False):
+            axes = " ".join(("%s=const" if isinstance(a, Const) else "%s=var") % a.name for a in t.axes)
+            print(f"{k:<90} {t.fi_api or '(unbound)':<70} ref={'yes' if t.reference else 'no '} init={'yes' if t.init else 'no '} {axes}")
+        else:
+            print(k)
     return 0
 
 
@@ -150,7 +154,9 @@ def main(argv=None) -> int:
     r.add_argument("path")
     r.add_argument("--sequence", action="store_true")
     r.set_defaults(fn=_cmd_replay)
-    sub.add_parser("trace-templates").set_defaults(fn=_cmd_trace_templates)
+    t = sub.add_parser("trace-templates", help="list the fi_trace templates (-v: bound API, reference / init presence, axes)")
+    t.add_argument("-v", "--verbose", action="store_true")
+    t.set_defaults(fn=_cmd_trace_templates)
     e = sub.add_parser("export-compile-commands", help="write compile_commands.json for the native modules")
     e.add_argument("modules", nargs="*")
     e.add_argument("-o", "--output", default=None)
