@@ -167,3 +167,47 @@ segment_gemm_trace = TraceTemplate(
     outputs=[Tensor("y", ("total_rows", "d_out"), dtype_from="x")], reference=_segment_gemm_reference, init=_segment_gemm_init,
     tags=("gemm", "grouped"), constraints=("len_indptr == batch_size + 1",), description="Per-segment GEMM (LoRA / grouped experts)",
     tolerance="cos", test_sizes={"d_in": 64, "d_out": 48})
+
+
+# ---- block-scaled FP4 GEMM (scales in the 128x4-tiled layout the tensor core's scale path reads)
+def _mm_fp4_reference(a, b, a_descale, b_descale, alpha=None, block_size=16):
+    """a [M, K/2] and b [K/2, N] (= w.t() of an [N, K/2] weight) hold two e2m1 codes per byte (low nibble first).
+    Scales are e4m3 bytes in the 128x4-tiled layout: byte of (row r, k-block c) sits at
+    ((r // 128) * ceil(kb / 4) + c // 4) * 512 + (r % 32) * 16 + ((r % 128) // 32) * 4 + c % 4.   out = alpha * deq(a) @ deq(w).T"""
+    grid = torch.tensor([0.0, 0.5, 1.0, 1.5, 2.0, 3.0, 4.0, 6.0], device=a.device)
+
+    def dequant(packed, sf):
+        rows, kb = packed.shape[0], packed.shape[1] * 2 // block_size
+        r = torch.arange(rows, device=packed.device)[:, None]
+        c = torch.arange(kb, device=packed.device)[None, :]
+        off = ((r // 128) * ((kb + 3) // 4) + c // 4) * 512 + (r % 32) * 16 + ((r % 128) // 32) * 4 + c % 4
+        scale = sf.reshape(-1).view(torch.uint8)[off].view(torch.float8_e4m3fn).to(torch.float32).repeat_interleave(block_size, dim=1)
+        codes = torch.stack([packed & 0xF, packed >> 4], dim=-1).reshape(rows, -1).long()
+        return grid[codes & 7] * torch.where(codes >= 8, -1.0, 1.0) * scale
+
+    out = dequant(a, a_descale) @ dequant(b.t(), b_descale).t()
+    if alpha is not None:
+        out = out * alpha.to(torch.float32)
+    return out.to(torch.bfloat16)
+
+
+def _mm_fp4_init(*, M=64, N=4096, K=4096, device="cuda", seed=0):
+    import flashinfer_b200 as fi
+
+    _, a, w = _ab(M, N, K, device, seed)
+    ga, gw = (448.0 * 6.0) / a.float().abs().max(), (448.0 * 6.0) / w.float().abs().max()
+    aq, asf = fi.fp4_quantize(a, ga.reshape(1))                  # swizzled scales (the default)
+    wq, wsf = fi.fp4_quantize(w, gw.reshape(1))
+    return {"a": aq, "b": wq.t(), "a_descale": asf.reshape(-1), "b_descale": wsf.reshape(-1), "alpha": (1.0 / (ga * gw)).reshape(1).to(device),
+            "out_dtype": torch.bfloat16}
+
+
+mm_fp4_trace = TraceTemplate(
+    op_type="gemm", name_fmt="mm_fp4_n{N}_k{K}", axes=[Var("M"), Const("N"), Const("K")],
+    inputs=[Tensor("a", ("M", "K_half"), "uint8"), Tensor("b", ("K_half", "N"), "uint8"), Tensor("a_descale", ("a_scale_bytes",), "uint8"),
+            Tensor("b_descale", ("b_scale_bytes",), "uint8"), Tensor("alpha", ("one",), "float32", optional=True), Scalar("block_size", "int32", optional=True)],
+    outputs=[Tensor("out", ("M", "N"), dtype="bfloat16")], reference=_mm_fp4_reference, init=_mm_fp4_init, tags=("gemm", "nvfp4"),
+    constraints=("K_half == K / 2", "a_scale_bytes == round_up(M, 128) * round_up(K / 16, 4)", "b_scale_bytes == round_up(N, 128) * round_up(K / 16, 4)",
+                 "one == 1"), derive=lambda s: {"K": 2 * s["K_half"]} if "K_half" in s else {},
+    description="NVFP4 block-scaled GEMM (tcgen05 kind::mxf4nvf4): e2m1 operands, e4m3 scale per 16 elements, global alpha",
+    tolerance="cos", test_sizes={"N": 128, "K": 128})
