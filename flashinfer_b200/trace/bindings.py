@@ -80,6 +80,7 @@ BINDINGS: List[Tuple[str, str, "_t.TraceTemplate"]] = [
     ("rope", "rope_quantize_fp8", T.rope_quantize_fp8_trace),
     ("rope", "mla_rope_quantize_fp8", T.mla_rope_quantize_fp8_trace),
     ("gemm.lowp", "mm_fp4", T.mm_fp4_trace),
+    ("gemm.lowp", "mm_mxfp8", T.mm_mxfp8_trace),
 ]
 
 _PKG = __name__.rsplit(".", 2)[0]

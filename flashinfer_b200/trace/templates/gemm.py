@@ -211,3 +211,36 @@ mm_fp4_trace = TraceTemplate(
                  "one == 1"), derive=lambda s: {"K": 2 * s["K_half"]} if "K_half" in s else {},
     description="NVFP4 block-scaled GEMM (tcgen05 kind::mxf4nvf4): e2m1 operands, e4m3 scale per 16 elements, global alpha",
     tolerance="cos", test_sizes={"N": 128, "K": 128})
+
+
+def _mm_mxfp8_reference(a, b, a_descale, b_descale):
+    """a [M, K] e4m3, b [K, N] (= w.t() of an [N, K] e4m3 weight); UE8M0 scale bytes per 32 elements in the 128x4-tiled layout
+    (see mm_fp4): value = 2^(byte - 127)."""
+    def dequant(x, sf):
+        rows, kb = x.shape[0], x.shape[1] // 32
+        r = torch.arange(rows, device=x.device)[:, None]
+        c = torch.arange(kb, device=x.device)[None, :]
+        off = ((r // 128) * ((kb + 3) // 4) + c // 4) * 512 + (r % 32) * 16 + ((r % 128) // 32) * 4 + c % 4
+        scale = torch.exp2(sf.reshape(-1).view(torch.uint8)[off].to(torch.float32) - 127.0).repeat_interleave(32, dim=1)
+        return x.to(torch.float32) * scale
+
+    return (dequant(a, a_descale) @ dequant(b.t(), b_descale).t()).to(torch.bfloat16)
+
+
+def _mm_mxfp8_init(*, M=64, N=4096, K=4096, device="cuda", seed=0):
+    import flashinfer_b200 as fi
+
+    _, a, w = _ab(M, N, K, device, seed)
+    aq, asf = fi.mxfp8_quantize(a)
+    wq, wsf = fi.mxfp8_quantize(w)
+    return {"a": aq, "b": wq.t(), "a_descale": asf.reshape(-1), "b_descale": wsf.reshape(-1), "out_dtype": torch.bfloat16}
+
+
+mm_mxfp8_trace = TraceTemplate(
+    op_type="gemm", name_fmt="mm_mxfp8_n{N}_k{K}", axes=[Var("M"), Const("N"), Const("K")],
+    inputs=[Tensor("a", ("M", "K"), "float8_e4m3fn"), Tensor("b", ("K", "N"), "float8_e4m3fn"), Tensor("a_descale", ("a_scale_bytes",), "uint8"),
+            Tensor("b_descale", ("b_scale_bytes",), "uint8")],
+    outputs=[Tensor("out", ("M", "N"), dtype="bfloat16")], reference=_mm_mxfp8_reference, init=_mm_mxfp8_init, tags=("gemm", "mxfp8"),
+    constraints=("a_scale_bytes == round_up(M, 128) * round_up(K / 32, 4)", "b_scale_bytes == round_up(N, 128) * round_up(K / 32, 4)"),
+    description="MXFP8 block-scaled GEMM (tcgen05 kind::mxf8f6f4): e4m3 operands with a power-of-two scale per 32 elements",
+    tolerance="cos", test_sizes={"N": 128, "K": 128})
