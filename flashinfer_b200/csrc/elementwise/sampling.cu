@@ -10,6 +10,7 @@
 //    from the probability mass above `low`, then count/sum the entries above pivot0 = p[token] and
 //    pivot1 = (pivot0 + high) / 2 to either accept or shrink (low, high).  No sort, O(rounds * V).
 //  * renorm / mask: bisection on the probability (logit) threshold with fused count + sum reductions.
+#include <float.h>
 #include <curand_kernel.h>
 #include <fib200/common.cuh>
 #include <fib200/ptx.cuh>
@@ -357,15 +358,20 @@ renorm_kernel(const float* __restrict__ in, float* __restrict__ outp, const floa
   int top_k = top_k_arr ? top_k_arr[row] : top_k_val;
   if (top_k <= 0 || top_k > V) top_k = V;
   float mx = -INFINITY, mn = INFINITY;
+  // min over FINITE entries only: rows pre-masked with -inf (banned tokens, grammar masks) are the normal input of
+  // top_k_mask_logits, and a -inf lower bound would stop the bisection on its first step (mid = -inf <= lo)
   for (int i = threadIdx.x; i < V; i += blockDim.x) {
-    mx = fmaxf(mx, x[i]);
-    mn = fminf(mn, x[i]);
+    const float v = x[i];
+    if (v == v) mx = fmaxf(mx, v);                    // NaN never moves a bound
+    if (v > -FLT_MAX && v < FLT_MAX) mn = fminf(mn, v);
   }
   mx = block_reduce_max(mx, smf);
   mn = -block_reduce_max(-mn, smf);
+  if (!(mn < FLT_MAX)) mn = -FLT_MAX * 0.5f;          // no finite entry at all
+  if (mode == 2 && mn < -FLT_MAX * 0.25f) mn = -FLT_MAX * 0.25f;
   // find the largest threshold `lo` such that the kept set {x >= ... } still satisfies the constraint:
   //  top-p: sum(x > t) >= p  (keep everything above t);  top-k: count(x > t) >= k
-  float lo = (mode == 2) ? mn - 1.f : 0.f, hi = mx;
+  float lo = (mode == 2) ? mn - fmaxf(1.f, fabsf(mn) * 1e-6f) : 0.f, hi = mx;
   // invariant: constraint(lo) holds (kept set large enough), constraint(hi) fails
   for (int it = 0; it < 40; ++it) {
     const float mid = 0.5f * (lo + hi);

@@ -16,6 +16,7 @@ from typing import Optional, Tuple, Union
 import torch
 
 from . import jit, reference
+from .utils import host_i32 as _host_i32
 from .utils import (
     check_kv_layout,
     check_pos_encoding_mode,
@@ -202,11 +203,11 @@ class BatchDecodeWithPagedKVCacheWrapper:
         self._sm_scale = sm_scale if sm_scale is not None else 1.0 / math.sqrt(head_dim)
         self._batch_size = batch_size
 
-        indptr_host = indptr.to("cpu", torch.int32)
-        last_host = last_page_len.to("cpu", torch.int32)
+        indptr_host = _host_i32(indptr)
+        last_host = _host_i32(last_page_len)
         n_pages = indptr_host[1:] - indptr_host[:-1]
         kv_lens_host = (torch.clamp(n_pages - 1, min=0) * page_size + torch.where(n_pages > 0, last_host, 0)).to(torch.int32)
-        qo_host = qo_indptr.to("cpu", torch.int32).contiguous() if qo_indptr is not None else None
+        qo_host = _host_i32(qo_indptr) if qo_indptr is not None else None
         self._qo_indptr_host = qo_host
         self._kv_lens_host = kv_lens_host
 
@@ -221,6 +222,7 @@ class BatchDecodeWithPagedKVCacheWrapper:
             self._kv_indices = indices.to(self.device, torch.int32, non_blocking=non_blocking)
         self._kv_indptr_host = indptr_host
         self._kv_last_host = last_host
+        self._gen_key = None  # device copies cached by the generic path belong to the previous plan
 
         # ---- C++ planner into the pinned buffer, then ONE H2D copy ----
         num_ctas = device_sm_count(self.device if self.device.type == "cuda" else None)

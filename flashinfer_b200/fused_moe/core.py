@@ -411,6 +411,38 @@ def _dequant_nvfp4(w: torch.Tensor, sf: torch.Tensor, global_scale, vec: int = 1
 
 
 # ------------------------------------------------------------------ trtllm-gen style entry points
+
+def _activation_name(activation_type) -> str:
+    a = int(activation_type)
+    if a in (int(ActivationType.Swiglu), int(ActivationType.Silu)):
+        return "silu"
+    if a in (int(ActivationType.Geglu), int(ActivationType.Gelu)):
+        return "gelu"
+    if a == int(ActivationType.Relu2):
+        return "relu2"
+    raise NotImplementedError(f"activation_type {ActivationType(a).name} is not implemented")
+
+
+def _fold_gate_scale(s1, s_gate, s2):
+    """Per-expert output scales of the trtllm-gen MoE contract -> (alpha1, alpha2) of a pipeline that applies ONE scale to
+    both halves of FC1.  Contract (reference tests/moe/test_trtllm_gen_fused_moe.py): ``act = silu(gate * s_gate) * (up * s1)``,
+    ``out = (act @ W2^T) * s2``.  The up factor is linear, so ``s1 / s_gate`` moves to FC2's output scale exactly:
+    alpha1 = s_gate on both halves, alpha2 = s2 * s1 / s_gate.  Device-side [E] arithmetic, no host sync."""
+    if s_gate is None:
+        return s1, s2
+    dev = next((t.device for t in (s_gate, s1, s2) if isinstance(t, torch.Tensor)), None)
+    s1t = torch.as_tensor(s1, dtype=torch.float32, device=dev)
+    sg = torch.as_tensor(s_gate, dtype=torch.float32, device=dev)
+    s2t = torch.as_tensor(s2, dtype=torch.float32, device=dev)
+    return sg, s2t * (s1t / sg)
+
+
+def _reject_unsupported(name: str, **kw):
+    """Arguments the native pipelines do not implement must fail loudly instead of being ignored."""
+    bad = [k for k, v in kw.items() if v is not None and v is not False]
+    if bad:
+        raise NotImplementedError(f"{name}: unsupported argument(s) {bad}")
+
 def trtllm_bf16_moe(routing_logits, routing_bias, hidden_states, gemm1_weights, gemm2_weights, num_experts, top_k,
                     n_group, topk_group, intermediate_size, local_expert_offset, local_num_experts,
                     routed_scaling_factor=None, routing_method_type: int = 0, use_shuffled_weight: bool = False,
@@ -427,7 +459,7 @@ def trtllm_bf16_moe(routing_logits, routing_bias, hidden_states, gemm1_weights, 
     if routing_replay_out is not None:
         routing_replay_out.copy_(ids)
     return moe_forward(hidden_states, ids, w, gemm1_weights, gemm2_weights, local_expert_offset, num_experts,
-                       do_finalize=do_finalize)
+                       activation=_activation_name(activation_type), do_finalize=do_finalize)
 
 
 def _unpack_routed(topk_ids: torch.Tensor):
@@ -453,9 +485,11 @@ def trtllm_fp8_per_tensor_scale_moe(routing_logits, routing_bias, hidden_states,
                                     routed_scaling_factor, use_routing_scales_on_input: bool = False,
                                     routing_method_type: int = 0, **kw):
     """fp8 per-tensor MoE: de-quantised to bf16 (scales folded into the weights) and run on the bf16 pipeline."""
+    _reject_unsupported("trtllm_fp8_per_tensor_scale_moe", use_routing_scales_on_input=use_routing_scales_on_input)
     ids, w = route(routing_logits, routing_bias, top_k, routing_method_type, n_group, topk_group, routed_scaling_factor)
-    s1 = output1_scales_scalar.float().reshape(-1, 1, 1)
-    s2 = output2_scales_scalar.float().reshape(-1, 1, 1)
+    a1, a2 = _fold_gate_scale(output1_scales_scalar, output1_scales_gate_scalar, output2_scales_scalar)
+    s1 = a1.float().reshape(-1, 1, 1)
+    s2 = a2.float().reshape(-1, 1, 1)
     w1 = (gemm1_weights.float() * s1).to(torch.bfloat16)
     w2 = (gemm2_weights.float() * s2).to(torch.bfloat16)
     x = hidden_states.float().to(torch.bfloat16)
@@ -489,12 +523,15 @@ def trtllm_fp4_block_scale_moe(routing_logits, routing_bias, hidden_states, hidd
                                local_expert_offset, local_num_experts, routed_scaling_factor,
                                routing_method_type: int = 0, do_finalize: bool = True, **kw):
     """NVFP4 weights (``[E, N, K/2]`` packed e2m1 + linear UE4M3 block scales) with bf16 or nvfp4 activations."""
+    _reject_unsupported("trtllm_fp4_block_scale_moe", gemm1_bias=gemm1_bias, gemm1_alpha=gemm1_alpha, gemm1_beta=gemm1_beta,
+                        gemm1_clamp_limit=gemm1_clamp_limit, gemm2_bias=gemm2_bias)
     ids, w = route(routing_logits, routing_bias, top_k, routing_method_type, n_group, topk_group, routed_scaling_factor)
     x = hidden_states
     if x.dtype == torch.uint8:
         x = _dequant_nvfp4(x, hidden_states_scale, 1.0)
     g1 = output1_scale_scalar if output1_scale_scalar is not None else 1.0
     g2 = output2_scale_scalar if output2_scale_scalar is not None else 1.0
+    g1, g2 = _fold_gate_scale(g1, output1_scale_gate_scalar, g2)
     if x.is_cuda and do_finalize and hidden_states.shape[-1] % 64 == 0 and intermediate_size % 64 == 0:
         return moe_forward_nvfp4(x, ids, w, gemm1_weights, gemm1_weights_scale, g1, gemm2_weights, gemm2_weights_scale, g2,
                                  local_expert_offset, num_experts)
@@ -509,12 +546,15 @@ def trtllm_fp4_block_scale_routed_moe(topk_ids, routing_bias, hidden_states, hid
                                       output1_scale_gate_scalar, output2_scale_scalar, num_experts, top_k, n_group,
                                       topk_group, intermediate_size, local_expert_offset, local_num_experts,
                                       routed_scaling_factor, routing_method_type: int = 1, do_finalize: bool = True, **kw):
+    _reject_unsupported("trtllm_fp4_block_scale_routed_moe", gemm1_bias=gemm1_bias, gemm1_alpha=gemm1_alpha,
+                        gemm1_beta=gemm1_beta, gemm1_clamp_limit=gemm1_clamp_limit, gemm2_bias=gemm2_bias)
     ids, w = _unpack_routed(topk_ids)
     x = hidden_states
     if x.dtype == torch.uint8:
         x = _dequant_nvfp4(x, hidden_states_scale, 1.0)
     g1 = output1_scale_scalar if output1_scale_scalar is not None else 1.0
     g2 = output2_scale_scalar if output2_scale_scalar is not None else 1.0
+    g1, g2 = _fold_gate_scale(g1, output1_scale_gate_scalar, g2)
     return moe_forward(x.to(torch.bfloat16), ids, w, _dequant_nvfp4(gemm1_weights, gemm1_weights_scale, g1),
                        _dequant_nvfp4(gemm2_weights, gemm2_weights_scale, g2), local_expert_offset, num_experts,
                        do_finalize=do_finalize)

@@ -51,7 +51,15 @@ def _sf_swizzled(sf: torch.Tensor, rows: int, kc: int, batch: int = 1, swizzled:
     if swizzled:
         if sf.numel() != batch * per:
             raise ValueError(f"swizzled scale tensor has {sf.numel()} bytes, expected {batch * per}")
-        return sf.reshape(batch, per).contiguous()
+        if not sf.is_contiguous():
+            # the reference idiom mm_fp4(a, b.T, a_sf, b_sf.T, ...) hands over a transposed VIEW of the swizzled buffer: the
+            # bytes are already in storage order, so undo the view instead of letting reshape() linearise it in logical order
+            if sf.dim() >= 2 and sf.transpose(-1, -2).is_contiguous():
+                sf = sf.transpose(-1, -2)
+            else:
+                raise ValueError("swizzled scale tensors must be contiguous (or a plain .T view of a contiguous buffer); "
+                                 f"got shape {tuple(sf.shape)} strides {tuple(sf.stride())}")
+        return sf.reshape(batch, per)
     if sf.shape[-2:] == (rows, kc):
         return block_scale_interleave(sf.contiguous()).reshape(batch, per)
     if sf.shape[-2:] == (kc, rows):  # transposed linear scales ([k/vec, n])

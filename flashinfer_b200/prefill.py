@@ -14,6 +14,7 @@ from typing import Optional, Tuple, Union
 import torch
 
 from . import jit, reference
+from .utils import host_i32 as _host_i32
 from .utils import (
     check_kv_layout,
     check_pos_encoding_mode,
@@ -164,8 +165,9 @@ class _BatchPrefillBase:
         self._q_dtype = _canon_dtype(q_data_type)
         self._kv_dtype = _canon_dtype(kv_data_type) if kv_data_type is not None else self._q_dtype
         self._custom_mask = custom_mask
-        qo_host = qo_indptr.to("cpu", torch.int32).contiguous()
+        qo_host = _host_i32(qo_indptr)
         self._qo_indptr_host = qo_host
+        self._gen_cache_key = None  # device copies cached by the generic path belong to the previous plan
         self._kv_lens_host = kv_lens_host.to(torch.int32).contiguous()
         self._batch_size = qo_host.numel() - 1
         # ---- C++ LPT planner: (request, q-tile, q-head) units over the persistent grid ----
@@ -392,8 +394,8 @@ class BatchPrefillWithPagedKVCacheWrapper(_BatchPrefillBase):
         if pos_encoding_mode != "NONE":
             raise NotImplementedError("in-kernel positional encoding")
         self._page_size = page_size
-        indptr_host = paged_kv_indptr.to("cpu", torch.int32)
-        last_host = paged_kv_last_page_len.to("cpu", torch.int32)
+        indptr_host = _host_i32(paged_kv_indptr)
+        last_host = _host_i32(paged_kv_last_page_len)
         n_pages = indptr_host[1:] - indptr_host[:-1]
         kv_lens = torch.clamp(n_pages - 1, min=0) * page_size + torch.where(n_pages > 0, last_host, 0)
         self._kv_indptr_host, self._kv_last_host = indptr_host, last_host

@@ -58,7 +58,7 @@ def _quant_cpu(x: torch.Tensor, gs: float, vec: int, ue8m0: bool):
     idx = torch.bucketize(mag, (grid[1:] + grid[:-1]) / 2)
     mids = (grid[1:] + grid[:-1]) / 2
     tie = (mag[..., None] == mids).any(-1)
-    idx = torch.where(tie & (idx % 2 == 1), idx - 1, idx)
+    idx = torch.where(tie & (idx % 2 == 1), idx + 1, idx)  # bucketize returns the LOWER code on an exact tie: step up to the even one
     code = idx.to(torch.uint8) | ((y < 0).to(torch.uint8) << 3)
     code = code.view(m, k)
     packed = code[:, 0::2] | (code[:, 1::2] << 4)

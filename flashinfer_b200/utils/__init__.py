@@ -97,6 +97,16 @@ def unpack_paged_kv_cache(
     return k, v
 
 
+def host_i32(t: torch.Tensor) -> torch.Tensor:
+    """Private int32 CPU copy of plan() metadata.  ``Tensor.to`` returns the SAME object when the input already is CPU int32,
+    so a caller that edits its preallocated indptr in place would silently change planned state (and id()-keyed caches would
+    never notice): always detach from the caller's storage."""
+    h = t.to("cpu", torch.int32).contiguous()
+    if h.data_ptr() == t.data_ptr():
+        h = h.clone()
+    return h
+
+
 def paged_kv_strides(k_cache: torch.Tensor, kv_layout: str):
     """(stride_page, stride_n, stride_h, page_size, num_kv_heads, head_dim) in elements."""
     if kv_layout == "NHD":

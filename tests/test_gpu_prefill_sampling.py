@@ -74,6 +74,13 @@ def test_softmax_and_renorm():
     assert (((r > 0).sum(-1) - nkeep).abs() <= 1).all()
     m = sampling.top_k_mask_logits(logits, 10)
     assert (torch.isfinite(m).sum(-1) == 10).all()
+    # rows that already carry -inf (banned tokens / grammar masks) must still be cut down to k entries
+    pre = logits.clone()
+    pre[:, ::3] = float("-inf")
+    m = sampling.top_k_mask_logits(pre, 10)
+    assert (torch.isfinite(m).sum(-1) == 10).all()
+    kept = torch.where(torch.isfinite(m), m, torch.full_like(m, -1e30)).topk(10).values
+    torch.testing.assert_close(kept, pre.topk(10).values)
 
 
 def test_sampling_distributions():

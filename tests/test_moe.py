@@ -271,3 +271,35 @@ def test_moe_sort_paths_gpu(T, E, K, off, local):
         assert (p2t_c[ref_off[e] + idx.numel():ref_off[e + 1]] == -1).all()
         assert (te[ref_off[e] // tile:ref_off[e + 1] // tile] == e).all()
     assert (p2t_c[ref_off[-1]:] == -1).all() and (te[ref_off[-1] // tile:] == -1).all()
+
+
+def test_fp8_per_tensor_moe_gate_scale_cpu():
+    """``act = silu(gate * s_gate) * (up * s1)``, ``out = act @ W2 * s2`` with s_gate != s1 (c_global_sf != 1)."""
+    import flashinfer_b200 as fi
+    from flashinfer_b200.fused_moe import core
+
+    torch.manual_seed(1)
+    T, H, I, E, K = 16, 64, 32, 4, 2
+    x = torch.randn(T, H).to(torch.bfloat16)
+    w1 = (torch.randn(E, 2 * I, H) * 0.2).to(torch.float8_e4m3fn)
+    w2 = (torch.randn(E, H, I) * 0.2).to(torch.float8_e4m3fn)
+    logits = torch.randn(T, E)
+    c_gs = 3.0
+    s_gate = torch.full((E,), 0.5)
+    s1 = s_gate * c_gs
+    s2 = torch.full((E,), 0.25) / c_gs
+    out = core.trtllm_fp8_per_tensor_scale_moe(logits, None, x, w1, s1, s_gate, w2, s2, E, K, None, None, I, 0, E, None,
+                                               routing_method_type=int(core.RoutingMethodType.Renormalize))
+    ids, wts = core.route(logits, None, K, int(core.RoutingMethodType.Renormalize))
+    ref = torch.zeros(T, H)
+    for t in range(T):
+        for j in range(K):
+            e = int(ids[t, j])
+            h = x[t].float() @ w1[e].float().t()
+            up, gate = h[:I], h[I:]
+            act = torch.nn.functional.silu(gate * s_gate[e]) * (up * s1[e])
+            ref[t] += wts[t, j] * (act @ w2[e].float().t()) * s2[e]
+    torch.testing.assert_close(out.float(), ref, rtol=5e-2, atol=5e-2)
+    with pytest.raises(NotImplementedError):
+        core.trtllm_fp8_per_tensor_scale_moe(logits, None, x, w1, s1, s_gate, w2, s2, E, K, None, None, I, 0, E, None,
+                                             use_routing_scales_on_input=True)

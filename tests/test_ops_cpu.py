@@ -89,3 +89,37 @@ def test_page_append_and_positions_cpu():
     torch.testing.assert_close(kk[30:33], k[5:])
     torch.testing.assert_close(vv[30:33], v[5:])
     assert page.get_seq_lens(indptr, last, 16).tolist() == kv_lens
+
+
+def test_fp4_oracle_rounds_ties_to_even():
+    """All 7 midpoints of the e2m1 grid round to the even code (cvt.rn semantics) - ADVICE r1."""
+    from flashinfer_b200.quantization.fp4 import E2M1_VALUES, fp4_quantize
+
+    mids = [0.25, 0.75, 1.25, 1.75, 2.5, 3.5, 5.0]
+    x = torch.tensor([mids + [6.0] + [0.0] * 8], dtype=torch.bfloat16)  # amax 6 -> block scale 1
+    q, _ = fp4_quantize(x, torch.tensor([1.0]), 16, False, False)
+    codes = torch.stack([q[0] & 0xF, q[0] >> 4], -1).reshape(-1)[:7]
+    assert [E2M1_VALUES[int(c)] for c in codes] == [0.0, 1.0, 1.0, 2.0, 2.0, 4.0, 4.0]
+    qn, _ = fp4_quantize(-x, torch.tensor([1.0]), 16, False, False)
+    assert torch.equal(qn[0, :4] & 0x77, q[0, :4] & 0x77)  # magnitudes symmetric
+
+
+def test_mm_fp4_accepts_transposed_scale_view():
+    """The reference idiom mm_fp4(a, b.T, a_sf, b_sf.T, alpha) (tests/gemm/test_mm_fp4.py) passes a transposed VIEW of the
+    swizzled weight scales: the result must match the call with the plain tensor."""
+    torch.manual_seed(0)
+    m, n, k = 48, 256, 128
+    a = torch.randn(m, k, dtype=torch.bfloat16)
+    w = torch.randn(n, k, dtype=torch.bfloat16)
+    ga = (448.0 * 6.0) / a.float().abs().amax()
+    gw = (448.0 * 6.0) / w.float().abs().amax()
+    aq, asf = fi.nvfp4_quantize(a, ga.reshape(1))
+    wq, wsf = fi.nvfp4_quantize(w, gw.reshape(1))
+    assert wsf.dim() == 2
+    alpha = 1.0 / (ga * gw)
+    plain = fi.mm_fp4(aq, wq.T, asf, wsf, alpha, torch.bfloat16)
+    viewed = fi.mm_fp4(aq, wq.T, asf, wsf.T, alpha, torch.bfloat16)
+    assert torch.equal(plain, viewed)
+    ref = a.float() @ w.float().t()
+    cos = torch.nn.functional.cosine_similarity(plain.float().reshape(-1), ref.reshape(-1), dim=0)
+    assert cos > 0.97
