@@ -84,7 +84,7 @@ def run_ours(args, rank, world):
         from flashinfer_b200.comm import TPCommunicator
         comm = TPCommunicator(dist.group.WORLD, max_tokens=BATCH, hidden=cfg.hidden_size, dtype=torch.bfloat16)
     indptr, indices, last, n_pages = _kv_layout(BATCH, KV_LEN, PAGE, torch)
-    eng = LlamaDecodeEngine(cfg, BATCH, n_pages, PAGE, tp_rank=rank, tp_size=world, comm=comm)
+    eng = LlamaDecodeEngine(cfg, BATCH, n_pages, PAGE, tp_rank=rank, tp_size=world, comm=comm, fused=not args.unfused)
     eng.fill_kv_random()
     eng.plan(indptr, indices, last)
     # host-side inputs in pinned memory (e2e path) + device staging
@@ -95,7 +95,8 @@ def run_ours(args, rank, world):
     eng.step()
     torch.cuda.synchronize()
     native_per_step = jit.native_launch_count() - c0
-    torch_per_step = 4 if world == 1 else 6  # index_select, zero_, argmax(+max/gather)
+    # torch-launched kernels per step: op-by-op path index_select, zero_, argmax (+ max / gather glue at tp > 1); fused path: argmax
+    torch_per_step = (1 if world == 1 else 3) if eng.fused else (4 if world == 1 else 6)
     if args.eager_steps > 0:  # ncu / profiler mode: plain eager launches, no timing contract
         for _ in range(args.eager_steps):
             eng.step()
@@ -157,10 +158,18 @@ def run_ours(args, rank, world):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic (random-init weights, random KV cache, random token ids)", "impl": "flashinfer_b200",
+            # same keys as the reference arm's config (the driver compares the two dicts)
             "config": {"model": "llama-3-8b", "global_batch": BATCH, "seq_len": KV_LEN, "page_size": PAGE,
                        "parallelism": f"tp{world}", "kv_layout": "NHD", "cuda_graph": True,
                        "l2_policy": "inputs larger than L2 (34 GB KV + 16 GB weights streamed per step)",
-                       "attention_kv_tb_per_s_equiv": kv_bytes / world / (ms_per_step / 1e3) / 1e12},
+                       "attention_kv_tb_per_s_equiv": kv_bytes / world / (ms_per_step / 1e3) / 1e12,
+                       "attention_backend": "flashinfer_b200 tcgen05 paged decode (decode_sm100)",
+                       "ref_attention_candidates": None,
+                       "linear": ("flashinfer_b200 decode_linear_sm100 (RMSNorm / RoPE+append / SwiGLU / residual epilogues)"
+                                  if eng.fused else "flashinfer_b200 gemm_sm100"),
+                       "allreduce": (("in-kernel NVLS all-reduce inside the O / down GEMM epilogue (multimem.red + ld_reduce)"
+                                      if eng.fused else "in-kernel NVLS all-reduce + add + RMSNorm kernel") if world > 1 else None),
+                       "ref_allreduce_candidates": None},
             "clocks": _summarise_clocks(clk.get("rows")),
             "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": BATCH * 8, "d2h_bytes_per_step": BATCH * 8},
             "gpu_launches": int((native_per_step + torch_per_step) * args.steps),
@@ -192,6 +201,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--eager-steps", type=int, default=0, help="run N eager steps and exit (for ncu)")
+    ap.add_argument("--ref-attn", default="auto", choices=["auto", "fa2", "fa2_tc", "trtllm-gen", "cudnn"],
+                    help="reference arm: decode attention backend (auto = fastest that runs)")
+    ap.add_argument("--ref-ar", default="auto", choices=["auto", "nccl", "trtllm_fusion"],
+                    help="reference arm: TP all-reduce path (auto = faster of the two)")
+    ap.add_argument("--unfused", action="store_true", help="ours: op-by-op decode path (round-1 composition) instead of decode_linear")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))

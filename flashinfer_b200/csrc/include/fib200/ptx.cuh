@@ -632,6 +632,22 @@ __device__ __forceinline__ uint32_t atom_add_acqrel_sys(uint32_t* p, uint32_t v)
   return old;
 }
 __device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+
+// Spin until the monotonic counter at `p` (written by peers with release semantics) reaches `want`, with a watchdog: a
+// peer that never arrives (crashed rank, mismatched launch) traps this kernel after `kSpinTimeoutNs` instead of hanging
+// the GPU forever (the reference's comm kernels spin unbounded).  globaltimer ticks in ns.
+constexpr unsigned long long kSpinTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
+__device__ __forceinline__ void spin_until_ge_sys(const uint32_t* p, uint32_t want) {
+  if (int32_t(ld_acquire_sys(p) - want) >= 0) return;
+  const uint64_t t0 = globaltimer();
+  uint32_t polls = 0;
+  while (int32_t(ld_acquire_sys(p) - want) < 0) {
+    if ((++polls & 0x3ff) == 0 && globaltimer() - t0 > kSpinTimeoutNs) {
+      printf("fib200: comm watchdog: flag %p stuck at %u (want %u) for 20 s -> trap\n", (const void*)p, ld_relaxed_sys(p), want);
+      __trap();
+    }
+  }
+}
 __device__ __forceinline__ int4 ld_volatile_v4(const void* p) {
   int4 v;
   asm volatile("ld.volatile.global.v4.s32 {%0, %1, %2, %3}, [%4];"

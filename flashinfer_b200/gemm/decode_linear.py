@@ -1,0 +1,249 @@
+"""Decode-layer linears: the small-M GEMM of a decode step with the neighbouring ops folded into its epilogue
+(csrc/gemm/decode_linear_sm100.cu).  A Llama layer becomes five launches: QKV (+RMSNorm +RoPE +paged-KV append), attention,
+O (+all-reduce +residual +norm statistics), gate/up (+RMSNorm +SwiGLU), down (+all-reduce +residual +norm statistics).
+
+Parity: the reference composes these from ``tgv_gemm_sm100`` / ``mm_bf16`` (flashinfer/gemm/gemm_base.py:485,1446),
+``fused_add_rmsnorm`` (flashinfer/norm.py), ``apply_llama31_rope_pos_ids_inplace`` + ``append_paged_kv_cache``
+(flashinfer/rope.py, flashinfer/page.py), ``silu_and_mul`` (flashinfer/activation.py) and
+``trtllm_allreduce_fusion(kARResidualRMSNorm)`` (flashinfer/comm/trtllm_ar.py:951-1060).
+
+RMSNorm folding: ``rmsnorm(x) * g @ W^T == rstd(x) * (x @ (W * g)^T)`` - ``fold_rmsnorm_weight`` bakes ``g`` into ``W`` once, the
+kernel applies ``rstd`` per token to the fp32 accumulators; the sum of squares comes from the residual epilogue of the previous
+GEMM (or :func:`decode_prep` for the embedding rows).  Every function has a fp32 PyTorch path (CPU tensors) that is the oracle of
+the CUDA kernels.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+
+from .. import jit
+from ..utils import dtype_code, stream_ptr
+
+EPI_PLAIN, EPI_GATED_SILU, EPI_RESIDUAL, EPI_ROPE_APPEND = 0, 1, 2, 3
+_SUMSQ_ROWS = 64  # row pitch of the sum-of-squares accumulators (= max decode batch of the kernel)
+
+
+# ------------------------------------------------------------------ weight preparation (load time)
+def fold_rmsnorm_weight(w: torch.Tensor, norm_weight: torch.Tensor, weight_bias: float = 0.0) -> torch.Tensor:
+    """``W [N, K]`` -> ``W * (g + weight_bias)[None, :]`` (the RMSNorm gain moves into the weight columns)."""
+    return (w.float() * (norm_weight.float() + weight_bias)[None, :]).to(w.dtype).contiguous()
+
+
+def permute_rope_rows(wqkv: torch.Tensor, num_q_heads: int, num_kv_heads: int, head_dim: int) -> torch.Tensor:
+    """NeoX-style RoPE rotates ``(j, j + head_dim/2)``: re-order the Q and K rows of every head to ``(0, hd/2, 1, hd/2+1, ...)`` so
+    that a rotation pair sits in adjacent accumulator columns of the QKV GEMM (the epilogue writes them back un-permuted)."""
+    k = wqkv.shape[1]
+    nqk = (num_q_heads + num_kv_heads) * head_dim
+    qk = wqkv[:nqk].view(num_q_heads + num_kv_heads, 2, head_dim // 2, k).transpose(1, 2).reshape(nqk, k)
+    return torch.cat([qk, wqkv[nqk:]], 0).contiguous()
+
+
+# ------------------------------------------------------------------ tensor-parallel context
+class FusedLinearTP:
+    """Symmetric staging buffers + flags of the in-kernel all-reduce (``epi="residual"`` with tp > 1).  Two ping-pong sets: a
+    rank may start the next all-reduce GEMM while a slow peer still reads the previous staging buffer; by the time the set
+    is reused every peer has finished the GEMM before (its own stores to the other set are proof)."""
+
+    MAX_CTAS = 1024
+
+    def __init__(self, group, max_tokens: int, hidden: int, dtype: torch.dtype = torch.bfloat16, heap=None):
+        import torch.distributed as dist
+
+        from ..comm.symm import SymmetricHeap
+
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        esz = torch.empty(0, dtype=dtype).element_size()
+        self.rows = _SUMSQ_ROWS
+        buf_bytes = self.rows * hidden * esz
+        need = 2 * (buf_bytes + self.MAX_CTAS * 4) + 16384
+        self.heap = heap if heap is not None else SymmetricHeap(self.group, need)
+        self.hidden, self.dtype = hidden, dtype
+        self.sets = []
+        for _ in range(2):
+            stage, s_off = self.heap.alloc(buf_bytes)
+            flags, f_off = self.heap.alloc(self.MAX_CTAS * 4)
+            self.sets.append({
+                "stage": stage.view(dtype).view(self.rows, hidden), "flags": flags.view(torch.int32),
+                "mc_stage": self.heap.mc(s_off), "mc_flags": self.heap.mc(f_off),
+                "peer_stage": self.heap.peer_ptr_table(s_off), "peer_flags": self.heap.peer_ptr_table(f_off),
+                "expect": torch.zeros(self.MAX_CTAS, dtype=torch.int32, device=self.heap.device),
+            })
+        self._turn = 0
+        self.heap.barrier()
+
+    def next_set(self) -> dict:
+        self._turn ^= 1
+        return self.sets[self._turn]
+
+
+class _ptr:
+    """Raw device address through the uniform C ABI (void*)."""
+
+    def __init__(self, v: int):
+        self.v = int(v)
+
+
+# ------------------------------------------------------------------ the op
+def _rstd(row_sumsq: Optional[torch.Tensor], m: int, norm_dim: int, eps: float) -> Optional[torch.Tensor]:
+    if row_sumsq is None:
+        return None
+    return torch.rsqrt(row_sumsq[:m].float() / norm_dim + eps)
+
+
+def _reference(x, w, epi, out, bias, row_sumsq, norm_dim, eps, residual, sumsq_out, tp, cos_sin, cache_row, k_cache, v_cache,
+               hq, hkv, head_dim, interleave, c_sh=0):
+    m = x.shape[0]
+    acc = x.float() @ w.float().t()
+    rs = _rstd(row_sumsq, m, norm_dim, eps)
+    if rs is not None and epi != EPI_RESIDUAL:
+        acc = acc * rs[:, None]
+    if epi == EPI_PLAIN:
+        if bias is not None:
+            acc = acc + bias.float()
+        out.copy_(acc.to(out.dtype))
+        return out
+    if epi == EPI_GATED_SILU:
+        out.copy_((torch.nn.functional.silu(acc[:, 0::2]) * acc[:, 1::2]).to(out.dtype))
+        return out
+    if epi == EPI_RESIDUAL:
+        if tp is not None and tp.world > 1:
+            import torch.distributed as dist
+
+            part = acc.to(x.dtype).float()  # partials travel in the activation dtype
+            dist.all_reduce(part, group=tp.group)
+            acc = part
+        new = (residual[:m].float() + acc).to(residual.dtype)
+        residual[:m].copy_(new)
+        if sumsq_out is not None:
+            sumsq_out[:m] += new.float().pow(2).sum(-1)
+        return residual
+    # rope + append
+    n_q, n_k = hq * head_dim, hkv * head_dim
+    half = head_dim // 2
+    cs, sn = cos_sin[:m, :half].float(), cos_sin[:m, half:].float()
+
+    def rope(t, heads):
+        t = t.view(m, heads, head_dim)
+        if interleave:
+            x1, x2 = t[..., 0::2], t[..., 1::2]
+            o = torch.stack([x1 * cs[:, None] - x2 * sn[:, None], x2 * cs[:, None] + x1 * sn[:, None]], -1).flatten(-2)
+        else:  # weights were permuted: column 2j = element j, column 2j+1 = element j + hd/2
+            x1, x2 = t[..., 0::2], t[..., 1::2]
+            o = torch.cat([x1 * cs[:, None] - x2 * sn[:, None], x2 * cs[:, None] + x1 * sn[:, None]], -1)
+        return o
+
+    q = rope(acc[:, :n_q], hq)
+    k = rope(acc[:, n_q:n_q + n_k], hkv)
+    v = acc[:, n_q + n_k:].view(m, hkv, head_dim)
+    out.view(m, hq, head_dim).copy_(q.to(out.dtype))
+    kf, vf = k_cache.view(-1), v_cache.view(-1)
+    for i in range(m):
+        base = int(cache_row[i])
+        for h in range(hkv):
+            kf[base + h * c_sh: base + h * c_sh + head_dim] = k[i, h].to(k_cache.dtype)
+            vf[base + h * c_sh: base + h * c_sh + head_dim] = v[i, h].to(v_cache.dtype)
+    return out
+
+
+def _head_stride(cache: torch.Tensor, head_dim: int) -> int:
+    """Element stride between KV heads inside one (page, slot) row of an NHD cache ``[P, page, H, D]`` (HND callers pass
+    ``head_stride=`` explicitly: ``page_size * D``)."""
+    return int(cache.stride(-2)) if cache.dim() == 4 else head_dim
+
+
+def decode_linear(x: torch.Tensor, w: torch.Tensor, epi: int = EPI_PLAIN, *, out: Optional[torch.Tensor] = None,
+                  bias: Optional[torch.Tensor] = None, row_sumsq: Optional[torch.Tensor] = None, norm_dim: Optional[int] = None,
+                  eps: float = 1e-5, residual: Optional[torch.Tensor] = None, sumsq_out: Optional[torch.Tensor] = None,
+                  tp: Optional[FusedLinearTP] = None, cos_sin: Optional[torch.Tensor] = None,
+                  cache_row: Optional[torch.Tensor] = None, k_cache: Optional[torch.Tensor] = None,
+                  v_cache: Optional[torch.Tensor] = None, head_stride: Optional[int] = None, num_q_heads: int = 0,
+                  num_kv_heads: int = 0, head_dim: int = 0, interleave: bool = False, bn: int = 0, split_k: int = 0,
+                  smem_kb: int = 0, enable_pdl: bool = True) -> torch.Tensor:
+    """``epilogue(x[M<=64, K] @ w[N, K]^T)``; see the module docstring for the four epilogues.
+
+    * ``row_sumsq`` (fp32 ``[>=M]``): per-token sum of squares of the un-normalised input over ``norm_dim`` columns; the output is
+      scaled by ``rsqrt(row_sumsq / norm_dim + eps)`` (RMSNorm folded; pass weights from :func:`fold_rmsnorm_weight`).
+    * ``EPI_GATED_SILU``: ``w`` rows interleaved (gate_0, up_0, ...) (:func:`flashinfer_b200.gemm.dense.interleave_gate_up`),
+      ``out [M, N/2]``.
+    * ``EPI_RESIDUAL``: ``residual[:M] += x @ w^T`` (summed over the ``tp`` ranks in-kernel), ``sumsq_out[:M] += sum(residual^2)``.
+    * ``EPI_ROPE_APPEND``: ``w`` from :func:`permute_rope_rows` (unless ``interleave``), ``out [M, Hq * D]`` receives RoPE(Q),
+      RoPE(K) and V are written into ``k_cache`` / ``v_cache`` at ``cache_row`` (from :func:`decode_prep`)."""
+    m, k = x.shape
+    n = w.shape[0]
+    if w.shape[1] != k:
+        raise ValueError(f"decode_linear: K mismatch {tuple(w.shape)} vs {tuple(x.shape)}")
+    if m > _SUMSQ_ROWS:
+        raise ValueError("decode_linear handles decode batches of at most 64 tokens (use gemm.linear beyond)")
+    norm_dim = norm_dim or k
+    if epi == EPI_RESIDUAL:
+        if residual is None:
+            raise ValueError("EPI_RESIDUAL needs residual=")
+        out = residual
+    elif out is None:
+        cols = n // 2 if epi == EPI_GATED_SILU else (num_q_heads * head_dim if epi == EPI_ROPE_APPEND else n)
+        out = torch.empty(m, cols, dtype=x.dtype, device=x.device)
+    if epi == EPI_ROPE_APPEND and (cos_sin is None or cache_row is None or k_cache is None or v_cache is None):
+        raise ValueError("EPI_ROPE_APPEND needs cos_sin / cache_row / k_cache / v_cache")
+    c_sh = 0
+    if epi == EPI_ROPE_APPEND:
+        c_sh = head_stride if head_stride is not None else _head_stride(k_cache, head_dim)
+    if not x.is_cuda:
+        return _reference(x, w, epi, out, bias, row_sumsq, norm_dim, eps, residual, sumsq_out, tp, cos_sin, cache_row, k_cache,
+                          v_cache, num_q_heads, num_kv_heads, head_dim, interleave, c_sh)
+    if x.dtype not in (torch.float16, torch.bfloat16) or w.dtype != x.dtype:
+        raise TypeError("decode_linear: x / w must both be float16 or bfloat16")
+    if x.stride(-1) != 1 or w.stride(-1) != 1 or out.stride(-1) != 1:
+        raise ValueError("decode_linear: innermost dimensions must be contiguous")
+    world, rank = (tp.world, tp.rank) if (tp is not None and epi == EPI_RESIDUAL) else (1, 0)
+    st = tp.next_set() if world > 1 else None
+    jit.load("decode_linear_sm100").call(
+        "dlinear_run", x, w, m, n, k, x.stride(0), w.stride(0), int(epi), out, out.stride(0), bias, row_sumsq,
+        1.0 / float(norm_dim), float(eps), residual, residual.stride(0) if residual is not None else 0, sumsq_out, world, rank,
+        st["stage"] if st else None, st["stage"].stride(0) if st else 0, _ptr(st["mc_stage"]) if st else None,
+        st["flags"] if st else None, _ptr(st["mc_flags"]) if st else None, st["expect"] if st else None,
+        st["peer_stage"] if st else None, st["peer_flags"] if st else None, cos_sin, cache_row, k_cache, v_cache, int(c_sh),
+        int(num_q_heads), int(num_kv_heads), int(head_dim), 1 if interleave else 0, int(bn), int(split_k), int(smem_kb),
+        dtype_code(x.dtype), 1 if enable_pdl else 0, stream_ptr(x))
+    return out
+
+
+def decode_prep(tokens: torch.Tensor, embed: torch.Tensor, residual: torch.Tensor, sumsq: torch.Tensor, positions: torch.Tensor,
+                kv_indptr: torch.Tensor, kv_indices: torch.Tensor, page_size: int, page_stride: int, slot_stride: int,
+                cos_sin: torch.Tensor, cache_row: torch.Tensor, head_dim: int, batch_indices: Optional[torch.Tensor] = None,
+                interleave: bool = False, rope_scale: float = 1.0, rope_theta: float = 1e4,
+                llama31: Optional[Tuple[float, float, float]] = None, enable_pdl: bool = False) -> None:
+    """One launch at the top of a decode step: ``residual[m] = embed[tokens[m]]``, ``sumsq[0, m] = sum(residual[m]^2)``,
+    ``sumsq[1:] = 0`` (the per-layer accumulators), ``cos_sin[m] = cos | sin`` of ``positions[m]`` (Llama-3.1 scaling optional),
+    ``cache_row[m]`` = element offset of the token's KV slot (``page * page_stride + slot * slot_stride``)."""
+    m = tokens.numel()
+    n_sumsq = sumsq.shape[0]
+    if not tokens.is_cuda:
+        residual[:m].copy_(embed[tokens.long()])
+        sumsq.zero_()
+        sumsq[0, :m] = residual[:m].float().pow(2).sum(-1)
+        half = head_dim // 2
+        inv = torch.pow(torch.tensor(float(rope_theta)), -torch.arange(0, half, dtype=torch.float32) * 2 / head_dim)
+        if llama31 is not None:
+            low, high, old_ctx = llama31
+            smooth = (inv * (old_ctx / (2 * math.pi * (high - low))) - 1.0 / (high / low - 1.0)).clamp(0, 1)
+            inv = (1 - smooth) * (inv / rope_scale) + smooth * inv
+        else:
+            inv = inv / rope_scale
+        ang = positions[:m].float()[:, None] * inv[None]
+        cos_sin[:m, :half] = torch.cos(ang)
+        cos_sin[:m, half:] = torch.sin(ang)
+        b = batch_indices.long() if batch_indices is not None else torch.arange(m)
+        pos = positions[:m].long()
+        page = kv_indices.long()[kv_indptr.long()[b] + pos // page_size]
+        cache_row[:m] = page * page_stride + (pos % page_size) * slot_stride
+        return
+    low, high, old_ctx = llama31 if llama31 is not None else (1.0, 1.0, 1.0)
+    jit.load("decode_linear_sm100").call(
+        "decode_prep_run", tokens, embed, residual, embed.stride(0), residual.stride(0), embed.shape[1], sumsq, n_sumsq,
+        positions, batch_indices, kv_indptr, kv_indices, int(page_size), int(page_stride), int(slot_stride), cos_sin, cache_row,
+        int(head_dim), 1 if interleave else 0, float(rope_scale), float(rope_theta), 1 if llama31 is not None else 0, float(low),
+        float(high), float(old_ctx), m, dtype_code(embed.dtype), 1 if enable_pdl else 0, stream_ptr(embed))

@@ -29,8 +29,8 @@ def _workspace(device) -> torch.Tensor:
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
            out: Optional[torch.Tensor] = None, enable_pdl: bool = True) -> torch.Tensor:
     """``x[..., K] @ weight[N, K]^T (+ bias[N])`` — the nn.Linear contraction, tcgen05 on CUDA."""
-    if x.dtype not in (torch.float16, torch.bfloat16) or weight.dtype != x.dtype:
-        raise TypeError("linear: x/weight must both be float16 or bfloat16")
+    if weight.dtype != x.dtype or (x.is_cuda and x.dtype not in (torch.float16, torch.bfloat16)):
+        raise TypeError("linear: x/weight must both be float16 or bfloat16 (fp32 only on the CPU oracle path)")
     k = x.shape[-1]
     n = weight.shape[0]
     if weight.shape[1] != k:

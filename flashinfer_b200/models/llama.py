@@ -15,6 +15,8 @@ import torch
 
 from .. import activation, norm, page, rope
 from ..decode import BatchDecodeWithPagedKVCacheWrapper
+from ..gemm.decode_linear import (EPI_GATED_SILU, EPI_RESIDUAL, EPI_ROPE_APPEND, FusedLinearTP, decode_linear, decode_prep,
+                                  fold_rmsnorm_weight, permute_rope_rows)
 from ..gemm.dense import interleave_gate_up, linear, linear_gated_silu
 
 
@@ -51,11 +53,23 @@ class LlamaDecodeEngine:
     """Random-init Llama decoder running batched single-token decode over a paged KV cache."""
 
     def __init__(self, cfg: LlamaConfig, max_batch: int, max_pages: int, page_size: int = 16, tp_rank: int = 0,
-                 tp_size: int = 1, device: str = "cuda", dtype: torch.dtype = torch.bfloat16, comm=None, seed: int = 0):
+                 tp_size: int = 1, device: str = "cuda", dtype: torch.dtype = torch.bfloat16, comm=None, seed: int = 0,
+                 fused: Optional[bool] = None, random_norms: bool = False, tp_group=None):
+        """``fused`` (default: on for batches of at most 64 tokens): five launches per layer through
+        :mod:`flashinfer_b200.gemm.decode_linear` - RMSNorm folded into the QKV / gate-up weights, RoPE + paged-KV append in the
+        QKV epilogue, SwiGLU in the gate-up epilogue, residual add + norm statistics (+ the tensor-parallel all-reduce over
+        NVLink) in the O / down epilogues.  ``fused=False`` keeps the op-by-op composition (any batch size)."""
         self.cfg, self.tp_rank, self.tp_size = cfg, tp_rank, tp_size
         self.device, self.dtype = torch.device(device), dtype
         self.page_size, self.max_batch = page_size, max_batch
         self.comm = comm
+        self.fused = (max_batch <= 64 and cfg.head_dim % 32 == 0) if fused is None else bool(fused)
+        if self.fused and max_batch > 64:
+            raise ValueError("the fused decode path handles at most 64 tokens per step")
+        self.tp_fused = None
+        if self.fused and tp_size > 1:
+            self.tp_fused = FusedLinearTP(tp_group if tp_group is not None else (comm.group if comm is not None else None),
+                                          max_batch, cfg.hidden_size, dtype) if self.device.type == "cuda" else _CpuTP(tp_group)
         assert cfg.num_kv_heads % tp_size == 0 and cfg.intermediate_size % tp_size == 0
         self.hq = cfg.num_qo_heads // tp_size
         self.hkv = cfg.num_kv_heads // tp_size
@@ -70,19 +84,28 @@ class LlamaDecodeEngine:
         self.embed = rnd((cfg.vocab_size, h), gs, 1.0)
         self.vocab_shard = (cfg.vocab_size + tp_size - 1) // tp_size
         self.lm_head = rnd((self.vocab_shard, h), g, h ** -0.5)
-        self.final_norm = torch.ones(h, device=self.device, dtype=dtype)
+        def norm_w():
+            if random_norms:  # tests: a non-trivial gain makes the folded and the op-by-op paths distinguishable
+                return (1.0 + 0.2 * torch.randn(h, device=self.device, dtype=torch.float32, generator=gs)).to(dtype)
+            return torch.ones(h, device=self.device, dtype=dtype)
+
+        self.final_norm = norm_w()
         self.layers = []
         for _ in range(cfg.num_layers):
-            self.layers.append({
-                "ln1": torch.ones(h, device=self.device, dtype=dtype),
-                "ln2": torch.ones(h, device=self.device, dtype=dtype),
+            l = {
+                "ln1": norm_w(),
+                "ln2": norm_w(),
                 "wqkv": rnd(((self.hq + 2 * self.hkv) * d, h), g, h ** -0.5),
                 "wo": rnd((h, self.hq * d), g, (cfg.num_qo_heads * d) ** -0.5),
                 "wgu": interleave_gate_up(rnd((2 * self.inter, h), g, h ** -0.5)),  # (g0, u0, g1, u1, ...) rows
                 "wd": rnd((h, self.inter), g, cfg.intermediate_size ** -0.5),
                 "k_cache": torch.zeros(max_pages, page_size, self.hkv, d, device=self.device, dtype=dtype),
                 "v_cache": torch.zeros(max_pages, page_size, self.hkv, d, device=self.device, dtype=dtype),
-            })
+            }
+            if self.fused:  # load-time weight preparation of the fused path (replaces the originals: no second copy)
+                l["wqkv"] = permute_rope_rows(fold_rmsnorm_weight(l["wqkv"], l["ln1"]), self.hq, self.hkv, d)
+                l["wgu"] = fold_rmsnorm_weight(l["wgu"], l["ln2"])
+            self.layers.append(l)
         self._ws = torch.empty(64 << 20, dtype=torch.uint8, device=self.device)
         self.wrapper = BatchDecodeWithPagedKVCacheWrapper(self._ws, "NHD")
         self.launches_per_step = 0
@@ -114,8 +137,13 @@ class LlamaDecodeEngine:
         self._res = torch.empty(b, h, device=self.device, dtype=self.dtype)
         self._qkv = torch.empty(b, (self.hq + 2 * self.hkv) * cfg.head_dim, device=self.device, dtype=self.dtype)
         self._attn = torch.empty(b, self.hq, cfg.head_dim, device=self.device, dtype=self.dtype)
+        self._attn_q = torch.empty(b, self.hq, cfg.head_dim, device=self.device, dtype=self.dtype)
         self._act = torch.empty(b, self.inter, device=self.device, dtype=self.dtype)
         self._logits = torch.empty(b, self.vocab_shard, device=self.device, dtype=self.dtype)
+        if self.fused:
+            self._sumsq = torch.zeros(2 * cfg.num_layers + 1, 64, device=self.device, dtype=torch.float32)
+            self._cos_sin = torch.zeros(64, cfg.head_dim, device=self.device, dtype=torch.float32)
+            self._cache_row = torch.zeros(64, device=self.device, dtype=torch.int64)
         self._graph = None
 
     # ------------------------------------------------------------------ one decode step
@@ -131,8 +159,53 @@ class LlamaDecodeEngine:
         else:
             self.comm.allreduce_add_rmsnorm(part, self._res, weight, self.cfg.rms_eps, out=self._x)
 
+    def _step_fused(self) -> torch.Tensor:
+        """Five launches per layer (see the class docstring); the residual stream ``self._res`` is the A operand of the
+        QKV / gate-up GEMMs and is updated in place by the O / down GEMM epilogues."""
+        cfg = self.cfg
+        d, hq, hkv, h, b = cfg.head_dim, self.hq, self.hkv, cfg.hidden_size, self.batch
+        res, ss = self._res, self._sumsq
+        kc0 = self.layers[0]["k_cache"]
+        decode_prep(self.tokens, self.embed, res, ss, self.positions, self.kv_indptr, self.kv_indices, self.page_size,
+                    kc0.stride(0), kc0.stride(1), self._cos_sin, self._cache_row, d, batch_indices=self.batch_indices,
+                    rope_scale=cfg.rope_scale, rope_theta=cfg.rope_theta, llama31=(1.0, 4.0, 8192.0))
+        q2d = self._attn_q.view(b, hq * d)
+        for li, l in enumerate(self.layers):
+            decode_linear(res, l["wqkv"], EPI_ROPE_APPEND, out=q2d, row_sumsq=ss[2 * li], norm_dim=h, eps=cfg.rms_eps,
+                          cos_sin=self._cos_sin, cache_row=self._cache_row, k_cache=l["k_cache"], v_cache=l["v_cache"],
+                          num_q_heads=hq, num_kv_heads=hkv, head_dim=d)
+            self.wrapper.run(self._attn_q, (l["k_cache"], l["v_cache"]), out=self._attn)
+            decode_linear(self._attn.view(b, hq * d), l["wo"], EPI_RESIDUAL, residual=res, sumsq_out=ss[2 * li + 1],
+                          tp=self.tp_fused)
+            decode_linear(res, l["wgu"], EPI_GATED_SILU, out=self._act, row_sumsq=ss[2 * li + 1], norm_dim=h, eps=cfg.rms_eps)
+            decode_linear(self._act, l["wd"], EPI_RESIDUAL, residual=res, sumsq_out=ss[2 * li + 2], tp=self.tp_fused)
+        norm.rmsnorm(res, self.final_norm, cfg.rms_eps, out=self._x)
+        linear(self._x, self.lm_head, out=self._logits)
+        if self.tp_size == 1:
+            torch.argmax(self._logits, dim=-1, out=self.next_tokens)
+        else:
+            val, idx = torch.max(self._logits.float(), dim=-1)
+            self.next_tokens.copy_(self._argmax_gather(val, idx + self.tp_rank * self.vocab_shard))
+        self.launches_per_step = 1 + 5 * len(self.layers) + 3
+        return self.next_tokens
+
+    def _argmax_gather(self, val: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+        if self.comm is not None:
+            return self.comm.argmax_gather(val, idx)
+        import torch.distributed as dist  # CPU / gloo tests
+
+        grp = self.tp_fused.group if self.tp_fused is not None else None
+        vals = [torch.empty_like(val) for _ in range(self.tp_size)]
+        idxs = [torch.empty_like(idx) for _ in range(self.tp_size)]
+        dist.all_gather(vals, val, group=grp)
+        dist.all_gather(idxs, idx, group=grp)
+        best = torch.stack(vals, 0).argmax(0)
+        return torch.stack(idxs, 0).gather(0, best[None])[0]
+
     def step(self) -> torch.Tensor:
         """tokens (self.tokens) -> next tokens (self.next_tokens); greedy sampling."""
+        if self.fused:
+            return self._step_fused()
         cfg = self.cfg
         d, hq, hkv = cfg.head_dim, self.hq, self.hkv
         x = self._x
@@ -191,3 +264,13 @@ class LlamaDecodeEngine:
             return self.step()
         self._graph.replay()
         return self.next_tokens
+
+
+class _CpuTP:
+    """Process-group handle of the fused path's fp32 oracle (CPU tensors, gloo): the all-reduce of the residual epilogue."""
+
+    def __init__(self, group):
+        import torch.distributed as dist
+
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
