@@ -37,7 +37,9 @@ def _time_us(fn, iters=20, warm=3):
 def run(args, rank, world, BATCH, KV_LEN, PAGE, kv_layout_fn, clock_sampler, summarise_clocks):
     import flashinfer  # resolved from baseline/_ref (bench.py put it first on sys.path)
 
-    assert "baseline/_ref" in flashinfer.__file__.replace("\\", "/"), flashinfer.__file__
+    src = getattr(args, "ref_src", "tree")
+    if src == "tree":
+        assert "baseline/_ref" in flashinfer.__file__.replace("\\", "/"), flashinfer.__file__
     dev = torch.device("cuda", torch.cuda.current_device())
     dt = torch.bfloat16
     hidden, inter_full, layers_n, hq_full, hkv_full, d, vocab = 4096, 14336, 32, 32, 8, 128, 128256
@@ -73,6 +75,16 @@ def run(args, rank, world, BATCH, KV_LEN, PAGE, kv_layout_fn, clock_sampler, sum
 
     # ------------------------------------------------------------------ attention backends of the reference
     def make_wrapper(backend, tc):
+        if backend == "trtllm-gen":
+            # the launcher would try to DOWNLOAD the cubins of the reference's own artifact hash (minutes of retries, no network):
+            # check the cubin directory first and report precisely what is missing
+            from flashinfer.artifacts import ArtifactPath
+            from flashinfer.jit.env import FLASHINFER_CUBIN_DIR
+
+            need = FLASHINFER_CUBIN_DIR / ArtifactPath.TRTLLM_GEN_FMHA
+            if not need.exists():
+                raise FileNotFoundError(f"trtllm-gen FMHA cubins {ArtifactPath.TRTLLM_GEN_FMHA} are not on this box (cubin dir "
+                                        f"{FLASHINFER_CUBIN_DIR} ships other hashes; no network to fetch them)")
         ws = torch.zeros(256 << 20, dtype=torch.uint8, device=dev)  # trtllm-gen wants a zero-initialised workspace
         w = flashinfer.BatchDecodeWithPagedKVCacheWrapper(ws, "HND", use_tensor_cores=tc, backend=backend)
         w.plan(kv_indptr, kv_indices, kv_last, hq, hkv, d, PAGE, q_data_type=dt, kv_data_type=dt)
@@ -91,7 +103,8 @@ def run(args, rank, world, BATCH, KV_LEN, PAGE, kv_layout_fn, clock_sampler, sum
     makers = {"trtllm-gen": lambda: make_wrapper("trtllm-gen", True), "cudnn": make_cudnn,
               "fa2_tc": lambda: make_wrapper("fa2", True), "fa2": lambda: make_wrapper("fa2", False)}
     want_attn = getattr(args, "ref_attn", "auto")
-    order = ["fa2_tc", "trtllm-gen", "cudnn", "fa2"] if want_attn == "auto" else [want_attn]
+    # auto: fa2 on CUDA cores is left out (published 0.050 ms vs 0.022 ms for fa2_tc at B=16: never the best; one JIT build less)
+    order = ["fa2_tc", "trtllm-gen", "cudnn"] if want_attn == "auto" else [want_attn]
     qprobe = torch.randn(BATCH, hq, d, device=dev, dtype=dt)
     cands, fns, oracle = {}, {}, None
     for name in order:
@@ -304,4 +317,5 @@ def run(args, rank, world, BATCH, KV_LEN, PAGE, kv_layout_fn, clock_sampler, sum
             "e2e": {"value": BATCH / (e2e_ms / args.steps / 1e3), "unit": "tokens/s", "h2d_bytes_per_step": BATCH * 8,
                     "d2h_bytes_per_step": BATCH * 8},
             "flashinfer_version": flashinfer.__version__,
+            "reference_source": "baseline/_ref (pip install of /root/reference)" if src == "tree" else f"installed wheel ({flashinfer.__file__})",
         }), flush=True)

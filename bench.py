@@ -84,7 +84,8 @@ def run_ours(args, rank, world):
         from flashinfer_b200.comm import TPCommunicator
         comm = TPCommunicator(dist.group.WORLD, max_tokens=BATCH, hidden=cfg.hidden_size, dtype=torch.bfloat16)
     indptr, indices, last, n_pages = _kv_layout(BATCH, KV_LEN, PAGE, torch)
-    eng = LlamaDecodeEngine(cfg, BATCH, n_pages, PAGE, tp_rank=rank, tp_size=world, comm=comm, fused=not args.unfused)
+    eng = LlamaDecodeEngine(cfg, BATCH, n_pages, PAGE, tp_rank=rank, tp_size=world, comm=comm, fused=not args.unfused,
+                            kv_layout=args.kv_layout)
     eng.fill_kv_random()
     eng.plan(indptr, indices, last)
     # host-side inputs in pinned memory (e2e path) + device staging
@@ -160,7 +161,7 @@ def run_ours(args, rank, world):
             "data": "synthetic (random-init weights, random KV cache, random token ids)", "impl": "flashinfer_b200",
             # same keys as the reference arm's config (the driver compares the two dicts)
             "config": {"model": "llama-3-8b", "global_batch": BATCH, "seq_len": KV_LEN, "page_size": PAGE,
-                       "parallelism": f"tp{world}", "kv_layout": "NHD", "cuda_graph": True,
+                       "parallelism": f"tp{world}", "kv_layout": args.kv_layout, "cuda_graph": True,
                        "l2_policy": "inputs larger than L2 (34 GB KV + 16 GB weights streamed per step)",
                        "attention_kv_tb_per_s_equiv": kv_bytes / world / (ms_per_step / 1e3) / 1e12,
                        "attention_backend": "flashinfer_b200 tcgen05 paged decode (decode_sm100)",
@@ -180,12 +181,13 @@ def run_ours(args, rank, world):
 
 def run_reference(args, rank, world):
     ref = os.path.join(ROOT, "baseline", "_ref")
-    if not os.path.isdir(os.path.join(ref, "flashinfer")):
+    if args.ref_src == "tree" and not os.path.isdir(os.path.join(ref, "flashinfer")):
         print(json.dumps({"impl": "reference", "unavailable": "baseline/_ref not installed"}))
         return
     os.environ.setdefault("FLASHINFER_DISABLE_VERSION_CHECK", "1")
-    os.environ.setdefault("FLASHINFER_WORKSPACE_BASE", os.path.join(ROOT, "baseline", "_ref_cache"))
-    sys.path.insert(0, ref)
+    os.environ.setdefault("FLASHINFER_WORKSPACE_BASE", os.path.join(ROOT, "baseline", "_ref_cache" if args.ref_src == "tree" else "_wheel_cache"))
+    if args.ref_src == "tree":
+        sys.path.insert(0, ref)
     try:
         from baseline.reference_arm import run as ref_run
         ref_run(args, rank, world, BATCH, KV_LEN, PAGE, _kv_layout, _clock_sampler, _summarise_clocks)
@@ -205,6 +207,12 @@ def main():
                     help="reference arm: decode attention backend (auto = fastest that runs)")
     ap.add_argument("--ref-ar", default="auto", choices=["auto", "nccl", "trtllm_fusion"],
                     help="reference arm: TP all-reduce path (auto = faster of the two)")
+    ap.add_argument("--ref-src", default="tree", choices=["tree", "wheel"],
+                    help="reference arm: tree = baseline/_ref (the unmodified /root/reference, default and the driver's arm); wheel = "
+                         "the pip-installed flashinfer-python 0.6.11.post2 + flashinfer-cubin (diagnostic: the only build whose "
+                         "trtllm-gen cubins exist offline)")
+    ap.add_argument("--kv-layout", default=os.environ.get("FIB200_BENCH_KV_LAYOUT", "HND"), choices=["NHD", "HND"],
+                    help="ours: paged KV-cache layout (HND: one contiguous 4 KB chunk per (page, head))")
     ap.add_argument("--unfused", action="store_true", help="ours: op-by-op decode path (round-1 composition) instead of decode_linear")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

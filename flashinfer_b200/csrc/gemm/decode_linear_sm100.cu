@@ -44,6 +44,7 @@ enum Epi : int { kPlain = 0, kGated = 1, kResid = 2, kRope = 3 };
 
 struct DLP {
   int M, N, K, BN, S, kblocks, stages, epi;
+  int w_blockk;  // weights stored BlockMajorK: [K / 64, N, 64] (every TMA box is one contiguous BN x 128 B chunk)
   void* out;
   int64_t ldo;
   const void* bias;
@@ -70,7 +71,7 @@ struct DLP {
 };
 
 __host__ __device__ inline int dl_stage_bytes(int BN) { return kABytes + BN * BK * 2; }
-__host__ __device__ inline int dl_xbuf_bytes(int BN, int S) { return S > 1 ? (BN / S) * BM * 4 : 0; }
+__host__ __device__ inline int dl_xbuf_bytes(int BN, int S) { return S > 1 ? (S - 1) * (BN / S) * BM * 4 : 0; }
 
 template <typename T>
 __device__ __forceinline__ void store16(T* dst, const float* v) {  // 16 values -> two 16-byte stores
@@ -146,7 +147,8 @@ dlinear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int npre = nkb < kStages ? nkb : kStages;
       for (int i = 0; i < npre; ++i) {  // weights first: independent of the previous kernel
         ptx::mbar_arrive_expect_tx(&full_bar[i], uint32_t(stage_bytes));
-        ptx::tma_load_2d(smem + i * stage_bytes + kABytes, &tmB, &full_bar[i], (kb0 + i) * BK, tb * BN, ptx::kEvictFirst);
+        if (p.w_blockk) ptx::tma_load_3d(smem + i * stage_bytes + kABytes, &tmB, &full_bar[i], 0, tb * BN, kb0 + i, ptx::kEvictFirst);
+        else ptx::tma_load_2d(smem + i * stage_bytes + kABytes, &tmB, &full_bar[i], (kb0 + i) * BK, tb * BN, ptx::kEvictFirst);
       }
       ptx::grid_dep_wait();
       for (int i = 0; i < npre; ++i)
@@ -158,7 +160,8 @@ dlinear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint8_t* sa = smem + stage * stage_bytes;
         ptx::mbar_arrive_expect_tx(&full_bar[stage], uint32_t(stage_bytes));
         ptx::tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, 0, ptx::kEvictLast);
-        ptx::tma_load_2d(sa + kABytes, &tmB, &full_bar[stage], kb * BK, tb * BN, ptx::kEvictFirst);
+        if (p.w_blockk) ptx::tma_load_3d(sa + kABytes, &tmB, &full_bar[stage], 0, tb * BN, kb, ptx::kEvictFirst);
+        else ptx::tma_load_2d(sa + kABytes, &tmB, &full_bar[stage], kb * BK, tb * BN, ptx::kEvictFirst);
         if (++stage == kStages) {
           stage = 0;
           phase ^= 1;
@@ -201,24 +204,28 @@ dlinear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     ptx::mbar_wait(tmem_full, 0);
     ptx::tc_fence_after();
     if (S > 1) {
-      const int peer = crank ^ 1;
-      const uint32_t rx = ptx::mapa(ptx::smem_u32(xbuf), uint32_t(peer));
-      const uint32_t rbar = ptx::mapa(ptx::smem_u32(xbar), uint32_t(peer));
-      for (int c = 0; c < own_w; c += 16) {
-        uint32_t r[16];
-        ptx::tmem_ld_x16(taddr + peer * own_w + c, r);
-        ptx::tmem_ld_wait();
-        if (row_ok) {
-          const uint32_t base = rx + uint32_t(((c >> 4) * BM + m) * 64);
+      // push my partial of every peer's columns into that peer's exchange slot (slot index = my rank, skipping the owner)
+      for (int pi = 1; pi < S; ++pi) {
+        const int peer = (crank + pi) % S;
+        const int slot = crank < peer ? crank : crank - 1;
+        const uint32_t rx = ptx::mapa(ptx::smem_u32(xbuf), uint32_t(peer)) + uint32_t(slot * own_w * BM * 4);
+        const uint32_t rbar = ptx::mapa(ptx::smem_u32(xbar), uint32_t(peer));
+        for (int c = 0; c < own_w; c += 16) {
+          uint32_t r[16];
+          ptx::tmem_ld_x16(taddr + peer * own_w + c, r);
+          ptx::tmem_ld_wait();
+          if (row_ok) {
+            const uint32_t base = rx + uint32_t(((c >> 4) * BM + m) * 64);
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            ptx::st_async_v4(base + uint32_t((j ^ xsw) * 16),
-                             make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
-                                         __uint_as_float(r[4 * j + 3])),
-                             rbar);
+            for (int j = 0; j < 4; ++j)
+              ptx::st_async_v4(base + uint32_t((j ^ xsw) * 16),
+                               make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                           __uint_as_float(r[4 * j + 3])),
+                               rbar);
+          }
         }
       }
-      ptx::mbar_wait(xbar, 0);  // tx-count completion (like a TMA write): the peer's partial of my columns has landed
+      ptx::mbar_wait(xbar, 0);  // tx-count completion (like a TMA write): all peers' partials of my columns have landed
     }
     float rs = 1.f;
     if (p.row_sumsq != nullptr && m_ok) rs = rsqrtf(p.row_sumsq[m] * p.inv_dim + p.eps);
@@ -231,14 +238,16 @@ dlinear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
       if (S > 1 && row_ok) {
-        const float4* src = reinterpret_cast<const float4*>(xbuf + ((c >> 4) * BM + m) * 64);
+        for (int sl = 0; sl < S - 1; ++sl) {
+          const float4* src = reinterpret_cast<const float4*>(xbuf + sl * own_w * BM * 4 + ((c >> 4) * BM + m) * 64);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 x = src[j ^ xsw];
-          v[4 * j] += x.x;
-          v[4 * j + 1] += x.y;
-          v[4 * j + 2] += x.z;
-          v[4 * j + 3] += x.w;
+          for (int j = 0; j < 4; ++j) {
+            const float4 x = src[j ^ xsw];
+            v[4 * j] += x.x;
+            v[4 * j + 1] += x.y;
+            v[4 * j + 2] += x.z;
+            v[4 * j + 3] += x.w;
+          }
         }
       }
     };
@@ -528,8 +537,8 @@ extern "C" int dlinear_run(void* A, void* W, int64_t M, int64_t N, int64_t K, in
                            void* sumsq_out, int64_t world, int64_t rank, void* stage, int64_t lds, void* mc_stage, void* flags,
                            void* mc_flags, void* expect, void* peer_stage_host, void* peer_flags_host, void* cos_sin,
                            void* cache_row, void* k_cache, void* v_cache, int64_t c_sh, int64_t hq, int64_t hkv, int64_t head_dim,
-                           int64_t interleave, int64_t force_bn, int64_t force_s, int64_t smem_kb, int64_t dtype, int64_t pdl,
-                           int64_t stream_) {
+                           int64_t interleave, int64_t force_bn, int64_t force_s, int64_t smem_kb, int64_t w_blockk, int64_t dtype,
+                           int64_t pdl, int64_t stream_) {
   FIB_CHECK(M >= 1 && M <= BM, "dlinear: 1 <= M <= 64 (decode batch); larger batches use gemm_nt");
   FIB_CHECK(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "dlinear: K / lda / ldw must be multiples of 8 (16 B TMA alignment)");
   FIB_CHECK((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0, "dlinear: A / W must be 16 B aligned");
@@ -552,17 +561,40 @@ extern "C" int dlinear_run(void* A, void* W, int64_t M, int64_t N, int64_t K, in
   int S = 1;
   int BN = int(((N + sms - 1) / sms + 15) / 16 * 16);
   if (BN < 32) BN = 32;
+  if (BN > 256) {
+    // several waves of one-tile CTAs (e.g. the LM head): time ~ waves x (weight rows + the 64 activation rows) per k-block
+    int best = 256;
+    long best_cost = 1L << 60;
+    for (int bn = 256; bn >= 192; bn -= 16) {
+      const long t = (N + bn - 1) / bn;
+      const long cost = ((t + sms - 1) / sms) * long(bn + BM);
+      if (cost < best_cost) {
+        best_cost = cost;
+        best = bn;
+      }
+    }
+    BN = best;
+  }
   if (BN <= 64 && K >= 2048 && kblocks >= 8) {
     S = 2;
     BN = int(((N * 2 + sms - 1) / sms + 31) / 32 * 32);
     if (BN < 64) BN = 64;
+    // 128-wide tiles over a 4-CTA cluster when that still fills the (132 usable) SMs: the activation tile is re-read from L2
+    // once per 128 weight rows instead of once per 64 (measured on B200, M = 64: o_proj 12.5 -> 11.4 us, down_proj 30.0 -> 24.2 us)
+    const int t128 = int((N + 127) / 128);
+    if (kblocks >= 16 && t128 * 4 <= (sms * 132) / 148 && t128 * 4 >= 96) {
+      S = 4;
+      BN = 128;
+    }
   }
   static const int env_bn = env_int("FIB200_DL_BN", 0), env_s = env_int("FIB200_DL_S", 0), env_kb = env_int("FIB200_DL_SMEM_KB", 0);
   if (force_s > 0 || env_s > 0) S = force_s > 0 ? int(force_s) : env_s;
   if (force_bn > 0 || env_bn > 0) BN = force_bn > 0 ? int(force_bn) : env_bn;
-  FIB_CHECK(S == 1 || S == 2, "dlinear: cluster split-K factor must be 1 or 2");
+  FIB_CHECK(S == 1 || S == 2 || S == 4 || S == 8, "dlinear: cluster split-K factor must be 1, 2, 4 or 8");
+  if (w_blockk) FIB_CHECK(K % BK == 0, "dlinear: BlockMajorK weights need K % 64 == 0");
   FIB_CHECK(BN % (16 * S) == 0 && BN >= 16 * S && BN <= 256, "dlinear: BN must be a multiple of 16 * S in [16 S, 256]");
-  if (S == 2) FIB_CHECK(kblocks >= 2, "dlinear: split-K needs >= 2 k-blocks");
+  if (S > 1) FIB_CHECK(kblocks >= S, "dlinear: split-K needs >= S k-blocks");
+  if (S >= 4) FIB_CHECK(int((N + BN - 1) / BN) * S <= (sms * 132) / 148, "dlinear: clusters of 4 / 8 fit only 132 of the 148 SMs");
   const int tiles = int((N + BN - 1) / BN);
   FIB_CHECK(int64_t(tiles) * S <= 65535, "dlinear: too many tiles");
   if (epi == kResid && world > 1) FIB_CHECK(tiles * S <= 1024, "dlinear (all-reduce): at most 1024 CTAs (flag slots)");
@@ -580,7 +612,7 @@ extern "C" int dlinear_run(void* A, void* W, int64_t M, int64_t N, int64_t K, in
 
   DLP p;
   memset(&p, 0, sizeof(p));
-  p.M = int(M); p.N = int(N); p.K = int(K); p.BN = BN; p.S = S; p.kblocks = kblocks; p.stages = stages; p.epi = int(epi);
+  p.M = int(M); p.N = int(N); p.K = int(K); p.BN = BN; p.S = S; p.kblocks = kblocks; p.stages = stages; p.epi = int(epi); p.w_blockk = int(w_blockk);
   p.out = out; p.ldo = ldo; p.bias = bias;
   p.row_sumsq = reinterpret_cast<const float*>(row_sumsq); p.inv_dim = float(inv_dim); p.eps = float(eps);
   p.resid = resid; p.ldr = ldr; p.sumsq_out = reinterpret_cast<float*>(sumsq_out);
@@ -610,7 +642,12 @@ extern "C" int dlinear_run(void* A, void* W, int64_t M, int64_t N, int64_t K, in
     uint32_t box[2] = {BK, BM};
     if (make_tmap(&tmA, dt, 2, A, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   }
-  {
+  if (w_blockk) {  // [K / 64, N, 64]: ldw = elements between consecutive N rows (64 when dense)
+    uint64_t dims[3] = {(uint64_t)BK, (uint64_t)N, (uint64_t)(K / BK)};
+    uint64_t str[2] = {(uint64_t)ldw * 2, (uint64_t)N * (uint64_t)ldw * 2};
+    uint32_t box[3] = {BK, (uint32_t)BN, 1};
+    if (make_tmap(&tmB, dt, 3, W, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  } else {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
     uint64_t str[1] = {(uint64_t)ldw * 2};
     uint32_t box[2] = {BK, (uint32_t)BN};

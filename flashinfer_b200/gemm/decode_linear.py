@@ -41,6 +41,21 @@ def permute_rope_rows(wqkv: torch.Tensor, num_q_heads: int, num_kv_heads: int, h
     return torch.cat([qk, wqkv[nqk:]], 0).contiguous()
 
 
+def to_block_major_k(w: torch.Tensor, block_k: int = 64) -> torch.Tensor:
+    """``W [N, K]`` -> BlockMajorK ``[K / 64, N, 64]`` (reference WeightLayout.BlockMajorK, flashinfer/tllm_enums.py:141-150): all N rows
+    of one 64-wide K block are contiguous, so the TMA box of a weight tile is ONE contiguous ``BN x 128 B`` chunk of HBM instead of
+    ``BN`` 128-byte pieces a whole row pitch apart."""
+    n, k = w.shape
+    if k % block_k:
+        raise ValueError("to_block_major_k: K must be a multiple of 64")
+    return w.view(n, k // block_k, block_k).transpose(0, 1).contiguous()
+
+
+def from_block_major_k(wb: torch.Tensor) -> torch.Tensor:
+    kb, n, bk = wb.shape
+    return wb.transpose(0, 1).reshape(n, kb * bk)
+
+
 # ------------------------------------------------------------------ tensor-parallel context
 class FusedLinearTP:
     """Symmetric staging buffers + flags of the in-kernel all-reduce (``epi="residual"`` with tp > 1).  Two ping-pong sets: a
@@ -173,8 +188,9 @@ def decode_linear(x: torch.Tensor, w: torch.Tensor, epi: int = EPI_PLAIN, *, out
     * ``EPI_ROPE_APPEND``: ``w`` from :func:`permute_rope_rows` (unless ``interleave``), ``out [M, Hq * D]`` receives RoPE(Q),
       RoPE(K) and V are written into ``k_cache`` / ``v_cache`` at ``cache_row`` (from :func:`decode_prep`)."""
     m, k = x.shape
-    n = w.shape[0]
-    if w.shape[1] != k:
+    blockk = w.dim() == 3  # BlockMajorK weights from to_block_major_k: [K / 64, N, 64]
+    n = w.shape[1] if blockk else w.shape[0]
+    if (w.shape[0] * w.shape[2] if blockk else w.shape[1]) != k:
         raise ValueError(f"decode_linear: K mismatch {tuple(w.shape)} vs {tuple(x.shape)}")
     if m > _SUMSQ_ROWS:
         raise ValueError("decode_linear handles decode batches of at most 64 tokens (use gemm.linear beyond)")
@@ -192,7 +208,7 @@ def decode_linear(x: torch.Tensor, w: torch.Tensor, epi: int = EPI_PLAIN, *, out
     if epi == EPI_ROPE_APPEND:
         c_sh = head_stride if head_stride is not None else _head_stride(k_cache, head_dim)
     if not x.is_cuda:
-        return _reference(x, w, epi, out, bias, row_sumsq, norm_dim, eps, residual, sumsq_out, tp, cos_sin, cache_row, k_cache,
+        return _reference(x, from_block_major_k(w) if blockk else w, epi, out, bias, row_sumsq, norm_dim, eps, residual, sumsq_out, tp, cos_sin, cache_row, k_cache,
                           v_cache, num_q_heads, num_kv_heads, head_dim, interleave, c_sh)
     if x.dtype not in (torch.float16, torch.bfloat16) or w.dtype != x.dtype:
         raise TypeError("decode_linear: x / w must both be float16 or bfloat16")
@@ -201,13 +217,13 @@ def decode_linear(x: torch.Tensor, w: torch.Tensor, epi: int = EPI_PLAIN, *, out
     world, rank = (tp.world, tp.rank) if (tp is not None and epi == EPI_RESIDUAL) else (1, 0)
     st = tp.next_set() if world > 1 else None
     jit.load("decode_linear_sm100").call(
-        "dlinear_run", x, w, m, n, k, x.stride(0), w.stride(0), int(epi), out, out.stride(0), bias, row_sumsq,
+        "dlinear_run", x, w, m, n, k, x.stride(0), w.stride(1) if blockk else w.stride(0), int(epi), out, out.stride(0), bias, row_sumsq,
         1.0 / float(norm_dim), float(eps), residual, residual.stride(0) if residual is not None else 0, sumsq_out, world, rank,
         st["stage"] if st else None, st["stage"].stride(0) if st else 0, _ptr(st["mc_stage"]) if st else None,
         st["flags"] if st else None, _ptr(st["mc_flags"]) if st else None, st["expect"] if st else None,
         st["peer_stage"] if st else None, st["peer_flags"] if st else None, cos_sin, cache_row, k_cache, v_cache, int(c_sh),
         int(num_q_heads), int(num_kv_heads), int(head_dim), 1 if interleave else 0, int(bn), int(split_k), int(smem_kb),
-        dtype_code(x.dtype), 1 if enable_pdl else 0, stream_ptr(x))
+        1 if blockk else 0, dtype_code(x.dtype), 1 if enable_pdl else 0, stream_ptr(x))
     return out
 
 

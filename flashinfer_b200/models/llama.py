@@ -16,7 +16,7 @@ import torch
 from .. import activation, norm, page, rope
 from ..decode import BatchDecodeWithPagedKVCacheWrapper
 from ..gemm.decode_linear import (EPI_GATED_SILU, EPI_RESIDUAL, EPI_ROPE_APPEND, FusedLinearTP, decode_linear, decode_prep,
-                                  fold_rmsnorm_weight, permute_rope_rows)
+                                  fold_rmsnorm_weight, permute_rope_rows, to_block_major_k)
 from ..gemm.dense import interleave_gate_up, linear, linear_gated_silu
 
 
@@ -54,7 +54,8 @@ class LlamaDecodeEngine:
 
     def __init__(self, cfg: LlamaConfig, max_batch: int, max_pages: int, page_size: int = 16, tp_rank: int = 0,
                  tp_size: int = 1, device: str = "cuda", dtype: torch.dtype = torch.bfloat16, comm=None, seed: int = 0,
-                 fused: Optional[bool] = None, random_norms: bool = False, tp_group=None):
+                 fused: Optional[bool] = None, random_norms: bool = False, tp_group=None, kv_layout: str = "NHD",
+                 block_major_k: Optional[bool] = None):
         """``fused`` (default: on for batches of at most 64 tokens): five launches per layer through
         :mod:`flashinfer_b200.gemm.decode_linear` - RMSNorm folded into the QKV / gate-up weights, RoPE + paged-KV append in the
         QKV epilogue, SwiGLU in the gate-up epilogue, residual add + norm statistics (+ the tensor-parallel all-reduce over
@@ -64,6 +65,11 @@ class LlamaDecodeEngine:
         self.page_size, self.max_batch = page_size, max_batch
         self.comm = comm
         self.fused = (max_batch <= 64 and cfg.head_dim % 32 == 0) if fused is None else bool(fused)
+        if kv_layout not in ("NHD", "HND"):
+            raise ValueError("kv_layout must be NHD or HND")
+        self.kv_layout = kv_layout
+        # BlockMajorK weights ([K / 64, N, 64]: every TMA box of a weight tile is one contiguous chunk of HBM) for the fused path
+        self.block_major_k = (self.fused and self.device.type == "cuda") if block_major_k is None else bool(block_major_k)
         if self.fused and max_batch > 64:
             raise ValueError("the fused decode path handles at most 64 tokens per step")
         self.tp_fused = None
@@ -90,7 +96,12 @@ class LlamaDecodeEngine:
             return torch.ones(h, device=self.device, dtype=dtype)
 
         self.final_norm = norm_w()
+        if self.fused:
+            self.lm_head = fold_rmsnorm_weight(self.lm_head, self.final_norm)
+            if self.block_major_k:
+                self.lm_head = to_block_major_k(self.lm_head)
         self.layers = []
+        cache_shape = (max_pages, page_size, self.hkv, d) if kv_layout == "NHD" else (max_pages, self.hkv, page_size, d)
         for _ in range(cfg.num_layers):
             l = {
                 "ln1": norm_w(),
@@ -99,15 +110,18 @@ class LlamaDecodeEngine:
                 "wo": rnd((h, self.hq * d), g, (cfg.num_qo_heads * d) ** -0.5),
                 "wgu": interleave_gate_up(rnd((2 * self.inter, h), g, h ** -0.5)),  # (g0, u0, g1, u1, ...) rows
                 "wd": rnd((h, self.inter), g, cfg.intermediate_size ** -0.5),
-                "k_cache": torch.zeros(max_pages, page_size, self.hkv, d, device=self.device, dtype=dtype),
-                "v_cache": torch.zeros(max_pages, page_size, self.hkv, d, device=self.device, dtype=dtype),
+                "k_cache": torch.zeros(*cache_shape, device=self.device, dtype=dtype),
+                "v_cache": torch.zeros(*cache_shape, device=self.device, dtype=dtype),
             }
             if self.fused:  # load-time weight preparation of the fused path (replaces the originals: no second copy)
                 l["wqkv"] = permute_rope_rows(fold_rmsnorm_weight(l["wqkv"], l["ln1"]), self.hq, self.hkv, d)
                 l["wgu"] = fold_rmsnorm_weight(l["wgu"], l["ln2"])
+                if self.block_major_k:
+                    for key in ("wqkv", "wo", "wgu", "wd"):
+                        l[key] = to_block_major_k(l[key])
             self.layers.append(l)
         self._ws = torch.empty(64 << 20, dtype=torch.uint8, device=self.device)
-        self.wrapper = BatchDecodeWithPagedKVCacheWrapper(self._ws, "NHD")
+        self.wrapper = BatchDecodeWithPagedKVCacheWrapper(self._ws, kv_layout)
         self.launches_per_step = 0
         self._graph = None
 
@@ -166,27 +180,28 @@ class LlamaDecodeEngine:
         d, hq, hkv, h, b = cfg.head_dim, self.hq, self.hkv, cfg.hidden_size, self.batch
         res, ss = self._res, self._sumsq
         kc0 = self.layers[0]["k_cache"]
+        slot_stride, head_stride = (kc0.stride(1), kc0.stride(2)) if self.kv_layout == "NHD" else (kc0.stride(2), kc0.stride(1))
         decode_prep(self.tokens, self.embed, res, ss, self.positions, self.kv_indptr, self.kv_indices, self.page_size,
-                    kc0.stride(0), kc0.stride(1), self._cos_sin, self._cache_row, d, batch_indices=self.batch_indices,
+                    kc0.stride(0), slot_stride, self._cos_sin, self._cache_row, d, batch_indices=self.batch_indices,
                     rope_scale=cfg.rope_scale, rope_theta=cfg.rope_theta, llama31=(1.0, 4.0, 8192.0))
         q2d = self._attn_q.view(b, hq * d)
         for li, l in enumerate(self.layers):
             decode_linear(res, l["wqkv"], EPI_ROPE_APPEND, out=q2d, row_sumsq=ss[2 * li], norm_dim=h, eps=cfg.rms_eps,
                           cos_sin=self._cos_sin, cache_row=self._cache_row, k_cache=l["k_cache"], v_cache=l["v_cache"],
-                          num_q_heads=hq, num_kv_heads=hkv, head_dim=d)
+                          num_q_heads=hq, num_kv_heads=hkv, head_dim=d, head_stride=head_stride)
             self.wrapper.run(self._attn_q, (l["k_cache"], l["v_cache"]), out=self._attn)
             decode_linear(self._attn.view(b, hq * d), l["wo"], EPI_RESIDUAL, residual=res, sumsq_out=ss[2 * li + 1],
                           tp=self.tp_fused)
             decode_linear(res, l["wgu"], EPI_GATED_SILU, out=self._act, row_sumsq=ss[2 * li + 1], norm_dim=h, eps=cfg.rms_eps)
             decode_linear(self._act, l["wd"], EPI_RESIDUAL, residual=res, sumsq_out=ss[2 * li + 2], tp=self.tp_fused)
-        norm.rmsnorm(res, self.final_norm, cfg.rms_eps, out=self._x)
-        linear(self._x, self.lm_head, out=self._logits)
+        # LM head with the final RMSNorm folded in (weights prepared at load time)
+        decode_linear(res, self.lm_head, out=self._logits, row_sumsq=ss[2 * len(self.layers)], norm_dim=h, eps=cfg.rms_eps)
         if self.tp_size == 1:
             torch.argmax(self._logits, dim=-1, out=self.next_tokens)
         else:
             val, idx = torch.max(self._logits.float(), dim=-1)
             self.next_tokens.copy_(self._argmax_gather(val, idx + self.tp_rank * self.vocab_shard))
-        self.launches_per_step = 1 + 5 * len(self.layers) + 3
+        self.launches_per_step = 1 + 5 * len(self.layers) + 2
         return self.next_tokens
 
     def _argmax_gather(self, val: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
@@ -223,7 +238,7 @@ class LlamaDecodeEngine:
             q, k, v = qkv[:, :hq], qkv[:, hq : hq + hkv], qkv[:, hq + hkv :]
             # one kernel: RoPE(q) in place, RoPE(k) and v straight into the cache pages
             rope.apply_rope_append_paged_kv_cache(q, k, v, self.positions, self.batch_indices, (l["k_cache"], l["v_cache"]),
-                                                  self.kv_indices, self.kv_indptr, "NHD", rope_scale=cfg.rope_scale,
+                                                  self.kv_indices, self.kv_indptr, self.kv_layout, rope_scale=cfg.rope_scale,
                                                   rope_theta=cfg.rope_theta, llama31=(1.0, 4.0, 8192.0))
             self.wrapper.run(q, (l["k_cache"], l["v_cache"]), out=self._attn)
             part = self._row_parallel(self._attn.view(self.batch, hq * d), l["wo"])

@@ -26,7 +26,8 @@ def _xw(m, n, k, dtype, seed=0):
 
 @pytest.mark.parametrize("m,n,k,bn,s", [(64, 4096, 4096, 0, 0), (64, 6144, 4096, 0, 0), (17, 4096, 2048, 64, 2), (64, 4096, 512, 0, 0),
                                         (1, 1024, 256, 32, 1), (64, 4096, 14336, 0, 0), (33, 4112, 1024, 48, 1), (64, 768, 4096, 0, 0),
-                                        (64, 2048, 1024, 128, 2), (64, 512, 8192, 256, 2)])
+                                        (64, 2048, 1024, 128, 2), (64, 512, 8192, 256, 2), (64, 4096, 4096, 128, 4), (50, 4096, 14336, 128, 4),
+                                        (64, 6144, 4096, 192, 4), (20, 1024, 512, 64, 4)])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 def test_plain_and_rowscale(m, n, k, bn, s, dtype):
     x, w = _xw(m, n, k, dtype)
@@ -38,6 +39,9 @@ def test_plain_and_rowscale(m, n, k, bn, s, dtype):
     out = dl.decode_linear(x, w, dl.EPI_PLAIN, bias=bias, row_sumsq=ss, norm_dim=k, eps=1e-5, bn=bn, split_k=s)
     ref2 = ref * torch.rsqrt(ss[:m] / k + 1e-5)[:, None] + bias.float()
     assert _rel(out, ref2) < 1.5e-2
+    # BlockMajorK weight layout ([K / 64, N, 64], one contiguous chunk per TMA box)
+    out = dl.decode_linear(x, dl.to_block_major_k(w), dl.EPI_PLAIN, bn=bn, split_k=s)
+    assert _rel(out, ref) < 1.5e-2
 
 
 @pytest.mark.parametrize("m,n,k,bn,s", [(64, 28672, 4096, 0, 0), (40, 3584, 4096, 0, 0), (64, 2048, 2048, 64, 2), (5, 256, 512, 32, 1)])
