@@ -9,11 +9,16 @@
 //   * kGated: gate/up projection -> SwiGLU on the accumulators (row-interleaved gate / up weights);
 //   * kResid: O / down projection -> (tensor-parallel: in-kernel all-reduce over NVLink, see below) -> residual += sum,
 //     per-token sum of squares of the new residual accumulated for the next folded RMSNorm.
-// Tensor parallelism (world > 1, kResid): the epilogue stores its bf16 partial tile into a symmetric staging buffer, bumps a
-// per-CTA flag on every rank with ONE `multimem.red` through the NVSwitch, waits until all ranks have arrived and pulls the
-// in-switch sum of its own columns with `multimem.ld_reduce` - GEMM, all-reduce, residual add and norm statistics are one
-// kernel and no NCCL call or separate all-reduce launch exists on the path (P2P loads / per-peer signals when the fabric has
-// no multicast).  Every spin has a watchdog (ptx::spin_until_ge_sys).
+// Tensor parallelism (world > 1, kResid): the all-reduce is a one-shot PUSH inside the epilogue, Lamport style.  Every rank
+// owns `world` receive slots per rotating buffer in a symmetric heap; the epilogue multicasts its bf16 partial tile straight from
+// registers into slot [rank] of EVERY rank with `multimem.st` through the NVSwitch (per-peer stores when the fabric has no
+// multicast), then polls its own columns of all slots until no sentinel (-0.0, which the sender never emits) is left, sums them
+// in rank order (bitwise identical on all ranks: the replicated residual stream cannot drift), adds the residual and
+// accumulates the norm statistics.  No flags, no system-scope fences, no staging round trip: the data is its own arrival signal,
+// the cost over the local GEMM is one NVLink one-way latency plus world x tile bytes of ingress.  Three rotating buffers selected
+// by a device-side epoch (CUDA-graph replay safe); the buffer of the next call is reset to the sentinel here (it was last read
+// two calls ago).  Polls carry a watchdog.  GEMM, all-reduce, residual add and norm statistics are ONE kernel; no NCCL call or
+// separate all-reduce launch exists on the path.
 //
 // Parity targets: reference include/flashinfer/gemm/tgv_gemm.cuh (low-latency small-M GEMM, PDL), the fused
 // allreduce + residual + RMSNorm patterns of include/flashinfer/comm/trtllm_allreduce_fusion.cuh:1336-1466, the
@@ -53,15 +58,14 @@ struct DLP {
   void* resid;             // kResid: residual stream in / out
   int64_t ldr;
   float* sumsq_out;        // kResid: += sum_n resid_new[m, n]^2
-  int world, rank;         // kResid all-reduce
-  void* stage;             // local symmetric staging [M, lds]
-  int64_t lds;
-  const void* mc_stage;    // multicast alias (or null)
-  uint32_t* flags;         // local symmetric flags [grid]
-  uint32_t* mc_flags;      // multicast alias (or null)
-  uint32_t* expect;        // local (non-symmetric) expected flag value per CTA
-  void* peer_stage[kMaxRanks];
-  uint32_t* peer_flags[kMaxRanks];
+  int world, rank;         // kResid all-reduce (Lamport push)
+  void* recv;              // local receive buffers [3][world][rows][lds] (symmetric heap)
+  int64_t lds;             // row pitch of a slot (elements)
+  int64_t slot_elems;      // elements per rank slot
+  int64_t buf_elems;       // elements per rotating buffer (= world * slot_elems)
+  void* mc_recv;           // multicast alias of `recv` (or null)
+  uint32_t* epoch;         // local device word: number of all-reduce calls so far (selects the rotating buffer)
+  void* peer_recv[kMaxRanks];
   const float* cos_sin;      // kRope: [M, head_dim] fp32 = cos[0:hd/2] | sin[0:hd/2] of the token's position
   const int64_t* cache_row;  // kRope: [M] element offset of the token's (page, slot) row in k_cache / v_cache
   void* k_cache;
@@ -84,13 +88,6 @@ __device__ __forceinline__ void store16(T* dst, const float* v) {  // 16 values 
   st16(dst, a);
   st16(dst + 8, b);
 }
-
-template <typename T>
-__device__ __forceinline__ int4 mc_ld_reduce(const void* p);
-template <>
-__device__ __forceinline__ int4 mc_ld_reduce<__nv_bfloat16>(const void* p) { return ptx::multimem_ld_reduce_bf16x8(p); }
-template <>
-__device__ __forceinline__ int4 mc_ld_reduce<__half>(const void* p) { return ptx::multimem_ld_reduce_f16x8(p); }
 
 template <typename T>
 __global__ void __launch_bounds__(256, 1)
@@ -312,70 +309,121 @@ dlinear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       } else {
-        // ---- in-kernel all-reduce of this CTA's columns over NVLink ----
-        T* stage = reinterpret_cast<T*>(p.stage);
-        for (int c = 0; c < own_w; c += 16) {
+        // ---- in-kernel all-reduce of this CTA's columns over NVLink: one-shot push, the data is its own arrival signal ----
+        constexpr uint32_t kSent = 0x80008000u;  // two -0.0 halves
+        uint32_t* s_epoch = tmem_ptr + 1;
+        if (etid == 0) *s_epoch = *reinterpret_cast<volatile uint32_t*>(p.epoch);
+        ptx::named_bar_sync(1, 128);
+        const uint32_t ep = *s_epoch;
+        T* recv = reinterpret_cast<T*>(p.recv);
+        const int64_t cur = int64_t(ep % 3u) * p.buf_elems, nxt = int64_t((ep + 1u) % 3u) * p.buf_elems;
+        for (int c = 0; c < own_w; c += 16) {  // (1) push my partial into slot [rank] of every rank
           float v[16];
           load_chunk(c, v);
           const int n0 = n_base + c;
-          if (m_ok && n0 < p.N) store16<T>(stage + int64_t(m) * p.lds + n0, v);
-        }
-        __threadfence_system();
-        ptx::named_bar_sync(1, 128);
-        if (etid == 0) {
-          if (p.mc_flags) {
-            ptx::multimem_red_add_u32(p.mc_flags + blockIdx.x, 1u);
-          } else {
-            for (int r = 0; r < p.world; ++r) ptx::red_add_release_sys(p.peer_flags[(p.rank + r) % p.world] + blockIdx.x, 1u);
+          if (m_ok && n0 < p.N) {
+            Vec16<T> a, b;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              a.v[e] = from_f32<T>(v[e]);
+              b.v[e] = from_f32<T>(v[8 + e]);
+            }
+            uint32_t* wa = reinterpret_cast<uint32_t*>(&a);
+            uint32_t* wb = reinterpret_cast<uint32_t*>(&b);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {  // -0.0 is the sentinel: never send it
+              if ((wa[e] & 0xffffu) == 0x8000u) wa[e] &= 0xffff0000u;
+              if ((wa[e] >> 16) == 0x8000u) wa[e] &= 0x0000ffffu;
+              if ((wb[e] & 0xffffu) == 0x8000u) wb[e] &= 0xffff0000u;
+              if ((wb[e] >> 16) == 0x8000u) wb[e] &= 0x0000ffffu;
+            }
+            const int64_t off = cur + int64_t(p.rank) * p.slot_elems + int64_t(m) * p.lds + n0;
+            if (p.mc_recv) {
+              T* d = reinterpret_cast<T*>(p.mc_recv) + off;
+              ptx::multimem_st_v4(d, *reinterpret_cast<const int4*>(&a));
+              ptx::multimem_st_v4(d + 8, *reinterpret_cast<const int4*>(&b));
+            } else {
+              for (int r = 0; r < p.world; ++r) {
+                T* d = reinterpret_cast<T*>(p.peer_recv[(p.rank + r) % p.world]) + off;
+                ptx::st_na_v4(d, *reinterpret_cast<const int4*>(&a));
+                ptx::st_na_v4(d + 8, *reinterpret_cast<const int4*>(&b));
+              }
+            }
           }
-          const uint32_t want = p.expect[blockIdx.x] + uint32_t(p.world);
-          ptx::spin_until_ge_sys(p.flags + blockIdx.x, want);
-          p.expect[blockIdx.x] = want;
         }
-        ptx::named_bar_sync(1, 128);
-        for (int c = 0; c < own_w; c += 16) {
+        if (row_ok) {  // (2) while the pushes fly: reset my columns (all 64 rows: the next call may carry more tokens) of the NEXT call's buffer,
+                       //     last read two calls ago
+          const int4 sent = make_int4(int(kSent), int(kSent), int(kSent), int(kSent));
+          for (int r = 0; r < p.world; ++r)
+            for (int c = 0; c < own_w; c += 16) {
+              const int n0 = n_base + c;
+              if (n0 < p.N) {
+                T* d = recv + nxt + int64_t(r) * p.slot_elems + int64_t(m) * p.lds + n0;
+                *reinterpret_cast<int4*>(d) = sent;
+                *reinterpret_cast<int4*>(d + 8) = sent;
+              }
+            }
+        }
+        for (int c = 0; c < own_w; c += 16) {  // (3) gather all ranks' partials of my columns, reduce in rank order
           const int n0 = n_base + c;
           if (m_ok && n0 < p.N) {
-            const int64_t off = int64_t(m) * p.lds + n0;
-            float v[16];
-            if (p.mc_stage) {
-              const int4 x0 = mc_ld_reduce<T>(reinterpret_cast<const T*>(p.mc_stage) + off);
-              const int4 x1 = mc_ld_reduce<T>(reinterpret_cast<const T*>(p.mc_stage) + off + 8);
-              const T* h0 = reinterpret_cast<const T*>(&x0);
-              const T* h1 = reinterpret_cast<const T*>(&x1);
+            const T* src = recv + cur + int64_t(m) * p.lds + n0;
+            int4 x[2 * 8];
+            uint32_t polls = 0;
+            uint64_t t0 = 0;
+            bool done;
+            do {
+              done = true;
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                v[e] = to_f32(h0[e]);
-                v[8 + e] = to_f32(h1[e]);
+              for (int r = 0; r < 8; ++r)
+                if (r < p.world) {
+                  x[2 * r] = ptx::ld_volatile_v4(src + int64_t(r) * p.slot_elems);
+                  x[2 * r + 1] = ptx::ld_volatile_v4(src + int64_t(r) * p.slot_elems + 8);
+                }
+#pragma unroll
+              for (int r = 0; r < 8; ++r)
+                if (r < p.world) {
+                  const uint32_t* w = reinterpret_cast<const uint32_t*>(&x[2 * r]);
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) done = done && ((w[e] & 0xffffu) != 0x8000u) && ((w[e] >> 16) != 0x8000u);
+                }
+              if (!done && (++polls & 0x3ffu) == 0) {  // watchdog: a peer that never sends traps this kernel instead of hanging the GPU
+                if (t0 == 0) t0 = ptx::globaltimer();
+                else if (ptx::globaltimer() - t0 > ptx::kSpinTimeoutNs) {
+                  printf("fib200: decode_linear all-reduce watchdog: rank %d cta %d waited 20 s for peer data -> trap\n", p.rank, int(blockIdx.x));
+                  __trap();
+                }
               }
-            } else {
+            } while (!done);
+            float v[16];
 #pragma unroll
-              for (int e = 0; e < 16; ++e) v[e] = 0.f;
-              for (int r = 0; r < p.world; ++r) {
-                const T* src = reinterpret_cast<const T*>(p.peer_stage[(p.rank + r) % p.world]) + off;
-                const int4 x0 = ptx::ld_volatile_v4(src), x1 = ptx::ld_volatile_v4(src + 8);
-                const T* h0 = reinterpret_cast<const T*>(&x0);
-                const T* h1 = reinterpret_cast<const T*>(&x1);
+            for (int e = 0; e < 16; ++e) v[e] = 0.f;
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+              if (r < p.world) {
+                const T* h0 = reinterpret_cast<const T*>(&x[2 * r]);
+                const T* h1 = reinterpret_cast<const T*>(&x[2 * r + 1]);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                   v[e] += to_f32(h0[e]);
                   v[8 + e] += to_f32(h1[e]);
                 }
               }
-            }
             T* rp = resid + int64_t(m) * p.ldr + n0;
             Vec16<T> a = ld16(rp), b = ld16(rp + 8);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               a.v[e] = from_f32<T>(to_f32(a.v[e]) + v[e]);
               b.v[e] = from_f32<T>(to_f32(b.v[e]) + v[8 + e]);
-              const float x = to_f32(a.v[e]), y = to_f32(b.v[e]);
-              ss += x * x + y * y;
+              const float xx = to_f32(a.v[e]), yy = to_f32(b.v[e]);
+              ss += xx * xx + yy * yy;
             }
             st16(rp, a);
             st16(rp + 8, b);
           }
         }
+        // all CTAs read the epoch at the top of their epilogue, microseconds ago (single wave: grid <= #SM): bump it for the next call
+        if (blockIdx.x == 0 && etid == 0) *reinterpret_cast<volatile uint32_t*>(p.epoch) = ep + 1u;
       }
       if (m_ok && p.sumsq_out) atomicAdd(p.sumsq_out + m, ss);
     } else {  // kRope
@@ -531,11 +579,11 @@ inline int env_int(const char* name, int dflt) {
 }  // namespace
 
 // A [M, K] (lda), W [N, K] (ldw), both K-major 16-bit.  `epi`: 0 plain, 1 gated SiLU (out [M, N/2]), 2 residual (+ all-reduce),
-// 3 RoPE + paged-KV append.  peer_stage / peer_flags: host int64 arrays of `world` device pointers (or null).
+// 3 RoPE + paged-KV append.  peer_recv_host: host int64 array of `world` device pointers (or null when multicast is used).
 extern "C" int dlinear_run(void* A, void* W, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldw, int64_t epi, void* out,
                            int64_t ldo, void* bias, void* row_sumsq, double inv_dim, double eps, void* resid, int64_t ldr,
-                           void* sumsq_out, int64_t world, int64_t rank, void* stage, int64_t lds, void* mc_stage, void* flags,
-                           void* mc_flags, void* expect, void* peer_stage_host, void* peer_flags_host, void* cos_sin,
+                           void* sumsq_out, int64_t world, int64_t rank, void* recv, int64_t lds, int64_t slot_elems,
+                           void* mc_recv, void* epoch, void* peer_recv_host, void* cos_sin,
                            void* cache_row, void* k_cache, void* v_cache, int64_t c_sh, int64_t hq, int64_t hkv, int64_t head_dim,
                            int64_t interleave, int64_t force_bn, int64_t force_s, int64_t smem_kb, int64_t w_blockk, int64_t dtype,
                            int64_t pdl, int64_t stream_) {
@@ -551,9 +599,8 @@ extern "C" int dlinear_run(void* A, void* W, int64_t M, int64_t N, int64_t K, in
                   c_sh % 8 == 0,
               "dlinear (rope): cos_sin / cache_row / caches required, N = (hq + 2 hkv) * head_dim, head_dim % 32 == 0");
   if (epi == kResid && world > 1)
-    FIB_CHECK(world <= kMaxRanks && stage && flags && expect && lds % 8 == 0 && (mc_stage != nullptr) == (mc_flags != nullptr) &&
-                  (mc_stage || (peer_stage_host && peer_flags_host)),
-              "dlinear (all-reduce): symmetric staging / flags (multicast or peer tables) required");
+    FIB_CHECK(world <= 8 && recv && epoch && lds % 8 == 0 && slot_elems >= M * lds && (mc_recv || peer_recv_host),
+              "dlinear (all-reduce): world <= 8, symmetric receive buffers (multicast alias or peer table) and the epoch word required");
   const int sms = num_sms();
   const int kblocks = int((K + BK - 1) / BK);
   // ---- tile plan: one wave, one tile per cluster.  BN = narrowest multiple of 16 (32 with the 2-CTA K split) that covers N with
@@ -597,7 +644,7 @@ extern "C" int dlinear_run(void* A, void* W, int64_t M, int64_t N, int64_t K, in
   if (S >= 4) FIB_CHECK(int((N + BN - 1) / BN) * S <= (sms * 132) / 148, "dlinear: clusters of 4 / 8 fit only 132 of the 148 SMs");
   const int tiles = int((N + BN - 1) / BN);
   FIB_CHECK(int64_t(tiles) * S <= 65535, "dlinear: too many tiles");
-  if (epi == kResid && world > 1) FIB_CHECK(tiles * S <= 1024, "dlinear (all-reduce): at most 1024 CTAs (flag slots)");
+  if (epi == kResid && world > 1) FIB_CHECK(tiles * S <= sms, "dlinear (all-reduce): the grid must be a single wave (<= #SM CTAs)");
   int budget_kb = smem_kb > 0 ? int(smem_kb) : (env_kb > 0 ? env_kb : 216);
   const int stage_bytes = dl_stage_bytes(BN);
   const int xbytes = dl_xbuf_bytes(BN, S);
@@ -617,16 +664,11 @@ extern "C" int dlinear_run(void* A, void* W, int64_t M, int64_t N, int64_t K, in
   p.row_sumsq = reinterpret_cast<const float*>(row_sumsq); p.inv_dim = float(inv_dim); p.eps = float(eps);
   p.resid = resid; p.ldr = ldr; p.sumsq_out = reinterpret_cast<float*>(sumsq_out);
   p.world = int(world); p.rank = int(rank);
-  p.stage = stage; p.lds = lds; p.mc_stage = mc_stage;
-  p.flags = reinterpret_cast<uint32_t*>(flags); p.mc_flags = reinterpret_cast<uint32_t*>(mc_flags);
-  p.expect = reinterpret_cast<uint32_t*>(expect);
-  if (peer_stage_host && peer_flags_host) {
-    const int64_t* ps = reinterpret_cast<const int64_t*>(peer_stage_host);
-    const int64_t* pf = reinterpret_cast<const int64_t*>(peer_flags_host);
-    for (int i = 0; i < world && i < kMaxRanks; ++i) {
-      p.peer_stage[i] = reinterpret_cast<void*>(ps[i]);
-      p.peer_flags[i] = reinterpret_cast<uint32_t*>(pf[i]);
-    }
+  p.recv = recv; p.lds = lds; p.slot_elems = slot_elems; p.buf_elems = slot_elems * world; p.mc_recv = mc_recv;
+  p.epoch = reinterpret_cast<uint32_t*>(epoch);
+  if (peer_recv_host) {
+    const int64_t* ps = reinterpret_cast<const int64_t*>(peer_recv_host);
+    for (int i = 0; i < world && i < kMaxRanks; ++i) p.peer_recv[i] = reinterpret_cast<void*>(ps[i]);
   }
   p.cos_sin = reinterpret_cast<const float*>(cos_sin); p.cache_row = reinterpret_cast<const int64_t*>(cache_row);
   p.k_cache = k_cache; p.v_cache = v_cache; p.c_sh = c_sh;

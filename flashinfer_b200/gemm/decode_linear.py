@@ -58,11 +58,9 @@ def from_block_major_k(wb: torch.Tensor) -> torch.Tensor:
 
 # ------------------------------------------------------------------ tensor-parallel context
 class FusedLinearTP:
-    """Symmetric staging buffers + flags of the in-kernel all-reduce (``epi="residual"`` with tp > 1).  Two ping-pong sets: a
-    rank may start the next all-reduce GEMM while a slow peer still reads the previous staging buffer; by the time the set
-    is reused every peer has finished the GEMM before (its own stores to the other set are proof)."""
-
-    MAX_CTAS = 1024
+    """Receive buffers of the in-kernel all-reduce (``EPI_RESIDUAL`` with tp > 1): ``[3 rotating][world slots][64 rows][hidden]``
+    in a symmetric heap (+ its NVLS multicast alias), pre-filled with the sentinel (-0.0), and the device-side epoch word that
+    selects the rotating buffer (CUDA-graph replay safe: nothing about the rotation is baked into the launch arguments)."""
 
     def __init__(self, group, max_tokens: int, hidden: int, dtype: torch.dtype = torch.bfloat16, heap=None):
         import torch.distributed as dist
@@ -71,28 +69,20 @@ class FusedLinearTP:
 
         self.group = group if group is not None else dist.group.WORLD
         self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        if self.world > 8:
+            raise ValueError("FusedLinearTP: the one-shot push all-reduce supports at most 8 ranks")
         esz = torch.empty(0, dtype=dtype).element_size()
-        self.rows = _SUMSQ_ROWS
-        buf_bytes = self.rows * hidden * esz
-        need = 2 * (buf_bytes + self.MAX_CTAS * 4) + 16384
-        self.heap = heap if heap is not None else SymmetricHeap(self.group, need)
-        self.hidden, self.dtype = hidden, dtype
-        self.sets = []
-        for _ in range(2):
-            stage, s_off = self.heap.alloc(buf_bytes)
-            flags, f_off = self.heap.alloc(self.MAX_CTAS * 4)
-            self.sets.append({
-                "stage": stage.view(dtype).view(self.rows, hidden), "flags": flags.view(torch.int32),
-                "mc_stage": self.heap.mc(s_off), "mc_flags": self.heap.mc(f_off),
-                "peer_stage": self.heap.peer_ptr_table(s_off), "peer_flags": self.heap.peer_ptr_table(f_off),
-                "expect": torch.zeros(self.MAX_CTAS, dtype=torch.int32, device=self.heap.device),
-            })
-        self._turn = 0
+        self.rows, self.hidden, self.dtype = _SUMSQ_ROWS, hidden, dtype
+        self.slot_elems = self.rows * hidden
+        nbytes = 3 * self.world * self.slot_elems * esz
+        self.heap = heap if heap is not None else SymmetricHeap(self.group, nbytes + 16384)
+        buf, off = self.heap.alloc(nbytes)
+        buf.view(torch.int16).fill_(-32768)  # 0x8000 = -0.0 in bf16 / fp16: "nothing has arrived yet"
+        self.recv = buf.view(dtype)
+        self.mc_recv = self.heap.mc(off)
+        self.peer_recv = self.heap.peer_ptr_table(off)
+        self.epoch = torch.zeros(4, dtype=torch.int32, device=self.heap.device)
         self.heap.barrier()
-
-    def next_set(self) -> dict:
-        self._turn ^= 1
-        return self.sets[self._turn]
 
 
 class _ptr:
@@ -215,13 +205,14 @@ def decode_linear(x: torch.Tensor, w: torch.Tensor, epi: int = EPI_PLAIN, *, out
     if x.stride(-1) != 1 or w.stride(-1) != 1 or out.stride(-1) != 1:
         raise ValueError("decode_linear: innermost dimensions must be contiguous")
     world, rank = (tp.world, tp.rank) if (tp is not None and epi == EPI_RESIDUAL) else (1, 0)
-    st = tp.next_set() if world > 1 else None
+    ar = tp if world > 1 else None
+    if ar is not None and (n != ar.hidden or x.dtype != ar.dtype):
+        raise ValueError("decode_linear: the all-reduce context was built for another hidden size / dtype")
     jit.load("decode_linear_sm100").call(
         "dlinear_run", x, w, m, n, k, x.stride(0), w.stride(1) if blockk else w.stride(0), int(epi), out, out.stride(0), bias, row_sumsq,
         1.0 / float(norm_dim), float(eps), residual, residual.stride(0) if residual is not None else 0, sumsq_out, world, rank,
-        st["stage"] if st else None, st["stage"].stride(0) if st else 0, _ptr(st["mc_stage"]) if st else None,
-        st["flags"] if st else None, _ptr(st["mc_flags"]) if st else None, st["expect"] if st else None,
-        st["peer_stage"] if st else None, st["peer_flags"] if st else None, cos_sin, cache_row, k_cache, v_cache, int(c_sh),
+        ar.recv if ar else None, ar.hidden if ar else 0, ar.slot_elems if ar else 0, _ptr(ar.mc_recv) if ar else None,
+        ar.epoch if ar else None, ar.peer_recv if ar else None, cos_sin, cache_row, k_cache, v_cache, int(c_sh),
         int(num_q_heads), int(num_kv_heads), int(head_dim), 1 if interleave else 0, int(bn), int(split_k), int(smem_kb),
         1 if blockk else 0, dtype_code(x.dtype), 1 if enable_pdl else 0, stream_ptr(x))
     return out
