@@ -143,4 +143,5 @@ def get_fp4_quantization_module(backend: str = "100"):
     return jit.load("quantization")
 
 
+api_logging.instrument()  # @flashinfer_api on every public op and wrapper plan / run (no-op wrappers at FLASHINFER_LOGLEVEL=0)
 trace.attach()  # bind op templates (wraps the ops only when FLASHINFER_TRACE_DUMP / FLASHINFER_TRACE_DIR is set)

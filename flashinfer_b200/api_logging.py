@@ -235,3 +235,88 @@ def replay_from_dump(dump_dir: str, device: str = "cuda", compare: bool = True, 
 def replay_sequence(root: str, device: str = "cuda", **kw) -> List[Dict[str, Any]]:
     return [replay_from_dump(os.path.join(root, d), device, **kw) for d in sorted(os.listdir(root))
             if os.path.isdir(os.path.join(root, d))]
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Package-wide instrumentation.  The reference puts ``@flashinfer_api`` on every public function and on the wrappers'
+# plan / run methods (flashinfer/api_logging.py:2364-2455 lists what replay can re-create).  Here the same set is decorated
+# in one sweep at package import: with FLASHINFER_LOGLEVEL=0 ``flashinfer_api`` hands the function back unchanged (zero
+# overhead) and only fills the replay registry; with a level > 0 - at import or later through ``set_level`` - the public
+# names are rebound to the logging wrappers in their home module and wherever the package re-exports them.
+# ------------------------------------------------------------------------------------------------------------------
+PUBLIC_API_MODULES = (
+    "activation", "cascade", "concat_ops", "decode", "deep_gemm", "dsv3_ops", "gdn", "norm", "page", "pod", "prefill", "rope",
+    "sampling", "sparse", "topk", "xqa", "attention._core", "mla._core", "gemm.dense", "gemm.lowp", "gemm.grouped",
+    "gemm.decode_linear", "fused_moe.core", "quantization.fp4", "quantization.fp8", "quantization.packbits",
+    "mamba.selective_state_update", "mamba.ssd_combined", "comm.allreduce", "comm.compat", "comm.alltoall", "comm.collectives",
+    "comm.gemm_allreduce", "logits_processor.pipeline",
+)
+_WRAPPER_METHODS = ("plan", "run", "forward", "begin_forward", "dispatch", "combine")
+_ORIGINALS: Dict[str, Any] = {}     # api name -> (owner object, attribute, undecorated callable)
+_PKG = __name__.rsplit(".", 1)[0]
+
+
+def _rebind_everywhere(old, new) -> None:
+    for name, mod in list(sys.modules.items()):
+        if mod is None or not (name == _PKG or name.startswith(_PKG + ".")):
+            continue
+        for attr, val in list(vars(mod).items()):
+            if val is old:
+                setattr(mod, attr, new)
+
+
+def instrument() -> int:
+    """Decorate every public op / wrapper method of the package (idempotent).  Returns the number of instrumented callables."""
+    import importlib
+
+    n = 0
+    for short in PUBLIC_API_MODULES:
+        try:
+            mod = importlib.import_module(f"{_PKG}.{short}")
+        except Exception:  # noqa: BLE001  (optional sub-module)
+            continue
+        for attr, obj in list(vars(mod).items()):
+            if attr.startswith("_"):
+                continue
+            if inspect.isfunction(obj) and getattr(obj, "__module__", None) == mod.__name__:
+                api = f"{short}.{attr}"
+                base = _ORIGINALS.setdefault(api, (mod, attr, getattr(obj, "__wrapped__", obj)))[2]
+                new = flashinfer_api(base, name=api)
+                if new is not obj:
+                    _rebind_everywhere(obj, new)
+                n += 1
+            elif inspect.isclass(obj) and getattr(obj, "__module__", None) == mod.__name__:
+                for meth in _WRAPPER_METHODS:
+                    f = obj.__dict__.get(meth)
+                    if not inspect.isfunction(f):
+                        continue
+                    api = f"{short}.{attr}.{meth}"
+                    base = _ORIGINALS.setdefault(api, (obj, meth, getattr(f, "__wrapped__", f)))[2]
+                    new = flashinfer_api(base, name=api)
+                    if new is not f:
+                        setattr(obj, meth, new)
+                    n += 1
+    return n
+
+
+def set_level(level: int, dest: Optional[str] = None, dump_dir: Optional[str] = None) -> int:
+    """Change the log level at run time (the environment variables are only the defaults) and re-instrument the package."""
+    global _LEVEL, _DEST, _DUMP_DIR, _stream
+    _LEVEL = int(level)
+    if dest is not None:
+        _DEST, _stream = dest, None
+    if dump_dir is not None:
+        _DUMP_DIR = dump_dir or None
+    # put the undecorated callables back first, then decorate at the new level
+    for api, (owner, attr, base) in _ORIGINALS.items():
+        cur = getattr(owner, attr, None)
+        if cur is not base and cur is not None:
+            if inspect.isclass(owner):
+                setattr(owner, attr, base)
+            else:
+                _rebind_everywhere(cur, base)
+    return instrument()
+
+
+def registered_apis() -> List[str]:
+    return sorted(_REGISTRY)

@@ -35,6 +35,7 @@
 #include <math.h>
 #include <fib200/common.cuh>
 #include <fib200/ptx.cuh>
+#include <fib200/profiler.cuh>
 
 using namespace fib200;
 
@@ -46,9 +47,13 @@ constexpr int BM = 64, BK = 64, kMaxRanks = 16;
 constexpr int kABytes = BM * BK * 2;  // 8 KB activation tile per stage
 
 enum Epi : int { kPlain = 0, kGated = 1, kResid = 2, kRope = 3 };
+// intra-kernel profiler: groups = warp roles (0 TMA producer, 1 MMA issuer, 2 epilogue), events below
+enum ProfEvent : int { kEvSetup = 0, kEvWaitPrevGrid = 1, kEvWeightPrefetch = 2, kEvMainLoop = 3, kEvSplitKExchange = 4, kEvEpilogue = 5, kEvAllReduce = 6 };
 
 struct DLP {
   int M, N, K, BN, S, kblocks, stages, epi;
+  uint64_t* prof;  // intra-kernel profiler buffer (FIB200_ENABLE_PROFILER builds; see fib200/profiler.cuh)
+  int prof_events;
   int w_blockk;  // weights stored BlockMajorK: [K / 64, N, 64] (every TMA box is one contiguous BN x 128 B chunk)
   void* out;
   int64_t ldo;
@@ -108,6 +113,15 @@ dlinear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int crank = S > 1 ? int(ptx::cluster_ctarank()) : 0;
   const int tb = blockIdx.x / S;  // output tile (N direction)
 
+  FIB_PROFILER_DECL
+#ifdef FIB200_ENABLE_PROFILER
+  {
+    const int grp = warp == 0 ? 0 : (warp == 1 ? 1 : 2);
+    const bool wr = p.prof != nullptr && lane == 0 && (warp == 0 || warp == 1 || warp == 4);
+    FIB_PROFILER_INIT(p.prof ? p.prof : reinterpret_cast<uint64_t*>(smem_raw), grp, 3, wr, p.prof_events);
+  }
+#endif
+  FIB_PROFILER_EVENT_START(kEvSetup);
   if (threadIdx.x == 0) {
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
@@ -132,8 +146,13 @@ dlinear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
+  FIB_PROFILER_EVENT_END(kEvSetup);
   // PDL: only the activation loads and the epilogue inputs depend on the previous kernel
-  if (warp != 0) ptx::grid_dep_wait();
+  if (warp != 0) {
+    FIB_PROFILER_EVENT_START(kEvWaitPrevGrid);
+    ptx::grid_dep_wait();
+    FIB_PROFILER_EVENT_END(kEvWaitPrevGrid);
+  }
   ptx::grid_dep_launch();
 
   const int kb0 = (crank * p.kblocks) / S, kb1 = ((crank + 1) * p.kblocks) / S;
@@ -147,7 +166,11 @@ dlinear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (p.w_blockk) ptx::tma_load_3d(smem + i * stage_bytes + kABytes, &tmB, &full_bar[i], 0, tb * BN, kb0 + i, ptx::kEvictFirst);
         else ptx::tma_load_2d(smem + i * stage_bytes + kABytes, &tmB, &full_bar[i], (kb0 + i) * BK, tb * BN, ptx::kEvictFirst);
       }
+      FIB_PROFILER_EVENT_INSTANT(kEvWeightPrefetch);
+      FIB_PROFILER_EVENT_START(kEvWaitPrevGrid);
       ptx::grid_dep_wait();
+      FIB_PROFILER_EVENT_END(kEvWaitPrevGrid);
+      FIB_PROFILER_EVENT_START(kEvMainLoop);
       for (int i = 0; i < npre; ++i)
         ptx::tma_load_2d(smem + i * stage_bytes, &tmA, &full_bar[i], (kb0 + i) * BK, 0, ptx::kEvictLast);
       int stage = npre == kStages ? 0 : npre;
@@ -164,10 +187,12 @@ dlinear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           phase ^= 1;
         }
       }
+      FIB_PROFILER_EVENT_END(kEvMainLoop);
     }
   } else if (warp == 1) {
     int stage = 0;
     uint32_t phase = 0;
+    FIB_PROFILER_EVENT_START(kEvMainLoop);
     for (int kb = kb0; kb < kb1; ++kb) {
       ptx::mbar_wait(&full_bar[stage], phase);
       ptx::tc_fence_after();
@@ -188,6 +213,7 @@ dlinear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         phase ^= 1;
       }
     }
+    FIB_PROFILER_EVENT_END(kEvMainLoop);
   } else if (warp >= 4) {
     // ===================== epilogue: thread = token row (UMMA M = 64: rows 16q..16q+15 in lanes 0-15 of quadrant q) ==========
     const int q = warp - 4, etid = threadIdx.x - 128;
@@ -198,8 +224,11 @@ dlinear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int own_w = BN / S;
     const int own_lo = crank * own_w;
     const int xsw = (m >> 1) & 3;  // 16-byte slot swizzle of the exchange rows (bank spread)
+    FIB_PROFILER_EVENT_START(kEvMainLoop);
     ptx::mbar_wait(tmem_full, 0);
     ptx::tc_fence_after();
+    FIB_PROFILER_EVENT_END(kEvMainLoop);
+    FIB_PROFILER_EVENT_START(kEvSplitKExchange);
     if (S > 1) {
       // push my partial of every peer's columns into that peer's exchange slot (slot index = my rank, skipping the owner)
       for (int pi = 1; pi < S; ++pi) {
@@ -224,6 +253,8 @@ dlinear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       ptx::mbar_wait(xbar, 0);  // tx-count completion (like a TMA write): all peers' partials of my columns have landed
     }
+    FIB_PROFILER_EVENT_END(kEvSplitKExchange);
+    FIB_PROFILER_EVENT_START(kEvEpilogue);
     float rs = 1.f;
     if (p.row_sumsq != nullptr && m_ok) rs = rsqrtf(p.row_sumsq[m] * p.inv_dim + p.eps);
 
@@ -483,6 +514,7 @@ dlinear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   }
 
+  if (warp >= 4) { FIB_PROFILER_EVENT_END(kEvEpilogue); }
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 2) {
@@ -570,6 +602,12 @@ __global__ void __launch_bounds__(256) decode_prep_kernel(const PrepParams p) {
     p.cos_sin[int64_t(m) * p.head_dim + half + i] = sn;
   }
 }
+
+struct ProfArm {
+  uint64_t* buf = nullptr;
+  int max_events = 0;
+};
+thread_local ProfArm g_prof;  // consumed (and cleared) by the next dlinear_run of this thread
 
 inline int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
@@ -660,6 +698,8 @@ extern "C" int dlinear_run(void* A, void* W, int64_t M, int64_t N, int64_t K, in
   DLP p;
   memset(&p, 0, sizeof(p));
   p.M = int(M); p.N = int(N); p.K = int(K); p.BN = BN; p.S = S; p.kblocks = kblocks; p.stages = stages; p.epi = int(epi); p.w_blockk = int(w_blockk);
+  p.prof = g_prof.buf; p.prof_events = g_prof.max_events;
+  g_prof = ProfArm();
   p.out = out; p.ldo = ldo; p.bias = bias;
   p.row_sumsq = reinterpret_cast<const float*>(row_sumsq); p.inv_dim = float(inv_dim); p.eps = float(eps);
   p.resid = resid; p.ldr = ldr; p.sumsq_out = reinterpret_cast<float*>(sumsq_out);
@@ -753,5 +793,16 @@ extern "C" int decode_prep_run(void* tokens, void* embed, void* resid, int64_t l
   } else {
     return set_error("decode_prep: f16 / bf16 only");
   }
+  return 0;
+}
+
+// Arms the intra-kernel profiler for the NEXT dlinear_run of this thread: `buf` from profiler.alloc_profiler_buffer(grid, 3, max_events).
+// Only the FIB200_ENABLE_PROFILER build (module decode_linear_sm100_prof) records anything.
+extern "C" int dlinear_set_profiler(void* buf, int64_t max_events) {
+#ifndef FIB200_ENABLE_PROFILER
+  if (buf) return set_error("dlinear_set_profiler: this library was built without FIB200_ENABLE_PROFILER (load decode_linear_sm100_prof)");
+#endif
+  g_prof.buf = reinterpret_cast<uint64_t*>(buf);
+  g_prof.max_events = int(max_events);
   return 0;
 }

@@ -14,6 +14,7 @@ the CUDA kernels.
 """
 from __future__ import annotations
 
+import contextlib
 import math
 from typing import Optional, Tuple
 
@@ -254,3 +255,19 @@ def decode_prep(tokens: torch.Tensor, embed: torch.Tensor, residual: torch.Tenso
         positions, batch_indices, kv_indptr, kv_indices, int(page_size), int(page_stride), int(slot_stride), cos_sin, cache_row,
         int(head_dim), 1 if interleave else 0, float(rope_scale), float(rope_theta), 1 if llama31 is not None else 0, float(low),
         float(high), float(old_ctx), m, dtype_code(embed.dtype), 1 if enable_pdl else 0, stream_ptr(embed))
+
+
+PROFILER_EVENTS = ("setup", "wait_prev_grid", "weight_prefetch_issued", "main_loop", "splitk_exchange", "epilogue", "all_reduce")
+PROFILER_GROUPS = ("tma_producer", "mma_issuer", "epilogue")
+
+
+@contextlib.contextmanager
+def profiled(buf: torch.Tensor, max_events: int = 32):
+    """Record the NEXT :func:`decode_linear` call of this thread with the intra-kernel profiler (reference flashinfer/profiler,
+    include/flashinfer/profiler.cuh): inside the block the op runs from the ``-DFIB200_ENABLE_PROFILER`` build of the kernel
+    (module ``decode_linear_sm100_prof``) and writes (event, globaltimer) pairs per (CTA, warp role) into ``buf``
+    (``profiler.alloc_profiler_buffer(grid, 3, max_events)``); ``profiler.export_to_perfetto_trace(buf, PROFILER_EVENTS, path,
+    max_events, PROFILER_GROUPS)`` turns it into a Perfetto timeline."""
+    with jit.redirect({"decode_linear_sm100": "decode_linear_sm100_prof"}):
+        jit.load("decode_linear_sm100").call("dlinear_set_profiler", buf, int(max_events))
+        yield

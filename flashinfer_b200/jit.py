@@ -144,6 +144,7 @@ register(ModuleSpec("planner", ["runtime/planner.cpp"]))
 register(ModuleSpec("runtime", ["runtime/runtime.cu"]))
 register(ModuleSpec("gemm_sm100", ["gemm/gemm_bf16_sm100.cu"]))
 register(ModuleSpec("decode_linear_sm100", ["gemm/decode_linear_sm100.cu"]))
+register(ModuleSpec("decode_linear_sm100_prof", ["gemm/decode_linear_sm100.cu"], extra_flags=["-DFIB200_ENABLE_PROFILER"]))  # intra-kernel profiler build
 register(ModuleSpec("decode_sm100", ["attention/decode_sm100.cu"]))
 register(ModuleSpec("prefill_sm100", ["attention/prefill_sm100.cu"]))
 register(ModuleSpec("mla_sm100", ["attention/mla_sm100.cu"]))

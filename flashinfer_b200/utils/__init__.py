@@ -444,3 +444,13 @@ def prepare_jit_additional_args(*args, **kwargs):
     tensors = [a for a in args if hasattr(a, "data_ptr")]
     scalars = [a for a in args if not hasattr(a, "data_ptr")]
     return tensors, scalars
+
+
+def register_custom_op(name, fn=None, /, *, mutates_args, device_types=None, schema=None):
+    """Reference name (flashinfer/utils.py:330): real ``torch.library.custom_op`` registration (see flashinfer_b200/torch_ops.py)."""
+    return torch.library.custom_op(name, fn, mutates_args=mutates_args, device_types=device_types, schema=schema)
+
+
+def register_fake_op(name, fn=None):
+    """Reference name (flashinfer/utils.py:365): ``torch.library.register_fake``."""
+    return torch.library.register_fake(name, fn)
