@@ -34,7 +34,7 @@ def _time_us(fn, iters=20, warm=3):
     return e0.elapsed_time(e1) * 1e3 / iters
 
 
-def run(args, rank, world, BATCH, KV_LEN, PAGE, kv_layout_fn, clock_sampler, summarise_clocks):
+def run(args, rank, world, BATCH, KV_LEN, PAGE, kv_layout_fn, clock_sampler, summarise_clocks, extras=None):
     import flashinfer  # resolved from baseline/_ref (bench.py put it first on sys.path)
 
     src = getattr(args, "ref_src", "tree")
@@ -298,6 +298,11 @@ def run(args, rank, world, BATCH, KV_LEN, PAGE, kv_layout_fn, clock_sampler, sum
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms = tm.tolist()
+    extra = None
+    if extras is not None:
+        del layers, embed, lm_head  # the extra configs allocate their own tensors
+        torch.cuda.empty_cache()
+        extra = extras()
     if rank == 0:
         ms = dev_ms / args.steps
         kv_bytes = BATCH * KV_LEN * hkv_full * d * 2 * 2 * layers_n
@@ -317,5 +322,6 @@ def run(args, rank, world, BATCH, KV_LEN, PAGE, kv_layout_fn, clock_sampler, sum
             "e2e": {"value": BATCH / (e2e_ms / args.steps / 1e3), "unit": "tokens/s", "h2d_bytes_per_step": BATCH * 8,
                     "d2h_bytes_per_step": BATCH * 8},
             "flashinfer_version": flashinfer.__version__,
+            "extra": extra,
             "reference_source": "baseline/_ref (pip install of /root/reference)" if src == "tree" else f"installed wheel ({flashinfer.__file__})",
         }), flush=True)

@@ -149,6 +149,7 @@ def run_ours(args, rank, world):
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms = tm.tolist()
     del flush
+    extra = _run_extras(args, "ours", rank, world)
     if rank == 0:
         ms_per_step = dev_ms / args.steps
         value = BATCH / (ms_per_step / 1e3)
@@ -175,8 +176,42 @@ def run_ours(args, rank, world):
             "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": BATCH * 8, "d2h_bytes_per_step": BATCH * 8},
             "gpu_launches": int((native_per_step + torch_per_step) * args.steps),
             "gpu_launches_native_per_step": int(native_per_step),
+            # the other BASELINE.json configs, measured after the timed region (benchmarks/extra_configs.py; same code both arms)
+            "extra": extra,
         }
         print(json.dumps(res), flush=True)
+
+
+def _run_extras(args, impl, rank, world):
+    """BASELINE.json configs 3 / 4 / 5 (benchmarks/extra_configs.py) after the headline measurement; never fatal.  The reference's
+    single-GPU config needs several JIT builds: it runs in a subprocess with a time limit so that the headline line is never at risk."""
+    if args.no_extras or os.environ.get("FIB200_BENCH_EXTRAS", "1") == "0":
+        return None
+    try:
+        import torch
+
+        torch.cuda.empty_cache()
+        if impl == "reference" and world == 1:
+            import tempfile
+
+            if args.ref_src != "tree":
+                return None
+            out = os.path.join(tempfile.gettempdir(), f"fib200_ref_extras_{os.getpid()}.json")
+            cmd = [sys.executable, os.path.join(ROOT, "benchmarks", "extra_configs.py"), "--impl", "reference", "--config",
+                   "prefill_pod_fp8", "--json-out", out]
+            try:
+                subprocess.run(cmd, timeout=float(os.environ.get("FIB200_REF_EXTRAS_TIMEOUT", "540")), stdout=subprocess.DEVNULL,
+                               stderr=subprocess.DEVNULL, check=False)
+                with open(out) as f:
+                    return json.load(f)["extra"]
+            except subprocess.TimeoutExpired:
+                return {"prefill_pod_fp8": {"unavailable": "reference JIT builds + run exceeded the extras time limit"}}
+        sys.path.insert(0, ROOT)
+        from benchmarks.extra_configs import run_extras
+
+        return run_extras(impl, rank, world)
+    except Exception as e:  # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {str(e)[:200]}"}
 
 
 def run_reference(args, rank, world):
@@ -190,7 +225,8 @@ def run_reference(args, rank, world):
         sys.path.insert(0, ref)
     try:
         from baseline.reference_arm import run as ref_run
-        ref_run(args, rank, world, BATCH, KV_LEN, PAGE, _kv_layout, _clock_sampler, _summarise_clocks)
+        ref_run(args, rank, world, BATCH, KV_LEN, PAGE, _kv_layout, _clock_sampler, _summarise_clocks,
+                extras=lambda: _run_extras(args, "reference", rank, world))
     except Exception as e:  # noqa: BLE001
         if rank == 0:
             print(json.dumps({"impl": "reference", "unavailable": f"{type(e).__name__}: {str(e)[:300]}"}))
@@ -211,8 +247,9 @@ def main():
                     help="reference arm: tree = baseline/_ref (the unmodified /root/reference, default and the driver's arm); wheel = "
                          "the pip-installed flashinfer-python 0.6.11.post2 + flashinfer-cubin (diagnostic: the only build whose "
                          "trtllm-gen cubins exist offline)")
-    ap.add_argument("--kv-layout", default=os.environ.get("FIB200_BENCH_KV_LAYOUT", "HND"), choices=["NHD", "HND"],
+    ap.add_argument("--kv-layout", default=os.environ.get("FIB200_BENCH_KV_LAYOUT", "NHD"), choices=["NHD", "HND"],
                     help="ours: paged KV-cache layout (HND: one contiguous 4 KB chunk per (page, head))")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra BASELINE configs (extra block of the JSON line)")
     ap.add_argument("--unfused", action="store_true", help="ours: op-by-op decode path (round-1 composition) instead of decode_linear")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -163,6 +163,7 @@ def flashinfer_api(fn: Optional[Callable] = None, *, name: Optional[str] = None)
                     _PENDING_GRAPH_DUMPS.append(deferred)
             return out
 
+        wrapper.__fib200_api_wrapper__ = True
         return wrapper
 
     return deco(fn) if fn is not None else deco
@@ -265,6 +266,11 @@ def _rebind_everywhere(old, new) -> None:
                 setattr(mod, attr, new)
 
 
+def _unwrap(f):
+    """Undo OUR logging wrapper only (functools.wraps also leaves ``__wrapped__`` on contextmanagers, lru_caches, ...)."""
+    return f.__wrapped__ if getattr(f, "__fib200_api_wrapper__", False) else f
+
+
 def instrument() -> int:
     """Decorate every public op / wrapper method of the package (idempotent).  Returns the number of instrumented callables."""
     import importlib
@@ -280,7 +286,7 @@ def instrument() -> int:
                 continue
             if inspect.isfunction(obj) and getattr(obj, "__module__", None) == mod.__name__:
                 api = f"{short}.{attr}"
-                base = _ORIGINALS.setdefault(api, (mod, attr, getattr(obj, "__wrapped__", obj)))[2]
+                base = _ORIGINALS.setdefault(api, (mod, attr, _unwrap(obj)))[2]
                 new = flashinfer_api(base, name=api)
                 if new is not obj:
                     _rebind_everywhere(obj, new)
@@ -291,7 +297,7 @@ def instrument() -> int:
                     if not inspect.isfunction(f):
                         continue
                     api = f"{short}.{attr}.{meth}"
-                    base = _ORIGINALS.setdefault(api, (obj, meth, getattr(f, "__wrapped__", f)))[2]
+                    base = _ORIGINALS.setdefault(api, (obj, meth, _unwrap(f)))[2]
                     new = flashinfer_api(base, name=api)
                     if new is not f:
                         setattr(obj, meth, new)
