@@ -169,7 +169,7 @@ def run_ours(args, rank, world):
                        "ref_attention_candidates": None,
                        "linear": ("flashinfer_b200 decode_linear_sm100 (RMSNorm / RoPE+append / SwiGLU / residual epilogues)"
                                   if eng.fused else "flashinfer_b200 gemm_sm100"),
-                       "allreduce": (("in-kernel NVLS all-reduce inside the O / down GEMM epilogue (multimem.red + ld_reduce)"
+                       "allreduce": (("one-shot push all-reduce inside the O / down GEMM epilogue (multimem.st into every rank's slot, sentinel polling)"
                                       if eng.fused else "in-kernel NVLS all-reduce + add + RMSNorm kernel") if world > 1 else None),
                        "ref_allreduce_candidates": None},
             "clocks": _summarise_clocks(clk.get("rows")),

@@ -140,7 +140,8 @@ def tp_gemm_rs(impl, rank, world):
         res = torch.randn(M // world, hidden, device="cuda").bfloat16()
         if impl == "ours":
             fn = lambda: comm.reduce_scatter(a, w, residual=res, rms_weight=gamma, eps=1e-5)  # noqa: E731
-            path = "one kernel: tcgen05 GEMM + NVLS multimem.ld_reduce reduce-scatter + residual; + rs_rmsnorm scale pass"
+            path = ("chunk-pipelined: persistent tcgen05 GEMM (gemm_nt) into symmetric staging || in-switch multimem.ld_reduce pull + residual "
+                    "+ row sum-of-squares on a side stream (rs_pull_rows); + rs_rmsnorm scale pass; no NCCL")
         else:
             def fn():
                 c = fi.mm_bf16(a, w.t()) if hasattr(fi, "mm_bf16") and os.environ.get("FIB200_REF_MM", "torch") == "flashinfer" else a @ w.t()

@@ -51,6 +51,7 @@ class TPCommunicator:
         self._small_tab = self.heap.peer_ptr_table(self._small_off)
         self._epochs = torch.zeros(2 * _MAX_BLOCKS, dtype=torch.int32, device=self.heap.device)
         self.use_nvls = bool(use_nvls and self.heap.mc_ptr)
+        self._push = None  # receive buffers of the one-shot push all-reduce: allocated on first use (3 x world x tokens x hidden)
         self._turn = 0
         self._mod = jit.load("comm_allreduce")
         self.heap.barrier()
@@ -101,6 +102,69 @@ class TPCommunicator:
         if two_shot:
             out.copy_(target)
         return out
+
+    # ------------------------------------------------------------------ one-shot push (Lamport) with fused prologue / epilogue
+    PUSH_MAX_TOKENS = 256
+    SF_LAYOUT = {"128x4": 0, "8x4": 1, "linear": 2}
+
+    def _push_state(self):
+        if self._push is None:
+            from .symm import SymmetricHeap
+
+            esz = torch.empty(0, dtype=self.dtype).element_size()
+            rows = min(self.max_tokens, self.PUSH_MAX_TOKENS)
+            slot = rows * self.hidden
+            nbytes = 3 * self.world * slot * esz
+            heap = SymmetricHeap(self.group, nbytes + 8192)
+            buf, off = heap.alloc(nbytes)
+            buf.view(torch.int16).fill_(-32768)  # -0.0 sentinel: "nothing has arrived"
+            self._push = {"heap": heap, "recv": buf.view(self.dtype), "mc": heap.mc(off) if self.use_nvls else 0,
+                          "peers": heap.peer_ptr_table(off), "epoch": torch.zeros(4, dtype=torch.int32, device=heap.device),
+                          "rows": rows, "slot": slot}
+            heap.barrier()
+        return self._push
+
+    def push_supported(self, tokens: int, hidden: int, dtype: torch.dtype) -> bool:
+        return (hidden == self.hidden and dtype == self.dtype and tokens <= min(self.max_tokens, self.PUSH_MAX_TOKENS)
+                and hidden % 16 == 0 and hidden <= 16384 and dtype in (torch.float16, torch.bfloat16))
+
+    def push_allreduce(self, x: Optional[torch.Tensor], *, tokens: Optional[int] = None, ar_out: Optional[torch.Tensor] = None,
+                       residual_in: Optional[torch.Tensor] = None, residual_out: Optional[torch.Tensor] = None,
+                       rms_gamma: Optional[torch.Tensor] = None, norm_out: Optional[torch.Tensor] = None, eps: float = 1e-6,
+                       weight_bias: float = 0.0, quant: str = "none", quant_out: Optional[torch.Tensor] = None,
+                       scale_out: Optional[torch.Tensor] = None, scale_factor: Optional[torch.Tensor] = None,
+                       sf_layout: str = "128x4", moe_reduction=None, moe_finalize=None, enable_pdl: bool = True) -> None:
+        """One kernel: [MoE reduction | MoE finalize |] all-reduce (one-shot push over NVLink) [+ residual][+ RMSNorm][+ e4m3 / NVFP4
+        quantisation with linear / 128x4 / 8x4 scale layout] (csrc/comm/allreduce.cu: allreduce_push_kernel).
+
+        ``moe_reduction = (active_experts_token [E, T, H], scale [E, T], token_input [T, H])``;
+        ``moe_finalize = (permuted_rows [P, H], expanded_idx_to_permuted_idx [T, K], expert_weights [T, K] or None, shared [T, H] or None)``."""
+        st = self._push_state()
+        mode, src, msc, mtok, e2p, mn = 0, x, None, None, None, 0
+        if moe_reduction is not None:
+            act, sc, tok = moe_reduction
+            mode, src, msc, mtok, mn = 1, act.contiguous(), sc.float().contiguous(), tok.contiguous(), act.shape[0]
+            tokens = tok.shape[0]
+        elif moe_finalize is not None:
+            rows, idx, w, shared = moe_finalize
+            mode, src, e2p, mn = 2, rows.contiguous(), idx.int().contiguous(), idx.shape[1]
+            msc = w.float().contiguous() if w is not None else None
+            mtok = shared.contiguous() if shared is not None else None
+            tokens = idx.shape[0]
+        else:
+            src = x.contiguous()
+            tokens = x.shape[0] if tokens is None else tokens
+        ref = src
+        q = {"none": 0, "fp8": 1, "nvfp4": 2}[quant]
+        sf = None
+        if q:
+            sf = scale_factor if isinstance(scale_factor, torch.Tensor) else torch.tensor([float(scale_factor if scale_factor is not None else 1.0)],
+                                                                                         device=ref.device)
+            sf = sf.float().reshape(-1)[:1].contiguous()
+        self._mod.call("allreduce_push_run", mode, src, msc, mtok, e2p, mn, st["recv"], _ptr(st["mc"]), st["peers"], st["epoch"], st["slot"],
+                       self.rank, self.world, tokens, self.hidden, st["rows"], ar_out, residual_in, residual_out, rms_gamma, norm_out,
+                       float(eps), float(weight_bias), q, quant_out, scale_out, sf, self.SF_LAYOUT[sf_layout], dtype_code(self.dtype),
+                       1 if enable_pdl else 0, stream_ptr(ref))
 
     def all_reduce(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Plain sum all-reduce through the same kernel."""

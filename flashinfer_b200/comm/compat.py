@@ -140,7 +140,7 @@ trtllm_destroy_ipc_workspace_for_all_reduce = trtllm_destroy_ipc_workspace_for_a
 
 
 def trtllm_lamport_initialize(buffer_ptr: int, size: int, dtype: torch.dtype) -> None:
-    """No-op: the NVLS kernels use epoch barriers instead of Lamport sentinels, nothing needs re-initialising."""
+    """No-op for callers: the one-shot push kernel keeps its own sentinel-initialised rotating buffers and re-arms them itself."""
 
 
 def trtllm_lamport_initialize_all(buffer_0_ptr: int, buffer_1_ptr: int, buffer_2_ptr: int, size: int, dtype: torch.dtype) -> None:
@@ -170,6 +170,26 @@ def _quant_after(norm: torch.Tensor, pattern: int, quant_out, scale_out, scale_f
     return None
 
 
+_SF_LAYOUT_NAME = {QuantizationSFLayout.SWIZZLED_128x4: "128x4", QuantizationSFLayout.SWIZZLED_8x4: "8x4", QuantizationSFLayout.LINEAR: "linear"}
+
+
+def _push_fused(comm: TPCommunicator, x, pattern: int, *, allreduce_out=None, residual_in=None, residual_out=None, rms_gamma=None,
+                rms_eps=1e-6, norm_out=None, quant_out=None, scale_out=None, scale_factor=None, layout_code=None, pdl=True,
+                moe_reduction=None, moe_finalize=None) -> None:
+    """Every pattern of the reference in ONE kernel (one-shot push all-reduce with fused prologue / epilogue)."""
+    P = AllReduceFusionPattern
+    quant = "none"
+    if pattern in (P.kARResidualRMSNormFP8Quant, P.kARResidualRMSNormOutFP8Quant):
+        quant = "fp8"
+    elif pattern in (P.kARResidualRMSNormFP4Quant, P.kARResidualRMSNormOutFP4Quant) or (quant_out is not None and pattern in (
+            P.kMoEReductionARResidualRMSNorm, P.kMoEFinalizeARResidualRMSNorm)):
+        quant = "nvfp4"
+    comm.push_allreduce(x, ar_out=allreduce_out, residual_in=residual_in, residual_out=residual_out, rms_gamma=rms_gamma,
+                        norm_out=norm_out, eps=rms_eps, quant=quant, quant_out=quant_out, scale_out=scale_out, scale_factor=scale_factor,
+                        sf_layout=_SF_LAYOUT_NAME.get(layout_code, "128x4"), moe_reduction=moe_reduction, moe_finalize=moe_finalize,
+                        enable_pdl=pdl)
+
+
 def allreduce_fusion(input: torch.Tensor, workspace: AllReduceFusionWorkspace, pattern: int, launch_with_pdl: bool = False,
                      trigger_completion_at_end: bool = True, output: Optional[torch.Tensor] = None,
                      residual_out: Optional[torch.Tensor] = None, norm_out: Optional[torch.Tensor] = None,
@@ -177,19 +197,42 @@ def allreduce_fusion(input: torch.Tensor, workspace: AllReduceFusionWorkspace, p
                      residual_in: Optional[torch.Tensor] = None, rms_gamma: Optional[torch.Tensor] = None, rms_eps: float = 1e-6,
                      scale_factor: Optional[Union[torch.Tensor, float]] = None, layout_code: Optional[int] = None,
                      use_oneshot: Optional[bool] = None, fp32_acc: bool = False, **moe_kwargs) -> torch.Tensor:
-    """Unified fused all-reduce (patterns 0-5): sum over ranks [+ residual add + RMSNorm [+ fp8 / nvfp4 quant]]."""
+    """Unified fused all-reduce (patterns 0-5): sum over ranks [+ residual add + RMSNorm [+ fp8 / nvfp4 quant]].
+
+    Up to ``TPCommunicator.PUSH_MAX_TOKENS`` tokens every pattern - quantisation and scale-factor layout included - is ONE
+    kernel (one-shot push, :meth:`TPCommunicator.push_allreduce`).  Larger messages use the in-switch ``multimem.ld_reduce``
+    kernel (AR + residual + RMSNorm + fp8) and, for NVFP4 only, the native quantiser as a second launch."""
     P = AllReduceFusionPattern
     comm = workspace.comm
     tokens, hidden = input.shape
-    if pattern == P.kAllReduce:
-        res = comm.allreduce_add_rmsnorm(input, None, None, out=output, enable_pdl=launch_with_pdl)
-        return res
     if pattern in (P.kMoEReductionARResidualRMSNorm, P.kMoEFinalizeARResidualRMSNorm):
         raise ValueError("use trtllm_moe_allreduce_fusion / trtllm_moe_finalize_allreduce_fusion for MoE patterns")
-    if residual_in is None or rms_gamma is None:
+    if pattern != P.kAllReduce and (residual_in is None or rms_gamma is None):
         raise ValueError("residual_in and rms_gamma are required for the RMSNorm patterns")
-    # one-shot keeps the residual replicated (reference semantics); the token-sharded two-shot flavour is exposed by
-    # TPCommunicator directly because it changes the residual layout
+    if input.is_cuda and use_oneshot is not False and comm.push_supported(tokens, hidden, input.dtype):
+        if pattern == P.kAllReduce:
+            out = output if output is not None else torch.empty_like(input)
+            _push_fused(comm, input, pattern, allreduce_out=out, pdl=launch_with_pdl)
+            return out
+        res_out = residual_out if residual_out is not None else residual_in  # in place when no separate output is given
+        need_norm = norm_out is not None or pattern in (P.kARResidualRMSNorm, P.kARResidualRMSNormOutFP8Quant, P.kARResidualRMSNormOutFP4Quant)
+        if need_norm and norm_out is None:
+            norm_out = torch.empty_like(input)
+        if pattern in (P.kARResidualRMSNormFP8Quant, P.kARResidualRMSNormOutFP8Quant) and quant_out is None:
+            quant_out = torch.empty(tokens, hidden, dtype=torch.float8_e4m3fn, device=input.device)
+        if pattern in (P.kARResidualRMSNormFP4Quant, P.kARResidualRMSNormOutFP4Quant):
+            if quant_out is None:
+                quant_out = torch.empty(tokens, hidden // 2, dtype=torch.uint8, device=input.device)
+            if scale_out is None:
+                n_sf = compute_fp4_swizzled_layout_sf_size(tokens, hidden // 16) if layout_code != QuantizationSFLayout.LINEAR else tokens * hidden // 16
+                scale_out = torch.empty(n_sf, dtype=torch.uint8, device=input.device)
+        _push_fused(comm, input, pattern, allreduce_out=output, residual_in=residual_in, residual_out=res_out, rms_gamma=rms_gamma,
+                    rms_eps=rms_eps, norm_out=norm_out, quant_out=quant_out, scale_out=scale_out, scale_factor=scale_factor,
+                    layout_code=layout_code, pdl=launch_with_pdl)
+        return norm_out if norm_out is not None else quant_out
+    # ---- large messages: in-switch pull kernel
+    if pattern == P.kAllReduce:
+        return comm.allreduce_add_rmsnorm(input, None, None, out=output, enable_pdl=launch_with_pdl)
     res = residual_in if residual_out is None else residual_out
     if residual_out is not None and residual_out.data_ptr() != residual_in.data_ptr():
         residual_out.copy_(residual_in)
@@ -208,17 +251,16 @@ def trtllm_allreduce_fusion(allreduce_in: torch.Tensor, world_size: int, world_r
                             block_quant_group_size: Optional[int] = None) -> None:
     ws = workspace_ptrs[0] if isinstance(workspace_ptrs, (list, tuple)) else workspace_ptrs
     x = allreduce_in.view(token_num, hidden_dim)
-    if pattern_code == AllReduceFusionPattern.kAllReduce:
-        allreduce_fusion(x, ws, pattern_code, launch_with_pdl, output=allreduce_out.view(token_num, hidden_dim) if allreduce_out is not None else None)
-        return
-    if norm_out is None:
-        norm_out = torch.empty_like(x)
-    allreduce_fusion(x, ws, pattern_code, launch_with_pdl, trigger_completion_at_end, None,
-                     residual_out.view(token_num, hidden_dim) if residual_out is not None else None,
-                     norm_out.view(token_num, hidden_dim), quant_out, scale_out,
-                     residual_in.view(token_num, hidden_dim) if residual_in is not None else None, rms_gamma,
-                     rms_eps if rms_eps is not None else 1e-6, scale_factor, layout_code, use_oneshot, fp32_acc)
-    if allreduce_out is not None and residual_out is not None and residual_in is not None:
+    v = lambda t: t.view(token_num, hidden_dim) if t is not None else None  # noqa: E731
+    if pattern_code in (AllReduceFusionPattern.kARResidualRMSNormPerTokenGroupFP8PackedQuant,
+                        AllReduceFusionPattern.kARResidualRMSNormOutPerTokenGroupFP8PackedQuant):
+        raise NotImplementedError("per-token-group fp8 packed quantisation pattern")
+    big = not (x.is_cuda and use_oneshot is not False and ws.comm.push_supported(token_num, hidden_dim, x.dtype))
+    allreduce_fusion(x, ws, pattern_code, launch_with_pdl, trigger_completion_at_end, v(allreduce_out), v(residual_out), v(norm_out),
+                     quant_out, scale_out, v(residual_in), rms_gamma, rms_eps if rms_eps is not None else 1e-6, scale_factor, layout_code,
+                     use_oneshot, fp32_acc)
+    if big and allreduce_out is not None and residual_out is not None and residual_in is not None and pattern_code != AllReduceFusionPattern.kAllReduce:
+        # pull kernel (large messages) has no separate raw-sum output: recover it from the residual stream
         allreduce_out.view(token_num, hidden_dim).copy_((residual_out.view(token_num, hidden_dim).float() -
                                                          residual_in.view(token_num, hidden_dim).float()).to(allreduce_out.dtype))
 
@@ -253,6 +295,15 @@ def trtllm_moe_allreduce_fusion(world_size: int, world_rank: int, token_num: int
     all-reduce + residual + RMSNorm (reference trtllm_ar.py:1062)."""
     ws = workspace_ptrs[0] if isinstance(workspace_ptrs, (list, tuple)) else workspace_ptrs
     E = moe_reduction_device_num_experts
+    if residual_in.is_cuda and ws.comm.push_supported(token_num, hidden_dim, residual_in.dtype):
+        # ONE kernel: expert-weighted reduction -> one-shot push all-reduce -> + residual -> RMSNorm (-> NVFP4 quant)
+        v = lambda t: t.view(token_num, hidden_dim) if t is not None else None  # noqa: E731
+        _push_fused(ws.comm, None, AllReduceFusionPattern.kMoEReductionARResidualRMSNorm, allreduce_out=v(moe_allreduce_out),
+                    residual_in=v(residual_in), residual_out=v(residual_out), rms_gamma=rms_gamma, rms_eps=rms_eps, norm_out=v(norm_out),
+                    quant_out=quant_out, scale_out=scale_out, scale_factor=scale_factor, layout_code=layout_code, pdl=launch_with_pdl,
+                    moe_reduction=(moe_reduction_active_experts_token_input.view(E, token_num, hidden_dim),
+                                   moe_reduction_scale_input.view(E, token_num), moe_reduction_token_input.view(token_num, hidden_dim)))
+        return
     act = moe_reduction_active_experts_token_input.view(E, token_num, hidden_dim).float()
     sc = moe_reduction_scale_input.view(E, token_num).float()
     x = (act * sc[..., None]).sum(0) + moe_reduction_token_input.view(token_num, hidden_dim).float()
@@ -281,6 +332,14 @@ def trtllm_moe_finalize_allreduce_fusion(allreduce_in: torch.Tensor, residual_in
     ws = workspace[0] if isinstance(workspace, (list, tuple)) else workspace
     T, K = expanded_idx_to_permuted_idx.shape
     H = allreduce_in.shape[-1]
+    if allreduce_in.is_cuda and ws.comm.push_supported(T, H, allreduce_in.dtype):
+        # ONE kernel: top-k weighted un-permute (+ shared expert) -> one-shot push all-reduce -> + residual -> RMSNorm (-> NVFP4 quant)
+        _push_fused(ws.comm, None, AllReduceFusionPattern.kMoEFinalizeARResidualRMSNorm, residual_in=residual_in.view(T, H),
+                    residual_out=residual_out.view(T, H), rms_gamma=norm_weight, rms_eps=eps, norm_out=norm_out.view(T, H),
+                    quant_out=quant_out, scale_out=scale_out, scale_factor=scale_factor, layout_code=layout_code, pdl=launch_with_pdl,
+                    moe_finalize=(allreduce_in.reshape(-1, H), expanded_idx_to_permuted_idx, expert_scale_factor,
+                                  shared_expert_output.view(T, H) if shared_expert_output is not None else None))
+        return
     x = torch.empty(T, H, dtype=allreduce_in.dtype, device=allreduce_in.device) if shared_expert_output is None \
         else shared_expert_output.clone().view(T, H)
     w = expert_scale_factor.float().contiguous() if expert_scale_factor is not None else torch.ones(T, K, device=x.device)

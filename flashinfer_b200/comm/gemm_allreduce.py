@@ -36,7 +36,7 @@ class GemmAllReduce:
         cbytes = (max_m * n * esz + 1023) // 1024 * 1024
         fbytes = _MAX_TILES * 4
         dbytes = _MAX_CTAS * 16 * 4
-        self.heap = SymmetricHeap(self.group, 3 * cbytes + fbytes + dbytes + 16384)
+        self.heap = SymmetricHeap(self.group, 3 * cbytes + fbytes + 2 * dbytes + 16384)
         self._stage = []
         for _ in range(2):
             v, off = self.heap.alloc(cbytes)
@@ -48,7 +48,11 @@ class GemmAllReduce:
         self._flag_tab = self.heap.peer_ptr_table(self._flag_off)
         _, self._done_off = self.heap.alloc(dbytes)
         self._done_tab = self.heap.peer_ptr_table(self._done_off)
+        _, self._rs_sig_off = self.heap.alloc(dbytes)  # epoch slots of the chunk-pipelined reduce-scatter (rs_pull_rows)
+        self._rs_sig_tab = self.heap.peer_ptr_table(self._rs_sig_off)
         dev = self.heap.device
+        self._rs_epoch = torch.zeros(_MAX_CTAS, dtype=torch.int32, device=dev)
+        self._side = None
         self._expect = torch.zeros(_MAX_TILES, dtype=torch.int32, device=dev)
         self._done_epoch = torch.zeros(_MAX_CTAS, dtype=torch.int32, device=dev)
         self.use_nvls = bool(use_nvls and self.heap.mc_ptr)
@@ -87,7 +91,7 @@ class GemmAllReduce:
 
     def reduce_scatter(self, a: torch.Tensor, w: torch.Tensor, residual: Optional[torch.Tensor] = None,
                        rms_weight: Optional[torch.Tensor] = None, eps: float = 1e-6, out: Optional[torch.Tensor] = None,
-                       bn: int = 0):
+                       bn: int = 0, pipelined: Optional[int] = None):
         """``GEMM -> reduce-scatter (-> + residual -> RMSNorm)`` of sequence-parallel tensor parallelism, one GEMM kernel per
         rank: rank ``r`` ends up with rows ``[r * M / world, (r + 1) * M / world)`` of ``sum_ranks(a @ w.T)``.
 
@@ -122,15 +126,65 @@ class GemmAllReduce:
         self._turn ^= 1
         stage, soff, stab = self._stage[self._turn]
         mc = self.heap.mc if self.use_nvls else (lambda off: 0)
-        self._mod.call("gemm_allreduce_nt", a, w, stage, shard, M, N, K, a.stride(0), w.stride(0), N, dtype_code(a.dtype), stab,
-                       self._flag_tab, None, self._done_tab, _ptr(mc(soff)), _ptr(mc(self._flag_off)), _ptr(0), self._expect,
-                       self._done_epoch, self.rank, self.world, 2, _MAX_TILES, bn, rpr, N, residual, sumsq, 1, stream_ptr(a))
+        chunks = self._pipeline_chunks(M, N, K) if pipelined is None else (int(pipelined) if pipelined else 0)
+        if chunks:
+            self._reduce_scatter_pipelined(a, w, stage, soff, stab, shard, residual, sumsq, rpr, chunks)
+        else:
+            self._mod.call("gemm_allreduce_nt", a, w, stage, shard, M, N, K, a.stride(0), w.stride(0), N, dtype_code(a.dtype), stab,
+                           self._flag_tab, None, self._done_tab, _ptr(mc(soff)), _ptr(mc(self._flag_off)), _ptr(0), self._expect,
+                           self._done_epoch, self.rank, self.world, 2, _MAX_TILES, bn, rpr, N, residual, sumsq, 1, stream_ptr(a))
         if rms_weight is None:
             return shard
         normed = torch.empty_like(shard)
         self._mod.call("rs_rmsnorm", shard, normed, rms_weight.to(a.dtype).contiguous(), sumsq, rpr, N, N, N, float(eps),
                        dtype_code(a.dtype), 1, stream_ptr(a))
         return normed, shard
+
+
+    # ------------------------------------------------------------------ prefill sizes: chunk-pipelined GEMM / in-switch pull
+    def _pipeline_chunks(self, M: int, N: int, K: int) -> int:
+        """Number of pipeline chunks (0 = the one-kernel path).  From a few thousand rows on, the GEMM is long enough that pulling
+        chunk c through the switch while the tensor cores work on chunk c + 1 hides the whole reduce-scatter (or, at TP = 8 where
+        the link is the bound, the whole GEMM)."""
+        rpr = M // self.world
+        if not self.use_nvls and self.world > 4:
+            return 0
+        if M < 2048 or N % 256 or rpr % 128:
+            return 0
+        for c in (4, 8, 2):
+            if rpr % (c * 128) == 0 and rpr // c >= 256:
+                return c
+        return 0
+
+    def _reduce_scatter_pipelined(self, a, w, stage, soff, stab, shard, residual, sumsq, rpr: int, chunks: int) -> None:
+        from ..gemm.dense import linear
+
+        M, K = a.shape
+        N = w.shape[0]
+        mc = self.heap.mc(soff) if self.use_nvls else 0
+        main = torch.cuda.current_stream(a.device)
+        if self._side is None:
+            self._side = torch.cuda.Stream(a.device)
+        side = self._side
+        m_c = rpr // chunks
+        evs = []
+        for c in range(chunks):
+            for r in range(self.world):  # chunk c of EVERY rank's row range: all ranks pull concurrently, links stay evenly loaded
+                lo = r * rpr + c * m_c
+                linear(a[lo: lo + m_c], w, out=stage[lo: lo + m_c])
+            ev = torch.cuda.Event()
+            ev.record(main)
+            evs.append(ev)
+            side.wait_event(ev)
+            lo = self.rank * rpr + c * m_c
+            self._mod.call("rs_pull_rows", _ptr(mc), stab, self._rs_sig_tab, self._rs_epoch, self.rank, self.world, N, lo, m_c, N,
+                           shard[c * m_c: (c + 1) * m_c], N, residual[c * m_c: (c + 1) * m_c] if residual is not None else None,
+                           N, sumsq[c * m_c:] if sumsq is not None else None, _MAX_CTAS, dtype_code(a.dtype), side.cuda_stream)
+        main.wait_stream(side)
+        for t in (a, w, shard, stage):
+            t.record_stream(side)
+        if residual is not None:
+            residual.record_stream(side)
 
 
 _CACHE: dict = {}

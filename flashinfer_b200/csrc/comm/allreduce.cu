@@ -19,6 +19,7 @@
 //    `st.release.sys` to the peer's slot, `ld.acquire.sys` spin on the local slot; epochs are kept in
 //    device memory so the kernels are CUDA-graph replay safe and never need a reset.
 //  * PDL: griddepcontrol.wait precedes the first signal (the producer GEMM may still be running).
+#include <cuda_fp4.h>
 #include <fib200/common.cuh>
 #include <fib200/ptx.cuh>
 
@@ -279,4 +280,322 @@ extern "C" int allreduce_fusion_run(void* peer_in_host, void* peer_sig_host, voi
   if (dtype == kF16) return launch_ar<__half>(p, nvls, two_shot != 0, blocks, threads, pdl != 0, stream);
   if (dtype == kF32) return launch_ar<float>(p, nvls, two_shot != 0, blocks, threads, pdl != 0, stream);
   return set_error("allreduce: unsupported dtype");
+}
+
+// =====================================================================================================================
+// One-shot PUSH all-reduce (Lamport style) with fused prologue and epilogue - the small-message path (<= 128-256 tokens).
+//
+// Parity: reference include/flashinfer/comm/trtllm_allreduce_fusion.cuh:1336-1403 (one-shot Lamport kernel),
+// :487-740 (fp8 / nvfp4 quantisation epilogues with linear / 128x4 / 8x4 scale layouts) and
+// include/flashinfer/comm/trtllm_moe_allreduce_fusion.cuh:938,1239 (MoE reduction / finalize fused in front of the all-reduce).
+//
+// One CTA per token.  Prologue (registers only): plain input row | MoE reduction  sum_e scale[e, t] * act[e, t, :] + token[t, :]
+// | MoE finalize  sum_k w[t, k] * permuted[e2p[t, k], :] (+ shared[t, :]).  The bf16 / fp16 row is multicast with
+// `multimem.st` into slot [rank] of EVERY rank's receive buffer (per-peer stores without NVLS); -0.0 is the "not yet
+// arrived" sentinel, the sender flushes real -0.0 to +0.0.  Every rank then polls its own copy of all slots, sums them in rank
+// order (bitwise identical everywhere), and runs the epilogue on the fp32 row: raw sum out | + residual -> residual out |
+// RMSNorm -> norm out | e4m3 quantisation | NVFP4 quantisation with the scale factors written in the requested layout.
+// No flags, no system fences.  Three rotating buffers, selected by a device-side epoch (CUDA-graph replay safe); the buffer
+// of the NEXT call is reset to the sentinel while the pushes are in flight.  Polls carry the 20 s watchdog.
+// =====================================================================================================================
+namespace {
+
+struct PushParams {
+  // prologue
+  int mode;                       // 0 plain | 1 MoE reduction | 2 MoE finalize
+  const void* in;                 // mode 0: [T, H];  mode 1: active-expert outputs [E, T, H];  mode 2: permuted rows [P, H]
+  const float* moe_scale;         // mode 1: [E, T];  mode 2: expert weights [T, K] (null = 1)
+  const void* moe_token_in;       // mode 1: [T, H] added to the reduction;  mode 2: shared-expert output [T, H] (or null)
+  const int32_t* e2p;             // mode 2: expanded (t * K + k) -> permuted row
+  int moe_n;                      // mode 1: experts E;  mode 2: top-k K
+  // exchange
+  void* recv;                     // local [3][world][max_tokens][hidden]
+  void* mc_recv;                  // multicast alias (or null)
+  void* peer_recv[kMaxRanks];
+  uint32_t* epoch;                // local device word
+  int64_t slot_elems, buf_elems;
+  int rank, world;
+  int tokens, hidden, max_tokens;
+  // epilogue
+  void* ar_out;                   // raw all-reduce sum [T, H] (or null)
+  const void* residual_in;        // (or null)
+  void* residual_out;             // (or null)
+  const void* gamma;              // RMSNorm weight (or null: no norm)
+  void* norm_out;                 // (or null)
+  float eps, weight_bias;
+  int quant;                      // 0 none | 1 e4m3 (quant_out [T, H]) | 2 nvfp4 (quant_out [T, H/2] + scale_out)
+  void* quant_out;
+  uint8_t* scale_out;
+  const float* scale_factor;      // device scalar: fp8: y / scale;  nvfp4: global scale (448 * 6 / amax)
+  int sf_layout;                  // 0 = 128x4 swizzled, 1 = 8x4 swizzled, 2 = linear
+};
+
+__device__ __forceinline__ int64_t sf_offset(int layout, int row, int c, int ncols_sf) {
+  const int pad4 = (ncols_sf + 3) / 4 * 4;
+  if (layout == 2) return int64_t(row) * ncols_sf + c;
+  if (layout == 1) return (int64_t(row / 8) * (pad4 / 4) + c / 4) * 32 + (row % 8) * 4 + (c % 4);
+  return (int64_t(row / 128) * (pad4 / 4) + c / 4) * 512 + (row % 32) * 16 + ((row % 128) / 32) * 4 + (c % 4);
+}
+
+template <typename T, int kVecPerThread>
+__global__ void __launch_bounds__(1024) allreduce_push_kernel(const PushParams p) {
+  constexpr int VN = 8;  // 16-bit elements per 16-byte vector
+  __shared__ float red[32];
+  __shared__ uint32_t s_epoch;
+  const int row = blockIdx.x;
+  const int nvec = p.hidden / VN;
+  ptx::grid_dep_wait();
+  __shared__ int s_dirty;
+  if (threadIdx.x == 0) {
+    s_epoch = *reinterpret_cast<volatile uint32_t*>(p.epoch);
+    s_dirty = int(*reinterpret_cast<volatile uint32_t*>(p.epoch + 1 + (s_epoch + 1u) % 3u));  // rows the NEXT buffer still holds
+  }
+  __syncthreads();
+  const uint32_t ep = s_epoch;
+  const int dirty_next = s_dirty;
+  T* recv = reinterpret_cast<T*>(p.recv);
+  const int64_t cur = int64_t(ep % 3u) * p.buf_elems, nxt = int64_t((ep + 1u) % 3u) * p.buf_elems;
+
+  // ---------------- prologue + push
+  int4 mine[kVecPerThread];
+#pragma unroll
+  for (int it = 0; it < kVecPerThread; ++it) {
+    const int v = threadIdx.x + it * blockDim.x;
+    if (v >= nvec) continue;
+    const int64_t off = int64_t(row) * p.hidden + int64_t(v) * VN;
+    float x[VN];
+    if (p.mode == 0) {
+      const Vec16<T> a = ld16(reinterpret_cast<const T*>(p.in) + off);
+#pragma unroll
+      for (int e = 0; e < VN; ++e) x[e] = to_f32(a.v[e]);
+    } else if (p.mode == 1) {
+      const Vec16<T> t0 = ld16(reinterpret_cast<const T*>(p.moe_token_in) + off);
+#pragma unroll
+      for (int e = 0; e < VN; ++e) x[e] = to_f32(t0.v[e]);
+      for (int ex = 0; ex < p.moe_n; ++ex) {
+        const float sc = p.moe_scale[int64_t(ex) * p.tokens + row];
+        const Vec16<T> a = ld16(reinterpret_cast<const T*>(p.in) + int64_t(ex) * p.tokens * p.hidden + off);
+#pragma unroll
+        for (int e = 0; e < VN; ++e) x[e] += sc * to_f32(a.v[e]);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < VN; ++e) x[e] = 0.f;
+      if (p.moe_token_in) {
+        const Vec16<T> t0 = ld16(reinterpret_cast<const T*>(p.moe_token_in) + off);
+#pragma unroll
+        for (int e = 0; e < VN; ++e) x[e] = to_f32(t0.v[e]);
+      }
+      for (int k = 0; k < p.moe_n; ++k) {
+        const int pr = p.e2p[int64_t(row) * p.moe_n + k];
+        if (pr < 0) continue;
+        const float w = p.moe_scale ? p.moe_scale[int64_t(row) * p.moe_n + k] : 1.f;
+        const Vec16<T> a = ld16(reinterpret_cast<const T*>(p.in) + int64_t(pr) * p.hidden + int64_t(v) * VN);
+#pragma unroll
+        for (int e = 0; e < VN; ++e) x[e] += w * to_f32(a.v[e]);
+      }
+    }
+    Vec16<T> o;
+#pragma unroll
+    for (int e = 0; e < VN; ++e) o.v[e] = from_f32<T>(x[e]);
+    uint32_t* w32 = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {  // -0.0 is the sentinel: never send it
+      if ((w32[e] & 0xffffu) == 0x8000u) w32[e] &= 0xffff0000u;
+      if ((w32[e] >> 16) == 0x8000u) w32[e] &= 0x0000ffffu;
+    }
+    mine[it] = *reinterpret_cast<const int4*>(&o);
+    const int64_t dst = cur + int64_t(p.rank) * p.slot_elems + off;
+    if (p.mc_recv) {
+      ptx::multimem_st_v4(reinterpret_cast<T*>(p.mc_recv) + dst, mine[it]);
+    } else {
+      for (int r = 0; r < p.world; ++r) ptx::st_na_v4(reinterpret_cast<T*>(p.peer_recv[(p.rank + r) % p.world]) + dst, mine[it]);
+    }
+  }
+  // ---------------- while the pushes fly: reset the rows the NEXT call's buffer still holds from its last use (two calls ago);
+  //                  the per-buffer dirty row count lives next to the epoch, so the work is what was actually written
+  {
+    const int4 sent = make_int4(int(0x80008000u), int(0x80008000u), int(0x80008000u), int(0x80008000u));
+    for (int rr = row; rr < dirty_next; rr += gridDim.x)
+      for (int r = 0; r < p.world; ++r)
+        for (int v = threadIdx.x; v < nvec; v += blockDim.x)
+          *reinterpret_cast<int4*>(recv + nxt + int64_t(r) * p.slot_elems + int64_t(rr) * p.hidden + int64_t(v) * VN) = sent;
+  }
+  // ---------------- gather + reduce (rank order) + epilogue
+  float acc[kVecPerThread][VN];
+  float ss = 0.f;
+#pragma unroll
+  for (int it = 0; it < kVecPerThread; ++it) {
+    const int v = threadIdx.x + it * blockDim.x;
+    if (v >= nvec) continue;
+    const int64_t off = int64_t(row) * p.hidden + int64_t(v) * VN;
+#pragma unroll
+    for (int e = 0; e < VN; ++e) acc[it][e] = 0.f;
+    for (int r = 0; r < p.world; ++r) {
+      int4 x;
+      if (r == p.rank) {
+        x = mine[it];  // my own contribution is already in registers (its multicast copy is never waited for)
+      } else {
+        const T* src = recv + cur + int64_t(r) * p.slot_elems + off;
+        uint32_t polls = 0;
+        uint64_t t0 = 0;
+        bool done;
+        do {
+          x = ptx::ld_volatile_v4(src);
+          const uint32_t* w = reinterpret_cast<const uint32_t*>(&x);
+          done = true;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) done = done && ((w[e] & 0xffffu) != 0x8000u) && ((w[e] >> 16) != 0x8000u);
+          if (!done && (++polls & 0x3ffu) == 0) {
+            if (t0 == 0) t0 = ptx::globaltimer();
+            else if (ptx::globaltimer() - t0 > ptx::kSpinTimeoutNs) {
+              printf("fib200: allreduce_push watchdog: rank %d row %d waited 20 s for rank %d -> trap\n", p.rank, row, r);
+              __trap();
+            }
+          }
+        } while (!done);
+      }
+      const T* h = reinterpret_cast<const T*>(&x);
+#pragma unroll
+      for (int e = 0; e < VN; ++e) acc[it][e] += to_f32(h[e]);
+    }
+    if (p.ar_out) {
+      Vec16<T> o;
+#pragma unroll
+      for (int e = 0; e < VN; ++e) o.v[e] = from_f32<T>(acc[it][e]);
+      st16(reinterpret_cast<T*>(p.ar_out) + off, o);
+    }
+    if (p.residual_in) {
+      Vec16<T> rv = ld16(reinterpret_cast<const T*>(p.residual_in) + off);
+#pragma unroll
+      for (int e = 0; e < VN; ++e) {
+        rv.v[e] = from_f32<T>(acc[it][e] + to_f32(rv.v[e]));
+        acc[it][e] = to_f32(rv.v[e]);
+      }
+      if (p.residual_out) st16(reinterpret_cast<T*>(p.residual_out) + off, rv);
+    }
+#pragma unroll
+    for (int e = 0; e < VN; ++e) ss += acc[it][e] * acc[it][e];
+  }
+  float rstd = 1.f;
+  if (p.gamma) {
+    ss = block_sum_ar<T>(ss, red);
+    rstd = rsqrtf(ss / float(p.hidden) + p.eps);
+  }
+  const float qs = p.scale_factor ? *p.scale_factor : 1.f;
+#pragma unroll
+  for (int it = 0; it < kVecPerThread; ++it) {
+    const int v = threadIdx.x + it * blockDim.x;
+    const bool live = v < nvec;
+    const int64_t off = int64_t(row) * p.hidden + int64_t(live ? v : 0) * VN;
+    float y[VN];
+#pragma unroll
+    for (int e = 0; e < VN; ++e) y[e] = 0.f;
+    if (live) {
+      if (p.gamma) {
+        const Vec16<T> g = ldg16(reinterpret_cast<const T*>(p.gamma) + int64_t(v) * VN);
+#pragma unroll
+        for (int e = 0; e < VN; ++e) y[e] = to_f32(from_f32<T>(acc[it][e] * rstd * (to_f32(g.v[e]) + p.weight_bias)));
+      } else {
+#pragma unroll
+        for (int e = 0; e < VN; ++e) y[e] = acc[it][e];
+      }
+      if (p.norm_out) {
+        Vec16<T> o;
+#pragma unroll
+        for (int e = 0; e < VN; ++e) o.v[e] = from_f32<T>(y[e]);
+        st16(reinterpret_cast<T*>(p.norm_out) + off, o);
+      }
+      if (p.quant == 1) {
+        uint8_t q8[VN];
+        const float inv = 1.f / qs;
+#pragma unroll
+        for (int e = 0; e < VN; ++e) {
+          const __nv_fp8_e4m3 q(fminf(fmaxf(y[e] * inv, -448.f), 448.f));
+          q8[e] = *reinterpret_cast<const uint8_t*>(&q);
+        }
+        *reinterpret_cast<int2*>(reinterpret_cast<uint8_t*>(p.quant_out) + off) = *reinterpret_cast<const int2*>(q8);
+      }
+    }
+    if (p.quant == 2) {
+      // NVFP4: 16-element blocks = two neighbouring vectors (lanes 2j, 2j + 1); every lane takes part in the shuffle
+      float amax = 0.f;
+#pragma unroll
+      for (int e = 0; e < VN; ++e) amax = fmaxf(amax, fabsf(y[e]));
+      amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+      const __nv_fp8_e4m3 s8(qs * (amax * (1.f / 6.f)));
+      const float sfv = float(s8);
+      const float out_scale = sfv != 0.f ? qs / sfv : 0.f;
+      if (live) {
+        uint8_t pk[4];
+#pragma unroll
+        for (int e = 0; e < VN; e += 2)
+          pk[e / 2] = (uint8_t)__nv_cvt_float2_to_fp4x2(make_float2(y[e] * out_scale, y[e + 1] * out_scale), __NV_E2M1, cudaRoundNearest);
+        *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(p.quant_out) + (int64_t(row) * p.hidden + int64_t(v) * VN) / 2) =
+            *reinterpret_cast<const uint32_t*>(pk);
+        if ((v & 1) == 0 && p.scale_out)
+          p.scale_out[sf_offset(p.sf_layout, row, v / 2, p.hidden / 16)] = *reinterpret_cast<const uint8_t*>(&s8);
+      }
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    volatile uint32_t* e = reinterpret_cast<volatile uint32_t*>(p.epoch);
+    // rows [0, tokens) of `cur` are dirty now; with fewer CTAs than dirty rows of `nxt` the strided loop above covered them all
+    e[1 + ep % 3u] = uint32_t(p.tokens);
+    e[1 + (ep + 1u) % 3u] = 0u;
+    e[0] = ep + 1u;
+  }
+  ptx::grid_dep_launch();
+}
+
+}  // namespace
+
+extern "C" int allreduce_push_run(int64_t mode, void* in, void* moe_scale, void* moe_token_in, void* e2p, int64_t moe_n, void* recv,
+                                  void* mc_recv, void* peer_recv_host, void* epoch, int64_t slot_elems, int64_t rank, int64_t world,
+                                  int64_t tokens, int64_t hidden, int64_t max_tokens, void* ar_out, void* residual_in,
+                                  void* residual_out, void* gamma, void* norm_out, double eps, double weight_bias, int64_t quant,
+                                  void* quant_out, void* scale_out, void* scale_factor, int64_t sf_layout, int64_t dtype, int64_t pdl,
+                                  int64_t stream_) {
+  FIB_CHECK(world >= 1 && world <= kMaxRanks, "allreduce_push: world size must be in [1, 16]");
+  FIB_CHECK(dtype == kF16 || dtype == kBF16, "allreduce_push: f16 / bf16 only");
+  FIB_CHECK(hidden % 16 == 0 && hidden <= 16384, "allreduce_push: hidden must be a multiple of 16 and <= 16384");
+  FIB_CHECK(tokens >= 1 && tokens <= max_tokens && slot_elems >= max_tokens * hidden, "allreduce_push: token count exceeds the workspace");
+  FIB_CHECK(mode >= 0 && mode <= 2 && quant >= 0 && quant <= 2 && sf_layout >= 0 && sf_layout <= 2, "allreduce_push: bad mode / quant / layout");
+  FIB_CHECK(recv && epoch && (mc_recv || peer_recv_host || world == 1), "allreduce_push: receive buffers required");
+  if (mode == 1) FIB_CHECK(moe_scale && moe_token_in && moe_n >= 1, "allreduce_push (MoE reduction): scale / token input required");
+  if (mode == 2) FIB_CHECK(e2p && moe_n >= 1, "allreduce_push (MoE finalize): expanded_idx_to_permuted_idx required");
+  if (quant) FIB_CHECK(quant_out != nullptr, "allreduce_push: quant_out required");
+  PushParams p;
+  memset(&p, 0, sizeof(p));
+  p.mode = int(mode); p.in = in; p.moe_scale = reinterpret_cast<const float*>(moe_scale); p.moe_token_in = moe_token_in;
+  p.e2p = reinterpret_cast<const int32_t*>(e2p); p.moe_n = int(moe_n);
+  p.recv = recv; p.mc_recv = mc_recv; p.epoch = reinterpret_cast<uint32_t*>(epoch);
+  if (peer_recv_host) {
+    const int64_t* ps = reinterpret_cast<const int64_t*>(peer_recv_host);
+    for (int i = 0; i < world; ++i) p.peer_recv[i] = reinterpret_cast<void*>(ps[i]);
+  }
+  p.slot_elems = slot_elems; p.buf_elems = slot_elems * world; p.rank = int(rank); p.world = int(world);
+  p.tokens = int(tokens); p.hidden = int(hidden); p.max_tokens = int(max_tokens);
+  p.ar_out = ar_out; p.residual_in = residual_in; p.residual_out = residual_out; p.gamma = gamma; p.norm_out = norm_out;
+  p.eps = float(eps); p.weight_bias = float(weight_bias); p.quant = int(quant); p.quant_out = quant_out;
+  p.scale_out = reinterpret_cast<uint8_t*>(scale_out); p.scale_factor = reinterpret_cast<const float*>(scale_factor);
+  p.sf_layout = int(sf_layout);
+  const int nvec = int(hidden / 8);
+  int threads = (nvec + 31) / 32 * 32;
+  int vpt = 1;
+  if (threads > 1024) {
+    vpt = 2;
+    threads = ((nvec + 1) / 2 + 31) / 32 * 32;
+  }
+  if (threads < 32) threads = 32;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  LaunchCfg lc(dim3((unsigned)tokens), dim3(threads), 0, stream, pdl != 0);
+#define FIB_PUSH(TT, V) FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, allreduce_push_kernel<TT, V>, p))
+  if (dtype == kBF16) {
+    if (vpt == 1) { FIB_PUSH(__nv_bfloat16, 1); } else { FIB_PUSH(__nv_bfloat16, 2); }
+  } else {
+    if (vpt == 1) { FIB_PUSH(__half, 1); } else { FIB_PUSH(__half, 2); }
+  }
+#undef FIB_PUSH
+  return 0;
 }

@@ -512,3 +512,141 @@ extern "C" int rs_rmsnorm(void* x, void* y, void* weight, void* sumsq, int64_t r
   }
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Prefill-size GEMM -> reduce-scatter: chunk-pipelined.  For M in the thousands the one-kernel version above is bound by
+// how many in-switch reductions its 4 reduce warps keep in flight; here the row range of every rank is cut into chunks, the
+// persistent tcgen05 GEMM (gemm_nt) writes chunk c of every rank's rows into the symmetric staging buffer on the main stream
+// and THIS kernel pulls the chunk on a side stream while the GEMM of chunk c + 1 runs: all 148 SMs issue
+// `multimem.ld_reduce` (4 per thread in flight; it co-resides with the GEMM CTAs: no shared memory, 512 threads), adds the
+// residual shard, writes the local shard and accumulates the per-row sums of squares for rs_rmsnorm.  A per-CTA cross-rank
+// epoch barrier at the top (with a watchdog) makes sure every rank has stored the chunk.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct RSPull {
+  const uint8_t* mc_stage;          // multicast alias of the staging buffer (or null)
+  const uint8_t* peer_stage[kMaxRanks];
+  uint32_t* peer_sig[kMaxRanks];    // [max_ctas][world] epoch slots of every rank
+  uint32_t* epochs;                 // local [max_ctas]
+  int rank, world;
+  int64_t ld;                       // staging row pitch (elements)
+  int row_lo, rows, n;              // global rows [row_lo, row_lo + rows) of the staging buffer are mine in this chunk
+  void* out;                        // local shard rows [out_row, out_row + rows)
+  int64_t ldo;
+  const void* residual;
+  int64_t ldr;
+  float* sumsq;                     // per local row (already offset to the chunk's first row) or null
+};
+
+template <typename T>
+__global__ void __launch_bounds__(512) rs_pull_kernel(const RSPull p) {
+  constexpr int VN = 16 / sizeof(T);
+  constexpr int U = 4;
+  // ---- every rank has finished storing this chunk (stream order on each rank + this barrier)
+  __syncthreads();
+  if (int(threadIdx.x) < p.world) {
+    const int peer = threadIdx.x;
+    const uint32_t epoch = p.epochs[blockIdx.x] + 1;
+    __threadfence_system();
+    ptx::st_release_sys(p.peer_sig[peer] + blockIdx.x * p.world + p.rank, epoch);
+    ptx::spin_until_ge_sys(p.peer_sig[p.rank] + blockIdx.x * p.world + peer, epoch);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) p.epochs[blockIdx.x] += 1;
+  const int vpr = p.n / VN;
+  const int64_t total = int64_t(p.rows) * vpr;
+  T* out = reinterpret_cast<T*>(p.out);
+  const T* residual = reinterpret_cast<const T*>(p.residual);
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t i0 = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i0 - (threadIdx.x & 31) < total; i0 += stride * U) {
+    int4 red[U];
+    bool ok[U];
+    int r[U], col[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + int64_t(u) * stride;
+      ok[u] = i < total;
+      r[u] = ok[u] ? int(i / vpr) : 0;
+      col[u] = ok[u] ? int(i - int64_t(r[u]) * vpr) * VN : 0;
+      red[u] = make_int4(0, 0, 0, 0);
+      if (ok[u] && p.mc_stage) {
+        const uint8_t* a = p.mc_stage + (int64_t(p.row_lo + r[u]) * p.ld + col[u]) * sizeof(T);
+        if constexpr (std::is_same<T, __half>::value) red[u] = ptx::multimem_ld_reduce_f16x8(a);
+        else red[u] = ptx::multimem_ld_reduce_bf16x8(a);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float sq = 0.f;
+      if (ok[u]) {
+        float acc[VN];
+        if (p.mc_stage) {
+          const T* h = reinterpret_cast<const T*>(&red[u]);
+#pragma unroll
+          for (int e = 0; e < VN; ++e) acc[e] = to_f32(h[e]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < VN; ++e) acc[e] = 0.f;
+          for (int q = 0; q < p.world; ++q) {
+            const int4 x = ptx::ld_volatile_v4(p.peer_stage[(p.rank + q) % p.world] + (int64_t(p.row_lo + r[u]) * p.ld + col[u]) * sizeof(T));
+            const T* h = reinterpret_cast<const T*>(&x);
+#pragma unroll
+            for (int e = 0; e < VN; ++e) acc[e] += to_f32(h[e]);
+          }
+        }
+        if (residual) {
+          const Vec16<T> rv = ld16(residual + int64_t(r[u]) * p.ldr + col[u]);
+#pragma unroll
+          for (int e = 0; e < VN; ++e) acc[e] += to_f32(rv.v[e]);
+        }
+        Vec16<T> o;
+#pragma unroll
+        for (int e = 0; e < VN; ++e) {
+          o.v[e] = from_f32<T>(acc[e]);
+          sq += acc[e] * acc[e];
+        }
+        st16(out + int64_t(r[u]) * p.ldo + col[u], o);
+      }
+      if (p.sumsq) {
+        // a warp covers 32 consecutive vectors: one row when vpr % 32 == 0 (checked on the host) -> one atomic per warp
+        sq = warp_reduce_sum(sq);
+        if ((threadIdx.x & 31) == 0 && ok[u]) atomicAdd(p.sumsq + r[u], sq);
+      }
+    }
+  }
+}
+
+}  // namespace
+
+// One chunk of the pipelined GEMM -> reduce-scatter: pull rows [row_lo, row_lo + rows) of the symmetric staging buffer.
+extern "C" int rs_pull_rows(void* mc_stage, void* peer_stage_host, void* peer_sig_host, void* epochs, int64_t rank, int64_t world,
+                            int64_t ld, int64_t row_lo, int64_t rows, int64_t n, void* out, int64_t ldo, void* residual, int64_t ldr,
+                            void* sumsq, int64_t max_ctas, int64_t dtype, int64_t stream_) {
+  FIB_CHECK(dtype == kF16 || dtype == kBF16, "rs_pull_rows: dtype must be f16 / bf16");
+  FIB_CHECK(world >= 1 && world <= kMaxRanks && n % 256 == 0 && ld % 8 == 0 && ldo % 8 == 0 && ldr % 8 == 0,
+            "rs_pull_rows: n must be a multiple of 256 (one row per warp step), strides multiples of 8");
+  if (rows == 0) return 0;
+  RSPull p;
+  memset(&p, 0, sizeof(p));
+  p.mc_stage = reinterpret_cast<const uint8_t*>(mc_stage);
+  const int64_t* ps = reinterpret_cast<const int64_t*>(peer_stage_host);
+  const int64_t* pg = reinterpret_cast<const int64_t*>(peer_sig_host);
+  for (int i = 0; i < world; ++i) {
+    p.peer_stage[i] = reinterpret_cast<const uint8_t*>(ps[i]);
+    p.peer_sig[i] = reinterpret_cast<uint32_t*>(pg[i]);
+  }
+  p.epochs = reinterpret_cast<uint32_t*>(epochs);
+  p.rank = int(rank); p.world = int(world); p.ld = ld; p.row_lo = int(row_lo); p.rows = int(rows); p.n = int(n);
+  p.out = out; p.ldo = ldo; p.residual = residual; p.ldr = ldr; p.sumsq = reinterpret_cast<float*>(sumsq);
+  int grid = num_sms();
+  if (grid > max_ctas) grid = int(max_ctas);
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  LaunchCfg lc(dim3(grid), dim3(512), 0, stream, false);
+  if (dtype == kF16) {
+    FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, rs_pull_kernel<__half>, p));
+  } else {
+    FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, rs_pull_kernel<__nv_bfloat16>, p));
+  }
+  return 0;
+}

@@ -28,7 +28,8 @@ namespace {
 constexpr int BM = 128;
 constexpr int BKB = 128;  // K slab in bytes per stage (one SWIZZLE_128B row)
 
-enum Kind { kFp8 = 0, kMxFp8 = 1, kNvFp4 = 2, kMxFp4 = 3 };
+enum Kind { kFp8 = 0, kMxFp8 = 1, kNvFp4 = 2, kMxFp4 = 3, kDense16 = 4 /* bf16 / f16 operands, CTA-pair kernel only */ };
+__host__ __device__ constexpr bool kind_scaled(int k) { return k == kMxFp8 || k == kNvFp4 || k == kMxFp4; }
 
 struct Geo {
   int stages, stage_bytes, a_bytes, b_bytes, sfa_bytes, sfb_bytes, bar_offset, total;
@@ -698,7 +699,7 @@ bs_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (threadIdx.x == 0) {
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
-    if constexpr (KIND != kFp8) {
+    if constexpr (kind_scaled(KIND)) {
       ptx::prefetch_tmap(&tmSFA);
       ptx::prefetch_tmap(&tmSFB);
     }
@@ -733,6 +734,18 @@ bs_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int num_tiles = tiles_per_batch * p.batch;
   const int num_kb = (p.Kb + BKB - 1) / BKB;
   const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  // grouped rasterisation: the pairs that run concurrently cover a compact (8 M-tiles x n) block of the output, so the A rows
+  // they stream stay L2 resident across the N sweep (walking all of M for one N column re-reads A from DRAM per column)
+  auto tile_coords = [&](int r, int& tm, int& tn) {
+    constexpr int kGroup = 8;
+    const int per_group = kGroup * tiles_n;
+    const int g = r / per_group;
+    const int first = g * kGroup;
+    const int rows = min(kGroup, tiles_m - first);
+    const int in = r - g * per_group;
+    tm = first + in % rows;
+    tn = in / rows;
+  };
   const uint32_t stage_tx = 2u * uint32_t(G.a_bytes + G.b_bytes + G.sfa_bytes + G.sfb_bytes);
 
   if (warp == 0) {
@@ -741,7 +754,8 @@ bs_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       uint32_t phase = 0;
       for (int t = pair; t < num_tiles; t += num_pairs) {
         const int b = t / tiles_per_batch, r = t % tiles_per_batch;
-        const int tm = r % tiles_m, tn = r / tiles_m;
+        int tm, tn;
+        tile_coords(r, tm, tn);
         const int n0 = tn * BN;
         const int row0 = tm * 2 * BM + crank * BM;
         const int sfa_row = (tm * 2 + crank);
@@ -763,13 +777,14 @@ bs_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else if (warp == 2) {
     // ---- second producer warp: scale-factor tiles (UTMALDG issue costs ~100 clk each; with A, B, SFA, SFB on one warp
     //      an nvfp4 slab (393 clk of MMA) was issue-bound).  Same full barrier; warp 0 arms the byte count.
-    if constexpr (KIND != kFp8) {
+    if constexpr (kind_scaled(KIND)) {
       if (ptx::elect_one()) {
         int stage = 0;
         uint32_t phase = 0;
         for (int t = pair; t < num_tiles; t += num_pairs) {
           const int b = t / tiles_per_batch, r = t % tiles_per_batch;
-          const int tm = r % tiles_m, tn = r / tiles_m;
+          int tm, tn;
+          tile_coords(r, tm, tn);
           const int sfa_row = tm * 2 + crank;
           const int rb0 = (tn * BN) / 128;
           for (int kb = 0; kb < num_kb; ++kb) {
@@ -797,7 +812,9 @@ bs_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const uint32_t sf_stride = uint32_t(G.nchunk * 4 * (1 + G.rb));
     for (int t = pair; t < num_tiles; t += num_pairs) {
       const int r = t % tiles_per_batch;
-      const int n0 = (r / tiles_m) * BN;
+      int tm_, tn_;
+      tile_coords(r, tm_, tn_);
+      const int n0 = tn_ * BN;
       const uint32_t sfb_off = uint32_t((n0 % 128) / 32);
       ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       ptx::tc_fence_after();
@@ -812,7 +829,7 @@ bs_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const uint32_t sb = sa + G.a_bytes;
           const uint64_t da = ptx::make_smem_desc(sa, 16, 1024, ptx::kSwz128);
           const uint64_t db = ptx::make_smem_desc(sb, 16, 1024, ptx::kSwz128);
-          if constexpr (KIND != kFp8 && !kCopyWarp) {
+          if constexpr (kind_scaled(KIND) && !kCopyWarp) {
             const uint32_t ssfa = sb + G.b_bytes, ssfb = ssfa + G.sfa_bytes;
             for (int c = 0; c < G.nchunk; ++c) {
               ptx::tmem_cp2_32x128b_warpx4(sfa_t + c * 4, ptx::make_smem_desc(ssfa + c * 512, 0, 128, ptx::kSwzNone));
@@ -827,6 +844,8 @@ bs_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const uint64_t dak = ptx::desc_advance(da, k * 32), dbk = ptx::desc_advance(db, k * 32);
             if constexpr (KIND == kFp8) {
               ptx::mma_f8f6f4_ss<2>(d_tmem, dak, dbk, p.idesc, accum);
+            } else if constexpr (KIND == kDense16) {  // a 128-byte slab is 64 16-bit elements: 4 MMAs of K = 16, same 32-byte steps
+              ptx::mma_f16_ss<2>(d_tmem, dak, dbk, p.idesc, accum);
             } else if constexpr (KIND == kMxFp8) {
               const uint32_t id = p.idesc | (uint32_t(k) << 4) | (uint32_t(k) << 29);
               ptx::mma2_mxf8f6f4_ss(d_tmem, dak, dbk, id, sfa_t, sfb_t + sfb_off, accum);
@@ -899,7 +918,8 @@ bs_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const uint32_t leader_empty = ptx::mapa(ptx::smem_u32(&tmem_empty[0]), 0);
     for (int t = pair; t < num_tiles; t += num_pairs) {
       const int b = t / tiles_per_batch, r = t % tiles_per_batch;
-      const int tm = r % tiles_m, tn = r / tiles_m;
+      int tm, tn;
+      tile_coords(r, tm, tn);
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
       const int row = tm * 2 * BM + crank * BM + q * 32 + lane;
@@ -983,14 +1003,14 @@ extern "C" int gemm_lowp_nt(void* A, void* B, void* C, void* sfa, void* sfb, voi
                             int64_t sfa_batch_stride, int64_t sfb_batch_stride, int64_t kind, int64_t a_fmt,
                             int64_t b_fmt, int64_t out_dtype, int64_t bn, void* tile_expert, void* meta, void* row_map, int64_t pdl,
                             int64_t stream_) {
-  FIB_CHECK(kind >= 0 && kind <= 3, "gemm_lowp: kind must be 0..3");
+  FIB_CHECK(kind >= 0 && kind <= 4, "gemm_lowp: kind must be 0..4");
   FIB_CHECK(out_dtype == kF16 || out_dtype == kBF16, "gemm_lowp: output must be f16/bf16");
   const bool fp4 = kind == kNvFp4 || kind == kMxFp4;
-  FIB_CHECK(K % (fp4 ? 32 : 16) == 0, "gemm_lowp: K must be a multiple of 16 (fp8) / 32 (fp4)");
+  FIB_CHECK(K % (fp4 ? 32 : (kind == kDense16 ? 8 : 16)) == 0, "gemm_lowp: K must be a multiple of 16 (fp8) / 32 (fp4) / 8 (16-bit)");
   FIB_CHECK(lda % 16 == 0 && ldb % 16 == 0, "gemm_lowp: row strides must be multiples of 16 bytes");
   if (M == 0 || N == 0 || batch == 0) return 0;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  const int64_t Kb = fp4 ? K / 2 : K;
+  const int64_t Kb = fp4 ? K / 2 : (kind == kDense16 ? 2 * K : K);
   const int tiles_m = int((M + BM - 1) / BM);
   const int64_t eb = tile_expert ? 1 : batch;  // grouped mode: `batch` counts experts (B / SFB), A and C are one matrix
   int BN = (int)bn;
@@ -1024,11 +1044,12 @@ extern "C" int gemm_lowp_nt(void* A, void* B, void* C, void* sfa, void* sfb, voi
   // ---- CTA-pair (cta_group::2) path for large problems ----
   {
     const char* env2 = getenv("FIB200_LOWP_2CTA");
-    const int BN2 = bn ? (int)bn : (kind == kFp8 ? 256 : 192);
+    const int BN2 = bn ? (int)bn : ((kind == kFp8 || kind == kDense16) ? 256 : 192);
     const int64_t tiles2 = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN2 - 1) / BN2) * batch;
     bool use2 = !tile_expert && M >= 512 && tiles2 >= num_sms() / 2 && K >= 512;
     if (env2) use2 = atoi(env2) != 0 && !tile_expert;
-    if (use2 && BN2 % 64 == 0 && BN2 >= 64 && BN2 <= 256 && (kind == kFp8 || 2 * BN2 + 2 * Geo2::make(BN2, (int)kind).nchunk * 4 * (1 + Geo2::make(BN2, (int)kind).rb) <= 512)) {
+    if (kind == kDense16 && !env2) use2 = !tile_expert;
+    if (use2 && BN2 % 64 == 0 && BN2 >= 64 && BN2 <= 256 && (!kind_scaled((int)kind) || 2 * BN2 + 2 * Geo2::make(BN2, (int)kind).nchunk * 4 * (1 + Geo2::make(BN2, (int)kind).rb) <= 512)) {
       const Geo2 G2 = Geo2::make(BN2, (int)kind);
       CUtensorMap tmA, tmB, tmSFA, tmSFB;
       {
@@ -1045,10 +1066,10 @@ extern "C" int gemm_lowp_nt(void* A, void* B, void* C, void* sfa, void* sfb, voi
       }
       Params2 p2;
       const int vec2 = kind == kNvFp4 ? 16 : 32;
-      p2.sf_k_tiles = kind == kFp8 ? 0 : int(((K + vec2 - 1) / vec2 + 3) / 4);
+      p2.sf_k_tiles = !kind_scaled((int)kind) ? 0 : int(((K + vec2 - 1) / vec2 + 3) / 4);
       p2.sfa_row_tiles = int((M + 127) / 128);
       p2.sfb_row_tiles = int((N + 127) / 128);
-      if (kind != kFp8) {
+      if (kind_scaled((int)kind)) {
         FIB_CHECK(sfa && sfb, "gemm_lowp: block-scaled kinds need scale tensors");
         FIB_CHECK(sfa_batch_stride == int64_t(p2.sfa_row_tiles) * p2.sf_k_tiles * 512 || batch == 1, "gemm_lowp: SFA must be contiguous per batch");
         FIB_CHECK(sfb_batch_stride == int64_t(p2.sfb_row_tiles) * p2.sf_k_tiles * 512 || batch == 1, "gemm_lowp: SFB must be contiguous per batch");
@@ -1070,11 +1091,15 @@ extern "C" int gemm_lowp_nt(void* A, void* B, void* C, void* sfa, void* sfb, voi
       p2.ldc = ldc;
       p2.M = (int)M; p2.N = (int)N; p2.Kb = (int)Kb; p2.batch = (int)batch; p2.BN = BN2;
       if (kind == kFp8) p2.idesc = ptx::make_idesc_f8((uint32_t)a_fmt, (uint32_t)b_fmt, 2 * BM, BN2, 0, 0);
+      else if (kind == kDense16) p2.idesc = ptx::make_idesc_f16(a_fmt == 0 ? ptx::kFmtF16 : ptx::kFmtBF16, 2 * BM, BN2, 0, 0);
       else if (kind == kMxFp8) p2.idesc = ptx::make_idesc_blockscaled((uint32_t)a_fmt, (uint32_t)b_fmt, 2 * BM, BN2, 1, 0, 0);
       else p2.idesc = ptx::make_idesc_blockscaled(1, 1, 2 * BM, BN2, kind == kMxFp4 ? 1 : 0, 0, 0);
       const int pairs = (int)(tiles2 < num_sms() / 2 ? tiles2 : num_sms() / 2);
       const bool f16o = out_dtype == kF16;
       switch (kind) {
+        case kDense16:
+          return f16o ? launch2<kDense16, __half>(tmA, tmB, tmSFA, tmSFB, C, p2, 2 * pairs, G2.total, pdl != 0, stream)
+                      : launch2<kDense16, __nv_bfloat16>(tmA, tmB, tmSFA, tmSFB, C, p2, 2 * pairs, G2.total, pdl != 0, stream);
         case kFp8:
           return f16o ? launch2<kFp8, __half>(tmA, tmB, tmSFA, tmSFB, C, p2, 2 * pairs, G2.total, pdl != 0, stream)
                       : launch2<kFp8, __nv_bfloat16>(tmA, tmB, tmSFA, tmSFB, C, p2, 2 * pairs, G2.total, pdl != 0, stream);
@@ -1090,6 +1115,7 @@ extern "C" int gemm_lowp_nt(void* A, void* B, void* C, void* sfa, void* sfb, voi
       }
     }
   }
+  FIB_CHECK(kind != kDense16, "gemm_lowp: 16-bit operands run on the CTA-pair kernel only (N tile multiple of 64)");
   FIB_CHECK(BN % 32 == 0 && BN >= 32 && BN <= 256, "gemm_lowp: N tile must be a multiple of 32 in [32, 256]");
   FIB_CHECK(kind == kFp8 || BN % 64 == 0, "gemm_lowp: block-scaled N tile must be a multiple of 64");
   const Geo G = Geo::make(BN, (int)kind);

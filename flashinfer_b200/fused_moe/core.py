@@ -7,9 +7,9 @@ Pipeline on B200 (all hand-written sm_100a kernels, PDL-chained):
   routing (9 methods, warp per token)  ->  sort / tile-padded permutation  ->  row gather  ->
   grouped tcgen05 GEMM (FC1, expert id = TMA coordinate)  ->  gated activation  ->  grouped GEMM (FC2)  ->
   finalize (top-k weighted un-permute).
-Quantised entry points (fp8 per-tensor / block-scale, nvfp4, mxint4) currently de-quantise the expert weights to
-bf16 on the fly and reuse the bf16 grouped GEMM (numerically equivalent reference semantics; the block-scaled
-tcgen05 grouped GEMM replaces this in a later round).  Gate/up convention follows the reference tests:
+Quantised entry points run natively: fp8 block-scale and fp8 per-tensor on the fp8 group-scaled tcgen05 grouped GEMM, NVFP4 on the
+block-scaled (kind::mxf4nvf4) grouped GEMM; weight layout conversions (trtllm-gen shuffled / BlockMajorK) and the one format
+without a tensor-core path (mxint4) are load-time preparations cached per weight tensor - nothing is de-quantised per call.  Gate/up convention follows the reference tests:
 ``h = x @ W1^T ; out = act(h[:, I:]) * h[:, :I]`` (second half is the gate).
 """
 from __future__ import annotations
@@ -410,6 +410,109 @@ def _dequant_nvfp4(w: torch.Tensor, sf: torch.Tensor, global_scale, vec: int = 1
     return (vals * s * g).to(dtype)
 
 
+# ------------------------------------------------------------------ load-time weight preparation (cached per weight tensor)
+_PREP_CACHE: dict = {}
+
+
+def _prepared(tag: str, tensors, fn):
+    """One-time transformation of STATIC expert weights, cached on (tag, data_ptr, shape, dtype, version) of the inputs: layout
+    conversions (un-shuffle, BlockMajorK -> MajorK) and the few formats without a native tensor-core path (mxint4) are prepared
+    on first use - never per call (the quantised entry points used to de-quantise every expert weight in eager
+    torch on every call)."""
+    key = (tag,) + tuple((t.data_ptr(), tuple(t.shape), str(t.dtype), t._version) for t in tensors if isinstance(t, torch.Tensor))
+    hit = _PREP_CACHE.get(key)
+    if hit is None:
+        if len(_PREP_CACHE) > 256:
+            _PREP_CACHE.clear()
+        hit = fn()
+        _PREP_CACHE[key] = hit
+    return hit
+
+
+def _shuffle_block_rows(m: int, epilogue_tile_m: int) -> torch.Tensor:
+    """``row_indices[new_row] = old_row`` of the trtllm-gen ``shuffle_matrix_a`` row permutation: rows move inside blocks of 16
+    (32 when ``epilogue_tile_m % 128 == 0``) so that row ``i`` of a block lands at ``(i % (B / 8)) * 8 + i // (B / 8)``."""
+    b = 32 if epilogue_tile_m % 128 == 0 else 16
+    if m % b:
+        raise ValueError(f"shuffled weights need a row count that is a multiple of {b}")
+    old = torch.arange(m)
+    i = old % b
+    new = (old // b) * b + (i % (b // 8)) * 8 + i // (b // 8)
+    idx = torch.empty(m, dtype=torch.long)
+    idx[new] = old
+    return idx
+
+
+def _unshuffle_expert_weights(w: torch.Tensor, epilogue_tile_m: int, block_major_k: bool, gated_interleaved: bool,
+                              block_k_bytes: int = 128) -> torch.Tensor:
+    """Undo the trtllm-gen weight pre-processing (reference fused_moe/core.py:133-233, tests/moe/test_trtllm_gen_fused_moe.py:1004):
+    ``[E, K/bk, N, bk]`` BlockMajorK -> ``[E, N, K]``, inverse ``shuffle_matrix_a`` row permutation, inverse gated-row interleave
+    (``reorder_rows_for_gated_act_gemm``).  The TMA-fed grouped GEMM here needs none of them."""
+    raw = w.view(torch.uint8)
+    if block_major_k:
+        e, kb, n, bk = raw.shape
+        raw = raw.permute(0, 2, 1, 3).reshape(e, n, kb * bk)
+    e, n, kbytes = raw.shape
+    idx = _shuffle_block_rows(n, epilogue_tile_m).to(raw.device)      # new -> old
+    out = torch.empty_like(raw)
+    out[:, idx] = raw                                                   # old row <- new row
+    if gated_interleaved:                                               # rows (r0, rN/2, r1, ...) -> [first half | second half]
+        out = torch.cat([out[:, 0::2], out[:, 1::2]], 1)
+    return out.contiguous().view(w.dtype) if w.dtype != torch.uint8 else out.contiguous()
+
+
+def _plain_weights(name: str, w: torch.Tensor, use_shuffled_weight: bool, weight_layout: int, epilogue_tile_m: int,
+                   gated_interleaved: bool = False) -> torch.Tensor:
+    bmk = int(weight_layout) == int(WeightLayout.BlockMajorK)
+    if int(weight_layout) == int(WeightLayout.MajorMn):
+        raise NotImplementedError(f"{name}: WeightLayout.MajorMn is not supported")
+    if not use_shuffled_weight and not bmk:
+        return w
+    if bmk and not use_shuffled_weight:
+        return _prepared("bmk", [w], lambda: _unshuffle_expert_weights_noperm(w))
+    return _prepared(f"unshuffle{epilogue_tile_m}{int(bmk)}{int(gated_interleaved)}", [w],
+                     lambda: _unshuffle_expert_weights(w, epilogue_tile_m, bmk, gated_interleaved))
+
+
+def _unshuffle_expert_weights_noperm(w: torch.Tensor) -> torch.Tensor:
+    raw = w.view(torch.uint8)
+    e, kb, n, bk = raw.shape
+    out = raw.permute(0, 2, 1, 3).reshape(e, n, kb * bk).contiguous()
+    return out.view(w.dtype) if w.dtype != torch.uint8 else out
+
+
+def _scalar_block_scales(scale: torch.Tensor, e: int, n: int, k: int) -> torch.Tensor:
+    """Per-expert scalar de-quantisation scale as a (stride-0) ``[E, N/128, K/128]`` block-scale view: lets fp8 per-tensor weights
+    run on the native fp8 group-scaled tensor-core pipeline without touching the weights."""
+    return scale.float().reshape(-1, 1, 1).expand(e, (n + 127) // 128, (k + 127) // 128)
+
+
+def moe_forward_fp8_per_tensor(x: torch.Tensor, topk_ids: torch.Tensor, topk_w: torch.Tensor, w1: torch.Tensor, alpha1,
+                               w2: torch.Tensor, alpha2, local_expert_offset: int = 0, num_experts: Optional[int] = None,
+                               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp8 (e4m3) expert weights with ONE de-quantisation scale per expert and GEMM: ``h = (x @ W1^T) * alpha1[e]``,
+    ``out = (swiglu(h) @ W2^T) * alpha2[e]``.  Runs on the fp8 tensor-core MoE pipeline (:func:`moe_forward_fp8_block`): the
+    scalar scales become stride-0 block-scale views and the activations are quantised per 1 x 128 group on the fly (finer than
+    the per-tensor activation scale of the reference kernels, so at least as accurate).  ``x`` may already be e4m3 (its values
+    are used as they are: the caller's activation scale is part of ``alpha1``, reference contract)."""
+    e_local, n1, h = w1.shape
+    inter = w2.shape[2]
+    dev = x.device
+    a1 = torch.as_tensor(alpha1, dtype=torch.float32, device=dev).reshape(-1)
+    a2 = torch.as_tensor(alpha2, dtype=torch.float32, device=dev).reshape(-1)
+    if a1.numel() == 1:
+        a1 = a1.expand(e_local)
+    if a2.numel() == 1:
+        a2 = a2.expand(e_local)
+    xb = x.to(torch.bfloat16) if x.dtype not in (torch.float16, torch.bfloat16) else x
+    if (not x.is_cuda) or h % 128 or inter % 128 or n1 != 2 * inter:
+        w1d = _prepared("fp8pt", [w1, a1], lambda: (w1.float() * a1.reshape(-1, 1, 1)).to(xb.dtype))
+        w2d = _prepared("fp8pt", [w2, a2], lambda: (w2.float() * a2.reshape(-1, 1, 1)).to(xb.dtype))
+        return moe_forward(xb, topk_ids, topk_w, w1d, w2d, local_expert_offset, num_experts, out=out)
+    return moe_forward_fp8_block(xb, None, topk_ids, topk_w, w1, _scalar_block_scales(a1, e_local, n1, h), w2,
+                                 _scalar_block_scales(a2, e_local, h, inter), local_expert_offset, num_experts, out=out)
+
+
 # ------------------------------------------------------------------ trtllm-gen style entry points
 
 def _activation_name(activation_type) -> str:
@@ -451,9 +554,10 @@ def trtllm_bf16_moe(routing_logits, routing_bias, hidden_states, gemm1_weights, 
                     norm_topk_prob: bool = True, routing_replay_out=None):
     """bf16 MoE with fused routing.  Weights are plain K-major ``[E_local, 2I, H]`` / ``[E_local, H, I]``
     (no pre-shuffling is needed by the TMA-fed grouped GEMM)."""
-    if use_shuffled_weight or int(weight_layout) != int(WeightLayout.MajorK):
-        raise NotImplementedError("pass plain MajorK weights (use_shuffled_weight=False): the tcgen05 grouped GEMM "
-                                  "needs no weight pre-shuffle")
+    # trtllm-gen pre-processed weights (gated-row interleave + shuffle_matrix_a(epilogue_tile_m=128) [+ BlockMajorK]) are
+    # converted back to plain MajorK ONCE per weight tensor (cached); the TMA-fed grouped GEMM needs no pre-shuffle
+    gemm1_weights = _plain_weights("trtllm_bf16_moe", gemm1_weights, use_shuffled_weight, weight_layout, 128, gated_interleaved=True)
+    gemm2_weights = _plain_weights("trtllm_bf16_moe", gemm2_weights, use_shuffled_weight, weight_layout, 128)
     ids, w = route(routing_logits, routing_bias, top_k, routing_method_type, n_group, topk_group, routed_scaling_factor,
                    norm_topk_prob)
     if routing_replay_out is not None:
@@ -475,8 +579,10 @@ def trtllm_bf16_routed_moe(topk_ids, hidden_states, gemm1_weights, gemm2_weights
                            weight_layout: int = WeightLayout.MajorK, do_finalize: bool = True, enable_pdl: bool = True,
                            tune_max_num_tokens: int = 8192, activation_type: int = ActivationType.Swiglu.value):
     ids, w = _unpack_routed(topk_ids)
+    gemm1_weights = _plain_weights("trtllm_bf16_routed_moe", gemm1_weights, use_shuffled_weight, weight_layout, 128, gated_interleaved=True)
+    gemm2_weights = _plain_weights("trtllm_bf16_routed_moe", gemm2_weights, use_shuffled_weight, weight_layout, 128)
     return moe_forward(hidden_states, ids, w, gemm1_weights, gemm2_weights, local_expert_offset, num_experts,
-                       do_finalize=do_finalize)
+                       activation=_activation_name(activation_type), do_finalize=do_finalize)
 
 
 def trtllm_fp8_per_tensor_scale_moe(routing_logits, routing_bias, hidden_states, gemm1_weights, output1_scales_scalar,
@@ -484,16 +590,11 @@ def trtllm_fp8_per_tensor_scale_moe(routing_logits, routing_bias, hidden_states,
                                     n_group, topk_group, intermediate_size, local_expert_offset, local_num_experts,
                                     routed_scaling_factor, use_routing_scales_on_input: bool = False,
                                     routing_method_type: int = 0, **kw):
-    """fp8 per-tensor MoE: de-quantised to bf16 (scales folded into the weights) and run on the bf16 pipeline."""
+    """fp8 per-tensor MoE on the native fp8 tensor-core pipeline (:func:`moe_forward_fp8_per_tensor`); no weight de-quantisation."""
     _reject_unsupported("trtllm_fp8_per_tensor_scale_moe", use_routing_scales_on_input=use_routing_scales_on_input)
     ids, w = route(routing_logits, routing_bias, top_k, routing_method_type, n_group, topk_group, routed_scaling_factor)
     a1, a2 = _fold_gate_scale(output1_scales_scalar, output1_scales_gate_scalar, output2_scales_scalar)
-    s1 = a1.float().reshape(-1, 1, 1)
-    s2 = a2.float().reshape(-1, 1, 1)
-    w1 = (gemm1_weights.float() * s1).to(torch.bfloat16)
-    w2 = (gemm2_weights.float() * s2).to(torch.bfloat16)
-    x = hidden_states.float().to(torch.bfloat16)
-    return moe_forward(x, ids, w, w1, w2, local_expert_offset, num_experts)
+    return moe_forward_fp8_per_tensor(hidden_states, ids, w, gemm1_weights, a1, gemm2_weights, a2, local_expert_offset, num_experts)
 
 
 def trtllm_fp8_block_scale_moe(routing_logits, routing_bias, hidden_states, hidden_states_scale, gemm1_weights,
@@ -501,7 +602,10 @@ def trtllm_fp8_block_scale_moe(routing_logits, routing_bias, hidden_states, hidd
                                topk_group, intermediate_size, local_expert_offset, local_num_experts,
                                routed_scaling_factor, routing_method_type: int = 0, use_shuffled_weight: bool = False,
                                weight_layout: int = 0, **kw):
-    """DeepSeek-style fp8 (1x128 activation scales ``[H/128, T]``, 128x128 weight scales)."""
+    """DeepSeek-style fp8 (1x128 activation scales ``[H/128, T]``, 128x128 weight scales).  ``use_shuffled_weight`` / BlockMajorK weights
+    (shuffle_matrix_a with epilogue_tile_m = 64, reference tests/moe/test_dpsk_fused_moe_fp8.py:684) are converted back once."""
+    gemm1_weights = _plain_weights("trtllm_fp8_block_scale_moe", gemm1_weights, use_shuffled_weight, weight_layout, 64)
+    gemm2_weights = _plain_weights("trtllm_fp8_block_scale_moe", gemm2_weights, use_shuffled_weight, weight_layout, 64)
     ids, w = route(routing_logits, routing_bias, top_k, routing_method_type, n_group, topk_group, routed_scaling_factor)
     return moe_forward_fp8_block(hidden_states, hidden_states_scale, ids, w, gemm1_weights, gemm1_weights_scale, gemm2_weights,
                                  gemm2_weights_scale, local_expert_offset, num_experts)
@@ -535,8 +639,8 @@ def trtllm_fp4_block_scale_moe(routing_logits, routing_bias, hidden_states, hidd
     if x.is_cuda and do_finalize and hidden_states.shape[-1] % 64 == 0 and intermediate_size % 64 == 0:
         return moe_forward_nvfp4(x, ids, w, gemm1_weights, gemm1_weights_scale, g1, gemm2_weights, gemm2_weights_scale, g2,
                                  local_expert_offset, num_experts)
-    w1 = _dequant_nvfp4(gemm1_weights, gemm1_weights_scale, g1)
-    w2 = _dequant_nvfp4(gemm2_weights, gemm2_weights_scale, g2)
+    w1 = _prepared("nvfp4deq", [gemm1_weights, gemm1_weights_scale], lambda: _dequant_nvfp4(gemm1_weights, gemm1_weights_scale, g1))
+    w2 = _prepared("nvfp4deq", [gemm2_weights, gemm2_weights_scale], lambda: _dequant_nvfp4(gemm2_weights, gemm2_weights_scale, g2))
     return moe_forward(x.to(torch.bfloat16), ids, w, w1, w2, local_expert_offset, num_experts, do_finalize=do_finalize)
 
 
@@ -555,9 +659,12 @@ def trtllm_fp4_block_scale_routed_moe(topk_ids, routing_bias, hidden_states, hid
     g1 = output1_scale_scalar if output1_scale_scalar is not None else 1.0
     g2 = output2_scale_scalar if output2_scale_scalar is not None else 1.0
     g1, g2 = _fold_gate_scale(g1, output1_scale_gate_scalar, g2)
-    return moe_forward(x.to(torch.bfloat16), ids, w, _dequant_nvfp4(gemm1_weights, gemm1_weights_scale, g1),
-                       _dequant_nvfp4(gemm2_weights, gemm2_weights_scale, g2), local_expert_offset, num_experts,
-                       do_finalize=do_finalize)
+    if x.is_cuda and do_finalize and hidden_states.shape[-1] % 64 == 0 and intermediate_size % 64 == 0:
+        return moe_forward_nvfp4(x, ids, w, gemm1_weights, gemm1_weights_scale, g1, gemm2_weights, gemm2_weights_scale, g2,
+                                 local_expert_offset, num_experts)
+    w1 = _prepared("nvfp4deq", [gemm1_weights, gemm1_weights_scale], lambda: _dequant_nvfp4(gemm1_weights, gemm1_weights_scale, g1))
+    w2 = _prepared("nvfp4deq", [gemm2_weights, gemm2_weights_scale], lambda: _dequant_nvfp4(gemm2_weights, gemm2_weights_scale, g2))
+    return moe_forward(x.to(torch.bfloat16), ids, w, w1, w2, local_expert_offset, num_experts, do_finalize=do_finalize)
 
 
 def trtllm_mxint4_block_scale_moe(routing_logits, routing_bias, hidden_states, gemm1_weights, gemm1_weights_scale,
@@ -577,8 +684,12 @@ def trtllm_mxint4_block_scale_moe(routing_logits, routing_bias, hidden_states, g
         s = sc.float().repeat_interleave(32, -1)[..., : vals.shape[-1]]
         return (vals * s).to(torch.bfloat16)
 
-    return moe_forward(hidden_states, ids, w, deq(gemm1_weights, gemm1_weights_scale),
-                       deq(gemm2_weights, gemm2_weights_scale), local_expert_offset, num_experts)
+    _reject_unsupported("trtllm_mxint4_block_scale_moe", gemm1_alpha=gemm1_alpha, gemm1_beta=gemm1_beta, gemm1_clamp_limit=gemm1_clamp_limit)
+    # Blackwell has no int4 tensor-core path and bf16 block scales are not representable as UE8M0 / UE4M3 MMA scale factors:
+    # the weights are expanded to bf16 ONCE per weight tensor (cached load-time preparation), the MoE itself is the native pipeline
+    w1 = _prepared("mxint4", [gemm1_weights, gemm1_weights_scale], lambda: deq(gemm1_weights, gemm1_weights_scale))
+    w2 = _prepared("mxint4", [gemm2_weights, gemm2_weights_scale], lambda: deq(gemm2_weights, gemm2_weights_scale))
+    return moe_forward(hidden_states, ids, w, w1, w2, local_expert_offset, num_experts)
 
 
 # ------------------------------------------------------------------ cutlass-style entry point
@@ -595,17 +706,38 @@ def cutlass_fused_moe(input: torch.Tensor, token_selected_experts: torch.Tensor,
     ``ep_rank`` selects the local expert range; ``tp_*`` only describe how the caller sharded I."""
     e_local = fc1_expert_weights.shape[0]
     w1, w2 = fc1_expert_weights, fc2_expert_weights
+    _reject_unsupported("cutlass_fused_moe", fc1_expert_biases=fc1_expert_biases, fc2_expert_biases=fc2_expert_biases,
+                        swiglu_alpha=swiglu_alpha, swiglu_beta=swiglu_beta, swiglu_limit=swiglu_limit,
+                        use_w4_group_scaling=use_w4_group_scaling, use_mxfp8_act_scaling=use_mxfp8_act_scaling,
+                        min_latency_mode=min_latency_mode, enable_alltoall=enable_alltoall)
+    ids, wts = token_selected_experts.int(), token_final_scales.float()
+    off, total = ep_rank * e_local, e_local * ep_size
+    act = "silu" if int(activation_type) in (int(ActivationType.Swiglu), int(ActivationType.Silu)) else "gelu"
+    x = input
     if use_deepseek_fp8_block_scale and quant_scales is not None:
-        w1 = _dequant_fp8_block(w1, quant_scales[0])
-        w2 = _dequant_fp8_block(w2, quant_scales[1])
+        # [fc1 128x128 block scales, fc2 128x128 block scales]: native fp8 tensor-core pipeline
+        xb = x if x.dtype in (torch.float16, torch.bfloat16) else x.to(output_dtype)
+        res = moe_forward_fp8_block(xb, None, ids, wts, w1, quant_scales[0], w2, quant_scales[1], off, total, out=output)
     elif w1.dtype == torch.float8_e4m3fn and quant_scales is not None:
-        w1 = (w1.float() * quant_scales[0].float().reshape(-1, 1, 1)).to(output_dtype)
-        w2 = (w2.float() * quant_scales[2].float().reshape(-1, 1, 1)).to(output_dtype) if len(quant_scales) > 2 else w2.to(output_dtype)
-    x = input if input.dtype == output_dtype else input.to(output_dtype)
-    res = moe_forward(x, token_selected_experts.int(), token_final_scales.float(), w1.to(output_dtype), w2.to(output_dtype),
-                      local_expert_offset=ep_rank * e_local, num_experts=e_local * ep_size,
-                      activation="silu" if int(activation_type) in (int(ActivationType.Swiglu), int(ActivationType.Silu)) else "gelu",
-                      out=output)
+        # [fc1_dequant [E], fc2_quant (activation scale), fc2_dequant [E], fc1_input_dequant]: act_q = act * fc2_quant, so the true
+        # FC2 de-quantisation scale of a pipeline that quantises activations per group on the fly is fc2_dequant * fc2_quant
+        a1 = quant_scales[0].float().reshape(-1)
+        a2 = quant_scales[2].float().reshape(-1) * quant_scales[1].float().reshape(-1) if len(quant_scales) > 2 else torch.ones_like(a1)
+        res = moe_forward_fp8_per_tensor(x, ids, wts, w1, a1, w2, a2, off, total, out=output)
+    elif quant_scales is not None and len(quant_scales) >= 6 and w1.dtype in (torch.uint8, torch.int64, torch.int32):
+        # NVFP4: [fc1_act_global, fc1_weight_block, fc1_global, fc2_act_global, fc2_weight_block, fc2_global]; *_global =
+        # 1 / (act_global * weight_global): this pipeline quantises activations with a unit global scale, so alpha = global * act_global
+        w1q, w2q = w1.view(torch.uint8).reshape(e_local, w1.shape[1], -1), w2.view(torch.uint8).reshape(e_local, w2.shape[1], -1)
+        a1 = (quant_scales[2].float() * quant_scales[0].float()).reshape(-1)
+        a2 = (quant_scales[5].float() * quant_scales[3].float()).reshape(-1)
+        xb = _dequant_nvfp4(x, input_sf, 1.0 / quant_scales[0].float()).to(output_dtype) if x.dtype == torch.uint8 else x.to(output_dtype)
+        res = moe_forward_nvfp4(xb, ids, wts, w1q, quant_scales[1], a1, w2q, quant_scales[4], a2, off, total, out=output)
+    else:
+        xb = x if x.dtype == output_dtype else x.to(output_dtype)
+        res = moe_forward(xb, ids, wts, w1.to(output_dtype), w2.to(output_dtype), local_expert_offset=off, num_experts=total,
+                          activation=act, out=output)
+    if res.dtype != output_dtype:
+        res = res.to(output_dtype)
     return [res]
 
 
@@ -613,12 +745,18 @@ def cute_dsl_fused_moe_nvfp4(x, x_sf, token_selected_experts, token_final_scales
                              fc2_input_scale, w2_weight, w2_weight_sf, w2_alpha, num_experts: int, top_k: int,
                              num_local_experts: Optional[int] = None, local_expert_offset: int = 0, output_dtype=torch.bfloat16,
                              **kw):
-    """NVFP4 MoE with pre-computed routing (reference fused_moe/cute_dsl/fused_moe.py)."""
-    xd = _dequant_nvfp4(x, x_sf, 1.0) if x.dtype == torch.uint8 else x
-    w1 = _dequant_nvfp4(w1_weight, w1_weight_sf, w1_alpha if w1_alpha is not None else 1.0)
-    w2 = _dequant_nvfp4(w2_weight, w2_weight_sf, w2_alpha if w2_alpha is not None else 1.0)
-    return moe_forward(xd.to(output_dtype), token_selected_experts.int(), token_final_scales.float(), w1.to(output_dtype),
-                       w2.to(output_dtype), local_expert_offset, num_experts)
+    """NVFP4 MoE with pre-computed routing (reference fused_moe/cute_dsl/fused_moe.py) on the native block-scaled grouped tcgen05
+    GEMMs (:func:`moe_forward_nvfp4`): gather + activation quantisation, FC1, SwiGLU + re-quantisation, FC2, finalize."""
+    xd = _dequant_nvfp4(x, x_sf, 1.0).to(output_dtype) if x.dtype == torch.uint8 else x.to(output_dtype)
+    e_local = w1_weight.shape[0]
+    ids, wts = token_selected_experts.int(), token_final_scales.float()
+    if xd.is_cuda and xd.shape[-1] % 64 == 0 and (w2_weight.shape[2] * 2) % 64 == 0:
+        return moe_forward_nvfp4(xd, ids, wts, w1_weight.view(torch.uint8).reshape(e_local, w1_weight.shape[1], -1), w1_weight_sf,
+                                 w1_alpha if w1_alpha is not None else 1.0, w2_weight.view(torch.uint8).reshape(e_local, w2_weight.shape[1], -1),
+                                 w2_weight_sf, w2_alpha if w2_alpha is not None else 1.0, local_expert_offset, num_experts)
+    w1 = _prepared("nvfp4deq", [w1_weight, w1_weight_sf], lambda: _dequant_nvfp4(w1_weight, w1_weight_sf, w1_alpha if w1_alpha is not None else 1.0))
+    w2 = _prepared("nvfp4deq", [w2_weight, w2_weight_sf], lambda: _dequant_nvfp4(w2_weight, w2_weight_sf, w2_alpha if w2_alpha is not None else 1.0))
+    return moe_forward(xd, ids, wts, w1.to(output_dtype), w2.to(output_dtype), local_expert_offset, num_experts)
 
 
 class CuteDslMoEWrapper:

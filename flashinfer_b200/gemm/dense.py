@@ -6,6 +6,7 @@
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -50,12 +51,34 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
         x2 = x2.contiguous()
     if weight.stride(-1) != 1:
         weight = weight.contiguous()
+    if _use_cta_pair(m, n, k, bias, x2, weight, out2):
+        # large problems: CTA-pair kernel (tcgen05.mma cta_group::2, 256 x 256 tile per SM pair, half the B tile per SM)
+        esz = x2.element_size()
+        jit.load("gemm_blockscaled_sm100").call(
+            "gemm_lowp_nt", x2, weight, out2, None, None, None, None, 1, m, n, k, x2.stride(0) * esz, weight.stride(0) * esz,
+            out2.stride(0), 0, 0, 0, 0, 0, 4, 0 if x.dtype == torch.float16 else 1, 0, dtype_code(x.dtype), 0, None, None, None,
+            1 if enable_pdl else 0, stream_ptr(x))
+        return out
     ws = _workspace(x.device)
     jit.load("gemm_sm100").call(
         "gemm_nt", x2, weight, out2, bias, m, n, k, x2.stride(0), weight.stride(0), out2.stride(0),
         dtype_code(x.dtype), ws, ws.numel(), 1 if enable_pdl else 0, stream_ptr(x),
     )
     return out
+
+
+_CTA_PAIR = os.environ.get("FIB200_GEMM_2CTA", "1") != "0"
+
+
+def _use_cta_pair(m, n, k, bias, x2, w, out2) -> bool:
+    """Route to the cta_group::2 kernel (csrc/gemm/gemm_blockscaled_sm100.cu, kind 4) when the problem fills the machine with
+    256 x 256 pair tiles: per-SM operand traffic per FLOP is half that of the 1-CTA 128 x 256 tile."""
+    if not _CTA_PAIR or bias is not None or m < 512 or n < 256 or k < 256:
+        return False
+    if (x2.stride(0) | w.stride(0) | out2.stride(0)) % 8 or (x2.data_ptr() | w.data_ptr() | out2.data_ptr()) % 16:
+        return False
+    tiles = ((m + 255) // 256) * ((n + 255) // 256)
+    return tiles >= 148  # at least two waves of SM pairs (below that the 1-CTA kernel's finer tiles win)
 
 
 def interleave_gate_up(w: torch.Tensor) -> torch.Tensor:

@@ -352,7 +352,7 @@ def grouped_gemm_fp8_groupwise(a: torch.Tensor, a_scale: torch.Tensor, w: torch.
     a = a if a.stride(1) == 1 else a.contiguous()
     w = w.contiguous()
     sa = a_scale.float()
-    sb = w_scale.float().contiguous()
+    sb = w_scale if w_scale.dtype == torch.float32 else w_scale.float()  # strides are passed: stride-0 (per-expert scalar) views are fine
     res = out if out is not None else torch.empty(M, N, dtype=out_dtype, device=a.device)
     jit.load("gemm_blockscaled_sm100").call(
         "gemm_fp8_groupwise_nt", a, w, res, sa, sb, M, N, K, a.stride(0), K, res.stride(0), sa.stride(0), sa.stride(1), sb.stride(1),

@@ -236,13 +236,17 @@ def shuffle_matrix_sf_a(input_tensor: torch.Tensor, epilogue_tile_m: int, num_el
 
 
 def _shuffle_row_indices(m: int, epilogue_tile_m: int, device) -> torch.Tensor:
-    if m % epilogue_tile_m:
-        return torch.arange(m, device=device)
-    half = epilogue_tile_m // 2
-    base = torch.arange(epilogue_tile_m, device=device)
-    perm = torch.where(base % 2 == 0, base // 2, half + base // 2)
-    tiles = torch.arange(0, m, epilogue_tile_m, device=device)[:, None]
-    return (tiles + perm[None]).reshape(-1)
+    """``idx[new_row] = old_row`` of the trtllm-gen weight shuffle (reference flashinfer/utils.py:801-867): rows are permuted inside
+    blocks of 16 rows (32 when ``epilogue_tile_m % 128 == 0``); row ``i`` of a block moves to ``(i % (B/8)) * 8 + i // (B/8)``."""
+    b = 32 if epilogue_tile_m % 128 == 0 else 16
+    if m % b:
+        raise ValueError(f"shuffle_matrix_a: the row count must be a multiple of {b}")
+    old = torch.arange(m, device=device)
+    i = old % b
+    new = (old // b) * b + (i % (b // 8)) * 8 + i // (b // 8)
+    idx = torch.empty(m, dtype=torch.long, device=device)
+    idx[new] = old
+    return idx
 
 
 def nvfp4_quantize_paged_kv_cache(k_cache: torch.Tensor, v_cache: torch.Tensor, kv_layout: str = "HND",

@@ -303,3 +303,117 @@ def test_fp8_per_tensor_moe_gate_scale_cpu():
     with pytest.raises(NotImplementedError):
         core.trtllm_fp8_per_tensor_scale_moe(logits, None, x, w1, s1, s_gate, w2, s2, E, K, None, None, I, 0, E, None,
                                              use_routing_scales_on_input=True)
+
+
+def test_trtllm_weight_shuffle_roundtrip_cpu():
+    """use_shuffled_weight / BlockMajorK: the load-time un-shuffle is the exact inverse of the reference pre-processing
+    (reorder_rows_for_gated_act_gemm -> shuffle_matrix_a -> convert_to_block_layout, flashinfer/fused_moe/core.py:133-233)."""
+    from flashinfer_b200.fused_moe import core
+    from flashinfer_b200.quantization.fp4 import shuffle_matrix_a
+
+    torch.manual_seed(0)
+    E, N, K = 3, 128, 256
+    w = torch.randn(E, N, K).to(torch.bfloat16)
+    # block-16 mapping table of the reference (srcToDstBlk16RowMap): row i of a block goes to map[i]
+    x = torch.arange(16)[:, None].float()
+    sh = shuffle_matrix_a(x, 64)
+    table = [0, 8, 1, 9, 2, 10, 3, 11, 4, 12, 5, 13, 6, 14, 7, 15]
+    for old, new in enumerate(table):
+        assert int(sh[new, 0]) == old
+    for tile_m, gated, bmk in ((128, True, False), (64, False, True), (128, True, True), (64, False, False)):
+        prep = []
+        for e in range(E):
+            t = core.reorder_rows_for_gated_act_gemm(w[e]) if gated else w[e]
+            t = shuffle_matrix_a(t.view(torch.uint8), tile_m)
+            if bmk:
+                t = t.view(N, t.shape[1] // 128, 128).permute(1, 0, 2).contiguous()
+            prep.append(t)
+        prep = torch.stack(prep).view(torch.bfloat16)
+        back = core._plain_weights("test", prep, True, int(core.WeightLayout.BlockMajorK if bmk else core.WeightLayout.MajorK), tile_m,
+                                   gated_interleaved=gated)
+        assert torch.equal(back.view(E, N, K), w), (tile_m, gated, bmk)
+    # cached: the second call returns the same prepared tensor
+    again = core._plain_weights("test", prep, True, int(core.WeightLayout.MajorK), 64, gated_interleaved=False)
+    assert again is back
+
+
+def test_bf16_moe_accepts_shuffled_weights_cpu():
+    from flashinfer_b200.fused_moe import core
+    from flashinfer_b200.quantization.fp4 import shuffle_matrix_a
+
+    x, w1, w2, logits = _mk(9, 4, 64, 32, "cpu", torch.float32)
+    w1 = w1.to(torch.bfloat16)
+    w2 = w2.to(torch.bfloat16)
+    x = x.to(torch.bfloat16)
+    ref = trtllm_bf16_moe(logits, None, x, w1, w2, 4, 2, None, None, 32, 0, 4, routing_method_type=1)
+    w1s = torch.stack([shuffle_matrix_a(core.reorder_rows_for_gated_act_gemm(w1[e]).view(torch.uint8), 128) for e in range(4)]).view(torch.bfloat16)
+    w2s = torch.stack([shuffle_matrix_a(w2[e].view(torch.uint8), 128) for e in range(4)]).view(torch.bfloat16)
+    got = trtllm_bf16_moe(logits, None, x, w1s, w2s, 4, 2, None, None, 32, 0, 4, routing_method_type=1, use_shuffled_weight=True)
+    torch.testing.assert_close(got.float(), ref.float())
+
+
+@pytest.mark.gpu
+def test_fp8_per_tensor_moe_native_gpu():
+    """fp8 per-tensor entry points on the fp8 tensor-core pipeline (no per-call weight de-quantisation) vs the expert-loop oracle."""
+    from flashinfer_b200.fused_moe import core
+
+    torch.manual_seed(3)
+    T, H, I, E, K = 200, 1024, 512, 16, 4
+    x = (torch.randn(T, H, device="cuda") * 0.5).bfloat16()
+    w1f = torch.randn(E, 2 * I, H, device="cuda") / H ** 0.5
+    w2f = torch.randn(E, H, I, device="cuda") / I ** 0.5
+    g1 = 448.0 / w1f.abs().amax((1, 2))
+    g2 = 448.0 / w2f.abs().amax((1, 2))
+    w1 = (w1f * g1[:, None, None]).to(torch.float8_e4m3fn)
+    w2 = (w2f * g2[:, None, None]).to(torch.float8_e4m3fn)
+    logits = torch.randn(T, E, device="cuda")
+    c_gs = 2.0
+    s_gate = 1.0 / g1
+    out = core.trtllm_fp8_per_tensor_scale_moe(logits, None, x, w1, s_gate * c_gs, s_gate, w2, 1.0 / (g2 * c_gs), E, K, None, None, I, 0, E, None,
+                                               routing_method_type=int(core.RoutingMethodType.Renormalize))
+    ids, wts = core.route(logits, None, K, int(core.RoutingMethodType.Renormalize))
+    ref = moe_reference(x, ids, wts, w1.float() / g1[:, None, None], w2.float() / g2[:, None, None])
+    rel = (out.float() - ref).norm() / ref.norm()
+    assert rel < 0.06, float(rel)
+    n0 = len(core._PREP_CACHE)
+    core.trtllm_fp8_per_tensor_scale_moe(logits, None, x, w1, s_gate * c_gs, s_gate, w2, 1.0 / (g2 * c_gs), E, K, None, None, I, 0, E, None,
+                                         routing_method_type=int(core.RoutingMethodType.Renormalize))
+    assert len(core._PREP_CACHE) == n0  # nothing de-quantised, nothing cached: fully native
+    # cutlass-style entry point with fp8 per-tensor scales: [fc1_dequant, fc2_quant, fc2_dequant, fc1_input_dequant]
+    res = cutlass_fused_moe(x, ids, wts, w1, w2, torch.bfloat16, quant_scales=[1.0 / g1, torch.tensor(c_gs, device="cuda"), 1.0 / (g2 * c_gs),
+                                                                             torch.tensor(1.0, device="cuda")])[0]
+    rel = (res.float() - ref).norm() / ref.norm()
+    assert rel < 0.06, float(rel)
+
+
+@pytest.mark.gpu
+def test_cute_dsl_and_cutlass_nvfp4_native_gpu():
+    from flashinfer_b200.fused_moe import core
+    from flashinfer_b200.quantization.fp4 import fp4_quantize
+
+    torch.manual_seed(4)
+    T, H, I, E, K = 64, 1024, 512, 8, 2
+    x, w1, w2, logits = _mk(T, E, H, I, "cuda")
+    ids, wts = route(logits, None, K, 1)
+
+    def quant_w(wt):
+        gs = (448.0 * 6.0) / wt.float().abs().amax((1, 2))
+        qs, sfs = [], []
+        for e in range(wt.shape[0]):
+            q, sf = fp4_quantize(wt[e], gs[e].reshape(1), 16, False, False)
+            qs.append(q)
+            sfs.append(sf)
+        return torch.stack(qs), torch.stack(sfs), (1.0 / gs).float()
+
+    w1q, w1sf, a1 = quant_w(w1)
+    w2q, w2sf, a2 = quant_w(w2)
+    ref = moe_reference(x, ids, wts, core._dequant_nvfp4(w1q, w1sf, a1), core._dequant_nvfp4(w2q, w2sf, a2))
+    n0 = len(core._PREP_CACHE)
+    out = core.cute_dsl_fused_moe_nvfp4(x, None, ids, wts, w1q, w1sf, a1, None, w2q, w2sf, a2, E, K)
+    assert len(core._PREP_CACHE) == n0
+    cos = torch.nn.functional.cosine_similarity(out.float().flatten(), ref.flatten(), dim=0)
+    assert cos > 0.97, float(cos)
+    one = torch.ones(1, device="cuda")
+    res = cutlass_fused_moe(x, ids, wts, w1q, w2q, torch.bfloat16, quant_scales=[one, w1sf, a1, one, w2sf, a2])[0]
+    cos = torch.nn.functional.cosine_similarity(res.float().flatten(), ref.flatten(), dim=0)
+    assert cos > 0.97, float(cos)
