@@ -35,7 +35,9 @@ class TPCommunicator:
         buf_bytes = max_tokens * hidden * esz
         sig_bytes = 2 * _MAX_BLOCKS * 16 * 4
         small_bytes = 1 << 20
-        self.heap = SymmetricHeap(self.group, sig_bytes + 3 * buf_bytes + small_bytes + 16384)
+        self._argmax_rows = max(256, max_tokens)
+        argmax_bytes = 2 * self.world * self._argmax_rows * 16
+        self.heap = SymmetricHeap(self.group, sig_bytes + 3 * buf_bytes + small_bytes + argmax_bytes + 16384)
         sig, self._sig_off = self.heap.alloc(sig_bytes)
         self._in = []
         for _ in range(2):
@@ -45,6 +47,9 @@ class TPCommunicator:
         self._out_sym = v.view(dtype).view(max_tokens, hidden)
         v, self._small_off = self.heap.alloc(small_bytes)
         self._small = v
+        self._argmax_box, argmax_off = self.heap.alloc(argmax_bytes)  # zero-filled by the heap: tag 0 = "nothing has arrived"
+        self._argmax_tab = self.heap.peer_ptr_table(argmax_off)
+        self._argmax_epoch = torch.zeros(4, dtype=torch.int32, device=self.heap.device)
         self._sig_tab = self.heap.peer_ptr_table(self._sig_off)
         self._in_tab = [self.heap.peer_ptr_table(off) for _, off in self._in]
         self._out_tab = self.heap.peer_ptr_table(self._out_off)
@@ -204,6 +209,23 @@ class TPCommunicator:
             self._epochs, None, 0 + 1, 4, self.rank, self.world, _MAX_BLOCKS, 0.0, 0.0, 0.0, 0,
             dtype_code(torch.float32), 1, stream_ptr(ref),
         )
+
+    def argmax_logits(self, logits: torch.Tensor, index_offset: int, out: Optional[torch.Tensor] = None,
+                      out_val: Optional[torch.Tensor] = None, enable_pdl: bool = True) -> torch.Tensor:
+        """Greedy sampling over a vocabulary-sharded LM head, one kernel: ``out[b] = argmax over all ranks' shards`` (global index
+        = ``index_offset`` + local column; lowest index on ties, identical on every rank).  ``logits [B, shard]`` (f16 / bf16 / f32,
+        row-contiguous), ``out`` int64 ``[B]`` (csrc/comm/allreduce.cu: argmax_push_kernel)."""
+        b, shard = logits.shape
+        if b > self._argmax_rows:
+            raise ValueError(f"argmax_logits: at most {self._argmax_rows} rows")
+        if logits.stride(-1) != 1:
+            logits = logits.contiguous()
+        if out is None:
+            out = torch.empty(b, dtype=torch.int64, device=logits.device)
+        self._mod.call("argmax_push_run", logits, logits.stride(0), shard, int(index_offset), self._argmax_box, self._argmax_tab,
+                       self._argmax_epoch, self.rank, self.world, b, self._argmax_rows, out, out_val, dtype_code(logits.dtype),
+                       1 if enable_pdl else 0, stream_ptr(logits))
+        return out
 
     def argmax_gather(self, val: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
         """Global argmax over vocab shards: every rank contributes (max value, global index)."""

@@ -599,3 +599,165 @@ extern "C" int allreduce_push_run(int64_t mode, void* in, void* moe_scale, void*
 #undef FIB_PUSH
   return 0;
 }
+
+// =====================================================================================================================
+// Greedy sampling over a vocabulary-sharded LM head in ONE kernel: per-row argmax of the local logits shard, (value, global
+// index) pushed to every rank (8-byte {payload, tag} stores, LL style: the tag is the call epoch, so there is nothing to reset),
+// poll the `world` pairs of the row, pick the winner (largest value, lowest index on ties: identical on all ranks).
+// Replaces torch.max + a small all-reduce + a barrier kernel + gather glue at the end of a tensor-parallel decode step.
+// Parity: the reference leaves this to the serving engine (vLLM / SGLang gather the vocab-parallel logits with NCCL).
+// =====================================================================================================================
+namespace {
+
+struct ArgmaxParams {
+  const void* logits;        // [rows, ld] local shard
+  int64_t ld;
+  int shard;                 // valid columns of the shard
+  int64_t index_offset;      // global index of column 0
+  uint2* inbox;              // local [2 parity][world][max_rows][2]
+  uint2* peer_inbox[kMaxRanks];
+  uint32_t* epoch;           // local device word
+  int rank, world, rows, max_rows;
+  int64_t* out;              // [rows] winning global index
+  float* out_val;            // [rows] winning value (or null)
+};
+
+__device__ __forceinline__ void st_volatile_v2(uint2* p, uint2 v) {
+  asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ uint2 ld_volatile_v2(const uint2* p) {
+  uint2 v;
+  asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+  return v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) argmax_push_kernel(const ArgmaxParams p) {
+  constexpr int VN = 16 / sizeof(T);
+  __shared__ float s_val[8];
+  __shared__ int s_idx[8];
+  __shared__ float r_val[kMaxRanks];
+  __shared__ int64_t r_idx[kMaxRanks];
+  __shared__ uint32_t s_epoch;
+  const int row = blockIdx.x;
+  ptx::grid_dep_wait();
+  if (threadIdx.x == 0) s_epoch = *reinterpret_cast<volatile uint32_t*>(p.epoch);
+  const T* src = reinterpret_cast<const T*>(p.logits) + int64_t(row) * p.ld;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  const bool vec_ok = (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+  const int nfull = vec_ok ? p.shard / VN * VN : 0;
+  for (int c = threadIdx.x * VN; c < nfull; c += blockDim.x * VN) {
+    const Vec16<T> v = ldg16(src + c);
+#pragma unroll
+    for (int e = 0; e < VN; ++e) {
+      const float x = to_f32(v.v[e]);
+      if (x > best) {  // ascending scan: the first occurrence of the maximum wins
+        best = x;
+        bi = c + e;
+      }
+    }
+  }
+  for (int c = nfull + threadIdx.x; c < p.shard; c += blockDim.x) {
+    const float x = to_f32(src[c]);
+    if (x > best || (x == best && c < bi)) {
+      best = x;
+      bi = c;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) {
+      best = ov;
+      bi = oi;
+    }
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s_val[threadIdx.x >> 5] = best;
+    s_idx[threadIdx.x >> 5] = bi;
+  }
+  __syncthreads();
+  const uint32_t tag = s_epoch + 1u;
+  const int par = int(s_epoch & 1u);
+  if (threadIdx.x < p.world) {
+    float v = s_val[0];
+    int i = s_idx[0];
+    for (int w = 1; w < int(blockDim.x >> 5); ++w)
+      if (s_val[w] > v || (s_val[w] == v && s_idx[w] < i)) {
+        v = s_val[w];
+        i = s_idx[w];
+      }
+    const int64_t gi = p.index_offset + (i == 0x7fffffff ? 0 : i);
+    // push my pair into slot [rank] of peer `threadIdx.x`, then wait for that peer's pair in my inbox
+    const int peer = threadIdx.x;
+    uint2* dst = p.peer_inbox[peer] + ((int64_t(par) * p.world + p.rank) * p.max_rows + row) * 2;
+    st_volatile_v2(dst, make_uint2(__float_as_uint(v), tag));
+    st_volatile_v2(dst + 1, make_uint2(uint32_t(gi), tag));
+    const uint2* in = p.inbox + ((int64_t(par) * p.world + peer) * p.max_rows + row) * 2;
+    uint2 a, b;
+    uint32_t polls = 0;
+    uint64_t t0 = 0;
+    for (;;) {
+      a = ld_volatile_v2(in);
+      b = ld_volatile_v2(in + 1);
+      if (a.y == tag && b.y == tag) break;
+      if ((++polls & 0x3ffu) == 0) {
+        if (t0 == 0) t0 = ptx::globaltimer();
+        else if (ptx::globaltimer() - t0 > ptx::kSpinTimeoutNs) {
+          printf("fib200: argmax_push watchdog: rank %d row %d waited 20 s for rank %d -> trap\n", p.rank, row, peer);
+          __trap();
+        }
+      }
+    }
+    r_val[peer] = __uint_as_float(a.x);
+    r_idx[peer] = int64_t(b.x);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = r_val[0];
+    int64_t i = r_idx[0];
+    for (int r = 1; r < p.world; ++r)
+      if (r_val[r] > v || (r_val[r] == v && r_idx[r] < i)) {
+        v = r_val[r];
+        i = r_idx[r];
+      }
+    p.out[row] = i;
+    if (p.out_val) p.out_val[row] = v;
+    if (blockIdx.x == 0) *reinterpret_cast<volatile uint32_t*>(p.epoch) = tag;  // every block read the epoch before its scan
+  }
+  ptx::grid_dep_launch();
+}
+
+}  // namespace
+
+extern "C" int argmax_push_run(void* logits, int64_t ld, int64_t shard, int64_t index_offset, void* inbox, void* peer_inbox_host,
+                               void* epoch, int64_t rank, int64_t world, int64_t rows, int64_t max_rows, void* out, void* out_val,
+                               int64_t dtype, int64_t pdl, int64_t stream_) {
+  FIB_CHECK(world >= 1 && world <= kMaxRanks, "argmax_push: world size must be in [1, 16]");
+  FIB_CHECK(rows >= 1 && rows <= max_rows && shard >= 1 && shard < (int64_t(1) << 31) && index_offset + shard < (int64_t(1) << 32),
+            "argmax_push: bad shape (rows <= max_rows, global vocabulary index must fit 32 bits)");
+  FIB_CHECK(inbox && peer_inbox_host && epoch && out, "argmax_push: inbox / peer table / epoch / out required");
+  ArgmaxParams p;
+  memset(&p, 0, sizeof(p));
+  p.logits = logits; p.ld = ld; p.shard = int(shard); p.index_offset = index_offset;
+  p.inbox = reinterpret_cast<uint2*>(inbox);
+  const int64_t* ps = reinterpret_cast<const int64_t*>(peer_inbox_host);
+  for (int i = 0; i < world; ++i) p.peer_inbox[i] = reinterpret_cast<uint2*>(ps[i]);
+  p.epoch = reinterpret_cast<uint32_t*>(epoch);
+  p.rank = int(rank); p.world = int(world); p.rows = int(rows); p.max_rows = int(max_rows);
+  p.out = reinterpret_cast<int64_t*>(out); p.out_val = reinterpret_cast<float*>(out_val);
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  LaunchCfg lc(dim3((unsigned)rows), dim3(256), 0, stream, pdl != 0);
+  if (dtype == kBF16) {
+    FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, argmax_push_kernel<__nv_bfloat16>, p));
+  } else if (dtype == kF16) {
+    FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, argmax_push_kernel<__half>, p));
+  } else if (dtype == kF32) {
+    FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, argmax_push_kernel<float>, p));
+  } else {
+    return set_error("argmax_push: f16 / bf16 / f32 logits only");
+  }
+  return 0;
+}

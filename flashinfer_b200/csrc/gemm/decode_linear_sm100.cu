@@ -64,6 +64,7 @@ struct DLP {
   int64_t ldr;
   float* sumsq_out;        // kResid: += sum_n resid_new[m, n]^2
   int world, rank;         // kResid all-reduce (Lamport push)
+  int ar_algo;             // 1 one-shot (gather all partials), 2 two-shot (reduce-scatter push + multicast all-gather)
   void* recv;              // local receive buffers [3][world][rows][lds] (symmetric heap)
   int64_t lds;             // row pitch of a slot (elements)
   int64_t slot_elems;      // elements per rank slot
@@ -224,6 +225,9 @@ dlinear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int own_w = BN / S;
     const int own_lo = crank * own_w;
     const int xsw = (m >> 1) & 3;  // 16-byte slot swizzle of the exchange rows (bank spread)
+    // all-reduce: the rotating-buffer epoch is read here, right after griddepcontrol.wait and long before any CTA of this grid can
+    // finish its all-reduce and bump it (published to the other epilogue threads by the named barrier after the tile staging)
+    if (p.epi == kResid && p.world > 1 && etid == 0) tmem_ptr[1] = *reinterpret_cast<volatile uint32_t*>(p.epoch);
     FIB_PROFILER_EVENT_START(kEvMainLoop);
     ptx::mbar_wait(tmem_full, 0);
     ptx::tc_fence_after();
@@ -340,19 +344,19 @@ dlinear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       } else {
-        // ---- in-kernel all-reduce of this CTA's columns over NVLink: one-shot push, the data is its own arrival signal ----
+        // ---- in-kernel all-reduce of this CTA's column strip over NVLink; the data is its own arrival signal (Lamport) ----
+        // (0) fp32 accumulators -> 16-bit partial (never the sentinel) -> shared-memory tile [64][own_w] in the idle TMA ring, so
+        //     that the exchange below runs with 16-byte pieces of one row in neighbouring lanes: every NVLink packet carries
+        //     own_w * 2 contiguous bytes of a row instead of one 16-byte piece per token row.
         constexpr uint32_t kSent = 0x80008000u;  // two -0.0 halves
-        uint32_t* s_epoch = tmem_ptr + 1;
-        if (etid == 0) *s_epoch = *reinterpret_cast<volatile uint32_t*>(p.epoch);
-        ptx::named_bar_sync(1, 128);
-        const uint32_t ep = *s_epoch;
-        T* recv = reinterpret_cast<T*>(p.recv);
-        const int64_t cur = int64_t(ep % 3u) * p.buf_elems, nxt = int64_t((ep + 1u) % 3u) * p.buf_elems;
-        for (int c = 0; c < own_w; c += 16) {  // (1) push my partial into slot [rank] of every rank
+        uint32_t* s_epoch = tmem_ptr + 1;        // read right after griddepcontrol.wait (top of this warp role)
+        uint8_t* tile = smem;
+        const int P = own_w >> 3;                // 16-byte pieces per strip row
+        const int pmask = (P & (P - 1)) == 0 ? P - 1 : 0;
+        for (int c = 0; c < own_w; c += 16) {
           float v[16];
           load_chunk(c, v);
-          const int n0 = n_base + c;
-          if (m_ok && n0 < p.N) {
+          if (row_ok) {
             Vec16<T> a, b;
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
@@ -368,95 +372,187 @@ dlinear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if ((wb[e] & 0xffffu) == 0x8000u) wb[e] &= 0xffff0000u;
               if ((wb[e] >> 16) == 0x8000u) wb[e] &= 0x0000ffffu;
             }
-            const int64_t off = cur + int64_t(p.rank) * p.slot_elems + int64_t(m) * p.lds + n0;
-            if (p.mc_recv) {
-              T* d = reinterpret_cast<T*>(p.mc_recv) + off;
-              ptx::multimem_st_v4(d, *reinterpret_cast<const int4*>(&a));
-              ptx::multimem_st_v4(d + 8, *reinterpret_cast<const int4*>(&b));
-            } else {
-              for (int r = 0; r < p.world; ++r) {
-                T* d = reinterpret_cast<T*>(p.peer_recv[(p.rank + r) % p.world]) + off;
-                ptx::st_na_v4(d, *reinterpret_cast<const int4*>(&a));
-                ptx::st_na_v4(d + 8, *reinterpret_cast<const int4*>(&b));
-              }
-            }
+            const int sw = (m >> 1) & pmask, pc = c >> 3;
+            *reinterpret_cast<int4*>(tile + ((m * P + (pc ^ sw)) << 4)) = *reinterpret_cast<const int4*>(&a);
+            *reinterpret_cast<int4*>(tile + ((m * P + ((pc + 1) ^ sw)) << 4)) = *reinterpret_cast<const int4*>(&b);
           }
         }
-        if (row_ok) {  // (2) while the pushes fly: reset my columns (all 64 rows: the next call may carry more tokens) of the NEXT call's buffer,
-                       //     last read two calls ago
-          const int4 sent = make_int4(int(kSent), int(kSent), int(kSent), int(kSent));
-          for (int r = 0; r < p.world; ++r)
-            for (int c = 0; c < own_w; c += 16) {
-              const int n0 = n_base + c;
-              if (n0 < p.N) {
-                T* d = recv + nxt + int64_t(r) * p.slot_elems + int64_t(m) * p.lds + n0;
-                *reinterpret_cast<int4*>(d) = sent;
-                *reinterpret_cast<int4*>(d + 8) = sent;
-              }
-            }
-        }
-        for (int c = 0; c < own_w; c += 16) {  // (3) gather all ranks' partials of my columns, reduce in rank order
-          const int n0 = n_base + c;
-          if (m_ok && n0 < p.N) {
-            const T* src = recv + cur + int64_t(m) * p.lds + n0;
-            int4 x[2 * 8];
-            uint32_t polls = 0;
-            uint64_t t0 = 0;
-            bool done;
-            do {
-              done = true;
-#pragma unroll
-              for (int r = 0; r < 8; ++r)
-                if (r < p.world) {
-                  x[2 * r] = ptx::ld_volatile_v4(src + int64_t(r) * p.slot_elems);
-                  x[2 * r + 1] = ptx::ld_volatile_v4(src + int64_t(r) * p.slot_elems + 8);
-                }
-#pragma unroll
-              for (int r = 0; r < 8; ++r)
-                if (r < p.world) {
-                  const uint32_t* w = reinterpret_cast<const uint32_t*>(&x[2 * r]);
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) done = done && ((w[e] & 0xffffu) != 0x8000u) && ((w[e] >> 16) != 0x8000u);
-                }
-              if (!done && (++polls & 0x3ffu) == 0) {  // watchdog: a peer that never sends traps this kernel instead of hanging the GPU
-                if (t0 == 0) t0 = ptx::globaltimer();
-                else if (ptx::globaltimer() - t0 > ptx::kSpinTimeoutNs) {
-                  printf("fib200: decode_linear all-reduce watchdog: rank %d cta %d waited 20 s for peer data -> trap\n", p.rank, int(blockIdx.x));
-                  __trap();
-                }
-              }
-            } while (!done);
-            float v[16];
-#pragma unroll
-            for (int e = 0; e < 16; ++e) v[e] = 0.f;
+        ptx::named_bar_sync(1, 128);
+        const uint32_t ep = *s_epoch;
+        T* recv = reinterpret_cast<T*>(p.recv);
+        const int W = p.world;
+        const int64_t cur = int64_t(ep % 3u) * p.buf_elems, nxt = int64_t((ep + 1u) % 3u) * p.buf_elems;
+        const int nvec = BM * P;  // vectors of the strip; thread -> (row = vi / P, piece = vi % P)
+        const int4 sent = make_int4(int(kSent), int(kSent), int(kSent), int(kSent));
+        auto tile_vec = [&](int row, int pc) { return *reinterpret_cast<const int4*>(tile + ((row * P + (pc ^ ((row >> 1) & pmask))) << 4)); };
+        // poll `n` 16-byte vectors (src + r * stride) until none holds a sentinel half; all loads of a round are in flight together
+        auto poll = [&](const T* src, int64_t stride, int n, int4* x) {
+          uint32_t polls = 0;
+          uint64_t t0 = 0;
+          bool done;
+          do {
+            done = true;
 #pragma unroll
             for (int r = 0; r < 8; ++r)
-              if (r < p.world) {
-                const T* h0 = reinterpret_cast<const T*>(&x[2 * r]);
-                const T* h1 = reinterpret_cast<const T*>(&x[2 * r + 1]);
+              if (r < n) x[r] = ptx::ld_volatile_v4(src + int64_t(r) * stride);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  v[e] += to_f32(h0[e]);
-                  v[8 + e] += to_f32(h1[e]);
-                }
+            for (int r = 0; r < 8; ++r)
+              if (r < n) {
+                const uint32_t* w = reinterpret_cast<const uint32_t*>(&x[r]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) done = done && ((w[e] & 0xffffu) != 0x8000u) && ((w[e] >> 16) != 0x8000u);
               }
-            T* rp = resid + int64_t(m) * p.ldr + n0;
-            Vec16<T> a = ld16(rp), b = ld16(rp + 8);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              a.v[e] = from_f32<T>(to_f32(a.v[e]) + v[e]);
-              b.v[e] = from_f32<T>(to_f32(b.v[e]) + v[8 + e]);
-              const float xx = to_f32(a.v[e]), yy = to_f32(b.v[e]);
-              ss += xx * xx + yy * yy;
+            if (!done && (++polls & 0x3ffu) == 0) {  // watchdog: a peer that never sends traps this kernel instead of hanging the GPU
+              if (t0 == 0) t0 = ptx::globaltimer();
+              else if (ptx::globaltimer() - t0 > ptx::kSpinTimeoutNs) {
+                printf("fib200: decode_linear all-reduce watchdog: rank %d cta %d waited 20 s for peer data -> trap\n", p.rank, int(blockIdx.x));
+                __trap();
+              }
             }
-            st16(rp, a);
-            st16(rp + 8, b);
+          } while (!done);
+        };
+        // residual += sum (16-bit rounding of the new residual), returns the sum of squares of the 8 new values
+        auto add_resid = [&](int row, int col, const float* sum) {
+          T* rp = resid + int64_t(row) * p.ldr + col;
+          Vec16<T> a = ld16(rp);
+          float s2 = 0.f;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            a.v[e] = from_f32<T>(to_f32(a.v[e]) + sum[e]);
+            const float x = to_f32(a.v[e]);
+            s2 += x * x;
+          }
+          st16(rp, a);
+          return s2;
+        };
+        // per-row sum of squares: the P lanes of a row are neighbours when P is a power of two
+        auto row_ss = [&](float s2, int row, int pc, bool ok) {
+          if (pmask) {
+            for (int o = 1; o < P && o < 32; o <<= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+            if (ok && pc == 0 && p.sumsq_out) atomicAdd(p.sumsq_out + row, s2);
+          } else if (ok && p.sumsq_out) {
+            atomicAdd(p.sumsq_out + row, s2);
+          }
+        };
+        if (p.ar_algo != 2) {
+          // ======== one-shot: multicast my strip into slot [rank] of every rank, gather all `world` slots, reduce in rank order ========
+          for (int vi = etid; vi < nvec; vi += 128) {
+            const int row = vi / P, pc = vi - row * P, col = n_base + pc * 8;
+            if (row < p.M && col < p.N) {
+              const int4 x = tile_vec(row, pc);
+              const int64_t off = cur + int64_t(p.rank) * p.slot_elems + int64_t(row) * p.lds + col;
+              if (p.mc_recv) {
+                ptx::multimem_st_v4(reinterpret_cast<T*>(p.mc_recv) + off, x);
+              } else {
+                for (int r = 0; r < W; ++r) ptx::st_na_v4(reinterpret_cast<T*>(p.peer_recv[(p.rank + r) % W]) + off, x);
+              }
+            }
+          }
+          // while the pushes fly: reset my strip (all 64 rows: the next call may carry more tokens) of the NEXT call's buffer, last read two calls ago
+          for (int vi = etid; vi < nvec; vi += 128) {
+            const int row = vi / P, pc = vi - row * P, col = n_base + pc * 8;
+            if (col < p.N)
+              for (int r = 0; r < W; ++r) *reinterpret_cast<int4*>(recv + nxt + int64_t(r) * p.slot_elems + int64_t(row) * p.lds + col) = sent;
+          }
+          for (int vi = etid; vi < nvec; vi += 128) {
+            const int row = vi / P, pc = vi - row * P, col = n_base + pc * 8;
+            const bool ok = row < p.M && col < p.N;
+            float s2 = 0.f;
+            if (ok) {
+              int4 x[8];
+              poll(recv + cur + int64_t(row) * p.lds + col, p.slot_elems, W, x);
+              float sum[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) sum[e] = 0.f;
+#pragma unroll
+              for (int r = 0; r < 8; ++r)
+                if (r < W) {
+                  const T* h = reinterpret_cast<const T*>(&x[r]);
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) sum[e] += to_f32(h[e]);
+                }
+              s2 = add_resid(row, col, sum);
+            }
+            row_ss(s2, row, pc, ok);
+          }
+        } else {
+          // ======== two-shot: reduce-scatter by push (row m is owned by rank m % world), the owner adds the residual and multicasts
+          //          the NEW residual rows to every rank.  Two one-way NVLink hops, (1 + 1/world) x strip bytes of ingress per rank
+          //          instead of world x: the choice for world >= 4.  Slot 0 of the rotating buffer is the reduce-scatter inbox
+          //          [src rank][owned row][hidden], slot 1 the all-gather inbox [row][hidden]. ========
+          const int R = BM / W;  // rows per owner (world is 2, 4 or 8)
+          for (int vi = etid; vi < nvec; vi += 128) {
+            const int row = vi / P, pc = vi - row * P, col = n_base + pc * 8;
+            if (row < p.M && col < p.N) {
+              const int dst = row % W, lr = row / W;
+              ptx::st_na_v4(reinterpret_cast<T*>(p.peer_recv[dst]) + cur + int64_t(p.rank * R + lr) * p.lds + col, tile_vec(row, pc));
+            }
+          }
+          for (int vi = etid; vi < nvec; vi += 128) {  // reset both inboxes of the NEXT call's buffer (my strip, all 64 rows)
+            const int row = vi / P, pc = vi - row * P, col = n_base + pc * 8;
+            if (col < p.N) {
+              *reinterpret_cast<int4*>(recv + nxt + int64_t(row) * p.lds + col) = sent;
+              *reinterpret_cast<int4*>(recv + nxt + p.slot_elems + int64_t(row) * p.lds + col) = sent;
+            }
+          }
+          for (int it = etid; it < R * P; it += 128) {  // owner: gather the `world` partials of my rows, reduce, + residual, broadcast
+            const int lr = it / P, pc = it - lr * P, col = n_base + pc * 8, row = lr * W + p.rank;
+            if (row < p.M && col < p.N) {
+              int4 x[8];
+              poll(recv + cur + int64_t(lr) * p.lds + col, int64_t(R) * p.lds, W, x);
+              float sum[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) sum[e] = 0.f;
+#pragma unroll
+              for (int r = 0; r < 8; ++r)
+                if (r < W) {
+                  const T* h = reinterpret_cast<const T*>(&x[r]);
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) sum[e] += to_f32(h[e]);
+                }
+              const Vec16<T> old = ld16(resid + int64_t(row) * p.ldr + col);
+              Vec16<T> nw;
+#pragma unroll
+              for (int e = 0; e < 8; ++e) nw.v[e] = from_f32<T>(to_f32(old.v[e]) + sum[e]);
+              uint32_t* w = reinterpret_cast<uint32_t*>(&nw);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                if ((w[e] & 0xffffu) == 0x8000u) w[e] &= 0xffff0000u;
+                if ((w[e] >> 16) == 0x8000u) w[e] &= 0x0000ffffu;
+              }
+              const int64_t off = cur + p.slot_elems + int64_t(row) * p.lds + col;
+              if (p.mc_recv) {
+                ptx::multimem_st_v4(reinterpret_cast<T*>(p.mc_recv) + off, *reinterpret_cast<const int4*>(&nw));
+              } else {
+                for (int r = 0; r < W; ++r)
+                  ptx::st_na_v4(reinterpret_cast<T*>(p.peer_recv[(p.rank + r) % W]) + off, *reinterpret_cast<const int4*>(&nw));
+              }
+            }
+          }
+          for (int vi = etid; vi < nvec; vi += 128) {  // everyone: the new residual rows of my strip arrive from their owners
+            const int row = vi / P, pc = vi - row * P, col = n_base + pc * 8;
+            const bool ok = row < p.M && col < p.N;
+            float s2 = 0.f;
+            if (ok) {
+              int4 x[8];
+              poll(recv + cur + p.slot_elems + int64_t(row) * p.lds + col, 0, 1, x);
+              const T* h = reinterpret_cast<const T*>(&x[0]);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float f = to_f32(h[e]);
+                s2 += f * f;
+              }
+              *reinterpret_cast<int4*>(resid + int64_t(row) * p.ldr + col) = x[0];
+            }
+            row_ss(s2, row, pc, ok);
           }
         }
-        // all CTAs read the epoch at the top of their epilogue, microseconds ago (single wave: grid <= #SM): bump it for the next call
+        // every CTA read the epoch right after griddepcontrol.wait, long before any CTA can get here: bump it for the next call
         if (blockIdx.x == 0 && etid == 0) *reinterpret_cast<volatile uint32_t*>(p.epoch) = ep + 1u;
       }
-      if (m_ok && p.sumsq_out) atomicAdd(p.sumsq_out + m, ss);
+      if (p.world <= 1) {
+        if (m_ok && p.sumsq_out) atomicAdd(p.sumsq_out + m, ss);
+      }
     } else {  // kRope
       const int hd = p.head_dim, half = hd / 2;
       T* k_cache = reinterpret_cast<T*>(p.k_cache);
@@ -621,7 +717,7 @@ inline int env_int(const char* name, int dflt) {
 extern "C" int dlinear_run(void* A, void* W, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldw, int64_t epi, void* out,
                            int64_t ldo, void* bias, void* row_sumsq, double inv_dim, double eps, void* resid, int64_t ldr,
                            void* sumsq_out, int64_t world, int64_t rank, void* recv, int64_t lds, int64_t slot_elems,
-                           void* mc_recv, void* epoch, void* peer_recv_host, void* cos_sin,
+                           void* mc_recv, void* epoch, void* peer_recv_host, int64_t ar_algo, void* cos_sin,
                            void* cache_row, void* k_cache, void* v_cache, int64_t c_sh, int64_t hq, int64_t hkv, int64_t head_dim,
                            int64_t interleave, int64_t force_bn, int64_t force_s, int64_t smem_kb, int64_t w_blockk, int64_t dtype,
                            int64_t pdl, int64_t stream_) {
@@ -636,9 +732,13 @@ extern "C" int dlinear_run(void* A, void* W, int64_t M, int64_t N, int64_t K, in
     FIB_CHECK(cos_sin && cache_row && k_cache && v_cache && head_dim % 32 == 0 && N == (hq + 2 * hkv) * head_dim && ldo % 8 == 0 &&
                   c_sh % 8 == 0,
               "dlinear (rope): cos_sin / cache_row / caches required, N = (hq + 2 hkv) * head_dim, head_dim % 32 == 0");
-  if (epi == kResid && world > 1)
-    FIB_CHECK(world <= 8 && recv && epoch && lds % 8 == 0 && slot_elems >= M * lds && (mc_recv || peer_recv_host),
+  if (epi == kResid && world > 1) {
+    FIB_CHECK(world <= 8 && recv && epoch && lds % 8 == 0 && slot_elems >= BM * lds && (mc_recv || peer_recv_host),
               "dlinear (all-reduce): world <= 8, symmetric receive buffers (multicast alias or peer table) and the epoch word required");
+    if (ar_algo == 0) ar_algo = (world >= 4 && BM % world == 0 && peer_recv_host) ? 2 : 1;
+    FIB_CHECK(ar_algo == 1 || ar_algo == 2, "dlinear (all-reduce): ar_algo must be 0 (auto), 1 (one-shot) or 2 (two-shot)");
+    if (ar_algo == 2) FIB_CHECK(BM % world == 0 && peer_recv_host, "dlinear (two-shot all-reduce): world must divide 64 and the peer table is required");
+  }
   const int sms = num_sms();
   const int kblocks = int((K + BK - 1) / BK);
   // ---- tile plan: one wave, one tile per cluster.  BN = narrowest multiple of 16 (32 with the 2-CTA K split) that covers N with
@@ -660,15 +760,23 @@ extern "C" int dlinear_run(void* A, void* W, int64_t M, int64_t N, int64_t K, in
     }
     BN = best;
   }
-  if (BN <= 64 && K >= 2048 && kblocks >= 8) {
+  if (BN <= 64 && kblocks >= 16) {
+    // split-K over a cluster: per-SM ingest (activation tile + weight tile per k-block) is the limiter of these single-wave
+    // GEMMs, and the 64 activation rows weigh as much as 64 weight rows.  Plans below are the winners of tools/dl_sweep.py on
+    // B200 for the Llama-3-8B decode shapes at TP 1 / 2 / 4 / 8 (gpurun_out/r14_sweep.log, profiles/decode_linear_plans.md).
     S = 2;
     BN = int(((N * 2 + sms - 1) / sms + 31) / 32 * 32);
     if (BN < 64) BN = 64;
-    // 128-wide tiles over a 4-CTA cluster when that still fills the (132 usable) SMs: the activation tile is re-read from L2
-    // once per 128 weight rows instead of once per 64 (measured on B200, M = 64: o_proj 12.5 -> 11.4 us, down_proj 30.0 -> 24.2 us)
     const int t128 = int((N + 127) / 128);
-    if (kblocks >= 16 && t128 * 4 <= (sms * 132) / 148 && t128 * 4 >= 96) {
+    const int cl_sms = (sms * 132) / 148;  // clusters of 4 / 8 CTAs can be placed on 132 of the 148 SMs
+    if (kblocks >= 32 && t128 * 4 <= cl_sms && t128 * 4 >= 96) {
+      // 128-wide tiles over a 4-CTA cluster when that still fills the SMs: the activation tile is re-read from L2 once per 128
+      // weight rows instead of once per 64 (M = 64: o_proj 12.5 -> 11.4 us, down_proj 30.0 -> 24.2 us)
       S = 4;
+      BN = 128;
+    } else if (kblocks >= 32 && t128 * 4 < 96 && t128 * 8 <= cl_sms) {
+      // narrow N (the QKV projection of a TP 4 / 8 shard): only an 8-way K split reaches enough SMs (TP8 qkv 10.6 -> 6.9 us)
+      S = 8;
       BN = 128;
     }
   }
@@ -703,7 +811,7 @@ extern "C" int dlinear_run(void* A, void* W, int64_t M, int64_t N, int64_t K, in
   p.out = out; p.ldo = ldo; p.bias = bias;
   p.row_sumsq = reinterpret_cast<const float*>(row_sumsq); p.inv_dim = float(inv_dim); p.eps = float(eps);
   p.resid = resid; p.ldr = ldr; p.sumsq_out = reinterpret_cast<float*>(sumsq_out);
-  p.world = int(world); p.rank = int(rank);
+  p.world = int(world); p.rank = int(rank); p.ar_algo = int(ar_algo);
   p.recv = recv; p.lds = lds; p.slot_elems = slot_elems; p.buf_elems = slot_elems * world; p.mc_recv = mc_recv;
   p.epoch = reinterpret_cast<uint32_t*>(epoch);
   if (peer_recv_host) {

@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import contextlib
 import math
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -63,7 +64,14 @@ class FusedLinearTP:
     in a symmetric heap (+ its NVLS multicast alias), pre-filled with the sentinel (-0.0), and the device-side epoch word that
     selects the rotating buffer (CUDA-graph replay safe: nothing about the rotation is baked into the launch arguments)."""
 
-    def __init__(self, group, max_tokens: int, hidden: int, dtype: torch.dtype = torch.bfloat16, heap=None):
+    ONE_SHOT, TWO_SHOT = 1, 2
+
+    def __init__(self, group, max_tokens: int, hidden: int, dtype: torch.dtype = torch.bfloat16, heap=None, algo: Optional[int] = None):
+        """``algo``: ``ONE_SHOT`` - every rank multicasts its partial strip and gathers all ``world`` partials (one NVLink hop,
+        ``world x`` ingress: best for 2 ranks); ``TWO_SHOT`` - reduce-scatter by push to the row owner (row ``m`` belongs to rank
+        ``m % world``), the owner adds the residual and multicasts the new residual rows (two hops, ``(1 + 1/world) x`` ingress:
+        best for 4 / 8 ranks); ``None`` / 0 - by world size (env ``FIB200_DL_AR_ALGO`` overrides).  The algorithm is a property
+        of the context because the two use the rotating receive buffers differently: do not change it between calls."""
         import torch.distributed as dist
 
         from ..comm.symm import SymmetricHeap
@@ -83,6 +91,12 @@ class FusedLinearTP:
         self.mc_recv = self.heap.mc(off)
         self.peer_recv = self.heap.peer_ptr_table(off)
         self.epoch = torch.zeros(4, dtype=torch.int32, device=self.heap.device)
+        algo = int(algo or os.environ.get("FIB200_DL_AR_ALGO", "0"))
+        if algo == 0:
+            algo = self.TWO_SHOT if (self.world >= 4 and 64 % self.world == 0) else self.ONE_SHOT
+        if algo == self.TWO_SHOT and 64 % self.world:
+            raise ValueError("FusedLinearTP: the two-shot all-reduce needs a world size that divides 64")
+        self.algo = algo
         self.heap.barrier()
 
 
@@ -213,7 +227,7 @@ def decode_linear(x: torch.Tensor, w: torch.Tensor, epi: int = EPI_PLAIN, *, out
         "dlinear_run", x, w, m, n, k, x.stride(0), w.stride(1) if blockk else w.stride(0), int(epi), out, out.stride(0), bias, row_sumsq,
         1.0 / float(norm_dim), float(eps), residual, residual.stride(0) if residual is not None else 0, sumsq_out, world, rank,
         ar.recv if ar else None, ar.hidden if ar else 0, ar.slot_elems if ar else 0, _ptr(ar.mc_recv) if ar else None,
-        ar.epoch if ar else None, ar.peer_recv if ar else None, cos_sin, cache_row, k_cache, v_cache, int(c_sh),
+        ar.epoch if ar else None, ar.peer_recv if ar else None, int(ar.algo) if ar else 0, cos_sin, cache_row, k_cache, v_cache, int(c_sh),
         int(num_q_heads), int(num_kv_heads), int(head_dim), 1 if interleave else 0, int(bn), int(split_k), int(smem_kb),
         1 if blockk else 0, dtype_code(x.dtype), 1 if enable_pdl else 0, stream_ptr(x))
     return out

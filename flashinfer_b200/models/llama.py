@@ -198,6 +198,9 @@ class LlamaDecodeEngine:
         decode_linear(res, self.lm_head, out=self._logits, row_sumsq=ss[2 * len(self.layers)], norm_dim=h, eps=cfg.rms_eps)
         if self.tp_size == 1:
             torch.argmax(self._logits, dim=-1, out=self.next_tokens)
+        elif self.comm is not None and hasattr(self.comm, "argmax_logits"):
+            # one kernel: shard argmax + (value, index) exchange over NVLink + winner selection
+            self.comm.argmax_logits(self._logits, self.tp_rank * self.vocab_shard, out=self.next_tokens)
         else:
             val, idx = torch.max(self._logits.float(), dim=-1)
             self.next_tokens.copy_(self._argmax_gather(val, idx + self.tp_rank * self.vocab_shard))
@@ -254,6 +257,8 @@ class LlamaDecodeEngine:
         n += 1
         if self.tp_size == 1:
             torch.argmax(self._logits, dim=-1, out=self.next_tokens)
+        elif hasattr(self.comm, "argmax_logits"):
+            self.comm.argmax_logits(self._logits, self.tp_rank * self.vocab_shard, out=self.next_tokens)
         else:
             val, idx = torch.max(self._logits.float(), dim=-1)
             self.next_tokens.copy_(self.comm.argmax_gather(val, idx + self.tp_rank * self.vocab_shard))

@@ -170,7 +170,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _tp_worker(rank, world, port, errs):
+def _tp_worker(rank, world, port, errs, algo=0):
     import torch.distributed as dist
 
     torch.cuda.set_device(rank)
@@ -179,8 +179,8 @@ def _tp_worker(rank, world, port, errs):
     try:
         worst = 0.0
         n = 4096
-        tp = dl.FusedLinearTP(None, 64, n, torch.bfloat16)
-        for it, (m, k, bn, s) in enumerate([(64, 512, 0, 0), (64, 1792, 0, 0), (3, 4096, 0, 0), (64, 2048, 64, 2), (33, 1024, 32, 1)] * 2):
+        tp = dl.FusedLinearTP(None, 64, n, torch.bfloat16, algo=algo)
+        for it, (m, k, bn, s) in enumerate([(64, 512, 0, 0), (64, 1792, 0, 0), (3, 4096, 0, 0), (64, 2048, 64, 2), (33, 1024, 32, 1), (17, 2048, 128, 4)] * 2):
             torch.manual_seed(100 + it)
             res = torch.randn(m, n, device="cuda").bfloat16()  # replicated residual stream
             torch.manual_seed(7 * it + rank)
@@ -222,12 +222,13 @@ def _tp_worker(rank, world, port, errs):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("algo", [1, 2], ids=["one_shot", "two_shot"])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_tp_residual_allreduce(world):
+def test_tp_residual_allreduce(world, algo):
     import torch.multiprocessing as mp
 
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     errs = mp.get_context("spawn").Manager().dict()
-    mp.spawn(_tp_worker, args=(world, _free_port(), errs), nprocs=world, join=True)
+    mp.spawn(_tp_worker, args=(world, _free_port(), errs, algo), nprocs=world, join=True)
     assert len(errs) == world and max(errs.values()) < 3e-2, dict(errs)

@@ -94,7 +94,8 @@ res["lm_head"] = timed(lambda i: dl.decode_linear(x, w[i % 2], out=lo, row_sumsq
 res["lm_head_floor"] = round(vs * H * 2 / 6.57e12 * 1e6, 2)
 del w
 # ---- o / down
-tp = dl.FusedLinearTP(None, 64, H) if world > 1 else None
+tp = dl.FusedLinearTP(None, 64, H, algo=1) if world > 1 else None
+tp2 = dl.FusedLinearTP(None, 64, H, algo=2) if world > 1 and 64 % world == 0 else None
 comm = None
 if world > 1:
     from flashinfer_b200.comm import TPCommunicator
@@ -109,7 +110,9 @@ for name, k in (("o", hq * D), ("down", inter)):
     res[f"{name}_local"] = timed(lambda i: dl.decode_linear(a, w[i % NB], dl.EPI_RESIDUAL, residual=resid, sumsq_out=sq), 16)
     res[f"{name}_floor"] = round(H * k * 2 / 6.57e12 * 1e6, 2)
     if world > 1:
-        res[f"{name}_fused_ar"] = timed(lambda i: dl.decode_linear(a, w[i % NB], dl.EPI_RESIDUAL, residual=resid, sumsq_out=sq, tp=tp), 16)
+        res[f"{name}_fused_ar_one_shot"] = timed(lambda i: dl.decode_linear(a, w[i % NB], dl.EPI_RESIDUAL, residual=resid, sumsq_out=sq, tp=tp), 16)
+        if tp2 is not None:
+            res[f"{name}_fused_ar_two_shot"] = timed(lambda i: dl.decode_linear(a, w[i % NB], dl.EPI_RESIDUAL, residual=resid, sumsq_out=sq, tp=tp2), 16)
         xo = torch.empty(B, H, device=dev, dtype=torch.bfloat16)
 
         def sep(i):
