@@ -140,8 +140,9 @@ def tp_gemm_rs(impl, rank, world):
         res = torch.randn(M // world, hidden, device="cuda").bfloat16()
         if impl == "ours":
             fn = lambda: comm.reduce_scatter(a, w, residual=res, rms_weight=gamma, eps=1e-5)  # noqa: E731
-            path = ("chunk-pipelined: persistent tcgen05 GEMM (gemm_nt) into symmetric staging || in-switch multimem.ld_reduce pull + residual "
-                    "+ row sum-of-squares on a side stream (rs_pull_rows); + rs_rmsnorm scale pass; no NCCL")
+            path = ("tcgen05 GEMM (cta_group::2 gemm_nt) into symmetric staging, in-switch multimem.ld_reduce pull + residual + row "
+                    "sum-of-squares (rs_pull_rows), rs_rmsnorm scale pass; schedule (one kernel / sequential / c pipeline chunks with "
+                    "the pull on a side stream) picked per shape by the tuner; no NCCL")
         else:
             def fn():
                 c = fi.mm_bf16(a, w.t()) if hasattr(fi, "mm_bf16") and os.environ.get("FIB200_REF_MM", "torch") == "flashinfer" else a @ w.t()
@@ -157,6 +158,11 @@ def tp_gemm_rs(impl, rank, world):
             t_link = M * hidden * 2 * (world - 1) / world / 770e9 * 1e3
             out[name] = {"ms": round(ms, 4), "k_local": K, "roofline_ms": round(max(t_compute, t_link), 4),
                          "fraction_of_roofline": round(max(t_compute, t_link) / ms, 3), "path": path}
+            if impl == "ours":  # schedule chosen by the per-shape tuner (0 one kernel | 1 GEMM then pull | c pipeline chunks) and its timings
+                out[name]["schedule_ms"] = {str(k): v for k, v in next(iter(getattr(comm, "_rs_tuning_log", {}).values()), {}).items()}
+                out[name]["schedule"] = next(iter(getattr(comm, "_rs_tuned", {}).values()), None)
+                comm.__dict__.pop("_rs_tuning_log", None)
+                comm.__dict__.pop("_rs_tuned", None)
         except Exception as e:  # noqa: BLE001
             out[name] = {"unavailable": f"{type(e).__name__}: {str(e)[:160]}"}
         del a, w, res

@@ -126,13 +126,11 @@ class GemmAllReduce:
         self._turn ^= 1
         stage, soff, stab = self._stage[self._turn]
         mc = self.heap.mc if self.use_nvls else (lambda off: 0)
-        chunks = self._pipeline_chunks(M, N, K) if pipelined is None else (int(pipelined) if pipelined else 0)
-        if chunks:
-            self._reduce_scatter_pipelined(a, w, stage, soff, stab, shard, residual, sumsq, rpr, chunks)
+        if pipelined is None:
+            chunks = self._tuned_chunks(a, w, stage, soff, stab, shard, residual, sumsq, rpr, bn)
         else:
-            self._mod.call("gemm_allreduce_nt", a, w, stage, shard, M, N, K, a.stride(0), w.stride(0), N, dtype_code(a.dtype), stab,
-                           self._flag_tab, None, self._done_tab, _ptr(mc(soff)), _ptr(mc(self._flag_off)), _ptr(0), self._expect,
-                           self._done_epoch, self.rank, self.world, 2, _MAX_TILES, bn, rpr, N, residual, sumsq, 1, stream_ptr(a))
+            chunks = int(pipelined) if pipelined else 0
+        self._run_rs(chunks, a, w, stage, soff, stab, shard, residual, sumsq, rpr, bn)
         if rms_weight is None:
             return shard
         normed = torch.empty_like(shard)
@@ -142,19 +140,75 @@ class GemmAllReduce:
 
 
     # ------------------------------------------------------------------ prefill sizes: chunk-pipelined GEMM / in-switch pull
-    def _pipeline_chunks(self, M: int, N: int, K: int) -> int:
-        """Number of pipeline chunks (0 = the one-kernel path).  From a few thousand rows on, the GEMM is long enough that pulling
-        chunk c through the switch while the tensor cores work on chunk c + 1 hides the whole reduce-scatter (or, at TP = 8 where
-        the link is the bound, the whole GEMM)."""
+    def _run_rs(self, chunks, a, w, stage, soff, stab, shard, residual, sumsq, rpr, bn) -> None:
+        M, K = a.shape
+        N = w.shape[0]
+        if chunks:
+            self._reduce_scatter_pipelined(a, w, stage, soff, stab, shard, residual, sumsq, rpr, chunks)
+            return
+        mc = self.heap.mc if self.use_nvls else (lambda off: 0)
+        self._mod.call("gemm_allreduce_nt", a, w, stage, shard, M, N, K, a.stride(0), w.stride(0), N, dtype_code(a.dtype), stab,
+                       self._flag_tab, None, self._done_tab, _ptr(mc(soff)), _ptr(mc(self._flag_off)), _ptr(0), self._expect,
+                       self._done_epoch, self.rank, self.world, 2, _MAX_TILES, bn, rpr, N, residual, sumsq, 1, stream_ptr(a))
+
+    def _chunk_candidates(self, M: int, N: int, K: int):
+        """Schedules of GEMM -> reduce-scatter for this shape: 0 = the one-kernel version (tile-by-tile overlap inside one
+        launch: wins at decode / small-prefill sizes), 1 = one full-size GEMM followed by one full-machine in-switch pull,
+        c >= 2 = c pipeline chunks (the pull of chunk i on a side stream under the GEMM of chunk i + 1)."""
         rpr = M // self.world
-        if not self.use_nvls and self.world > 4:
-            return 0
-        if M < 2048 or N % 256 or rpr % 128:
-            return 0
-        for c in (4, 8, 2):
-            if rpr % (c * 128) == 0 and rpr // c >= 256:
-                return c
-        return 0
+        if (not self.use_nvls and self.world > 4) or M < 2048 or N % 256 or rpr % 128:
+            return [0]
+        cands = [c for c in (4, 2, 8, 1) if rpr % (c * 128) == 0 and rpr // c >= 256]
+        if M <= 8192:
+            cands.append(0)
+        return cands or [0]
+
+    def _pipeline_chunks(self, M: int, N: int, K: int) -> int:
+        """Default schedule without tuning (first admissible candidate)."""
+        return self._chunk_candidates(M, N, K)[0]
+
+    def _tuned_chunks(self, a, w, stage, soff, stab, shard, residual, sumsq, rpr, bn) -> int:
+        """Schedule for this (M, N, K): the candidates of :meth:`_chunk_candidates` are timed once per shape on the live
+        tensors (device events, median of 3, max over ranks through one all-reduce so that every rank takes the same
+        decision) and the winner is cached - the communication / compute balance depends on the group size and on K, and a
+        wrong static choice costs integer factors at TP = 8 (profiles/tp_gemm_rs.md).  ``FIB200_RS_CHUNKS`` pins a schedule."""
+        import os
+
+        M, K = a.shape
+        N = w.shape[0]
+        key = (M, N, K, residual is not None, sumsq is not None)
+        tuned = self.__dict__.setdefault("_rs_tuned", {})
+        if key in tuned:
+            return tuned[key]
+        env = os.environ.get("FIB200_RS_CHUNKS")
+        cands = self._chunk_candidates(M, N, K)
+        if env is not None:
+            tuned[key] = int(env)
+            return tuned[key]
+        if len(cands) == 1 or torch.cuda.is_current_stream_capturing():
+            return cands[0]
+        times = []
+        for c in cands:
+            ts = []
+            for it in range(4):
+                if sumsq is not None:
+                    sumsq.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                self._run_rs(c, a, w, stage, soff, stab, shard, residual, sumsq, rpr, bn)
+                e1.record()
+                torch.cuda.synchronize()
+                if it:
+                    ts.append(e0.elapsed_time(e1))
+            times.append(sorted(ts)[len(ts) // 2])
+        t = torch.tensor(times, device=a.device, dtype=torch.float32)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        best = int(torch.argmin(t).item())
+        tuned[key] = cands[best]
+        self.__dict__.setdefault("_rs_tuning_log", {})[key] = {int(c): round(float(x), 4) for c, x in zip(cands, t.tolist())}
+        if sumsq is not None:
+            sumsq.zero_()
+        return tuned[key]
 
     def _reduce_scatter_pipelined(self, a, w, stage, soff, stab, shard, residual, sumsq, rpr: int, chunks: int) -> None:
         from ..gemm.dense import linear
@@ -167,6 +221,12 @@ class GemmAllReduce:
             self._side = torch.cuda.Stream(a.device)
         side = self._side
         m_c = rpr // chunks
+        if chunks == 1:  # one full-size GEMM, then one full-machine pull, same stream
+            linear(a, w, out=stage[:M])
+            lo = self.rank * rpr
+            self._mod.call("rs_pull_rows", _ptr(mc), stab, self._rs_sig_tab, self._rs_epoch, self.rank, self.world, N, lo, rpr, N,
+                           shard, N, residual, N, sumsq, _MAX_CTAS, dtype_code(a.dtype), main.cuda_stream)
+            return
         evs = []
         for c in range(chunks):
             for r in range(self.world):  # chunk c of EVERY rank's row range: all ranks pull concurrently, links stay evenly loaded

@@ -46,6 +46,9 @@ struct DecodeParams {
   int64_t q_stride_n, q_stride_h, o_stride_n, o_stride_h;
   int num_qo_heads, num_kv_heads, group, page_size, layout_hnd, rows_per_slot;
   int window_left, causal;
+  int kv_early;          // PDL: the preceding kernel only APPENDS the q_len newest tokens of every request to the cache, so the TMA
+                         // producers may fetch every older KV tile before griddepcontrol.wait (pipeline fill under the tail of the
+                         // previous kernel); they wait right before the first tile that can hold an appended token
   float sm_scale_log2;   // sm_scale * log2(e)
   float soft_cap;        // 0 = off ; else logits = cap * tanh(x * sm_scale / cap)
   float sm_scale;
@@ -205,12 +208,14 @@ __device__ __forceinline__ void decode_body(const CUtensorMap& tmK, const CUtens
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  ptx::grid_dep_wait();
+  const bool is_producer = warp == 0 || warp == 2 || warp == 3 || warp == 8;
+  bool dep_waited = !(p.kv_early && is_producer);
+  if (dep_waited) ptx::grid_dep_wait();
   ptx::grid_dep_launch();  // early trigger: dependents overlap their prologue, they still wait for our completion
 
   const int ps = p.page_size;
 
-  if (warp == 0 || warp == 2 || warp == 3 || warp == 8) {
+  if (is_producer) {
     // ============================ TMA producers (4 warps) ============================
     // ncu showed one producer warp saturating on UTMALDG issue (the per-lane page boxes are serialised
     // through an ELECT/R2UR loop, ~100 cycles each), so the 32 boxes of a tile are split over four
@@ -232,8 +237,13 @@ __device__ __forceinline__ void decode_body(const CUtensorMap& tmK, const CUtens
     for (int seg = seg_begin; seg < seg_end; ++seg) {
       const int32_t* si = p.seg_info + seg * kSegInts;
       const int kv_head = si[1], t0 = si[2], t1 = si[3], page_start = si[8], num_pages = si[9];
+      const int first_new = si[7] - si[6];  // kv_len - q_len: position of the oldest token the preceding kernel may have written
       for (int ti = t0; ti < t1; ++ti) {
         const TileGeom g2 = tile_geom(ti, ps);
+        if (!dep_waited && g2.token_start + g2.rows > first_new) {
+          ptx::grid_dep_wait();
+          dep_waited = true;
+        }
         int n_boxes, box_rows;
         if (ps <= kTileKV) {
           n_boxes = min(kTileKV / ps, num_pages - g2.first_page);
@@ -735,6 +745,7 @@ extern "C" int decode_paged_run(void* q, void* k_cache, void* v_cache, void* out
   p.layout_hnd = (int)layout_hnd;
   p.window_left = (int)window_left;
   p.causal = (int)causal;
+  p.kv_early = (pdl == 2) ? 1 : 0;
   p.sm_scale = (float)sm_scale;
   p.sm_scale_log2 = (float)(sm_scale * 1.4426950408889634);
   p.soft_cap = (float)soft_cap;

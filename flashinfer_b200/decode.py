@@ -290,7 +290,12 @@ class BatchDecodeWithPagedKVCacheWrapper:
         window_left: Optional[int] = None,
         sinks: Optional[torch.Tensor] = None,
         kv_cache_sf=None,
+        kv_prefetch: bool = False,
     ):
+        """``kv_prefetch=True`` (with PDL): promise that the kernel launched just before this one on the stream only APPENDS the
+        newest ``q_len`` tokens of each request to the cache (an append / fused QKV+RoPE+append kernel): the TMA producers then
+        stream all older KV tiles before the programmatic dependency resolves, filling the pipeline under the previous
+        kernel's tail."""
         if not self._planned:
             raise RuntimeError("plan() must be called before run()")
         k_cache, v_cache = unpack_paged_kv_cache(paged_kv_cache, self._kv_layout)
@@ -329,7 +334,8 @@ class BatchDecodeWithPagedKVCacheWrapper:
             if want_lse:
                 lse.copy_(lse_ref)
         else:
-            self._run_sm100(q, k_cache, v_cache, out, lse if want_lse else None, sm_scale, window_left, enable_pdl)
+            self._run_sm100(q, k_cache, v_cache, out, lse if want_lse else None, sm_scale, window_left,
+                            2 if (kv_prefetch and (enable_pdl is None or enable_pdl)) else enable_pdl)
         if sinks is not None:
             # the sink only adds exp(sink) to the softmax denominator: fold it in from (o, lse)
             from .attention._core import apply_attention_sink
@@ -389,7 +395,7 @@ class BatchDecodeWithPagedKVCacheWrapper:
             self._num_qo_heads, self._num_kv_heads, self._head_dim, page_size, k_cache.shape[0], sp, sn, sh,
             1 if self._kv_layout == "HND" else 0, q.stride(0), q.stride(1), out.stride(0), out.stride(1),
             float(sm_scale), float(self._logits_soft_cap), int(window_left), causal, dtype_code(q.dtype),
-            dtype_code(k_cache.dtype), 1 if (enable_pdl is None or enable_pdl) else 0, stream_ptr(q),
+            dtype_code(k_cache.dtype), 2 if enable_pdl == 2 else (1 if (enable_pdl is None or enable_pdl) else 0), stream_ptr(q),
         )
 
 

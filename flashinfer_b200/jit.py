@@ -492,8 +492,7 @@ _GEN_MAP = {
     "gen_act_and_mul_module": "activation", "gen_batch_attention_module": "prefill_sm100", "gen_batch_decode_mla_module": "mla_sm100",
     "gen_batch_decode_module": "decode_sm100", "gen_batch_mla_module": "mla_sm100", "gen_batch_pod_module": "pod_sm100",
     "gen_batch_prefill_module": "prefill_sm100", "gen_comm_alltoall_module": "comm_alltoall", "gen_cudnn_fmha_module": "prefill_sm100",
-    "gen_customize_batch_decode_module": "attention_generic", "gen_customize_batch_prefill_module": "attention_generic",
-    "gen_customize_single_decode_module": "attention_generic", "gen_customize_single_prefill_module": "attention_generic",
+    "gen_customize_batch_decode_module": "attention_generic", "gen_customize_single_decode_module": "attention_generic",
     "gen_dcp_alltoall_module": "comm_collectives", "gen_dsv3_fused_routing_module": "moe", "gen_dsv3_router_gemm_module": "gemm_sm100",
     "gen_fmha_cutlass_sm100a_module": "prefill_sm100", "gen_fmha_v2_module": "prefill_sm100", "gen_fp4_kv_dequantization_module": "quantization",
     "gen_fp4_kv_quantization_module": "quantization", "gen_moe_alltoall_module": "comm_alltoall", "gen_moe_utils_module": "moe",
@@ -515,6 +514,92 @@ def _make_gen(fn_name: str, module: str):
 
 for _fn, _mod in _GEN_MAP.items():
     globals()[_fn] = _make_gen(_fn, _mod)
+
+
+# ----------------------------------------------------------------------------
+# User attention variants compiled INTO the tcgen05 prefill kernel.
+# Reference: flashinfer/jit/attention/modules.py gen_customize_batch_prefill_module / gen_customize_single_prefill_module
+# (:1189-1708) + include/flashinfer/attention/variant_helper.cuh (REGISTER_LOGITS_TRANSFORM / REGISTER_LOGITS_MASK).
+# ----------------------------------------------------------------------------
+_VARIANT_CTYPES = {"float": "float", "float32": "float", "double": "double", "half": "__half", "float16": "__half",
+                   "bfloat16": "__nv_bfloat16", "nv_bfloat16": "__nv_bfloat16", "int32_t": "int32_t", "int32": "int32_t", "int": "int32_t",
+                   "int64_t": "int64_t", "int64": "int64_t", "uint8_t": "uint8_t", "uint8": "uint8_t", "bool": "bool", "uint32_t": "uint32_t"}
+
+_VARIANT_PRELUDE = """// generated by flashinfer_b200.jit.gen_customize_batch_prefill_module - do not edit
+// A variant is a struct with two static device hooks evaluated for every logit in the softmax pass of the tcgen05 prefill kernel:
+//   static __device__ float LogitsTransform(const VariantCtx& ctx, float logits, int kv_idx);   // logits = q.k * sm_scale (after soft-cap)
+//   static __device__ bool  LogitsMask(const VariantCtx& ctx, int kv_idx);                       // false = masked out
+// ctx carries batch_idx, qo_idx (row inside the request), qo_head_idx, kv_head_idx, qo_len, kv_len.  The additional tensors / scalars
+// declared to the generator are visible under their names (tensors as typed const pointers, scalars as float).
+// The reference's REGISTER_* macros are accepted for the two hooks this kernel implements.
+#define REGISTER_LOGITS_TRANSFORM(params, logits, batch_idx, qo_idx, kv_idx, qo_head_idx, kv_head_idx, ...)                          \
+  static __device__ __forceinline__ float LogitsTransform(const VariantCtx& ctx, float logits, int kv_idx) {                       \
+    const int batch_idx = ctx.batch_idx, qo_idx = ctx.qo_idx, qo_head_idx = ctx.qo_head_idx, kv_head_idx = ctx.kv_head_idx;        \
+    (void)batch_idx; (void)qo_idx; (void)qo_head_idx; (void)kv_head_idx;                                                           \
+    __VA_ARGS__                                                                                                                    \
+  }
+#define REGISTER_LOGITS_MASK(params, batch_idx, qo_idx, kv_idx, qo_head_idx, kv_head_idx, ...)                                       \
+  static __device__ __forceinline__ bool LogitsMask(const VariantCtx& ctx, int kv_idx) {                                           \
+    const int batch_idx = ctx.batch_idx, qo_idx = ctx.qo_idx, qo_head_idx = ctx.qo_head_idx, kv_head_idx = ctx.kv_head_idx;        \
+    (void)batch_idx; (void)qo_idx; (void)qo_head_idx; (void)kv_head_idx;                                                           \
+    __VA_ARGS__                                                                                                                    \
+  }
+struct VariantDefaults {
+  static __device__ __forceinline__ float LogitsTransform(const VariantCtx&, float logits, int) { return logits; }
+  static __device__ __forceinline__ bool LogitsMask(const VariantCtx&, int) { return true; }
+};
+"""
+
+
+class AttentionVariantSpec(JitSpec):
+    """JitSpec of a prefill module with a compiled-in variant; remembers the declared extra arguments of ``run()``."""
+
+    additional_tensor_names: Sequence[str] = ()
+    additional_scalar_names: Sequence[str] = ()
+
+
+def gen_customize_batch_prefill_module(backend, uri: str, dtype_q=None, dtype_kv=None, dtype_o=None, idtype=None, head_dim_qk: int = 128,
+                                       head_dim_vo: int = 128, additional_tensor_names: Sequence[str] = (),
+                                       additional_tensor_dtypes: Sequence[str] = (), additional_scalar_names: Sequence[str] = (),
+                                       additional_scalar_dtypes: Sequence[str] = (), variant_name: str = "Variant",
+                                       variant_decl: str = "", **kwargs) -> AttentionVariantSpec:
+    """Compile ``variant_decl`` (C++: ``struct <variant_name> : VariantDefaults { ... }`` overriding ``LogitsTransform`` and / or
+    ``LogitsMask``, see the generated header's prelude) into a private copy of the tcgen05 prefill kernel and return its spec;
+    ``BatchPrefillWith{Paged,Ragged}KVCacheWrapper(..., jit_args=[uri, dtype_q, dtype_kv, dtype_o, idtype, head_dim_qk, head_dim_vo,
+    tensor_names, tensor_dtypes, scalar_names, scalar_dtypes, variant_name, variant_decl])`` builds and uses it, the extra
+    tensors / scalars follow ``q, kv`` in ``run()`` (at most 8 of each; scalars reach the device as float)."""
+    if len(additional_tensor_names) > 8 or len(additional_scalar_names) > 8:
+        raise ValueError("attention variants take at most 8 additional tensors and 8 additional scalars")
+    if len(additional_tensor_names) != len(additional_tensor_dtypes) or len(additional_scalar_names) != len(additional_scalar_dtypes):
+        raise ValueError("names / dtypes of the additional arguments must pair up")
+    gen_dir = LIB_DIR / "gen"
+    gen_dir.mkdir(parents=True, exist_ok=True)
+    name = "prefill_variant_" + "".join(c if c.isalnum() or c == "_" else "_" for c in str(uri))
+    lines = [_VARIANT_PRELUDE]
+    for i, (n, dt) in enumerate(zip(additional_tensor_names, additional_tensor_dtypes)):
+        ct = _VARIANT_CTYPES.get(str(dt).replace("torch.", ""), None)
+        if ct is None:
+            raise ValueError(f"unsupported additional tensor dtype {dt!r}")
+        lines.append(f"#define {n} (reinterpret_cast<const {ct}*>(ctx.params->var_ptr[{i}]))")
+    for i, n in enumerate(additional_scalar_names):
+        lines.append(f"#define {n} (ctx.params->var_f[{i}])")
+    lines.append(variant_decl)
+    header = gen_dir / f"{name}.cuh"
+    text = "\n".join(lines) + "\n"
+    if not header.exists() or header.read_text() != text:
+        header.write_text(text)
+    flags = [f"-DFIB_PREFILL_VARIANT={variant_name}", f'-DFIB_PREFILL_VARIANT_HEADER="{header}"']
+    spec = AttentionVariantSpec(name, ["attention/prefill_sm100.cu"], extra_flags=flags, deps=[str(header)])
+    spec.additional_tensor_names = tuple(additional_tensor_names)
+    spec.additional_scalar_names = tuple(additional_scalar_names)
+    REGISTRY[name] = spec
+    _USER_SPECS[name] = spec
+    return spec
+
+
+def gen_customize_single_prefill_module(backend, uri: str, *args, **kwargs) -> AttentionVariantSpec:
+    """Single-request flavour: the same module (a single request is a batch of one)."""
+    return gen_customize_batch_prefill_module(backend, uri, *args, **kwargs)
 
 
 def _uri(prefix: str):

@@ -8,6 +8,7 @@ CUDA graph by ``LlamaDecodeEngine.capture()``.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -72,6 +73,7 @@ class LlamaDecodeEngine:
         self.block_major_k = (self.fused and self.device.type == "cuda") if block_major_k is None else bool(block_major_k)
         if self.fused and max_batch > 64:
             raise ValueError("the fused decode path handles at most 64 tokens per step")
+        self.kv_prefetch = os.environ.get("FIB200_KV_PREFETCH", "1") != "0"
         self.tp_fused = None
         if self.fused and tp_size > 1:
             self.tp_fused = FusedLinearTP(tp_group if tp_group is not None else (comm.group if comm is not None else None),
@@ -189,7 +191,8 @@ class LlamaDecodeEngine:
             decode_linear(res, l["wqkv"], EPI_ROPE_APPEND, out=q2d, row_sumsq=ss[2 * li], norm_dim=h, eps=cfg.rms_eps,
                           cos_sin=self._cos_sin, cache_row=self._cache_row, k_cache=l["k_cache"], v_cache=l["v_cache"],
                           num_q_heads=hq, num_kv_heads=hkv, head_dim=d, head_stride=head_stride)
-            self.wrapper.run(self._attn_q, (l["k_cache"], l["v_cache"]), out=self._attn)
+            # the QKV kernel just before only appended this step's token: older KV tiles are prefetched under its tail
+            self.wrapper.run(self._attn_q, (l["k_cache"], l["v_cache"]), out=self._attn, kv_prefetch=self.kv_prefetch)
             decode_linear(self._attn.view(b, hq * d), l["wo"], EPI_RESIDUAL, residual=res, sumsq_out=ss[2 * li + 1],
                           tp=self.tp_fused)
             decode_linear(res, l["wgu"], EPI_GATED_SILU, out=self._act, row_sumsq=ss[2 * li + 1], norm_dim=h, eps=cfg.rms_eps)

@@ -67,8 +67,8 @@ def single_prefill_with_kv_cache(
     or ``[Hkv, kv_len, D]`` (HND).  Returns ``o`` (and base-2 ``lse [qo_len, Hq]``)."""
     check_kv_layout(kv_layout)
     check_pos_encoding_mode(pos_encoding_mode)
-    if pos_encoding_mode != "NONE":
-        raise NotImplementedError("in-kernel RoPE/ALiBi: apply flashinfer_b200.rope first")
+    if pos_encoding_mode not in ("NONE", "ALIBI"):
+        raise NotImplementedError("in-kernel RoPE: apply flashinfer_b200.rope first (ALiBi runs inside the kernel)")
     d = q.shape[-1]
     if sm_scale is None:
         sm_scale = 1.0 / math.sqrt(d)
@@ -80,11 +80,14 @@ def single_prefill_with_kv_cache(
         mask = _unpack_bits(packed_custom_mask, qo_len * kv_len).view(qo_len, kv_len)
     elif custom_mask is not None:
         mask = custom_mask.view(qo_len, kv_len)
-    fast = q.is_cuda and mask is None and q.shape[-1] in (128, 192) and v.shape[-1] == 128 and q.dtype in (
+    fast = q.is_cuda and q.shape[-1] in (128, 192) and v.shape[-1] == 128 and q.dtype in (
         torch.float16, torch.bfloat16) and k.dtype == q.dtype
+    alibi = pos_encoding_mode == "ALIBI"
     if not q.is_cuda:
+        from .utils import get_alibi_slopes
+
         o, lse = reference.attention_ref(q, k, v, causal and mask is None, sm_scale, logits_soft_cap or 0.0,
-                                         window_left, custom_mask=mask)
+                                         window_left, custom_mask=mask, alibi_slopes=get_alibi_slopes(q.shape[1]) if alibi else None)
     elif not fast:
         from .attention import generic as _g
 
@@ -100,16 +103,19 @@ def single_prefill_with_kv_cache(
         mi = torch.tensor([0, qo_len * kv_len], dtype=torch.int32, device=q.device) if mask is not None else None
         ks = float(scale_k) if scale_k is not None else 1.0
         qs_ = float(scale_q) if scale_q is not None else 1.0
+        from .utils import get_alibi_slopes
+
         _g.run(q, k, v, o, lse, qi, ki, None, None, 1, (0, k.stride(0), k.stride(1)), (0, v.stride(0), v.stride(1)), k.shape[1],
-               causal and mask is None, window_left, sm_scale * qs_, logits_soft_cap or 0.0, pm, mi, None, ks,
-               float(scale_v) if scale_v is not None else 1.0)
+               causal and mask is None, window_left, sm_scale * qs_, logits_soft_cap or 0.0, pm, mi,
+               get_alibi_slopes(q.shape[1], q.device) if alibi else None, ks, float(scale_v) if scale_v is not None else 1.0)
     else:
         ws = torch.empty(16 * 1024 * 1024, dtype=torch.uint8, device=q.device)
         w = BatchPrefillWithRaggedKVCacheWrapper(ws, "NHD")
         qo_indptr = torch.tensor([0, qo_len], dtype=torch.int32)
         kv_indptr = torch.tensor([0, kv_len], dtype=torch.int32)
         w.plan(qo_indptr, kv_indptr, q.shape[1], k.shape[1], d, head_dim_vo=v.shape[-1], causal=causal, sm_scale=sm_scale,
-               window_left=window_left, logits_soft_cap=logits_soft_cap, q_data_type=q.dtype)
+               window_left=window_left, logits_soft_cap=logits_soft_cap, q_data_type=q.dtype,
+               custom_mask=mask.flatten() if mask is not None else None, pos_encoding_mode=pos_encoding_mode)
         o, lse = w.run(q, k, v, return_lse=True)
     if o_dtype is not None and o.dtype != o_dtype:
         o = o.to(o_dtype)
@@ -141,6 +147,17 @@ class _BatchPrefillBase:
         self._planned = False
         self._backend = "sm100"
         self._cta_budget: Optional[int] = None  # POD: restrict the persistent grid to this many SMs
+        # user attention variant (reference: jit_args of the wrappers + flashinfer/jit/attention/modules.py gen_customize_*):
+        # LogitsTransform / LogitsMask hooks compiled INTO the tcgen05 prefill kernel (csrc/attention/prefill_sm100.cu)
+        self._variant_mod = None
+        self._variant_tensor_names, self._variant_scalar_names = [], []
+        if jit_args is not None:
+            spec = jit.gen_customize_batch_prefill_module(backend, *jit_args, **(jit_kwargs or {}))
+            self._variant_mod = spec.build_and_load()
+            self._variant_tensor_names = list(spec.additional_tensor_names)
+            self._variant_scalar_names = list(spec.additional_scalar_names)
+        self._alibi = None
+        self._mask_words = self._mask_bit_indptr = None
 
     @property
     def is_cuda_graph_enabled(self) -> bool:
@@ -158,7 +175,8 @@ class _BatchPrefillBase:
             raise ValueError("num_qo_heads must be a multiple of num_kv_heads")
         self._num_qo_heads, self._num_kv_heads = num_qo_heads, num_kv_heads
         self._head_dim_qk, self._head_dim_vo = head_dim_qk, head_dim_vo or head_dim_qk
-        self._causal = bool(causal)
+        self._causal = bool(causal) and custom_mask is None  # MaskMode::kCustom overrides causal (reference prefill.cuh)
+        causal = self._causal
         self._sm_scale = sm_scale if sm_scale is not None else 1.0 / math.sqrt(head_dim_qk)
         self._window_left = window_left
         self._logits_soft_cap = float(logits_soft_cap or 0.0)
@@ -193,6 +211,18 @@ class _BatchPrefillBase:
         dev32[:need].copy_(pin32[:need], non_blocking=non_blocking and self.device.type == "cuda")
         self._work_info = dev32[: max(max_work, 1) * _WORK_INTS]
         self._cta_work_indptr = dev32[max(max_work, 1) * _WORK_INTS : need]
+        self._mask_words = self._mask_bit_indptr = None
+        if custom_mask is not None and self.device.type == "cuda":
+            # packed little-endian bit stream (bit i = element i of the concatenated [q_len, kv_len] masks) as 32-bit words with two
+            # spare words at the end (the kernel funnel-shifts 32 bits out of two neighbouring words), int64 bit offset per request
+            from .attention.generic import pack_mask_bits
+
+            by = pack_mask_bits(custom_mask.to(self.device).bool())
+            pad = (-by.numel()) % 4 + 8
+            self._mask_words = torch.cat([by, torch.zeros(pad, dtype=torch.uint8, device=self.device)]).view(torch.int32)
+            bits = torch.zeros(self._batch_size + 1, dtype=torch.int64)
+            bits[1:] = torch.cumsum((qo_host[1:] - qo_host[:-1]).long() * self._kv_lens_host.long(), 0)
+            self._mask_bit_indptr = bits.to(self.device)
         self._planned = True
 
     def _run_reference(self, q, get_kv, out, lse, sm_scale, window_left):
@@ -212,7 +242,8 @@ class _BatchPrefillBase:
                 l_b = torch.full((qe - qs, self._num_qo_heads), float("-inf"), device=q.device)
             else:
                 o_b, l_b = reference.attention_ref(q[qs:qe], k, v, self._causal and mask is None, sm_scale,
-                                                   self._logits_soft_cap, window_left, custom_mask=mask)
+                                                   self._logits_soft_cap, window_left, custom_mask=mask,
+                                                   alibi_slopes=self._alibi)
             out[qs:qe] = o_b.to(out.dtype)
             if lse is not None:
                 lse[qs:qe] = l_b
@@ -220,8 +251,7 @@ class _BatchPrefillBase:
 
     def _launch_sm100(self, q, k, v, out, lse, sm_scale, window_left, paged, kv_indices, page_args, enable_pdl,
                       k_scale=None, v_scale=None):
-        shape_ok = (self._head_dim_qk in (128, 192) and self._head_dim_vo == 128 and q.dtype in (torch.float16, torch.bfloat16)
-                    and self._custom_mask is None)
+        shape_ok = self._head_dim_qk in (128, 192) and self._head_dim_vo == 128 and q.dtype in (torch.float16, torch.bfloat16)
         if shape_ok and k.dtype in (torch.float8_e4m3fn, torch.float8_e5m2) and q.shape[0] >= 4 * self._batch_size:
             # fp8 KV with a compute-bound (prefill-sized) query: widen the KV that this call touches to the query dtype
             # once (1 B read + 2 B write per element, negligible next to the O(q * kv) attention work) and stay on the
@@ -240,17 +270,42 @@ class _BatchPrefillBase:
                 page_args = (1, k.shape[0], k.stride(0), k.stride(0), k.stride(1), 0, v.stride(0), v.stride(0), v.stride(1))
         fast = shape_ok and k.dtype == q.dtype and v.dtype == q.dtype
         if not fast:
+            if self._variant_mod is not None:
+                raise NotImplementedError("user attention variants run on the tcgen05 prefill kernel: f16 / bf16, head_dim 128 (192 qk)")
             return self._launch_generic(q, k, v, out, lse, sm_scale, window_left, paged, kv_indices, page_args, enable_pdl,
                                         k_scale, v_scale)
         page_size, num_pages_total, sp, sn, sh, hnd = page_args[:6]
         vsp, vsn, vsh = page_args[6:9] if len(page_args) >= 9 else (sp, sn, sh)
-        jit.load("prefill_sm100").call(
+        var_ptrs = var_scalars = None
+        if self._variant_mod is not None:
+            extra = list(getattr(self, "_variant_args", ()))
+            nt, ns = len(self._variant_tensor_names), len(self._variant_scalar_names)
+            if len(extra) != nt + ns:
+                raise ValueError(f"variant expects {nt} tensors {self._variant_tensor_names} + {ns} scalars {self._variant_scalar_names} "
+                                 f"after the q / kv arguments of run(), got {len(extra)}")
+            self._variant_keepalive = [t.contiguous() for t in extra[:nt]]
+            var_ptrs = torch.tensor([t.data_ptr() for t in self._variant_keepalive] + [0] * (8 - nt), dtype=torch.int64)
+            var_scalars = torch.tensor([float(x) for x in extra[nt:]] + [0.0] * (8 - ns), dtype=torch.float64)
+        (self._variant_mod or jit.load("prefill_sm100")).call(
             "prefill_run", q, k, v, out, lse, kv_indices, self._kv_page_indptr_dev if paged else None,
             self._work_info, self._cta_work_indptr, self._num_ctas, q.shape[0], self._num_qo_heads, self._num_kv_heads,
             self._head_dim_qk, 1 if paged else 0, page_size, num_pages_total, sp, sn, sh, vsp, vsn, vsh, hnd, q.stride(0),
             q.stride(1), out.stride(0), out.stride(1), float(sm_scale), float(self._logits_soft_cap), int(window_left),
-            1 if self._causal else 0, dtype_code(q.dtype), 1 if (enable_pdl is None or enable_pdl) else 0, stream_ptr(q),
+            1 if self._causal else 0, self._mask_words, self._mask_bit_indptr, self._alibi,
+            1 if self._variant_mod is not None else 0, var_ptrs, var_scalars,
+            dtype_code(q.dtype), 1 if (enable_pdl is None or enable_pdl) else 0, stream_ptr(q),
         )
+
+    def _set_pos_encoding(self, pos_encoding_mode: str, num_qo_heads: int) -> None:
+        """ALiBi is a logits transform of the softmax pass (slopes per head); RoPE has to be applied by flashinfer_b200.rope."""
+        check_pos_encoding_mode(pos_encoding_mode)
+        if pos_encoding_mode not in ("NONE", "ALIBI"):
+            raise NotImplementedError("in-kernel RoPE: apply flashinfer_b200.rope to q / k first (ALiBi runs inside the kernel)")
+        self._alibi = None
+        if pos_encoding_mode == "ALIBI":
+            from .utils import get_alibi_slopes
+
+            self._alibi = get_alibi_slopes(num_qo_heads, self.device).float().contiguous()
 
     def _launch_generic(self, q, k, v, out, lse, sm_scale, window_left, paged, kv_indices, page_args, enable_pdl, k_scale, v_scale):
         """Catch-all CUDA-core kernel: other head dims, fp8 KV, custom masks."""
@@ -281,7 +336,7 @@ class _BatchPrefillBase:
             page_size, _, sp, sn, sh, _ = page_args[:6]
             _g.run(q, k, v, out, lse, self._gen_qo, self._gen_kv, kv_indices, self._gen_last, page_size, (sp, sn, sh), (sp, sn, sh),
                    self._num_kv_heads, causal, window_left, sm_scale, self._logits_soft_cap, self._gen_mask,
-                   getattr(self, "_gen_mask_indptr", None), None, 1.0, 1.0, enable_pdl is None or enable_pdl)
+                   getattr(self, "_gen_mask_indptr", None), self._alibi, 1.0, 1.0, enable_pdl is None or enable_pdl)
         else:
             # ragged: requests may be non-contiguous in k, so each request is one launch over its [start, start+len) slice
             for b in range(self._batch_size):
@@ -298,7 +353,7 @@ class _BatchPrefillBase:
                     mi = torch.tensor([0, (qe - qs) * ln], dtype=torch.int32, device=dev)
                 _g.run(q[qs:qe], k[st:st + ln], v[st:st + ln], out[qs:qe], lse[qs:qe] if lse is not None else None, qi, ki, None,
                        None, 1, (0, k.stride(0), k.stride(1)), (0, v.stride(0), v.stride(1)), self._num_kv_heads, causal,
-                       window_left, sm_scale, self._logits_soft_cap, pm, mi, None, 1.0, 1.0, enable_pdl is None or enable_pdl)
+                       window_left, sm_scale, self._logits_soft_cap, pm, mi, self._alibi, 1.0, 1.0, enable_pdl is None or enable_pdl)
 
     def end_forward(self) -> None:
         pass
@@ -312,7 +367,7 @@ class BatchPrefillWithRaggedKVCacheWrapper(_BatchPrefillBase):
                  backend: str = "auto", jit_args=None, jit_kwargs=None):
         super().__init__(float_workspace_buffer, kv_layout, use_cuda_graph, qo_indptr_buf=qo_indptr_buf,
                          kv_indptr_buf=kv_indptr_buf, custom_mask_buf=custom_mask_buf, mask_indptr_buf=mask_indptr_buf,
-                         backend=backend)
+                         backend=backend, jit_args=jit_args, jit_kwargs=jit_kwargs)
 
     def plan(self, qo_indptr, kv_indptr, num_qo_heads, num_kv_heads, head_dim_qk, head_dim_vo=None, custom_mask=None,
              packed_custom_mask=None, causal=False, pos_encoding_mode="NONE", use_fp16_qk_reduction=False,
@@ -320,9 +375,7 @@ class BatchPrefillWithRaggedKVCacheWrapper(_BatchPrefillBase):
              q_data_type="float16", kv_data_type=None, o_data_type=None, non_blocking=True, prefix_len_ptr=None,
              token_pos_in_items_ptr=None, token_pos_in_items_len=0, max_item_len_ptr=None, fixed_split_size=None,
              disable_split_kv=False) -> None:
-        check_pos_encoding_mode(pos_encoding_mode)
-        if pos_encoding_mode != "NONE":
-            raise NotImplementedError("in-kernel positional encoding")
+        self._set_pos_encoding(pos_encoding_mode, num_qo_heads)
         kv_host = kv_indptr.to("cpu", torch.int32)
         self._kv_start_host = kv_host[:-1].contiguous()
         self._kv_indptr_ragged_host = kv_host
@@ -340,6 +393,7 @@ class BatchPrefillWithRaggedKVCacheWrapper(_BatchPrefillBase):
             enable_pdl=None, window_left=None):
         if not self._planned:
             raise RuntimeError("plan() must be called before run()")
+        self._variant_args = args
         if self._kv_layout == "HND":
             k, v = k.transpose(0, 1), v.transpose(0, 1)
         sm_scale = self._sm_scale * (q_scale or 1.0) * (k_scale or 1.0)
@@ -381,7 +435,7 @@ class BatchPrefillWithPagedKVCacheWrapper(_BatchPrefillBase):
         super().__init__(float_workspace_buffer, kv_layout, use_cuda_graph, qo_indptr_buf=qo_indptr_buf,
                          paged_kv_indptr_buf=paged_kv_indptr_buf, paged_kv_indices_buf=paged_kv_indices_buf,
                          paged_kv_last_page_len_buf=paged_kv_last_page_len_buf, custom_mask_buf=custom_mask_buf,
-                         mask_indptr_buf=mask_indptr_buf, backend=backend)
+                         mask_indptr_buf=mask_indptr_buf, backend=backend, jit_args=jit_args, jit_kwargs=jit_kwargs)
 
     def plan(self, qo_indptr, paged_kv_indptr, paged_kv_indices, paged_kv_last_page_len, num_qo_heads, num_kv_heads,
              head_dim_qk, page_size, head_dim_vo=None, custom_mask=None, packed_custom_mask=None, causal=False,
@@ -390,9 +444,7 @@ class BatchPrefillWithPagedKVCacheWrapper(_BatchPrefillBase):
              o_data_type=None, non_blocking=True, prefix_len_ptr=None, token_pos_in_items_ptr=None,
              token_pos_in_items_len=0, max_item_len_ptr=None, seq_lens=None, seq_lens_q=None, block_tables=None,
              max_token_per_sequence=None, max_sequence_kv=None, fixed_split_size=None, disable_split_kv=False) -> None:
-        check_pos_encoding_mode(pos_encoding_mode)
-        if pos_encoding_mode != "NONE":
-            raise NotImplementedError("in-kernel positional encoding")
+        self._set_pos_encoding(pos_encoding_mode, num_qo_heads)
         self._page_size = page_size
         indptr_host = _host_i32(paged_kv_indptr)
         last_host = _host_i32(paged_kv_last_page_len)
@@ -415,6 +467,7 @@ class BatchPrefillWithPagedKVCacheWrapper(_BatchPrefillBase):
             return_lse=False, enable_pdl=None, window_left=None, sinks=None):
         if not self._planned:
             raise RuntimeError("plan() must be called before run()")
+        self._variant_args = args
         user_return_lse = return_lse
         return_lse = return_lse or sinks is not None
         k_cache, v_cache = unpack_paged_kv_cache(paged_kv_cache, self._kv_layout)

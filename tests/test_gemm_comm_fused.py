@@ -50,6 +50,12 @@ def _worker(rank, world, port, errs):
                 got = gar.reduce_scatter(a, w)
                 torch.cuda.synchronize()
                 worst = max(worst, float((got.float() - mine).abs().max() / full.abs().max()))
+                if M == 2048:  # every schedule of the prefill-size path: one kernel, full GEMM + full pull, 2 / 4 pipeline chunks
+                    for sched in (0, 1, 2, 4):
+                        normed, shard = gar.reduce_scatter(a, w, residual=res, rms_weight=gamma, eps=1e-5, pipelined=sched)
+                        torch.cuda.synchronize()
+                        x = mine + res.float()
+                        worst = max(worst, float((shard.float() - x).abs().max() / x.abs().max()))
                 for _ in range(2):  # twice: the sum-of-squares scratch must be left clean
                     normed, shard = gar.reduce_scatter(a, w, residual=res, rms_weight=gamma, eps=1e-5)
                     torch.cuda.synchronize()

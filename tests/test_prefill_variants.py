@@ -1,0 +1,161 @@
+"""Attention variants inside the tcgen05 prefill kernel (csrc/attention/prefill_sm100.cu softmax passes): packed / dense custom masks,
+ALiBi, and user LogitsTransform / LogitsMask hooks JIT-compiled into the kernel through jit.gen_customize_batch_prefill_module.
+Reference parity: tests/attention/test_batch_prefill_kernels.py (custom mask), test_alibi.py, tests/utils/test_jit_example.py."""
+import math
+
+import pytest
+import torch
+
+import flashinfer_b200 as fi
+from flashinfer_b200 import jit, reference
+
+VARIANT_DECL = r"""
+struct SoftBiasVariant : VariantDefaults {
+  // logits * temp + bias[head] * (kv position - query position);   every 7th key (except key 0) is masked out
+  static __device__ __forceinline__ float LogitsTransform(const VariantCtx& ctx, float logits, int kv_idx) {
+    return logits * temp + bias[ctx.qo_head_idx] * float(kv_idx - (ctx.kv_len - ctx.qo_len + ctx.qo_idx));
+  }
+  REGISTER_LOGITS_MASK(params, batch_idx, qo_idx, kv_idx, qo_head_idx, kv_head_idx, { return (kv_idx % 7) != 3 || kv_idx == 0; })
+};
+"""
+JIT_ARGS = ["test_softbias", torch.bfloat16, torch.bfloat16, torch.bfloat16, torch.int32, 128, 128, ["bias"], ["float"], ["temp"],
+            ["double"], "SoftBiasVariant", VARIANT_DECL]
+
+
+def test_variant_module_builds():
+    """CPU-side: the generator writes the header and nvcc cross-compiles the private prefill module for sm_100a (the .so stays
+    in-tree next to the other native modules, so a GPU box loads it without compiling)."""
+    if not jit.have_nvcc():
+        pytest.skip("nvcc not available")
+    spec = jit.gen_customize_batch_prefill_module("auto", *JIT_ARGS)
+    jit.build_module(spec)
+    assert spec.so_path.exists() and spec.is_fresh()
+    assert spec.additional_tensor_names == ("bias",) and spec.additional_scalar_names == ("temp",)
+    with pytest.raises(ValueError):
+        jit.gen_customize_batch_prefill_module("auto", "bad", None, None, None, None, 128, 128, ["a"] * 9, ["float"] * 9, [], [], "V", "")
+
+
+def _no_generic(monkeypatch):
+    """The SIMT catch-all kernel must not serve these configurations any more."""
+    from flashinfer_b200.attention import generic
+
+    def boom(*a, **k):
+        raise AssertionError("generic (CUDA-core) attention kernel was used")
+
+    monkeypatch.setattr(generic, "run", boom)
+
+
+def _ragged_case(seed, lens, hq, hkv, d=128, dtype=torch.bfloat16):
+    torch.manual_seed(seed)
+    qo = torch.tensor([0] + [a for a, _ in lens]).cumsum(0).int()
+    kv = torch.tensor([0] + [b for _, b in lens]).cumsum(0).int()
+    q = torch.randn(int(qo[-1]), hq, d, device="cuda", dtype=dtype)
+    k = torch.randn(int(kv[-1]), hkv, d, device="cuda", dtype=dtype)
+    v = torch.randn(int(kv[-1]), hkv, d, device="cuda", dtype=dtype)
+    return qo, kv, q, k, v
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("packed", [False, True])
+def test_custom_mask_ragged_tcgen05(monkeypatch, packed):
+    _no_generic(monkeypatch)
+    lens = [(37, 90), (300, 300), (1, 513), (129, 140)]
+    qo, kv, q, k, v = _ragged_case(0, lens, 8, 2)
+    masks = []
+    for ql, kl in lens:
+        m = torch.rand(ql, kl, device="cuda") > 0.35
+        m[:, 0] = True
+        masks.append(m)
+    masks[1][5, :] = False  # a fully masked row: output 0, lse -inf
+    flat = torch.cat([m.flatten() for m in masks])
+    w = fi.BatchPrefillWithRaggedKVCacheWrapper(torch.empty(32 << 20, dtype=torch.uint8, device="cuda"))
+    kw = {"packed_custom_mask": fi.packbits(flat, bitorder="little")} if packed else {"custom_mask": flat}
+    w.plan(qo, kv, 8, 2, 128, causal=True, q_data_type=torch.bfloat16, **kw)  # causal is overridden by the custom mask
+    out, lse = w.run(q, k, v, return_lse=True)
+    for b, (ql, kl) in enumerate(lens):
+        qs, ks = int(qo[b]), int(kv[b])
+        ref, lref = reference.attention_ref(q[qs:qs + ql], k[ks:ks + kl], v[ks:ks + kl], False, 1 / math.sqrt(128), custom_mask=masks[b])
+        ref = torch.nan_to_num(ref.float(), nan=0.0)
+        assert (out[qs:qs + ql].float() - ref).abs().max() < 2e-2
+        fin = torch.isfinite(lref)
+        assert (lse[qs:qs + ql][fin] - lref[fin]).abs().max() < 2e-2
+        assert torch.isinf(lse[qs:qs + ql][~fin]).all()
+
+
+@pytest.mark.gpu
+def test_custom_mask_paged_and_single_tcgen05(monkeypatch):
+    _no_generic(monkeypatch)
+    torch.manual_seed(3)
+    hq, hkv, d, ps = 4, 4, 128, 8
+    qo_len, kv_len = 37, 90
+    mask = torch.rand(qo_len, kv_len, device="cuda") > 0.4
+    mask[:, 0] = True
+    q = torch.randn(qo_len, hq, d, device="cuda", dtype=torch.float16)
+    k = torch.randn(kv_len, hkv, d, device="cuda", dtype=torch.float16)
+    v = torch.randn(kv_len, hkv, d, device="cuda", dtype=torch.float16)
+    ref, _ = reference.attention_ref(q, k, v, False, 1 / math.sqrt(d), custom_mask=mask)
+    out = fi.single_prefill_with_kv_cache(q, k, v, custom_mask=mask)
+    assert (out.float() - ref.float()).abs().max() < 2e-2
+    n_pages = (kv_len + ps - 1) // ps
+    kc = torch.zeros(n_pages, ps, hkv, d, device="cuda", dtype=torch.float16)
+    vc = torch.zeros_like(kc)
+    kc.view(-1, hkv, d)[:kv_len] = k
+    vc.view(-1, hkv, d)[:kv_len] = v
+    w = fi.BatchPrefillWithPagedKVCacheWrapper(torch.empty(32 << 20, dtype=torch.uint8, device="cuda"))
+    w.plan(torch.tensor([0, qo_len], dtype=torch.int32), torch.tensor([0, n_pages], dtype=torch.int32),
+           torch.arange(n_pages, dtype=torch.int32), torch.tensor([(kv_len - 1) % ps + 1], dtype=torch.int32), hq, hkv, d, ps,
+           custom_mask=mask.flatten(), q_data_type=torch.float16)
+    out2 = w.run(q, (kc, vc))
+    assert (out2.float() - ref.float()).abs().max() < 2e-2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("causal", [False, True])
+def test_alibi_tcgen05(monkeypatch, causal):
+    _no_generic(monkeypatch)
+    lens = [(64, 200), (257, 257), (5, 1000)]
+    hq, hkv = 12, 4  # non power-of-two head count: both slope series
+    qo, kv, q, k, v = _ragged_case(1, lens, hq, hkv)
+    w = fi.BatchPrefillWithRaggedKVCacheWrapper(torch.empty(32 << 20, dtype=torch.uint8, device="cuda"))
+    w.plan(qo, kv, hq, hkv, 128, causal=causal, pos_encoding_mode="ALIBI", logits_soft_cap=0.0, q_data_type=torch.bfloat16)
+    out = w.run(q, k, v)
+    slopes = fi.utils.get_alibi_slopes(hq, q.device)
+    for b, (ql, kl) in enumerate(lens):
+        qs, ks = int(qo[b]), int(kv[b])
+        ref, _ = reference.attention_ref(q[qs:qs + ql], k[ks:ks + kl], v[ks:ks + kl], causal, 1 / math.sqrt(128), alibi_slopes=slopes)
+        assert (out[qs:qs + ql].float() - ref.float()).abs().max() < 2e-2
+    o1 = fi.single_prefill_with_kv_cache(q[:64], k[:200], v[:200], causal=causal, pos_encoding_mode="ALIBI")
+    ref, _ = reference.attention_ref(q[:64], k[:200], v[:200], causal, 1 / math.sqrt(128), alibi_slopes=slopes)
+    assert (o1.float() - ref.float()).abs().max() < 2e-2
+
+
+@pytest.mark.gpu
+def test_user_variant_jit_tcgen05(monkeypatch):
+    """LogitsTransform + LogitsMask supplied as C++ and compiled into the tensor-core kernel (reference tests/utils/test_jit_example.py)."""
+    _no_generic(monkeypatch)
+    lens = [(100, 260), (33, 33)]
+    hq, hkv = 8, 2
+    qo, kv, q, k, v = _ragged_case(2, lens, hq, hkv)
+    bias = (torch.rand(hq, device="cuda") * 0.02).float()
+    temp = 0.7
+    w = fi.BatchPrefillWithRaggedKVCacheWrapper(torch.empty(32 << 20, dtype=torch.uint8, device="cuda"), jit_args=JIT_ARGS)
+    w.plan(qo, kv, hq, hkv, 128, causal=True, q_data_type=torch.bfloat16)
+    out, lse = w.run(q, k, v, bias, temp, return_lse=True)
+    sm = 1 / math.sqrt(128)
+    for b, (ql, kl) in enumerate(lens):
+        qs, ks = int(qo[b]), int(kv[b])
+        qq = q[qs:qs + ql].float().transpose(0, 1)                                     # [hq, ql, d]
+        kk = k[ks:ks + kl].float().transpose(0, 1).repeat_interleave(hq // hkv, 0)     # [hq, kl, d]
+        vv = v[ks:ks + kl].float().transpose(0, 1).repeat_interleave(hq // hkv, 0)
+        logits = qq @ kk.transpose(1, 2) * sm
+        qpos = (kl - ql + torch.arange(ql, device="cuda"))[:, None]
+        kpos = torch.arange(kl, device="cuda")[None, :]
+        logits = logits * temp + bias[:, None, None] * (kpos - qpos)[None].float()
+        keep = (kpos <= qpos) & ((kpos % 7 != 3) | (kpos == 0))
+        logits = logits.masked_fill(~keep[None], float("-inf"))
+        ref = (torch.softmax(logits, -1) @ vv).transpose(0, 1)
+        assert (out[qs:qs + ql].float() - ref).abs().max() < 2e-2
+        lref = (torch.logsumexp(logits, -1) * math.log2(math.e)).transpose(0, 1)
+        assert (lse[qs:qs + ql] - lref).abs().max() < 2e-2
+    with pytest.raises(ValueError):
+        w.run(q, k, v, bias)  # the scalar is missing
