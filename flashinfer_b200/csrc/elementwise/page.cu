@@ -155,3 +155,43 @@ extern "C" int get_batch_indices_positions(void* append_indptr, void* seq_lens, 
   FIB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Row gather: dst[i, :] = idx[i] >= 0 ? src[idx[i], :] : 0   (rows of `row_bytes` bytes, multiple of 16).  The compaction
+// step of sparse (top-k) MLA: the selected KV tokens of every query are packed into a dense per-query cache that the tcgen05
+// MLA kernel streams with full-size TMA boxes (reference: sparse_mla_top_k of trtllm_batch_decode_with_kv_cache_mla,
+// flashinfer/mla/_core.py:631-940, where the closed kernel gathers by token index).
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) gather_rows_kernel(const uint8_t* __restrict__ src, const int32_t* __restrict__ idx,
+                                                          uint8_t* __restrict__ dst, int64_t n_rows, int64_t src_rows, int vecs,
+                                                          int64_t src_pitch, int64_t dst_pitch) {
+  ptx::grid_dep_wait();
+  ptx::grid_dep_launch();
+  const int64_t total = n_rows * vecs;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t r = i / vecs;
+    const int v = int(i - r * vecs);
+    const int32_t s = idx[r];
+    int4 val = make_int4(0, 0, 0, 0);
+    if (s >= 0 && s < src_rows) val = __ldg(reinterpret_cast<const int4*>(src + int64_t(s) * src_pitch) + v);
+    reinterpret_cast<int4*>(dst + r * dst_pitch)[v] = val;
+  }
+}
+}  // namespace
+
+extern "C" int gather_rows(void* src, void* idx, void* dst, int64_t n_rows, int64_t src_rows, int64_t row_bytes, int64_t src_pitch,
+                           int64_t dst_pitch, int64_t pdl, int64_t stream_) {
+  FIB_CHECK(row_bytes % 16 == 0 && src_pitch % 16 == 0 && dst_pitch % 16 == 0, "gather_rows: row size / pitches must be multiples of 16 bytes");
+  FIB_CHECK((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0, "gather_rows: 16-byte aligned tensors");
+  if (n_rows == 0) return 0;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const int vecs = int(row_bytes / 16);
+  int64_t blocks = (n_rows * vecs + 255) / 256;
+  const int64_t cap = int64_t(num_sms()) * 16;
+  if (blocks > cap) blocks = cap;
+  LaunchCfg lc(dim3((unsigned)blocks), dim3(256), 0, stream, pdl != 0);
+  FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, gather_rows_kernel, (const uint8_t*)src, (const int32_t*)idx, (uint8_t*)dst, n_rows,
+                                    src_rows, vecs, src_pitch, dst_pitch));
+  return 0;
+}

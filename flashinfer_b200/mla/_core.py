@@ -201,7 +201,8 @@ def trtllm_batch_decode_with_kv_cache_mla(query: torch.Tensor, kv_cache: torch.T
     """Function-style MLA decode (reference :631): ``query [B, q_len, H, 576]`` (nope|rope concatenated),
     ``kv_cache [pages, (1,) page, 576]``, ``block_tables [B, max_pages]``."""
     if sparse_mla_top_k:
-        raise NotImplementedError("sparse MLA")
+        return _sparse_mla_decode(query, kv_cache, workspace_buffer, kv_lora_rank, qk_rope_head_dim, block_tables, sparse_mla_top_k,
+                                  float(bmm1_scale), float(bmm2_scale), out, lse, return_lse)
     b, ql, h, _ = query.shape
     kvc = kv_cache.squeeze(1) if kv_cache.ndim == 4 else kv_cache
     page_size = kvc.shape[1]
@@ -225,6 +226,61 @@ def trtllm_batch_decode_with_kv_cache_mla(query: torch.Tensor, kv_cache: torch.T
         out.copy_(o)
         o = out
     return (o, res[1].view(b, ql, h)) if return_lse else o
+
+
+def _sparse_mla_decode(query, kv_cache, workspace_buffer, kv_lora_rank, qk_rope_head_dim, block_tables, top_k, bmm1_scale,
+                       bmm2_scale, out, lse, return_lse):
+    """Sparse (top-k) MLA decode, DeepSeek-V3.2 style (reference flashinfer/mla/_core.py:631-940 ``sparse_mla_top_k``):
+    ``block_tables [B, q_len, top_k]`` holds, for every query token, the row indices of its selected KV tokens in the flattened
+    cache ``[pages * page_size, 576]`` (-1 = unused).  Two native kernels: ``gather_rows`` (csrc/elementwise/page.cu) packs the
+    selected rows of every query token into a dense per-query cache, then the tcgen05 MLA kernel (csrc/attention/mla_sm100.cu)
+    runs over it with full-size TMA boxes, every query token as its own request."""
+    b, ql, h, dqk = query.shape
+    if block_tables.shape != (b, ql, top_k):
+        raise ValueError(f"Expected page_table.shape == (num_seqs, num_tokens, sparse_mla_top_k), got {tuple(block_tables.shape)}")
+    kvc = kv_cache.squeeze(1) if kv_cache.ndim == 4 else kv_cache
+    flat = kvc.reshape(-1, kvc.shape[-1])
+    n = b * ql
+    idx = block_tables.reshape(n, top_k).to(torch.int32)
+    valid = idx >= 0
+    lens = valid.sum(-1).to(torch.int32)
+    if bool((valid[:, 1:] & ~valid[:, :-1]).any()):  # unused slots in the middle: move the valid indices to the front (stable)
+        order = torch.argsort((~valid).to(torch.int8), dim=-1, stable=True)
+        idx = torch.gather(idx, 1, order)
+    page = 64
+    kpad = (top_k + page - 1) // page * page
+    if kpad != top_k:
+        idx = torch.nn.functional.pad(idx, (0, kpad - top_k), value=-1)
+    idx = idx.contiguous()
+    dense = torch.empty(n * kpad, flat.shape[-1], dtype=flat.dtype, device=flat.device)
+    if flat.is_cuda:
+        esz = flat.element_size()
+        if flat.stride(-1) != 1:
+            flat = flat.contiguous()
+        jit.load("page").call("gather_rows", flat, idx, dense, n * kpad, flat.shape[0], flat.shape[-1] * esz, flat.stride(0) * esz,
+                              dense.stride(0) * esz, 1, stream_ptr(flat))
+    else:
+        dense.copy_(torch.where((idx >= 0).reshape(-1, 1), flat[idx.reshape(-1).clamp(min=0).long()], torch.zeros((), dtype=flat.dtype)))
+    dense = dense.view(n * kpad // page, page, flat.shape[-1])
+    ppr = kpad // page
+    w = BatchMLAPagedAttentionWrapper(workspace_buffer)
+    w.plan(torch.arange(0, n + 1, dtype=torch.int32), torch.arange(0, (n + 1) * ppr, ppr, dtype=torch.int32),
+           torch.arange(0, n * ppr, dtype=torch.int32), lens.to("cpu"), h, kv_lora_rank, qk_rope_head_dim, page, False, bmm1_scale,
+           query.dtype, dense.dtype)
+    q = query.reshape(n, h, dqk)
+    res = w.run(q[..., :kv_lora_rank], q[..., kv_lora_rank:], dense[..., :kv_lora_rank], dense[..., kv_lora_rank:],
+                return_lse=return_lse, o_scale=bmm2_scale if bmm2_scale != 1.0 else None)
+    o = (res[0] if return_lse else res).view(b, ql, h, kv_lora_rank)
+    if out is not None:
+        out.copy_(o)
+        o = out
+    if return_lse:
+        l2 = res[1].view(b, ql, h)
+        if lse is not None:
+            lse.copy_(l2)
+            l2 = lse
+        return o, l2
+    return o
 
 
 def xqa_batch_decode_with_kv_cache_mla(*args, **kwargs):
