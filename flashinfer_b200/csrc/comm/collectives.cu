@@ -189,3 +189,114 @@ extern "C" int p2p_all_to_all(void* peer_buf_host, void* peer_sig_host, void* ep
   FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, all_to_all_kernel, p, (const int4*)src, out_off, rows, row_bytes / 16));
   return 0;
 }
+
+// =====================================================================================================================
+// Indexed all-to-all-v of the legacy MoE "prepare + comm" protocol (reference flashinfer/comm/trtllm_alltoall.py moe_comm,
+// include/flashinfer/comm/trtllm_alltoall.cuh: moeAllToAllKernel).  Entry e of the send list goes to the rank j with
+// send_cumsum[j - 1] <= e < send_cumsum[j] and carries row send_idx[e] of `src`; the k-th row received from rank i lands in row
+// recv_idx[recv_cumsum[i - 1] + k] of `out`.  Two launches over a symmetric staging region [world][cap_rows][row]:
+//   push: cross-rank barrier (every rank has left its previous pull), rows are stored straight into the target's staging slot
+//         [me][k] with 16-byte peer stores over NVLink;
+//   pull: cross-rank barrier (every rank's push kernel has completed), staging rows are scattered into `out`.
+// Both grids have the same fixed size on every rank (the barriers are per CTA index); spins carry the watchdog.
+// =====================================================================================================================
+namespace {
+
+struct MoeCommParams {
+  CollParams c;
+  const uint8_t* src;
+  int64_t src_pitch;
+  const int32_t* send_cumsum;
+  const int32_t* send_idx;
+  uint8_t* out;
+  int64_t out_pitch;
+  const int32_t* recv_cumsum;
+  const int32_t* recv_idx;
+  int vecs;
+  int64_t cap_rows, src_rows, out_rows;
+};
+
+__device__ __forceinline__ void coll_barrier_wd(const CollParams& p, int phase) {
+  __threadfence_system();
+  __syncthreads();
+  if (int(threadIdx.x) < p.world) {
+    const int peer = threadIdx.x;
+    const int slot_base = (phase * p.max_blocks + blockIdx.x) * p.world;
+    const uint32_t epoch = p.epochs[phase * p.max_blocks + blockIdx.x] + 1;
+    ptx::st_release_sys(p.peer_sig[peer] + slot_base + p.rank, epoch);
+    ptx::spin_until_ge_sys(p.peer_sig[p.rank] + slot_base + peer, epoch);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) p.epochs[phase * p.max_blocks + blockIdx.x] += 1;
+}
+
+// rank owning entry e of an inclusive cumulative count list, and the entry's offset inside that rank's run
+__device__ __forceinline__ int owner_of(const int32_t* cumsum, int world, int e, int* k) {
+  int j = 0, lo = 0;
+  while (j < world - 1 && e >= cumsum[j]) {
+    lo = cumsum[j];
+    ++j;
+  }
+  *k = e - lo;
+  return j;
+}
+
+__global__ void __launch_bounds__(512) moe_comm_push_kernel(const MoeCommParams p) {
+  ptx::grid_dep_wait();
+  coll_barrier_wd(p.c, 0);
+  const int total = p.send_cumsum[p.c.world - 1];
+  const int64_t work = int64_t(total) * p.vecs;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < work; i += int64_t(gridDim.x) * blockDim.x) {
+    const int e = int(i / p.vecs), v = int(i - int64_t(e) * p.vecs);
+    int k;
+    const int j = owner_of(p.send_cumsum, p.c.world, e, &k);
+    const int row = p.send_idx[e];
+    if (k >= p.cap_rows || row < 0 || row >= p.src_rows) {
+      if (v == 0) printf("fib200: moe_comm: rank %d entry %d (row %d, slot %d of peer %d) outside the workspace / input -> trap\n", p.c.rank, e, row, k, j);
+      __trap();
+    }
+    const int4 val = *(reinterpret_cast<const int4*>(p.src + int64_t(row) * p.src_pitch) + v);
+    *(reinterpret_cast<int4*>(p.c.peer_buf[j]) + (int64_t(p.c.rank) * p.cap_rows + k) * p.vecs + v) = val;
+  }
+  ptx::grid_dep_launch();
+}
+
+__global__ void __launch_bounds__(512) moe_comm_pull_kernel(const MoeCommParams p) {
+  ptx::grid_dep_wait();
+  coll_barrier_wd(p.c, 1);
+  const int total = p.recv_cumsum[p.c.world - 1];
+  const int64_t work = int64_t(total) * p.vecs;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < work; i += int64_t(gridDim.x) * blockDim.x) {
+    const int e = int(i / p.vecs), v = int(i - int64_t(e) * p.vecs);
+    int k;
+    const int src_rank = owner_of(p.recv_cumsum, p.c.world, e, &k);
+    const int row = p.recv_idx[e];
+    if (row < 0 || row >= p.out_rows || k >= p.cap_rows) continue;
+    const int4 val = ld_sys16(reinterpret_cast<const int4*>(p.c.peer_buf[p.c.rank]) + (int64_t(src_rank) * p.cap_rows + k) * p.vecs + v);
+    *(reinterpret_cast<int4*>(p.out + int64_t(row) * p.out_pitch) + v) = val;
+  }
+  ptx::grid_dep_launch();
+}
+
+}  // namespace
+
+extern "C" int moe_comm_run(void* peer_buf_host, void* peer_sig_host, void* epochs, void* src, int64_t src_rows, int64_t src_pitch,
+                            void* send_cumsum, void* send_idx, void* out, int64_t out_rows, int64_t out_pitch, void* recv_cumsum,
+                            void* recv_idx, int64_t row_bytes, int64_t cap_rows, int64_t rank, int64_t world, int64_t max_blocks,
+                            int64_t stream_) {
+  FIB_CHECK(row_bytes % 16 == 0 && src_pitch % 16 == 0 && out_pitch % 16 == 0, "moe_comm: rows / pitches must be multiples of 16 bytes");
+  FIB_CHECK(cap_rows >= 1, "moe_comm: the workspace is too small for one row per rank pair");
+  MoeCommParams p;
+  memset(&p, 0, sizeof(p));
+  if (fill(p.c, (const int64_t*)peer_buf_host, (const int64_t*)peer_sig_host, nullptr, epochs, rank, world, max_blocks)) return 1;
+  p.src = reinterpret_cast<const uint8_t*>(src); p.src_pitch = src_pitch; p.src_rows = src_rows;
+  p.send_cumsum = reinterpret_cast<const int32_t*>(send_cumsum); p.send_idx = reinterpret_cast<const int32_t*>(send_idx);
+  p.out = reinterpret_cast<uint8_t*>(out); p.out_pitch = out_pitch; p.out_rows = out_rows;
+  p.recv_cumsum = reinterpret_cast<const int32_t*>(recv_cumsum); p.recv_idx = reinterpret_cast<const int32_t*>(recv_idx);
+  p.vecs = int(row_bytes / 16); p.cap_rows = cap_rows;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  LaunchCfg lc(dim3((unsigned)max_blocks), dim3(512), 0, stream, false);
+  FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, moe_comm_push_kernel, p));
+  FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, moe_comm_pull_kernel, p));
+  return 0;
+}

@@ -22,6 +22,8 @@ using namespace fib200;
 FIB_EXPORT_LAST_ERROR()
 
 namespace {
+thread_local int g_sm_budget = 0;  // gemm_set_sm_budget: persistent-grid size of the next launches of this thread (0 = all SMs)
+
 
 constexpr int BK = 64;   // 64 x 2B = one 128B swizzle span
 
@@ -670,6 +672,7 @@ int launch_gemm(int BN, int cluster_split, int mcast_g, int gated, const CUtenso
   sk.kblocks = (K + BK - 1) / BK;
   const int tiles = sk.tiles_a * sk.tiles_b;
   int grid = num_sms();
+  if (g_sm_budget > 0 && g_sm_budget < grid) grid = g_sm_budget;  // SM-constrained GEMM: the persistent grid is the budget
   if (tiles < grid && (!kSwap || workspace == nullptr || int64_t(tiles) * sk.kblocks < 2 * grid)) grid = tiles;
   sk.grid = grid;
   sk.W = tiles / grid;
@@ -789,6 +792,7 @@ int gemm_dispatch(const void* A, const void* B, OutT* C, const OutT* bias, int M
     BN = (N >= 256 && (int64_t(M) * N >= int64_t(256) * 256 * 64)) ? 256 : 128;
   }
   if (gated) Ssel = 1;
+  if (g_sm_budget > 0) Ssel = 1;  // SM-constrained: plain persistent tiles (cluster split-K assumes one tile per cluster on the full machine)
   if (force_swap == 1 && M <= 128 && !gated) {
     swap = true;
     BMsel = 128;
@@ -881,4 +885,13 @@ extern "C" int gemm_nt_gated_silu(void* A, void* B, void* C, int64_t M, int64_t 
     return gemm_dispatch<__nv_bfloat16>(A, B, (__nv_bfloat16*)C, nullptr, (int)M, (int)N, (int)K, lda, ldb, ldc, false, nullptr, 0,
                                         pdl != 0, s, true);
   return set_error("gemm_nt_gated_silu: unsupported dtype");
+}
+
+// SM-constrained GEMM (reference flashinfer/triton/sm_constraint_gemm.py gemm_persistent(num_sms=...)): the persistent tcgen05
+// kernel runs with `n` CTAs (one per SM) until the budget is reset to 0, leaving the other SMs to a concurrent kernel
+// (communication, another stream's GEMM).  Thread-local, like the launch itself.
+extern "C" int gemm_set_sm_budget(int64_t n) {
+  FIB_CHECK(n >= 0, "gemm_set_sm_budget: n >= 0 (0 = no constraint)");
+  g_sm_budget = int(n);
+  return 0;
 }

@@ -122,3 +122,21 @@ def test_linear_gated_silu(mnk, dtype):
     out = linear_gated_silu(x, interleave_gate_up(w))
     assert out.shape == (m, n2 // 2)
     torch.testing.assert_close(out.float(), ref, rtol=2e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("m,n,k,sms", [(4096, 4096, 1024, 32), (300, 1000, 512, 7), (64, 4096, 4096, 40), (2048, 8192, 2048, None)])
+def test_sm_constrained_gemm(m, n, k, sms):
+    """reference flashinfer/triton/sm_constraint_gemm.py gemm_persistent(num_sms=...): same result on a capped persistent grid."""
+    from flashinfer_b200.triton import gemm_persistent
+
+    torch.manual_seed(0)
+    a = (torch.randn(m, k, device="cuda") * 0.5).bfloat16()
+    w = (torch.randn(n, k, device="cuda") / k ** 0.5).bfloat16()
+    ref = a.float() @ w.float().t()
+    out = gemm_persistent(a, w.t(), num_sms=sms)
+    assert (out.float() - ref).abs().max() / ref.abs().max() < 1e-2
+    c = torch.randn(m, n, device="cuda").bfloat16()
+    c0 = c.clone()
+    gemm_persistent(a, w.t(), c, alpha=0.5, beta=2.0, num_sms=sms)
+    ref2 = 0.5 * ref + 2.0 * c0.float()
+    assert (c.float() - ref2).abs().max() / ref2.abs().max() < 1e-2
