@@ -21,16 +21,18 @@ class TopKTieBreak(IntEnum):
 
 
 def _run(input, k, mode, lengths=None, row_starts=None, row_to_batch=None, page_table=None, ragged_offsets=None,
-         tie_break=0, want_values=False):
+         tie_break=0, want_values=False, clusters=0, pdl=False):
+    """``clusters``: 0 = auto (one row per thread-block cluster of 2 / 4 / 8 CTAs when the rows alone cannot fill the SMs),
+    1 = one CTA per row, 2 / 4 / 8 = cluster size (csrc/elementwise/topk.cu: topk_kernel / topk_cluster_kernel)."""
     rows, max_len = input.shape
     x = input if input.stride(-1) == 1 else input.contiguous()
     idx = torch.empty(rows, k, dtype=torch.int32, device=x.device)
     vals = torch.empty(rows, k, dtype=x.dtype, device=x.device) if want_values else None
     i32 = lambda t: t.to(torch.int32).contiguous() if t is not None else None  # noqa: E731
     jit.load("topk").call(
-        "topk_run", x, x.stride(0), vals, idx, i32(lengths), i32(row_starts), i32(row_to_batch), i32(page_table),
+        "topk_run_ex", x, x.stride(0), vals, idx, i32(lengths), i32(row_starts), i32(row_to_batch), i32(page_table),
         page_table.stride(0) if page_table is not None else 0, i32(ragged_offsets), rows, max_len, k, mode,
-        int(tie_break), dtype_code(x.dtype), stream_ptr(x),
+        int(tie_break), dtype_code(x.dtype), int(clusters), 1 if pdl else 0, stream_ptr(x),
     )
     return vals, idx
 
@@ -118,19 +120,34 @@ def can_use_clusters_topk(device, deterministic: bool, dsa_graph_safe: bool) -> 
     return not dsa_graph_safe and not deterministic
 
 
+def _cluster_size(rows: int) -> int:
+    return max(2, get_fast_topk_clusters(rows))
+
+
 def topk_clusters_exact(logits: torch.Tensor, top_k: int, output_values: bool = False, out_dtype=torch.int32, pdl: bool = False):
-    """Exact top-k indices (and optionally values) per row; the radix-select kernel of :func:`top_k` serves this entry point."""
-    vals, idx = globals()["top_k"](logits, top_k)
+    """Exact top-k indices (and optionally values) per row on the cluster kernel: one row per thread-block cluster, slices of
+    the row per CTA, histograms and compaction bases merged through distributed shared memory
+    (reference include/flashinfer/fast_topk_clusters_exact.cuh:408-497)."""
+    if not logits.is_cuda:
+        vals, idx = torch.topk(logits, top_k, dim=-1, sorted=False)
+        return (idx.to(out_dtype), vals) if output_values else idx.to(out_dtype)
+    vals, idx = _run(logits, top_k, 0, want_values=output_values, clusters=_cluster_size(logits.shape[0]), pdl=pdl)
     idx = idx.to(out_dtype)
     return (idx, vals) if output_values else idx
 
 
 def topk_clusters_page_table_transform(logits, seq_lens, src_page_table, top_k: int, pdl: bool = False):
-    return top_k_page_table_transform(logits, src_page_table, seq_lens, top_k)
+    """Cluster flavour of :func:`top_k_page_table_transform` (rows = query tokens, one request each)."""
+    if not logits.is_cuda:
+        return top_k_page_table_transform(logits, src_page_table, seq_lens, top_k)
+    return _run(logits, top_k, 1, lengths=seq_lens, page_table=src_page_table, clusters=_cluster_size(logits.shape[0]), pdl=pdl)[1]
 
 
 def topk_clusters_ragged_transform(logits, seq_lens, offsets, top_k: int, pdl: bool = False):
-    return top_k_ragged_transform(logits, offsets, seq_lens, top_k)
+    """Cluster flavour of :func:`top_k_ragged_transform`."""
+    if not logits.is_cuda:
+        return top_k_ragged_transform(logits, offsets, seq_lens, top_k)
+    return _run(logits, top_k, 2, lengths=seq_lens, ragged_offsets=offsets, clusters=_cluster_size(logits.shape[0]), pdl=pdl)[1]
 
 
 def get_topk_module(*args, **kwargs):

@@ -85,3 +85,41 @@ def test_top_k_transforms_and_ties():
     assert sorted(i[0].tolist()) == list(range(7))
     _, i = TK.top_k(t, 7, tie_break=TK.TopKTieBreak.LARGE)
     assert sorted(i[0].tolist()) == list(range(493, 500))
+
+
+@pytest.mark.parametrize("rows,n,k,cs", [(1, 131072, 2048, 8), (3, 65536, 2048, 4), (2, 40000, 512, 2), (5, 9000, 64, 8), (1, 450000, 2048, 8),
+                                         (4, 131072, 2048, 0)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_top_k_cluster_kernel(rows, n, k, cs, dtype):
+    """One row per thread-block cluster (csrc/elementwise/topk.cu: topk_cluster_kernel): same selection as the one-CTA kernel and
+    torch.topk, for slices that fit the shared-memory key cache and for slices that do not (n = 450000 over 8 CTAs = 56 K keys per slice)."""
+    torch.manual_seed(rows * 1000 + k)
+    x = torch.randn(rows, n, device="cuda").to(dtype)
+    vals, idx = TK._run(x, k, 0, want_values=True, clusters=cs)
+    v1, i1 = TK._run(x, k, 0, want_values=True, clusters=1)
+    assert torch.equal(idx, i1) and torch.equal(vals, v1)  # deterministic, index-ordered: bit-identical to the single-CTA kernel
+    vr = torch.topk(x.float(), k, dim=-1).values
+    assert torch.equal(vals.float().sort(-1, descending=True).values, vr)
+    assert torch.equal(x.gather(1, idx.long()), vals)
+
+
+def test_top_k_cluster_transforms_ties_lengths():
+    torch.manual_seed(1)
+    rows, n, k = 3, 50000, 1024
+    x = torch.randn(rows, n, device="cuda")
+    x[:, ::3] = 0.25  # heavy ties around the threshold
+    lengths = torch.tensor([50000, 20001, 700], dtype=torch.int32, device="cuda")
+    table = torch.randint(0, 1 << 20, (rows, n), dtype=torch.int32, device="cuda")
+    offs = torch.tensor([5, 100000, 7], dtype=torch.int32, device="cuda")
+    for tb in (TK.TopKTieBreak.NONE, TK.TopKTieBreak.SMALL, TK.TopKTieBreak.LARGE):
+        a = TK._run(x, k, 1, lengths=lengths, page_table=table, tie_break=tb, clusters=8)[1]
+        b = TK._run(x, k, 1, lengths=lengths, page_table=table, tie_break=tb, clusters=1)[1]
+        assert torch.equal(a, b)
+        a = TK._run(x, k, 2, lengths=lengths, ragged_offsets=offs, tie_break=tb, clusters=4)[1]
+        b = TK._run(x, k, 2, lengths=lengths, ragged_offsets=offs, tie_break=tb, clusters=1)[1]
+        assert torch.equal(a, b)
+    assert (a[2, 700:] == -1).all()
+    idx = TK.topk_clusters_exact(x, k)
+    assert idx.dtype == torch.int32 and torch.equal(idx, TK._run(x, k, 0, clusters=1)[1])
+    assert torch.equal(TK.topk_clusters_page_table_transform(x, lengths, table, k), TK.top_k_page_table_transform(x, table, lengths, k))
+    assert torch.equal(TK.topk_clusters_ragged_transform(x, lengths, offs, k), TK.top_k_ragged_transform(x, offs, lengths, k))

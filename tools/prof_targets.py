@@ -55,4 +55,21 @@ elif mode in ("gemm_o", "gemm_qkv", "cublas_o", "cublas_qkv"):
     a = torch.randn(64, K, device="cuda", dtype=torch.bfloat16)
     for w in ws:
         (fi.mm_bf16(a, w.t()) if mode.startswith("gemm") else a @ w.t())
+elif mode in ("dlinear_gate_up", "dlinear_down", "dlinear_qkv", "dlinear_o"):
+    # the flagship decode linears (csrc/gemm/decode_linear_sm100.cu) on the Llama-3-8B shapes, rotating weights (cold L2)
+    from flashinfer_b200.gemm import decode_linear as dl
+    H, I, D = 4096, 14336, 128
+    n, k = {"dlinear_gate_up": (2 * I, H), "dlinear_down": (H, I), "dlinear_qkv": (6144, H), "dlinear_o": (H, H)}[mode]
+    ws = [dl.to_block_major_k(torch.randn(n, k, device="cuda", dtype=torch.bfloat16) * 0.02) for _ in range(6)]
+    a = torch.randn(64, k, device="cuda", dtype=torch.bfloat16)
+    ss = torch.rand(64, device="cuda") * H + 1
+    resid = torch.zeros(64, H, device="cuda", dtype=torch.bfloat16); sq = torch.zeros(64, device="cuda")
+    act = torch.empty(64, I, device="cuda", dtype=torch.bfloat16)
+    for w in ws:
+        if mode == "dlinear_gate_up":
+            dl.decode_linear(a, w, dl.EPI_GATED_SILU, out=act, row_sumsq=ss)
+        elif mode in ("dlinear_down", "dlinear_o"):
+            dl.decode_linear(a, w, dl.EPI_RESIDUAL, residual=resid, sumsq_out=sq)
+        else:
+            dl.decode_linear(a, w, out=torch.empty(64, n, device="cuda", dtype=torch.bfloat16), row_sumsq=ss)
 torch.cuda.synchronize()
