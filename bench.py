@@ -96,8 +96,8 @@ def run_ours(args, rank, world):
     eng.step()
     torch.cuda.synchronize()
     native_per_step = jit.native_launch_count() - c0
-    # torch-launched kernels per step: op-by-op path index_select, zero_, argmax (+ max / gather glue at tp > 1); fused path: argmax
-    torch_per_step = (1 if world == 1 else 3) if eng.fused else (4 if world == 1 else 6)
+    # torch-launched kernels per step: op-by-op path index_select, zero_ (+ argmax on one GPU)
+    torch_per_step = 0 if eng.fused else (3 if world == 1 else 2)  # fused path: every launch is native (argmax included)
     if args.eager_steps > 0:  # ncu / profiler mode: plain eager launches, no timing contract
         for _ in range(args.eager_steps):
             eng.step()
@@ -169,8 +169,11 @@ def run_ours(args, rank, world):
                        "ref_attention_candidates": None,
                        "linear": ("flashinfer_b200 decode_linear_sm100 (RMSNorm / RoPE+append / SwiGLU / residual epilogues)"
                                   if eng.fused else "flashinfer_b200 gemm_sm100"),
-                       "allreduce": (("one-shot push all-reduce inside the O / down GEMM epilogue (multimem.st into every rank's slot, sentinel polling)"
-                                      if eng.fused else "in-kernel NVLS all-reduce + add + RMSNorm kernel") if world > 1 else None),
+                       "allreduce": ((("two-shot Lamport all-reduce inside the O / down GEMM epilogue (reduce-scatter push to the row owner, "
+                                       "multimem.st all-gather of the new residual rows, sentinel polling)" if eng.tp_fused.algo == 2 else
+                                       "one-shot push all-reduce inside the O / down GEMM epilogue (multimem.st into every rank's slot, "
+                                       "sentinel polling)") if eng.fused else "in-kernel NVLS all-reduce + add + RMSNorm kernel")
+                                     if world > 1 else None),
                        "ref_allreduce_candidates": None},
             "clocks": _summarise_clocks(clk.get("rows")),
             "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": BATCH * 8, "d2h_bytes_per_step": BATCH * 8},

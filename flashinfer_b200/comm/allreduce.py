@@ -238,6 +238,37 @@ class TPCommunicator:
         return table[:, 1].gather(0, best[None])[0].long()
 
 
+_LOCAL_ARGMAX: dict = {}
+
+
+def local_argmax(logits: torch.Tensor, out: Optional[torch.Tensor] = None, out_val: Optional[torch.Tensor] = None,
+                 enable_pdl: bool = True) -> torch.Tensor:
+    """Row-wise argmax of ``logits [B, V]`` (greedy sampling on one GPU) through the same kernel as
+    :meth:`TPCommunicator.argmax_logits` with a group of one: one CTA of 1024 threads per row, lowest index on ties."""
+    b, v = logits.shape
+    if not logits.is_cuda:
+        res = logits.float().argmax(-1)
+        if out is not None:
+            out.copy_(res)
+            return out
+        return res
+    dev = logits.device
+    st = _LOCAL_ARGMAX.get(dev.index)
+    if st is None or st["rows"] < b:
+        rows = max(256, b)
+        box = torch.zeros(2 * rows * 16, dtype=torch.uint8, device=dev)
+        st = {"rows": rows, "box": box, "tab": torch.tensor([box.data_ptr()], dtype=torch.int64),
+              "epoch": torch.zeros(4, dtype=torch.int32, device=dev), "mod": jit.load("comm_allreduce")}
+        _LOCAL_ARGMAX[dev.index] = st
+    if logits.stride(-1) != 1:
+        logits = logits.contiguous()
+    if out is None:
+        out = torch.empty(b, dtype=torch.int64, device=dev)
+    st["mod"].call("argmax_push_run", logits, logits.stride(0), v, 0, st["box"], st["tab"], st["epoch"], 0, 1, b, st["rows"], out, out_val,
+                   dtype_code(logits.dtype), 1 if enable_pdl else 0, stream_ptr(logits))
+    return out
+
+
 class _ptr:
     """Marshal a raw device address through the uniform C ABI (void*)."""
 

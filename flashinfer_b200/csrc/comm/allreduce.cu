@@ -632,10 +632,10 @@ __device__ __forceinline__ uint2 ld_volatile_v2(const uint2* p) {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) argmax_push_kernel(const ArgmaxParams p) {
+__global__ void __launch_bounds__(1024) argmax_push_kernel(const ArgmaxParams p) {
   constexpr int VN = 16 / sizeof(T);
-  __shared__ float s_val[8];
-  __shared__ int s_idx[8];
+  __shared__ float s_val[32];
+  __shared__ int s_idx[32];
   __shared__ float r_val[kMaxRanks];
   __shared__ int64_t r_idx[kMaxRanks];
   __shared__ uint32_t s_epoch;
@@ -749,7 +749,8 @@ extern "C" int argmax_push_run(void* logits, int64_t ld, int64_t shard, int64_t 
   p.rank = int(rank); p.world = int(world); p.rows = int(rows); p.max_rows = int(max_rows);
   p.out = reinterpret_cast<int64_t*>(out); p.out_val = reinterpret_cast<float*>(out_val);
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  LaunchCfg lc(dim3((unsigned)rows), dim3(256), 0, stream, pdl != 0);
+  // few long rows (a decode batch over a 128 K vocabulary shard): 1024 threads per row keep enough loads in flight
+  LaunchCfg lc(dim3((unsigned)rows), dim3(shard >= 16384 ? 1024 : 256), 0, stream, pdl != 0);
   if (dtype == kBF16) {
     FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, argmax_push_kernel<__nv_bfloat16>, p));
   } else if (dtype == kF16) {

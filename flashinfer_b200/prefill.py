@@ -80,7 +80,7 @@ def single_prefill_with_kv_cache(
         mask = _unpack_bits(packed_custom_mask, qo_len * kv_len).view(qo_len, kv_len)
     elif custom_mask is not None:
         mask = custom_mask.view(qo_len, kv_len)
-    fast = q.is_cuda and q.shape[-1] in (128, 192) and v.shape[-1] == 128 and q.dtype in (
+    fast = q.is_cuda and (q.shape[-1], v.shape[-1]) in ((128, 128), (192, 128), (64, 64)) and q.dtype in (
         torch.float16, torch.bfloat16) and k.dtype == q.dtype
     alibi = pos_encoding_mode == "ALIBI"
     if not q.is_cuda:
@@ -251,7 +251,8 @@ class _BatchPrefillBase:
 
     def _launch_sm100(self, q, k, v, out, lse, sm_scale, window_left, paged, kv_indices, page_args, enable_pdl,
                       k_scale=None, v_scale=None):
-        shape_ok = self._head_dim_qk in (128, 192) and self._head_dim_vo == 128 and q.dtype in (torch.float16, torch.bfloat16)
+        shape_ok = ((self._head_dim_qk, self._head_dim_vo) in ((128, 128), (192, 128), (64, 64))
+                    and q.dtype in (torch.float16, torch.bfloat16))
         if shape_ok and k.dtype in (torch.float8_e4m3fn, torch.float8_e5m2) and q.shape[0] >= 4 * self._batch_size:
             # fp8 KV with a compute-bound (prefill-sized) query: widen the KV that this call touches to the query dtype
             # once (1 B read + 2 B write per element, negligible next to the O(q * kv) attention work) and stay on the
@@ -271,7 +272,7 @@ class _BatchPrefillBase:
         fast = shape_ok and k.dtype == q.dtype and v.dtype == q.dtype
         if not fast:
             if self._variant_mod is not None:
-                raise NotImplementedError("user attention variants run on the tcgen05 prefill kernel: f16 / bf16, head_dim 128 (192 qk)")
+                raise NotImplementedError("user attention variants run on the tcgen05 prefill kernel: f16 / bf16, head_dim 64 / 128 (192 qk)")
             return self._launch_generic(q, k, v, out, lse, sm_scale, window_left, paged, kv_indices, page_args, enable_pdl,
                                         k_scale, v_scale)
         page_size, num_pages_total, sp, sn, sh, hnd = page_args[:6]

@@ -79,3 +79,19 @@ def test_argmax_push(world):
     errs = mp.get_context("spawn").Manager().dict()
     mp.spawn(_worker, args=(world, _free_port(), errs), nprocs=world, join=True)
     assert len(errs) == world and max(errs.values()) == 0, dict(errs)
+
+
+@pytest.mark.parametrize("rows,v,dt", [(64, 128256, torch.bfloat16), (3, 1000, torch.float32), (64, 16032, torch.float16)])
+def test_local_argmax(rows, v, dt):
+    """Single-GPU flavour (group of one) used by the decode engine for greedy sampling."""
+    from flashinfer_b200.comm.allreduce import local_argmax
+
+    torch.manual_seed(rows)
+    x = torch.randn(rows, v, device="cuda").to(dt)
+    x[0, 5] = x[0, 9] = 100.0  # tie: lowest index wins
+    val = torch.empty(rows, device="cuda")
+    for _ in range(3):  # epoch / parity rotation
+        out = local_argmax(x, out_val=val)
+    assert int(out[0]) == 5
+    assert torch.equal(val, x.float().max(-1).values)
+    assert torch.equal(x.float().gather(1, out[:, None])[:, 0], val)

@@ -159,3 +159,44 @@ def test_user_variant_jit_tcgen05(monkeypatch):
         assert (lse[qs:qs + ql] - lref).abs().max() < 2e-2
     with pytest.raises(ValueError):
         w.run(q, k, v, bias)  # the scalar is missing
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_head_dim_64_tcgen05(monkeypatch, causal, dtype):
+    """head_dim 64 (qk = vo) runs on the tcgen05 prefill kernel (128 x 64 PV tiles), ragged and paged, with soft-cap / window."""
+    _no_generic(monkeypatch)
+    lens = [(200, 200), (1, 777), (300, 1200), (129, 129)]
+    hq, hkv, d = 8, 2, 64
+    qo, kv, q, k, v = _ragged_case(7, lens, hq, hkv, d=d, dtype=dtype)
+    w = fi.BatchPrefillWithRaggedKVCacheWrapper(torch.empty(32 << 20, dtype=torch.uint8, device="cuda"))
+    w.plan(qo, kv, hq, hkv, d, causal=causal, q_data_type=dtype)
+    out, lse = w.run(q, k, v, return_lse=True)
+    for b, (ql, kl) in enumerate(lens):
+        qs, ks = int(qo[b]), int(kv[b])
+        ref, lref = reference.attention_ref(q[qs:qs + ql], k[ks:ks + kl], v[ks:ks + kl], causal, 1 / math.sqrt(d))
+        assert (out[qs:qs + ql].float() - ref.float()).abs().max() < 2e-2
+        assert (lse[qs:qs + ql] - lref).abs().max() < 2e-2
+    # paged, page_size 16, soft-cap + sliding window
+    ps, kl, ql = 16, 1000, 260
+    n_pages = (kl + ps - 1) // ps
+    perm = torch.randperm(n_pages + 5)[:n_pages].int()
+    kc = torch.zeros(n_pages + 5, ps, hkv, d, device="cuda", dtype=dtype)
+    vc = torch.zeros_like(kc)
+    kk, vv = torch.randn(kl, hkv, d, device="cuda").to(dtype), torch.randn(kl, hkv, d, device="cuda").to(dtype)
+    for i in range(n_pages):
+        n = min(ps, kl - i * ps)
+        kc[perm[i], :n] = kk[i * ps:i * ps + n]
+        vc[perm[i], :n] = vv[i * ps:i * ps + n]
+    qq = torch.randn(ql, hq, d, device="cuda").to(dtype)
+    wp = fi.BatchPrefillWithPagedKVCacheWrapper(torch.empty(32 << 20, dtype=torch.uint8, device="cuda"))
+    wp.plan(torch.tensor([0, ql], dtype=torch.int32), torch.tensor([0, n_pages], dtype=torch.int32), perm,
+            torch.tensor([(kl - 1) % ps + 1], dtype=torch.int32), hq, hkv, d, ps, causal=True, window_left=300, logits_soft_cap=20.0,
+            q_data_type=dtype)
+    o2 = wp.run(qq, (kc, vc))
+    ref, _ = reference.attention_ref(qq, kk, vv, True, 1 / math.sqrt(d), 20.0, 300)
+    assert (o2.float() - ref.float()).abs().max() < 2e-2
+    o3 = fi.single_prefill_with_kv_cache(qq, kk, vv, causal=causal)
+    ref, _ = reference.attention_ref(qq, kk, vv, causal, 1 / math.sqrt(d))
+    assert (o3.float() - ref.float()).abs().max() < 2e-2
