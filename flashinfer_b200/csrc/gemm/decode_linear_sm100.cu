@@ -228,6 +228,22 @@ dlinear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // all-reduce: the rotating-buffer epoch is read here, right after griddepcontrol.wait and long before any CTA of this grid can
     // finish its all-reduce and bump it (published to the other epilogue threads by the named barrier after the tile staging)
     if (p.epi == kResid && p.world > 1 && etid == 0) tmem_ptr[1] = *reinterpret_cast<volatile uint32_t*>(p.epoch);
+    // epilogue inputs that do not depend on the accumulators are fetched while the main loop runs: the folded-RMSNorm scale of
+    // the row, and (single-GPU residual epilogue, strips of <= 64 columns) the residual values this thread will update
+    float rs_pre = 1.f;
+    if (p.row_sumsq != nullptr && m_ok) rs_pre = rsqrtf(p.row_sumsq[m] * p.inv_dim + p.eps);
+    constexpr int kResPre = 4;  // 16-column chunks of the residual held in registers
+    Vec16<T> res_pre[2 * kResPre];
+    const bool res_prefetched = p.epi == kResid && p.world <= 1 && own_w <= 16 * kResPre;
+    if (res_prefetched && m_ok) {
+      const T* rp0 = reinterpret_cast<const T*>(p.resid) + int64_t(m) * p.ldr + tb * BN + own_lo;
+#pragma unroll
+      for (int c = 0; c < kResPre; ++c)
+        if (c * 16 < own_w && tb * BN + own_lo + c * 16 < p.N) {
+          res_pre[2 * c] = ld16(rp0 + c * 16);
+          res_pre[2 * c + 1] = ld16(rp0 + c * 16 + 8);
+        }
+    }
     FIB_PROFILER_EVENT_START(kEvMainLoop);
     ptx::mbar_wait(tmem_full, 0);
     ptx::tc_fence_after();
@@ -259,8 +275,7 @@ dlinear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     FIB_PROFILER_EVENT_END(kEvSplitKExchange);
     FIB_PROFILER_EVENT_START(kEvEpilogue);
-    float rs = 1.f;
-    if (p.row_sumsq != nullptr && m_ok) rs = rsqrtf(p.row_sumsq[m] * p.inv_dim + p.eps);
+    const float rs = rs_pre;
 
     // fp32 values of 16 owned columns starting at tile column own_lo + c (warp-collective TMEM load)
     auto load_chunk = [&](int c, float* v) {
@@ -279,6 +294,31 @@ dlinear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             v[4 * j + 1] += x.y;
             v[4 * j + 2] += x.z;
             v[4 * j + 3] += x.w;
+          }
+        }
+      }
+    };
+    // 32 columns per TMEM round trip (tcgen05.wait::ld waits for every outstanding load of the thread, so the way to have fewer
+    // serialized round trips is wider loads): the wide epilogues (gate/up: 208 columns per thread) are bound by that latency chain
+    auto load_chunk32 = [&](int c, float* v) {
+      uint32_t r[32];
+      ptx::tmem_ld_x32(taddr + own_lo + c, r);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      if (S > 1 && row_ok) {
+        for (int sl = 0; sl < S - 1; ++sl) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const float4* src = reinterpret_cast<const float4*>(xbuf + sl * own_w * BM * 4 + (((c >> 4) + h) * BM + m) * 64);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 x = src[j ^ xsw];
+              v[16 * h + 4 * j] += x.x;
+              v[16 * h + 4 * j + 1] += x.y;
+              v[16 * h + 4 * j + 2] += x.z;
+              v[16 * h + 4 * j + 3] += x.w;
+            }
           }
         }
       }
@@ -307,7 +347,27 @@ dlinear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     } else if (p.epi == kGated) {
-      for (int c = 0; c < own_w; c += 16) {
+      int c = 0;
+      for (; c + 32 <= own_w; c += 32) {
+        float v[32];
+        load_chunk32(c, v);
+        const int n0 = n_base + c;
+        if (m_ok && n0 < p.N) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (n0 + 16 * h < p.N) {
+              Vec16<T> o;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float g = v[16 * h + 2 * j] * rs, u = v[16 * h + 2 * j + 1] * rs;
+                o.v[j] = from_f32<T>(g / (1.f + __expf(-g)) * u);
+              }
+              st16(reinterpret_cast<T*>(p.out) + int64_t(m) * p.ldo + (n0 + 16 * h) / 2, o);
+            }
+          }
+        }
+      }
+      for (; c < own_w; c += 16) {
         float v[16];
         load_chunk(c, v);
         const int n0 = n_base + c;
@@ -331,7 +391,21 @@ dlinear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int n0 = n_base + c;
           if (m_ok && n0 < p.N) {
             T* rp = resid + int64_t(m) * p.ldr + n0;
-            Vec16<T> a = ld16(rp), b = ld16(rp + 8);
+            Vec16<T> a, b;
+            if (res_prefetched) {
+              // (compile-time indices: the chunk loop is at most kResPre long on this path)
+              a = res_pre[0];
+              b = res_pre[1];
+#pragma unroll
+              for (int q2 = 1; q2 < kResPre; ++q2)
+                if (c == 16 * q2) {
+                  a = res_pre[2 * q2];
+                  b = res_pre[2 * q2 + 1];
+                }
+            } else {
+              a = ld16(rp);
+              b = ld16(rp + 8);
+            }
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               a.v[e] = from_f32<T>(to_f32(a.v[e]) + v[e]);
@@ -353,28 +427,40 @@ dlinear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint8_t* tile = smem;
         const int P = own_w >> 3;                // 16-byte pieces per strip row
         const int pmask = (P & (P - 1)) == 0 ? P - 1 : 0;
-        for (int c = 0; c < own_w; c += 16) {
-          float v[16];
-          load_chunk(c, v);
-          if (row_ok) {
-            Vec16<T> a, b;
+        auto stage16 = [&](const float* v, int c) {  // 16 accumulator columns -> two 16-byte pieces of the staged strip
+          Vec16<T> a, b;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              a.v[e] = from_f32<T>(v[e]);
-              b.v[e] = from_f32<T>(v[8 + e]);
-            }
-            uint32_t* wa = reinterpret_cast<uint32_t*>(&a);
-            uint32_t* wb = reinterpret_cast<uint32_t*>(&b);
+          for (int e = 0; e < 8; ++e) {
+            a.v[e] = from_f32<T>(v[e]);
+            b.v[e] = from_f32<T>(v[8 + e]);
+          }
+          uint32_t* wa = reinterpret_cast<uint32_t*>(&a);
+          uint32_t* wb = reinterpret_cast<uint32_t*>(&b);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {  // -0.0 is the sentinel: never send it
-              if ((wa[e] & 0xffffu) == 0x8000u) wa[e] &= 0xffff0000u;
-              if ((wa[e] >> 16) == 0x8000u) wa[e] &= 0x0000ffffu;
-              if ((wb[e] & 0xffffu) == 0x8000u) wb[e] &= 0xffff0000u;
-              if ((wb[e] >> 16) == 0x8000u) wb[e] &= 0x0000ffffu;
+          for (int e = 0; e < 4; ++e) {  // -0.0 is the sentinel: never send it
+            if ((wa[e] & 0xffffu) == 0x8000u) wa[e] &= 0xffff0000u;
+            if ((wa[e] >> 16) == 0x8000u) wa[e] &= 0x0000ffffu;
+            if ((wb[e] & 0xffffu) == 0x8000u) wb[e] &= 0xffff0000u;
+            if ((wb[e] >> 16) == 0x8000u) wb[e] &= 0x0000ffffu;
+          }
+          const int sw = (m >> 1) & pmask, pc = c >> 3;
+          *reinterpret_cast<int4*>(tile + ((m * P + (pc ^ sw)) << 4)) = *reinterpret_cast<const int4*>(&a);
+          *reinterpret_cast<int4*>(tile + ((m * P + ((pc + 1) ^ sw)) << 4)) = *reinterpret_cast<const int4*>(&b);
+        };
+        {
+          int c = 0;
+          for (; c + 32 <= own_w; c += 32) {
+            float v[32];
+            load_chunk32(c, v);
+            if (row_ok) {
+              stage16(v, c);
+              stage16(v + 16, c + 16);
             }
-            const int sw = (m >> 1) & pmask, pc = c >> 3;
-            *reinterpret_cast<int4*>(tile + ((m * P + (pc ^ sw)) << 4)) = *reinterpret_cast<const int4*>(&a);
-            *reinterpret_cast<int4*>(tile + ((m * P + ((pc + 1) ^ sw)) << 4)) = *reinterpret_cast<const int4*>(&b);
+          }
+          for (; c < own_w; c += 16) {
+            float v[16];
+            load_chunk(c, v);
+            if (row_ok) stage16(v, c);
           }
         }
         ptx::named_bar_sync(1, 128);
@@ -412,9 +498,9 @@ dlinear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           } while (!done);
         };
         // residual += sum (16-bit rounding of the new residual), returns the sum of squares of the 8 new values
-        auto add_resid = [&](int row, int col, const float* sum) {
+        auto add_resid = [&](int row, int col, const float* sum, bool have, Vec16<T> a) {
           T* rp = resid + int64_t(row) * p.ldr + col;
-          Vec16<T> a = ld16(rp);
+          if (!have) a = ld16(rp);
           float s2 = 0.f;
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
@@ -448,6 +534,18 @@ dlinear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             }
           }
+          // the residual values this thread will update do not depend on the peers: fetch them now, under the NVLink latency
+          constexpr int kPre = 4;
+          Vec16<T> rpre[kPre];
+          const bool pre_ok = nvec <= kPre * 128;
+          if (pre_ok) {
+#pragma unroll
+            for (int q2 = 0; q2 < kPre; ++q2) {
+              const int vi = etid + q2 * 128;
+              const int row = vi / P, pc = vi - row * P, col = n_base + pc * 8;
+              if (vi < nvec && row < p.M && col < p.N) rpre[q2] = ld16(resid + int64_t(row) * p.ldr + col);
+            }
+          }
           // while the pushes fly: reset my strip (all 64 rows: the next call may carry more tokens) of the NEXT call's buffer, last read two calls ago
           for (int vi = etid; vi < nvec; vi += 128) {
             const int row = vi / P, pc = vi - row * P, col = n_base + pc * 8;
@@ -471,7 +569,11 @@ dlinear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                   for (int e = 0; e < 8; ++e) sum[e] += to_f32(h[e]);
                 }
-              s2 = add_resid(row, col, sum);
+              Vec16<T> rv = rpre[0];
+#pragma unroll
+              for (int q2 = 1; q2 < kPre; ++q2)
+                if (vi == etid + q2 * 128) rv = rpre[q2];
+              s2 = add_resid(row, col, sum, pre_ok, rv);
             }
             row_ss(s2, row, pc, ok);
           }
@@ -499,6 +601,7 @@ dlinear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int lr = it / P, pc = it - lr * P, col = n_base + pc * 8, row = lr * W + p.rank;
             if (row < p.M && col < p.N) {
               int4 x[8];
+              const Vec16<T> old = ld16(resid + int64_t(row) * p.ldr + col);  // issued before the poll: hidden under the NVLink hop
               poll(recv + cur + int64_t(lr) * p.lds + col, int64_t(R) * p.lds, W, x);
               float sum[8];
 #pragma unroll
@@ -510,7 +613,6 @@ dlinear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                   for (int e = 0; e < 8; ++e) sum[e] += to_f32(h[e]);
                 }
-              const Vec16<T> old = ld16(resid + int64_t(row) * p.ldr + col);
               Vec16<T> nw;
 #pragma unroll
               for (int e = 0; e < 8; ++e) nw.v[e] = from_f32<T>(to_f32(old.v[e]) + sum[e]);
