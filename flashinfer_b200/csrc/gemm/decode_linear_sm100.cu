@@ -580,7 +580,7 @@ dlinear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         } else {
           // ======== two-shot: reduce-scatter by push (row m is owned by rank m % world), the owner adds the residual and multicasts
           //          the NEW residual rows to every rank.  Two one-way NVLink hops, (1 + 1/world) x strip bytes of ingress per rank
-          //          instead of world x: the choice for world >= 4.  Slot 0 of the rotating buffer is the reduce-scatter inbox
+          //          instead of world x: the choice for world >= 8 (measured equal at 4).  Slot 0 of the rotating buffer is the reduce-scatter inbox
           //          [src rank][owned row][hidden], slot 1 the all-gather inbox [row][hidden]. ========
           const int R = BM / W;  // rows per owner (world is 2, 4 or 8)
           for (int vi = etid; vi < nvec; vi += 128) {
@@ -837,7 +837,7 @@ extern "C" int dlinear_run(void* A, void* W, int64_t M, int64_t N, int64_t K, in
   if (epi == kResid && world > 1) {
     FIB_CHECK(world <= 8 && recv && epoch && lds % 8 == 0 && slot_elems >= BM * lds && (mc_recv || peer_recv_host),
               "dlinear (all-reduce): world <= 8, symmetric receive buffers (multicast alias or peer table) and the epoch word required");
-    if (ar_algo == 0) ar_algo = (world >= 4 && BM % world == 0 && peer_recv_host) ? 2 : 1;
+    if (ar_algo == 0) ar_algo = (world >= 8 && BM % world == 0 && peer_recv_host) ? 2 : 1;
     FIB_CHECK(ar_algo == 1 || ar_algo == 2, "dlinear (all-reduce): ar_algo must be 0 (auto), 1 (one-shot) or 2 (two-shot)");
     if (ar_algo == 2) FIB_CHECK(BM % world == 0 && peer_recv_host, "dlinear (two-shot all-reduce): world must divide 64 and the peer table is required");
   }

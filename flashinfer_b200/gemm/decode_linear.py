@@ -70,7 +70,7 @@ class FusedLinearTP:
         """``algo``: ``ONE_SHOT`` - every rank multicasts its partial strip and gathers all ``world`` partials (one NVLink hop,
         ``world x`` ingress: best for 2 ranks); ``TWO_SHOT`` - reduce-scatter by push to the row owner (row ``m`` belongs to rank
         ``m % world``), the owner adds the residual and multicasts the new residual rows (two hops, ``(1 + 1/world) x`` ingress:
-        best for 4 / 8 ranks); ``None`` / 0 - by world size (env ``FIB200_DL_AR_ALGO`` overrides).  The algorithm is a property
+        best for 8 ranks); ``None`` / 0 - by world size (env ``FIB200_DL_AR_ALGO`` overrides).  The algorithm is a property
         of the context because the two use the rotating receive buffers differently: do not change it between calls."""
         import torch.distributed as dist
 
@@ -93,7 +93,9 @@ class FusedLinearTP:
         self.epoch = torch.zeros(4, dtype=torch.int32, device=self.heap.device)
         algo = int(algo or os.environ.get("FIB200_DL_AR_ALGO", "0"))
         if algo == 0:
-            algo = self.TWO_SHOT if (self.world >= 4 and 64 % self.world == 0) else self.ONE_SHOT
+            # measured on B200 (tools/tp_breakdown.py, O projection, fused GEMM + all-reduce): world 2: 12.6 (one-shot) vs 13.9 us,
+            # world 4: 14.1 vs 14.3 us; at world 8 the one-shot ingress is 8 x the strip and the two-shot wins
+            algo = self.TWO_SHOT if (self.world >= 8 and 64 % self.world == 0) else self.ONE_SHOT
         if algo == self.TWO_SHOT and 64 % self.world:
             raise ValueError("FusedLinearTP: the two-shot all-reduce needs a world size that divides 64")
         self.algo = algo
