@@ -161,6 +161,7 @@ def tp_gemm_rs(impl, rank, world):
             if impl == "ours":  # schedule chosen by the per-shape tuner (0 one kernel | 1 GEMM then pull | c pipeline chunks) and its timings
                 out[name]["schedule_ms"] = {str(k): v for k, v in next(iter(getattr(comm, "_rs_tuning_log", {}).values()), {}).items()}
                 out[name]["schedule"] = next(iter(getattr(comm, "_rs_tuned", {}).values()), None)
+                out[name]["nvls_multicast"] = bool(comm.use_nvls)
                 comm.__dict__.pop("_rs_tuning_log", None)
                 comm.__dict__.pop("_rs_tuned", None)
         except Exception as e:  # noqa: BLE001

@@ -156,12 +156,14 @@ class GemmAllReduce:
         launch: wins at decode / small-prefill sizes), 1 = one full-size GEMM followed by one full-machine in-switch pull,
         c >= 2 = c pipeline chunks (the pull of chunk i on a side stream under the GEMM of chunk i + 1)."""
         rpr = M // self.world
-        if (not self.use_nvls and self.world > 4) or M < 2048 or N % 256 or rpr % 128:
+        if M < 2048 or N % 256 or rpr % 128:
             return [0]
+        # (without an NVLS multicast mapping of the staging buffer - e.g. a heap too large for the multicast object - the pull
+        # kernel reads the `world` partials with direct peer loads: same bytes over NVLink, still far ahead of the one-kernel
+        # version whose 4 reduce warps cannot keep a prefill-sized pull in flight: 4.4 ms at TP 8, M = 32768)
         cands = [c for c in (4, 2, 8, 1) if rpr % (c * 128) == 0 and rpr // c >= 256]
-        if M <= 8192:
-            cands.append(0)
-        return cands or [0]
+        cands.append(0)
+        return cands
 
     def _pipeline_chunks(self, M: int, N: int, K: int) -> int:
         """Default schedule without tuning (first admissible candidate)."""
