@@ -45,40 +45,55 @@ class BlockSparseAttentionWrapper:
              kv_data_type=None, o_data_type="float16", non_blocking: bool = True) -> None:
         if M % R or N % C:
             raise ValueError("M must be a multiple of R and N of C")
-        if mask is not None or packed_mask is not None:
-            raise NotImplementedError("element-level masks inside blocks")
+        # element-level mask inside the non-zero blocks: ``mask [nnz, R, C]`` (or already in the flattened per-block-row layout of
+        # convert_bsr_mask_layout) / its little-endian bit-packed form -> the custom-mask stream of the tcgen05 prefill kernel
+        flat_mask = None
+        if mask is not None:
+            flat_mask = (convert_bsr_mask_layout(mask.bool(), indptr) if mask.dim() == 3 else mask.flatten().bool())
+        elif packed_mask is not None:
+            from .prefill import _unpack_bits
+
+            flat_mask = _unpack_bits(packed_mask, int(indices.numel()) * R * C)
         self._M, self._N, self._R, self._C = M, N, R, C
         self._hq, self._hkv, self._d = num_qo_heads, num_kv_heads, head_dim
         mb = M // R
-        self._indptr_host = indptr.to("cpu", torch.int32)
-        self._indices = indices.to(torch.int32)
-        last = torch.full((mb,), C, dtype=torch.int32)
-        self._use_decode = (R * (num_qo_heads // num_kv_heads) <= 32) and not causal
-        if self._use_decode:
-            qo = torch.arange(0, (mb + 1) * R, R, dtype=torch.int32) if R > 1 else None
-            self._decode.plan(indptr, indices, last, num_qo_heads, num_kv_heads, head_dim, C, q_data_type=q_data_type,
-                              logits_soft_cap=logits_soft_cap, sm_scale=sm_scale, qo_indptr=qo)
-            self._decode_noncausal = R > 1
+        # page granularity of the paged kernels: a page must tile the 128-token KV tile (power of two <= 128) or be a multiple of
+        # 128; any other block width C is cut into C / g pages of g = largest power of two dividing C
+        if (C <= 128 and C & (C - 1) == 0) or C % 128 == 0:
+            g = C
         else:
-            if C & (C - 1) and C % 128:
-                raise NotImplementedError("block-sparse prefill needs C to be a power of two or a multiple of 128")
+            g = C & -C
+            g = min(g, 128)
+        ppb = C // g
+        self._g = g
+        indptr_i = indptr.to("cpu", torch.int64)
+        indices_i = indices.to("cpu", torch.int64)
+        if ppb > 1:
+            indices_i = (indices_i[:, None] * ppb + torch.arange(ppb)[None, :]).reshape(-1)
+            indptr_i = indptr_i * ppb
+        self._indptr_host = indptr_i.to(torch.int32)
+        self._indices = indices_i.to(torch.int32)
+        last = torch.full((mb,), g, dtype=torch.int32)
+        # one query row per block row and no intra-block mask: the decode kernel (swap-AB, bandwidth-bound); otherwise prefill
+        self._use_decode = R == 1 and (num_qo_heads // num_kv_heads) <= 32 and not causal and flat_mask is None
+        if self._use_decode:
+            self._decode.plan(self._indptr_host, self._indices, last, num_qo_heads, num_kv_heads, head_dim, g, q_data_type=q_data_type,
+                              logits_soft_cap=logits_soft_cap, sm_scale=sm_scale)
+        else:
             qo = torch.arange(0, (mb + 1) * R, R, dtype=torch.int32)
-            self._prefill.plan(qo, indptr, indices, last, num_qo_heads, num_kv_heads, head_dim, C, causal=causal,
-                               logits_soft_cap=logits_soft_cap, sm_scale=sm_scale, q_data_type=q_data_type)
+            self._prefill.plan(qo, self._indptr_host, self._indices, last, num_qo_heads, num_kv_heads, head_dim, g, causal=causal,
+                               logits_soft_cap=logits_soft_cap, sm_scale=sm_scale, q_data_type=q_data_type, custom_mask=flat_mask,
+                               pos_encoding_mode=pos_encoding_mode)
 
     begin_forward = plan
 
     def run(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale_q=None, scale_k=None, scale_v=None,
             out: Optional[torch.Tensor] = None, lse: Optional[torch.Tensor] = None, return_lse: bool = False,
             enable_pdl=None):
-        C = self._C
-        kc = k.reshape(-1, C, self._hkv, self._d)
-        vc = v.reshape(-1, C, self._hkv, self._d)
+        g = self._g
+        kc = k.reshape(-1, g, self._hkv, self._d)
+        vc = v.reshape(-1, g, self._hkv, self._d)
         if self._use_decode:
-            if self._decode_noncausal:
-                # decode kernel applies causal masking among the R new tokens; block-sparse rows see whole blocks,
-                # so run row by row semantics through the prefill wrapper instead when R > 1
-                raise NotImplementedError("R > 1 with small groups: plan with causal=False uses the prefill kernel")
             res = self._decode.run(q, (kc, vc), out=out, lse=lse, return_lse=return_lse)
         else:
             res = self._prefill.run(q, (kc, vc), out=out, lse=lse, return_lse=return_lse)
@@ -108,8 +123,6 @@ class VariableBlockSparseAttentionWrapper:
              q_data_type="float16", kv_data_type=None) -> None:
         """``block_mask_map [num_kv_heads, MB, NB]`` bool, ``block_row_sz [num_kv_heads, MB]``,
         ``block_col_sz [num_kv_heads, NB]``.  Heads are folded into the batch dimension."""
-        if causal:
-            raise NotImplementedError("causal variable block-sparse")
         hkv, mb, nb = block_mask_map.shape
         self._hq, self._hkv, self._d = num_qo_heads, num_kv_heads, head_dim
         bm = block_mask_map.cpu().bool()
@@ -130,7 +143,7 @@ class VariableBlockSparseAttentionWrapper:
         n_req = len(qo) - 1
         group = num_qo_heads // num_kv_heads
         self._prefill.plan(torch.tensor(qo, dtype=torch.int32), torch.tensor(kvp, dtype=torch.int32), kv_indices,
-                           torch.ones(n_req, dtype=torch.int32), group, 1, head_dim, 1, causal=False,
+                           torch.ones(n_req, dtype=torch.int32), group, 1, head_dim, 1, causal=causal,  # causal over the gathered keys, like the reference
                            logits_soft_cap=logits_soft_cap, sm_scale=sm_scale, q_data_type=q_data_type)
 
     def run(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out=None, lse=None, return_lse: bool = False,

@@ -81,6 +81,14 @@ BINDINGS: List[Tuple[str, str, "_t.TraceTemplate"]] = [
     ("rope", "mla_rope_quantize_fp8", T.mla_rope_quantize_fp8_trace),
     ("gemm.lowp", "mm_fp4", T.mm_fp4_trace),
     ("gemm.lowp", "mm_mxfp8", T.mm_mxfp8_trace),
+    ("gemm.decode_linear", "decode_linear", T.decode_linear_trace),
+    ("topk", "topk_clusters_exact", T.topk_clusters_exact_trace),
+    ("topk", "top_k_page_table_transform", T.top_k_page_table_transform_trace),
+    ("topk", "top_k_ragged_transform", T.top_k_ragged_transform_trace),
+    ("triton.sm_constraint_gemm", "gemm_persistent", T.gemm_persistent_trace),
+    ("comm.allreduce", "local_argmax", T.local_argmax_trace),
+    ("comm.trtllm_alltoall", "moe_local_gather", T.moe_local_gather_trace),
+    ("mla._core", "trtllm_batch_decode_with_kv_cache_mla", T.sparse_mla_decode_trace),
 ]
 
 _PKG = __name__.rsplit(".", 2)[0]
