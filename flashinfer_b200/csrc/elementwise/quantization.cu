@@ -121,7 +121,10 @@ fp4_quantize_kernel(const T* __restrict__ x, uint8_t* __restrict__ q, uint8_t* _
     }
     uint8_t* dst = q + (b * M + m) * (K / 2) + kc * (VEC / 2);
     const uint8_t sf_byte = fp4_quantize_block<VEC, kUE8M0>(v, gs, dst);
-    const int64_t sf_off = swizzled ? sf_swizzled_offset(m, kc, kc_pad) : m * kc_total + kc;
+    // swizzled: 0 linear [M, K / vec] | 1 the 128x4 tile layout of tcgen05 block-scaled MMA | 2 the 8x4 tile layout
+    // (reference SfLayout.layout_8x4: tiles of 8 rows x 4 scale columns, 32 bytes each, row-major inside the tile)
+    const int64_t sf_off = swizzled == 2 ? ((m / 8) * (kc_pad / 4) + kc / 4) * 32 + (m % 8) * 4 + (kc % 4)
+                                         : (swizzled ? sf_swizzled_offset(m, kc, kc_pad) : m * kc_total + kc);
     sf[b * sf_batch_stride + sf_off] = sf_byte;
   }
   ptx::grid_dep_launch();

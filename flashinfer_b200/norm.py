@@ -126,8 +126,22 @@ def fused_rmsnorm_silu(input, weight, eps: float = 1e-6, out=None, block_scale=N
     """``out = SiLU(RMSNorm(input) * weight)`` (bf16 or fp8 output)."""
     if out is None:
         out = torch.empty_like(input)
+    fp4_dt = getattr(torch, "float4_e2m1fn_x2", None)
+    if out.dtype == torch.uint8 or (fp4_dt is not None and out.dtype == fp4_dt):
+        # NVFP4 output (reference norm/__init__.py:639-658): linear [tokens, hidden / 16] e4m3 block scales, global scale 1.
+        # Two native kernels: norm + SiLU, then the block quantiser.
+        from .quantization.fp4 import fp4_quantize
+
+        y = fused_rmsnorm_silu(input, weight, eps)
+        q, sf = fp4_quantize(y, None, 16, False, False)
+        out.view(torch.uint8).copy_(q)
+        if block_scale is None:
+            block_scale = sf.view(torch.float8_e4m3fn)
+        else:
+            block_scale.view(torch.uint8).copy_(sf)
+        return out, block_scale
     if out.dtype not in (input.dtype, torch.float8_e4m3fn):
-        raise NotImplementedError("fused_rmsnorm_silu: nvfp4 output not implemented yet")
+        raise TypeError(f"fused_rmsnorm_silu: unsupported output dtype {out.dtype}")
     if not input.is_cuda:
         y = reference.rmsnorm_ref(input.float(), weight, eps)
         out.copy_(torch.nn.functional.silu(y).to(out.dtype))

@@ -36,6 +36,14 @@ def _unswizzle_index(m: int, kc: int) -> torch.Tensor:
     return (tile * 512 + (r % 32) * 16 + ((r % 128) // 32) * 4 + c % 4).reshape(-1)
 
 
+def _index_8x4(m: int, kc: int) -> torch.Tensor:
+    """flat offset of every (row, scale-column) pair in the 8x4 tile layout, row-major ``[m*kc]``."""
+    kc_pad = round_up(kc, 4)
+    r = torch.arange(m)[:, None]
+    c = torch.arange(kc)[None, :]
+    return (((r // 8) * (kc_pad // 4) + c // 4) * 32 + (r % 8) * 4 + c % 4).reshape(-1)
+
+
 def _quant_cpu(x: torch.Tensor, gs: float, vec: int, ue8m0: bool):
     m, k = x.shape
     xf = x.float().view(m, k // vec, vec)
@@ -70,8 +78,6 @@ def fp4_quantize(input: torch.Tensor, global_scale: Optional[torch.Tensor] = Non
                  is_global_scale_inversed: bool = False, enable_pdl: Optional[bool] = None,
                  backend: str = "cuda", row_map: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """Quantise ``[..., k]`` f16/bf16 to FP4.  Returns (packed uint8 ``[..., k/2]``, uint8 scale factors)."""
-    if is_sf_8x4_layout:
-        raise NotImplementedError("8x4 scale-factor layout")
     if sf_vec_size not in (16, 32):
         raise ValueError("sf_vec_size must be 16 or 32")
     shape = input.shape
@@ -82,10 +88,14 @@ def fp4_quantize(input: torch.Tensor, global_scale: Optional[torch.Tensor] = Non
     if gs is not None and is_global_scale_inversed:
         gs = 1.0 / gs
     sf_size = _swizzled_sf_size(m, kc) if is_sf_swizzled_layout else m * kc
+    if is_sf_8x4_layout:  # tiles of 8 rows x 4 scale columns (reference SfLayout.layout_8x4)
+        sf_size = round_up(m, 8) * round_up(kc, 4)
     if not x.is_cuda:
         packed, sfb = _quant_cpu(x, float(gs) if gs is not None else 1.0, sf_vec_size, sf_use_ue8m0)
         sf = torch.zeros(sf_size, dtype=torch.uint8)
-        if is_sf_swizzled_layout:
+        if is_sf_8x4_layout:
+            sf[_index_8x4(m, kc)] = sfb.reshape(-1)
+        elif is_sf_swizzled_layout:
             sf[_unswizzle_index(m, kc)] = sfb.reshape(-1)
         else:
             sf.copy_(sfb.reshape(-1))
@@ -96,9 +106,10 @@ def fp4_quantize(input: torch.Tensor, global_scale: Optional[torch.Tensor] = Non
         gst = gs.float().reshape(1).contiguous() if gs is not None else None
         jit.load("quantization").call(
             "fp4_quantize", x, packed, sf, gst, 1, m, k, x.stride(0), 0, sf_vec_size, 1 if sf_use_ue8m0 else 0,
-            1 if is_sf_swizzled_layout else 0, 0, row_map, 0, 0, None, 0, 1, dtype_code(x.dtype), 1, stream_ptr(x),
+            2 if is_sf_8x4_layout else (1 if is_sf_swizzled_layout else 0), 0, row_map, 0, 0, None, 0, 1, dtype_code(x.dtype), 1,
+            stream_ptr(x),
         )
-    sf = sf.view(-1, round_up(kc, 4)) if is_sf_swizzled_layout else sf.view(m, kc)
+    sf = sf.view(-1, round_up(kc, 4)) if (is_sf_swizzled_layout or is_sf_8x4_layout) else sf.view(m, kc)
     return packed.view(*shape[:-1], k // 2), sf
 
 

@@ -16,7 +16,7 @@ def _launch(q, k, q_out, k_out, *, pos_ids=None, indptr=None, offsets=None, cos_
             interleave=False, rope_scale=1.0, rope_theta=1e4, llama31=None, q_out_scale=1.0, k_out_scale=1.0):
     nnz, hq, d = q.shape
     hk = k.shape[1] if k is not None else 0
-    rd = rotary_dim or (cos_sin_cache.shape[-1] if cos_sin_cache is not None else d)
+    rd = rotary_dim if rotary_dim is not None else (cos_sin_cache.shape[-1] if cos_sin_cache is not None else d)
     if not q.is_cuda:
         if pos_ids is None:
             lens = (indptr[1:] - indptr[:-1]).long()
@@ -142,6 +142,16 @@ def rope_quantize_fp8(q_rope, k_rope, q_nope, k_nope, cos_sin_cache, pos_ids, is
     _launch(q_rope, kr, q_rope_out, kro, pos_ids=pos_ids, cos_sin_cache=cos_sin_cache, interleave=not is_neox,
             q_out_scale=quant_scale_q, k_out_scale=quant_scale_kv)
     lim = 448.0 if qd == torch.float8_e4m3fn else 57344.0
+    if q_nope is not None and q_nope.is_cuda and q_nope.shape[-1] % 8 == 0 and (k_nope is None or kn.shape[-1] == q_nope.shape[-1]):
+        # the no-rope slices ride the same native kernel with rotary_dim = 0: a saturating scale + fp8 cast, no rotation
+        q_nope_out = q_nope_out if q_nope_out is not None else torch.empty_like(q_nope, dtype=qd)
+        kno = None
+        if k_nope is not None:
+            k_nope_out = k_nope_out if k_nope_out is not None else torch.empty_like(k_nope, dtype=qd)
+            kno = k_nope_out.unsqueeze(1) if k_nope.ndim == 2 else k_nope_out
+        _launch(q_nope, kn if k_nope is not None else None, q_nope_out, kno, pos_ids=pos_ids, rotary_dim=0, interleave=False,
+                q_out_scale=quant_scale_q, k_out_scale=quant_scale_kv)
+        return q_rope_out, k_rope_out, q_nope_out, k_nope_out
     if q_nope is not None:
         qn = (q_nope.float() * quant_scale_q).clamp(-lim, lim).to(qd)
         q_nope_out = qn if q_nope_out is None else q_nope_out.copy_(qn)
@@ -203,7 +213,20 @@ def rope_quantize_fp8_append_paged_kv_cache(q_rope, k_rope, q_nope, k_nope, v, c
     ``mla_rope_quantize_fp8`` + ``append_paged_mla_kv_cache``.)"""
     qdt = quantize_dtype or torch.float8_e4m3fn
     if v is None:
-        raise NotImplementedError("MLA layout: use mla_rope_quantize_fp8 + append_paged_mla_kv_cache")
+        # MLA layout (reference rope.py:1600-1691): k_rope [T, 64] is the shared rope key (kpe), k_nope [T, 512] the compressed
+        # latent (ckv); paged_kv_cache = (ckv_cache [pages, page, 512], kpe_cache [pages, page, 64]).  Two native kernels: RoPE +
+        # fp8 quantisation of q / k (rope_quantize_fp8), then the latent-cache append.
+        from . import page as _page
+
+        ckv_cache, kpe_cache = paged_kv_cache
+        qr, kr, qn, kn = rope_quantize_fp8(q_rope, k_rope, q_nope, k_nope, cos_sin_cache, pos_ids, is_neox, qdt, quant_scale_q,
+                                           quant_scale_kv, q_rope_out, None, q_nope_out, None, enable_pdl)
+        kr2 = kr.reshape(kr.shape[0], -1)
+        kn2 = kn.reshape(kn.shape[0], -1)
+        if ckv_cache.dtype != kn2.dtype or kpe_cache.dtype != kr2.dtype:
+            raise ValueError("cache dtype must equal quantize_dtype")
+        _page.append_paged_mla_kv_cache(kn2, kr2, batch_indices, positions, ckv_cache, kpe_cache, kv_indices, kv_indptr, None)
+        return qr, qn
     rd = q_rope.shape[-1]
     # assemble full heads [nope | rope]?  the reference keeps rope dims first in memory for GQA: [rope | nope]
     q_full = torch.cat([q_rope, q_nope], -1) if q_nope is not None and q_nope.shape[-1] else q_rope

@@ -133,3 +133,49 @@ def test_merge_states(dtype):
     cascade.merge_state_in_place(va2, sa2, vb, sb, mask)
     torch.testing.assert_close(va2[mask], vr[mask], rtol=2e-2, atol=2e-2)
     torch.testing.assert_close(va2[~mask], va[~mask])
+
+
+def test_fused_rmsnorm_silu_nvfp4_output_gpu():
+    from flashinfer_b200.quantization.fp4 import e2m1_and_ufp8sf_scale_to_float
+
+    torch.manual_seed(0)
+    x, w = torch.randn(300, 512, device="cuda").bfloat16(), (1 + 0.1 * torch.randn(512, device="cuda")).bfloat16()
+    q, sf = fi.norm.fused_rmsnorm_silu(x, w, 1e-6, out=torch.empty(300, 256, dtype=torch.uint8, device="cuda"))
+    ref = fi.norm.fused_rmsnorm_silu(x, w, 1e-6).float()
+    d = e2m1_and_ufp8sf_scale_to_float(q.view(torch.uint8), sf.view(torch.uint8), None, 16, 1, False)
+    assert torch.nn.functional.cosine_similarity(d.flatten(), ref.flatten(), dim=0) > 0.99
+
+
+def test_rope_quantize_fp8_nope_slices_and_mla_append():
+    """No-rope slices are scaled / cast by the native kernel (rotary_dim = 0); the MLA flavour of the fused append writes
+    (ckv, kpe) into the latent caches.  Oracle: the same ops on CPU tensors."""
+    torch.manual_seed(0)
+    T, H, dr, dn, page = 37, 16, 64, 512, 16
+    q_rope, q_nope = torch.randn(T, H, dr).bfloat16(), torch.randn(T, H, dn).bfloat16()
+    k_rope, k_nope = torch.randn(T, dr).bfloat16(), torch.randn(T, dn).bfloat16()
+    pos = torch.arange(T, dtype=torch.int32)
+    inv = 1.0 / (1e4 ** (torch.arange(0, dr, 2).float() / dr))
+    ang = torch.arange(64).float()[:, None] * inv[None]
+    cache = torch.cat([ang.cos(), ang.sin()], -1)
+    cpu = rope.mla_rope_quantize_fp8(q_rope, k_rope, q_nope, k_nope, cache, pos, quant_scale_q=0.5, quant_scale_kv=2.0)
+    gpu = rope.mla_rope_quantize_fp8(q_rope.cuda(), k_rope.cuda(), q_nope.cuda(), k_nope.cuda(), cache.cuda(), pos.cuda(),
+                                     quant_scale_q=0.5, quant_scale_kv=2.0)
+    for c, g in zip(cpu, gpu):
+        assert g.dtype == torch.float8_e4m3fn and g.shape == c.shape
+        assert (g.float().cpu() - c.float()).abs().max() <= 0.07 * c.float().abs().max()  # one e4m3 step on rare rounding ties
+    # fused append, MLA layout: one request of T tokens
+    n_pages = (T + page - 1) // page
+    kv_indices = torch.randperm(n_pages).int()
+    kv_indptr = torch.tensor([0, n_pages], dtype=torch.int32)
+    bi = torch.zeros(T, dtype=torch.int32)
+    outs = {}
+    for dev in ("cpu", "cuda"):
+        ckv = torch.zeros(n_pages, page, dn, dtype=torch.float8_e4m3fn, device=dev)
+        kpe = torch.zeros(n_pages, page, dr, dtype=torch.float8_e4m3fn, device=dev)
+        qr, qn = rope.rope_quantize_fp8_append_paged_kv_cache(
+            q_rope.to(dev), k_rope.to(dev), q_nope.to(dev), k_nope.to(dev), None, cache.to(dev), pos.to(dev), (ckv, kpe),
+            kv_indices.to(dev), kv_indptr.to(dev), bi.to(dev), pos.to(dev), quant_scale_kv=2.0, page_size=page)
+        outs[dev] = (ckv.float().cpu(), kpe.float().cpu(), qr.float().cpu(), qn.float().cpu())
+    for a, b in zip(outs["cpu"], outs["cuda"]):
+        assert (a - b).abs().max() <= 0.07 * a.abs().max()
+    assert outs["cuda"][0].abs().sum() > 0 and outs["cuda"][1].abs().sum() > 0

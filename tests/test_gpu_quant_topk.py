@@ -123,3 +123,21 @@ def test_top_k_cluster_transforms_ties_lengths():
     assert idx.dtype == torch.int32 and torch.equal(idx, TK._run(x, k, 0, clusters=1)[1])
     assert torch.equal(TK.topk_clusters_page_table_transform(x, lengths, table, k), TK.top_k_page_table_transform(x, table, lengths, k))
     assert torch.equal(TK.topk_clusters_ragged_transform(x, lengths, offs, k), TK.top_k_ragged_transform(x, offs, lengths, k))
+
+
+@pytest.mark.parametrize("shape", [(8, 64), (37, 256), (200, 4096)])
+def test_nvfp4_quantize_8x4_layout(shape):
+    """SfLayout.layout_8x4 (tiles of 8 rows x 4 scale columns): same codes and scale bytes as the linear layout, at the 8x4 offsets."""
+    from flashinfer_b200.quantization.fp4 import SfLayout, _index_8x4, nvfp4_quantize
+
+    torch.manual_seed(shape[0])
+    x = torch.randn(*shape, device="cuda").bfloat16()
+    gs = torch.tensor([448.0 * 6.0 / float(x.float().abs().max())], device="cuda")
+    q8, sf8 = nvfp4_quantize(x, gs, sfLayout=SfLayout.layout_8x4)
+    ql, sfl = nvfp4_quantize(x, gs, sfLayout=SfLayout.layout_linear)
+    assert torch.equal(q8, ql)
+    m, kc = shape[0], shape[1] // 16
+    assert sf8.numel() == (m + 7) // 8 * 8 * ((kc + 3) // 4 * 4)
+    assert torch.equal(sf8.reshape(-1)[_index_8x4(m, kc).to("cuda")], sfl.reshape(-1))
+    qc, sfc = nvfp4_quantize(x.cpu(), gs.cpu(), sfLayout=SfLayout.layout_8x4)
+    assert (sfc.reshape(-1) == sf8.reshape(-1).cpu()).float().mean() > 0.999  # rare 1-ulp differences in the scale

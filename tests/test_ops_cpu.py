@@ -123,3 +123,19 @@ def test_mm_fp4_accepts_transposed_scale_view():
     ref = a.float() @ w.float().t()
     cos = torch.nn.functional.cosine_similarity(plain.float().reshape(-1), ref.reshape(-1), dim=0)
     assert cos > 0.97
+
+
+def test_fused_rmsnorm_silu_nvfp4_output_and_fp4_8x4_layout():
+    import flashinfer_b200 as fi
+    from flashinfer_b200.quantization.fp4 import SfLayout, _index_8x4, e2m1_and_ufp8sf_scale_to_float, nvfp4_quantize
+
+    torch.manual_seed(0)
+    x, w = torch.randn(20, 128).bfloat16(), (1 + 0.1 * torch.randn(128)).bfloat16()
+    q, sf = fi.norm.fused_rmsnorm_silu(x, w, 1e-6, out=torch.empty(20, 64, dtype=torch.uint8))
+    ref = fi.norm.fused_rmsnorm_silu(x, w, 1e-6).float()
+    d = e2m1_and_ufp8sf_scale_to_float(q.view(torch.uint8), sf.view(torch.uint8), None, 16, 1, False)
+    assert sf.shape == (20, 8) and torch.nn.functional.cosine_similarity(d.flatten(), ref.flatten(), dim=0) > 0.99
+    gs = torch.tensor([100.0])
+    q8, sf8 = nvfp4_quantize(x, gs, sfLayout=SfLayout.layout_8x4)
+    ql, sfl = nvfp4_quantize(x, gs, sfLayout=SfLayout.layout_linear)
+    assert torch.equal(q8, ql) and sf8.numel() == 24 * 8 and torch.equal(sf8.reshape(-1)[_index_8x4(20, 8)], sfl.reshape(-1))
