@@ -52,6 +52,7 @@ struct DecodeParams {
   float sm_scale_log2;   // sm_scale * log2(e)
   float soft_cap;        // 0 = off ; else logits = cap * tanh(x * sm_scale / cap)
   float sm_scale;
+  const float* sinks;    // [num_qo_heads] attention-sink logits (natural log units) or null: exp(sink) joins the softmax denominator
 };
 
 // KVB = bytes per KV element: 2 (f16 / bf16 cache) or 1 (fp8 cache: Q and P are converted to e4m3 and both MMAs run
@@ -544,11 +545,21 @@ __device__ __forceinline__ void decode_body(const CUtensorMap& tmK, const CUtens
       for (int c = 0; c < NV; ++c) {
         if (c < nq) {
           const float4 w = *reinterpret_cast<const float4*>(red_sum + c * 4);
-          const float lt = w.x + w.y + w.z + w.w;
+          float lt = w.x + w.y + w.z + w.w;
+          float mc = m[c];
+          const int qi = c / G, g = c % G;
+          if (slot < 0 && p.sinks) {  // final (unsplit) state: fold the attention sink into the denominator
+            const float s2 = p.sinks[kv_head * G + g] * 1.4426950408889634f;
+            if (!(lt > 0.f)) {
+              mc = s2;
+              lt = 1.f;
+            } else {
+              lt += ptx::ex2(s2 - mc);
+            }
+          }
           const float inv = lt > 0.f ? 1.f / lt : 0.f;
           const float val = o[c] * inv;
-          const float lse = lt > 0.f ? m[c] + ptx::lg2(lt) : -INFINITY;
-          const int qi = c / G, g = c % G;
+          const float lse = lt > 0.f ? mc + ptx::lg2(lt) : -INFINITY;
           if (slot < 0) {
             obase[int64_t(q_start + qi) * p.o_stride_n + int64_t(kv_head * G + g) * p.o_stride_h + row] = from_f32<T>(val);
             if (p.lse && row == 0) p.lse[int64_t(q_start + qi) * p.num_qo_heads + kv_head * G + g] = lse;
@@ -584,8 +595,17 @@ __device__ __forceinline__ void decode_body(const CUtensorMap& tmK, const CUtens
               acc += w * __ldcg(p.partial_o + (int64_t(first_slot + sidx) * p.rows_per_slot + c) * D + row);
               den += w;
             }
-            const float val = den > 0.f ? acc / den : 0.f;
             const int qi = c / G, g = c % G;
+            if (p.sinks) {
+              const float s2 = p.sinks[kv_head * G + g] * 1.4426950408889634f;
+              if (mx == -INFINITY) {
+                mx = s2;
+                den = 1.f;
+              } else {
+                den += ptx::ex2(s2 - mx);
+              }
+            }
+            const float val = den > 0.f ? acc / den : 0.f;
             obase[int64_t(q_start + qi) * p.o_stride_n + int64_t(kv_head * G + g) * p.o_stride_h + row] = from_f32<T>(val);
             if (p.lse && row == 0)
               p.lse[int64_t(q_start + qi) * p.num_qo_heads + kv_head * G + g] = den > 0.f ? mx + ptx::lg2(den) : -INFINITY;
@@ -617,7 +637,8 @@ template <int D, typename T>
 __global__ void __launch_bounds__(D)
 decode_merge_kernel(const int32_t* __restrict__ items, int num_items, const float* __restrict__ partial_o,
                     const float* __restrict__ partial_lse, T* __restrict__ out, float* __restrict__ lse_out,
-                    int rows_per_slot, int group, int num_qo_heads, int64_t o_stride_n, int64_t o_stride_h) {
+                    int rows_per_slot, int group, int num_qo_heads, int64_t o_stride_n, int64_t o_stride_h,
+                    const float* __restrict__ sinks) {
   ptx::grid_dep_wait();
   ptx::grid_dep_launch();  // early trigger: dependents overlap their prologue, they still wait for our completion
   for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
@@ -635,8 +656,17 @@ decode_merge_kernel(const int32_t* __restrict__ items, int num_items, const floa
         acc += w * partial_o[(int64_t(slot0 + s) * rows_per_slot + c) * D + d];
         den += w;
       }
-      const float val = den > 0.f ? acc / den : 0.f;
       const int qi = c / group, g = c % group;
+      if (sinks) {
+        const float s2 = sinks[kv_head * group + g] * 1.4426950408889634f;
+        if (mx == -INFINITY) {
+          mx = s2;
+          den = 1.f;
+        } else {
+          den += ptx::ex2(s2 - mx);
+        }
+      }
+      const float val = den > 0.f ? acc / den : 0.f;
       out[int64_t(q_start + qi) * o_stride_n + int64_t(kv_head * group + g) * o_stride_h + d] = from_f32<T>(val);
       if (lse_out && d == 0)
         lse_out[int64_t(q_start + qi) * num_qo_heads + kv_head * group + g] = den > 0.f ? mx + ptx::lg2(den) : -INFINITY;
@@ -692,7 +722,7 @@ extern "C" int decode_paged_run(void* q, void* k_cache, void* v_cache, void* out
                                 int64_t num_pages_total, int64_t kv_stride_page, int64_t kv_stride_n,
                                 int64_t kv_stride_h, int64_t layout_hnd, int64_t q_stride_n, int64_t q_stride_h,
                                 int64_t o_stride_n, int64_t o_stride_h, double sm_scale, double soft_cap,
-                                int64_t window_left, int64_t causal, int64_t dtype, int64_t kv_dtype, int64_t pdl,
+                                int64_t window_left, int64_t causal, void* sinks, int64_t dtype, int64_t kv_dtype, int64_t pdl,
                                 int64_t stream_) {
   FIB_CHECK(head_dim == 128, "decode_sm100: only head_dim 128 is specialised");
   FIB_CHECK(dtype == kF16 || dtype == kBF16, "decode_sm100: q dtype must be f16/bf16");
@@ -746,6 +776,7 @@ extern "C" int decode_paged_run(void* q, void* k_cache, void* v_cache, void* out
   p.window_left = (int)window_left;
   p.causal = (int)causal;
   p.kv_early = (pdl == 2) ? 1 : 0;
+  p.sinks = reinterpret_cast<const float*>(sinks);
   p.sm_scale = (float)sm_scale;
   p.sm_scale_log2 = (float)(sm_scale * 1.4426950408889634);
   p.soft_cap = (float)soft_cap;
@@ -781,12 +812,12 @@ extern "C" int decode_paged_run(void* q, void* k_cache, void* v_cache, void* out
       FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, decode_merge_kernel<128, __half>, (const int32_t*)merge_items,
                                         (int)num_merge_items, (const float*)partial_o, (const float*)partial_lse,
                                         (__half*)out, (float*)lse, p.rows_per_slot, p.group, p.num_qo_heads, o_stride_n,
-                                        o_stride_h));
+                                        o_stride_h, p.sinks));
     } else {
       FIB_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, decode_merge_kernel<128, __nv_bfloat16>, (const int32_t*)merge_items,
                                         (int)num_merge_items, (const float*)partial_o, (const float*)partial_lse,
                                         (__nv_bfloat16*)out, (float*)lse, p.rows_per_slot, p.group, p.num_qo_heads,
-                                        o_stride_n, o_stride_h));
+                                        o_stride_n, o_stride_h, p.sinks));
     }
   }
   return 0;

@@ -334,8 +334,9 @@ class BatchDecodeWithPagedKVCacheWrapper:
             if want_lse:
                 lse.copy_(lse_ref)
         else:
-            self._run_sm100(q, k_cache, v_cache, out, lse if want_lse else None, sm_scale, window_left,
-                            2 if (kv_prefetch and (enable_pdl is None or enable_pdl)) else enable_pdl)
+            if self._run_sm100(q, k_cache, v_cache, out, lse if want_lse else None, sm_scale, window_left,
+                               2 if (kv_prefetch and (enable_pdl is None or enable_pdl)) else enable_pdl, sinks=sinks):
+                sinks = None  # folded into the softmax denominator by the kernel
         if sinks is not None:
             # the sink only adds exp(sink) to the softmax denominator: fold it in from (o, lse)
             from .attention._core import apply_attention_sink
@@ -374,11 +375,13 @@ class BatchDecodeWithPagedKVCacheWrapper:
                (sp, sn, sh), (vsp, vsn, vsh), self._num_kv_heads, True, window_left, sm_scale, self._logits_soft_cap,
                enable_pdl=enable_pdl is None or enable_pdl)
 
-    def _run_sm100(self, q, k_cache, v_cache, out, lse, sm_scale, window_left, enable_pdl):
+    def _run_sm100(self, q, k_cache, v_cache, out, lse, sm_scale, window_left, enable_pdl, sinks=None):
+        """Returns True when ``sinks`` were folded in by the kernel."""
         kv_ok = k_cache.dtype == q.dtype or k_cache.dtype in (torch.float8_e4m3fn, torch.float8_e5m2)
         if (self._head_dim != 128 or q.dtype not in (torch.float16, torch.bfloat16) or not kv_ok or v_cache.dtype != k_cache.dtype
                 or self._max_q_rows > _MAX_Q_ROWS):
-            return self._run_generic(q, k_cache, v_cache, out, lse, sm_scale, window_left, enable_pdl)
+            self._run_generic(q, k_cache, v_cache, out, lse, sm_scale, window_left, enable_pdl)
+            return False
         sp, sn, sh, page_size, hkv, d = paged_kv_strides(k_cache, self._kv_layout)
         if paged_kv_strides(v_cache, self._kv_layout)[:3] != (sp, sn, sh):
             raise ValueError("k_cache and v_cache must share strides")
@@ -394,9 +397,11 @@ class BatchDecodeWithPagedKVCacheWrapper:
             self._num_merge, self._partial_o, self._partial_lse, self._merge_counters, self._num_ctas, self._max_q_rows,
             self._num_qo_heads, self._num_kv_heads, self._head_dim, page_size, k_cache.shape[0], sp, sn, sh,
             1 if self._kv_layout == "HND" else 0, q.stride(0), q.stride(1), out.stride(0), out.stride(1),
-            float(sm_scale), float(self._logits_soft_cap), int(window_left), causal, dtype_code(q.dtype),
+            float(sm_scale), float(self._logits_soft_cap), int(window_left), causal,
+            sinks.float().contiguous() if sinks is not None else None, dtype_code(q.dtype),
             dtype_code(k_cache.dtype), 2 if enable_pdl == 2 else (1 if (enable_pdl is None or enable_pdl) else 0), stream_ptr(q),
         )
+        return sinks is not None
 
 
 class CUDAGraphBatchDecodeWithPagedKVCacheWrapper(BatchDecodeWithPagedKVCacheWrapper):

@@ -250,7 +250,8 @@ class _BatchPrefillBase:
         return outs
 
     def _launch_sm100(self, q, k, v, out, lse, sm_scale, window_left, paged, kv_indices, page_args, enable_pdl,
-                      k_scale=None, v_scale=None):
+                      k_scale=None, v_scale=None, sinks=None):
+        """Returns True when ``sinks`` were folded in by the kernel (tcgen05 path), False when the caller still has to."""
         shape_ok = ((self._head_dim_qk, self._head_dim_vo) in ((128, 128), (192, 128), (64, 64))
                     and q.dtype in (torch.float16, torch.bfloat16))
         if shape_ok and k.dtype in (torch.float8_e4m3fn, torch.float8_e5m2) and q.shape[0] >= 4 * self._batch_size:
@@ -273,8 +274,8 @@ class _BatchPrefillBase:
         if not fast:
             if self._variant_mod is not None:
                 raise NotImplementedError("user attention variants run on the tcgen05 prefill kernel: f16 / bf16, head_dim 64 / 128 (192 qk)")
-            return self._launch_generic(q, k, v, out, lse, sm_scale, window_left, paged, kv_indices, page_args, enable_pdl,
-                                        k_scale, v_scale)
+            self._launch_generic(q, k, v, out, lse, sm_scale, window_left, paged, kv_indices, page_args, enable_pdl, k_scale, v_scale)
+            return False
         page_size, num_pages_total, sp, sn, sh, hnd = page_args[:6]
         vsp, vsn, vsh = page_args[6:9] if len(page_args) >= 9 else (sp, sn, sh)
         var_ptrs = var_scalars = None
@@ -294,8 +295,10 @@ class _BatchPrefillBase:
             q.stride(1), out.stride(0), out.stride(1), float(sm_scale), float(self._logits_soft_cap), int(window_left),
             1 if self._causal else 0, self._mask_words, self._mask_bit_indptr, self._alibi,
             1 if self._variant_mod is not None else 0, var_ptrs, var_scalars,
+            sinks.float().contiguous() if sinks is not None else None,
             dtype_code(q.dtype), 1 if (enable_pdl is None or enable_pdl) else 0, stream_ptr(q),
         )
+        return sinks is not None
 
     def _set_pos_encoding(self, pos_encoding_mode: str, num_qo_heads: int) -> None:
         """ALiBi is a logits transform of the softmax pass (slopes per head); RoPE has to be applied by flashinfer_b200.rope."""
@@ -488,8 +491,10 @@ class BatchPrefillWithPagedKVCacheWrapper(_BatchPrefillBase):
             if paged_kv_strides(v_cache, self._kv_layout)[:3] != (sp, sn, sh):
                 raise ValueError("k_cache and v_cache must share strides")
             page_args = (page_size, k_cache.shape[0], sp, sn, sh, 1 if self._kv_layout == "HND" else 0)
-            self._launch_sm100(q, k_cache, v_cache, out, lse if return_lse else None, sm_scale, window_left, True,
-                               self._kv_indices, page_args, enable_pdl)
+            folded = self._launch_sm100(q, k_cache, v_cache, out, lse if return_lse else None, sm_scale, window_left, True,
+                                        self._kv_indices, page_args, enable_pdl, sinks=sinks)
+            if folded:
+                sinks = None  # exp(sink) joined the softmax denominator inside the kernel
         if sinks is not None:
             from .attention._core import apply_attention_sink
 

@@ -200,3 +200,54 @@ def test_head_dim_64_tcgen05(monkeypatch, causal, dtype):
     o3 = fi.single_prefill_with_kv_cache(qq, kk, vv, causal=causal)
     ref, _ = reference.attention_ref(qq, kk, vv, causal, 1 / math.sqrt(d))
     assert (o3.float() - ref.float()).abs().max() < 2e-2
+
+
+@pytest.mark.gpu
+def test_attention_sinks_in_kernel(monkeypatch):
+    """`sinks=` joins the softmax denominator inside the tcgen05 kernels (decode: unsplit segments, in-kernel split-KV merge;
+    paged prefill epilogue) - the torch post-processing of (o, lse) must not run."""
+    _no_generic(monkeypatch)
+    from flashinfer_b200.attention import _core
+
+    def boom(*a, **k):
+        raise AssertionError("attention sink applied post hoc in torch")
+
+    monkeypatch.setattr(_core, "apply_attention_sink", boom)
+    torch.manual_seed(11)
+    hq, hkv, d, ps = 8, 2, 128, 16
+    sinks = torch.randn(hq, device="cuda") * 2
+    # ---- decode: a long request (split over CTAs, merged in-kernel) and short ones (unsplit)
+    kv_lens = [9000, 17, 300, 1]
+    n_pages = [(l + ps - 1) // ps for l in kv_lens]
+    indptr = torch.tensor([0] + list(torch.tensor(n_pages).cumsum(0)), dtype=torch.int32)
+    indices = torch.randperm(sum(n_pages)).int()
+    last = torch.tensor([(l - 1) % ps + 1 for l in kv_lens], dtype=torch.int32)
+    kc = torch.randn(sum(n_pages), ps, hkv, d, device="cuda").bfloat16()
+    vc = torch.randn(sum(n_pages), ps, hkv, d, device="cuda").bfloat16()
+    q = torch.randn(len(kv_lens), hq, d, device="cuda").bfloat16()
+    w = fi.BatchDecodeWithPagedKVCacheWrapper(torch.empty(64 << 20, dtype=torch.uint8, device="cuda"))
+    w.plan(indptr, indices, last, hq, hkv, d, ps, q_data_type=torch.bfloat16)
+    out, lse = w.run(q, (kc, vc), sinks=sinks, return_lse=True)
+    for b, L in enumerate(kv_lens):
+        pages = indices[int(indptr[b]):int(indptr[b + 1])].long().cuda()
+        k = kc[pages].reshape(-1, hkv, d)[:L]
+        v = vc[pages].reshape(-1, hkv, d)[:L]
+        ref, lref = reference.attention_ref(q[b:b + 1], k, v, False, 1 / math.sqrt(d), sinks=sinks)
+        assert (out[b:b + 1].float() - ref.float()).abs().max() < 2e-2
+        assert (lse[b:b + 1] - lref).abs().max() < 2e-2
+    # ---- paged prefill (causal) with sinks
+    ql, kl = 200, 700
+    npg = (kl + ps - 1) // ps
+    perm = torch.randperm(npg).int()
+    qq = torch.randn(ql, hq, d, device="cuda").bfloat16()
+    wp = fi.BatchPrefillWithPagedKVCacheWrapper(torch.empty(32 << 20, dtype=torch.uint8, device="cuda"))
+    wp.plan(torch.tensor([0, ql], dtype=torch.int32), torch.tensor([0, npg], dtype=torch.int32), perm,
+            torch.tensor([(kl - 1) % ps + 1], dtype=torch.int32), hq, hkv, d, ps, causal=True, q_data_type=torch.bfloat16)
+    kcp = torch.randn(npg, ps, hkv, d, device="cuda").bfloat16()
+    vcp = torch.randn(npg, ps, hkv, d, device="cuda").bfloat16()
+    o2, l2 = wp.run(qq, (kcp, vcp), sinks=sinks, return_lse=True)
+    k = kcp[perm.long().cuda()].reshape(-1, hkv, d)[:kl]
+    v = vcp[perm.long().cuda()].reshape(-1, hkv, d)[:kl]
+    ref, lref = reference.attention_ref(qq, k, v, True, 1 / math.sqrt(d), sinks=sinks)
+    assert (o2.float() - ref.float()).abs().max() < 2e-2
+    assert (l2 - lref).abs().max() < 2e-2
