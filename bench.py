@@ -170,10 +170,13 @@ def run_ours(args, rank, world):
                        "linear": ("flashinfer_b200 decode_linear_sm100 (RMSNorm / RoPE+append / SwiGLU / residual epilogues)"
                                   if eng.fused else "flashinfer_b200 gemm_sm100"),
                        "allreduce": ((("two-shot Lamport all-reduce inside the O / down GEMM epilogue (reduce-scatter push to the row owner, "
-                                       "multimem.st all-gather of the new residual rows, sentinel polling)" if eng.tp_fused.algo == 2 else
-                                       "one-shot push all-reduce inside the O / down GEMM epilogue (multimem.st into every rank's slot, "
-                                       "sentinel polling)") if eng.fused else "in-kernel NVLS all-reduce + add + RMSNorm kernel")
-                                     if world > 1 else None),
+                                       "all-gather push of the new residual rows, sentinel polling; "
+                                       + ("multimem.st" if eng.tp_fused.mc_recv else "peer stores: no NVLS multicast mapping on this box") + ")"
+                                       if eng.tp_fused.algo == 2 else
+                                       "one-shot push all-reduce inside the O / down GEMM epilogue (every rank's strip into slot [rank] of all "
+                                       "ranks, sentinel polling; "
+                                       + ("multimem.st" if eng.tp_fused.mc_recv else "peer stores: no NVLS multicast mapping on this box") + ")")
+                                      if eng.fused else "in-kernel all-reduce + add + RMSNorm kernel") if world > 1 else None),
                        "ref_allreduce_candidates": None},
             "clocks": _summarise_clocks(clk.get("rows")),
             "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": BATCH * 8, "d2h_bytes_per_step": BATCH * 8},
