@@ -47,6 +47,10 @@ class BatchAttention:
         kvp = kv_indptr.to("cpu", torch.int64)
         kvl = kv_len_arr.to("cpu", torch.int64)
         idx = kv_indices.to("cpu", torch.int32)
+        # plan()-time state read by the fi_trace template of run()
+        self._qo_indptr_host, self._kv_indptr_host, self._kv_len_host, self._kv_indices_host = qo.int(), kvp.int(), kvl.int(), idx
+        self._causal = bool(causal)
+        self._sm_scale = float(sm_scale) if sm_scale is not None else 1.0 / (head_dim_qk ** 0.5)
         group = num_qo_heads // num_kv_heads
         q_lens = qo[1:] - qo[:-1]
         is_dec = (q_lens * group <= 32) & (q_lens > 0) & bool(causal or (q_lens == 1).all())

@@ -56,6 +56,8 @@ class BlockSparseAttentionWrapper:
             flat_mask = _unpack_bits(packed_mask, int(indices.numel()) * R * C)
         self._M, self._N, self._R, self._C = M, N, R, C
         self._hq, self._hkv, self._d = num_qo_heads, num_kv_heads, head_dim
+        self._bsr_indptr, self._bsr_indices = indptr.to("cpu", torch.int32), indices.to("cpu", torch.int32)  # (fi_trace: run() inputs)
+        self._sm_scale = float(sm_scale) if sm_scale is not None else 1.0 / (head_dim ** 0.5)
         mb = M // R
         # page granularity of the paged kernels: a page must tile the 128-token KV tile (power of two <= 128) or be a multiple of
         # 128; any other block width C is cut into C / g pages of g = largest power of two dividing C

@@ -89,6 +89,8 @@ BINDINGS: List[Tuple[str, str, "_t.TraceTemplate"]] = [
     ("comm.allreduce", "local_argmax", T.local_argmax_trace),
     ("comm.trtllm_alltoall", "moe_local_gather", T.moe_local_gather_trace),
     ("mla._core", "trtllm_batch_decode_with_kv_cache_mla", T.sparse_mla_decode_trace),
+    ("sparse", "BlockSparseAttentionWrapper.run", T.block_sparse_attention_trace),
+    ("attention._core", "BatchAttention.run", T.batch_attention_trace),
 ]
 
 _PKG = __name__.rsplit(".", 2)[0]

@@ -236,3 +236,113 @@ sparse_mla_decode_trace = TraceTemplate(
     test_sizes={"num_heads": 4, "top_k": 48, "seq_len": 100, "page_size": 32})
 
 __all__ = [n for n in dir() if n.endswith("_trace")]
+
+
+# ------------------------------------------------------------------ block-sparse attention (BSR mask, wrapper state from plan())
+def _block_sparse_reference(q, k, v, bsr_indptr, bsr_indices, R, C, sm_scale):
+    """Dense oracle: row block i attends the column blocks bsr_indices[bsr_indptr[i]:bsr_indptr[i + 1]] (no intra-block mask)."""
+    M, hq, d = q.shape
+    N, hkv = k.shape[0], k.shape[1]
+    mask = torch.zeros(M, N, dtype=torch.bool, device=q.device)
+    for i in range(M // R):
+        for j in bsr_indices[int(bsr_indptr[i]):int(bsr_indptr[i + 1])].tolist():
+            mask[i * R:(i + 1) * R, j * C:(j + 1) * C] = True
+    g = hq // hkv
+    kk = k.to(torch.float32).repeat_interleave(g, dim=1)
+    vv = v.to(torch.float32).repeat_interleave(g, dim=1)
+    logits = torch.einsum("mhd,nhd->hmn", q.to(torch.float32), kk) * sm_scale
+    logits = logits.masked_fill(~mask[None], float("-inf"))
+    return torch.einsum("hmn,nhd->mhd", torch.softmax(logits, -1), vv).to(q.dtype)
+
+
+def _block_sparse_init(*, num_row_blocks=6, num_col_blocks=7, R=16, C=16, num_qo_heads=8, num_kv_heads=2, head_dim=128, device="cuda", seed=0):
+    import flashinfer_b200 as fi
+
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    dense = torch.rand(num_row_blocks, num_col_blocks, generator=g) < 0.4
+    dense[:, 0] = True
+    indptr = torch.zeros(num_row_blocks + 1, dtype=torch.int32)
+    indptr[1:] = dense.sum(1).cumsum(0)
+    indices = dense.nonzero()[:, 1].int()
+    M, N = num_row_blocks * R, num_col_blocks * C
+    mk = lambda *s: torch.randn(*s, generator=g).to(torch.bfloat16).to(device)  # noqa: E731
+    w = fi.BlockSparseAttentionWrapper(torch.empty(32 << 20, dtype=torch.uint8, device=device))
+    w.plan(indptr, indices, M, N, R, C, num_qo_heads, num_kv_heads, head_dim, q_data_type=torch.bfloat16)
+    return {"self": w, "q": mk(M, num_qo_heads, head_dim), "k": mk(N, num_kv_heads, head_dim), "v": mk(N, num_kv_heads, head_dim)}
+
+
+block_sparse_attention_trace = TraceTemplate(
+    op_type="block_sparse", name_fmt="block_sparse_h{num_qo_heads}_kv{num_kv_heads}_d{head_dim}",
+    axes=[Var("M"), Var("N"), Var("len_indptr"), Var("nnz_blocks"), Const("num_qo_heads", abbrev="h"), Const("num_kv_heads", abbrev="kv"),
+          Const("head_dim", abbrev="d")],
+    inputs=[Tensor("q", ("M", "num_qo_heads", "head_dim")), Tensor("k", ("N", "num_kv_heads", "head_dim")),
+            Tensor("v", ("N", "num_kv_heads", "head_dim")), Tensor("bsr_indptr", ("len_indptr",), "int32", param="self._bsr_indptr"),
+            Tensor("bsr_indices", ("nnz_blocks",), "int32", param="self._bsr_indices"), Scalar("R", "int32", param="self._R"),
+            Scalar("C", "int32", param="self._C"), Scalar("sm_scale", param="self._sm_scale")],
+    outputs=[Tensor("output", ("M", "num_qo_heads", "head_dim"), dtype_from="q")], reference=_block_sparse_reference, init=_block_sparse_init,
+    tags=("attention", "block-sparse"), tolerance="bf16",
+    description="Attention under a fixed-size block-sparse (BSR) mask: every row block is a request whose KV pages are its non-zero column blocks",
+    test_sizes={"R": 4, "C": 8, "num_qo_heads": 4, "num_kv_heads": 2, "head_dim": 32})
+
+
+# ------------------------------------------------------------------ BatchAttention (mixed prefill / decode batch)
+def _batch_attention_reference(q, k_cache, v_cache, qo_indptr, kv_indptr, kv_indices, kv_len_arr, causal, sm_scale):
+    h, d = q.shape[1:]
+    page_size, hkv = k_cache.shape[1], k_cache.shape[2]
+    g = h // hkv
+    out = torch.zeros(q.shape, dtype=torch.float32, device=q.device)
+    lse = torch.full((q.shape[0], h), float("-inf"), dtype=torch.float32, device=q.device)
+    for b in range(qo_indptr.numel() - 1):
+        qs, qe = int(qo_indptr[b]), int(qo_indptr[b + 1])
+        n = int(kv_len_arr[b])
+        if qe == qs or n == 0:
+            continue
+        pages = kv_indices[int(kv_indptr[b]): int(kv_indptr[b + 1])].long()
+        k = k_cache[pages].reshape(-1, hkv, d)[:n].to(torch.float32).repeat_interleave(g, dim=1)
+        v = v_cache[pages].reshape(-1, hkv, d)[:n].to(torch.float32).repeat_interleave(g, dim=1)
+        logits = torch.einsum("qhd,nhd->hqn", q[qs:qe].to(torch.float32), k) * sm_scale
+        if causal:
+            qpos = (n - (qe - qs) + torch.arange(qe - qs, device=q.device))[:, None]
+            logits = logits.masked_fill((torch.arange(n, device=q.device)[None, :] > qpos)[None], float("-inf"))
+        out[qs:qe] = torch.einsum("hqn,nhd->qhd", torch.softmax(logits, -1), v)
+        lse[qs:qe] = (torch.logsumexp(logits, -1) * 1.4426950408889634).transpose(0, 1)
+    return out.to(q.dtype), lse
+
+
+def _batch_attention_init(*, batch_size=6, num_qo_heads=8, num_kv_heads=2, head_dim=128, page_size=16, device="cuda", seed=0):
+    import flashinfer_b200 as fi
+
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    kv_lens = [int(x) for x in torch.randint(1, 5 * page_size, (batch_size,), generator=g)]
+    q_lens = [1 if i % 2 == 0 else min(kv_lens[i], int(torch.randint(2, 40, (1,), generator=g))) for i in range(batch_size)]
+    n_pages = [(n + page_size - 1) // page_size for n in kv_lens]
+    total = sum(n_pages)
+    kv_indptr = torch.tensor([0] + list(torch.tensor(n_pages).cumsum(0)), dtype=torch.int32)
+    qo_indptr = torch.tensor([0] + list(torch.tensor(q_lens).cumsum(0)), dtype=torch.int32)
+    kv_indices = torch.randperm(total + 2, generator=g)[:total].to(torch.int32)
+    mk = lambda *s: torch.randn(*s, generator=g).to(torch.bfloat16).to(device)  # noqa: E731
+    w = fi.BatchAttention("NHD", device=device)
+    w.plan(qo_indptr, kv_indptr, kv_indices, torch.tensor(kv_lens, dtype=torch.int32), num_qo_heads, num_kv_heads, head_dim, head_dim, page_size,
+           causal=True, q_data_type=torch.bfloat16, kv_data_type=torch.bfloat16)
+    return {"self": w, "q": mk(int(qo_indptr[-1]), num_qo_heads, head_dim),
+            "kv_cache": (mk(total + 2, page_size, num_kv_heads, head_dim), mk(total + 2, page_size, num_kv_heads, head_dim))}
+
+
+_PAGED2 = ("num_pages", "page_size", "num_kv_heads", "head_dim")
+batch_attention_trace = TraceTemplate(
+    op_type="batch_attention", name_fmt="batch_attention_h{num_qo_heads}_kv{num_kv_heads}_d{head_dim}_ps{page_size}",
+    axes=[Var("total_q"), Var("num_pages"), Var("len_indptr"), Var("num_kv_indices"), Var("batch_size"), Const("num_qo_heads", abbrev="h"),
+          Const("num_kv_heads", abbrev="kv"), Const("head_dim", abbrev="d"), Const("page_size", abbrev="ps")],
+    inputs=[Tensor("q", ("total_q", "num_qo_heads", "head_dim")), Tensor("k_cache", _PAGED2, param="kv_cache", tuple_idx=0),
+            Tensor("v_cache", _PAGED2, param="kv_cache", tuple_idx=1), Tensor("qo_indptr", ("len_indptr",), "int32", param="self._qo_indptr_host"),
+            Tensor("kv_indptr", ("len_indptr",), "int32", param="self._kv_indptr_host"),
+            Tensor("kv_indices", ("num_kv_indices",), "int32", param="self._kv_indices_host"),
+            Tensor("kv_len_arr", ("batch_size",), "int32", param="self._kv_len_host"), Scalar("causal", "bool", param="self._causal"),
+            Scalar("sm_scale", param="self._sm_scale")],
+    outputs=[Tensor("output", ("total_q", "num_qo_heads", "head_dim"), dtype_from="q"), Tensor("lse", ("total_q", "num_qo_heads"), dtype="float32")],
+    reference=_batch_attention_reference, init=_batch_attention_init, tags=("attention", "prefill", "decode", "paged", "mixed-batch"),
+    constraints=("len_indptr == batch_size + 1",), tolerance="bf16",
+    description="Mixed prefill / decode batch over one paged KV cache (decode-sized requests on the decode kernel, the rest on the prefill kernel)",
+    test_sizes={"num_qo_heads": 4, "num_kv_heads": 2, "head_dim": 32, "page_size": 8})
+
+__all__ = [n for n in dir() if n.endswith("_trace")]
