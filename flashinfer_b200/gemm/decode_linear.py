@@ -109,6 +109,50 @@ class _ptr:
         self.v = int(v)
 
 
+# ------------------------------------------------------------------ autotuner client: the tile plan (BN, split-K cluster size)
+def admissible_plans(n: int, k: int, sms: int = 148):
+    """Single-wave tile plans of the kernel for ``W [N, K]``: weight-tile width BN (multiple of 16 x S) and split-K cluster size S
+    (clusters of 4 / 8 CTAs are placeable on 132 of 148 SMs); the same enumeration as tools/dl_sweep.py.  A plan is encoded as
+    ``BN * 16 + S`` (tactic ``-1`` = the planner in ``dlinear_run``)."""
+    kb = k // 64
+    out = []
+    for s in (1, 2, 4, 8):
+        if kb < s:
+            continue
+        for bn in range(16 * s, 257, 16 * s):
+            tiles = (n + bn - 1) // bn
+            lim = sms if s < 4 else sms * 132 // 148
+            if tiles * s > lim or tiles * s < min(40, lim // 2):
+                continue
+            out.append(bn * 16 + s)
+    return out
+
+
+def _tuned_plan(x: torch.Tensor, w: torch.Tensor, n: int, k: int, epi: int, launch):
+    """``(bn, split_k)`` for this call: (0, 0) = the built-in planner, unless the autotuner is profiling (``with autotune():``) or
+    holds a tuned choice for this (bucketed M, N, K, epilogue) - the plan table in the kernel was swept on the Llama-3-8B shapes
+    (profiles/decode_linear_plans.md); other models tune theirs once and ship the JSON.  ``launch(bn, split_k)`` runs the op on
+    the live tensors (the caller gives idempotent scratch outputs to the residual epilogue while profiling)."""
+    from ..autotuner import AutoTuner, DynamicTensorSpec, TunableRunner, TuningConfig
+
+    tuner = AutoTuner.get()
+    if not (tuner.is_tuning_mode or tuner.profiling_cache):
+        return 0, 0
+
+    class _PlanRunner(TunableRunner):
+        def get_valid_tactics(self, inputs, profile):
+            return [-1] + admissible_plans(n, k)
+
+        def forward(self, inputs, tactic=-1, do_preparation=False, **kwargs):
+            t = int(tactic)
+            return launch(0, 0) if t < 0 else launch(t // 16, t % 16)
+
+    cfg = TuningConfig(dynamic_tensor_specs=(DynamicTensorSpec((0,), (0,)),), use_cold_l2_cache=True, synthesize_buckets=False)
+    _, tactic = tuner.choose_one("decode_linear", [_PlanRunner()], cfg, [x, w], extras=(int(epi), int(n), int(k), str(x.dtype), w.dim()))
+    t = int(tactic)
+    return (0, 0) if t < 0 else (t // 16, t % 16)
+
+
 # ------------------------------------------------------------------ the op
 def _rstd(row_sumsq: Optional[torch.Tensor], m: int, norm_dim: int, eps: float) -> Optional[torch.Tensor]:
     if row_sumsq is None:
@@ -225,13 +269,31 @@ def decode_linear(x: torch.Tensor, w: torch.Tensor, epi: int = EPI_PLAIN, *, out
     ar = tp if world > 1 else None
     if ar is not None and (n != ar.hidden or x.dtype != ar.dtype):
         raise ValueError("decode_linear: the all-reduce context was built for another hidden size / dtype")
-    jit.load("decode_linear_sm100").call(
-        "dlinear_run", x, w, m, n, k, x.stride(0), w.stride(1) if blockk else w.stride(0), int(epi), out, out.stride(0), bias, row_sumsq,
-        1.0 / float(norm_dim), float(eps), residual, residual.stride(0) if residual is not None else 0, sumsq_out, world, rank,
-        ar.recv if ar else None, ar.hidden if ar else 0, ar.slot_elems if ar else 0, _ptr(ar.mc_recv) if ar else None,
-        ar.epoch if ar else None, ar.peer_recv if ar else None, int(ar.algo) if ar else 0, cos_sin, cache_row, k_cache, v_cache, int(c_sh),
-        int(num_q_heads), int(num_kv_heads), int(head_dim), 1 if interleave else 0, int(bn), int(split_k), int(smem_kb),
-        1 if blockk else 0, dtype_code(x.dtype), 1 if enable_pdl else 0, stream_ptr(x))
+    mod = jit.load("decode_linear_sm100")
+
+    def launch(bn_, s_, residual_=residual, sumsq_=sumsq_out, out_=out):
+        mod.call(
+            "dlinear_run", x, w, m, n, k, x.stride(0), w.stride(1) if blockk else w.stride(0), int(epi), out_, out_.stride(0), bias,
+            row_sumsq, 1.0 / float(norm_dim), float(eps), residual_, residual_.stride(0) if residual_ is not None else 0, sumsq_, world,
+            rank, ar.recv if ar else None, ar.hidden if ar else 0, ar.slot_elems if ar else 0, _ptr(ar.mc_recv) if ar else None,
+            ar.epoch if ar else None, ar.peer_recv if ar else None, int(ar.algo) if ar else 0, cos_sin, cache_row, k_cache, v_cache,
+            int(c_sh), int(num_q_heads), int(num_kv_heads), int(head_dim), 1 if interleave else 0, int(bn_), int(s_), int(smem_kb),
+            1 if blockk else 0, dtype_code(x.dtype), 1 if enable_pdl else 0, stream_ptr(x))
+        return out_
+
+    if bn == 0 and split_k == 0 and ar is None and not torch.cuda.is_current_stream_capturing():
+        scratch = {}
+
+        def probe(bn_, s_):  # profiling runs must not accumulate into the caller's residual stream
+            if epi != EPI_RESIDUAL:
+                return launch(bn_, s_)
+            if not scratch:
+                scratch["r"] = residual.clone()
+                scratch["s"] = torch.zeros_like(sumsq_out) if sumsq_out is not None else None
+            return launch(bn_, s_, scratch["r"], scratch["s"], scratch["r"])
+
+        bn, split_k = _tuned_plan(x, w, n, k, epi, probe)
+    launch(bn, split_k)
     return out
 
 

@@ -157,3 +157,29 @@ def test_shipped_and_env_configs_seed_the_singleton(tmp_path, monkeypatch):
     t = AutoTuner.get()
     assert t.profiling_cache[("op_s", "R", ((8,),), ())][1] == 64 and t.profiling_cache[("op_u", "R", ((8,),), ())][1] == 128
     monkeypatch.setattr(AutoTuner, "_instance", None)          # the next get() builds a clean singleton for the other tests
+
+
+def test_decode_linear_plan_is_a_tuner_client(tuner):
+    """The flagship decode GEMM asks the tuner for its tile plan (BN, split-K cluster) only while tuning or with loaded configs;
+    tactics are the admissible single-wave plans, the choice is cached per (M bucket, N, K, epilogue)."""
+    from flashinfer_b200.gemm import decode_linear as dl
+
+    plans = dl.admissible_plans(768, 4096)
+    assert plans == [16 * 16 + 1, 32 * 16 + 2, 64 * 16 + 4, 128 * 16 + 8]          # narrow N: only deeper K splits reach more SMs
+    assert all((p // 16) % (16 * (p % 16)) == 0 for p in dl.admissible_plans(6144, 4096))
+    x, w = torch.zeros(48, 4096), torch.zeros(768, 4096)
+    seen = []
+
+    def launch(bn, s):
+        seen.append((bn, s))
+        time.sleep({(0, 0): 6e-3, (16, 1): 8e-3, (32, 2): 6e-3, (64, 4): 5e-3, (128, 8): 2e-4}[(bn, s)])
+
+    assert dl._tuned_plan(x, w, 768, 4096, dl.EPI_PLAIN, launch) == (0, 0) and not seen     # idle tuner: planner default, no probing
+    with autotune():
+        assert dl._tuned_plan(x, w, 768, 4096, dl.EPI_PLAIN, launch) == (128, 8)
+    assert set(seen) == {(0, 0), (16, 1), (32, 2), (64, 4), (128, 8)}
+    seen.clear()
+    assert dl._tuned_plan(torch.zeros(60, 4096), w, 768, 4096, dl.EPI_PLAIN, launch) == (128, 8) and not seen   # same M bucket: cached
+    with autotune():
+        dl._tuned_plan(x, w, 768, 4096, dl.EPI_GATED_SILU, launch)                         # another epilogue is another key
+    assert seen
