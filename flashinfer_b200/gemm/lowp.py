@@ -67,6 +67,18 @@ def _sf_swizzled(sf: torch.Tensor, rows: int, kc: int, batch: int = 1, swizzled:
     raise ValueError(f"scale tensor of shape {tuple(sf.shape)} is neither swizzled ({per} bytes) nor linear [{rows}, {kc}]")
 
 
+def _sf_8x4_to_128x4(sf: torch.Tensor, rows: int, kc: int) -> torch.Tensor:
+    """Scale bytes stored in 8 x 4 tiles (``SfLayout.layout_8x4``: tile (r / 8, c / 4), 32 bytes, row-major inside) -> linear
+    ``[rows, kc]`` uint8 (a gather over rows * kc bytes) -> the 128x4 layout (native ``sf_interleave`` kernel)."""
+    from ..quantization.fp4 import _index_8x4
+
+    flat = sf.view(torch.uint8).reshape(-1)
+    need = (rows + 7) // 8 * 8 * ((kc + 3) // 4 * 4)
+    if flat.numel() < need:
+        raise ValueError(f"8x4 scale tensor has {flat.numel()} bytes, expected at least {need} for [{rows}, {kc}] scales")
+    return block_scale_interleave(flat[_index_8x4(rows, kc).to(flat.device)].view(rows, kc).contiguous())
+
+
 def _launch_raw(kind: str, a, b_nk, out, sfa, sfb, alpha_a, alpha_b, K: int, bn: int, tile_expert, meta, row_map):
     B, M, _ = a.shape
     if tile_expert is not None:
@@ -208,8 +220,8 @@ def bmm_mxfp8(A: torch.Tensor, B: torch.Tensor, A_scale: torch.Tensor, B_scale: 
 def mm_mxfp8(a: torch.Tensor, b: torch.Tensor, a_descale: torch.Tensor, b_descale: torch.Tensor,
              out: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.bfloat16, use_8x4_sf_layout: bool = False,
              backend: str = "auto") -> torch.Tensor:
-    if use_8x4_sf_layout:
-        raise NotImplementedError("mm_mxfp8: only the 128x4 scale layout is supported")
+    if use_8x4_sf_layout:  # activation scales in 8x4 tiles (small-M layout of the reference): re-tiled to the 128x4 layout of tcgen05.cp
+        a_descale = _sf_8x4_to_128x4(a_descale, a.shape[-2], a.shape[-1] // 32)
     return bmm_mxfp8(a, b, a_descale, b_descale, out_dtype, out)
 
 
@@ -220,10 +232,10 @@ def mm_fp4(a: torch.Tensor, b: torch.Tensor, a_descale: torch.Tensor, b_descale:
            enable_pdl: bool = True) -> torch.Tensor:
     """``a [m, k/2]`` packed e2m1, ``b [k/2, n]`` column-major packed e2m1, 128x4-swizzled block scales
     (UE4M3 / 16 for NVFP4, UE8M0 / 32 for MXFP4), ``alpha`` = 1 / (global_sf_a * global_sf_b)."""
-    if use_8x4_sf_layout:
-        raise NotImplementedError("mm_fp4: only the 128x4 scale layout is supported")
     nv = use_nvfp4 and block_size == 16
     vec = 16 if nv else 32
+    if use_8x4_sf_layout:  # activation scales in 8x4 tiles (small-M layout of the reference): re-tiled to the 128x4 layout of tcgen05.cp
+        a_descale = _sf_8x4_to_128x4(a_descale, a.shape[0], a.shape[1] * 2 // vec)
     a3, bnk = _prep(a.view(torch.uint8), b.view(torch.uint8))
     _, M, K2 = a3.shape
     N = bnk.shape[1]

@@ -139,3 +139,21 @@ def test_fused_rmsnorm_silu_nvfp4_output_and_fp4_8x4_layout():
     q8, sf8 = nvfp4_quantize(x, gs, sfLayout=SfLayout.layout_8x4)
     ql, sfl = nvfp4_quantize(x, gs, sfLayout=SfLayout.layout_linear)
     assert torch.equal(q8, ql) and sf8.numel() == 24 * 8 and torch.equal(sf8.reshape(-1)[_index_8x4(20, 8)], sfl.reshape(-1))
+
+
+def test_mm_fp4_accepts_8x4_activation_scales():
+    """use_8x4_sf_layout (reference mm_fp4 / mm_mxfp8): activation scales in 8x4 tiles give the same product as the 128x4 layout."""
+    import flashinfer_b200 as fi
+    from flashinfer_b200.quantization.fp4 import SfLayout, nvfp4_quantize
+
+    torch.manual_seed(0)
+    m, n, k = 24, 64, 128
+    a, w = torch.randn(m, k).bfloat16(), torch.randn(n, k).bfloat16()
+    ga, gw = torch.tensor([448 * 6 / float(a.abs().max())]), torch.tensor([448 * 6 / float(w.abs().max())])
+    aq8, asf8 = nvfp4_quantize(a, ga, sfLayout=SfLayout.layout_8x4)
+    aq, asf = nvfp4_quantize(a, ga)
+    wq, wsf = nvfp4_quantize(w, gw)
+    alpha = 1 / (ga * gw)
+    o8 = fi.mm_fp4(aq8, wq.t(), asf8, wsf.t(), alpha, torch.bfloat16, use_8x4_sf_layout=True)
+    assert torch.equal(o8, fi.mm_fp4(aq, wq.t(), asf, wsf.t(), alpha, torch.bfloat16))
+    assert torch.nn.functional.cosine_similarity(o8.float().flatten(), (a.float() @ w.float().t()).flatten(), dim=0) > 0.98
