@@ -288,3 +288,82 @@ extern "C" int prefill_plan(const int32_t* qo_indptr, const int32_t* kv_lens, co
   counts[1] = max_load;
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// MLA decode plan (reference include/flashinfer/attention/scheduler.cuh MLAPlan :1440-1710).
+//   One work item = (query token, KV chunk); a chunk is a multiple of the 32-token MLA tile.  The chunk length is the smallest
+//   one for which all items fit ONE wave of CTA pairs (every query token is at least one item), found by bisection.
+//   qo_indptr / kv_page_indptr [batch + 1], kv_lens [batch] (int64).  causal: token i of a q_len-token request sees
+//   kv_len - (q_len - 1 - i) keys (MTP / speculative decode).
+// Outputs: work [num_work][8] = {q_row, page_start, kv_lo, kv_hi, kv_visible, partial_slot, num_pages, (kmax << 16) | nsplits},
+//          row_parts [n_q] = splits of every query row, counts = {num_work, kmax, n_q, chunk}.
+// ---------------------------------------------------------------------------------------------
+extern "C" int mla_plan(const int64_t* qo_indptr, const int64_t* kv_page_indptr, const int64_t* kv_lens, int64_t batch, int64_t causal,
+                        int64_t num_ctas, int64_t tile, int32_t* work, int64_t max_work, int32_t* row_parts, int64_t max_rows,
+                        int64_t* counts) {
+  if (batch < 0 || num_ctas <= 0 || tile <= 0) return fail("mla_plan: bad arguments");
+  struct Row {
+    int64_t q_row, page_start, vis, npages;
+  };
+  std::vector<Row> rows;
+  int64_t total_tokens = 0, max_vis = tile;
+  for (int64_t b = 0; b < batch; ++b) {
+    const int64_t ql = qo_indptr[b + 1] - qo_indptr[b];
+    if (kv_lens[b] < 0 || ql < 0) return fail("mla_plan: negative length");
+    for (int64_t i = 0; i < ql; ++i) {
+      int64_t vis = causal ? kv_lens[b] - (ql - 1 - i) : kv_lens[b];
+      if (vis < 0) vis = 0;
+      rows.push_back({qo_indptr[b] + i, kv_page_indptr[b], vis, kv_page_indptr[b + 1] - kv_page_indptr[b]});
+      total_tokens += vis;
+      max_vis = std::max(max_vis, vis);
+    }
+  }
+  const int64_t n_q = batch > 0 ? qo_indptr[batch] : 0;
+  if (n_q > max_rows) return fail("mla_plan: row_parts capacity exceeded");
+  auto ceil_div = [](int64_t a, int64_t b) { return (a + b - 1) / b; };
+  auto count = [&](int64_t c) {
+    int64_t n = 0;
+    for (const Row& r : rows) n += std::max<int64_t>(1, ceil_div(r.vis, c));
+    return n;
+  };
+  int64_t chunk = std::max<int64_t>(4 * tile, ceil_div(total_tokens, num_ctas));
+  chunk = ceil_div(chunk, tile) * tile;
+  const int64_t target = std::max<int64_t>(num_ctas, (int64_t)rows.size());
+  if (count(chunk) > target) {
+    int64_t lo = chunk / tile, hi = std::max<int64_t>(chunk / tile, ceil_div(max_vis, tile));
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) / 2;
+      if (count(mid * tile) > target) lo = mid + 1;
+      else hi = mid;
+    }
+    chunk = lo * tile;
+  }
+  int64_t kmax = 1;
+  for (const Row& r : rows) kmax = std::max<int64_t>(kmax, ceil_div(r.vis, chunk));
+  if (kmax >= (int64_t(1) << 15)) return fail("mla_plan: too many KV splits");
+  for (int64_t i = 0; i < n_q; ++i) row_parts[i] = 1;
+  int64_t nw = 0;
+  for (const Row& r : rows) {
+    const int64_t nsp = std::max<int64_t>(1, ceil_div(r.vis, chunk));
+    row_parts[r.q_row] = (int32_t)nsp;
+    for (int64_t s = 0; s < nsp; ++s) {
+      if (nw >= max_work) return fail("mla_plan: work capacity exceeded");
+      const int64_t lo = s * chunk, hi = std::min<int64_t>(r.vis, (s + 1) * chunk);
+      int32_t* w = work + nw * 8;
+      w[0] = (int32_t)r.q_row;
+      w[1] = (int32_t)r.page_start;
+      w[2] = (int32_t)lo;
+      w[3] = (int32_t)std::max(hi, lo);
+      w[4] = (int32_t)r.vis;
+      w[5] = (int32_t)(r.q_row * kmax + s);
+      w[6] = (int32_t)std::max<int64_t>(r.npages, 1);
+      w[7] = (int32_t)((kmax << 16) | nsp);
+      ++nw;
+    }
+  }
+  counts[0] = nw;
+  counts[1] = kmax;
+  counts[2] = n_q;
+  counts[3] = chunk;
+  return 0;
+}

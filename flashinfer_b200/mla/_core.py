@@ -89,49 +89,26 @@ class BatchMLAPagedAttentionWrapper:
         self._qo_host, self._kvp_host, self._kvl_host = qo, kvp, kvl
         self._kv_indices = kv_indices.to(self.device, torch.int32)
         batch = kvl.numel()
-        # ---- flatten query tokens (q_len > 1: MTP / speculative decode, causal inside the new tokens) ----
-        rows = []  # (q_row, page_start, kv_len_visible, num_pages)
-        for b in range(batch):
-            ql = int(qo[b + 1] - qo[b])
-            for i in range(ql):
-                vis = int(kvl[b]) - (ql - 1 - i) if causal else int(kvl[b])
-                rows.append((int(qo[b]) + i, int(kvp[b]), max(vis, 0), int(kvp[b + 1] - kvp[b])))
-        self._n_q = int(qo[-1])
-        total_tokens = sum(r[2] for r in rows)
+        # ---- C++ planner (csrc/runtime/planner.cpp mla_plan): query tokens are flattened (q_len > 1: MTP / speculative decode, causal
+        #      inside the new tokens), the KV chunk is the smallest multiple of the tile for which all (token, chunk) items fit one wave
+        self._n_q = int(qo[-1]) if batch else 0
         ctas = max(1, device_sm_count(self.device if self.device.type == "cuda" else None) // 2)
-        chunk = max(4 * _TILE, -(-total_tokens // ctas))
-        chunk = -(-chunk // _TILE) * _TILE
-        # one wave: grow the chunk until the number of (row, split) work items fits the CTA pairs of the device
-        # (every row is at least one item, so the target is max(ctas, rows); bisect instead of stepping)
-        target = max(ctas, len(rows))
-        count = lambda c: sum(max(1, -(-r[2] // c)) for r in rows)  # noqa: E731
-        if count(chunk) > target:
-            lo, hi = chunk // _TILE, max(chunk // _TILE, -(-max((r[2] for r in rows), default=_TILE) // _TILE))
-            while lo < hi:
-                mid = (lo + hi) // 2
-                if count(mid * _TILE) > target:
-                    lo = mid + 1
-                else:
-                    hi = mid
-            chunk = lo * _TILE
-        kmax = max(1, max((-(-r[2] // chunk) for r in rows), default=1))
-        self._kmax = kmax
-        work = []
-        row_parts = [1] * max(self._n_q, 1)
-        for (qr, pstart, vis, npages) in rows:
-            nsp = max(1, -(-vis // chunk))
-            row_parts[qr] = nsp
-            for s in range(nsp):
-                lo, hi = s * chunk, min(vis, (s + 1) * chunk)
-                work.append([qr, pstart, lo, max(hi, lo), vis, qr * kmax + s, max(npages, 1), (kmax << 16) | nsp])
-        self._num_work = len(work)
-        w = torch.cat([torch.tensor(work, dtype=torch.int32).reshape(-1), torch.tensor(row_parts, dtype=torch.int32)])
+        max_work = max(ctas, self._n_q, 1)
         pin = self._pin_int_workspace_buffer.view(torch.int32)
-        pin[: w.numel()].copy_(w)
+        if max_work * 8 + max(self._n_q, 1) > pin.numel():
+            raise RuntimeError("int workspace too small for this MLA batch")
+        work_h = pin[: max_work * 8]
+        parts_h = pin[max_work * 8: max_work * 8 + max(self._n_q, 1)]
+        counts = torch.zeros(4, dtype=torch.int64)
+        jit.load("planner").call("mla_plan", qo.contiguous(), kvp.contiguous(), kvl.contiguous(), batch, 1 if causal else 0, ctas, _TILE,
+                                 work_h, max_work, parts_h, max(self._n_q, 1), counts)
+        self._num_work, kmax = int(counts[0]), int(counts[1])
+        self._kmax = kmax
+        n_used = max_work * 8 + max(self._n_q, 1)
         dev = self._int_workspace_buffer.view(torch.int32)
-        dev[: w.numel()].copy_(pin[: w.numel()], non_blocking=self.device.type == "cuda")
-        self._work = dev[: len(work) * 8]
-        self._row_parts = dev[len(work) * 8 : w.numel()]
+        dev[:n_used].copy_(pin[:n_used], non_blocking=self.device.type == "cuda")
+        self._work = dev[: self._num_work * 8]
+        self._row_parts = dev[max_work * 8: n_used]
         if kmax > 1:
             need = self._n_q * kmax * num_heads * (512 + 2) * 4
             if need > self._float_workspace_buffer.numel() * self._float_workspace_buffer.element_size():

@@ -113,3 +113,59 @@ def test_wrapper_plan_cpu_reference_roundtrip():
         o1, l1 = fi.single_decode_with_kv_cache(q[b], k, v, return_lse=True)
         torch.testing.assert_close(o[b], o1)
         torch.testing.assert_close(lse[b], l1)
+
+
+def _mla_plan_py(qo, kvp, kvl, causal, ctas, tile=32):
+    """The planner as it was written in Python (mla/_core.py before the C++ port): the oracle of mla_plan."""
+    rows = []
+    for b in range(len(kvl)):
+        ql = qo[b + 1] - qo[b]
+        for i in range(ql):
+            vis = kvl[b] - (ql - 1 - i) if causal else kvl[b]
+            rows.append((qo[b] + i, kvp[b], max(vis, 0), kvp[b + 1] - kvp[b]))
+    total = sum(r[2] for r in rows)
+    chunk = max(4 * tile, -(-total // ctas))
+    chunk = -(-chunk // tile) * tile
+    target = max(ctas, len(rows))
+    count = lambda c: sum(max(1, -(-r[2] // c)) for r in rows)  # noqa: E731
+    if count(chunk) > target:
+        lo, hi = chunk // tile, max(chunk // tile, -(-max((r[2] for r in rows), default=tile) // tile))
+        while lo < hi:
+            mid = (lo + hi) // 2
+            if count(mid * tile) > target:
+                lo = mid + 1
+            else:
+                hi = mid
+        chunk = lo * tile
+    kmax = max(1, max((-(-r[2] // chunk) for r in rows), default=1))
+    work, parts = [], [1] * max(qo[-1], 1)
+    for (qr, ps, vis, npg) in rows:
+        nsp = max(1, -(-vis // chunk))
+        parts[qr] = nsp
+        for s in range(nsp):
+            lo, hi = s * chunk, min(vis, (s + 1) * chunk)
+            work.append([qr, ps, lo, max(hi, lo), vis, qr * kmax + s, max(npg, 1), (kmax << 16) | nsp])
+    return work, parts, kmax, chunk
+
+
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("q_lens,kv_lens", [([1] * 64, [4096] * 64), ([1, 3, 1, 8], [5, 700, 0, 33000]), ([2] * 300, [17] * 300), ([1], [100000]),
+                                            ([4, 4], [2, 1])])
+def test_mla_plan_matches_python_oracle(causal, q_lens, kv_lens):
+    page = 64
+    qo = [0] + torch.tensor(q_lens).cumsum(0).tolist()
+    npg = [(l + page - 1) // page for l in kv_lens]
+    kvp = [0] + torch.tensor(npg).cumsum(0).tolist()
+    for ctas in (74, 8):
+        n_q = qo[-1]
+        max_work = max(ctas, n_q, 1)
+        work = torch.zeros(max_work * 8, dtype=torch.int32)
+        parts = torch.zeros(max(n_q, 1), dtype=torch.int32)
+        counts = torch.zeros(4, dtype=torch.int64)
+        jit.load("planner").call("mla_plan", torch.tensor(qo), torch.tensor(kvp), torch.tensor(kv_lens), len(kv_lens), 1 if causal else 0, ctas, 32,
+                                 work, max_work, parts, max(n_q, 1), counts)
+        w_ref, p_ref, kmax, chunk = _mla_plan_py(qo, kvp, kv_lens, causal, ctas)
+        assert int(counts[0]) == len(w_ref) and int(counts[1]) == kmax and int(counts[3]) == chunk
+        assert work.view(-1, 8)[: len(w_ref)].tolist() == w_ref
+        assert parts.tolist() == p_ref
+        assert len(w_ref) <= max_work                                   # one wave of CTA pairs (or one item per query row)
