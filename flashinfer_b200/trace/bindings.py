@@ -91,6 +91,7 @@ BINDINGS: List[Tuple[str, str, "_t.TraceTemplate"]] = [
     ("mla._core", "trtllm_batch_decode_with_kv_cache_mla", T.sparse_mla_decode_trace),
     ("sparse", "BlockSparseAttentionWrapper.run", T.block_sparse_attention_trace),
     ("attention._core", "BatchAttention.run", T.batch_attention_trace),
+    ("fused_moe.core", "trtllm_bf16_routed_moe", T.trtllm_bf16_routed_moe_trace),
 ]
 
 _PKG = __name__.rsplit(".", 2)[0]

@@ -346,3 +346,53 @@ batch_attention_trace = TraceTemplate(
     test_sizes={"num_qo_heads": 4, "num_kv_heads": 2, "head_dim": 32, "page_size": 8})
 
 __all__ = [n for n in dir() if n.endswith("_trace")]
+
+
+# ------------------------------------------------------------------ trtllm-style pre-routed bf16 MoE (packed routing words)
+def _routed_moe_reference(topk_ids, hidden_states, gemm1_weights, gemm2_weights):
+    """topk_ids [T, K] int32 = (expert_id << 16) | bf16 bits of the routing weight; gemm1 [E, 2I, H] = [up | gate] rows."""
+    ids = (topk_ids >> 16).to(torch.int64)
+    wts = (topk_ids & 0xFFFF).to(torch.int16).view(torch.bfloat16).to(torch.float32)
+    t_, h = hidden_states.shape
+    inter = gemm2_weights.shape[2]
+    out = torch.zeros(t_, h, dtype=torch.float32, device=hidden_states.device)
+    for e in range(gemm1_weights.shape[0]):
+        tok, slot = torch.nonzero(ids == e, as_tuple=True)
+        if tok.numel() == 0:
+            continue
+        hid = hidden_states[tok].to(torch.float32) @ gemm1_weights[e].to(torch.float32).t()
+        act = torch.nn.functional.silu(hid[:, inter:]) * hid[:, :inter]
+        out.index_add_(0, tok, (act @ gemm2_weights[e].to(torch.float32).t()) * wts[tok, slot][:, None])
+    return out.to(hidden_states.dtype)
+
+
+def _routed_moe_init(*, seq_len=64, num_experts=8, hidden_size=4096, intermediate_size=1024, top_k=2, device="cuda", seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = (torch.randn(seq_len, hidden_size, generator=g) * 0.5).to(torch.bfloat16)
+    w1 = (torch.randn(num_experts, 2 * intermediate_size, hidden_size, generator=g) / hidden_size ** 0.5).to(torch.bfloat16)
+    w2 = (torch.randn(num_experts, hidden_size, intermediate_size, generator=g) / intermediate_size ** 0.5).to(torch.bfloat16)
+    scales, ids = torch.topk(torch.softmax(torch.randn(seq_len, num_experts, generator=g), -1), top_k)
+    packed = (ids.to(torch.int32) << 16) | (scales.to(torch.bfloat16).view(torch.int16).to(torch.int32) & 0xFFFF)
+    return {"topk_ids": packed.to(device), "hidden_states": x.to(device), "gemm1_weights": w1.to(device), "gemm2_weights": w2.to(device),
+            "num_experts": num_experts, "top_k": top_k, "n_group": None, "topk_group": None, "intermediate_size": intermediate_size,
+            "local_expert_offset": 0, "local_num_experts": num_experts}
+
+
+def _moe_first(got, expected, kwargs):
+    out = got[0][0] if isinstance(got[0], (list, tuple)) else got[0]
+    torch.testing.assert_close(out.float(), expected[0].float(), atol=3e-2, rtol=3e-2)
+
+
+trtllm_bf16_routed_moe_trace = TraceTemplate(
+    op_type="moe", name_fmt="trtllm_bf16_routed_moe_e{num_experts}_h{hidden_size}_i{intermediate_size}_k{top_k}",
+    axes=[Var("seq_len"), Const("num_experts", abbrev="e"), Const("hidden_size", abbrev="h"), Const("intermediate_size", abbrev="i"),
+          Const("top_k", abbrev="k"), Var("gemm1_rows")],
+    inputs=[Tensor("topk_ids", ("seq_len", "top_k"), dtype="int32"), Tensor("hidden_states", ("seq_len", "hidden_size")),
+            Tensor("gemm1_weights", ("num_experts", "gemm1_rows", "hidden_size")),
+            Tensor("gemm2_weights", ("num_experts", "hidden_size", "intermediate_size"))],
+    outputs=[Tensor("output", ("seq_len", "hidden_size"), dtype_from="hidden_states")], reference=_routed_moe_reference, init=_routed_moe_init,
+    compare=_moe_first, tags=("moe", "bf16", "pre-routed"), constraints=("gemm1_rows == 2 * intermediate_size",),
+    description="trtllm-style bf16 MoE with packed pre-computed routing ((expert << 16) | bf16 weight), SwiGLU experts",
+    test_sizes={"num_experts": 4, "hidden_size": 64, "intermediate_size": 32, "top_k": 2})
+
+__all__ = [n for n in dir() if n.endswith("_trace")]
