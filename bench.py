@@ -149,7 +149,7 @@ def run_ours(args, rank, world):
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms = tm.tolist()
     del flush
-    extra = _run_extras(args, "ours", rank, world)
+    res = None
     if rank == 0:
         ms_per_step = dev_ms / args.steps
         value = BATCH / (ms_per_step / 1e3)
@@ -183,9 +183,41 @@ def run_ours(args, rank, world):
             "gpu_launches": int((native_per_step + torch_per_step) * args.steps),
             "gpu_launches_native_per_step": int(native_per_step),
             # the other BASELINE.json configs, measured after the timed region (benchmarks/extra_configs.py; same code both arms)
-            "extra": extra,
+            "extra": None,
         }
-        print(json.dumps(res), flush=True)
+    _emit_guarded(res, lambda: _run_extras(args, "ours", rank, world))
+
+
+def _emit_guarded(res, extras_fn, limit_s=None):
+    """The headline line must never be lost to the extras: they run under a wall-clock guard.  If they raise, the error goes into the
+    ``extra`` block; if they hang (a collective that never completes at some world size), every rank gives up after ``limit_s``
+    seconds, rank 0 prints the headline with an error note, and the processes exit cleanly."""
+    limit_s = float(os.environ.get("FIB200_BENCH_EXTRAS_LIMIT", "300")) if limit_s is None else limit_s
+    lock, state = threading.Lock(), {"printed": False}
+
+    def emit(extra):
+        with lock:
+            if state["printed"]:
+                return
+            state["printed"] = True
+            if res is not None:
+                res["extra"] = extra
+                print(json.dumps(res), flush=True)
+
+    def bail():
+        emit({"error": f"extras exceeded {limit_s:.0f} s and were abandoned"})
+        sys.stdout.flush()
+        os._exit(0)
+
+    timer = threading.Timer(limit_s, bail)
+    timer.daemon = True
+    timer.start()
+    try:
+        extra = extras_fn()
+    except BaseException as e:  # noqa: BLE001
+        extra = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+    timer.cancel()
+    emit(extra)
 
 
 def _run_extras(args, impl, rank, world):
@@ -276,8 +308,11 @@ def main():
         run_ours(args, rank, world)
     if world > 1:
         import torch.distributed as dist
-        dist.barrier()
-        dist.destroy_process_group()
+        try:  # (after a failed extra the CUDA context may be unusable: the JSON line is out, leave quietly)
+            dist.barrier()
+            dist.destroy_process_group()
+        except Exception:  # noqa: BLE001
+            pass
 
 
 if __name__ == "__main__":
