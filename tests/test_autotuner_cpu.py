@@ -183,3 +183,25 @@ def test_decode_linear_plan_is_a_tuner_client(tuner):
     with autotune():
         dl._tuned_plan(x, w, 768, 4096, dl.EPI_GATED_SILU, launch)                         # another epilogue is another key
     assert seen
+
+
+def test_example_tuned_config_feeds_decode_linear(tuner):
+    """The shipped example (measured B200 sweep) loads and answers the keys decode_linear asks with."""
+    import os
+    import warnings
+
+    import flashinfer_b200
+    from flashinfer_b200.gemm import decode_linear as dl
+
+    path = os.path.join(os.path.dirname(flashinfer_b200.__file__), "tuning_configs", "examples", "llama3_8b_decode_linear_NVIDIA_B200.json")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")                     # measured on a B200, loaded on whatever runs the test
+        assert tuner.load_configs(path) == 16
+    calls = []
+    launch = lambda bn, s: calls.append((bn, s))  # noqa: E731
+    x = torch.zeros(64, 4096, dtype=torch.bfloat16)
+    w_qkv_tp8 = torch.zeros(64, 768, 64, dtype=torch.bfloat16)       # BlockMajorK [K / 64, N, 64]
+    assert dl._tuned_plan(x, w_qkv_tp8, 768, 4096, dl.EPI_ROPE_APPEND, launch) == (128, 8)
+    w_gu = torch.zeros(64, 28672, 64, dtype=torch.bfloat16)
+    assert dl._tuned_plan(x, w_gu, 28672, 4096, dl.EPI_GATED_SILU, launch) == (0, 0)      # planner default was the best plan
+    assert not calls                                                                     # cache hits never launch anything
