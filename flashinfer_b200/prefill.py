@@ -41,6 +41,19 @@ def _unpack_bits(packed: torch.Tensor, n: int) -> torch.Tensor:
     return bits.bool()
 
 
+def _unpack_segmented(packed: torch.Tensor, seg_bits) -> torch.Tensor:
+    """Inverse of ``segment_packbits(mask, indptr, "little")`` (the format of ``packed_custom_mask`` in the reference: every
+    request's ``q_len x kv_len`` bits start on a byte boundary, reference prefill.py ``_compute_page_mask_indptr``):
+    concatenated bool bits of all segments."""
+    out, off = [], 0
+    flat = packed.reshape(-1)
+    for n in seg_bits:
+        nb = (int(n) + 7) // 8
+        out.append(_unpack_bits(flat[off: off + nb], int(n)))
+        off += nb
+    return torch.cat(out) if out else torch.empty(0, dtype=torch.bool, device=packed.device)
+
+
 def single_prefill_with_kv_cache(
     q: torch.Tensor,
     k: torch.Tensor,
@@ -385,8 +398,7 @@ class BatchPrefillWithRaggedKVCacheWrapper(_BatchPrefillBase):
         self._kv_indptr_ragged_host = kv_host
         if packed_custom_mask is not None and custom_mask is None:
             qo_h = qo_indptr.to("cpu")
-            n = int(((qo_h[1:] - qo_h[:-1]) * (kv_host[1:] - kv_host[:-1])).sum())
-            custom_mask = _unpack_bits(packed_custom_mask, n)
+            custom_mask = _unpack_segmented(packed_custom_mask, ((qo_h[1:] - qo_h[:-1]) * (kv_host[1:] - kv_host[:-1])).tolist())
         self._plan_common(qo_indptr, kv_host[1:] - kv_host[:-1], num_qo_heads, num_kv_heads, head_dim_qk, head_dim_vo,
                           causal, sm_scale, window_left, logits_soft_cap, q_data_type, kv_data_type, custom_mask,
                           non_blocking)
@@ -460,8 +472,7 @@ class BatchPrefillWithPagedKVCacheWrapper(_BatchPrefillBase):
         self._kv_page_indptr_dev = indptr_host.to(self.device, non_blocking=non_blocking)
         if packed_custom_mask is not None and custom_mask is None:
             qo_h = qo_indptr.to("cpu")
-            n = int(((qo_h[1:] - qo_h[:-1]) * kv_lens).sum())
-            custom_mask = _unpack_bits(packed_custom_mask, n)
+            custom_mask = _unpack_segmented(packed_custom_mask, ((qo_h[1:] - qo_h[:-1]) * kv_lens).tolist())
         self._plan_common(qo_indptr, kv_lens, num_qo_heads, num_kv_heads, head_dim_qk, head_dim_vo, causal, sm_scale,
                           window_left, logits_soft_cap, q_data_type, kv_data_type, custom_mask, non_blocking)
 

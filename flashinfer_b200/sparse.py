@@ -51,9 +51,10 @@ class BlockSparseAttentionWrapper:
         if mask is not None:
             flat_mask = (convert_bsr_mask_layout(mask.bool(), indptr) if mask.dim() == 3 else mask.flatten().bool())
         elif packed_mask is not None:
-            from .prefill import _unpack_bits
+            from .prefill import _unpack_segmented
 
-            flat_mask = _unpack_bits(packed_mask, int(indices.numel()) * R * C)
+            ip = indptr.to("cpu", torch.int64)
+            flat_mask = _unpack_segmented(packed_mask, ((ip[1:] - ip[:-1]) * (R * C)).tolist())  # one byte-aligned segment per block row
         self._M, self._N, self._R, self._C = M, N, R, C
         self._hq, self._hkv, self._d = num_qo_heads, num_kv_heads, head_dim
         self._bsr_indptr, self._bsr_indices = indptr.to("cpu", torch.int32), indices.to("cpu", torch.int32)  # (fi_trace: run() inputs)

@@ -40,7 +40,8 @@ def _run_case(device, dtype, R, C, hq, hkv, d, mb, nb, elem_mask=False, packed=F
                 blk += 1
         if packed:
             flat = fi.sparse.convert_bsr_mask_layout(em, indptr)
-            kw["packed_mask"] = fi.packbits(flat.to(device), bitorder="little")
+            seg = (indptr.long() * (R * C)).int()     # reference format: one byte-aligned segment per block row (segment_packbits)
+            kw["packed_mask"] = fi.segment_packbits(flat.cpu(), seg, bitorder="little")[0].to(device)
         else:
             kw["mask"] = em.to(device)
     w = fi.BlockSparseAttentionWrapper(torch.empty(32 << 20, dtype=torch.uint8, device=device))
@@ -50,9 +51,10 @@ def _run_case(device, dtype, R, C, hq, hkv, d, mb, nb, elem_mask=False, packed=F
     assert (out.float() - ref.float()).abs().max() < tol
 
 
-@pytest.mark.parametrize("R,C,elem", [(1, 16, False), (4, 8, False), (16, 16, True), (2, 24, False)])
-def test_block_sparse_cpu(R, C, elem):
-    _run_case("cpu", torch.float32, R, C, 4, 2, 32, 6, 5, elem_mask=elem, tol=1e-4)
+@pytest.mark.parametrize("R,C,elem,packed", [(1, 16, False, False), (4, 8, False, False), (16, 16, True, False), (2, 24, False, False),
+                                             (3, 3, True, True)])          # 9 bits per block: segments end inside a byte
+def test_block_sparse_cpu(R, C, elem, packed):
+    _run_case("cpu", torch.float32, R, C, 4, 2, 32, 6, 5, elem_mask=elem, packed=packed, tol=1e-4)
 
 
 @pytest.mark.gpu

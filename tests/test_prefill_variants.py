@@ -69,7 +69,9 @@ def test_custom_mask_ragged_tcgen05(monkeypatch, packed):
     masks[1][5, :] = False  # a fully masked row: output 0, lse -inf
     flat = torch.cat([m.flatten() for m in masks])
     w = fi.BatchPrefillWithRaggedKVCacheWrapper(torch.empty(32 << 20, dtype=torch.uint8, device="cuda"))
-    kw = {"packed_custom_mask": fi.packbits(flat, bitorder="little")} if packed else {"custom_mask": flat}
+    # packed form = segment_packbits: every request's q_len x kv_len bits start on a byte boundary (3330 / 513 bits here are not multiples of 8)
+    bits = torch.tensor([0] + [a * b for a, b in lens]).cumsum(0).int()
+    kw = {"packed_custom_mask": fi.segment_packbits(flat.cpu(), bits, bitorder="little")[0].cuda()} if packed else {"custom_mask": flat}
     w.plan(qo, kv, 8, 2, 128, causal=True, q_data_type=torch.bfloat16, **kw)  # causal is overridden by the custom mask
     out, lse = w.run(q, k, v, return_lse=True)
     for b, (ql, kl) in enumerate(lens):
@@ -251,3 +253,27 @@ def test_attention_sinks_in_kernel(monkeypatch):
     ref, lref = reference.attention_ref(qq, k, v, True, 1 / math.sqrt(d), sinks=sinks)
     assert (o2.float() - ref.float()).abs().max() < 2e-2
     assert (l2 - lref).abs().max() < 2e-2
+
+
+def test_packed_custom_mask_is_segment_packed_cpu():
+    """`packed_custom_mask` follows the reference format (segment_packbits: byte-aligned per request), on the wrappers' CPU path."""
+    torch.manual_seed(0)
+    lens = [(5, 7), (3, 11), (8, 8)]            # 35 / 33 / 64 bits: the first two segments end inside a byte
+    hq, hkv, d = 2, 1, 16
+    qo = torch.tensor([0] + [a for a, _ in lens]).cumsum(0).int()
+    kv = torch.tensor([0] + [b for _, b in lens]).cumsum(0).int()
+    q, k, v = torch.randn(int(qo[-1]), hq, d), torch.randn(int(kv[-1]), hkv, d), torch.randn(int(kv[-1]), hkv, d)
+    masks = [torch.rand(a, b) > 0.4 for a, b in lens]
+    for m in masks:
+        m[:, 0] = True
+    flat = torch.cat([m.flatten() for m in masks])
+    bits = torch.tensor([0] + [a * b for a, b in lens]).cumsum(0).int()
+    packed, _ = fi.segment_packbits(flat, bits, bitorder="little")
+    assert packed.numel() == 5 + 5 + 8
+    w = fi.BatchPrefillWithRaggedKVCacheWrapper(torch.empty(1 << 20, dtype=torch.uint8))
+    w.plan(qo, kv, hq, hkv, d, packed_custom_mask=packed, q_data_type=torch.float32)
+    out = w.run(q, k, v)
+    for b, (ql, kl) in enumerate(lens):
+        ref, _ = reference.attention_ref(q[int(qo[b]):int(qo[b + 1])], k[int(kv[b]):int(kv[b + 1])], v[int(kv[b]):int(kv[b + 1])], False,
+                                         1 / math.sqrt(d), custom_mask=masks[b])
+        assert (out[int(qo[b]):int(qo[b + 1])] - ref).abs().max() < 1e-4
