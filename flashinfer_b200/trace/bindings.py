@@ -92,6 +92,7 @@ BINDINGS: List[Tuple[str, str, "_t.TraceTemplate"]] = [
     ("sparse", "BlockSparseAttentionWrapper.run", T.block_sparse_attention_trace),
     ("attention._core", "BatchAttention.run", T.batch_attention_trace),
     ("fused_moe.core", "trtllm_bf16_routed_moe", T.trtllm_bf16_routed_moe_trace),
+    ("xqa", "xqa", T.xqa_trace),
 ]
 
 _PKG = __name__.rsplit(".", 2)[0]

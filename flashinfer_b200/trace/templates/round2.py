@@ -396,3 +396,48 @@ trtllm_bf16_routed_moe_trace = TraceTemplate(
     test_sizes={"num_experts": 4, "hidden_size": 64, "intermediate_size": 32, "top_k": 2})
 
 __all__ = [n for n in dir() if n.endswith("_trace")]
+
+
+# ------------------------------------------------------------------ XQA decode (page table + sequence lengths, reference xqa.py:155)
+def _xqa_reference(q, k_cache, v_cache, page_table, seq_lens):
+    """q [B, 1, Hq, D]; k_cache / v_cache [pages, page_size, Hkv, D] (NHD); page_table [B, max_pages]; seq_lens [B, 1]."""
+    b, _, hq, d = q.shape
+    page_size, hkv = k_cache.shape[1], k_cache.shape[2]
+    g = hq // hkv
+    out = torch.zeros(b, 1, hq, d, dtype=torch.float32, device=q.device)
+    for i in range(b):
+        n = int(seq_lens.reshape(-1)[i])
+        pages = page_table[i, : (n + page_size - 1) // page_size].long()
+        k = k_cache[pages].reshape(-1, hkv, d)[:n].to(torch.float32).repeat_interleave(g, dim=1)
+        v = v_cache[pages].reshape(-1, hkv, d)[:n].to(torch.float32).repeat_interleave(g, dim=1)
+        logits = torch.einsum("hd,nhd->hn", q[i, 0].to(torch.float32), k) / (d ** 0.5)
+        out[i, 0] = torch.einsum("hn,nhd->hd", torch.softmax(logits, -1), v)
+    return out.to(q.dtype)
+
+
+def _xqa_init(*, batch_size=8, num_qo_heads=32, num_kv_heads=8, head_dim=128, page_size=16, max_pages=8, device="cuda", seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    lens = torch.randint(1, max_pages * page_size + 1, (batch_size,), generator=g)
+    total = batch_size * max_pages
+    table = torch.randperm(total, generator=g).view(batch_size, max_pages).to(torch.int32)
+    mk = lambda *s: torch.randn(*s, generator=g).to(torch.bfloat16).to(device)  # noqa: E731
+    return {"q": mk(batch_size, 1, num_qo_heads, head_dim), "k_cache": mk(total, page_size, num_kv_heads, head_dim),
+            "v_cache": mk(total, page_size, num_kv_heads, head_dim), "page_table": table.to(device),
+            "seq_lens": lens.to(torch.int32).view(batch_size, 1).to(device),
+            "output": torch.empty(batch_size, 1, num_qo_heads, head_dim, dtype=torch.bfloat16, device=device),
+            "workspace_buffer": torch.zeros(16 << 20, dtype=torch.uint8, device=device)}
+
+
+xqa_trace = TraceTemplate(
+    op_type="xqa", name_fmt="xqa_h{num_qo_heads}_kv{num_kv_heads}_d{head_dim}_ps{page_size}",
+    axes=[Var("batch_size"), Var("num_pages"), Var("max_pages"), Const("num_qo_heads", abbrev="h"), Const("num_kv_heads", abbrev="kv"),
+          Const("head_dim", abbrev="d"), Const("page_size", abbrev="ps")],
+    inputs=[Tensor("q", ("batch_size", "one", "num_qo_heads", "head_dim")), Tensor("k_cache", ("num_pages", "page_size", "num_kv_heads", "head_dim")),
+            Tensor("v_cache", ("num_pages", "page_size", "num_kv_heads", "head_dim")), Tensor("page_table", ("batch_size", "max_pages"), dtype="int32"),
+            Tensor("seq_lens", ("batch_size", "one"), dtype="int32")],
+    outputs=[Tensor("out", ("batch_size", "one", "num_qo_heads", "head_dim"), dtype_from="q", param="output")],
+    reference=_xqa_reference, init=_xqa_init, tags=("attention", "decode", "paged", "xqa"), constraints=("one == 1",), tolerance="bf16",
+    description="XQA-style batch decode: per-request page table rows + sequence lengths (served by the tcgen05 paged decode kernel)",
+    test_sizes={"num_qo_heads": 4, "num_kv_heads": 2, "head_dim": 32, "page_size": 8, "max_pages": 5})
+
+__all__ = [n for n in dir() if n.endswith("_trace")]
