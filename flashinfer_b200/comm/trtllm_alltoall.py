@@ -159,10 +159,20 @@ def moe_comm(input: torch.Tensor, send_rank_cum_sum: torch.Tensor, send_indices:
     if input.dim() != 2 or output.dim() != 2 or input.shape[1] != output.shape[1] or input.dtype != output.dtype:
         raise ValueError("moe_comm: input / output must be 2-D with the same row size and dtype")
     if not input.is_cuda:
-        if ep_size != 1:
-            raise NotImplementedError("moe_comm on CPU tensors: single rank only (the oracle of the native kernel)")
-        n = int(send_rank_cum_sum[0])
-        output[recv_indices[:n].long()] = input[send_indices[:n].long()]
+        # CPU tensors: the oracle of the native kernel; several ranks go through torch.distributed (gloo) all_to_all_single
+        n_send, n_recv = int(send_rank_cum_sum[ep_size - 1]), int(recv_rank_cum_sum[ep_size - 1])
+        rows = input[send_indices[:n_send].long()].contiguous()
+        if ep_size == 1:
+            output[recv_indices[:n_recv].long()] = rows
+            return
+        import torch.distributed as dist
+
+        sc, rc = send_rank_cum_sum.tolist(), recv_rank_cum_sum.tolist()
+        in_split = [sc[0]] + [sc[i] - sc[i - 1] for i in range(1, ep_size)]
+        out_split = [rc[0]] + [rc[i] - rc[i - 1] for i in range(1, ep_size)]
+        recv = torch.empty(n_recv, input.shape[1], dtype=input.dtype)
+        dist.all_to_all_single(recv, rows, output_split_sizes=out_split, input_split_sizes=in_split, group=group)
+        output[recv_indices[:n_recv].long()] = recv
         return
     row_bytes = input.shape[1] * input.element_size()
     if row_bytes % 16 or input.stride(1) != 1 or output.stride(1) != 1:
@@ -196,16 +206,13 @@ def moe_prepare(experts_ids: torch.Tensor, scales: Optional[torch.Tensor], exper
     if ep_size > 1:
         import torch.distributed as dist
 
-        g_ids = torch.empty(ep_size * max_token_count_per_rank, top_k, dtype=torch.int32, device=dev)
-        g_sc = torch.empty(ep_size * max_token_count_per_rank, top_k, dtype=torch.float32, device=dev)
-        g_cnt = torch.empty(ep_size, dtype=torch.int32, device=dev)
-        dist.all_gather_into_tensor(g_ids, ids, group=group)
-        dist.all_gather_into_tensor(g_sc, sc, group=group)
-        dist.all_gather_into_tensor(g_cnt, cnt, group=group)
-        stat = None
-        if experts_statics is not None:
-            stat = torch.empty(ep_size, *experts_statics.shape, dtype=experts_statics.dtype, device=dev)
-            dist.all_gather_into_tensor(stat, experts_statics.contiguous(), group=group)
+        def gather(t):  # all_gather (list form: works on every backend, gloo included), rank-major concatenation
+            parts = [torch.empty_like(t) for _ in range(ep_size)]
+            dist.all_gather(parts, t.contiguous(), group=group)
+            return parts
+
+        g_ids, g_sc, g_cnt = torch.cat(gather(ids)), torch.cat(gather(sc)), torch.cat(gather(cnt))
+        stat = torch.stack(gather(experts_statics)) if experts_statics is not None else None
     else:
         g_ids, g_sc, g_cnt = ids, sc, cnt
         stat = experts_statics[None] if experts_statics is not None else None

@@ -141,3 +141,45 @@ def test_legacy_alltoall_round_trip(world):
     errs = mp.get_context("spawn").Manager().dict()
     mp.spawn(_worker, args=(world, _free_port(), errs), nprocs=world, join=True)
     assert len(errs) == world and max(errs.values()) < 2e-2, dict(errs)
+
+
+def _gloo_worker(rank, world, port, errs):
+    """Host-side logic of the legacy protocol across ranks, on CPU tensors over gloo: prepare (all-gathered routing tables, index
+    lists), dispatch, "experts", combine == a local oracle."""
+    import torch.distributed as dist
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        E, K, H, max_tok = 4 * world, 3, 16, 12
+        epr = E // world
+        worst = 0.0
+        for it in range(3):
+            torch.manual_seed(10 * it + rank)
+            T = [max_tok, 1 + 5 * rank, 7][it]
+            x = torch.randn(T, H)
+            ids = torch.stack([torch.randperm(E)[:K] for _ in range(T)]).int()
+            sc = torch.rand(T, K)
+            info, lids, lsc, _ = ta.MnnvlMoe.mnnvl_moe_alltoallv_prepare_without_allgather(ids, sc, None, None, max_tok, rank, world, E, E, K)
+            ws = torch.zeros(8)
+            recv = ta.MnnvlMoe.mnnvl_moe_alltoallv(x, info, ws, rank, world)
+            n_recv = int(info.recv_rank_count_cumsum[-1])
+            here = (lids[:n_recv] >= rank * epr) & (lids[:n_recv] < (rank + 1) * epr)
+            coef = torch.where(here, (lids[:n_recv] + 1).float() * lsc[:n_recv], torch.zeros_like(lsc[:n_recv])).sum(-1)
+            y = torch.zeros_like(recv)
+            y[:n_recv] = recv[:n_recv] * coef[:, None]
+            out = ta.MnnvlMoe.mnnvl_moe_alltoallv_combine(y, info, ws, rank, world, K, T)
+            ref = x * ((ids + 1).float() * sc).sum(-1)[:, None]          # every expert e scales by (e + 1) * routing weight
+            worst = max(worst, float((out - ref).abs().max() / ref.abs().max()))
+        errs[rank] = worst
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_legacy_alltoall_round_trip_gloo(world):
+    import torch.multiprocessing as mp
+
+    errs = mp.Manager().dict()
+    mp.spawn(_gloo_worker, args=(world, _free_port(), errs), nprocs=world, join=True)
+    assert len(errs) == world and max(errs.values()) < 1e-5, dict(errs)
