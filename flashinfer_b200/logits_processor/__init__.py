@@ -35,4 +35,4 @@ from .pipeline import (  # noqa: F401
 
 from .. import _alias  # noqa: E402
 
-_alias.install(__name__, ['types', 'op', 'operators', 'processors', 'compiler', 'fusion_rules', 'legalization', 'validators'])  # the reference's per-file module paths
+from . import compiler, fusion_rules, legalization, op, operators, processors, types, validators  # noqa: E402,F401  (the reference's module layout)

@@ -1,0 +1,32 @@
+"""Processors -> typed primitive ops, with type inference of the pipeline input (reference flashinfer/logits_processor/legalization.py)."""
+from __future__ import annotations
+
+from typing import List, Sequence
+
+from .op import Op
+from .processors import LogitsProcessor, Sample, Softmax, Temperature, TopK
+from .types import LegalizationError, TensorType
+
+
+def infer_initial_type(processors: Sequence[LogitsProcessor]) -> TensorType:
+    first = processors[0]
+    if isinstance(first, (Temperature, Softmax)):
+        return TensorType.LOGITS
+    if isinstance(first, (TopP, MinP)):
+        return TensorType.PROBS
+    raise LegalizationError(f"cannot infer the input type from {type(first).__name__}; pass input_type=")
+
+
+def legalize_processors(processors: Sequence[LogitsProcessor], input_type: TensorType) -> List[Op]:
+    ops: List[Op] = []
+    cur = input_type
+    for p in processors:
+        if cur == TensorType.INDICES:
+            raise LegalizationError("no processor may follow Sample")
+        lowered = p.legalize(cur)
+        for op in lowered:
+            if op.IN != cur:
+                raise LegalizationError(f"{op} does not accept {cur.value}")
+            cur = op.OUT
+        ops += lowered
+    return ops

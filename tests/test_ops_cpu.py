@@ -157,3 +157,30 @@ def test_mm_fp4_accepts_8x4_activation_scales():
     o8 = fi.mm_fp4(aq8, wq.t(), asf8, wsf.t(), alpha, torch.bfloat16, use_8x4_sf_layout=True)
     assert torch.equal(o8, fi.mm_fp4(aq, wq.t(), asf, wsf.t(), alpha, torch.bfloat16))
     assert torch.nn.functional.cosine_similarity(o8.float().flatten(), (a.float() @ w.float().t()).flatten(), dim=0) > 0.98
+
+
+def test_logits_processor_modules_and_validators():
+    """The pipeline is split like the reference (types / op / operators / processors / legalization / fusion_rules / compiler /
+    validators); validators reject pipelines that cannot be lowered; custom checks and custom fusion rules plug in."""
+    from flashinfer_b200.logits_processor import LogitsPipe, Sample, Softmax, Temperature, TopK
+    from flashinfer_b200.logits_processor.fusion_rules import DEFAULT_RULES, FusionRule
+    from flashinfer_b200.logits_processor.legalization import legalize_processors
+    from flashinfer_b200.logits_processor.operators import TempSoftmaxOp
+    from flashinfer_b200.logits_processor.types import LegalizationError, TensorType
+    from flashinfer_b200.logits_processor.validators import validate_pipeline
+
+    with pytest.raises(LegalizationError):
+        LogitsPipe([Sample(), Softmax()])
+    with pytest.raises(LegalizationError):
+        validate_pipeline([Softmax(), Sample(), Sample()])
+    with pytest.raises(RuntimeError):
+        LogitsPipe([Softmax()], custom_validity_checks=[lambda ps: (_ for _ in ()).throw(RuntimeError("nope"))])
+    ops = legalize_processors([Temperature(), Softmax(), TopK()], TensorType.LOGITS)
+    assert [o.name for o in ops] == ["temperature", "softmax", "topk_renorm_probs"]
+    pipe = LogitsPipe([Temperature(), Softmax(), TopK()])
+    assert [o.name for o in pipe.compiled_ops] == ["temperature_softmax", "topk_renorm_probs"] and isinstance(pipe.compiled_ops[0], TempSoftmaxOp)
+    extra = FusionRule(("temperature_softmax", "topk_renorm_probs"), lambda ops: ops[0], priority=0)   # user rule: runs after the defaults
+    assert len(LogitsPipe([Temperature(), Softmax(), TopK()], custom_fusion_rules=[extra]).compiled_ops) == 1 and len(DEFAULT_RULES) == 6
+    x = torch.randn(3, 50)
+    probs = pipe(x, temperature=0.7, top_k=4)
+    assert torch.allclose(probs.sum(-1), torch.ones(3), atol=1e-5) and int((probs > 0).sum(-1).max()) <= 4
