@@ -14,6 +14,7 @@ without a tensor-core path (mxint4) are load-time preparations cached per weight
 """
 from __future__ import annotations
 
+import weakref
 from enum import IntEnum
 from typing import List, Optional, Tuple, Union
 
@@ -418,15 +419,25 @@ def _prepared(tag: str, tensors, fn):
     """One-time transformation of STATIC expert weights, cached on (tag, data_ptr, shape, dtype, version) of the inputs: layout
     conversions (un-shuffle, BlockMajorK -> MajorK) and the few formats without a native tensor-core path (mxint4) are prepared
     on first use - never per call (the quantised entry points used to de-quantise every expert weight in eager
-    torch on every call)."""
-    key = (tag,) + tuple((t.data_ptr(), tuple(t.shape), str(t.dtype), t._version) for t in tensors if isinstance(t, torch.Tensor))
+    torch on every call).
+
+    An entry is only trusted while the tensors it was computed from (their view bases) are still alive: once they are freed
+    the allocator may hand the same address to different weights of the same shape, and the key alone would match them."""
+    live = [t for t in tensors if isinstance(t, torch.Tensor)]
+    key = (tag,) + tuple((t.data_ptr(), tuple(t.shape), tuple(t.stride()), str(t.dtype), t._version) for t in live)
     hit = _PREP_CACHE.get(key)
-    if hit is None:
-        if len(_PREP_CACHE) > 256:
-            _PREP_CACHE.clear()
-        hit = fn()
-        _PREP_CACHE[key] = hit
-    return hit
+    if hit is not None and all(r() is not None for r in hit[0]):
+        return hit[1]
+    if len(_PREP_CACHE) > 256:
+        _PREP_CACHE.clear()
+    value = fn()
+    _PREP_CACHE[key] = ([weakref.ref(t._base if t._base is not None else t) for t in live], value)
+    return value
+
+
+def _scale_tag(tag: str, scale) -> str:
+    """Cache tag that carries a python-number global scale (tensor scales are part of the key through the tensor list)."""
+    return tag if (scale is None or isinstance(scale, torch.Tensor)) else f"{tag}:{float(scale)!r}"
 
 
 def _shuffle_block_rows(m: int, epilogue_tile_m: int) -> torch.Tensor:
@@ -639,8 +650,8 @@ def trtllm_fp4_block_scale_moe(routing_logits, routing_bias, hidden_states, hidd
     if x.is_cuda and do_finalize and hidden_states.shape[-1] % 64 == 0 and intermediate_size % 64 == 0:
         return moe_forward_nvfp4(x, ids, w, gemm1_weights, gemm1_weights_scale, g1, gemm2_weights, gemm2_weights_scale, g2,
                                  local_expert_offset, num_experts)
-    w1 = _prepared("nvfp4deq", [gemm1_weights, gemm1_weights_scale], lambda: _dequant_nvfp4(gemm1_weights, gemm1_weights_scale, g1))
-    w2 = _prepared("nvfp4deq", [gemm2_weights, gemm2_weights_scale], lambda: _dequant_nvfp4(gemm2_weights, gemm2_weights_scale, g2))
+    w1 = _prepared(_scale_tag("nvfp4deq", g1), [gemm1_weights, gemm1_weights_scale, g1], lambda: _dequant_nvfp4(gemm1_weights, gemm1_weights_scale, g1))
+    w2 = _prepared(_scale_tag("nvfp4deq", g2), [gemm2_weights, gemm2_weights_scale, g2], lambda: _dequant_nvfp4(gemm2_weights, gemm2_weights_scale, g2))
     return moe_forward(x.to(torch.bfloat16), ids, w, w1, w2, local_expert_offset, num_experts, do_finalize=do_finalize)
 
 
@@ -662,8 +673,8 @@ def trtllm_fp4_block_scale_routed_moe(topk_ids, routing_bias, hidden_states, hid
     if x.is_cuda and do_finalize and hidden_states.shape[-1] % 64 == 0 and intermediate_size % 64 == 0:
         return moe_forward_nvfp4(x, ids, w, gemm1_weights, gemm1_weights_scale, g1, gemm2_weights, gemm2_weights_scale, g2,
                                  local_expert_offset, num_experts)
-    w1 = _prepared("nvfp4deq", [gemm1_weights, gemm1_weights_scale], lambda: _dequant_nvfp4(gemm1_weights, gemm1_weights_scale, g1))
-    w2 = _prepared("nvfp4deq", [gemm2_weights, gemm2_weights_scale], lambda: _dequant_nvfp4(gemm2_weights, gemm2_weights_scale, g2))
+    w1 = _prepared(_scale_tag("nvfp4deq", g1), [gemm1_weights, gemm1_weights_scale, g1], lambda: _dequant_nvfp4(gemm1_weights, gemm1_weights_scale, g1))
+    w2 = _prepared(_scale_tag("nvfp4deq", g2), [gemm2_weights, gemm2_weights_scale, g2], lambda: _dequant_nvfp4(gemm2_weights, gemm2_weights_scale, g2))
     return moe_forward(x.to(torch.bfloat16), ids, w, w1, w2, local_expert_offset, num_experts, do_finalize=do_finalize)
 
 
@@ -754,8 +765,8 @@ def cute_dsl_fused_moe_nvfp4(x, x_sf, token_selected_experts, token_final_scales
         return moe_forward_nvfp4(xd, ids, wts, w1_weight.view(torch.uint8).reshape(e_local, w1_weight.shape[1], -1), w1_weight_sf,
                                  w1_alpha if w1_alpha is not None else 1.0, w2_weight.view(torch.uint8).reshape(e_local, w2_weight.shape[1], -1),
                                  w2_weight_sf, w2_alpha if w2_alpha is not None else 1.0, local_expert_offset, num_experts)
-    w1 = _prepared("nvfp4deq", [w1_weight, w1_weight_sf], lambda: _dequant_nvfp4(w1_weight, w1_weight_sf, w1_alpha if w1_alpha is not None else 1.0))
-    w2 = _prepared("nvfp4deq", [w2_weight, w2_weight_sf], lambda: _dequant_nvfp4(w2_weight, w2_weight_sf, w2_alpha if w2_alpha is not None else 1.0))
+    w1 = _prepared(_scale_tag("nvfp4deq", w1_alpha), [w1_weight, w1_weight_sf, w1_alpha], lambda: _dequant_nvfp4(w1_weight, w1_weight_sf, w1_alpha if w1_alpha is not None else 1.0))
+    w2 = _prepared(_scale_tag("nvfp4deq", w2_alpha), [w2_weight, w2_weight_sf, w2_alpha], lambda: _dequant_nvfp4(w2_weight, w2_weight_sf, w2_alpha if w2_alpha is not None else 1.0))
     return moe_forward(xd, ids, wts, w1.to(output_dtype), w2.to(output_dtype), local_expert_offset, num_experts)
 
 

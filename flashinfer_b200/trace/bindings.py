@@ -93,7 +93,19 @@ BINDINGS: List[Tuple[str, str, "_t.TraceTemplate"]] = [
     ("attention._core", "BatchAttention.run", T.batch_attention_trace),
     ("fused_moe.core", "trtllm_bf16_routed_moe", T.trtllm_bf16_routed_moe_trace),
     ("xqa", "xqa", T.xqa_trace),
+    ("fused_moe.core", "trtllm_bf16_moe", T.trtllm_bf16_moe_trace),
+    ("fused_moe.core", "trtllm_fp8_per_tensor_scale_moe", T.trtllm_fp8_per_tensor_scale_moe_trace),
+    ("fused_moe.core", "trtllm_fp8_block_scale_moe", T.trtllm_fp8_block_scale_moe_trace_dispatch),
+    ("fused_moe.core", "trtllm_fp8_block_scale_routed_moe", T.trtllm_fp8_block_scale_routed_moe_trace),
+    ("fused_moe.core", "trtllm_fp4_block_scale_moe", T.trtllm_fp4_block_scale_moe_trace_dispatch),
+    ("fused_moe.core", "trtllm_fp4_block_scale_routed_moe", T.trtllm_fp4_block_scale_routed_moe_trace),
+    ("fused_moe.core", "trtllm_mxint4_block_scale_moe", T.trtllm_mxint4_block_scale_moe_trace),
+    ("fused_moe.core", "cute_dsl_fused_moe_nvfp4", T.cute_dsl_fused_moe_nvfp4_trace),
+    ("fused_moe.core", "CuteDslMoEWrapper.run", T.cute_dsl_moe_wrapper_run_trace),
 ]
+
+# one row per concrete template (a dispatch contributes one row per member): what the generic tests iterate over
+FLAT_BINDINGS: List[Tuple[str, str, "_t.TraceTemplate"]] = [(m, p, c) for m, p, t in BINDINGS for c in _t.concrete_templates(t)]
 
 _PKG = __name__.rsplit(".", 2)[0]
 _originals: Dict[Tuple[str, str], object] = {}

@@ -127,6 +127,7 @@ class TraceTemplate:
     derive: Optional[Callable] = None  # derive(sizes) -> extra axis sizes computed from the resolved ones
     test_sizes: Optional[Dict[str, int]] = None   # small axis sizes for the generic reference-correctness test
     compare: Optional[Callable] = None  # compare(got, expected, kwargs): op-specific check replacing the tolerance class
+    helpers: Sequence[Callable] = field(default_factory=tuple)   # functions ``reference`` calls: their source is emitted in front of it
 
     def __post_init__(self):
         _TEMPLATES[self.key] = self
@@ -208,7 +209,8 @@ class TraceTemplate:
         for label, fn in (("reference", self.reference), ("init", self.init)):
             if fn is not None:
                 try:
-                    out[label] = inspect.getsource(fn)
+                    parts = [inspect.getsource(h) for h in self.helpers] if label == "reference" else []
+                    out[label] = "\n\n".join(parts + [inspect.getsource(fn)])
                 except (OSError, TypeError):
                     out[label] = None
         return out
@@ -271,12 +273,59 @@ class TraceTemplate:
         return trace
 
 
+class TemplateDispatch:
+    """Several templates behind one API: ``select(bound)`` names the member that describes a given call (reference
+    flashinfer/api_logging.py:2182-2291, the ``trace=<callable>`` form - e.g. one MoE entry point whose definition depends
+    on ``routing_method_type``).  Offers the subset of :class:`TraceTemplate` the binding / tracing code uses."""
+
+    def __init__(self, templates: Sequence["TraceTemplate"], select: Callable[[Dict[str, Any]], "TraceTemplate"]):
+        self.templates = tuple(templates)
+        self._select = select
+
+    def pick(self, bound: Dict[str, Any]) -> "TraceTemplate":
+        tpl = self._select(bound)
+        if tpl not in self.templates:
+            raise ValueError("dispatch returned a template that is not one of its members")
+        return tpl
+
+    @property
+    def fi_api(self) -> str:
+        return self.templates[0].fi_api
+
+    @fi_api.setter
+    def fi_api(self, value: str) -> None:
+        for t in self.templates:
+            t.fi_api = value
+
+    def definition(self, bound: Dict[str, Any]) -> Dict[str, Any]:
+        return self.pick(bound).definition(bound)
+
+    def dump(self, bound: Dict[str, Any], save_dir: Optional[str] = None) -> Dict[str, Any]:
+        return self.pick(bound).dump(bound, save_dir)
+
+    def build_fi_trace_fn(self, fi_api: str = "") -> Callable[..., Dict[str, Any]]:
+        if fi_api:
+            self.fi_api = fi_api
+
+        def trace(save_dir: Optional[str] = None, **kwargs) -> Dict[str, Any]:
+            return self.dump(kwargs, save_dir) if (save_dir or _State.dump_dir) else self.definition(kwargs)
+
+        return trace
+
+
+def concrete_templates(tpl) -> Tuple["TraceTemplate", ...]:
+    """The member templates of a dispatch, or the template itself."""
+    return tuple(tpl.templates) if isinstance(tpl, TemplateDispatch) else (tpl,)
+
+
 def registered_templates() -> Dict[str, TraceTemplate]:
     return dict(_TEMPLATES)
 
 
-def _emit_once(template: TraceTemplate, bound: Dict[str, Any], out_dir: str) -> None:
+def _emit_once(template, bound: Dict[str, Any], out_dir: str) -> None:
     try:
+        if isinstance(template, TemplateDispatch):
+            template = template.pick(bound)
         sizes = template.resolve_axes(bound)
         key = (template.op_type, template.definition_name(sizes), out_dir)
         with _lock:

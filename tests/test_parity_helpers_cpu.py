@@ -248,3 +248,31 @@ def test_module_accessors_and_moe_layout_helpers():
     calls = []
     cached = prefill.make_hashable_cache(lambda names, opts=None: calls.append(1) or len(calls))
     assert cached(["a", "b"], opts={"k": [1]}) == cached(["a", "b"], opts={"k": [1]}) == 1 and cached(["a"]) == 2
+
+
+def test_moe_prepared_cache_is_tied_to_the_live_weight_tensors():
+    """Load-time weight preparation is cached per weight tensor; an entry must die with the tensor it was computed from
+    (the allocator hands the same address to the next tensor of that shape) and must survive fresh views of a live base."""
+    import gc
+
+    from flashinfer_b200.fused_moe import core
+
+    calls = []
+
+    def prep(t):
+        return core._prepared("unit-test", [t], lambda: (calls.append(1), t.clone())[1])
+
+    base = torch.arange(64, dtype=torch.float32)
+    first = prep(base.view(8, 8))                      # temporary view: its base stays alive
+    assert prep(base.view(8, 8)) is first and len(calls) == 1
+    base.add_(1)                                       # in-place update of the weights -> new version -> recomputed
+    assert prep(base.view(8, 8)) is not first and len(calls) == 2
+
+    a = torch.full((32,), 1.0)
+    ptr = a.data_ptr()
+    got_a = prep(a)
+    del a
+    gc.collect()
+    b = torch.full((32,), 2.0)
+    if b.data_ptr() == ptr:                            # address reuse is what usually happens; the rule is checked when it does
+        assert torch.equal(prep(b), b) and prep(b) is not got_a

@@ -10,7 +10,7 @@ import pytest
 import torch
 
 import flashinfer_b200 as fi
-from flashinfer_b200.trace import BINDINGS, Const, Scalar, Tensor, Var
+from flashinfer_b200.trace import FLAT_BINDINGS as BINDINGS, Const, Scalar, Tensor, Var
 from flashinfer_b200.trace.bindings import _resolve
 
 # FIB200_TRACE_TEST_DEVICE=cuda runs the same checks against the native kernels (opt-in: not part of the gpu-marked suite yet)
@@ -27,7 +27,7 @@ TOLERANCE = {
     "support": None,                            # stochastic: the reference is the mask of tokens that may be emitted
 }
 
-_IDS = [f"{m}.{p}" for m, p, _ in BINDINGS]
+_IDS = [f"{m}.{p}" + (f"[{t.name_fmt.split('{')[0].rstrip('_e')}]" if sum(1 for b in BINDINGS if b[:2] == (m, p)) > 1 else "") for m, p, t in BINDINGS]
 
 
 def _api(mod, path):
