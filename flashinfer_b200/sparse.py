@@ -132,6 +132,8 @@ class VariableBlockSparseAttentionWrapper:
         rs, cs = block_row_sz.cpu().long(), block_col_sz.cpu().long()
         self._seq_q = int(rs[0].sum())
         self._seq_kv = int(cs[0].sum())
+        self._block_mask_map, self._block_row_sz, self._block_col_sz = bm, rs, cs   # host copies (read by the fi_trace template)
+        self._sm_scale = sm_scale if sm_scale is not None else head_dim ** -0.5
         qo, kvp, idx = [0], [0], []
         for h in range(hkv):
             col_start = torch.cat([torch.zeros(1, dtype=torch.long), cs[h].cumsum(0)])

@@ -88,7 +88,7 @@ BINDINGS: List[Tuple[str, str, "_t.TraceTemplate"]] = [
     ("triton.sm_constraint_gemm", "gemm_persistent", T.gemm_persistent_trace),
     ("comm.allreduce", "local_argmax", T.local_argmax_trace),
     ("comm.trtllm_alltoall", "moe_local_gather", T.moe_local_gather_trace),
-    ("mla._core", "trtllm_batch_decode_with_kv_cache_mla", T.sparse_mla_decode_trace),
+    ("mla._core", "trtllm_batch_decode_with_kv_cache_mla", T.trtllm_batch_decode_mla_trace_dispatch),
     ("sparse", "BlockSparseAttentionWrapper.run", T.block_sparse_attention_trace),
     ("attention._core", "BatchAttention.run", T.batch_attention_trace),
     ("fused_moe.core", "trtllm_bf16_routed_moe", T.trtllm_bf16_routed_moe_trace),
@@ -102,6 +102,15 @@ BINDINGS: List[Tuple[str, str, "_t.TraceTemplate"]] = [
     ("fused_moe.core", "trtllm_mxint4_block_scale_moe", T.trtllm_mxint4_block_scale_moe_trace),
     ("fused_moe.core", "cute_dsl_fused_moe_nvfp4", T.cute_dsl_fused_moe_nvfp4_trace),
     ("fused_moe.core", "CuteDslMoEWrapper.run", T.cute_dsl_moe_wrapper_run_trace),
+    ("pod", "PODWithPagedKVCacheWrapper.run", T.pod_with_paged_kv_cache_run_trace),
+    ("pod", "BatchPODWithPagedKVCacheWrapper.run", T.batch_pod_with_paged_kv_cache_run_trace),
+    ("cascade", "MultiLevelCascadeAttentionWrapper.run", T.multi_level_cascade_run_trace),
+    ("sparse", "VariableBlockSparseAttentionWrapper.run", T.variable_block_sparse_attention_run_trace),
+    ("prefill", "trtllm_batch_context_with_kv_cache", T.trtllm_batch_context_trace),
+    ("prefill", "cudnn_batch_prefill_with_kv_cache", T.cudnn_batch_prefill_trace),
+    ("prefill", "trtllm_ragged_attention_deepseek", T.trtllm_ragged_attention_deepseek_trace),
+    ("prefill", "fmha_v2_prefill_deepseek", T.fmha_v2_prefill_deepseek_trace),
+    ("xqa", "xqa_mla", T.xqa_mla_trace),
 ]
 
 # one row per concrete template (a dispatch contributes one row per member): what the generic tests iterate over

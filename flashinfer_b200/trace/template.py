@@ -100,8 +100,11 @@ def _pick(bound: Dict[str, Any], spec) -> Any:
     src = spec.source
     if src.startswith("self."):                      # plan()-time state of a wrapper object: "self._kv_indptr_host"
         v = bound.get("self")
-        for part in src[5:].split("."):
-            v = getattr(v, part, None)
+        for part in src[5:].split("."):                # a numeric part indexes a list / tuple held by the wrapper
+            if part.isdigit():
+                v = v[int(part)] if isinstance(v, (list, tuple)) and len(v) > int(part) else None
+            else:
+                v = getattr(v, part, None)
     else:
         v = bound.get(src)
     idx = getattr(spec, "tuple_idx", None)

@@ -191,7 +191,7 @@ def _gqa_ragged_prefill_reference(q, k, v, qo_indptr, kv_indptr, causal=True, sm
     h, d = q.shape[1:]
     group = h // k.shape[1]
     scale = sm_scale if sm_scale is not None else 1.0 / (d ** 0.5)
-    out = torch.zeros(q.shape, dtype=torch.float32, device=q.device)
+    out = torch.zeros(q.shape[0], h, v.shape[-1], dtype=torch.float32, device=q.device)
     lse = torch.zeros(q.shape[0], h, dtype=torch.float32, device=q.device)
     for i in range(qo_indptr.numel() - 1):
         qs, qe, ks, ke = int(qo_indptr[i]), int(qo_indptr[i + 1]), int(kv_indptr[i]), int(kv_indptr[i + 1])
