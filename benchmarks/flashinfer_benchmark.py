@@ -30,7 +30,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
 import flashinfer_b200 as fi  # noqa: E402
-from flashinfer_b200.trace import BINDINGS, Const  # noqa: E402
+from flashinfer_b200.trace import FLAT_BINDINGS as BINDINGS, Const  # noqa: E402  (one row per concrete template)
 from flashinfer_b200.trace.bindings import _resolve  # noqa: E402
 
 COLUMNS = ["routine", "fi_api", "definition", "axes", "device", "median_ms", "std_ms", "iters", "bytes", "tb_per_sec", "flops",
