@@ -1,5 +1,5 @@
 """Reference flashinfer/artifacts.py downloads pre-built cubins (trtllm-gen FMHA / GEMM / MoE) from an artifact server.
-This library ships no binary kernels: every kernel is compiled from ``csrc/`` (see ``jit.py`` / ``aot.py``), so the artifact
+This library ships no binary kernels: every kernel is compiled from ``csrc/`` (see ``jit/`` / ``aot.py``), so the artifact
 functions report an empty set."""
 from typing import List
 

@@ -472,9 +472,17 @@ def trtllm_batch_decode_with_kv_cache(query: torch.Tensor, kv_cache, workspace_b
     return res
 
 
-def xqa_batch_decode_with_kv_cache(*args, **kwargs):
-    """XQA entry point of the reference (flashinfer/decode.py:2727): same kernel here."""
-    return trtllm_batch_decode_with_kv_cache(*args, **kwargs)
+def xqa_batch_decode_with_kv_cache(query: torch.Tensor, kv_cache, workspace_buffer: torch.Tensor, block_tables: torch.Tensor,
+                                   seq_lens: torch.Tensor, max_seq_len: int, bmm1_scale: float = 1.0, bmm2_scale: float = 1.0,
+                                   window_left: int = -1, out: Optional[torch.Tensor] = None, sinks=None, kv_layout: str = "NHD",
+                                   enable_pdl=None, q_len_per_req: Optional[int] = 1, o_scale: Optional[float] = 1.0, mask=None,
+                                   kv_cache_sf=None):
+    """XQA entry point of the reference (flashinfer/decode.py:2727; note its ``kv_layout`` default is NHD): same kernel here.
+    ``o_scale`` cancels in the result (the reference multiplies the V scale by it and the output by its reciprocal; it only
+    positions the fp8 output range of that kernel), so it is accepted and not applied."""
+    return trtllm_batch_decode_with_kv_cache(query, kv_cache, workspace_buffer, block_tables, seq_lens, max_seq_len, bmm1_scale,
+                                             bmm2_scale, window_left, out=out, sinks=sinks, kv_layout=kv_layout,
+                                             enable_pdl=enable_pdl, q_len_per_req=q_len_per_req, mask=mask, kv_cache_sf=kv_cache_sf)
 
 
 def cudnn_batch_decode_with_kv_cache(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, scale: float,

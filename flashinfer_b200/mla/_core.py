@@ -260,6 +260,12 @@ def _sparse_mla_decode(query, kv_cache, workspace_buffer, kv_lora_rank, qk_rope_
     return o
 
 
-def xqa_batch_decode_with_kv_cache_mla(*args, **kwargs):
-    """sm120-only path in the reference; on B200 the tcgen05 MLA kernel serves the same API."""
-    return trtllm_batch_decode_with_kv_cache_mla(*args, **kwargs)
+def xqa_batch_decode_with_kv_cache_mla(query: torch.Tensor, kv_cache: torch.Tensor, workspace_buffer: torch.Tensor,
+                                       qk_nope_head_dim: int, kv_lora_rank: int, qk_rope_head_dim: int, block_tables: torch.Tensor,
+                                       seq_lens: torch.Tensor, max_seq_len: int, out: Optional[torch.Tensor] = None,
+                                       bmm1_scale: Union[float, torch.Tensor] = 1.0, bmm2_scale: Union[float, torch.Tensor] = 1.0,
+                                       sinks=None, enable_pdl=None):
+    """sm120-only path in the reference (mla/_core.py:943); on B200 the tcgen05 MLA kernel serves the same API."""
+    return trtllm_batch_decode_with_kv_cache_mla(query, kv_cache, workspace_buffer, qk_nope_head_dim, kv_lora_rank, qk_rope_head_dim,
+                                                 block_tables, seq_lens, max_seq_len, out=out, bmm1_scale=bmm1_scale,
+                                                 bmm2_scale=bmm2_scale, sinks=sinks, enable_pdl=enable_pdl)

@@ -111,6 +111,22 @@ BINDINGS: List[Tuple[str, str, "_t.TraceTemplate"]] = [
     ("prefill", "trtllm_ragged_attention_deepseek", T.trtllm_ragged_attention_deepseek_trace),
     ("prefill", "fmha_v2_prefill_deepseek", T.fmha_v2_prefill_deepseek_trace),
     ("xqa", "xqa_mla", T.xqa_mla_trace),
+    ("decode", "xqa_batch_decode_with_kv_cache", T.xqa_batch_decode_trace),
+    ("mla._core", "xqa_batch_decode_with_kv_cache_mla", T.xqa_batch_decode_mla_trace),
+    ("norm", "rmsnorm_fp4quant", T.rmsnorm_fp4quant_trace),
+    ("norm", "add_rmsnorm_fp4quant", T.add_rmsnorm_fp4quant_trace),
+    ("norm", "fused_rmsnorm_silu", T.fused_rmsnorm_silu_trace),
+    ("gemm.lowp", "bmm_mxfp8", T.bmm_mxfp8_trace),
+    ("gemm.grouped", "batch_deepgemm_fp8_nt_groupwise", T.batch_deepgemm_fp8_nt_groupwise_trace),
+    ("gemm.grouped", "grouped_gemm_nt_masked", T.grouped_gemm_nt_masked_trace),
+    ("dsv3_ops", "tinygemm_bf16", T.tinygemm_bf16_trace),
+    ("quantization.fp4", "nvfp4_quantize", T.nvfp4_quantize_trace),
+    ("quantization.fp4", "nvfp4_kv_quantize", T.nvfp4_kv_quantize_trace),
+    ("activation", "silu_and_mul_scaled_nvfp4_experts_quantize", T.silu_and_mul_scaled_nvfp4_experts_quantize_trace),
+    ("gdn", "gated_delta_rule_mtp", T.gdn_mtp_trace),
+    ("mamba.ssd_combined", "SSDCombined.run", T.selective_scan_ssd_prefill_trace),
+    ("rope", "rope_quantize_fp8_append_paged_kv_cache", T.rope_quantize_fp8_append_paged_kv_cache_trace),
+    ("comm.collectives", "decode_cp_a2a_alltoall", T.decode_cp_a2a_alltoall_trace),
 ]
 
 # one row per concrete template (a dispatch contributes one row per member): what the generic tests iterate over

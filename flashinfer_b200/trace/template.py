@@ -149,6 +149,12 @@ class TraceTemplate:
                     dims = t.shape[t.dim() - len(spec.axes):] if spec.axes else ()
                     for ax, n in zip(spec.axes, dims):
                         sizes.setdefault(ax, int(n))
+        names = {a.name for a in self.axes}
+        for spec in self.inputs:                          # integer scalars named like an axis (also plan()-time state: "self.chunk_size")
+            if isinstance(spec, Scalar) and spec.name in names:
+                v = _pick(bound, spec)
+                if isinstance(v, int) and not isinstance(v, bool):
+                    sizes.setdefault(spec.name, v)
         for ax in self.axes:
             v = bound.get(ax.name)
             if isinstance(v, int) and not isinstance(v, bool):

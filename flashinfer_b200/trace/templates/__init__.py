@@ -1,5 +1,5 @@
 """Op templates, one module per category (reference flashinfer/trace/templates/*.py)."""
-from . import activation, attention, attention_more, cascade, gdn, gemm, misc, moe, moe_trtllm, norm, page, quantize, rope, round2, sampling  # noqa: F401
+from . import activation, attention, attention_more, cascade, gdn, gemm, misc, moe, moe_trtllm, more_ops, norm, page, quantize, rope, round2, sampling  # noqa: F401
 from .comm import *  # noqa: F401,F403
 from .activation import *  # noqa: F401,F403
 from .norm import *  # noqa: F401,F403
@@ -16,3 +16,4 @@ from .misc import *  # noqa: F401,F403
 from .gdn import *  # noqa: F401,F403
 from .round2 import *  # noqa: F401,F403
 from .attention_more import *  # noqa: F401,F403
+from .more_ops import *  # noqa: F401,F403

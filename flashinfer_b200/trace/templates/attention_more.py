@@ -512,4 +512,59 @@ xqa_mla_trace = TraceTemplate(
     description="XQA-style MLA decode: per-request page table rows + sequence lengths over a 576-wide latent cache (tcgen05 MLA kernel)",
     test_sizes={"num_heads": 4, "page_size": 16})
 
+
+# ------------------------------------------------------------------ XQA batch decode entry points (block table; NHD pages by default)
+def _xqa_batch_decode_reference(query, k_cache, v_cache, block_tables, seq_lens, bmm1_scale, bmm2_scale):
+    """NHD pages [pages, page_size, Hkv, D] (the XQA entry point's default layout); one query token per request."""
+    b, h, d = query.shape
+    page_size, hkv = k_cache.shape[1], k_cache.shape[2]
+    grp = h // hkv
+    out = torch.zeros(b, h, d, dtype=torch.float32, device=query.device)
+    for i in range(b):
+        n = int(seq_lens[i])
+        pages = block_tables[i, : (n + page_size - 1) // page_size].long()
+        k = k_cache[pages].reshape(-1, hkv, d)[:n].float().repeat_interleave(grp, dim=1)
+        v = v_cache[pages].reshape(-1, hkv, d)[:n].float().repeat_interleave(grp, dim=1)
+        p = torch.softmax(torch.einsum("hd,nhd->hn", query[i].float(), k) * bmm1_scale, -1)
+        out[i] = torch.einsum("hn,nhd->hd", p, v) * bmm2_scale
+    return out.to(query.dtype)
+
+
+def _xqa_batch_decode_init(*, batch_size=8, num_qo_heads=32, num_kv_heads=8, head_dim=128, page_size=16, device="cuda", seed=0):
+    t = _block_table_context_inputs(batch_size, num_qo_heads, num_kv_heads, head_dim, page_size, device, seed)
+    g = torch.Generator(device="cpu").manual_seed(seed + 3)
+    return {"query": _mk(g, device)(batch_size, num_qo_heads, head_dim), "kv_cache": (t["k"].transpose(1, 2).contiguous(), t["v"].transpose(1, 2).contiguous()),
+            "workspace_buffer": torch.zeros(32 << 20, dtype=torch.uint8, device=device), "block_tables": t["table"],
+            "seq_lens": torch.tensor(t["kv_lens"], dtype=torch.int32, device=device), "max_seq_len": max(t["kv_lens"]),
+            "bmm1_scale": 1.0 / math.sqrt(head_dim), "bmm2_scale": 1.0}
+
+
+xqa_batch_decode_trace = TraceTemplate(
+    op_type="gqa_paged", name_fmt="xqa_batch_decode_h{num_qo_heads}_kv{num_kv_heads}_d{head_dim}_ps{page_size}",
+    axes=[Var("batch_size"), Var("num_pages"), Var("max_pages_per_seq")] + _H + [Const("page_size", abbrev="ps")],
+    inputs=[Tensor("query", ("batch_size", "num_qo_heads", "head_dim")), Tensor("k_cache", _NHD, param="kv_cache", tuple_idx=0),
+            Tensor("v_cache", _NHD, param="kv_cache", tuple_idx=1), Tensor("block_tables", ("batch_size", "max_pages_per_seq"), "int32"),
+            Tensor("seq_lens", ("batch_size",), "int32"), Scalar("bmm1_scale"), Scalar("bmm2_scale")],
+    outputs=[Tensor("output", ("batch_size", "num_qo_heads", "head_dim"), dtype_from="query")], reference=_xqa_batch_decode_reference,
+    init=_xqa_batch_decode_init, tags=("attention", "decode", "paged", "block_table", "xqa"), tolerance="bf16",
+    description="XQA-named batch decode entry point (NHD pages by default); the tcgen05 paged decode kernel on B200", test_sizes=_SIZES)
+
+
+def _xqa_batch_mla_init(*, batch_size=4, q_len=1, num_heads=128, page_size=64, device="cuda", seed=0):
+    kw = _mla_block_table_init(batch_size=batch_size, q_len=q_len, num_heads=num_heads, page_size=page_size, device=device, seed=seed)
+    return kw
+
+
+xqa_batch_decode_mla_trace = TraceTemplate(
+    op_type="mla_paged", name_fmt="xqa_batch_decode_mla_h{num_heads}_ps{page_size}",
+    axes=[Var("batch_size"), Var("q_len"), Var("num_pages"), Var("max_pages_per_seq"), Const("num_heads", abbrev="h"), Const("page_size", abbrev="ps")],
+    inputs=[Tensor("query", ("batch_size", "q_len", "num_heads", "qk_dim")), Tensor("kv_cache", ("num_pages", "one", "page_size", "qk_dim")),
+            Tensor("block_tables", ("batch_size", "max_pages_per_seq"), "int32"), Tensor("seq_lens", ("batch_size",), "int32"), Scalar("bmm1_scale"),
+            Scalar("bmm2_scale")],
+    outputs=[Tensor("out", ("batch_size", "q_len", "num_heads", "kv_lora_rank"), dtype_from="query")], reference=_mla_block_table_reference,
+    init=_xqa_batch_mla_init, tags=("mla", "decode", "paged", "block_table", "xqa"), tolerance="bf16",
+    constraints=("one == 1", "qk_dim == 576", "kv_lora_rank == 512"),
+    description="XQA-named MLA batch decode (an sm_120 kernel in the reference; the tcgen05 MLA kernel here)",
+    test_sizes={"num_heads": 4, "page_size": 16, "q_len": 1})
+
 __all__ = [n for n in dir() if n.endswith("_trace") or n.endswith("_trace_dispatch")]

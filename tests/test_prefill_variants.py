@@ -35,6 +35,24 @@ def test_variant_module_builds():
         jit.gen_customize_batch_prefill_module("auto", "bad", None, None, None, None, 128, 128, ["a"] * 9, ["float"] * 9, [], [], "V", "")
 
 
+def test_variant_argument_names_do_not_leak_into_the_kernel():
+    """Additional tensors / scalars are visible to the hooks as macros; they are undefined again after the variant struct, so a
+    user scalar called like one of the kernel's own locals (``alpha``, ``l``) compiles."""
+    if not jit.have_nvcc():
+        pytest.skip("nvcc not available")
+    decl = ("struct Clash : VariantDefaults { static __device__ __forceinline__ float LogitsTransform(const VariantCtx& ctx, float logits, "
+            "int kv_idx) { return logits * alpha + l[kv_idx]; } };")
+    spec = jit.gen_customize_batch_prefill_module("auto", "unit_name_clash", None, None, None, None, 128, 128, ["l"], ["float"], ["alpha"],
+                                                  ["double"], "Clash", decl)
+    try:
+        jit.build_module(spec)
+        assert spec.is_fresh()
+    finally:
+        for p in (spec.so_path, spec.hash_path):
+            if p.exists():
+                p.unlink()
+
+
 def _no_generic(monkeypatch):
     """The SIMT catch-all kernel must not serve these configurations any more."""
     from flashinfer_b200.attention import generic
