@@ -550,9 +550,21 @@ def trtllm_ragged_attention_deepseek(query, key, value, workspace_buffer, seq_le
     w = BatchPrefillWithRaggedKVCacheWrapper(workspace_buffer)
     w.plan(cum_seq_lens_q, cum_seq_lens_kv, query.shape[1], key.shape[1], query.shape[2], head_dim_vo=value.shape[2],
            causal=is_causal, sm_scale=float(bmm1_scale), window_left=window_left, q_data_type=query.dtype)
-    res = w.run(query, key, value, out=out, lse=lse, return_lse=return_lse,
-                v_scale=float(bmm2_scale) if float(bmm2_scale) != 1.0 else None)
-    return res
+    vs = float(bmm2_scale) if float(bmm2_scale) != 1.0 else None
+    if attention_sinks is None:
+        return w.run(query, key, value, out=out, lse=lse, return_lse=return_lse, v_scale=vs)
+    # per-head sink logits join the softmax denominator through the (out, lse) state
+    from .attention._core import apply_attention_sink
+
+    o, l = w.run(query, key, value, lse=lse, return_lse=True, v_scale=vs)
+    o2, l2 = apply_attention_sink(o, l, attention_sinks.to(o.device))
+    if out is not None:
+        out.copy_(o2)
+        o2 = out
+    if lse is not None:
+        lse.copy_(l2)
+        l2 = lse
+    return (o2, l2) if return_lse else o2
 
 
 def trtllm_batch_context_with_kv_cache(query, kv_cache, workspace_buffer, block_tables, seq_lens, max_q_len, max_kv_len,

@@ -1,0 +1,119 @@
+"""GPU tests written AFTER this round's GPU budget was spent: they have never run on a B200.  They carry the ``gpu_pending`` marker
+(not ``gpu``), so the round-end ``pytest -m gpu`` does not pick up unverified assertions; the first GPU call of the next round should
+be ``python -m pytest tests/test_gpu_pending.py -m gpu_pending -q`` - whatever passes is re-marked ``gpu`` and moved next to its
+module's tests."""
+import math
+import os
+
+import pytest
+import torch
+
+import flashinfer_b200 as fi
+
+pytestmark = pytest.mark.gpu_pending
+
+
+def _ragged(lens, hq, hkv, d=128, dv=None, seed=0):
+    torch.manual_seed(seed)
+    ind = torch.tensor([0] + lens).cumsum(0).int()
+    n = int(ind[-1])
+    mk = lambda h, dd: torch.randn(n, h, dd, device="cuda", dtype=torch.bfloat16)  # noqa: E731
+    return ind, mk(hq, d), mk(hkv, d), mk(hkv, dv or d)
+
+
+def _attn_ref(q, k, v, ind, sm, bias_fn=None, sinks=None):
+    out = torch.zeros(q.shape[0], q.shape[1], v.shape[-1], device=q.device)
+    g = q.shape[1] // k.shape[1]
+    for i in range(ind.numel() - 1):
+        s, e = int(ind[i]), int(ind[i + 1])
+        n = e - s
+        lg = torch.einsum("qhd,khd->hqk", q[s:e].float(), k[s:e].float().repeat_interleave(g, 1)) * sm
+        pos = torch.arange(n, device=q.device)
+        if bias_fn is not None:
+            lg = lg + bias_fn(pos[None, :] - pos[:, None])
+        lg = lg.masked_fill(pos[None, :] > pos[:, None], float("-inf"))
+        if sinks is not None:
+            p = torch.softmax(torch.cat([lg, sinks.float()[:, None, None].expand(-1, n, 1)], -1), -1)[..., :-1]
+        else:
+            p = torch.softmax(lg, -1)
+        out[s:e] = torch.einsum("hqk,khd->qhd", p, v[s:e].float().repeat_interleave(g, 1))
+    return out
+
+
+def test_rpe_variant_on_the_tcgen05_prefill_kernel():
+    from flashinfer_b200.cute_dsl.attention import BatchPrefillCuteDSLWrapper, RPEAttention
+
+    ind, q, k, v = _ragged([200, 77, 513], 8, 2)
+    table = torch.randn(8, 2 * 64 + 1, device="cuda") * 0.5
+    w = BatchPrefillCuteDSLWrapper(torch.empty(64 << 20, dtype=torch.uint8, device="cuda"))
+    w.plan(ind, ind, 8, 2, 128, causal=True, sm_scale=128 ** -0.5, q_data_type=torch.bfloat16, kv_data_type=torch.bfloat16,
+           variant=RPEAttention(table, 64))
+    out = w.run(q, k, v)
+    ref = _attn_ref(q, k, v, ind, 128 ** -0.5, bias_fn=lambda rel: table[:, (rel + 64).clamp(0, 128)])
+    torch.testing.assert_close(out.float(), ref, atol=3e-2, rtol=3e-2)
+
+
+def test_cute_dsl_prefill_wrapper_builtin_variants():
+    from flashinfer_b200.cute_dsl.attention import ALiBiAttention, AttentionWithSink, BatchPrefillCuteDSLWrapper
+
+    ind, q, k, v = _ragged([130, 300], 8, 4, seed=1)
+    w = BatchPrefillCuteDSLWrapper(torch.empty(64 << 20, dtype=torch.uint8, device="cuda"))
+    slopes = torch.rand(8, device="cuda") * 0.2
+    w.plan(ind, ind, 8, 4, 128, causal=True, sm_scale=128 ** -0.5, q_data_type=torch.bfloat16, kv_data_type=torch.bfloat16,
+           variant=ALiBiAttention(slopes))
+    torch.testing.assert_close(w.run(q, k, v).float(), _attn_ref(q, k, v, ind, 128 ** -0.5, bias_fn=lambda rel: slopes[:, None, None] * rel),
+                               atol=3e-2, rtol=3e-2)
+    sinks = torch.randn(8, device="cuda")
+    w.plan(ind, ind, 8, 4, 128, causal=True, sm_scale=128 ** -0.5, q_data_type=torch.bfloat16, kv_data_type=torch.bfloat16,
+           variant=AttentionWithSink(sinks))
+    torch.testing.assert_close(w.run(q, k, v).float(), _attn_ref(q, k, v, ind, 128 ** -0.5, sinks=sinks), atol=3e-2, rtol=3e-2)
+
+
+def test_ragged_deepseek_entry_point_applies_attention_sinks():
+    ind, q, k, v = _ragged([90, 260], 16, 16, d=192, dv=128, seed=2)
+    sinks = torch.randn(16, device="cuda")
+    sm = 192 ** -0.5
+    lens = (ind[1:] - ind[:-1]).cuda()
+    out = fi.prefill.trtllm_ragged_attention_deepseek(q, k, v, torch.empty(64 << 20, dtype=torch.uint8, device="cuda"), lens, 260, 260, sm, 1.0, -1.0,
+                                                      2, -1, ind.cuda(), ind.cuda(), attention_sinks=sinks)
+    torch.testing.assert_close(out.float(), _attn_ref(q, k, v, ind, sm, sinks=sinks), atol=3e-2, rtol=3e-2)
+
+
+def test_cute_dsl_mla_wrapper_and_xqa_batch_entry_points():
+    from flashinfer_b200.cute_dsl.attention import BatchMLADecodeCuteDSLWrapper
+    from flashinfer_b200.trace import templates as T
+
+    for tpl, api in ((T.trtllm_batch_decode_mla_trace, fi.mla.trtllm_batch_decode_with_kv_cache_mla),
+                     (T.xqa_batch_decode_mla_trace, fi.mla.xqa_batch_decode_with_kv_cache_mla),
+                     (T.xqa_batch_decode_trace, fi.decode.xqa_batch_decode_with_kv_cache)):
+        kw = tpl.make_inputs(device="cuda", seed=3, batch_size=5)
+        ref = tpl.run_reference({k_: (v_.clone() if isinstance(v_, torch.Tensor) else v_) for k_, v_ in kw.items()})
+        torch.testing.assert_close(api(**kw).float(), ref.float(), atol=3e-2, rtol=3e-2)
+    kw = T.trtllm_batch_decode_mla_trace.make_inputs(device="cuda", seed=4, batch_size=6)
+    w = BatchMLADecodeCuteDSLWrapper(torch.zeros(64 << 20, dtype=torch.int8, device="cuda"))
+    w.plan(512, 64, kw["query"].shape[2], kw["kv_cache"].shape[2], torch.bfloat16)
+    got = w.run(kw["query"], kw["kv_cache"], kw["block_tables"], kw["seq_lens"], kw["max_seq_len"], kw["bmm1_scale"])
+    torch.testing.assert_close(got.float(), T.trtllm_batch_decode_mla_trace.run_reference(kw).float(), atol=3e-2, rtol=3e-2)
+
+
+def test_every_trace_template_against_the_native_kernels():
+    """tests/test_trace_templates.py on the device: every template's reference against the API it is bound to, with CUDA inputs
+    (the template suite had only ever run through the CPU paths).  Failures are collected, not raised one by one."""
+    import importlib
+    import sys
+
+    sys.path.insert(0, os.path.dirname(__file__))
+    os.environ["FIB200_TRACE_TEST_DEVICE"] = "cuda"
+    mod = importlib.import_module("test_trace_templates")
+    mod = importlib.reload(mod)
+    failures = []
+    for (m, p, tpl), tid in zip(mod.BINDINGS, mod._IDS):
+        if tpl.init is None:
+            continue
+        try:
+            mod.test_reference_matches_api(m, p, tpl)
+            torch.cuda.synchronize()
+        except Exception as exc:  # noqa: BLE001
+            failures.append(f"{tid}: {type(exc).__name__}: {str(exc)[:200]}")
+    os.environ["FIB200_TRACE_TEST_DEVICE"] = "cpu"
+    assert not failures, "\n".join(failures)
