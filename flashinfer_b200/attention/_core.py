@@ -57,6 +57,7 @@ class BatchAttention:
         self._sel_d = torch.nonzero(is_dec).flatten()
         self._sel_p = torch.nonzero(~is_dec & (q_lens > 0)).flatten()
         self._hq, self._dvo = num_qo_heads, head_dim_vo
+        self._soft_cap = float(logits_soft_cap or 0.0)
 
         def sub(sel):
             qi, kpi, ind, last, rows = [0], [0], [], [], []
@@ -94,6 +95,12 @@ class BatchAttention:
 
     def run(self, q: torch.Tensor, kv_cache, out: Optional[torch.Tensor] = None, lse: Optional[torch.Tensor] = None,
             k_scale=None, v_scale=None, logits_soft_cap: float = 0.0, profiler_buffer=None, kv_cache_sf=None):
+        from ..utils import reject_unsupported
+
+        reject_unsupported("BatchAttention.run", kv_cache_sf=kv_cache_sf)
+        if logits_soft_cap and float(logits_soft_cap) != float(getattr(self, "_soft_cap", 0.0) or 0.0):
+            raise ValueError("BatchAttention.run: logits_soft_cap differs from the value given to plan() (it is compiled into the plan)")
+        scales = {k_: v_ for k_, v_ in (("k_scale", k_scale), ("v_scale", v_scale)) if v_ is not None}
         if out is None:
             out = torch.empty(q.shape[0], self._hq, self._dvo, dtype=q.dtype, device=q.device)
         if lse is None:
@@ -104,11 +111,11 @@ class BatchAttention:
         if self._rows_d is not None:
             ctx = torch.cuda.stream(self._side.stream) if both else _null()
             with ctx:
-                o_d, l_d = self._decode.run(q[self._rows_d], kv_cache, return_lse=True)
+                o_d, l_d = self._decode.run(q[self._rows_d], kv_cache, return_lse=True, **scales)
                 out[self._rows_d] = o_d
                 lse[self._rows_d] = l_d
         if self._rows_p is not None:
-            o_p, l_p = self._prefill.run(q[self._rows_p], kv_cache, return_lse=True)
+            o_p, l_p = self._prefill.run(q[self._rows_p], kv_cache, return_lse=True, **scales)
             out[self._rows_p] = o_p
             lse[self._rows_p] = l_p
         if both:
@@ -140,6 +147,8 @@ class BatchAttentionWithAttentionSinkWrapper(BatchPrefillWithPagedKVCacheWrapper
         super().__init__(float_workspace_buffer, kv_layout, use_cuda_graph)
 
     def run(self, q, paged_kv_cache, sinks: Optional[torch.Tensor] = None, sm_scale=None, *args, return_lse=False, **kw):
+        if sm_scale is not None:
+            self._sm_scale = float(sm_scale)          # the reference passes the softmax scale at run() time for this wrapper
         o, l = super().run(q, paged_kv_cache, return_lse=True, **kw)
         if sinks is not None:
             o, l = apply_attention_sink(o, l, sinks)

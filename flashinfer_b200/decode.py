@@ -452,6 +452,12 @@ def trtllm_batch_decode_with_kv_cache(query: torch.Tensor, kv_cache, workspace_b
                                       lse=None, return_lse: bool = False):
     """``query [B * q_len_per_req, Hq, D]``; ``kv_cache`` a ``(k, v)`` tuple or ``[pages, 2, ...]`` tensor in
     ``kv_layout``; ``block_tables [B, max_pages]``; ``bmm1_scale`` is the softmax scale (q/k scales folded in)."""
+    from .utils import reject_unsupported
+
+    # NVFP4 output (o_sf_*), tree masks of speculative decoding and ragged query lengths are not implemented; the skip-softmax
+    # threshold is a pure speed hint of the reference kernel (exact softmax here) and o_scale cancels in the result
+    reject_unsupported("trtllm_batch_decode_with_kv_cache", o_sf_scale=o_sf_scale, o_sf_vec_size=o_sf_vec_size, mask=mask,
+                       cum_seq_lens_q=cum_seq_lens_q, uses_shared_paged_kv_idx=(uses_shared_paged_kv_idx, True))
     k_cache, v_cache = unpack_paged_kv_cache(kv_cache, kv_layout)
     _, _, _, page_size, hkv, d = paged_kv_strides(k_cache, kv_layout)
     if k_cache.dtype == torch.uint8:
@@ -466,9 +472,22 @@ def trtllm_batch_decode_with_kv_cache(query: torch.Tensor, kv_cache, workspace_b
     res = w.run(query, (k_cache, v_cache), out=out if (out is not None and out.dtype == query.dtype) else None,
                 return_lse=return_lse, sinks=sinks, v_scale=float(bmm2_scale) if float(bmm2_scale) != 1.0 else None,
                 kv_cache_sf=kv_cache_sf)
-    if out is not None and not return_lse and res.data_ptr() != out.data_ptr():
+    if return_lse:
+        o, l = res
+        if lse is not None:
+            lse.copy_(l.view_as(lse))
+            l = lse
+        if out is not None and o.data_ptr() != out.data_ptr():
+            out.copy_(o)
+            o = out
+        elif out_dtype is not None and o.dtype != out_dtype:
+            o = o.to(out_dtype)
+        return o, l
+    if out is not None and res.data_ptr() != out.data_ptr():
         out.copy_(res)
         return out
+    if out is None and out_dtype is not None and res.dtype != out_dtype:
+        return res.to(out_dtype)
     return res
 
 
@@ -521,10 +540,15 @@ class BatchDecodeMlaWithPagedKVCacheWrapper:
     def plan(self, indptr, indices, last_page_len, num_qo_heads, head_dim_compressed_kv, page_size, sm_scale,
              window_left: int = -1, logits_soft_cap=None, data_type="float16", q_data_type=None, rope_scale=None,
              rope_theta=None) -> None:
+        if window_left is not None and window_left >= 0:
+            raise NotImplementedError("BatchDecodeMlaWithPagedKVCacheWrapper: sliding windows are not implemented by the MLA kernel")
+        if logits_soft_cap:
+            raise NotImplementedError("BatchDecodeMlaWithPagedKVCacheWrapper: logits_soft_cap is not implemented by the MLA kernel")
         n_pages = (indptr[1:] - indptr[:-1]).to("cpu", torch.int64)
         kv_len = torch.clamp(n_pages - 1, min=0) * page_size + last_page_len.to("cpu", torch.int64)
         b = kv_len.numel()
         dt = _canon_dtype(q_data_type or data_type)
+        self._plan_args, self._sm_scale = (indptr, indices, kv_len.int(), num_qo_heads, head_dim_compressed_kv, page_size, dt, b), float(sm_scale)
         self._w.plan(torch.arange(b + 1, dtype=torch.int32), indptr, indices, kv_len.int(), num_qo_heads,
                      head_dim_compressed_kv, 64, page_size, False, sm_scale, dt, dt)
 
@@ -532,7 +556,15 @@ class BatchDecodeMlaWithPagedKVCacheWrapper:
 
     def run(self, q_nope, q_pe, paged_ckv_cache, paged_kpe_cache, q_scale=None, k_scale=None, v_scale=None, out=None,
             lse=None, return_lse: bool = False, enable_pdl: bool = False):
-        return self._w.run(q_nope, q_pe, paged_ckv_cache, paged_kpe_cache, out=out, lse=lse, return_lse=return_lse)
+        # q / k de-quantisation scales fold into the softmax scale (a re-plan of the host-side work list when they change the
+        # planned value); the v scale multiplies the output
+        sm = self._sm_scale * (float(q_scale) if q_scale is not None else 1.0) * (float(k_scale) if k_scale is not None else 1.0)
+        if sm != getattr(self, "_sm_planned", self._sm_scale):
+            indptr, indices, kv_len, h, dckv, page_size, dt, b = self._plan_args
+            self._w.plan(torch.arange(b + 1, dtype=torch.int32), indptr, indices, kv_len, h, dckv, 64, page_size, False, sm, dt, dt)
+            self._sm_planned = sm
+        return self._w.run(q_nope, q_pe, paged_ckv_cache, paged_kpe_cache, out=out, lse=lse, return_lse=return_lse,
+                           o_scale=float(v_scale) if (v_scale is not None and float(v_scale) != 1.0) else None)
 
     forward = run
 

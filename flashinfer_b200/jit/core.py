@@ -69,6 +69,10 @@ def gen_jit_spec(name: str, sources: Sequence, extra_cflags: Optional[Sequence[s
     """Declare a native module from ``sources`` (paths relative to ``csrc/`` or absolute: user kernels are welcome).  The
     result builds with the sm_100a flags of this package and loads through the uniform C-ABI caller (``spec.build_and_load()``)."""
     flags = list(extra_cuda_cflags or [])
+    for f in extra_cflags or []:                       # host-compiler flags travel through nvcc
+        flags += ["-Xcompiler", str(f)]
+    if needs_device_linking:
+        flags.append("-rdc=true")
     for inc in extra_include_paths or []:
         flags += ["-I", str(inc)]
     spec = JitSpec(name, [str(s) for s in sources], extra_flags=flags, ldflags=list(extra_ldflags or []))

@@ -56,9 +56,12 @@ def selective_state_update(state: torch.Tensor, x: torch.Tensor, dt: torch.Tenso
                            intermediate_state_scales=None, rand_seed=None, philox_rounds: int = 10, cache_steps: int = 0,
                            algorithm: str = "auto", dst_state_batch_indices: Optional[torch.Tensor] = None,
                            cu_seqlens: Optional[torch.Tensor] = None, num_accepted_tokens=None) -> torch.Tensor:
-    if state_scale is not None or intermediate_states_buffer is not None or cu_seqlens is not None or rand_seed is not None:
-        raise NotImplementedError("int16 block-scaled states, intermediate-state caching, varlen and stochastic rounding "
-                                  "are not implemented")
+    if (state_scale is not None or intermediate_states_buffer is not None or cu_seqlens is not None or rand_seed is not None
+            or intermediate_state_indices is not None or intermediate_state_scales is not None or num_accepted_tokens is not None
+            or cache_steps):
+        raise NotImplementedError("int16 block-scaled states, intermediate-state caching (buffer / indices / scales / cache_steps / "
+                                  "num_accepted_tokens), varlen and stochastic rounding are not implemented")
+    # ``algorithm`` selects between the reference's kernel variants (same result) and ``philox_rounds`` only matters with rand_seed
     orig_shape = x.shape
     has_heads = state.dim() == 4
     # canonicalise to state [N,H,dim,ds], x [B,T,H,dim]

@@ -177,6 +177,10 @@ def trtllm_batch_decode_with_kv_cache_mla(query: torch.Tensor, kv_cache: torch.T
                                           lse: Optional[torch.Tensor] = None, return_lse: bool = False):
     """Function-style MLA decode (reference :631): ``query [B, q_len, H, 576]`` (nope|rope concatenated),
     ``kv_cache [pages, (1,) page, 576]``, ``block_tables [B, max_pages]``."""
+    if sinks is not None:
+        raise NotImplementedError("trtllm_batch_decode_with_kv_cache_mla: attention sinks are not implemented by the MLA kernel")
+    if not uses_shared_paged_kv_idx:
+        raise NotImplementedError("trtllm_batch_decode_with_kv_cache_mla: separate K / V page indices are not implemented")
     if sparse_mla_top_k:
         return _sparse_mla_decode(query, kv_cache, workspace_buffer, kv_lora_rank, qk_rope_head_dim, block_tables, sparse_mla_top_k,
                                   float(bmm1_scale), float(bmm2_scale), out, lse, return_lse)

@@ -17,7 +17,7 @@ import torch
 from . import jit
 from .decode import BatchDecodeWithPagedKVCacheWrapper
 from .prefill import BatchPrefillWithPagedKVCacheWrapper, BatchPrefillWithRaggedKVCacheWrapper
-from .utils import device_sm_count
+from .utils import check_pos_encoding_mode, device_sm_count
 
 _PEAK_FLOPS = 1.1e15  # achieved FMHA rate (profiles/), not the datasheet number
 _PEAK_BW = 6.0e12
@@ -103,6 +103,9 @@ class PODWithPagedKVCacheWrapper:
     def plan(self, indptr, indices, last_page_len, num_qo_heads, num_kv_heads, head_dim, page_size,
              pos_encoding_mode="NONE", window_left=-1, q_data_type="float16", kv_data_type=None, data_type=None,
              sm_scale=None, rope_scale=None, rope_theta=None, non_blocking=True) -> None:
+        check_pos_encoding_mode(pos_encoding_mode)
+        if pos_encoding_mode != "NONE":
+            raise NotImplementedError("POD: in-kernel positional encodings are not implemented (apply flashinfer_b200.rope first)")
         self._dargs = (indptr, indices, last_page_len, num_qo_heads, num_kv_heads, head_dim, page_size)
         self._dkw = dict(window_left=window_left, q_data_type=data_type or q_data_type, kv_data_type=kv_data_type,
                          sm_scale=sm_scale)
@@ -119,8 +122,21 @@ class PODWithPagedKVCacheWrapper:
             kv_layout_d="NHD", pos_encoding_mode_d="NONE", sm_scale_d=None, window_left_d=-1, rope_scale_d=None,
             rope_theta_d=None, q_scale=None, k_scale=None, v_scale=None, return_lse_d=False,
             use_fp16_qk_reduction=False, enable_pdl=None):
-        if custom_mask_p is not None or packed_custom_mask_p is not None:
+        if custom_mask_p is not None or packed_custom_mask_p is not None or custom_mask_d is not None or packed_custom_mask_d is not None:
             raise NotImplementedError("POD with custom masks")
+        if pos_encoding_mode_p != "NONE" or pos_encoding_mode_d != "NONE":
+            raise NotImplementedError("POD: in-kernel positional encodings are not implemented (apply flashinfer_b200.rope first)")
+        if kv_layout_d != self._kv_layout:
+            raise ValueError(f"POD: kv_layout_d={kv_layout_d!r} differs from the wrapper's layout {self._kv_layout!r}")
+        # run()-time decode parameters override what plan() recorded (the decode side is planned lazily, below); causal_d is
+        # immaterial for one query token per request
+        dkw = dict(self._dkw)
+        if sm_scale_d is not None:
+            dkw["sm_scale"] = sm_scale_d
+        if window_left_d != -1:
+            dkw["window_left"] = window_left_d
+        if dkw != self._dkw:
+            self._dkw, self._decode_planned_for = dkw, None
         total = device_sm_count(self.device if self.device.type == "cuda" else None)
         qo_len, kv_len = q_p.shape[0], (k_p.shape[0] if kv_layout_p == "NHD" else k_p.shape[1])
         flops = 4.0 * qo_len * kv_len * self._hq * self._d * (0.5 if causal_p else 1.0)
@@ -176,7 +192,16 @@ class BatchPODWithPagedKVCacheWrapper:
     def plan(self, qo_indptr_p, kv_indptr_p, kv_indices_p, last_page_len_p, qo_indptr_d, kv_indptr_d, kv_indices_d,
              last_page_len_d, num_qo_heads, num_kv_heads, head_dim, page_size, pos_encoding_mode="NONE",
              window_left=-1, q_data_type="float16", kv_data_type=None, data_type=None, sm_scale=None, rope_scale=None,
-             rope_theta=None, non_blocking=True, causal_p: bool = True) -> None:
+             rope_theta=None, non_blocking=True, causal_p: Optional[bool] = None) -> None:
+        """``causal_p``: the reference chooses the prefill mask at run() time (``run(causal_p=...)``, default non-causal).  The tcgen05
+        prefill plan bakes the mask in, so it can also be given here; run() re-plans the prefill side when it asks for the other
+        mask.  Left at None in both places, the reference's default (non-causal) applies."""
+        check_pos_encoding_mode(pos_encoding_mode)
+        if pos_encoding_mode != "NONE":
+            raise NotImplementedError("POD: in-kernel positional encodings are not implemented (apply flashinfer_b200.rope first)")
+        self._causal_arg = causal_p
+        causal_p = True if causal_p is None else bool(causal_p)       # plan for the common case; run() corrects it if needed
+        self._causal_planned = causal_p
         total = device_sm_count(self.device if self.device.type == "cuda" else None)
         qo_p = qo_indptr_p.to("cpu", torch.int64)
         q_lens = qo_p[1:] - qo_p[:-1]
@@ -187,9 +212,9 @@ class BatchPODWithPagedKVCacheWrapper:
         sp, sd = _split_sms(total, flops, dbytes)
         self._prefill._cta_budget, self._decode._cta_budget = sp or None, sd or None
         dt = data_type or q_data_type
-        self._prefill.plan(qo_indptr_p, kv_indptr_p, kv_indices_p, last_page_len_p, num_qo_heads, num_kv_heads, head_dim,
-                           page_size, causal=causal_p, sm_scale=sm_scale, window_left=window_left, q_data_type=dt,
-                           kv_data_type=kv_data_type)
+        self._pplan = ((qo_indptr_p, kv_indptr_p, kv_indices_p, last_page_len_p, num_qo_heads, num_kv_heads, head_dim, page_size),
+                       dict(sm_scale=sm_scale, window_left=window_left, q_data_type=dt, kv_data_type=kv_data_type))
+        self._prefill.plan(*self._pplan[0], causal=causal_p, **self._pplan[1])
         qo_d = qo_indptr_d.to("cpu", torch.int64)
         plain_decode = bool(((qo_d[1:] - qo_d[:-1]) == 1).all())
         self._decode.plan(kv_indptr_d, kv_indices_d, last_page_len_d, num_qo_heads, num_kv_heads, head_dim, page_size,
@@ -201,10 +226,14 @@ class BatchPODWithPagedKVCacheWrapper:
     begin_forward = plan
 
     def run(self, q_p, paged_kv_cache_p, q_d, paged_kv_cache_d, custom_mask_p=None, packed_custom_mask_p=None,
-            causal_p: bool = False, q_scale=None, k_scale=None, v_scale=None, return_lse: bool = False,
+            causal_p: Optional[bool] = None, q_scale=None, k_scale=None, v_scale=None, return_lse: bool = False,
             use_fp16_qk_reduction: bool = False, enable_pdl=None):
         if custom_mask_p is not None or packed_custom_mask_p is not None:
             raise NotImplementedError("POD with custom masks")
+        want = bool(causal_p) if causal_p is not None else (bool(self._causal_arg) if self._causal_arg is not None else False)
+        if want != self._causal_planned:
+            self._prefill.plan(*self._pplan[0], causal=want, **self._pplan[1])
+            self._causal_planned = want
         kp = paged_kv_cache_p[0] if isinstance(paged_kv_cache_p, (tuple, list)) else paged_kv_cache_p
         if self._fused and self._plain_decode and _fusable(q_p, q_d, paged_kv_cache_d, self._hq, self._hkv, self._d) \
                 and kp.dtype == q_p.dtype and q_scale is None and k_scale is None and v_scale is None:

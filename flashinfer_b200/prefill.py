@@ -313,6 +313,16 @@ class _BatchPrefillBase:
         )
         return sinks is not None
 
+    @staticmethod
+    def _check_plan_extras(q_data_type, o_data_type, prefix_len_ptr, token_pos_in_items_ptr, max_item_len_ptr) -> None:
+        """Multi-item scoring masks and an output dtype different from the query's are not implemented: refuse them at plan() time
+        instead of computing plain attention in the query dtype."""
+        from .utils import reject_unsupported
+
+        reject_unsupported("plan", prefix_len_ptr=prefix_len_ptr, token_pos_in_items_ptr=token_pos_in_items_ptr, max_item_len_ptr=max_item_len_ptr)
+        if o_data_type is not None and _canon_dtype(o_data_type) != _canon_dtype(q_data_type):
+            raise NotImplementedError(f"plan: o_data_type {o_data_type} != q_data_type {q_data_type} (convert the output after run())")
+
     def _set_pos_encoding(self, pos_encoding_mode: str, num_qo_heads: int) -> None:
         """ALiBi is a logits transform of the softmax pass (slopes per head); RoPE has to be applied by flashinfer_b200.rope."""
         check_pos_encoding_mode(pos_encoding_mode)
@@ -393,6 +403,7 @@ class BatchPrefillWithRaggedKVCacheWrapper(_BatchPrefillBase):
              token_pos_in_items_ptr=None, token_pos_in_items_len=0, max_item_len_ptr=None, fixed_split_size=None,
              disable_split_kv=False) -> None:
         self._set_pos_encoding(pos_encoding_mode, num_qo_heads)
+        self._check_plan_extras(q_data_type, o_data_type, prefix_len_ptr, token_pos_in_items_ptr, max_item_len_ptr)
         kv_host = kv_indptr.to("cpu", torch.int32)
         self._kv_start_host = kv_host[:-1].contiguous()
         self._kv_indptr_ragged_host = kv_host
@@ -461,6 +472,7 @@ class BatchPrefillWithPagedKVCacheWrapper(_BatchPrefillBase):
              token_pos_in_items_len=0, max_item_len_ptr=None, seq_lens=None, seq_lens_q=None, block_tables=None,
              max_token_per_sequence=None, max_sequence_kv=None, fixed_split_size=None, disable_split_kv=False) -> None:
         self._set_pos_encoding(pos_encoding_mode, num_qo_heads)
+        self._check_plan_extras(q_data_type, o_data_type, prefix_len_ptr, token_pos_in_items_ptr, max_item_len_ptr)
         self._page_size = page_size
         indptr_host = _host_i32(paged_kv_indptr)
         last_host = _host_i32(paged_kv_last_page_len)
@@ -547,6 +559,8 @@ def trtllm_ragged_attention_deepseek(query, key, value, workspace_buffer, seq_le
                                      bmm2_scale, o_sf_scale, batch_size, window_left, cum_seq_lens_q, cum_seq_lens_kv,
                                      enable_pdl=False, is_causal=True, return_lse=False, attention_sinks=None, out=None,
                                      lse=None, skip_softmax_threshold_scale_factor=None):
+    if o_sf_scale is not None and float(o_sf_scale) > 0:
+        raise NotImplementedError("trtllm_ragged_attention_deepseek: NVFP4 output (o_sf_scale > 0) is not implemented")
     w = BatchPrefillWithRaggedKVCacheWrapper(workspace_buffer)
     w.plan(cum_seq_lens_q, cum_seq_lens_kv, query.shape[1], key.shape[1], query.shape[2], head_dim_vo=value.shape[2],
            causal=is_causal, sm_scale=float(bmm1_scale), window_left=window_left, q_data_type=query.dtype)
@@ -575,6 +589,11 @@ def trtllm_batch_context_with_kv_cache(query, kv_cache, workspace_buffer, block_
                                        uses_shared_paged_kv_idx: bool = True, lse=None, return_lse: bool = False):
     """Paged context attention with a block-table interface (causal)."""
     from .decode import _block_tables_to_indices
+    from .utils import reject_unsupported
+
+    # NVFP4 output / NVFP4 KV scale factors are not implemented on the context path; skip-softmax is a speed hint (exact here)
+    reject_unsupported("trtllm_batch_context_with_kv_cache", o_sf_scale=o_sf_scale, o_sf_vec_size=o_sf_vec_size, kv_cache_sf=kv_cache_sf,
+                       uses_shared_paged_kv_idx=(uses_shared_paged_kv_idx, True))
 
     k_cache, v_cache = unpack_paged_kv_cache(kv_cache, kv_layout)
     _, _, _, page_size, hkv, d = paged_kv_strides(k_cache, kv_layout)
@@ -582,8 +601,16 @@ def trtllm_batch_context_with_kv_cache(query, kv_cache, workspace_buffer, block_
     w = BatchPrefillWithPagedKVCacheWrapper(workspace_buffer, kv_layout)
     w.plan(cum_seq_lens_q, indptr, indices, last, query.shape[1], hkv, d, page_size, causal=True,
            sm_scale=float(bmm1_scale), window_left=window_left, q_data_type=query.dtype)
-    return w.run(query, (k_cache, v_cache), out=out, lse=lse, return_lse=return_lse, sinks=sinks,
-                 v_scale=float(bmm2_scale) if float(bmm2_scale) != 1.0 else None)
+    res = w.run(query, (k_cache, v_cache), out=out if (out is None or out.dtype == query.dtype) else None, lse=lse,
+                return_lse=return_lse, sinks=sinks, v_scale=float(bmm2_scale) if float(bmm2_scale) != 1.0 else None)
+    want = out.dtype if out is not None else out_dtype
+    if want is None or want == query.dtype:
+        return res
+    o = (res[0] if return_lse else res).to(want)          # output dtype other than the query's (e.g. fp8 out): converted after the kernel
+    if out is not None:
+        out.copy_(o)
+        o = out
+    return (o, res[1]) if return_lse else o
 
 
 def fmha_v2_prefill_deepseek(query: torch.Tensor, key: torch.Tensor, value: torch.Tensor, out: torch.Tensor, num_heads: int,

@@ -116,6 +116,9 @@ def fp4_quantize(input: torch.Tensor, global_scale: Optional[torch.Tensor] = Non
 def nvfp4_quantize(a, a_global_sf, sfLayout=SfLayout.layout_128x4, do_shuffle=False, sf_vec_size=16, enable_pdl=None,
                    backend: str = "cuda", *, per_token_activation: bool = False, expanded_idx_to_permuted_idx=None):
     """NVFP4 quantisation with explicit scale-factor layout (reference :1077)."""
+    if per_token_activation or expanded_idx_to_permuted_idx is not None:
+        raise NotImplementedError("nvfp4_quantize: per-token activation scales / fused MoE row permutation are not implemented "
+                                  "(the MoE pipeline quantises inside its gather kernel)")
     q, sf = fp4_quantize(a, a_global_sf, sf_vec_size, False, sfLayout == SfLayout.layout_128x4,
                          sfLayout == SfLayout.layout_8x4)
     if do_shuffle:

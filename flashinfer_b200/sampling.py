@@ -98,11 +98,16 @@ def _sample_cpu(probs, mode, indices, top_k, top_p, min_p, generator, return_val
     return out
 
 
+def _check_nan(probs, check_nan: bool) -> None:
+    """``check_nan=True`` of the reference's samplers: refuse NaN probabilities (one device reduction + a host sync, opt-in)."""
+    if check_nan and torch.isnan(probs).any():
+        raise ValueError("Input probs contains NaN.")
+
+
 def sampling_from_probs(probs, indices=None, deterministic=True, generator=None, check_nan=False, seed=None,
                         offset=None, return_valid=False):
     """Category sampling from ``probs [batch, vocab]`` (inverse-CDF)."""
-    if check_nan and torch.isnan(probs).any():
-        raise ValueError("Input probs contains NaN.")
+    _check_nan(probs, check_nan)
     return _sample(probs, 0, indices, generator=generator, seed=seed, offset=offset, return_valid=return_valid)
 
 
@@ -114,18 +119,21 @@ def sampling_from_logits(logits, indices=None, deterministic=True, generator=Non
 
 def top_p_sampling_from_probs(probs, top_p, indices=None, deterministic=True, generator=None, check_nan=False,
                               seed=None, offset=None, return_valid=False):
+    _check_nan(probs, check_nan)
     return _sample(probs, 2, indices, top_p=top_p, generator=generator, seed=seed, offset=offset,
                    return_valid=return_valid)
 
 
 def top_k_sampling_from_probs(probs, top_k, indices=None, deterministic=True, generator=None, check_nan=False,
                               seed=None, offset=None, return_valid=False):
+    _check_nan(probs, check_nan)
     return _sample(probs, 1, indices, top_k=top_k, generator=generator, seed=seed, offset=offset,
                    return_valid=return_valid)
 
 
 def min_p_sampling_from_probs(probs, min_p, indices=None, deterministic=True, generator=None, check_nan=False,
                               seed=None, offset=None, return_valid=False):
+    _check_nan(probs, check_nan)
     return _sample(probs, 3, indices, min_p=min_p, generator=generator, seed=seed, offset=offset,
                    return_valid=return_valid)
 
@@ -138,6 +146,7 @@ def top_k_top_p_sampling_from_probs(probs, top_k, top_p, indices=None, filter_ap
         return top_p_sampling_from_probs(renorm, top_p, indices, deterministic, generator, check_nan, seed, offset,
                                          return_valid)
     if filter_apply_order == "joint":
+        _check_nan(probs, check_nan)
         return _sample(probs, 4, indices, top_k=top_k, top_p=top_p, generator=generator, seed=seed, offset=offset,
                        return_valid=return_valid)
     raise ValueError(f"Invalid filter_apply_order: {filter_apply_order}")

@@ -96,10 +96,11 @@ class BlockSparseAttentionWrapper:
         g = self._g
         kc = k.reshape(-1, g, self._hkv, self._d)
         vc = v.reshape(-1, g, self._hkv, self._d)
+        scales = {n: v_ for n, v_ in (("q_scale", scale_q), ("k_scale", scale_k), ("v_scale", scale_v)) if v_ is not None}
         if self._use_decode:
-            res = self._decode.run(q, (kc, vc), out=out, lse=lse, return_lse=return_lse)
+            res = self._decode.run(q, (kc, vc), out=out, lse=lse, return_lse=return_lse, **scales)
         else:
-            res = self._prefill.run(q, (kc, vc), out=out, lse=lse, return_lse=return_lse)
+            res = self._prefill.run(q, (kc, vc), out=out, lse=lse, return_lse=return_lse, **scales)
         return res
 
     forward = run
@@ -169,6 +170,9 @@ class VariableBlockSparseAttentionWrapper:
             o = out
         if return_lse:
             l = res[1].view(hkv, sq, g).permute(0, 2, 1).reshape(hq, sq)
+            if lse is not None:
+                lse.copy_(l)
+                l = lse
             return o, l
         return o
 

@@ -454,3 +454,18 @@ def register_custom_op(name, fn=None, /, *, mutates_args, device_types=None, sch
 def register_fake_op(name, fn=None):
     """Reference name (flashinfer/utils.py:365): ``torch.library.register_fake``."""
     return torch.library.register_fake(name, fn)
+
+
+def reject_unsupported(api: str, **arguments) -> None:
+    """Raise for arguments an entry point accepts for signature parity but does not implement.  An argument counts as "set" when it is
+    not None / False (pass ``name=(value, default)`` to compare against another default): accepting it silently would return a
+    result computed without it."""
+    bad = []
+    for name, v in arguments.items():
+        if isinstance(v, tuple) and len(v) == 2:
+            if v[0] is not None and v[0] != v[1]:
+                bad.append(name)
+        elif v is not None and v is not False:
+            bad.append(name)
+    if bad:
+        raise NotImplementedError(f"{api}: argument(s) {bad} are not implemented by this library")

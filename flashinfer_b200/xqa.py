@@ -15,6 +15,10 @@ def xqa(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, page_tabl
         kv_layout: str = "NHD", sm_count=None, enable_pdl=None, rcp_out_scale: float = 1.0, q_seq_len: int = 1, mask=None,
         k_sf_cache=None, v_sf_cache=None):
     """q ``[B, beam(=1), Hq, D]`` -> output of the same shape; paged K/V + page table (reference semantics)."""
+    from .utils import reject_unsupported
+
+    # speculative-decoding tree masks and NVFP4 KV scale factors of the reference's XQA kernel are not implemented here
+    reject_unsupported("xqa", mask=mask, k_sf_cache=k_sf_cache, v_sf_cache=v_sf_cache)
     b = q.shape[0]
     d = q.shape[-1]
     qq = q.reshape(b * q_seq_len, -1, d)
@@ -22,7 +26,8 @@ def xqa(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, page_tabl
     res = trtllm_batch_decode_with_kv_cache(qq, (k_cache, v_cache), workspace_buffer, page_table, seq_lens.reshape(-1),
                                             int(seq_lens.max()), bmm1_scale=sm_scale,
                                             window_left=sliding_win_size - 1 if sliding_win_size > 0 else -1,
-                                            kv_layout=kv_layout, sinks=sinks, q_len_per_req=q_seq_len)
+                                            kv_layout=kv_layout, sinks=sinks, q_len_per_req=q_seq_len,
+                                            bmm2_scale=(float(kv_scale) if kv_scale is not None else 1.0) * float(rcp_out_scale))
     output.copy_(res.reshape(output.shape))
     return output
 

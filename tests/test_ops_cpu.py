@@ -184,3 +184,50 @@ def test_logits_processor_modules_and_validators():
     x = torch.randn(3, 50)
     probs = pipe(x, temperature=0.7, top_k=4)
     assert torch.allclose(probs.sum(-1), torch.ones(3), atol=1e-5) and int((probs > 0).sum(-1).max()) <= 4
+
+
+def test_entry_points_refuse_arguments_they_do_not_implement():
+    """Signature-parity arguments that would change the result must fail loudly instead of being dropped (ADVICE r1 class of
+    bug: silently ignored parameters)."""
+    from flashinfer_b200.utils import reject_unsupported
+
+    reject_unsupported("f", a=None, b=False, c=(True, True), d=(None, 3))
+    with pytest.raises(NotImplementedError, match="mask', 'c"):
+        reject_unsupported("f", mask=torch.zeros(1), c=(False, True))
+    q = torch.randn(2, 4, 64, dtype=torch.bfloat16)
+    kc = torch.randn(3, 2, 8, 64, dtype=torch.bfloat16)
+    ws = torch.empty(1 << 20, dtype=torch.uint8)
+    table, lens = torch.tensor([[0, 1], [2, 0]], dtype=torch.int32), torch.tensor([12, 5], dtype=torch.int32)
+    with pytest.raises(NotImplementedError):
+        fi.decode.trtllm_batch_decode_with_kv_cache(q, (kc, kc), ws, table, lens, 12, mask=torch.zeros(1))
+    with pytest.raises(NotImplementedError):
+        fi.decode.trtllm_batch_decode_with_kv_cache(q, (kc, kc), ws, table, lens, 12, o_sf_scale=1.0)
+    o16 = fi.decode.trtllm_batch_decode_with_kv_cache(q, (kc, kc), ws, table, lens, 12, bmm1_scale=0.125, out_dtype=torch.float16)
+    assert o16.dtype == torch.float16
+    o, l = fi.decode.trtllm_batch_decode_with_kv_cache(q, (kc, kc), ws, table, lens, 12, bmm1_scale=0.125, return_lse=True,
+                                                       lse=torch.empty(2, 4))
+    assert l.shape == (2, 4) and torch.allclose(o.float(), o16.float(), atol=2e-2)
+    w = fi.BatchPrefillWithRaggedKVCacheWrapper(ws)
+    ind = torch.tensor([0, 2], dtype=torch.int32)
+    with pytest.raises(NotImplementedError):
+        w.plan(ind, ind, 4, 2, 64, q_data_type=torch.bfloat16, prefix_len_ptr=torch.zeros(1, dtype=torch.int32))
+    with pytest.raises(NotImplementedError):
+        w.plan(ind, ind, 4, 2, 64, q_data_type=torch.bfloat16, o_data_type=torch.float8_e4m3fn)
+    w.plan(ind, ind, 4, 2, 64, q_data_type=torch.bfloat16, o_data_type="bfloat16")
+    with pytest.raises(ValueError, match="NaN"):
+        fi.sampling.top_k_sampling_from_probs(torch.tensor([[0.5, float("nan"), 0.5]]), 2, check_nan=True)
+    with pytest.raises(NotImplementedError):
+        fi.quantization.fp4.nvfp4_quantize(torch.randn(4, 64), torch.ones(1), per_token_activation=True)
+
+
+def test_xqa_batch_decode_default_layout_is_nhd():
+    """The reference's XQA batch entry point defaults to NHD pages (its trtllm sibling to HND)."""
+    torch.manual_seed(0)
+    q = torch.randn(2, 4, 64, dtype=torch.bfloat16)
+    k_nhd, v_nhd = torch.randn(3, 8, 2, 64, dtype=torch.bfloat16), torch.randn(3, 8, 2, 64, dtype=torch.bfloat16)
+    ws = torch.empty(1 << 20, dtype=torch.uint8)
+    table, lens = torch.tensor([[0, 1], [2, 0]], dtype=torch.int32), torch.tensor([12, 5], dtype=torch.int32)
+    a = fi.decode.xqa_batch_decode_with_kv_cache(q, (k_nhd, v_nhd), ws, table, lens, 12, bmm1_scale=0.125)
+    b = fi.decode.trtllm_batch_decode_with_kv_cache(q, (k_nhd.transpose(1, 2).contiguous(), v_nhd.transpose(1, 2).contiguous()), ws, table,
+                                                    lens, 12, bmm1_scale=0.125)
+    torch.testing.assert_close(a.float(), b.float(), atol=1e-2, rtol=1e-2)
