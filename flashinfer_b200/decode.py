@@ -549,6 +549,7 @@ class BatchDecodeMlaWithPagedKVCacheWrapper:
         b = kv_len.numel()
         dt = _canon_dtype(q_data_type or data_type)
         self._plan_args, self._sm_scale = (indptr, indices, kv_len.int(), num_qo_heads, head_dim_compressed_kv, page_size, dt, b), float(sm_scale)
+        self._sm_planned = self._sm_scale
         self._w.plan(torch.arange(b + 1, dtype=torch.int32), indptr, indices, kv_len.int(), num_qo_heads,
                      head_dim_compressed_kv, 64, page_size, False, sm_scale, dt, dt)
 
