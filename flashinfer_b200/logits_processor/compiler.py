@@ -21,7 +21,7 @@ class Compiler:
                 n = len(rule.pattern)
                 for i in range(len(ops) - n + 1):
                     window = ops[i:i + n]
-                    if tuple(o.name for o in window) == rule.pattern and (rule.guard is None or rule.guard(window)):
+                    if rule.matches(window):
                         ops[i:i + n] = [rule.build(window)]
                         changed = True
                         break

@@ -4,7 +4,7 @@ from __future__ import annotations
 from typing import List, Sequence
 
 from .op import Op
-from .processors import LogitsProcessor, Sample, Softmax, Temperature, TopK
+from .processors import LogitsProcessor, MinP, Softmax, Temperature, TopP
 from .types import LegalizationError, TensorType
 
 
@@ -30,3 +30,15 @@ def legalize_processors(processors: Sequence[LogitsProcessor], input_type: Tenso
             cur = op.OUT
         ops += lowered
     return ops
+
+
+def validate_processor_chain(processors: Sequence[LogitsProcessor]) -> None:
+    """Raises :class:`LegalizationError` when the chain is empty, its input type cannot be inferred, or it cannot be lowered."""
+    if not processors:
+        raise LegalizationError("Processor chain cannot be empty")
+    try:
+        legalize_processors(processors, infer_initial_type(processors))
+    except LegalizationError:
+        raise
+    except Exception as exc:  # noqa: BLE001
+        raise LegalizationError(f"Processor chain validation failed: {exc}") from exc

@@ -60,4 +60,11 @@ TopKTopPSampleOp = _make_op("topk_topp_sample", TensorType.PROBS, TensorType.IND
                                 filter_apply_order="joint" if self.static.get("joint") else "top_k_first", **_gen(kw)),
                             ("top_k", "top_p"))
 
+# the reference's class names for the same ops (flashinfer/logits_processor/operators.py), so user fusion rules / validity checks written
+# against ``isinstance(op, ProbsTopKOp)`` work unchanged
+LogitsTopKOp, ProbsTopKOp, TopPOp, MinPOp = TopKLogitsOp, TopKProbsOp, TopPProbsOp, MinPProbsOp
+ProbsSampleOp, LogitsSampleOp = SampleProbsOp, SampleLogitsOp
+FusedTemperatureSoftmaxOp, FusedProbsTopKSampleOp, FusedProbsTopPSampleOp = TempSoftmaxOp, TopKSampleOp, TopPSampleOp
+FusedProbsMinPSampleOp, FusedProbsTopKTopPSampleOp = MinPSampleOp, TopKTopPSampleOp
+
 __all__ = [n for n in dir() if n.endswith("Op")]

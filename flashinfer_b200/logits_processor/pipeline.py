@@ -16,7 +16,7 @@ from .op import Op, ParameterizedOp  # noqa: F401
 from .operators import *  # noqa: F401,F403
 from .processors import LogitsProcessor, MinP, Sample, Softmax, Temperature, TopK, TopP  # noqa: F401
 from .types import CompileError, LegalizationError, TaggedTensor, TensorType  # noqa: F401
-from .validators import validate_pipeline
+from .validators import validate_ops, validate_pipeline
 
 
 class LogitsPipe:
@@ -25,9 +25,10 @@ class LogitsPipe:
         if not processors:
             raise ValueError("Pipeline cannot be empty")
         self.processors = list(processors)
-        validate_pipeline(self.processors, custom_validity_checks)
+        validate_pipeline(self.processors)
         self._initial_type = input_type or infer_initial_type(self.processors)
         self.ops = legalize_processors(self.processors, self._initial_type)
+        validate_ops(self.ops, custom_validity_checks)
         self._rules = custom_fusion_rules
         self.compiled_ops: Optional[List[Op]] = None
         if compile:

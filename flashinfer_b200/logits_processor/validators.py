@@ -1,10 +1,16 @@
-"""Pipeline validity checks run before legalisation (reference flashinfer/logits_processor/validators.py)."""
+"""Pipeline validity checks (reference flashinfer/logits_processor/validators.py).  Two layers: checks on the processor list before
+legalisation (a pipeline samples at most once, and last) and - the reference's form, also what ``custom_validity_checks`` receive -
+checks on the legalised op list (``single_softmax_rule``, ``indices_terminal_rule``)."""
 from __future__ import annotations
 
 from typing import Callable, List, Optional, Sequence
 
+from .op import Op
+from .operators import SoftmaxOp, TempSoftmaxOp
 from .processors import LogitsProcessor, Sample
-from .types import LegalizationError
+from .types import CompileError, LegalizationError, TensorType  # noqa: F401  (CompileError is the reference's export of this module)
+
+ValidityCheck = Callable[[List[Op]], None]
 
 
 def _sample_is_last(processors: Sequence[LogitsProcessor]) -> None:
@@ -21,7 +27,30 @@ def _no_duplicate_sample(processors: Sequence[LogitsProcessor]) -> None:
 DEFAULT_VALIDATORS: List[Callable[[Sequence[LogitsProcessor]], None]] = [_no_duplicate_sample, _sample_is_last]
 
 
-def validate_pipeline(processors: Sequence[LogitsProcessor], custom_validity_checks: Optional[Sequence[Callable]] = None) -> None:
-    """Raises :class:`LegalizationError` (or whatever a custom check raises) for pipelines that cannot be lowered."""
-    for check in list(DEFAULT_VALIDATORS) + list(custom_validity_checks or []):
+def single_softmax_rule(ops: List[Op]) -> None:
+    """At most one softmax (plain or fused with the temperature) per pipeline."""
+    if sum(isinstance(o, (SoftmaxOp, TempSoftmaxOp)) for o in ops) > 1:
+        raise CompileError("Multiple Softmax operators found. Only one Softmax is allowed per pipeline.")
+
+
+def indices_terminal_rule(ops: List[Op]) -> None:
+    """Nothing may follow an op that produces token ids."""
+    for op, nxt in zip(ops, ops[1:]):
+        if op.OUT == TensorType.INDICES:
+            raise CompileError(f"No operator may follow one that outputs Indices: found {nxt} after {op}")
+
+
+def get_default_validity_checks() -> List[ValidityCheck]:
+    return [single_softmax_rule, indices_terminal_rule]
+
+
+def validate_pipeline(processors: Sequence[LogitsProcessor]) -> None:
+    """Processor-level checks: raises :class:`LegalizationError` for pipelines that cannot be lowered."""
+    for check in DEFAULT_VALIDATORS:
         check(processors)
+
+
+def validate_ops(ops: List[Op], custom_validity_checks: Optional[Sequence[ValidityCheck]] = None) -> None:
+    """Op-level checks on the legalised pipeline: the defaults, then the caller's (they raise whatever they like)."""
+    for check in get_default_validity_checks() + list(custom_validity_checks or []):
+        check(ops)

@@ -231,3 +231,48 @@ def test_xqa_batch_decode_default_layout_is_nhd():
     b = fi.decode.trtllm_batch_decode_with_kv_cache(q, (k_nhd.transpose(1, 2).contiguous(), v_nhd.transpose(1, 2).contiguous()), ws, table,
                                                     lens, 12, bmm1_scale=0.125)
     torch.testing.assert_close(a.float(), b.float(), atol=1e-2, rtol=1e-2)
+
+
+def test_logits_processor_accepts_rules_and_checks_written_for_the_reference():
+    """Reference-style extension points: FusionRule(pattern=<op classes>, guard=, build=, prio=), validity checks over the legalised op
+    list, the reference's op class and builder names."""
+    from flashinfer_b200.logits_processor import LogitsPipe, MinP, Sample, Softmax, Temperature, TopK, TopP
+    from flashinfer_b200.logits_processor.fusion_rules import (FusionRule, build_topk_sampling, get_default_fusion_rules,
+                                                              joint_topk_topp_sampleprobs_guard)
+    from flashinfer_b200.logits_processor.legalization import validate_processor_chain
+    from flashinfer_b200.logits_processor.operators import (FusedProbsTopKSampleOp, FusedProbsTopKTopPSampleOp, FusedTemperatureSoftmaxOp,
+                                                           ProbsSampleOp, ProbsTopKOp, SoftmaxOp, TemperatureOp, TopPOp)
+    from flashinfer_b200.logits_processor.types import LegalizationError, TensorType
+    from flashinfer_b200.logits_processor.validators import (CompileError, get_default_validity_checks, indices_terminal_rule,
+                                                            single_softmax_rule)
+
+    assert len(get_default_fusion_rules()) == 6 and [c.__name__ for c in get_default_validity_checks()] == ["single_softmax_rule", "indices_terminal_rule"]
+    seen = []
+    rule = FusionRule(pattern=(TemperatureOp, SoftmaxOp), guard=lambda w: seen.append(len(w)) or False, build=lambda w: w[0], prio=1000)
+    pipe = LogitsPipe([Temperature(), Softmax(), TopK(), Sample()], custom_fusion_rules=[rule])
+    assert seen and isinstance(pipe.compiled_ops[0], FusedTemperatureSoftmaxOp) and isinstance(pipe.compiled_ops[1], FusedProbsTopKSampleOp)
+    joint = LogitsPipe([TopK(joint_topk_topp=True), TopP(), Sample()], input_type=TensorType.PROBS)
+    assert isinstance(joint.compiled_ops[0], FusedProbsTopKTopPSampleOp) and joint_topk_topp_sampleprobs_guard(joint.ops)
+    assert isinstance(build_topk_sampling(LogitsPipe([TopK(), Sample()], input_type=TensorType.PROBS, compile=False).ops), FusedProbsTopKSampleOp)
+
+    def no_top_p(ops):                                  # a check in the reference's form: it sees Op objects
+        assert all(hasattr(o, "OUT") for o in ops)
+        if any(isinstance(o, TopPOp) for o in ops):
+            raise CompileError("top-p is not allowed here")
+
+    LogitsPipe([Softmax(), TopK(), Sample()], custom_validity_checks=[no_top_p])
+    with pytest.raises(CompileError):
+        LogitsPipe([Softmax(), TopP(), Sample()], custom_validity_checks=[no_top_p])
+    ops = LogitsPipe([Temperature(), Softmax(), TopK(), Sample()], compile=False).ops
+    assert isinstance(ops[2], ProbsTopKOp) and isinstance(ops[3], ProbsSampleOp)
+    single_softmax_rule(ops)
+    indices_terminal_rule(ops)
+    with pytest.raises(CompileError):
+        single_softmax_rule(ops + [ops[1]])
+    with pytest.raises(CompileError):
+        indices_terminal_rule(ops + [ops[2]])
+    validate_processor_chain([MinP(), Sample()])         # input type inferred from a probs-only processor
+    with pytest.raises(LegalizationError):
+        validate_processor_chain([])
+    with pytest.raises(LegalizationError):
+        validate_processor_chain([Sample(), Softmax()])
