@@ -32,6 +32,24 @@ def convert_to_block_layout(input_tensor, blockK: int):
     *lead, M, K = input_tensor.shape
     return input_tensor.reshape(*lead, M, K // blockK, blockK).transpose(-3, -2).contiguous()
 
+from . import moe_utils  # noqa: E402,F401  (standalone building blocks: moe_sort / moe_permute / moe_unpermute / moe_activation ...)
+from .moe_utils import (  # noqa: E402,F401
+    MoeActivationType,
+    allocate_moe_sort_buffers,
+    get_max_num_permuted_tokens,
+    get_max_num_tiles,
+    moe_activation,
+    moe_geglu,
+    moe_gelu,
+    moe_output_memset,
+    moe_output_memset_inplace,
+    moe_permute,
+    moe_relu,
+    moe_silu,
+    moe_sort,
+    moe_swiglu,
+    moe_unpermute,
+)
 from .. import _alias  # noqa: E402
 
 _alias.install(__name__, ['fused_routing_dsv3'])  # the reference's per-file module paths
