@@ -11,18 +11,16 @@ from .moe_alltoall import (  # noqa: F401,E402
     moe_a2a_sanitize_expert_ids,
     moe_a2a_wrap_payload_tensor_in_workspace,
 )
-from .compat import (  # noqa: F401,E402
+from .workspace_base import AllReduceFusionWorkspace  # noqa: F401,E402
+from .trtllm_ar import (  # noqa: F401,E402
     AllReduceFusionOp,
     AllReduceFusionPattern,
-    AllReduceFusionWorkspace,
     AllReduceStrategyConfig,
     AllReduceStrategyType,
-    MNNVLAllReduceFusionWorkspace,
     QuantizationSFLayout,
     TRTLLMAllReduceFusionWorkspace,
     allreduce_fusion,
     compute_fp4_swizzled_layout_sf_size,
-    create_allreduce_fusion_workspace,
     trtllm_allreduce_fusion,
     trtllm_create_ipc_workspace_for_all_reduce,
     trtllm_create_ipc_workspace_for_all_reduce_fusion,
@@ -33,6 +31,10 @@ from .compat import (  # noqa: F401,E402
     trtllm_lamport_initialize_all,
     trtllm_moe_allreduce_fusion,
     trtllm_moe_finalize_allreduce_fusion,
+)
+from .allreduce import create_allreduce_fusion_workspace  # noqa: F401,E402
+from .trtllm_mnnvl_ar import MNNVLAllReduceFusionWorkspace  # noqa: F401,E402
+from .vllm_ar import (  # noqa: F401,E402
     vllm_all_reduce,
     vllm_dispose,
     vllm_get_graph_buffer_ipc_meta,
@@ -54,7 +56,8 @@ from .collectives import (  # noqa: F401,E402
 )
 from .gemm_allreduce import GemmAllReduce, gemm_allreduce, gemm_reduce_scatter  # noqa: F401,E402
 from .all_gather_matmul import AllGatherMatmul, all_gather_matmul  # noqa: F401,E402
-from .compat import CudaRTLibrary, create_shared_buffer, free_shared_buffer, pack_strided_memory  # noqa: F401,E402
+from .cuda_ipc import CudaRTLibrary, create_shared_buffer, free_shared_buffer  # noqa: F401,E402
+from .dlpack_utils import pack_strided_memory  # noqa: F401,E402
 from . import mixed_comm, mnnvl, nvshmem, trtllm_alltoall, trtllm_mnnvl_ar  # noqa: F401,E402
 from .trtllm_mnnvl_ar import (  # noqa: F401,E402
     MNNVLAllreduceFusionStrategy,

@@ -274,3 +274,23 @@ class _ptr:
 
     def __init__(self, v: int):
         self.v = int(v)
+
+
+# ------------------------------------------------------------------ unified fused all-reduce API (reference flashinfer/comm/allreduce.py:
+# AllReduceFusionWorkspace / TRTLLMAllReduceFusionWorkspace / MNNVLAllReduceFusionWorkspace, create_allreduce_fusion_workspace :286,
+# allreduce_fusion :460).  The pattern implementation is shared with the TRT-LLM named entry points (trtllm_ar.py).
+from .workspace_base import AllReduceFusionWorkspace  # noqa: E402,F401
+from .trtllm_ar import AllReduceFusionPattern, QuantizationSFLayout, TRTLLMAllReduceFusionWorkspace, allreduce_fusion  # noqa: E402,F401
+from .trtllm_mnnvl_ar import MNNVLAllReduceFusionWorkspace  # noqa: E402,F401
+
+
+def create_allreduce_fusion_workspace(backend: str = "auto", world_size: Optional[int] = None, rank: Optional[int] = None,
+                                      max_token_num: Optional[int] = None, hidden_dim: Optional[int] = None,
+                                      dtype: Optional[torch.dtype] = None, gpus_per_node: Optional[int] = None,
+                                      comm_backend=None, force_oneshot_support: bool = False,
+                                      group: Optional[dist.ProcessGroup] = None) -> AllReduceFusionWorkspace:
+    g = group if group is not None else dist.group.WORLD
+    world_size = world_size or dist.get_world_size(g)
+    rank = dist.get_rank(g) if rank is None else rank
+    cls = {"trtllm": TRTLLMAllReduceFusionWorkspace, "mnnvl": MNNVLAllReduceFusionWorkspace}.get(backend, AllReduceFusionWorkspace)
+    return cls(world_size, rank, max_token_num, hidden_dim, dtype or torch.bfloat16, g)

@@ -147,7 +147,7 @@ class MnnvlMemory:
 
     def as_torch_strided_tensor(self, dtype: torch.dtype) -> torch.Tensor:
         """``[world, size / itemsize]``: row ``r`` is rank ``r``'s slice (peer memory, addressable from this rank)."""
-        from .compat import pack_strided_memory
+        from .dlpack_utils import pack_strided_memory
 
         esz = torch.empty(0, dtype=dtype).element_size()
         rows = [pack_strided_memory(p, self.segment_size, self.segment_size, 1, dtype, self.heap.device)[0] for p in self.heap.peer_ptrs]

@@ -8,7 +8,12 @@ from typing import Optional, Tuple
 import torch
 import torch.distributed as dist
 
-from .compat import AllReduceFusionPattern, MNNVLAllReduceFusionWorkspace, allreduce_fusion  # noqa: F401
+from .trtllm_ar import AllReduceFusionPattern, allreduce_fusion  # noqa: F401
+from .workspace_base import AllReduceFusionWorkspace
+
+
+class MNNVLAllReduceFusionWorkspace(AllReduceFusionWorkspace):
+    backend = "mnnvl"
 
 
 class MNNVLAllreduceFusionStrategy(Enum):
