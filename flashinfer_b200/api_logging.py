@@ -249,7 +249,7 @@ PUBLIC_API_MODULES = (
     "activation", "cascade", "concat_ops", "decode", "deep_gemm", "dsv3_ops", "gdn", "norm", "page", "pod", "prefill", "rope",
     "sampling", "sparse", "topk", "xqa", "attention._core", "mla._core", "gemm.dense", "gemm.lowp", "gemm.grouped",
     "gemm.decode_linear", "fused_moe.core", "quantization.fp4", "quantization.fp8", "quantization.packbits",
-    "mamba.selective_state_update", "mamba.ssd_combined", "comm.allreduce", "comm.trtllm_ar", "comm.vllm_ar", "comm.cuda_ipc", "comm.dlpack_utils", "comm.trtllm_mnnvl_ar", "comm.alltoall", "comm.collectives",
+    "mamba.selective_state_update", "mamba.ssd_combined", "comm.allreduce", "comm.trtllm_ar", "comm.vllm_ar", "comm.cuda_ipc", "comm.dlpack_utils", "comm.trtllm_mnnvl_ar", "comm.alltoall", "comm.collectives", "comm.dcp_alltoall", "comm.mixed_comm",
     "comm.gemm_allreduce", "logits_processor.pipeline",
 )
 _WRAPPER_METHODS = ("plan", "run", "forward", "begin_forward", "dispatch", "combine")

@@ -43,16 +43,13 @@ from .vllm_ar import (  # noqa: F401,E402
     vllm_register_buffer,
     vllm_register_graph_buffers,
 )
-from .collectives import (  # noqa: F401,E402
-    MixedCommHandler,
-    MixedCommMode,
-    MixedCommOp,
-    NVLSCollectives,
+from .collectives import NVLSCollectives  # noqa: F401,E402
+from .mixed_comm import MixedCommHandler, MixedCommMode, MixedCommOp, run_mixed_comm  # noqa: F401,E402
+from .dcp_alltoall import (  # noqa: F401,E402
     decode_cp_a2a_allocate_mnnvl_workspace,
     decode_cp_a2a_alltoall,
     decode_cp_a2a_init_workspace,
     decode_cp_a2a_workspace_size,
-    run_mixed_comm,
 )
 from .gemm_allreduce import GemmAllReduce, gemm_allreduce, gemm_reduce_scatter  # noqa: F401,E402
 from .all_gather_matmul import AllGatherMatmul, all_gather_matmul  # noqa: F401,E402

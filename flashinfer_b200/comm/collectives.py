@@ -138,117 +138,3 @@ class NVLSCollectives:
         self._mod.call("p2p_all_to_all", tab, self._sig_tab, self._epochs, xc, 0, rows, row_bytes, self.rank, self.world,
                        _MAX_BLOCKS, 1, stream_ptr(xc))
         return region[:nbytes].view(x.dtype).view(x.shape)
-
-
-# ------------------------------------------------------------------ DCP (decode context parallel) all-to-all
-_DCP: dict = {}
-
-
-def decode_cp_a2a_workspace_size(cp_size: int) -> int:
-    return 2 * (16 << 20) + 2 * _MAX_BLOCKS * 16 * 4 + 8192
-
-
-def decode_cp_a2a_allocate_mnnvl_workspace(mapping, *, mnnvl_config=None, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
-    """Allocates the symmetric workspace for the CP group and returns an opaque handle tensor (int64 id)."""
-    coll = NVLSCollectives(group, 16 << 20)
-    h = torch.tensor([len(_DCP) + 1], dtype=torch.int64)
-    _DCP[int(h)] = coll
-    return h
-
-
-def decode_cp_a2a_init_workspace(workspace: torch.Tensor, cp_rank: int, cp_size: int) -> None:
-    """Nothing to reset (epoch barriers); kept for API compatibility.  Synchronises like the reference."""
-    if torch.cuda.is_available():
-        torch.cuda.current_stream().synchronize()
-
-
-def decode_cp_a2a_alltoall(partial_o: torch.Tensor, softmax_stats: torch.Tensor, workspace: torch.Tensor, cp_rank: int,
-                           cp_size: int, enable_pdl: Optional[bool] = None) -> Tuple[torch.Tensor, torch.Tensor]:
-    """``partial_o [..., cp, D]`` and ``softmax_stats [..., cp, S]``: slice ``[..., j, :]`` goes to rank j.  Both tensors
-    travel in ONE kernel launch (stats are packed behind the output rows)."""
-    coll: NVLSCollectives = _DCP[int(workspace.reshape(-1)[0])]
-    lead = partial_o.shape[:-2]
-    rows = 1
-    for d in lead:
-        rows *= d
-    D, S = partial_o.shape[-1], softmax_stats.shape[-1]
-    ob = D * partial_o.element_size()
-    sb = S * 4
-    pad = (-(ob + sb)) % 16
-    packed = torch.empty(rows, cp_size, ob + sb + pad, dtype=torch.uint8, device=partial_o.device)
-    packed[..., :ob] = partial_o.reshape(rows, cp_size, D).contiguous().view(torch.uint8).view(rows, cp_size, ob)
-    packed[..., ob:ob + sb] = softmax_stats.reshape(rows, cp_size, S).float().contiguous().view(torch.uint8).view(rows, cp_size, sb)
-    recv = coll.all_to_all(packed)
-    o = recv[..., :ob].contiguous().view(partial_o.dtype).view(*lead, cp_size, D)
-    st = recv[..., ob:ob + sb].contiguous().view(torch.float32).view(*lead, cp_size, S)
-    return o, st
-
-
-# ------------------------------------------------------------------ mixed_comm front end
-class MixedCommOp(Enum):
-    ALLREDUCE = 0
-    ALLGATHER = 1
-    REDUCESCATTER = 2
-    ALLREDUCE_ALLGATHER = 3
-    REDUCESCATTER_ALLREDUCE = 4
-
-
-class MixedCommMode(Enum):
-    FUSED_NVLS = 0
-    FUSED_P2P = 1
-    NCCL = 2
-    AUTOTUNE = 3
-
-
-class MixedCommHandler:
-    """TP x DP collectives on one NVSwitch domain.  ``local_tp_size * local_dp_size`` ranks form the group: AR / RS run
-    inside each TP sub-group, AG across the DP sub-group (reference mixed_comm.py:143-421 topology model; the
-    inter-node NVSHMEM legs do not exist on a single node)."""
-
-    def __init__(self, group: Optional[dist.ProcessGroup] = None, capacity_bytes: int = 64 << 20, hidden: int = 4096,
-                 dtype: torch.dtype = torch.bfloat16, max_tokens: int = 8192, mode: MixedCommMode = MixedCommMode.FUSED_NVLS) -> None:
-        from .allreduce import TPCommunicator
-
-        self.group = group if group is not None else dist.group.WORLD
-        self.mode = mode
-        self.coll = NVLSCollectives(self.group, capacity_bytes, use_nvls=mode != MixedCommMode.FUSED_P2P)
-        self.ar = TPCommunicator(self.group, max_tokens, hidden, dtype, use_nvls=mode != MixedCommMode.FUSED_P2P) \
-            if self.coll._cuda else None
-
-    def run(self, op: MixedCommOp, x: torch.Tensor) -> torch.Tensor:
-        if self.mode == MixedCommMode.NCCL or not self.coll._cuda:
-            return self._nccl(op, x)
-        if op == MixedCommOp.ALLREDUCE:
-            return self.ar.all_reduce(x)
-        if op == MixedCommOp.ALLGATHER:
-            return self.coll.all_gather(x)
-        if op == MixedCommOp.REDUCESCATTER:
-            return self.coll.reduce_scatter(x)
-        if op == MixedCommOp.ALLREDUCE_ALLGATHER:
-            return self.coll.all_gather(self.ar.all_reduce(x))
-        if op == MixedCommOp.REDUCESCATTER_ALLREDUCE:
-            return self.coll.reduce_scatter(x)
-        raise ValueError(op)
-
-    def _nccl(self, op: MixedCommOp, x: torch.Tensor) -> torch.Tensor:
-        w = dist.get_world_size(self.group)
-        if op == MixedCommOp.ALLREDUCE:
-            y = x.clone()
-            dist.all_reduce(y, group=self.group)
-            return y
-        if op in (MixedCommOp.ALLGATHER, MixedCommOp.ALLREDUCE_ALLGATHER):
-            y = x.clone()
-            if op == MixedCommOp.ALLREDUCE_ALLGATHER:
-                dist.all_reduce(y, group=self.group)
-            parts = [torch.empty_like(y) for _ in range(w)]
-            dist.all_gather(parts, y, group=self.group)
-            return torch.cat(parts, 0)
-        y = x.clone()
-        dist.all_reduce(y, group=self.group)
-        n = x.shape[0] // w
-        r = dist.get_rank(self.group)
-        return y[r * n:(r + 1) * n].clone()
-
-
-def run_mixed_comm(handler: MixedCommHandler, op: MixedCommOp, x: torch.Tensor) -> torch.Tensor:
-    return handler.run(op, x)

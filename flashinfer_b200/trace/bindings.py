@@ -126,7 +126,7 @@ BINDINGS: List[Tuple[str, str, "_t.TraceTemplate"]] = [
     ("gdn", "gated_delta_rule_mtp", T.gdn_mtp_trace),
     ("mamba.ssd_combined", "SSDCombined.run", T.selective_scan_ssd_prefill_trace),
     ("rope", "rope_quantize_fp8_append_paged_kv_cache", T.rope_quantize_fp8_append_paged_kv_cache_trace),
-    ("comm.collectives", "decode_cp_a2a_alltoall", T.decode_cp_a2a_alltoall_trace),
+    ("comm.dcp_alltoall", "decode_cp_a2a_alltoall", T.decode_cp_a2a_alltoall_trace),
 ]
 
 # one row per concrete template (a dispatch contributes one row per member): what the generic tests iterate over
