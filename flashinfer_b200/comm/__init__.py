@@ -2,7 +2,7 @@
 from .allreduce import TPCommunicator  # noqa: F401
 from .symm import SymmetricHeap  # noqa: F401
 from .mapping import Mapping  # noqa: F401,E402
-from .moe_alltoall import (  # noqa: F401,E402
+from .trtllm_moe_alltoall import (  # noqa: F401,E402
     MoeAlltoAll,
     moe_a2a_combine,
     moe_a2a_dispatch,

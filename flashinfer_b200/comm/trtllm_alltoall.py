@@ -21,7 +21,7 @@ import torch
 
 from .. import jit
 from ..utils import stream_ptr
-from .moe_alltoall import MoeAlltoAll, moe_a2a_get_workspace_size_per_rank  # noqa: F401
+from .trtllm_moe_alltoall import MoeAlltoAll, moe_a2a_get_workspace_size_per_rank  # noqa: F401
 
 _MAX_BLOCKS = 148
 _max_sms = {"value": None}

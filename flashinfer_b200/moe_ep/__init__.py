@@ -60,6 +60,6 @@ def create_fleet(mapping, max_num_tokens: int, top_k: int, num_experts: int, hid
     """Build the dispatch / combine object for one EP group.  ``backend='nvlink_a2a'`` returns a
     :class:`~flashinfer_b200.comm.MoeAlltoAll`; the plugin backends raise :class:`MoEEpNotBuiltError`."""
     _require_built(backend)
-    from ..comm.moe_alltoall import MoeAlltoAll
+    from ..comm.trtllm_moe_alltoall import MoeAlltoAll
 
     return MoeAlltoAll(mapping, max_num_tokens, top_k, num_experts, hidden_size=hidden_size, **kwargs)
