@@ -19,7 +19,7 @@ from .utils import (  # noqa: F401
     sleep_after_kernel_run,
 )
 
-from .utils import bench_gpu_time as bench_gpu_time_with_cupti  # noqa: F401,E402  (CUPTI is not required: CUDA events / graphs)
+from .utils import bench_gpu_time_with_cupti  # noqa: F401,E402  (CUPTI activity records through torch.profiler)
 from .utils import (  # noqa: F401,E402
     aggregate_gpu_time_across_ranks,
     bench_kineto,

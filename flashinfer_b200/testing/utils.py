@@ -151,14 +151,86 @@ def bench_gpu_time_with_cudagraph(fn: Callable, dry_run_iters: Optional[int] = N
     return out
 
 
+def bench_gpu_time_with_cupti(fn: Callable, dry_run_iters: Optional[int] = None, repeat_iters: Optional[int] = None,
+                              dry_run_time_ms: int = 25, repeat_time_ms: int = 100, l2_flush: bool = True, sleep_after_run: bool = False,
+                              input_args: Tuple = (), input_kwargs: Optional[dict] = None, cold_l2_cache: Optional[bool] = None,
+                              use_cuda_graph: bool = False) -> List[float]:
+    """Per-iteration DEVICE time (ms) from CUPTI activity records: the sum of the durations of the kernels / copies an iteration
+    launches, so launch gaps and host overhead are excluded (reference testing/utils.py:937, which reads the records through
+    cupti-python; here through torch.profiler, whose Kineto backend records the same CUPTI activities).  Every iteration runs inside a
+    ``record_function`` range; a device activity belongs to the iteration whose range contains its launch.  Falls back to
+    :func:`bench_gpu_time_with_cuda_event` when no device activity can be attributed (profiler unavailable, graph replays)."""
+    input_kwargs = input_kwargs or {}
+    if cold_l2_cache is not None:
+        l2_flush = cold_l2_cache
+    fallback = lambda: bench_gpu_time_with_cuda_event(fn, dry_run_iters, repeat_iters, dry_run_time_ms, repeat_time_ms, l2_flush,  # noqa: E731
+                                                      sleep_after_run, input_args, input_kwargs)
+    if use_cuda_graph:
+        return fallback()
+    try:
+        from torch.profiler import ProfilerActivity, profile, record_function
+    except ImportError:
+        return fallback()
+    call = lambda: fn(*input_args, **input_kwargs)  # noqa: E731
+    flush = _L2Flusher(torch.cuda.current_device()) if l2_flush else None
+    call()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(3):
+        call()
+    e.record()
+    torch.cuda.synchronize()
+    est = max(s.elapsed_time(e) / 3, 1e-3)
+    dry = dry_run_iters if dry_run_iters is not None else max(3, int(dry_run_time_ms / est))
+    rep = repeat_iters if repeat_iters is not None else max(5, min(2000, int(repeat_time_ms / est)))
+    for _ in range(max(dry, 3)):
+        call()
+    torch.cuda.synchronize()
+    tag = "fib200_bench_iteration"
+    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+        for _ in range(rep):
+            if flush is not None:
+                flush()
+            with record_function(tag):
+                call()
+            if sleep_after_run:
+                torch.cuda.synchronize()
+        torch.cuda.synchronize()
+    events = prof.events()
+    ranges = sorted((ev.time_range.start, ev.time_range.end) for ev in events if ev.name == tag)
+    if len(ranges) != rep:
+        return fallback()
+    totals = [0.0] * rep
+    starts = [r[0] for r in ranges]
+    import bisect
+
+    attributed = 0
+    for ev in events:
+        kernels = getattr(ev, "kernels", None)
+        if not kernels or ev.name == tag:
+            continue
+        i = bisect.bisect_right(starts, ev.time_range.start) - 1
+        if i < 0 or ev.time_range.start > ranges[i][1]:
+            continue                                          # launched outside the timed ranges (the L2 flush)
+        totals[i] += sum(k.duration for k in kernels)         # microseconds
+        attributed += len(kernels)
+    if attributed == 0:
+        return fallback()
+    return [t / 1e3 for t in totals]
+
+
 def bench_gpu_time(fn: Callable, dry_run_iters: Optional[int] = None, repeat_iters: Optional[int] = None,
                    dry_run_time_ms: int = 25, repeat_time_ms: int = 100, l2_flush: bool = True, use_cuda_graph: bool = False,
                    num_iters_within_graph: int = 10, sleep_after_run: bool = False, enable_cupti: bool = False,
                    input_args: Tuple = (), input_kwargs: Optional[dict] = None, cold_l2_cache: Optional[bool] = None,
                    aggregate_op: Optional[str] = None, group=None) -> List[float]:
-    """Unified entry (reference testing/utils.py:1546).  ``enable_cupti`` is accepted but events are used (CUPTI python
-    bindings are not in this image).  ``aggregate_op='max'`` reduces every sample over the ranks of ``group``."""
-    if use_cuda_graph:
+    """Unified entry (reference testing/utils.py:1546).  ``enable_cupti`` measures device time from CUPTI activity records
+    (:func:`bench_gpu_time_with_cupti`).  ``aggregate_op='max'`` reduces every sample over the ranks of ``group``."""
+    if enable_cupti and not use_cuda_graph:
+        times = bench_gpu_time_with_cupti(fn, dry_run_iters, repeat_iters, dry_run_time_ms, repeat_time_ms, l2_flush, sleep_after_run,
+                                          input_args, input_kwargs, cold_l2_cache)
+    elif use_cuda_graph:
         times = bench_gpu_time_with_cudagraph(fn, dry_run_iters, repeat_iters, dry_run_time_ms, repeat_time_ms,
                                               num_iters_within_graph, l2_flush, sleep_after_run, input_args, input_kwargs,
                                               None, cold_l2_cache)

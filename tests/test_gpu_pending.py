@@ -117,3 +117,18 @@ def test_every_trace_template_against_the_native_kernels():
             failures.append(f"{tid}: {type(exc).__name__}: {str(exc)[:200]}")
     os.environ["FIB200_TRACE_TEST_DEVICE"] = "cpu"
     assert not failures, "\n".join(failures)
+
+
+def test_cupti_timing_excludes_launch_gaps():
+    from flashinfer_b200.testing import bench_gpu_time_with_cuda_event, bench_gpu_time_with_cupti
+
+    a = torch.randn(2048, 2048, device="cuda", dtype=torch.bfloat16)
+
+    def fn():
+        for _ in range(4):
+            torch.mm(a, a)
+
+    dev = bench_gpu_time_with_cupti(fn, dry_run_iters=3, repeat_iters=20)
+    wall = bench_gpu_time_with_cuda_event(fn, dry_run_iters=3, repeat_iters=20)
+    med = lambda xs: sorted(xs)[len(xs) // 2]  # noqa: E731
+    assert len(dev) == 20 and 0 < med(dev) <= med(wall) * 1.05
