@@ -276,3 +276,24 @@ def test_moe_prepared_cache_is_tied_to_the_live_weight_tensors():
     b = torch.full((32,), 2.0)
     if b.data_ptr() == ptr:                            # address reuse is what usually happens; the rule is checked when it does
         assert torch.equal(prep(b), b) and prep(b) is not got_a
+
+
+def test_artifacts_describe_the_in_tree_libraries():
+    """The artifact vocabulary of the reference mapped onto the compiled modules: checksums are the content hashes of the build."""
+    import os
+
+    from flashinfer_b200 import artifacts, jit
+
+    status = dict(artifacts.get_artifacts_status())
+    assert len(status) == len(jit.REGISTRY) and set(artifacts.get_checksums()) == set(status)
+    name, digest = next(artifacts.get_subdir_file_list())
+    assert name.endswith(".so") and len(digest) == 64
+    assert set(artifacts.get_checksums(["comm"])) == {k for k in status if k.startswith("comm/")} != set()
+    built = set(artifacts.get_available_cubin_files())
+    assert built <= set(status) and all(status[k] for k in built if artifacts.CheckSumHash.recorded().get(k.split("/")[1][:-3]) ==
+                                        artifacts.CheckSumHash.expected()[k.split("/")[1][:-3]])
+    assert any(h.endswith(".cuh") for h in artifacts.get_available_header_files())
+    assert artifacts.ArtifactPath().TRTLLM_GEN_FMHA == "" and artifacts.ArtifactPath.GEMM == "gemm"
+    with artifacts.temp_env_var("FIB200_UNIT_ENV", "x"):
+        assert os.environ["FIB200_UNIT_ENV"] == "x"
+    assert "FIB200_UNIT_ENV" not in os.environ
