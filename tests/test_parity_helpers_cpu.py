@@ -1,4 +1,7 @@
 """CPU checks of the host-side / reference paths of ops added late in the round (their CUDA kernels have GPU tests)."""
+import math
+
+import pytest
 import torch
 
 import flashinfer_b200 as fi
@@ -297,3 +300,58 @@ def test_artifacts_describe_the_in_tree_libraries():
     with artifacts.temp_env_var("FIB200_UNIT_ENV", "x"):
         assert os.environ["FIB200_UNIT_ENV"] == "x"
     assert "FIB200_UNIT_ENV" not in os.environ
+
+
+def test_triton_path_helpers_on_native_ops():
+    """flashinfer.triton.{activation,norm,cascade}: unscaled forms equal the native ops, scales follow the Triton kernels' semantics
+    (inputs multiplied by in-scale, result multiplied by out-scale and clamped to the output dtype)."""
+    from flashinfer_b200.triton import activation as ta
+    from flashinfer_b200.triton import cascade as tc
+    from flashinfer_b200.triton import norm as tn
+
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(5, 64, generator=g).to(torch.bfloat16)
+    ref = torch.nn.functional.silu(x[:, :32].float()) * x[:, 32:].float()
+    torch.testing.assert_close(ta.silu_and_mul(x).float(), ref, atol=2e-2, rtol=2e-2)
+    xs, os_ = torch.tensor(0.5), torch.tensor(300.0)
+    q = ta.silu_and_mul(x, xs, os_, torch.float8_e4m3fn)
+    want = (torch.nn.functional.silu(x[:, :32].float() * 0.5) * (x[:, 32:].float() * 0.5) * 300.0).clamp(-448, 448).to(torch.float8_e4m3fn)
+    assert q.dtype == torch.float8_e4m3fn and torch.equal(q.float(), want.float())
+    with pytest.raises(TypeError):
+        ta.scale_and_clamp(x, 1.0, torch.int8)
+
+    w = (1 + 0.1 * torch.randn(64, generator=g)).to(torch.bfloat16)
+    out = torch.empty_like(x)
+    tn.rms_norm(x, w, out, 1e-6)
+    nref = w.float() * x.float() * torch.rsqrt((x.float() ** 2).mean(-1, keepdim=True) + 1e-6)
+    torch.testing.assert_close(out.float(), nref, atol=2e-2, rtol=2e-2)
+    o8 = torch.empty(5, 64, dtype=torch.float8_e4m3fn)
+    tn.rms_norm(x, w, o8, 1e-6, in_scale=torch.tensor(2.0), out_scale=torch.tensor(100.0))
+    x2 = x.float() * 2
+    want = (w.float() * x2 * torch.rsqrt((x2 ** 2).mean(-1, keepdim=True) + 1e-6) * 100).clamp(-448, 448).to(torch.float8_e4m3fn)
+    assert torch.equal(o8.float(), want.float())
+    xr, res = x.clone(), torch.randn(5, 64, generator=g).to(torch.bfloat16)
+    r0 = res.clone()
+    tn.rms_norm_add_residual(xr, res, w, 1e-6)
+    summed = (x.float() + r0.float()).to(torch.bfloat16)
+    torch.testing.assert_close(res.float(), summed.float(), atol=1e-2, rtol=1e-2)
+    torch.testing.assert_close(xr.float(), w.float() * summed.float() * torch.rsqrt((summed.float() ** 2).mean(-1, keepdim=True) + 1e-6), atol=3e-2, rtol=3e-2)
+    xo = torch.empty(5, 64, dtype=torch.float8_e4m3fn)
+    res2 = r0.clone()
+    tn.rms_norm_add_residual(x, res2, w, 1e-6, x_out=xo, x_in_scale=torch.tensor(0.5), x_out_scale=torch.tensor(50.0))
+    assert torch.equal(res2, (r0.float() + 0.5 * x.float()).to(torch.bfloat16)) and xo.dtype == torch.float8_e4m3fn
+
+    # segmented merge against merging each segment by hand
+    v = torch.randn(9, 3, 8, generator=g)
+    s = torch.randn(9, 3, generator=g) * 3
+    indptr = torch.tensor([0, 4, 4, 5, 9], dtype=torch.int32)               # segment 1 is empty
+    vo, so = tc.variable_length_merge_states(v, s, indptr)
+    for i, (a, b) in enumerate(zip(indptr.tolist()[:-1], indptr.tolist()[1:])):
+        if a == b:
+            assert float(vo[i].abs().sum()) == 0.0 and bool(torch.isinf(so[i]).all())
+            continue
+        wts = torch.exp2(s[a:b] - torch.logsumexp(s[a:b] * math.log(2.0), 0) / math.log(2.0))
+        torch.testing.assert_close(vo[i], (wts[..., None] * v[a:b]).sum(0), atol=1e-5, rtol=1e-5)
+        torch.testing.assert_close(so[i], torch.logsumexp(s[a:b] * math.log(2.0), 0) / math.log(2.0), atol=1e-5, rtol=1e-5)
+    v2, s2 = tc.merge_states(v[:4].unsqueeze(0).transpose(0, 1).reshape(1, 4, 3, 8), s[:4].reshape(1, 4, 3))
+    torch.testing.assert_close(v2[0], vo[0], atol=1e-4, rtol=1e-4)
