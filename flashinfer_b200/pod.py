@@ -126,8 +126,7 @@ class PODWithPagedKVCacheWrapper:
             raise NotImplementedError("POD with custom masks")
         if pos_encoding_mode_p != "NONE" or pos_encoding_mode_d != "NONE":
             raise NotImplementedError("POD: in-kernel positional encodings are not implemented (apply flashinfer_b200.rope first)")
-        if kv_layout_d != self._kv_layout:
-            raise ValueError(f"POD: kv_layout_d={kv_layout_d!r} differs from the wrapper's layout {self._kv_layout!r}")
+        # kv_layout_d is not consulted: like in the reference, the decode cache has the layout the wrapper was constructed with
         # run()-time decode parameters override what plan() recorded (the decode side is planned lazily, below); causal_d is
         # immaterial for one query token per request
         dkw = dict(self._dkw)
