@@ -122,6 +122,9 @@ def batch_paged_attention_ref(
         o, l = attention_ref(q[qs:qe], k, v, causal, sm_scale, logits_soft_cap, window_left)
         outs.append(o)
         lses.append(l)
+    if not outs:                                           # an empty batch
+        return (torch.zeros(0, q.shape[1], v_cache.shape[-1], dtype=q.dtype, device=q.device),
+                torch.zeros(0, q.shape[1], dtype=torch.float32, device=q.device))
     return torch.cat(outs, 0), torch.cat(lses, 0)
 
 
