@@ -355,3 +355,38 @@ def test_triton_path_helpers_on_native_ops():
         torch.testing.assert_close(so[i], torch.logsumexp(s[a:b] * math.log(2.0), 0) / math.log(2.0), atol=1e-5, rtol=1e-5)
     v2, s2 = tc.merge_states(v[:4].unsqueeze(0).transpose(0, 1).reshape(1, 4, 3, 8), s[:4].reshape(1, 4, 3))
     torch.testing.assert_close(v2[0], vo[0], atol=1e-4, rtol=1e-4)
+
+
+def test_dit_fusions_match_their_definitions():
+    """diffusion_ops: gated residual + LayerNorm + modulation (reference norm/__init__.py:1057-1440) against plain PyTorch."""
+    import flashinfer_b200.diffusion_ops as dit
+    from flashinfer_b200 import norm
+
+    assert norm.fused_dit_residual_layernorm_scale_shift is dit.fused_dit_residual_layernorm_scale_shift
+    g = torch.Generator().manual_seed(0)
+    b, s, h = 2, 5, 64
+    r = lambda *sh: torch.randn(*sh, generator=g)  # noqa: E731
+    x, res, gate = r(b, s, h).to(torch.bfloat16), r(b, s, h).to(torch.bfloat16), r(b, 1, h).to(torch.bfloat16)
+    gamma, beta, scale, shift = r(h), r(h), r(b, 1, h) * 0.1, r(b, 1, h) * 0.1
+    ln = lambda t: torch.nn.functional.layer_norm(t.float(), (h,), eps=1e-6)  # noqa: E731
+
+    ro, no = dit.fused_dit_gate_residual_layernorm_gamma_beta(x, res, gate, gamma, beta, gate_bias=torch.ones(h))
+    want_r = (res.float() + x.float() * (gate.float() + 1.0)).to(torch.bfloat16)
+    torch.testing.assert_close(ro.float(), want_r.float(), atol=1e-2, rtol=1e-2)
+    torch.testing.assert_close(no.float(), ln(want_r) * gamma + beta, atol=4e-2, rtol=4e-2)
+
+    ro, no = dit.fused_dit_gate_residual_layernorm_scale_shift(x, res, gate, scale, shift, scale_bias=torch.zeros(h), shift_bias=torch.ones(h))
+    want_r = (res.float() + x.float() * gate.float()).to(torch.bfloat16)
+    torch.testing.assert_close(no.float(), ln(want_r) * (1 + scale) + shift + 1.0, atol=4e-2, rtol=4e-2)
+
+    rbuf, nbuf = torch.empty_like(x), torch.empty_like(x)
+    ro, no = dit.fused_dit_residual_layernorm_scale_shift(x, res, scale, shift, residual_out=rbuf, norm_out=nbuf, input_global_scaling_factor=0.5)
+    assert ro is rbuf and no is nbuf
+    want_r = (res.float() + 0.5 * x.float()).to(torch.bfloat16)
+    torch.testing.assert_close(rbuf.float(), want_r.float(), atol=1e-2, rtol=1e-2)
+    torch.testing.assert_close(nbuf.float(), ln(want_r) * (1 + scale) + shift, atol=4e-2, rtol=4e-2)
+
+    _, q8, sf8 = dit.fused_dit_residual_layernorm_scale_shift(x, res, scale, shift, use_mxfp8=True)
+    assert q8.dtype == torch.float8_e4m3fn and q8.shape == x.shape and sf8.dtype == torch.uint8
+    _, q4, sf4 = dit.fused_dit_residual_layernorm_scale_shift(x, res, scale, shift, use_nvfp4=True, global_scaling_factor=torch.tensor([100.0]))
+    assert q4.dtype == torch.uint8 and q4.shape == (b, s, h // 2)
