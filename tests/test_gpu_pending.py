@@ -132,3 +132,70 @@ def test_cupti_timing_excludes_launch_gaps():
     wall = bench_gpu_time_with_cuda_event(fn, dry_run_iters=3, repeat_iters=20)
     med = lambda xs: sorted(xs)[len(xs) // 2]  # noqa: E731
     assert len(dev) == 20 and 0 < med(dev) <= med(wall) * 1.05
+
+
+def test_moe_building_blocks_on_cuda():
+    """moe_utils on the device: static-shape sort, native activation + finalize kernels, composed against the fused bf16 MoE."""
+    from flashinfer_b200.fused_moe import moe_utils as mu
+    from flashinfer_b200.fused_moe.core import moe_forward
+
+    torch.manual_seed(0)
+    t, k, e, h, inter, tile = 257, 4, 16, 512, 256, 128
+    x = (torch.randn(t, h, device="cuda") * 0.5).to(torch.bfloat16)
+    w1 = (torch.randn(e, 2 * inter, h, device="cuda") / h ** 0.5).to(torch.bfloat16)
+    w2 = (torch.randn(e, h, inter, device="cuda") / inter ** 0.5).to(torch.bfloat16)
+    scales, ids = torch.topk(torch.softmax(torch.randn(t, e, device="cuda"), -1), k)
+    ids = ids.int()
+    te, lim, e2p, p2e, total, ntiles = mu.moe_sort(ids, scales, e, k, tile_tokens_dim=tile)
+    rows = mu.get_max_num_permuted_tokens(t, k, e, tile)
+    xp = torch.empty(rows, h, dtype=torch.bfloat16, device="cuda")
+    mu.moe_permute(x, xp, lim, p2e, ntiles, rows, k, tile)
+    h1 = torch.zeros(rows, 2 * inter, dtype=torch.bfloat16, device="cuda")
+    for tl in range(int(ntiles)):
+        h1[tl * tile:(tl + 1) * tile] = xp[tl * tile:(tl + 1) * tile] @ w1[int(te[tl])].t()
+    a = torch.empty(rows, inter, dtype=torch.bfloat16, device="cuda")
+    mu.moe_swiglu(h1, a, lim, ntiles, rows, tile)
+    h2 = torch.zeros(rows, h, dtype=torch.bfloat16, device="cuda")
+    for tl in range(int(ntiles)):
+        h2[tl * tile:(tl + 1) * tile] = a[tl * tile:(tl + 1) * tile] @ w2[int(te[tl])].t()
+    out = torch.empty(t, h, dtype=torch.bfloat16, device="cuda")
+    mu.moe_unpermute(h2, out, e2p, scales, t, k)
+    ref = moe_forward(x, ids, scales.float(), w1, w2)
+    torch.testing.assert_close(out.float(), ref.float(), atol=5e-2, rtol=5e-2)
+
+
+def _pa_worker(rank, world, port, errs):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world)
+    try:
+        from flashinfer_b200.parallel_attention import ParallelAttention, get_parallel_groups
+
+        g = torch.Generator().manual_seed(0)
+        H, S, D = 8, 4096, 128
+        q, k, v = (torch.randn(H, S, D, generator=g).to(torch.bfloat16).cuda() for _ in range(3))
+        ref = torch.nn.functional.scaled_dot_product_attention(q[None].float(), k[None].float(), v[None].float())[0]
+        shard = lambda t_: t_.chunk(world, dim=1)[rank].contiguous()  # noqa: E731
+        for mode in ("ulysses", "ring"):
+            rg, ug = get_parallel_groups(world if mode == "ulysses" else 1, world if mode == "ring" else 1)
+            out = ParallelAttention("sm100", ug, rg, fuse_qkv=True).run(shard(q), shard(k), shard(v), "HND")
+            errs[(rank, mode)] = float((out.float() - shard(ref)).abs().max())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_parallel_attention_nccl_two_gpus():
+    import socket
+
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    errs = mp.Manager().dict()
+    mp.spawn(_pa_worker, args=(2, port, errs), nprocs=2, join=True)
+    assert len(errs) == 4 and max(errs.values()) < 3e-2, dict(errs)
