@@ -1,0 +1,12 @@
+"""Decode engines assembled from this library's ops.
+
+* :mod:`.llama` - the flagship: Llama-family step on the fused decode GEMM family (5 launches per layer, in-GEMM tensor-parallel
+  all-reduce), what ``bench.py`` measures;
+* :mod:`.deepseek` - DeepSeek-V2 / V3: absorbed Multi-head Latent Attention over a paged latent cache + grouped-top-k MoE with a shared expert;
+* :mod:`.transformer` - a configurable GQA decoder: Mixtral / Qwen-MoE (renormalised top-k experts), Qwen3 (q / k norm), Gemma-2 / 3
+  (soft-caps, sliding-window layers, post norms, GeGLU), plain Llama / Mistral.
+
+The last two are op-by-op and device agnostic (native kernels on CUDA, eager paths on CPU) and are tested against plain PyTorch models."""
+from .deepseek import DeepSeekConfig, DeepSeekDecodeEngine  # noqa: F401
+from .llama import LlamaConfig, LlamaDecodeEngine  # noqa: F401
+from .transformer import TransformerConfig, TransformerDecodeEngine  # noqa: F401

@@ -199,3 +199,36 @@ def test_parallel_attention_nccl_two_gpus():
     errs = mp.Manager().dict()
     mp.spawn(_pa_worker, args=(2, port, errs), nprocs=2, join=True)
     assert len(errs) == 4 and max(errs.values()) < 3e-2, dict(errs)
+
+
+@pytest.mark.parametrize("family", ["deepseek", "mixtral_8x7b", "qwen3_30b_a3b", "gemma2_9b"])
+def test_model_engines_on_cuda_match_their_cpu_runs(family):
+    """models.deepseek / models.transformer: the same random-init engine on CUDA (native kernels) and on CPU (eager paths)."""
+    from flashinfer_b200.models import DeepSeekConfig, DeepSeekDecodeEngine, TransformerConfig, TransformerDecodeEngine
+
+    page_size = 64 if family == "deepseek" else 16
+    lens = [70, 1, 200, 33]
+    per = [(n + page_size - 1) // page_size for n in lens]
+    g = torch.Generator().manual_seed(0)
+    ids = torch.randperm(sum(per) + 2, generator=g)[: sum(per)].int()
+    indptr = torch.tensor([0] + list(torch.tensor(per).cumsum(0)), dtype=torch.int32)
+    last = torch.tensor([(n - 1) % page_size + 1 for n in lens], dtype=torch.int32)
+    tokens = torch.randint(0, 300, (4,), generator=g)
+    logits = {}
+    for dev in ("cpu", "cuda"):
+        if family == "deepseek":
+            eng = DeepSeekDecodeEngine(DeepSeekConfig.tiny(), 4, sum(per) + 2, page_size, dev, torch.bfloat16, seed=1)
+            caches = ("ckv_cache", "kpe_cache")
+        else:
+            eng = TransformerDecodeEngine(getattr(TransformerConfig, family)().tiny(), 4, sum(per) + 2, page_size, dev, torch.bfloat16, seed=1)
+            caches = ("k_cache", "v_cache")
+        fill = torch.Generator().manual_seed(2)
+        for l in eng.layers:
+            for name in caches:
+                l[name].copy_((torch.randn(l[name].shape, generator=fill) * 0.5).to(torch.bfloat16))
+        eng.plan(indptr, ids, last)
+        eng.tokens.copy_(tokens)
+        eng.step()
+        logits[dev] = eng.logits.float().cpu()
+    cos = torch.nn.functional.cosine_similarity(logits["cpu"].flatten(), logits["cuda"].flatten(), dim=0)
+    assert cos > 0.995, float(cos)

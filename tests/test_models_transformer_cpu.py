@@ -1,0 +1,116 @@
+"""The configurable GQA decode engine (Mixtral / Qwen3 / Qwen3-MoE / Gemma-2 switches) against a plain PyTorch implementation of
+the same architecture options: q/k norm, (1 + w) norms, post norms, GeGLU, embedding scale, soft-caps, sliding-window layers,
+renormalised top-k MoE routing."""
+import math
+
+import pytest
+import torch
+
+from flashinfer_b200.models.transformer import TransformerConfig, TransformerDecodeEngine
+
+
+def _norm(x, w, eps, gemma):
+    x = x.float()
+    return x * torch.rsqrt((x * x).mean(-1, keepdim=True) + eps) * (w.float() + (1.0 if gemma else 0.0))
+
+
+def _rope_neox(x, pos, theta):
+    d = x.shape[-1]
+    inv = theta ** (-torch.arange(0, d, 2).float() / d)
+    ang = pos.float()[..., None] * inv
+    cos, sin = ang.cos(), ang.sin()
+    x1, x2 = x[..., : d // 2].float(), x[..., d // 2:].float()
+    return torch.cat([x1 * cos - x2 * sin, x2 * cos + x1 * sin], -1)
+
+
+def _reference_step(eng, tokens, history):
+    cfg, dt = eng.cfg, eng.dtype
+    rd = lambda t: t.to(dt).float()  # noqa: E731  (round like the engine's bf16 activations)
+    b, hq, hkv, d = tokens.numel(), cfg.num_qo_heads, cfg.num_kv_heads, cfg.head_dim
+    res = rd(eng.embed[tokens].float() * cfg.embed_scale)
+    for li, l in enumerate(eng.layers):
+        x = rd(_norm(res, l["ln1"], cfg.rms_eps, cfg.gemma_norm))
+        qkv = rd(x @ l["wqkv"].float().t()).view(b, hq + 2 * hkv, d)
+        q, k, v = qkv[:, :hq], qkv[:, hq:hq + hkv], qkv[:, hq + hkv:]
+        if cfg.qk_norm:
+            q, k = rd(_norm(q, l["q_norm"], cfg.rms_eps, cfg.gemma_norm)), rd(_norm(k, l["k_norm"], cfg.rms_eps, cfg.gemma_norm))
+        attn = torch.zeros(b, hq, d)
+        for r in range(b):
+            k_old, v_old = history[li][r]
+            pos = k_old.shape[0]
+            qr = rd(_rope_neox(q[r], torch.full((hq,), pos), cfg.rope_theta))
+            kr = rd(_rope_neox(k[r], torch.full((hkv,), pos), cfg.rope_theta))
+            keys, vals = torch.cat([k_old.float(), kr[None]]), torch.cat([v_old.float(), v[r][None]])         # [n, hkv, d]
+            if cfg.is_sliding(li):
+                keys, vals = keys[-cfg.sliding_window:], vals[-cfg.sliding_window:]
+            keys, vals = keys.repeat_interleave(hq // hkv, 1), vals.repeat_interleave(hq // hkv, 1)
+            lg = torch.einsum("hd,nhd->hn", qr, keys) * cfg.softmax_scale
+            if cfg.attn_logit_softcap:
+                lg = cfg.attn_logit_softcap * torch.tanh(lg / cfg.attn_logit_softcap)
+            attn[r] = torch.einsum("hn,nhd->hd", torch.softmax(lg, -1), vals)
+        a = rd(rd(attn).reshape(b, -1) @ l["wo"].float().t())
+        if cfg.post_norms:
+            a = rd(_norm(a, l["post_attn"], cfg.rms_eps, cfg.gemma_norm))
+        res = rd(res + a)
+        x = rd(_norm(res, l["ln2"], cfg.rms_eps, cfg.gemma_norm))
+        if cfg.num_experts:
+            lg = rd(x @ l["router"].float().t())
+            top, ids = lg.topk(cfg.num_experts_per_tok, -1)
+            wts = torch.softmax(top, -1)
+            i = cfg.intermediate_size
+            f = torch.zeros(b, cfg.hidden_size)
+            for r in range(b):
+                for j in range(cfg.num_experts_per_tok):
+                    hid = l["w1"][int(ids[r, j])].float() @ x[r]
+                    f[r] += wts[r, j] * (l["w2"][int(ids[r, j])].float() @ (torch.nn.functional.silu(hid[i:]) * hid[:i]))
+        else:
+            gu = rd(x @ l["w_gu"].float().t())
+            i = gu.shape[-1] // 2
+            act = torch.nn.functional.silu(gu[:, :i]) if cfg.activation == "silu" else torch.nn.functional.gelu(gu[:, :i], approximate="tanh")
+            f = rd(act * gu[:, i:]) @ l["w_d"].float().t()
+        f = rd(f)
+        if cfg.post_norms:
+            f = rd(_norm(f, l["post_ffn"], cfg.rms_eps, cfg.gemma_norm))
+        res = rd(res + f)
+    logits = rd(rd(_norm(res, eng.final_norm, cfg.rms_eps, cfg.gemma_norm)) @ eng.lm_head.float().t())
+    if cfg.final_logit_softcap:
+        logits = torch.tanh(logits / cfg.final_logit_softcap) * cfg.final_logit_softcap
+    return logits
+
+
+@pytest.mark.parametrize("preset", ["mixtral_8x7b", "qwen3_8b", "qwen3_30b_a3b", "gemma2_9b", "plain"])
+def test_engine_matches_plain_pytorch(preset):
+    cfg = (TransformerConfig() if preset == "plain" else getattr(TransformerConfig, preset)()).tiny()
+    page_size, lens = 4, [9, 1, 15]                                   # longer than the tiny sliding window (6)
+    per = [(n + page_size - 1) // page_size for n in lens]
+    g = torch.Generator().manual_seed(11)
+    ids = torch.randperm(sum(per) + 2, generator=g)[: sum(per)].int()
+    indptr = torch.tensor([0] + list(torch.tensor(per).cumsum(0)), dtype=torch.int32)
+    last = torch.tensor([(n - 1) % page_size + 1 for n in lens], dtype=torch.int32)
+    eng = TransformerDecodeEngine(cfg, max_batch=4, max_pages=sum(per) + 2, page_size=page_size, device="cpu", dtype=torch.bfloat16, seed=5)
+    history = []
+    for l in eng.layers:
+        for name in ("k_cache", "v_cache"):
+            l[name].copy_((torch.randn(l[name].shape, generator=g) * 0.5).to(torch.bfloat16))
+        per_req = []
+        for r, n in enumerate(lens):
+            pages = ids[int(indptr[r]): int(indptr[r + 1])].long()
+            per_req.append(tuple(l[name][pages].reshape(-1, cfg.num_kv_heads, cfg.head_dim)[: n - 1].clone() for name in ("k_cache", "v_cache")))
+        history.append(per_req)
+    eng.plan(indptr, ids, last)
+    eng.tokens.copy_(torch.randint(0, cfg.vocab_size, (3,), generator=g))
+    ref = _reference_step(eng, eng.tokens.clone(), history)
+    nxt = eng.step()
+    got = eng.logits.float()
+    cos = torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0)
+    assert cos > 0.998, float(cos)
+    torch.testing.assert_close(got, ref, atol=0.08 * float(ref.abs().max()), rtol=0.05)
+    assert nxt.shape == (3,)
+
+
+def test_presets_and_layer_pattern():
+    g2 = TransformerConfig.gemma2_9b()
+    assert g2.head_dim == 256 and [g2.is_sliding(i) for i in range(4)] == [True, False, True, False] and abs(g2.softmax_scale - 1 / 16) < 1e-9
+    assert not TransformerConfig.mixtral_8x7b().is_sliding(0) and TransformerConfig.qwen3_30b_a3b().num_experts == 128
+    t = g2.tiny()
+    assert t.sliding_window == 6 and t.embed_scale == math.sqrt(t.hidden_size) and t.name.endswith("-tiny")
