@@ -232,3 +232,22 @@ def test_model_engines_on_cuda_match_their_cpu_runs(family):
         logits[dev] = eng.logits.float().cpu()
     cos = torch.nn.functional.cosine_similarity(logits["cpu"].flatten(), logits["cuda"].flatten(), dim=0)
     assert cos > 0.995, float(cos)
+
+
+@pytest.mark.parametrize("family", ["mamba2", "gdn"])
+def test_recurrent_engines_on_cuda_match_their_cpu_runs(family):
+    from flashinfer_b200.models import GDNConfig, GDNDecodeEngine, Mamba2Config, Mamba2DecodeEngine
+
+    slots = torch.tensor([3, 0, 5], dtype=torch.int32)
+    g = torch.Generator().manual_seed(0)
+    toks = [torch.randint(0, 200, (3,), generator=g) for _ in range(4)]
+    logits = {}
+    for dev in ("cpu", "cuda"):
+        eng = (Mamba2DecodeEngine(Mamba2Config.tiny(), 6, dev, torch.bfloat16, seed=1) if family == "mamba2"
+               else GDNDecodeEngine(GDNConfig.tiny(), 6, dev, torch.bfloat16, seed=1))
+        eng.plan(slots)
+        for t in toks:
+            eng.tokens.copy_(t)
+            eng.step()
+        logits[dev] = eng.logits.float().cpu()
+    assert torch.nn.functional.cosine_similarity(logits["cpu"].flatten(), logits["cuda"].flatten(), dim=0) > 0.995
