@@ -19,6 +19,7 @@ import torch
 
 from .. import activation, norm, page, rope
 from ..decode import BatchDecodeWithPagedKVCacheWrapper
+from ..prefill import BatchPrefillWithPagedKVCacheWrapper
 from ..fused_moe.core import RoutingMethodType, moe_forward, route
 from ..gemm.dense import linear
 
@@ -131,6 +132,9 @@ class TransformerDecodeEngine:
         ws = lambda: torch.empty(32 << 20, dtype=torch.uint8, device=self.device)  # noqa: E731
         self.attn_global = BatchDecodeWithPagedKVCacheWrapper(ws(), "NHD")
         self.attn_sliding = BatchDecodeWithPagedKVCacheWrapper(ws(), "NHD") if cfg.sliding_window else None
+        self.prefill_global = BatchPrefillWithPagedKVCacheWrapper(ws(), "NHD")
+        self.prefill_sliding = BatchPrefillWithPagedKVCacheWrapper(ws(), "NHD") if cfg.sliding_window else None
+        self._mode = "decode"
         self.logits: Optional[torch.Tensor] = None
 
     def _norm(self, x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
@@ -156,19 +160,23 @@ class TransformerDecodeEngine:
         self.next_tokens = torch.zeros(b, dtype=torch.int64, device=self.device)
 
     def _attention(self, li: int, l: dict, x: torch.Tensor) -> torch.Tensor:
-        cfg, b = self.cfg, self.batch
+        """``x [rows, hidden]``: one row per request in decode, all prompt tokens in prefill (``self._mode``)."""
+        cfg, n = self.cfg, x.shape[0]
         hq, hkv, d = cfg.num_qo_heads, cfg.num_kv_heads, cfg.head_dim
-        qkv = linear(x, l["wqkv"]).view(b, hq + 2 * hkv, d)
+        qkv = linear(x, l["wqkv"]).view(n, hq + 2 * hkv, d)
         q, k, v = qkv[:, :hq].contiguous(), qkv[:, hq:hq + hkv].contiguous(), qkv[:, hq + hkv:].contiguous()
         if cfg.qk_norm:
-            q = self._norm(q.view(b * hq, d), l["q_norm"]).view(b, hq, d)
-            k = self._norm(k.view(b * hkv, d), l["k_norm"]).view(b, hkv, d)
+            q = self._norm(q.view(n * hq, d), l["q_norm"]).view(n, hq, d)
+            k = self._norm(k.view(n * hkv, d), l["k_norm"]).view(n, hkv, d)
         q, k = rope.apply_rope_pos_ids(q, k, self.positions, rope_theta=cfg.rope_theta)
         page.append_paged_kv_cache(k, v, self.batch_indices, self.positions, (l["k_cache"], l["v_cache"]), self.kv_indices, self.kv_indptr,
                                    self.kv_last, "NHD")
-        wrapper = self.attn_sliding if cfg.is_sliding(li) else self.attn_global
+        if self._mode == "prefill":
+            wrapper = self.prefill_sliding if cfg.is_sliding(li) else self.prefill_global
+        else:
+            wrapper = self.attn_sliding if cfg.is_sliding(li) else self.attn_global
         o = wrapper.run(q, (l["k_cache"], l["v_cache"]))
-        return linear(o.reshape(b, hq * d), l["wo"])
+        return linear(o.reshape(n, hq * d), l["wo"])
 
     def _ffn(self, l: dict, x: torch.Tensor) -> torch.Tensor:
         cfg = self.cfg
@@ -179,9 +187,10 @@ class TransformerDecodeEngine:
         act = activation.silu_and_mul if cfg.activation == "silu" else activation.gelu_tanh_and_mul
         return linear(act(linear(x, l["w_gu"])), l["w_d"])
 
-    def step(self) -> torch.Tensor:
+    def _forward(self, tokens: torch.Tensor) -> torch.Tensor:
+        """Hidden states after the last layer for ``tokens`` (rows laid out as the current plan says)."""
         cfg = self.cfg
-        res = self.embed[self.tokens]
+        res = self.embed[tokens]
         if cfg.embed_scale != 1.0:
             res = (res.float() * cfg.embed_scale).to(self.dtype)
         for li, l in enumerate(self.layers):
@@ -193,9 +202,44 @@ class TransformerDecodeEngine:
             if cfg.post_norms:
                 f = self._norm(f, l["post_ffn"])
             res = res + f
-        logits = linear(self._norm(res, self.final_norm), self.lm_head)
+        return res
+
+    def _head(self, hidden: torch.Tensor) -> torch.Tensor:
+        cfg = self.cfg
+        logits = linear(self._norm(hidden, self.final_norm), self.lm_head)
         if cfg.final_logit_softcap:
             logits = (torch.tanh(logits.float() / cfg.final_logit_softcap) * cfg.final_logit_softcap).to(logits.dtype)
-        self.logits = logits
-        torch.argmax(logits, dim=-1, out=self.next_tokens)
+        return logits
+
+    def step(self) -> torch.Tensor:
+        self._mode = "decode"
+        self.logits = self._head(self._forward(self.tokens))
+        torch.argmax(self.logits, dim=-1, out=self.next_tokens)
         return self.next_tokens
+
+    # ------------------------------------------------------------------ prompt processing
+    def prefill(self, tokens: torch.Tensor, qo_indptr: torch.Tensor, kv_indptr: torch.Tensor, kv_indices: torch.Tensor,
+                kv_last_page_len: torch.Tensor) -> torch.Tensor:
+        """Append the packed prompt ``tokens`` (``qo_indptr [B + 1]`` splits them per request) to the paged cache described by ``kv_*``
+        (lengths INCLUDE these tokens; earlier cache contents are the prefix) and run causal attention over prefix + prompt.  Returns the
+        greedy next token of every request; ``self.logits`` holds the logits of each request's last prompt token."""
+        cfg = self.cfg
+        self._mode = "prefill"
+        b = kv_last_page_len.numel()
+        self.kv_indptr = kv_indptr.to(self.device, torch.int32)
+        self.kv_indices = kv_indices.to(self.device, torch.int32)
+        self.kv_last = kv_last_page_len.to(self.device, torch.int32)
+        seq_lens = page.get_seq_lens(self.kv_indptr, self.kv_last, self.page_size).int()
+        qo = qo_indptr.to(self.device, torch.int32)
+        self.batch_indices, self.positions = page.get_batch_indices_positions(qo, seq_lens, int(tokens.numel()))
+        common = dict(causal=True, q_data_type=self.dtype, sm_scale=cfg.softmax_scale, logits_soft_cap=cfg.attn_logit_softcap or None)
+        self.prefill_global.plan(qo_indptr, kv_indptr, kv_indices, kv_last_page_len, cfg.num_qo_heads, cfg.num_kv_heads, cfg.head_dim,
+                                 self.page_size, **common)
+        if self.prefill_sliding is not None:
+            self.prefill_sliding.plan(qo_indptr, kv_indptr, kv_indices, kv_last_page_len, cfg.num_qo_heads, cfg.num_kv_heads, cfg.head_dim,
+                                      self.page_size, window_left=cfg.sliding_window - 1, **common)
+        hidden = self._forward(tokens.to(self.device))
+        last = (qo[1:] - 1).long()
+        self.logits = self._head(hidden[last])
+        self._mode = "decode"
+        return torch.argmax(self.logits, dim=-1)

@@ -114,3 +114,128 @@ def test_presets_and_layer_pattern():
     assert not TransformerConfig.mixtral_8x7b().is_sliding(0) and TransformerConfig.qwen3_30b_a3b().num_experts == 128
     t = g2.tiny()
     assert t.sliding_window == 6 and t.embed_scale == math.sqrt(t.hidden_size) and t.name.endswith("-tiny")
+
+
+def _full_forward_logits(eng, seq):
+    """Plain causal forward of a whole token sequence (no cache): logits of the LAST position.  Reuses _reference_step token by
+    token with an explicit per-layer K / V history (keys stored after RoPE, like the cache)."""
+    cfg = eng.cfg
+    hist = [[(torch.zeros(0, cfg.num_kv_heads, cfg.head_dim), torch.zeros(0, cfg.num_kv_heads, cfg.head_dim))] for _ in eng.layers]
+    logits = None
+    for pos, tok in enumerate(seq):
+        # run one step and capture the k / v this step appends, by replaying the projection of the reference
+        logits = _reference_step(eng, torch.tensor([tok]), hist)
+        dt = eng.dtype
+        rd = lambda t: t.to(dt).float()  # noqa: E731
+        res = rd(eng.embed[torch.tensor([tok])].float() * cfg.embed_scale)
+        new_hist = []
+        for li, l in enumerate(eng.layers):
+            x = rd(_norm(res, l["ln1"], cfg.rms_eps, cfg.gemma_norm))
+            hq, hkv, d = cfg.num_qo_heads, cfg.num_kv_heads, cfg.head_dim
+            qkv = rd(x @ l["wqkv"].float().t()).view(1, hq + 2 * hkv, d)
+            k, v = qkv[:, hq:hq + hkv], qkv[:, hq + hkv:]
+            if cfg.qk_norm:
+                k = rd(_norm(k, l["k_norm"], cfg.rms_eps, cfg.gemma_norm))
+            kr = rd(_rope_neox(k[0], torch.full((hkv,), pos), cfg.rope_theta))
+            k_old, v_old = hist[li][0]
+            new_hist.append([(torch.cat([k_old, kr[None]]), torch.cat([v_old, v[0][None]]))])
+            # advance the residual exactly like _reference_step does (recompute this layer)
+            single = _LayerOnly(eng, li)
+            res = single(res, hist[li][0], pos)
+        hist = new_hist
+    return logits
+
+
+class _LayerOnly:
+    """One layer of the plain model on one token (used to advance the residual while collecting K / V history)."""
+
+    def __init__(self, eng, li):
+        self.eng, self.li = eng, li
+
+    def __call__(self, res, kv_hist, pos):
+        eng, cfg, l = self.eng, self.eng.cfg, self.eng.layers[self.li]
+        sub = type("E", (), {})()
+        sub.cfg, sub.dtype, sub.embed, sub.final_norm, sub.lm_head = cfg, eng.dtype, eng.embed, eng.final_norm, eng.lm_head
+        sub.layers = [l]
+        # run the single layer through the same reference code path: feed the residual as the "embedding" of a fake token
+        rd = lambda t: t.to(eng.dtype).float()  # noqa: E731
+        hq, hkv, d = cfg.num_qo_heads, cfg.num_kv_heads, cfg.head_dim
+        x = rd(_norm(res, l["ln1"], cfg.rms_eps, cfg.gemma_norm))
+        qkv = rd(x @ l["wqkv"].float().t()).view(1, hq + 2 * hkv, d)
+        q, k, v = qkv[:, :hq], qkv[:, hq:hq + hkv], qkv[:, hq + hkv:]
+        if cfg.qk_norm:
+            q, k = rd(_norm(q, l["q_norm"], cfg.rms_eps, cfg.gemma_norm)), rd(_norm(k, l["k_norm"], cfg.rms_eps, cfg.gemma_norm))
+        qr = rd(_rope_neox(q[0], torch.full((hq,), pos), cfg.rope_theta))
+        kr = rd(_rope_neox(k[0], torch.full((hkv,), pos), cfg.rope_theta))
+        keys, vals = torch.cat([kv_hist[0], kr[None]]), torch.cat([kv_hist[1], v[0][None]])
+        if cfg.is_sliding(self.li):
+            keys, vals = keys[-cfg.sliding_window:], vals[-cfg.sliding_window:]
+        keys, vals = keys.repeat_interleave(hq // hkv, 1), vals.repeat_interleave(hq // hkv, 1)
+        lg = torch.einsum("hd,nhd->hn", qr, keys) * cfg.softmax_scale
+        if cfg.attn_logit_softcap:
+            lg = cfg.attn_logit_softcap * torch.tanh(lg / cfg.attn_logit_softcap)
+        a = rd(rd(torch.einsum("hn,nhd->hd", torch.softmax(lg, -1), vals)).reshape(1, -1) @ l["wo"].float().t())
+        if cfg.post_norms:
+            a = rd(_norm(a, l["post_attn"], cfg.rms_eps, cfg.gemma_norm))
+        res = rd(res + a)
+        x = rd(_norm(res, l["ln2"], cfg.rms_eps, cfg.gemma_norm))
+        if cfg.num_experts:
+            lgts = rd(x @ l["router"].float().t())
+            top, ids = lgts.topk(cfg.num_experts_per_tok, -1)
+            wts = torch.softmax(top, -1)
+            i = cfg.intermediate_size
+            f = torch.zeros(1, cfg.hidden_size)
+            for j in range(cfg.num_experts_per_tok):
+                hid = l["w1"][int(ids[0, j])].float() @ x[0]
+                f[0] += wts[0, j] * (l["w2"][int(ids[0, j])].float() @ (torch.nn.functional.silu(hid[i:]) * hid[:i]))
+        else:
+            gu = rd(x @ l["w_gu"].float().t())
+            i = gu.shape[-1] // 2
+            act = torch.nn.functional.silu(gu[:, :i]) if cfg.activation == "silu" else torch.nn.functional.gelu(gu[:, :i], approximate="tanh")
+            f = rd(act * gu[:, i:]) @ l["w_d"].float().t()
+        f = rd(f)
+        if cfg.post_norms:
+            f = rd(_norm(f, l["post_ffn"], cfg.rms_eps, cfg.gemma_norm))
+        return rd(res + f)
+
+
+@pytest.mark.parametrize("preset", ["plain", "gemma2_9b", "qwen3_30b_a3b"])
+def test_prefill_then_decode_equals_full_sequence_forward(preset):
+    """Serve a request end to end: prefill a prompt into the paged cache, then decode two tokens; the logits after every stage equal a
+    plain causal forward over the whole sequence so far (sliding-window layers included)."""
+    cfg = (TransformerConfig() if preset == "plain" else getattr(TransformerConfig, preset)()).tiny()
+    page_size = 4
+    prompts = [[5, 17, 3, 99, 42, 7, 250, 11, 8], [200, 1, 64]]
+    g = torch.Generator().manual_seed(3)
+    max_pages = 12
+    eng = TransformerDecodeEngine(cfg, max_batch=2, max_pages=max_pages, page_size=page_size, device="cpu", dtype=torch.bfloat16, seed=8)
+    free = torch.randperm(max_pages, generator=g).tolist()
+    pages = [[], []]
+
+    def tables(lens):
+        for r, n in enumerate(lens):
+            while len(pages[r]) * page_size < n:
+                pages[r].append(free.pop())
+        indptr = torch.tensor([0, len(pages[0]), len(pages[0]) + len(pages[1])], dtype=torch.int32)
+        indices = torch.tensor(pages[0] + pages[1], dtype=torch.int32)
+        last = torch.tensor([(n - 1) % page_size + 1 for n in lens], dtype=torch.int32)
+        return indptr, indices, last
+
+    lens = [len(p) for p in prompts]
+    qo = torch.tensor([0, lens[0], lens[0] + lens[1]], dtype=torch.int32)
+    nxt = eng.prefill(torch.tensor(prompts[0] + prompts[1]), qo, *tables(lens))
+    seqs = [list(p) for p in prompts]
+    for r in range(2):
+        want = _full_forward_logits(eng, seqs[r])[0]
+        got = eng.logits[r].float()
+        assert torch.nn.functional.cosine_similarity(got, want, dim=0) > 0.998, (preset, "prefill", r)
+    for _ in range(2):
+        for r in range(2):
+            seqs[r].append(int(nxt[r]))
+        lens = [len(s) for s in seqs]
+        eng.plan(*tables(lens))
+        eng.tokens.copy_(torch.tensor([s[-1] for s in seqs]))
+        nxt = eng.step().clone()
+        for r in range(2):
+            want = _full_forward_logits(eng, seqs[r])[0]
+            assert torch.nn.functional.cosine_similarity(eng.logits[r].float(), want, dim=0) > 0.998, (preset, "decode", r)
