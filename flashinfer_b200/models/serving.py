@@ -1,0 +1,85 @@
+"""Minimal serving loop around the op-by-op engines: a page allocator for the paged KV cache and greedy continuous generation
+(prefill the prompts of a batch, then decode step by step, growing every request's page list on demand).  It is the glue an inference
+server wraps around this library's ``plan`` / ``run`` calls, reduced to what a test or an example needs."""
+from __future__ import annotations
+
+from typing import Dict, List, Sequence, Tuple
+
+import torch
+
+
+class PagedKVAllocator:
+    """Free-list page pool with per-request page tables; emits the ``(kv_indptr, kv_indices, kv_last_page_len)`` triple the wrappers plan
+    with.  Pages are handed out in a shuffled order (nothing may depend on contiguity)."""
+
+    def __init__(self, num_pages: int, page_size: int, seed: int = 0) -> None:
+        self.page_size = page_size
+        g = torch.Generator().manual_seed(seed)
+        self._free: List[int] = torch.randperm(num_pages, generator=g).tolist()
+        self._tables: Dict[int, List[int]] = {}
+        self._lens: Dict[int, int] = {}
+
+    @property
+    def free_pages(self) -> int:
+        return len(self._free)
+
+    def add_request(self, rid: int) -> None:
+        if rid in self._tables:
+            raise KeyError(f"request {rid} already exists")
+        self._tables[rid], self._lens[rid] = [], 0
+
+    def grow(self, rid: int, new_tokens: int) -> None:
+        """Reserve room for ``new_tokens`` more tokens of request ``rid`` (raises MemoryError when the pool is exhausted)."""
+        want = self._lens[rid] + new_tokens
+        need = -(-want // self.page_size) - len(self._tables[rid])
+        if need > len(self._free):
+            raise MemoryError(f"KV pool exhausted: request {rid} needs {need} pages, {len(self._free)} free")
+        for _ in range(need):
+            self._tables[rid].append(self._free.pop())
+        self._lens[rid] = want
+
+    def release(self, rid: int) -> None:
+        self._free.extend(self._tables.pop(rid))
+        self._lens.pop(rid)
+
+    def length(self, rid: int) -> int:
+        return self._lens[rid]
+
+    def tables(self, rids: Sequence[int]) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        counts = [len(self._tables[r]) for r in rids]
+        indptr = torch.tensor([0] + list(torch.tensor(counts).cumsum(0).tolist()) if counts else [0], dtype=torch.int32)
+        indices = torch.tensor([p for r in rids for p in self._tables[r]], dtype=torch.int32)
+        last = torch.tensor([(self._lens[r] - 1) % self.page_size + 1 if self._lens[r] else 0 for r in rids], dtype=torch.int32)
+        return indptr, indices, last
+
+
+def generate(engine, prompts: Sequence[Sequence[int]], max_new_tokens: int, allocator: PagedKVAllocator = None, eos_token: int = -1) -> List[List[int]]:
+    """Greedy generation with a :class:`~flashinfer_b200.models.transformer.TransformerDecodeEngine`: one batched prefill of all prompts,
+    then batched decode steps; a request that emits ``eos_token`` leaves the batch and returns its pages.  Returns the generated tokens
+    (without the prompts)."""
+    alloc = allocator or PagedKVAllocator(engine.layers[0]["k_cache"].shape[0], engine.page_size)
+    rids = list(range(len(prompts)))
+    for r, p in zip(rids, prompts):
+        alloc.add_request(r)
+        alloc.grow(r, len(p))
+    qo = torch.tensor([0] + list(torch.tensor([len(p) for p in prompts]).cumsum(0).tolist()), dtype=torch.int32)
+    flat = torch.tensor([t for p in prompts for t in p], dtype=torch.int64)
+    nxt = engine.prefill(flat, qo, *alloc.tables(rids)).tolist()
+    out: List[List[int]] = [[] for _ in prompts]
+    active = list(rids)
+    for _ in range(max_new_tokens):
+        emitted = dict(zip(active, nxt))
+        for r, t in emitted.items():
+            out[r].append(int(t))
+        active = [r for r in active if emitted[r] != eos_token]
+        for r in list(emitted):
+            if emitted[r] == eos_token:
+                alloc.release(r)
+        if not active or len(out[active[0]]) >= max_new_tokens:
+            break
+        for r in active:
+            alloc.grow(r, 1)
+        engine.plan(*alloc.tables(active))
+        engine.tokens.copy_(torch.tensor([emitted[r] for r in active], dtype=torch.int64))
+        nxt = engine.step().tolist()
+    return out

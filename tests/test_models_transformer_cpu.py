@@ -239,3 +239,29 @@ def test_prefill_then_decode_equals_full_sequence_forward(preset):
         for r in range(2):
             want = _full_forward_logits(eng, seqs[r])[0]
             assert torch.nn.functional.cosine_similarity(eng.logits[r].float(), want, dim=0) > 0.998, (preset, "decode", r)
+
+
+def test_generation_loop_and_page_allocator():
+    """models.serving: batched prefill + greedy decode with on-demand page growth gives, per request, the same tokens as serving the
+    request alone; pages return to the pool."""
+    from flashinfer_b200.models.serving import PagedKVAllocator, generate
+
+    cfg = TransformerConfig.qwen3_8b().tiny()
+    prompts = [[3, 14, 15, 92, 65, 35, 89], [79, 32], [38, 46, 26, 43, 38]]
+    eng = TransformerDecodeEngine(cfg, max_batch=3, max_pages=24, page_size=4, device="cpu", dtype=torch.bfloat16, seed=4)
+    alloc = PagedKVAllocator(24, 4, seed=1)
+    batched = generate(eng, prompts, 5, alloc)
+    assert [len(o) for o in batched] == [5, 5, 5] and alloc.free_pages == 24 - sum(-(-(len(p) + 4) // 4) for p in prompts)
+    for i, p in enumerate(prompts):
+        solo = TransformerDecodeEngine(cfg, max_batch=1, max_pages=24, page_size=4, device="cpu", dtype=torch.bfloat16, seed=4)
+        assert generate(solo, [p], 5)[0] == batched[i]                       # batching and page placement do not change the result
+    a = PagedKVAllocator(4, 4)
+    a.add_request(0)
+    a.grow(0, 9)
+    assert a.free_pages == 1 and a.tables([0])[2].tolist() == [1] and a.length(0) == 9
+    with pytest.raises(MemoryError):
+        a.grow(0, 8)
+    a.release(0)
+    assert a.free_pages == 4
+    with pytest.raises(KeyError):
+        a.add_request(1) or a.add_request(1)
