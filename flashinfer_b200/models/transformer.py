@@ -96,9 +96,18 @@ class TransformerDecodeEngine:
     """Random-init decoder: batched single-token decode over a paged KV cache (``plan`` / ``step`` like the other engines)."""
 
     def __init__(self, cfg: TransformerConfig, max_batch: int, max_pages: int, page_size: int = 16, device: str = "cuda",
-                 dtype: torch.dtype = torch.bfloat16, seed: int = 0) -> None:
+                 dtype: torch.dtype = torch.bfloat16, seed: int = 0, tp_group=None) -> None:
+        """``tp_group``: tensor / expert parallelism over a ``torch.distributed`` group - attention heads, MLP columns and whole experts
+        are sharded over its ranks (weights are drawn for the full model from ``seed`` and sliced, so every world size computes the same
+        function); the two partial sums per layer are all-reduced (NCCL over NVLink on CUDA, gloo on CPU)."""
         self.cfg, self.page_size, self.max_batch = cfg, page_size, max_batch
         self.device, self.dtype = torch.device(device), dtype
+        self.tp_group = tp_group
+        self.tp_size = torch.distributed.get_world_size(tp_group) if tp_group is not None else 1
+        self.tp_rank = torch.distributed.get_rank(tp_group) if tp_group is not None else 0
+        tp, rk = self.tp_size, self.tp_rank
+        if cfg.num_qo_heads % tp or cfg.num_kv_heads % tp or (cfg.num_experts or tp) % tp or cfg.intermediate_size % tp:
+            raise ValueError(f"heads ({cfg.num_qo_heads} / {cfg.num_kv_heads}), experts and the MLP width must be divisible by the TP size {tp}")
         g = torch.Generator(device="cpu").manual_seed(seed)
 
         def w(rows: int, cols: int) -> torch.Tensor:
@@ -109,25 +118,40 @@ class TransformerDecodeEngine:
             return (base if cfg.gemma_norm else 1.0 + base).to(dtype).to(self.device)
 
         h, d, hq, hkv = cfg.hidden_size, cfg.head_dim, cfg.num_qo_heads, cfg.num_kv_heads
+        self.hq, self.hkv = hq // tp, hkv // tp                      # local head counts
         self.embed = (torch.randn(cfg.vocab_size, h, generator=g) * 0.5).to(dtype).to(self.device)
         self.lm_head = w(cfg.vocab_size, h)
         self.final_norm = norm_w(h)
         self.layers: List[dict] = []
+
+        def rows(t: torch.Tensor, blocks: int) -> torch.Tensor:
+            """Rank slice of a row-stacked weight made of ``blocks`` equal blocks (each block is sharded on its own)."""
+            parts = t.view(blocks, -1, t.shape[-1])
+            n = parts.shape[1] // tp
+            return parts[:, rk * n:(rk + 1) * n].reshape(-1, t.shape[-1]).contiguous()
+
         for _ in range(cfg.num_layers):
-            l = {"ln1": norm_w(h), "ln2": norm_w(h), "wqkv": w((hq + 2 * hkv) * d, h), "wo": w(h, hq * d),
-                 "k_cache": torch.zeros(max_pages, page_size, hkv, d, dtype=dtype, device=self.device),
-                 "v_cache": torch.zeros(max_pages, page_size, hkv, d, dtype=dtype, device=self.device)}
+            wq, wk, wv = w(hq * d, h), w(hkv * d, h), w(hkv * d, h)
+            wo = w(h, hq * d)
+            l = {"ln1": norm_w(h), "ln2": norm_w(h), "wqkv": torch.cat([rows(wq, 1), rows(wk, 1), rows(wv, 1)]).contiguous(),
+                 "wo": wo[:, rk * self.hq * d:(rk + 1) * self.hq * d].contiguous(),
+                 "k_cache": torch.zeros(max_pages, page_size, self.hkv, d, dtype=dtype, device=self.device),
+                 "v_cache": torch.zeros(max_pages, page_size, self.hkv, d, dtype=dtype, device=self.device)}
             if cfg.qk_norm:
                 l.update(q_norm=norm_w(d), k_norm=norm_w(d))
             if cfg.post_norms:
                 l.update(post_attn=norm_w(h), post_ffn=norm_w(h))
             if cfg.num_experts:
                 e, i = cfg.num_experts, cfg.intermediate_size
+                el = e // tp                                           # expert parallel: whole experts per rank
+                w1 = (torch.randn(e, 2 * i, h, generator=g) / h ** 0.5).to(dtype)                                    # rows = [up | gate]
+                w2 = (torch.randn(e, h, i, generator=g) / i ** 0.5).to(dtype)
                 l.update(router=(torch.randn(e, h, generator=g) / h ** 0.5).to(dtype).to(self.device),
-                         w1=(torch.randn(e, 2 * i, h, generator=g) / h ** 0.5).to(dtype).to(self.device),           # rows = [up | gate]
-                         w2=(torch.randn(e, h, i, generator=g) / i ** 0.5).to(dtype).to(self.device))
+                         w1=w1[rk * el:(rk + 1) * el].contiguous().to(self.device), w2=w2[rk * el:(rk + 1) * el].contiguous().to(self.device))
             else:
-                l.update(w_gu=w(2 * cfg.intermediate_size, h), w_d=w(h, cfg.intermediate_size))                      # rows = [gate | up]
+                w_gu, w_d = w(2 * cfg.intermediate_size, h), w(h, cfg.intermediate_size)                             # rows = [gate | up]
+                il = cfg.intermediate_size // tp
+                l.update(w_gu=rows(w_gu, 2), w_d=w_d[:, rk * il:(rk + 1) * il].contiguous())
             self.layers.append(l)
         ws = lambda: torch.empty(32 << 20, dtype=torch.uint8, device=self.device)  # noqa: E731
         self.attn_global = BatchDecodeWithPagedKVCacheWrapper(ws(), "NHD")
@@ -152,9 +176,9 @@ class TransformerDecodeEngine:
         self.positions = (page.get_seq_lens(self.kv_indptr, self.kv_last, self.page_size).int() - 1).contiguous()
         self.batch_indices = torch.arange(b, device=self.device, dtype=torch.int32)
         common = dict(q_data_type=self.dtype, sm_scale=cfg.softmax_scale, logits_soft_cap=cfg.attn_logit_softcap or None)
-        self.attn_global.plan(kv_indptr, kv_indices, kv_last_page_len, cfg.num_qo_heads, cfg.num_kv_heads, cfg.head_dim, self.page_size, **common)
+        self.attn_global.plan(kv_indptr, kv_indices, kv_last_page_len, self.hq, self.hkv, cfg.head_dim, self.page_size, **common)
         if self.attn_sliding is not None:                       # a window of W tokens = the query plus W - 1 tokens to its left
-            self.attn_sliding.plan(kv_indptr, kv_indices, kv_last_page_len, cfg.num_qo_heads, cfg.num_kv_heads, cfg.head_dim, self.page_size,
+            self.attn_sliding.plan(kv_indptr, kv_indices, kv_last_page_len, self.hq, self.hkv, cfg.head_dim, self.page_size,
                                    window_left=cfg.sliding_window - 1, **common)
         self.tokens = torch.zeros(b, dtype=torch.int64, device=self.device)
         self.next_tokens = torch.zeros(b, dtype=torch.int64, device=self.device)
@@ -162,7 +186,7 @@ class TransformerDecodeEngine:
     def _attention(self, li: int, l: dict, x: torch.Tensor) -> torch.Tensor:
         """``x [rows, hidden]``: one row per request in decode, all prompt tokens in prefill (``self._mode``)."""
         cfg, n = self.cfg, x.shape[0]
-        hq, hkv, d = cfg.num_qo_heads, cfg.num_kv_heads, cfg.head_dim
+        hq, hkv, d = self.hq, self.hkv, cfg.head_dim
         qkv = linear(x, l["wqkv"]).view(n, hq + 2 * hkv, d)
         q, k, v = qkv[:, :hq].contiguous(), qkv[:, hq:hq + hkv].contiguous(), qkv[:, hq + hkv:].contiguous()
         if cfg.qk_norm:
@@ -176,16 +200,25 @@ class TransformerDecodeEngine:
         else:
             wrapper = self.attn_sliding if cfg.is_sliding(li) else self.attn_global
         o = wrapper.run(q, (l["k_cache"], l["v_cache"]))
-        return linear(o.reshape(n, hq * d), l["wo"])
+        return self._all_reduce(linear(o.reshape(n, hq * d), l["wo"]))
 
     def _ffn(self, l: dict, x: torch.Tensor) -> torch.Tensor:
         cfg = self.cfg
         if cfg.num_experts:
             logits = linear(x, l["router"])
             ids, wts = route(logits, None, cfg.num_experts_per_tok, int(RoutingMethodType.Renormalize))
-            return moe_forward(x, ids, wts, l["w1"], l["w2"], 0, cfg.num_experts)
+            local = cfg.num_experts // self.tp_size
+            return self._all_reduce(moe_forward(x, ids, wts, l["w1"], l["w2"], self.tp_rank * local, cfg.num_experts))
         act = activation.silu_and_mul if cfg.activation == "silu" else activation.gelu_tanh_and_mul
-        return linear(act(linear(x, l["w_gu"])), l["w_d"])
+        return self._all_reduce(linear(act(linear(x, l["w_gu"])), l["w_d"]))
+
+    def _all_reduce(self, partial: torch.Tensor) -> torch.Tensor:
+        """Sum of the ranks' partial results (fp32 on the wire so that the result does not depend on the reduction order)."""
+        if self.tp_size == 1:
+            return partial
+        buf = partial.float()
+        torch.distributed.all_reduce(buf, group=self.tp_group)
+        return buf.to(partial.dtype)
 
     def _forward(self, tokens: torch.Tensor) -> torch.Tensor:
         """Hidden states after the last layer for ``tokens`` (rows laid out as the current plan says)."""
@@ -233,10 +266,10 @@ class TransformerDecodeEngine:
         qo = qo_indptr.to(self.device, torch.int32)
         self.batch_indices, self.positions = page.get_batch_indices_positions(qo, seq_lens, int(tokens.numel()))
         common = dict(causal=True, q_data_type=self.dtype, sm_scale=cfg.softmax_scale, logits_soft_cap=cfg.attn_logit_softcap or None)
-        self.prefill_global.plan(qo_indptr, kv_indptr, kv_indices, kv_last_page_len, cfg.num_qo_heads, cfg.num_kv_heads, cfg.head_dim,
+        self.prefill_global.plan(qo_indptr, kv_indptr, kv_indices, kv_last_page_len, self.hq, self.hkv, cfg.head_dim,
                                  self.page_size, **common)
         if self.prefill_sliding is not None:
-            self.prefill_sliding.plan(qo_indptr, kv_indptr, kv_indices, kv_last_page_len, cfg.num_qo_heads, cfg.num_kv_heads, cfg.head_dim,
+            self.prefill_sliding.plan(qo_indptr, kv_indptr, kv_indices, kv_last_page_len, self.hq, self.hkv, cfg.head_dim,
                                       self.page_size, window_left=cfg.sliding_window - 1, **common)
         hidden = self._forward(tokens.to(self.device))
         last = (qo[1:] - 1).long()
