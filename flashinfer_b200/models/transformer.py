@@ -22,6 +22,7 @@ from ..decode import BatchDecodeWithPagedKVCacheWrapper
 from ..prefill import BatchPrefillWithPagedKVCacheWrapper
 from ..fused_moe.core import RoutingMethodType, moe_forward, route
 from ..gemm.dense import linear
+from ..parallel import all_reduce_fp32, shard_cols, shard_rows
 
 
 @dataclass
@@ -124,17 +125,13 @@ class TransformerDecodeEngine:
         self.final_norm = norm_w(h)
         self.layers: List[dict] = []
 
-        def rows(t: torch.Tensor, blocks: int) -> torch.Tensor:
-            """Rank slice of a row-stacked weight made of ``blocks`` equal blocks (each block is sharded on its own)."""
-            parts = t.view(blocks, -1, t.shape[-1])
-            n = parts.shape[1] // tp
-            return parts[:, rk * n:(rk + 1) * n].reshape(-1, t.shape[-1]).contiguous()
+        rows = lambda t, blocks: shard_rows(t, rk, tp, blocks)  # noqa: E731
 
         for _ in range(cfg.num_layers):
             wq, wk, wv = w(hq * d, h), w(hkv * d, h), w(hkv * d, h)
             wo = w(h, hq * d)
             l = {"ln1": norm_w(h), "ln2": norm_w(h), "wqkv": torch.cat([rows(wq, 1), rows(wk, 1), rows(wv, 1)]).contiguous(),
-                 "wo": wo[:, rk * self.hq * d:(rk + 1) * self.hq * d].contiguous(),
+                 "wo": shard_cols(wo, rk, tp),
                  "k_cache": torch.zeros(max_pages, page_size, self.hkv, d, dtype=dtype, device=self.device),
                  "v_cache": torch.zeros(max_pages, page_size, self.hkv, d, dtype=dtype, device=self.device)}
             if cfg.qk_norm:
@@ -150,8 +147,7 @@ class TransformerDecodeEngine:
                          w1=w1[rk * el:(rk + 1) * el].contiguous().to(self.device), w2=w2[rk * el:(rk + 1) * el].contiguous().to(self.device))
             else:
                 w_gu, w_d = w(2 * cfg.intermediate_size, h), w(h, cfg.intermediate_size)                             # rows = [gate | up]
-                il = cfg.intermediate_size // tp
-                l.update(w_gu=rows(w_gu, 2), w_d=w_d[:, rk * il:(rk + 1) * il].contiguous())
+                l.update(w_gu=rows(w_gu, 2), w_d=shard_cols(w_d, rk, tp))
             self.layers.append(l)
         ws = lambda: torch.empty(32 << 20, dtype=torch.uint8, device=self.device)  # noqa: E731
         self.attn_global = BatchDecodeWithPagedKVCacheWrapper(ws(), "NHD")
@@ -213,12 +209,7 @@ class TransformerDecodeEngine:
         return self._all_reduce(linear(act(linear(x, l["w_gu"])), l["w_d"]))
 
     def _all_reduce(self, partial: torch.Tensor) -> torch.Tensor:
-        """Sum of the ranks' partial results (fp32 on the wire so that the result does not depend on the reduction order)."""
-        if self.tp_size == 1:
-            return partial
-        buf = partial.float()
-        torch.distributed.all_reduce(buf, group=self.tp_group)
-        return buf.to(partial.dtype)
+        return all_reduce_fp32(partial, self.tp_group)
 
     def _forward(self, tokens: torch.Tensor) -> torch.Tensor:
         """Hidden states after the last layer for ``tokens`` (rows laid out as the current plan says)."""

@@ -76,3 +76,17 @@ def test_sharding_requirements():
             TransformerDecodeEngine(cfg, 1, 4, 4, "cpu", torch.bfloat16, tp_group=_G())
     finally:
         dist.get_world_size, dist.get_rank = orig_ws, orig_rk
+
+
+def test_parallel_helpers():
+    from flashinfer_b200 import parallel
+
+    w = torch.arange(24.0).view(6, 4)                                         # two stacked blocks of three rows
+    assert parallel.shard_rows(w, 1, 3, blocks=2)[:, 0].tolist() == [4.0, 16.0] and parallel.shard_rows(w, 0, 2)[:, 0].tolist() == [0.0, 4.0, 8.0]
+    assert torch.equal(torch.cat([parallel.shard_cols(w, r, 2) for r in range(2)], -1), w)
+    with pytest.raises(ValueError):
+        parallel.shard_rows(w, 0, 4)
+    with pytest.raises(ValueError):
+        parallel.shard_cols(w, 0, 3)
+    x = torch.randn(3, 5)
+    assert parallel.all_reduce_fp32(x, None) is x
