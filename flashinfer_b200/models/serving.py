@@ -38,6 +38,12 @@ class PagedKVAllocator:
             self._tables[rid].append(self._free.pop())
         self._lens[rid] = want
 
+    def truncate(self, rid: int, length: int) -> None:
+        """Forget the tokens beyond ``length`` (rejected speculative tokens); their pages stay reserved for the request."""
+        if length > self._lens[rid]:
+            raise ValueError("truncate cannot grow a request")
+        self._lens[rid] = length
+
     def release(self, rid: int) -> None:
         self._free.extend(self._tables.pop(rid))
         self._lens.pop(rid)
@@ -83,3 +89,70 @@ def generate(engine, prompts: Sequence[Sequence[int]], max_new_tokens: int, allo
         engine.tokens.copy_(torch.tensor([emitted[r] for r in active], dtype=torch.int64))
         nxt = engine.step().tolist()
     return out
+
+
+def _probs(logits: torch.Tensor, temperature: float) -> torch.Tensor:
+    """Sampling distribution of a logits row: softmax at ``temperature``, the one-hot argmax at temperature 0 (greedy)."""
+    if temperature <= 0:
+        return torch.nn.functional.one_hot(logits.argmax(-1), logits.shape[-1]).float()
+    return torch.softmax(logits.float() / temperature, -1)
+
+
+def speculative_generate(target, draft, prompts: Sequence[Sequence[int]], max_new_tokens: int, num_draft_tokens: int = 3,
+                         temperature: float = 0.0, generator=None) -> Tuple[List[List[int]], float]:
+    """Speculative decoding with two :class:`~flashinfer_b200.models.transformer.TransformerDecodeEngine` s (same vocabulary): per
+    round the draft proposes ``num_draft_tokens`` tokens with single-token decode steps, the target scores the pending token and all
+    proposals in ONE multi-token pass over its paged cache, and ``sampling.chain_speculative_sampling`` accepts a prefix and emits one
+    corrected / bonus token.  Rejected tokens are dropped from both caches by truncating the requests' lengths.  Returns the generated
+    tokens and the mean number of tokens emitted per round.  At ``temperature`` 0 the output equals greedy decoding of the target,
+    whatever the draft proposes."""
+    from ..sampling import chain_speculative_sampling
+
+    k, b = num_draft_tokens, len(prompts)
+    pools = {e: PagedKVAllocator(e.layers[0]["k_cache"].shape[0], e.page_size) for e in (target, draft)}
+    rids = list(range(b))
+    qo = torch.tensor([0] + list(torch.tensor([len(p) for p in prompts]).cumsum(0).tolist()), dtype=torch.int32)
+    flat = torch.tensor([t for p in prompts for t in p], dtype=torch.int64)
+    pending = None
+    for e in (draft, target):                                                 # both caches hold the prompts; the target picks the first token
+        for r, p in zip(rids, prompts):
+            pools[e].add_request(r)
+            pools[e].grow(r, len(p))
+        e.prefill(flat, qo, *pools[e].tables(rids))
+        pending = torch.multinomial(_probs(e.logits, temperature), 1, generator=generator)[:, 0]
+    out: List[List[int]] = [[int(t)] for t in pending]
+    rounds = emitted_total = 0
+    while min(len(o) for o in out) < max_new_tokens:
+        base = [pools[target].length(r) for r in rids]                        # tokens in the caches; ``pending`` is not among them yet
+        # ---- draft: k proposals (+ one more step that only writes the last proposal into the draft cache)
+        cur, d_ids, d_probs = pending.clone(), [], []
+        for i in range(k + 1):
+            for r in rids:
+                pools[draft].grow(r, 1)
+            draft.plan(*pools[draft].tables(rids))
+            draft.tokens.copy_(cur)
+            draft.step()
+            if i < k:
+                pr = _probs(draft.logits, temperature)
+                cur = torch.multinomial(pr, 1, generator=generator)[:, 0]
+                d_ids.append(cur.clone())
+                d_probs.append(pr)
+        d_ids, d_probs = torch.stack(d_ids, 1), torch.stack(d_probs, 1)       # [b, k], [b, k, vocab]
+        # ---- target: score [pending, d_1 .. d_k] in one pass
+        for r in rids:
+            pools[target].grow(r, k + 1)
+        seq = torch.cat([pending[:, None], d_ids], 1).reshape(-1)
+        target.prefill(seq, torch.arange(0, (b + 1) * (k + 1), k + 1, dtype=torch.int32), *pools[target].tables(rids), all_logits=True)
+        t_probs = _probs(target.logits, temperature).view(b, k + 1, -1)
+        tokens = chain_speculative_sampling(d_probs.float(), d_ids.int(), t_probs, generator=generator)[0]   # [b, k + 1], -1 padded
+        n_emit = (tokens >= 0).sum(1)
+        for i, r in enumerate(rids):
+            new = tokens[i, : int(n_emit[i])].tolist()
+            out[i].extend(int(t) for t in new)
+            keep = base[i] + int(n_emit[i])                                   # pending + the accepted proposals stay cached
+            pools[target].truncate(r, keep)
+            pools[draft].truncate(r, keep)
+        pending = torch.stack([tokens[i, int(n_emit[i]) - 1] for i in range(b)]).long()
+        rounds += 1
+        emitted_total += int(n_emit.sum())
+    return [o[:max_new_tokens] for o in out], emitted_total / max(rounds * b, 1)

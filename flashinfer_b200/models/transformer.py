@@ -243,10 +243,11 @@ class TransformerDecodeEngine:
 
     # ------------------------------------------------------------------ prompt processing
     def prefill(self, tokens: torch.Tensor, qo_indptr: torch.Tensor, kv_indptr: torch.Tensor, kv_indices: torch.Tensor,
-                kv_last_page_len: torch.Tensor) -> torch.Tensor:
+                kv_last_page_len: torch.Tensor, all_logits: bool = False) -> torch.Tensor:
         """Append the packed prompt ``tokens`` (``qo_indptr [B + 1]`` splits them per request) to the paged cache described by ``kv_*``
         (lengths INCLUDE these tokens; earlier cache contents are the prefix) and run causal attention over prefix + prompt.  Returns the
-        greedy next token of every request; ``self.logits`` holds the logits of each request's last prompt token."""
+        greedy next token of every request; ``self.logits`` holds the logits of each request's last prompt token (``all_logits``: of every
+        appended token - what speculative decoding verifies drafts against)."""
         cfg = self.cfg
         self._mode = "prefill"
         b = kv_last_page_len.numel()
@@ -264,6 +265,6 @@ class TransformerDecodeEngine:
                                       self.page_size, window_left=cfg.sliding_window - 1, **common)
         hidden = self._forward(tokens.to(self.device))
         last = (qo[1:] - 1).long()
-        self.logits = self._head(hidden[last])
+        self.logits = self._head(hidden if all_logits else hidden[last])      # all_logits: one row per appended token (verification of drafts)
         self._mode = "decode"
-        return torch.argmax(self.logits, dim=-1)
+        return torch.argmax(self.logits[last] if all_logits else self.logits, dim=-1)

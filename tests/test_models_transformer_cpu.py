@@ -265,3 +265,20 @@ def test_generation_loop_and_page_allocator():
     assert a.free_pages == 4
     with pytest.raises(KeyError):
         a.add_request(1) or a.add_request(1)
+
+
+@pytest.mark.parametrize("same_draft", [True, False])
+def test_speculative_decoding_reproduces_greedy_target(same_draft):
+    """models.serving.speculative_generate: at temperature 0 the accepted + corrected tokens are exactly the target's greedy tokens for
+    ANY draft model; with the target as its own draft every proposal is accepted (k + 1 tokens per round)."""
+    from flashinfer_b200.models.serving import generate, speculative_generate
+
+    cfg = TransformerConfig.qwen3_8b().tiny()
+    prompts = [[3, 14, 15, 92, 65], [35, 89, 79]]
+    mk = lambda seed: TransformerDecodeEngine(cfg, max_batch=2, max_pages=32, page_size=4, device="cpu", dtype=torch.bfloat16, seed=seed)  # noqa: E731
+    want = generate(mk(4), prompts, 9)
+    got, per_round = speculative_generate(mk(4), mk(4 if same_draft else 5), prompts, 9, num_draft_tokens=3, temperature=0.0)
+    assert got == want
+    assert per_round == 4.0 if same_draft else 1.0 <= per_round <= 4.0
+    sampled, rate = speculative_generate(mk(4), mk(5), prompts, 6, num_draft_tokens=2, temperature=0.8, generator=torch.Generator().manual_seed(0))
+    assert all(len(o) == 6 and all(0 <= t < cfg.vocab_size for t in o) for o in sampled) and 1.0 <= rate <= 3.0
