@@ -211,26 +211,33 @@ class TransformerDecodeEngine:
     def _all_reduce(self, partial: torch.Tensor) -> torch.Tensor:
         return all_reduce_fp32(partial, self.tp_group)
 
+    def _add_norm(self, delta: torch.Tensor, res: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+        """``res += delta`` and the RMSNorm of the new residual, in one kernel (in place on both; returns the normalised tensor)."""
+        (norm.gemma_fused_add_rmsnorm if self.cfg.gemma_norm else norm.fused_add_rmsnorm)(delta, res, weight, self.cfg.rms_eps)
+        return delta
+
     def _forward(self, tokens: torch.Tensor) -> torch.Tensor:
-        """Hidden states after the last layer for ``tokens`` (rows laid out as the current plan says)."""
+        """Final-norm-ed hidden states for ``tokens`` (rows laid out as the current plan says).  Every residual update is fused with the
+        RMSNorm that follows it (the next block's input norm, at the end the final norm)."""
         cfg = self.cfg
         res = self.embed[tokens]
         if cfg.embed_scale != 1.0:
             res = (res.float() * cfg.embed_scale).to(self.dtype)
+        x = self._norm(res, self.layers[0]["ln1"])
         for li, l in enumerate(self.layers):
-            a = self._attention(li, l, self._norm(res, l["ln1"]))
+            a = self._attention(li, l, x)
             if cfg.post_norms:
                 a = self._norm(a, l["post_attn"])
-            res = res + a
-            f = self._ffn(l, self._norm(res, l["ln2"]))
+            x = self._add_norm(a, res, l["ln2"])
+            f = self._ffn(l, x)
             if cfg.post_norms:
                 f = self._norm(f, l["post_ffn"])
-            res = res + f
-        return res
+            x = self._add_norm(f, res, self.layers[li + 1]["ln1"] if li + 1 < len(self.layers) else self.final_norm)
+        return x
 
     def _head(self, hidden: torch.Tensor) -> torch.Tensor:
         cfg = self.cfg
-        logits = linear(self._norm(hidden, self.final_norm), self.lm_head)
+        logits = linear(hidden, self.lm_head)                      # ``hidden`` already carries the final norm
         if cfg.final_logit_softcap:
             logits = (torch.tanh(logits.float() / cfg.final_logit_softcap) * cfg.final_logit_softcap).to(logits.dtype)
         return logits
