@@ -142,9 +142,28 @@ class DeepSeekDecodeEngine:
         self.tokens = torch.zeros(b, dtype=torch.int64, device=self.device)
         self.next_tokens = torch.zeros(b, dtype=torch.int64, device=self.device)
 
+    def prefill(self, tokens: torch.Tensor, qo_indptr: torch.Tensor, kv_indptr: torch.Tensor, kv_indices: torch.Tensor,
+                kv_last_page_len: torch.Tensor, all_logits: bool = False) -> torch.Tensor:
+        """Append the packed prompt ``tokens`` (split per request by ``qo_indptr``) to the latent cache described by ``kv_*`` (lengths
+        INCLUDE these tokens) and run causal absorbed MLA over prefix + prompt.  Returns the greedy next token per request; ``self.logits``:
+        logits of every request's last token (``all_logits``: of every appended token)."""
+        cfg = self.cfg
+        self.kv_indptr = kv_indptr.to(self.device, torch.int32)
+        self.kv_indices = kv_indices.to(self.device, torch.int32)
+        self.kv_last = kv_last_page_len.to(self.device, torch.int32)
+        seq_lens = page.get_seq_lens(self.kv_indptr, self.kv_last, self.page_size).int()
+        qo = qo_indptr.to(self.device, torch.int32)
+        self.batch_indices, self.positions = page.get_batch_indices_positions(qo, seq_lens, int(tokens.numel()))
+        self.attn.plan(qo_indptr.to("cpu", torch.int32), kv_indptr.to("cpu", torch.int32), kv_indices.to("cpu", torch.int32), seq_lens.to("cpu"),
+                       cfg.num_heads, cfg.kv_lora_rank, cfg.qk_rope_head_dim, self.page_size, True, cfg.softmax_scale, self.dtype, self.dtype)
+        hidden = self._forward(tokens.to(self.device))
+        last = (qo[1:] - 1).long()
+        self.logits = linear(hidden if all_logits else hidden[last], self.lm_head)
+        return torch.argmax(self.logits[last] if all_logits else self.logits, dim=-1)
+
     # ------------------------------------------------------------------ one decode step
     def _attention(self, l: dict, x: torch.Tensor) -> torch.Tensor:
-        cfg, b, hq = self.cfg, self.batch, self.cfg.num_heads
+        cfg, b, hq = self.cfg, x.shape[0], self.cfg.num_heads          # b = rows: requests in decode, prompt tokens in prefill
         if cfg.q_lora_rank:
             q = linear(norm.rmsnorm(linear(x, l["q_a"]), l["q_norm"], cfg.rms_eps), l["q_b"])
         else:
@@ -173,9 +192,10 @@ class DeepSeekDecodeEngine:
         shared = linear(activation.silu_and_mul(linear(x, l["shared_gu"])), l["shared_d"])
         return routed + shared
 
-    def step(self) -> torch.Tensor:
+    def _forward(self, tokens: torch.Tensor) -> torch.Tensor:
+        """Final-norm-ed hidden states (every residual update is fused with the RMSNorm that follows it)."""
         cfg = self.cfg
-        res = self.embed[self.tokens]                                   # residual stream [b, hidden]
+        res = self.embed[tokens]                                        # residual stream [rows, hidden]
         x = norm.rmsnorm(res, self.layers[0]["ln1"], cfg.rms_eps)
         for li, l in enumerate(self.layers):
             a = self._attention(l, x)
@@ -184,6 +204,9 @@ class DeepSeekDecodeEngine:
             nxt = self.layers[li + 1]["ln1"] if li + 1 < len(self.layers) else self.final_norm
             norm.fused_add_rmsnorm(f, res, nxt, cfg.rms_eps)            # res += f ; f <- rmsnorm(res) = next layer's input
             x = f
-        self.logits = linear(x, self.lm_head)
+        return x
+
+    def step(self) -> torch.Tensor:
+        self.logits = linear(self._forward(self.tokens), self.lm_head)
         torch.argmax(self.logits, dim=-1, out=self.next_tokens)
         return self.next_tokens

@@ -59,11 +59,18 @@ class PagedKVAllocator:
         return indptr, indices, last
 
 
+def _num_pages(engine) -> int:
+    """Pages of an engine's paged cache (GQA engines: ``k_cache``, the MLA engine: ``ckv_cache``)."""
+    layer = engine.layers[0]
+    return (layer["k_cache"] if "k_cache" in layer else layer["ckv_cache"]).shape[0]
+
+
 def generate(engine, prompts: Sequence[Sequence[int]], max_new_tokens: int, allocator: PagedKVAllocator = None, eos_token: int = -1) -> List[List[int]]:
-    """Greedy generation with a :class:`~flashinfer_b200.models.transformer.TransformerDecodeEngine`: one batched prefill of all prompts,
+    """Greedy generation with an engine that has ``prefill`` / ``plan`` / ``step`` over a paged cache
+    (:class:`~flashinfer_b200.models.transformer.TransformerDecodeEngine`, :class:`~flashinfer_b200.models.deepseek.DeepSeekDecodeEngine`): one batched prefill of all prompts,
     then batched decode steps; a request that emits ``eos_token`` leaves the batch and returns its pages.  Returns the generated tokens
     (without the prompts)."""
-    alloc = allocator or PagedKVAllocator(engine.layers[0]["k_cache"].shape[0], engine.page_size)
+    alloc = allocator or PagedKVAllocator(_num_pages(engine), engine.page_size)
     rids = list(range(len(prompts)))
     for r, p in zip(rids, prompts):
         alloc.add_request(r)
@@ -109,7 +116,7 @@ def speculative_generate(target, draft, prompts: Sequence[Sequence[int]], max_ne
     from ..sampling import chain_speculative_sampling
 
     k, b = num_draft_tokens, len(prompts)
-    pools = {e: PagedKVAllocator(e.layers[0]["k_cache"].shape[0], e.page_size) for e in (target, draft)}
+    pools = {e: PagedKVAllocator(_num_pages(e), e.page_size) for e in (target, draft)}
     rids = list(range(b))
     qo = torch.tensor([0] + list(torch.tensor([len(p) for p in prompts]).cumsum(0).tolist()), dtype=torch.int32)
     flat = torch.tensor([t for p in prompts for t in p], dtype=torch.int64)

@@ -133,3 +133,45 @@ def test_config_presets():
     assert v3.qk_head_dim == 192 and abs(v3.softmax_scale - 1 / math.sqrt(192)) < 1e-9 and v3.num_experts % v3.n_group == 0
     t = DeepSeekConfig.tiny()
     assert t.kv_lora_rank == 512 and t.qk_rope_head_dim == 64 and t.first_k_dense < t.num_layers
+
+
+def test_prefill_equals_token_by_token_decode():
+    """One causal multi-token pass over the latent cache gives the logits of feeding the same tokens one decode step at a time."""
+    cfg = DeepSeekConfig.tiny()
+    page_size, prompts = 8, [[5, 9, 2, 77, 41, 3, 8, 120, 6, 1], [300, 4, 18]]
+    pages = [[0, 3], [2]]
+    mk = lambda: DeepSeekDecodeEngine(cfg, max_batch=2, max_pages=5, page_size=page_size, device="cpu", dtype=torch.bfloat16, seed=9)  # noqa: E731
+
+    def tables(lens):
+        used = [pages[r][: -(-n // page_size)] for r, n in enumerate(lens)]
+        indptr = torch.tensor([0, len(used[0]), len(used[0]) + len(used[1])], dtype=torch.int32)
+        return indptr, torch.tensor(used[0] + used[1], dtype=torch.int32), torch.tensor([(n - 1) % page_size + 1 for n in lens], dtype=torch.int32)
+
+    a = mk()
+    lens = [len(p) for p in prompts]
+    a.prefill(torch.tensor(prompts[0] + prompts[1]), torch.tensor([0, lens[0], lens[0] + lens[1]], dtype=torch.int32), *tables(lens), all_logits=True)
+    all_rows = a.logits.float().clone()
+    b = mk()
+    for r, p in enumerate(prompts):                                  # request by request, token by token
+        for i, tok in enumerate(p):
+            cur = [0, 0]
+            cur[r] = i + 1
+            indptr, idx, last = tables([max(cur[0], 1), max(cur[1], 1)])
+            sel = slice(int(indptr[r]), int(indptr[r + 1]))
+            b.plan(torch.tensor([0, -(-(i + 1) // page_size)], dtype=torch.int32), idx[sel], last[r:r + 1])
+            b.tokens.copy_(torch.tensor([tok]))
+            b.step()
+            row = (0 if r == 0 else lens[0]) + i
+            cos = torch.nn.functional.cosine_similarity(b.logits[0].float(), all_rows[row], dim=0)
+            assert cos > 0.999, (r, i, float(cos))
+
+
+def test_generate_with_the_mla_engine():
+    from flashinfer_b200.models.serving import generate
+
+    cfg = DeepSeekConfig.tiny()
+    prompts = [[5, 9, 2, 77, 41], [300, 4]]
+    mk = lambda b: DeepSeekDecodeEngine(cfg, max_batch=b, max_pages=8, page_size=8, device="cpu", dtype=torch.bfloat16, seed=9)  # noqa: E731
+    batched = generate(mk(2), prompts, 4)
+    assert [len(o) for o in batched] == [4, 4]
+    assert generate(mk(1), [prompts[1]], 4)[0] == batched[1]             # batching does not change a request's tokens
