@@ -421,8 +421,9 @@ def _prepared(tag: str, tensors, fn):
     on first use - never per call (the quantised entry points used to de-quantise every expert weight in eager
     torch on every call).
 
-    An entry is only trusted while the tensors it was computed from (their view bases) are still alive: once they are freed
-    the allocator may hand the same address to different weights of the same shape, and the key alone would match them."""
+    An entry is only trusted while the STORAGE it was computed from is still alive (weak references to the storage objects, which
+    PyTorch keeps for as long as any tensor - parameter, ``.data`` alias, view - uses the memory): once it is freed the allocator may
+    hand the same address to different weights of the same shape, and the key alone would match them."""
     live = [t for t in tensors if isinstance(t, torch.Tensor)]
     key = (tag,) + tuple((t.data_ptr(), tuple(t.shape), tuple(t.stride()), str(t.dtype), t._version) for t in live)
     hit = _PREP_CACHE.get(key)
@@ -431,7 +432,7 @@ def _prepared(tag: str, tensors, fn):
     if len(_PREP_CACHE) > 256:
         _PREP_CACHE.clear()
     value = fn()
-    _PREP_CACHE[key] = ([weakref.ref(t._base if t._base is not None else t) for t in live], value)
+    _PREP_CACHE[key] = ([weakref.ref(t.untyped_storage()) for t in live], value)
     return value
 
 

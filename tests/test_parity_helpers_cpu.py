@@ -265,9 +265,10 @@ def test_moe_prepared_cache_is_tied_to_the_live_weight_tensors():
     def prep(t):
         return core._prepared("unit-test", [t], lambda: (calls.append(1), t.clone())[1])
 
-    base = torch.arange(64, dtype=torch.float32)
-    first = prep(base.view(8, 8))                      # temporary view: its base stays alive
-    assert prep(base.view(8, 8)) is first and len(calls) == 1
+    base = torch.nn.Parameter(torch.arange(64, dtype=torch.float32))
+    first = prep(base.view(8, 8))                      # temporary view: the storage stays alive
+    assert prep(base.view(8, 8)) is first and prep(base.data.view(8, 8)) is first and prep(base.detach().view(8, 8)) is first and len(calls) == 1
+    base = base.data
     base.add_(1)                                       # in-place update of the weights -> new version -> recomputed
     assert prep(base.view(8, 8)) is not first and len(calls) == 2
 
