@@ -59,8 +59,8 @@ def single_decode_with_kv_cache(
     """Decode attention for one request: q [Hq, D], k/v [kv_len, Hkv, D] (NHD) or [Hkv, kv_len, D] (HND)."""
     check_kv_layout(kv_layout)
     check_pos_encoding_mode(pos_encoding_mode)
-    if pos_encoding_mode != "NONE":
-        raise NotImplementedError("in-kernel RoPE/ALiBi for decode: apply flashinfer_b200.rope first")
+    if pos_encoding_mode == "ALIBI":
+        raise NotImplementedError("decode with ALiBi: use single_prefill_with_kv_cache (q_len 1) - the decode kernel has no bias pass")
     head_dim = q.shape[-1]
     if sm_scale is None:
         sm_scale = 1.0 / math.sqrt(head_dim)
@@ -70,6 +70,12 @@ def single_decode_with_kv_cache(
         sm_scale *= k_scale
     kn = k if kv_layout == "NHD" else k.transpose(0, 1)
     vn = v if kv_layout == "NHD" else v.transpose(0, 1)
+    if pos_encoding_mode == "ROPE_LLAMA":              # rotate q (the newest position) and k, then plain attention
+        from .attention.rope_on_the_fly import rope_params, rotate_rows
+
+        rs, rt = rope_params(rope_scale, rope_theta)
+        q = rotate_rows(q.unsqueeze(0), torch.tensor([kn.shape[0] - 1]), rs, rt)[0]
+        kn = rotate_rows(kn.contiguous(), torch.arange(kn.shape[0]), rs, rt)
     if not q.is_cuda:
         o, lse = reference.attention_ref(
             q.unsqueeze(0), kn, vn, False, sm_scale, logits_soft_cap or 0.0, window_left
@@ -185,8 +191,13 @@ class BatchDecodeWithPagedKVCacheWrapper:
         """Host-side planning.  ``qo_indptr`` (extension) allows q_len>1 per request
         (speculative decode / small append) as long as ``q_len * group <= 32``."""
         check_pos_encoding_mode(pos_encoding_mode)
-        if pos_encoding_mode != "NONE":
-            raise NotImplementedError("decode with in-kernel positional encoding; use flashinfer_b200.rope ops")
+        if pos_encoding_mode == "ALIBI":
+            raise NotImplementedError("decode with ALiBi: use the prefill wrappers (q_len 1) - the decode kernel has no bias pass")
+        self._rope = None                                   # ROPE_LLAMA: (scale, theta); served by attention/rope_on_the_fly.py
+        if pos_encoding_mode == "ROPE_LLAMA":
+            from .attention.rope_on_the_fly import rope_params
+
+            self._rope = rope_params(rope_scale, rope_theta)
         if num_qo_heads % num_kv_heads != 0:
             raise ValueError("num_qo_heads must be a multiple of num_kv_heads")
         batch_size = last_page_len.numel()
@@ -299,6 +310,12 @@ class BatchDecodeWithPagedKVCacheWrapper:
         if not self._planned:
             raise RuntimeError("plan() must be called before run()")
         k_cache, v_cache = unpack_paged_kv_cache(paged_kv_cache, self._kv_layout)
+        if getattr(self, "_rope", None) is not None:     # ROPE_LLAMA: rotate q and the batch's key pages, then the plain kernel
+            from .attention.rope_on_the_fly import query_positions, rotate_rows, rotated_paged_keys
+
+            qo = self._qo_indptr_host if self._qo_indptr_host is not None else torch.arange(self._batch_size + 1, dtype=torch.int32)
+            q = rotate_rows(q, query_positions(qo, self._kv_lens_host), *self._rope)
+            k_cache = rotated_paged_keys(k_cache, self._kv_indices, self._kv_indptr_host, self._kv_layout, *self._rope)
         if k_cache.dtype == torch.uint8 or v_cache.dtype == torch.uint8:
             # NVFP4 KV cache (reference decode.py:1293): block scales come in ``kv_cache_sf`` in the cache layout, the global
             # scales in k_scale / v_scale.  Composed path: the cache is widened to the query dtype, then the tcgen05 kernel runs.

@@ -80,14 +80,19 @@ def single_prefill_with_kv_cache(
     or ``[Hkv, kv_len, D]`` (HND).  Returns ``o`` (and base-2 ``lse [qo_len, Hq]``)."""
     check_kv_layout(kv_layout)
     check_pos_encoding_mode(pos_encoding_mode)
-    if pos_encoding_mode not in ("NONE", "ALIBI"):
-        raise NotImplementedError("in-kernel RoPE: apply flashinfer_b200.rope first (ALiBi runs inside the kernel)")
     d = q.shape[-1]
     if sm_scale is None:
         sm_scale = 1.0 / math.sqrt(d)
     if kv_layout == "HND":
         k, v = k.transpose(0, 1), v.transpose(0, 1)
     qo_len, kv_len = q.shape[0], k.shape[0]
+    if pos_encoding_mode == "ROPE_LLAMA":              # rotate q (the last qo_len positions) and k, then plain attention
+        from .attention.rope_on_the_fly import rope_params, rotate_rows
+
+        rs, rt = rope_params(rope_scale, rope_theta)
+        q = rotate_rows(q, torch.arange(kv_len - qo_len, kv_len), rs, rt)
+        k = rotate_rows(k.contiguous(), torch.arange(kv_len), rs, rt)
+        pos_encoding_mode = "NONE"
     mask = None
     if packed_custom_mask is not None and custom_mask is None:
         mask = _unpack_bits(packed_custom_mask, qo_len * kv_len).view(qo_len, kv_len)
@@ -323,16 +328,20 @@ class _BatchPrefillBase:
         if o_data_type is not None and _canon_dtype(o_data_type) != _canon_dtype(q_data_type):
             raise NotImplementedError(f"plan: o_data_type {o_data_type} != q_data_type {q_data_type} (convert the output after run())")
 
-    def _set_pos_encoding(self, pos_encoding_mode: str, num_qo_heads: int) -> None:
-        """ALiBi is a logits transform of the softmax pass (slopes per head); RoPE has to be applied by flashinfer_b200.rope."""
+    def _set_pos_encoding(self, pos_encoding_mode: str, num_qo_heads: int, rope_scale=None, rope_theta=None) -> None:
+        """ALiBi is a logits transform of the softmax pass (slopes per head); ROPE_LLAMA rotates q and the touched keys before the
+        kernel runs in its plain mode (attention/rope_on_the_fly.py)."""
         check_pos_encoding_mode(pos_encoding_mode)
-        if pos_encoding_mode not in ("NONE", "ALIBI"):
-            raise NotImplementedError("in-kernel RoPE: apply flashinfer_b200.rope to q / k first (ALiBi runs inside the kernel)")
+        self._rope = None                                   # ROPE_LLAMA: (scale, theta); served by attention/rope_on_the_fly.py
         self._alibi = None
         if pos_encoding_mode == "ALIBI":
             from .utils import get_alibi_slopes
 
             self._alibi = get_alibi_slopes(num_qo_heads, self.device).float().contiguous()
+        if pos_encoding_mode == "ROPE_LLAMA":
+            from .attention.rope_on_the_fly import rope_params
+
+            self._rope = rope_params(rope_scale, rope_theta)
 
     def _launch_generic(self, q, k, v, out, lse, sm_scale, window_left, paged, kv_indices, page_args, enable_pdl, k_scale, v_scale):
         """Catch-all CUDA-core kernel: other head dims, fp8 KV, custom masks."""
@@ -402,7 +411,7 @@ class BatchPrefillWithRaggedKVCacheWrapper(_BatchPrefillBase):
              q_data_type="float16", kv_data_type=None, o_data_type=None, non_blocking=True, prefix_len_ptr=None,
              token_pos_in_items_ptr=None, token_pos_in_items_len=0, max_item_len_ptr=None, fixed_split_size=None,
              disable_split_kv=False) -> None:
-        self._set_pos_encoding(pos_encoding_mode, num_qo_heads)
+        self._set_pos_encoding(pos_encoding_mode, num_qo_heads, rope_scale, rope_theta)
         self._check_plan_extras(q_data_type, o_data_type, prefix_len_ptr, token_pos_in_items_ptr, max_item_len_ptr)
         kv_host = kv_indptr.to("cpu", torch.int32)
         self._kv_start_host = kv_host[:-1].contiguous()
@@ -423,6 +432,11 @@ class BatchPrefillWithRaggedKVCacheWrapper(_BatchPrefillBase):
         self._variant_args = args
         if self._kv_layout == "HND":
             k, v = k.transpose(0, 1), v.transpose(0, 1)
+        if self._rope is not None:                       # ROPE_LLAMA: rotate q and k, the kernel below runs in its plain mode
+            from .attention.rope_on_the_fly import query_positions, ragged_key_positions, rotate_rows
+
+            q = rotate_rows(q, query_positions(self._qo_indptr_host, self._kv_lens_host), *self._rope)
+            k = rotate_rows(k.contiguous(), ragged_key_positions(self._kv_indptr_ragged_host), *self._rope)
         sm_scale = self._sm_scale * (q_scale or 1.0) * (k_scale or 1.0)
         window_left = self._window_left if window_left is None else window_left
         if out is None:
@@ -471,7 +485,7 @@ class BatchPrefillWithPagedKVCacheWrapper(_BatchPrefillBase):
              o_data_type=None, non_blocking=True, prefix_len_ptr=None, token_pos_in_items_ptr=None,
              token_pos_in_items_len=0, max_item_len_ptr=None, seq_lens=None, seq_lens_q=None, block_tables=None,
              max_token_per_sequence=None, max_sequence_kv=None, fixed_split_size=None, disable_split_kv=False) -> None:
-        self._set_pos_encoding(pos_encoding_mode, num_qo_heads)
+        self._set_pos_encoding(pos_encoding_mode, num_qo_heads, rope_scale, rope_theta)
         self._check_plan_extras(q_data_type, o_data_type, prefix_len_ptr, token_pos_in_items_ptr, max_item_len_ptr)
         self._page_size = page_size
         indptr_host = _host_i32(paged_kv_indptr)
@@ -498,6 +512,11 @@ class BatchPrefillWithPagedKVCacheWrapper(_BatchPrefillBase):
         user_return_lse = return_lse
         return_lse = return_lse or sinks is not None
         k_cache, v_cache = unpack_paged_kv_cache(paged_kv_cache, self._kv_layout)
+        if self._rope is not None:                       # ROPE_LLAMA: rotate q and the batch's key pages (scratch copy of the cache)
+            from .attention.rope_on_the_fly import query_positions, rotate_rows, rotated_paged_keys
+
+            q = rotate_rows(q, query_positions(self._qo_indptr_host, self._kv_lens_host), *self._rope)
+            k_cache = rotated_paged_keys(k_cache, self._kv_indices, self._kv_indptr_host, self._kv_layout, *self._rope)
         sm_scale = self._sm_scale * (q_scale or 1.0) * (k_scale or 1.0)
         window_left = self._window_left if window_left is None else window_left
         if out is None:

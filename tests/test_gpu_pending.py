@@ -251,3 +251,17 @@ def test_recurrent_engines_on_cuda_match_their_cpu_runs(family):
             eng.step()
         logits[dev] = eng.logits.float().cpu()
     assert torch.nn.functional.cosine_similarity(logits["cpu"].flatten(), logits["cuda"].flatten(), dim=0) > 0.995
+
+
+def test_rope_llama_mode_on_cuda():
+    """pos_encoding_mode="ROPE_LLAMA" (rotate, then the plain kernel) on the device against rotating q / k by hand."""
+    from flashinfer_b200.attention.rope_on_the_fly import rotate_rows
+
+    torch.manual_seed(0)
+    q, k, v = (torch.randn(n, h, 128, device="cuda", dtype=torch.bfloat16) for n, h in ((100, 8), (300, 2), (300, 2)))
+    got = fi.single_prefill_with_kv_cache(q, k, v, causal=True, pos_encoding_mode="ROPE_LLAMA")
+    want = fi.single_prefill_with_kv_cache(rotate_rows(q, torch.arange(200, 300), 1.0, 1e4), rotate_rows(k, torch.arange(300), 1.0, 1e4), v, causal=True)
+    torch.testing.assert_close(got.float(), want.float(), atol=2e-2, rtol=2e-2)
+    got = fi.single_decode_with_kv_cache(q[0], k, v, pos_encoding_mode="ROPE_LLAMA")
+    want = fi.single_decode_with_kv_cache(rotate_rows(q[:1], torch.tensor([299]), 1.0, 1e4)[0], rotate_rows(k, torch.arange(300), 1.0, 1e4), v)
+    torch.testing.assert_close(got.float(), want.float(), atol=2e-2, rtol=2e-2)
