@@ -59,8 +59,14 @@ def single_decode_with_kv_cache(
     """Decode attention for one request: q [Hq, D], k/v [kv_len, Hkv, D] (NHD) or [Hkv, kv_len, D] (HND)."""
     check_kv_layout(kv_layout)
     check_pos_encoding_mode(pos_encoding_mode)
-    if pos_encoding_mode == "ALIBI":
-        raise NotImplementedError("decode with ALiBi: use single_prefill_with_kv_cache (q_len 1) - the decode kernel has no bias pass")
+    if pos_encoding_mode == "ALIBI":                    # the bias pass lives in the prefill kernel: one query row there
+        from .prefill import single_prefill_with_kv_cache
+
+        scale = (sm_scale if sm_scale is not None else 1.0 / math.sqrt(q.shape[-1])) * (q_scale or 1.0) * (k_scale or 1.0)
+        res = single_prefill_with_kv_cache(q.unsqueeze(0), k, v, causal=False, kv_layout=kv_layout, pos_encoding_mode="ALIBI", sm_scale=scale,
+                                           window_left=window_left, logits_soft_cap=logits_soft_cap, return_lse=True)
+        o = res[0][0] if v_scale is None else (res[0][0].float() * v_scale).to(q.dtype)
+        return (o, res[1][0]) if return_lse else o
     head_dim = q.shape[-1]
     if sm_scale is None:
         sm_scale = 1.0 / math.sqrt(head_dim)
@@ -191,8 +197,18 @@ class BatchDecodeWithPagedKVCacheWrapper:
         """Host-side planning.  ``qo_indptr`` (extension) allows q_len>1 per request
         (speculative decode / small append) as long as ``q_len * group <= 32``."""
         check_pos_encoding_mode(pos_encoding_mode)
-        if pos_encoding_mode == "ALIBI":
-            raise NotImplementedError("decode with ALiBi: use the prefill wrappers (q_len 1) - the decode kernel has no bias pass")
+        self._alibi_delegate = None
+        if pos_encoding_mode == "ALIBI":                # the bias pass lives in the prefill kernel: delegate with one query row per request
+            from .prefill import BatchPrefillWithPagedKVCacheWrapper
+
+            bsz = last_page_len.numel()
+            self._alibi_delegate = BatchPrefillWithPagedKVCacheWrapper(self._float_workspace_buffer, self._kv_layout)
+            self._alibi_delegate.plan(qo_indptr if qo_indptr is not None else torch.arange(bsz + 1, dtype=torch.int32), indptr, indices, last_page_len,
+                                      num_qo_heads, num_kv_heads, head_dim, page_size, causal=qo_indptr is not None, pos_encoding_mode="ALIBI",
+                                      sm_scale=sm_scale, window_left=window_left, logits_soft_cap=logits_soft_cap,
+                                      q_data_type=data_type if data_type is not None else q_data_type, kv_data_type=kv_data_type)
+            self._planned = True
+            return
         self._rope = None                                   # ROPE_LLAMA: (scale, theta); served by attention/rope_on_the_fly.py
         if pos_encoding_mode == "ROPE_LLAMA":
             from .attention.rope_on_the_fly import rope_params
@@ -309,6 +325,9 @@ class BatchDecodeWithPagedKVCacheWrapper:
         kernel's tail."""
         if not self._planned:
             raise RuntimeError("plan() must be called before run()")
+        if getattr(self, "_alibi_delegate", None) is not None:
+            return self._alibi_delegate.run(q, paged_kv_cache, q_scale=q_scale, k_scale=k_scale, v_scale=v_scale, out=out, lse=lse,
+                                            return_lse=return_lse, enable_pdl=enable_pdl, window_left=window_left, sinks=sinks)
         k_cache, v_cache = unpack_paged_kv_cache(paged_kv_cache, self._kv_layout)
         if getattr(self, "_rope", None) is not None:     # ROPE_LLAMA: rotate q and the batch's key pages, then the plain kernel
             from .attention.rope_on_the_fly import query_positions, rotate_rows, rotated_paged_keys

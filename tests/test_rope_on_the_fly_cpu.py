@@ -27,8 +27,6 @@ def test_single_request_forms():
     want = fi.single_decode_with_kv_cache(_rot(qd[None], torch.tensor([11]))[0], _rot(k, torch.arange(12)), v)
     got = fi.single_decode_with_kv_cache(qd, k, v, pos_encoding_mode="ROPE_LLAMA")
     torch.testing.assert_close(got.float(), want.float(), atol=2e-2, rtol=2e-2)
-    with pytest.raises(NotImplementedError):
-        fi.single_decode_with_kv_cache(qd, k, v, pos_encoding_mode="ALIBI")
 
 
 @pytest.mark.parametrize("layout", ["NHD", "HND"])
@@ -80,3 +78,24 @@ def test_batched_wrappers(layout):
         want = wr.run(q_rot, kr_rot, vr)
         wr.plan(qo, kvp, hq, hkv, d, causal=True, q_data_type=torch.bfloat16, pos_encoding_mode="ROPE_LLAMA")
         torch.testing.assert_close(wr.run(q, kr, vr).float(), want.float(), atol=2e-2, rtol=2e-2)
+
+
+def test_decode_alibi_is_served_by_the_prefill_kernel():
+    from flashinfer_b200.utils import get_alibi_slopes
+
+    g = torch.Generator().manual_seed(2)
+    hq, hkv, d, n = 4, 2, 64, 11
+    q, k, v = torch.randn(hq, d, generator=g).to(torch.bfloat16), torch.randn(n, hkv, d, generator=g).to(torch.bfloat16), torch.randn(n, hkv, d, generator=g).to(torch.bfloat16)
+    slopes = get_alibi_slopes(hq).float()
+    lg = torch.einsum("hd,nhd->hn", q.float(), k.float().repeat_interleave(2, 1)) / 8.0 + slopes[:, None] * (torch.arange(n) - (n - 1))[None, :]
+    want = torch.einsum("hn,nhd->hd", torch.softmax(lg, -1), v.float().repeat_interleave(2, 1))
+    got = fi.single_decode_with_kv_cache(q, k, v, pos_encoding_mode="ALIBI")
+    torch.testing.assert_close(got.float(), want, atol=2e-2, rtol=2e-2)
+    page_size = 4
+    kc = torch.zeros(3, page_size, hkv, d, dtype=torch.bfloat16)
+    vc = torch.zeros_like(kc)
+    kc.view(-1, hkv, d)[:n], vc.view(-1, hkv, d)[:n] = k, v
+    w = fi.BatchDecodeWithPagedKVCacheWrapper(torch.empty(1 << 20, dtype=torch.uint8), "NHD")
+    w.plan(torch.tensor([0, 3], dtype=torch.int32), torch.arange(3, dtype=torch.int32), torch.tensor([3], dtype=torch.int32), hq, hkv, d, page_size,
+           pos_encoding_mode="ALIBI", q_data_type=torch.bfloat16)
+    torch.testing.assert_close(w.run(q[None], (kc, vc))[0].float(), want, atol=2e-2, rtol=2e-2)
