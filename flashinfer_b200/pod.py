@@ -104,11 +104,11 @@ class PODWithPagedKVCacheWrapper:
              pos_encoding_mode="NONE", window_left=-1, q_data_type="float16", kv_data_type=None, data_type=None,
              sm_scale=None, rope_scale=None, rope_theta=None, non_blocking=True) -> None:
         check_pos_encoding_mode(pos_encoding_mode)
-        if pos_encoding_mode != "NONE":
-            raise NotImplementedError("POD: in-kernel positional encodings are not implemented (apply flashinfer_b200.rope first)")
+        # like in the reference, the decode side uses the positional encoding recorded here (run(pos_encoding_mode_d=) is not consulted)
         self._dargs = (indptr, indices, last_page_len, num_qo_heads, num_kv_heads, head_dim, page_size)
         self._dkw = dict(window_left=window_left, q_data_type=data_type or q_data_type, kv_data_type=kv_data_type,
-                         sm_scale=sm_scale)
+                         sm_scale=sm_scale, pos_encoding_mode=pos_encoding_mode, rope_scale=rope_scale, rope_theta=rope_theta)
+        self._plain = pos_encoding_mode == "NONE"
         self._hq, self._hkv, self._d, self._ps = num_qo_heads, num_kv_heads, head_dim, page_size
         n_pages = (indptr[1:] - indptr[:-1]).to("cpu")
         self._decode_tokens = int(n_pages.sum()) * page_size
@@ -122,10 +122,13 @@ class PODWithPagedKVCacheWrapper:
             kv_layout_d="NHD", pos_encoding_mode_d="NONE", sm_scale_d=None, window_left_d=-1, rope_scale_d=None,
             rope_theta_d=None, q_scale=None, k_scale=None, v_scale=None, return_lse_d=False,
             use_fp16_qk_reduction=False, enable_pdl=None):
-        if custom_mask_p is not None or packed_custom_mask_p is not None or custom_mask_d is not None or packed_custom_mask_d is not None:
-            raise NotImplementedError("POD with custom masks")
-        if pos_encoding_mode_p != "NONE" or pos_encoding_mode_d != "NONE":
-            raise NotImplementedError("POD: in-kernel positional encodings are not implemented (apply flashinfer_b200.rope first)")
+        # custom_mask_d / packed_custom_mask_d / pos_encoding_mode_d are accepted and not consulted, as in the reference (one query
+        # token per request sees its whole history; the decode positional encoding is the one given to plan()).  A custom prefill
+        # mask or a positional encoding on either side runs the two phases as two launches (side stream) - the single-launch
+        # fusion covers the plain kernels
+        check_pos_encoding_mode(pos_encoding_mode_p)
+        masked = custom_mask_p is not None or packed_custom_mask_p is not None
+        plain = self._plain and pos_encoding_mode_p == "NONE" and not masked
         # kv_layout_d is not consulted: like in the reference, the decode cache has the layout the wrapper was constructed with
         # run()-time decode parameters override what plan() recorded (the decode side is planned lazily, below); causal_d is
         # immaterial for one query token per request
@@ -147,9 +150,11 @@ class PODWithPagedKVCacheWrapper:
             self._decode_planned_for = sd
         self._prefill._kv_layout = kv_layout_p
         self._prefill.plan(torch.tensor([0, qo_len], dtype=torch.int32), torch.tensor([0, kv_len], dtype=torch.int32),
-                           self._hq, self._hkv, self._d, causal=causal_p, sm_scale=sm_scale_p,
-                           window_left=window_left_p, q_data_type=q_p.dtype)
-        if _fusable(q_p, q_d, paged_kv_cache_d, self._hq, self._hkv, self._d) and k_p.dtype == q_p.dtype \
+                           self._hq, self._hkv, self._d, causal=causal_p and not masked, sm_scale=sm_scale_p,
+                           window_left=window_left_p, q_data_type=q_p.dtype, custom_mask=custom_mask_p,
+                           packed_custom_mask=packed_custom_mask_p, pos_encoding_mode=pos_encoding_mode_p,
+                           rope_scale=rope_scale_p, rope_theta=rope_theta_p)
+        if plain and _fusable(q_p, q_d, paged_kv_cache_d, self._hq, self._hkv, self._d) and k_p.dtype == q_p.dtype \
                 and q_scale is None and k_scale is None and v_scale is None and self._fused:
             res_p, res_d = _run_fused(lambda: self._prefill.run(q_p, k_p, v_p, return_lse=return_lse_p),
                                       lambda: self._decode.run(q_d, paged_kv_cache_d, return_lse=return_lse_d))
@@ -196,8 +201,7 @@ class BatchPODWithPagedKVCacheWrapper:
         prefill plan bakes the mask in, so it can also be given here; run() re-plans the prefill side when it asks for the other
         mask.  Left at None in both places, the reference's default (non-causal) applies."""
         check_pos_encoding_mode(pos_encoding_mode)
-        if pos_encoding_mode != "NONE":
-            raise NotImplementedError("POD: in-kernel positional encodings are not implemented (apply flashinfer_b200.rope first)")
+        self._plain = pos_encoding_mode == "NONE"
         self._causal_arg = causal_p
         causal_p = True if causal_p is None else bool(causal_p)       # plan for the common case; run() corrects it if needed
         self._causal_planned = causal_p
@@ -212,13 +216,16 @@ class BatchPODWithPagedKVCacheWrapper:
         self._prefill._cta_budget, self._decode._cta_budget = sp or None, sd or None
         dt = data_type or q_data_type
         self._pplan = ((qo_indptr_p, kv_indptr_p, kv_indices_p, last_page_len_p, num_qo_heads, num_kv_heads, head_dim, page_size),
-                       dict(sm_scale=sm_scale, window_left=window_left, q_data_type=dt, kv_data_type=kv_data_type))
+                       dict(sm_scale=sm_scale, window_left=window_left, q_data_type=dt, kv_data_type=kv_data_type,
+                            pos_encoding_mode=pos_encoding_mode, rope_scale=rope_scale, rope_theta=rope_theta))
+        self._mask_planned = None
         self._prefill.plan(*self._pplan[0], causal=causal_p, **self._pplan[1])
         qo_d = qo_indptr_d.to("cpu", torch.int64)
         plain_decode = bool(((qo_d[1:] - qo_d[:-1]) == 1).all())
         self._decode.plan(kv_indptr_d, kv_indices_d, last_page_len_d, num_qo_heads, num_kv_heads, head_dim, page_size,
                           window_left=window_left, q_data_type=dt, kv_data_type=kv_data_type, sm_scale=sm_scale,
-                          qo_indptr=None if plain_decode else qo_indptr_d)
+                          qo_indptr=None if plain_decode else qo_indptr_d, pos_encoding_mode=pos_encoding_mode,
+                          rope_scale=rope_scale, rope_theta=rope_theta)
         self._sm_split = (sp, sd)
         self._hq, self._hkv, self._d, self._plain_decode = num_qo_heads, num_kv_heads, head_dim, plain_decode
 
@@ -227,14 +234,18 @@ class BatchPODWithPagedKVCacheWrapper:
     def run(self, q_p, paged_kv_cache_p, q_d, paged_kv_cache_d, custom_mask_p=None, packed_custom_mask_p=None,
             causal_p: Optional[bool] = None, q_scale=None, k_scale=None, v_scale=None, return_lse: bool = False,
             use_fp16_qk_reduction: bool = False, enable_pdl=None):
-        if custom_mask_p is not None or packed_custom_mask_p is not None:
-            raise NotImplementedError("POD with custom masks")
         want = bool(causal_p) if causal_p is not None else (bool(self._causal_arg) if self._causal_arg is not None else False)
-        if want != self._causal_planned:
+        mask = custom_mask_p if custom_mask_p is not None else packed_custom_mask_p
+        if mask is not None:                              # the prefill plan owns the mask (as in the prefill wrappers): re-plan with it
+            if self._mask_planned is not mask:
+                self._prefill.plan(*self._pplan[0], causal=False, custom_mask=custom_mask_p,
+                                   packed_custom_mask=None if custom_mask_p is not None else packed_custom_mask_p, **self._pplan[1])
+                self._mask_planned, self._causal_planned = mask, None
+        elif want != self._causal_planned:
             self._prefill.plan(*self._pplan[0], causal=want, **self._pplan[1])
-            self._causal_planned = want
+            self._causal_planned, self._mask_planned = want, None
         kp = paged_kv_cache_p[0] if isinstance(paged_kv_cache_p, (tuple, list)) else paged_kv_cache_p
-        if self._fused and self._plain_decode and _fusable(q_p, q_d, paged_kv_cache_d, self._hq, self._hkv, self._d) \
+        if self._fused and self._plain and mask is None and self._plain_decode and _fusable(q_p, q_d, paged_kv_cache_d, self._hq, self._hkv, self._d) \
                 and kp.dtype == q_p.dtype and q_scale is None and k_scale is None and v_scale is None:
             res_p, res_d = _run_fused(lambda: self._prefill.run(q_p, paged_kv_cache_p, return_lse=return_lse),
                                       lambda: self._decode.run(q_d, paged_kv_cache_d, return_lse=return_lse))

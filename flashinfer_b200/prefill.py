@@ -318,15 +318,27 @@ class _BatchPrefillBase:
         )
         return sinks is not None
 
-    @staticmethod
-    def _check_plan_extras(q_data_type, o_data_type, prefix_len_ptr, token_pos_in_items_ptr, max_item_len_ptr) -> None:
-        """Multi-item scoring masks and an output dtype different from the query's are not implemented: refuse them at plan() time
-        instead of computing plain attention in the query dtype."""
+    def _check_plan_extras(self, q_data_type, o_data_type, prefix_len_ptr, token_pos_in_items_ptr, max_item_len_ptr) -> None:
+        """Multi-item scoring masks are not implemented: refuse them at plan() time instead of computing plain attention.  An output
+        dtype different from the query's is a conversion of the kernel's output (``_cast_output``)."""
         from .utils import reject_unsupported
 
         reject_unsupported("plan", prefix_len_ptr=prefix_len_ptr, token_pos_in_items_ptr=token_pos_in_items_ptr, max_item_len_ptr=max_item_len_ptr)
+        self._o_cast = None
         if o_data_type is not None and _canon_dtype(o_data_type) != _canon_dtype(q_data_type):
-            raise NotImplementedError(f"plan: o_data_type {o_data_type} != q_data_type {q_data_type} (convert the output after run())")
+            self._o_cast = _canon_dtype(o_data_type)
+
+    def _cast_output(self, run, out):
+        """run() with ``o_data_type != q_data_type``: the kernel writes the query dtype; the result is converted (into ``out`` when the
+        caller passed a buffer of the planned output dtype)."""
+        cast, self._o_cast = self._o_cast, None
+        try:
+            res = run()
+        finally:
+            self._o_cast = cast
+        o = res[0] if isinstance(res, tuple) else res
+        o = out.copy_(o) if out is not None else o.to(cast)
+        return (o, *res[1:]) if isinstance(res, tuple) else o
 
     def _set_pos_encoding(self, pos_encoding_mode: str, num_qo_heads: int, rope_scale=None, rope_theta=None) -> None:
         """ALiBi is a logits transform of the softmax pass (slopes per head); ROPE_LLAMA rotates q and the touched keys before the
@@ -429,6 +441,9 @@ class BatchPrefillWithRaggedKVCacheWrapper(_BatchPrefillBase):
             enable_pdl=None, window_left=None):
         if not self._planned:
             raise RuntimeError("plan() must be called before run()")
+        if getattr(self, "_o_cast", None) is not None:
+            return self._cast_output(lambda: self.run(q, k, v, *args, q_scale=q_scale, k_scale=k_scale, v_scale=v_scale, lse=lse,
+                                                      return_lse=return_lse, enable_pdl=enable_pdl, window_left=window_left), out)
         self._variant_args = args
         if self._kv_layout == "HND":
             k, v = k.transpose(0, 1), v.transpose(0, 1)
@@ -508,6 +523,9 @@ class BatchPrefillWithPagedKVCacheWrapper(_BatchPrefillBase):
             return_lse=False, enable_pdl=None, window_left=None, sinks=None):
         if not self._planned:
             raise RuntimeError("plan() must be called before run()")
+        if getattr(self, "_o_cast", None) is not None:
+            return self._cast_output(lambda: self.run(q, paged_kv_cache, *args, q_scale=q_scale, k_scale=k_scale, v_scale=v_scale, lse=lse,
+                                                      return_lse=return_lse, enable_pdl=enable_pdl, window_left=window_left, sinks=sinks), out)
         self._variant_args = args
         user_return_lse = return_lse
         return_lse = return_lse or sinks is not None

@@ -211,8 +211,8 @@ def test_entry_points_refuse_arguments_they_do_not_implement():
     ind = torch.tensor([0, 2], dtype=torch.int32)
     with pytest.raises(NotImplementedError):
         w.plan(ind, ind, 4, 2, 64, q_data_type=torch.bfloat16, prefix_len_ptr=torch.zeros(1, dtype=torch.int32))
-    with pytest.raises(NotImplementedError):
-        w.plan(ind, ind, 4, 2, 64, q_data_type=torch.bfloat16, o_data_type=torch.float8_e4m3fn)
+    w.plan(ind, ind, 4, 2, 64, q_data_type=torch.bfloat16, o_data_type=torch.float8_e4m3fn)      # a conversion of the kernel's output
+    assert w.run(torch.randn(2, 4, 64).bfloat16(), torch.randn(2, 2, 64).bfloat16(), torch.randn(2, 2, 64).bfloat16()).dtype == torch.float8_e4m3fn
     w.plan(ind, ind, 4, 2, 64, q_data_type=torch.bfloat16, o_data_type="bfloat16")
     with pytest.raises(ValueError, match="NaN"):
         fi.sampling.top_k_sampling_from_probs(torch.tensor([[0.5, float("nan"), 0.5]]), 2, check_nan=True)

@@ -99,3 +99,81 @@ def test_decode_alibi_is_served_by_the_prefill_kernel():
     w.plan(torch.tensor([0, 3], dtype=torch.int32), torch.arange(3, dtype=torch.int32), torch.tensor([3], dtype=torch.int32), hq, hkv, d, page_size,
            pos_encoding_mode="ALIBI", q_data_type=torch.bfloat16)
     torch.testing.assert_close(w.run(q[None], (kc, vc))[0].float(), want, atol=2e-2, rtol=2e-2)
+
+
+def test_pod_wrappers_pass_masks_and_positional_encodings_through():
+    """POD with a custom prefill mask / ROPE_LLAMA equals the standalone prefill and decode calls with the same options."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(__file__))
+    from helpers import make_paged
+    from flashinfer_b200.pod import BatchPODWithPagedKVCacheWrapper, PODWithPagedKVCacheWrapper
+
+    torch.manual_seed(5)
+    dt, ps, hq, hkv, d = torch.float32, 4, 4, 2, 64
+    ws = torch.empty(1 << 22, dtype=torch.uint8)
+    q_p, k_p, v_p = torch.randn(9, hq, d), torch.randn(13, hkv, d), torch.randn(13, hkv, d)
+    indptr, indices, last, kc, vc = make_paged([7, 10], hkv, d, ps, "NHD", dt)
+    q_d = torch.randn(2, hq, d)
+    mask = torch.rand(9, 13) > 0.4
+    mask[:, 0] = True
+    # custom mask on the prefill side
+    w = PODWithPagedKVCacheWrapper(ws)
+    w.plan(indptr, indices, last, hq, hkv, d, ps, q_data_type=dt)
+    o_p, o_d = w.run(q_p, k_p, v_p, q_d, (kc, vc), custom_mask_p=mask)
+    torch.testing.assert_close(o_p, fi.single_prefill_with_kv_cache(q_p, k_p, v_p, custom_mask=mask), atol=1e-4, rtol=1e-4)
+    dw = fi.BatchDecodeWithPagedKVCacheWrapper(ws, "NHD")
+    dw.plan(indptr, indices, last, hq, hkv, d, ps, q_data_type=dt)
+    torch.testing.assert_close(o_d, dw.run(q_d, (kc, vc)), atol=1e-4, rtol=1e-4)
+    # ROPE_LLAMA on both sides (the decode side takes it from plan(), as in the reference)
+    w.plan(indptr, indices, last, hq, hkv, d, ps, q_data_type=dt, pos_encoding_mode="ROPE_LLAMA")
+    o_p, o_d = w.run(q_p, k_p, v_p, q_d, (kc, vc), causal_p=True, pos_encoding_mode_p="ROPE_LLAMA")
+    torch.testing.assert_close(o_p, fi.single_prefill_with_kv_cache(q_p, k_p, v_p, causal=True, pos_encoding_mode="ROPE_LLAMA"), atol=1e-4, rtol=1e-4)
+    dw.plan(indptr, indices, last, hq, hkv, d, ps, q_data_type=dt, pos_encoding_mode="ROPE_LLAMA")
+    want_d = dw.run(q_d, (kc, vc))
+    torch.testing.assert_close(o_d, want_d, atol=1e-4, rtol=1e-4)
+    # batched POD: packed mask + rope from plan()
+    qo_p = torch.tensor([0, 4, 9], dtype=torch.int32)
+    ip, ii, il, kcp, vcp = make_paged([6, 9], hkv, d, ps, "NHD", dt)
+    flat = torch.cat([(torch.rand(4, 6) > 0.3).flatten(), (torch.rand(5, 9) > 0.3).flatten()])
+    flat[0], flat[24] = True, True
+    wb = BatchPODWithPagedKVCacheWrapper(ws)
+    wb.plan(qo_p, ip, ii, il, torch.arange(3, dtype=torch.int32), indptr, indices, last, hq, hkv, d, ps, q_data_type=dt, pos_encoding_mode="ROPE_LLAMA")
+    o_p2, o_d2 = wb.run(q_p, (kcp, vcp), q_d, (kc, vc), custom_mask_p=flat)
+    pw = fi.BatchPrefillWithPagedKVCacheWrapper(ws, "NHD")
+    pw.plan(qo_p, ip, ii, il, hq, hkv, d, ps, custom_mask=flat, q_data_type=dt, pos_encoding_mode="ROPE_LLAMA")
+    torch.testing.assert_close(o_p2, pw.run(q_p, (kcp, vcp)), atol=1e-4, rtol=1e-4)
+    torch.testing.assert_close(o_d2, want_d, atol=1e-4, rtol=1e-4)
+    # causal after a mask re-plans back
+    o_p3, _ = wb.run(q_p, (kcp, vcp), q_d, (kc, vc), causal_p=True)
+    pw.plan(qo_p, ip, ii, il, hq, hkv, d, ps, causal=True, q_data_type=dt, pos_encoding_mode="ROPE_LLAMA")
+    torch.testing.assert_close(o_p3, pw.run(q_p, (kcp, vcp)), atol=1e-4, rtol=1e-4)
+
+
+def test_prefill_wrappers_honour_o_data_type():
+    torch.manual_seed(1)
+    hq, hkv, d = 4, 2, 64
+    q, k, v = torch.randn(6, hq, d).bfloat16(), torch.randn(10, hkv, d).bfloat16(), torch.randn(10, hkv, d).bfloat16()
+    ws = torch.empty(1 << 20, dtype=torch.uint8)
+    w = fi.BatchPrefillWithRaggedKVCacheWrapper(ws, "NHD")
+    qo, kv = torch.tensor([0, 6], dtype=torch.int32), torch.tensor([0, 10], dtype=torch.int32)
+    w.plan(qo, kv, hq, hkv, d, causal=True, q_data_type=torch.bfloat16)
+    base = w.run(q, k, v)
+    w.plan(qo, kv, hq, hkv, d, causal=True, q_data_type=torch.bfloat16, o_data_type=torch.float32)
+    o, lse = w.run(q, k, v, return_lse=True)
+    assert o.dtype == torch.float32 and lse.shape == (6, hq)
+    torch.testing.assert_close(o, base.float())
+    buf = torch.empty(6, hq, d, dtype=torch.float16)
+    w.plan(qo, kv, hq, hkv, d, causal=True, q_data_type=torch.bfloat16, o_data_type=torch.float16)
+    assert w.run(q, k, v, out=buf) is buf
+    torch.testing.assert_close(buf.float(), base.float(), atol=1e-2, rtol=1e-2)
+    # planning again without o_data_type goes back to the query dtype
+    w.plan(qo, kv, hq, hkv, d, causal=True, q_data_type=torch.bfloat16)
+    assert w.run(q, k, v).dtype == torch.bfloat16
+    kc, vc = torch.zeros(3, 4, hkv, d, dtype=torch.bfloat16), torch.zeros(3, 4, hkv, d, dtype=torch.bfloat16)
+    kc.view(-1, hkv, d)[:10], vc.view(-1, hkv, d)[:10] = k, v
+    pw = fi.BatchPrefillWithPagedKVCacheWrapper(ws, "NHD")
+    pw.plan(qo, torch.tensor([0, 3], dtype=torch.int32), torch.arange(3, dtype=torch.int32), torch.tensor([2], dtype=torch.int32), hq, hkv, d, 4,
+            causal=True, q_data_type=torch.bfloat16, o_data_type=torch.float32)
+    o = pw.run(q, (kc, vc))
+    assert o.dtype == torch.float32
+    torch.testing.assert_close(o, base.float(), atol=2e-2, rtol=2e-2)
