@@ -139,31 +139,92 @@ def _run(q, k, v, state, a, bgate, g_log, A_log, dt_bias, scale, l2norm, beta_is
     return res
 
 
+def _check_layout(state_layout: str) -> bool:
+    if state_layout not in ("VK", "KV"):
+        raise ValueError(f"state_layout must be 'VK' (reference: K-last) or 'KV' (native: K-major), got {state_layout!r}")
+    return state_layout == "VK"
+
+
 def gated_delta_rule_decode(q, k, v, state, A_log, a, dt_bias, b, scale: Optional[float] = None,
                             output: Optional[torch.Tensor] = None, use_qk_l2norm: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
-    """One decode step; ``state [B, HV, K, V]`` fp32 is updated in place.  Returns ``(output [B,1,HV,V], state)``."""
+    """One decode step; ``state [B, HV, K, V]`` fp32 (K-major, the kernel's native layout) is updated in place.  Returns
+    ``(output [B,1,HV,V], state)``."""
     o = _run(q, k, v, state, a, b, None, A_log, dt_bias, scale, use_qk_l2norm, True, True, out=output)
     return o, state
 
 
 def gated_delta_rule_decode_pretranspose(q, k, v, state, A_log, a, dt_bias, b, scale: Optional[float] = None,
-                                         output: Optional[torch.Tensor] = None, use_qk_l2norm: bool = True):
-    """Same step for a V-major state ``[B, HV, V, K]`` (transposed on the fly; prefer the K-major entry point)."""
-    st = state.transpose(-1, -2).contiguous()
+                                         output: Optional[torch.Tensor] = None, use_qk_l2norm: bool = True,
+                                         initial_state: Optional[torch.Tensor] = None, initial_state_indices: Optional[torch.Tensor] = None,
+                                         output_state_indices: Optional[torch.Tensor] = None):
+    """Same step for a V-major (K-last) state ``[B, HV, V, K]``, transposed on the fly (prefer the K-major entry point).
+
+    Pool form (reference gdn_decode.py :118): ``state=None``, ``initial_state [pool, HV, V, K]`` gathered through
+    ``initial_state_indices [B]`` and written back to ``output_state_indices`` (default: the same slots).  Entries whose index is
+    ``-1`` are padding: their slot is not touched and their output row is zero (the reference's float32-path semantics)."""
+    if initial_state is None:
+        if state is None:
+            raise ValueError("gated_delta_rule_decode_pretranspose: pass state, or initial_state with initial_state_indices")
+        if initial_state_indices is not None or output_state_indices is not None:
+            raise ValueError("initial_state_indices / output_state_indices need the initial_state pool")
+        st = state.float().transpose(-1, -2).contiguous()
+        o = _run(q, k, v, st, a, b, None, A_log, dt_bias, scale, use_qk_l2norm, True, True, out=output)
+        state.copy_(st.transpose(-1, -2))
+        return o, state
+    if state is not None:
+        raise ValueError("gated_delta_rule_decode_pretranspose: state and initial_state are mutually exclusive")
+    if initial_state_indices is None:
+        raise ValueError("initial_state needs initial_state_indices")
+    src = initial_state_indices.long()
+    dst = output_state_indices.long() if output_state_indices is not None else src
+    live = (src >= 0) & (dst >= 0)
+    st = initial_state[src.clamp(min=0)].float().transpose(-1, -2).contiguous()
     o = _run(q, k, v, st, a, b, None, A_log, dt_bias, scale, use_qk_l2norm, True, True, out=output)
-    state.copy_(st.transpose(-1, -2))
-    return o, state
+    o.mul_(live.view(-1, 1, 1, 1).to(o.dtype))
+    initial_state.index_copy_(0, dst[live], st.transpose(-1, -2)[live].to(initial_state.dtype))
+    return o, initial_state
 
 
 def gated_delta_rule_mtp(q, k, v, initial_state, initial_state_indices, A_log, a, dt_bias, b, scale: Optional[float] = None,
-                         output: Optional[torch.Tensor] = None, intermediate_states_buffer=None,
-                         disable_state_update: Optional[bool] = None, use_qk_l2norm: bool = True):
-    """T > 1 tokens per sequence (speculative verification); ``initial_state [pool, HV, K, V]`` indexed by
-    ``initial_state_indices [B]``."""
-    if intermediate_states_buffer is not None:
-        raise NotImplementedError("intermediate state caching is not implemented")
-    o = _run(q, k, v, initial_state, a, b, None, A_log, dt_bias, scale, use_qk_l2norm, True, not bool(disable_state_update),
-             state_idx=initial_state_indices, out=output)
+                         output: Optional[torch.Tensor] = None, intermediate_states_buffer: Optional[torch.Tensor] = None,
+                         disable_state_update: Optional[bool] = None, use_qk_l2norm: bool = True, state_layout: str = "VK"):
+    """T > 1 tokens per sequence (speculative verification); the state pool is indexed by ``initial_state_indices [B]``.
+
+    ``state_layout="VK"`` (default, the reference's convention): ``initial_state [pool, HV, V, K]`` (K-last); the touched slots are
+    gathered and transposed around the kernel.  ``state_layout="KV"``: ``[pool, HV, K, V]``, the kernel's native layout - it
+    indexes the pool itself, nothing is copied (what ``models.gdn`` uses).  ``disable_state_update=None`` means True with a
+    warning, like in the reference (its default flips in a later release: pass it explicitly).  ``intermediate_states_buffer
+    [>= B, >= T, HV, V, K]`` receives the state after every token (row ``b`` of the call, not the pool slot), for roll-back after
+    partial acceptance; with it the tokens run as T single-token launches."""
+    vk = _check_layout(state_layout)
+    if disable_state_update is None:
+        import warnings
+
+        warnings.warn("gated_delta_rule_mtp(): disable_state_update defaults to True (the state pool is NOT updated); pass it "
+                      "explicitly - the reference flips this default in 0.7.0", FutureWarning, stacklevel=2)
+        disable_state_update = True
+    update = not disable_state_update
+    B, T = q.shape[0], q.shape[1]
+    if intermediate_states_buffer is None and not vk:
+        o = _run(q, k, v, initial_state, a, b, None, A_log, dt_bias, scale, use_qk_l2norm, True, update,
+                 state_idx=initial_state_indices, out=output)
+        return o, initial_state
+    idx = initial_state_indices.long()
+    st = initial_state[idx].float()
+    st = st.transpose(-1, -2).contiguous() if vk else st.contiguous()           # working copy [B, HV, K, V]
+    if intermediate_states_buffer is None:
+        o = _run(q, k, v, st, a, b, None, A_log, dt_bias, scale, use_qk_l2norm, True, True, out=output)
+    else:
+        buf = intermediate_states_buffer
+        if buf.shape[0] < B or buf.shape[1] < T:
+            raise ValueError(f"intermediate_states_buffer {tuple(buf.shape)} must hold at least [B={B}, T={T}] states")
+        o = output if output is not None else torch.empty(B, T, v.shape[2], v.shape[3], dtype=q.dtype, device=q.device)
+        for t in range(T):
+            sl = slice(t, t + 1)
+            o[:, sl] = _run(q[:, sl], k[:, sl], v[:, sl], st, a[:, sl], b[:, sl], None, A_log, dt_bias, scale, use_qk_l2norm, True, True)
+            buf[:B, t] = st.transpose(-1, -2).to(buf.dtype)
+    if update:
+        initial_state.index_copy_(0, idx, (st.transpose(-1, -2) if vk else st).to(initial_state.dtype))
     return o, initial_state
 
 
@@ -171,16 +232,31 @@ def chunk_gated_delta_rule(q, k, v, g: Optional[torch.Tensor] = None, beta: Opti
                            scale: Optional[float] = None, initial_state: Optional[torch.Tensor] = None,
                            output_final_state: bool = False, cu_seqlens: Optional[torch.Tensor] = None,
                            use_qk_l2norm_in_kernel: bool = False, output: Optional[torch.Tensor] = None,
-                           output_state: Optional[torch.Tensor] = None, state_checkpoints=None, checkpoint_cu_starts=None,
-                           checkpoint_every_n_tokens: int = 0, chunked: Optional[bool] = None,
-                           chunk_size: int = 64) -> Union[torch.Tensor, Tuple[torch.Tensor, torch.Tensor]]:
+                           output_state: Optional[torch.Tensor] = None, state_checkpoints: Optional[torch.Tensor] = None,
+                           checkpoint_cu_starts: Optional[torch.Tensor] = None, checkpoint_every_n_tokens: int = 0,
+                           chunked: Optional[bool] = None, chunk_size: int = 64,
+                           state_layout: str = "VK") -> Union[torch.Tensor, Tuple[torch.Tensor, torch.Tensor]]:
     """Prefill: ``q/k [total, H, K]``, ``v [total, HV, V]``, ``g`` (multiplicative forget gate) / ``beta`` ``[total, HV]``
     fp32, packed sequences described by ``cu_seqlens``.
 
+    States (``initial_state``, ``output_state`` / the returned final state, ``state_checkpoints``) are ``[*, HV, V, K]`` (K-last,
+    the reference's layout: gdn_prefill.py :186) by default and transposed around the kernel; ``state_layout="KV"`` takes and
+    returns the kernel's native ``[*, HV, K, V]`` without copies.
+
+    ``checkpoint_every_n_tokens = n > 0`` (a multiple of 64): the state after every n tokens of sequence ``i`` is written to
+    ``state_checkpoints[checkpoint_cu_starts[i] + j]`` (``seq_len_i // n`` checkpoints per sequence).  The sequences then run in
+    rounds of n tokens - round j processes the j-th segment of every sequence that has one, as one packed launch.
+
     ``chunked=True`` (or ``FIB200_GDN_CHUNKED=1``) runs the chunk-parallel WY algorithm (:func:`gated_delta_rule_chunked`:
     batched GEMMs + a triangular solve per 64-token chunk) instead of the token-sequential kernel."""
-    if state_checkpoints is not None:
-        raise NotImplementedError("state checkpoints are not implemented")
+    vk = _check_layout(state_layout)
+    if checkpoint_every_n_tokens < 0:
+        raise ValueError(f"checkpoint_every_n_tokens must be non-negative, got {checkpoint_every_n_tokens}")
+    if checkpoint_every_n_tokens > 0:
+        if checkpoint_every_n_tokens % 64 != 0:
+            raise ValueError(f"checkpoint_every_n_tokens must be a multiple of the chunk size (64), got {checkpoint_every_n_tokens}")
+        if state_checkpoints is None or checkpoint_cu_starts is None:
+            raise ValueError("state_checkpoints and checkpoint_cu_starts must both be provided when checkpoint_every_n_tokens > 0")
     total, H, K = q.shape
     HV, V = v.shape[1], v.shape[2]
     dev = q.device
@@ -192,29 +268,66 @@ def chunk_gated_delta_rule(q, k, v, g: Optional[torch.Tensor] = None, beta: Opti
         HV = H
     g_log = torch.log(g.float()) if g is not None else torch.zeros(total, HV, device=dev)
     bt = beta.float() if beta is not None else torch.ones(total, HV, device=dev)
-    state = output_state if output_state is not None else torch.zeros(n, HV, K, V, dtype=torch.float32, device=dev)
+    native_out = output_state is not None and not vk                      # the kernel may work in the caller's buffer
+    state = output_state if native_out else torch.zeros(n, HV, K, V, dtype=torch.float32, device=dev)
     if initial_state is not None:
-        state.copy_(initial_state)
-    elif output_state is not None:
+        state.copy_(initial_state.transpose(-1, -2) if vk else initial_state)
+    elif native_out:
         state.zero_()
     import os
 
     if chunked is None:
         chunked = os.environ.get("FIB200_GDN_CHUNKED", "0") == "1"
-    if chunked:
-        sc = scale if scale is not None else 1.0 / math.sqrt(K)
-        o = torch.empty(total, HV, V, dtype=torch.float32, device=dev)
+
+    def segment(qs, ks, vs, gs, bs, st, cu, out):
+        """One packed launch: tokens ``[0, cu[-1])`` of the given tensors, sequence ``i`` continuing ``st[i]`` (updated in place)."""
+        if chunked:
+            sc = scale if scale is not None else 1.0 / math.sqrt(K)
+            o = torch.empty(qs.shape[0], HV, V, dtype=torch.float32, device=dev)
+            cl = cu.tolist()
+            for i in range(len(cl) - 1):
+                sl = slice(cl[i], cl[i + 1])
+                if cl[i + 1] > cl[i]:
+                    o[sl] = gated_delta_rule_chunked(qs[None, sl], ks[None, sl], vs[None, sl], st[i:i + 1], gs[None, sl], bs[None, sl], sc,
+                                                     use_qk_l2norm_in_kernel, chunk_size)[0]
+            o = o.to(q.dtype)
+            if out is not None:
+                out.copy_(o)
+                o = out
+            return o
+        return _run(qs[None], ks[None], vs[None], st, None, bs[None], gs[None], None, None, scale, use_qk_l2norm_in_kernel, False, True,
+                    cu_seqlens=cu, out=out[None] if out is not None else None)[0]
+
+    if checkpoint_every_n_tokens == 0:
+        o = segment(q, k, v, g_log, bt, state, cu_seqlens, output)
+    else:
+        step = checkpoint_every_n_tokens
         cu = cu_seqlens.tolist()
+        starts = checkpoint_cu_starts.tolist()
+        lens = [cu[i + 1] - cu[i] for i in range(n)]
         for i in range(n):
-            sl = slice(cu[i], cu[i + 1])
-            if cu[i + 1] > cu[i]:
-                o[sl] = gated_delta_rule_chunked(q[None, sl], k[None, sl], v[None, sl], state[i:i + 1], g_log[None, sl], bt[None, sl], sc,
-                                                 use_qk_l2norm_in_kernel, chunk_size)[0]
-        o = o.to(q.dtype)
-        if output is not None:
-            output.copy_(o)
-            o = output
+            if starts[i + 1] - starts[i] != lens[i] // step:
+                raise ValueError(f"checkpoint_cu_starts: sequence {i} of {lens[i]} tokens has {lens[i] // step} checkpoints, "
+                                 f"got {starts[i + 1] - starts[i]}")
+        o = output if output is not None else torch.empty(total, HV, V, dtype=q.dtype, device=dev)
+        for j in range((max(lens) + step - 1) // step if lens else 0):
+            act = [i for i in range(n) if lens[i] > j * step]
+            seg = [min(step, lens[i] - j * step) for i in act]
+            tok = torch.cat([torch.arange(cu[i] + j * step, cu[i] + j * step + m, device=dev) for i, m in zip(act, seg)])
+            cu_j = torch.tensor([0] + torch.tensor(seg).cumsum(0).tolist(), dtype=torch.int32, device=dev)
+            act_t = torch.tensor(act, device=dev)
+            st = state[act_t].contiguous()
+            o[tok] = segment(q[tok], k[tok], v[tok], g_log[tok], bt[tok], st, cu_j, None).to(o.dtype)
+            state[act_t] = st
+            full = [x for x, (i, m) in enumerate(zip(act, seg)) if m == step]
+            if full:
+                rows = torch.tensor([starts[act[x]] + j for x in full], device=dev)
+                snap = st[torch.tensor(full, device=dev)]
+                state_checkpoints[rows] = (snap.transpose(-1, -2) if vk else snap).to(state_checkpoints.dtype)
+    if native_out:
         return (o, state) if output_final_state else o
-    o = _run(q[None], k[None], v[None], state, None, bt[None], g_log[None], None, None, scale, use_qk_l2norm_in_kernel, False, True,
-             cu_seqlens=cu_seqlens, out=output[None] if output is not None else None)[0]
-    return (o, state) if output_final_state else o
+    final = state.transpose(-1, -2) if vk else state
+    if output_state is not None:
+        output_state.copy_(final)
+        final = output_state
+    return (o, final.contiguous()) if output_final_state else o

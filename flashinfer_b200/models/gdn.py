@@ -86,7 +86,7 @@ class GDNDecodeEngine:
         k = qkv[:, hk * kd: 2 * hk * kd].reshape(b, 1, hk, kd)
         v = qkv[:, 2 * hk * kd:].reshape(b, 1, hv, vd)
         o, _ = gated_delta_rule_mtp(q.contiguous(), k.contiguous(), v.contiguous(), l["state"], self.slots, l["A_log"], a.reshape(b, 1, hv).contiguous(),
-                                    l["dt_bias"], bgate.reshape(b, 1, hv).contiguous())
+                                    l["dt_bias"], bgate.reshape(b, 1, hv).contiguous(), disable_state_update=False, state_layout="KV")
         o = norm.rmsnorm(o.reshape(b * hv, vd).to(self.dtype), l["o_norm"], cfg.rms_eps).view(b, hv * vd)
         gated = (o.float() * torch.nn.functional.silu(z.float())).to(self.dtype)
         return linear(gated, l["out_proj"])

@@ -58,14 +58,14 @@ gated_delta_rule_decode_trace = TraceTemplate(
 
 def _gdn_prefill_reference(q, k, v, g, beta, cu_seqlens, scale=None, initial_state=None, use_qk_l2norm_in_kernel=False):
     """q, k [total, H, K]; v [total, HV, V]; g (multiplicative gate), beta [total, HV]; packed sequences in cu_seqlens.
-    Returns (output [total, HV, V], final state [num_seqs, HV, K, V])."""
+    States are K-last: initial_state and the returned final state [num_seqs, HV, V, K].  Returns (output [total, HV, V], final state)."""
     total, h, kd = q.shape
     hv, vd = v.shape[1], v.shape[2]
     rep = hv // h
     sc = scale if scale is not None else kd ** -0.5
     n = cu_seqlens.numel() - 1
     out = torch.zeros(total, hv, vd, dtype=torch.float32, device=q.device)
-    states = torch.zeros(n, hv, kd, vd, dtype=torch.float32, device=q.device) if initial_state is None else initial_state.to(torch.float32).clone()
+    states = torch.zeros(n, hv, kd, vd, dtype=torch.float32, device=q.device) if initial_state is None else initial_state.to(torch.float32).transpose(-1, -2).clone()
     for i in range(n):
         s = states[i]
         for t in range(int(cu_seqlens[i]), int(cu_seqlens[i + 1])):
@@ -79,7 +79,7 @@ def _gdn_prefill_reference(q, k, v, g, beta, cu_seqlens, scale=None, initial_sta
             s = s + kt[:, :, None] * delta[:, None, :]
             out[t] = torch.einsum("hk,hkv->hv", qt * sc, s)
         states[i] = s
-    return out.to(q.dtype), states
+    return out.to(q.dtype), states.transpose(-1, -2).contiguous()
 
 
 def _gdn_prefill_init(*, num_seqs=4, seq_len=None, num_q_heads=16, num_v_heads=32, head_dim_k=128, head_dim_v=128, device="cuda", seed=0):
@@ -101,10 +101,10 @@ chunk_gated_delta_rule_trace = TraceTemplate(
     inputs=[Tensor("q", ("total_tokens", "num_q_heads", "head_dim_k")), Tensor("k", ("total_tokens", "num_q_heads", "head_dim_k")),
             Tensor("v", ("total_tokens", "num_v_heads", "head_dim_v")), Tensor("g", ("total_tokens", "num_v_heads"), "float32"),
             Tensor("beta", ("total_tokens", "num_v_heads"), "float32"), Tensor("cu_seqlens", ("len_cu",), "int32"), Scalar("scale", optional=True),
-            Tensor("initial_state", ("num_seqs", "num_v_heads", "head_dim_k", "head_dim_v"), "float32", optional=True),
+            Tensor("initial_state", ("num_seqs", "num_v_heads", "head_dim_v", "head_dim_k"), "float32", optional=True),
             Scalar("use_qk_l2norm_in_kernel", "bool", optional=True)],
     outputs=[Tensor("output", ("total_tokens", "num_v_heads", "head_dim_v"), dtype_from="q"),
-             Tensor("final_state", ("num_seqs", "num_v_heads", "head_dim_k", "head_dim_v"), dtype="float32")],
+             Tensor("final_state", ("num_seqs", "num_v_heads", "head_dim_v", "head_dim_k"), dtype="float32")],
     reference=_gdn_prefill_reference, init=_gdn_prefill_init, tags=("gdn", "prefill"), constraints=("len_cu == num_seqs + 1",),
     description="Gated delta rule over packed sequences (token-sequential or chunk-parallel WY execution, same result)", tolerance="bf16",
     test_sizes=_SIZES)

@@ -346,9 +346,9 @@ silu_and_mul_scaled_nvfp4_experts_quantize_trace = TraceTemplate(
 
 
 # ------------------------------------------------------------------ GDN multi-token (speculative) decode
-def _gdn_mtp_reference(q, k, v, initial_state, initial_state_indices, A_log, a, dt_bias, b, scale=None, use_qk_l2norm=True):
-    """q, k [B, T, H, K]; v [B, T, HV, V]; state pool [pool, HV, K, V] fp32 addressed by initial_state_indices [B]; a, b [B, T, HV].
-    Token t sees the state left by token t - 1; the pool row is updated with the state after the last token."""
+def _gdn_mtp_reference(q, k, v, initial_state, initial_state_indices, A_log, a, dt_bias, b, scale=None, use_qk_l2norm=True, disable_state_update=False):
+    """q, k [B, T, H, K]; v [B, T, HV, V]; state pool [pool, HV, V, K] fp32 (K-last) addressed by initial_state_indices [B]; a, b [B, T, HV].
+    Token t sees the state left by token t - 1; the pool row is updated with the state after the last token unless disable_state_update."""
     bsz, t_, h, kd = q.shape
     hv = v.shape[2]
     rep = hv // h
@@ -358,7 +358,7 @@ def _gdn_mtp_reference(q, k, v, initial_state, initial_state_indices, A_log, a, 
     out = torch.zeros(bsz, t_, hv, v.shape[3], dtype=torch.float32, device=q.device)
     pool = initial_state.float().clone()
     for i in range(bsz):
-        s = pool[int(initial_state_indices[i])].clone()
+        s = pool[int(initial_state_indices[i])].transpose(-1, -2).clone()            # [HV, K, V]
         for t in range(t_):
             qt = q[i, t].float().repeat_interleave(rep, 0)
             kt = k[i, t].float().repeat_interleave(rep, 0)
@@ -369,7 +369,8 @@ def _gdn_mtp_reference(q, k, v, initial_state, initial_state_indices, A_log, a, 
             delta = (v[i, t].float() - torch.einsum("hk,hkv->hv", kt, s)) * beta[i, t][:, None]
             s = s + kt[:, :, None] * delta[:, None, :]
             out[i, t] = torch.einsum("hk,hkv->hv", qt * sc, s)
-        pool[int(initial_state_indices[i])] = s
+        if not disable_state_update:
+            pool[int(initial_state_indices[i])] = s.transpose(-1, -2)
     return out.to(q.dtype), pool
 
 
@@ -379,20 +380,21 @@ def _gdn_mtp_init(*, batch_size=4, num_tokens=4, num_q_heads=16, num_v_heads=32,
     bf = lambda t: t.to(torch.bfloat16).to(device)  # noqa: E731
     pool = batch_size + 3
     return {"q": bf(r(batch_size, num_tokens, num_q_heads, head_dim_k)), "k": bf(r(batch_size, num_tokens, num_q_heads, head_dim_k)),
-            "v": bf(r(batch_size, num_tokens, num_v_heads, head_dim_v)), "initial_state": (r(pool, num_v_heads, head_dim_k, head_dim_v) * 0.1).to(device),
+            "v": bf(r(batch_size, num_tokens, num_v_heads, head_dim_v)), "initial_state": (r(pool, num_v_heads, head_dim_v, head_dim_k) * 0.1).to(device),
             "initial_state_indices": torch.randperm(pool, generator=g)[:batch_size].int().to(device), "A_log": (r(num_v_heads) * 0.5).to(device),
-            "a": bf(r(batch_size, num_tokens, num_v_heads)), "dt_bias": (r(num_v_heads) * 0.1).to(device), "b": bf(r(batch_size, num_tokens, num_v_heads))}
+            "a": bf(r(batch_size, num_tokens, num_v_heads)), "dt_bias": (r(num_v_heads) * 0.1).to(device), "b": bf(r(batch_size, num_tokens, num_v_heads)), "disable_state_update": False}
 
 
 gdn_mtp_trace = TraceTemplate(
     op_type="gdn", name_fmt="gdn_mtp_h{num_q_heads}_hv{num_v_heads}_k{head_dim_k}_v{head_dim_v}", axes=[Var("batch_size"), Var("num_tokens"), Var("pool_size")] + list(_GDN_AXES),
     inputs=[Tensor("q", ("batch_size", "num_tokens", "num_q_heads", "head_dim_k")), Tensor("k", ("batch_size", "num_tokens", "num_q_heads", "head_dim_k")),
             Tensor("v", ("batch_size", "num_tokens", "num_v_heads", "head_dim_v")),
-            Tensor("initial_state", ("pool_size", "num_v_heads", "head_dim_k", "head_dim_v"), "float32"), Tensor("initial_state_indices", ("batch_size",), "int32"),
+            Tensor("initial_state", ("pool_size", "num_v_heads", "head_dim_v", "head_dim_k"), "float32"), Tensor("initial_state_indices", ("batch_size",), "int32"),
             Tensor("A_log", ("num_v_heads",)), Tensor("a", ("batch_size", "num_tokens", "num_v_heads")), Tensor("dt_bias", ("num_v_heads",)),
-            Tensor("b", ("batch_size", "num_tokens", "num_v_heads")), Scalar("scale", optional=True), Scalar("use_qk_l2norm", "bool", optional=True)],
+            Tensor("b", ("batch_size", "num_tokens", "num_v_heads")), Scalar("scale", optional=True), Scalar("use_qk_l2norm", "bool", optional=True),
+            Scalar("disable_state_update", "bool", optional=True)],
     outputs=[Tensor("output", ("batch_size", "num_tokens", "num_v_heads", "head_dim_v"), dtype_from="q"),
-             Tensor("state_out", ("pool_size", "num_v_heads", "head_dim_k", "head_dim_v"), dtype="float32", param="initial_state")],
+             Tensor("state_out", ("pool_size", "num_v_heads", "head_dim_v", "head_dim_k"), dtype="float32", param="initial_state")],
     reference=_gdn_mtp_reference, init=_gdn_mtp_init, tags=("gdn", "decode", "mtp", "inplace"), tolerance="bf16",
     description="Gated delta rule over several draft tokens per sequence (speculative verification), state pool updated in place",
     test_sizes={"num_q_heads": 2, "num_v_heads": 4, "head_dim_k": 16, "head_dim_v": 8})

@@ -265,3 +265,43 @@ def test_rope_llama_mode_on_cuda():
     got = fi.single_decode_with_kv_cache(q[0], k, v, pos_encoding_mode="ROPE_LLAMA")
     want = fi.single_decode_with_kv_cache(rotate_rows(q[:1], torch.tensor([299]), 1.0, 1e4)[0], rotate_rows(k, torch.arange(300), 1.0, 1e4), v)
     torch.testing.assert_close(got.float(), want.float(), atol=2e-2, rtol=2e-2)
+
+
+def test_gdn_reference_state_conventions_on_cuda():
+    """K-last pools, intermediate states, pool-form pretranspose decode and prefill checkpoints on the device against the CPU run
+    of the same calls (the CUDA kernel works on K-major copies of the touched slots)."""
+    from flashinfer_b200.gdn import chunk_gated_delta_rule, gated_delta_rule_decode_pretranspose, gated_delta_rule_mtp
+
+    torch.manual_seed(0)
+    B, T, H, HV, K, V = 3, 4, 4, 8, 128, 128
+    mk = lambda *s: torch.randn(*s)  # noqa: E731
+    x = dict(q=mk(B, T, H, K).bfloat16(), k=mk(B, T, H, K).bfloat16(), v=mk(B, T, HV, V).bfloat16(), a=mk(B, T, HV).bfloat16(), b=mk(B, T, HV).bfloat16())
+    A_log, dt_bias, pool = mk(HV) * 0.5, mk(HV) * 0.1, mk(6, HV, V, K) * 0.1
+    idx = torch.tensor([4, 0, 5], dtype=torch.int32)
+    res = {}
+    for dev in ("cpu", "cuda"):
+        d = {n: t.to(dev) for n, t in x.items()}
+        p, buf = pool.clone().to(dev), torch.zeros(B, T, HV, V, K, device=dev)
+        o, _ = gated_delta_rule_mtp(d["q"], d["k"], d["v"], p, idx.to(dev), A_log.to(dev), d["a"], dt_bias.to(dev), d["b"],
+                                    intermediate_states_buffer=buf, disable_state_update=False)
+        p2 = pool.clone().to(dev)
+        o1, _ = gated_delta_rule_decode_pretranspose(d["q"][:, :1], d["k"][:, :1], d["v"][:, :1], None, A_log.to(dev), d["a"][:, :1], dt_bias.to(dev), d["b"][:, :1],
+                                                     initial_state=p2, initial_state_indices=torch.tensor([4, -1, 5], device=dev))
+        res[dev] = [t.float().cpu() for t in (o, p, buf, o1, p2)]
+    for got, want in zip(res["cuda"], res["cpu"]):
+        torch.testing.assert_close(got, want, atol=3e-2, rtol=3e-2)
+    lens = [150, 64, 130]
+    cu = torch.tensor([0] + torch.tensor(lens).cumsum(0).tolist(), dtype=torch.int32)
+    total = int(cu[-1])
+    q, k, v = mk(total, H, K).bfloat16(), mk(total, H, K).bfloat16(), mk(total, HV, V).bfloat16()
+    g, beta, init = torch.exp(-torch.rand(total, HV) * 0.3), torch.rand(total, HV), mk(3, HV, V, K) * 0.1
+    starts = torch.tensor([0, 2, 3, 5])
+    res = {}
+    for dev in ("cpu", "cuda"):
+        ck = torch.zeros(5, HV, V, K, device=dev)
+        o, s = chunk_gated_delta_rule(q.to(dev), k.to(dev), v.to(dev), g.to(dev), beta.to(dev), initial_state=init.to(dev), output_final_state=True,
+                                      cu_seqlens=cu.to(dev), use_qk_l2norm_in_kernel=True, state_checkpoints=ck, checkpoint_cu_starts=starts,
+                                      checkpoint_every_n_tokens=64)
+        res[dev] = [t.float().cpu() for t in (o, s, ck)]
+    for got, want in zip(res["cuda"], res["cpu"]):
+        torch.testing.assert_close(got, want, atol=3e-2, rtol=3e-2)
