@@ -305,3 +305,34 @@ def test_gdn_reference_state_conventions_on_cuda():
         res[dev] = [t.float().cpu() for t in (o, s, ck)]
     for got, want in zip(res["cuda"], res["cpu"]):
         torch.testing.assert_close(got, want, atol=3e-2, rtol=3e-2)
+
+
+def test_mamba_spec_decoding_forms_on_cuda():
+    """Intermediate-state caching and the varlen / num_accepted_tokens form of selective_state_update on the device against the
+    CPU run of the same call (rounds of single-token launches of the CUDA kernel on an fp32 working copy)."""
+    from flashinfer_b200.mamba import selective_state_update
+
+    torch.manual_seed(0)
+    H, DIM, DS, G, POOL, T = 8, 64, 128, 2, 16, 4
+    A, D, dtb = -torch.rand(H, DIM, DS), torch.randn(H, DIM), torch.randn(H, DIM) * 0.1
+    state = (torch.randn(POOL, H, DIM, DS) * 0.1).bfloat16()
+    mk = lambda *s: torch.randn(*s).bfloat16()  # noqa: E731
+    x, dt, B, C, z = mk(3, T, H, DIM), mk(3, T, H, DIM), mk(3, T, G, DS), mk(3, T, G, DS), mk(3, T, H, DIM)
+    idx = torch.tensor([7, -1, 2], dtype=torch.int32)
+    lens = [1, 4, 2]
+    cu = torch.tensor([0, 1, 5, 7], dtype=torch.int32)
+    src = torch.arange(12, dtype=torch.int32).view(3, 4)
+    acc = torch.tensor([1, 3, 2])
+    res = {}
+    for dev in ("cpu", "cuda"):
+        mv = lambda t: t.to(dev)  # noqa: E731
+        st, buf = mv(state.clone()), torch.zeros(3, T, H, DIM, DS, device=dev)
+        y = selective_state_update(st, mv(x), mv(dt), mv(A), mv(B), mv(C), mv(D), mv(z), mv(dtb), True, state_batch_indices=mv(idx),
+                                   intermediate_states_buffer=buf, cache_steps=T)
+        st2 = mv(state.clone())
+        f = lambda t: mv(t.reshape(12, *t.shape[2:])[:7])  # noqa: E731
+        y2 = selective_state_update(st2, f(x), f(dt), mv(A), f(B), f(C), mv(D), f(z), mv(dtb), True, state_batch_indices=mv(src),
+                                    cu_seqlens=mv(cu), num_accepted_tokens=mv(acc), cache_steps=4)
+        res[dev] = [t.float().cpu() for t in (y, st, buf, y2, st2)]
+    for got, want in zip(res["cuda"], res["cpu"]):
+        torch.testing.assert_close(got, want, atol=3e-2, rtol=3e-2)
