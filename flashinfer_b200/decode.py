@@ -17,6 +17,7 @@ import torch
 
 from . import jit, reference
 from .utils import host_i32 as _host_i32
+from .utils import legacy_forward_replan, remember_plan
 from .utils import (
     check_kv_layout,
     check_pos_encoding_mode,
@@ -196,6 +197,8 @@ class BatchDecodeWithPagedKVCacheWrapper:
     ) -> None:
         """Host-side planning.  ``qo_indptr`` (extension) allows q_len>1 per request
         (speculative decode / small append) as long as ``q_len * group <= 32``."""
+        remember_plan(self, locals())
+        self._qlen_planned = 1
         check_pos_encoding_mode(pos_encoding_mode)
         self._alibi_delegate = None
         if pos_encoding_mode == "ALIBI":                # the bias pass lives in the prefill kernel: delegate with one query row per request
@@ -318,13 +321,28 @@ class BatchDecodeWithPagedKVCacheWrapper:
         sinks: Optional[torch.Tensor] = None,
         kv_cache_sf=None,
         kv_prefetch: bool = False,
+        q_len_per_req: Optional[int] = 1,
+        skip_softmax_threshold_scale_factor: Optional[float] = None,
     ):
-        """``kv_prefetch=True`` (with PDL): promise that the kernel launched just before this one on the stream only APPENDS the
+        """``q_len_per_req`` (reference decode.py :1285): query tokens per request, ``q [batch * q_len_per_req, H, D]`` - more than
+        one (speculative verification, causal over the newest tokens) plans the multi-token form again from the remembered
+        ``plan()`` arguments.  ``skip_softmax_threshold_scale_factor`` (an approximation knob of the reference's trtllm-gen backend)
+        is accepted and not used: every KV tile is computed exactly.
+
+        ``kv_prefetch=True`` (with PDL): promise that the kernel launched just before this one on the stream only APPENDS the
         newest ``q_len`` tokens of each request to the cache (an append / fused QKV+RoPE+append kernel): the TMA producers then
         stream all older KV tiles before the programmatic dependency resolves, filling the pipeline under the previous
         kernel's tail."""
         if not self._planned:
             raise RuntimeError("plan() must be called before run()")
+        qlen = 1 if q_len_per_req is None else int(q_len_per_req)
+        if qlen != getattr(self, "_qlen_planned", 1):
+            bsz = self._plan_locals["last_page_len"].numel()
+            if q.shape[0] != bsz * qlen:
+                raise ValueError(f"q.shape[0] ({q.shape[0]}) does not match batch_size * q_len_per_req ({bsz} * {qlen} = {bsz * qlen}). "
+                                 "For batch decode, q must have shape [batch_size * q_len_per_req, num_heads, head_dim].")
+            self.plan(**{**self._plan_locals, "qo_indptr": None if qlen == 1 else torch.arange(0, (bsz + 1) * qlen, qlen, dtype=torch.int32)})
+            self._qlen_planned = qlen
         if getattr(self, "_alibi_delegate", None) is not None:
             return self._alibi_delegate.run(q, paged_kv_cache, q_scale=q_scale, k_scale=k_scale, v_scale=v_scale, out=out, lse=lse,
                                             return_lse=return_lse, enable_pdl=enable_pdl, window_left=window_left, sinks=sinks)
@@ -384,10 +402,19 @@ class BatchDecodeWithPagedKVCacheWrapper:
             out.copy_((out.float() * v_scale).to(out.dtype))
         return (out, lse) if return_lse else out
 
-    forward = run
+    def forward(self, q, paged_kv_cache, pos_encoding_mode="NONE", q_scale=None, k_scale=None, v_scale=None, window_left=-1, logits_soft_cap=None,
+                sm_scale=None, rope_scale=None, rope_theta=None):
+        """Deprecated (use :meth:`run`): the attention parameters given here replace the planned ones, defaults included."""
+        legacy_forward_replan(self, pos_encoding_mode=pos_encoding_mode, window_left=window_left, logits_soft_cap=logits_soft_cap, sm_scale=sm_scale,
+                              rope_scale=rope_scale, rope_theta=rope_theta)
+        return self.run(q, paged_kv_cache, q_scale=q_scale, k_scale=k_scale, v_scale=v_scale)
 
-    def forward_return_lse(self, q, paged_kv_cache, **kw):
-        return self.run(q, paged_kv_cache, return_lse=True, **kw)
+    def forward_return_lse(self, q, paged_kv_cache, pos_encoding_mode="NONE", q_scale=None, k_scale=None, v_scale=None, window_left=-1,
+                           logits_soft_cap=None, sm_scale=None, rope_scale=None, rope_theta=None):
+        """Deprecated (use :meth:`run_return_lse`)."""
+        legacy_forward_replan(self, pos_encoding_mode=pos_encoding_mode, window_left=window_left, logits_soft_cap=logits_soft_cap, sm_scale=sm_scale,
+                              rope_scale=rope_scale, rope_theta=rope_theta)
+        return self.run(q, paged_kv_cache, q_scale=q_scale, k_scale=k_scale, v_scale=v_scale, return_lse=True)
 
     def end_forward(self) -> None:
         pass

@@ -15,6 +15,7 @@ import torch
 
 from . import jit, reference
 from .utils import host_i32 as _host_i32
+from .utils import legacy_forward_replan, remember_plan
 from .utils import (
     check_kv_layout,
     check_pos_encoding_mode,
@@ -75,14 +76,22 @@ def single_prefill_with_kv_cache(
     rope_theta: Optional[float] = None,
     backend: str = "auto",
     return_lse: bool = False,
+    kv_cache_sf=None,
+    k_scale: Optional[float] = None,
+    v_scale: Optional[float] = None,
 ):
     """Prefill/append attention for one request.  q ``[qo_len, Hq, D]``; k/v ``[kv_len, Hkv, D]`` (NHD)
-    or ``[Hkv, kv_len, D]`` (HND).  Returns ``o`` (and base-2 ``lse [qo_len, Hq]``)."""
+    or ``[Hkv, kv_len, D]`` (HND).  Returns ``o`` (and base-2 ``lse [qo_len, Hq]``).  ``k_scale`` folds into the softmax scale and
+    ``v_scale`` multiplies the output (de-quantisation scales of a low-precision K / V); NVFP4 K / V (``kv_cache_sf``) is refused."""
+    if kv_cache_sf is not None:
+        raise NotImplementedError("single_prefill_with_kv_cache: NVFP4 K / V (kv_cache_sf) is not implemented")
     check_kv_layout(kv_layout)
     check_pos_encoding_mode(pos_encoding_mode)
     d = q.shape[-1]
     if sm_scale is None:
         sm_scale = 1.0 / math.sqrt(d)
+    if k_scale is not None:
+        sm_scale = sm_scale * float(k_scale)
     if kv_layout == "HND":
         k, v = k.transpose(0, 1), v.transpose(0, 1)
     qo_len, kv_len = q.shape[0], k.shape[0]
@@ -135,6 +144,8 @@ def single_prefill_with_kv_cache(
                window_left=window_left, logits_soft_cap=logits_soft_cap, q_data_type=q.dtype,
                custom_mask=mask.flatten() if mask is not None else None, pos_encoding_mode=pos_encoding_mode)
         o, lse = w.run(q, k, v, return_lse=True)
+    if v_scale is not None and float(v_scale) != 1.0:
+        o = (o.float() * float(v_scale)).to(o.dtype)
     if o_dtype is not None and o.dtype != o_dtype:
         o = o.to(o_dtype)
     return (o, lse) if return_lse else o
@@ -422,7 +433,14 @@ class BatchPrefillWithRaggedKVCacheWrapper(_BatchPrefillBase):
              window_left=-1, logits_soft_cap=None, sm_scale=None, rope_scale=None, rope_theta=None,
              q_data_type="float16", kv_data_type=None, o_data_type=None, non_blocking=True, prefix_len_ptr=None,
              token_pos_in_items_ptr=None, token_pos_in_items_len=0, max_item_len_ptr=None, fixed_split_size=None,
-             disable_split_kv=False) -> None:
+             disable_split_kv=False, seq_lens=None, seq_lens_q=None, max_token_per_sequence=None, max_sequence_kv=None,
+             v_indptr=None, o_indptr=None) -> None:
+        """``seq_lens`` / ``seq_lens_q`` / ``max_token_per_sequence`` / ``max_sequence_kv`` restate what the indptr arrays say (the cuDNN
+        backend of the reference wants them); separate element offsets for V and O (``v_indptr`` / ``o_indptr``) are refused."""
+        from .utils import reject_unsupported
+
+        reject_unsupported("BatchPrefillWithRaggedKVCacheWrapper.plan", v_indptr=v_indptr, o_indptr=o_indptr)
+        remember_plan(self, locals())
         self._set_pos_encoding(pos_encoding_mode, num_qo_heads, rope_scale, rope_theta)
         self._check_plan_extras(q_data_type, o_data_type, prefix_len_ptr, token_pos_in_items_ptr, max_item_len_ptr)
         kv_host = kv_indptr.to("cpu", torch.int32)
@@ -437,10 +455,16 @@ class BatchPrefillWithRaggedKVCacheWrapper(_BatchPrefillBase):
 
     begin_forward = plan
 
-    def run(self, q, k, v, *args, q_scale=None, k_scale=None, v_scale=None, out=None, lse=None, return_lse=False,
-            enable_pdl=None, window_left=None):
+    def run(self, q, k, v, *args, q_scale=None, k_scale=None, v_scale=None, o_scale=None, out=None, lse=None, return_lse=False,
+            enable_pdl=None, window_left=None, kv_cache_sf=None):
+        """``o_scale``: calibration scale of the output - the result is multiplied by ``v_scale / o_scale``.  NVFP4 K / V
+        (``kv_cache_sf``) is refused."""
         if not self._planned:
             raise RuntimeError("plan() must be called before run()")
+        if kv_cache_sf is not None:
+            raise NotImplementedError("BatchPrefillWithRaggedKVCacheWrapper.run: NVFP4 K / V (kv_cache_sf) is not implemented")
+        if o_scale is not None:
+            v_scale = (1.0 if v_scale is None else float(v_scale)) / float(o_scale)
         if getattr(self, "_o_cast", None) is not None:
             return self._cast_output(lambda: self.run(q, k, v, *args, q_scale=q_scale, k_scale=k_scale, v_scale=v_scale, lse=lse,
                                                       return_lse=return_lse, enable_pdl=enable_pdl, window_left=window_left), out)
@@ -473,10 +497,19 @@ class BatchPrefillWithRaggedKVCacheWrapper(_BatchPrefillBase):
             out.copy_((out.float() * v_scale).to(out.dtype))
         return (out, lse) if return_lse else out
 
-    forward = run
+    def forward(self, q, k, v, causal=False, pos_encoding_mode="NONE", use_fp16_qk_reduction=False, window_left=-1, logits_soft_cap=None,
+                sm_scale=None, rope_scale=None, rope_theta=None):
+        """Deprecated (use :meth:`run`): the attention parameters given here replace the planned ones, defaults included."""
+        legacy_forward_replan(self, causal=causal, pos_encoding_mode=pos_encoding_mode, window_left=window_left, logits_soft_cap=logits_soft_cap,
+                              sm_scale=sm_scale, rope_scale=rope_scale, rope_theta=rope_theta)
+        return self.run(q, k, v)
 
-    def forward_return_lse(self, q, k, v, **kw):
-        return self.run(q, k, v, return_lse=True, **kw)
+    def forward_return_lse(self, q, k, v, causal=False, pos_encoding_mode="NONE", use_fp16_qk_reduction=False, window_left=-1,
+                           logits_soft_cap=None, sm_scale=None, rope_scale=None, rope_theta=None):
+        """Deprecated (use :meth:`run_return_lse`)."""
+        legacy_forward_replan(self, causal=causal, pos_encoding_mode=pos_encoding_mode, window_left=window_left, logits_soft_cap=logits_soft_cap,
+                              sm_scale=sm_scale, rope_scale=rope_scale, rope_theta=rope_theta)
+        return self.run(q, k, v, return_lse=True)
 
 
 class BatchPrefillWithPagedKVCacheWrapper(_BatchPrefillBase):
@@ -500,6 +533,7 @@ class BatchPrefillWithPagedKVCacheWrapper(_BatchPrefillBase):
              o_data_type=None, non_blocking=True, prefix_len_ptr=None, token_pos_in_items_ptr=None,
              token_pos_in_items_len=0, max_item_len_ptr=None, seq_lens=None, seq_lens_q=None, block_tables=None,
              max_token_per_sequence=None, max_sequence_kv=None, fixed_split_size=None, disable_split_kv=False) -> None:
+        remember_plan(self, locals())
         self._set_pos_encoding(pos_encoding_mode, num_qo_heads, rope_scale, rope_theta)
         self._check_plan_extras(q_data_type, o_data_type, prefix_len_ptr, token_pos_in_items_ptr, max_item_len_ptr)
         self._page_size = page_size
@@ -520,9 +554,16 @@ class BatchPrefillWithPagedKVCacheWrapper(_BatchPrefillBase):
     begin_forward = plan
 
     def run(self, q, paged_kv_cache, *args, q_scale=None, k_scale=None, v_scale=None, out=None, lse=None,
-            return_lse=False, enable_pdl=None, window_left=None, sinks=None):
+            return_lse=False, enable_pdl=None, window_left=None, sinks=None, kv_cache_sf=None,
+            skip_softmax_threshold_scale_factor=None):
+        """``skip_softmax_threshold_scale_factor`` (an approximation knob of the reference's trtllm-gen backend: KV tiles whose
+        logits fall below a threshold skip the softmax) is accepted and not used - every tile is computed exactly.  NVFP4 KV
+        pages (``kv_cache_sf``) are refused here (the decode wrapper reads them)."""
         if not self._planned:
             raise RuntimeError("plan() must be called before run()")
+        if kv_cache_sf is not None:
+            raise NotImplementedError("BatchPrefillWithPagedKVCacheWrapper.run: NVFP4 KV pages (kv_cache_sf) are not implemented; "
+                                      "BatchDecodeWithPagedKVCacheWrapper reads them")
         if getattr(self, "_o_cast", None) is not None:
             return self._cast_output(lambda: self.run(q, paged_kv_cache, *args, q_scale=q_scale, k_scale=k_scale, v_scale=v_scale, lse=lse,
                                                       return_lse=return_lse, enable_pdl=enable_pdl, window_left=window_left, sinks=sinks), out)
@@ -565,10 +606,19 @@ class BatchPrefillWithPagedKVCacheWrapper(_BatchPrefillBase):
             out.copy_((out.float() * v_scale).to(out.dtype))
         return (out, lse) if user_return_lse else out
 
-    forward = run
+    def forward(self, q, paged_kv_cache, causal=False, pos_encoding_mode="NONE", use_fp16_qk_reduction=False, k_scale=None, v_scale=None,
+                window_left=-1, logits_soft_cap=None, sm_scale=None, rope_scale=None, rope_theta=None):
+        """Deprecated (use :meth:`run`): the attention parameters given here replace the planned ones, defaults included."""
+        legacy_forward_replan(self, causal=causal, pos_encoding_mode=pos_encoding_mode, window_left=window_left, logits_soft_cap=logits_soft_cap,
+                              sm_scale=sm_scale, rope_scale=rope_scale, rope_theta=rope_theta)
+        return self.run(q, paged_kv_cache, k_scale=k_scale, v_scale=v_scale)
 
-    def forward_return_lse(self, q, paged_kv_cache, **kw):
-        return self.run(q, paged_kv_cache, return_lse=True, **kw)
+    def forward_return_lse(self, q, paged_kv_cache, causal=False, pos_encoding_mode="NONE", use_fp16_qk_reduction=False, k_scale=None,
+                           v_scale=None, window_left=-1, logits_soft_cap=None, sm_scale=None, rope_scale=None, rope_theta=None):
+        """Deprecated (use :meth:`run_return_lse`)."""
+        legacy_forward_replan(self, causal=causal, pos_encoding_mode=pos_encoding_mode, window_left=window_left, logits_soft_cap=logits_soft_cap,
+                              sm_scale=sm_scale, rope_scale=rope_scale, rope_theta=rope_theta)
+        return self.run(q, paged_kv_cache, k_scale=k_scale, v_scale=v_scale, return_lse=True)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -578,13 +628,16 @@ class BatchPrefillWithPagedKVCacheWrapper(_BatchPrefillBase):
 # ------------------------------------------------------------------------------------------------
 def fmha_varlen(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, qo_segment_offsets: torch.Tensor,
                 kv_segment_offsets: torch.Tensor, plan_info=None, max_qo_len: Optional[int] = None, out=None, lse=None,
-                causal: bool = False, sm_scale: Optional[float] = None, return_lse: bool = False):
-    """Ragged variable-length FMHA (q/k/v ``[nnz, H, D]`` + segment offsets)."""
+                causal: bool = False, sm_scale: Optional[float] = None, q_scale: Optional[float] = None,
+                k_scale: Optional[float] = None, v_scale: Optional[float] = None, o_scale: Optional[float] = None,
+                return_lse: bool = False):
+    """Ragged variable-length FMHA (q/k/v ``[nnz, H, D]`` + segment offsets).  ``q_scale * k_scale`` folds into the softmax scale;
+    the output is multiplied by ``v_scale / o_scale`` (reference prefill.py :3600)."""
     ws = torch.empty(16 << 20, dtype=torch.uint8, device=q.device)
     w = BatchPrefillWithRaggedKVCacheWrapper(ws)
     w.plan(qo_segment_offsets, kv_segment_offsets, q.shape[1], k.shape[1], q.shape[2], head_dim_vo=v.shape[2],
            causal=causal, sm_scale=sm_scale, q_data_type=q.dtype)
-    return w.run(q, k, v, out=out, lse=lse, return_lse=return_lse)
+    return w.run(q, k, v, out=out, lse=lse, return_lse=return_lse, q_scale=q_scale, k_scale=k_scale, v_scale=v_scale, o_scale=o_scale)
 
 
 def fmha_varlen_plan(module, qo_segment_offsets, kv_segment_offsets, num_qo_heads, causal):
@@ -595,7 +648,11 @@ def fmha_varlen_plan(module, qo_segment_offsets, kv_segment_offsets, num_qo_head
 def trtllm_ragged_attention_deepseek(query, key, value, workspace_buffer, seq_lens, max_q_len, max_kv_len, bmm1_scale,
                                      bmm2_scale, o_sf_scale, batch_size, window_left, cum_seq_lens_q, cum_seq_lens_kv,
                                      enable_pdl=False, is_causal=True, return_lse=False, attention_sinks=None, out=None,
-                                     lse=None, skip_softmax_threshold_scale_factor=None):
+                                     lse=None, skip_softmax_threshold_scale_factor=None, sage_attn_sfs=(None, None, None, None),
+                                     num_elts_per_sage_attn_blk=(0, 0, 0, 0), backend: str = "trtllm-gen"):
+    """``backend`` names the reference's kernel family (one native kernel here); SageAttention block scales are refused."""
+    if any(t is not None for t in sage_attn_sfs) or any(int(n) != 0 for n in num_elts_per_sage_attn_blk):
+        raise NotImplementedError("trtllm_ragged_attention_deepseek: SageAttention block scales (sage_attn_sfs) are not implemented")
     if o_sf_scale is not None and float(o_sf_scale) > 0:
         raise NotImplementedError("trtllm_ragged_attention_deepseek: NVFP4 output (o_sf_scale > 0) is not implemented")
     w = BatchPrefillWithRaggedKVCacheWrapper(workspace_buffer)
@@ -623,8 +680,12 @@ def trtllm_batch_context_with_kv_cache(query, kv_cache, workspace_buffer, block_
                                        window_left: int = -1, out=None, out_dtype=None, o_sf_scale=None,
                                        o_sf_vec_size=None, kv_layout: str = "HND", enable_pdl=None, sinks=None,
                                        kv_cache_sf=None, skip_softmax_threshold_scale_factor=None,
-                                       uses_shared_paged_kv_idx: bool = True, lse=None, return_lse: bool = False):
-    """Paged context attention with a block-table interface (causal)."""
+                                       uses_shared_paged_kv_idx: bool = True, causal: bool = True, lse=None,
+                                       return_lse: bool = False):
+    """Paged context attention with a block-table interface; ``causal=False`` = dense / bidirectional attention (no sliding
+    window then, like the reference :4155)."""
+    if not causal and window_left >= 0:
+        raise ValueError("Sliding-window non-causal attention is not supported for the paged context path")
     from .decode import _block_tables_to_indices
     from .utils import reject_unsupported
 
@@ -636,7 +697,7 @@ def trtllm_batch_context_with_kv_cache(query, kv_cache, workspace_buffer, block_
     _, _, _, page_size, hkv, d = paged_kv_strides(k_cache, kv_layout)
     indptr, indices, last = _block_tables_to_indices(block_tables, seq_lens, page_size)
     w = BatchPrefillWithPagedKVCacheWrapper(workspace_buffer, kv_layout)
-    w.plan(cum_seq_lens_q, indptr, indices, last, query.shape[1], hkv, d, page_size, causal=True,
+    w.plan(cum_seq_lens_q, indptr, indices, last, query.shape[1], hkv, d, page_size, causal=bool(causal),
            sm_scale=float(bmm1_scale), window_left=window_left, q_data_type=query.dtype)
     res = w.run(query, (k_cache, v_cache), out=out if (out is None or out.dtype == query.dtype) else None, lse=lse,
                 return_lse=return_lse, sinks=sinks, v_scale=float(bmm2_scale) if float(bmm2_scale) != 1.0 else None)

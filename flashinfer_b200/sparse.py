@@ -12,6 +12,7 @@ import torch
 from . import reference
 from .decode import BatchDecodeWithPagedKVCacheWrapper
 from .prefill import BatchPrefillWithPagedKVCacheWrapper
+from .utils import legacy_forward_replan, remember_plan
 
 
 def convert_bsr_mask_layout(mask: torch.Tensor, indptr: torch.Tensor) -> torch.Tensor:
@@ -43,6 +44,7 @@ class BlockSparseAttentionWrapper:
              use_fp16_qk_reduction: bool = False, logits_soft_cap: Optional[float] = None,
              sm_scale: Optional[float] = None, rope_scale=None, rope_theta=None, q_data_type="float16",
              kv_data_type=None, o_data_type="float16", non_blocking: bool = True) -> None:
+        remember_plan(self, locals())
         if M % R or N % C:
             raise ValueError("M must be a multiple of R and N of C")
         # element-level mask inside the non-zero blocks: ``mask [nnz, R, C]`` (or already in the flattened per-block-row layout of
@@ -103,7 +105,12 @@ class BlockSparseAttentionWrapper:
             res = self._prefill.run(q, (kc, vc), out=out, lse=lse, return_lse=return_lse, **scales)
         return res
 
-    forward = run
+    def forward(self, q, k, v, scale_q=None, scale_k=None, scale_v=None, pos_encoding_mode="NONE", use_fp16_qk_reduction=False,
+                logits_soft_cap=None, sm_scale=None, rope_scale=None, rope_theta=None):
+        """Deprecated (use :meth:`run`): the attention parameters given here replace the planned ones, defaults included."""
+        legacy_forward_replan(self, pos_encoding_mode=pos_encoding_mode, logits_soft_cap=logits_soft_cap, sm_scale=sm_scale, rope_scale=rope_scale,
+                              rope_theta=rope_theta)
+        return self.run(q, k, v, scale_q, scale_k, scale_v)
 
     def end_forward(self) -> None:
         pass
@@ -127,6 +134,7 @@ class VariableBlockSparseAttentionWrapper:
              q_data_type="float16", kv_data_type=None) -> None:
         """``block_mask_map [num_kv_heads, MB, NB]`` bool, ``block_row_sz [num_kv_heads, MB]``,
         ``block_col_sz [num_kv_heads, NB]``.  Heads are folded into the batch dimension."""
+        remember_plan(self, locals())
         hkv, mb, nb = block_mask_map.shape
         self._hq, self._hkv, self._d = num_qo_heads, num_kv_heads, head_dim
         bm = block_mask_map.cpu().bool()
@@ -176,4 +184,9 @@ class VariableBlockSparseAttentionWrapper:
             return o, l
         return o
 
-    forward = run
+    def forward(self, q, k, v, pos_encoding_mode="NONE", use_fp16_qk_reduction=False, logits_soft_cap=None, sm_scale=None, rope_scale=None,
+                rope_theta=None):
+        """Deprecated (use :meth:`run`): the attention parameters given here replace the planned ones, defaults included."""
+        legacy_forward_replan(self, pos_encoding_mode=pos_encoding_mode, logits_soft_cap=logits_soft_cap, sm_scale=sm_scale, rope_scale=rope_scale,
+                              rope_theta=rope_theta)
+        return self.run(q, k, v)

@@ -462,10 +462,37 @@ def reject_unsupported(api: str, **arguments) -> None:
     result computed without it."""
     bad = []
     for name, v in arguments.items():
-        if isinstance(v, tuple) and len(v) == 2:
-            if v[0] is not None and v[0] != v[1]:
+        if isinstance(v, tuple) and len(v) == 2 and not any(isinstance(e, torch.Tensor) for e in v):     # (value, default); a pair of
+            if v[0] is not None and v[0] != v[1]:                                                          # tensors is a value
                 bad.append(name)
         elif v is not None and v is not False:
             bad.append(name)
     if bad:
         raise NotImplementedError(f"{api}: argument(s) {bad} are not implemented by this library")
+
+
+def remember_plan(wrapper, local_vars: dict) -> None:
+    """First line of a wrapper's ``plan()``: keep its arguments so the deprecated ``forward()`` entry points can plan again."""
+    cls = type(wrapper)
+    names = _PLAN_PARAMS.get(cls)
+    if names is None:
+        import inspect
+
+        names = _PLAN_PARAMS[cls] = tuple(n for n in inspect.signature(inspect.unwrap(cls.plan)).parameters if n != "self")
+    wrapper._plan_locals = {k: local_vars[k] for k in names}
+
+
+_PLAN_PARAMS: dict = {}
+
+
+def legacy_forward_replan(wrapper, **overrides) -> None:
+    """The reference's deprecated ``forward(...)`` methods take the attention parameters (causal, pos_encoding_mode, window_left,
+    logits_soft_cap, sm_scale, rope_scale, rope_theta) at call time and they REPLACE what ``begin_forward`` recorded - defaults
+    included (reference prefill.py :2117, decode.py :1159, sparse.py :469).  The plans here bake those parameters in, so a value
+    that differs from the planned one is a new plan with the remembered arguments."""
+    args = getattr(wrapper, "_plan_locals", None)
+    if args is None:
+        raise RuntimeError("begin_forward() / plan() must be called before forward()")
+    diff = {k: v for k, v in overrides.items() if k in args and args[k] != v}
+    if diff:
+        wrapper.plan(**{**args, **diff})

@@ -177,3 +177,82 @@ def test_prefill_wrappers_honour_o_data_type():
     o = pw.run(q, (kc, vc))
     assert o.dtype == torch.float32
     torch.testing.assert_close(o, base.float(), atol=2e-2, rtol=2e-2)
+
+
+def test_deprecated_forward_replaces_the_planned_parameters():
+    """begin_forward() + forward(causal=..., sm_scale=..., ...) of the reference era: the call-time parameters win, defaults included."""
+    torch.manual_seed(3)
+    hq, hkv, d, ps = 4, 2, 64, 4
+    q, k, v = torch.randn(6, hq, d), torch.randn(10, hkv, d), torch.randn(10, hkv, d)
+    ws = torch.empty(1 << 20, dtype=torch.uint8)
+    qo, kv = torch.tensor([0, 6], dtype=torch.int32), torch.tensor([0, 10], dtype=torch.int32)
+    w = fi.BatchPrefillWithRaggedKVCacheWrapper(ws, "NHD")
+    w.begin_forward(qo, kv, hq, hkv, d, causal=True, q_data_type=torch.float32)
+    torch.testing.assert_close(w.forward(q, k, v), fi.single_prefill_with_kv_cache(q, k, v, causal=False))       # forward's default: non-causal
+    torch.testing.assert_close(w.forward(q, k, v, causal=True, sm_scale=0.05, logits_soft_cap=8.0),
+                               fi.single_prefill_with_kv_cache(q, k, v, causal=True, sm_scale=0.05, logits_soft_cap=8.0))
+    o, lse = w.forward_return_lse(q, k, v, causal=True, pos_encoding_mode="ROPE_LLAMA")
+    want = fi.single_prefill_with_kv_cache(q, k, v, causal=True, pos_encoding_mode="ROPE_LLAMA", return_lse=True)
+    torch.testing.assert_close(o, want[0])
+    torch.testing.assert_close(lse, want[1])
+    with pytest.raises(RuntimeError):
+        fi.BatchPrefillWithRaggedKVCacheWrapper(ws, "NHD").forward(q, k, v)
+    kc, vc = torch.zeros(3, ps, hkv, d), torch.zeros(3, ps, hkv, d)
+    kc.view(-1, hkv, d)[:10], vc.view(-1, hkv, d)[:10] = k, v
+    pw = fi.BatchPrefillWithPagedKVCacheWrapper(ws, "NHD")
+    pw.begin_forward(qo, torch.tensor([0, 3], dtype=torch.int32), torch.arange(3, dtype=torch.int32), torch.tensor([2], dtype=torch.int32), hq, hkv, d, ps,
+                     q_data_type=torch.float32)
+    torch.testing.assert_close(pw.forward(q, (kc, vc), causal=True, window_left=3), fi.single_prefill_with_kv_cache(q, k, v, causal=True, window_left=3))
+    dw = fi.BatchDecodeWithPagedKVCacheWrapper(ws, "NHD")
+    dw.begin_forward(torch.tensor([0, 3], dtype=torch.int32), torch.arange(3, dtype=torch.int32), torch.tensor([2], dtype=torch.int32), hq, hkv, d, ps,
+                     q_data_type=torch.float32, sm_scale=0.5)
+    torch.testing.assert_close(dw.forward(q[:1], (kc, vc))[0], fi.single_decode_with_kv_cache(q[0], k, v))     # planned sm_scale replaced by the default
+    o, lse = dw.forward_return_lse(q[:1], (kc, vc), sm_scale=0.05, window_left=4, v_scale=2.0)
+    torch.testing.assert_close(o[0], 2.0 * fi.single_decode_with_kv_cache(q[0], k, v, sm_scale=0.05, window_left=4))
+    assert lse.shape == (1, hq)
+    from flashinfer_b200.sparse import BlockSparseAttentionWrapper
+
+    bw = BlockSparseAttentionWrapper(ws)
+    qs, ks, vs = torch.randn(8, hq, d), torch.randn(8, hkv, d), torch.randn(8, hkv, d)
+    bw.begin_forward(torch.tensor([0, 2, 3], dtype=torch.int32), torch.tensor([0, 1, 1], dtype=torch.int32), 8, 8, 4, 4, hq, hkv, d, q_data_type=torch.float32,
+                     sm_scale=0.3)
+    dense = torch.tensor([[1, 1], [0, 1]], dtype=torch.bool).repeat_interleave(4, 0).repeat_interleave(4, 1)
+    torch.testing.assert_close(bw.forward(qs, ks, vs, sm_scale=0.07), fi.single_prefill_with_kv_cache(qs, ks, vs, custom_mask=dense, sm_scale=0.07))
+
+
+def test_reference_era_keyword_arguments():
+    """Keyword arguments of the reference signatures that were missing: scales of single prefill / fmha_varlen, q_len_per_req of the
+    decode wrapper, causal=False of the trtllm context entry point, the restating plan() arguments of the ragged wrapper."""
+    torch.manual_seed(9)
+    hq, hkv, d, ps = 4, 2, 64, 4
+    q, k, v = torch.randn(6, hq, d), torch.randn(10, hkv, d), torch.randn(10, hkv, d)
+    base = fi.single_prefill_with_kv_cache(q, k, v, causal=True, sm_scale=0.1)
+    torch.testing.assert_close(fi.single_prefill_with_kv_cache(q, k, v, causal=True, sm_scale=0.05, k_scale=2.0, v_scale=3.0), 3.0 * base)
+    with pytest.raises(NotImplementedError):
+        fi.single_prefill_with_kv_cache(q, k, v, kv_cache_sf=(k, v))
+    qo, kv = torch.tensor([0, 6], dtype=torch.int32), torch.tensor([0, 10], dtype=torch.int32)
+    o = fi.prefill.fmha_varlen(q, k, v, qo, kv, causal=True, sm_scale=0.05, q_scale=4.0, k_scale=0.5, v_scale=3.0, o_scale=1.5)
+    torch.testing.assert_close(o, 2.0 * base)
+    ws = torch.empty(1 << 20, dtype=torch.uint8)
+    w = fi.BatchPrefillWithRaggedKVCacheWrapper(ws, "NHD")
+    w.plan(qo, kv, hq, hkv, d, causal=True, sm_scale=0.1, q_data_type=torch.float32, seq_lens=torch.tensor([10]), seq_lens_q=torch.tensor([6]),
+           max_token_per_sequence=6, max_sequence_kv=10)
+    torch.testing.assert_close(w.run(q, k, v, o_scale=0.5), 2.0 * base)
+    with pytest.raises(NotImplementedError):
+        w.plan(qo, kv, hq, hkv, d, v_indptr=kv)
+    # decode wrapper: two query tokens per request == causal append of the newest two
+    kc, vc = torch.zeros(3, ps, hkv, d), torch.zeros(3, ps, hkv, d)
+    kc.view(-1, hkv, d)[:10], vc.view(-1, hkv, d)[:10] = k, v
+    dw = fi.BatchDecodeWithPagedKVCacheWrapper(ws, "NHD")
+    dw.plan(torch.tensor([0, 3], dtype=torch.int32), torch.arange(3, dtype=torch.int32), torch.tensor([2], dtype=torch.int32), hq, hkv, d, ps, q_data_type=torch.float32)
+    got = dw.run(q[:2], (kc, vc), q_len_per_req=2, skip_softmax_threshold_scale_factor=1.0)
+    torch.testing.assert_close(got, fi.single_prefill_with_kv_cache(q[:2], k, v, causal=True))
+    torch.testing.assert_close(dw.run(q[:1], (kc, vc))[0], fi.single_decode_with_kv_cache(q[0], k, v))          # back to one token per request
+    with pytest.raises(ValueError):
+        dw.run(q[:3], (kc, vc), q_len_per_req=2)
+    # trtllm context entry point, bidirectional
+    tables, lens = torch.arange(3, dtype=torch.int32)[None], torch.tensor([10], dtype=torch.int32)
+    o = fi.prefill.trtllm_batch_context_with_kv_cache(q, (kc, vc), ws, tables, lens, 6, 10, 0.1, 1.0, 1, qo, kv, kv_layout="NHD", causal=False)
+    torch.testing.assert_close(o, fi.single_prefill_with_kv_cache(q, k, v, causal=False, sm_scale=0.1))
+    with pytest.raises(ValueError):
+        fi.prefill.trtllm_batch_context_with_kv_cache(q, (kc, vc), ws, tables, lens, 6, 10, 0.1, 1.0, 1, qo, kv, window_left=4, kv_layout="NHD", causal=False)
