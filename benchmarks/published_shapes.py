@@ -154,7 +154,8 @@ def moe():
     w2 = torch.randn(E, H, I, device="cuda", dtype=torch.bfloat16) * 0.03
     logits = torch.randn(T, E, device="cuda")
     bias = torch.randn(E, device="cuda") * 0.1
-    ms = timeit(lambda: trtllm_bf16_moe(logits, bias, x, w1, w2, E, K, 8, 4, I, 0, E, 2.5, RoutingMethodType.DeepSeekV3), graph=True)
+    ms = timeit(lambda: trtllm_bf16_moe(logits, bias, x, w1, w2, E, K, 8, 4, I, 0, E, 2.5, RoutingMethodType.DeepSeekV3,
+                                        use_shuffled_weight=False, weight_layout=0), graph=True)
     row("fused MoE (bf16 weights) T=1024 h=1024 i=1024 E=256 top8 DSv3 routing", ms, 0.131, "trtllm fp4", round(2.0 * T * K * H * I * 3 / ms / 1e9, 1))
     # NVFP4 weights + on-the-fly NVFP4 activations on the block-scaled grouped tcgen05 GEMM (the reference's configuration)
     from flashinfer_b200.fused_moe import trtllm_fp4_block_scale_moe

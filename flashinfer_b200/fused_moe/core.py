@@ -158,9 +158,12 @@ def _route_cpu(logits, bias, k, method, n_group, topk_group, scale, norm):
 
 def fused_topk_deepseek(scores: torch.Tensor, bias: torch.Tensor, n_group: int, topk_group: int, topk: int,
                         routed_scaling_factor: float, topk_values: Optional[torch.Tensor] = None,
-                        topk_indices: Optional[torch.Tensor] = None, launch_with_pdl: bool = True):
-    """DeepSeek-V3 no-aux-loss routing (reference fused_routing_dsv3.py): sigmoid + bias, grouped top-k."""
+                        topk_indices: Optional[torch.Tensor] = None, launch_with_pdl: bool = True,
+                        routing_replay_out: Optional[torch.Tensor] = None):
+    """DeepSeek-V3 no-aux-loss routing (reference fused_routing_dsv3.py): sigmoid + bias, grouped top-k.  ``routing_replay_out``
+    (int16 ``[>= T, topk]``) also receives the selected expert ids."""
     ids, w = route(scores, bias, topk, RoutingMethodType.DeepSeekV3, n_group, topk_group, routed_scaling_factor, True)
+    _replay(routing_replay_out, ids)
     if topk_values is not None:
         topk_values.copy_(w)
         w = topk_values
@@ -560,22 +563,73 @@ def _reject_unsupported(name: str, **kw):
 
 def trtllm_bf16_moe(routing_logits, routing_bias, hidden_states, gemm1_weights, gemm2_weights, num_experts, top_k,
                     n_group, topk_group, intermediate_size, local_expert_offset, local_num_experts,
-                    routed_scaling_factor=None, routing_method_type: int = 0, use_shuffled_weight: bool = False,
-                    weight_layout: int = WeightLayout.MajorK, do_finalize: bool = True, enable_pdl: bool = True,
+                    routed_scaling_factor=None, routing_method_type: int = 0, use_shuffled_weight: bool = True,
+                    weight_layout: int = WeightLayout.BlockMajorK, do_finalize: bool = True, enable_pdl: bool = True,
                     tune_max_num_tokens: int = 8192, activation_type: int = ActivationType.Swiglu.value,
                     norm_topk_prob: bool = True, routing_replay_out=None):
-    """bf16 MoE with fused routing.  Weights are plain K-major ``[E_local, 2I, H]`` / ``[E_local, H, I]``
-    (no pre-shuffling is needed by the TMA-fed grouped GEMM)."""
+    """bf16 MoE with fused routing.  The defaults are the reference's (core.py :2560): weights pre-processed for trtllm-gen
+    (``use_shuffled_weight=True``, ``WeightLayout.BlockMajorK``) - they are converted back ONCE per tensor (cached).  The TMA-fed
+    grouped GEMM itself needs no pre-shuffling: pass ``use_shuffled_weight=False, weight_layout=WeightLayout.MajorK`` with plain
+    K-major ``[E_local, 2I, H]`` / ``[E_local, H, I]`` weights to skip the conversion."""
     # trtllm-gen pre-processed weights (gated-row interleave + shuffle_matrix_a(epilogue_tile_m=128) [+ BlockMajorK]) are
     # converted back to plain MajorK ONCE per weight tensor (cached); the TMA-fed grouped GEMM needs no pre-shuffle
     gemm1_weights = _plain_weights("trtllm_bf16_moe", gemm1_weights, use_shuffled_weight, weight_layout, 128, gated_interleaved=True)
     gemm2_weights = _plain_weights("trtllm_bf16_moe", gemm2_weights, use_shuffled_weight, weight_layout, 128)
     ids, w = route(routing_logits, routing_bias, top_k, routing_method_type, n_group, topk_group, routed_scaling_factor,
                    norm_topk_prob)
-    if routing_replay_out is not None:
-        routing_replay_out.copy_(ids)
+    _replay(routing_replay_out, ids)
     return moe_forward(hidden_states, ids, w, gemm1_weights, gemm2_weights, local_expert_offset, num_experts,
                        activation=_activation_name(activation_type), do_finalize=do_finalize)
+
+
+def _replay(routing_replay_out: Optional[torch.Tensor], ids: torch.Tensor) -> None:
+    """Routing replay (reference fused_routing_dsv3.py :45): the selected expert ids of every token, int16 ``[>= T, top_k]``."""
+    if routing_replay_out is None:
+        return
+    t, k = ids.shape
+    if routing_replay_out.dtype != torch.int16:
+        raise ValueError(f"routing_replay_out must be int16, got {routing_replay_out.dtype}")
+    if routing_replay_out.shape[0] < t or routing_replay_out.shape[1] != k:
+        raise ValueError(f"routing_replay_out shape[0] must be >= {t} and shape[1] must be {k}, got {tuple(routing_replay_out.shape)}")
+    routing_replay_out[:t].copy_(ids)
+
+
+_TAIL_KEYS = frozenset({"do_finalize", "enable_pdl", "tune_max_num_tokens", "activation_type", "norm_topk_prob", "routing_replay_out", "output",
+                        "per_token_scale", "fp8_quantization_type", "use_shuffled_weight", "weight_layout"})
+
+
+def _tail(name: str, kw: dict, ids: Optional[torch.Tensor] = None, supports: Tuple[str, ...] = ()) -> None:
+    """Keyword tail of the trtllm_* entry points (the reference's trailing optional arguments).  Launch / tuning hints (``enable_pdl``,
+    ``tune_max_num_tokens``) do not change the result and are accepted; ``routing_replay_out`` is written; anything that would
+    change the result and is not implemented by this entry point is refused, and an unknown name is a TypeError as usual."""
+    unknown = set(kw) - _TAIL_KEYS
+    if unknown:
+        raise TypeError(f"{name}() got unexpected keyword argument(s) {sorted(unknown)}")
+    bad = []
+    if kw.get("do_finalize", True) is False and "do_finalize" not in supports:
+        bad.append("do_finalize=False")
+    act = kw.get("activation_type")
+    if act is not None and int(act) != int(ActivationType.Swiglu) and "activation_type" not in supports:
+        bad.append(f"activation_type={ActivationType(int(act)).name}")
+    if kw.get("per_token_scale") is not None:
+        bad.append("per_token_scale")
+    fq = kw.get("fp8_quantization_type")
+    if fq is not None and int(fq) != int(Fp8QuantizationType.DeepSeekFp8):
+        bad.append(f"fp8_quantization_type={Fp8QuantizationType(int(fq)).name}")
+    if (kw.get("use_shuffled_weight") or kw.get("weight_layout")) and "weights" not in supports:
+        bad.append("use_shuffled_weight / weight_layout")
+    if bad:
+        raise NotImplementedError(f"{name}: unsupported argument(s) {bad}")
+    if ids is not None:
+        _replay(kw.get("routing_replay_out"), ids)
+
+
+def _into(output: Optional[torch.Tensor], res):
+    """``output=`` of the trtllm_* entry points: the finalized result is written into the caller's buffer."""
+    if output is None:
+        return res
+    output.copy_(res[0] if isinstance(res, (list, tuple)) else res)
+    return output
 
 
 def _unpack_routed(topk_ids: torch.Tensor):
@@ -587,10 +641,14 @@ def _unpack_routed(topk_ids: torch.Tensor):
 
 def trtllm_bf16_routed_moe(topk_ids, hidden_states, gemm1_weights, gemm2_weights, num_experts, top_k, n_group,
                            topk_group, intermediate_size, local_expert_offset, local_num_experts,
-                           routed_scaling_factor=None, routing_method_type: int = 1, use_shuffled_weight: bool = False,
-                           weight_layout: int = WeightLayout.MajorK, do_finalize: bool = True, enable_pdl: bool = True,
-                           tune_max_num_tokens: int = 8192, activation_type: int = ActivationType.Swiglu.value):
+                           routed_scaling_factor=None, routing_method_type: int = 0, use_shuffled_weight: bool = True,
+                           weight_layout: int = WeightLayout.BlockMajorK, do_finalize: bool = True, enable_pdl: bool = True,
+                           tune_max_num_tokens: int = 8192, activation_type: int = ActivationType.Swiglu.value,
+                           routing_replay_out=None):
+    """Pre-routed bf16 MoE (packed ``(expert << 16) | bf16 weight`` words); weight defaults as in :func:`trtllm_bf16_moe`.
+    ``routing_replay_out [>= T, top_k]`` int16 receives the expert ids."""
     ids, w = _unpack_routed(topk_ids)
+    _replay(routing_replay_out, ids)
     gemm1_weights = _plain_weights("trtllm_bf16_routed_moe", gemm1_weights, use_shuffled_weight, weight_layout, 128, gated_interleaved=True)
     gemm2_weights = _plain_weights("trtllm_bf16_routed_moe", gemm2_weights, use_shuffled_weight, weight_layout, 128)
     return moe_forward(hidden_states, ids, w, gemm1_weights, gemm2_weights, local_expert_offset, num_experts,
@@ -604,7 +662,9 @@ def trtllm_fp8_per_tensor_scale_moe(routing_logits, routing_bias, hidden_states,
                                     routing_method_type: int = 0, **kw):
     """fp8 per-tensor MoE on the native fp8 tensor-core pipeline (:func:`moe_forward_fp8_per_tensor`); no weight de-quantisation."""
     _reject_unsupported("trtllm_fp8_per_tensor_scale_moe", use_routing_scales_on_input=use_routing_scales_on_input)
-    ids, w = route(routing_logits, routing_bias, top_k, routing_method_type, n_group, topk_group, routed_scaling_factor)
+    ids, w = route(routing_logits, routing_bias, top_k, routing_method_type, n_group, topk_group, routed_scaling_factor,
+                   kw.get("norm_topk_prob", True))
+    _tail("trtllm_fp8_per_tensor_scale_moe", kw, ids)
     a1, a2 = _fold_gate_scale(output1_scales_scalar, output1_scales_gate_scalar, output2_scales_scalar)
     return moe_forward_fp8_per_tensor(hidden_states, ids, w, gemm1_weights, a1, gemm2_weights, a2, local_expert_offset, num_experts)
 
@@ -618,7 +678,9 @@ def trtllm_fp8_block_scale_moe(routing_logits, routing_bias, hidden_states, hidd
     (shuffle_matrix_a with epilogue_tile_m = 64, reference tests/moe/test_dpsk_fused_moe_fp8.py:684) are converted back once."""
     gemm1_weights = _plain_weights("trtllm_fp8_block_scale_moe", gemm1_weights, use_shuffled_weight, weight_layout, 64)
     gemm2_weights = _plain_weights("trtllm_fp8_block_scale_moe", gemm2_weights, use_shuffled_weight, weight_layout, 64)
-    ids, w = route(routing_logits, routing_bias, top_k, routing_method_type, n_group, topk_group, routed_scaling_factor)
+    ids, w = route(routing_logits, routing_bias, top_k, routing_method_type, n_group, topk_group, routed_scaling_factor,
+                   kw.get("norm_topk_prob", True))
+    _tail("trtllm_fp8_block_scale_moe", kw, ids)
     return moe_forward_fp8_block(hidden_states, hidden_states_scale, ids, w, gemm1_weights, gemm1_weights_scale, gemm2_weights,
                                  gemm2_weights_scale, local_expert_offset, num_experts)
 
@@ -626,10 +688,15 @@ def trtllm_fp8_block_scale_moe(routing_logits, routing_bias, hidden_states, hidd
 def trtllm_fp8_block_scale_routed_moe(topk_ids, routing_bias, hidden_states, hidden_states_scale, gemm1_weights,
                                       gemm1_weights_scale, gemm2_weights, gemm2_weights_scale, num_experts, top_k,
                                       n_group, topk_group, intermediate_size, local_expert_offset, local_num_experts,
-                                      routed_scaling_factor, routing_method_type: int = 1, **kw):
+                                      routed_scaling_factor, routing_method_type: int = 0, use_shuffled_weight: bool = False,
+                                      weight_layout: int = 0, **kw):
+    """Pre-routed form of :func:`trtllm_fp8_block_scale_moe` (packed ``(expert << 16) | bf16 weight`` words)."""
+    gemm1_weights = _plain_weights("trtllm_fp8_block_scale_routed_moe", gemm1_weights, use_shuffled_weight, weight_layout, 64)
+    gemm2_weights = _plain_weights("trtllm_fp8_block_scale_routed_moe", gemm2_weights, use_shuffled_weight, weight_layout, 64)
     ids, w = _unpack_routed(topk_ids)
-    return moe_forward_fp8_block(hidden_states, hidden_states_scale, ids, w, gemm1_weights, gemm1_weights_scale, gemm2_weights,
-                                 gemm2_weights_scale, local_expert_offset, num_experts)
+    _tail("trtllm_fp8_block_scale_routed_moe", kw, ids)
+    return _into(kw.get("output"), moe_forward_fp8_block(hidden_states, hidden_states_scale, ids, w, gemm1_weights, gemm1_weights_scale,
+                                                         gemm2_weights, gemm2_weights_scale, local_expert_offset, num_experts))
 
 
 def trtllm_fp4_block_scale_moe(routing_logits, routing_bias, hidden_states, hidden_states_scale, gemm1_weights,
@@ -641,7 +708,18 @@ def trtllm_fp4_block_scale_moe(routing_logits, routing_bias, hidden_states, hidd
     """NVFP4 weights (``[E, N, K/2]`` packed e2m1 + linear UE4M3 block scales) with bf16 or nvfp4 activations."""
     _reject_unsupported("trtllm_fp4_block_scale_moe", gemm1_bias=gemm1_bias, gemm1_alpha=gemm1_alpha, gemm1_beta=gemm1_beta,
                         gemm1_clamp_limit=gemm1_clamp_limit, gemm2_bias=gemm2_bias)
-    ids, w = route(routing_logits, routing_bias, top_k, routing_method_type, n_group, topk_group, routed_scaling_factor)
+    ids, w = route(routing_logits, routing_bias, top_k, routing_method_type, n_group, topk_group, routed_scaling_factor,
+                   kw.get("norm_topk_prob", True))
+    _tail("trtllm_fp4_block_scale_moe", kw, ids, supports=("do_finalize",))
+    return _into(kw.get("output"), _fp4_block_scale_core(hidden_states, hidden_states_scale, ids, w, gemm1_weights, gemm1_weights_scale, gemm2_weights,
+                                                         gemm2_weights_scale, output1_scale_scalar, output1_scale_gate_scalar, output2_scale_scalar,
+                                                         num_experts, intermediate_size, local_expert_offset, do_finalize))
+
+
+def _fp4_block_scale_core(hidden_states, hidden_states_scale, ids, w, gemm1_weights, gemm1_weights_scale, gemm2_weights, gemm2_weights_scale,
+                          output1_scale_scalar, output1_scale_gate_scalar, output2_scale_scalar, num_experts, intermediate_size,
+                          local_expert_offset, do_finalize):
+    """Shared body of the fused-routing and pre-routed NVFP4 entry points (routing already resolved to ``ids`` / ``w``)."""
     x = hidden_states
     if x.dtype == torch.uint8:
         x = _dequant_nvfp4(x, hidden_states_scale, 1.0)
@@ -661,22 +739,15 @@ def trtllm_fp4_block_scale_routed_moe(topk_ids, routing_bias, hidden_states, hid
                                       gemm2_weights, gemm2_weights_scale, gemm2_bias, output1_scale_scalar,
                                       output1_scale_gate_scalar, output2_scale_scalar, num_experts, top_k, n_group,
                                       topk_group, intermediate_size, local_expert_offset, local_num_experts,
-                                      routed_scaling_factor, routing_method_type: int = 1, do_finalize: bool = True, **kw):
+                                      routed_scaling_factor, routing_method_type: int = 0, do_finalize: bool = True, **kw):
+    """Pre-routed form of :func:`trtllm_fp4_block_scale_moe` (packed ``(expert << 16) | bf16 weight`` words)."""
     _reject_unsupported("trtllm_fp4_block_scale_routed_moe", gemm1_bias=gemm1_bias, gemm1_alpha=gemm1_alpha,
                         gemm1_beta=gemm1_beta, gemm1_clamp_limit=gemm1_clamp_limit, gemm2_bias=gemm2_bias)
     ids, w = _unpack_routed(topk_ids)
-    x = hidden_states
-    if x.dtype == torch.uint8:
-        x = _dequant_nvfp4(x, hidden_states_scale, 1.0)
-    g1 = output1_scale_scalar if output1_scale_scalar is not None else 1.0
-    g2 = output2_scale_scalar if output2_scale_scalar is not None else 1.0
-    g1, g2 = _fold_gate_scale(g1, output1_scale_gate_scalar, g2)
-    if x.is_cuda and do_finalize and hidden_states.shape[-1] % 64 == 0 and intermediate_size % 64 == 0:
-        return moe_forward_nvfp4(x, ids, w, gemm1_weights, gemm1_weights_scale, g1, gemm2_weights, gemm2_weights_scale, g2,
-                                 local_expert_offset, num_experts)
-    w1 = _prepared(_scale_tag("nvfp4deq", g1), [gemm1_weights, gemm1_weights_scale, g1], lambda: _dequant_nvfp4(gemm1_weights, gemm1_weights_scale, g1))
-    w2 = _prepared(_scale_tag("nvfp4deq", g2), [gemm2_weights, gemm2_weights_scale, g2], lambda: _dequant_nvfp4(gemm2_weights, gemm2_weights_scale, g2))
-    return moe_forward(x.to(torch.bfloat16), ids, w, w1, w2, local_expert_offset, num_experts, do_finalize=do_finalize)
+    _tail("trtllm_fp4_block_scale_routed_moe", kw, ids, supports=("do_finalize",))
+    return _into(kw.get("output"), _fp4_block_scale_core(hidden_states, hidden_states_scale, ids, w, gemm1_weights, gemm1_weights_scale, gemm2_weights,
+                                                         gemm2_weights_scale, output1_scale_scalar, output1_scale_gate_scalar, output2_scale_scalar,
+                                                         num_experts, intermediate_size, local_expert_offset, do_finalize))
 
 
 def trtllm_mxint4_block_scale_moe(routing_logits, routing_bias, hidden_states, gemm1_weights, gemm1_weights_scale,
@@ -684,7 +755,9 @@ def trtllm_mxint4_block_scale_moe(routing_logits, routing_bias, hidden_states, g
                                   num_experts, top_k, n_group, topk_group, intermediate_size, local_expert_offset,
                                   local_num_experts, routed_scaling_factor, routing_method_type: int = 0, **kw):
     """MXINT4 weights: int4 pairs in uint8 + bf16 scales per 32 elements."""
-    ids, w = route(routing_logits, routing_bias, top_k, routing_method_type, n_group, topk_group, routed_scaling_factor)
+    ids, w = route(routing_logits, routing_bias, top_k, routing_method_type, n_group, topk_group, routed_scaling_factor,
+                   kw.get("norm_topk_prob", True))
+    _tail("trtllm_mxint4_block_scale_moe", kw, ids)
 
     def deq(wq, sc):
         b = wq.view(torch.uint8)
@@ -701,7 +774,7 @@ def trtllm_mxint4_block_scale_moe(routing_logits, routing_bias, hidden_states, g
     # the weights are expanded to bf16 ONCE per weight tensor (cached load-time preparation), the MoE itself is the native pipeline
     w1 = _prepared("mxint4", [gemm1_weights, gemm1_weights_scale], lambda: deq(gemm1_weights, gemm1_weights_scale))
     w2 = _prepared("mxint4", [gemm2_weights, gemm2_weights_scale], lambda: deq(gemm2_weights, gemm2_weights_scale))
-    return moe_forward(hidden_states, ids, w, w1, w2, local_expert_offset, num_experts)
+    return _into(kw.get("output"), moe_forward(hidden_states, ids, w, w1, w2, local_expert_offset, num_experts))
 
 
 # ------------------------------------------------------------------ cutlass-style entry point

@@ -129,9 +129,10 @@ def mm_bf16(a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = Non
 mm_fp16 = mm_bf16
 
 
-def bmm_bf16(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None,
+def bmm_bf16(A: torch.Tensor, B: torch.Tensor, out: Optional[torch.Tensor] = None,
              out_dtype: torch.dtype = torch.bfloat16, backend: str = "auto"):
-    """a [B, m, k], b [B, k, n] (column-major per batch) -> [B, m, n]."""
+    """A [B, m, k], B [B, k, n] (column-major per batch) -> [B, m, n]."""
+    a, b = A, B
     bsz, m, _ = a.shape
     n = b.shape[-1]
     if out is None:
@@ -141,7 +142,8 @@ def bmm_bf16(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = Non
     return out if out_dtype == out.dtype else out.to(out_dtype)
 
 
-def tgv_gemm_sm100(a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = None, pdl: bool = False):
+def tgv_gemm_sm100(a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = None, pdl: bool = False,
+                   out: Optional[torch.Tensor] = None):
     """Low-latency small-M GEMM (reference tgv_gemm_sm100, gemm_base.py:1446): a [m,k], b [k,n] col-major.
     The swap-AB + split-K + PDL path of gemm_nt is the low-latency kernel here."""
-    return mm_bf16(a, b, bias=bias, pdl=pdl, out_dtype=a.dtype)
+    return mm_bf16(a, b, bias=bias, pdl=pdl, out=out, out_dtype=a.dtype)

@@ -105,10 +105,63 @@ class SegmentGEMMWrapper:
 
 
 def grouped_mm_bf16(a: torch.Tensor, b: torch.Tensor, m_indptr: torch.Tensor, out: Optional[torch.Tensor] = None,
-                    out_dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
-    """``a [cum_m, K]``, ``b [G, N, K]``, ``m_indptr [G+1]`` -> ``[cum_m, N]`` (reference grouped_mm/core.py)."""
+                    out_dtype: torch.dtype = torch.bfloat16, *, backend: str = "auto", tactic: int = -1) -> torch.Tensor:
+    """``a [cum_m, K]``, ``b [G, N, K]``, ``m_indptr [G+1]`` -> ``[cum_m, N]`` (reference grouped_mm/core.py :82).  ``backend`` /
+    ``tactic`` select a cuDNN plan in the reference; there is one native grouped tcgen05 GEMM here."""
     y = segment_gemm(a, b, m_indptr, None, True)
     y = y if y.dtype == out_dtype else y.to(out_dtype)
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
+
+
+def grouped_mm_fp8(a: torch.Tensor, b: torch.Tensor, m_indptr: torch.Tensor, alpha: Optional[torch.Tensor] = None,
+                   out: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.bfloat16, *, backend: str = "auto",
+                   tactic: int = -1) -> torch.Tensor:
+    """Per-tensor FP8 grouped GEMM (reference grouped_mm/core.py :204): ``a [cum_m, k]`` / ``b [G, n, k]`` e4m3 or e5m2, ``alpha [1]``
+    scales the output.  Composed: fp8 values are exact in bf16, so the operands are widened and the bf16 grouped tcgen05 GEMM
+    (fp32 accumulation, bf16 store) runs on the m_indptr segments; ``alpha`` multiplies that result in fp32."""
+    if out is not None:
+        out_dtype = out.dtype
+    y = grouped_mm_bf16(a.to(torch.bfloat16), b.to(torch.bfloat16), m_indptr, None, torch.float32 if alpha is not None else out_dtype)
+    if alpha is not None:
+        y = (y * alpha.float().reshape(())).to(out_dtype)
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
+
+
+def grouped_mm_fp4(a: torch.Tensor, b: torch.Tensor, a_descale: torch.Tensor, b_descale: torch.Tensor, m_indptr: torch.Tensor,
+                   alpha: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.bfloat16,
+                   block_size: int = 16, *, backend: str = "auto", tactic: int = -1) -> torch.Tensor:
+    """Block-scaled FP4 grouped GEMM (reference grouped_mm/core.py :503): ``a [cum_m, k/2]`` / ``b [G, n, k/2]`` packed e2m1 with
+    128x4-swizzled block scales ``a_descale [cum_m, k/block_size]`` / ``b_descale [G, n, k/block_size]`` (ue4m3 for
+    ``block_size=16`` = NVFP4, ue8m0 for 32 = MXFP4), ``alpha [1]`` scales the output.  Composed: the operands are de-quantised
+    (scales un-swizzled) and the bf16 grouped tcgen05 GEMM runs on the m_indptr segments."""
+    from ..quantization.fp4 import _swizzled_sf_size, _unswizzle_index
+
+    if block_size not in (16, 32):
+        raise ValueError(f"grouped_mm_fp4: block_size must be 16 (NVFP4) or 32 (MXFP4), got {block_size}")
+    kind = "ue4m3" if block_size == 16 else "ue8m0"
+
+    def linear_sf(sf, rows, kc):
+        flat = sf.reshape(-1).view(torch.uint8)
+        if flat.numel() < _swizzled_sf_size(rows, kc):
+            raise ValueError(f"block scales hold {flat.numel()} bytes, a 128x4-swizzled [{rows}, {kc}] table needs {_swizzled_sf_size(rows, kc)}")
+        return flat[_unswizzle_index(rows, kc).to(flat.device)].view(rows, kc)
+
+    cum_m, k = a.shape[0], a.shape[1] * 2
+    G, n = b.shape[0], b.shape[1]
+    kc = k // block_size
+    ad = _dq_fp4(a, linear_sf(a_descale, cum_m, kc), block_size, kind)
+    bd = torch.stack([_dq_fp4(b[g], linear_sf(b_descale[g], n, kc), block_size, kind) for g in range(G)])
+    if out is not None:
+        out_dtype = out.dtype
+    y = grouped_mm_bf16(ad, bd, m_indptr, None, torch.float32 if alpha is not None else out_dtype)
+    if alpha is not None:
+        y = (y * alpha.float().reshape(())).to(out_dtype)
     if out is not None:
         out.copy_(y)
         return out

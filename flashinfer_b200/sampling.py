@@ -193,8 +193,9 @@ def _renorm(x, mode, top_p=1.0, top_k=0):
     return out
 
 
-def top_p_renorm_probs(probs, top_p):
-    """Keep the smallest set of entries whose mass reaches ``top_p`` and renormalise."""
+def top_p_renorm_probs(probs, top_p, is_deterministic: bool = False):
+    """Keep the smallest set of entries whose mass reaches ``top_p`` and renormalise.  ``is_deterministic`` selects integer
+    histograms in the reference's radix search; the threshold search here has a fixed reduction order - always deterministic."""
     return _renorm(probs, 0, top_p=top_p)
 
 

@@ -47,18 +47,18 @@ tgv_gemm_sm100_trace = TraceTemplate(
     description="Latency-oriented small-M GEMM with bias (decode projections)", tolerance="cos", test_sizes=_SIZES)
 
 
-def _bmm_bf16_reference(a, b):
-    return torch.bmm(a.to(torch.float32), b.to(torch.float32)).to(torch.bfloat16)
+def _bmm_bf16_reference(A, B):
+    return torch.bmm(A.to(torch.float32), B.to(torch.float32)).to(torch.bfloat16)
 
 
 def _bmm_bf16_init(*, batch=4, M=64, N=1024, K=1024, device="cuda", seed=0):
     _, a, w = _ab(M, N, K, device, seed, batch)
-    return {"a": a, "b": w.transpose(-1, -2)}
+    return {"A": a, "B": w.transpose(-1, -2)}
 
 
 bmm_bf16_trace = TraceTemplate(
     op_type="gemm", name_fmt="bmm_bf16_n{N}_k{K}", axes=[Var("batch"), Var("M"), Const("N"), Const("K")],
-    inputs=[Tensor("a", ("batch", "M", "K")), Tensor("b", ("batch", "K", "N"))], outputs=[Tensor("out", ("batch", "M", "N"), dtype="bfloat16")],
+    inputs=[Tensor("A", ("batch", "M", "K")), Tensor("B", ("batch", "K", "N"))], outputs=[Tensor("out", ("batch", "M", "N"), dtype="bfloat16")],
     reference=_bmm_bf16_reference, init=_bmm_bf16_init, tags=("gemm", "bf16", "batched"), description="Batched bf16 GEMM",
     tolerance="cos", test_sizes=_SIZES)
 

@@ -186,7 +186,7 @@ def _bf16_moe_init(*, seq_len=64, num_experts=8, hidden_size=4096, intermediate_
     w1, w2 = _bf16_weights(g, num_experts, hidden_size, intermediate_size)
     kw = _routing_inputs(g, method, seq_len, num_experts, top_k, 4, 2)
     kw.update(hidden_states=_rand(g, seq_len, hidden_size, scale=0.5).to(torch.bfloat16), gemm1_weights=w1, gemm2_weights=w2,
-              intermediate_size=intermediate_size)
+              intermediate_size=intermediate_size, use_shuffled_weight=False, weight_layout=0)     # plain K-major weights
     return _to(device, kw)
 
 

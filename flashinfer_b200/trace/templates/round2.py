@@ -375,7 +375,7 @@ def _routed_moe_init(*, seq_len=64, num_experts=8, hidden_size=4096, intermediat
     packed = (ids.to(torch.int32) << 16) | (scales.to(torch.bfloat16).view(torch.int16).to(torch.int32) & 0xFFFF)
     return {"topk_ids": packed.to(device), "hidden_states": x.to(device), "gemm1_weights": w1.to(device), "gemm2_weights": w2.to(device),
             "num_experts": num_experts, "top_k": top_k, "n_group": None, "topk_group": None, "intermediate_size": intermediate_size,
-            "local_expert_offset": 0, "local_num_experts": num_experts}
+            "local_expert_offset": 0, "local_num_experts": num_experts, "use_shuffled_weight": False, "weight_layout": 0}     # plain K-major weights
 
 
 def _moe_first(got, expected, kwargs):

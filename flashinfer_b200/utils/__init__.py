@@ -70,12 +70,12 @@ def next_positive_power_of_2(x: int) -> int:
     return 1 << (x - 1).bit_length()
 
 
-def ceil_div(a: int, b: int) -> int:
-    return (a + b - 1) // b
+def ceil_div(x: int, y: int) -> int:
+    return (x + y - 1) // y
 
 
-def round_up(a: int, b: int) -> int:
-    return ceil_div(a, b) * b
+def round_up(x: int, y: int) -> int:
+    return ceil_div(x, y) * y
 
 
 def unpack_paged_kv_cache(

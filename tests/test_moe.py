@@ -9,6 +9,8 @@ from flashinfer_b200.fused_moe import (RoutingMethodType, cutlass_fused_moe, fus
 from flashinfer_b200.fused_moe.core import _route_cpu
 from flashinfer_b200.gemm import SegmentGEMMWrapper, grouped_gemm_nt_masked, grouped_mm_bf16
 
+PLAIN = dict(use_shuffled_weight=False, weight_layout=0)      # plain K-major weights (the reference's defaults are shuffled BlockMajorK)
+
 
 def _mk(T, E, H, I, dev, dtype=torch.bfloat16, seed=0):
     g = torch.Generator(device="cpu").manual_seed(seed)
@@ -35,7 +37,7 @@ def test_route_cpu_methods():
 
 def test_moe_cpu_matches_dense_expert_loop():
     x, w1, w2, logits = _mk(9, 4, 32, 16, "cpu", torch.float32)
-    out = trtllm_bf16_moe(logits, None, x, w1, w2, 4, 2, None, None, 16, 0, 4, routing_method_type=1)
+    out = trtllm_bf16_moe(logits, None, x, w1, w2, 4, 2, None, None, 16, 0, 4, routing_method_type=1, **PLAIN)
     ids, w = route(logits, None, 2, 1)
     ref = torch.zeros_like(x)
     for t in range(9):
@@ -108,7 +110,7 @@ def test_trtllm_bf16_moe_deepseek_routing_gpu():
     T, E, K, H, I = 65, 256, 8, 1024, 256
     x, w1, w2, logits = _mk(T, E, H, I, "cuda")
     bias = (torch.randn(E) * 0.1).cuda()
-    out = trtllm_bf16_moe(logits, bias, x, w1, w2, E, K, 8, 4, I, 0, E, 2.5, RoutingMethodType.DeepSeekV3)
+    out = trtllm_bf16_moe(logits, bias, x, w1, w2, E, K, 8, 4, I, 0, E, 2.5, RoutingMethodType.DeepSeekV3, **PLAIN)
     w_, ids = fused_topk_deepseek(logits, bias, 8, 4, K, 2.5)
     ref = moe_reference(x, ids, w_, w1, w2)
     assert (out.float() - ref).abs().max().item() < 3e-2 * max(1.0, ref.abs().max().item())
@@ -345,10 +347,10 @@ def test_bf16_moe_accepts_shuffled_weights_cpu():
     w1 = w1.to(torch.bfloat16)
     w2 = w2.to(torch.bfloat16)
     x = x.to(torch.bfloat16)
-    ref = trtllm_bf16_moe(logits, None, x, w1, w2, 4, 2, None, None, 32, 0, 4, routing_method_type=1)
+    ref = trtllm_bf16_moe(logits, None, x, w1, w2, 4, 2, None, None, 32, 0, 4, routing_method_type=1, **PLAIN)
     w1s = torch.stack([shuffle_matrix_a(core.reorder_rows_for_gated_act_gemm(w1[e]).view(torch.uint8), 128) for e in range(4)]).view(torch.bfloat16)
     w2s = torch.stack([shuffle_matrix_a(w2[e].view(torch.uint8), 128) for e in range(4)]).view(torch.bfloat16)
-    got = trtllm_bf16_moe(logits, None, x, w1s, w2s, 4, 2, None, None, 32, 0, 4, routing_method_type=1, use_shuffled_weight=True)
+    got = trtllm_bf16_moe(logits, None, x, w1s, w2s, 4, 2, None, None, 32, 0, 4, routing_method_type=1, use_shuffled_weight=True, weight_layout=0)
     torch.testing.assert_close(got.float(), ref.float())
 
 
@@ -417,3 +419,44 @@ def test_cute_dsl_and_cutlass_nvfp4_native_gpu():
     res = cutlass_fused_moe(x, ids, wts, w1q, w2q, torch.bfloat16, quant_scales=[one, w1sf, a1, one, w2sf, a2])[0]
     cos = torch.nn.functional.cosine_similarity(res.float().flatten(), ref.flatten(), dim=0)
     assert cos > 0.97, float(cos)
+
+
+def test_trtllm_moe_keyword_tail_cpu():
+    """Trailing keyword arguments of the trtllm_* entry points: hints accepted, routing replay written, output= honoured, unknown names
+    and unimplemented semantics refused (they used to be swallowed by **kw)."""
+    from flashinfer_b200.fused_moe import core
+
+    x, w1, w2, logits = _mk(9, 4, 32, 16, "cpu", torch.float32)
+    replay = torch.full((12, 2), -1, dtype=torch.int16)
+    out = trtllm_bf16_moe(logits, None, x, w1, w2, 4, 2, None, None, 16, 0, 4, routing_method_type=1, routing_replay_out=replay, **PLAIN)
+    ids, w = route(logits, None, 2, 1)
+    assert torch.equal(replay[:9].int(), ids.int()) and (replay[9:] == -1).all()
+    packed = (ids.to(torch.int32) << 16) | (w.to(torch.bfloat16).view(torch.int16).to(torch.int32) & 0xFFFF)
+    replay2 = torch.zeros(9, 2, dtype=torch.int16)
+    out2 = core.trtllm_bf16_routed_moe(packed, x, w1, w2, 4, 2, None, None, 16, 0, 4, routing_replay_out=replay2, **PLAIN)
+    assert torch.equal(replay2.int(), ids.int())
+    torch.testing.assert_close(out2, out, atol=2e-2, rtol=2e-2)
+    with pytest.raises(ValueError):
+        trtllm_bf16_moe(logits, None, x, w1, w2, 4, 2, None, None, 16, 0, 4, routing_method_type=1, routing_replay_out=torch.zeros(9, 2, dtype=torch.int32), **PLAIN)
+    w_, i_ = fused_topk_deepseek(torch.randn(5, 16), torch.zeros(16), 4, 2, 3, 1.0, routing_replay_out=(r3 := torch.zeros(5, 3, dtype=torch.int16)))
+    assert torch.equal(r3.int(), i_.int())
+    # mxint4 entry point (pure torch preparation + the bf16 pipeline): hints, output=, replay; unknown / unimplemented refused
+    E, H, I = 4, 64, 32
+    g = torch.Generator().manual_seed(0)
+    q1, q2 = torch.randint(0, 256, (E, 2 * I, H // 2), generator=g, dtype=torch.uint8), torch.randint(0, 256, (E, H, I // 2), generator=g, dtype=torch.uint8)
+    s1, s2 = torch.rand(E, 2 * I, H // 32, generator=g).bfloat16() * 0.02, torch.rand(E, H, I // 32, generator=g).bfloat16() * 0.02
+    xx, lg = torch.randn(7, H, generator=g).bfloat16(), torch.randn(7, E, generator=g)
+    args = (lg, None, xx, q1, s1, None, None, None, q2, s2, E, 2, None, None, I, 0, E, None)
+    base = core.trtllm_mxint4_block_scale_moe(*args, routing_method_type=1)
+    buf, rep = torch.empty(7, H, dtype=torch.bfloat16), torch.zeros(7, 2, dtype=torch.int16)
+    got = core.trtllm_mxint4_block_scale_moe(*args, routing_method_type=1, enable_pdl=True, tune_max_num_tokens=64, output=buf, routing_replay_out=rep,
+                                             norm_topk_prob=True, do_finalize=True)
+    assert got is buf and torch.equal(buf, base if torch.is_tensor(base) else base[0])
+    assert torch.equal(rep.int(), route(lg, None, 2, 1)[0].int())
+    with pytest.raises(TypeError):
+        core.trtllm_mxint4_block_scale_moe(*args, routing_method_type=1, not_an_argument=1)
+    with pytest.raises(NotImplementedError):
+        core.trtllm_mxint4_block_scale_moe(*args, routing_method_type=1, do_finalize=False)
+    with pytest.raises(NotImplementedError):
+        core.trtllm_fp8_block_scale_moe(lg, None, xx, None, q1, s1, q2, s2, E, 2, None, None, I, 0, E, None, routing_method_type=1,
+                                        fp8_quantization_type=core.Fp8QuantizationType.MxFp8)
