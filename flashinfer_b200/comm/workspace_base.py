@@ -25,11 +25,15 @@ class AllReduceFusionWorkspace:
         self.comm = TPCommunicator(group, max_token_num, hidden_dim, dtype)
         self._destroyed = False
 
-    def is_buffer_size_sufficient(self, token_num: int, hidden_dim: int, tp_size: Optional[int] = None,
-                                  dtype: Optional[torch.dtype] = None) -> bool:
+    def is_buffer_size_sufficient(self, tp_size: int, num_tokens: int, hidden_dim: int, dtype: Optional[torch.dtype] = None,
+                                  use_oneshot=None, strategy=None) -> bool:
+        """Argument order of the reference (workspace_base.py :54): ``(tp_size, num_tokens, hidden_dim, dtype, use_oneshot)``; the MNNVL
+        workspace names its last argument ``strategy``.  One-shot / two-shot use the same heap here, so neither changes the answer."""
+        if tp_size != self.world_size:
+            return False
         esz = torch.empty(0, dtype=dtype or self.dtype).element_size()
         cap = self.max_token_num * self.hidden_dim * torch.empty(0, dtype=self.dtype).element_size()
-        return token_num * hidden_dim * esz <= cap and hidden_dim == self.hidden_dim
+        return num_tokens * hidden_dim * esz <= cap and hidden_dim == self.hidden_dim
 
     def destroy(self) -> None:
         self._destroyed = True

@@ -336,3 +336,41 @@ def test_mamba_spec_decoding_forms_on_cuda():
         res[dev] = [t.float().cpu() for t in (y, st, buf, y2, st2)]
     for got, want in zip(res["cuda"], res["cpu"]):
         torch.testing.assert_close(got, want, atol=3e-2, rtol=3e-2)
+
+
+def _mc_worker(rank, world, port, errs):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world)
+    try:
+        from flashinfer_b200.comm.mixed_comm import MixedCommHandler, MixedCommMode, MixedCommOp, run_mixed_comm
+
+        x = lambda r, rows: (torch.arange(rows * 1024, dtype=torch.float32).view(rows, 1024) % 7 * (r + 1)).bfloat16().cuda()  # noqa: E731
+        for tp, dp, ops in ((world, None, (MixedCommOp.ALLREDUCE,)), (None, world, (MixedCommOp.ALLGATHER, MixedCommOp.REDUCESCATTER))):
+            h = MixedCommHandler(rank, world, rank, world, 0, 1, tp, dp, None, None, torch.bfloat16, torch.device("cuda", rank), max_tokens=256, hidden=1024)
+            assert MixedCommMode.FUSED_OPT_WAITS_MC in h.valid_mode_list
+            for op in ops:
+                rows = 64 * world if op == MixedCommOp.REDUCESCATTER else 64
+                fused = run_mixed_comm(op, h, x(rank, rows))                                   # autotune -> the NVLS kernels
+                nccl = run_mixed_comm(op, h, x(rank, rows), None, MixedCommMode.NCCL_ONE)
+                errs[(rank, op.name)] = float((fused.float() - nccl.float()).abs().max())
+            h.shutdown()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_mixed_comm_fused_modes_two_gpus():
+    import socket
+
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    errs = mp.Manager().dict()
+    mp.spawn(_mc_worker, args=(2, port, errs), nprocs=2, join=True)
+    assert len(errs) == 6 and max(errs.values()) < 0.5, dict(errs)

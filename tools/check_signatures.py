@@ -28,7 +28,10 @@ def ref_functions(path: Path):
     def params(fn):
         a = fn.args
         names = [x.arg for x in a.posonlyargs + a.args + a.kwonlyargs]
-        return [n for n in names if n not in ("self", "cls")], a.vararg is not None, a.kwarg is not None
+        pos = a.posonlyargs + a.args
+        defaults = {x.arg: ast.unparse(d) for x, d in zip(pos[len(pos) - len(a.defaults):], a.defaults)}
+        defaults.update({x.arg: ast.unparse(d) for x, d in zip(a.kwonlyargs, a.kw_defaults) if d is not None})
+        return [n for n in names if n not in ("self", "cls")], defaults, [x.arg for x in pos if x.arg not in ("self", "cls")]
 
     for node in tree.body:
         if isinstance(node, (ast.FunctionDef, ast.AsyncFunctionDef)) and not node.name.startswith("_"):
@@ -40,8 +43,23 @@ def ref_functions(path: Path):
     return out
 
 
+def _norm(text: str) -> str:
+    """Comparable spelling of a default: enum members by their last name component, quotes unified, dtype prefixes dropped."""
+    t = text.strip().replace('"', "'")
+    if t.startswith("<") and ":" in t:                       # <Enum.Member: 3>
+        t = t[1:].split(":")[0]
+    for pre in ("torch.", "ActivationType.", "WeightLayout.", "RoutingMethodType.", "Fp8QuantizationType.", "SfLayout.", "GatedActType."):
+        t = t.replace(pre, "")
+    t = t.replace(".value", "")
+    try:
+        return repr(float(t)) if t.replace(".", "", 1).replace("-", "", 1).replace("e", "", 1).isdigit() else t
+    except ValueError:
+        return t
+
+
 def main() -> int:
-    root = Path(sys.argv[1] if len(sys.argv) > 1 else "/root/reference/flashinfer")
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    root = Path(args[0] if args else "/root/reference/flashinfer")
     files = sorted(p for p in root.rglob("*.py") if "gdn_kernels" not in p.parts and "data" not in p.parts and "triton" not in p.parts
                    and "cute_dsl" not in p.parts and "jit" not in p.parts and "tuning_configs" not in p.parts)
     n_checked = n_missing_fn = n_gap = 0
@@ -56,7 +74,7 @@ def main() -> int:
             mod = importlib.import_module("flashinfer_b200" + ("." + mod_name if mod_name else ""))
         except Exception:
             continue
-        for qual, (names, _, _) in ref_functions(f).items():
+        for qual, (names, ref_defaults, ref_pos) in ref_functions(f).items():
             obj = mod
             try:
                 for part in qual.split("."):
@@ -77,6 +95,21 @@ def main() -> int:
             if lack:
                 n_gap += 1
                 print(f"PARAMS   {mod_name}.{qual}: {', '.join(lack)}")
+            if "--defaults" in sys.argv:
+                diffs = []
+                for n, d in ref_defaults.items():
+                    p = ours.get(n)
+                    if p is None or p.default is inspect.Parameter.empty:
+                        continue
+                    if _norm(d) != _norm(repr(p.default)):
+                        diffs.append(f"{n}: ref {d} / here {p.default!r}")
+                if diffs:
+                    print(f"DEFAULTS {mod_name}.{qual}: " + "; ".join(diffs))
+            if "--order" in sys.argv:
+                mine = [n for n, p in ours.items() if p.kind in (p.POSITIONAL_ONLY, p.POSITIONAL_OR_KEYWORD) and n not in ("self", "cls")]
+                common = [n for n in ref_pos if n in mine]
+                if common != [n for n in mine if n in common]:
+                    print(f"ORDER    {mod_name}.{qual}: ref {common} / here {[n for n in mine if n in common]}")
     print(f"{n_checked} callables compared, {n_gap} with missing parameters, {n_missing_fn} missing callables")
     return 0
 
