@@ -71,8 +71,11 @@ class TRTLLMAllReduceFusionWorkspace(AllReduceFusionWorkspace):
 
 def trtllm_create_ipc_workspace_for_all_reduce_fusion(tp_rank: int, tp_size: int, max_token_num: int, hidden_dim: int,
                                                       use_fp32_lamport: bool = False, group: Optional[dist.ProcessGroup] = None,
-                                                      create_metadata: bool = False, dtype: torch.dtype = torch.bfloat16):
-    """Returns ``(handles, workspace)`` like the reference; ``workspace`` is the object to pass as ``workspace_ptrs``."""
+                                                      create_metadata: bool = False, comm_backend=None, use_symm_dev_mem: bool = False,
+                                                      *, dtype: torch.dtype = torch.bfloat16):
+    """Returns ``(handles, workspace)`` like the reference; ``workspace`` is the object to pass as ``workspace_ptrs``.
+    ``comm_backend`` (how the reference exchanges IPC handles) and ``use_symm_dev_mem`` (its allocator choice) have no counterpart:
+    the heap is always a symmetric allocation of this library."""
     ws = TRTLLMAllReduceFusionWorkspace(tp_size, tp_rank, max_token_num, hidden_dim, dtype, group)
     if create_metadata:
         return [ws], ws, ws.metadata
@@ -84,8 +87,38 @@ def trtllm_destroy_ipc_workspace_for_all_reduce_fusion(workspace, group=None) ->
         w.destroy()
 
 
-trtllm_create_ipc_workspace_for_all_reduce = trtllm_create_ipc_workspace_for_all_reduce_fusion
-trtllm_destroy_ipc_workspace_for_all_reduce = trtllm_destroy_ipc_workspace_for_all_reduce_fusion
+# ------------------------------------------------------------------ legacy pointer-table workspace (reference trtllm_ar.py :430, :809)
+_LEGACY: dict = {}          # handle value -> workspace
+
+
+class _IpcHandles(list):
+    """What ``trtllm_create_ipc_workspace_for_all_reduce`` returns: seven rows of ``tp_size`` integers, shaped like the reference's
+    peer pointer tables (comm buffers x2, barrier flags x2, Lamport buffers x3).  The integers are opaque handles of this library's
+    symmetric heap (NOT device addresses): ``trtllm_custom_all_reduce`` resolves the communicator from any of them."""
+
+    workspace = None
+
+
+def trtllm_create_ipc_workspace_for_all_reduce(rank: int, tp_size: int, max_token_num: int, hidden_dim: int,
+                                               group: Optional[dist.ProcessGroup] = None, *, dtype: torch.dtype = torch.bfloat16):
+    ws = TRTLLMAllReduceFusionWorkspace(tp_size, rank, max_token_num, hidden_dim, dtype, group)
+    base = (id(ws) & 0xFFFFFFFFFF) << 16
+    handles = _IpcHandles([base + row * 256 + r for r in range(tp_size)] for row in range(7))
+    handles.workspace = ws
+    for row in handles:
+        for h in row:
+            _LEGACY[h] = ws
+    return handles
+
+
+def trtllm_destroy_ipc_workspace_for_all_reduce(workspace, group=None) -> None:
+    seen = set()
+    for row in workspace:
+        for h in (row if isinstance(row, (list, tuple)) else [row]):
+            ws = _LEGACY.pop(h, None) if isinstance(h, int) else h
+            if ws is not None and id(ws) not in seen:
+                seen.add(id(ws))
+                ws.destroy()
 
 
 def trtllm_lamport_initialize(buffer_ptr: int, size: int, dtype: torch.dtype) -> None:
@@ -214,22 +247,57 @@ def trtllm_allreduce_fusion(allreduce_in: torch.Tensor, world_size: int, world_r
                                                          residual_in.view(token_num, hidden_dim).float()).to(allreduce_out.dtype))
 
 
-def trtllm_custom_all_reduce(inp: torch.Tensor, world_size: int, world_rank: int, token_num: int, hidden_dim: int,
-                             workspace_ptrs, launch_with_pdl: bool = False, flag_value: int = 0,
-                             peer_comm_buffer_ptrs=None, peer_barrier_ptrs_in=None, peer_barrier_ptrs_out=None,
-                             bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
-                             weight: Optional[torch.Tensor] = None, weight_pre_residual_norm=None, eps: Optional[float] = None,
-                             intermediate_buffer=None, lamport_peer_comm_buffer_ptrs_0=None, lamport_peer_comm_buffer_ptrs_1=None,
-                             lamport_peer_comm_buffer_ptrs_2=None, out: Optional[torch.Tensor] = None, strategy_code=None,
-                             config_code=None, fusion_op_code: int = AllReduceFusionOp.NONE) -> torch.Tensor:
-    ws = workspace_ptrs[0] if isinstance(workspace_ptrs, (list, tuple)) else workspace_ptrs
-    x = inp.view(token_num, hidden_dim)
-    if fusion_op_code == AllReduceFusionOp.RESIDUAL_RMS_NORM:
-        if bias is not None:
-            x = x + bias
-        return ws.comm.allreduce_add_rmsnorm(x, residual.view(token_num, hidden_dim), weight, eps or 1e-6,
-                                             out=out.view(token_num, hidden_dim) if out is not None else None, two_shot=False)
-    return ws.comm.allreduce_add_rmsnorm(x, None, None, out=out.view(token_num, hidden_dim) if out is not None else None)
+def trtllm_custom_all_reduce(inp: torch.Tensor, out: torch.Tensor, tp_size: int, tp_rank: int, token_num: int, fusion_op_code: int,
+                             strategy_code, config_code, launch_with_pdl: bool, flag_value: int, peer_comm_buffer_ptrs,
+                             peer_barrier_ptrs_in=None, peer_barrier_ptrs_out=None, bias: Optional[torch.Tensor] = None,
+                             residual: Optional[torch.Tensor] = None, weight: Optional[torch.Tensor] = None,
+                             weight_pre_residual_norm: Optional[torch.Tensor] = None, eps: Optional[float] = None,
+                             intermediate_buffer: Optional[torch.Tensor] = None, lamport_peer_comm_buffer_ptrs_0=None,
+                             lamport_peer_comm_buffer_ptrs_1=None, lamport_peer_comm_buffer_ptrs_2=None) -> None:
+    """Legacy custom all-reduce in the reference's calling convention (trtllm_ar.py :809): ``out [token_num, hidden]`` receives the sum of
+    ``inp`` over the TP group; with ``fusion_op_code = RESIDUAL_RMS_NORM`` it receives ``rmsnorm(sum + bias + residual) * weight`` and
+    ``intermediate_buffer`` the pre-norm sum.  ``peer_comm_buffer_ptrs`` is a row (tensor or list) of the table returned by
+    :func:`trtllm_create_ipc_workspace_for_all_reduce`, or that table / its workspace object.  The strategy / config codes pick between
+    the reference's one-shot / two-shot kernels; the communicator chooses by message size here.  The other pointer rows and
+    ``flag_value`` belong to the reference's barrier protocol (the communicator keeps its own epoch)."""
+    ws = _resolve_legacy(peer_comm_buffer_ptrs)
+    if ws.world_size != tp_size:
+        raise ValueError(f"workspace was created for tp_size {ws.world_size}, called with {tp_size}")
+    hidden = inp.numel() // token_num
+    x = inp.view(token_num, hidden)
+    o = out.view(token_num, hidden)
+    op = int(fusion_op_code)
+    if op == AllReduceFusionOp.NONE:
+        ws.comm.allreduce_add_rmsnorm(x, None, None, out=o)
+        return
+    if op != AllReduceFusionOp.RESIDUAL_RMS_NORM:
+        raise NotImplementedError(f"trtllm_custom_all_reduce: fusion_op_code {op} (use trtllm_allreduce_fusion for the quantising patterns)")
+    if weight_pre_residual_norm is not None:
+        raise NotImplementedError("trtllm_custom_all_reduce: weight_pre_residual_norm")
+    if bias is not None:
+        x = x + bias
+    # the communicator updates its residual operand in place (residual += sum): that operand is the caller's intermediate_buffer
+    # (the reference's output for the pre-norm sum) or a scratch copy - the caller's residual stays an input
+    pre = intermediate_buffer.view(token_num, hidden) if intermediate_buffer is not None else torch.empty_like(x)
+    pre.copy_(residual.view(token_num, hidden))
+    ws.comm.allreduce_add_rmsnorm(x, pre, weight, eps or 1e-6, out=o, two_shot=False)
+
+
+def _resolve_legacy(ptrs):
+    if isinstance(ptrs, AllReduceFusionWorkspace):
+        return ptrs
+    if isinstance(ptrs, _IpcHandles):
+        return ptrs.workspace
+    first = ptrs
+    while isinstance(first, (list, tuple)):
+        first = first[0]
+    if isinstance(first, AllReduceFusionWorkspace):
+        return first
+    key = int(first.flatten()[0]) if isinstance(first, torch.Tensor) else int(first)
+    ws = _LEGACY.get(key)
+    if ws is None:
+        raise ValueError("peer_comm_buffer_ptrs does not come from trtllm_create_ipc_workspace_for_all_reduce (or the workspace was destroyed)")
+    return ws
 
 
 # ------------------------------------------------------------------ MoE fusions
@@ -270,17 +338,23 @@ def trtllm_moe_allreduce_fusion(world_size: int, world_rank: int, token_num: int
 
 def trtllm_moe_finalize_allreduce_fusion(allreduce_in: torch.Tensor, residual_in: torch.Tensor, norm_weight: torch.Tensor,
                                          expanded_idx_to_permuted_idx: torch.Tensor, norm_out: torch.Tensor,
-                                         residual_out: torch.Tensor, launch_with_pdl: bool, workspace, world_rank: int,
-                                         world_size: int, eps: float, shared_expert_output: Optional[torch.Tensor] = None,
-                                         expert_scale_factor: Optional[torch.Tensor] = None, quant_out=None, scale_out=None,
-                                         scale_factor=None, layout_code=None) -> None:
-    """MoE finalize (top-k weighted un-permute, native kernel) + shared-expert add, then AR + residual + RMSNorm."""
+                                         residual_out: torch.Tensor, quant_out: Optional[torch.Tensor], scale_out: Optional[torch.Tensor],
+                                         workspace_ptrs, launch_with_pdl: bool, world_rank: int, world_size: int, eps: float,
+                                         shared_expert_output: Optional[torch.Tensor] = None,
+                                         expert_scale_factor: Optional[torch.Tensor] = None,
+                                         routed_scaling_factor: Optional[float] = None, *, scale_factor=None, layout_code=None) -> None:
+    """MoE finalize (top-k weighted un-permute, native kernel) + shared-expert add, then AR + residual + RMSNorm; argument order of the
+    reference (trtllm_ar.py :1140).  ``routed_scaling_factor`` multiplies the routed sum before the shared expert is added - it is
+    folded into the per-slot scales."""
     from .. import jit
     from ..utils import dtype_code, stream_ptr
 
-    ws = workspace[0] if isinstance(workspace, (list, tuple)) else workspace
+    ws = workspace_ptrs[0] if isinstance(workspace_ptrs, (list, tuple)) else workspace_ptrs
     T, K = expanded_idx_to_permuted_idx.shape
     H = allreduce_in.shape[-1]
+    if routed_scaling_factor is not None and float(routed_scaling_factor) != 1.0:
+        base = expert_scale_factor.float() if expert_scale_factor is not None else torch.ones(T, K, device=allreduce_in.device)
+        expert_scale_factor = base * float(routed_scaling_factor)
     if allreduce_in.is_cuda and ws.comm.push_supported(T, H, allreduce_in.dtype):
         # ONE kernel: top-k weighted un-permute (+ shared expert) -> one-shot push all-reduce -> + residual -> RMSNorm (-> NVFP4 quant)
         _push_fused(ws.comm, None, AllReduceFusionPattern.kMoEFinalizeARResidualRMSNorm, residual_in=residual_in.view(T, H),

@@ -510,8 +510,8 @@ def trtllm_batch_decode_with_kv_cache(query: torch.Tensor, kv_cache, workspace_b
                                       out: Optional[torch.Tensor] = None, out_dtype=None, o_sf_scale=None,
                                       o_sf_vec_size=None, sinks=None, kv_layout: str = "HND", enable_pdl=None,
                                       backend: str = "auto", q_len_per_req: Optional[int] = 1, o_scale=None,
-                                      mask=None, max_q_len=None, cum_seq_lens_q=None, kv_cache_sf=None,
-                                      skip_softmax_threshold_scale_factor=None, uses_shared_paged_kv_idx: bool = True,
+                                      mask=None, max_q_len=None, cum_seq_lens_q=None, skip_softmax_threshold_scale_factor=None,
+                                      kv_cache_sf=None, uses_shared_paged_kv_idx: bool = True,
                                       lse=None, return_lse: bool = False):
     """``query [B * q_len_per_req, Hq, D]``; ``kv_cache`` a ``(k, v)`` tuple or ``[pages, 2, ...]`` tensor in
     ``kv_layout``; ``block_tables [B, max_pages]``; ``bmm1_scale`` is the softmax scale (q/k scales folded in)."""

@@ -647,8 +647,8 @@ def fmha_varlen_plan(module, qo_segment_offsets, kv_segment_offsets, num_qo_head
 
 def trtllm_ragged_attention_deepseek(query, key, value, workspace_buffer, seq_lens, max_q_len, max_kv_len, bmm1_scale,
                                      bmm2_scale, o_sf_scale, batch_size, window_left, cum_seq_lens_q, cum_seq_lens_kv,
-                                     enable_pdl=False, is_causal=True, return_lse=False, attention_sinks=None, out=None,
-                                     lse=None, skip_softmax_threshold_scale_factor=None, sage_attn_sfs=(None, None, None, None),
+                                     enable_pdl=False, is_causal=True, return_lse=False, attention_sinks=None,
+                                     skip_softmax_threshold_scale_factor=None, out=None, lse=None, sage_attn_sfs=(None, None, None, None),
                                      num_elts_per_sage_attn_blk=(0, 0, 0, 0), backend: str = "trtllm-gen"):
     """``backend`` names the reference's kernel family (one native kernel here); SageAttention block scales are refused."""
     if any(t is not None for t in sage_attn_sfs) or any(int(n) != 0 for n in num_elts_per_sage_attn_blk):

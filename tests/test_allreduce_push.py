@@ -123,7 +123,7 @@ def _worker(rank, world, port, errs):
         local = ((rows[idx.long()].float() * wts[..., None]).sum(1) + shared.float()).bfloat16().float()
         tot = local.clone()
         dist.all_reduce(tot)
-        comm.trtllm_moe_finalize_allreduce_fusion(rows, res, gamma, idx, norm_out, res_out, True, ws, rank, world, eps, shared, wts)
+        comm.trtllm_moe_finalize_allreduce_fusion(rows, res, gamma, idx, norm_out, res_out, None, None, ws, True, rank, world, eps, shared, wts)
         torch.cuda.synchronize()
         r_ref = tot.bfloat16().float() + res.float()
         n_ref = r_ref * torch.rsqrt(r_ref.pow(2).mean(-1, keepdim=True) + eps) * gamma.float()
