@@ -92,8 +92,8 @@ class MoEInputs:
         return [getattr(self, n) for n in MoEInputs._FIELDS]
 
     @classmethod
-    def from_list(cls, values):
-        return cls(**dict(zip(cls._FIELDS, values)))
+    def from_list(cls, lst):
+        return cls(**dict(zip(cls._FIELDS, lst)))
 
     @classmethod
     def idx(cls, name: str) -> int:
@@ -786,7 +786,8 @@ def cutlass_fused_moe(input: torch.Tensor, token_selected_experts: torch.Tensor,
                       output: Optional[torch.Tensor] = None, enable_alltoall: bool = False,
                       use_deepseek_fp8_block_scale: bool = False, use_w4_group_scaling: bool = False,
                       use_mxfp8_act_scaling: bool = False, min_latency_mode: bool = False, use_packed_weights: bool = False,
-                      tune_max_num_tokens: int = 8192, enable_pdl=None, activation_type=ActivationType.Swiglu):
+                      tune_max_num_tokens: int = 8192, enable_pdl=None, activation_type=ActivationType.Swiglu,
+                      swizzled_input_sf: bool = True):
     """Pre-routed MoE (reference core.py:775): ``fc1 [E_local, 2I, H]`` (= cat([w3/up, w1/gate])), ``fc2 [E_local, H, I]``.
     ``ep_rank`` selects the local expert range; ``tp_*`` only describe how the caller sharded I."""
     e_local = fc1_expert_weights.shape[0]
@@ -815,7 +816,18 @@ def cutlass_fused_moe(input: torch.Tensor, token_selected_experts: torch.Tensor,
         w1q, w2q = w1.view(torch.uint8).reshape(e_local, w1.shape[1], -1), w2.view(torch.uint8).reshape(e_local, w2.shape[1], -1)
         a1 = (quant_scales[2].float() * quant_scales[0].float()).reshape(-1)
         a2 = (quant_scales[5].float() * quant_scales[3].float()).reshape(-1)
-        xb = _dequant_nvfp4(x, input_sf, 1.0 / quant_scales[0].float()).to(output_dtype) if x.dtype == torch.uint8 else x.to(output_dtype)
+        if x.dtype == torch.uint8:                  # NVFP4 activations: block scales 128x4-swizzled by default (reference :916), linear after an
+            if input_sf is None:                    # FP4 all-gather / all-to-all (swizzled_input_sf=False)
+                raise ValueError("cutlass_fused_moe: NVFP4 input needs input_sf")
+            sf = input_sf
+            if swizzled_input_sf:
+                from ..quantization.fp4 import _unswizzle_index
+
+                kc = x.shape[-1] * 2 // 16
+                sf = input_sf.reshape(-1).view(torch.uint8)[_unswizzle_index(x.shape[0], kc).to(input_sf.device)].view(x.shape[0], kc)
+            xb = _dequant_nvfp4(x, sf, 1.0 / quant_scales[0].float()).to(output_dtype)
+        else:
+            xb = x.to(output_dtype)
         res = moe_forward_nvfp4(xb, ids, wts, w1q, quant_scales[1], a1, w2q, quant_scales[4], a2, off, total, out=output)
     else:
         xb = x if x.dtype == output_dtype else x.to(output_dtype)

@@ -47,8 +47,16 @@ def mxfp8_quantize(input: torch.Tensor, is_sf_swizzled_layout: bool = True, alig
     return q, sf
 
 
-def mxfp8_dequantize_host(input: torch.Tensor, scale_tensor: torch.Tensor, is_sf_swizzled_layout: bool = True) -> torch.Tensor:
-    """Reference dequantiser (any device): returns fp32 ``[m, k]``."""
+def mxfp8_dequantize_host(input: torch.Tensor, scale_tensor: torch.Tensor, is_sf_swizzled_layout: bool = True,
+                          sf_swizzle_layout=None) -> torch.Tensor:
+    """Reference dequantiser (any device): returns fp32 ``[m, k]``.  ``sf_swizzle_layout`` (``SfLayout.layout_128x4`` or
+    ``layout_linear``) overrides ``is_sf_swizzled_layout`` when given."""
+    if sf_swizzle_layout is not None:
+        from .fp4 import SfLayout
+
+        if sf_swizzle_layout not in (SfLayout.layout_128x4, SfLayout.layout_linear):
+            raise ValueError(f"mxfp8_dequantize_host: sf_swizzle_layout must be layout_128x4 or layout_linear, got {sf_swizzle_layout}")
+        is_sf_swizzled_layout = sf_swizzle_layout == SfLayout.layout_128x4
     m, k = input.shape
     kc = k // 32
     sf = scale_tensor.reshape(-1)

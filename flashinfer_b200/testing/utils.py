@@ -60,8 +60,11 @@ class _L2Flusher:
 def bench_gpu_time_with_cuda_event(fn: Callable, dry_run_iters: Optional[int] = None, repeat_iters: Optional[int] = None,
                                    dry_run_time_ms: int = 25, repeat_time_ms: int = 100, l2_flush: bool = True,
                                    sleep_after_run: bool = False, input_args: Tuple = (), input_kwargs: Optional[dict] = None,
-                                   cold_l2_cache: Optional[bool] = None) -> List[float]:
-    """Per-iteration times (ms) measured with CUDA events; the L2 is flushed before every timed call."""
+                                   cold_l2_cache: Optional[bool] = None, *, l2_flush_size_mb: Optional[int] = None,
+                                   l2_flush_device: Optional[str] = None, aggregate_op=None) -> List[float]:
+    """Per-iteration times (ms) measured with CUDA events; the L2 is flushed before every timed call.  ``l2_flush_size_mb`` /
+    ``l2_flush_device`` (deprecated in the reference too) are accepted: the flush buffer is sized from the device's L2 here.
+    ``aggregate_op`` is applied by :func:`bench_gpu_time` (cross-rank reduction of the samples)."""
     input_kwargs = input_kwargs or {}
     if cold_l2_cache is not None:
         l2_flush = cold_l2_cache
@@ -102,7 +105,8 @@ def bench_gpu_time_with_cudagraph(fn: Callable, dry_run_iters: Optional[int] = N
                                   dry_run_time_ms: int = 25, repeat_time_ms: int = 100, num_iters_within_graph: int = 10,
                                   l2_flush: bool = True, sleep_after_run: bool = False, input_args: Tuple = (),
                                   input_kwargs: Optional[dict] = None, rotate_inputs: Optional[Sequence[Tuple]] = None,
-                                  cold_l2_cache: Optional[bool] = None) -> List[float]:
+                                  cold_l2_cache: Optional[bool] = None, *, l2_flush_size_mb: Optional[int] = None,
+                                  l2_flush_device: Optional[str] = None, aggregate_op=None) -> List[float]:
     """Times a CUDA graph holding ``num_iters_within_graph`` calls (launch overhead amortised).  With
     ``rotate_inputs`` (a list of argument tuples whose total footprint exceeds the L2) every call inside the
     graph sees cold inputs; otherwise the L2 is flushed between graph replays only."""
@@ -154,7 +158,8 @@ def bench_gpu_time_with_cudagraph(fn: Callable, dry_run_iters: Optional[int] = N
 def bench_gpu_time_with_cupti(fn: Callable, dry_run_iters: Optional[int] = None, repeat_iters: Optional[int] = None,
                               dry_run_time_ms: int = 25, repeat_time_ms: int = 100, l2_flush: bool = True, sleep_after_run: bool = False,
                               input_args: Tuple = (), input_kwargs: Optional[dict] = None, cold_l2_cache: Optional[bool] = None,
-                              use_cuda_graph: bool = False) -> List[float]:
+                              use_cuda_graph: bool = False, *, l2_flush_size_mb: Optional[int] = None,
+                              l2_flush_device: Optional[str] = None, aggregate_op=None) -> List[float]:
     """Per-iteration DEVICE time (ms) from CUPTI activity records: the sum of the durations of the kernels / copies an iteration
     launches, so launch gaps and host overhead are excluded (reference testing/utils.py:937, which reads the records through
     cupti-python; here through torch.profiler, whose Kineto backend records the same CUPTI activities).  Every iteration runs inside a
@@ -224,7 +229,8 @@ def bench_gpu_time(fn: Callable, dry_run_iters: Optional[int] = None, repeat_ite
                    dry_run_time_ms: int = 25, repeat_time_ms: int = 100, l2_flush: bool = True, use_cuda_graph: bool = False,
                    num_iters_within_graph: int = 10, sleep_after_run: bool = False, enable_cupti: bool = False,
                    input_args: Tuple = (), input_kwargs: Optional[dict] = None, cold_l2_cache: Optional[bool] = None,
-                   aggregate_op: Optional[str] = None, group=None) -> List[float]:
+                   aggregate_op: Optional[str] = None, group=None, *, l2_flush_size_mb: Optional[int] = None,
+                   l2_flush_device: Optional[str] = None) -> List[float]:
     """Unified entry (reference testing/utils.py:1546).  ``enable_cupti`` measures device time from CUPTI activity records
     (:func:`bench_gpu_time_with_cupti`).  ``aggregate_op='max'`` reduces every sample over the ranks of ``group``."""
     if enable_cupti and not use_cuda_graph:
@@ -243,7 +249,7 @@ def bench_gpu_time(fn: Callable, dry_run_iters: Optional[int] = None, repeat_ite
         torch.distributed.all_reduce(n, op=torch.distributed.ReduceOp.MIN, group=group)
         t = t[: int(n)]
         op = {"max": torch.distributed.ReduceOp.MAX, "min": torch.distributed.ReduceOp.MIN,
-              "sum": torch.distributed.ReduceOp.SUM}[aggregate_op]
+              "sum": torch.distributed.ReduceOp.SUM}[getattr(aggregate_op, "__name__", aggregate_op)]      # "max" or the builtin max (reference)
         torch.distributed.all_reduce(t, op=op, group=group)
         times = t.tolist()
     return times

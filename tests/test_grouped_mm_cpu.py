@@ -61,3 +61,47 @@ def test_grouped_mm_fp4_swizzled_scales(block_size):
         fi.grouped_mm.grouped_mm_fp4(aq, bq, asf, bsf, indptr, block_size=8)
     with pytest.raises(ValueError):
         fi.grouped_mm.grouped_mm_fp4(aq, bq, asf.reshape(-1)[:100], bsf, indptr, block_size=block_size)
+
+
+def test_cutlass_fused_moe_input_sf_layouts_and_small_parity_arguments(monkeypatch):
+    """NVFP4 activations: ``input_sf`` is 128x4-swizzled by default (reference core.py :916), linear with ``swizzled_input_sf=False`` - both
+    must give the same result; plus ``mxfp8_dequantize_host(sf_swizzle_layout=)`` and ``MoEInputs.from_list(lst=)``."""
+    from flashinfer_b200.fused_moe import core
+    from flashinfer_b200.quantization.fp4 import SfLayout
+    from flashinfer_b200.quantization.fp8 import mxfp8_dequantize_host, mxfp8_quantize
+
+    torch.manual_seed(2)
+    T, H, I, E, K = 5, 64, 32, 4, 2
+    x = torch.randn(T, H).bfloat16()
+    one = torch.tensor([1.0])
+    xq_s, sf_s = fp4_quantize(x, one, 16, False, True)
+    xq_l, sf_l = fp4_quantize(x, one, 16, False, False)
+    assert torch.equal(xq_s, xq_l)
+    w1, w2 = (torch.randn(E, 2 * I, H) * 0.1).bfloat16(), (torch.randn(E, H, I) * 0.1).bfloat16()
+    q1 = [fp4_quantize(w1[e], one, 16, False, False) for e in range(E)]
+    q2 = [fp4_quantize(w2[e], one, 16, False, False) for e in range(E)]
+    w1q, w1sf = torch.stack([a for a, _ in q1]), torch.stack([b.view(2 * I, H // 16) for _, b in q1])
+    w2q, w2sf = torch.stack([a for a, _ in q2]), torch.stack([b.view(H, I // 16) for _, b in q2])
+    ids = torch.randint(0, E, (T, K), dtype=torch.int32)
+    wts = torch.rand(T, K)
+    ones = torch.ones(E)
+    scales = [one, w1sf, ones, one, w2sf, ones]
+    # the NVFP4 pipeline itself is CUDA-only: stand in for it and look at the activations it is handed
+    monkeypatch.setattr(core, "moe_forward_nvfp4", lambda xb, *a, **k: xb.clone())
+    a = core.cutlass_fused_moe(xq_s, ids, wts, w1q, w2q, torch.bfloat16, quant_scales=scales, input_sf=sf_s)
+    b = core.cutlass_fused_moe(xq_l, ids, wts, w1q, w2q, torch.bfloat16, quant_scales=scales, input_sf=sf_l, swizzled_input_sf=False)
+    a, b = (t[0] if isinstance(t, (list, tuple)) else t for t in (a, b))
+    torch.testing.assert_close(a, b)
+    assert torch.nn.functional.cosine_similarity(a.float().flatten(), x.float().flatten(), dim=0) > 0.98           # = the de-quantised input
+    with pytest.raises(ValueError):
+        core.cutlass_fused_moe(xq_s, ids, wts, w1q, w2q, torch.bfloat16, quant_scales=scales)
+    y = torch.randn(130, 64).bfloat16()
+    yq, ysf = mxfp8_quantize(y, True)
+    d0 = mxfp8_dequantize_host(yq, ysf)
+    torch.testing.assert_close(mxfp8_dequantize_host(yq, ysf, False, sf_swizzle_layout=SfLayout.layout_128x4), d0)
+    yq2, ysf2 = mxfp8_quantize(y, False)
+    torch.testing.assert_close(mxfp8_dequantize_host(yq2, ysf2, True, sf_swizzle_layout=SfLayout.layout_linear), d0)
+    with pytest.raises(ValueError):
+        mxfp8_dequantize_host(yq, ysf, sf_swizzle_layout=SfLayout.layout_8x4)
+    fields = core.MoEInputs._FIELDS
+    assert core.MoEInputs.from_list(lst=list(range(len(fields)))).__dict__[fields[1]] == 1
