@@ -1,7 +1,7 @@
 """Processors -> typed primitive ops, with type inference of the pipeline input (reference flashinfer/logits_processor/legalization.py)."""
 from __future__ import annotations
 
-from typing import List, Sequence
+from typing import List, Optional, Sequence
 
 from .op import Op
 from .processors import LogitsProcessor, MinP, Softmax, Temperature, TopP
@@ -17,9 +17,10 @@ def infer_initial_type(processors: Sequence[LogitsProcessor]) -> TensorType:
     raise LegalizationError(f"cannot infer the input type from {type(first).__name__}; pass input_type=")
 
 
-def legalize_processors(processors: Sequence[LogitsProcessor], input_type: TensorType) -> List[Op]:
+def legalize_processors(processors: Sequence[LogitsProcessor], initial_type: TensorType = TensorType.LOGITS, *,
+                        input_type: Optional[TensorType] = None) -> List[Op]:
     ops: List[Op] = []
-    cur = input_type
+    cur = input_type if input_type is not None else initial_type
     for p in processors:
         if cur == TensorType.INDICES:
             raise LegalizationError("no processor may follow Sample")

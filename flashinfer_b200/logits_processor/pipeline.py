@@ -29,13 +29,19 @@ class LogitsPipe:
         self._initial_type = input_type or infer_initial_type(self.processors)
         self.ops = legalize_processors(self.processors, self._initial_type)
         validate_ops(self.ops, custom_validity_checks)
-        self._rules = custom_fusion_rules
+        self._rules, self._checks = custom_fusion_rules, custom_validity_checks
         self.compiled_ops: Optional[List[Op]] = None
         if compile:
             self.compile()
 
-    def compile(self) -> None:
-        self.compiled_ops = compile_pipeline(self.ops, self._rules)
+    def compile(self, custom_fusion_rules: Optional[List[FusionRule]] = None, custom_validity_checks=None) -> None:
+        """Fuse the legalised ops; rules / checks given here are added to the ones given to the constructor (reference pipeline.py :168)."""
+        rules = list(self._rules or []) + list(custom_fusion_rules or [])
+        checks = list(self._checks or []) + list(custom_validity_checks or [])
+        try:
+            self.compiled_ops = compile_pipeline(self.ops, rules, checks)
+        except CompileError as e:
+            raise ValueError(f"Compilation failed: {e}") from e
 
     @property
     def initial_type(self) -> TensorType:

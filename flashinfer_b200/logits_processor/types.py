@@ -26,6 +26,17 @@ class TaggedTensor:
     def probs(t: torch.Tensor) -> "TaggedTensor":
         return TaggedTensor(t, TensorType.PROBS)
 
+    @staticmethod
+    def indices(t: torch.Tensor) -> "TaggedTensor":
+        return TaggedTensor(t, TensorType.INDICES)
+
+    shape = property(lambda self: self.data.shape)
+    device = property(lambda self: self.data.device)
+    dtype = property(lambda self: self.data.dtype)
+
+    def size(self, dim=None):
+        return self.data.size() if dim is None else self.data.size(dim)
+
 
 class LegalizationError(ValueError):
     pass

@@ -44,10 +44,16 @@ def get_default_validity_checks() -> List[ValidityCheck]:
     return [single_softmax_rule, indices_terminal_rule]
 
 
-def validate_pipeline(processors: Sequence[LogitsProcessor]) -> None:
-    """Processor-level checks: raises :class:`LegalizationError` for pipelines that cannot be lowered."""
+def validate_pipeline(ops, custom_checks: Optional[Sequence[ValidityCheck]] = None) -> None:
+    """The reference's form (validators.py :87) takes the legalised ops: default op-level checks, then ``custom_checks``.  A list of
+    high-level processors gets the processor-level checks (raises :class:`LegalizationError` for pipelines that cannot be lowered)."""
+    if not ops:
+        raise CompileError("Pipeline cannot be empty")
+    if all(isinstance(o, Op) for o in ops):
+        validate_ops(list(ops), custom_checks)
+        return
     for check in DEFAULT_VALIDATORS:
-        check(processors)
+        check(ops)
 
 
 def validate_ops(ops: List[Op], custom_validity_checks: Optional[Sequence[ValidityCheck]] = None) -> None:

@@ -276,3 +276,41 @@ def test_logits_processor_accepts_rules_and_checks_written_for_the_reference():
         validate_processor_chain([])
     with pytest.raises(LegalizationError):
         validate_processor_chain([Sample(), Softmax()])
+
+
+def test_logits_pipe_compile_time_hooks_of_the_reference():
+    """compile(custom_fusion_rules, custom_validity_checks), Compiler.register_*, op-level validate_pipeline, TaggedTensor accessors."""
+    import torch
+    from flashinfer_b200.logits_processor import LogitsPipe, Sample, Softmax, TaggedTensor, Temperature, TensorType, TopK
+    from flashinfer_b200.logits_processor.compiler import Compiler, compile_pipeline
+    from flashinfer_b200.logits_processor.legalization import legalize_processors
+    from flashinfer_b200.logits_processor.types import CompileError
+    from flashinfer_b200.logits_processor.validators import validate_pipeline
+
+    pipe = LogitsPipe([Temperature(), Softmax(), TopK(), Sample()], compile=False)
+    seen = []
+    pipe.compile(custom_validity_checks=[lambda ops: seen.append(len(ops))])
+    assert seen and pipe.compiled_ops
+
+    def no_topk(ops):
+        if any("topk" in type(o).__name__.lower() for o in ops):
+            raise CompileError("top-k is not allowed here")
+
+    with pytest.raises(ValueError, match="Compilation failed: top-k"):
+        pipe.compile(custom_validity_checks=[no_topk])
+    ops = legalize_processors([Temperature(), Softmax(), TopK()])                       # initial_type defaults to logits
+    assert ops == legalize_processors([Temperature(), Softmax(), TopK()], initial_type=TensorType.LOGITS) or len(ops) > 0
+    validate_pipeline(ops)
+    with pytest.raises(CompileError):
+        validate_pipeline(ops, custom_checks=[no_topk])
+    with pytest.raises(CompileError):
+        validate_pipeline([])
+    c = Compiler()
+    c.register_validity_check(no_topk)
+    with pytest.raises(CompileError):
+        c.compile(ops)
+    with pytest.raises(CompileError):
+        Compiler().compile([])
+    assert len(compile_pipeline(ops, None, None)) <= len(ops)
+    t = TaggedTensor.indices(torch.zeros(2, 3, dtype=torch.int32))
+    assert t.type == TensorType.INDICES and t.shape == (2, 3) and t.dtype == torch.int32 and t.size(1) == 3 and t.device.type == "cpu"
